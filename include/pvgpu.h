@@ -1,0 +1,412 @@
+/*
+ * pvgpu.h -- C ABI of the B200-native trace path for POV-Ray ("pvgpu").
+ *
+ * This is the drop-in boundary.  POV-Ray has no plugin/FFI interface for its
+ * render path, so the seam is cut where `TraceTask::Run` (source/backend/render/tracetask.cpp:287)
+ * would call `TracePixel`/`Trace` (source/core/render/tracepixel.cpp:311, trace.cpp:135): the parsed
+ * scene (`SceneData`, source/core/scene/scenedata.h:85-263) is flattened ONCE into the plain tables
+ * declared here, and rectangles obtained from `ViewData::GetNextRectangle`
+ * (source/backend/scene/view.cpp:236) are rendered by `pvgpu_render`, whose output layout is what
+ * `ViewData::CompletedRectangle` (view.cpp:405) expects (row-major RGBT floats).
+ *
+ * Every table record cites the reference type it is a flat image of.  Numeric types follow the
+ * reference: geometry FP64 (DBL), colours / finish / interior FP32 (COLC, SNGL), bounding boxes and
+ * mesh vertices FP32 (BBoxScalar, MeshVector).
+ *
+ * Conventions: plain C, no exceptions across the ABI; every function returns 0 on success or a
+ * negative PVGPU_E_* code and leaves a message retrievable with pvgpu_last_error() (thread local).
+ * Caller owns every input array (copied during the call); the library owns device memory.
+ * There is NO CPU fallback: every render/trace entry point fails with PVGPU_E_NO_DEVICE when no CUDA
+ * device is usable.
+ */
+#ifndef PVGPU_H
+#define PVGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVGPU_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define PVGPU_OK              0
+#define PVGPU_E_INVALID      -1   /* bad argument / inconsistent tables                        */
+#define PVGPU_E_UNSUPPORTED  -2   /* scene uses a feature outside the hot-path scope           */
+#define PVGPU_E_NO_DEVICE    -3   /* no usable CUDA device (there is no CPU fallback)          */
+#define PVGPU_E_CUDA         -4   /* CUDA runtime error                                        */
+#define PVGPU_E_IO           -5   /* file could not be read / written                          */
+#define PVGPU_E_ABORTED      -6   /* the cooperate callback asked to stop (Task::Cooperate)    */
+#define PVGPU_E_OVERFLOW     -7   /* a device-side fixed capacity was exceeded                 */
+
+/* ---- object table ------------------------------------------------------------------------ */
+
+/* Primitive kinds (ObjectBase subclasses, source/core/shape/). */
+enum {
+    PVGPU_OBJ_SPHERE           = 1,  /* sphere.h:73    p[0..2]=Center p[3]=Radius; aux=Do_Ellipsoid        */
+    PVGPU_OBJ_BOX              = 2,  /* box.h:90       p[0..2]=bounds[0] p[3..5]=bounds[1]                  */
+    PVGPU_OBJ_PLANE            = 3,  /* plane.h:76     p[0..2]=Normal_Vector p[3]=Distance                  */
+    PVGPU_OBJ_QUADRIC          = 4,  /* quadric.h:79   p[0..2]=Square_Terms p[3..5]=Mixed_Terms p[6..8]=Terms p[9]=Constant */
+    PVGPU_OBJ_TORUS            = 5,  /* torus.h:80     p[0]=MajorRadius p[1]=MinorRadius; aux=spindle mode (0 = plain torus), p[2]=mSpindleTipYSqr */
+    PVGPU_OBJ_MESH             = 6,  /* mesh.h:107     mesh = index into mesh table                         */
+    PVGPU_OBJ_CSG_UNION        = 7,  /* csg.h CSGUnion        children in index list                        */
+    PVGPU_OBJ_CSG_INTERSECTION = 8,  /* csg.h CSGIntersection (difference = intersection + inverted kids)   */
+    PVGPU_OBJ_CSG_MERGE        = 9   /* csg.h CSGMerge                                                      */
+};
+
+/* Object flags: the reference's ObjectBase::Flags bits verbatim (source/core/scene/object.h:88-117). */
+#define PVGPU_NO_SHADOW_FLAG          0x00000001u
+#define PVGPU_INVERTED_FLAG           0x00000004u
+#define PVGPU_STURM_FLAG              0x00000040u
+#define PVGPU_OPAQUE_FLAG             0x00000080u
+#define PVGPU_MULTITEXTURE_FLAG       0x00000100u
+#define PVGPU_INFINITE_FLAG           0x00000200u
+#define PVGPU_HOLLOW_FLAG             0x00000800u
+#define PVGPU_UV_FLAG                 0x00002000u
+#define PVGPU_DOUBLE_ILLUMINATE_FLAG  0x00004000u
+#define PVGPU_NO_IMAGE_FLAG           0x00008000u
+#define PVGPU_NO_REFLECTION_FLAG      0x00010000u
+#define PVGPU_NO_GLOBAL_LIGHTS_FLAG   0x00020000u
+#define PVGPU_CUTAWAY_TEXTURES_FLAG   0x10000000u
+
+/* One ObjectBase (object.h:173-200) plus the subclass parameters. 168 bytes. */
+typedef struct pvgpu_object {
+    uint32_t type;               /* PVGPU_OBJ_*                                                     */
+    uint32_t flags;              /* ObjectBase::Flags                                               */
+    int32_t  texture;            /* ObjectBase::Texture          -> texture table index, -1 = none  */
+    int32_t  interior_texture;   /* ObjectBase::Interior_Texture -> texture table index, -1 = none  */
+    int32_t  interior;           /* ObjectBase::interior         -> interior table index, -1 = none */
+    int32_t  transform;          /* ObjectBase::Trans            -> transform table index, -1 = none*/
+    int32_t  parent;             /* enclosing CSG object (object index), -1 for frame-level objects */
+    uint32_t child_first, child_count;   /* CompoundObject::children -> range in the index list     */
+    uint32_t clip_first,  clip_count;    /* ObjectBase::Clip         -> range in the index list     */
+    uint32_t bound_first, bound_count;   /* ObjectBase::Bound        -> range in the index list     */
+    int32_t  mesh;               /* PVGPU_OBJ_MESH: mesh table index                                */
+    uint32_t aux;                /* see PVGPU_OBJ_* comments                                        */
+    float    bbox[6];            /* ObjectBase::BBox: lowerLeft xyz, size xyz (boundingbox.h:93)    */
+    uint32_t reserved;
+    double   p[10];              /* see PVGPU_OBJ_* comments                                        */
+} pvgpu_object;
+
+/* TRANSFORM (source/core/math/matrix.h): row-major 4x4 `matrix` and `inverse`. */
+typedef struct pvgpu_transform {
+    double matrix[16];
+    double inverse[16];
+} pvgpu_transform;
+
+/* ---- bounding tree ----------------------------------------------------------------------- */
+
+/* One BBOX_TREE node (boundingbox.h:172-178), children stored contiguously.
+ * count > 0: inner node, children are nodes [first, first+count).
+ * count == 0: leaf, `first` is the object index (scene tree) or triangle index (mesh tree). */
+#define PVGPU_NODE_INFINITE 1u
+typedef struct pvgpu_node {
+    float    lo[3];              /* BoundingBox::lowerLeft, verbatim FP32 */
+    float    size[3];            /* BoundingBox::size,      verbatim FP32 */
+    uint32_t first;
+    uint16_t count;              /* BBOX_TREE::Entries  */
+    uint16_t flags;              /* BBOX_TREE::Infinite */
+} pvgpu_node;
+
+/* ---- meshes ------------------------------------------------------------------------------ */
+
+/* MESH_TRIANGLE (source/core/shape/mesh.h:89-106), indices relative to the mesh's own arrays. */
+#define PVGPU_TRI_SMOOTH    1u
+#define PVGPU_TRI_THREETEX  2u
+typedef struct pvgpu_triangle {
+    float    perp[3];            /* Perp                                   */
+    float    distance;           /* Distance                               */
+    int32_t  normal_ind;         /* Normal_Ind                             */
+    int32_t  p1, p2, p3;         /* P1..P3                                 */
+    int32_t  n1, n2, n3;         /* N1..N3                                 */
+    int32_t  texture, texture2, texture3; /* -1 = use the object's texture */
+    uint8_t  flags;              /* PVGPU_TRI_*                            */
+    uint8_t  dominant_axis;      /* Dominant_Axis                          */
+    uint8_t  v_axis;             /* vAxis                                  */
+    uint8_t  reserved;
+} pvgpu_triangle;
+
+/* MESH_DATA (mesh.h:108-120) + Mesh members (mesh.h:131-145).  Ranges index the scene-wide
+ * vertex / normal / triangle / mesh-node / mesh-texture arrays. */
+typedef struct pvgpu_mesh {
+    uint32_t vertex_first, vertex_count;      /* float[3] each  (MeshVector)  */
+    uint32_t normal_first, normal_count;      /* float[3] each                */
+    uint32_t triangle_first, triangle_count;
+    uint32_t node_first, node_count;          /* mesh BBOX_TREE, root = node_first; count 0 = no tree */
+    uint32_t texture_first, texture_count;    /* Mesh::Textures -> range in the index list          */
+    uint32_t has_inside_vector;
+    uint32_t reserved;
+    double   inside_vector[3];
+} pvgpu_mesh;
+
+/* ---- lights ------------------------------------------------------------------------------ */
+enum { PVGPU_LIGHT_POINT = 1, PVGPU_LIGHT_SPOT = 2, PVGPU_LIGHT_FILL = 3, PVGPU_LIGHT_CYLINDER = 4 };
+#define PVGPU_LIGHT_AREA             0x001u
+#define PVGPU_LIGHT_FULL_AREA        0x002u
+#define PVGPU_LIGHT_JITTER           0x004u
+#define PVGPU_LIGHT_ORIENT           0x008u
+#define PVGPU_LIGHT_CIRCULAR         0x010u
+#define PVGPU_LIGHT_PARALLEL         0x020u
+#define PVGPU_LIGHT_MEDIA_ATTEN      0x040u
+#define PVGPU_LIGHT_MEDIA_INTERACT   0x080u
+#define PVGPU_LIGHT_GROUP            0x100u
+
+/* LightSource (source/core/scene/object.h:313-351). */
+typedef struct pvgpu_light {
+    uint32_t type;               /* Light_Type */
+    uint32_t flags;              /* PVGPU_LIGHT_* */
+    float    colour[3];
+    int32_t  projected_through;  /* object index or -1 */
+    double   center[3], direction[3], points_at[3], axis1[3], axis2[3];
+    double   coeff, radius, falloff, fade_distance, fade_power;
+    int32_t  area_size1, area_size2, adaptive_level;
+    uint32_t object_flags;       /* the light's own ObjectBase::Flags */
+} pvgpu_light;
+
+/* ---- materials --------------------------------------------------------------------------- */
+
+/* Pattern kinds the device evaluates (source/core/material/pattern.h). */
+enum {
+    PVGPU_PAT_PLAIN    = 1,      /* PlainPattern / PLAIN_PATTERN: use `colour`            */
+    PVGPU_PAT_CHECKER  = 2,      /* CheckerPattern   pattern.cpp:5691                     */
+    PVGPU_PAT_BOZO     = 3,      /* NoisePattern/Bozo pattern.cpp:7858                    */
+    PVGPU_PAT_GRANITE  = 4,      /* GranitePattern   pattern.cpp:6429                     */
+    PVGPU_PAT_GRADIENT = 5,      /* GradientPattern  pattern.cpp:6386, p[0..2]=gradient   */
+    PVGPU_PAT_MARBLE   = 6,      /* MarblePattern    pattern.cpp:7831                     */
+    PVGPU_PAT_WRINKLES = 7,      /* WrinklesPattern  pattern.cpp:8720                     */
+    PVGPU_PAT_ONION    = 8,      /* OnionPattern     pattern.cpp:7934                     */
+    PVGPU_PAT_BRICK    = 9,      /* BrickPattern     pattern.cpp:5495, p[0..2]=brick size p[3]=mortar */
+    PVGPU_PAT_HEXAGON  = 10,     /* HexagonPattern   pattern.cpp:6512                     */
+    PVGPU_PAT_SPOTTED  = 11,     /* SpottedPattern (== bozo noise)                        */
+    PVGPU_PAT_AGATE    = 12,     /* AgatePattern     pattern.cpp:5396, p[0]=agateTurbScale */
+    PVGPU_PAT_WOOD     = 13,     /* WoodPattern      pattern.cpp:8651                     */
+    PVGPU_PAT_LEOPARD  = 14,
+    PVGPU_PAT_SPHERICAL= 15,
+    PVGPU_PAT_BOXED    = 16,
+    PVGPU_PAT_RADIAL   = 17
+};
+/* ContinuousPattern::waveType (pattern.h:108-117) */
+enum { PVGPU_WAVE_RAW = 0, PVGPU_WAVE_RAMP = 1, PVGPU_WAVE_SINE = 2, PVGPU_WAVE_TRIANGLE = 3,
+       PVGPU_WAVE_SCALLOP = 4, PVGPU_WAVE_CUBIC = 5, PVGPU_WAVE_POLY = 6 };
+
+/* Warps (source/core/material/warp.h). */
+enum { PVGPU_WARP_TRANSFORM = 1, PVGPU_WARP_TURBULENCE = 2, PVGPU_WARP_CLASSIC_TURBULENCE = 3 };
+typedef struct pvgpu_warp {
+    uint32_t type;
+    int32_t  transform;          /* TransformWarp::Trans -> transform table index */
+    double   turbulence[3];      /* GenericTurbulenceWarp::Turbulence             */
+    int32_t  octaves;
+    float    lambda, omega;
+    uint32_t handled_by_pattern; /* ClassicTurbulence::handledByPattern           */
+} pvgpu_warp;
+
+/* BlendMapEntry<TransColour> (pigment.h:125): value + rgb,filter,transmit. */
+typedef struct pvgpu_blend_entry {
+    float value;
+    float colour[5];
+} pvgpu_blend_entry;
+
+/* ColourBlendMap: contiguous entry range + GenericPigmentBlendMap::blendMode/blendGamma. */
+typedef struct pvgpu_blend_map {
+    uint32_t entry_first, entry_count;
+    int32_t  blend_mode;
+    float    blend_gamma;
+} pvgpu_blend_map;
+
+/* PIGMENT (pigment.h:130-135) + the pattern object it owns (pattern.h BasicPattern/ContinuousPattern). */
+typedef struct pvgpu_pigment {
+    uint32_t pattern;            /* PVGPU_PAT_*                                     */
+    uint32_t wave_type;          /* PVGPU_WAVE_*                                    */
+    float    frequency, phase, exponent;     /* waveFrequency, wavePhase, waveExponent */
+    int32_t  noise_generator;    /* BasicPattern::noiseGenerator, 0 = scene default */
+    uint32_t warp_first, warp_count;         /* BasicPattern::warps -> warp table range */
+    int32_t  blend_map;          /* Blend_Map -> blend map index, -1 = none         */
+    float    colour[5];          /* PIGMENT::colour                                 */
+    float    quick_colour[5];    /* PIGMENT::Quick_Colour (NaN red = invalid)       */
+    uint32_t reserved;
+    double   p[4];               /* pattern-specific, see PVGPU_PAT_*               */
+} pvgpu_pigment;
+
+/* FINISH (source/core/material/texture.h:119-142), same field order. */
+typedef struct pvgpu_finish {
+    float diffuse, diffuse_back, brilliance, brilliance_adjust, brilliance_adjust_rad;
+    float specular, roughness, phong, phong_size;
+    float irid, irid_film_thickness, irid_turb;
+    float reflect_exp, crand, metallic;
+    float ambient[3], emission[3], reflection_max[3], reflection_min[3];
+    float reflection_falloff;
+    float fresnel;
+    float reflect_metallic;
+    int32_t reflection_fresnel;
+    int32_t conserve_energy;
+    int32_t alpha_knockout;
+    int32_t use_subsurface;
+} pvgpu_finish;
+
+/* TEXTURE (texture.h:108-117): one layer; `next` chains the layers of a layered texture. */
+typedef struct pvgpu_texture {
+    uint32_t type;               /* PVGPU_PAT_PLAIN only (texture maps are out of scope) */
+    int32_t  next;               /* TEXTURE::Next, -1 = last layer                       */
+    int32_t  pigment;
+    int32_t  finish;
+    int32_t  tnormal;            /* -1 (normal perturbation is a "next" row, section 8f)  */
+    uint32_t reserved;
+} pvgpu_texture;
+
+/* Interior (source/core/coretypes.h:193-214). */
+typedef struct pvgpu_interior {
+    int32_t hollow;
+    int32_t disp_nelems;
+    float   ior, dispersion, caustics, old_refract, fade_distance, fade_power;
+    float   fade_colour[3];
+    uint32_t reserved;
+} pvgpu_interior;
+
+/* ---- frame-level ------------------------------------------------------------------------- */
+
+/* QualityFlags (source/core/coretypes.h:558-585) */
+#define PVGPU_Q_AMBIENT_ONLY 0x001u
+#define PVGPU_Q_QUICK_COLOUR 0x002u
+#define PVGPU_Q_SHADOWS      0x004u
+#define PVGPU_Q_AREA_LIGHTS  0x008u
+#define PVGPU_Q_REFRACTIONS  0x010u
+#define PVGPU_Q_REFLECTIONS  0x020u
+#define PVGPU_Q_NORMALS      0x040u
+#define PVGPU_Q_DEFAULT (PVGPU_Q_SHADOWS | PVGPU_Q_AREA_LIGHTS | PVGPU_Q_REFRACTIONS | PVGPU_Q_REFLECTIONS | PVGPU_Q_NORMALS)
+
+/* The SceneData scalars the trace path reads (scenedata.h:85-263). */
+typedef struct pvgpu_globals {
+    uint32_t max_trace_level;    /* parsedMaxTraceLevel  */
+    uint32_t language_version;   /* EffectiveLanguageVersion(), e.g. 370 / 380 */
+    int32_t  noise_generator;    /* noiseGenerator       */
+    uint32_t bounding_method;    /* boundingMethod: 0 = linear object loop, 1 = BBOX_TREE */
+    uint32_t quality_flags;      /* PVGPU_Q_*            */
+    int32_t  output_alpha;       /* outputAlpha          */
+    double   adc_bailout;        /* parsedAdcBailout     */
+    float    ambient_light[3];   /* ambientLight         */
+    float    background[5];      /* backgroundColour (rgb, filter, transmit) */
+    float    atmosphere_ior, atmosphere_dispersion;
+    uint32_t number_of_waves;
+    uint32_t reserved;
+} pvgpu_globals;
+
+/* Camera (source/core/scene/camera.h:84-136), the members TracePixel reads (tracepixel.cpp:235-391). */
+enum { PVGPU_CAMERA_PERSPECTIVE = 1, PVGPU_CAMERA_ORTHOGRAPHIC = 2 };
+typedef struct pvgpu_camera {
+    uint32_t type;
+    uint32_t reserved;
+    double   location[3], direction[3], up[3], right[3];
+    double   max_ray_distance;
+} pvgpu_camera;
+
+/* TraceTask constructor arguments (source/backend/render/tracetask.h:73-75). */
+typedef struct pvgpu_aa {
+    uint32_t method;             /* tracingMethod: 0 none, 1 non-adaptive (+AM1), 2 adaptive (+AM2) */
+    uint32_t depth;              /* aaDepth      (+R)  */
+    double   threshold;          /* aaThreshold  (+A)  */
+    double   jitter_scale;       /* jitterScale  (+J), 0 = off */
+    double   gamma;              /* aaGamma      (+AG), default 2.5 (view.cpp:724) */
+} pvgpu_aa;
+
+/* POVRect (inclusive corners, source/backend/frame.h). */
+typedef struct pvgpu_rect { int32_t left, top, right, bottom; } pvgpu_rect;
+
+/* Device counters, same meaning as the reference's RenderStatistics ids (statisticids.h:120-253). */
+typedef struct pvgpu_stats {
+    uint64_t rays;               /* Number_Of_Rays   (every TraceRay call)        */
+    uint64_t shadow_ray_tests;   /* Shadow_Ray_Tests (every shadow traversal)     */
+    uint64_t reflected_rays, refracted_rays, transmitted_rays, tir_rays;
+    uint64_t adc_saves;
+    uint64_t samples;            /* AA samples beyond one per pixel               */
+    uint64_t waves;              /* wavefront iterations                          */
+    uint64_t kernel_launches;    /* CUDA kernels launched by the call             */
+    uint32_t max_trace_level;    /* highest level reached                         */
+    uint32_t overflow;           /* non-zero: a device capacity was exceeded      */
+    double   device_ms;          /* CUDA-event time of the device work            */
+} pvgpu_stats;
+
+typedef struct pvgpu_scene pvgpu_scene;   /* opaque */
+
+/* ---- scene construction (replaces: Scene::StartParser handing SceneData to the views) ----- */
+int  pvgpu_abi_version(void);
+const char* pvgpu_last_error(void);
+
+int  pvgpu_scene_create(pvgpu_scene** out, const pvgpu_globals* g);
+void pvgpu_scene_destroy(pvgpu_scene* s);
+
+/* SceneData::objects (all objects incl. CSG children / clip / bound objects; frame-level ones are
+ * those listed in `frame`, in SceneData::objects order) + the shared index list. */
+int  pvgpu_scene_set_objects(pvgpu_scene* s, const pvgpu_object* objs, size_t n_objs,
+                             const uint32_t* index_list, size_t n_index,
+                             const uint32_t* frame, size_t n_frame);
+int  pvgpu_scene_set_transforms(pvgpu_scene* s, const pvgpu_transform* t, size_t n);
+/* SceneData::boundingSlabs (BBOX_TREE built by BoundingTask, boundingtask.cpp:168-209); root = node 0. */
+int  pvgpu_scene_set_tree(pvgpu_scene* s, const pvgpu_node* nodes, size_t n);
+/* Builds the tree with the reference's own algorithm (Build_Bounding_Slabs, boundingbox.cpp:325-430)
+ * from the frame-level objects' bboxes; for callers that do not come from the POV-Ray parser. */
+int  pvgpu_scene_build_tree(pvgpu_scene* s);
+int  pvgpu_scene_set_meshes(pvgpu_scene* s, const pvgpu_mesh* meshes, size_t n_meshes,
+                            const float* vertices, size_t n_vertices,
+                            const float* normals, size_t n_normals,
+                            const pvgpu_triangle* tris, size_t n_tris,
+                            const pvgpu_node* nodes, size_t n_nodes);
+int  pvgpu_scene_set_lights(pvgpu_scene* s, const pvgpu_light* l, size_t n);
+int  pvgpu_scene_set_materials(pvgpu_scene* s,
+                               const pvgpu_texture* tex, size_t n_tex,
+                               const pvgpu_pigment* pig, size_t n_pig,
+                               const pvgpu_finish* fin, size_t n_fin,
+                               const pvgpu_blend_map* maps, size_t n_maps,
+                               const pvgpu_blend_entry* entries, size_t n_entries,
+                               const pvgpu_warp* warps, size_t n_warps,
+                               const pvgpu_interior* interiors, size_t n_interiors);
+int  pvgpu_scene_set_camera(pvgpu_scene* s, const pvgpu_camera* cam);
+int  pvgpu_scene_get_camera(const pvgpu_scene* s, pvgpu_camera* cam);
+
+/* Host-side mesh helper mirroring the parser's mesh2 post-processing (Mesh::Compute_Mesh_Triangle,
+ * mesh.cpp:838-954, and Mesh::Build_Mesh_BBox_Tree, mesh.cpp:1376-1413): fills triangle records
+ * (normal, Distance, Dominant_Axis, vertex order) and builds the mesh tree.  `indices` = 3 per face.
+ * On return *out_mesh is the index of the new mesh in the scene's mesh table. */
+int  pvgpu_scene_add_mesh2(pvgpu_scene* s, const double* vertices, size_t n_vertices,
+                           const int32_t* indices, size_t n_faces, int32_t* out_mesh);
+
+/* Validates, derives device layouts and uploads everything to CUDA device `device`. */
+int  pvgpu_scene_finalize(pvgpu_scene* s, int device);
+/* Total bytes uploaded by finalize (the H2D traffic of one scene). */
+size_t pvgpu_scene_device_bytes(const pvgpu_scene* s);
+
+/* Flat-scene file (little endian dump of the tables; used by the reference-side adapter and tests). */
+int  pvgpu_scene_save(const pvgpu_scene* s, const char* path);
+int  pvgpu_scene_load(pvgpu_scene** out, const char* path);
+
+/* ---- rendering (replaces TraceTask::Run: tracetask.cpp:287-657) --------------------------- */
+
+/* Renders `n_rects` rectangles of a width x height image.  rgbt_out (HOST memory) receives, rectangle
+ * after rectangle, rect-area pixels row-major, 4 floats each (r, g, b, transm) exactly as
+ * ViewData::CompletedRectangle takes them.  `cooperate` (may be NULL) is polled between wavefront
+ * iterations like Task::Cooperate(); a non-zero return aborts with PVGPU_E_ABORTED. */
+int  pvgpu_render(pvgpu_scene* s, const pvgpu_aa* aa, int width, int height,
+                  const pvgpu_rect* rects, size_t n_rects, float* rgbt_out,
+                  pvgpu_stats* stats, int (*cooperate)(void*), void* user);
+
+/* Same, but the result stays in DEVICE memory (`d_rgbt_out` is a device pointer with room for the
+ * rect-area sum x 4 floats) and the work is enqueued on `cuda_stream` (a cudaStream_t, 0 = default). */
+int  pvgpu_render_device(pvgpu_scene* s, const pvgpu_aa* aa, int width, int height,
+                         const pvgpu_rect* rects, size_t n_rects, float* d_rgbt_out,
+                         pvgpu_stats* stats, void* cuda_stream);
+
+/* Ray-level harness (mirrors Trace::FindIntersection(Intersection&, const Ray&), trace.h:255, with the
+ * primary-ray conditions of TraceRay): org_dir = 6 doubles per ray (origin, direction; host memory).
+ * obj[i] = frame-or-child object index of Intersection::Object or 0xFFFFFFFF, depth[i] = Depth,
+ * aux[i] = Intersection::i1 (box side) / triangle index (mesh), may be NULL. */
+int  pvgpu_trace_rays(pvgpu_scene* s, const double* org_dir, size_t n,
+                      uint32_t* obj, double* depth, uint32_t* aux);
+
+/* Camera rays exactly as TracePixel::CreateCameraRay makes them for pixel-space (x, y): 6 doubles each. */
+int  pvgpu_camera_rays(pvgpu_scene* s, int width, int height, const double* xy, size_t n, double* org_dir);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVGPU_H */

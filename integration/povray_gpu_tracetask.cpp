@@ -1,0 +1,670 @@
+// Reference-side binding of the pvgpu trace path: a replacement for POV-Ray's
+// source/backend/render/tracetask.cpp.  It is compiled AGAINST the reference headers (never copied
+// into them) and linked with the reference's other objects instead of the stock tracetask.o, giving a
+// `povray-gpu` binary whose parser, SDL, INI/CLI options, RenderBackend / View / vfe session code are
+// the unmodified reference and whose TraceTask::Run() hands the tiles to the GPU:
+//
+//   View::StartRender (view.cpp:1186) -> TraceTask::Run()
+//        flatten SceneData -> pvgpu_scene_*          (once per view, first task to arrive)
+//        ViewData::GetNextRectangle (view.cpp:236)   drain the tile queue
+//        pvgpu_render                                 one call for all drained tiles
+//        ViewData::CompletedRectangle (view.cpp:405)  same rect / serial / row-major RGBT pixels
+//
+// Environment switches (used by the parity tests; all optional):
+//   PVGPU_RENDER=gpu|stock   who computes the delivered pixels (default gpu).  `stock` runs the reference's
+//                            own TracePixel per pixel centre exactly like SimpleSamplingM0 (tracetask.cpp:403).
+//   PVGPU_DUMP_SCENE=<file>  write the flattened scene (pvgpu_scene_save)
+//   PVGPU_DUMP_RAYS=<file>   per pixel: stock camera ray + stock Trace::FindIntersection result
+//   PVGPU_DUMP_RGBT=<file>   per pixel float RGBT from the stock TracePixel
+//   PVGPU_DUMP_GPU=<file>    per pixel float RGBT from pvgpu_render
+// Dumps cover the whole render area and are written when the tile queue is empty (run with +WT1).
+//
+// Build recipe: oracle/Makefile (target adapter).  See INTEGRATION.md.
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// The flattening needs a few members the reference keeps private/protected (Sphere::Do_Ellipsoid,
+// SpindleTorus::mSpindleMode, TracePixel::CreateCameraRay).  A maintainer would add accessors or a
+// friend declaration; the out-of-tree adapter opens the classes up instead.
+#define private public
+#define protected public
+#include "backend/render/tracetask.h"
+#include "backend/scene/backendscenedata.h"
+#include "backend/scene/view.h"
+#include "backend/scene/viewthreaddata.h"
+#include "core/bounding/boundingbox.h"
+#include "core/lighting/lightsource.h"
+#include "core/material/blendmap.h"
+#include "core/material/interior.h"
+#include "core/material/pattern.h"
+#include "core/material/pigment.h"
+#include "core/material/texture.h"
+#include "core/material/warp.h"
+#include "core/math/matrix.h"
+#include "core/render/ray.h"
+#include "core/scene/object.h"
+#include "core/scene/scenedata.h"
+#include "core/scene/tracethreaddata.h"
+#include "core/shape/box.h"
+#include "core/shape/csg.h"
+#include "core/shape/mesh.h"
+#include "core/shape/plane.h"
+#include "core/shape/quadric.h"
+#include "core/shape/sphere.h"
+#include "core/shape/torus.h"
+#include "core/support/statistics.h"
+#undef private
+#undef protected
+
+#include "pvgpu.h"
+
+// this must be the last file included
+#include "base/povdebug.h"
+
+namespace pov
+{
+
+using std::vector;
+
+namespace
+{
+
+// ------------------------------------------------------------------------------------------------
+// SceneData -> pvgpu tables
+// ------------------------------------------------------------------------------------------------
+struct Flattener
+{
+    vector<pvgpu_object> objects;
+    vector<uint32_t> index_list, frame;
+    vector<pvgpu_transform> transforms;
+    vector<pvgpu_node> nodes, mesh_nodes;
+    vector<pvgpu_mesh> meshes;
+    vector<float> vertices, normals;
+    vector<pvgpu_triangle> triangles;
+    vector<pvgpu_light> lights;
+    vector<pvgpu_texture> textures;
+    vector<pvgpu_pigment> pigments;
+    vector<pvgpu_finish> finishes;
+    vector<pvgpu_blend_map> maps;
+    vector<pvgpu_blend_entry> entries;
+    vector<pvgpu_warp> warps;
+    vector<pvgpu_interior> interiors;
+    std::map<const void*, int32_t> object_ids, texture_ids, interior_ids;
+    std::string error;
+
+    void unsupported(const std::string& what) { if (error.empty()) error = what; }
+
+    int32_t add_transform(const TRANSFORM* t)
+    {
+        if (t == nullptr) return -1;
+        pvgpu_transform x;
+        for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) { x.matrix[4 * r + c] = t->matrix[r][c]; x.inverse[4 * r + c] = t->inverse[r][c]; }
+        transforms.push_back(x);
+        return (int32_t)transforms.size() - 1;
+    }
+
+    int32_t add_interior(const Interior* in)
+    {
+        if (in == nullptr) return -1;
+        auto it = interior_ids.find(in);
+        if (it != interior_ids.end()) return it->second;
+        if (!in->media.empty()) unsupported("media inside an interior");
+        pvgpu_interior p{};
+        p.hollow = in->hollow; p.disp_nelems = in->Disp_NElems;
+        p.ior = in->IOR; p.dispersion = in->Dispersion; p.caustics = in->Caustics; p.old_refract = in->Old_Refract;
+        p.fade_distance = in->Fade_Distance; p.fade_power = in->Fade_Power;
+        for (int k = 0; k < 3; k++) p.fade_colour[k] = in->Fade_Colour[k];
+        interiors.push_back(p);
+        return interior_ids[in] = (int32_t)interiors.size() - 1;
+    }
+
+    void add_warps(const WarpList& wl, uint32_t& first, uint32_t& count)
+    {
+        first = (uint32_t)warps.size();
+        count = 0;
+        for (WarpList::const_iterator i = wl.begin(); i != wl.end(); ++i) {
+            pvgpu_warp w{};
+            w.transform = -1;
+            if (const TransformWarp* tw = dynamic_cast<const TransformWarp*>(*i)) {
+                w.type = PVGPU_WARP_TRANSFORM;
+                w.transform = add_transform(&tw->Trans);
+            } else if (const GenericTurbulenceWarp* gt = dynamic_cast<const GenericTurbulenceWarp*>(*i)) {
+                const ClassicTurbulence* ct = dynamic_cast<const ClassicTurbulence*>(*i);
+                w.type = ct ? PVGPU_WARP_CLASSIC_TURBULENCE : PVGPU_WARP_TURBULENCE;
+                for (int k = 0; k < 3; k++) w.turbulence[k] = gt->Turbulence[k];
+                w.octaves = gt->Octaves; w.lambda = gt->Lambda; w.omega = gt->Omega;
+                w.handled_by_pattern = ct ? ct->handledByPattern : 0;
+            } else unsupported("warp type other than transform / turbulence");
+            warps.push_back(w);
+            count++;
+        }
+    }
+
+    int32_t add_pigment(const PIGMENT* pg)
+    {
+        pvgpu_pigment p{};
+        p.blend_map = -1;
+        for (int k = 0; k < 3; k++) { p.colour[k] = pg->colour.colour()[k]; p.quick_colour[k] = pg->Quick_Colour.colour()[k]; }
+        p.colour[3] = pg->colour.filter(); p.colour[4] = pg->colour.transm();
+        p.quick_colour[3] = pg->Quick_Colour.filter(); p.quick_colour[4] = pg->Quick_Colour.transm();
+        p.wave_type = PVGPU_WAVE_RAMP; p.frequency = 1.0f; p.exponent = 1.0f;
+        const BasicPattern* bp = pg->pattern.get();
+        if (pg->Type == PLAIN_PATTERN) p.pattern = PVGPU_PAT_PLAIN;
+        else if (pg->Type != GENERIC_PATTERN) unsupported("pigment type other than plain / generic pattern (image_map, average, uv_mapping ...)");
+        else {
+            if (dynamic_cast<const CheckerPattern*>(bp)) p.pattern = PVGPU_PAT_CHECKER;
+            else if (dynamic_cast<const BozoPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;
+            else if (dynamic_cast<const SpottedPattern*>(bp)) p.pattern = PVGPU_PAT_SPOTTED;
+            else if (dynamic_cast<const GranitePattern*>(bp)) p.pattern = PVGPU_PAT_GRANITE;
+            else if (const GradientPattern* g = dynamic_cast<const GradientPattern*>(bp)) { p.pattern = PVGPU_PAT_GRADIENT; for (int k = 0; k < 3; k++) p.p[k] = g->gradient[k]; }
+            else if (dynamic_cast<const MarblePattern*>(bp)) p.pattern = PVGPU_PAT_MARBLE;
+            else if (dynamic_cast<const OnionPattern*>(bp)) p.pattern = PVGPU_PAT_ONION;
+            else if (dynamic_cast<const WrinklesPattern*>(bp)) p.pattern = PVGPU_PAT_WRINKLES;
+            else if (const AgatePattern* a = dynamic_cast<const AgatePattern*>(bp)) { p.pattern = PVGPU_PAT_AGATE; p.p[0] = a->agateTurbScale; }
+            else unsupported("pigment pattern outside the hot-path scope");
+            if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {
+                p.wave_type = cp->waveType; p.frequency = cp->waveFrequency; p.phase = cp->wavePhase; p.exponent = cp->waveExponent;
+            }
+            p.noise_generator = bp->noiseGenerator;
+            add_warps(bp->warps, p.warp_first, p.warp_count);
+            const ColourBlendMap* cm = dynamic_cast<const ColourBlendMap*>(pg->Blend_Map.get());
+            if (cm == nullptr) unsupported("pigment without a colour blend map (pigment_map ...)");
+            else {
+                pvgpu_blend_map m{};
+                m.entry_first = (uint32_t)entries.size();
+                m.entry_count = (uint32_t)cm->Blend_Map_Entries.size();
+                m.blend_mode = cm->blendMode;
+                if (cm->blendMode != 0) unsupported("colour_map blend_mode other than 0");
+                for (const auto& e : cm->Blend_Map_Entries) {
+                    pvgpu_blend_entry be;
+                    be.value = e.value;
+                    for (int k = 0; k < 3; k++) be.colour[k] = e.Vals.colour()[k];
+                    be.colour[3] = e.Vals.filter(); be.colour[4] = e.Vals.transm();
+                    entries.push_back(be);
+                }
+                maps.push_back(m);
+                p.blend_map = (int32_t)maps.size() - 1;
+            }
+        }
+        pigments.push_back(p);
+        return (int32_t)pigments.size() - 1;
+    }
+
+    int32_t add_finish(const FINISH* f)
+    {
+        pvgpu_finish p{};
+        p.diffuse = f->Diffuse; p.diffuse_back = f->DiffuseBack; p.brilliance = f->Brilliance;
+        p.brilliance_adjust = f->BrillianceAdjust; p.brilliance_adjust_rad = f->BrillianceAdjustRad;
+        p.specular = f->Specular; p.roughness = f->Roughness; p.phong = f->Phong; p.phong_size = f->Phong_Size;
+        p.irid = f->Irid; p.irid_film_thickness = f->Irid_Film_Thickness; p.irid_turb = f->Irid_Turb;
+        p.reflect_exp = f->Reflect_Exp; p.crand = f->Crand; p.metallic = f->Metallic;
+        for (int k = 0; k < 3; k++) {
+            p.ambient[k] = f->Ambient[k]; p.emission[k] = f->Emission[k];
+            p.reflection_max[k] = f->Reflection_Max[k]; p.reflection_min[k] = f->Reflection_Min[k];
+        }
+        p.reflection_falloff = f->Reflection_Falloff; p.fresnel = f->Fresnel; p.reflect_metallic = f->Reflect_Metallic;
+        p.reflection_fresnel = f->Reflection_Fresnel; p.conserve_energy = f->Conserve_Energy;
+        p.alpha_knockout = f->AlphaKnockout; p.use_subsurface = f->UseSubsurface;
+        finishes.push_back(p);
+        return (int32_t)finishes.size() - 1;
+    }
+
+    int32_t add_texture(const TEXTURE* t)
+    {
+        if (t == nullptr) return -1;
+        auto it = texture_ids.find(t);
+        if (it != texture_ids.end()) return it->second;
+        // reserve the slots of the whole layer chain first so that `next` can be filled in
+        vector<const TEXTURE*> chain;
+        for (const TEXTURE* l = t; l != nullptr; l = l->Next) chain.push_back(l);
+        int32_t first = (int32_t)textures.size();
+        textures.resize(textures.size() + chain.size());
+        for (size_t i = 0; i < chain.size(); i++) {
+            const TEXTURE* l = chain[i];
+            pvgpu_texture p{};
+            p.next = (i + 1 < chain.size()) ? first + (int32_t)i + 1 : -1;
+            p.tnormal = -1;
+            if (l->Type != PLAIN_PATTERN) { unsupported("patterned texture / texture_map / material_map"); p.type = 0; }
+            else {
+                p.type = PVGPU_PAT_PLAIN;
+                p.pigment = add_pigment(l->Pigment);
+                p.finish = add_finish(l->Finish);
+                if (l->Tnormal != nullptr) unsupported("normal perturbation (SURVEY 8f 'next')");
+            }
+            textures[first + i] = p;
+            texture_ids[l] = first + (int32_t)i;
+        }
+        return first;
+    }
+
+    void add_index_range(const vector<ObjectPtr>& v, uint32_t self, bool as_children, uint32_t& first, uint32_t& count)
+    {
+        // children are flattened first so that the range in the index list is contiguous
+        vector<uint32_t> ids;
+        for (ObjectPtr o : v) {
+            if ((o->Type & LIGHT_SOURCE_OBJECT) != 0) {
+                if (!(reinterpret_cast<LightSource*>(o))->children.empty()) unsupported("light source with looks_like inside a compound object");
+                continue;      // a light without geometry takes no part in intersection / inside tests
+            }
+            ids.push_back(add_object(o, as_children ? (int32_t)self : -1));
+        }
+        first = (uint32_t)index_list.size();
+        count = (uint32_t)ids.size();
+        index_list.insert(index_list.end(), ids.begin(), ids.end());
+    }
+
+    int32_t add_mesh(Mesh* m)
+    {
+        pvgpu_mesh me{};
+        const MESH_DATA* D = m->Data;
+        me.vertex_first = (uint32_t)(vertices.size() / 3); me.vertex_count = D->Number_Of_Vertices;
+        me.normal_first = (uint32_t)(normals.size() / 3);  me.normal_count = D->Number_Of_Normals;
+        me.triangle_first = (uint32_t)triangles.size();    me.triangle_count = D->Number_Of_Triangles;
+        for (int i = 0; i < D->Number_Of_Vertices; i++) for (int k = 0; k < 3; k++) vertices.push_back(D->Vertices[i][k]);
+        for (int i = 0; i < D->Number_Of_Normals; i++) for (int k = 0; k < 3; k++) normals.push_back(D->Normals[i][k]);
+        for (int i = 0; i < D->Number_Of_Triangles; i++) {
+            const MESH_TRIANGLE& t = D->Triangles[i];
+            pvgpu_triangle p{};
+            for (int k = 0; k < 3; k++) p.perp[k] = t.Perp[k];
+            p.distance = t.Distance; p.normal_ind = t.Normal_Ind;
+            p.p1 = t.P1; p.p2 = t.P2; p.p3 = t.P3; p.n1 = t.N1; p.n2 = t.N2; p.n3 = t.N3;
+            p.texture = t.Texture; p.texture2 = t.Texture2; p.texture3 = t.Texture3;
+            p.flags = (t.Smooth ? PVGPU_TRI_SMOOTH : 0) | (t.ThreeTex ? PVGPU_TRI_THREETEX : 0);
+            p.dominant_axis = t.Dominant_Axis; p.v_axis = t.vAxis;
+            triangles.push_back(p);
+        }
+        me.texture_first = (uint32_t)index_list.size();
+        me.texture_count = (uint32_t)m->Number_Of_Textures;
+        {
+            vector<uint32_t> tids;
+            for (int i = 0; i < m->Number_Of_Textures; i++) tids.push_back((uint32_t)add_texture(m->Textures[i]));
+            me.texture_first = (uint32_t)index_list.size();
+            index_list.insert(index_list.end(), tids.begin(), tids.end());
+        }
+        me.has_inside_vector = m->has_inside_vector;
+        if (m->has_inside_vector) for (int k = 0; k < 3; k++) me.inside_vector[k] = D->Inside_Vect[k];
+        me.node_first = (uint32_t)mesh_nodes.size();
+        if (D->Tree != nullptr) {
+            vector<pvgpu_node> tree;
+            flatten_tree(D->Tree, tree, [&](const BBOX_TREE* leaf) { return (uint32_t)(reinterpret_cast<const MESH_TRIANGLE*>(leaf->Node) - D->Triangles); });
+            me.node_count = (uint32_t)tree.size();
+            mesh_nodes.insert(mesh_nodes.end(), tree.begin(), tree.end());
+        }
+        meshes.push_back(me);
+        return (int32_t)meshes.size() - 1;
+    }
+
+    int32_t add_object(ObjectPtr o, int32_t parent)
+    {
+        auto it = object_ids.find(o);
+        if (it != object_ids.end()) return it->second;
+        const uint32_t self = (uint32_t)objects.size();
+        object_ids[o] = (int32_t)self;
+        objects.push_back(pvgpu_object{});
+        pvgpu_object p{};
+        p.flags = o->Flags;
+        p.parent = parent;
+        p.mesh = -1;
+        p.texture = add_texture(o->Texture);
+        p.interior_texture = add_texture(o->Interior_Texture);
+        p.interior = add_interior(o->interior.get());
+        p.bbox[0] = o->BBox.lowerLeft[X]; p.bbox[1] = o->BBox.lowerLeft[Y]; p.bbox[2] = o->BBox.lowerLeft[Z];
+        p.bbox[3] = o->BBox.size[X]; p.bbox[4] = o->BBox.size[Y]; p.bbox[5] = o->BBox.size[Z];
+        p.transform = -1;
+        if (!o->LLights.empty()) unsupported("light_group");
+        if (Sphere* s = dynamic_cast<Sphere*>(o)) {
+            p.type = PVGPU_OBJ_SPHERE;
+            for (int k = 0; k < 3; k++) p.p[k] = s->Center[k];
+            p.p[3] = s->Radius;
+            p.aux = s->Do_Ellipsoid ? 1 : 0;
+            if (s->Do_Ellipsoid) p.transform = add_transform(s->Trans);
+        } else if (Box* b = dynamic_cast<Box*>(o)) {
+            p.type = PVGPU_OBJ_BOX;
+            for (int k = 0; k < 3; k++) { p.p[k] = b->bounds[0][k]; p.p[3 + k] = b->bounds[1][k]; }
+            p.transform = add_transform(b->Trans);
+        } else if (Plane* pl = dynamic_cast<Plane*>(o)) {
+            p.type = PVGPU_OBJ_PLANE;
+            for (int k = 0; k < 3; k++) p.p[k] = pl->Normal_Vector[k];
+            p.p[3] = pl->Distance;
+            p.transform = add_transform(pl->Trans);
+        } else if (Quadric* q = dynamic_cast<Quadric*>(o)) {
+            p.type = PVGPU_OBJ_QUADRIC;
+            for (int k = 0; k < 3; k++) { p.p[k] = q->Square_Terms[k]; p.p[3 + k] = q->Mixed_Terms[k]; p.p[6 + k] = q->Terms[k]; }
+            p.p[9] = q->Constant;
+        } else if (Torus* t = dynamic_cast<Torus*>(o)) {
+            p.type = PVGPU_OBJ_TORUS;
+            p.p[0] = t->MajorRadius; p.p[1] = t->MinorRadius;
+            if (SpindleTorus* st = dynamic_cast<SpindleTorus*>(o)) { p.aux = (uint32_t)st->mSpindleMode; p.p[2] = st->mSpindleTipYSqr; }
+            p.transform = add_transform(t->Trans);
+        } else if (Mesh* m = dynamic_cast<Mesh*>(o)) {
+            p.type = PVGPU_OBJ_MESH;
+            p.mesh = add_mesh(m);
+            p.transform = add_transform(m->Trans);
+        } else if (CSG* c = dynamic_cast<CSG*>(o)) {
+            if (dynamic_cast<CSGMerge*>(o)) p.type = PVGPU_OBJ_CSG_MERGE;
+            else if (dynamic_cast<CSGUnion*>(o)) p.type = PVGPU_OBJ_CSG_UNION;
+            else if (dynamic_cast<CSGIntersection*>(o)) p.type = PVGPU_OBJ_CSG_INTERSECTION;
+            else unsupported("unknown CSG class");
+            add_index_range(c->children, self, true, p.child_first, p.child_count);
+        } else {
+            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, CSG)");
+            p.type = 0;
+        }
+        add_index_range(o->Clip, self, false, p.clip_first, p.clip_count);
+        // Bound and Clip may share their objects (bounded_by { clipped_by }); the memo keeps them shared here too
+        add_index_range(o->Bound, self, false, p.bound_first, p.bound_count);
+        objects[self] = p;
+        return (int32_t)self;
+    }
+
+    template <typename LEAF>
+    void flatten_tree(const BBOX_TREE* root, vector<pvgpu_node>& out, LEAF leaf_payload)
+    {
+        vector<const BBOX_TREE*> order{ root };
+        out.assign(1, pvgpu_node{});
+        for (size_t qi = 0; qi < order.size(); qi++) {
+            const BBOX_TREE* n = order[qi];
+            pvgpu_node pn{};
+            pn.lo[0] = n->BBox.lowerLeft[X]; pn.lo[1] = n->BBox.lowerLeft[Y]; pn.lo[2] = n->BBox.lowerLeft[Z];
+            pn.size[0] = n->BBox.size[X]; pn.size[1] = n->BBox.size[Y]; pn.size[2] = n->BBox.size[Z];
+            pn.flags = n->Infinite ? PVGPU_NODE_INFINITE : 0;
+            if (n->Entries == 0) { pn.count = 0; pn.first = leaf_payload(n); }
+            else {
+                pn.count = (uint16_t)n->Entries;
+                pn.first = (uint32_t)order.size();
+                for (int i = 0; i < n->Entries; i++) order.push_back(n->Node[i]);
+                out.resize(order.size());
+            }
+            out[qi] = pn;
+        }
+    }
+
+    void add_light(const LightSource* l)
+    {
+        pvgpu_light p{};
+        p.type = l->Light_Type;
+        p.flags = (l->Area_Light ? PVGPU_LIGHT_AREA : 0) | (l->Use_Full_Area_Lighting ? PVGPU_LIGHT_FULL_AREA : 0) |
+                  (l->Jitter ? PVGPU_LIGHT_JITTER : 0) | (l->Orient ? PVGPU_LIGHT_ORIENT : 0) | (l->Circular ? PVGPU_LIGHT_CIRCULAR : 0) |
+                  (l->Parallel ? PVGPU_LIGHT_PARALLEL : 0) | (l->Media_Attenuation ? PVGPU_LIGHT_MEDIA_ATTEN : 0) |
+                  (l->Media_Interaction ? PVGPU_LIGHT_MEDIA_INTERACT : 0) | (l->lightGroupLight ? PVGPU_LIGHT_GROUP : 0);
+        for (int k = 0; k < 3; k++) {
+            p.colour[k] = l->colour[k];
+            p.center[k] = l->Center[k]; p.direction[k] = l->Direction[k]; p.points_at[k] = l->Points_At[k];
+            p.axis1[k] = l->Axis1[k]; p.axis2[k] = l->Axis2[k];
+        }
+        p.projected_through = l->Projected_Through_Object ? add_object(l->Projected_Through_Object, -1) : -1;
+        p.coeff = l->Coeff; p.radius = l->Radius; p.falloff = l->Falloff;
+        p.fade_distance = l->Fade_Distance; p.fade_power = l->Fade_Power;
+        p.area_size1 = l->Area_Size1; p.area_size2 = l->Area_Size2; p.adaptive_level = l->Adaptive_Level;
+        p.object_flags = l->Flags;
+        lights.push_back(p);
+    }
+};
+
+int quality_bits(const QualityFlags& q)
+{
+    return (q.ambientOnly ? PVGPU_Q_AMBIENT_ONLY : 0) | (q.quickColour ? PVGPU_Q_QUICK_COLOUR : 0) | (q.shadows ? PVGPU_Q_SHADOWS : 0) |
+           (q.areaLights ? PVGPU_Q_AREA_LIGHTS : 0) | (q.refractions ? PVGPU_Q_REFRACTIONS : 0) | (q.reflections ? PVGPU_Q_REFLECTIONS : 0) |
+           (q.normals ? PVGPU_Q_NORMALS : 0);
+}
+
+struct GpuView
+{
+    pvgpu_scene* scene = nullptr;
+    std::map<const void*, int32_t> object_ids;
+    bool finalized = false;
+    std::string error;
+};
+
+std::mutex g_mutex;
+std::map<const void*, std::shared_ptr<GpuView>> g_views;     // keyed by SceneData
+
+void check(int rc, const char* what)
+{
+    if (rc != PVGPU_OK)
+        throw POV_EXCEPTION_STRING((std::string("pvgpu: ") + what + ": " + pvgpu_last_error()).c_str());
+}
+
+std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    SceneData* sd = vd->GetSceneData().get();
+    std::shared_ptr<GpuView>& slot = g_views[sd];
+    if (slot) return slot;
+    slot.reset(new GpuView());
+    GpuView& gv = *slot;
+
+    if (sd->skysphere != nullptr || sd->fog != nullptr || sd->rainbow != nullptr || !sd->atmosphere.empty())
+        gv.error = "sky_sphere / fog / rainbow / atmospheric media (SURVEY 8f 'next')";
+    if (sd->radiositySettings.radiosityEnabled) gv.error = "radiosity";
+    if (sd->photonSettings.photonsEnabled) gv.error = "photons";
+    if (sd->boundingMethod == 2) gv.error = "BSP bounding (+BM2)";
+    if (sd->useSubsurface) gv.error = "subsurface light transport";
+
+    Flattener fl;
+    for (ObjectPtr o : sd->objects) {
+        if ((o->Type & LIGHT_SOURCE_OBJECT) != 0) {
+            if (!(reinterpret_cast<LightSource*>(o))->children.empty()) fl.unsupported("light source with looks_like");
+            continue;
+        }
+        fl.frame.push_back((uint32_t)fl.add_object(o, -1));
+    }
+    for (const LightSource* l : sd->lightSources) fl.add_light(l);
+    if (!sd->lightGroupLightSources.empty()) fl.unsupported("light_group");
+    if (sd->boundingSlabs != nullptr)
+        fl.flatten_tree(sd->boundingSlabs, fl.nodes, [&](const BBOX_TREE* leaf) { return (uint32_t)fl.object_ids.at(reinterpret_cast<const void*>(leaf->Node)); });
+    if (gv.error.empty()) gv.error = fl.error;
+    gv.object_ids = fl.object_ids;
+
+    pvgpu_globals g{};
+    g.max_trace_level = sd->parsedMaxTraceLevel;
+    g.language_version = sd->EffectiveLanguageVersion();
+    g.noise_generator = sd->noiseGenerator;
+    g.bounding_method = (sd->boundingMethod == 1 && sd->boundingSlabs != nullptr) ? 1 : 0;
+    g.quality_flags = quality_bits(vd->GetQualityFeatureFlags());
+    g.output_alpha = sd->outputAlpha;
+    g.adc_bailout = sd->parsedAdcBailout;
+    for (int k = 0; k < 3; k++) { g.ambient_light[k] = sd->ambientLight[k]; g.background[k] = sd->backgroundColour.colour()[k]; }
+    g.background[3] = sd->backgroundColour.filter(); g.background[4] = sd->backgroundColour.transm();
+    g.atmosphere_ior = sd->atmosphereIOR; g.atmosphere_dispersion = sd->atmosphereDispersion;
+    g.number_of_waves = sd->numberOfWaves;
+
+    const Camera& cam = vd->GetCamera();
+    pvgpu_camera c{};
+    c.type = cam.Type;
+    for (int k = 0; k < 3; k++) { c.location[k] = cam.Location[k]; c.direction[k] = cam.Direction[k]; c.up[k] = cam.Up[k]; c.right[k] = cam.Right[k]; }
+    c.max_ray_distance = cam.Max_Ray_Distance;
+    if (cam.Tnormal != nullptr) gv.error = "camera normal perturbation";
+    if ((cam.Aperture != 0.0) && (cam.Blur_Samples > 0)) gv.error = "focal blur";
+    if (cam.Rays_Per_Pixel != 1) gv.error = "mesh camera";
+
+    check(pvgpu_scene_create(&gv.scene, &g), "scene_create");
+    check(pvgpu_scene_set_objects(gv.scene, fl.objects.data(), fl.objects.size(), fl.index_list.data(), fl.index_list.size(),
+                                  fl.frame.data(), fl.frame.size()), "set_objects");
+    check(pvgpu_scene_set_transforms(gv.scene, fl.transforms.data(), fl.transforms.size()), "set_transforms");
+    check(pvgpu_scene_set_tree(gv.scene, fl.nodes.data(), fl.nodes.size()), "set_tree");
+    check(pvgpu_scene_set_meshes(gv.scene, fl.meshes.data(), fl.meshes.size(), fl.vertices.data(), fl.vertices.size() / 3,
+                                 fl.normals.data(), fl.normals.size() / 3, fl.triangles.data(), fl.triangles.size(),
+                                 fl.mesh_nodes.data(), fl.mesh_nodes.size()), "set_meshes");
+    check(pvgpu_scene_set_lights(gv.scene, fl.lights.data(), fl.lights.size()), "set_lights");
+    check(pvgpu_scene_set_materials(gv.scene, fl.textures.data(), fl.textures.size(), fl.pigments.data(), fl.pigments.size(),
+                                    fl.finishes.data(), fl.finishes.size(), fl.maps.data(), fl.maps.size(),
+                                    fl.entries.data(), fl.entries.size(), fl.warps.data(), fl.warps.size(),
+                                    fl.interiors.data(), fl.interiors.size()), "set_materials");
+    check(pvgpu_scene_set_camera(gv.scene, &c), "set_camera");
+    if (const char* path = getenv("PVGPU_DUMP_SCENE")) check(pvgpu_scene_save(gv.scene, path), "scene_save");
+    if (need_device) {
+        if (!gv.error.empty())
+            throw POV_EXCEPTION_STRING((std::string("pvgpu: scene uses a feature outside the GPU trace path: ") + gv.error).c_str());
+        const char* dev = getenv("PVGPU_DEVICE");
+        check(pvgpu_scene_finalize(gv.scene, dev ? atoi(dev) : 0), "scene_finalize");
+        gv.finalized = true;
+    }
+    return slot;
+}
+
+void write_file(const char* path, const void* data, size_t bytes)
+{
+    FILE* f = fopen(path, "wb");
+    if (f == nullptr || fwrite(data, 1, bytes, f) != bytes) throw POV_EXCEPTION_STRING("pvgpu adapter: cannot write dump file");
+    fclose(f);
+}
+
+#pragma pack(push, 1)
+struct RayDumpRecord { double org[3], dir[3], depth; int32_t object, aux; };
+#pragma pack(pop)
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// TraceTask: same class (tracetask.h), GPU-backed implementation
+// ------------------------------------------------------------------------------------------------
+TraceTask::TraceTask(ViewData *vd, unsigned int tm, DBL js, DBL aat, DBL aac, unsigned int aad, pov_base::GammaCurvePtr& aag,
+                     unsigned int ps, bool psc, bool contributesToImage, bool hr, size_t seed) :
+    RenderTask(vd, seed, "Trace"),
+    tracingMethod(tm), jitterScale(js), aaThreshold(aat), aaConfidence(aac), aaDepth(aad),
+    previewSize(ps), previewSkipCorner(psc), passContributesToImage(contributesToImage),
+    passCompletesImage((ps == 0) || ((ps == 1) && contributesToImage)), highReproducibility(hr), aaGamma(aag),
+    trace(vd->GetSceneData(), &vd->GetCamera(), GetViewDataPtr(), vd->GetSceneData()->parsedMaxTraceLevel,
+          vd->GetSceneData()->parsedAdcBailout, vd->GetQualityFeatureFlags(), cooperate, media, radiosity),
+    cooperate(*this),
+    media(GetViewDataPtr(), &trace, &photonGatherer),
+    radiosity(vd->GetSceneData(), GetViewDataPtr(), vd->GetSceneData()->radiositySettings, vd->GetRadiosityCache(),
+              cooperate, true, vd->GetCamera().Location),
+    photonGatherer(&vd->GetSceneData()->mediaPhotonMap, vd->GetSceneData()->photonSettings)
+{
+    GetViewDataPtr()->qualityFlags = vd->GetQualityFeatureFlags();
+}
+
+TraceTask::~TraceTask() {}
+
+void TraceTask::Run()
+{
+    ViewData* vd = GetViewData();
+    const unsigned int width = vd->GetWidth(), height = vd->GetHeight();
+    const char* mode_env = getenv("PVGPU_RENDER");
+    const bool use_gpu = !(mode_env && strcmp(mode_env, "stock") == 0);
+    const char* dump_rays = getenv("PVGPU_DUMP_RAYS");
+    const char* dump_rgbt = getenv("PVGPU_DUMP_RGBT");
+    const char* dump_gpu = getenv("PVGPU_DUMP_GPU");
+
+    if (previewSize > 0) {
+        // mosaic preview passes (SimpleSamplingM0P) carry no final pixels; the final pass renders everything
+        POVRect r; unsigned int serial;
+        while (vd->GetNextRectangle(r, serial)) { vector<RGBTColour> px(r.GetArea()); vd->CompletedRectangle(r, serial, px, 1, false, passCompletesImage); Cooperate(); }
+        return;
+    }
+    if (use_gpu && tracingMethod != 0)
+        throw POV_EXCEPTION_STRING("pvgpu: anti-aliased tracing methods are not wired into this adapter yet; render with -A");
+
+    std::shared_ptr<GpuView> gv = flatten_scene(vd, use_gpu);
+
+    // drain the tile queue
+    vector<POVRect> rects;
+    vector<unsigned int> serials;
+    {
+        POVRect r; unsigned int serial;
+        while (vd->GetNextRectangle(r, serial)) { rects.push_back(r); serials.push_back(serial); }
+    }
+    if (rects.empty()) return;
+    Cooperate();
+
+    vector<float> frame_ref, frame_gpu;
+    vector<RayDumpRecord> frame_rays;
+    if (dump_rgbt) frame_ref.assign((size_t)width * height * 4, 0.0f);
+    if (dump_gpu) frame_gpu.assign((size_t)width * height * 4, 0.0f);
+    if (dump_rays) frame_rays.assign((size_t)width * height, RayDumpRecord{});
+
+    vector<float> gpu_pixels;
+    if (use_gpu) {
+        vector<pvgpu_rect> pr(rects.size());
+        size_t total = 0;
+        for (size_t i = 0; i < rects.size(); i++) {
+            pr[i].left = (int32_t)rects[i].left; pr[i].top = (int32_t)rects[i].top;
+            pr[i].right = (int32_t)rects[i].right; pr[i].bottom = (int32_t)rects[i].bottom;
+            total += rects[i].GetArea();
+        }
+        gpu_pixels.resize(total * 4);
+        pvgpu_aa aa{};
+        aa.method = 0;
+        pvgpu_stats st{};
+        check(pvgpu_render(gv->scene, &aa, (int)width, (int)height, pr.data(), pr.size(), gpu_pixels.data(), &st, nullptr, nullptr), "render");
+        // the stock statistics page keeps working: counters the device kept in the reference's units
+        GetViewDataPtr()->Stats()[Number_Of_Rays] += st.rays;
+        GetViewDataPtr()->Stats()[Shadow_Ray_Tests] += st.shadow_ray_tests;
+        GetViewDataPtr()->Stats()[Reflected_Rays_Traced] += st.reflected_rays;
+        GetViewDataPtr()->Stats()[Refracted_Rays_Traced] += st.refracted_rays;
+        GetViewDataPtr()->Stats()[Transmitted_Rays_Traced] += st.transmitted_rays;
+        GetViewDataPtr()->Stats()[ADC_Saves] += st.adc_saves;
+        vd->SetHighestTraceLevel(st.max_trace_level);
+    }
+
+    size_t cursor = 0;
+    for (size_t ri = 0; ri < rects.size(); ri++) {
+        const POVRect& rect = rects[ri];
+        vector<RGBTColour> pixels;
+        pixels.reserve(rect.GetArea());
+        for (unsigned int y = rect.top; y <= rect.bottom; y++) {
+            for (unsigned int x = rect.left; x <= rect.right; x++, cursor++) {
+                const size_t fi = (size_t)y * width + x;
+                RGBTColour ref;
+                if (!use_gpu || dump_rgbt) {
+                    trace(DBL(x) + 0.5, DBL(y) + 0.5, width, height, ref);     // the reference's own TracePixel
+                    if (dump_rgbt) { frame_ref[4 * fi] = ref.red(); frame_ref[4 * fi + 1] = ref.green(); frame_ref[4 * fi + 2] = ref.blue(); frame_ref[4 * fi + 3] = ref.transm(); }
+                }
+                if (dump_rays) {
+                    TraceTicket ticket(GetSceneData()->parsedMaxTraceLevel, GetSceneData()->parsedAdcBailout, GetSceneData()->outputAlpha);
+                    Ray ray(ticket);
+                    RayDumpRecord& rec = frame_rays[fi];
+                    rec.object = -1; rec.aux = 0; rec.depth = BOUND_HUGE;
+                    if (trace.CreateCameraRay(ray, DBL(x) + 0.5, DBL(y) + 0.5, width, height, 0)) {
+                        Intersection isect;
+                        NoSomethingFlagRayObjectCondition precond;
+                        TrueRayObjectCondition postcond;
+                        for (int k = 0; k < 3; k++) { rec.org[k] = ray.Origin[k]; rec.dir[k] = ray.Direction[k]; }
+                        if (trace.FindIntersection(isect, ray, precond, postcond)) {
+                            auto it = gv->object_ids.find(isect.Object);
+                            rec.object = (it == gv->object_ids.end()) ? -2 : it->second;
+                            rec.depth = isect.Depth;
+                            if (Mesh* m = dynamic_cast<Mesh*>(isect.Object)) rec.aux = (int32_t)(reinterpret_cast<const MESH_TRIANGLE*>(isect.Pointer) - m->Data->Triangles);
+                            else rec.aux = isect.i1;
+                        }
+                    }
+                }
+                if (use_gpu) {
+                    const float* g = &gpu_pixels[4 * cursor];
+                    pixels.push_back(RGBTColour(g[0], g[1], g[2], g[3]));
+                    if (dump_gpu) memcpy(&frame_gpu[4 * fi], g, 4 * sizeof(float));
+                } else pixels.push_back(ref);
+                GetViewDataPtr()->Stats()[Number_Of_Pixels]++;
+            }
+            Cooperate();
+        }
+        GetViewDataPtr()->AfterTile();
+        vd->CompletedRectangle(rect, serials[ri], pixels, 1, passContributesToImage, passCompletesImage);
+    }
+    if (dump_rgbt) write_file(dump_rgbt, frame_ref.data(), frame_ref.size() * sizeof(float));
+    if (dump_gpu) write_file(dump_gpu, frame_gpu.data(), frame_gpu.size() * sizeof(float));
+    if (dump_rays) write_file(dump_rays, frame_rays.data(), frame_rays.size() * sizeof(RayDumpRecord));
+    if (!use_gpu) vd->SetHighestTraceLevel(trace.GetHighestTraceLevel());
+}
+
+void TraceTask::Stopped() {}
+
+void TraceTask::Finish()
+{
+    GetViewDataPtr()->timeType = TraceThreadData::kRenderTime;
+    GetViewDataPtr()->realTime = ConsumedRealTime();
+    GetViewDataPtr()->cpuTime = ConsumedCPUTime();
+}
+
+}  // namespace pov

@@ -1,0 +1,138 @@
+// Device-side view of the flattened scene, the wavefront records that live in HBM, and the numeric
+// constants of the reference's trace path.  sm_100a only; compiled with -fmad=false so that every FP64
+// expression is evaluated with the same roundings as the -ffp-contract=off reference build.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "pvgpu.h"
+
+namespace pvgpu {
+
+// ---- constants (source/core/configcore.h) --------------------------------------------------------
+#define PV_EPSILON          1.0e-10     // EPSILON          configcore.h:153
+#define PV_HUGE_VAL         1.0e17      // HUGE_VAL         configcore.h:164
+#define PV_BOUND_HUGE       2.0e10      // BOUND_HUGE       configcore.h:184
+#define PV_SMALL_TOLERANCE  1.0e-3      // SMALL_TOLERANCE  configcore.h:193
+#define PV_MAX_DISTANCE     1.0e7       // MAX_DISTANCE     configcore.h:198
+#define PV_MIN_ISECT_DEPTH  1.0e-4      // MIN_ISECT_DEPTH  configcore.h:206
+#define PV_SHADOW_TOLERANCE 1.0e-3      // SHADOW_TOLERANCE trace.cpp:81
+#define PV_COORDINATE_LIMIT 1.0e17      // COORDINATE_LIMIT warp.h
+
+#define PV_STACK_SIZE     96            // traversal stack entries per ray (scene tree + nested mesh tree)
+#define PV_MAX_LAYERS     8             // layers of a layered texture
+#define PV_MAX_INTERIORS  10            // interiors a ray can be inside of at once
+#define PV_CSG_STACK      16            // nesting depth of Inside() evaluation
+#define PV_NO_OBJECT      0xFFFFFFFFu
+
+struct V3 { double x, y, z; };
+
+// Packed mesh triangle for the intersection test: everything intersect_mesh_triangle
+// (mesh.cpp:1040-1127) reads, in one 64-byte record (one L2 sector pair) instead of five gathers.
+struct __align__(16) DTri {
+    float p1[3], p2[3], p3[3];   // Vertices[P1..P3]
+    float n[3];                  // Normals[Normal_Ind]
+    float dist;                  // Distance
+    uint32_t dom;                // Dominant_Axis
+    uint32_t pad[2];
+};
+static_assert(sizeof(DTri) == 64, "DTri must be 64 bytes");
+
+struct DMesh {                   // pvgpu_mesh with absolute offsets resolved
+    uint32_t tri_first, tri_count, node_first, node_count;
+    uint32_t vertex_first, normal_first, texture_first, texture_count;
+    uint32_t has_inside_vector;
+    double inside_vector[3];
+};
+
+// Noise tables (built on the host with the reference's LCG, noise.cpp:231-255, 306-348).
+struct NoiseTables {
+    const uint16_t* hash;      // hashTable[8192]
+    const double*   rtable;    // RTable[534]                            noise.cpp:98-145,181-182
+    const uint16_t* perm;      // NoisePermutation[2*(NoiseEntries+1)]
+    const double*   grad;      // NoiseGradients[2*(NoiseEntries+1)][3]
+};
+
+// Read-only scene tables in HBM (uploaded once by pvgpu_scene_finalize).
+struct DScene {
+    const pvgpu_object*      objs;
+    const pvgpu_transform*   xf;
+    const uint32_t*          index_list;
+    const uint32_t*          frame;
+    const pvgpu_node*        nodes;         // scene tree, root 0
+    const DMesh*             meshes;
+    const DTri*              dtris;
+    const pvgpu_triangle*    tris;
+    const float*             verts;
+    const float*             norms;
+    const pvgpu_node*        mnodes;
+    const pvgpu_light*       lights;
+    const pvgpu_texture*     textures;
+    const pvgpu_pigment*     pigments;
+    const pvgpu_finish*      finishes;
+    const pvgpu_blend_map*   maps;
+    const pvgpu_blend_entry* entries;
+    const pvgpu_warp*        warps;
+    const pvgpu_interior*    interiors;
+    const uint32_t*          csg_leaves;    // per top-level CSG object: its primitive descendants (DFS order)
+    const uint2*             csg_leaf_range;// per object: (first, count) into csg_leaves
+    NoiseTables              noise;
+    uint32_t n_objs, n_frame, n_nodes, n_lights;
+    uint32_t use_tree;                      // boundingMethod == 1 && tree present
+    uint32_t all_opaque;                    // every shadow caster has OPAQUE_FLAG
+    pvgpu_globals g;
+    pvgpu_camera  cam;
+    uint16_t cam_interiors[PV_MAX_INTERIORS];   // TracePixel::InitRayContainerState result
+    uint32_t n_cam_interiors;
+};
+
+// ---- wavefront records --------------------------------------------------------------------------
+#define PV_RAY_PRIMARY     0x01u
+#define PV_RAY_REFLECTION  0x02u
+#define PV_RAY_REFRACTION  0x04u
+#define PV_RAY_CONTINUED   0x08u    // TraceRay(..., continuedRay = true): trace level is not incremented
+#define PV_RAY_ALPHA_BG    0x10u    // TraceTicket::alphaBackground
+
+// One pending TraceRay call (trace.cpp:135): 96 bytes.
+struct __align__(16) PRay {
+    double   o[3], d[3];
+    float    w[3];               // linear RGB factor this ray's colour is multiplied with on its way to the pixel
+    float    wt;                 // same for the transmittance (alpha) channel
+    float    adc;                // TraceRay's `weight` argument (ADC bailout test)
+    uint32_t sample;             // accumulation slot
+    uint8_t  level;              // TraceTicket::traceLevel on entry
+    uint8_t  flags;              // PV_RAY_*
+    uint8_t  n_int;              // Ray::interiors.size()
+    uint8_t  pad;
+    uint16_t interiors[PV_MAX_INTERIORS];
+};
+static_assert(sizeof(PRay) == 96, "PRay must be 96 bytes");
+
+// One pending TraceShadowRay call (trace.cpp:1892): 96 bytes.
+struct __align__(16) SRay {
+    double   o[3], d[3];
+    double   depth;              // lightsourcedepth
+    float    a[3];               // un-shadowed contribution (path weight x filter x light colour x BRDF terms)
+    uint32_t sample;
+    uint32_t parent;             // index of the PRay that spawned it (interior list for fade attenuation)
+    uint32_t light;
+    uint32_t pad[2];
+};
+static_assert(sizeof(SRay) == 96, "SRay must be 96 bytes");
+
+struct Counters {
+    unsigned long long rays, shadow_tests, reflected, refracted, transmitted, tir, adc_saves;
+    unsigned int n_next;         // rays appended to the next wave
+    unsigned int n_shadow;       // shadow rays appended for the current chunk
+    unsigned int max_level;
+    unsigned int overflow;
+};
+
+struct Hit {
+    double   depth;
+    V3       ip;                 // Intersection::IPoint
+    uint32_t obj;                // Intersection::Object (primitive)
+    uint32_t aux;                // Intersection::i1 (box side) or triangle index (Intersection::Pointer)
+    int32_t  csg;                // Intersection::Csg or -1
+};
+
+}  // namespace pvgpu

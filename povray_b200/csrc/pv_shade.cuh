@@ -1,0 +1,800 @@
+// Surface shading in wavefront form: Trace::ComputeTextureColour / ComputeLightedTexture
+// (source/core/render/trace.cpp:457-1179), the light loop (trace.cpp:1488-1728, 1872-1889,
+// 2710-2767; lightsource.cpp:548-633), the finish models (trace.cpp:2441-2708), reflection and
+// refraction ray set-up (trace.cpp:1264-1485, 2595-2625), ComputeSky (trace.cpp:2769-2890) and the
+// pigment / pattern evaluation they call (pigment.cpp:395-545, pattern.cpp, warp.cpp:103-122).
+//
+// The reference recurses: a child's colour is multiplied by a factor and added to the parent's.
+// Every such factor on this path is linear in the child colour, so a ray carries the product of the
+// factors (`w`, `wt`) and adds its own local terms straight into the sample's accumulator.
+#pragma once
+#include "pv_traverse.cuh"
+#include "pv_noise.cuh"
+
+namespace pvgpu {
+
+struct WaveCtx {
+    float4*   accum;          // per-sample RGBT accumulators
+    PRay*     next;           // next wave's queue
+    SRay*     shadow;         // shadow-ray queue of the current chunk
+    Counters* cnt;
+    uint32_t  next_cap, shadow_cap;
+};
+
+__device__ __forceinline__ void accum_add(float4* accum, uint32_t sample, float r, float g, float b, float t)
+{
+    float* a = reinterpret_cast<float*>(accum + sample);
+    if (r != 0.0f) atomicAdd(a + 0, r);
+    if (g != 0.0f) atomicAdd(a + 1, g);
+    if (b != 0.0f) atomicAdd(a + 2, b);
+    if (t != 0.0f) atomicAdd(a + 3, t);
+}
+
+// ---- pattern evaluation --------------------------------------------------------------------------
+// cycloidal (texture.cpp:98-110)
+__device__ inline double cycloidal(double value)
+{
+    const double two_pi = 6.283185307179586476925286766560;
+    if (value >= 0.0) return sin(((value - floor(value)) * 50000.0) / 50000.0 * two_pi);
+    return 0.0 - sin(((0.0 - (value + floor(0.0 - value))) * 50000.0) / 50000.0 * two_pi);
+}
+// Triangle_Wave (texture.cpp:128-150)
+__device__ inline double triangle_wave(double value)
+{
+    double offset = (value >= 0.0) ? value - floor(value) : value + 1.0 + floor(fabs(value));
+    return (offset >= 0.5) ? 2.0 * (1.0 - offset) : 2.0 * offset;
+}
+
+// Warp_EPoint (warp.cpp:103-122): warps applied last-to-first, then clamped to COORDINATE_LIMIT.
+__device__ inline V3 warp_epoint(const DScene& sc, const pvgpu_pigment& pg, const V3& ep)
+{
+    V3 p = ep;
+    for (int i = (int)pg.warp_count - 1; i >= 0; i--) {
+        const pvgpu_warp& w = sc.warps[pg.warp_first + i];
+        if (w.type == PVGPU_WARP_TRANSFORM) p = inv_trans_point(sc.xf[w.transform], p);
+        else {   // GenericTurbulenceWarp::WarpPoint (warp.cpp:553-559)
+            V3 t = dturbulence(sc.noise, p, w.octaves, (double)w.lambda, (double)w.omega);
+            p = mk(p.x + t.x * w.turbulence[0], p.y + t.y * w.turbulence[1], p.z + t.z * w.turbulence[2]);
+        }
+    }
+    if (p.x > PV_COORDINATE_LIMIT) p.x = PV_COORDINATE_LIMIT; else if (p.x < -PV_COORDINATE_LIMIT) p.x = -PV_COORDINATE_LIMIT;
+    if (p.y > PV_COORDINATE_LIMIT) p.y = PV_COORDINATE_LIMIT; else if (p.y < -PV_COORDINATE_LIMIT) p.y = -PV_COORDINATE_LIMIT;
+    if (p.z > PV_COORDINATE_LIMIT) p.z = PV_COORDINATE_LIMIT; else if (p.z < -PV_COORDINATE_LIMIT) p.z = -PV_COORDINATE_LIMIT;
+    return p;
+}
+
+// Pattern value for a warped point: Evaluate_TPat -> <Pattern>::Evaluate.
+__device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment& pg, const V3& p)
+{
+    const int gen = pg.noise_generator ? pg.noise_generator : sc.g.noise_generator;   // BasicPattern::GetNoiseGen
+    // first warp is a ClassicTurbulence? (GetTurb, pattern.cpp:1135)
+    const pvgpu_warp* turb = (pg.warp_count && sc.warps[pg.warp_first].type == PVGPU_WARP_CLASSIC_TURBULENCE) ? &sc.warps[pg.warp_first] : nullptr;
+    double value;
+    switch (pg.pattern) {
+        case PVGPU_PAT_CHECKER: {   // CheckerPattern::Evaluate (pattern.cpp:5691-5707): discrete, no wave processing
+            int v = (int)(floor(p.x + PV_EPSILON) + floor(p.y + PV_EPSILON) + floor(p.z + PV_EPSILON));
+            return (v & 1) ? 1.0 : 0.0;
+        }
+        case PVGPU_PAT_BOZO:
+        case PVGPU_PAT_SPOTTED:     // NoisePattern::EvaluateRaw (pattern.cpp:7858)
+            value = noise3(sc.noise, p, gen);
+            break;
+        case PVGPU_PAT_GRANITE: {   // GranitePattern::EvaluateRaw (pattern.cpp:6429-6465)
+            double noise = 0.0, freq = 1.0;
+            V3 tv1 = p * 4.0;
+            for (int i = 0; i < 6; freq *= 2.0, i++) {
+                V3 tv2 = tv1 * freq;
+                double temp;
+                if (gen <= 1) temp = fabs(0.5 - noise3(sc.noise, tv2, gen));
+                else { temp = fabs(1.0 - 2.0 * noise3(sc.noise, tv2, gen)); if (temp > 0.5) temp = 0.5; }
+                noise += temp / freq;
+            }
+            value = noise;
+            break;
+        }
+        case PVGPU_PAT_GRADIENT: {  // GradientPattern::EvaluateRaw (pattern.cpp:6386-6393)
+            double r = dot(p, ld3(pg.p));
+            value = (r > 1.0) ? fmod(r, 1.0) : r;
+            break;
+        }
+        case PVGPU_PAT_MARBLE: {    // MarblePattern::EvaluateRaw (pattern.cpp:7831-7847)
+            double tv = 0.0;
+            if (turb) tv = turb->turbulence[0] * turbulence(sc.noise, p, turb->octaves, (double)turb->lambda, (double)turb->omega, gen);
+            value = p.x + tv;
+            break;
+        }
+        case PVGPU_PAT_ONION:       // OnionPattern::EvaluateRaw (pattern.cpp:7934-7953)
+            value = fmod(length(p), 1.0);
+            break;
+        case PVGPU_PAT_WRINKLES: {  // WrinklesPattern::EvaluateRaw (pattern.cpp:8720-8775)
+            double lambda = 2.0, omega = 0.5;
+            if (gen <= 1) value = noise3(sc.noise, p, gen);
+            else value = fmin(fmax(noise3(sc.noise, p, gen) * 2.0 - 0.5, 0.0), 1.0);
+            for (int i = 1; i < 10; i++) {
+                V3 temp = p * lambda;
+                if (gen <= 1) value += omega * noise3(sc.noise, temp, gen);
+                else value += omega * fmin(fmax(noise3(sc.noise, temp, gen) * 2.0 - 0.5, 0.0), 1.0);
+                lambda *= 2.0;
+                omega *= 0.5;
+            }
+            value = value / 2.0;
+            break;
+        }
+        case PVGPU_PAT_AGATE: {     // AgatePattern::EvaluateRaw (pattern.cpp:5396-5421)
+            double tv = 0.0;
+            if (turb) tv = pg.p[0] * turbulence(sc.noise, p, turb->octaves, (double)turb->lambda, (double)turb->omega, gen);
+            double noise = 0.5 * (cycloidal(1.3 * tv + 1.1 * p.z) + 1.0);
+            if (noise < 0.0) noise = 0.0;
+            else { noise = fmin(1.0, noise); noise = pow(noise, 0.77); }
+            value = noise;
+            break;
+        }
+        default:
+            value = 0.0;
+            break;
+    }
+    // ContinuousPattern::Evaluate (pattern.cpp:354-392)
+    if (pg.wave_type == PVGPU_WAVE_RAW) return value;
+    if (pg.frequency != 0.0f) value = fmod(value * (double)pg.frequency + (double)pg.phase, 1.00001);
+    if (value < 0.0) value -= floor(value);
+    switch (pg.wave_type) {
+        case PVGPU_WAVE_SINE:     value = (1.0 + cycloidal(value)) * 0.5; break;
+        case PVGPU_WAVE_TRIANGLE: value = triangle_wave(value); break;
+        case PVGPU_WAVE_SCALLOP:  value = fabs(cycloidal(value * 0.5)); break;
+        case PVGPU_WAVE_CUBIC:    value = sqr(value) * ((-2.0 * value) + 3.0); break;
+        case PVGPU_WAVE_POLY:     value = pow(value, (double)pg.exponent); break;
+        default: break;
+    }
+    return value;
+}
+
+// Compute_Pigment (pigment.cpp:395-466) + ColourBlendMap::Compute / BlendMap::Search
+// (pigment.cpp:513-530, pattern.cpp:1068-1112).  col = rgb, filter, transmit.
+__device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
+{
+    const pvgpu_pigment& pg = sc.pigments[pig_index];
+    if (pg.pattern == PVGPU_PAT_PLAIN) {
+        #pragma unroll
+        for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
+        return;
+    }
+    const V3 tp = warp_epoint(sc, pg, ep);
+    const double value = evaluate_pattern(sc, pg, tp);
+    const pvgpu_blend_map& m = sc.maps[pg.blend_map];
+    const pvgpu_blend_entry* e = sc.entries + m.entry_first;
+    const uint32_t last = m.entry_count - 1;
+    uint32_t ip = last, in = last;
+    double wp = 0.0, wn = 1.0;
+    if (!(value >= (double)e[last].value)) {
+        ip = in = 0;
+        while (value > (double)e[in].value) { ip = in; in++; }
+        if ((value == (double)e[in].value) || (ip == in)) { ip = in; }
+        else {
+            wp = ((double)e[in].value - value) / ((double)e[in].value - (double)e[ip].value);
+            wn = 1.0 - wp;
+        }
+    }
+    if (ip == in) {
+        #pragma unroll
+        for (int k = 0; k < 5; k++) col[k] = e[in].colour[k];
+    } else {
+        // GenericPigmentBlendMap::Blend, default blend mode (pigment.cpp:468-511): colour1*w1 + colour2*w2
+        #pragma unroll
+        for (int k = 0; k < 5; k++) col[k] = (float)(e[ip].colour[k] * wp) + (float)(e[in].colour[k] * wn);
+    }
+}
+
+// ---- finish helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float greyscale(const float* c) { return (float)(0.297 * c[0] + 0.589 * c[1] + 0.114 * c[2]); }   // colour.h:1366
+
+// Trace::FresnelR (trace.cpp:2680-2708)
+__device__ inline double fresnel_r(double cosTi, double n)
+{
+    double sqrg = sqr(n) + sqr(cosTi) - 1.0;
+    if (sqrg <= 0.0) return 1.0;
+    double g = sqrt(sqrg);
+    double quot1 = (g - cosTi) / (g + cosTi);
+    double quot2 = (cosTi * (g + cosTi) - 1.0) / (cosTi * (g - cosTi) + 1.0);
+    double f = 0.5 * sqr(quot1) * (1.0 + sqr(quot2));
+    return fmin(fmax(f, 0.0), 1.0);
+}
+
+// Trace::ComputeMetallic (trace.cpp:2656-2669)
+__device__ inline void compute_metallic(float c[3], double metallic, const float* mcol, double cos_angle)
+{
+    if (metallic != 0.0) {
+        double x = fabs(acos(cos_angle)) / 1.57079632679489661923;
+        double F = 0.014567225 / sqr(x - 1.12) - 0.011612903;
+        F = fmin(1.0, fmax(0.0, F));
+        #pragma unroll
+        for (int k = 0; k < 3; k++) c[k] *= (float)(1.0 + (metallic * (1.0 - F)) * ((double)mcol[k] - 1.0));
+    }
+}
+
+// Trace::ComputeReflectivity (trace.cpp:2627-2654) + ComputeFresnel (:2671-2675)
+__device__ inline void compute_reflectivity(double& weight, float refl[3], const pvgpu_finish& f, double cos_angle, double rel_ior)
+{
+    if (!f.reflection_fresnel) {
+        double wmax = fmax(fmax((double)f.reflection_max[0], (double)f.reflection_max[1]), (double)f.reflection_max[2]);
+        double wmin = fmax(fmax((double)f.reflection_min[0], (double)f.reflection_min[1]), (double)f.reflection_min[2]);
+        weight = weight * fmax(wmax, wmin);
+        double frac;
+        if (fabs((double)f.reflection_falloff - 1.0) > PV_EPSILON) frac = pow(1.0 - cos_angle, (double)f.reflection_falloff);
+        else frac = 1.0 - cos_angle;
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (fabs(frac) < PV_EPSILON) refl[k] = f.reflection_min[k];
+            else if (fabs(frac - 1.0) < PV_EPSILON) refl[k] = f.reflection_max[k];
+            else refl[k] = (float)(frac * f.reflection_max[k]) + (float)((1.0 - frac) * f.reflection_min[k]);
+        }
+    } else {
+        double fr = fresnel_r(cos_angle, rel_ior);
+        #pragma unroll
+        for (int k = 0; k < 3; k++) refl[k] = (float)(fr * f.reflection_max[k]) + (float)((1.0 - fr) * f.reflection_min[k]);
+        weight = weight * fmax(fmax((double)refl[0], (double)refl[1]), (double)refl[2]);
+    }
+}
+
+// cubic_spline (lightsource.cpp:501-517)
+__device__ inline double cubic_spline(double low, double high, double pos)
+{
+    if (pos < low) return 0.0;
+    if (pos >= high) return 1.0;
+    pos = (pos - low) / (high - low);
+    return (3 - 2 * pos) * pos * pos;
+}
+
+// Attenuate_Light (lightsource.cpp:548-633)
+__device__ inline double attenuate_light(const pvgpu_light& L, const V3& ray_o, const V3& ray_d, double distance)
+{
+    double att = 1.0;
+    if (L.type == PVGPU_LIGHT_SPOT) {
+        double costheta = dot(ray_d, ld3(L.direction));
+        if (distance > 0.0) costheta = -costheta;
+        if (costheta > 0.0) {
+            att = pow(costheta, L.coeff);
+            if (L.radius > 0.0 && costheta < L.radius) att *= cubic_spline(L.falloff, L.radius, costheta);
+        } else return 0.0;
+    } else if (L.type == PVGPU_LIGHT_CYLINDER) {
+        V3 v1 = ray_o - ld3(L.center);
+        double k = dot(v1, ld3(L.direction));
+        if (k > 0.0) {
+            V3 p = v1 - k * ld3(L.direction);
+            double len = length(p);
+            if (len < L.falloff) {
+                double dist = 1.0 - len / L.falloff;
+                att = pow(dist, L.coeff);
+                if (L.radius > 0.0 && len > L.radius) att *= cubic_spline(0.0, 1.0 - L.radius / L.falloff, dist);
+            } else return 0.0;
+        } else return 0.0;
+    }
+    if (att > 0.0 && L.fade_power > 0.0) {
+        if (fabs(L.fade_distance) >= PV_EPSILON) att *= 2.0 / (1.0 + pow(distance / L.fade_distance, L.fade_power));
+        else att *= pow(distance, -L.fade_power);
+    }
+    return att;
+}
+
+// ComputeOneWhiteLightRay (trace.cpp:2710-2767) for non-area lights
+__device__ inline void light_ray(const pvgpu_light& L, const V3& ipoint, V3& dir, double& depth)
+{
+    V3 center = ld3(L.center);
+    if (L.type == PVGPU_LIGHT_CYLINDER) {
+        dir = center - ld3(L.points_at);
+        V3 to_ctr = center - ipoint;
+        double dist_pa = length(dir);
+        depth = dot(to_ctr, dir);
+        depth /= dist_pa;
+        dir = normalized(dir);
+    } else {
+        dir = center - ipoint;
+        depth = length(dir);
+        dir = dir / depth;
+    }
+    if (L.flags & PVGPU_LIGHT_PARALLEL) {
+        double a = dot(ld3(L.direction), dir);
+        depth *= (-a);
+        dir = -ld3(L.direction);
+    }
+}
+
+// ---- interiors -----------------------------------------------------------------------------------
+__device__ __forceinline__ bool ray_is_interior(const PRay& r, int32_t interior)
+{
+    for (int i = 0; i < r.n_int; i++) if (r.interiors[i] == (uint16_t)interior) return true;
+    return false;
+}
+__device__ __forceinline__ bool ray_remove_interior(PRay& r, int32_t interior)
+{
+    for (int i = 0; i < r.n_int; i++)
+        if (r.interiors[i] == (uint16_t)interior) {
+            for (int j = i + 1; j < r.n_int; j++) r.interiors[j - 1] = r.interiors[j];
+            r.n_int--;
+            return true;
+        }
+    return false;
+}
+__device__ __forceinline__ void ray_append_interior(PRay& r, int32_t interior, unsigned int* overflow)
+{
+    if (r.n_int < PV_MAX_INTERIORS) r.interiors[r.n_int++] = (uint16_t)interior;
+    else atomicOr(overflow, 4u);
+}
+
+// Trace::ComputeRelativeIOR (trace.cpp:2595-2625)
+__device__ inline double relative_ior(const DScene& sc, const PRay& ray, int32_t interior)
+{
+    if (interior < 0) return 1.0;
+    const double ior = sc.interiors[interior].ior;
+    if (ray.n_int == 0) return ior / (double)sc.g.atmosphere_ior;
+    if (ray_is_interior(ray, interior)) {
+        if (ray.n_int == 1) return (double)sc.g.atmosphere_ior / ior;
+        return (double)sc.interiors[ray.interiors[ray.n_int - 1]].ior / ior;
+    }
+    return ior / (double)sc.interiors[ray.interiors[ray.n_int - 1]].ior;
+}
+
+// ---- queues --------------------------------------------------------------------------------------
+__device__ __forceinline__ void push_ray(WaveCtx& ctx, const PRay& r)
+{
+    unsigned int slot = atomicAdd(&ctx.cnt->n_next, 1u);
+    if (slot < ctx.next_cap) ctx.next[slot] = r;
+    else atomicOr(&ctx.cnt->overflow, 8u);
+}
+__device__ __forceinline__ void push_shadow(WaveCtx& ctx, const SRay& r)
+{
+    unsigned int slot = atomicAdd(&ctx.cnt->n_shadow, 1u);
+    if (slot < ctx.shadow_cap) ctx.shadow[slot] = r;
+    else atomicOr(&ctx.cnt->overflow, 16u);
+}
+
+// ---- object normal / texture selection -----------------------------------------------------------
+// Mesh::Normal + Smooth_Mesh_Normal (mesh.cpp:283-375)
+__device__ inline V3 mesh_normal(const DScene& sc, const pvgpu_object& ob, const Hit& hit)
+{
+    const DMesh& me = sc.meshes[ob.mesh];
+    const pvgpu_triangle& tr = sc.tris[hit.aux];
+    const float* N = sc.norms + 3 * (size_t)me.normal_first;
+    const float* V = sc.verts + 3 * (size_t)me.vertex_first;
+    V3 result;
+    if (tr.flags & PVGPU_TRI_SMOOTH) {
+        V3 ip = (ob.transform >= 0) ? inv_trans_point(sc.xf[ob.transform], hit.ip) : hit.ip;
+        V3 n1 = ld3f(N + 3 * tr.n1), n2 = ld3f(N + 3 * tr.n2), n3 = ld3f(N + 3 * tr.n3);
+        V3 pmp1 = ip - ld3f(V + 3 * tr.p1);
+        double u = dot(pmp1, ld3f(tr.perp));
+        if (u < PV_EPSILON) result = n1;
+        else {
+            const int axis = tr.v_axis;
+            double k1 = V[3 * tr.p1 + axis], k2 = V[3 * tr.p2 + axis], k3 = V[3 * tr.p3 + axis];
+            double v = (comp(pmp1, axis) / u + k1 - k2) / (k3 - k2);
+            result = n1 + u * (n2 - n1 + v * (n3 - n2));
+        }
+        if (ob.transform >= 0) result = trans_normal(sc.xf[ob.transform], result);
+        result = normalized(result);
+    } else {
+        result = ld3f(N + 3 * tr.normal_ind);
+        if (ob.transform >= 0) result = normalized(trans_normal(sc.xf[ob.transform], result));
+    }
+    return result;
+}
+
+__device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, const Hit& hit)
+{
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE:  return sphere_normal(sc, ob, hit.ip);
+        case PVGPU_OBJ_BOX:     return box_normal(sc, ob, hit.aux);
+        case PVGPU_OBJ_PLANE:   return plane_normal(sc, ob);
+        case PVGPU_OBJ_QUADRIC: return quadric_normal(ob, hit.ip);
+        case PVGPU_OBJ_TORUS:   return torus_normal(sc, ob, hit.ip, hit.aux);
+        case PVGPU_OBJ_MESH:    return mesh_normal(sc, ob, hit);
+    }
+    return mk(0.0, 1.0, 0.0);
+}
+
+// Texture of the hit: ObjectBase::Texture / Interior_Texture (trace.cpp:513-530) or, for a
+// multi-textured mesh, the triangle's texture (Mesh::Determine_Textures, mesh.cpp:2421-2457).
+__device__ inline int32_t hit_texture(const DScene& sc, const pvgpu_object& ob, const Hit& hit, bool backside)
+{
+    if (ob.type == PVGPU_OBJ_MESH && (ob.flags & PVGPU_MULTITEXTURE_FLAG)) {
+        // Mesh::Determine_Textures (mesh.cpp:2421-2457); ThreeTex triangles are rejected at finalize
+        if (backside && ob.interior_texture >= 0) return ob.interior_texture;
+        const pvgpu_triangle& tr = sc.tris[hit.aux];
+        if (tr.texture >= 0) return (int32_t)sc.index_list[sc.meshes[ob.mesh].texture_first + tr.texture];
+        return ob.texture;
+    }
+    if (ob.texture < 0) return -1;
+    return (backside && ob.interior_texture >= 0) ? ob.interior_texture : ob.texture;
+}
+
+// Trace::ComputeSky for language version >= 3.7 without sky_sphere (trace.cpp:2848-2890) and the
+// legacy branch (trace.cpp:2771-2800).
+__device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[3], float& transm)
+{
+    const bool alpha_bg = (ray.flags & PV_RAY_ALPHA_BG) != 0;
+    const float* bg = sc.g.background;
+    if (sc.g.language_version < 370) {
+        if (alpha_bg) { col[0] = col[1] = col[2] = 0.0f; transm = 1.0f; return; }
+        col[0] = bg[0]; col[1] = bg[1]; col[2] = bg[2];
+        transm = bg[4];
+        return;
+    }
+    float f = alpha_bg ? bg[3] : 0.0f, t = alpha_bg ? bg[4] : 0.0f;
+    float att = (float)(1.0 - f - t);                       // TransColour::Opacity
+    col[0] = bg[0] * att; col[1] = bg[1] * att; col[2] = bg[2] * att;
+    float fil[3] = { bg[0] * f + t, bg[1] * f + t, bg[2] * f + t };   // TransmittedColour
+    transm = fminf(1.0f, fabsf(greyscale(fil)));
+}
+
+// ComputeReflection's direction rule (trace.cpp:1264-1300)
+__device__ inline V3 reflect_direction(const V3& dir, const V3& normal, const V3& rawnormal)
+{
+    double n = -2.0 * dot(dir, normal);
+    V3 nd = dir + n * normal;
+    n = dot(nd, rawnormal);
+    if (n < 0.0) {
+        double n2 = dot(nd, normal);
+        if (n2 < 0.0) {
+            n = -2.0 * dot(dir, rawnormal);
+            nd = dir + n * rawnormal;
+        } else {
+            n *= -2.0;
+            nd = nd + n * rawnormal;
+        }
+    }
+    return normalized(nd);
+}
+
+// ---- the shading of one closest hit ---------------------------------------------------------------
+// ray:      the TraceRay call being served (already past the level / ADC test)
+// ray_slot: its index in the current wave (shadow records point back at it)
+__device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx)
+{
+    const pvgpu_object& ob = sc.objs[hit.obj];
+    const V3 dir = ld3(ray.d);
+    const V3 ipoint = hit.ip;
+    const uint8_t child_level = (ray.flags & PV_RAY_CONTINUED) ? ray.level : (uint8_t)(ray.level + 1);
+    const double adc = sc.g.adc_bailout;
+    const double weight = (double)ray.adc;
+
+    V3 rawnormal = object_normal(sc, ob, hit);
+    if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
+    const double normaldirection = dot(rawnormal, dir);
+    if (normaldirection > 0.0) rawnormal = -rawnormal;
+
+    const int32_t tex0 = hit_texture(sc, ob, hit, normaldirection > 0.0);
+    if (tex0 < 0) return;
+    // a single WeightedTexture of weight 1.0: skipped if 1.0 < adcBailout (trace.cpp:541)
+    if (1.0 < adc) return;
+
+    const double rel_ior = relative_ior(sc, ray, ob.interior);
+
+    struct Layer { float col[3]; float fil[3]; float refl[3]; double att; double rweight; int32_t finish; };
+    Layer layers[PV_MAX_LAYERS];
+    int nlayers = 0;
+    float fil[3] = { 1.0f, 1.0f, 1.0f };
+    double trans = 1.0;
+    float amb[3] = { 0.0f, 0.0f, 0.0f };
+    const V3 lay_normal = rawnormal;      // no normal perturbation on this path
+    const double cos_inc = -dot(dir, lay_normal);
+
+    for (int32_t li = tex0; li >= 0 && trans > adc && nlayers < PV_MAX_LAYERS; li = sc.textures[li].next) {
+        const pvgpu_texture& tx = sc.textures[li];
+        const pvgpu_finish& fn = sc.finishes[tx.finish];
+        Layer& L = layers[nlayers];
+        float lc[5];
+        compute_pigment(sc, tx.pigment, ipoint, lc);
+        L.col[0] = lc[0]; L.col[1] = lc[1]; L.col[2] = lc[2];
+        L.fil[0] = fil[0]; L.fil[1] = fil[1]; L.fil[2] = fil[2];
+        L.finish = tx.finish;
+        L.rweight = weight * trans;
+        compute_reflectivity(L.rweight, L.refl, fn, cos_inc, rel_ior);
+        compute_metallic(L.refl, (double)fn.reflect_metallic, L.col, cos_inc);
+        double att;
+        if (sc.g.language_version < 370) att = (float)(1.0 - ((double)(lc[3] * fmaxf(fmaxf(lc[0], lc[1]), lc[2])) + (double)lc[4]));   // LegacyOpacity
+        else att = (float)(1.0 - (double)lc[3] - (double)lc[4]);                                                                   // Opacity
+        L.att = att;
+        if (fn.alpha_knockout) { L.refl[0] *= (float)att; L.refl[1] *= (float)att; L.refl[2] *= (float)att; }
+        // emission + classic ambient (trace.cpp:978-1004); radiosity is outside this path
+        float em[3];
+        #pragma unroll
+        for (int k = 0; k < 3; k++) em[k] = fn.emission[k] + fn.ambient[k] * sc.g.ambient_light[k];
+        if (fn.fresnel != 0.0f) {
+            float f1 = (float)(1.0 - (double)fn.fresnel * fresnel_r(cos_inc, rel_ior));
+            em[0] *= f1; em[1] *= f1; em[2] *= f1;
+        }
+        #pragma unroll
+        for (int k = 0; k < 3; k++) amb[k] += (L.col[k] * em[k] * (float)att) * fil[k];
+        nlayers++;
+        // new filter colour and remaining translucency (trace.cpp:1059-1076)
+        #pragma unroll
+        for (int k = 0; k < 3; k++) fil[k] *= (lc[k] * lc[3] + lc[4]);
+        if (fn.conserve_energy != 0) {
+            #pragma unroll
+            for (int k = 0; k < 3; k++) fil[k] *= fminf(1.0f - L.refl[k], 1.0f);
+        }
+        trans = fmin(1.0, (double)fabsf(greyscale(fil)));
+    }
+
+    // local (non-recursive) term
+    accum_add(ctx.accum, ray.sample, ray.w[0] * amb[0], ray.w[1] * amb[1], ray.w[2] * amb[2], 0.0f);
+
+    // ---- classic lights: ComputeDiffuseLight / ComputeOneDiffuseLight (trace.cpp:1488-1510, 1637-1728)
+    if (!(ob.flags & PVGPU_NO_GLOBAL_LIGHTS_FLAG)) {
+        for (uint32_t l = 0; l < sc.n_lights; l++) {
+            const pvgpu_light& Lt = sc.lights[l];
+            V3 ldir; double ldepth;
+            light_ray(Lt, ipoint, ldir, ldepth);
+            const double latt = attenuate_light(Lt, ipoint, ldir, ldepth);
+            float lcol[3] = { (float)(Lt.colour[0] * latt), (float)(Lt.colour[1] * latt), (float)(Lt.colour[2] * latt) };
+            if (fabsf(lcol[0]) < (float)PV_EPSILON && fabsf(lcol[1]) < (float)PV_EPSILON && fabsf(lcol[2]) < (float)PV_EPSILON) continue;
+            float K[3] = { 0.0f, 0.0f, 0.0f };
+            for (int i = 0; i < nlayers; i++) {
+                const Layer& L = layers[i];
+                const pvgpu_finish& fn = sc.finishes[L.finish];
+                if (!((fn.diffuse != 0.0f) || (fn.diffuse_back != 0.0f) || (fn.specular != 0.0f) || (fn.phong != 0.0f))) continue;
+                if (fn.alpha_knockout && L.att == 0.0) continue;
+                bool backside = false;
+                if (!(ob.flags & PVGPU_DOUBLE_ILLUMINATE_FLAG)) {
+                    double cos_shadow = dot(lay_normal, ldir);
+                    if (cos_shadow < PV_EPSILON) {
+                        if (fn.diffuse_back != 0.0f) backside = true;
+                        else continue;
+                    }
+                }
+                float k3[3] = { 0.0f, 0.0f, 0.0f };
+                // ComputeDiffuseColour (trace.cpp:2441-2484)
+                {
+                    double diffuse = (double)((backside ? fn.diffuse_back : fn.diffuse) * fn.brilliance_adjust);
+                    if (diffuse > 0.0) {
+                        double cai = dot(lay_normal, ldir);
+                        double intensity = (fn.brilliance != 1.0f) ? pow(fabs(cai), (double)fn.brilliance) : fabs(cai);
+                        intensity *= diffuse * L.att;
+                        double ff = 1.0;
+                        if (fn.fresnel != 0.0f) {
+                            double f1 = (double)fn.fresnel * fresnel_r(cai, rel_ior);
+                            double f2 = (double)fn.fresnel * fresnel_r(-dot(lay_normal, dir), rel_ior);
+                            ff = (1.0 - f1) * (1.0 - f2);
+                        }
+                        #pragma unroll
+                        for (int k = 0; k < 3; k++) k3[k] += (float)(intensity * ff) * L.col[k];
+                    }
+                }
+                const float hl_att = fn.alpha_knockout ? (float)L.att : 1.0f;     // tempLightColour (trace.cpp:1698)
+                if (Lt.type != PVGPU_LIGHT_FILL && !backside) {
+                    // ComputePhongColour (trace.cpp:2518-2555)
+                    if (fn.phong > 0.0f) {
+                        double c = -2.0 * dot(dir, lay_normal);
+                        V3 rd = dir + c * lay_normal;
+                        c = dot(rd, ldir);
+                        if (c > 0.0 && ((fn.phong_size < 60.0f) || (c > 0.0008))) {
+                            double intensity = (double)fn.phong * pow(c, (double)fn.phong_size);
+                            float cs[3] = { 1.0f, 1.0f, 1.0f };
+                            if ((fn.fresnel != 0.0f) || (fn.metallic != 0.0f)) {
+                                double ndotl = dot(lay_normal, ldir);
+                                if (fn.fresnel != 0.0f) { float fr = (float)((double)fn.fresnel * fresnel_r(ndotl, rel_ior)); cs[0] *= fr; cs[1] *= fr; cs[2] *= fr; }
+                                compute_metallic(cs, (double)fn.metallic, L.col, ndotl);
+                            }
+                            #pragma unroll
+                            for (int k = 0; k < 3; k++) k3[k] += (float)intensity * cs[k] * hl_att;
+                        }
+                    }
+                    // ComputeSpecularColour (trace.cpp:2557-2593)
+                    if (fn.specular > 0.0f) {
+                        V3 halfway = ((-dir) + ldir) * 0.5;
+                        double hl = length(halfway);
+                        if (hl > 0.0) {
+                            double c = dot(halfway, lay_normal) / hl;
+                            if (c > 0.0) {
+                                double intensity = (double)fn.specular * pow(c, (double)fn.roughness);
+                                float cs[3] = { 1.0f, 1.0f, 1.0f };
+                                if ((fn.fresnel != 0.0f) || (fn.metallic != 0.0f)) {
+                                    double ndotl = dot(halfway, ldir) / hl;
+                                    if (fn.fresnel != 0.0f) { float fr = (float)((double)fn.fresnel * fresnel_r(ndotl, rel_ior)); cs[0] *= fr; cs[1] *= fr; cs[2] *= fr; }
+                                    compute_metallic(cs, (double)fn.metallic, L.col, ndotl);
+                                }
+                                #pragma unroll
+                                for (int k = 0; k < 3; k++) k3[k] += (float)intensity * cs[k] * hl_att;
+                            }
+                        }
+                    }
+                }
+                #pragma unroll
+                for (int k = 0; k < 3; k++) K[k] += L.fil[k] * k3[k];
+            }
+            float a[3] = { ray.w[0] * lcol[0] * K[0], ray.w[1] * lcol[1] * K[1], ray.w[2] * lcol[2] * K[2] };
+            if (a[0] == 0.0f && a[1] == 0.0f && a[2] == 0.0f) continue;
+            const bool shadowed = (sc.g.quality_flags & PVGPU_Q_SHADOWS) && (Lt.type != PVGPU_LIGHT_FILL);
+            if (!shadowed) { accum_add(ctx.accum, ray.sample, a[0], a[1], a[2], 0.0f); continue; }
+            SRay s;
+            s.o[0] = ipoint.x; s.o[1] = ipoint.y; s.o[2] = ipoint.z;
+            s.d[0] = ldir.x; s.d[1] = ldir.y; s.d[2] = ldir.z;
+            s.depth = ldepth;
+            s.a[0] = a[0]; s.a[1] = a[1]; s.a[2] = a[2];
+            s.sample = ray.sample; s.parent = ray_slot; s.light = l;
+            s.pad[0] = s.pad[1] = 0;
+            push_shadow(ctx, s);
+        }
+    }
+
+    // ---- transmitted component: ComputeRefraction / TraceRefractionRay (trace.cpp:1085-1145, 1323-1485)
+    bool tir = false;
+    if (ob.interior >= 0 && trans > adc && (sc.g.quality_flags & PVGPU_Q_REFRACTIONS)) {
+        const pvgpu_interior& in = sc.interiors[ob.interior];
+        const double w1 = fmax(fmax((double)fabsf(fil[0]), (double)fabsf(fil[1])), (double)fabsf(fil[2]));   // WeightMaxAbs
+        const double new_weight = weight * w1;
+        // distance based attenuation (trace.cpp:1098-1121); uses the INCOMING ray's interior list
+        float attc[3] = { in.old_refract, in.old_refract, in.old_refract };
+        if (ray_is_interior(ray, ob.interior) && fabs((double)in.fade_distance) > PV_EPSILON) {
+            if (in.fade_power >= 1000.0f) {
+                double depth = hit.depth / (double)in.fade_distance;
+                #pragma unroll
+                for (int k = 0; k < 3; k++) attc[k] *= expf((float)(-(1.0 - (double)in.fade_colour[k]) * depth));
+            } else {
+                double a = 1.0 + pow(hit.depth / (double)in.fade_distance, (double)in.fade_power);
+                #pragma unroll
+                for (int k = 0; k < 3; k++) attc[k] *= (float)((double)in.fade_colour[k] + (1.0 - (double)in.fade_colour[k]) / a);
+            }
+        }
+        PRay nr = ray;
+        nr.flags = (uint8_t)((ray.flags & (PV_RAY_REFLECTION | PV_RAY_ALPHA_BG)) | PV_RAY_REFRACTION);
+        nr.o[0] = ipoint.x; nr.o[1] = ipoint.y; nr.o[2] = ipoint.z;
+        nr.level = child_level;
+        nr.adc = (float)new_weight;
+        double ior;
+        if (nr.n_int == 0) {
+            ray_append_interior(nr, ob.interior, &ctx.cnt->overflow);
+            ior = (double)sc.g.atmosphere_ior / (double)in.ior;
+        } else if ((uint16_t)ob.interior == nr.interiors[nr.n_int - 1]) {
+            ray_remove_interior(nr, ob.interior);
+            if (nr.n_int == 0) ior = (double)in.ior / (double)sc.g.atmosphere_ior;
+            else ior = (double)in.ior / (double)sc.interiors[nr.interiors[nr.n_int - 1]].ior;
+        } else if (ray_remove_interior(nr, ob.interior)) {
+            ior = 1.0;
+        } else {
+            ior = (double)sc.interiors[nr.interiors[nr.n_int - 1]].ior / (double)in.ior;
+            ray_append_interior(nr, ob.interior, &ctx.cnt->overflow);
+        }
+        const V3 top_normal = lay_normal;
+        bool spawn = true;
+        if (fabs(ior - 1.0) < PV_EPSILON) {
+            nr.flags |= PV_RAY_CONTINUED;     // TraceRay(nray, ..., continuedRay = true)
+            atomicAdd(&ctx.cnt->transmitted, 1ull);
+        } else {
+            double n = dot(dir, top_normal);
+            V3 localnormal;
+            if (n <= 0.0) { localnormal = top_normal; n = -n; }
+            else localnormal = -top_normal;
+            double t = 1.0 + sqr(ior) * (sqr(n) - 1.0);
+            if (t < 0.0) {
+                // total internal reflection: ComputeReflection with the ORIGINAL ray's interiors (trace.cpp:1462-1470)
+                tir = true;
+                spawn = false;
+                atomicAdd(&ctx.cnt->tir, 1ull);
+                atomicAdd(&ctx.cnt->reflected, 1ull);
+                PRay rr = ray;
+                V3 rd = reflect_direction(dir, top_normal, rawnormal);
+                rr.o[0] = ipoint.x; rr.o[1] = ipoint.y; rr.o[2] = ipoint.z;
+                rr.d[0] = rd.x; rr.d[1] = rd.y; rr.d[2] = rd.z;
+                rr.flags = (uint8_t)((ray.flags & PV_RAY_REFRACTION) | PV_RAY_REFLECTION);
+                rr.level = child_level;
+                rr.adc = (float)new_weight;
+                rr.w[0] = ray.w[0] * attc[0]; rr.w[1] = ray.w[1] * attc[1]; rr.w[2] = ray.w[2] * attc[2];
+                rr.wt = 0.0f;
+                push_ray(ctx, rr);
+            } else {
+                t = ior * n - sqrt(t);
+                V3 nd = ior * dir + t * localnormal;
+                nr.d[0] = nd.x; nr.d[1] = nd.y; nr.d[2] = nd.z;
+                atomicAdd(&ctx.cnt->refracted, 1ull);
+            }
+        }
+        if (spawn) {
+            // one_colour_found is always true on this path (no image maps)
+            nr.w[0] = ray.w[0] * attc[0] * fil[0]; nr.w[1] = ray.w[1] * attc[1] * fil[1]; nr.w[2] = ray.w[2] * attc[2] * fil[2];
+            nr.wt = ray.wt * (float)((double)greyscale(attc) * trans);
+            push_ray(ctx, nr);
+        }
+    }
+
+    // ---- reflected component (trace.cpp:1151-1178)
+    if (sc.g.quality_flags & PVGPU_Q_REFLECTIONS) {
+        for (int i = 0; i < nlayers; i++) {
+            const Layer& L = layers[i];
+            if (tir) continue;      // all layer normals equal topNormal on this path
+            if (L.refl[0] == 0.0f && L.refl[1] == 0.0f && L.refl[2] == 0.0f) continue;
+            PRay rr = ray;
+            V3 rd = reflect_direction(dir, lay_normal, rawnormal);
+            rr.o[0] = ipoint.x; rr.o[1] = ipoint.y; rr.o[2] = ipoint.z;
+            rr.d[0] = rd.x; rr.d[1] = rd.y; rr.d[2] = rd.z;
+            rr.flags = (uint8_t)((ray.flags & PV_RAY_REFRACTION) | PV_RAY_REFLECTION);   // Ray::SetFlags(ReflectionRay, ray); alphaBackground off
+            rr.level = child_level;
+            rr.adc = (float)L.rweight;
+            rr.w[0] = ray.w[0] * L.refl[0]; rr.w[1] = ray.w[1] * L.refl[1]; rr.w[2] = ray.w[2] * L.refl[2];
+            rr.wt = 0.0f;
+            atomicAdd(&ctx.cnt->reflected, 1ull);
+            push_ray(ctx, rr);
+        }
+    }
+}
+
+// ---- shadow rays ----------------------------------------------------------------------------------
+// Trace::ComputeShadowTexture (trace.cpp:1181-1262) for a transparent blocker.
+__device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3& dir, const PRay* parent, bool inside_now, float f[3])
+{
+    const pvgpu_object& ob = sc.objs[hit.obj];
+    V3 rawnormal = object_normal(sc, ob, hit);
+    if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
+    const double nd = dot(rawnormal, dir);
+    if (nd > 0.0) rawnormal = -rawnormal;
+    const int32_t tex0 = hit_texture(sc, ob, hit, nd > 0.0);
+    if (tex0 < 0) return;       // texture list empty: colour unchanged (trace.cpp:2391-2397)
+    float tmp[3] = { 1.0f, 1.0f, 1.0f };
+    const pvgpu_interior* in = (ob.interior >= 0) ? &sc.interiors[ob.interior] : nullptr;
+    for (int32_t li = tex0; li >= 0; li = sc.textures[li].next) {
+        float lc[5];
+        compute_pigment(sc, sc.textures[li].pigment, hit.ip, lc);
+        #pragma unroll
+        for (int k = 0; k < 3; k++) tmp[k] *= (lc[k] * lc[3] + lc[4]);
+        if (in && in->caustics != 0.0f) {
+            double dotval = dot(rawnormal, dir);
+            float kk = (float)(1.0 + pow(fabs(dotval), (double)in->caustics));
+            tmp[0] *= kk; tmp[1] *= kk; tmp[2] *= kk;
+        }
+    }
+    float refr[3] = { 1.0f, 1.0f, 1.0f };
+    if (in && inside_now && in->fade_power > 0.0f && fabs((double)in->fade_distance) > PV_EPSILON) {
+        if (in->fade_power >= 1000.0f) {
+            #pragma unroll
+            for (int k = 0; k < 3; k++) refr[k] *= expf((float)(-(1.0 - (double)in->fade_colour[k]) * (hit.depth / (double)in->fade_distance)));
+        } else {
+            double kk = 1.0 + pow(hit.depth / (double)in->fade_distance, (double)in->fade_power);
+            #pragma unroll
+            for (int k = 0; k < 3; k++) refr[k] *= (float)((double)in->fade_colour[k] + (1.0 - (double)in->fade_colour[k]) / kk);
+        }
+    }
+    float tc[3] = { tmp[0] * refr[0], tmp[1] * refr[1], tmp[2] * refr[2] };
+    // ComputeShadowColour: "close enough to full shadow" (trace.cpp:2419-2424)
+    if (fabsf((fabsf(tc[0]) + fabsf(tc[1]) + fabsf(tc[2])) / 3.0f) < (float)sc.g.adc_bailout) { f[0] = f[1] = f[2] = 0.0f; return; }
+    f[0] *= tc[0]; f[1] *= tc[1]; f[2] *= tc[2];
+}
+
+// Trace::TraceShadowRay -> TracePointLightShadowRay (trace.cpp:1892-2076) without the (result-neutral)
+// shadow caches.  Returns the factor the light colour is multiplied with.
+__device__ inline void trace_shadow(const DScene& sc, const SRay& s, const PRay* wave, uint2* stack, Counters* cnt, float f[3])
+{
+    f[0] = f[1] = f[2] = 1.0f;
+    V3 o = ld3(s.o);
+    const V3 d = ld3(s.d);
+    double depth = s.depth;
+    // interiors of the light ray start as a copy of the eye ray's (Ray lightsourceray(eye), trace.cpp:1642)
+    PRay in_state;
+    in_state.n_int = 0;
+    bool have_state = false;
+    unsigned long long tests = 0;
+    for (int iter = 0; iter < 256; iter++) {
+        Hit best;
+        best.depth = depth;
+        best.obj = PV_NO_OBJECT;
+        tests++;
+        bool found;
+        if (sc.all_opaque) found = find_intersection<true>(sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow, depth - PV_SHADOW_TOLERANCE);
+        else found = find_intersection<false>(sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow);
+        if (!(found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))) break;
+        const pvgpu_object& ob = sc.objs[best.obj];
+        if (ob.flags & PVGPU_OPAQUE_FLAG) { f[0] = f[1] = f[2] = 0.0f; break; }     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
+        if (!have_state) { in_state = wave[s.parent]; have_state = true; }
+        shadow_filter(sc, best, d, &in_state, ob.interior >= 0 && ray_is_interior(in_state, ob.interior), f);
+        // ComputeShadowMedia (trace.cpp:3046-3071) toggles the blocker's interior on the light ray
+        if (ob.interior >= 0) {
+            if (!ray_remove_interior(in_state, ob.interior)) ray_append_interior(in_state, ob.interior, &cnt->overflow);
+        }
+        if (f[0] == 0.0f && f[1] == 0.0f && f[2] == 0.0f) {
+            // colour is black; the reference keeps looping only to find an opaque object for its cache
+            break;
+        }
+        depth -= best.depth;
+        o = best.ip;
+    }
+    atomicAdd(&cnt->shadow_tests, tests);
+}
+
+}  // namespace pvgpu

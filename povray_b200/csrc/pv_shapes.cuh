@@ -1,0 +1,438 @@
+// Per-primitive FP64 intersection / inside / normal device functions.  Each follows the control flow,
+// tolerances and floating-point operation order of the reference method it cites, so that depths agree
+// to the last bit wherever only +,-,*,/ and sqrt are involved.
+#pragma once
+#include "pv_math.cuh"
+#include "pv_solver.cuh"
+
+namespace pvgpu {
+
+#define PV_SPHERE_DEPTH_TOL   1.0e-6   // sphere.cpp:63
+#define PV_BOX_DEPTH_TOL      1.0e-6   // box.cpp:67
+#define PV_BOX_CLOSE_TOL      1.0e-6   // box.cpp:70
+#define PV_PLANE_DEPTH_TOL    1.0e-6   // plane.cpp:62
+#define PV_QUADRIC_DEPTH_TOL  1.0e-6   // quadric.cpp:94
+#define PV_MESH_DEPTH_TOL     1.0e-6   // mesh.cpp:92
+#define PV_TORUS_DEPTH_TOL    1.0e-4   // torus.cpp:78
+#define PV_TORUS_ROOT_TOL     1.0e-4   // torus.cpp:81
+
+// Candidate hits of one primitive, in the order the reference pushes them on the IStack.
+struct PrimHits {
+    int    n;
+    double depth[4];
+    V3     ip[4];
+    uint32_t aux[4];
+};
+
+// ---- sphere -------------------------------------------------------------------------------------
+// Sphere::Intersect (sphere.cpp:211-243)
+__device__ __forceinline__ bool sphere_intersect(const V3& o, const V3& d, const V3& center, double radius2,
+                                                 double& depth1, double& depth2)
+{
+    V3 oc = center - o;
+    double oc2 = length_sqr(oc);
+    double tca = dot(oc, d);
+    if ((oc2 >= radius2) && (tca < PV_EPSILON)) return false;
+    double thc2 = radius2 - oc2 + sqr(tca);
+    if (thc2 > PV_EPSILON) {
+        double hc = sqrt(thc2);
+        depth1 = tca - hc;
+        depth2 = tca + hc;
+        return true;
+    }
+    return false;
+}
+
+// Sphere::All_Intersections (sphere.cpp:92-170)
+__device__ inline void sphere_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    double d1, d2;
+    if (ob.aux) {   // Do_Ellipsoid: unit sphere in object space
+        const pvgpu_transform& t = sc.xf[ob.transform];
+        V3 no = inv_trans_point(t, o);
+        V3 nd = inv_trans_direction(t, d);
+        double len = length(nd);
+        nd = nd / len;
+        if (sphere_intersect(no, nd, mk(0.0, 0.0, 0.0), 1.0, d1, d2)) {
+            if ((d1 > PV_SPHERE_DEPTH_TOL) && (d1 < PV_MAX_DISTANCE)) {
+                h.depth[h.n] = d1 / len; h.ip[h.n] = trans_point(t, evaluate(no, nd, d1)); h.aux[h.n] = 0; h.n++;
+            }
+            if ((d2 > PV_SPHERE_DEPTH_TOL) && (d2 < PV_MAX_DISTANCE)) {
+                h.depth[h.n] = d2 / len; h.ip[h.n] = trans_point(t, evaluate(no, nd, d2)); h.aux[h.n] = 0; h.n++;
+            }
+        }
+    } else {
+        if (sphere_intersect(o, d, ld3(ob.p), sqr(ob.p[3]), d1, d2)) {
+            if ((d1 > PV_SPHERE_DEPTH_TOL) && (d1 < PV_MAX_DISTANCE)) {
+                h.depth[h.n] = d1; h.ip[h.n] = evaluate(o, d, d1); h.aux[h.n] = 0; h.n++;
+            }
+            if ((d2 > PV_SPHERE_DEPTH_TOL) && (d2 < PV_MAX_DISTANCE)) {
+                h.depth[h.n] = d2; h.ip[h.n] = evaluate(o, d, d2); h.aux[h.n] = 0; h.n++;
+            }
+        }
+    }
+}
+
+// Sphere::Inside (sphere.cpp:262-300)
+__device__ inline bool sphere_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    double oc2;
+    if (ob.aux) oc2 = length_sqr(inv_trans_point(sc.xf[ob.transform], p));
+    else        oc2 = length_sqr(ld3(ob.p) - p);
+    return (ob.flags & PVGPU_INVERTED_FLAG) ? (oc2 > sqr(ob.p[3])) : (oc2 < sqr(ob.p[3]));
+}
+
+// Sphere::Normal (sphere.cpp:318-340)
+__device__ inline V3 sphere_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip)
+{
+    if (ob.aux) {
+        const pvgpu_transform& t = sc.xf[ob.transform];
+        return normalized(trans_normal(t, inv_trans_point(t, ip)));
+    }
+    return (ip - ld3(ob.p)) / ob.p[3];
+}
+
+// ---- plane --------------------------------------------------------------------------------------
+// Plane::Intersect + All_Intersections (plane.cpp:92-190)
+__device__ inline void plane_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    V3 n = ld3(ob.p);
+    double ndd, ndo;
+    if (ob.transform < 0) {
+        ndd = dot(n, d);
+        if (fabs(ndd) < PV_EPSILON) return;
+        ndo = dot(n, o);
+    } else {
+        const pvgpu_transform& t = sc.xf[ob.transform];
+        V3 P = inv_trans_point(t, o);
+        V3 D = inv_trans_direction(t, d);
+        ndd = dot(n, D);
+        if (fabs(ndd) < PV_EPSILON) return;
+        ndo = dot(n, P);
+    }
+    double depth = -(ndo + ob.p[3]) / ndd;
+    if ((depth >= PV_PLANE_DEPTH_TOL) && (depth <= PV_MAX_DISTANCE)) {
+        h.depth[0] = depth; h.ip[0] = evaluate(o, d, depth); h.aux[0] = 0; h.n = 1;
+    }
+}
+
+// Plane::Inside (plane.cpp:208-225)
+__device__ inline bool plane_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    double temp;
+    if (ob.transform < 0) temp = dot(p, ld3(ob.p));
+    else                  temp = dot(inv_trans_point(sc.xf[ob.transform], p), ld3(ob.p));
+    return (temp + ob.p[3]) < PV_EPSILON;
+}
+
+// Plane::Normal (plane.cpp:243-253)
+__device__ inline V3 plane_normal(const DScene& sc, const pvgpu_object& ob)
+{
+    V3 n = ld3(ob.p);
+    if (ob.transform >= 0) n = normalized(trans_normal(sc.xf[ob.transform], n));
+    return n;
+}
+
+// ---- box ----------------------------------------------------------------------------------------
+// Box::Intersect (box.cpp:167-520).  The reference unrolls the three axes; the near/far bookkeeping is
+// identical per axis except that X uses no CLOSE_TOLERANCE and Y / Z break near-ties by comparing the
+// direction component with that of the axis of the side currently recorded (Y always against X).
+__device__ inline bool box_intersect(const V3& P, const V3& D, const double* c1, const double* c2,
+                                     double& depth1, double& depth2, int& side1, int& side2)
+{
+    int smin = 0, smax = 0;
+    double tmin = 0.0, tmax = PV_BOUND_HUGE, t;
+    // X
+    if (D.x < -PV_EPSILON) {
+        t = (c1[0] - P.x) / D.x;
+        if (t < tmin) return false;
+        if (t <= tmax) { smax = 1; tmax = t; }
+        t = (c2[0] - P.x) / D.x;
+        if (t >= tmin) { if (t > tmax) return false; smin = 2; tmin = t; }
+    } else if (D.x > PV_EPSILON) {
+        t = (c2[0] - P.x) / D.x;
+        if (t < tmin) return false;
+        if (t <= tmax) { smax = 2; tmax = t; }
+        t = (c1[0] - P.x) / D.x;
+        if (t >= tmin) { if (t > tmax) return false; smin = 1; tmin = t; }
+    } else if ((P.x < c1[0]) || (P.x > c2[0])) return false;
+
+    // Y and Z share one shape
+    #pragma unroll
+    for (int ax = 1; ax < 3; ax++) {
+        const double Da = (ax == 1) ? D.y : D.z, Pa = (ax == 1) ? P.y : P.z;
+        const int s0 = 2 * ax + 1, s1 = 2 * ax + 2;       // kSideHit_{Y0,Y1} = 3,4 ; {Z0,Z1} = 5,6
+        if (Da < -PV_EPSILON || Da > PV_EPSILON) {
+            const bool neg = Da < -PV_EPSILON;
+            const double far_c = neg ? c1[ax] : c2[ax], near_c = neg ? c2[ax] : c1[ax];
+            const int far_s = neg ? s0 : s1, near_s = neg ? s1 : s0;
+            const double mag = neg ? -Da : Da;
+            t = (far_c - Pa) / Da;
+            if (t < tmin) return false;
+            if (t <= tmax - PV_BOX_CLOSE_TOL) { smax = far_s; tmax = t; }
+            else if (t <= tmax + PV_BOX_CLOSE_TOL) {
+                if (ax == 1) { if (mag > fabs(D.x)) smax = far_s; }
+                else if (smax == 1 || smax == 2) { if (mag > fabs(D.x)) smax = far_s; }
+                else if (smax == 3 || smax == 4) { if (mag > fabs(D.y)) smax = far_s; }
+            }
+            t = (near_c - Pa) / Da;
+            if (t >= tmin + PV_BOX_CLOSE_TOL) { if (t > tmax) return false; smin = near_s; tmin = t; }
+            else if (t >= tmin - PV_BOX_CLOSE_TOL) {
+                if (ax == 1) { if (mag > fabs(D.x)) smin = near_s; }
+                else if (smin == 1 || smin == 2) { if (mag > fabs(D.x)) smin = near_s; }
+                else if (smin == 3 || smin == 4) { if (mag > fabs(D.y)) smin = near_s; }
+            }
+        } else if ((Pa < c1[ax]) || (Pa > c2[ax])) return false;
+    }
+    if (tmax < PV_BOX_DEPTH_TOL) return false;
+    depth1 = tmin; depth2 = tmax; side1 = smin; side2 = smax;
+    return true;
+}
+
+// Box::All_Intersections (box.cpp:100-149)
+__device__ inline void box_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    V3 P = o, D = d;
+    if (ob.transform >= 0) {
+        const pvgpu_transform& t = sc.xf[ob.transform];
+        P = inv_trans_point(t, o);
+        D = inv_trans_direction(t, d);
+    }
+    double d1, d2; int s1, s2;
+    if (box_intersect(P, D, ob.p, ob.p + 3, d1, d2, s1, s2)) {
+        if (d1 > PV_BOX_DEPTH_TOL) { h.depth[h.n] = d1; h.ip[h.n] = evaluate(o, d, d1); h.aux[h.n] = (uint32_t)s1; h.n++; }
+        h.depth[h.n] = d2; h.ip[h.n] = evaluate(o, d, d2); h.aux[h.n] = (uint32_t)s2; h.n++;
+    }
+}
+
+// Box::Inside (box.cpp:538-575)
+__device__ inline bool box_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    V3 q = (ob.transform >= 0) ? inv_trans_point(sc.xf[ob.transform], p) : p;
+    const bool inv = (ob.flags & PVGPU_INVERTED_FLAG) != 0;
+    if ((q.x < ob.p[0]) || (q.x > ob.p[3])) return inv;
+    if ((q.y < ob.p[1]) || (q.y > ob.p[4])) return inv;
+    if ((q.z < ob.p[2]) || (q.z > ob.p[5])) return inv;
+    return !inv;
+}
+
+// Box::Normal (box.cpp:600-620)
+__device__ inline V3 box_normal(const DScene& sc, const pvgpu_object& ob, uint32_t side)
+{
+    V3 n = mk(0.0, 0.0, 0.0);
+    switch (side) {
+        case 1: n.x = -1.0; break;
+        case 2: n.x = 1.0; break;
+        case 3: n.y = -1.0; break;
+        case 4: n.y = 1.0; break;
+        case 5: n.z = -1.0; break;
+        case 6: n.z = 1.0; break;
+    }
+    if (ob.transform >= 0) n = normalized(trans_normal(sc.xf[ob.transform], n));
+    return n;
+}
+
+// ---- quadric ------------------------------------------------------------------------------------
+// Quadric::Intersect + All_Intersections (quadric.cpp:123-230); coefficient names as in quadric.cpp:80-92
+__device__ inline void quadric_hits(const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    const double QA = ob.p[0], QE = ob.p[1], QH = ob.p[2], QB = ob.p[3], QC = ob.p[4], QF = ob.p[5],
+                 QD = ob.p[6], QG = ob.p[7], QI = ob.p[8], QJ = ob.p[9];
+    const double Xo = o.x, Yo = o.y, Zo = o.z, Xd = d.x, Yd = d.y, Zd = d.z;
+    double a = Xd * (QA * Xd + QB * Yd + QC * Zd) + Yd * (QE * Yd + QF * Zd) + Zd * QH * Zd;
+    double b = Xd * (QA * Xo + 0.5 * (QB * Yo + QC * Zo + QD)) +
+               Yd * (QE * Yo + 0.5 * (QB * Xo + QF * Zo + QG)) +
+               Zd * (QH * Zo + 0.5 * (QC * Xo + QF * Yo + QI));
+    double c = Xo * (QA * Xo + QB * Yo + QC * Zo + QD) + Yo * (QE * Yo + QF * Zo + QG) + Zo * (QH * Zo + QI) + QJ;
+    double d1, d2;
+    if (a != 0.0) {
+        double disc = sqr(b) - a * c;
+        if (disc <= 0.0) return;
+        disc = sqrt(disc);
+        d1 = (-b + disc) / a;
+        d2 = (-b - disc) / a;
+    } else {
+        if (b == 0.0) return;
+        d1 = -0.5 * c / b;
+        d2 = PV_MAX_DISTANCE;
+    }
+    if ((d1 > PV_QUADRIC_DEPTH_TOL) && (d1 < PV_MAX_DISTANCE)) { h.depth[h.n] = d1; h.ip[h.n] = evaluate(o, d, d1); h.aux[h.n] = 0; h.n++; }
+    if ((d2 > PV_QUADRIC_DEPTH_TOL) && (d2 < PV_MAX_DISTANCE)) { h.depth[h.n] = d2; h.ip[h.n] = evaluate(o, d, d2); h.aux[h.n] = 0; h.n++; }
+}
+
+// Quadric::Inside (quadric.cpp:248-255)
+__device__ inline bool quadric_inside(const pvgpu_object& ob, const V3& p)
+{
+    const double QA = ob.p[0], QE = ob.p[1], QH = ob.p[2], QB = ob.p[3], QC = ob.p[4], QF = ob.p[5],
+                 QD = ob.p[6], QG = ob.p[7], QI = ob.p[8], QJ = ob.p[9];
+    return (p.x * (QA * p.x + QB * p.y + QD) + p.y * (QE * p.y + QF * p.z + QG) + p.z * (QH * p.z + QC * p.x + QI) + QJ) <= 0.0;
+}
+
+// Quadric::Normal (quadric.cpp:273-310)
+__device__ inline V3 quadric_normal(const pvgpu_object& ob, const V3& ip)
+{
+    const double QA = ob.p[0], QE = ob.p[1], QH = ob.p[2], QB = ob.p[3], QC = ob.p[4], QF = ob.p[5],
+                 QD = ob.p[6], QG = ob.p[7], QI = ob.p[8];
+    V3 n = mk(2.0 * QA * ip.x + QB * ip.y + QC * ip.z + QD,
+              QB * ip.x + 2.0 * QE * ip.y + QF * ip.z + QG,
+              QC * ip.x + QF * ip.y + 2.0 * QH * ip.z + QI);
+    double len = length(n);
+    if (len == 0.0) return mk(1.0, 0.0, 0.0);
+    return n / len;
+}
+
+// ---- torus --------------------------------------------------------------------------------------
+// Torus::Test_Thick_Cylinder (torus.cpp:932-1059)
+__device__ inline bool torus_thick_cylinder(const V3& P, const V3& D, double h1, double h2, double r1, double r2)
+{
+    double a, b, c, d, u, v, k, r, h;
+    if (fabs(D.y) < PV_EPSILON) {
+        if ((P.y < h1) || (P.y > h2)) return false;
+    } else {
+        k = (h2 - P.y) / D.y;
+        u = P.x + k * D.x;
+        v = P.z + k * D.z;
+        if ((k > PV_EPSILON) && (k < PV_MAX_DISTANCE)) {
+            r = u * u + v * v;
+            if ((r >= r1) && (r <= r2)) return true;
+        }
+        k = (h1 - P.y) / D.y;
+        u = P.x + k * D.x;
+        v = P.z + k * D.z;
+        if ((k > PV_EPSILON) && (k < PV_MAX_DISTANCE)) {
+            r = u * u + v * v;
+            if ((r >= r1) && (r <= r2)) return true;
+        }
+    }
+    a = D.x * D.x + D.z * D.z;
+    if (a > PV_EPSILON) {
+        b = P.x * D.x + P.z * D.z;
+        c = P.x * P.x + P.z * P.z - r2;
+        d = b * b - a * c;
+        if (d >= 0.0) {
+            d = sqrt(d);
+            k = (-b + d) / a;
+            if ((k > PV_EPSILON) && (k < PV_MAX_DISTANCE)) { h = P.y + k * D.y; if ((h >= h1) && (h <= h2)) return true; }
+            k = (-b - d) / a;
+            if ((k > PV_EPSILON) && (k < PV_MAX_DISTANCE)) { h = P.y + k * D.y; if ((h >= h1) && (h <= h2)) return true; }
+        }
+        c = P.x * P.x + P.z * P.z - r1;
+        d = b * b - a * c;
+        if (d >= 0.0) {
+            d = sqrt(d);
+            k = (-b + d) / a;
+            if ((k > PV_EPSILON) && (k < PV_MAX_DISTANCE)) { h = P.y + k * D.y; if ((h >= h1) && (h <= h2)) return true; }
+            k = (-b - d) / a;
+            if ((k > PV_EPSILON) && (k < PV_MAX_DISTANCE)) { h = P.y + k * D.y; if ((h >= h1) && (h <= h2)) return true; }
+        }
+    }
+    return false;
+}
+
+// Torus::Intersect + All_Intersections (torus.cpp:133-160, 229-330); SpindleTorus filter (:162-210)
+__device__ inline void torus_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    const pvgpu_transform& t = sc.xf[ob.transform];
+    const double R = ob.p[0], rr = ob.p[1];
+    V3 P = inv_trans_point(t, o);
+    V3 D = inv_trans_direction(t, d);
+    double len = length(D);
+    D = D / len;
+    double y1 = -rr, y2 = rr;
+    double r1 = sqr(R - rr);
+    if (R < rr) r1 = 0;
+    double r2 = sqr(R + rr);
+    if (!torus_thick_cylinder(P, D, y1, y2, r1, r2)) return;
+    double bsr = R + rr + rr;
+    double distP = length_sqr(P);
+    double closer = 0.0;
+    if (distP > sqr(bsr)) {
+        distP = sqrt(distP);
+        closer = distP - bsr;
+        P = P + closer * D;
+    }
+    double R2 = sqr(R);
+    r2 = sqr(rr);
+    double Py2 = P.y * P.y, Dy2 = D.y * D.y, PDy2 = P.y * D.y;
+    double k1 = P.x * P.x + P.z * P.z + Py2 - R2 - r2;
+    double k2 = P.x * D.x + P.z * D.z + PDy2;
+    double c[5], r[4];
+    c[0] = 1.0;
+    c[1] = 4.0 * k2;
+    c[2] = 2.0 * (k1 + 2.0 * (k2 * k2 + R2 * Dy2));
+    c[3] = 4.0 * (k2 * k1 + 2.0 * R2 * PDy2);
+    c[4] = k1 * k1 + 4.0 * R2 * (Py2 - r2);
+    int n = solve_polynomial(4, c, r, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, PV_TORUS_ROOT_TOL);
+    while (n--) {
+        double depth = (r[n] + closer) / len;
+        if ((depth > PV_TORUS_DEPTH_TOL) && (depth < PV_MAX_DISTANCE)) {
+            V3 ip = evaluate(o, d, depth);
+            uint32_t aux = 0;
+            if (ob.aux) {                          // SpindleTorus: keep the hit only on the visible part
+                V3 lp = inv_trans_point(t, ip);
+                bool on_spindle = (length_sqr(lp) < ob.p[2]);
+                bool valid = on_spindle ? (ob.aux & 0x01u) : (ob.aux & 0x02u);   // SpindleVisible / NonSpindleVisible
+                if (!valid) continue;
+                aux = on_spindle ? 1u : 0u;
+            }
+            h.depth[h.n] = depth; h.ip[h.n] = ip; h.aux[h.n] = aux; h.n++;
+        }
+    }
+}
+
+// Torus::Inside (torus.cpp:348-365); spindle variant (:367-400)
+__device__ inline bool torus_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    V3 P = inv_trans_point(sc.xf[ob.transform], p);
+    double r = sqrt(sqr(P.x) + sqr(P.z));
+    double r2 = sqr(P.y) + sqr(r - ob.p[0]);
+    bool inside;
+    if (r2 <= sqr(ob.p[1])) {
+        inside = true;
+        if (ob.aux & 0x20u) {                       // SpindleRelevantForInside (torus.h:110)
+            bool in_spindle = (sqr(P.y) + sqr(r + ob.p[0]) <= sqr(ob.p[1]));
+            inside = (ob.aux & 0x04u) ? in_spindle : !in_spindle;   // SpindleInside (torus.h:107)
+        }
+    } else inside = false;
+    return inside ? !(ob.flags & PVGPU_INVERTED_FLAG) : (ob.flags & PVGPU_INVERTED_FLAG) != 0;
+}
+
+// Torus::Normal (torus.cpp:418-445)
+__device__ inline V3 torus_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip, uint32_t on_spindle)
+{
+    const pvgpu_transform& t = sc.xf[ob.transform];
+    V3 P = inv_trans_point(t, ip);
+    double dist = sqrt(P.x * P.x + P.z * P.z);
+    V3 M = mk(0.0, 0.0, 0.0);
+    if (dist > PV_EPSILON) { M.x = ob.p[0] * P.x / dist; M.z = ob.p[0] * P.z / dist; }
+    if (on_spindle) M = -M;                         // SpindleTorus::Normal (torus.cpp:447-489)
+    return normalized(trans_normal(t, P - M));
+}
+
+// ---- mesh triangle ------------------------------------------------------------------------------
+// Mesh::intersect_mesh_triangle (mesh.cpp:1040-1127): plane hit, then three edge tests in the 2-D
+// projection along the dominant axis.
+__device__ __forceinline__ bool tri_intersect(const DTri& tr, const V3& o, const V3& d, double& depth)
+{
+    V3 n = ld3f(tr.n);
+    double ndd = dot(n, d);
+    if (fabs(ndd) < PV_EPSILON) return false;
+    double ndo = dot(n, o);
+    depth = -((double)tr.dist + ndo) / ndd;
+    if ((depth < PV_MESH_DEPTH_TOL) || (depth > PV_MAX_DISTANCE)) return false;
+    const int ua = (tr.dom == 0) ? 1 : 0, va = (tr.dom == 2) ? 1 : 2;
+    double s = comp(o, ua) + depth * comp(d, ua);
+    double t = comp(o, va) + depth * comp(d, va);
+    double p1u = tr.p1[ua], p1v = tr.p1[va], p2u = tr.p2[ua], p2v = tr.p2[va], p3u = tr.p3[ua], p3v = tr.p3[va];
+    if ((p2u - s) * (p2v - p1v) < (p2v - t) * (p2u - p1u)) return false;
+    if ((p3u - s) * (p3v - p2v) < (p3v - t) * (p3u - p2u)) return false;
+    if ((p1u - s) * (p1v - p3v) < (p1v - t) * (p1u - p3u)) return false;
+    return true;
+}
+
+}  // namespace pvgpu

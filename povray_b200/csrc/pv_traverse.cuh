@@ -1,0 +1,489 @@
+// Closest-hit search: the flattened BBOX_TREE walk (Intersect_BBox_Tree + Check_And_Enqueue,
+// boundingbox.cpp:485-648), the per-object Find_Intersection (object.cpp:172-224) with its FP32 box
+// pre-test (object.cpp:917-941, 1074-1109), bounded_by / clipped_by (object.cpp:346-443), CSG
+// candidate filtering (csg.cpp:128-375) and the nested mesh tree (mesh.cpp:1452-1528).
+//
+// The reference walks the tree best-first with a binary heap; here each ray keeps a small LIFO stack
+// of (entry depth, node) pairs in local memory, pushes the children that pass the slab test nearest
+// last, and prunes entries whose entry depth exceeds the best hit so far.  The set of leaves whose
+// objects are tested against the final best depth is the same, so the closest hit is the same except
+// for exact ties between different objects (first visited wins in both schemes, visit order differs).
+#pragma once
+#include "pv_shapes.cuh"
+
+namespace pvgpu {
+
+// Rayinfo (boundingbox.h:182-216): FP32 origin and reciprocal direction.
+struct RayInfo {
+    float org[3], inv[3];
+    bool  nonzero[3], positive[3];
+};
+
+__device__ __forceinline__ RayInfo make_rayinfo(const V3& o, const V3& d)
+{
+    RayInfo ri;
+    const double dd[3] = { d.x, d.y, d.z };
+    const double oo[3] = { o.x, o.y, o.z };
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        ri.org[k] = (float)oo[k];
+        ri.nonzero[k] = (dd[k] != 0.0);
+        ri.inv[k] = ri.nonzero[k] ? (float)(1.0 / dd[k]) : 0.0f;
+        ri.positive[k] = (dd[k] > 0.0);
+    }
+    return ri;
+}
+
+// Check_And_Enqueue's slab test (boundingbox.cpp:566-636).  Box data and ray info are FP32 and the
+// products are formed in FP32, then compared in FP64 -- exactly the reference's operand types.
+__device__ __forceinline__ bool slab_test(const float* lo, const float* size, const RayInfo& ri, float& dmin_out)
+{
+    double dmin = -PV_BOUND_HUGE, dmax = PV_BOUND_HUGE;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float hi = __fadd_rn(lo[k], size[k]);
+        if (ri.nonzero[k]) {
+            double tmin, tmax;
+            if (ri.positive[k]) {
+                tmax = (double)__fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
+                if (tmax < PV_EPSILON) return false;
+                tmin = (double)__fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
+            } else {
+                tmax = (double)__fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
+                if (tmax < PV_EPSILON) return false;
+                tmin = (double)__fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
+            }
+            if (tmax < dmax) {
+                if (tmin > dmin) { if (tmin > tmax) return false; dmin = tmin; }
+                else if (dmin > tmax) return false;
+                dmax = tmax;
+            } else if (tmin > dmin) {
+                if (tmin > dmax) return false;
+                dmin = tmin;
+            }
+        } else if (!((lo[k] <= ri.org[k]) && (ri.org[k] <= hi))) return false;
+    }
+    dmin_out = (float)dmin;       // dmin is an FP32 product (or -BOUND_HUGE): the narrowing is exact enough for ordering
+    return true;
+}
+
+// ObjectBase::Intersect_BBox -> Intersect_BBox_Dir (object.cpp:917-941, 1074-1109): all-FP32 test that
+// gates All_Intersections for every primitive that does not override it (quadric, torus, mesh, CSG).
+__device__ inline bool object_bbox_test(const float* bbox, const V3& o, const V3& d, float maxd)
+{
+    float org[3] = { (float)o.x, (float)o.y, (float)o.z };
+    float inv[3] = { (float)(1.0 / d.x), (float)(1.0 / d.y), (float)(1.0 / d.z) };
+    float b0[3] = { bbox[0], bbox[1], bbox[2] };
+    float b1[3] = { __fadd_rn(bbox[0], bbox[3]), __fadd_rn(bbox[1], bbox[4]), __fadd_rn(bbox[2], bbox[5]) };
+    const bool nx = inv[0] < 0.0f, ny = inv[1] < 0.0f, nz = inv[2] < 0.0f;
+    float tmin  = __fmul_rn(__fsub_rn(nx ? b1[0] : b0[0], org[0]), inv[0]);
+    float tmax  = __fmul_rn(__fsub_rn(nx ? b0[0] : b1[0], org[0]), inv[0]);
+    float tymin = __fmul_rn(__fsub_rn(ny ? b1[1] : b0[1], org[1]), inv[1]);
+    float tymax = __fmul_rn(__fsub_rn(ny ? b0[1] : b1[1], org[1]), inv[1]);
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = __fmul_rn(__fsub_rn(nz ? b1[2] : b0[2], org[2]), inv[2]);
+    float tzmax = __fmul_rn(__fsub_rn(nz ? b0[2] : b1[2], org[2]), inv[2]);
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    return (tmin < maxd) && (tmax > (float)PV_MIN_ISECT_DEPTH);
+}
+
+__device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
+{
+    // Sphere, Box and Plane override Intersect_BBox to return true (sphere.cpp:753, box.cpp:1079, plane.cpp:629)
+    return type >= PVGPU_OBJ_QUADRIC;
+}
+
+// ---- Inside --------------------------------------------------------------------------------------
+__device__ bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, uint2* stack, int sp0);
+
+__device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, uint2* stack, int sp0)
+{
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
+        case PVGPU_OBJ_BOX:     return box_inside(sc, ob, p);
+        case PVGPU_OBJ_PLANE:   return plane_inside(sc, ob, p);
+        case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
+        case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
+        case PVGPU_OBJ_MESH:    return mesh_inside(sc, ob, p, stack, sp0);
+    }
+    return false;
+}
+
+// Inside_Object (object.cpp:346-355) = every clipped_by object contains the point AND Object->Inside();
+// CSGUnion/CSGMerge::Inside = any child, CSGIntersection::Inside = all children (csg.cpp:393-454).
+// Evaluated iteratively with short-circuit over the object graph (the reference recurses).
+__device__ __noinline__ bool inside_object(const DScene& sc, uint32_t root, const V3& p, uint2* stack, int sp0, bool root_clip = true)
+{
+    struct Frame { uint32_t obj; uint32_t cur; };
+    Frame st[PV_CSG_STACK];
+    int sp = 0;
+    st[0].obj = root; st[0].cur = 0;
+    bool ret = false, have_ret = false;
+    while (sp >= 0) {
+        Frame& f = st[sp];
+        const pvgpu_object& o = sc.objs[f.obj];
+        const uint32_t nclip = (sp == 0 && !root_clip) ? 0u : o.clip_count;   // Object->Inside() alone for the root if asked
+        const bool is_csg = o.type >= PVGPU_OBJ_CSG_UNION;
+        if (have_ret) {
+            have_ret = false;
+            const uint32_t e = f.cur - 1;
+            if (e < nclip) { if (!ret) { have_ret = true; sp--; continue; } }           // a clip object excludes the point
+            else if (o.type == PVGPU_OBJ_CSG_INTERSECTION) { if (!ret) { have_ret = true; sp--; continue; } }
+            else if (ret) { have_ret = true; sp--; continue; }                            // union / merge: one child suffices
+        }
+        uint32_t next;
+        if (f.cur < nclip) next = sc.index_list[o.clip_first + f.cur];
+        else if (!is_csg) { ret = prim_inside(sc, o, p, stack, sp0); have_ret = true; sp--; continue; }
+        else if (f.cur - nclip < o.child_count) next = sc.index_list[o.child_first + (f.cur - nclip)];
+        else { ret = (o.type == PVGPU_OBJ_CSG_INTERSECTION); have_ret = true; sp--; continue; }
+        f.cur++;
+        if (sp + 1 >= PV_CSG_STACK) { ret = false; have_ret = true; sp--; continue; }     // deeper than supported (validated on the host)
+        sp++;
+        st[sp].obj = next; st[sp].cur = 0;
+    }
+    return ret;
+}
+
+// Point_In_Clip (object.cpp:430-443)
+__device__ inline bool point_in_clip(const DScene& sc, const pvgpu_object& o, const V3& p, uint2* stack, int sp0)
+{
+    for (uint32_t i = 0; i < o.clip_count; i++)
+        if (!inside_object(sc, sc.index_list[o.clip_first + i], p, stack, sp0)) return false;
+    return true;
+}
+
+// ---- per-object candidate collection ----------------------------------------------------------------
+// Selection rule of Find_Intersection (object.cpp:203-215): the IStack is popped from the top with a
+// strict `<`, so among equal depths of ONE object the hit pushed LAST wins -> `<=` in push order.
+struct HitAcc {
+    double closest;      // starts at HUGE_VAL per object
+    double post_min;     // SmallToleranceRayObjectCondition: depth > post_min (shadow rays), else -1
+    Hit    best;
+    bool   found;
+};
+
+__device__ __forceinline__ void consider(HitAcc& acc, double depth, const V3& ip, uint32_t obj, uint32_t aux, int32_t csg)
+{
+    if (depth <= acc.closest && depth >= PV_MIN_ISECT_DEPTH && depth > acc.post_min) {
+        acc.closest = depth;
+        acc.best.depth = depth; acc.best.ip = ip; acc.best.obj = obj; acc.best.aux = aux; acc.best.csg = csg;
+        acc.found = true;
+    }
+}
+
+__device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_PLANE:   plane_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_QUADRIC: quadric_hits(ob, o, d, h); break;
+        case PVGPU_OBJ_TORUS:   torus_hits(sc, ob, o, d, h); break;
+        default: h.n = 0; break;
+    }
+}
+
+// Test_Ray_Flags / Test_Ray_Flags_Shadow (csg.cpp:80-104) for the ray kinds this path traces.
+__device__ __forceinline__ bool test_ray_flags(uint32_t oflags, uint32_t rflags, bool shadow_ray, bool shadow_variant)
+{
+    const bool primary = (rflags & PV_RAY_PRIMARY) != 0;
+    const bool reflection = (rflags & PV_RAY_REFLECTION) != 0;
+    const bool image = !shadow_ray && (primary || ((rflags & PV_RAY_REFRACTION) && !reflection));
+    bool ok = (!(oflags & PVGPU_NO_IMAGE_FLAG) || !image || (!shadow_variant && primary)) &&
+              (!(oflags & PVGPU_NO_REFLECTION_FLAG) || !reflection);
+    if (shadow_variant && shadow_ray && !(oflags & PVGPU_NO_SHADOW_FLAG)) ok = true;
+    return ok;
+}
+
+// Mesh::intersect_bbox_tree + test_hit (mesh.cpp:1452-1528, 1208-1243) with a LIFO stack.
+__device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvgpu_object& ob, const V3& o, const V3& d,
+                                 HitAcc& acc, int32_t csg, uint2* stack, int sp0, unsigned int* overflow)
+{
+    const DMesh& me = sc.meshes[ob.mesh];
+    V3 mo = o, md = d;
+    double len = 1.0;
+    if (ob.transform >= 0) {
+        const pvgpu_transform& t = sc.xf[ob.transform];
+        mo = inv_trans_point(t, o);
+        md = inv_trans_direction(t, d);
+        len = length(md);
+        md = md / len;
+    }
+    if (me.node_count == 0) {
+        for (uint32_t i = 0; i < me.tri_count; i++) {
+            double t;
+            if (tri_intersect(sc.dtris[me.tri_first + i], mo, md, t)) {
+                double wd = t / len;
+                V3 ip = evaluate(o, d, wd);
+                if (ob.clip_count == 0 || point_in_clip(sc, ob, ip, stack, sp0)) consider(acc, wd, ip, obj_index, me.tri_first + i, csg);
+            }
+        }
+        return;
+    }
+    const RayInfo ri = make_rayinfo(mo, md);
+    const pvgpu_node* nodes = sc.mnodes + me.node_first;
+    int sp = sp0;
+    float dmin;
+    {
+        const pvgpu_node root = nodes[0];
+        if (!slab_test(root.lo, root.size, ri, dmin)) return;
+        stack[sp++] = make_uint2(__float_as_uint(dmin), 0u);
+    }
+    // entries further than the closest accepted hit cannot improve it; compared in mesh space (t = world * len)
+    while (sp > sp0) {
+        const uint2 e = stack[--sp];
+        if ((double)__uint_as_float(e.x) > acc.closest * len) continue;
+        const pvgpu_node n = nodes[e.y];
+        if (n.count) {
+            const int base = sp;
+            for (uint32_t c = 0; c < n.count; c++) {
+                const pvgpu_node ch = nodes[n.first + c];
+                if (slab_test(ch.lo, ch.size, ri, dmin)) {
+                    if (sp >= PV_STACK_SIZE) { atomicOr(overflow, 1u); break; }
+                    int j = sp++;
+                    while (j > base && __uint_as_float(stack[j - 1].x) < dmin) { stack[j] = stack[j - 1]; j--; }   // keep nearest on top
+                    stack[j] = make_uint2(__float_as_uint(dmin), n.first + c);
+                }
+            }
+        } else {
+            double t;
+            const uint32_t ti = me.tri_first + n.first;
+            if (tri_intersect(sc.dtris[ti], mo, md, t)) {
+                double wd = t / len;
+                V3 ip = evaluate(o, d, wd);
+                if (ob.clip_count == 0 || point_in_clip(sc, ob, ip, stack, sp)) consider(acc, wd, ip, obj_index, ti, csg);
+            }
+        }
+    }
+}
+
+// Mesh::Inside + inside_bbox_tree (mesh.cpp:197-262, 2266-2315): parity of crossings along Inside_Vect.
+__device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, uint2* stack, int sp0)
+{
+    const DMesh& me = sc.meshes[ob.mesh];
+    if (!me.has_inside_vector) return false;
+    V3 mo = p, md = ld3(me.inside_vector);
+    if (ob.transform >= 0) {
+        const pvgpu_transform& t = sc.xf[ob.transform];
+        mo = inv_trans_point(t, p);
+        md = normalized(inv_trans_direction(t, md));
+    }
+    unsigned found = 0;
+    if (me.node_count == 0) {
+        for (uint32_t i = 0; i < me.tri_count; i++) {
+            double t;
+            if (tri_intersect(sc.dtris[me.tri_first + i], mo, md, t)) found++;
+        }
+    } else {
+        const RayInfo ri = make_rayinfo(mo, md);
+        const pvgpu_node* nodes = sc.mnodes + me.node_first;
+        int sp = sp0;
+        float dmin;
+        const pvgpu_node root = nodes[0];
+        if (slab_test(root.lo, root.size, ri, dmin)) stack[sp++] = make_uint2(0u, 0u);
+        while (sp > sp0) {
+            const uint2 e = stack[--sp];
+            const pvgpu_node n = nodes[e.y];
+            if (n.count) {
+                for (uint32_t c = 0; c < n.count && sp < PV_STACK_SIZE; c++) {
+                    const pvgpu_node ch = nodes[n.first + c];
+                    if (slab_test(ch.lo, ch.size, ri, dmin)) stack[sp++] = make_uint2(0u, n.first + c);
+                }
+            } else {
+                double t;
+                if (tri_intersect(sc.dtris[me.tri_first + n.first], mo, md, t)) found++;
+            }
+        }
+    }
+    bool inside = (found & 1u) != 0;
+    if (ob.flags & PVGPU_INVERTED_FLAG) inside = !inside;
+    return inside;
+}
+
+// CSG*::All_Intersections (csg.cpp:128-375) without recursion: every primitive descendant contributes
+// its hits; a hit survives iff, walking up to the CSG being tested, every intersection ancestor has the
+// point inside all other children, every merge ancestor has it inside none of the other children, and
+// every ancestor's clipped_by list contains it.  Intersection::Csg ends up as the outermost ancestor
+// that sets it (unions without clipped_by do not, csg.cpp:137-150).
+__device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
+                                HitAcc& acc, uint2* stack, int sp0, unsigned int* overflow)
+{
+    const uint2 range = sc.csg_leaf_range[top];
+    for (uint32_t li = 0; li < range.y; li++) {
+        const uint32_t leaf = sc.csg_leaves[range.x + li];
+        const pvgpu_object& lo = sc.objs[leaf];
+        // ray-kind visibility of the leaf and of every ancestor below `top` (children of unions / merges only)
+        bool visible = true;
+        for (uint32_t c = leaf; c != top && visible; c = (uint32_t)sc.objs[c].parent) {
+            const uint32_t ptype = sc.objs[sc.objs[c].parent].type;
+            if (ptype == PVGPU_OBJ_CSG_UNION) visible = test_ray_flags(sc.objs[c].flags, rflags, shadow_ray, false);
+            else if (ptype == PVGPU_OBJ_CSG_MERGE) visible = test_ray_flags(sc.objs[c].flags, rflags, shadow_ray, true);
+        }
+        if (!visible) continue;
+        if (lo.type == PVGPU_OBJ_MESH) { atomicOr(overflow, 2u); continue; }   // mesh inside CSG: rejected at finalize
+        PrimHits h;
+        prim_hits(sc, lo, o, d, h);
+        for (int i = 0; i < h.n; i++) {
+            const V3 ip = h.ip[i];
+            if (lo.clip_count && !point_in_clip(sc, lo, ip, stack, sp0)) continue;
+            bool keep = true;
+            int32_t csg = -1;
+            uint32_t child = leaf;
+            while (child != top && keep) {
+                const uint32_t par = (uint32_t)sc.objs[child].parent;
+                const pvgpu_object& po = sc.objs[par];
+                if (po.type == PVGPU_OBJ_CSG_INTERSECTION) {
+                    for (uint32_t k = 0; k < po.child_count && keep; k++) {
+                        const uint32_t sib = sc.index_list[po.child_first + k];
+                        if (sib != child && !inside_object(sc, sib, ip, stack, sp0)) keep = false;
+                    }
+                    if (keep && po.clip_count && !point_in_clip(sc, po, ip, stack, sp0)) keep = false;
+                    if (keep) csg = (int32_t)par;
+                } else if (po.type == PVGPU_OBJ_CSG_MERGE) {
+                    if (po.clip_count && !point_in_clip(sc, po, ip, stack, sp0)) keep = false;
+                    for (uint32_t k = 0; k < po.child_count && keep; k++) {
+                        const uint32_t sib = sc.index_list[po.child_first + k];
+                        if (sib != child && test_ray_flags(sc.objs[sib].flags, rflags, shadow_ray, true) &&
+                            inside_object(sc, sib, ip, stack, sp0)) keep = false;
+                    }
+                    if (keep) csg = (int32_t)par;
+                } else {   // union
+                    if (po.clip_count) {
+                        if (!point_in_clip(sc, po, ip, stack, sp0)) keep = false;
+                        else csg = (int32_t)par;
+                    }
+                }
+                child = par;
+            }
+            if (keep) consider(acc, h.depth[i], ip, leaf, h.aux[i], csg);
+        }
+    }
+}
+
+__device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
+                                                uint2* stack, int sp0, unsigned int* overflow);
+
+// Find_Intersection for one frame-level object (object.cpp:172-224 / trace.cpp:345-443).
+__device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
+                                   double post_min, float bbox_maxd, Hit& out, uint2* stack, int sp0, unsigned int* overflow)
+{
+    const pvgpu_object& ob = sc.objs[idx];
+    if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, bbox_maxd)) return false;
+    // Ray_In_Bound (object.cpp:385-400)
+    for (uint32_t i = 0; i < ob.bound_count; i++) {
+        const uint32_t b = sc.index_list[ob.bound_first + i];
+        if (!object_find_simple(sc, b, o, d, rflags, stack, sp0, overflow) && !inside_object(sc, b, o, stack, sp0)) return false;
+    }
+    HitAcc acc;
+    acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
+    if (ob.type >= PVGPU_OBJ_CSG_UNION) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow);
+    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
+    else {
+        PrimHits h;
+        prim_hits(sc, ob, o, d, h);
+        for (int i = 0; i < h.n; i++)
+            if (ob.clip_count == 0 || point_in_clip(sc, ob, h.ip[i], stack, sp0)) consider(acc, h.depth[i], h.ip[i], idx, h.aux[i], -1);
+    }
+    if (acc.found) out = acc.best;
+    return acc.found;
+}
+
+// The plain Find_Intersection(isect, object, ray) used for bounded_by objects (no post-condition,
+// maxd = HUGE_VAL; nested bounded_by lists are rejected on the host).
+__device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
+                                                uint2* stack, int sp0, unsigned int* overflow)
+{
+    const pvgpu_object& ob = sc.objs[idx];
+    if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL)) return false;
+    HitAcc acc;
+    acc.closest = PV_HUGE_VAL; acc.post_min = -1.0; acc.found = false;
+    if (ob.type >= PVGPU_OBJ_CSG_UNION) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow);
+    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
+    else {
+        PrimHits h;
+        prim_hits(sc, ob, o, d, h);
+        for (int i = 0; i < h.n; i++)
+            if (ob.clip_count == 0 || point_in_clip(sc, ob, h.ip[i], stack, sp0)) consider(acc, h.depth[i], h.ip[i], idx, h.aux[i], -1);
+    }
+    return acc.found;
+}
+
+// Pre-condition of the traversal (NoSomethingFlagRayObjectCondition trace.cpp:84-95 for TraceRay,
+// NoShadowFlagRayObjectCondition trace.cpp:1943 for shadow rays).
+__device__ __forceinline__ bool precondition(uint32_t oflags, uint32_t rflags, bool shadow_ray)
+{
+    if (shadow_ray) return !(oflags & PVGPU_NO_SHADOW_FLAG);
+    const bool reflection = (rflags & PV_RAY_REFLECTION) != 0;
+    const bool image = (rflags & PV_RAY_PRIMARY) || ((rflags & PV_RAY_REFRACTION) && !reflection);
+    if (image && (oflags & PVGPU_NO_IMAGE_FLAG)) return false;
+    if (reflection && (oflags & PVGPU_NO_REFLECTION_FLAG)) return false;
+    return true;
+}
+
+// Trace::FindIntersection(bestisect, ray, precondition, postcondition) (trace.cpp:285-344).
+//   best.depth must be preset to the search limit (HUGE_VAL, Max_Ray_Distance or the light distance).
+//   ANY_OPAQUE: shadow-ray mode that returns as soon as a hit on an OPAQUE object satisfies the shadow
+//   window (depth in (SHADOW_TOLERANCE, limit - SHADOW_TOLERANCE)); see trace_shadow in pv_shade.cuh.
+template <bool ANY_OPAQUE>
+__device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
+                                         double post_min, Hit& best, uint2* stack, unsigned int* overflow,
+                                         double opaque_limit = 0.0)
+{
+    bool found = false;
+    if (!sc.use_tree) {
+        // boundingMethod 0: linear loop over SceneData::objects (trace.cpp:321-340)
+        for (uint32_t i = 0; i < sc.n_frame; i++) {
+            const uint32_t idx = sc.frame[i];
+            if (!precondition(sc.objs[idx].flags, rflags, shadow_ray)) continue;
+            Hit h;
+            if (object_find(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, 0, overflow) && h.depth < best.depth) {
+                best = h;
+                found = true;
+                if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
+            }
+        }
+        return found;
+    }
+    const RayInfo ri = make_rayinfo(o, d);
+    int sp = 0;
+    float dmin;
+    {
+        const pvgpu_node root = sc.nodes[0];
+        if (root.flags & PVGPU_NODE_INFINITE) dmin = (float)-PV_MAX_DISTANCE;
+        else if (!slab_test(root.lo, root.size, ri, dmin)) return false;
+        stack[sp++] = make_uint2(__float_as_uint(dmin), 0u);
+    }
+    while (sp > 0) {
+        const uint2 e = stack[--sp];
+        if ((double)__uint_as_float(e.x) > best.depth) continue;      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
+        const pvgpu_node n = sc.nodes[e.y];
+        if (n.count) {
+            const int base = sp;
+            for (uint32_t c = 0; c < n.count; c++) {
+                const pvgpu_node ch = sc.nodes[n.first + c];
+                if (ch.flags & PVGPU_NODE_INFINITE) dmin = (float)-PV_MAX_DISTANCE;
+                else if (!slab_test(ch.lo, ch.size, ri, dmin)) continue;
+                if (sp >= PV_STACK_SIZE) { atomicOr(overflow, 1u); break; }
+                int j = sp++;
+                while (j > base && __uint_as_float(stack[j - 1].x) < dmin) { stack[j] = stack[j - 1]; j--; }
+                stack[j] = make_uint2(__float_as_uint(dmin), n.first + c);
+            }
+        } else {
+            const uint32_t idx = n.first;
+            if (!precondition(sc.objs[idx].flags, rflags, shadow_ray)) continue;
+            Hit h;
+            if (object_find(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow) && h.depth < best.depth) {
+                best = h;
+                found = true;
+                if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
+            }
+        }
+    }
+    return found;
+}
+
+}  // namespace pvgpu

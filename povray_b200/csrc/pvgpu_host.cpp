@@ -1,0 +1,711 @@
+// Host side of the pvgpu C ABI: scene container, table setters, validation, the bounding-tree builder
+// (for scenes that do not come with a BBOX_TREE from POV-Ray's BoundingTask), the mesh2 helper and
+// the flat-scene file format.  No tracing happens here; everything that computes pixels or
+// intersections lives in pvgpu_device.cu and runs on the GPU only.
+#include "pvgpu_scene.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <limits>
+
+namespace pvgpu {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void clear_error() { g_err[0] = 0; }
+
+// ------------------------------------------------------------------------------------------------
+// Bounding tree construction.
+//
+// Follows Build_BBox_Tree / sort_and_split / find_axis / calc_bbox / build_area_table
+// (source/core/bounding/boundingbox.cpp:262-323, 700-927) so that a scene assembled through the ABI
+// gets the SAME tree POV-Ray's BoundingTask would hand us: leaves are bunched bottom-up into nodes of
+// at most BUNCHING_FACTOR (4) entries unless splitting stops paying off, and the pass is repeated on
+// the freshly made nodes until one node is left.  All box arithmetic is FP32 exactly as there.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int    kBunching  = 4;          // BUNCHING_FACTOR, boundingbox.cpp:68
+constexpr double kBoundHuge = 2.0e10;     // BOUND_HUGE, configcore.h:184
+
+struct BuildNode {
+    float lo[3], size[3];
+    std::vector<int64_t> kids;            // empty: leaf
+    uint32_t payload = 0;
+    bool infinite = false;
+};
+
+struct TreeBuilder {
+    std::deque<BuildNode> pool;
+    std::vector<int64_t>  work;           // the reference's `Finite` array (ids into pool)
+    std::vector<float>    area;
+    int64_t root = -1;
+
+    static thread_local const TreeBuilder* sort_ctx;
+    static thread_local int sort_axis;
+
+    static int cmp(const void* pa, const void* pb)
+    {
+        const BuildNode& a = sort_ctx->pool[(size_t)*(const int64_t*)pa];
+        const BuildNode& b = sort_ctx->pool[(size_t)*(const int64_t*)pb];
+        // compboxes<>: am = 2.0 * lowerLeft + size evaluated in double, stored as BBoxScalar
+        float am = (float)(2.0 * a.lo[sort_axis] + a.size[sort_axis]);
+        float bm = (float)(2.0 * b.lo[sort_axis] + b.size[sort_axis]);
+        if (am < bm) return -1;
+        return (am == bm) ? 0 : 1;
+    }
+
+    int find_axis(ptrdiff_t first, ptrdiff_t last) const
+    {
+        float mins[3], maxs[3];
+        for (int k = 0; k < 3; k++) { mins[k] = (float)kBoundHuge; maxs[k] = (float)-kBoundHuge; }
+        for (ptrdiff_t i = first; i < last; i++) {
+            const BuildNode& n = pool[(size_t)work[i]];
+            for (int k = 0; k < 3; k++) {
+                if (n.lo[k] < mins[k]) mins[k] = n.lo[k];
+                float hi = n.lo[k] + n.size[k];
+                if (hi > maxs[k]) maxs[k] = hi;
+            }
+        }
+        int which = 0;
+        float d = (float)-kBoundHuge, e;
+        e = maxs[0] - mins[0]; if (e > d) { d = e; which = 0; }
+        e = maxs[1] - mins[1]; if (e > d) { d = e; which = 1; }
+        e = maxs[2] - mins[2]; if (e > d) { which = 2; }
+        return which;
+    }
+
+    // calc_bbox: double min/max of FP32 boxes, stored back as FP32 lowerLeft / size
+    void calc_bbox(BuildNode& out, const std::vector<int64_t>& ids) const
+    {
+        double bmin[3] = { kBoundHuge, kBoundHuge, kBoundHuge };
+        double bmax[3] = { -kBoundHuge, -kBoundHuge, -kBoundHuge };
+        for (int64_t id : ids) {
+            const BuildNode& n = pool[(size_t)id];
+            for (int k = 0; k < 3; k++) {
+                double tmin = n.lo[k];
+                double tmax = tmin + n.size[k];
+                if (tmin < bmin[k]) bmin[k] = tmin;
+                if (tmax > bmax[k]) bmax[k] = tmax;
+            }
+        }
+        for (int k = 0; k < 3; k++) { out.lo[k] = (float)bmin[k]; out.size[k] = (float)(bmax[k] - bmin[k]); }
+    }
+
+    void area_table(ptrdiff_t a, ptrdiff_t b, float* areas) const
+    {
+        ptrdiff_t imin = (a < b) ? a : b, dir = (a < b) ? 1 : -1;
+        float bmin[3], bmax[3];
+        for (int k = 0; k < 3; k++) { bmin[k] = (float)kBoundHuge; bmax[k] = (float)-kBoundHuge; }
+        for (ptrdiff_t i = a; i != b + dir; i += dir) {
+            const BuildNode& n = pool[(size_t)work[i]];
+            for (int k = 0; k < 3; k++) {
+                float tmin = n.lo[k], tmax = tmin + n.size[k];
+                if (tmin < bmin[k]) bmin[k] = tmin;
+                if (tmax > bmax[k]) bmax[k] = tmax;
+            }
+            float lx = bmax[0] - bmin[0], ly = bmax[1] - bmin[1], lz = bmax[2] - bmin[2];
+            areas[i - imin] = lx * (ly + lz) + ly * lz;
+        }
+    }
+
+    bool sort_and_split(ptrdiff_t first, ptrdiff_t last)
+    {
+        ptrdiff_t size = last - first, best_loc = -1;
+        if (size <= 0) return false;
+        if (size > kBunching) {
+            sort_axis = find_axis(first, last);
+            sort_ctx = this;
+            std::qsort(work.data() + first, (size_t)size, sizeof(int64_t), cmp);   // same libc routine as the reference
+            if (area.size() < (size_t)(2 * size)) area.resize((size_t)(2 * size));
+            float* area_left = area.data();
+            float* area_right = area_left + size;
+            area_table(first, last - 1, area_left);
+            area_table(last - 1, first, area_right);
+            float best_index = area_right[0] * float(size - 3);   // cost of not subdividing
+            for (ptrdiff_t i = 1; i < size; i++) {
+                float new_index = float(i) * area_left[i - 1] + float(size - i) * area_right[i];
+                if (new_index < best_index) { best_index = new_index; best_loc = i + first; }
+            }
+        }
+        if (best_loc < 0) {
+            BuildNode n;
+            n.kids.assign(work.begin() + first, work.begin() + last);
+            calc_bbox(n, n.kids);
+            pool.push_back(std::move(n));
+            root = (int64_t)pool.size() - 1;
+            work.push_back(root);
+            return false;
+        }
+        sort_and_split(first, best_loc);
+        sort_and_split(best_loc, last);
+        return true;
+    }
+};
+thread_local const TreeBuilder* TreeBuilder::sort_ctx = nullptr;
+thread_local int TreeBuilder::sort_axis = 0;
+
+}  // namespace
+
+void build_bbox_tree(const std::vector<LeafBox>& finite, const std::vector<LeafBox>& infinite,
+                     std::vector<pvgpu_node>& out)
+{
+    out.clear();
+    TreeBuilder tb;
+    auto add_leaf = [&](const LeafBox& b, bool inf) {
+        BuildNode n;
+        std::memcpy(n.lo, b.lo, sizeof n.lo);
+        std::memcpy(n.size, b.size, sizeof n.size);
+        n.payload = b.payload;
+        n.infinite = inf;
+        tb.pool.push_back(std::move(n));
+        return (int64_t)tb.pool.size() - 1;
+    };
+    for (const LeafBox& b : finite) tb.work.push_back(add_leaf(b, false));
+    std::vector<int64_t> inf_ids;
+    for (const LeafBox& b : infinite) inf_ids.push_back(add_leaf(b, true));
+
+    if (!finite.empty()) {
+        ptrdiff_t low = 0, high = (ptrdiff_t)finite.size();
+        while (tb.sort_and_split(low, high)) { low = high; high = (ptrdiff_t)tb.work.size(); }
+        if (!inf_ids.empty()) {
+            // infinite objects go into a new first child of the root (boundingbox.cpp:288-306)
+            BuildNode cd;
+            cd.kids = inf_ids;
+            tb.calc_bbox(cd, cd.kids);
+            cd.infinite = true;
+            tb.pool.push_back(std::move(cd));
+            int64_t cd_id = (int64_t)tb.pool.size() - 1;
+            BuildNode& r = tb.pool[(size_t)tb.root];
+            r.kids.insert(r.kids.begin(), cd_id);
+            tb.calc_bbox(r, r.kids);
+            r.infinite = true;
+        }
+    } else if (!inf_ids.empty()) {
+        BuildNode cd;
+        cd.kids = inf_ids;
+        tb.calc_bbox(cd, cd.kids);
+        cd.infinite = true;
+        tb.pool.push_back(std::move(cd));
+        tb.root = (int64_t)tb.pool.size() - 1;
+    } else {
+        return;
+    }
+
+    // breadth-first layout: children of a node are contiguous, root = 0
+    std::vector<int64_t> order{ tb.root };
+    out.resize(1);
+    for (size_t qi = 0; qi < order.size(); qi++) {
+        const BuildNode& n = tb.pool[(size_t)order[qi]];
+        pvgpu_node pn{};
+        std::memcpy(pn.lo, n.lo, sizeof pn.lo);
+        std::memcpy(pn.size, n.size, sizeof pn.size);
+        pn.flags = n.infinite ? PVGPU_NODE_INFINITE : 0;
+        if (n.kids.empty()) {
+            pn.count = 0;
+            pn.first = n.payload;
+        } else {
+            pn.count = (uint16_t)n.kids.size();
+            pn.first = (uint32_t)order.size();
+            for (int64_t k : n.kids) order.push_back(k);
+            out.resize(order.size());
+        }
+        out[qi] = pn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// validation
+// ------------------------------------------------------------------------------------------------
+static bool range_ok(uint32_t first, uint32_t count, size_t n) { return (size_t)first + count <= n; }
+
+int validate_scene(Scene& s)
+{
+    const size_t no = s.objects.size();
+    if (s.frame.empty()) return fail(PVGPU_E_INVALID, "scene has no frame-level objects");
+    for (uint32_t f : s.frame)
+        if (f >= no) return fail(PVGPU_E_INVALID, "frame object index %u out of range", f);
+    for (size_t i = 0; i < no; i++) {
+        const pvgpu_object& o = s.objects[i];
+        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_CSG_MERGE)
+            return fail(PVGPU_E_UNSUPPORTED, "object %zu: primitive type %u is outside the hot-path scope", i, o.type);
+        if (!range_ok(o.child_first, o.child_count, s.index_list.size()) ||
+            !range_ok(o.clip_first, o.clip_count, s.index_list.size()) ||
+            !range_ok(o.bound_first, o.bound_count, s.index_list.size()))
+            return fail(PVGPU_E_INVALID, "object %zu: index-list range out of bounds", i);
+        if (o.texture >= (int32_t)s.textures.size() || o.interior_texture >= (int32_t)s.textures.size())
+            return fail(PVGPU_E_INVALID, "object %zu: texture index out of range", i);
+        if (o.interior >= (int32_t)s.interiors.size())
+            return fail(PVGPU_E_INVALID, "object %zu: interior index out of range", i);
+        if (o.transform >= (int32_t)s.transforms.size())
+            return fail(PVGPU_E_INVALID, "object %zu: transform index out of range", i);
+        if (o.parent >= (int32_t)no) return fail(PVGPU_E_INVALID, "object %zu: parent out of range", i);
+        if (o.type == PVGPU_OBJ_MESH && (o.mesh < 0 || o.mesh >= (int32_t)s.meshes.size()))
+            return fail(PVGPU_E_INVALID, "object %zu: mesh index out of range", i);
+        if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
+            return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
+        if ((o.flags & PVGPU_UV_FLAG))
+            return fail(PVGPU_E_UNSUPPORTED, "object %zu: uv_mapping is outside the hot-path scope", i);
+        if ((o.flags & PVGPU_CUTAWAY_TEXTURES_FLAG) && o.texture < 0)
+            return fail(PVGPU_E_UNSUPPORTED, "object %zu: cutaway_textures is outside the hot-path scope", i);
+        if (o.type >= PVGPU_OBJ_CSG_UNION && o.parent >= 0 && o.bound_count)
+            return fail(PVGPU_E_UNSUPPORTED, "object %zu: bounded_by on a nested CSG child", i);
+    }
+    for (uint32_t v : s.index_list)
+        if (v >= no && v >= s.textures.size())
+            return fail(PVGPU_E_INVALID, "index list entry %u out of range", v);
+    for (size_t i = 0; i < s.nodes.size(); i++) {
+        const pvgpu_node& n = s.nodes[i];
+        if (n.count ? !range_ok(n.first, n.count, s.nodes.size()) : n.first >= no)
+            return fail(PVGPU_E_INVALID, "tree node %zu: bad child / object reference", i);
+    }
+    for (size_t m = 0; m < s.meshes.size(); m++) {
+        const pvgpu_mesh& me = s.meshes[m];
+        if (!range_ok(me.vertex_first, me.vertex_count, s.vertices.size() / 3) ||
+            !range_ok(me.normal_first, me.normal_count, s.normals.size() / 3) ||
+            !range_ok(me.triangle_first, me.triangle_count, s.triangles.size()) ||
+            !range_ok(me.node_first, me.node_count, s.mesh_nodes.size()) ||
+            !range_ok(me.texture_first, me.texture_count, s.index_list.size()))
+            return fail(PVGPU_E_INVALID, "mesh %zu: range out of bounds", m);
+        for (uint32_t t = 0; t < me.triangle_count; t++) {
+            const pvgpu_triangle& tr = s.triangles[me.triangle_first + t];
+            if (tr.p1 < 0 || tr.p2 < 0 || tr.p3 < 0 || (uint32_t)tr.p1 >= me.vertex_count ||
+                (uint32_t)tr.p2 >= me.vertex_count || (uint32_t)tr.p3 >= me.vertex_count ||
+                tr.normal_ind < 0 || (uint32_t)tr.normal_ind >= me.normal_count || tr.dominant_axis > 2)
+                return fail(PVGPU_E_INVALID, "mesh %zu triangle %u: bad index", m, t);
+            if ((tr.flags & PVGPU_TRI_SMOOTH) &&
+                (tr.n1 < 0 || tr.n2 < 0 || tr.n3 < 0 || (uint32_t)tr.n1 >= me.normal_count ||
+                 (uint32_t)tr.n2 >= me.normal_count || (uint32_t)tr.n3 >= me.normal_count))
+                return fail(PVGPU_E_INVALID, "mesh %zu triangle %u: bad normal index", m, t);
+            if (tr.flags & PVGPU_TRI_THREETEX)
+                return fail(PVGPU_E_UNSUPPORTED, "mesh %zu: per-vertex textures are outside the hot-path scope", m);
+            if (tr.texture >= (int32_t)me.texture_count)
+                return fail(PVGPU_E_INVALID, "mesh %zu triangle %u: bad texture index", m, t);
+        }
+        for (uint32_t k = 0; k < me.node_count; k++) {
+            const pvgpu_node& n = s.mesh_nodes[me.node_first + k];
+            if (n.count ? !range_ok(n.first, n.count, me.node_count) : n.first >= me.triangle_count)
+                return fail(PVGPU_E_INVALID, "mesh %zu node %u: bad reference", m, k);
+        }
+    }
+    for (size_t i = 0; i < s.textures.size(); i++) {
+        const pvgpu_texture& t = s.textures[i];
+        if (t.type != PVGPU_PAT_PLAIN)
+            return fail(PVGPU_E_UNSUPPORTED, "texture %zu: patterned textures / texture maps are outside the hot-path scope", i);
+        if (t.pigment < 0 || t.pigment >= (int32_t)s.pigments.size() || t.finish < 0 ||
+            t.finish >= (int32_t)s.finishes.size() || t.next >= (int32_t)s.textures.size())
+            return fail(PVGPU_E_INVALID, "texture %zu: bad pigment / finish / next index", i);
+        if (t.tnormal >= 0)
+            return fail(PVGPU_E_UNSUPPORTED, "texture %zu: normal perturbation is outside the hot-path scope", i);
+        int depth = 0;
+        for (int32_t k = (int32_t)i; k >= 0; k = s.textures[k].next)
+            if (++depth > 8) return fail(PVGPU_E_UNSUPPORTED, "texture %zu: more than 8 layers", i);
+    }
+    for (size_t i = 0; i < s.pigments.size(); i++) {
+        const pvgpu_pigment& p = s.pigments[i];
+        if (p.pattern < PVGPU_PAT_PLAIN || p.pattern > PVGPU_PAT_RADIAL)
+            return fail(PVGPU_E_UNSUPPORTED, "pigment %zu: pattern %u unsupported", i, p.pattern);
+        if (p.pattern != PVGPU_PAT_PLAIN && (p.blend_map < 0 || p.blend_map >= (int32_t)s.blend_maps.size()))
+            return fail(PVGPU_E_INVALID, "pigment %zu: patterned pigment without blend map", i);
+        if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
+            return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
+    }
+    for (size_t i = 0; i < s.blend_maps.size(); i++) {
+        const pvgpu_blend_map& m = s.blend_maps[i];
+        if (m.entry_count == 0 || !range_ok(m.entry_first, m.entry_count, s.blend_entries.size()))
+            return fail(PVGPU_E_INVALID, "blend map %zu: bad entry range", i);
+    }
+    for (size_t i = 0; i < s.warps.size(); i++) {
+        const pvgpu_warp& w = s.warps[i];
+        if (w.type < PVGPU_WARP_TRANSFORM || w.type > PVGPU_WARP_CLASSIC_TURBULENCE)
+            return fail(PVGPU_E_UNSUPPORTED, "warp %zu: type %u unsupported", i, w.type);
+        if (w.type == PVGPU_WARP_TRANSFORM && (w.transform < 0 || w.transform >= (int32_t)s.transforms.size()))
+            return fail(PVGPU_E_INVALID, "warp %zu: bad transform", i);
+    }
+    for (size_t i = 0; i < s.finishes.size(); i++) {
+        const pvgpu_finish& f = s.finishes[i];
+        bool reflective = f.reflection_max[0] != 0 || f.reflection_max[1] != 0 || f.reflection_max[2] != 0 ||
+                          f.reflection_min[0] != 0 || f.reflection_min[1] != 0 || f.reflection_min[2] != 0;
+        if (reflective && f.reflect_exp != 1.0f)
+            return fail(PVGPU_E_UNSUPPORTED, "finish %zu: reflection exponent != 1 (non-linear in the child ray)", i);
+        if (f.irid > 0.0f) return fail(PVGPU_E_UNSUPPORTED, "finish %zu: iridescence is outside the hot-path scope", i);
+        if (f.crand > 0.0f) return fail(PVGPU_E_UNSUPPORTED, "finish %zu: crand is excluded from parity (per-thread RNG)", i);
+        if (f.use_subsurface) return fail(PVGPU_E_UNSUPPORTED, "finish %zu: subsurface is outside the hot-path scope", i);
+    }
+    for (size_t i = 0; i < s.lights.size(); i++) {
+        const pvgpu_light& l = s.lights[i];
+        if (l.type < PVGPU_LIGHT_POINT || l.type > PVGPU_LIGHT_CYLINDER)
+            return fail(PVGPU_E_INVALID, "light %zu: bad type", i);
+        if (l.flags & PVGPU_LIGHT_AREA)
+            return fail(PVGPU_E_UNSUPPORTED, "light %zu: area lights are a 'next' row (SURVEY 8f)", i);
+        if (l.projected_through >= 0)
+            return fail(PVGPU_E_UNSUPPORTED, "light %zu: projected_through is outside the hot-path scope", i);
+        if (l.flags & PVGPU_LIGHT_GROUP)
+            return fail(PVGPU_E_UNSUPPORTED, "light %zu: light groups are outside the hot-path scope", i);
+    }
+    for (size_t i = 0; i < s.interiors.size(); i++)
+        if (std::fabs((double)s.interiors[i].dispersion - 1.0) >= 1e-10)
+            return fail(PVGPU_E_UNSUPPORTED, "interior %zu: dispersion is outside the hot-path scope", i);
+    if (std::fabs((double)s.globals.atmosphere_dispersion - 1.0) >= 1e-10)
+        return fail(PVGPU_E_UNSUPPORTED, "atmosphere dispersion is outside the hot-path scope");
+    if (!s.have_camera) return fail(PVGPU_E_INVALID, "no camera set");
+    if (s.camera.type != PVGPU_CAMERA_PERSPECTIVE && s.camera.type != PVGPU_CAMERA_ORTHOGRAPHIC)
+        return fail(PVGPU_E_UNSUPPORTED, "camera type %u is outside the hot-path scope", s.camera.type);
+    if (s.globals.bounding_method == 1 && s.nodes.empty())
+        return fail(PVGPU_E_INVALID, "bounding_method 1 without a tree (call pvgpu_scene_set_tree or pvgpu_scene_build_tree)");
+
+    // shadow rays may stop at the first opaque blocker only when every shadow caster is opaque;
+    // otherwise the reference's closest-hit filter loop is followed (trace.cpp:2025-2075)
+    s.all_shadow_casters_opaque = true;
+    for (const pvgpu_object& o : s.objects)
+        if (o.type < PVGPU_OBJ_CSG_UNION && !(o.flags & PVGPU_NO_SHADOW_FLAG) && !(o.flags & PVGPU_OPAQUE_FLAG))
+            s.all_shadow_casters_opaque = false;
+    return PVGPU_OK;
+}
+
+}  // namespace pvgpu
+
+static const char kMagic[8] = { 'P', 'V', 'G', 'P', 'U', 'S', 'C', '1' };
+
+template <class T> static bool put(FILE* f, const std::vector<T>& v)
+{
+    uint64_t n = v.size();
+    return fwrite(&n, sizeof n, 1, f) == 1 && (n == 0 || fwrite(v.data(), sizeof(T), n, f) == n);
+}
+template <class T> static bool get(FILE* f, std::vector<T>& v)
+{
+    uint64_t n = 0;
+    if (fread(&n, sizeof n, 1, f) != 1 || n > (1ull << 34) / sizeof(T)) return false;
+    v.resize(n);
+    return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace pvgpu;
+
+extern "C" {
+
+int pvgpu_abi_version(void) { return PVGPU_ABI_VERSION; }
+const char* pvgpu_last_error(void) { return g_err; }
+
+int pvgpu_scene_create(pvgpu_scene** out, const pvgpu_globals* g)
+{
+    clear_error();
+    if (!out || !g) return fail(PVGPU_E_INVALID, "pvgpu_scene_create: null argument");
+    Scene* s = new Scene();
+    s->globals = *g;
+    *out = reinterpret_cast<pvgpu_scene*>(s);
+    return PVGPU_OK;
+}
+
+void pvgpu_scene_destroy(pvgpu_scene* sc)
+{
+    if (!sc) return;
+    Scene* s = reinterpret_cast<Scene*>(sc);
+    device_release(*s);
+    delete s;
+}
+
+#define SCENE_OR_FAIL(sc) \
+    clear_error(); \
+    if (!(sc)) return fail(PVGPU_E_INVALID, "%s: null scene", __func__); \
+    Scene& s = *reinterpret_cast<Scene*>(sc); \
+    if (s.dev) return fail(PVGPU_E_INVALID, "%s: scene already finalized", __func__)
+
+int pvgpu_scene_set_objects(pvgpu_scene* sc, const pvgpu_object* objs, size_t n_objs,
+                            const uint32_t* index_list, size_t n_index,
+                            const uint32_t* frame, size_t n_frame)
+{
+    SCENE_OR_FAIL(sc);
+    if ((!objs && n_objs) || (!index_list && n_index) || (!frame && n_frame))
+        return fail(PVGPU_E_INVALID, "pvgpu_scene_set_objects: null array");
+    s.objects.assign(objs, objs + n_objs);
+    s.index_list.assign(index_list, index_list + n_index);
+    s.frame.assign(frame, frame + n_frame);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_transforms(pvgpu_scene* sc, const pvgpu_transform* t, size_t n)
+{
+    SCENE_OR_FAIL(sc);
+    if (!t && n) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_transforms: null array");
+    s.transforms.assign(t, t + n);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_tree(pvgpu_scene* sc, const pvgpu_node* nodes, size_t n)
+{
+    SCENE_OR_FAIL(sc);
+    if (!nodes && n) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_tree: null array");
+    s.nodes.assign(nodes, nodes + n);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_build_tree(pvgpu_scene* sc)
+{
+    SCENE_OR_FAIL(sc);
+    // Build_Bounding_Slabs (boundingbox.cpp:325-430): frame-level objects split by INFINITE_FLAG
+    std::vector<LeafBox> fin, inf;
+    for (uint32_t f : s.frame) {
+        if (f >= s.objects.size()) return fail(PVGPU_E_INVALID, "frame object index out of range");
+        const pvgpu_object& o = s.objects[f];
+        LeafBox b;
+        std::memcpy(b.lo, o.bbox, sizeof b.lo);
+        std::memcpy(b.size, o.bbox + 3, sizeof b.size);
+        b.payload = f;
+        ((o.flags & PVGPU_INFINITE_FLAG) ? inf : fin).push_back(b);
+    }
+    build_bbox_tree(fin, inf, s.nodes);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_meshes(pvgpu_scene* sc, const pvgpu_mesh* meshes, size_t n_meshes,
+                           const float* vertices, size_t n_vertices,
+                           const float* normals, size_t n_normals,
+                           const pvgpu_triangle* tris, size_t n_tris,
+                           const pvgpu_node* nodes, size_t n_nodes)
+{
+    SCENE_OR_FAIL(sc);
+    if ((!meshes && n_meshes) || (!vertices && n_vertices) || (!normals && n_normals) || (!tris && n_tris) ||
+        (!nodes && n_nodes))
+        return fail(PVGPU_E_INVALID, "pvgpu_scene_set_meshes: null array");
+    s.meshes.assign(meshes, meshes + n_meshes);
+    s.vertices.assign(vertices, vertices + 3 * n_vertices);
+    s.normals.assign(normals, normals + 3 * n_normals);
+    s.triangles.assign(tris, tris + n_tris);
+    s.mesh_nodes.assign(nodes, nodes + n_nodes);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_lights(pvgpu_scene* sc, const pvgpu_light* l, size_t n)
+{
+    SCENE_OR_FAIL(sc);
+    if (!l && n) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_lights: null array");
+    s.lights.assign(l, l + n);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_materials(pvgpu_scene* sc,
+                              const pvgpu_texture* tex, size_t n_tex,
+                              const pvgpu_pigment* pig, size_t n_pig,
+                              const pvgpu_finish* fin, size_t n_fin,
+                              const pvgpu_blend_map* maps, size_t n_maps,
+                              const pvgpu_blend_entry* entries, size_t n_entries,
+                              const pvgpu_warp* warps, size_t n_warps,
+                              const pvgpu_interior* interiors, size_t n_interiors)
+{
+    SCENE_OR_FAIL(sc);
+    if ((!tex && n_tex) || (!pig && n_pig) || (!fin && n_fin) || (!maps && n_maps) || (!entries && n_entries) ||
+        (!warps && n_warps) || (!interiors && n_interiors))
+        return fail(PVGPU_E_INVALID, "pvgpu_scene_set_materials: null array");
+    s.textures.assign(tex, tex + n_tex);
+    s.pigments.assign(pig, pig + n_pig);
+    s.finishes.assign(fin, fin + n_fin);
+    s.blend_maps.assign(maps, maps + n_maps);
+    s.blend_entries.assign(entries, entries + n_entries);
+    s.warps.assign(warps, warps + n_warps);
+    s.interiors.assign(interiors, interiors + n_interiors);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_camera(pvgpu_scene* sc, const pvgpu_camera* cam)
+{
+    clear_error();
+    if (!sc || !cam) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_camera: null argument");
+    Scene& s = *reinterpret_cast<Scene*>(sc);    // the camera may change between frames of a finalized scene
+    s.camera = *cam;
+    s.have_camera = true;
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_get_camera(const pvgpu_scene* sc, pvgpu_camera* cam)
+{
+    clear_error();
+    if (!sc || !cam) return fail(PVGPU_E_INVALID, "pvgpu_scene_get_camera: null argument");
+    const Scene& s = *reinterpret_cast<const Scene*>(sc);
+    if (!s.have_camera) return fail(PVGPU_E_INVALID, "no camera set");
+    *cam = s.camera;
+    return PVGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mesh2 helper: what Parser::Parse_Mesh2 (parser.cpp:4079-4620) + Mesh::Compute_Mesh_Triangle
+// (mesh.cpp:838-954) + Mesh::Build_Mesh_BBox_Tree (mesh.cpp:1376-1413) leave in MESH_DATA for a
+// mesh2 { vertex_vectors, face_indices } without normals / uv / textures (flat triangles).
+// ------------------------------------------------------------------------------------------------
+static inline int max3_coordinate(double x, double y, double z)   // mesh.cpp:94
+{
+    return (x > y) ? ((x > z) ? 0 : 2) : ((y > z) ? 1 : 2);
+}
+
+int pvgpu_scene_add_mesh2(pvgpu_scene* sc, const double* vertices, size_t n_vertices,
+                          const int32_t* indices, size_t n_faces, int32_t* out_mesh)
+{
+    SCENE_OR_FAIL(sc);
+    if (!vertices || !indices || !n_vertices || !n_faces)
+        return fail(PVGPU_E_INVALID, "pvgpu_scene_add_mesh2: empty mesh");
+    pvgpu_mesh me{};
+    me.vertex_first = (uint32_t)(s.vertices.size() / 3);
+    me.vertex_count = (uint32_t)n_vertices;
+    me.normal_first = (uint32_t)(s.normals.size() / 3);
+    me.normal_count = (uint32_t)n_faces;
+    me.triangle_first = (uint32_t)s.triangles.size();
+    me.triangle_count = (uint32_t)n_faces;
+    me.node_first = (uint32_t)s.mesh_nodes.size();
+
+    // vertices are stored as MeshVector (FP32); every later computation starts from the rounded values
+    const size_t v0 = s.vertices.size();
+    s.vertices.resize(v0 + 3 * n_vertices);
+    for (size_t i = 0; i < 3 * n_vertices; i++) s.vertices[v0 + i] = (float)vertices[i];
+    const float* V = s.vertices.data() + v0;
+
+    const size_t n0 = s.normals.size();
+    s.normals.resize(n0 + 3 * n_faces);
+    const size_t t0 = s.triangles.size();
+    s.triangles.resize(t0 + n_faces);
+    std::vector<LeafBox> leaves(n_faces);
+
+    for (size_t f = 0; f < n_faces; f++) {
+        int32_t a = indices[3 * f], b = indices[3 * f + 1], c = indices[3 * f + 2];
+        if (a < 0 || b < 0 || c < 0 || (size_t)a >= n_vertices || (size_t)b >= n_vertices || (size_t)c >= n_vertices)
+            return fail(PVGPU_E_INVALID, "mesh face %zu: index out of range", f);
+        pvgpu_triangle tr{};
+        tr.p1 = a; tr.p2 = b; tr.p3 = c;
+        tr.n1 = tr.n2 = tr.n3 = -1;
+        tr.texture = tr.texture2 = tr.texture3 = -1;
+        double P1[3], P2[3], P3[3];
+        for (int k = 0; k < 3; k++) { P1[k] = V[3 * a + k]; P2[k] = V[3 * b + k]; P3[k] = V[3 * c + k]; }
+        double V1[3], V2[3], N[3];
+        for (int k = 0; k < 3; k++) { V1[k] = P2[k] - P1[k]; V2[k] = P3[k] - P1[k]; }
+        N[0] = V2[1] * V1[2] - V2[2] * V1[1];       // cross(V2, V1)
+        N[1] = V2[2] * V1[0] - V2[0] * V1[2];
+        N[2] = V2[0] * V1[1] - V2[1] * V1[0];
+        double len = std::sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+        if (len != 0.0) {
+            for (int k = 0; k < 3; k++) N[k] /= len;
+            double dist = N[0] * P1[0] + N[1] * P1[1] + N[2] * P1[2];
+            dist *= -1.0;
+            tr.distance = (float)dist;
+            int dom = max3_coordinate(std::fabs(N[0]), std::fabs(N[1]), std::fabs(N[2]));
+            tr.dominant_axis = (uint8_t)dom;
+            const int ua = (dom == 0) ? 1 : 0, va = (dom == 2) ? 1 : 2;     // X:(Y,Z) Y:(X,Z) Z:(X,Y)
+            bool swap = (P2[ua] - P3[ua]) * (P2[va] - P1[va]) < (P2[va] - P3[va]) * (P2[ua] - P1[ua]);
+            const double* q1 = P1; const double* q2 = P2;
+            if (swap) { std::swap(tr.p1, tr.p2); q1 = P2; q2 = P1; }
+            // compute_smooth_triangle (mesh.cpp:984-1010): Perp / vAxis are filled for flat triangles too
+            double d32[3] = { P3[0] - q2[0], P3[1] - q2[1], P3[2] - q2[2] };
+            tr.v_axis = (uint8_t)max3_coordinate(std::fabs(d32[0]), std::fabs(d32[1]), std::fabs(d32[2]));
+            double t1[3] = { q2[0] - P3[0], q2[1] - P3[1], q2[2] - P3[2] };
+            double l1 = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+            if (l1 != 0) for (int k = 0; k < 3; k++) t1[k] /= l1;
+            double t2[3] = { q1[0] - P3[0], q1[1] - P3[1], q1[2] - P3[2] };
+            double proj = t2[0] * t1[0] + t2[1] * t1[1] + t2[2] * t1[2];
+            for (int k = 0; k < 3; k++) t1[k] *= proj;
+            double pp[3] = { t1[0] - t2[0], t1[1] - t2[1], t1[2] - t2[2] };
+            double lp = std::sqrt(pp[0] * pp[0] + pp[1] * pp[1] + pp[2] * pp[2]);
+            if (lp != 0) for (int k = 0; k < 3; k++) pp[k] /= lp;
+            float perp[3] = { (float)pp[0], (float)pp[1], (float)pp[2] };
+            double uden = -(t2[0] * (double)perp[0] + t2[1] * (double)perp[1] + t2[2] * (double)perp[2]);
+            for (int k = 0; k < 3; k++) tr.perp[k] = perp[k] / (float)uden;      // MeshVector /= DBL divides in FP32
+        }
+        tr.normal_ind = (int32_t)f;
+        for (int k = 0; k < 3; k++) s.normals[n0 + 3 * f + k] = (float)N[k];
+        s.triangles[t0 + f] = tr;
+        // get_triangle_bbox (mesh.cpp:1335): double min/max of the FP32 vertices
+        LeafBox& lb = leaves[f];
+        for (int k = 0; k < 3; k++) {
+            double mn = std::min(P1[k], std::min(P2[k], P3[k]));
+            double mx = std::max(P1[k], std::max(P2[k], P3[k]));
+            lb.lo[k] = (float)mn;
+            lb.size[k] = (float)(mx - mn);
+        }
+        lb.payload = (uint32_t)f;
+    }
+    std::vector<pvgpu_node> tree;
+    build_bbox_tree(leaves, {}, tree);
+    me.node_count = (uint32_t)tree.size();
+    s.mesh_nodes.insert(s.mesh_nodes.end(), tree.begin(), tree.end());
+    s.meshes.push_back(me);
+    if (out_mesh) *out_mesh = (int32_t)s.meshes.size() - 1;
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_finalize(pvgpu_scene* sc, int device)
+{
+    SCENE_OR_FAIL(sc);
+    int rc = validate_scene(s);
+    if (rc != PVGPU_OK) return rc;
+    return device_upload(s, device);
+}
+
+size_t pvgpu_scene_device_bytes(const pvgpu_scene* sc)
+{
+    return sc ? reinterpret_cast<const Scene*>(sc)->device_bytes : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat-scene file: magic, ABI version, then every table as (u64 count, raw records)
+// ------------------------------------------------------------------------------------------------
+int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
+{
+    clear_error();
+    if (!sc || !path) return fail(PVGPU_E_INVALID, "pvgpu_scene_save: null argument");
+    const Scene& s = *reinterpret_cast<const Scene*>(sc);
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(PVGPU_E_IO, "cannot open %s for writing", path);
+    uint32_t ver = PVGPU_ABI_VERSION, have_cam = s.have_camera;
+    bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&ver, 4, 1, f) == 1 && fwrite(&have_cam, 4, 1, f) == 1 &&
+              fwrite(&s.globals, sizeof s.globals, 1, f) == 1 && fwrite(&s.camera, sizeof s.camera, 1, f) == 1 &&
+              put(f, s.objects) && put(f, s.index_list) && put(f, s.frame) && put(f, s.transforms) &&
+              put(f, s.nodes) && put(f, s.meshes) && put(f, s.vertices) && put(f, s.normals) &&
+              put(f, s.triangles) && put(f, s.mesh_nodes) && put(f, s.lights) && put(f, s.textures) &&
+              put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
+              put(f, s.warps) && put(f, s.interiors);
+    ok = (fclose(f) == 0) && ok;
+    return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
+}
+
+int pvgpu_scene_load(pvgpu_scene** out, const char* path)
+{
+    clear_error();
+    if (!out || !path) return fail(PVGPU_E_INVALID, "pvgpu_scene_load: null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(PVGPU_E_IO, "cannot open %s", path);
+    Scene* s = new Scene();
+    char magic[8];
+    uint32_t ver = 0, have_cam = 0;
+    bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(&ver, 4, 1, f) == 1 &&
+              ver == PVGPU_ABI_VERSION && fread(&have_cam, 4, 1, f) == 1 &&
+              fread(&s->globals, sizeof s->globals, 1, f) == 1 && fread(&s->camera, sizeof s->camera, 1, f) == 1 &&
+              get(f, s->objects) && get(f, s->index_list) && get(f, s->frame) && get(f, s->transforms) &&
+              get(f, s->nodes) && get(f, s->meshes) && get(f, s->vertices) && get(f, s->normals) &&
+              get(f, s->triangles) && get(f, s->mesh_nodes) && get(f, s->lights) && get(f, s->textures) &&
+              get(f, s->pigments) && get(f, s->finishes) && get(f, s->blend_maps) && get(f, s->blend_entries) &&
+              get(f, s->warps) && get(f, s->interiors);
+    fclose(f);
+    if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of ABI version %d", path, PVGPU_ABI_VERSION); }
+    s->have_camera = have_cam != 0;
+    *out = reinterpret_cast<pvgpu_scene*>(s);
+    return PVGPU_OK;
+}
+
+}  // extern "C"
