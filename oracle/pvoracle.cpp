@@ -1,0 +1,1754 @@
+// pvoracle -- CPU restatement of POV-Ray's per-pixel trace path.  TEST INFRASTRUCTURE ONLY.
+//
+// This file is the checker, not the product: only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load it.  Nothing under povray_b200/ links or calls it.
+//
+// It restates, in plain recursive C++ that mirrors the reference's own control flow (priority-queue tree
+// walk, recursive TraceRay returning colours), the functions SURVEY.md section 8a lists; every function
+// cites the reference file:line it follows.  Its structure is deliberately different from the CUDA
+// wavefront implementation (heap instead of stack, recursion instead of ray queues, colours returned
+// instead of weighted accumulation), so agreement between the two is evidence, not tautology.
+//
+// Pinning: the reference holds no golden vectors for this path, so the oracle is
+// pinned against outputs of the UNMODIFIED reference built into oracle/_ref (ray-level object id + depth,
+// float RGBT per pixel) -- see tests/test_oracle_vs_reference.py and tests/golden/.
+//
+// Input: the flat tables of include/pvgpu.h (a .pvs file written by pvgpu_scene_save).
+// Build: make -C oracle oracle   (g++ -O2 -fno-fast-math -ffp-contract=off)
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "pvgpu.h"
+
+namespace {
+
+constexpr double EPSILON = 1.0e-10, HUGE_VALUE = 1.0e17, BOUND_HUGE = 2.0e10, SMALL_TOLERANCE = 1.0e-3,
+                 MAX_DISTANCE = 1.0e7, MIN_ISECT_DEPTH = 1.0e-4, SHADOW_TOLERANCE = 1.0e-3, COORDINATE_LIMIT = 1.0e17;
+
+struct V3 {
+    double x, y, z;
+    double operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline V3 v3(double x, double y, double z) { return V3{ x, y, z }; }
+inline V3 v3(const double* p) { return V3{ p[0], p[1], p[2] }; }
+inline V3 v3f(const float* p) { return V3{ (double)p[0], (double)p[1], (double)p[2] }; }
+inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+inline V3 operator*(V3 a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
+inline V3 operator*(double s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
+inline V3 operator/(V3 a, double s) { return v3(a.x / s, a.y / s, a.z / s); }
+inline double dot(V3 a, V3 b) { return ((a.x * b.x) + (a.y * b.y)) + (a.z * b.z); }        // vector.h:568
+inline double len2(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+inline double len(V3 a) { return std::sqrt(len2(a)); }
+inline V3 unit(V3 a) { double l = len(a); return l != 0.0 ? a / l : a; }                     // vector.h:531
+inline double sqr(double x) { return x * x; }
+
+struct Col { float r, g, b; };
+inline Col operator+(Col a, Col b) { return Col{ a.r + b.r, a.g + b.g, a.b + b.b }; }
+inline Col operator*(Col a, Col b) { return Col{ a.r * b.r, a.g * b.g, a.b * b.b }; }
+inline Col operator*(Col a, float s) { return Col{ a.r * s, a.g * s, a.b * s }; }
+inline float grey(Col c) { return (float)(0.297 * c.r + 0.589 * c.g + 0.114 * c.b); }        // colour.h:1366
+inline bool near_zero(Col c, float e) { return std::fabs(c.r) < e && std::fabs(c.g) < e && std::fabs(c.b) < e; }
+
+struct Scene {
+    pvgpu_globals g{};
+    pvgpu_camera cam{};
+    std::vector<pvgpu_object> objects;
+    std::vector<uint32_t> index_list, frame;
+    std::vector<pvgpu_transform> xf;
+    std::vector<pvgpu_node> nodes;
+    std::vector<pvgpu_mesh> meshes;
+    std::vector<float> verts, norms;
+    std::vector<pvgpu_triangle> tris;
+    std::vector<pvgpu_node> mnodes;
+    std::vector<pvgpu_light> lights;
+    std::vector<pvgpu_texture> textures;
+    std::vector<pvgpu_pigment> pigments;
+    std::vector<pvgpu_finish> finishes;
+    std::vector<pvgpu_blend_map> maps;
+    std::vector<pvgpu_blend_entry> entries;
+    std::vector<pvgpu_warp> warps;
+    std::vector<pvgpu_interior> interiors;
+    // noise tables
+    std::vector<unsigned short> hashTable;
+    std::vector<double> RTable;
+    std::vector<int> NoisePermutation;
+    std::vector<V3> NoiseGradients;
+    bool use_tree = false;
+};
+
+// ---- transforms (matrix.cpp:415-507, matrix.h:97-105) ------------------------------------------------
+inline V3 mpoint(const double* m, V3 v)
+{
+    return v3(v.x * m[0] + v.y * m[4] + v.z * m[8] + m[12], v.x * m[1] + v.y * m[5] + v.z * m[9] + m[13],
+              v.x * m[2] + v.y * m[6] + v.z * m[10] + m[14]);
+}
+inline V3 mdir(const double* m, V3 v)
+{
+    return v3(v.x * m[0] + v.y * m[4] + v.z * m[8], v.x * m[1] + v.y * m[5] + v.z * m[9], v.x * m[2] + v.y * m[6] + v.z * m[10]);
+}
+inline V3 mtransposed(const double* m, V3 v)
+{
+    return v3(v.x * m[0] + v.y * m[1] + v.z * m[2], v.x * m[4] + v.y * m[5] + v.z * m[6], v.x * m[8] + v.y * m[9] + v.z * m[10]);
+}
+inline V3 MTransPoint(const pvgpu_transform& t, V3 v) { return mpoint(t.matrix, v); }
+inline V3 MInvTransPoint(const pvgpu_transform& t, V3 v) { return mpoint(t.inverse, v); }
+inline V3 MInvTransDirection(const pvgpu_transform& t, V3 v) { return mdir(t.inverse, v); }
+inline V3 MTransNormal(const pvgpu_transform& t, V3 v) { return mtransposed(t.inverse, v); }
+
+// ---- polynomial solver (polynomialsolver.cpp) --------------------------------------------------------
+constexpr double SMALL_ENOUGH = 1.0e-10, RELERROR = 1.0e-12, FUDGE_FACTOR1 = 1.0e12;
+constexpr int MAX_ITERATIONS = 50, MAX_ORDER = 4;
+constexpr double TWO_M_PI_3 = 2.0943951023931954923084, FOUR_M_PI_3 = 4.1887902047863909846168;
+
+int solve_quadratic(const double* x, double* y)          // :810-861
+{
+    double a = x[0], b = -x[1], c = x[2];
+    if (a == 0.0) { if (b == 0.0) return 0; y[0] = c / b; return 1; }
+    b /= a; c /= a; a = 1.0;
+    double d = b * b - 4.0 * a * c;
+    if ((d > -SMALL_ENOUGH) && (d < SMALL_ENOUGH)) { y[0] = 0.5 * b / a; return 1; }
+    if (d < 0.0) return 0;
+    d = std::sqrt(d);
+    double t = 2.0 * a;
+    y[0] = (b + d) / t; y[1] = (b - d) / t;
+    return 2;
+}
+int solve_cubic(const double* x, double* y)              // :903-978
+{
+    double a0 = x[0], a1, a2, a3;
+    if (a0 == 0.0) return solve_quadratic(&x[1], y);
+    if (a0 != 1.0) { a1 = x[1] / a0; a2 = x[2] / a0; a3 = x[3] / a0; } else { a1 = x[1]; a2 = x[2]; a3 = x[3]; }
+    double A2 = a1 * a1, Q = (A2 - 3.0 * a2) / 9.0, R = (a1 * (A2 - 4.5 * a2) + 13.5 * a3) / 27.0;
+    double Q3 = Q * Q * Q, R2 = R * R, d = Q3 - R2, an = a1 / 3.0;
+    if (d >= 0.0) {
+        d = R / std::sqrt(Q3);
+        double theta = std::acos(d) / 3.0, sQ = -2.0 * std::sqrt(Q);
+        y[0] = sQ * std::cos(theta) - an; y[1] = sQ * std::cos(theta + TWO_M_PI_3) - an; y[2] = sQ * std::cos(theta + FOUR_M_PI_3) - an;
+        return 3;
+    }
+    double sQ = std::pow(std::sqrt(R2 - Q3) + std::fabs(R), 1.0 / 3.0);
+    y[0] = (R < 0) ? (sQ + Q / sQ) - an : -(sQ + Q / sQ) - an;
+    return 1;
+}
+int solve_quartic(const double* x, double* results)      // :1325-1450
+{
+    double cubic[4], roots[3], c0 = x[0], c1, c2, c3, c4;
+    if (c0 != 1.0) { c1 = x[1] / c0; c2 = x[2] / c0; c3 = x[3] / c0; c4 = x[4] / c0; } else { c1 = x[1]; c2 = x[2]; c3 = x[3]; c4 = x[4]; }
+    double c12 = c1 * c1, p = -0.375 * c12 + c2, q = 0.125 * c12 * c1 - 0.5 * c1 * c2 + c3;
+    double r = -0.01171875 * c12 * c12 + 0.0625 * c12 * c2 - 0.25 * c1 * c3 + c4;
+    cubic[0] = 1.0; cubic[1] = -0.5 * p; cubic[2] = -r; cubic[3] = 0.5 * r * p - 0.125 * q * q;
+    int i = solve_cubic(cubic, roots);
+    if (i <= 0) return 0;
+    double z = roots[0], d1 = 2.0 * z - p, d2;
+    if (d1 < 0.0) { if (d1 > -SMALL_ENOUGH) d1 = 0.0; else return 0; }
+    if (d1 < SMALL_ENOUGH) { d2 = z * z - r; if (d2 < 0.0) return 0; d2 = std::sqrt(d2); }
+    else { d1 = std::sqrt(d1); d2 = 0.5 * q / d1; }
+    double q1 = d1 * d1, q2 = -0.25 * c1;
+    i = 0;
+    p = q1 - 4.0 * (z - d2);
+    if (p == 0) results[i++] = -0.5 * d1 - q2;
+    else if (p > 0) { p = std::sqrt(p); results[i++] = -0.5 * (d1 + p) + q2; results[i++] = -0.5 * (d1 - p) + q2; }
+    p = q1 - 4.0 * (z + d2);
+    if (p == 0) results[i++] = 0.5 * d1 - q2;
+    else if (p > 0) { p = std::sqrt(p); results[i++] = 0.5 * (d1 + p) + q2; results[i++] = 0.5 * (d1 - p) + q2; }
+    return i;
+}
+int difficult_coeffs(int n, const double* x)             // :1075-1109 (variant without USE_NEW_DIFFICULT_COEFFS)
+{
+    double biggest = 0.0;
+    for (int i = 0; i <= n; i++) if (std::fabs(x[i]) > biggest) biggest = x[i];
+    if (biggest == 0.0) return 0;
+    for (int i = 0; i <= n; i++) if (x[i] != 0.0 && std::fabs(biggest / x[i]) > FUDGE_FACTOR1) return 1;
+    return 0;
+}
+struct polynomial { int ord; double coef[MAX_ORDER + 1]; };
+double polyeval(double x, int n, const double* c) { double v = c[n]; for (int i = n - 1; i >= 0; i--) v = v * x + c[i]; return v; }
+int modp(const polynomial* u, const polynomial* v, polynomial* r)          // :171-215
+{
+    *r = *u;
+    if (v->coef[v->ord] < 0.0) {
+        for (int k = u->ord - v->ord - 1; k >= 0; k -= 2) r->coef[k] = -r->coef[k];
+        for (int k = u->ord - v->ord; k >= 0; k--)
+            for (int j = v->ord + k - 1; j >= k; j--) r->coef[j] = -r->coef[j] - r->coef[v->ord + k] * v->coef[j - k];
+    } else {
+        for (int k = u->ord - v->ord; k >= 0; k--)
+            for (int j = v->ord + k - 1; j >= k; j--) r->coef[j] -= r->coef[v->ord + k] * v->coef[j - k];
+    }
+    int k = v->ord - 1;
+    while (k >= 0 && std::fabs(r->coef[k]) < SMALL_ENOUGH) { r->coef[k] = 0.0; k--; }
+    r->ord = (k < 0) ? 0 : k;
+    return r->ord;
+}
+int buildsturm(int ord, polynomial* sseq)                // :233-270
+{
+    sseq[0].ord = ord; sseq[1].ord = ord - 1;
+    double f = std::fabs(sseq[0].coef[ord] * ord);
+    double* fp = sseq[1].coef; double* fc = sseq[0].coef + 1;
+    for (int i = 1; i <= ord; i++) *fp++ = *fc++ * i / f;
+    polynomial* sp;
+    for (sp = sseq + 2; modp(sp - 2, sp - 1, sp); sp++) {
+        f = -std::fabs(sp->coef[sp->ord]);
+        for (fp = &sp->coef[sp->ord]; fp >= sp->coef; fp--) *fp /= f;
+    }
+    sp->coef[0] = -sp->coef[0];
+    return (int)(sp - sseq);
+}
+int numchanges(int np, const polynomial* sseq, double a) // :330-352
+{
+    int changes = 0;
+    double lf = polyeval(a, sseq[0].ord, sseq[0].coef);
+    for (const polynomial* s = sseq + 1; s <= sseq + np; s++) {
+        double f = polyeval(a, s->ord, s->coef);
+        if (lf == 0.0 || lf * f < 0) changes++;
+        lf = f;
+    }
+    return changes;
+}
+int visible_roots(int np, const polynomial* sseq)        // :288-328
+{
+    int atposinf = 0, atzero = 0;
+    double lf = sseq[0].coef[sseq[0].ord];
+    for (const polynomial* s = sseq + 1; s <= sseq + np; s++) { double f = s->coef[s->ord]; if (lf == 0.0 || lf * f < 0) atposinf++; lf = f; }
+    lf = sseq[0].coef[0];
+    for (const polynomial* s = sseq + 1; s <= sseq + np; s++) { double f = s->coef[0]; if (lf == 0.0 || lf * f < 0) atzero++; lf = f; }
+    return atzero - atposinf;
+}
+int regula_falsa(int order, const double* coef, double a, double b, double* val)     // :700-775
+{
+    double fa = polyeval(a, order, coef), fb = polyeval(b, order, coef);
+    if (fa * fb > 0.0) return 0;
+    if (std::fabs(fa) < SMALL_ENOUGH) { *val = a; return 1; }
+    if (std::fabs(fb) < SMALL_ENOUGH) { *val = b; return 1; }
+    double lfx = fa;
+    for (int its = 0; its < MAX_ITERATIONS; its++) {
+        double x = (fb * a - fa * b) / (fb - fa), fx = polyeval(x, order, coef);
+        if (std::fabs(x) > RELERROR) { if (std::fabs(fx / x) < RELERROR) { *val = x; return 1; } }
+        else if (std::fabs(fx) < RELERROR) { *val = x; return 1; }
+        if (fa < 0) {
+            if (fx < 0) { a = x; fa = fx; if ((lfx * fx) > 0) fb /= 2; } else { b = x; fb = fx; if ((lfx * fx) > 0) fa /= 2; }
+        } else {
+            if (fx < 0) { b = x; fb = fx; if ((lfx * fx) > 0) fa /= 2; } else { a = x; fa = fx; if ((lfx * fx) > 0) fb /= 2; }
+        }
+        if (std::fabs(b - a) < RELERROR) { *val = x; return 1; }
+        lfx = fx;
+    }
+    return 0;
+}
+int sbisect(int np, const polynomial* sseq, double min_value, double max_value, int atmin, int atmax, double* roots)   // :370-480
+{
+    double mid = 0;
+    int n1, n2, its, atmid;
+    if ((atmin - atmax) == 1) {
+        if (regula_falsa(sseq->ord, sseq->coef, min_value, max_value, roots)) return 1;
+        for (its = 0; its < MAX_ITERATIONS; its++) {
+            mid = (min_value + max_value) / 2;
+            atmid = numchanges(np, sseq, mid);
+            if ((atmid < atmax) || (atmid > atmin)) return 0;
+            if (std::fabs(mid) > RELERROR) { if (std::fabs((max_value - min_value) / mid) < RELERROR) { roots[0] = mid; return 1; } }
+            else if (std::fabs(max_value - min_value) < RELERROR) { roots[0] = mid; return 1; }
+            if ((atmin - atmid) == 0) min_value = mid; else max_value = mid;
+        }
+        roots[0] = mid;
+        return 1;
+    }
+    for (its = 0; its < MAX_ITERATIONS; its++) {
+        mid = (min_value + max_value) / 2;
+        atmid = numchanges(np, sseq, mid);
+        if ((atmid < atmax) || (atmid > atmin)) return 0;
+        if (std::fabs(mid) > RELERROR) { if (std::fabs((max_value - min_value) / mid) < RELERROR) { roots[0] = mid; return 1; } }
+        else if (std::fabs(max_value - min_value) < RELERROR) { roots[0] = mid; return 1; }
+        n1 = atmin - atmid; n2 = atmid - atmax;
+        if ((n1 != 0) && (n2 != 0)) {
+            n1 = sbisect(np, sseq, min_value, mid, atmin, atmid, roots);
+            n2 = sbisect(np, sseq, mid, max_value, atmid, atmax, &roots[n1]);
+            return n1 + n2;
+        }
+        if (n1 == 0) min_value = mid; else max_value = mid;
+    }
+    roots[0] = mid;
+    return 1;
+}
+int polysolve(int order, const double* Coeffs, double* roots)             // :1481-1523
+{
+    polynomial sseq[MAX_ORDER + 1];
+    for (int i = 0; i <= order; i++) sseq[0].coef[order - i] = Coeffs[i] / Coeffs[0];
+    int np = buildsturm(order, &sseq[0]);
+    if (visible_roots(np, sseq) == 0) return 0;
+    int atmin = numchanges(np, sseq, 0.0), atmax = numchanges(np, sseq, MAX_DISTANCE);
+    if (atmin - atmax == 0) return 0;
+    return sbisect(np, sseq, 0.0, MAX_DISTANCE, atmin, atmax, roots);
+}
+int Solve_Polynomial(int n, const double* c0, double* r, int sturm, double epsilon)   // :1585-1729 (n <= 4)
+{
+    int roots = 0, i = 0;
+    while ((i < n) && (std::fabs(c0[i]) < SMALL_ENOUGH)) i++;
+    n -= i;
+    const double* c = &c0[i];
+    switch (n) {
+        case 0: break;
+        case 1: if (c[0] != 0.0) r[roots++] = -c[1] / c[0]; break;
+        case 2: roots = solve_quadratic(c, r); break;
+        case 3:
+            if (epsilon > 0.0 && (c[2] != 0.0) && (std::fabs(c[3] / c[2]) < epsilon)) { roots = solve_quadratic(c, r); break; }
+            roots = sturm ? polysolve(3, c, r) : solve_cubic(c, r);
+            break;
+        case 4:
+            if (epsilon > 0.0 && (c[3] != 0.0) && (std::fabs(c[4] / c[3]) < epsilon)) { roots = sturm ? polysolve(3, c, r) : solve_cubic(c, r); break; }
+            if (difficult_coeffs(4, c)) sturm = 1;
+            roots = sturm ? polysolve(4, c, r) : solve_quartic(c, r);
+            break;
+    }
+    return roots;
+}
+
+// ---- noise (noise.cpp, portablenoise.cpp) ------------------------------------------------------------
+const double kRTableEven[267] = {
+#include "pv_rtable.inc"
+};
+void init_noise(Scene& s)
+{
+    s.hashTable.assign(8192, 0);                          // InitTextureTable noise.cpp:231-255
+    for (int i = 0; i < 4096; i++) s.hashTable[i] = (unsigned short)i;
+    int next_rand = 0;
+    for (int i = 4095; i >= 0; i--) {
+        next_rand = (int)((long long)next_rand * 1812433253LL + 12345LL);
+        unsigned short j = (unsigned short)(((int)(next_rand >> 16) & 0x7FFF) % 4096);
+        std::swap(s.hashTable[i], s.hashTable[j]);
+    }
+    for (int i = 0; i < 4096; i++) s.hashTable[4096 + i] = s.hashTable[i];
+    s.RTable.assign(534, 0.0);                            // Initialize_Noise noise.cpp:181-182
+    for (int i = 0; i < 267; i++) { s.RTable[2 * i] = kRTableEven[i]; s.RTable[2 * i + 1] = kRTableEven[i] * 0.5; }
+    const int NE = 2048;                                  // InitSolidNoise noise.cpp:306-348
+    s.NoisePermutation.assign(2 * (NE + 1), 0);
+    s.NoiseGradients.assign(2 * (NE + 1), v3(0, 0, 0));
+    next_rand = 1;
+    for (int i = 0; i < NE; i++) {
+        double v[3], q;
+        do {
+            for (int j = 0; j < 3; j++) {
+                next_rand = (int)((long long)next_rand * 1812433253LL + 12345LL);
+                v[j] = (double)((((int)(next_rand >> 16) & 0x7FFF) % (NE << 1)) - NE) / (double)NE;
+            }
+            q = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        } while ((q > 1.0) || (q < 1.0e-5));
+        double l = std::sqrt(q);
+        s.NoiseGradients[i] = v3(v[0] / l, v[1] / l, v[2] / l);
+    }
+    for (int i = 0; i < NE; i++) s.NoisePermutation[i] = i;
+    for (int i = NE; i > 0; i -= 2) {
+        int k = s.NoisePermutation[i];
+        next_rand = (int)((long long)next_rand * 1812433253LL + 12345LL);
+        int j = ((int)(next_rand >> 16) & 0x7FFF) % NE;
+        s.NoisePermutation[i] = s.NoisePermutation[j];
+        s.NoisePermutation[j] = k;
+    }
+    for (int i = 0; i < NE + 2; i++) { s.NoisePermutation[NE + i] = s.NoisePermutation[i]; s.NoiseGradients[NE + i] = s.NoiseGradients[i]; }
+}
+inline double SCURVE(double a) { return a * a * (3.0 - 2.0 * a); }
+inline double Lerp(double t, double a, double b) { return a + t * (b - a); }
+double SolidNoise(const Scene& s, V3 P)                   // noise.cpp:392-440
+{
+    const int NE = 2048;
+    const double ROLLOVER = 10000000.023157213;
+    int b0[3], b1[3]; double r0[3], r1[3];
+    for (int i = 0; i < 3; i++) {
+        double t = P[i] + ROLLOVER; int it = (int)std::floor(t);
+        b0[i] = it & (NE - 1); b1[i] = (b0[i] + 1) & (NE - 1); r0[i] = t - it; r1[i] = r0[i] - 1.0;
+    }
+    const std::vector<int>& NP = s.NoisePermutation;
+    int i = NP[b0[0]], j = NP[b1[0]];
+    int b00 = NP[i + b0[1]], b10 = NP[j + b0[1]], b01 = NP[i + b1[1]], b11 = NP[j + b1[1]];
+    double sx = SCURVE(r0[0]), sy = SCURVE(r0[1]), sz = SCURVE(r0[2]);
+    auto at = [&](int idx, double rx, double ry, double rz) { const V3& q = s.NoiseGradients[idx]; return rx * q.x + ry * q.y + rz * q.z; };
+    double u, v, a, b, c, d;
+    u = at(b00 + b0[2], r0[0], r0[1], r0[2]); v = at(b10 + b0[2], r1[0], r0[1], r0[2]); a = Lerp(sx, u, v);
+    u = at(b01 + b0[2], r0[0], r1[1], r0[2]); v = at(b11 + b0[2], r1[0], r1[1], r0[2]); b = Lerp(sx, u, v);
+    c = Lerp(sy, a, b);
+    u = at(b00 + b1[2], r0[0], r0[1], r1[2]); v = at(b10 + b1[2], r1[0], r0[1], r1[2]); a = Lerp(sx, u, v);
+    u = at(b01 + b1[2], r0[0], r1[1], r1[2]); v = at(b11 + b1[2], r1[0], r1[1], r1[2]); b = Lerp(sx, u, v);
+    d = Lerp(sy, a, b);
+    return Lerp(sz, c, d);
+}
+struct Lattice { int ix, iy, iz; double x_ix, y_iy, z_iz; };
+inline void lattice_axis(double x, int& i, double& f)     // portablenoise.cpp:128-138
+{
+    int tmp = (x >= 0) ? (int)x : (int)(x - (1 - EPSILON));
+    i = (int)((tmp - (-10000)) & 0xFFF);
+    f = x - tmp;
+}
+#define HASH2D(a, b) (hT[(int)(hT[(int)(a)] ^ (b))])
+#define RIDX(a, b) ((hT[(int)(a) ^ (b)] & 0xFF) * 2)
+#define INCRSUMP(mp, s, x, y, z) ((s) * ((mp)[1] + (mp)[2] * (x) + (mp)[4] * (y) + (mp)[6] * (z)))
+double Noise(const Scene& s, V3 P, int gen)               // PortableNoise portablenoise.cpp:103-225
+{
+    if (gen == 3) {
+        double sum = 0.5 * (1.59 * SolidNoise(s, P) + 0.985);
+        return std::min(std::max(sum, 0.0), 1.0);
+    }
+    const unsigned short* hT = s.hashTable.data();
+    const double* RT = s.RTable.data();
+    int ix, iy, iz; double x_ix, y_iy, z_iz;
+    lattice_axis(P.x, ix, x_ix); lattice_axis(P.y, iy, y_iy); lattice_axis(P.z, iz, z_iz);
+    double x_jx = x_ix - 1, y_jy = y_iy - 1, z_jz = z_iz - 1;
+    double sx = SCURVE(x_ix), sy = SCURVE(y_iy), sz = SCURVE(z_iz), tx = 1 - sx, ty = 1 - sy, tz = 1 - sz;
+    double txty = tx * ty, sxty = sx * ty, txsy = tx * sy, sxsy = sx * sy;
+    int ixiy = HASH2D(ix, iy), jxiy = HASH2D(ix + 1, iy), ixjy = HASH2D(ix, iy + 1), jxjy = HASH2D(ix + 1, iy + 1);
+    const double* mp; double sum;
+    mp = RT + RIDX(ixiy, iz);     sum  = INCRSUMP(mp, (txty * tz), x_ix, y_iy, z_iz);
+    mp = RT + RIDX(jxiy, iz);     sum += INCRSUMP(mp, (sxty * tz), x_jx, y_iy, z_iz);
+    mp = RT + RIDX(ixjy, iz);     sum += INCRSUMP(mp, (txsy * tz), x_ix, y_jy, z_iz);
+    mp = RT + RIDX(jxjy, iz);     sum += INCRSUMP(mp, (sxsy * tz), x_jx, y_jy, z_iz);
+    mp = RT + RIDX(ixiy, iz + 1); sum += INCRSUMP(mp, (txty * sz), x_ix, y_iy, z_jz);
+    mp = RT + RIDX(jxiy, iz + 1); sum += INCRSUMP(mp, (sxty * sz), x_jx, y_iy, z_jz);
+    mp = RT + RIDX(ixjy, iz + 1); sum += INCRSUMP(mp, (txsy * sz), x_ix, y_jy, z_jz);
+    mp = RT + RIDX(jxjy, iz + 1); sum += INCRSUMP(mp, (sxsy * sz), x_jx, y_jy, z_jz);
+    if (gen == 2) { sum += 1.05242; sum *= 0.48985582; } else sum = sum + 0.5;
+    if (sum < 0.0) sum = 0.0;
+    if (sum > 1.0) sum = 1.0;
+    return sum;
+}
+V3 DNoise(const Scene& s, V3 P)                           // PortableDNoise portablenoise.cpp:262-378
+{
+    const unsigned short* hT = s.hashTable.data();
+    const double* RT = s.RTable.data();
+    int ix, iy, iz; double x_ix, y_iy, z_iz;
+    lattice_axis(P.x, ix, x_ix); lattice_axis(P.y, iy, y_iy); lattice_axis(P.z, iz, z_iz);
+    double x_jx = x_ix - 1, y_jy = y_iy - 1, z_jz = z_iz - 1;
+    double sx = SCURVE(x_ix), sy = SCURVE(y_iy), sz = SCURVE(z_iz), tx = 1 - sx, ty = 1 - sy, tz = 1 - sz;
+    double txty = tx * ty, sxty = sx * ty, txsy = tx * sy, sxsy = sx * sy;
+    int ixiy = HASH2D(ix, iy), jxiy = HASH2D(ix + 1, iy), ixjy = HASH2D(ix, iy + 1), jxjy = HASH2D(ix + 1, iy + 1);
+    double r[3] = { 0, 0, 0 };
+    bool first = true;
+    auto corner = [&](int hash, int z, double sw, double fx, double fy, double fz) {
+        const double* mp = RT + RIDX(hash, z);
+        for (int k = 0; k < 3; k++, mp += 8) { double v = INCRSUMP(mp, sw, fx, fy, fz); if (first) r[k] = v; else r[k] += v; }
+        first = false;
+    };
+    corner(ixiy, iz, txty * tz, x_ix, y_iy, z_iz); corner(jxiy, iz, sxty * tz, x_jx, y_iy, z_iz);
+    corner(jxjy, iz, sxsy * tz, x_jx, y_jy, z_iz); corner(ixjy, iz, txsy * tz, x_ix, y_jy, z_iz);
+    corner(ixjy, iz + 1, txsy * sz, x_ix, y_jy, z_jz); corner(jxjy, iz + 1, sxsy * sz, x_jx, y_jy, z_jz);
+    corner(jxiy, iz + 1, sxty * sz, x_jx, y_iy, z_jz); corner(ixiy, iz + 1, txty * sz, x_ix, y_iy, z_jz);
+    return v3(r[0], r[1], r[2]);
+}
+double Turbulence(const Scene& s, V3 P, const pvgpu_warp& T, int gen)      // noise.cpp:500-560
+{
+    double value;
+    if (gen <= 1) value = Noise(s, P, gen);
+    else { value = 2.0 * Noise(s, P, gen) - 0.5; value = std::min(std::max(value, 0.0), 1.0); }
+    double Lambda = T.lambda, Omega = T.omega, l = Lambda, o = Omega;
+    for (int i = 2; i <= T.octaves; i++) {
+        V3 temp = P * l;
+        if (gen <= 1) value += o * Noise(s, temp, gen); else value += o * (2.0 * Noise(s, temp, gen) - 0.5);
+        if (i < T.octaves) { l *= Lambda; o *= Omega; }
+    }
+    return value;
+}
+V3 DTurbulence(const Scene& s, V3 P, const pvgpu_warp& T)                  // noise.cpp:580-610
+{
+    V3 result = DNoise(s, P);
+    double Lambda = T.lambda, Omega = T.omega, l = Lambda, o = Omega;
+    for (int i = 2; i <= T.octaves; i++) {
+        V3 value = DNoise(s, P * l);
+        result = result + o * value;
+        if (i < T.octaves) { l *= Lambda; o *= Omega; }
+    }
+    return result;
+}
+
+// ---- rays, intersections ------------------------------------------------------------------------------
+enum { RAY_PRIMARY = 1, RAY_REFLECTION = 2, RAY_REFRACTION = 4 };
+struct Ray {
+    V3 Origin, Direction;
+    unsigned flags = RAY_PRIMARY;
+    bool shadowTest = false;
+    std::vector<int> interiors;
+    bool IsImageRay() const { return (flags & RAY_PRIMARY) || ((flags & RAY_REFRACTION) && !(flags & RAY_REFLECTION)); }
+    bool IsInterior(int i) const { return std::find(interiors.begin(), interiors.end(), i) != interiors.end(); }
+    bool RemoveInterior(int i) { auto it = std::find(interiors.begin(), interiors.end(), i); if (it == interiors.end()) return false; interiors.erase(it); return true; }
+    V3 Evaluate(double t) const { return v3(Origin.x + Direction.x * t, Origin.y + Direction.y * t, Origin.z + Direction.z * t); }
+};
+struct Ticket { unsigned traceLevel = 0, maxAllowedTraceLevel; double adcBailout; bool alphaBackground; unsigned maxFound = 0; };
+struct Intersection { double Depth = BOUND_HUGE; V3 IPoint{ 0, 0, 0 }; int Object = -1, Csg = -1; uint32_t aux = 0; };
+typedef std::vector<Intersection> IStack;
+
+struct Stats { unsigned long long rays = 0, shadow_tests = 0; unsigned max_level = 0; };
+
+class Tracer {
+public:
+    const Scene& S;
+    Stats st;
+    explicit Tracer(const Scene& s) : S(s) {}
+
+    // ---- primitives ----
+    static bool sphere_intersect(V3 o, V3 d, V3 Center, double Radius2, double* Depth1, double* Depth2)   // sphere.cpp:211-243
+    {
+        V3 oc = Center - o;
+        double OCSquared = len2(oc), t_ca = dot(oc, d);
+        if ((OCSquared >= Radius2) && (t_ca < EPSILON)) return false;
+        double thc2 = Radius2 - OCSquared + sqr(t_ca);
+        if (thc2 > EPSILON) { double hc = std::sqrt(thc2); *Depth1 = t_ca - hc; *Depth2 = t_ca + hc; return true; }
+        return false;
+    }
+    bool box_intersect(V3 P, V3 D, const double* c1, const double* c2, double* Depth1, double* Depth2, int* Side1, int* Side2) const;
+    bool clip_ok(const pvgpu_object& o, V3 ip) const { return o.clip_count == 0 || Point_In_Clip(ip, o); }
+    bool Point_In_Clip(V3 ip, const pvgpu_object& o) const                                               // object.cpp:430-443
+    {
+        for (uint32_t i = 0; i < o.clip_count; i++) if (!Inside_Object(ip, S.index_list[o.clip_first + i])) return false;
+        return true;
+    }
+    bool Inside_Object(V3 ip, uint32_t idx) const                                                         // object.cpp:346-355
+    {
+        const pvgpu_object& o = S.objects[idx];
+        for (uint32_t i = 0; i < o.clip_count; i++) if (!Inside_Object(ip, S.index_list[o.clip_first + i])) return false;
+        return Inside(ip, idx);
+    }
+    bool Inside(V3 p, uint32_t idx) const;
+    bool All_Intersections(uint32_t idx, const Ray& ray, IStack& stack) const;
+    bool Find_Intersection(Intersection* isect, uint32_t idx, const Ray& ray, double post_min) const;
+    bool Ray_In_Bound(const Ray& ray, const pvgpu_object& o) const                                        // object.cpp:385-400
+    {
+        for (uint32_t i = 0; i < o.bound_count; i++) {
+            Intersection local;
+            uint32_t b = S.index_list[o.bound_first + i];
+            if (!Find_Intersection(&local, b, ray, -1.0) && !Inside_Object(ray.Origin, b)) return false;
+        }
+        return true;
+    }
+    bool tri_intersect(const pvgpu_mesh& me, const pvgpu_triangle& tr, V3 o, V3 d, double* Depth) const;
+    bool mesh_intersect(uint32_t idx, const Ray& ray, IStack& stack) const;
+    bool mesh_inside(const pvgpu_object& ob, V3 p) const;
+    V3 Normal(const Intersection& isect) const;
+
+    // ---- tree ----
+    struct Rayinfo { float origin[3], invDirection[3]; bool nonzero[3], positive[3]; };
+    static Rayinfo make_rayinfo(V3 o, V3 d)                                                               // boundingbox.h:182-216
+    {
+        Rayinfo ri;
+        for (int k = 0; k < 3; k++) {
+            ri.origin[k] = (float)o[k];
+            double t = d[k];
+            ri.nonzero[k] = (t != 0.0);
+            ri.invDirection[k] = ri.nonzero[k] ? (float)(1.0 / t) : 0.0f;
+            ri.positive[k] = (t > 0.0);
+        }
+        return ri;
+    }
+    struct Qelem { double depth; uint32_t node; };
+    static void heap_insert(std::vector<Qelem>& q, double depth, uint32_t node)                           // boundingbox.cpp:88-103
+    {
+        size_t i = q.size();
+        q.push_back(Qelem{});
+        while ((i > 1) && (depth < q[i / 2].depth)) { q[i] = q[i / 2]; i /= 2; }
+        q[i].depth = depth; q[i].node = node;
+    }
+    static bool heap_remove_min(std::vector<Qelem>& q, double& depth, uint32_t& node)                     // boundingbox.cpp:105-137
+    {
+        size_t size = q.size() - 1;
+        if (size == 0) return false;
+        depth = q[1].depth; node = q[1].node;
+        size_t i = 1, j;
+        while (i <= size / 2) {
+            if ((2 * i == size) || (q[2 * i].depth < q[2 * i + 1].depth)) j = 2 * i; else j = 2 * i + 1;
+            if (q[size].depth <= q[j].depth) break;
+            q[i] = q[j];
+            i = j;
+        }
+        if (i != size) q[i] = q[size];
+        q.pop_back();
+        return true;
+    }
+    static void Check_And_Enqueue(std::vector<Qelem>& q, const pvgpu_node* nodes, uint32_t ni, const Rayinfo& ri)   // boundingbox.cpp:541-648
+    {
+        const pvgpu_node& n = nodes[ni];
+        double dmin, dmax;
+        if (!(n.flags & PVGPU_NODE_INFINITE)) {
+            dmin = -BOUND_HUGE; dmax = BOUND_HUGE;
+            for (int dim = 0; dim < 3; dim++) {
+                const float lo = n.lo[dim], hi = n.lo[dim] + n.size[dim];
+                if (ri.nonzero[dim]) {
+                    double tmin, tmax;
+                    if (ri.positive[dim]) {
+                        tmax = (hi - ri.origin[dim]) * ri.invDirection[dim];
+                        if (tmax < EPSILON) return;
+                        tmin = (lo - ri.origin[dim]) * ri.invDirection[dim];
+                    } else {
+                        tmax = (lo - ri.origin[dim]) * ri.invDirection[dim];
+                        if (tmax < EPSILON) return;
+                        tmin = (hi - ri.origin[dim]) * ri.invDirection[dim];
+                    }
+                    if (tmax < dmax) {
+                        if (tmin > dmin) { if (tmin > tmax) return; dmin = tmin; }
+                        else if (dmin > tmax) return;
+                        dmax = tmax;
+                    } else if (tmin > dmin) { if (tmin > dmax) return; dmin = tmin; }
+                } else if (!((lo <= ri.origin[dim]) && (ri.origin[dim] <= hi))) return;
+            }
+        } else dmin = -MAX_DISTANCE;
+        heap_insert(q, dmin, ni);
+    }
+    bool precondition(const Ray& ray, const pvgpu_object& o) const
+    {
+        if (ray.shadowTest) return !(o.flags & PVGPU_NO_SHADOW_FLAG);                                     // trace.cpp:1943
+        if (ray.IsImageRay() && (o.flags & PVGPU_NO_IMAGE_FLAG)) return false;                            // trace.cpp:84-95
+        if ((ray.flags & RAY_REFLECTION) && (o.flags & PVGPU_NO_REFLECTION_FLAG)) return false;
+        return true;
+    }
+    bool FindIntersection(Intersection& best, const Ray& ray, double post_min) const;                     // trace.cpp:285-344
+
+    // ---- shading ----
+    double TraceRay(Ray& ray, Ticket& tk, Col& colour, float& transm, float weight, bool continuedRay, double maxDepth = 0.0);
+    void ComputeTextureColour(Intersection& isect, Col& colour, float& transm, Ray& ray, Ticket& tk, float weight);
+    void ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect);
+    void ComputeSky(const Ray& ray, const Ticket& tk, Col& colour, float& transm) const;
+    void Compute_Pigment(float col[5], int pigment, V3 EPoint) const;
+    double relative_ior(const Ray& ray, int interior) const;
+    void ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight);
+    bool ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight);
+    void ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn, V3 ipoint, const Ray& eye, Ticket& tk, V3 layer_normal,
+                                Col layer_pigment_colour, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor);
+    void TraceShadowRay(const pvgpu_light& L, double depth, Ray& lightsourceray, Ticket& tk, Col& colour);
+    void ComputeShadowColour(Intersection& isect, Ray& lightsourceray, const Ticket& tk, Col& colour);
+    int hit_texture(const pvgpu_object& ob, const Intersection& isect, bool backside) const;
+};
+
+// Box::Intersect (box.cpp:167-520)
+bool Tracer::box_intersect(V3 P, V3 D, const double* c1, const double* c2, double* Depth1, double* Depth2, int* Side1, int* Side2) const
+{
+    const double CLOSE_TOLERANCE = 1.0e-6, DEPTH_TOLERANCE = 1.0e-6;
+    int smin = 0, smax = 0;
+    double t, tmin = 0.0, tmax = BOUND_HUGE;
+    const double Pv[3] = { P.x, P.y, P.z }, Dv[3] = { D.x, D.y, D.z };
+    for (int ax = 0; ax < 3; ax++) {
+        const double close = (ax == 0) ? 0.0 : CLOSE_TOLERANCE;
+        const int s0 = 2 * ax + 1, s1 = 2 * ax + 2;
+        auto prefer = [&](int current) {
+            // which axis is the currently recorded side on?  Y compares against X unconditionally, Z against the recorded one
+            if (ax == 1) return std::fabs(Dv[1]) > std::fabs(Dv[0]);
+            if (current == 1 || current == 2) return std::fabs(Dv[2]) > std::fabs(Dv[0]);
+            if (current == 3 || current == 4) return std::fabs(Dv[2]) > std::fabs(Dv[1]);
+            return false;
+        };
+        if (Dv[ax] < -EPSILON || Dv[ax] > EPSILON) {
+            const bool neg = Dv[ax] < -EPSILON;
+            const double farc = neg ? c1[ax] : c2[ax], nearc = neg ? c2[ax] : c1[ax];
+            const int fars = neg ? s0 : s1, nears = neg ? s1 : s0;
+            t = (farc - Pv[ax]) / Dv[ax];
+            if (t < tmin) return false;
+            if (ax == 0) { if (t <= tmax) { smax = fars; tmax = t; } }
+            else if (t <= tmax - close) { smax = fars; tmax = t; }
+            else if (t <= tmax + close) { if (prefer(smax)) smax = fars; }
+            t = (nearc - Pv[ax]) / Dv[ax];
+            if (ax == 0) { if (t >= tmin) { if (t > tmax) return false; smin = nears; tmin = t; } }
+            else if (t >= tmin + close) { if (t > tmax) return false; smin = nears; tmin = t; }
+            else if (t >= tmin - close) { if (prefer(smin)) smin = nears; }
+        } else if ((Pv[ax] < c1[ax]) || (Pv[ax] > c2[ax])) return false;
+    }
+    if (tmax < DEPTH_TOLERANCE) return false;
+    *Depth1 = tmin; *Depth2 = tmax; *Side1 = smin; *Side2 = smax;
+    return true;
+}
+
+// Mesh::intersect_mesh_triangle (mesh.cpp:1040-1127)
+bool Tracer::tri_intersect(const pvgpu_mesh& me, const pvgpu_triangle& tr, V3 o, V3 d, double* Depth) const
+{
+    const float* N = S.norms.data() + 3 * (size_t)me.normal_first;
+    const float* V = S.verts.data() + 3 * (size_t)me.vertex_first;
+    V3 n = v3f(N + 3 * tr.normal_ind);
+    double ndd = dot(n, d);
+    if (std::fabs(ndd) < EPSILON) return false;
+    double ndo = dot(n, o);
+    *Depth = -((double)tr.distance + ndo) / ndd;
+    if ((*Depth < 1.0e-6) || (*Depth > MAX_DISTANCE)) return false;
+    V3 P1 = v3f(V + 3 * tr.p1), P2 = v3f(V + 3 * tr.p2), P3 = v3f(V + 3 * tr.p3);
+    const int a = (tr.dominant_axis == 0) ? 1 : 0, b = (tr.dominant_axis == 2) ? 1 : 2;
+    double s = o[a] + *Depth * d[a], t = o[b] + *Depth * d[b];
+    if ((P2[a] - s) * (P2[b] - P1[b]) < (P2[b] - t) * (P2[a] - P1[a])) return false;
+    if ((P3[a] - s) * (P3[b] - P2[b]) < (P3[b] - t) * (P3[a] - P2[a])) return false;
+    if ((P1[a] - s) * (P1[b] - P3[b]) < (P1[b] - t) * (P1[a] - P3[a])) return false;
+    return true;
+}
+
+// Mesh::Intersect + intersect_bbox_tree + test_hit (mesh.cpp:155-195, 1452-1528, 1208-1243)
+bool Tracer::mesh_intersect(uint32_t idx, const Ray& ray, IStack& stack) const
+{
+    const pvgpu_object& ob = S.objects[idx];
+    const pvgpu_mesh& me = S.meshes[ob.mesh];
+    V3 mo = ray.Origin, md = ray.Direction;
+    double len_ = 1.0;
+    if (ob.transform >= 0) {
+        const pvgpu_transform& t = S.xf[ob.transform];
+        mo = MInvTransPoint(t, ray.Origin); md = MInvTransDirection(t, ray.Direction);
+        len_ = len(md); md = md / len_;
+    }
+    bool found = false;
+    auto test_hit = [&](uint32_t ti, double Depth) {
+        double world_dist = Depth / len_;
+        V3 ip = ray.Evaluate(world_dist);
+        if (clip_ok(ob, ip)) { Intersection is; is.Depth = world_dist; is.IPoint = ip; is.Object = (int)idx; is.aux = me.triangle_first + ti; stack.push_back(is); return true; }
+        return false;
+    };
+    if (me.node_count == 0) {
+        for (uint32_t i = 0; i < me.triangle_count; i++) {
+            double t;
+            if (tri_intersect(me, S.tris[me.triangle_first + i], mo, md, &t) && test_hit(i, t)) found = true;
+        }
+        return found;
+    }
+    const pvgpu_node* nodes = S.mnodes.data() + me.node_first;
+    Rayinfo ri = make_rayinfo(mo, md);
+    std::vector<Qelem> q(1);
+    double Best = BOUND_HUGE, Depth;
+    const bool OldStyle = me.has_inside_vector != 0;
+    Check_And_Enqueue(q, nodes, 0, ri);
+    uint32_t ni;
+    while (heap_remove_min(q, Depth, ni)) {
+        if (!OldStyle && Depth > Best) break;
+        const pvgpu_node& n = nodes[ni];
+        if (n.count) { for (uint32_t i = 0; i < n.count; i++) Check_And_Enqueue(q, nodes, n.first + i, ri); }
+        else if (tri_intersect(me, S.tris[me.triangle_first + n.first], mo, md, &Depth) && test_hit(n.first, Depth)) { found = true; Best = Depth; }
+    }
+    return found;
+}
+
+// Mesh::Inside (mesh.cpp:197-262)
+bool Tracer::mesh_inside(const pvgpu_object& ob, V3 p) const
+{
+    const pvgpu_mesh& me = S.meshes[ob.mesh];
+    if (!me.has_inside_vector) return false;
+    V3 mo = p, md = v3(me.inside_vector);
+    if (ob.transform >= 0) { const pvgpu_transform& t = S.xf[ob.transform]; mo = MInvTransPoint(t, p); md = unit(MInvTransDirection(t, md)); }
+    unsigned found = 0;
+    // (the tree variant counts the same triangles; the linear form is enough for a checker)
+    for (uint32_t i = 0; i < me.triangle_count; i++) { double t; if (tri_intersect(me, S.tris[me.triangle_first + i], mo, md, &t)) found++; }
+    bool inside = (found & 1) != 0;
+    if (ob.flags & PVGPU_INVERTED_FLAG) inside = !inside;
+    return inside;
+}
+
+bool Tracer::Inside(V3 p, uint32_t idx) const
+{
+    const pvgpu_object& ob = S.objects[idx];
+    const bool inv = (ob.flags & PVGPU_INVERTED_FLAG) != 0;
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE: {                                                                          // sphere.cpp:262-300
+            double oc2 = ob.aux ? len2(MInvTransPoint(S.xf[ob.transform], p)) : len2(v3(ob.p) - p);
+            return inv ? (oc2 > sqr(ob.p[3])) : (oc2 < sqr(ob.p[3]));
+        }
+        case PVGPU_OBJ_BOX: {                                                                             // box.cpp:538-575
+            V3 q = (ob.transform >= 0) ? MInvTransPoint(S.xf[ob.transform], p) : p;
+            if ((q.x < ob.p[0]) || (q.x > ob.p[3])) return inv;
+            if ((q.y < ob.p[1]) || (q.y > ob.p[4])) return inv;
+            if ((q.z < ob.p[2]) || (q.z > ob.p[5])) return inv;
+            return !inv;
+        }
+        case PVGPU_OBJ_PLANE: {                                                                           // plane.cpp:208-225
+            double temp = (ob.transform < 0) ? dot(p, v3(ob.p)) : dot(MInvTransPoint(S.xf[ob.transform], p), v3(ob.p));
+            return (temp + ob.p[3]) < EPSILON;
+        }
+        case PVGPU_OBJ_QUADRIC: {                                                                         // quadric.cpp:248-255
+            const double* c = ob.p;
+            return (p.x * (c[0] * p.x + c[3] * p.y + c[6]) + p.y * (c[1] * p.y + c[5] * p.z + c[7]) + p.z * (c[2] * p.z + c[4] * p.x + c[8]) + c[9]) <= 0.0;
+        }
+        case PVGPU_OBJ_TORUS: {                                                                           // torus.cpp:348-400
+            V3 P = MInvTransPoint(S.xf[ob.transform], p);
+            double r = std::sqrt(sqr(P.x) + sqr(P.z)), r2 = sqr(P.y) + sqr(r - ob.p[0]);
+            bool inside = false;
+            if (r2 <= sqr(ob.p[1])) {
+                inside = true;
+                if (ob.aux & 0x20u) { bool insp = (sqr(P.y) + sqr(r + ob.p[0]) <= sqr(ob.p[1])); inside = (ob.aux & 0x04u) ? insp : !insp; }
+            }
+            return inside ? !inv : inv;
+        }
+        case PVGPU_OBJ_MESH: return mesh_inside(ob, p);
+        case PVGPU_OBJ_CSG_UNION:
+        case PVGPU_OBJ_CSG_MERGE:                                                                         // csg.cpp:393-410
+            for (uint32_t i = 0; i < ob.child_count; i++) if (Inside_Object(p, S.index_list[ob.child_first + i])) return true;
+            return false;
+        case PVGPU_OBJ_CSG_INTERSECTION:                                                                  // csg.cpp:428-440
+            for (uint32_t i = 0; i < ob.child_count; i++) if (!Inside_Object(p, S.index_list[ob.child_first + i])) return false;
+            return true;
+    }
+    return false;
+}
+
+static bool test_ray_flags(const Ray& ray, uint32_t oflags, bool shadow_variant)                          // csg.cpp:80-104
+{
+    const bool image = !ray.shadowTest && ray.IsImageRay(), primary = !ray.shadowTest && (ray.flags & RAY_PRIMARY), refl = !ray.shadowTest && (ray.flags & RAY_REFLECTION);
+    bool ok = (!(oflags & PVGPU_NO_IMAGE_FLAG) || !image || (!shadow_variant && primary)) && (!(oflags & PVGPU_NO_REFLECTION_FLAG) || !refl);
+    if (shadow_variant && ray.shadowTest && !(oflags & PVGPU_NO_SHADOW_FLAG)) ok = true;
+    return ok;
+}
+
+bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack) const
+{
+    const pvgpu_object& ob = S.objects[idx];
+    const V3 o = ray.Origin, d = ray.Direction;
+    auto push = [&](double depth, V3 ip, uint32_t aux) {
+        if (clip_ok(ob, ip)) { Intersection is; is.Depth = depth; is.IPoint = ip; is.Object = (int)idx; is.aux = aux; Depth_Stack.push_back(is); return true; }
+        return false;
+    };
+    bool found = false;
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE: {                                                                          // sphere.cpp:92-170
+            double d1, d2;
+            if (ob.aux) {
+                const pvgpu_transform& t = S.xf[ob.transform];
+                V3 no = MInvTransPoint(t, o), nd = MInvTransDirection(t, d);
+                double l = len(nd); nd = nd / l;
+                if (sphere_intersect(no, nd, v3(0, 0, 0), 1.0, &d1, &d2)) {
+                    if ((d1 > 1.0e-6) && (d1 < MAX_DISTANCE)) found |= push(d1 / l, MTransPoint(t, v3(no.x + nd.x * d1, no.y + nd.y * d1, no.z + nd.z * d1)), 0);
+                    if ((d2 > 1.0e-6) && (d2 < MAX_DISTANCE)) found |= push(d2 / l, MTransPoint(t, v3(no.x + nd.x * d2, no.y + nd.y * d2, no.z + nd.z * d2)), 0);
+                }
+            } else if (sphere_intersect(o, d, v3(ob.p), sqr(ob.p[3]), &d1, &d2)) {
+                if ((d1 > 1.0e-6) && (d1 < MAX_DISTANCE)) found |= push(d1, ray.Evaluate(d1), 0);
+                if ((d2 > 1.0e-6) && (d2 < MAX_DISTANCE)) found |= push(d2, ray.Evaluate(d2), 0);
+            }
+            return found;
+        }
+        case PVGPU_OBJ_BOX: {                                                                             // box.cpp:100-149
+            V3 P = o, D = d;
+            if (ob.transform >= 0) { P = MInvTransPoint(S.xf[ob.transform], o); D = MInvTransDirection(S.xf[ob.transform], d); }
+            double d1, d2; int s1, s2;
+            if (box_intersect(P, D, ob.p, ob.p + 3, &d1, &d2, &s1, &s2)) {
+                if (d1 > 1.0e-6) found |= push(d1, ray.Evaluate(d1), (uint32_t)s1);
+                found |= push(d2, ray.Evaluate(d2), (uint32_t)s2);
+            }
+            return found;
+        }
+        case PVGPU_OBJ_PLANE: {                                                                           // plane.cpp:92-190
+            V3 n = v3(ob.p);
+            double ndd, ndo;
+            if (ob.transform < 0) { ndd = dot(n, d); if (std::fabs(ndd) < EPSILON) return false; ndo = dot(n, o); }
+            else {
+                V3 P = MInvTransPoint(S.xf[ob.transform], o), D = MInvTransDirection(S.xf[ob.transform], d);
+                ndd = dot(n, D); if (std::fabs(ndd) < EPSILON) return false; ndo = dot(n, P);
+            }
+            double depth = -(ndo + ob.p[3]) / ndd;
+            if ((depth >= 1.0e-6) && (depth <= MAX_DISTANCE)) return push(depth, ray.Evaluate(depth), 0);
+            return false;
+        }
+        case PVGPU_OBJ_QUADRIC: {                                                                         // quadric.cpp:123-230
+            const double QA = ob.p[0], QE = ob.p[1], QH = ob.p[2], QB = ob.p[3], QC = ob.p[4], QF = ob.p[5], QD = ob.p[6], QG = ob.p[7], QI = ob.p[8], QJ = ob.p[9];
+            const double Xo = o.x, Yo = o.y, Zo = o.z, Xd = d.x, Yd = d.y, Zd = d.z;
+            double a = Xd * (QA * Xd + QB * Yd + QC * Zd) + Yd * (QE * Yd + QF * Zd) + Zd * QH * Zd;
+            double b = Xd * (QA * Xo + 0.5 * (QB * Yo + QC * Zo + QD)) + Yd * (QE * Yo + 0.5 * (QB * Xo + QF * Zo + QG)) + Zd * (QH * Zo + 0.5 * (QC * Xo + QF * Yo + QI));
+            double c = Xo * (QA * Xo + QB * Yo + QC * Zo + QD) + Yo * (QE * Yo + QF * Zo + QG) + Zo * (QH * Zo + QI) + QJ;
+            double d1, d2;
+            if (a != 0.0) { double dd = sqr(b) - a * c; if (dd <= 0.0) return false; dd = std::sqrt(dd); d1 = (-b + dd) / a; d2 = (-b - dd) / a; }
+            else { if (b == 0.0) return false; d1 = -0.5 * c / b; d2 = MAX_DISTANCE; }
+            if ((d1 > 1.0e-6) && (d1 < MAX_DISTANCE)) found |= push(d1, ray.Evaluate(d1), 0);
+            if ((d2 > 1.0e-6) && (d2 < MAX_DISTANCE)) found |= push(d2, ray.Evaluate(d2), 0);
+            return found;
+        }
+        case PVGPU_OBJ_TORUS: {                                                                           // torus.cpp:133-330, 932-1059
+            const pvgpu_transform& t = S.xf[ob.transform];
+            const double R = ob.p[0], r = ob.p[1];
+            V3 P = MInvTransPoint(t, o), D = MInvTransDirection(t, d);
+            double l = len(D); D = D / l;
+            double y1 = -r, y2 = r, r1 = sqr(R - r); if (R < r) r1 = 0; double r2 = sqr(R + r);
+            auto thick = [&]() {
+                double a, b, c, dd, u, v, k, rr, h;
+                if (std::fabs(D.y) < EPSILON) { if ((P.y < y1) || (P.y > y2)) return false; }
+                else {
+                    k = (y2 - P.y) / D.y; u = P.x + k * D.x; v = P.z + k * D.z;
+                    if ((k > EPSILON) && (k < MAX_DISTANCE)) { rr = u * u + v * v; if ((rr >= r1) && (rr <= r2)) return true; }
+                    k = (y1 - P.y) / D.y; u = P.x + k * D.x; v = P.z + k * D.z;
+                    if ((k > EPSILON) && (k < MAX_DISTANCE)) { rr = u * u + v * v; if ((rr >= r1) && (rr <= r2)) return true; }
+                }
+                a = D.x * D.x + D.z * D.z;
+                if (a > EPSILON) {
+                    b = P.x * D.x + P.z * D.z;
+                    for (int pass = 0; pass < 2; pass++) {
+                        c = P.x * P.x + P.z * P.z - (pass == 0 ? r2 : r1);
+                        dd = b * b - a * c;
+                        if (dd >= 0.0) {
+                            dd = std::sqrt(dd);
+                            k = (-b + dd) / a; if ((k > EPSILON) && (k < MAX_DISTANCE)) { h = P.y + k * D.y; if ((h >= y1) && (h <= y2)) return true; }
+                            k = (-b - dd) / a; if ((k > EPSILON) && (k < MAX_DISTANCE)) { h = P.y + k * D.y; if ((h >= y1) && (h <= y2)) return true; }
+                        }
+                    }
+                }
+                return false;
+            };
+            if (!thick()) return false;
+            double bsr = R + r + r, DistanceP = len2(P), Closer = 0.0;
+            if (DistanceP > sqr(bsr)) { DistanceP = std::sqrt(DistanceP); Closer = DistanceP - bsr; P = P + Closer * D; }
+            double R2 = sqr(R); r2 = sqr(r);
+            double Py2 = P.y * P.y, Dy2 = D.y * D.y, PDy2 = P.y * D.y;
+            double k1 = P.x * P.x + P.z * P.z + Py2 - R2 - r2, k2 = P.x * D.x + P.z * D.z + PDy2;
+            double c[5], rt[4];
+            c[0] = 1.0; c[1] = 4.0 * k2; c[2] = 2.0 * (k1 + 2.0 * (k2 * k2 + R2 * Dy2)); c[3] = 4.0 * (k2 * k1 + 2.0 * R2 * PDy2); c[4] = k1 * k1 + 4.0 * R2 * (Py2 - r2);
+            int n = Solve_Polynomial(4, c, rt, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, 1.0e-4);
+            while (n--) {
+                double depth = (rt[n] + Closer) / l;
+                if ((depth > 1.0e-4) && (depth < MAX_DISTANCE)) {
+                    V3 ip = ray.Evaluate(depth);
+                    uint32_t aux = 0;
+                    if (ob.aux) {
+                        if (!clip_ok(ob, ip)) continue;
+                        bool on = len2(MInvTransPoint(t, ip)) < ob.p[2];
+                        if (!(on ? (ob.aux & 1u) : (ob.aux & 2u))) continue;
+                        aux = on ? 1u : 0u;
+                    }
+                    found |= push(depth, ip, aux);
+                }
+            }
+            return found;
+        }
+        case PVGPU_OBJ_MESH: return mesh_intersect(idx, ray, Depth_Stack);
+        case PVGPU_OBJ_CSG_UNION: {                                                                       // csg.cpp:128-189
+            for (uint32_t i = 0; i < ob.child_count; i++) {
+                uint32_t ch = S.index_list[ob.child_first + i];
+                const pvgpu_object& co = S.objects[ch];
+                if (!test_ray_flags(ray, co.flags, false)) continue;
+                if (co.bound_count && !Ray_In_Bound(ray, co)) continue;
+                if (ob.clip_count == 0) { if (All_Intersections(ch, ray, Depth_Stack)) found = true; }
+                else {
+                    IStack local;
+                    if (All_Intersections(ch, ray, local))
+                        while (!local.empty()) {
+                            if (Point_In_Clip(local.back().IPoint, ob)) { local.back().Csg = (int)idx; Depth_Stack.push_back(local.back()); found = true; }
+                            local.pop_back();
+                        }
+                }
+            }
+            return found;
+        }
+        case PVGPU_OBJ_CSG_INTERSECTION: {                                                                // csg.cpp:219-277
+            for (uint32_t i = 0; i < ob.child_count; i++) {
+                uint32_t ch = S.index_list[ob.child_first + i];
+                const pvgpu_object& co = S.objects[ch];
+                if (co.bound_count && !Ray_In_Bound(ray, co)) continue;
+                IStack local;
+                if (All_Intersections(ch, ray, local))
+                    while (!local.empty()) {
+                        bool maybe = true;
+                        for (uint32_t k = 0; k < ob.child_count; k++) {
+                            uint32_t sib = S.index_list[ob.child_first + k];
+                            if (sib != ch && !Inside_Object(local.back().IPoint, sib)) { maybe = false; break; }
+                        }
+                        if (maybe && (ob.clip_count == 0 || Point_In_Clip(local.back().IPoint, ob))) { local.back().Csg = (int)idx; Depth_Stack.push_back(local.back()); found = true; }
+                        local.pop_back();
+                    }
+            }
+            return found;
+        }
+        case PVGPU_OBJ_CSG_MERGE: {                                                                       // csg.cpp:307-375
+            for (uint32_t i = 0; i < ob.child_count; i++) {
+                uint32_t ch = S.index_list[ob.child_first + i];
+                const pvgpu_object& co = S.objects[ch];
+                if (!test_ray_flags(ray, co.flags, true)) continue;
+                if (co.bound_count && !Ray_In_Bound(ray, co)) continue;
+                IStack local;
+                if (All_Intersections(ch, ray, local))
+                    while (!local.empty()) {
+                        if (ob.clip_count == 0 || Point_In_Clip(local.back().IPoint, ob)) {
+                            bool inside_flag = true;
+                            for (uint32_t k = 0; k < ob.child_count && inside_flag; k++) {
+                                uint32_t sib = S.index_list[ob.child_first + k];
+                                if (sib != ch && test_ray_flags(ray, S.objects[sib].flags, true) && Inside_Object(local.back().IPoint, sib)) inside_flag = false;
+                            }
+                            if (inside_flag) { local.back().Csg = (int)idx; found = true; Depth_Stack.push_back(local.back()); }
+                        }
+                        local.pop_back();
+                    }
+            }
+            return found;
+        }
+    }
+    return false;
+}
+
+// ObjectBase::Intersect_BBox / Intersect_BBox_Dir (object.cpp:917-941, 1074-1109)
+static bool Intersect_BBox(const pvgpu_object& ob, V3 o, V3 d, float maxd)
+{
+    if (ob.type < PVGPU_OBJ_QUADRIC) return true;          // Sphere / Box / Plane override it (sphere.cpp:753, box.cpp:1079, plane.cpp:629)
+    float origin[3] = { (float)o.x, (float)o.y, (float)o.z };
+    float invdir[3] = { (float)(1.0 / d.x), (float)(1.0 / d.y), (float)(1.0 / d.z) };
+    float b[2][3] = { { ob.bbox[0], ob.bbox[1], ob.bbox[2] }, { ob.bbox[0] + ob.bbox[3], ob.bbox[1] + ob.bbox[4], ob.bbox[2] + ob.bbox[5] } };
+    const int BX = invdir[0] < 0.0f, BY = invdir[1] < 0.0f, BZ = invdir[2] < 0.0f;
+    float tmin = (b[BX][0] - origin[0]) * invdir[0], tmax = (b[1 - BX][0] - origin[0]) * invdir[0];
+    float tymin = (b[BY][1] - origin[1]) * invdir[1], tymax = (b[1 - BY][1] - origin[1]) * invdir[1];
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    float tzmin = (b[BZ][2] - origin[2]) * invdir[2], tzmax = (b[1 - BZ][2] - origin[2]) * invdir[2];
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    if (tzmin > tmin) tmin = tzmin;
+    if (tzmax < tmax) tmax = tzmax;
+    return (tmin < maxd) && (tmax > (float)MIN_ISECT_DEPTH);
+}
+
+// Find_Intersection (object.cpp:118-224); post_min < 0: no post-condition, else SmallToleranceRayObjectCondition
+bool Tracer::Find_Intersection(Intersection* isect, uint32_t idx, const Ray& ray, double post_min) const
+{
+    const pvgpu_object& ob = S.objects[idx];
+    double closest = HUGE_VALUE;
+    if (!Intersect_BBox(ob, ray.Origin, ray.Direction, (float)closest)) return false;
+    if (ob.bound_count && !Ray_In_Bound(ray, ob)) return false;
+    IStack depthstack;
+    if (All_Intersections(idx, ray, depthstack)) {
+        bool found = false;
+        while (!depthstack.empty()) {
+            double tmpDepth = depthstack.back().Depth;
+            if (tmpDepth < closest && tmpDepth >= MIN_ISECT_DEPTH && tmpDepth > post_min) { *isect = depthstack.back(); closest = tmpDepth; found = true; }
+            depthstack.pop_back();
+        }
+        return found;
+    }
+    return false;
+}
+
+// Trace::FindIntersection + Intersect_BBox_Tree (trace.cpp:285-344, boundingbox.cpp:485-539)
+bool Tracer::FindIntersection(Intersection& best, const Ray& ray, double post_min) const
+{
+    bool found = false;
+    if (!S.use_tree) {
+        for (uint32_t f : S.frame) {
+            if (!precondition(ray, S.objects[f])) continue;
+            Intersection isect;
+            if (Find_Intersection(&isect, f, ray, post_min) && (isect.Depth < best.Depth)) { best = isect; found = true; }
+        }
+        return found;
+    }
+    Rayinfo ri = make_rayinfo(ray.Origin, ray.Direction);
+    std::vector<Qelem> q(1);
+    Check_And_Enqueue(q, S.nodes.data(), 0, ri);
+    double Depth; uint32_t ni;
+    while (heap_remove_min(q, Depth, ni)) {
+        if (Depth > best.Depth) break;
+        const pvgpu_node& n = S.nodes[ni];
+        if (n.count) { for (uint32_t i = 0; i < n.count; i++) Check_And_Enqueue(q, S.nodes.data(), n.first + i, ri); }
+        else if (precondition(ray, S.objects[n.first])) {
+            Intersection isect;
+            if (Find_Intersection(&isect, n.first, ray, post_min) && isect.Depth < best.Depth) { best = isect; found = true; }
+        }
+    }
+    return found;
+}
+
+// <Primitive>::Normal
+V3 Tracer::Normal(const Intersection& isect) const
+{
+    const pvgpu_object& ob = S.objects[isect.Object];
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE:                                                                            // sphere.cpp:318-340
+            if (ob.aux) { const pvgpu_transform& t = S.xf[ob.transform]; return unit(MTransNormal(t, MInvTransPoint(t, isect.IPoint))); }
+            return (isect.IPoint - v3(ob.p)) / ob.p[3];
+        case PVGPU_OBJ_BOX: {                                                                             // box.cpp:600-620
+            V3 n = v3(0, 0, 0);
+            switch (isect.aux) { case 1: n.x = -1; break; case 2: n.x = 1; break; case 3: n.y = -1; break; case 4: n.y = 1; break; case 5: n.z = -1; break; case 6: n.z = 1; break; }
+            if (ob.transform >= 0) n = unit(MTransNormal(S.xf[ob.transform], n));
+            return n;
+        }
+        case PVGPU_OBJ_PLANE: {                                                                           // plane.cpp:243-253
+            V3 n = v3(ob.p);
+            if (ob.transform >= 0) n = unit(MTransNormal(S.xf[ob.transform], n));
+            return n;
+        }
+        case PVGPU_OBJ_QUADRIC: {                                                                         // quadric.cpp:273-310
+            const double* c = ob.p; V3 ip = isect.IPoint;
+            V3 n = v3(2.0 * c[0] * ip.x + c[3] * ip.y + c[4] * ip.z + c[6], c[3] * ip.x + 2.0 * c[1] * ip.y + c[5] * ip.z + c[7], c[4] * ip.x + c[5] * ip.y + 2.0 * c[2] * ip.z + c[8]);
+            double l = len(n);
+            return l == 0.0 ? v3(1, 0, 0) : n / l;
+        }
+        case PVGPU_OBJ_TORUS: {                                                                           // torus.cpp:418-520
+            const pvgpu_transform& t = S.xf[ob.transform];
+            V3 P = MInvTransPoint(t, isect.IPoint);
+            double dist = std::sqrt(P.x * P.x + P.z * P.z);
+            V3 M = v3(0, 0, 0);
+            if (dist > EPSILON) { M.x = ob.p[0] * P.x / dist; M.z = ob.p[0] * P.z / dist; }
+            V3 N = isect.aux ? P + M : P - M;
+            return unit(MTransNormal(t, N));
+        }
+        case PVGPU_OBJ_MESH: {                                                                            // mesh.cpp:283-375
+            const pvgpu_mesh& me = S.meshes[ob.mesh];
+            const pvgpu_triangle& tr = S.tris[isect.aux];
+            const float* N = S.norms.data() + 3 * (size_t)me.normal_first;
+            const float* V = S.verts.data() + 3 * (size_t)me.vertex_first;
+            V3 result;
+            if (tr.flags & PVGPU_TRI_SMOOTH) {
+                V3 ip = (ob.transform >= 0) ? MInvTransPoint(S.xf[ob.transform], isect.IPoint) : isect.IPoint;
+                V3 N1 = v3f(N + 3 * tr.n1), N2 = v3f(N + 3 * tr.n2), N3 = v3f(N + 3 * tr.n3);
+                V3 PIMinusP1 = ip - v3f(V + 3 * tr.p1);
+                double u = dot(PIMinusP1, v3f(tr.perp));
+                if (u < EPSILON) result = N1;
+                else {
+                    int axis = tr.v_axis;
+                    double k1 = V[3 * tr.p1 + axis], k2 = V[3 * tr.p2 + axis], k3 = V[3 * tr.p3 + axis];
+                    double v = (PIMinusP1[axis] / u + k1 - k2) / (k3 - k2);
+                    result = N1 + u * (N2 - N1 + v * (N3 - N2));
+                }
+                if (ob.transform >= 0) result = MTransNormal(S.xf[ob.transform], result);
+                return unit(result);
+            }
+            result = v3f(N + 3 * tr.normal_ind);
+            if (ob.transform >= 0) result = unit(MTransNormal(S.xf[ob.transform], result));
+            return result;
+        }
+    }
+    return v3(0, 1, 0);
+}
+
+// ---- materials -------------------------------------------------------------------------------------------
+static double cycloidal(double value)                                                                     // texture.cpp:98-110
+{
+    const double TWO_M_PI = 6.283185307179586476925286766560;
+    if (value >= 0.0) return std::sin(((value - std::floor(value)) * 50000.0) / 50000.0 * TWO_M_PI);
+    return 0.0 - std::sin(((0.0 - (value + std::floor(0.0 - value))) * 50000.0) / 50000.0 * TWO_M_PI);
+}
+static double Triangle_Wave(double value)                                                                 // texture.cpp:128-150
+{
+    double offset = (value >= 0.0) ? value - std::floor(value) : value + 1.0 + std::floor(std::fabs(value));
+    return (offset >= 0.5) ? 2.0 * (1.0 - offset) : 2.0 * offset;
+}
+
+void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const                                  // pigment.cpp:395-466
+{
+    const pvgpu_pigment& pg = S.pigments[pigment];
+    if (pg.pattern == PVGPU_PAT_PLAIN) { for (int k = 0; k < 5; k++) col[k] = pg.colour[k]; return; }
+    // Warp_EPoint (warp.cpp:103-122)
+    V3 p = EPoint;
+    for (int i = (int)pg.warp_count - 1; i >= 0; i--) {
+        const pvgpu_warp& w = S.warps[pg.warp_first + i];
+        if (w.type == PVGPU_WARP_TRANSFORM) p = MInvTransPoint(S.xf[w.transform], p);
+        else { V3 t = DTurbulence(S, p, w); p = v3(p.x + t.x * w.turbulence[0], p.y + t.y * w.turbulence[1], p.z + t.z * w.turbulence[2]); }
+    }
+    auto clampc = [](double& c) { if (c > COORDINATE_LIMIT) c = COORDINATE_LIMIT; else if (c < -COORDINATE_LIMIT) c = -COORDINATE_LIMIT; };
+    clampc(p.x); clampc(p.y); clampc(p.z);
+    const int gen = pg.noise_generator ? pg.noise_generator : S.g.noise_generator;
+    const pvgpu_warp* turb = (pg.warp_count && S.warps[pg.warp_first].type == PVGPU_WARP_CLASSIC_TURBULENCE) ? &S.warps[pg.warp_first] : nullptr;
+    double value = 0.0;
+    bool discrete = false;
+    switch (pg.pattern) {
+        case PVGPU_PAT_CHECKER: {                                                                         // pattern.cpp:5691-5707
+            int v = (int)(std::floor(p.x + EPSILON) + std::floor(p.y + EPSILON) + std::floor(p.z + EPSILON));
+            value = (v & 1) ? 1.0 : 0.0; discrete = true; break;
+        }
+        case PVGPU_PAT_BOZO: case PVGPU_PAT_SPOTTED: value = Noise(S, p, gen); break;                     // pattern.cpp:7858
+        case PVGPU_PAT_GRANITE: {                                                                         // pattern.cpp:6429-6465
+            double noise = 0.0, freq = 1.0; V3 tv1 = p * 4.0;
+            for (int i = 0; i < 6; freq *= 2.0, i++) {
+                V3 tv2 = tv1 * freq; double temp;
+                if (gen <= 1) temp = std::fabs(0.5 - Noise(S, tv2, gen));
+                else { temp = std::fabs(1.0 - 2.0 * Noise(S, tv2, gen)); if (temp > 0.5) temp = 0.5; }
+                noise += temp / freq;
+            }
+            value = noise; break;
+        }
+        case PVGPU_PAT_GRADIENT: { double r = dot(p, v3(pg.p)); value = (r > 1.0) ? std::fmod(r, 1.0) : r; break; }   // pattern.cpp:6386
+        case PVGPU_PAT_MARBLE: value = p.x + (turb ? turb->turbulence[0] * Turbulence(S, p, *turb, gen) : 0.0); break; // pattern.cpp:7831
+        case PVGPU_PAT_ONION: value = std::fmod(len(p), 1.0); break;                                      // pattern.cpp:7934
+        case PVGPU_PAT_WRINKLES: {                                                                        // pattern.cpp:8720-8775
+            double lambda = 2.0, omega = 0.5;
+            auto n1 = [&](V3 q) { return gen <= 1 ? Noise(S, q, gen) : std::min(std::max(Noise(S, q, gen) * 2.0 - 0.5, 0.0), 1.0); };
+            value = n1(p);
+            for (int i = 1; i < 10; i++) { value += omega * n1(p * lambda); lambda *= 2.0; omega *= 0.5; }
+            value = value / 2.0; break;
+        }
+        case PVGPU_PAT_AGATE: {                                                                           // pattern.cpp:5396-5421
+            double tv = turb ? pg.p[0] * Turbulence(S, p, *turb, gen) : 0.0;
+            double noise = 0.5 * (cycloidal(1.3 * tv + 1.1 * p.z) + 1.0);
+            if (noise < 0.0) noise = 0.0; else { noise = std::min(1.0, noise); noise = std::pow(noise, 0.77); }
+            value = noise; break;
+        }
+    }
+    if (!discrete && pg.wave_type != PVGPU_WAVE_RAW) {                                                    // pattern.cpp:354-392
+        if (pg.frequency != 0.0f) value = std::fmod(value * (double)pg.frequency + (double)pg.phase, 1.00001);
+        if (value < 0.0) value -= std::floor(value);
+        switch (pg.wave_type) {
+            case PVGPU_WAVE_SINE: value = (1.0 + cycloidal(value)) * 0.5; break;
+            case PVGPU_WAVE_TRIANGLE: value = Triangle_Wave(value); break;
+            case PVGPU_WAVE_SCALLOP: value = std::fabs(cycloidal(value * 0.5)); break;
+            case PVGPU_WAVE_CUBIC: value = sqr(value) * ((-2.0 * value) + 3.0); break;
+            case PVGPU_WAVE_POLY: value = std::pow(value, (double)pg.exponent); break;
+        }
+    }
+    // BlendMap::Search + ColourBlendMap::Compute (pattern.cpp:1068-1112, pigment.cpp:513-530)
+    const pvgpu_blend_map& m = S.maps[pg.blend_map];
+    const pvgpu_blend_entry* e = S.entries.data() + m.entry_first;
+    const uint32_t Max_Ent = m.entry_count - 1;
+    uint32_t iP, iN; double prevW = 0.0, nextW = 1.0;
+    if (value >= e[Max_Ent].value) iP = iN = Max_Ent;
+    else {
+        iP = iN = 0;
+        while (value > e[iN].value) { iP = iN; iN++; }
+        if ((value == e[iN].value) || (iP == iN)) iP = iN;
+        else { prevW = (e[iN].value - value) / (e[iN].value - e[iP].value); nextW = 1.0 - prevW; }
+    }
+    if (iP == iN) for (int k = 0; k < 5; k++) col[k] = e[iN].colour[k];
+    else for (int k = 0; k < 5; k++) col[k] = (float)(e[iP].colour[k] * prevW) + (float)(e[iN].colour[k] * nextW);
+}
+
+static double FresnelR(double cosTi, double n)                                                            // trace.cpp:2680-2708
+{
+    double sqrg = sqr(n) + sqr(cosTi) - 1.0;
+    if (sqrg <= 0.0) return 1.0;
+    double g = std::sqrt(sqrg), quot1 = (g - cosTi) / (g + cosTi), quot2 = (cosTi * (g + cosTi) - 1.0) / (cosTi * (g - cosTi) + 1.0);
+    double f = 0.5 * sqr(quot1) * (1.0 + sqr(quot2));
+    return std::min(std::max(f, 0.0), 1.0);
+}
+static void ComputeMetallic(Col& c, double metallic, Col mc, double cosAngle)                             // trace.cpp:2656-2669
+{
+    if (metallic != 0.0) {
+        double x = std::fabs(std::acos(cosAngle)) / 1.57079632679489661923;
+        double F = 0.014567225 / sqr(x - 1.12) - 0.011612903;
+        F = std::min(1.0, std::max(0.0, F));
+        c.r *= (float)(1.0 + (metallic * (1.0 - F)) * (mc.r - 1.0)); c.g *= (float)(1.0 + (metallic * (1.0 - F)) * (mc.g - 1.0)); c.b *= (float)(1.0 + (metallic * (1.0 - F)) * (mc.b - 1.0));
+    }
+}
+static double cubic_spline(double low, double high, double pos)                                           // lightsource.cpp:501-517
+{
+    if (pos < low) return 0.0;
+    if (pos >= high) return 1.0;
+    pos = (pos - low) / (high - low);
+    return (3 - 2 * pos) * pos * pos;
+}
+static double Attenuate_Light(const pvgpu_light& L, const Ray& ray, double Distance)                      // lightsource.cpp:548-633
+{
+    double Attenuation = 1.0;
+    if (L.type == PVGPU_LIGHT_SPOT) {
+        double costheta = dot(ray.Direction, v3(L.direction));
+        if (Distance > 0.0) costheta = -costheta;
+        if (costheta > 0.0) { Attenuation = std::pow(costheta, L.coeff); if (L.radius > 0.0 && costheta < L.radius) Attenuation *= cubic_spline(L.falloff, L.radius, costheta); }
+        else return 0.0;
+    } else if (L.type == PVGPU_LIGHT_CYLINDER) {
+        V3 V1 = ray.Origin - v3(L.center);
+        double k = dot(V1, v3(L.direction));
+        if (k > 0.0) {
+            V3 P = V1 - k * v3(L.direction);
+            double l = len(P);
+            if (l < L.falloff) { double dist = 1.0 - l / L.falloff; Attenuation = std::pow(dist, L.coeff); if (L.radius > 0.0 && l > L.radius) Attenuation *= cubic_spline(0.0, 1.0 - L.radius / L.falloff, dist); }
+            else return 0.0;
+        } else return 0.0;
+    }
+    if (Attenuation > 0.0 && L.fade_power > 0.0) {
+        if (std::fabs(L.fade_distance) >= EPSILON) Attenuation *= 2.0 / (1.0 + std::pow(Distance / L.fade_distance, L.fade_power));
+        else Attenuation *= std::pow(Distance, -L.fade_power);
+    }
+    return Attenuation;
+}
+
+double Tracer::relative_ior(const Ray& ray, int interior) const                                           // trace.cpp:2595-2625
+{
+    if (interior < 0) return 1.0;
+    double ior = S.interiors[interior].ior;
+    if (ray.interiors.empty()) return ior / S.g.atmosphere_ior;
+    if (ray.IsInterior(interior)) {
+        if (ray.interiors.size() == 1) return S.g.atmosphere_ior / ior;
+        return S.interiors[ray.interiors.back()].ior / ior;
+    }
+    return ior / S.interiors[ray.interiors.back()].ior;
+}
+
+int Tracer::hit_texture(const pvgpu_object& ob, const Intersection& isect, bool backside) const
+{
+    if (ob.type == PVGPU_OBJ_MESH && (ob.flags & PVGPU_MULTITEXTURE_FLAG)) {                              // mesh.cpp:2421-2457
+        if (backside && ob.interior_texture >= 0) return ob.interior_texture;
+        const pvgpu_triangle& tr = S.tris[isect.aux];
+        if (tr.texture >= 0) return (int)S.index_list[S.meshes[ob.mesh].texture_first + tr.texture];
+        return ob.texture;
+    }
+    if (ob.texture < 0) return -1;
+    return (backside && ob.interior_texture >= 0) ? ob.interior_texture : ob.texture;                     // trace.cpp:513-530
+}
+
+void Tracer::ComputeSky(const Ray&, const Ticket& tk, Col& colour, float& transm) const                   // trace.cpp:2769-2890 (no sky_sphere)
+{
+    const float* bg = S.g.background;
+    if (S.g.language_version < 370) {
+        if (tk.alphaBackground) { colour = Col{ 0, 0, 0 }; transm = 1.0f; return; }
+        colour = Col{ bg[0], bg[1], bg[2] }; transm = bg[4];
+        return;
+    }
+    float f = tk.alphaBackground ? bg[3] : 0.0f, t = tk.alphaBackground ? bg[4] : 0.0f;
+    float att = (float)(1.0 - f - t);
+    colour = Col{ bg[0] * att, bg[1] * att, bg[2] * att };
+    Col fil{ bg[0] * f + t, bg[1] * f + t, bg[2] * f + t };
+    transm = std::min(1.0f, std::fabs(grey(fil)));
+}
+
+double Tracer::TraceRay(Ray& ray, Ticket& tk, Col& colour, float& transm, float weight, bool continuedRay, double maxDepth)   // trace.cpp:135-228
+{
+    st.rays++;
+    if ((tk.traceLevel >= tk.maxAllowedTraceLevel) || (weight < tk.adcBailout)) { colour = Col{ 0, 0, 0 }; transm = 0.0f; return HUGE_VALUE; }
+    Intersection bestisect;
+    if (maxDepth >= EPSILON) bestisect.Depth = maxDepth;
+    bool found = FindIntersection(bestisect, ray, -1.0);
+    const bool inc = !continuedRay;
+    if (inc) { tk.traceLevel++; tk.maxFound = std::max(tk.maxFound, tk.traceLevel); }
+    if (found) ComputeTextureColour(bestisect, colour, transm, ray, tk, weight);
+    else ComputeSky(ray, tk, colour, transm);
+    if (inc) tk.traceLevel--;
+    st.max_level = std::max(st.max_level, tk.maxFound);
+    return found ? bestisect.Depth : HUGE_VALUE;
+}
+
+void Tracer::ComputeTextureColour(Intersection& isect, Col& colour, float& transm, Ray& ray, Ticket& tk, float weight)       // trace.cpp:457-586
+{
+    const pvgpu_object& ob = S.objects[isect.Object];
+    V3 rawnormal = Normal(isect);
+    if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
+    double normaldirection = dot(rawnormal, ray.Direction);
+    if (normaldirection > 0.0) rawnormal = -rawnormal;
+    int tex = hit_texture(ob, isect, normaldirection > 0.0);
+    if (tex < 0) return;
+    Col tmpCol{ 0, 0, 0 }; float tmpTransm = 0.0f;
+    if (!(1.0 < tk.adcBailout)) {
+        Col c1{ 0, 0, 0 }; float t1 = 0.0f;
+        ComputeLightedTexture(c1, t1, tex, isect.IPoint, rawnormal, ray, tk, weight, isect);
+        tmpCol = tmpCol + c1 * 1.0f; tmpTransm += 1.0f * t1;
+    }
+    colour = colour + tmpCol; transm += tmpTransm;
+}
+
+void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect)   // trace.cpp:739-1179
+{
+    const pvgpu_object& ob = S.objects[isect.Object];
+    const double relativeIor = relative_ior(ray, ob.interior);
+    struct WNRX { double weight; V3 normal; Col reflec; float reflex; };
+    std::vector<WNRX> listWNRX;
+    resultColour = Col{ 0, 0, 0 }; resultTransm = 0.0f;
+    Col filCol{ 1, 1, 1 };
+    double trans = 1.0;
+    V3 topNormal = rawnormal;
+    int layer_number = 0;
+    for (int layer = texture; (layer >= 0) && (trans > tk.adcBailout); layer_number++, layer = S.textures[layer].next) {
+        const pvgpu_finish& fn = S.finishes[S.textures[layer].finish];
+        V3 layNormal = rawnormal;
+        if (layer_number == 0) topNormal = layNormal;
+        double new_Weight = weight * trans;
+        float lc[5];
+        Compute_Pigment(lc, S.textures[layer].pigment, ipoint);
+        Col layCol{ lc[0], lc[1], lc[2] };
+        listWNRX.push_back(WNRX{ new_Weight, layNormal, Col{ 0, 0, 0 }, fn.reflect_exp });
+        double cos_Angle_Incidence = -dot(ray.Direction, layNormal);
+        // ComputeReflectivity (trace.cpp:2627-2654)
+        WNRX& W = listWNRX.back();
+        if (!fn.reflection_fresnel) {
+            double wmax = std::max(std::max(fn.reflection_max[0], fn.reflection_max[1]), fn.reflection_max[2]);
+            double wmin = std::max(std::max(fn.reflection_min[0], fn.reflection_min[1]), fn.reflection_min[2]);
+            W.weight = W.weight * std::max(wmax, wmin);
+            double frac = (std::fabs(fn.reflection_falloff - 1.0) > EPSILON) ? std::pow(1.0 - cos_Angle_Incidence, (double)fn.reflection_falloff) : 1.0 - cos_Angle_Incidence;
+            float* o3 = &W.reflec.r;
+            for (int k = 0; k < 3; k++) {
+                if (std::fabs(frac) < EPSILON) o3[k] = fn.reflection_min[k];
+                else if (std::fabs(frac - 1.0) < EPSILON) o3[k] = fn.reflection_max[k];
+                else o3[k] = (float)(frac * fn.reflection_max[k]) + (float)((1.0 - frac) * fn.reflection_min[k]);
+            }
+        } else {
+            double f = FresnelR(cos_Angle_Incidence, relativeIor);
+            float* o3 = &W.reflec.r;
+            for (int k = 0; k < 3; k++) o3[k] = (float)(f * fn.reflection_max[k]) + (float)((1.0 - f) * fn.reflection_min[k]);
+            W.weight = W.weight * std::max(std::max(W.reflec.r, W.reflec.g), W.reflec.b);
+        }
+        ComputeMetallic(W.reflec, fn.reflect_metallic, layCol, cos_Angle_Incidence);
+        double att = (S.g.language_version < 370) ? (float)(1.0 - ((double)(lc[3] * std::max(std::max(lc[0], lc[1]), lc[2])) + (double)lc[4])) : (float)(1.0 - (double)lc[3] - (double)lc[4]);
+        if (fn.alpha_knockout) W.reflec = W.reflec * (float)att;
+        Col tmpCol{ 0, 0, 0 };
+        Col emission{ fn.emission[0] + fn.ambient[0] * S.g.ambient_light[0], fn.emission[1] + fn.ambient[1] * S.g.ambient_light[1], fn.emission[2] + fn.ambient[2] * S.g.ambient_light[2] };
+        if (fn.fresnel != 0.0f) emission = emission * (float)(1.0 - (double)fn.fresnel * FresnelR(cos_Angle_Incidence, relativeIor));
+        tmpCol = tmpCol + (layCol * emission) * (float)att;
+        if (((fn.diffuse != 0.0f) || (fn.diffuse_back != 0.0f) || (fn.specular != 0.0f) || (fn.phong != 0.0f)) && ((!fn.alpha_knockout) || (att != 0.0))) {
+            Col classic{ 0, 0, 0 };
+            if (!(ob.flags & PVGPU_NO_GLOBAL_LIGHTS_FLAG))                                               // ComputeDiffuseLight trace.cpp:1488-1510
+                for (const pvgpu_light& L : S.lights) ComputeOneDiffuseLight(L, fn, isect.IPoint, ray, tk, layNormal, layCol, classic, att, ob, relativeIor);
+            tmpCol = tmpCol + classic;
+        }
+        tmpCol = tmpCol * filCol;
+        resultColour = resultColour + tmpCol;
+        Col tc{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
+        filCol = filCol * tc;
+        if (fn.conserve_energy != 0) filCol = filCol * Col{ std::min(1.0f - W.reflec.r, 1.0f), std::min(1.0f - W.reflec.g, 1.0f), std::min(1.0f - W.reflec.b, 1.0f) };
+        trans = std::min(1.0, (double)std::fabs(grey(filCol)));
+    }
+    bool tir_occured = false;
+    if ((ob.interior >= 0) && (trans > tk.adcBailout) && (S.g.quality_flags & PVGPU_Q_REFRACTIONS)) {     // trace.cpp:1085-1145
+        const pvgpu_interior& in = S.interiors[ob.interior];
+        double w1 = std::max(std::max((double)std::fabs(filCol.r), (double)std::fabs(filCol.g)), (double)std::fabs(filCol.b));
+        double new_Weight = weight * w1;
+        Col rfrCol{ 0, 0, 0 }; float rfrTransm = 0.0f;
+        tir_occured = ComputeRefraction(ob.interior, isect.IPoint, ray, tk, topNormal, rawnormal, rfrCol, rfrTransm, (float)new_Weight);
+        Col attCol{ in.old_refract, in.old_refract, in.old_refract };
+        if (ray.IsInterior(ob.interior) && std::fabs(in.fade_distance) > EPSILON) {
+            if (in.fade_power >= 1000) {
+                double depth = isect.Depth / in.fade_distance;
+                attCol = attCol * Col{ std::exp((float)(-(1.0 - in.fade_colour[0]) * depth)), std::exp((float)(-(1.0 - in.fade_colour[1]) * depth)), std::exp((float)(-(1.0 - in.fade_colour[2]) * depth)) };
+            } else {
+                double a = 1.0 + std::pow(isect.Depth / in.fade_distance, (double)in.fade_power);
+                attCol = attCol * Col{ (float)(in.fade_colour[0] + (1.0 - in.fade_colour[0]) / a), (float)(in.fade_colour[1] + (1.0 - in.fade_colour[1]) / a), (float)(in.fade_colour[2] + (1.0 - in.fade_colour[2]) / a) };
+            }
+        }
+        if (tir_occured) resultColour = resultColour + attCol * rfrCol;
+        else { resultColour = resultColour + attCol * rfrCol * filCol; resultTransm = grey(attCol) * rfrTransm * (float)trans; }
+    }
+    if (S.g.quality_flags & PVGPU_Q_REFLECTIONS) {                                                        // trace.cpp:1151-1178
+        for (int i = 0; i < layer_number; i++) {
+            const WNRX& W = listWNRX[i];
+            if ((!tir_occured) || (std::fabs(topNormal.x - W.normal.x) > EPSILON) || (std::fabs(topNormal.y - W.normal.y) > EPSILON) || (std::fabs(topNormal.z - W.normal.z) > EPSILON)) {
+                if (!(W.reflec.r == 0.0f && W.reflec.g == 0.0f && W.reflec.b == 0.0f)) {
+                    Col rflCol{ 0, 0, 0 };
+                    ComputeReflection(isect.IPoint, ray, tk, W.normal, rawnormal, rflCol, (float)W.weight);
+                    if (W.reflex != 1.0f) resultColour = resultColour + W.reflec * Col{ std::pow(rflCol.r, W.reflex), std::pow(rflCol.g, W.reflex), std::pow(rflCol.b, W.reflex) };
+                    else resultColour = resultColour + W.reflec * rflCol;
+                }
+            }
+        }
+    }
+}
+
+void Tracer::ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight)           // trace.cpp:1264-1321
+{
+    Ray nray(ray);
+    nray.flags = RAY_REFLECTION | (ray.flags & RAY_REFRACTION);
+    double n = -2.0 * dot(ray.Direction, normal);
+    nray.Direction = ray.Direction + n * normal;
+    n = dot(nray.Direction, rawnormal);
+    if (n < 0.0) {
+        double n2 = dot(nray.Direction, normal);
+        if (n2 < 0.0) { n = -2.0 * dot(ray.Direction, rawnormal); nray.Direction = ray.Direction + n * rawnormal; }
+        else { n *= -2.0; nray.Direction = nray.Direction + n * rawnormal; }
+    }
+    nray.Direction = unit(nray.Direction);
+    nray.Origin = ipoint;
+    bool alphaBackground = tk.alphaBackground;
+    tk.alphaBackground = false;
+    float dummyTransm = 0.0f;
+    Col c{ 0, 0, 0 };
+    TraceRay(nray, tk, c, dummyTransm, weight, false);
+    colour = colour + c;
+    tk.alphaBackground = alphaBackground;
+}
+
+bool Tracer::ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight)   // trace.cpp:1323-1485
+{
+    const pvgpu_interior& in = S.interiors[interior];
+    Ray nray(ray);
+    nray.flags = RAY_REFRACTION | (ray.flags & RAY_REFLECTION);
+    nray.Origin = ipoint;
+    double ior;
+    if (nray.interiors.empty()) { nray.interiors.push_back(interior); ior = S.g.atmosphere_ior / in.ior; }
+    else if (interior == nray.interiors.back()) {
+        nray.RemoveInterior(interior);
+        if (nray.interiors.empty()) ior = in.ior / S.g.atmosphere_ior;
+        else ior = in.ior / S.interiors[nray.interiors.back()].ior;
+    } else if (nray.RemoveInterior(interior)) ior = 1.0;
+    else { ior = S.interiors[nray.interiors.back()].ior / in.ior; nray.interiors.push_back(interior); }
+    if (std::fabs(ior - 1.0) < EPSILON) {
+        nray.Direction = ray.Direction;
+        colour = Col{ 0, 0, 0 }; transm = 0.0f;
+        TraceRay(nray, tk, colour, transm, weight, true);
+        return false;
+    }
+    double n = dot(ray.Direction, normal);
+    V3 localnormal;
+    if (n <= 0.0) { localnormal = normal; n = -n; } else localnormal = -normal;
+    double t = 1.0 + sqr(ior) * (sqr(n) - 1.0);                                                           // TraceRefractionRay trace.cpp:1456-1485
+    if (t < 0.0) {
+        Col tempcolour{ 0, 0, 0 };
+        ComputeReflection(ipoint, ray, tk, normal, rawnormal, tempcolour, weight);
+        colour = colour + tempcolour;
+        return true;
+    }
+    t = ior * n - std::sqrt(t);
+    nray.Direction = ior * ray.Direction + t * localnormal;
+    colour = Col{ 0, 0, 0 }; transm = 0.0f;
+    TraceRay(nray, tk, colour, transm, weight, false);
+    return false;
+}
+
+void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn, V3 ipoint, const Ray& eye, Ticket& tk, V3 layer_normal,
+                                    Col pig, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor)     // trace.cpp:1637-1728
+{
+    Ray lray(eye);
+    double depth;
+    // ComputeOneWhiteLightRay (trace.cpp:2710-2767)
+    V3 center = v3(L.center);
+    lray.Origin = ipoint;
+    if (L.type == PVGPU_LIGHT_CYLINDER) {
+        lray.Direction = center - v3(L.points_at);
+        V3 toLightCtr = center - ipoint;
+        double distToPointsAt = len(lray.Direction);
+        depth = dot(toLightCtr, lray.Direction);
+        depth /= distToPointsAt;
+        lray.Direction = unit(lray.Direction);
+    } else { lray.Direction = center - ipoint; depth = len(lray.Direction); lray.Direction = lray.Direction / depth; }
+    if (L.flags & PVGPU_LIGHT_PARALLEL) { double a = dot(v3(L.direction), lray.Direction); depth *= (-a); lray.Direction = -v3(L.direction); }
+    double latt = Attenuate_Light(L, lray, depth);
+    Col lightcolour{ (float)(L.colour[0] * latt), (float)(L.colour[1] * latt), (float)(L.colour[2] * latt) };
+    if (near_zero(lightcolour, (float)EPSILON)) return;
+    bool backside = false;
+    if (!(object.flags & PVGPU_DOUBLE_ILLUMINATE_FLAG)) {
+        double cos_shadow_angle = dot(layer_normal, lray.Direction);
+        if (cos_shadow_angle < EPSILON) { if (fn.diffuse_back != 0.0f) backside = true; else return; }
+    }
+    if ((S.g.quality_flags & PVGPU_Q_SHADOWS) && (L.type != PVGPU_LIGHT_FILL)) TraceShadowRay(L, depth, lray, tk, lightcolour);
+    Col tmpCol{ 0, 0, 0 };
+    if (!near_zero(lightcolour, (float)EPSILON)) {
+        // ComputeDiffuseColour (trace.cpp:2441-2484)
+        double diffuse = (double)((backside ? fn.diffuse_back : fn.diffuse) * fn.brilliance_adjust);
+        if (diffuse > 0.0) {
+            double cai = dot(layer_normal, lray.Direction);
+            double intensity = (fn.brilliance != 1.0f) ? std::pow(std::fabs(cai), (double)fn.brilliance) : std::fabs(cai);
+            intensity *= diffuse * attenuation;
+            double ff = 1.0;
+            if (fn.fresnel != 0.0f) {
+                double f1 = fn.fresnel * FresnelR(cai, relativeIor), f2 = fn.fresnel * FresnelR(-dot(layer_normal, eye.Direction), relativeIor);
+                ff = (1.0 - f1) * (1.0 - f2);
+            }
+            tmpCol = tmpCol + (pig * lightcolour) * (float)(intensity * ff);
+        }
+        Col tempLight = fn.alpha_knockout ? lightcolour * (float)attenuation : lightcolour;
+        if ((L.type != PVGPU_LIGHT_FILL) && !backside) {
+            if (fn.phong > 0.0f) {                                                                        // ComputePhongColour trace.cpp:2518-2555
+                double c = -2.0 * dot(eye.Direction, layer_normal);
+                V3 rd = eye.Direction + c * layer_normal;
+                c = dot(rd, lray.Direction);
+                if (c > 0.0 && ((fn.phong_size < 60) || (c > 0.0008))) {
+                    double intensity = fn.phong * std::pow(c, (double)fn.phong_size);
+                    Col cs{ 1, 1, 1 };
+                    if ((fn.fresnel != 0.0f) || (fn.metallic != 0.0f)) {
+                        double ndotl = dot(layer_normal, lray.Direction);
+                        if (fn.fresnel != 0.0f) cs = cs * (float)(fn.fresnel * FresnelR(ndotl, relativeIor));
+                        ComputeMetallic(cs, fn.metallic, pig, ndotl);
+                    }
+                    tmpCol = tmpCol + (tempLight * cs) * (float)intensity;
+                }
+            }
+            if (fn.specular > 0.0f) {                                                                     // ComputeSpecularColour trace.cpp:2557-2593
+                V3 halfway = ((-eye.Direction) + lray.Direction) * 0.5;
+                double hl = len(halfway);
+                if (hl > 0.0) {
+                    double c = dot(halfway, layer_normal) / hl;
+                    if (c > 0.0) {
+                        double intensity = fn.specular * std::pow(c, (double)fn.roughness);
+                        Col cs{ 1, 1, 1 };
+                        if ((fn.fresnel != 0.0f) || (fn.metallic != 0.0f)) {
+                            double ndotl = dot(halfway, lray.Direction) / hl;
+                            if (fn.fresnel != 0.0f) cs = cs * (float)(fn.fresnel * FresnelR(ndotl, relativeIor));
+                            ComputeMetallic(cs, fn.metallic, pig, ndotl);
+                        }
+                        tmpCol = tmpCol + (tempLight * cs) * (float)intensity;
+                    }
+                }
+            }
+        }
+    }
+    colour = colour + tmpCol;
+}
+
+void Tracer::TraceShadowRay(const pvgpu_light&, double depth, Ray& lightsourceray, Ticket& tk, Col& colour)                  // trace.cpp:1892-2076 (no caches)
+{
+    if (tk.traceLevel > tk.maxAllowedTraceLevel) { colour = Col{ 0, 0, 0 }; return; }
+    tk.maxFound = std::max(tk.maxFound, tk.traceLevel);
+    tk.traceLevel++;
+    Ray newray(lightsourceray);
+    newray.flags = 0; newray.shadowTest = true;
+    double lightsourcedepth = depth;
+    while (true) {
+        Intersection bi;
+        bi.Depth = lightsourcedepth;
+        st.shadow_tests++;
+        bool found = FindIntersection(bi, newray, SMALL_TOLERANCE);
+        if (found && (bi.Depth < lightsourcedepth - SHADOW_TOLERANCE) && (lightsourcedepth - bi.Depth > 0.0) && (bi.Depth > SHADOW_TOLERANCE)) {
+            ComputeShadowColour(bi, newray, tk, colour);
+            int testObject = bi.Csg >= 0 ? bi.Csg : bi.Object;
+            if (near_zero(colour, (float)EPSILON) && (S.objects[testObject].flags & PVGPU_OPAQUE_FLAG)) break;
+            if (near_zero(colour, (float)EPSILON)) break;       // black already: further segments cannot change the result
+            lightsourcedepth -= bi.Depth;
+            newray.Origin = bi.IPoint;
+        } else break;
+    }
+    tk.traceLevel--;
+    st.max_level = std::max(st.max_level, tk.maxFound);
+}
+
+void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& tk, Col& colour)           // trace.cpp:2274-2439 + ComputeShadowTexture :1181-1262
+{
+    const pvgpu_object& ob = S.objects[isect.Object];
+    if (!(S.g.quality_flags & PVGPU_Q_SHADOWS)) return;
+    if (ob.flags & PVGPU_OPAQUE_FLAG) { colour = Col{ 0, 0, 0 }; return; }
+    V3 raw = Normal(isect);
+    if (ob.flags & PVGPU_INVERTED_FLAG) raw = -raw;
+    double nd = dot(raw, lray.Direction);
+    if (nd > 0.0) raw = -raw;
+    int tex = hit_texture(ob, isect, nd > 0.0);
+    if (tex < 0) return;
+    Col tmpCol{ 1, 1, 1 };
+    const pvgpu_interior* in = ob.interior >= 0 ? &S.interiors[ob.interior] : nullptr;
+    for (int layer = tex; layer >= 0; layer = S.textures[layer].next) {
+        float lc[5];
+        Compute_Pigment(lc, S.textures[layer].pigment, isect.IPoint);
+        tmpCol = tmpCol * Col{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
+        if (in && in->caustics != 0.0f) { double k = 1.0 + std::pow(std::fabs(dot(raw, lray.Direction)), (double)in->caustics); tmpCol = tmpCol * (float)k; }
+    }
+    Col refraction{ 1, 1, 1 };
+    if (in && lray.IsInterior(ob.interior) && (in->fade_power > 0.0f) && (std::fabs(in->fade_distance) > EPSILON)) {
+        if (in->fade_power >= 1000) {
+            double dd = isect.Depth / in->fade_distance;
+            refraction = refraction * Col{ std::exp((float)(-(1.0 - in->fade_colour[0]) * dd)), std::exp((float)(-(1.0 - in->fade_colour[1]) * dd)), std::exp((float)(-(1.0 - in->fade_colour[2]) * dd)) };
+        } else {
+            double k = 1.0 + std::pow(isect.Depth / in->fade_distance, (double)in->fade_power);
+            refraction = refraction * Col{ (float)(in->fade_colour[0] + (1.0 - in->fade_colour[0]) / k), (float)(in->fade_colour[1] + (1.0 - in->fade_colour[1]) / k), (float)(in->fade_colour[2] + (1.0 - in->fade_colour[2]) / k) };
+        }
+    }
+    Col temp = tmpCol * refraction;
+    if (std::fabs((std::fabs(temp.r) + std::fabs(temp.g) + std::fabs(temp.b)) / 3.0f) < tk.adcBailout) { colour = Col{ 0, 0, 0 }; return; }
+    colour = colour * temp;
+    // ComputeShadowMedia (trace.cpp:3046-3071): toggle the blocker's interior on the light ray
+    if (!near_zero(colour, (float)EPSILON) && ob.interior >= 0)
+        if (lray.interiors.empty() || !lray.RemoveInterior(ob.interior)) lray.interiors.push_back(ob.interior);
+}
+
+// TracePixel::CreateCameraRay (tracepixel.cpp:341-391, 917-927)
+void camera_ray(const pvgpu_camera& cam, double x, double y, double width, double height, V3& o, V3& d)
+{
+    double x0 = x / width - 0.5, y0 = 0.5 - y / height;
+    V3 loc = v3(cam.location), dir = v3(cam.direction), right = v3(cam.right), up = v3(cam.up);
+    if (cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) { d = dir; o = (loc + x0 * right) + y0 * up; }
+    else { o = loc; d = (dir + x0 * right) + y0 * up; }
+    d = unit(d);
+}
+
+// TracePixel::InitRayContainerState (tracepixel.cpp:929-1006)
+void container_state(const Scene& S, const Tracer& T, V3 p, std::vector<int>& out)
+{
+    out.clear();
+    auto inside_bbox = [&](const float* lo, const float* size) {
+        if (p.x < (double)lo[0] || p.y < (double)lo[1] || p.z < (double)lo[2]) return false;
+        if (p.x > (double)lo[0] + (double)size[0] || p.y > (double)lo[1] + (double)size[1] || p.z > (double)lo[2] + (double)size[2]) return false;
+        return true;
+    };
+    if (!S.use_tree) {
+        for (uint32_t f : S.frame) { const pvgpu_object& o = S.objects[f]; if (o.interior >= 0 && inside_bbox(o.bbox, o.bbox + 3) && T.Inside(p, f)) out.push_back(o.interior); }
+        return;
+    }
+    std::vector<uint32_t> st{ 0 };
+    while (!st.empty()) {
+        uint32_t ni = st.back(); st.pop_back();
+        const pvgpu_node& n = S.nodes[ni];
+        if (!inside_bbox(n.lo, n.size)) continue;
+        if (n.count == 0) { const pvgpu_object& o = S.objects[n.first]; if (o.interior >= 0 && T.Inside(p, n.first)) out.push_back(o.interior); }
+        else for (uint32_t c = n.count; c-- > 0;) st.push_back(n.first + c);
+    }
+}
+
+template <class T> bool get(FILE* f, std::vector<T>& v)
+{
+    uint64_t n = 0;
+    if (fread(&n, sizeof n, 1, f) != 1 || n > (1ull << 34) / sizeof(T)) return false;
+    v.resize(n);
+    return n == 0 || fread(v.data(), sizeof(T), n, f) == n;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// C interface (ctypes)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void* pvo_scene_load(const char* path)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) return nullptr;
+    Scene* s = new Scene();
+    char magic[8]; uint32_t ver = 0, have_cam = 0;
+    bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, "PVGPUSC1", 8) == 0 && fread(&ver, 4, 1, f) == 1 && fread(&have_cam, 4, 1, f) == 1 &&
+              fread(&s->g, sizeof s->g, 1, f) == 1 && fread(&s->cam, sizeof s->cam, 1, f) == 1 &&
+              get(f, s->objects) && get(f, s->index_list) && get(f, s->frame) && get(f, s->xf) && get(f, s->nodes) && get(f, s->meshes) &&
+              get(f, s->verts) && get(f, s->norms) && get(f, s->tris) && get(f, s->mnodes) && get(f, s->lights) && get(f, s->textures) &&
+              get(f, s->pigments) && get(f, s->finishes) && get(f, s->maps) && get(f, s->entries) && get(f, s->warps) && get(f, s->interiors);
+    fclose(f);
+    if (!ok) { delete s; return nullptr; }
+    s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());
+    init_noise(*s);
+    return s;
+}
+
+void pvo_scene_destroy(void* sc) { delete reinterpret_cast<Scene*>(sc); }
+
+// Renders pixel centres of the rectangle [left..right] x [top..bottom] (inclusive) of a width x height image,
+// row-major RGBT, with `threads` worker threads pulling rows.  stats[0] = rays, stats[1] = shadow ray tests,
+// stats[2] = highest trace level.
+int pvo_render(void* sc, int width, int height, int left, int top, int right, int bottom, float* rgbt, int threads, unsigned long long* stats)
+{
+    const Scene& S = *reinterpret_cast<Scene*>(sc);
+    if (threads < 1) threads = 1;
+    std::atomic<int> next_row(top);
+    std::vector<Stats> tstats(threads);
+    auto worker = [&](int ti) {
+        Tracer T(S);
+        std::vector<int> cam_interiors;
+        if (S.cam.type == PVGPU_CAMERA_PERSPECTIVE) container_state(S, T, v3(S.cam.location), cam_interiors);
+        const int w = right - left + 1;
+        for (;;) {
+            int y = next_row.fetch_add(1);
+            if (y > bottom) break;
+            for (int x = left; x <= right; x++) {
+                Ticket tk; tk.maxAllowedTraceLevel = S.g.max_trace_level; tk.adcBailout = S.g.adc_bailout; tk.alphaBackground = S.g.output_alpha != 0;
+                Ray ray;
+                camera_ray(S.cam, x + 0.5, y + 0.5, width, height, ray.Origin, ray.Direction);
+                if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) container_state(S, T, ray.Origin, cam_interiors);
+                ray.interiors = cam_interiors;
+                Col col{ 0, 0, 0 }; float transm = 0.0f;
+                T.TraceRay(ray, tk, col, transm, 1.0f, false, S.cam.max_ray_distance);
+                float* o = rgbt + 4 * ((size_t)(y - top) * w + (x - left));
+                o[0] = col.r; o[1] = col.g; o[2] = col.b; o[3] = transm;
+            }
+        }
+        tstats[ti] = T.st;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
+    if (stats) {
+        stats[0] = stats[1] = stats[2] = 0;
+        for (const Stats& s : tstats) { stats[0] += s.rays; stats[1] += s.shadow_tests; stats[2] = std::max<unsigned long long>(stats[2], s.max_level); }
+    }
+    return 0;
+}
+
+// Trace::FindIntersection under primary-ray conditions for explicit rays (6 doubles each).
+int pvo_trace_rays(void* sc, const double* org_dir, size_t n, int32_t* obj, double* depth, uint32_t* aux)
+{
+    const Scene& S = *reinterpret_cast<Scene*>(sc);
+    Tracer T(S);
+    for (size_t i = 0; i < n; i++) {
+        Ray ray; ray.Origin = v3(org_dir + 6 * i); ray.Direction = v3(org_dir + 6 * i + 3);
+        Intersection best;
+        bool found = T.FindIntersection(best, ray, -1.0);
+        obj[i] = found ? best.Object : -1; depth[i] = found ? best.Depth : BOUND_HUGE;
+        if (aux) aux[i] = found ? best.aux : 0;
+    }
+    return 0;
+}
+
+int pvo_camera_rays(void* sc, int width, int height, const double* xy, size_t n, double* org_dir)
+{
+    const Scene& S = *reinterpret_cast<Scene*>(sc);
+    for (size_t i = 0; i < n; i++) {
+        V3 o, d;
+        camera_ray(S.cam, xy[2 * i], xy[2 * i + 1], width, height, o, d);
+        double* r = org_dir + 6 * i;
+        r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
+    }
+    return 0;
+}
+
+// Solve_Polynomial / Noise / DNoise probes for unit tests
+int pvo_solve_polynomial(int n, const double* c, double* r, int sturm, double epsilon) { return Solve_Polynomial(n, c, r, sturm, epsilon); }
+double pvo_noise(void* sc, double x, double y, double z, int gen) { return Noise(*reinterpret_cast<Scene*>(sc), v3(x, y, z), gen); }
+void pvo_dnoise(void* sc, double x, double y, double z, double* out) { V3 r = DNoise(*reinterpret_cast<Scene*>(sc), v3(x, y, z)); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
+
+}  // extern "C"
