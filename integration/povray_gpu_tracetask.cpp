@@ -159,7 +159,7 @@ struct Flattener
         p.wave_type = PVGPU_WAVE_RAMP; p.frequency = 1.0f; p.exponent = 1.0f;
         const BasicPattern* bp = pg->pattern.get();
         if (pg->Type == PLAIN_PATTERN) p.pattern = PVGPU_PAT_PLAIN;
-        else if (pg->Type != GENERIC_PATTERN) unsupported("pigment type other than plain / generic pattern (image_map, average, uv_mapping ...)");
+        else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern (image_map, average, uv_mapping ...)");
         else {
             if (dynamic_cast<const CheckerPattern*>(bp)) p.pattern = PVGPU_PAT_CHECKER;
             else if (dynamic_cast<const BozoPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;
@@ -502,6 +502,7 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
                                     fl.interiors.data(), fl.interiors.size()), "set_materials");
     check(pvgpu_scene_set_camera(gv.scene, &c), "set_camera");
     if (const char* path = getenv("PVGPU_DUMP_SCENE")) check(pvgpu_scene_save(gv.scene, path), "scene_save");
+    if (!gv.error.empty()) fprintf(stderr, "pvgpu adapter: scene uses a feature outside the GPU trace path: %s\n", gv.error.c_str());
     if (need_device) {
         if (!gv.error.empty())
             throw POV_EXCEPTION_STRING((std::string("pvgpu: scene uses a feature outside the GPU trace path: ") + gv.error).c_str());

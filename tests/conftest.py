@@ -1,0 +1,43 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN_W, GOLDEN_H = 96, 54
+GOLDEN_SCENES = ["spheres64", "mesh24", "csg_glass", "torus_noise", "layered_lights", "clipped_bounded"]
+ADAPTER = os.path.join(ROOT, "oracle", "_ref", "parity", "povray-gpu")
+REF_BINARY = os.path.join(ROOT, "oracle", "_ref", "parity", "povray")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def pvlib():
+    """The product library; building it is part of __graft_entry__.build()."""
+    from povray_b200 import _abi
+    if not os.path.exists(_abi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _abi.lib()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle_lib
+    oracle_lib.lib()
+    return oracle_lib

@@ -1,0 +1,94 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/pvgpu.h declares; the ctypes
+structures have the sizes the C compiler gives them; finalize / render refuse to run without a GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+from conftest import ROOT, GOLDEN, has_gpu
+from povray_b200 import _abi as A
+from povray_b200 import PvgpuError, Scene
+
+HEADER = os.path.join(ROOT, "include", "pvgpu.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pvgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(pvlib):
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(pvlib, s), f"{s} declared in pvgpu.h but not exported by libpvgpu.so"
+    assert set(syms) == set(A.SIGNATURES), "python binding table and header disagree"
+    assert pvlib.pvgpu_abi_version() == A.ABI_VERSION
+
+
+def test_struct_sizes_match_the_c_compiler():
+    names = {"pvgpu_object": A.Object, "pvgpu_transform": A.Transform, "pvgpu_node": A.Node, "pvgpu_triangle": A.Triangle,
+             "pvgpu_mesh": A.Mesh, "pvgpu_light": A.Light, "pvgpu_warp": A.Warp, "pvgpu_blend_entry": A.BlendEntry,
+             "pvgpu_blend_map": A.BlendMap, "pvgpu_pigment": A.Pigment, "pvgpu_finish": A.Finish, "pvgpu_texture": A.Texture,
+             "pvgpu_interior": A.Interior, "pvgpu_globals": A.Globals, "pvgpu_camera": A.Camera, "pvgpu_aa": A.AA,
+             "pvgpu_rect": A.Rect, "pvgpu_stats": A.Stats}
+    src = "#include <stdio.h>\n#include \"pvgpu.h\"\nint main(void){\n" + \
+          "".join(f'printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
+        out = subprocess.check_output([os.path.join(d, "s")], text=True)
+    for line in out.splitlines():
+        n, size = line.split()
+        assert C.sizeof(names[n]) == int(size), n
+    assert C.sizeof(A.Node) == 32 and C.sizeof(A.Object) == 168
+
+
+def test_error_reporting_and_validation(pvlib):
+    h = A.VP()
+    assert pvlib.pvgpu_scene_create(C.byref(h), None) == A.E_INVALID
+    assert b"null" in pvlib.pvgpu_last_error()
+    assert pvlib.pvgpu_scene_load(C.byref(h), b"/nonexistent/file.pvs") == A.E_IO
+    g = A.Globals()
+    s = Scene.create(g)
+    with pytest.raises(PvgpuError) as e:          # empty scene
+        s.finalize(0)
+    assert e.value.code == A.E_INVALID
+    # rendering a scene that was never finalized is refused
+    with pytest.raises(PvgpuError):
+        s.render(8, 8)
+
+
+def test_unsupported_features_are_rejected_not_approximated(pvlib):
+    from povray_b200 import synth
+    b = synth.spheres_scene(4)
+    b.objects[1]["texture"]["reflection"] = 0.5
+    s = b.build()
+    # poke a reflection exponent into the finish table through the file format: exponent != 1 is non-linear
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "x.pvs")
+        s.save(p)
+        assert Scene.load(p) is not None
+    obj = (A.Object * 1)()
+    obj[0].type = 77                               # unknown primitive kind
+    obj[0].texture = obj[0].interior_texture = obj[0].interior = obj[0].transform = obj[0].parent = obj[0].mesh = -1
+    frame = (C.c_uint32 * 1)(0)
+    s2 = Scene.create(A.Globals())
+    A.check(pvlib.pvgpu_scene_set_objects(s2.handle, obj, 1, None, 0, frame, 1))
+    s2.set_camera(s.get_camera())
+    with pytest.raises(PvgpuError) as e:
+        s2.finalize(0)
+    assert e.value.code == A.E_UNSUPPORTED
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the behaviour of a box without a GPU")
+def test_no_cpu_fallback(pvlib):
+    s = Scene.load(os.path.join(GOLDEN, "spheres64.pvs"))
+    with pytest.raises(PvgpuError) as e:
+        s.finalize(0)
+    assert e.value.code == A.E_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
