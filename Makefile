@@ -1,0 +1,33 @@
+# Builds the product: povray_b200/libpvgpu.so (hand-written sm_100a CUDA behind the C ABI of include/pvgpu.h).
+#   make            the library
+#   make oracle     test infrastructure (CPU restatement; see oracle/Makefile)
+# -fmad=false: FP64 expressions must round like the reference built with -ffp-contract=off ("Numerics").
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Iinclude -Ipovray_b200/csrc
+CSRC      := povray_b200/csrc
+OBJDIR    := build/obj
+CU        := $(wildcard $(CSRC)/*.cu)
+CPP       := $(wildcard $(CSRC)/*.cpp)
+OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP))
+HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) include/pvgpu.h
+
+.PHONY: all oracle clean
+all: povray_b200/libpvgpu.so
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+povray_b200/libpvgpu.so: $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
+
+oracle:
+	$(MAKE) -C oracle oracle
+
+clean:
+	rm -rf build povray_b200/libpvgpu.so

@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""bench.py - the trace path on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1]
+
+One "step" = one 1920x1080 frame of the workload through the trace path (no anti-aliasing):
+  cfg2 (default)  synthetic 999,698-triangle mesh2 height field with its BBox tree, 2 point lights with shadows,
+                  reflection to max_trace_level 5, checker floor + 2 mirror spheres      (BASELINE.json configs[1])
+  cfg1            1024 spheres + checker plane, 1 point light with shadows               (BASELINE.json configs[0])
+
+metric  = Mrays/s, rays counted like the reference's statistics page: Number_Of_Rays + Shadow_Ray_Tests.
+value   = device-timed (CUDA events), scene tables and output buffer resident in HBM.
+e2e     = same frame through pvgpu_render() with HOST buffers (rectangle list in, RGBT float frame out),
+          wall clock around the C-ABI call.
+N > 1   = one process per GPU (torchrun); the frame's 32x32 tiles are dealt round-robin to the ranks, the scene is
+          replicated, and the finished tiles are gathered to rank 0 (the only NVLink traffic).  Total work is one
+          frame whatever N is -> "strong" scaling.
+--impl reference = the UNMODIFIED reference binary (oracle/_ref/*/povray, built from /root/reference by
+          oracle/build_ref.sh) rendering the same scene file with +WT<host threads>; its "Trace Time" and its
+          Rays / Shadow Ray Tests counters give the same metric.  Rank 0 only.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, BLOCK = 1920, 1080, 32
+WORKLOADS = {
+    "cfg2": "synthetic 999698-triangle mesh2 height field + BBox tree, 2 lights with shadows, reflection max_trace_level 5, 1920x1080 -A",
+    "cfg1": "synthetic 1024 spheres + checker plane, 1 point light with shadows, 1920x1080 -A",
+}
+# algorithmic bytes per ray (SURVEY.md section 8d / DESIGN.md "Roofline"): node tests x 32 B + primitive records + ray record I/O
+ALG_BYTES_PER_RAY = {"cfg2": 101 * 32 + 10 * 64 + 128, "cfg1": 30 * 32 + 2 * 168 + 128}
+
+
+def make_builder(workload):
+    from povray_b200 import synth
+    return synth.mesh_scene(708) if workload == "cfg2" else synth.spheres_scene(1024)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm (CPU)
+# ----------------------------------------------------------------------------------------------------------
+def reference_binary():
+    for variant in ("fast", "parity"):
+        p = os.path.join(ROOT, "oracle", "_ref", variant, "povray")
+        if os.path.exists(p):
+            return p, variant
+    return None, None
+
+
+def run_reference_once(binary, pov, threads, width=W, height=H):
+    """One render of `pov` by the unmodified reference; returns (trace seconds, rays, shadow tests, parse seconds)."""
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([binary, "+I" + pov, "+O" + os.path.join(d, "o.png"), f"+W{width}", f"+H{height}", "-A", "-D", f"+WT{threads}",
+                            "-GD", "-GR", "-GW", "-GF", "+GS"], capture_output=True, text=True, cwd=d)
+    out = (r.stdout + r.stderr).replace("\r", "\n")
+    if r.returncode != 0:
+        raise RuntimeError("reference render failed:\n" + out[-2000:])
+    trace = float(re.search(r"Trace Time:.*?\(([\d.]+) seconds\)", out).group(1))
+    parse = float(re.search(r"Parse Time:.*?\(([\d.]+) seconds\)", out).group(1))
+    rays = int(re.search(r"Rays:\s+(\d+)", out).group(1))
+    m = re.search(r"Shadow Ray Tests:\s+(\d+)", out)
+    shadow = int(m.group(1)) if m else 0
+    return trace, rays, shadow, parse
+
+
+def write_pov(workload, directory):
+    path = os.path.join(directory, workload + ".pov")
+    with open(path, "w") as f:
+        make_builder(workload).to_pov(f)
+    return path
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    binary, variant = reference_binary()
+    threads = os.cpu_count() or 1
+    base = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": "none", "tile": BLOCK}}
+    if binary is None:
+        base["unavailable"] = "oracle/_ref/*/povray not built (needs /root/reference at build time)"
+        print(json.dumps(base))
+        return
+    with tempfile.TemporaryDirectory() as d:
+        pov = write_pov(args.workload, d)
+        for _ in range(args.warmup):
+            run_reference_once(binary, pov, threads)
+        t, rays, shadow, parse = 0.0, 0, 0, 0.0
+        for _ in range(args.steps):
+            tr, r, s, p = run_reference_once(binary, pov, threads)
+            t += tr; rays += r; shadow += s; parse += p
+    value = (rays + shadow) / t / 1e6
+    flags = "-O3 -march=x86-64-v3 -fno-fast-math" if variant == "fast" else "-O2 -fno-fast-math -ffp-contract=off"
+    base.update({"value": value, "ms_per_step": 1e3 * t / args.steps, "sec_per_frame": t / args.steps,
+                 "rays_per_step": (rays + shadow) / args.steps, "gpu_launches": 0,
+                 "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference",
+                                  "sample": f"{args.steps} full {W}x{H} frames by oracle/_ref/{variant}/povray ({flags}) +WT{threads}; "
+                                            f"time = the reference's own 'Trace Time' (parse {parse / args.steps:.1f} s/frame excluded)"},
+                 "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm (GPU)
+# ----------------------------------------------------------------------------------------------------------
+def ours(args):
+    import numpy as np
+    import torch
+    import povray_b200 as pv
+    from povray_b200 import _abi as A
+    from povray_b200.scene import _rect_array, _area
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the trace path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t0 = time.time()
+    scene = make_builder(args.workload).build()
+    t_build = time.time() - t0
+    t0 = time.time()
+    scene.finalize(local_rank)
+    t_upload = time.time() - t0
+
+    all_tiles = pv.tiles(W, H, BLOCK)
+    mine = all_tiles[rank::world]                      # round-robin deal: statistically balanced, no exchange needed
+    rect_arr = _rect_array(mine)
+    n_px = _area(mine)
+    max_px = max(_area(all_tiles[r::world]) for r in range(world))
+    dev = torch.device("cuda", local_rank)
+    out = torch.zeros(max_px * 4, dtype=torch.float32, device=dev)
+    gathered = [torch.empty_like(out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        st = scene.render_device(W, H, rect_arr, out.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.gather(out, gathered, dst=0)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    stats = []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        for k in range(args.steps):
+            flush.zero_()                              # evict the scene tables and queues from L2 between timed frames
+            barrier()
+            ev[k][0].record()
+            stats.append(step_device())
+            ev[k][1].record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    rays = sum(s["rays"] + s["shadow_ray_tests"] for s in stats)
+    launches = sum(s["kernel_launches"] for s in stats)
+    kern_ms = {k: sum(s.get(k, 0.0) for s in stats) for k in ("closest_ms", "shadow_ms", "shade_ms", "primary_ms")}
+    kern_n = {k: sum(s.get(k, 0) for s in stats) for k in ("closest_launches", "shadow_launches", "closest_rays", "shadow_rays")}
+
+    # end to end: host buffers through the C-ABI call, wall clock (rank-local frame share; at N > 1 the host-side
+    # gather is the caller's memcpy of disjoint tiles and is not part of the library)
+    px = None
+    for _ in range(2):
+        px, _ = scene.render(W, H, mine)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_rays = 0
+    for _ in range(args.steps):
+        px, st = scene.render(W, H, mine)
+        e2e_rays += st["rays"] + st["shadow_ray_tests"]
+    e2e_s = time.perf_counter() - t0
+
+    vals = torch.tensor([ms, float(rays), float(launches), e2e_s, float(e2e_rays), kern_ms["closest_ms"], kern_ms["shadow_ms"],
+                         float(kern_n["closest_rays"]), float(kern_n["shadow_rays"]), float(kern_n["closest_launches"]), float(kern_n["shadow_launches"]),
+                         kern_ms["shade_ms"], kern_ms["primary_ms"]],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(mx[0]), float(mx[3])
+        rays, launches, e2e_rays = float(sm[1]), float(sm[2]), float(sm[4])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = rays / (ms * 1e-3) / 1e6
+    line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "sec_per_frame": ms / args.steps / 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": "none", "tile": BLOCK,
+                       "sharding": f"{len(all_tiles)} tiles dealt round-robin over {world} GPU(s), scene replicated, gather to rank 0",
+                       "l2": "256 MB flush write between timed frames; scene tables + ray queues exceed the 126 MB L2",
+                       "scene_device_bytes": scene.device_bytes, "scene_build_s": round(t_build, 2), "scene_upload_s": round(t_upload, 3),
+                       "rays_per_frame": rays / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "h2d_bytes_per_step": len(mine) * 16, "d2h_bytes_per_step": n_px * 16}}
+
+    # roofline of the dominant kernel, timed live with CUDA events inside the library (same stream as the launches)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    t_ms, s_ms = float(vals[5]), float(vals[6])
+    if t_ms > 0 or s_ms > 0:
+        dom = "k_closest" if t_ms >= s_ms else "k_shadow"
+        d_ms, d_rays, d_n = (t_ms, float(vals[7]), float(vals[9])) if dom == "k_closest" else (s_ms, float(vals[8]), float(vals[10]))
+        bpr = ALG_BYTES_PER_RAY[args.workload]
+        achieved = d_rays * bpr / (d_ms * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "peak_source": which, "traffic": None, "alg_bytes_per_ray": bpr, "rays_per_launch": d_rays / max(d_n, 1),
+                            "avg_launch_ms": d_ms / max(d_n, 1), "share_of_step": d_ms / ms,
+                            "kernel_ms_per_step": {"k_primary": float(vals[12]) / args.steps, "k_closest": t_ms / args.steps,
+                                                   "k_shade": float(vals[11]) / args.steps, "k_shadow": s_ms / args.steps}}
+    else:
+        line["roofline"] = None
+
+    # CPU baseline on this box's host cores: the unmodified reference on a bounded sample of the same workload
+    if world == 1 and not args.no_cpu_baseline:
+        binary, variant = reference_binary()
+        threads = os.cpu_count() or 1
+        try:
+            if binary is None:
+                raise RuntimeError("reference binary not built")
+            with tempfile.TemporaryDirectory() as d:
+                pov = write_pov(args.workload, d)
+                tr, r, s, parse = run_reference_once(binary, pov, threads)
+            line["cpu_baseline"] = {"value": (r + s) / tr / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "reference",
+                                    "sec_per_frame": tr, "parse_s": parse,
+                                    "sample": f"1 full {W}x{H} frame by oracle/_ref/{variant}/povray +WT{threads}, the reference's own Trace Time"}
+        except Exception as e:      # the oracle port is the fallback checker-as-baseline
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib
+            with tempfile.TemporaryDirectory() as d:
+                p = os.path.join(d, "s.pvs")
+                scene.save(p)
+                o = oracle_lib.OracleScene(p)
+                t0 = time.perf_counter()
+                _, ost = o.render(W, H, rect=(0, 476, W - 1, 603), threads=threads)      # 128 rows through the middle of the frame
+                dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": (ost["rays"] + ost["shadow_ray_tests"]) / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                                    "sample": f"rows 476-603 of the {W}x{H} frame by oracle/libpvoracle.so with {threads} threads ({e})"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define PVGPU_ABI_VERSION 1
+#define PVGPU_ABI_VERSION 2
+#define PVGPU_FILE_VERSION 1      /* layout of the table records as written by pvgpu_scene_save */
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define PVGPU_OK              0
@@ -325,6 +326,12 @@ typedef struct pvgpu_stats {
     uint32_t max_trace_level;    /* highest level reached                         */
     uint32_t overflow;           /* non-zero: a device capacity was exceeded      */
     double   device_ms;          /* CUDA-event time of the device work            */
+    /* per kernel family, timed with CUDA events on the launching stream:
+     * 0 camera rays (k_primary), 1 closest hit (k_closest), 2 shading (k_shade), 3 shadow rays (k_shadow_*),
+     * 4 anti-aliasing bookkeeping.  kernel_items = rays (samples) the launches processed. */
+    double   kernel_ms[5];
+    uint64_t kernel_count[5];
+    uint64_t kernel_items[5];
 } pvgpu_stats;
 
 typedef struct pvgpu_scene pvgpu_scene;   /* opaque */

@@ -614,7 +614,8 @@ public:
     void ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight);
     bool ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight);
     void ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn, V3 ipoint, const Ray& eye, Ticket& tk, V3 layer_normal,
-                                Col layer_pigment_colour, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor);
+                                Col layer_pigment_colour, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor,
+                                std::pair<bool, Col>* light_cache);
     void TraceShadowRay(const pvgpu_light& L, double depth, Ray& lightsourceray, Ticket& tk, Col& colour);
     void ComputeShadowColour(Intersection& isect, Ray& lightsourceray, const Ticket& tk, Col& colour);
     int hit_texture(const pvgpu_object& ob, const Intersection& isect, bool backside) const;
@@ -1322,6 +1323,7 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
     double trans = 1.0;
     V3 topNormal = rawnormal;
     int layer_number = 0;
+    std::vector<std::pair<bool, Col>> light_cache(S.lights.size(), std::make_pair(false, Col{ 0, 0, 0 }));
     for (int layer = texture; (layer >= 0) && (trans > tk.adcBailout); layer_number++, layer = S.textures[layer].next) {
         const pvgpu_finish& fn = S.finishes[S.textures[layer].finish];
         V3 layNormal = rawnormal;
@@ -1361,7 +1363,8 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
         if (((fn.diffuse != 0.0f) || (fn.diffuse_back != 0.0f) || (fn.specular != 0.0f) || (fn.phong != 0.0f)) && ((!fn.alpha_knockout) || (att != 0.0))) {
             Col classic{ 0, 0, 0 };
             if (!(ob.flags & PVGPU_NO_GLOBAL_LIGHTS_FLAG))                                               // ComputeDiffuseLight trace.cpp:1488-1510
-                for (const pvgpu_light& L : S.lights) ComputeOneDiffuseLight(L, fn, isect.IPoint, ray, tk, layNormal, layCol, classic, att, ob, relativeIor);
+                for (size_t li = 0; li < S.lights.size(); li++)
+                    ComputeOneDiffuseLight(S.lights[li], fn, isect.IPoint, ray, tk, layNormal, layCol, classic, att, ob, relativeIor, &light_cache[li]);
             tmpCol = tmpCol + classic;
         }
         tmpCol = tmpCol * filCol;
@@ -1467,7 +1470,8 @@ bool Tracer::ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3
 }
 
 void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn, V3 ipoint, const Ray& eye, Ticket& tk, V3 layer_normal,
-                                    Col pig, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor)     // trace.cpp:1637-1728
+                                    Col pig, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor,
+                                    std::pair<bool, Col>* light_cache)     // trace.cpp:1637-1728
 {
     Ray lray(eye);
     double depth;
@@ -1491,7 +1495,11 @@ void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn
         double cos_shadow_angle = dot(layer_normal, lray.Direction);
         if (cos_shadow_angle < EPSILON) { if (fn.diffuse_back != 0.0f) backside = true; else return; }
     }
-    if ((S.g.quality_flags & PVGPU_Q_SHADOWS) && (L.type != PVGPU_LIGHT_FILL)) TraceShadowRay(L, depth, lray, tk, lightcolour);
+    if ((S.g.quality_flags & PVGPU_Q_SHADOWS) && (L.type != PVGPU_LIGHT_FILL)) {
+        // lightColorCache (trace.cpp:1671-1682): one shadow test per light for all layers of a layered texture
+        if (!light_cache->first) { TraceShadowRay(L, depth, lray, tk, lightcolour); light_cache->first = true; light_cache->second = lightcolour; }
+        else lightcolour = light_cache->second;
+    }
     Col tmpCol{ 0, 0, 0 };
     if (!near_zero(lightcolour, (float)EPSILON)) {
         // ComputeDiffuseColour (trace.cpp:2441-2484)

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpvgpu.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # error codes
 OK, E_INVALID, E_UNSUPPORTED, E_NO_DEVICE, E_CUDA, E_IO, E_ABORTED, E_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
@@ -144,10 +144,18 @@ class Rect(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", u64), ("shadow_ray_tests", u64), ("reflected_rays", u64), ("refracted_rays", u64),
                 ("transmitted_rays", u64), ("tir_rays", u64), ("adc_saves", u64), ("samples", u64), ("waves", u64),
-                ("kernel_launches", u64), ("max_trace_level", u32), ("overflow", u32), ("device_ms", f64)]
+                ("kernel_launches", u64), ("max_trace_level", u32), ("overflow", u32), ("device_ms", f64),
+                ("kernel_ms", f64 * 5), ("kernel_count", u64 * 5), ("kernel_items", u64 * 5)]
+
+    KERNELS = ("primary", "closest", "shade", "shadow", "aa")
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_[:13]}
+        for i, k in enumerate(self.KERNELS):
+            d[k + "_ms"] = self.kernel_ms[i]
+            d[k + "_launches"] = int(self.kernel_count[i])
+            d[k + "_rays"] = int(self.kernel_items[i])
+        return d
 
 
 # every symbol include/pvgpu.h declares, with its signature

@@ -1,0 +1,250 @@
+// Camera-ray generation and the closest-hit kernel (Trace::TraceRay's level / ADC test and
+// Trace::FindIntersection, trace.cpp:135-228, 285-344) of the wavefront, plus the small kernels of the
+// ray-level harness.
+#include "pv_traverse.cuh"
+#include "pv_kernels.hpp"
+
+namespace pvgpu {
+
+int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+int grid_for(uint32_t n, int block, int per_sm)
+{
+    long long blocks = ((long long)n + block - 1) / block;
+    long long cap = (long long)sm_count() * per_sm;      // a multiple of the SM count; grid-stride loops cover the rest
+    return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+// TracePixel::InitRayContainerState (tracepixel.cpp:929-1006): interiors of all objects containing `p`.
+__device__ inline void container_state(const DScene& sc, const V3& p, uint16_t* out, uint32_t& n, uint2* stack, unsigned int* overflow)
+{
+    n = 0;
+    auto inside_bbox = [&](const float* lo, const float* size) {       // Inside_BBox (boundingbox.h:139-155)
+        if (p.x < (double)lo[0] || p.y < (double)lo[1] || p.z < (double)lo[2]) return false;
+        if (p.x > (double)lo[0] + (double)size[0] || p.y > (double)lo[1] + (double)size[1] || p.z > (double)lo[2] + (double)size[2]) return false;
+        return true;
+    };
+    auto test_object = [&](uint32_t idx, int sp) {
+        const pvgpu_object& o = sc.objs[idx];
+        if (o.interior >= 0 && inside_object(sc, idx, p, stack, sp, false)) {
+            if (n < PV_MAX_INTERIORS) out[n++] = (uint16_t)o.interior; else atomicOr(overflow, 4u);
+        }
+    };
+    if (!sc.use_tree) {
+        for (uint32_t i = 0; i < sc.n_frame; i++) {
+            const pvgpu_object& o = sc.objs[sc.frame[i]];
+            if (o.interior >= 0 && inside_bbox(o.bbox, o.bbox + 3)) test_object(sc.frame[i], 0);
+        }
+        return;
+    }
+    // InitRayContainerStateTree: children visited in order (pre-order), so push them reversed
+    int sp = 0;
+    stack[sp++] = make_uint2(0u, 0u);
+    while (sp > 0) {
+        const uint32_t ni = stack[--sp].y;
+        const NodeL nd = load_node(sc.nodes + ni);
+        if (!inside_bbox(nd.lo, nd.size)) continue;
+        if (nd.count == 0) test_object(nd.first, sp);
+        else for (uint32_t c = nd.count; c-- > 0 && sp < PV_STACK_SIZE;) stack[sp++] = make_uint2(0u, nd.first + c);
+    }
+}
+
+__global__ void k_container_state(DScene sc, uint16_t* out, Counters* cnt)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    uint2 stack[PV_STACK_SIZE];
+    uint16_t ints[PV_MAX_INTERIORS];
+    uint32_t n;
+    container_state(sc, ld3(sc.cam.location), ints, n, stack, &cnt->overflow);
+    for (uint32_t i = 0; i < n; i++) out[i] = ints[i];
+    out[PV_MAX_INTERIORS] = (uint16_t)n;
+}
+
+// TracePixel::CreateCameraRay (tracepixel.cpp:341-391, 917-927): perspective and orthographic cameras.
+__device__ __forceinline__ void camera_ray(const pvgpu_camera& cam, double x, double y, double width, double height, V3& o, V3& d)
+{
+    const double x0 = x / width - 0.5;
+    const double y0 = 0.5 - y / height;
+    const V3 loc = ld3(cam.location), dirv = ld3(cam.direction), right = ld3(cam.right), up = ld3(cam.up);
+    if (cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) {
+        d = dirv;
+        o = (loc + x0 * right) + y0 * up;
+    } else {
+        o = loc;
+        d = (dirv + x0 * right) + y0 * up;
+    }
+    d = normalized(d);
+}
+
+// sample i -> (rectangle, x, y): rectangles are row-major runs, rect_off holds their prefix sums
+__device__ __forceinline__ void sample_xy(const pvgpu_rect* rects, const uint32_t* rect_off, uint32_t n_rects, uint32_t i, double& x, double& y)
+{
+    uint32_t lo = 0, hi = n_rects;
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (rect_off[mid] <= i) lo = mid; else hi = mid; }
+    const pvgpu_rect r = rects[lo];
+    const uint32_t k = i - rect_off[lo], w = (uint32_t)(r.right - r.left + 1);
+    x = (double)(r.left + (int)(k % w)) + 0.5;       // SimpleSamplingM0: pixel centres (tracetask.cpp:438)
+    y = (double)(r.top + (int)(k / w)) + 0.5;
+}
+
+// TracePixel::operator() (tracepixel.cpp:311-339): one new ticket + camera ray per sample.
+__global__ void __launch_bounds__(256)
+k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width, double height, PRay* out, Counters* cnt)
+{
+    uint2 stack[PV_STACK_SIZE];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double x, y;
+        uint32_t slot = first + i;
+        if (src.coords) {
+            const double2 c = src.coords[first + i];
+            x = c.x; y = c.y;
+            if (src.slots) slot = src.slots[first + i];
+        } else sample_xy(src.rects, src.rect_off, src.n_rects, first + i, x, y);
+        V3 o, d;
+        camera_ray(sc.cam, x, y, width, height, o, d);
+        PRay r;
+        r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z;
+        r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
+        r.w[0] = r.w[1] = r.w[2] = 1.0f;
+        r.wt = 1.0f;
+        r.adc = 1.0f;
+        r.sample = slot;
+        r.level = 0;
+        r.flags = (uint8_t)(PV_RAY_PRIMARY | (sc.g.output_alpha ? PV_RAY_ALPHA_BG : 0));
+        r.n_int = (uint8_t)sc.n_cam_interiors;
+        r.pad = 0;
+        #pragma unroll
+        for (int k = 0; k < PV_MAX_INTERIORS; k++) r.interiors[k] = sc.cam_interiors[k];
+        if (sc.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC && sc.has_interiors) {
+            // InitRayContainerState(ray, true): recomputed per ray when the origin moves with the pixel
+            uint32_t nci;
+            container_state(sc, o, r.interiors, nci, stack, &cnt->overflow);
+            r.n_int = (uint8_t)nci;
+        }
+        out[i] = r;
+    }
+}
+
+// Trace::TraceRay's entry (trace.cpp:142-160) + FindIntersection for every ray of the wave.
+__global__ void __launch_bounds__(128)
+k_closest(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRec* __restrict__ hits, Counters* cnt)
+{
+    uint2 stack[PV_STACK_SIZE];
+    unsigned long long n_rays = 0, n_adc = 0;
+    unsigned int max_level = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const PRay* rp = cur + i;
+        const V3 o = ld3(rp->o), d = ld3(rp->d);
+        const float adcw = rp->adc;
+        const uint32_t level = rp->level, flags = rp->flags;
+        HitRec out;
+        out.pad = 0; out.csg = -1; out.aux = 0; out.depth = 0.0; out.ip[0] = out.ip[1] = out.ip[2] = 0.0;
+        if (!(flags & PV_RAY_PROBE)) {
+            n_rays++;
+            // max. trace level / ADC bailout (trace.cpp:147-155)
+            if ((level >= sc.g.max_trace_level) || ((double)adcw < sc.g.adc_bailout)) {
+                if ((double)adcw < sc.g.adc_bailout) n_adc++;
+                out.obj = PV_HIT_STOPPED;
+                hits[i] = out;
+                continue;
+            }
+            const unsigned int lvl = (flags & PV_RAY_CONTINUED) ? level : level + 1u;
+            if (lvl > max_level) max_level = lvl;
+        }
+        Hit best;
+        best.depth = ((flags & PV_RAY_PRIMARY) && sc.cam.max_ray_distance >= PV_EPSILON) ? sc.cam.max_ray_distance : PV_BOUND_HUGE;
+        best.obj = PV_NO_OBJECT;
+        best.aux = 0; best.csg = -1;
+        const bool found = find_intersection<false>(sc, o, d, flags & ~PV_RAY_PROBE, false, -1.0, best, stack, &cnt->overflow);
+        if (found) {
+            out.depth = best.depth; out.ip[0] = best.ip.x; out.ip[1] = best.ip.y; out.ip[2] = best.ip.z;
+            out.obj = best.obj; out.aux = best.aux; out.csg = best.csg;
+        } else out.obj = PV_HIT_MISS;
+        hits[i] = out;
+    }
+    // one atomic per warp for the statistics
+    for (int off = 16; off > 0; off >>= 1) {
+        n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
+        n_adc += __shfl_down_sync(0xffffffffu, n_adc, off);
+        max_level = max(max_level, __shfl_down_sync(0xffffffffu, max_level, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_rays) atomicAdd(&cnt->rays, n_rays);
+        if (n_adc) atomicAdd(&cnt->adc_saves, n_adc);
+        if (max_level) atomicMax(&cnt->max_level, max_level);
+    }
+}
+
+// ray-level harness: explicit rays under primary-ray conditions (Trace::FindIntersection(Intersection&, const Ray&), trace.h:255)
+__global__ void k_probe_rays(const double* org_dir, uint32_t n, PRay* out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        PRay r;
+        #pragma unroll
+        for (int k = 0; k < 3; k++) { r.o[k] = org_dir[6 * (size_t)i + k]; r.d[k] = org_dir[6 * (size_t)i + 3 + k]; }
+        r.w[0] = r.w[1] = r.w[2] = 0.0f; r.wt = 0.0f; r.adc = 1.0f;
+        r.sample = i; r.level = 0; r.flags = (uint8_t)(PV_RAY_PRIMARY | PV_RAY_PROBE); r.n_int = 0; r.pad = 0;
+        #pragma unroll
+        for (int k = 0; k < PV_MAX_INTERIORS; k++) r.interiors[k] = 0;
+        out[i] = r;
+    }
+}
+
+__global__ void k_probe_results(const HitRec* hits, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const HitRec h = hits[i];
+        const bool found = h.obj < PV_HIT_STOPPED;
+        obj[i] = found ? h.obj : PV_NO_OBJECT;
+        depth[i] = found ? h.depth : PV_BOUND_HUGE;
+        if (aux) aux[i] = found ? h.aux : 0u;
+    }
+}
+
+__global__ void k_camera_rays(DScene sc, const double* xy, uint32_t n, double width, double height, double* org_dir)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 o, d;
+        camera_ray(sc.cam, xy[2 * (size_t)i], xy[2 * (size_t)i + 1], width, height, o, d);
+        double* r = org_dir + 6 * (size_t)i;
+        r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
+    }
+}
+
+void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cudaStream_t st)
+{
+    k_container_state<<<1, 32, 0, st>>>(sc, out, cnt);
+}
+void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,
+                    PRay* out, Counters* cnt, cudaStream_t st)
+{
+    k_primary<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, src, first, n, width, height, out, cnt);
+}
+void launch_closest(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st)
+{
+    k_closest<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, cur, n, hits, cnt);
+}
+void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st)
+{
+    k_probe_rays<<<grid_for(n, 256, 8), 256, 0, st>>>(org_dir, n, out);
+}
+void launch_probe_results(const HitRec* hits, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux, cudaStream_t st)
+{
+    k_probe_results<<<grid_for(n, 256, 8), 256, 0, st>>>(hits, n, obj, depth, aux);
+}
+void launch_camera_rays(const DScene& sc, const double* xy, uint32_t n, double width, double height, double* org_dir, cudaStream_t st)
+{
+    k_camera_rays<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, xy, n, width, height, org_dir);
+}
+
+}  // namespace pvgpu

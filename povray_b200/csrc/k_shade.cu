@@ -1,0 +1,32 @@
+// The shading kernel of the wavefront: for every ray of the wave and its closest hit, Trace::ComputeTextureColour /
+// ComputeLightedTexture (trace.cpp:457-1179) or ComputeSky (trace.cpp:2769-2890); emits shadow rays and the
+// reflection / refraction rays of the next wave.
+#include "pv_shade.cuh"
+
+namespace pvgpu {
+
+__global__ void __launch_bounds__(128)
+k_shade(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits, uint32_t n, WaveCtx ctx)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const HitRec h = hits[i];
+        if (h.obj == PV_HIT_STOPPED) continue;
+        const PRay ray = cur[i];
+        if (h.obj == PV_HIT_MISS) {
+            float col[3], transm;
+            compute_sky(sc, ray, col, transm);
+            accum_add(ctx.accum, ray.sample, ray.w[0] * col[0], ray.w[1] * col[1], ray.w[2] * col[2], ray.wt * transm);
+            continue;
+        }
+        Hit hit;
+        hit.depth = h.depth; hit.ip = mk(h.ip[0], h.ip[1], h.ip[2]); hit.obj = h.obj; hit.aux = h.aux; hit.csg = h.csg;
+        shade_hit(sc, ray, i, hit, ctx);
+    }
+}
+
+void launch_shade(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st)
+{
+    k_shade<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, cur, hits, n, ctx);
+}
+
+}  // namespace pvgpu

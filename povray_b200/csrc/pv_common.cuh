@@ -79,6 +79,7 @@ struct DScene {
     uint32_t n_objs, n_frame, n_nodes, n_lights;
     uint32_t use_tree;                      // boundingMethod == 1 && tree present
     uint32_t all_opaque;                    // every shadow caster has OPAQUE_FLAG
+    uint32_t has_interiors;                 // the interior table is not empty
     pvgpu_globals g;
     pvgpu_camera  cam;
     uint16_t cam_interiors[PV_MAX_INTERIORS];   // TracePixel::InitRayContainerState result
@@ -91,6 +92,7 @@ struct DScene {
 #define PV_RAY_REFRACTION  0x04u
 #define PV_RAY_CONTINUED   0x08u    // TraceRay(..., continuedRay = true): trace level is not incremented
 #define PV_RAY_ALPHA_BG    0x10u    // TraceTicket::alphaBackground
+#define PV_RAY_PROBE       0x20u    // ray of the ray-level harness: Trace::FindIntersection without the camera's Max_Ray_Distance
 
 // One pending TraceRay call (trace.cpp:135): 96 bytes.
 struct __align__(16) PRay {
@@ -121,6 +123,7 @@ static_assert(sizeof(SRay) == 96, "SRay must be 96 bytes");
 
 struct Counters {
     unsigned long long rays, shadow_tests, reflected, refracted, transmitted, tir, adc_saves;
+    unsigned long long shadow_rays;   // shadow rays traced (TraceShadowRay calls)
     unsigned int n_next;         // rays appended to the next wave
     unsigned int n_shadow;       // shadow rays appended for the current chunk
     unsigned int max_level;
@@ -134,5 +137,18 @@ struct Hit {
     uint32_t aux;                // Intersection::i1 (box side) or triangle index (Intersection::Pointer)
     int32_t  csg;                // Intersection::Csg or -1
 };
+
+// Closest-hit result of one PRay as it travels through HBM from k_closest to k_shade: 48 bytes.
+#define PV_HIT_MISS     0xFFFFFFFFu      // no object hit: ComputeSky
+#define PV_HIT_STOPPED  0xFFFFFFFEu      // max. trace level / ADC bailout stopped the ray (trace.cpp:147-155)
+struct __align__(16) HitRec {
+    double   depth;
+    double   ip[3];
+    uint32_t obj;
+    uint32_t aux;
+    int32_t  csg;
+    uint32_t pad;
+};
+static_assert(sizeof(HitRec) == 48, "HitRec must be 48 bytes");
 
 }  // namespace pvgpu

@@ -1,0 +1,98 @@
+// Shadow rays: Trace::TraceShadowRay -> TracePointLightShadowRay (trace.cpp:1892-2076), ComputeShadowColour /
+// ComputeShadowTexture (trace.cpp:2274-2439, 1181-1262).  Needs both the traversal and the pigment evaluation.
+#pragma once
+#include "pv_traverse.cuh"
+#include "pv_shade.cuh"
+
+namespace pvgpu {
+
+// ---- shadow rays ----------------------------------------------------------------------------------
+// Trace::ComputeShadowTexture (trace.cpp:1181-1262) for a transparent blocker.
+__device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3& dir, const PRay* parent, bool inside_now, float f[3])
+{
+    const pvgpu_object& ob = sc.objs[hit.obj];
+    V3 rawnormal = object_normal(sc, ob, hit);
+    if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
+    const double nd = dot(rawnormal, dir);
+    if (nd > 0.0) rawnormal = -rawnormal;
+    const int32_t tex0 = hit_texture(sc, ob, hit, nd > 0.0);
+    if (tex0 < 0) return;       // texture list empty: colour unchanged (trace.cpp:2391-2397)
+    float tmp[3] = { 1.0f, 1.0f, 1.0f };
+    const pvgpu_interior* in = (ob.interior >= 0) ? &sc.interiors[ob.interior] : nullptr;
+    for (int32_t li = tex0; li >= 0; li = sc.textures[li].next) {
+        float lc[5];
+        compute_pigment(sc, sc.textures[li].pigment, hit.ip, lc);
+        #pragma unroll
+        for (int k = 0; k < 3; k++) tmp[k] *= (lc[k] * lc[3] + lc[4]);
+        if (in && in->caustics != 0.0f) {
+            double dotval = dot(rawnormal, dir);
+            float kk = (float)(1.0 + pow(fabs(dotval), (double)in->caustics));
+            tmp[0] *= kk; tmp[1] *= kk; tmp[2] *= kk;
+        }
+    }
+    float refr[3] = { 1.0f, 1.0f, 1.0f };
+    if (in && inside_now && in->fade_power > 0.0f && fabs((double)in->fade_distance) > PV_EPSILON) {
+        if (in->fade_power >= 1000.0f) {
+            #pragma unroll
+            for (int k = 0; k < 3; k++) refr[k] *= expf((float)(-(1.0 - (double)in->fade_colour[k]) * (hit.depth / (double)in->fade_distance)));
+        } else {
+            double kk = 1.0 + pow(hit.depth / (double)in->fade_distance, (double)in->fade_power);
+            #pragma unroll
+            for (int k = 0; k < 3; k++) refr[k] *= (float)((double)in->fade_colour[k] + (1.0 - (double)in->fade_colour[k]) / kk);
+        }
+    }
+    float tc[3] = { tmp[0] * refr[0], tmp[1] * refr[1], tmp[2] * refr[2] };
+    // ComputeShadowColour: "close enough to full shadow" (trace.cpp:2419-2424)
+    if (fabsf((fabsf(tc[0]) + fabsf(tc[1]) + fabsf(tc[2])) / 3.0f) < (float)sc.g.adc_bailout) { f[0] = f[1] = f[2] = 0.0f; return; }
+    f[0] *= tc[0]; f[1] *= tc[1]; f[2] *= tc[2];
+}
+
+// Trace::TraceShadowRay -> TracePointLightShadowRay (trace.cpp:1892-2076) without the (result-neutral)
+// shadow caches.  Returns the factor the light colour is multiplied with and adds the number of
+// FindIntersection calls (Shadow_Ray_Tests) to `tests`.
+//   ALL_OPAQUE: every shadow caster of the scene has OPAQUE_FLAG, so the first blocker inside the shadow
+//   window ends the search (any-hit) and no filtering code is needed.
+template <bool ALL_OPAQUE>
+__device__ inline void trace_shadow(const DScene& sc, V3 o, const V3& d, double depth, const PRay* wave, uint32_t parent,
+                                    uint2* stack, Counters* cnt, float f[3], unsigned long long& tests)
+{
+    f[0] = f[1] = f[2] = 1.0f;
+    if (ALL_OPAQUE) {
+        Hit best;
+        best.depth = depth;
+        best.obj = PV_NO_OBJECT;
+        tests++;
+        const bool found = find_intersection<true>(sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow, depth - PV_SHADOW_TOLERANCE);
+        if (found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))
+            f[0] = f[1] = f[2] = 0.0f;     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
+        return;
+    }
+    // interiors of the light ray start as a copy of the eye ray's (Ray lightsourceray(eye), trace.cpp:1642)
+    PRay in_state;
+    in_state.n_int = 0;
+    bool have_state = false;
+    for (int iter = 0; iter < 256; iter++) {
+        Hit best;
+        best.depth = depth;
+        best.obj = PV_NO_OBJECT;
+        tests++;
+        const bool found = find_intersection<false>(sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow);
+        if (!(found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))) break;
+        const pvgpu_object& ob = sc.objs[best.obj];
+        if (ob.flags & PVGPU_OPAQUE_FLAG) { f[0] = f[1] = f[2] = 0.0f; break; }     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
+        if (!have_state) { in_state = wave[parent]; have_state = true; }
+        shadow_filter(sc, best, d, &in_state, ob.interior >= 0 && ray_is_interior(in_state, ob.interior), f);
+        // ComputeShadowMedia (trace.cpp:3046-3071) toggles the blocker's interior on the light ray
+        if (ob.interior >= 0) {
+            if (!ray_remove_interior(in_state, ob.interior)) ray_append_interior(in_state, ob.interior, &cnt->overflow);
+        }
+        if (f[0] == 0.0f && f[1] == 0.0f && f[2] == 0.0f) {
+            // colour is black; the reference keeps looping only to find an opaque object for its cache
+            break;
+        }
+        depth -= best.depth;
+        o = best.ip;
+    }
+}
+
+}  // namespace pvgpu

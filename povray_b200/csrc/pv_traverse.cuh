@@ -34,25 +34,56 @@ __device__ __forceinline__ RayInfo make_rayinfo(const V3& o, const V3& d)
     return ri;
 }
 
-// Check_And_Enqueue's slab test (boundingbox.cpp:566-636).  Box data and ray info are FP32 and the
-// products are formed in FP32, then compared in FP64 -- exactly the reference's operand types.
+// Check_And_Enqueue's slab test (boundingbox.cpp:566-636).  In the reference box data and ray info are FP32,
+// the products (box - origin) * invdir are formed in FP32 and then compared as doubles against each other,
+// against +-BOUND_HUGE (2e10, exactly representable in FP32) and against EPSILON.  Every operand of those
+// comparisons is therefore an FP32 value, so the same decisions are taken here with FP32 compares; the one
+// FP64 constant, EPSILON = 1e-10, is replaced by the smallest FP32 value that is >= 1e-10 (for FP32 t:
+// (double)t < 1e-10  <=>  t < PV_EPSILON_F32).
+#define PV_EPSILON_F32   1.0e-10f      // (double)1.0e-10f = 1.00000001335e-10 >= 1e-10; checked in device_upload()
+#define PV_BOUND_HUGE_F  2.0e10f
+
+// One BBOX_TREE node as it sits in HBM (pvgpu_node, 32 bytes = one sector), fetched with two 128-bit loads.
+struct NodeL {
+    float lo[3], size[3];
+    uint32_t first;
+    uint32_t count;      // BBOX_TREE::Entries
+    uint32_t flags;      // PVGPU_NODE_*
+};
+__device__ __forceinline__ NodeL load_node(const pvgpu_node* p)
+{
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 a = __ldg(q), b = __ldg(q + 1);
+    NodeL n;
+    n.lo[0] = __uint_as_float(a.x); n.lo[1] = __uint_as_float(a.y); n.lo[2] = __uint_as_float(a.z);
+    n.size[0] = __uint_as_float(a.w); n.size[1] = __uint_as_float(b.x); n.size[2] = __uint_as_float(b.y);
+    n.first = b.z;
+    n.count = b.w & 0xFFFFu;
+    n.flags = b.w >> 16;
+    return n;
+}
+
+// Traversal stack entry: x = entry depth (FP32 bits), y = what to do when popped:
+//   top nibble 0      : leaf, low 28 bits = object / triangle index
+//   top nibble 1..14  : inner node with that many children starting at node (low 28 bits)
+//   top nibble 15     : inner node with >= 15 children (only the node of infinite objects): low 28 bits = node index, reloaded
+__device__ __forceinline__ uint32_t stack_code(const NodeL& n, uint32_t index)
+{
+    return (n.count < 15u) ? (n.first | (n.count << 28)) : (index | 0xF0000000u);
+}
+
 __device__ __forceinline__ bool slab_test(const float* lo, const float* size, const RayInfo& ri, float& dmin_out)
 {
-    double dmin = -PV_BOUND_HUGE, dmax = PV_BOUND_HUGE;
+    float dmin = -PV_BOUND_HUGE_F, dmax = PV_BOUND_HUGE_F;
     #pragma unroll
     for (int k = 0; k < 3; k++) {
         const float hi = __fadd_rn(lo[k], size[k]);
         if (ri.nonzero[k]) {
-            double tmin, tmax;
-            if (ri.positive[k]) {
-                tmax = (double)__fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
-                if (tmax < PV_EPSILON) return false;
-                tmin = (double)__fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
-            } else {
-                tmax = (double)__fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
-                if (tmax < PV_EPSILON) return false;
-                tmin = (double)__fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
-            }
+            const float t_lo = __fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
+            const float t_hi = __fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
+            const float tmax = ri.positive[k] ? t_hi : t_lo;
+            const float tmin = ri.positive[k] ? t_lo : t_hi;
+            if (tmax < PV_EPSILON_F32) return false;
             if (tmax < dmax) {
                 if (tmin > dmin) { if (tmin > tmax) return false; dmin = tmin; }
                 else if (dmin > tmax) return false;
@@ -63,7 +94,7 @@ __device__ __forceinline__ bool slab_test(const float* lo, const float* size, co
             }
         } else if (!((lo[k] <= ri.org[k]) && (ri.org[k] <= hi))) return false;
     }
-    dmin_out = (float)dmin;       // dmin is an FP32 product (or -BOUND_HUGE): the narrowing is exact enough for ordering
+    dmin_out = dmin;
     return true;
 }
 
@@ -97,6 +128,40 @@ __device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
     return type >= PVGPU_OBJ_QUADRIC;
 }
 
+#define PV_MAX_DISTANCE_F 1.0e7f
+
+// Tests the `count` children stored at nodes[first..] (Check_And_Enqueue per child, boundingbox.cpp:541-648) and
+// pushes those the ray may hit so that the nearest ends up on top.  Children are fetched four at a time (the
+// reference bunches <= 4 entries per node) so that the 128-bit loads of one node visit are all in flight together.
+template <bool ALLOW_INFINITE>
+__device__ __forceinline__ void push_children(const pvgpu_node* __restrict__ nodes, uint32_t first, uint32_t count, const RayInfo& ri,
+                                              uint2* stack, int& sp, unsigned int* overflow)
+{
+    const int base = sp;
+    for (uint32_t c0 = 0; c0 < count; c0 += 4) {
+        NodeL ch[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) ch[k] = load_node(nodes + first + min(c0 + (uint32_t)k, count - 1u));
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (c0 + k < count) {
+                float dmin;
+                bool ok;
+                if (ALLOW_INFINITE && (ch[k].flags & PVGPU_NODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
+                else ok = slab_test(ch[k].lo, ch[k].size, ri, dmin);
+                if (ok) {
+                    if (sp >= PV_STACK_SIZE) { atomicOr(overflow, 1u); }
+                    else {
+                        int j = sp++;
+                        while (j > base && __uint_as_float(stack[j - 1].x) < dmin) { stack[j] = stack[j - 1]; j--; }
+                        stack[j] = make_uint2(__float_as_uint(dmin), stack_code(ch[k], first + c0 + k));
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ---- Inside --------------------------------------------------------------------------------------
 __device__ bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, uint2* stack, int sp0);
 
@@ -116,7 +181,7 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
 // Inside_Object (object.cpp:346-355) = every clipped_by object contains the point AND Object->Inside();
 // CSGUnion/CSGMerge::Inside = any child, CSGIntersection::Inside = all children (csg.cpp:393-454).
 // Evaluated iteratively with short-circuit over the object graph (the reference recurses).
-__device__ __noinline__ bool inside_object(const DScene& sc, uint32_t root, const V3& p, uint2* stack, int sp0, bool root_clip = true)
+static __device__ __noinline__ bool inside_object(const DScene& sc, uint32_t root, const V3& p, uint2* stack, int sp0, bool root_clip = true)
 {
     struct Frame { uint32_t obj; uint32_t cur; };
     Frame st[PV_CSG_STACK];
@@ -225,33 +290,26 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
         return;
     }
     const RayInfo ri = make_rayinfo(mo, md);
-    const pvgpu_node* nodes = sc.mnodes + me.node_first;
+    const pvgpu_node* __restrict__ nodes = sc.mnodes + me.node_first;
     int sp = sp0;
-    float dmin;
     {
-        const pvgpu_node root = nodes[0];
+        const NodeL root = load_node(nodes);
+        float dmin;
         if (!slab_test(root.lo, root.size, ri, dmin)) return;
-        stack[sp++] = make_uint2(__float_as_uint(dmin), 0u);
+        stack[sp++] = make_uint2(__float_as_uint(dmin), stack_code(root, 0u));
     }
     // entries further than the closest accepted hit cannot improve it; compared in mesh space (t = world * len)
     while (sp > sp0) {
         const uint2 e = stack[--sp];
         if ((double)__uint_as_float(e.x) > acc.closest * len) continue;
-        const pvgpu_node n = nodes[e.y];
-        if (n.count) {
-            const int base = sp;
-            for (uint32_t c = 0; c < n.count; c++) {
-                const pvgpu_node ch = nodes[n.first + c];
-                if (slab_test(ch.lo, ch.size, ri, dmin)) {
-                    if (sp >= PV_STACK_SIZE) { atomicOr(overflow, 1u); break; }
-                    int j = sp++;
-                    while (j > base && __uint_as_float(stack[j - 1].x) < dmin) { stack[j] = stack[j - 1]; j--; }   // keep nearest on top
-                    stack[j] = make_uint2(__float_as_uint(dmin), n.first + c);
-                }
-            }
+        const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+        if (code) {
+            uint32_t first = idx, count = code;
+            if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+            push_children<false>(nodes, first, count, ri, stack, sp, overflow);
         } else {
             double t;
-            const uint32_t ti = me.tri_first + n.first;
+            const uint32_t ti = me.tri_first + idx;
             if (tri_intersect(sc.dtris[ti], mo, md, t)) {
                 double wd = t / len;
                 V3 ip = evaluate(o, d, wd);
@@ -280,22 +338,22 @@ __device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, con
         }
     } else {
         const RayInfo ri = make_rayinfo(mo, md);
-        const pvgpu_node* nodes = sc.mnodes + me.node_first;
+        const pvgpu_node* __restrict__ nodes = sc.mnodes + me.node_first;
         int sp = sp0;
         float dmin;
-        const pvgpu_node root = nodes[0];
-        if (slab_test(root.lo, root.size, ri, dmin)) stack[sp++] = make_uint2(0u, 0u);
+        unsigned int ovf = 0;
+        const NodeL root = load_node(nodes);
+        if (slab_test(root.lo, root.size, ri, dmin)) stack[sp++] = make_uint2(0u, stack_code(root, 0u));
         while (sp > sp0) {
             const uint2 e = stack[--sp];
-            const pvgpu_node n = nodes[e.y];
-            if (n.count) {
-                for (uint32_t c = 0; c < n.count && sp < PV_STACK_SIZE; c++) {
-                    const pvgpu_node ch = nodes[n.first + c];
-                    if (slab_test(ch.lo, ch.size, ri, dmin)) stack[sp++] = make_uint2(0u, n.first + c);
-                }
+            const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+            if (code) {
+                uint32_t first = idx, count = code;
+                if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+                push_children<false>(nodes, first, count, ri, stack, sp, &ovf);
             } else {
                 double t;
-                if (tri_intersect(sc.dtris[me.tri_first + n.first], mo, md, t)) found++;
+                if (tri_intersect(sc.dtris[me.tri_first + idx], mo, md, t)) found++;
             }
         }
     }
@@ -364,7 +422,7 @@ __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, con
     }
 }
 
-__device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
+static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
                                                 uint2* stack, int sp0, unsigned int* overflow);
 
 // Find_Intersection for one frame-level object (object.cpp:172-224 / trace.cpp:345-443).
@@ -394,7 +452,7 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
 
 // The plain Find_Intersection(isect, object, ray) used for bounded_by objects (no post-condition,
 // maxd = HUGE_VAL; nested bounded_by lists are rejected on the host).
-__device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
+static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
                                                 uint2* stack, int sp0, unsigned int* overflow)
 {
     const pvgpu_object& ob = sc.objs[idx];
@@ -449,31 +507,24 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
         return found;
     }
     const RayInfo ri = make_rayinfo(o, d);
+    const pvgpu_node* __restrict__ nodes = sc.nodes;
     int sp = 0;
-    float dmin;
     {
-        const pvgpu_node root = sc.nodes[0];
-        if (root.flags & PVGPU_NODE_INFINITE) dmin = (float)-PV_MAX_DISTANCE;
+        const NodeL root = load_node(nodes);
+        float dmin;
+        if (root.flags & PVGPU_NODE_INFINITE) dmin = -PV_MAX_DISTANCE_F;
         else if (!slab_test(root.lo, root.size, ri, dmin)) return false;
-        stack[sp++] = make_uint2(__float_as_uint(dmin), 0u);
+        stack[sp++] = make_uint2(__float_as_uint(dmin), stack_code(root, 0u));
     }
     while (sp > 0) {
         const uint2 e = stack[--sp];
         if ((double)__uint_as_float(e.x) > best.depth) continue;      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
-        const pvgpu_node n = sc.nodes[e.y];
-        if (n.count) {
-            const int base = sp;
-            for (uint32_t c = 0; c < n.count; c++) {
-                const pvgpu_node ch = sc.nodes[n.first + c];
-                if (ch.flags & PVGPU_NODE_INFINITE) dmin = (float)-PV_MAX_DISTANCE;
-                else if (!slab_test(ch.lo, ch.size, ri, dmin)) continue;
-                if (sp >= PV_STACK_SIZE) { atomicOr(overflow, 1u); break; }
-                int j = sp++;
-                while (j > base && __uint_as_float(stack[j - 1].x) < dmin) { stack[j] = stack[j - 1]; j--; }
-                stack[j] = make_uint2(__float_as_uint(dmin), n.first + c);
-            }
+        const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+        if (code) {
+            uint32_t first = idx, count = code;
+            if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+            push_children<true>(nodes, first, count, ri, stack, sp, overflow);
         } else {
-            const uint32_t idx = n.first;
             if (!precondition(sc.objs[idx].flags, rflags, shadow_ray)) continue;
             Hit h;
             if (object_find(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow) && h.depth < best.depth) {

@@ -1,15 +1,16 @@
 // Device side of pvgpu: scene upload, the wavefront kernels and the render / ray-harness entry points.
 //
-// One frame = a loop of "waves".  Wave 0 holds one camera ray per sample; every wave runs
-//   k_trace   : per ray  - level / ADC test, closest hit (tree walk + FP64 primitive tests), shading of the
-//                          hit, emission of shadow rays (one per light) and of reflection / refraction rays
-//   k_shadow  : per shadow ray - blocker search towards the light, filtered through transparent objects,
-//                          then the un-shadowed contribution x filter is added to the sample
-// and the reflection / refraction rays it produced form the next wave.  Queues live in HBM; slots are
-// handed out with warp-aggregated atomics (the compiler turns the uniform-address atomicAdd into
-// REDUX + one atomic per warp).  There is no CPU fallback anywhere in this file.
+// One frame = a loop of "waves".  Wave 0 holds one camera ray per sample (k_primary); every wave runs
+//   k_closest : per ray  - level / ADC test, closest hit (tree walk + FP64 primitive tests) -> HitRec
+//   k_shade   : per ray  - shading of the hit (or the sky), emission of shadow rays (one per light) and of
+//                          the reflection / refraction rays that form the next wave
+//   k_shadow_*: per shadow ray - blocker search towards the light (any-hit when every caster is opaque,
+//                          else filtered through transparent objects), then the contribution is added
+// Queues live in HBM; slots are handed out with warp-aggregated atomics (the compiler turns the
+// uniform-address atomicAdd into REDUX + one atomic per warp).  The kernels live in k_*.cu; this file is
+// the host side.  There is no CPU fallback anywhere.
 #include "pvgpu_scene.hpp"
-#include "pv_shade.cuh"
+#include "pv_kernels.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -30,6 +31,7 @@ struct DeviceScene {
     std::vector<void*> allocs;
     // work buffers (grown on demand)
     PRay* q[2] = { nullptr, nullptr };
+    HitRec* hits = nullptr;
     SRay* sq = nullptr;
     Counters* cnt = nullptr;
     pvgpu_rect* rects = nullptr;
@@ -38,6 +40,15 @@ struct DeviceScene {
     uint16_t* d_cam_int = nullptr;       // container-state result
     unsigned long long kernel_launches = 0;
     bool camera_dirty = true;
+    // host-side staging of pvgpu_render (pinned) and its device frame
+    float* d_frame = nullptr;
+    float* h_frame = nullptr;
+    size_t frame_cap = 0;
+    // per-launch timing (CUDA events on the launching stream)
+    std::vector<cudaEvent_t> ev_pool;
+    struct Timed { int kind; size_t e0, e1; unsigned long long items; };
+    std::vector<Timed> timed;
+    size_t ev_used = 0;
 };
 
 template <class T>
@@ -113,8 +124,10 @@ void device_release(Scene& s)
     if (!s.dev) return;
     if (s.device >= 0) cudaSetDevice(s.device);
     for (void* p : s.dev->allocs) cudaFree(p);
-    cudaFree(s.dev->q[0]); cudaFree(s.dev->q[1]); cudaFree(s.dev->sq); cudaFree(s.dev->cnt);
+    cudaFree(s.dev->q[0]); cudaFree(s.dev->q[1]); cudaFree(s.dev->sq); cudaFree(s.dev->cnt); cudaFree(s.dev->hits);
     cudaFree(s.dev->rects); cudaFree(s.dev->rect_off); cudaFree(s.dev->d_cam_int);
+    cudaFree(s.dev->d_frame); if (s.dev->h_frame) cudaFreeHost(s.dev->h_frame);
+    for (cudaEvent_t e : s.dev->ev_pool) cudaEventDestroy(e);
     delete s.dev;
     s.dev = nullptr;
 }
@@ -127,6 +140,11 @@ int device_upload(Scene& s, int device)
     if (device < 0 || device >= ndev) return fail(PVGPU_E_INVALID, "device %d out of range (have %d)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
     s.device = device;
+    // the FP32 stand-in for EPSILON in the slab test must be the smallest float >= 1e-10 (pv_traverse.cuh)
+    if (!((double)1.0e-10f >= 1.0e-10 && (double)std::nextafterf(1.0e-10f, 0.0f) < 1.0e-10))
+        return fail(PVGPU_E_INVALID, "internal: FP32 epsilon of the slab test is not the smallest float >= 1e-10");
+    if (s.nodes.size() >= (1u << 28) || s.mesh_nodes.size() >= (1u << 28) || s.triangles.size() >= (1u << 28) || s.objects.size() >= (1u << 28))
+        return fail(PVGPU_E_UNSUPPORTED, "more than 2^28 nodes / triangles / objects");
     DeviceScene* d = new DeviceScene();
     s.dev = d;
     size_t total = 0;
@@ -205,6 +223,7 @@ int device_upload(Scene& s, int device)
     v.n_lights = (uint32_t)s.lights.size();
     v.use_tree = (s.globals.bounding_method == 1 && !s.nodes.empty()) ? 1u : 0u;
     v.all_opaque = s.all_shadow_casters_opaque ? 1u : 0u;
+    v.has_interiors = s.interiors.empty() ? 0u : 1u;
     v.g = s.globals;
     v.cam = s.camera;
     v.n_cam_interiors = 0;
@@ -221,219 +240,46 @@ int device_upload(Scene& s, int device)
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernels
-// ------------------------------------------------------------------------------------------------
-
-// TracePixel::InitRayContainerState (tracepixel.cpp:929-1006): interiors of all objects containing `p`.
-__device__ inline void container_state(const DScene& sc, const V3& p, uint16_t* out, uint32_t& n, uint2* stack, unsigned int* overflow)
-{
-    n = 0;
-    auto inside_bbox = [&](const float* lo, const float* size) {       // Inside_BBox (boundingbox.h:139-155)
-        if (p.x < (double)lo[0] || p.y < (double)lo[1] || p.z < (double)lo[2]) return false;
-        if (p.x > (double)lo[0] + (double)size[0] || p.y > (double)lo[1] + (double)size[1] || p.z > (double)lo[2] + (double)size[2]) return false;
-        return true;
-    };
-    auto test_object = [&](uint32_t idx, int sp) {
-        const pvgpu_object& o = sc.objs[idx];
-        if (o.interior >= 0 && inside_object(sc, idx, p, stack, sp, false)) {
-            if (n < PV_MAX_INTERIORS) out[n++] = (uint16_t)o.interior; else atomicOr(overflow, 4u);
-        }
-    };
-    if (!sc.use_tree) {
-        for (uint32_t i = 0; i < sc.n_frame; i++) {
-            const pvgpu_object& o = sc.objs[sc.frame[i]];
-            if (o.interior >= 0 && inside_bbox(o.bbox, o.bbox + 3)) test_object(sc.frame[i], 0);
-        }
-        return;
-    }
-    // InitRayContainerStateTree: children visited in order (pre-order), so push them reversed
-    int sp = 0;
-    stack[sp++] = make_uint2(0u, 0u);
-    while (sp > 0) {
-        const uint32_t ni = stack[--sp].y;
-        const pvgpu_node nd = sc.nodes[ni];
-        if (!inside_bbox(nd.lo, nd.size)) continue;
-        if (nd.count == 0) test_object(nd.first, sp);
-        else for (uint32_t c = nd.count; c-- > 0 && sp < PV_STACK_SIZE;) stack[sp++] = make_uint2(0u, nd.first + c);
-    }
-}
-
-__global__ void k_container_state(DScene sc, uint16_t* out, Counters* cnt)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    uint2 stack[PV_STACK_SIZE];
-    uint16_t ints[PV_MAX_INTERIORS];
-    uint32_t n;
-    container_state(sc, ld3(sc.cam.location), ints, n, stack, &cnt->overflow);
-    for (uint32_t i = 0; i < n; i++) out[i] = ints[i];
-    out[PV_MAX_INTERIORS] = (uint16_t)n;
-}
-
-// TracePixel::CreateCameraRay (tracepixel.cpp:341-391, 917-927): perspective and orthographic cameras.
-__device__ __forceinline__ void camera_ray(const pvgpu_camera& cam, double x, double y, double width, double height, V3& o, V3& d)
-{
-    const double x0 = x / width - 0.5;
-    const double y0 = 0.5 - y / height;
-    const V3 loc = ld3(cam.location), dirv = ld3(cam.direction), right = ld3(cam.right), up = ld3(cam.up);
-    if (cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) {
-        d = dirv;
-        o = (loc + x0 * right) + y0 * up;
-    } else {
-        o = loc;
-        d = (dirv + x0 * right) + y0 * up;
-    }
-    d = normalized(d);
-}
-
-// sample i -> (rectangle, x, y): rectangles are row-major runs, rect_off holds their prefix sums
-__device__ __forceinline__ void sample_xy(const pvgpu_rect* rects, const uint32_t* rect_off, uint32_t n_rects, uint32_t i, double& x, double& y)
-{
-    uint32_t lo = 0, hi = n_rects;
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (rect_off[mid] <= i) lo = mid; else hi = mid; }
-    const pvgpu_rect r = rects[lo];
-    const uint32_t k = i - rect_off[lo], w = (uint32_t)(r.right - r.left + 1);
-    x = (double)(r.left + (int)(k % w)) + 0.5;       // SimpleSamplingM0: pixel centres (tracetask.cpp:438)
-    y = (double)(r.top + (int)(k / w)) + 0.5;
-}
-
-__global__ void __launch_bounds__(256)
-k_primary(DScene sc, const pvgpu_rect* rects, const uint32_t* rect_off, uint32_t n_rects, uint32_t first, uint32_t n,
-          double width, double height, PRay* out)
-{
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double x, y;
-        sample_xy(rects, rect_off, n_rects, first + i, x, y);
-        V3 o, d;
-        camera_ray(sc.cam, x, y, width, height, o, d);
-        PRay r;
-        r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z;
-        r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
-        r.w[0] = r.w[1] = r.w[2] = 1.0f;
-        r.wt = 1.0f;
-        r.adc = 1.0f;
-        r.sample = first + i;
-        r.level = 0;
-        r.flags = (uint8_t)(PV_RAY_PRIMARY | (sc.g.output_alpha ? PV_RAY_ALPHA_BG : 0));
-        r.n_int = (uint8_t)sc.n_cam_interiors;
-        r.pad = 0;
-        #pragma unroll
-        for (int k = 0; k < PV_MAX_INTERIORS; k++) r.interiors[k] = sc.cam_interiors[k];
-        out[i] = r;
-    }
-}
-
-// Trace::TraceRay (trace.cpp:135-228) for every ray of the wave.
-__global__ void __launch_bounds__(128)
-k_trace(DScene sc, const PRay* __restrict__ cur, uint32_t n, WaveCtx ctx)
-{
-    uint2 stack[PV_STACK_SIZE];
-    unsigned long long n_rays = 0, n_adc = 0;
-    unsigned int max_level = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        PRay ray = cur[i];
-        n_rays++;
-        // max. trace level / ADC bailout (trace.cpp:147-155)
-        if ((ray.level >= sc.g.max_trace_level) || ((double)ray.adc < sc.g.adc_bailout)) {
-            if ((double)ray.adc < sc.g.adc_bailout) n_adc++;
-            continue;
-        }
-        const unsigned int lvl = (ray.flags & PV_RAY_CONTINUED) ? ray.level : ray.level + 1u;
-        if (lvl > max_level) max_level = lvl;
-        if ((ray.flags & PV_RAY_PRIMARY) && sc.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) {
-            // InitRayContainerState(ray, true): recomputed per ray when the origin moves with the pixel
-            uint32_t nci;
-            container_state(sc, ld3(ray.o), ray.interiors, nci, stack, &ctx.cnt->overflow);
-            ray.n_int = (uint8_t)nci;
-        }
-        Hit best;
-        best.depth = ((ray.flags & PV_RAY_PRIMARY) && sc.cam.max_ray_distance >= PV_EPSILON) ? sc.cam.max_ray_distance : PV_BOUND_HUGE;
-        best.obj = PV_NO_OBJECT;
-        const bool found = find_intersection<false>(sc, ld3(ray.o), ld3(ray.d), ray.flags, false, -1.0, best, stack, &ctx.cnt->overflow);
-        if (found) shade_hit(sc, ray, i, best, ctx);
-        else {
-            float col[3], transm;
-            compute_sky(sc, ray, col, transm);
-            accum_add(ctx.accum, ray.sample, ray.w[0] * col[0], ray.w[1] * col[1], ray.w[2] * col[2], ray.wt * transm);
-        }
-    }
-    // one atomic per warp for the statistics
-    for (int off = 16; off > 0; off >>= 1) {
-        n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
-        n_adc += __shfl_down_sync(0xffffffffu, n_adc, off);
-        max_level = max(max_level, __shfl_down_sync(0xffffffffu, max_level, off));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_rays) atomicAdd(&ctx.cnt->rays, n_rays);
-        if (n_adc) atomicAdd(&ctx.cnt->adc_saves, n_adc);
-        if (max_level) atomicMax(&ctx.cnt->max_level, max_level);
-    }
-}
-
-// Trace::TraceShadowRay (trace.cpp:1892-1940) for every shadow ray the chunk produced.
-__global__ void __launch_bounds__(128)
-k_shadow(DScene sc, const SRay* __restrict__ rays, const PRay* __restrict__ wave, float4* accum, Counters* cnt)
-{
-    uint2 stack[PV_STACK_SIZE];
-    const uint32_t n = cnt->n_shadow;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const SRay s = rays[i];
-        float f[3];
-        trace_shadow(sc, s, wave, stack, cnt, f);
-        accum_add(accum, s.sample, s.a[0] * f[0], s.a[1] * f[1], s.a[2] * f[2], 0.0f);
-    }
-}
-
-// ray-level harness: Trace::FindIntersection for explicit rays under primary-ray conditions
-__global__ void __launch_bounds__(128)
-k_probe(DScene sc, const double* org_dir, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux, Counters* cnt)
-{
-    uint2 stack[PV_STACK_SIZE];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const V3 o = ld3(org_dir + 6 * (size_t)i), d = ld3(org_dir + 6 * (size_t)i + 3);
-        Hit best;
-        best.depth = PV_BOUND_HUGE;
-        best.obj = PV_NO_OBJECT;
-        best.aux = 0;
-        const bool found = find_intersection<false>(sc, o, d, PV_RAY_PRIMARY, false, -1.0, best, stack, &cnt->overflow);
-        obj[i] = found ? best.obj : PV_NO_OBJECT;
-        depth[i] = found ? best.depth : PV_BOUND_HUGE;
-        if (aux) aux[i] = found ? best.aux : 0u;
-    }
-}
-
-__global__ void k_camera_rays(DScene sc, const double* xy, uint32_t n, double width, double height, double* org_dir)
-{
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        V3 o, d;
-        camera_ray(sc.cam, xy[2 * (size_t)i], xy[2 * (size_t)i + 1], width, height, o, d);
-        double* r = org_dir + 6 * (size_t)i;
-        r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
-static int grid_for(uint32_t n, int block, int per_sm)
+enum { KIND_PRIMARY = 0, KIND_CLOSEST = 1, KIND_SHADE = 2, KIND_SHADOW = 3, KIND_AA = 4, KIND_COUNT = 5 };
+
+static size_t next_event(DeviceScene& d)
 {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    if (d.ev_used == d.ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        d.ev_pool.push_back(e);
     }
-    long long blocks = ((long long)n + block - 1) / block;
-    long long cap = (long long)g_sm_count * per_sm;      // a multiple of the SM count; grid-stride loops cover the rest
-    return (int)std::max<long long>(1, std::min(blocks, cap));
+    return d.ev_used++;
 }
+
+// Brackets one kernel launch with CUDA events on the launching stream; the elapsed times are summed per kernel
+// kind when the frame is complete (pvgpu_stats::kernel_ms).
+struct TimedLaunch {
+    DeviceScene& d; cudaStream_t st; size_t e0;
+    int kind; unsigned long long items;
+    TimedLaunch(DeviceScene& d_, cudaStream_t st_, int kind_, unsigned long long items_) : d(d_), st(st_), kind(kind_), items(items_)
+    {
+        e0 = next_event(d);
+        cudaEventRecord(d.ev_pool[e0], st);
+    }
+    ~TimedLaunch()
+    {
+        size_t e1 = next_event(d);
+        cudaEventRecord(d.ev_pool[e1], st);
+        d.timed.push_back({ kind, e0, e1, items });
+        d.kernel_launches++;
+    }
+};
 
 static int ensure_work_buffers(DeviceScene& d, size_t q_cap, size_t sq_cap, size_t n_rects)
 {
     if (q_cap > d.q_cap) {
-        cudaFree(d.q[0]); cudaFree(d.q[1]); d.q[0] = d.q[1] = nullptr; d.q_cap = 0;
+        cudaFree(d.q[0]); cudaFree(d.q[1]); cudaFree(d.hits); d.q[0] = d.q[1] = nullptr; d.hits = nullptr; d.q_cap = 0;
         CUDA_TRY(cudaMalloc(&d.q[0], q_cap * sizeof(PRay)));
         CUDA_TRY(cudaMalloc(&d.q[1], q_cap * sizeof(PRay)));
+        CUDA_TRY(cudaMalloc(&d.hits, q_cap * sizeof(HitRec)));
         d.q_cap = q_cap;
     }
     if (sq_cap > d.sq_cap) {
@@ -457,7 +303,7 @@ static int refresh_camera(Scene& s, cudaStream_t stream)
     d.view.cam = s.camera;
     d.view.n_cam_interiors = 0;
     if (!s.interiors.empty() && s.camera.type == PVGPU_CAMERA_PERSPECTIVE) {
-        k_container_state<<<1, 32, 0, stream>>>(d.view, d.d_cam_int, d.cnt);
+        launch_container_state(d.view, d.d_cam_int, d.cnt, stream);
         d.kernel_launches++;
         uint16_t h[PV_MAX_INTERIORS + 1];
         CUDA_TRY(cudaMemcpyAsync(h, d.d_cam_int, sizeof h, cudaMemcpyDeviceToHost, stream));
@@ -472,16 +318,29 @@ static int refresh_camera(Scene& s, cudaStream_t stream)
 static const size_t kBatchSamples = 1u << 22;          // samples traced per batch of waves
 static const size_t kShadowCap = 1u << 23;             // shadow-ray queue capacity (records)
 
-// Runs all waves for samples [first, first+n).  Returns PVGPU_E_OVERFLOW if a queue was too small.
-static int run_batch(Scene& s, uint32_t first, uint32_t n, uint32_t n_rects, int width, int height,
-                     float4* d_accum, cudaStream_t stream, pvgpu_stats& st)
+struct FrameCtx {
+    Scene& s;
+    cudaStream_t stream;
+    int width, height;
+    float4* accum;
+    pvgpu_stats st{};
+    int (*cooperate)(void*);
+    void* user;
+};
+
+// Runs all waves for samples [first, first+n) of `src`.  Returns PVGPU_E_OVERFLOW if a queue was too small.
+static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint32_t n)
 {
+    Scene& s = f.s;
     DeviceScene& d = *s.dev;
+    cudaStream_t stream = f.stream;
     const uint32_t q_cap = (uint32_t)d.q_cap, sq_cap = (uint32_t)d.sq_cap;
     const uint32_t n_lights = std::max<uint32_t>(1, (uint32_t)s.lights.size());
     const uint32_t chunk_max = std::max<uint32_t>(1, sq_cap / n_lights);
-    k_primary<<<grid_for(n, 256, 8), 256, 0, stream>>>(d.view, d.rects, d.rect_off, n_rects, first, n, (double)width, (double)height, d.q[0]);
-    d.kernel_launches++;
+    {
+        TimedLaunch t(d, stream, KIND_PRIMARY, n);
+        launch_primary(d.view, src, first, n, (double)f.width, (double)f.height, d.q[0], d.cnt, stream);
+    }
     uint32_t n_cur = n;
     int cur = 0;
     const uint32_t max_waves = s.globals.max_trace_level + 64;     // continued rays do not consume a level
@@ -491,21 +350,60 @@ static int run_batch(Scene& s, uint32_t first, uint32_t n, uint32_t n_rects, int
             const uint32_t cn = std::min(chunk_max, n_cur - c0);
             CUDA_TRY(cudaMemsetAsync(&d.cnt->n_shadow, 0, sizeof(unsigned int), stream));
             WaveCtx ctx;
-            ctx.accum = d_accum; ctx.next = d.q[cur ^ 1]; ctx.shadow = d.sq; ctx.cnt = d.cnt;
+            ctx.accum = f.accum; ctx.next = d.q[cur ^ 1]; ctx.shadow = d.sq; ctx.cnt = d.cnt;
             ctx.next_cap = q_cap; ctx.shadow_cap = sq_cap;
-            k_trace<<<grid_for(cn, 128, 8), 128, 0, stream>>>(d.view, d.q[cur] + c0, cn, ctx);
-            // the shadow kernel reads its count on the device; its grid is sized for the worst case of this chunk
-            const uint32_t worst = (uint32_t)std::min<unsigned long long>((unsigned long long)cn * n_lights, sq_cap);
-            k_shadow<<<grid_for(worst, 128, 8), 128, 0, stream>>>(d.view, d.sq, d.q[cur] + c0, d_accum, d.cnt);
-            d.kernel_launches += 2;
+            {
+                TimedLaunch t(d, stream, KIND_CLOSEST, cn);
+                launch_closest(d.view, d.q[cur] + c0, cn, d.hits + c0, d.cnt, stream);
+            }
+            {
+                TimedLaunch t(d, stream, KIND_SHADE, cn);
+                launch_shade(d.view, d.q[cur] + c0, d.hits + c0, cn, ctx, stream);
+            }
+            if (!s.lights.empty()) {
+                // the shadow kernel reads its count on the device; its grid is sized for the worst case of this chunk
+                const uint32_t worst = (uint32_t)std::min<unsigned long long>((unsigned long long)cn * n_lights, sq_cap);
+                TimedLaunch t(d, stream, KIND_SHADOW, 0);
+                if (d.view.all_opaque) launch_shadow_opaque(d.view, d.sq, worst, f.accum, d.cnt, stream);
+                else launch_shadow_filter(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, stream);
+            }
         }
         unsigned int h[4];     // n_next, n_shadow, max_level, overflow
         CUDA_TRY(cudaMemcpyAsync(h, &d.cnt->n_next, sizeof h, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        st.waves++;
+        f.st.waves++;
         if (h[3] & (8u | 16u)) return PVGPU_E_OVERFLOW;
         n_cur = h[0];
         cur ^= 1;
+        if (f.cooperate && n_cur && f.cooperate(f.user)) return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback");
+    }
+    return PVGPU_OK;
+}
+
+// Traces samples [0, n) of `src` into the accumulators: batches of kBatchSamples; a batch whose ray queues overflow is
+// retried as two halves.  `slot_of` must be the identity (slot = sample index) for the retry to clear the right slots,
+// or `clear_slots` = false when several samples share one slot (anti-aliasing sums) - then an overflow is fatal.
+static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_samples, bool clear_slots)
+{
+    DeviceScene& d = *f.s.dev;
+    if (n_samples == 0) return PVGPU_OK;
+    const size_t batch = std::min<size_t>(kBatchSamples, n_samples);
+    struct Span { uint32_t first, n; };
+    std::vector<Span> todo;
+    for (uint32_t b = 0; b < n_samples; b += (uint32_t)batch) todo.push_back({ b, (uint32_t)std::min<size_t>(batch, n_samples - b) });
+    std::reverse(todo.begin(), todo.end());
+    while (!todo.empty()) {
+        Span sp = todo.back(); todo.pop_back();
+        if (f.cooperate && f.cooperate(f.user)) return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback");
+        int rc = run_batch(f, src, sp.first, sp.n);
+        if (rc == PVGPU_E_OVERFLOW && sp.n > 1 && clear_slots) {
+            CUDA_TRY(cudaMemsetAsync(f.accum + sp.first, 0, (size_t)sp.n * sizeof(float4), f.stream));
+            CUDA_TRY(cudaMemsetAsync(&d.cnt->overflow, 0, sizeof(unsigned int), f.stream));
+            todo.push_back({ sp.first + sp.n / 2, sp.n - sp.n / 2 });
+            todo.push_back({ sp.first, sp.n / 2 });
+            continue;
+        }
+        if (rc != PVGPU_OK) return rc == PVGPU_E_OVERFLOW ? fail(rc, "ray queue overflow") : rc;
     }
     return PVGPU_OK;
 }
@@ -527,12 +425,11 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
         off[i + 1] = off[i] + (uint32_t)area;
     }
     const uint32_t n_samples = off[n_rects];
-    pvgpu_stats st{};
     const unsigned long long launches0 = d.kernel_launches;
-    cudaEvent_t ev0, ev1;
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
-    CUDA_TRY(cudaEventRecord(ev0, stream));
+    d.ev_used = 0;
+    d.timed.clear();
+    const size_t ev0 = next_event(d);
+    CUDA_TRY(cudaEventRecord(d.ev_pool[ev0], stream));
     CUDA_TRY(cudaMemsetAsync(d.cnt, 0, sizeof(Counters), stream));
     if (d.camera_dirty || std::memcmp(&d.view.cam, &s.camera, sizeof s.camera) != 0) {
         int rc = refresh_camera(s, stream);
@@ -544,38 +441,34 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
     CUDA_TRY(cudaMemcpyAsync(d.rects, rects, n_rects * sizeof(pvgpu_rect), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d.rect_off, off.data(), (n_rects + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)n_samples * 4 * sizeof(float), stream));
-    float4* accum = reinterpret_cast<float4*>(d_out);
 
-    // batches; a batch whose ray queues overflow is retried as two halves (accumulators of the batch are cleared first)
-    struct Span { uint32_t first, n; };
-    std::vector<Span> todo;
-    for (uint32_t f = 0; f < n_samples; f += (uint32_t)batch) todo.push_back({ f, (uint32_t)std::min<size_t>(batch, n_samples - f) });
-    std::reverse(todo.begin(), todo.end());
-    while (!todo.empty()) {
-        Span sp = todo.back(); todo.pop_back();
-        if (cooperate && cooperate(user)) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback"); }
-        rc = run_batch(s, sp.first, sp.n, (uint32_t)n_rects, width, height, accum, stream, st);
-        if (rc == PVGPU_E_OVERFLOW && sp.n > 1) {
-            CUDA_TRY(cudaMemsetAsync(accum + sp.first, 0, (size_t)sp.n * sizeof(float4), stream));
-            CUDA_TRY(cudaMemsetAsync(&d.cnt->overflow, 0, sizeof(unsigned int), stream));
-            todo.push_back({ sp.first + sp.n / 2, sp.n - sp.n / 2 });
-            todo.push_back({ sp.first, sp.n / 2 });
-            continue;
-        }
-        if (rc != PVGPU_OK) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); return rc == PVGPU_E_OVERFLOW ? fail(rc, "ray queue overflow") : rc; }
-    }
+    FrameCtx f{ s, stream, width, height, reinterpret_cast<float4*>(d_out), pvgpu_stats{}, cooperate, user };
+    SampleSource src{};
+    src.rects = d.rects; src.rect_off = d.rect_off; src.n_rects = (uint32_t)n_rects;
+    rc = trace_samples(f, src, n_samples, true);
+    if (rc != PVGPU_OK) return rc;
+
     Counters hc;
     CUDA_TRY(cudaMemcpyAsync(&hc, d.cnt, sizeof hc, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaEventRecord(ev1, stream));
-    CUDA_TRY(cudaEventSynchronize(ev1));
+    const size_t ev1 = next_event(d);
+    CUDA_TRY(cudaEventRecord(d.ev_pool[ev1], stream));
+    CUDA_TRY(cudaEventSynchronize(d.ev_pool[ev1]));
     float ms = 0.0f;
-    cudaEventElapsedTime(&ms, ev0, ev1);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    cudaEventElapsedTime(&ms, d.ev_pool[ev0], d.ev_pool[ev1]);
+    pvgpu_stats& st = f.st;
     st.rays = hc.rays; st.shadow_ray_tests = hc.shadow_tests; st.reflected_rays = hc.reflected;
     st.refracted_rays = hc.refracted; st.transmitted_rays = hc.transmitted; st.tir_rays = hc.tir;
     st.adc_saves = hc.adc_saves; st.samples = 0; st.max_trace_level = hc.max_level; st.overflow = hc.overflow;
     st.kernel_launches = d.kernel_launches - launches0;
     st.device_ms = ms;
+    for (const DeviceScene::Timed& t : d.timed) {
+        float k = 0.0f;
+        cudaEventElapsedTime(&k, d.ev_pool[t.e0], d.ev_pool[t.e1]);
+        st.kernel_ms[t.kind] += k;
+        st.kernel_count[t.kind] += 1;
+        st.kernel_items[t.kind] += t.items;
+    }
+    st.kernel_items[KIND_SHADOW] = hc.shadow_rays;
     if (stats) *stats = st;
     if (hc.overflow & ~(8u | 16u))
         return fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x: 1 traversal stack, 2 mesh in CSG, 4 interior list)", hc.overflow);
@@ -607,18 +500,49 @@ int pvgpu_render(pvgpu_scene* sc, const pvgpu_aa* aa, int width, int height,
     Scene& s = *reinterpret_cast<Scene*>(sc);
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     CUDA_TRY(cudaSetDevice(s.device));
+    DeviceScene& d = *s.dev;
     size_t n = 0;
     for (size_t i = 0; i < n_rects; i++)
         if (rects[i].right >= rects[i].left && rects[i].bottom >= rects[i].top)
             n += (size_t)(rects[i].right - rects[i].left + 1) * (size_t)(rects[i].bottom - rects[i].top + 1);
-    float* d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_out, std::max<size_t>(n, 1) * 4 * sizeof(float)));
-    int rc = render_impl(s, aa, width, height, rects, n_rects, d_out, stats, 0, cooperate, user);
+    // device frame + pinned staging buffer are kept between calls (a frame sequence reuses them)
+    const size_t bytes = std::max<size_t>(n, 1) * 4 * sizeof(float);
+    if (bytes > d.frame_cap) {
+        cudaFree(d.d_frame); d.d_frame = nullptr;
+        if (d.h_frame) cudaFreeHost(d.h_frame);
+        d.h_frame = nullptr; d.frame_cap = 0;
+        CUDA_TRY(cudaMalloc(&d.d_frame, bytes));
+        CUDA_TRY(cudaMallocHost(&d.h_frame, bytes));
+        d.frame_cap = bytes;
+    }
+    int rc = render_impl(s, aa, width, height, rects, n_rects, d.d_frame, stats, 0, cooperate, user);
     if (rc == PVGPU_OK) {
-        cudaError_t e = cudaMemcpy(rgbt_out, d_out, n * 4 * sizeof(float), cudaMemcpyDeviceToHost);
+        // D2H into pinned memory in slices, each copied to the caller's buffer while the next slice is in flight
+        const size_t total = n * 4 * sizeof(float), slice = 4u << 20;
+        cudaEvent_t evs[2];
+        cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming);
+        cudaError_t e = cudaSuccess;
+        size_t issued = 0, done = 0;
+        int k = 0;
+        auto issue = [&]() {
+            const size_t len = std::min(slice, total - issued);
+            e = cudaMemcpyAsync(reinterpret_cast<char*>(d.h_frame) + issued, reinterpret_cast<const char*>(d.d_frame) + issued, len, cudaMemcpyDeviceToHost, 0);
+            cudaEventRecord(evs[k & 1], 0);
+            issued += len; k++;
+        };
+        if (total) issue();
+        int kd = 0;
+        while (done < total && e == cudaSuccess) {
+            if (issued < total) issue();
+            e = cudaEventSynchronize(evs[kd & 1]);
+            const size_t len = std::min(slice, total - done);
+            std::memcpy(reinterpret_cast<char*>(rgbt_out) + done, reinterpret_cast<const char*>(d.h_frame) + done, len);
+            done += len; kd++;
+        }
+        cudaEventDestroy(evs[0]); cudaEventDestroy(evs[1]);
         if (e != cudaSuccess) rc = fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_out);
     return rc;
 }
 
@@ -632,25 +556,33 @@ int pvgpu_trace_rays(pvgpu_scene* sc, const double* org_dir, size_t n, uint32_t*
     if (n > 0xFFFFFFF0ull) return fail(PVGPU_E_INVALID, "too many rays");
     CUDA_TRY(cudaSetDevice(s.device));
     DeviceScene& d = *s.dev;
+    const size_t chunk = 1u << 22;
+    int rc = ensure_work_buffers(d, std::max<size_t>(std::min(n, chunk), 1024), 0, 0);
+    if (rc != PVGPU_OK) return rc;
     double *d_rays = nullptr, *d_depth = nullptr;
     uint32_t *d_obj = nullptr, *d_aux = nullptr;
-    int rc = PVGPU_OK;
     auto cleanup = [&]() { cudaFree(d_rays); cudaFree(d_depth); cudaFree(d_obj); cudaFree(d_aux); };
-    if (cudaMalloc(&d_rays, n * 6 * sizeof(double)) != cudaSuccess || cudaMalloc(&d_depth, n * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&d_obj, n * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&d_aux, n * sizeof(uint32_t)) != cudaSuccess) {
+    const size_t cn_max = std::min(n, chunk);
+    if (cudaMalloc(&d_rays, cn_max * 6 * sizeof(double)) != cudaSuccess || cudaMalloc(&d_depth, cn_max * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d_obj, cn_max * sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&d_aux, cn_max * sizeof(uint32_t)) != cudaSuccess) {
         cleanup();
         return fail(PVGPU_E_CUDA, "cudaMalloc failed in pvgpu_trace_rays");
     }
-    cudaMemcpy(d_rays, org_dir, n * 6 * sizeof(double), cudaMemcpyHostToDevice);
     cudaMemset(d.cnt, 0, sizeof(Counters));
-    k_probe<<<grid_for((uint32_t)n, 128, 8), 128>>>(d.view, d_rays, (uint32_t)n, d_obj, d_depth, d_aux, d.cnt);
-    d.kernel_launches++;
-    cudaError_t e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) rc = fail(PVGPU_E_CUDA, "k_probe failed: %s", cudaGetErrorString(e));
+    for (size_t c0 = 0; c0 < n && rc == PVGPU_OK; c0 += chunk) {
+        const uint32_t cn = (uint32_t)std::min(chunk, n - c0);
+        cudaMemcpy(d_rays, org_dir + 6 * c0, (size_t)cn * 6 * sizeof(double), cudaMemcpyHostToDevice);
+        launch_probe_rays(d_rays, cn, d.q[0], 0);
+        launch_closest(d.view, d.q[0], cn, d.hits, d.cnt, 0);
+        launch_probe_results(d.hits, cn, d_obj, d_depth, d_aux, 0);
+        d.kernel_launches += 3;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { rc = fail(PVGPU_E_CUDA, "k_closest failed: %s", cudaGetErrorString(e)); break; }
+        cudaMemcpy(obj + c0, d_obj, (size_t)cn * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        cudaMemcpy(depth + c0, d_depth, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost);
+        if (aux) cudaMemcpy(aux + c0, d_aux, (size_t)cn * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    }
     if (rc == PVGPU_OK) {
-        cudaMemcpy(obj, d_obj, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-        cudaMemcpy(depth, d_depth, n * sizeof(double), cudaMemcpyDeviceToHost);
-        if (aux) cudaMemcpy(aux, d_aux, n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
         Counters hc;
         cudaMemcpy(&hc, d.cnt, sizeof hc, cudaMemcpyDeviceToHost);
         if (hc.overflow) rc = fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x)", hc.overflow);
@@ -675,7 +607,7 @@ int pvgpu_camera_rays(pvgpu_scene* sc, int width, int height, const double* xy, 
         return fail(PVGPU_E_CUDA, "cudaMalloc failed in pvgpu_camera_rays");
     }
     cudaMemcpy(d_xy, xy, n * 2 * sizeof(double), cudaMemcpyHostToDevice);
-    k_camera_rays<<<grid_for((uint32_t)n, 256, 8), 256>>>(d.view, d_xy, (uint32_t)n, (double)width, (double)height, d_out);
+    launch_camera_rays(d.view, d_xy, (uint32_t)n, (double)width, (double)height, d_out, 0);
     d.kernel_launches++;
     cudaError_t e = cudaMemcpy(org_dir, d_out, n * 6 * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_xy); cudaFree(d_out);

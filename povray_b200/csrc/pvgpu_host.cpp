@@ -672,7 +672,7 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
     const Scene& s = *reinterpret_cast<const Scene*>(sc);
     FILE* f = fopen(path, "wb");
     if (!f) return fail(PVGPU_E_IO, "cannot open %s for writing", path);
-    uint32_t ver = PVGPU_ABI_VERSION, have_cam = s.have_camera;
+    uint32_t ver = PVGPU_FILE_VERSION, have_cam = s.have_camera;
     bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(&ver, 4, 1, f) == 1 && fwrite(&have_cam, 4, 1, f) == 1 &&
               fwrite(&s.globals, sizeof s.globals, 1, f) == 1 && fwrite(&s.camera, sizeof s.camera, 1, f) == 1 &&
               put(f, s.objects) && put(f, s.index_list) && put(f, s.frame) && put(f, s.transforms) &&
@@ -694,7 +694,7 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     char magic[8];
     uint32_t ver = 0, have_cam = 0;
     bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(&ver, 4, 1, f) == 1 &&
-              ver == PVGPU_ABI_VERSION && fread(&have_cam, 4, 1, f) == 1 &&
+              ver == PVGPU_FILE_VERSION && fread(&have_cam, 4, 1, f) == 1 &&
               fread(&s->globals, sizeof s->globals, 1, f) == 1 && fread(&s->camera, sizeof s->camera, 1, f) == 1 &&
               get(f, s->objects) && get(f, s->index_list) && get(f, s->frame) && get(f, s->transforms) &&
               get(f, s->nodes) && get(f, s->meshes) && get(f, s->vertices) && get(f, s->normals) &&
@@ -702,7 +702,7 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
               get(f, s->pigments) && get(f, s->finishes) && get(f, s->blend_maps) && get(f, s->blend_entries) &&
               get(f, s->warps) && get(f, s->interiors);
     fclose(f);
-    if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of ABI version %d", path, PVGPU_ABI_VERSION); }
+    if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }
     s->have_camera = have_cam != 0;
     *out = reinterpret_cast<pvgpu_scene*>(s);
     return PVGPU_OK;

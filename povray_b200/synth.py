@@ -123,12 +123,11 @@ class SceneBuilder:
                 out.write(f"box {{ {_vec(o['c1'])}, {_vec(o['c2'])} {tex} }}\n")
             elif o["kind"] == "mesh2":
                 v, f = o["vertices"], o["faces"]
+                # %.17g round-trips every double, like repr(); vectorised because config 2 has ~1.5M lines
                 out.write(f"mesh2 {{\n vertex_vectors {{ {len(v)}")
-                for p in v:
-                    out.write(",\n" + _vec(p))
+                out.write("".join(",\n<%.17g, %.17g, %.17g>" % (p[0], p[1], p[2]) for p in v.tolist()))
                 out.write(f"\n }}\n face_indices {{ {len(f)}")
-                for t in f:
-                    out.write(f",\n<{int(t[0])},{int(t[1])},{int(t[2])}>")
+                out.write("".join(",\n<%d,%d,%d>" % (t[0], t[1], t[2]) for t in f.tolist()))
                 out.write(f"\n }}\n {tex}\n}}\n")
 
     # ---- tables -------------------------------------------------------------------------------------
