@@ -1727,6 +1727,200 @@ int pvo_render(void* sc, int width, int height, int left, int top, int right, in
     return 0;
 }
 
+// ---- anti-aliasing (tracetask.cpp:521-657, 838-1074) -------------------------------------------------
+static const float JitterTable[256] = {
+#include "pv_jitter.inc"
+};
+
+// Jitter2d(DBL x, DBL y, DBL& jx, DBL& jy) (jitter.h:92-96); hashTable is the noise hash table
+static void Jitter2d(const Scene& S, double x, double y, double& jx, double& jy)
+{
+    const unsigned short* h = S.hashTable.data();
+    jx = JitterTable[int(h[int(h[(int(x * 1021.0) & 0xfff)] ^ int(y * 1019.0)) & 0xfff]) & 0xff];
+    jy = JitterTable[int(h[int(h[(int(x * 1019.0) & 0xfff)] ^ int(y * 1021.0)) & 0xfff]) & 0xff];
+}
+
+struct Px { float r, g, b, t; };
+static inline Px px_add(Px a, Px b) { return Px{ a.r + b.r, a.g + b.g, a.b + b.b, a.t + b.t }; }
+static inline Px px_div(Px a, double d) { return Px{ (float)(a.r / d), (float)(a.g / d), (float)(a.b / d), (float)(a.t / d) }; }   // colour.h:531-536,1167
+// GammaCurve::Encode(aaGamma, RGBTColour) with a power-law curve (colourspace.h:163-169, colourspace.cpp:306-313): transm is not encoded
+static inline Px px_encode(Px a, float enc_gamma, bool neutral)
+{
+    if (neutral) return a;
+    return Px{ std::pow(std::max(a.r, 0.0f), enc_gamma), std::pow(std::max(a.g, 0.0f), enc_gamma), std::pow(std::max(a.b, 0.0f), enc_gamma), a.t };
+}
+// ColourDistanceRGBT (colour.h:616-621, 1221-1224)
+static inline float px_dist(Px a, Px b) { return std::fabs(a.r - b.r) + std::fabs(a.g - b.g) + std::fabs(a.b - b.b) + std::fabs(a.t - b.t); }
+
+struct AAParams { int method; int depth; double threshold; double jitter_scale; double gamma; };
+
+struct AATracer {
+    const Scene& S; Tracer& T; int width, height; std::vector<int>& cam_interiors;
+    float enc_gamma; bool neutral; AAParams aa; double jitterScale;
+    unsigned long long samples = 0;
+    Px trace(double x, double y)                          // TracePixel::operator() (tracepixel.cpp:311-339)
+    {
+        Ticket tk; tk.maxAllowedTraceLevel = S.g.max_trace_level; tk.adcBailout = S.g.adc_bailout; tk.alphaBackground = S.g.output_alpha != 0;
+        Ray ray;
+        camera_ray(S.cam, x, y, width, height, ray.Origin, ray.Direction);
+        if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) container_state(S, T, ray.Origin, cam_interiors);
+        ray.interiors = cam_interiors;
+        Col col{ 0, 0, 0 }; float transm = 0.0f;
+        T.TraceRay(ray, tk, col, transm, 1.0f, false, S.cam.max_ray_distance);
+        return Px{ col.r, col.g, col.b, transm };
+    }
+    bool differs(Px a, Px b) const { return px_dist(px_encode(a, enc_gamma, neutral), px_encode(b, enc_gamma, neutral)) >= aa.threshold; }
+
+    // SupersampleOnePixel (tracetask.cpp:860-890)
+    void supersample(double x, double y, Px& col)
+    {
+        const double step = 1.0 / double(aa.depth), range = 0.5 - (step * 0.5);
+        for (double yy = -range; yy <= (range + EPSILON); yy += step)
+            for (double xx = -range; xx <= (range + EPSILON); xx += step) {
+                Px t;
+                if (jitterScale > 0.0) {
+                    double rx, ry;
+                    Jitter2d(S, x + xx, y + yy, rx, ry);
+                    t = trace(x + 0.5 + xx + (rx * jitterScale), y + 0.5 + yy + (ry * jitterScale));
+                } else t = trace(x + 0.5 + xx, y + 0.5 + yy);
+                col = px_add(col, t);
+                samples++;
+            }
+        col = px_div(col, double(aa.depth * aa.depth + 1));
+    }
+
+    // NonAdaptiveSupersamplingM1 for one rectangle (tracetask.cpp:521-602, 838-858)
+    void method1(int left, int top, int right, int bottom, float* out)
+    {
+        const int w = right - left + 1, h = bottom - top + 1, W1 = w + 1;
+        std::vector<Px> px((size_t)W1 * (h + 1));
+        std::vector<char> flag((size_t)W1 * (h + 1), 0);
+        auto at = [&](int x, int y) -> size_t { return (size_t)(y - (top - 1)) * W1 + (x - (left - 1)); };
+        for (int x = left; x <= right; x++) { px[at(x, top - 1)] = trace(x + 0.5, top - 0.5); flag[at(x, top - 1)] = 1; }
+        for (int y = top; y <= bottom; y++) {
+            px[at(left - 1, y)] = trace(left - 0.5, y + 0.5); flag[at(left - 1, y)] = 1;
+            for (int x = left; x <= right; x++) {
+                Px& cur = px[at(x, y)]; Px& lft = px[at(x - 1, y)]; Px& tp = px[at(x, y - 1)];
+                cur = trace(x + 0.5, y + 0.5);
+                bool sampleleft = !flag[at(x - 1, y)], sampletop = !flag[at(x, y - 1)];
+                const bool leftdiff = differs(lft, cur), topdiff = differs(tp, cur);
+                sampleleft = sampleleft && leftdiff;
+                sampletop = sampletop && topdiff;
+                const bool samplecurrent = leftdiff || topdiff;
+                if (sampleleft) { supersample(x - 1.0, y, lft); flag[at(x - 1, y)] = 1; }
+                if (sampletop) { supersample(x, y - 1.0, tp); flag[at(x, y - 1)] = 1; }
+                if (samplecurrent) { supersample(x, y, cur); flag[at(x, y)] = 1; }
+            }
+        }
+        for (int y = top; y <= bottom; y++)
+            for (int x = left; x <= right; x++) { Px p = px[at(x, y)]; float* o = out + 4 * ((size_t)(y - top) * w + (x - left)); o[0] = p.r; o[1] = p.g; o[2] = p.b; o[3] = p.t; }
+    }
+
+    // SubdivideOnePixel (tracetask.cpp:892-1074): buf is the (subsize+1)^2 sample buffer of one pixel
+    struct SubBuf { int n; std::vector<Px> v; std::vector<char> have; };
+    Px subdivide(double x, double y, double d, int bx, int by, int bstep, SubBuf& buf, int level)
+    {
+        auto idx = [&](int i, int j) { return (size_t)j * buf.n + i; };
+        const Px c00 = buf.v[idx(bx, by)], c02 = buf.v[idx(bx, by + bstep)], c20 = buf.v[idx(bx + bstep, by)], c22 = buf.v[idx(bx + bstep, by + bstep)];
+        const int half = bstep / 2;
+        if ((level > 0) && (differs(c00, c02) || differs(c00, c20) || differs(c00, c22) || differs(c02, c20) || differs(c02, c22) || differs(c20, c22))) {
+            auto need = [&](int i, int j, double ox, double oy) {
+                if (buf.have[idx(i, j)]) return;
+                Px t;
+                if (jitterScale > 0.0) {
+                    double rx, ry;
+                    Jitter2d(S, x + ox, y + oy, rx, ry);
+                    t = trace(x + 0.5 + ox + (rx * jitterScale), y + 0.5 + oy + (ry * jitterScale));
+                } else t = trace(x + 0.5 + ox, y + 0.5 + oy);
+                buf.v[idx(i, j)] = t; buf.have[idx(i, j)] = 1;
+                samples++;
+            };
+            need(bx, by + half, -d, 0.0);
+            need(bx + half, by, 0.0, -d);
+            need(bx + bstep, by + half, d, 0.0);
+            need(bx + half, by + bstep, 0.0, d);
+            need(bx + half, by + half, 0.0, 0.0);
+            const double d2 = d * 0.5;
+            const Px r00 = subdivide(x - d2, y - d2, d2, bx, by, half, buf, level - 1);
+            const Px r01 = subdivide(x - d2, y + d2, d2, bx, by + half, half, buf, level - 1);
+            const Px r10 = subdivide(x + d2, y - d2, d2, bx + half, by, half, buf, level - 1);
+            const Px r11 = subdivide(x + d2, y + d2, d2, bx + half, by + half, half, buf, level - 1);
+            return px_div(px_add(px_add(px_add(r00, r01), r10), r11), 4.0);
+        }
+        return px_div(px_add(px_add(px_add(c00, c02), c20), c22), 4.0);
+    }
+
+    // AdaptiveSupersamplingM2 for one rectangle (tracetask.cpp:604-657)
+    void method2(int left, int top, int right, int bottom, float* out)
+    {
+        const int w = right - left + 1, h = bottom - top + 1, W1 = w + 1, subsize = 1 << aa.depth;
+        std::vector<Px> corner((size_t)W1 * (h + 1));
+        for (int y = top; y <= bottom + 1; y++)
+            for (int x = left; x <= right + 1; x++) corner[(size_t)(y - top) * W1 + (x - left)] = trace(x, y);
+        SubBuf buf; buf.n = subsize + 1; buf.v.resize((size_t)buf.n * buf.n); buf.have.resize(buf.v.size());
+        for (int y = top; y <= bottom; y++)
+            for (int x = left; x <= right; x++) {
+                std::fill(buf.have.begin(), buf.have.end(), 0);
+                auto set = [&](int i, int j, Px p) { buf.v[(size_t)j * buf.n + i] = p; buf.have[(size_t)j * buf.n + i] = 1; };
+                set(0, 0, corner[(size_t)(y - top) * W1 + (x - left)]);
+                set(0, subsize, corner[(size_t)(y + 1 - top) * W1 + (x - left)]);
+                set(subsize, 0, corner[(size_t)(y - top) * W1 + (x + 1 - left)]);
+                set(subsize, subsize, corner[(size_t)(y + 1 - top) * W1 + (x + 1 - left)]);
+                Px p = subdivide(double(x), double(y), 0.5, 0, 0, subsize, buf, aa.depth - 1);
+                float* o = out + 4 * ((size_t)(y - top) * w + (x - left)); o[0] = p.r; o[1] = p.g; o[2] = p.b; o[3] = p.t;
+            }
+    }
+};
+
+// Anti-aliased render of a list of rectangles (left, top, right, bottom each), rect-major output like
+// ViewData::CompletedRectangle.  method 1 = NonAdaptiveSupersamplingM1, 2 = AdaptiveSupersamplingM2, 0 = SimpleSamplingM0.
+// jitter_scale is TraceTask's constructor argument (0 = no jitter); gamma = decoding gamma of the AA curve (<= 0 or 1: neutral).
+// stats: [0] rays, [1] shadow tests, [2] max level, [3] samples (Number_Of_Samples).
+int pvo_render_aa(void* sc, int width, int height, const int* rects, int n_rects, int method, int depth, double threshold,
+                  double jitter_scale, double gamma, float* rgbt, int threads, unsigned long long* stats)
+{
+    const Scene& S = *reinterpret_cast<Scene*>(sc);
+    if (threads < 1) threads = 1;
+    std::vector<size_t> off(n_rects + 1, 0);
+    for (int i = 0; i < n_rects; i++) off[i + 1] = off[i] + (size_t)(rects[4 * i + 2] - rects[4 * i] + 1) * (rects[4 * i + 3] - rects[4 * i + 1] + 1);
+    std::atomic<int> next(0);
+    std::vector<Stats> tstats(threads);
+    std::vector<unsigned long long> tsamples(threads, 0);
+    auto worker = [&](int ti) {
+        Tracer T(S);
+        std::vector<int> cam_interiors;
+        if (S.cam.type == PVGPU_CAMERA_PERSPECTIVE) container_state(S, T, v3(S.cam.location), cam_interiors);
+        AATracer A{ S, T, width, height, cam_interiors, 1.0f, true, AAParams{ method, depth, threshold, jitter_scale, gamma }, 0.0 };
+        if (gamma > 0.0 && gamma != 1.0) { A.enc_gamma = 1.0f / (float)gamma; A.neutral = false; }
+        // jitterScale = jitterScale / aaDepth (M1, tracetask.cpp:526) or / ((1 << aaDepth) + 1) (M2, tracetask.cpp:611)
+        A.jitterScale = (method == 1) ? jitter_scale / double(depth) : jitter_scale / double((1 << depth) + 1);
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n_rects) break;
+            const int l = rects[4 * i], t = rects[4 * i + 1], r = rects[4 * i + 2], b = rects[4 * i + 3];
+            float* out = rgbt + 4 * off[i];
+            if (method == 1) A.method1(l, t, r, b, out);
+            else if (method == 2) A.method2(l, t, r, b, out);
+            else {
+                const int w = r - l + 1;
+                for (int y = t; y <= b; y++)
+                    for (int x = l; x <= r; x++) { Px p = A.trace(x + 0.5, y + 0.5); float* o = out + 4 * ((size_t)(y - t) * w + (x - l)); o[0] = p.r; o[1] = p.g; o[2] = p.b; o[3] = p.t; }
+            }
+        }
+        tstats[ti] = T.st;
+        tsamples[ti] = A.samples;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
+    if (stats) {
+        stats[0] = stats[1] = stats[2] = stats[3] = 0;
+        for (int t = 0; t < threads; t++) { stats[0] += tstats[t].rays; stats[1] += tstats[t].shadow_tests; stats[2] = std::max<unsigned long long>(stats[2], tstats[t].max_level); stats[3] += tsamples[t]; }
+    }
+    return 0;
+}
+
 // Trace::FindIntersection under primary-ray conditions for explicit rays (6 doubles each).
 int pvo_trace_rays(void* sc, const double* org_dir, size_t n, int32_t* obj, double* depth, uint32_t* aux)
 {

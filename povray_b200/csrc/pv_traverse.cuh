@@ -72,30 +72,28 @@ __device__ __forceinline__ uint32_t stack_code(const NodeL& n, uint32_t index)
     return (n.count < 15u) ? (n.first | (n.count << 28)) : (index | 0xF0000000u);
 }
 
+// Branch-free form: the reference's cascade of early exits is, as its own comment says (boundingbox.cpp:597-603),
+// "if (tmax < dmax) dmax = tmax; if (tmin > dmin) dmin = tmin; if (dmin > dmax) return;" per axis; dmin only grows
+// and dmax only shrinks, so one final dmin > dmax test gives the same verdict, and the strict compares leave
+// dmin / dmax untouched for NaN products exactly like the reference's else-branches.
 __device__ __forceinline__ bool slab_test(const float* lo, const float* size, const RayInfo& ri, float& dmin_out)
 {
     float dmin = -PV_BOUND_HUGE_F, dmax = PV_BOUND_HUGE_F;
+    bool ok = true;
     #pragma unroll
     for (int k = 0; k < 3; k++) {
         const float hi = __fadd_rn(lo[k], size[k]);
-        if (ri.nonzero[k]) {
-            const float t_lo = __fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
-            const float t_hi = __fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
-            const float tmax = ri.positive[k] ? t_hi : t_lo;
-            const float tmin = ri.positive[k] ? t_lo : t_hi;
-            if (tmax < PV_EPSILON_F32) return false;
-            if (tmax < dmax) {
-                if (tmin > dmin) { if (tmin > tmax) return false; dmin = tmin; }
-                else if (dmin > tmax) return false;
-                dmax = tmax;
-            } else if (tmin > dmin) {
-                if (tmin > dmax) return false;
-                dmin = tmin;
-            }
-        } else if (!((lo[k] <= ri.org[k]) && (ri.org[k] <= hi))) return false;
+        const float t_lo = __fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
+        const float t_hi = __fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
+        const float tmax = ri.positive[k] ? t_hi : t_lo;
+        const float tmin = ri.positive[k] ? t_lo : t_hi;
+        const bool nz = ri.nonzero[k];
+        ok = ok && (nz ? !(tmax < PV_EPSILON_F32) : ((lo[k] <= ri.org[k]) && (ri.org[k] <= hi)));
+        dmax = (nz && tmax < dmax) ? tmax : dmax;
+        dmin = (nz && tmin > dmin) ? tmin : dmin;
     }
     dmin_out = dmin;
-    return true;
+    return ok && !(dmin > dmax);
 }
 
 // ObjectBase::Intersect_BBox -> Intersect_BBox_Dir (object.cpp:917-941, 1074-1109): all-FP32 test that
@@ -131,32 +129,43 @@ __device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
 #define PV_MAX_DISTANCE_F 1.0e7f
 
 // Tests the `count` children stored at nodes[first..] (Check_And_Enqueue per child, boundingbox.cpp:541-648) and
-// pushes those the ray may hit so that the nearest ends up on top.  Children are fetched four at a time (the
-// reference bunches <= 4 entries per node) so that the 128-bit loads of one node visit are all in flight together.
+// pushes those the ray may hit so that the nearest ends up on top (equal depths: the later child on top, the order
+// an insertion of one child after the other produces).  Children are fetched four at a time (the reference bunches
+// <= 4 entries per node): 8 x LDG.128 in flight, four branch-free slab tests, a 5-comparator sorting network, and
+// predicated pushes - no data-dependent loop, so the lanes of a warp stay converged through a node visit.
 template <bool ALLOW_INFINITE>
 __device__ __forceinline__ void push_children(const pvgpu_node* __restrict__ nodes, uint32_t first, uint32_t count, const RayInfo& ri,
                                               uint2* stack, int& sp, unsigned int* overflow)
 {
-    const int base = sp;
+    const float kInvalid = __int_as_float(0x7f800000);     // +inf: sorts first, never pushed
     for (uint32_t c0 = 0; c0 < count; c0 += 4) {
         NodeL ch[4];
         #pragma unroll
         for (int k = 0; k < 4; k++) ch[k] = load_node(nodes + first + min(c0 + (uint32_t)k, count - 1u));
+        float key[4];
+        uint32_t val[4];
         #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (c0 + k < count) {
-                float dmin;
-                bool ok;
-                if (ALLOW_INFINITE && (ch[k].flags & PVGPU_NODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
-                else ok = slab_test(ch[k].lo, ch[k].size, ri, dmin);
-                if (ok) {
-                    if (sp >= PV_STACK_SIZE) { atomicOr(overflow, 1u); }
-                    else {
-                        int j = sp++;
-                        while (j > base && __uint_as_float(stack[j - 1].x) < dmin) { stack[j] = stack[j - 1]; j--; }
-                        stack[j] = make_uint2(__float_as_uint(dmin), stack_code(ch[k], first + c0 + k));
-                    }
-                }
+            float dmin;
+            bool ok = slab_test(ch[k].lo, ch[k].size, ri, dmin);
+            if (ALLOW_INFINITE && (ch[k].flags & PVGPU_NODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
+            ok = ok && (c0 + k < count);
+            key[k] = ok ? dmin : kInvalid;
+            val[k] = stack_code(ch[k], first + c0 + k) ;
+        }
+        // descending by entry depth; equal depths keep the child order (the ordinal rides in the comparison)
+        uint32_t ord[4] = { 0u, 1u, 2u, 3u };
+        #define PV_CSWAP(i, j) { const bool sw = (key[i] < key[j]) || (key[i] == key[j] && ord[i] > ord[j]); \
+                                 const float tk = sw ? key[j] : key[i]; key[j] = sw ? key[i] : key[j]; key[i] = tk; \
+                                 const uint32_t tv = sw ? val[j] : val[i]; val[j] = sw ? val[i] : val[j]; val[i] = tv; \
+                                 const uint32_t to = sw ? ord[j] : ord[i]; ord[j] = sw ? ord[i] : ord[j]; ord[i] = to; }
+        PV_CSWAP(0, 1) PV_CSWAP(2, 3) PV_CSWAP(0, 2) PV_CSWAP(1, 3) PV_CSWAP(1, 2)
+        #undef PV_CSWAP
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (key[k] != kInvalid) {
+                if (sp >= PV_STACK_SIZE) atomicOr(overflow, 1u);
+                else stack[sp++] = make_uint2(__float_as_uint(key[k]), val[k]);
             }
         }
     }
@@ -265,8 +274,11 @@ __device__ __forceinline__ bool test_ray_flags(uint32_t oflags, uint32_t rflags,
 }
 
 // Mesh::intersect_bbox_tree + test_hit (mesh.cpp:1452-1528, 1208-1243) with a LIFO stack.
+//   ANY_HIT (shadow rays, every caster opaque): return at the first accepted hit inside (SHADOW_TOLERANCE, any_limit) -
+//   the closest hit the reference would find is then inside the same window, i.e. the light is blocked either way.
+template <bool ANY_HIT>
 __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvgpu_object& ob, const V3& o, const V3& d,
-                                 HitAcc& acc, int32_t csg, uint2* stack, int sp0, unsigned int* overflow)
+                                 HitAcc& acc, int32_t csg, uint2* stack, int sp0, unsigned int* overflow, double any_limit = 0.0)
 {
     const DMesh& me = sc.meshes[ob.mesh];
     V3 mo = o, md = d;
@@ -298,23 +310,30 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
         if (!slab_test(root.lo, root.size, ri, dmin)) return;
         stack[sp++] = make_uint2(__float_as_uint(dmin), stack_code(root, 0u));
     }
-    // entries further than the closest accepted hit cannot improve it; compared in mesh space (t = world * len)
-    while (sp > sp0) {
-        const uint2 e = stack[--sp];
-        if ((double)__uint_as_float(e.x) > acc.closest * len) continue;
-        const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
-        if (code) {
+    // "while-while" traversal: every lane first walks inner nodes until it holds a leaf (or runs out of work); the
+    // warp reconverges behind that loop and the lanes that found a triangle run the FP64 test together, instead of
+    // paying for both code paths on every iteration.
+    // Entries further than the closest accepted hit cannot improve it; compared in mesh space (t = world * len).
+    const bool any_ok = ANY_HIT && (ob.flags & PVGPU_OPAQUE_FLAG) && ob.clip_count == 0;
+    for (;;) {
+        uint32_t leaf = 0xFFFFFFFFu;
+        while (sp > sp0) {
+            const uint2 e = stack[--sp];
+            if ((double)__uint_as_float(e.x) > acc.closest * len) continue;
+            const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+            if (code == 0u) { leaf = idx; break; }
             uint32_t first = idx, count = code;
             if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
             push_children<false>(nodes, first, count, ri, stack, sp, overflow);
-        } else {
-            double t;
-            const uint32_t ti = me.tri_first + idx;
-            if (tri_intersect(sc.dtris[ti], mo, md, t)) {
-                double wd = t / len;
-                V3 ip = evaluate(o, d, wd);
-                if (ob.clip_count == 0 || point_in_clip(sc, ob, ip, stack, sp)) consider(acc, wd, ip, obj_index, ti, csg);
-            }
+        }
+        if (leaf == 0xFFFFFFFFu) break;
+        double t;
+        const uint32_t ti = me.tri_first + leaf;
+        if (tri_intersect(sc.dtris[ti], mo, md, t)) {
+            double wd = t / len;
+            V3 ip = evaluate(o, d, wd);
+            if (ob.clip_count == 0 || point_in_clip(sc, ob, ip, stack, sp)) consider(acc, wd, ip, obj_index, ti, csg);
+            if (any_ok && acc.found && acc.closest > PV_SHADOW_TOLERANCE && acc.closest < any_limit) return;
         }
     }
 }
@@ -426,8 +445,10 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
                                                 uint2* stack, int sp0, unsigned int* overflow);
 
 // Find_Intersection for one frame-level object (object.cpp:172-224 / trace.cpp:345-443).
+template <bool ANY_OPAQUE>
 __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
-                                   double post_min, float bbox_maxd, Hit& out, uint2* stack, int sp0, unsigned int* overflow)
+                                   double post_min, float bbox_maxd, Hit& out, uint2* stack, int sp0, unsigned int* overflow,
+                                   double opaque_limit = 0.0)
 {
     const pvgpu_object& ob = sc.objs[idx];
     if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, bbox_maxd)) return false;
@@ -439,7 +460,7 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
     if (ob.type >= PVGPU_OBJ_CSG_UNION) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow);
-    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
+    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
     else {
         PrimHits h;
         prim_hits(sc, ob, o, d, h);
@@ -460,7 +481,7 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = -1.0; acc.found = false;
     if (ob.type >= PVGPU_OBJ_CSG_UNION) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow);
-    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
+    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
     else {
         PrimHits h;
         prim_hits(sc, ob, o, d, h);
@@ -498,7 +519,7 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
             const uint32_t idx = sc.frame[i];
             if (!precondition(sc.objs[idx].flags, rflags, shadow_ray)) continue;
             Hit h;
-            if (object_find(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, 0, overflow) && h.depth < best.depth) {
+            if (object_find<ANY_OPAQUE>(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, 0, overflow, opaque_limit) && h.depth < best.depth) {
                 best = h;
                 found = true;
                 if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
@@ -516,22 +537,24 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
         else if (!slab_test(root.lo, root.size, ri, dmin)) return false;
         stack[sp++] = make_uint2(__float_as_uint(dmin), stack_code(root, 0u));
     }
-    while (sp > 0) {
-        const uint2 e = stack[--sp];
-        if ((double)__uint_as_float(e.x) > best.depth) continue;      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
-        const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
-        if (code) {
+    for (;;) {
+        uint32_t leaf = 0xFFFFFFFFu;
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if ((double)__uint_as_float(e.x) > best.depth) continue;      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
+            const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+            if (code == 0u) { leaf = idx; break; }
             uint32_t first = idx, count = code;
             if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
             push_children<true>(nodes, first, count, ri, stack, sp, overflow);
-        } else {
-            if (!precondition(sc.objs[idx].flags, rflags, shadow_ray)) continue;
-            Hit h;
-            if (object_find(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow) && h.depth < best.depth) {
-                best = h;
-                found = true;
-                if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
-            }
+        }
+        if (leaf == 0xFFFFFFFFu) break;
+        if (!precondition(sc.objs[leaf].flags, rflags, shadow_ray)) continue;
+        Hit h;
+        if (object_find<ANY_OPAQUE>(sc, leaf, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow, opaque_limit) && h.depth < best.depth) {
+            best = h;
+            found = true;
+            if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
         }
     }
     return found;

@@ -79,3 +79,21 @@ class OracleScene:
         out = np.empty((len(xy), 6), dtype=np.float64)
         lib().pvo_camera_rays(self._h, width, height, xy.ctypes.data_as(C.POINTER(C.c_double)), len(xy), out.ctypes.data_as(C.POINTER(C.c_double)))
         return out
+
+
+def _setup_aa(l):
+    l.pvo_render_aa.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_ulonglong)]
+
+
+def render_aa(scene, width, height, rects, method, depth=3, threshold=0.3, jitter=1.0, gamma=2.5, threads=1):
+    """Anti-aliased render of `rects` [(l, t, r, b)] by the oracle; returns (rect-major [n,4] float32 pixels, stats)."""
+    l = lib()
+    _setup_aa(l)
+    ra = np.ascontiguousarray(np.array(rects, dtype=np.int32).reshape(-1, 4))
+    n = int(((ra[:, 2] - ra[:, 0] + 1) * (ra[:, 3] - ra[:, 1] + 1)).sum())
+    out = np.zeros((n, 4), dtype=np.float32)
+    st = (C.c_ulonglong * 4)()
+    l.pvo_render_aa(scene._h, width, height, ra.ctypes.data_as(C.POINTER(C.c_int)), len(ra), method, depth, threshold, jitter, gamma,
+                    out.ctypes.data_as(C.POINTER(C.c_float)), threads, st)
+    return out, dict(rays=st[0], shadow_ray_tests=st[1], max_trace_level=st[2], samples=st[3])
