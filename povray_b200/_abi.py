@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpvgpu.so")
+LIB_PATH = os.environ.get("PVGPU_LIB") or os.path.join(HERE, "libpvgpu.so")
 
 ABI_VERSION = 2
 

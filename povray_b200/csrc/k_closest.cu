@@ -26,7 +26,7 @@ int grid_for(uint32_t n, int block, int per_sm)
 }
 
 // TracePixel::InitRayContainerState (tracepixel.cpp:929-1006): interiors of all objects containing `p`.
-__device__ inline void container_state(const DScene& sc, const V3& p, uint16_t* out, uint32_t& n, uint2* stack, unsigned int* overflow)
+__device__ inline void container_state(const DScene& sc, const V3& p, uint16_t* out, uint32_t& n, TStack stack, unsigned int* overflow)
 {
     n = 0;
     auto inside_bbox = [&](const float* lo, const float* size) {       // Inside_BBox (boundingbox.h:139-155)
@@ -49,20 +49,21 @@ __device__ inline void container_state(const DScene& sc, const V3& p, uint16_t* 
     }
     // InitRayContainerStateTree: children visited in order (pre-order), so push them reversed
     int sp = 0;
-    stack[sp++] = make_uint2(0u, 0u);
+    stack.set(sp++, make_uint2(0u, 0u));
     while (sp > 0) {
-        const uint32_t ni = stack[--sp].y;
+        const uint32_t ni = stack.get(--sp).y;
         const NodeL nd = load_node(sc.nodes + ni);
         if (!inside_bbox(nd.lo, nd.size)) continue;
         if (nd.count == 0) test_object(nd.first, sp);
-        else for (uint32_t c = nd.count; c-- > 0 && sp < PV_STACK_SIZE;) stack[sp++] = make_uint2(0u, nd.first + c);
+        else for (uint32_t c = nd.count; c-- > 0 && sp < PV_STACK_SIZE;) stack.set(sp++, make_uint2(0u, nd.first + c));
     }
 }
 
 __global__ void k_container_state(DScene sc, uint16_t* out, Counters* cnt)
 {
     if (threadIdx.x || blockIdx.x) return;
-    uint2 stack[PV_STACK_SIZE];
+    uint2 stack_mem[PV_STACK_SIZE];
+    const TStack stack{ nullptr, stack_mem, 0 };
     uint16_t ints[PV_MAX_INTERIORS];
     uint32_t n;
     container_state(sc, ld3(sc.cam.location), ints, n, stack, &cnt->overflow);
@@ -101,7 +102,8 @@ __device__ __forceinline__ void sample_xy(const pvgpu_rect* rects, const uint32_
 __global__ void __launch_bounds__(256)
 k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width, double height, PRay* out, Counters* cnt)
 {
-    uint2 stack[PV_STACK_SIZE];
+    uint2 stack_mem[PV_STACK_SIZE];
+    const TStack stack{ nullptr, stack_mem, 0 };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double x, y;
         uint32_t slot = first + i;
@@ -136,41 +138,57 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
 }
 
 // Trace::TraceRay's entry (trace.cpp:142-160) + FindIntersection for every ray of the wave.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
 k_closest(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRec* __restrict__ hits, Counters* cnt)
 {
-    uint2 stack[PV_STACK_SIZE];
+#if PV_SSTACK > 0
+    __shared__ uint2 stack_sh[PV_SSTACK * PV_TRAV_BLOCK];
+    uint2 stack_lo[PV_STACK_SIZE - PV_SSTACK];
+    const TStack stack{ stack_sh + threadIdx.x, stack_lo, PV_SSTACK };
+#else
+    uint2 stack_lo[PV_STACK_SIZE];
+    const TStack stack{ nullptr, stack_lo, 0 };
+#endif
     unsigned long long n_rays = 0, n_adc = 0;
     unsigned int max_level = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const PRay* rp = cur + i;
-        const V3 o = ld3(rp->o), d = ld3(rp->d);
-        const float adcw = rp->adc;
-        const uint32_t level = rp->level, flags = rp->flags;
+    // warp-uniform trip count: all 32 lanes stay in the loop (and in the warp-synchronous traversal) together
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        bool alive = i < n;
+        V3 o = mk(0.0, 0.0, 0.0), d = mk(0.0, 0.0, 1.0);
+        uint32_t flags = 0;
         HitRec out;
-        out.pad = 0; out.csg = -1; out.aux = 0; out.depth = 0.0; out.ip[0] = out.ip[1] = out.ip[2] = 0.0;
-        if (!(flags & PV_RAY_PROBE)) {
-            n_rays++;
-            // max. trace level / ADC bailout (trace.cpp:147-155)
-            if ((level >= sc.g.max_trace_level) || ((double)adcw < sc.g.adc_bailout)) {
-                if ((double)adcw < sc.g.adc_bailout) n_adc++;
-                out.obj = PV_HIT_STOPPED;
-                hits[i] = out;
-                continue;
+        out.pad = 0; out.csg = -1; out.aux = 0; out.depth = 0.0; out.ip[0] = out.ip[1] = out.ip[2] = 0.0; out.obj = PV_HIT_MISS;
+        if (alive) {
+            const PRay* rp = cur + i;
+            o = ld3(rp->o); d = ld3(rp->d);
+            const float adcw = rp->adc;
+            const uint32_t level = rp->level;
+            flags = rp->flags;
+            if (!(flags & PV_RAY_PROBE)) {
+                n_rays++;
+                // max. trace level / ADC bailout (trace.cpp:147-155)
+                if ((level >= sc.g.max_trace_level) || ((double)adcw < sc.g.adc_bailout)) {
+                    if ((double)adcw < sc.g.adc_bailout) n_adc++;
+                    out.obj = PV_HIT_STOPPED;
+                    alive = false;
+                } else {
+                    const unsigned int lvl = (flags & PV_RAY_CONTINUED) ? level : level + 1u;
+                    if (lvl > max_level) max_level = lvl;
+                }
             }
-            const unsigned int lvl = (flags & PV_RAY_CONTINUED) ? level : level + 1u;
-            if (lvl > max_level) max_level = lvl;
         }
         Hit best;
-        best.depth = ((flags & PV_RAY_PRIMARY) && sc.cam.max_ray_distance >= PV_EPSILON) ? sc.cam.max_ray_distance : PV_BOUND_HUGE;
+        best.depth = ((flags & PV_RAY_PRIMARY) && !(flags & PV_RAY_PROBE) && sc.cam.max_ray_distance >= PV_EPSILON) ? sc.cam.max_ray_distance : PV_BOUND_HUGE;
         best.obj = PV_NO_OBJECT;
         best.aux = 0; best.csg = -1;
-        const bool found = find_intersection<false>(sc, o, d, flags & ~PV_RAY_PROBE, false, -1.0, best, stack, &cnt->overflow);
+        const bool found = find_intersection_sync<false>(alive, sc, o, d, flags & ~PV_RAY_PROBE, false, -1.0, best, stack, &cnt->overflow);
         if (found) {
             out.depth = best.depth; out.ip[0] = best.ip.x; out.ip[1] = best.ip.y; out.ip[2] = best.ip.z;
             out.obj = best.obj; out.aux = best.aux; out.csg = best.csg;
-        } else out.obj = PV_HIT_MISS;
-        hits[i] = out;
+        }
+        if (i < n) hits[i] = out;
     }
     // one atomic per warp for the statistics
     for (int off = 16; off > 0; off >>= 1) {
@@ -232,7 +250,7 @@ void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, u
 }
 void launch_closest(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st)
 {
-    k_closest<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, cur, n, hits, cnt);
+    k_closest<<<grid_for(n, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, n, hits, cnt);
 }
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st)
 {

@@ -18,6 +18,9 @@ namespace pvgpu {
 #define PV_SHADOW_TOLERANCE 1.0e-3      // SHADOW_TOLERANCE trace.cpp:81
 #define PV_COORDINATE_LIMIT 1.0e17      // COORDINATE_LIMIT warp.h
 
+#ifndef PV_TRAV_MIN_BLOCKS
+#define PV_TRAV_MIN_BLOCKS 8           // resident CTAs per SM the traversal kernels are compiled for (register budget)
+#endif
 #define PV_STACK_SIZE     96            // traversal stack entries per ray (scene tree + nested mesh tree)
 #define PV_MAX_LAYERS     8             // layers of a layered texture
 #define PV_MAX_INTERIORS  10            // interiors a ray can be inside of at once
@@ -25,6 +28,22 @@ namespace pvgpu {
 #define PV_NO_OBJECT      0xFFFFFFFFu
 
 struct V3 { double x, y, z; };
+
+// Per-ray traversal stack.  The first `nsh` entries of a thread live in shared memory (entry-major, one 8-byte
+// column per thread: lanes never collide on a bank whatever their stack depths are), deeper entries in local memory.
+#define PV_TRAV_BLOCK   128            // threads per CTA of the traversal kernels
+#ifndef PV_SSTACK
+#define PV_SSTACK       0              // shared-memory entries per thread.  0: the whole stack stays in local memory - measured
+                                       // faster on B200: 24 entries (24 KB per CTA, 8 CTAs per SM) shrink the L1 that serves the
+                                       // node fetches and the register spills (cfg2 28.4 -> 30.0 ms)
+#endif
+struct TStack {
+    uint2* sh;      // shared column of this thread (stride PV_TRAV_BLOCK), or nullptr
+    uint2* lo;      // local-memory part
+    int    nsh;     // entries held in shared memory (0 or PV_SSTACK)
+    __device__ __forceinline__ uint2 get(int i) const { return (i < nsh) ? sh[i * PV_TRAV_BLOCK] : lo[i - nsh]; }
+    __device__ __forceinline__ void set(int i, uint2 v) const { if (i < nsh) sh[i * PV_TRAV_BLOCK] = v; else lo[i - nsh] = v; }
+};
 
 // Packed mesh triangle for the intersection test: everything intersect_mesh_triangle
 // (mesh.cpp:1040-1127) reads, in one 64-byte record (one L2 sector pair) instead of five gathers.

@@ -53,16 +53,17 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
 //   ALL_OPAQUE: every shadow caster of the scene has OPAQUE_FLAG, so the first blocker inside the shadow
 //   window ends the search (any-hit) and no filtering code is needed.
 template <bool ALL_OPAQUE>
-__device__ inline void trace_shadow(const DScene& sc, V3 o, const V3& d, double depth, const PRay* wave, uint32_t parent,
-                                    uint2* stack, Counters* cnt, float f[3], unsigned long long& tests)
+__device__ inline void trace_shadow(bool alive, const DScene& sc, V3 o, const V3& d, double depth, const PRay* wave, uint32_t parent,
+                                    TStack stack, Counters* cnt, float f[3], unsigned long long& tests)
 {
+    // all 32 lanes of the warp are here together (the traversal is warp-synchronous); `alive` lanes carry a shadow ray
     f[0] = f[1] = f[2] = 1.0f;
     if (ALL_OPAQUE) {
         Hit best;
         best.depth = depth;
         best.obj = PV_NO_OBJECT;
-        tests++;
-        const bool found = find_intersection<true>(sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow, depth - PV_SHADOW_TOLERANCE);
+        if (alive) tests++;
+        const bool found = find_intersection_sync<true>(alive, sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow, depth - PV_SHADOW_TOLERANCE);
         if (found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))
             f[0] = f[1] = f[2] = 0.0f;     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
         return;
@@ -72,14 +73,16 @@ __device__ inline void trace_shadow(const DScene& sc, V3 o, const V3& d, double 
     in_state.n_int = 0;
     bool have_state = false;
     for (int iter = 0; iter < 256; iter++) {
+        if (!__any_sync(PV_FULL_MASK, alive)) break;
         Hit best;
         best.depth = depth;
         best.obj = PV_NO_OBJECT;
-        tests++;
-        const bool found = find_intersection<false>(sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow);
-        if (!(found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))) break;
+        if (alive) tests++;
+        const bool found = find_intersection_sync<false>(alive, sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow);
+        if (!alive) continue;
+        if (!(found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))) { alive = false; continue; }
         const pvgpu_object& ob = sc.objs[best.obj];
-        if (ob.flags & PVGPU_OPAQUE_FLAG) { f[0] = f[1] = f[2] = 0.0f; break; }     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
+        if (ob.flags & PVGPU_OPAQUE_FLAG) { f[0] = f[1] = f[2] = 0.0f; alive = false; continue; }     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
         if (!have_state) { in_state = wave[parent]; have_state = true; }
         shadow_filter(sc, best, d, &in_state, ob.interior >= 0 && ray_is_interior(in_state, ob.interior), f);
         // ComputeShadowMedia (trace.cpp:3046-3071) toggles the blocker's interior on the light ray
@@ -88,7 +91,8 @@ __device__ inline void trace_shadow(const DScene& sc, V3 o, const V3& d, double 
         }
         if (f[0] == 0.0f && f[1] == 0.0f && f[2] == 0.0f) {
             // colour is black; the reference keeps looping only to find an opaque object for its cache
-            break;
+            alive = false;
+            continue;
         }
         depth -= best.depth;
         o = best.ip;

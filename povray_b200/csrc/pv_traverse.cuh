@@ -13,10 +13,13 @@
 
 namespace pvgpu {
 
-// Rayinfo (boundingbox.h:182-216): FP32 origin and reciprocal direction.
+// Rayinfo (boundingbox.h:182-216): FP32 origin and reciprocal direction, plus per-axis constants that let the
+// slab test run without per-axis branches.
 struct RayInfo {
     float org[3], inv[3];
+    float cmin[3], cmax[3];       // 0 for axes the ray moves along; -/+BOUND_HUGE for axes with a zero direction component
     bool  nonzero[3], positive[3];
+    bool  any_zero;               // some direction component is exactly zero (containment test needed)
 };
 
 __device__ __forceinline__ RayInfo make_rayinfo(const V3& o, const V3& d)
@@ -24,12 +27,16 @@ __device__ __forceinline__ RayInfo make_rayinfo(const V3& o, const V3& d)
     RayInfo ri;
     const double dd[3] = { d.x, d.y, d.z };
     const double oo[3] = { o.x, o.y, o.z };
+    ri.any_zero = false;
     #pragma unroll
     for (int k = 0; k < 3; k++) {
         ri.org[k] = (float)oo[k];
         ri.nonzero[k] = (dd[k] != 0.0);
         ri.inv[k] = ri.nonzero[k] ? (float)(1.0 / dd[k]) : 0.0f;
         ri.positive[k] = (dd[k] > 0.0);
+        ri.cmin[k] = ri.nonzero[k] ? 0.0f : -2.0e10f;
+        ri.cmax[k] = ri.nonzero[k] ? 0.0f : 2.0e10f;
+        ri.any_zero = ri.any_zero || !ri.nonzero[k];
     }
     return ri;
 }
@@ -73,27 +80,34 @@ __device__ __forceinline__ uint32_t stack_code(const NodeL& n, uint32_t index)
 }
 
 // Branch-free form: the reference's cascade of early exits is, as its own comment says (boundingbox.cpp:597-603),
-// "if (tmax < dmax) dmax = tmax; if (tmin > dmin) dmin = tmin; if (dmin > dmax) return;" per axis; dmin only grows
-// and dmax only shrinks, so one final dmin > dmax test gives the same verdict, and the strict compares leave
-// dmin / dmax untouched for NaN products exactly like the reference's else-branches.
+// "if (tmax < dmax) dmax = tmax; if (tmin > dmin) dmin = tmin; if (dmin > dmax) return;" per axis.  dmin only grows and
+// dmax only shrinks, so one final dmin > dmax test gives the same verdict; "tmax < EPSILON on some axis" is
+// "dmax < EPSILON" at the end; fmaxf / fminf ignore a NaN product exactly like the reference's strict compares do.
+// Axes with a zero direction component do not take part in the reference (containment test instead): their
+// products are 0 * finite = 0 here and the per-ray constants cmin / cmax (-/+BOUND_HUGE) neutralise them, while for
+// all other axes the constants are 0 and adding them changes nothing.
 __device__ __forceinline__ bool slab_test(const float* lo, const float* size, const RayInfo& ri, float& dmin_out)
 {
     float dmin = -PV_BOUND_HUGE_F, dmax = PV_BOUND_HUGE_F;
-    bool ok = true;
+    float hi[3];
     #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const float hi = __fadd_rn(lo[k], size[k]);
-        const float t_lo = __fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
-        const float t_hi = __fmul_rn(__fsub_rn(hi, ri.org[k]), ri.inv[k]);
-        const float tmax = ri.positive[k] ? t_hi : t_lo;
-        const float tmin = ri.positive[k] ? t_lo : t_hi;
-        const bool nz = ri.nonzero[k];
-        ok = ok && (nz ? !(tmax < PV_EPSILON_F32) : ((lo[k] <= ri.org[k]) && (ri.org[k] <= hi)));
-        dmax = (nz && tmax < dmax) ? tmax : dmax;
-        dmin = (nz && tmin > dmin) ? tmin : dmin;
+        hi[k] = __fadd_rn(lo[k], size[k]);
+        const float near_p = ri.positive[k] ? lo[k] : hi[k];
+        const float far_p = ri.positive[k] ? hi[k] : lo[k];
+        const float tmin = __fadd_rn(__fmul_rn(__fsub_rn(near_p, ri.org[k]), ri.inv[k]), ri.cmin[k]);
+        const float tmax = __fadd_rn(__fmul_rn(__fsub_rn(far_p, ri.org[k]), ri.inv[k]), ri.cmax[k]);
+        dmin = fmaxf(dmin, tmin);
+        dmax = fminf(dmax, tmax);
+    }
+    bool ok = !(dmax < PV_EPSILON_F32) && !(dmin > dmax);
+    if (ri.any_zero) {
+        #pragma unroll
+        for (int k = 0; k < 3; k++)
+            if (!ri.nonzero[k]) ok = ok && (lo[k] <= ri.org[k]) && (ri.org[k] <= hi[k]);
     }
     dmin_out = dmin;
-    return ok && !(dmin > dmax);
+    return ok;
 }
 
 // ObjectBase::Intersect_BBox -> Intersect_BBox_Dir (object.cpp:917-941, 1074-1109): all-FP32 test that
@@ -133,9 +147,12 @@ __device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
 // an insertion of one child after the other produces).  Children are fetched four at a time (the reference bunches
 // <= 4 entries per node): 8 x LDG.128 in flight, four branch-free slab tests, a 5-comparator sorting network, and
 // predicated pushes - no data-dependent loop, so the lanes of a warp stay converged through a node visit.
-template <bool ALLOW_INFINITE>
+//   ORDERED = false (any-hit searches): no sorting, children are pushed in storage order.
+//   limit: children entered beyond this depth are not pushed at all (a conservative FP32 upper bound of the best depth
+//   so far; the exact test is repeated when an entry is popped, so this only saves stack traffic).
+template <bool ALLOW_INFINITE, bool ORDERED>
 __device__ __forceinline__ void push_children(const pvgpu_node* __restrict__ nodes, uint32_t first, uint32_t count, const RayInfo& ri,
-                                              uint2* stack, int& sp, unsigned int* overflow)
+                                              const TStack& stack, int& sp, unsigned int* overflow, float limit = 3.0e38f)
 {
     const float kInvalid = __int_as_float(0x7f800000);     // +inf: sorts first, never pushed
     for (uint32_t c0 = 0; c0 < count; c0 += 4) {
@@ -149,32 +166,34 @@ __device__ __forceinline__ void push_children(const pvgpu_node* __restrict__ nod
             float dmin;
             bool ok = slab_test(ch[k].lo, ch[k].size, ri, dmin);
             if (ALLOW_INFINITE && (ch[k].flags & PVGPU_NODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
-            ok = ok && (c0 + k < count);
+            ok = ok && (c0 + k < count) && !(dmin > limit);
             key[k] = ok ? dmin : kInvalid;
-            val[k] = stack_code(ch[k], first + c0 + k) ;
+            val[k] = stack_code(ch[k], first + c0 + k);
         }
-        // descending by entry depth; equal depths keep the child order (the ordinal rides in the comparison)
-        uint32_t ord[4] = { 0u, 1u, 2u, 3u };
-        #define PV_CSWAP(i, j) { const bool sw = (key[i] < key[j]) || (key[i] == key[j] && ord[i] > ord[j]); \
-                                 const float tk = sw ? key[j] : key[i]; key[j] = sw ? key[i] : key[j]; key[i] = tk; \
-                                 const uint32_t tv = sw ? val[j] : val[i]; val[j] = sw ? val[i] : val[j]; val[i] = tv; \
-                                 const uint32_t to = sw ? ord[j] : ord[i]; ord[j] = sw ? ord[i] : ord[j]; ord[i] = to; }
-        PV_CSWAP(0, 1) PV_CSWAP(2, 3) PV_CSWAP(0, 2) PV_CSWAP(1, 3) PV_CSWAP(1, 2)
-        #undef PV_CSWAP
+        if (ORDERED) {
+            // descending by entry depth; equal depths keep the child order (the ordinal rides in the comparison)
+            uint32_t ord[4] = { 0u, 1u, 2u, 3u };
+            #define PV_CSWAP(i, j) { const bool sw = (key[i] < key[j]) || (key[i] == key[j] && ord[i] > ord[j]); \
+                                     const float tk = sw ? key[j] : key[i]; key[j] = sw ? key[i] : key[j]; key[i] = tk; \
+                                     const uint32_t tv = sw ? val[j] : val[i]; val[j] = sw ? val[i] : val[j]; val[i] = tv; \
+                                     const uint32_t to = sw ? ord[j] : ord[i]; ord[j] = sw ? ord[i] : ord[j]; ord[i] = to; }
+            PV_CSWAP(0, 1) PV_CSWAP(2, 3) PV_CSWAP(0, 2) PV_CSWAP(1, 3) PV_CSWAP(1, 2)
+            #undef PV_CSWAP
+        }
         #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (key[k] != kInvalid) {
                 if (sp >= PV_STACK_SIZE) atomicOr(overflow, 1u);
-                else stack[sp++] = make_uint2(__float_as_uint(key[k]), val[k]);
+                else stack.set(sp++, make_uint2(__float_as_uint(key[k]), val[k]));
             }
         }
     }
 }
 
 // ---- Inside --------------------------------------------------------------------------------------
-__device__ bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, uint2* stack, int sp0);
+__device__ bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, TStack stack, int sp0);
 
-__device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, uint2* stack, int sp0)
+__device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, TStack stack, int sp0)
 {
     switch (ob.type) {
         case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
@@ -190,7 +209,7 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
 // Inside_Object (object.cpp:346-355) = every clipped_by object contains the point AND Object->Inside();
 // CSGUnion/CSGMerge::Inside = any child, CSGIntersection::Inside = all children (csg.cpp:393-454).
 // Evaluated iteratively with short-circuit over the object graph (the reference recurses).
-static __device__ __noinline__ bool inside_object(const DScene& sc, uint32_t root, const V3& p, uint2* stack, int sp0, bool root_clip = true)
+static __device__ __noinline__ bool inside_object(const DScene& sc, uint32_t root, const V3& p, TStack stack, int sp0, bool root_clip = true)
 {
     struct Frame { uint32_t obj; uint32_t cur; };
     Frame st[PV_CSG_STACK];
@@ -223,7 +242,7 @@ static __device__ __noinline__ bool inside_object(const DScene& sc, uint32_t roo
 }
 
 // Point_In_Clip (object.cpp:430-443)
-__device__ inline bool point_in_clip(const DScene& sc, const pvgpu_object& o, const V3& p, uint2* stack, int sp0)
+__device__ inline bool point_in_clip(const DScene& sc, const pvgpu_object& o, const V3& p, TStack stack, int sp0)
 {
     for (uint32_t i = 0; i < o.clip_count; i++)
         if (!inside_object(sc, sc.index_list[o.clip_first + i], p, stack, sp0)) return false;
@@ -278,7 +297,7 @@ __device__ __forceinline__ bool test_ray_flags(uint32_t oflags, uint32_t rflags,
 //   the closest hit the reference would find is then inside the same window, i.e. the light is blocked either way.
 template <bool ANY_HIT>
 __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvgpu_object& ob, const V3& o, const V3& d,
-                                 HitAcc& acc, int32_t csg, uint2* stack, int sp0, unsigned int* overflow, double any_limit = 0.0)
+                                 HitAcc& acc, int32_t csg, TStack stack, int sp0, unsigned int* overflow, double any_limit = 0.0)
 {
     const DMesh& me = sc.meshes[ob.mesh];
     V3 mo = o, md = d;
@@ -308,7 +327,7 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
         const NodeL root = load_node(nodes);
         float dmin;
         if (!slab_test(root.lo, root.size, ri, dmin)) return;
-        stack[sp++] = make_uint2(__float_as_uint(dmin), stack_code(root, 0u));
+        stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
     }
     // "while-while" traversal: every lane first walks inner nodes until it holds a leaf (or runs out of work); the
     // warp reconverges behind that loop and the lanes that found a triangle run the FP64 test together, instead of
@@ -318,13 +337,13 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
     for (;;) {
         uint32_t leaf = 0xFFFFFFFFu;
         while (sp > sp0) {
-            const uint2 e = stack[--sp];
+            const uint2 e = stack.get(--sp);
             if ((double)__uint_as_float(e.x) > acc.closest * len) continue;
             const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
             if (code == 0u) { leaf = idx; break; }
             uint32_t first = idx, count = code;
             if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
-            push_children<false>(nodes, first, count, ri, stack, sp, overflow);
+            push_children<false, true>(nodes, first, count, ri, stack, sp, overflow);
         }
         if (leaf == 0xFFFFFFFFu) break;
         double t;
@@ -338,8 +357,85 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
     }
 }
 
+// Warp-synchronous form of mesh_hits for the hot path.  ALL 32 lanes of the warp call it together; lanes with
+// `active` hold a mesh object, the others idle.  The loops have warp-uniform conditions (votes), so the warp
+// provably reconverges between the two phases: every lane walks inner nodes until it holds a triangle (or runs out
+// of work), then the lanes that found one run the FP64 triangle test together.
+#define PV_FULL_MASK 0xffffffffu
+#define PV_NONE      0xFFFFFFFFu
+template <bool ANY_HIT>
+__device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t obj_index, const V3& o, const V3& d,
+                                      HitAcc& acc, TStack stack, int sp0, unsigned int* overflow, double any_limit, double limit0)
+{
+    V3 mo = o, md = d;
+    double len = 1.0;
+    RayInfo ri;
+    const pvgpu_node* __restrict__ nodes = sc.mnodes;
+    uint32_t tri_first = 0;
+    bool any_ok = false, clipped = false;
+    int sp = sp0;
+    if (active) {
+        const pvgpu_object& ob = sc.objs[obj_index];
+        const DMesh& me = sc.meshes[ob.mesh];
+        if (me.node_count == 0) {
+            // a mesh without its own tree (mesh.cpp:1490-1500): the generic, divergent form does it
+            mesh_hits<ANY_HIT>(sc, obj_index, ob, o, d, acc, -1, stack, sp0, overflow, any_limit);
+            active = false;
+        } else {
+            if (ob.transform >= 0) {
+                const pvgpu_transform& t = sc.xf[ob.transform];
+                mo = inv_trans_point(t, o);
+                md = inv_trans_direction(t, d);
+                len = length(md);
+                md = md / len;
+            }
+            ri = make_rayinfo(mo, md);
+            nodes = sc.mnodes + me.node_first;
+            tri_first = me.tri_first;
+            clipped = ob.clip_count != 0;
+            any_ok = ANY_HIT && (ob.flags & PVGPU_OPAQUE_FLAG) && !clipped;
+            const NodeL root = load_node(nodes);
+            float dmin;
+            if (slab_test(root.lo, root.size, ri, dmin)) stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
+        }
+    }
+    uint32_t tri = PV_NONE;
+    for (;;) {
+        for (;;) {
+            const bool want = active && tri == PV_NONE && sp > sp0;
+            if (!__any_sync(PV_FULL_MASK, want)) break;
+            if (want) {
+                const uint2 e = stack.get(--sp);
+                // entries further than the closest accepted hit cannot improve it; compared in mesh space (t = world * len)
+                if (!((double)__uint_as_float(e.x) > fmin(acc.closest, limit0) * len)) {
+                    const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+                    if (code == 0u) tri = idx;
+                    else {
+                        uint32_t first = idx, count = code;
+                        if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+                        const double lim = fmin(acc.closest, limit0) * len;
+                        push_children<false, !ANY_HIT>(nodes, first, count, ri, stack, sp, overflow, (lim < 3.0e38) ? __double2float_ru(lim) : 3.0e38f);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(PV_FULL_MASK, tri != PV_NONE)) break;
+        if (tri != PV_NONE) {
+            double t;
+            const uint32_t ti = tri_first + tri;
+            tri = PV_NONE;
+            if (tri_intersect(sc.dtris[ti], mo, md, t)) {
+                const double wd = t / len;
+                const V3 ip = evaluate(o, d, wd);
+                if (!clipped || point_in_clip(sc, sc.objs[obj_index], ip, stack, sp)) consider(acc, wd, ip, obj_index, ti, -1);
+                if (any_ok && acc.found && acc.closest > PV_SHADOW_TOLERANCE && acc.closest < any_limit) sp = sp0;   // blocked: drop the rest
+            }
+        }
+    }
+}
+
 // Mesh::Inside + inside_bbox_tree (mesh.cpp:197-262, 2266-2315): parity of crossings along Inside_Vect.
-__device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, uint2* stack, int sp0)
+__device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, TStack stack, int sp0)
 {
     const DMesh& me = sc.meshes[ob.mesh];
     if (!me.has_inside_vector) return false;
@@ -362,14 +458,14 @@ __device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, con
         float dmin;
         unsigned int ovf = 0;
         const NodeL root = load_node(nodes);
-        if (slab_test(root.lo, root.size, ri, dmin)) stack[sp++] = make_uint2(0u, stack_code(root, 0u));
+        if (slab_test(root.lo, root.size, ri, dmin)) stack.set(sp++, make_uint2(0u, stack_code(root, 0u)));
         while (sp > sp0) {
-            const uint2 e = stack[--sp];
+            const uint2 e = stack.get(--sp);
             const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
             if (code) {
                 uint32_t first = idx, count = code;
                 if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
-                push_children<false>(nodes, first, count, ri, stack, sp, &ovf);
+                push_children<false, false>(nodes, first, count, ri, stack, sp, &ovf);
             } else {
                 double t;
                 if (tri_intersect(sc.dtris[me.tri_first + idx], mo, md, t)) found++;
@@ -387,7 +483,7 @@ __device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, con
 // every ancestor's clipped_by list contains it.  Intersection::Csg ends up as the outermost ancestor
 // that sets it (unions without clipped_by do not, csg.cpp:137-150).
 __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
-                                HitAcc& acc, uint2* stack, int sp0, unsigned int* overflow)
+                                HitAcc& acc, TStack stack, int sp0, unsigned int* overflow)
 {
     const uint2 range = sc.csg_leaf_range[top];
     for (uint32_t li = 0; li < range.y; li++) {
@@ -442,12 +538,12 @@ __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, con
 }
 
 static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
-                                                uint2* stack, int sp0, unsigned int* overflow);
+                                                TStack stack, int sp0, unsigned int* overflow);
 
 // Find_Intersection for one frame-level object (object.cpp:172-224 / trace.cpp:345-443).
 template <bool ANY_OPAQUE>
 __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
-                                   double post_min, float bbox_maxd, Hit& out, uint2* stack, int sp0, unsigned int* overflow,
+                                   double post_min, float bbox_maxd, Hit& out, TStack stack, int sp0, unsigned int* overflow,
                                    double opaque_limit = 0.0)
 {
     const pvgpu_object& ob = sc.objs[idx];
@@ -474,7 +570,7 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
 // The plain Find_Intersection(isect, object, ray) used for bounded_by objects (no post-condition,
 // maxd = HUGE_VAL; nested bounded_by lists are rejected on the host).
 static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags,
-                                                uint2* stack, int sp0, unsigned int* overflow)
+                                                TStack stack, int sp0, unsigned int* overflow)
 {
     const pvgpu_object& ob = sc.objs[idx];
     if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL)) return false;
@@ -509,7 +605,7 @@ __device__ __forceinline__ bool precondition(uint32_t oflags, uint32_t rflags, b
 //   window (depth in (SHADOW_TOLERANCE, limit - SHADOW_TOLERANCE)); see trace_shadow in pv_shade.cuh.
 template <bool ANY_OPAQUE>
 __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
-                                         double post_min, Hit& best, uint2* stack, unsigned int* overflow,
+                                         double post_min, Hit& best, TStack stack, unsigned int* overflow,
                                          double opaque_limit = 0.0)
 {
     bool found = false;
@@ -535,18 +631,18 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
         float dmin;
         if (root.flags & PVGPU_NODE_INFINITE) dmin = -PV_MAX_DISTANCE_F;
         else if (!slab_test(root.lo, root.size, ri, dmin)) return false;
-        stack[sp++] = make_uint2(__float_as_uint(dmin), stack_code(root, 0u));
+        stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
     }
     for (;;) {
         uint32_t leaf = 0xFFFFFFFFu;
         while (sp > 0) {
-            const uint2 e = stack[--sp];
+            const uint2 e = stack.get(--sp);
             if ((double)__uint_as_float(e.x) > best.depth) continue;      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
             const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
             if (code == 0u) { leaf = idx; break; }
             uint32_t first = idx, count = code;
             if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
-            push_children<true>(nodes, first, count, ri, stack, sp, overflow);
+            push_children<true, true>(nodes, first, count, ri, stack, sp, overflow);
         }
         if (leaf == 0xFFFFFFFFu) break;
         if (!precondition(sc.objs[leaf].flags, rflags, shadow_ray)) continue;
@@ -556,6 +652,97 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
             found = true;
             if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
         }
+    }
+    return found;
+}
+
+// Warp-synchronous form of find_intersection used by the wavefront kernels.  ALL 32 lanes of the warp call it
+// together; lanes with `alive` carry a ray.  Phase A walks the scene tree until every lane holds a leaf object or has
+// run out of work, phase B runs the per-object tests (meshes through mesh_hits_sync, so the nested traversal stays
+// converged as well).  Same results as find_intersection(); only the scheduling of the work inside the warp differs.
+template <bool ANY_OPAQUE>
+__device__ inline bool find_intersection_sync(bool alive, const DScene& sc, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
+                                              double post_min, Hit& best, TStack stack, unsigned int* overflow,
+                                              double opaque_limit = 0.0)
+{
+    bool found = false;
+    int sp = 0;
+    // phase B for the lanes that hold `leaf`; returns true when an ANY_OPAQUE search is satisfied
+    auto leaf_phase = [&](bool has_leaf, uint32_t leaf) -> bool {
+        bool is_mesh = false, done = false;
+        HitAcc acc;
+        acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
+        if (has_leaf) {
+            const pvgpu_object& ob = sc.objs[leaf];
+            if (ob.type == PVGPU_OBJ_MESH) {
+                // object_find's prelude: FP32 box test and Ray_In_Bound (object.cpp:186-193, 385-400)
+                is_mesh = object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL);
+                for (uint32_t i = 0; is_mesh && i < ob.bound_count; i++) {
+                    const uint32_t b = sc.index_list[ob.bound_first + i];
+                    if (!object_find_simple(sc, b, o, d, rflags, stack, sp, overflow) && !inside_object(sc, b, o, stack, sp)) is_mesh = false;
+                }
+            } else {
+                Hit h;
+                if (object_find<ANY_OPAQUE>(sc, leaf, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow, opaque_limit) && h.depth < best.depth) {
+                    best = h;
+                    found = true;
+                    if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) done = true;
+                }
+            }
+        }
+        if (__any_sync(PV_FULL_MASK, is_mesh)) {
+            mesh_hits_sync<ANY_OPAQUE>(is_mesh, sc, leaf, o, d, acc, stack, sp, overflow, opaque_limit, best.depth);
+            if (is_mesh && acc.found && acc.best.depth < best.depth) {
+                best = acc.best;
+                found = true;
+                if (ANY_OPAQUE && (sc.objs[best.obj].flags & PVGPU_OPAQUE_FLAG) && best.depth > PV_SHADOW_TOLERANCE && best.depth < opaque_limit) done = true;
+            }
+        }
+        return done;
+    };
+
+    if (!sc.use_tree) {
+        // boundingMethod 0: linear loop over SceneData::objects (trace.cpp:321-340); the trip count is uniform
+        for (uint32_t i = 0; i < sc.n_frame; i++) {
+            const uint32_t idx = sc.frame[i];
+            const bool cand = alive && precondition(sc.objs[idx].flags, rflags, shadow_ray);
+            if (leaf_phase(cand, idx)) alive = false;
+        }
+        return found;
+    }
+    RayInfo ri;
+    const pvgpu_node* __restrict__ nodes = sc.nodes;
+    if (alive) {
+        ri = make_rayinfo(o, d);
+        const NodeL root = load_node(nodes);
+        float dmin;
+        bool ok = true;
+        if (root.flags & PVGPU_NODE_INFINITE) dmin = -PV_MAX_DISTANCE_F;
+        else ok = slab_test(root.lo, root.size, ri, dmin);
+        if (ok) stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
+    }
+    uint32_t leaf = PV_NONE;
+    for (;;) {
+        for (;;) {
+            const bool want = alive && leaf == PV_NONE && sp > 0;
+            if (!__any_sync(PV_FULL_MASK, want)) break;
+            if (want) {
+                const uint2 e = stack.get(--sp);
+                if (!((double)__uint_as_float(e.x) > best.depth)) {      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
+                    const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+                    if (code == 0u) { if (precondition(sc.objs[idx].flags, rflags, shadow_ray)) leaf = idx; }
+                    else {
+                        uint32_t first = idx, count = code;
+                        if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+                        push_children<true, !ANY_OPAQUE>(nodes, first, count, ri, stack, sp, overflow, (best.depth < 3.0e38) ? __double2float_ru(best.depth) : 3.0e38f);
+                    }
+                }
+            }
+        }
+        if (!__any_sync(PV_FULL_MASK, leaf != PV_NONE)) break;
+        const uint32_t cur = leaf;
+        leaf = PV_NONE;
+        if (leaf_phase(cur != PV_NONE, cur)) { alive = false; sp = 0; }
     }
     return found;
 }

@@ -193,6 +193,19 @@ def test_full_size_properties_config2(pv, oracle):
         assert (np.abs(depth[hit] - odepth[hit]) / odepth[hit]).max() <= DEPTH_RTOL
 
 
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_full_size_frame_matches_reference_lattice(pv, name):
+    """BASELINE.json configs 1 and 2 at the full 1920x1080: every 8th pixel in x and y of the frame the UNMODIFIED
+    reference's TracePixel produced (tests/golden/make_golden_1080.py) against the GPU frame."""
+    from povray_b200 import synth
+    w, h = 1920, 1080
+    ref = np.fromfile(os.path.join(GOLDEN, f"{name}_1080_lattice8.rgbt"), dtype="<f4").reshape(135, 240, 4)
+    s = (synth.spheres_scene(1024) if name == "cfg1" else synth.mesh_scene(708)).build().finalize(0)
+    img, st = s.render_image(w, h)
+    d = check_pixels(img[5::8, 3::8], ref, name + " 1080p lattice")
+    assert np.quantile(d, 0.999) < 1e-4
+
+
 def read_ppm(path):
     with open(path, "rb") as f:
         data = f.read()
