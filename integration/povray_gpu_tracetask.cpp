@@ -67,6 +67,7 @@
 #include "pvgpu.h"
 
 // this must be the last file included
+#include "base/image/colourspace.h"
 #include "base/povdebug.h"
 
 namespace pov
@@ -564,8 +565,17 @@ void TraceTask::Run()
         while (vd->GetNextRectangle(r, serial)) { vector<RGBTColour> px(r.GetArea()); vd->CompletedRectangle(r, serial, px, 1, false, passCompletesImage); Cooperate(); }
         return;
     }
-    if (use_gpu && tracingMethod != 0)
-        throw POV_EXCEPTION_STRING("pvgpu: anti-aliased tracing methods are not wired into this adapter yet; render with -A");
+    // anti-aliasing: methods 1 and 2 run on the device; the aaGamma curve must be neutral or a power law
+    double aa_decoding_gamma = 1.0;
+    if (use_gpu && tracingMethod != 0) {
+        if (tracingMethod > 2)
+            throw POV_EXCEPTION_STRING("pvgpu: sampling method 3 (stochastic supersampling) is outside the GPU trace path; use +AM1 or +AM2");
+        if (!GammaCurve::IsNeutral(aaGamma)) {
+            if (dynamic_cast<PowerLawGammaCurve*>(aaGamma.get()) == nullptr)
+                throw POV_EXCEPTION_STRING("pvgpu: Antialias_Gamma combined with a non-power-law working gamma is outside the GPU trace path");
+            aa_decoding_gamma = aaGamma->ApproximateDecodingGamma();
+        }
+    }
 
     std::shared_ptr<GpuView> gv = flatten_scene(vd, use_gpu);
 
@@ -596,7 +606,11 @@ void TraceTask::Run()
         }
         gpu_pixels.resize(total * 4);
         pvgpu_aa aa{};
-        aa.method = 0;
+        aa.method = tracingMethod;
+        aa.depth = aaDepth;
+        aa.threshold = aaThreshold;
+        aa.jitter_scale = jitterScale;
+        aa.gamma = aa_decoding_gamma;
         pvgpu_stats st{};
         check(pvgpu_render(gv->scene, &aa, (int)width, (int)height, pr.data(), pr.size(), gpu_pixels.data(), &st, nullptr, nullptr), "render");
         // the stock statistics page keeps working: counters the device kept in the reference's units
@@ -606,6 +620,7 @@ void TraceTask::Run()
         GetViewDataPtr()->Stats()[Refracted_Rays_Traced] += st.refracted_rays;
         GetViewDataPtr()->Stats()[Transmitted_Rays_Traced] += st.transmitted_rays;
         GetViewDataPtr()->Stats()[ADC_Saves] += st.adc_saves;
+        GetViewDataPtr()->Stats()[Number_Of_Samples] += st.samples;
         vd->SetHighestTraceLevel(st.max_trace_level);
     }
 

@@ -106,7 +106,7 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
     const TStack stack{ nullptr, stack_mem, 0 };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double x, y;
-        uint32_t slot = first + i;
+        uint32_t slot = src.slot_base + first + i;
         if (src.coords) {
             const double2 c = src.coords[first + i];
             x = c.x; y = c.y;

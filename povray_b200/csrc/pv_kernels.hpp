@@ -18,8 +18,29 @@ struct SampleSource {
     const pvgpu_rect* rects;      // mode 0: pixel centres of rectangles, rect-major (SimpleSamplingM0, tracetask.cpp:438)
     const uint32_t*   rect_off;
     uint32_t          n_rects;
-    const double2*    coords;     // mode 1: explicit image-plane coordinates (anti-aliasing passes), slot = slots[i] or first + i
-    const uint32_t*   slots;
+    const double2*    coords;     // mode 1: explicit image-plane coordinates (anti-aliasing passes)
+    const uint32_t*   slots;      // accumulator slot per sample, or nullptr: slot = slot_base + sample index
+    uint32_t          slot_base;
+};
+
+// Anti-aliasing parameters as the kernels use them (TraceTask members, tracetask.h:107-118)
+struct AAParams {
+    int      method;
+    uint32_t depth;               // aaDepth
+    double   threshold;           // aaThreshold
+    double   jitter_scale;        // jitterScale after the per-method division (tracetask.cpp:526, 611); 0 = no jitter
+    float    enc_gamma;           // encoding exponent of the power-law aaGamma curve
+    int      neutral;             // aaGamma is neutral (no encoding)
+};
+
+// Slot layout of one anti-aliased render call
+struct AALayout {
+    const pvgpu_rect* rects;
+    const uint32_t*   rect_off;   // pixels of the rectangles before rectangle r
+    const uint32_t*   frame_off;  // method 1: frame samples (w + h per rectangle) before rectangle r
+    const uint32_t*   corner_off; // method 2: corner samples ((w+1)(h+1) per rectangle) before rectangle r
+    uint32_t n_rects, n_px, n_frame, n_corner;
+    uint32_t s_base;              // first slot of the supersampling sums (method 1) / sample buffers (method 2)
 };
 
 int  sm_count();
@@ -35,6 +56,17 @@ void launch_shadow_opaque(const DScene& sc, const SRay* rays, uint32_t n_max, fl
 void launch_shadow_filter(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st);
 void launch_probe_results(const HitRec* hits, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux, cudaStream_t st);
+void launch_aa1_frame_coords(const AALayout& L, double2* coords, cudaStream_t st);
+void launch_aa1_candidates(const AALayout& L, const AAParams& aa, const float4* accum, int32_t* s_slot, uint32_t* cand_list, unsigned int* n_cand, cudaStream_t st);
+void launch_aa1_sample_coords(const AALayout& L, const AAParams& aa, const uint16_t* hash, const uint32_t* cand_list, uint32_t first, uint32_t n,
+                              const double2* offsets, uint32_t n_off, double2* coords, uint32_t* slots, cudaStream_t st);
+void launch_aa1_decide(const AALayout& L, const AAParams& aa, const float4* accum, int32_t* s_slot, uint32_t* cand_list, unsigned int* n_cand,
+                       float4* out, uint8_t* flag, unsigned int* n_supersampled, cudaStream_t st);
+void launch_aa2_corner_coords(const AALayout& L, double2* coords, cudaStream_t st);
+void launch_aa2_mark(const AALayout& L, const AAParams& aa, const float4* accum, int32_t* act_idx, uint32_t* act_list, unsigned int* n_active, cudaStream_t st);
+void launch_aa2_expand(const AALayout& L, const AAParams& aa, const uint16_t* hash, const float4* accum, const uint32_t* act_list, uint32_t n_active,
+                       int target, uint32_t* sampled, double2* coords, uint32_t* slots, unsigned int* n_samples, uint32_t cap, cudaStream_t st);
+void launch_aa2_resolve(const AALayout& L, const AAParams& aa, const float4* accum, const int32_t* act_idx, float4* out, cudaStream_t st);
 void launch_camera_rays(const DScene& sc, const double* xy, uint32_t n, double width, double height, double* org_dir, cudaStream_t st);
 
 }  // namespace pvgpu

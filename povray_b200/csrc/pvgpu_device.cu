@@ -388,6 +388,10 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
     DeviceScene& d = *f.s.dev;
     if (n_samples == 0) return PVGPU_OK;
     const size_t batch = std::min<size_t>(kBatchSamples, n_samples);
+    {
+        int rc = ensure_work_buffers(d, std::max<size_t>(3 * batch, 1024), kShadowCap, 0);
+        if (rc != PVGPU_OK) return rc;
+    }
     struct Span { uint32_t first, n; };
     std::vector<Span> todo;
     for (uint32_t b = 0; b < n_samples; b += (uint32_t)batch) todo.push_back({ b, (uint32_t)std::min<size_t>(batch, n_samples - b) });
@@ -396,8 +400,8 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
         Span sp = todo.back(); todo.pop_back();
         if (f.cooperate && f.cooperate(f.user)) return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback");
         int rc = run_batch(f, src, sp.first, sp.n);
-        if (rc == PVGPU_E_OVERFLOW && sp.n > 1 && clear_slots) {
-            CUDA_TRY(cudaMemsetAsync(f.accum + sp.first, 0, (size_t)sp.n * sizeof(float4), f.stream));
+        if (rc == PVGPU_E_OVERFLOW && sp.n > 1 && clear_slots && !src.slots) {
+            CUDA_TRY(cudaMemsetAsync(f.accum + src.slot_base + sp.first, 0, (size_t)sp.n * sizeof(float4), f.stream));
             CUDA_TRY(cudaMemsetAsync(&d.cnt->overflow, 0, sizeof(unsigned int), f.stream));
             todo.push_back({ sp.first + sp.n / 2, sp.n - sp.n / 2 });
             todo.push_back({ sp.first, sp.n / 2 });
@@ -408,12 +412,199 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
     return PVGPU_OK;
 }
 
+// Device scratch of one anti-aliased call, freed on scope exit.
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> int alloc(T*& out, size_t n)
+    {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        ptrs.push_back(p);
+        out = reinterpret_cast<T*>(p);
+        return PVGPU_OK;
+    }
+};
+#define AA_TRY(expr) do { int rc__ = (expr); if (rc__ != PVGPU_OK) return rc__; } while (0)
+
+static int read_counter(const unsigned int* d_ptr, cudaStream_t stream, unsigned int& out)
+{
+    CUDA_TRY(cudaMemcpyAsync(&out, d_ptr, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return PVGPU_OK;
+}
+
+static AAParams make_aa_params(const pvgpu_aa& aa)
+{
+    AAParams p{};
+    p.method = (int)aa.method;
+    p.depth = aa.depth;
+    p.threshold = aa.threshold;
+    // jitterScale = jitterScale / aaDepth (tracetask.cpp:526) resp. / ((1 << aaDepth) + 1) (tracetask.cpp:611)
+    p.jitter_scale = (aa.method == 1) ? aa.jitter_scale / (double)aa.depth : aa.jitter_scale / (double)((1u << aa.depth) + 1u);
+    p.neutral = !(aa.gamma > 0.0 && aa.gamma != 1.0);
+    p.enc_gamma = p.neutral ? 1.0f : 1.0f / (float)aa.gamma;       // PowerLawGammaCurve::GetByDecodingGamma (colourspace.cpp:306)
+    return p;
+}
+
+// NonAdaptiveSupersamplingM1 (tracetask.cpp:521-602) for all rectangles of the call; see k_aa.cu for the scheme.
+static int render_aa1(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, size_t n_rects, const std::vector<uint32_t>& off, float4* d_out,
+                      unsigned long long& n_extra_samples)
+{
+    Scene& s = f.s;
+    DeviceScene& d = *s.dev;
+    cudaStream_t stream = f.stream;
+    const uint32_t n_px = off[n_rects];
+    std::vector<uint32_t> foff(n_rects + 1, 0);
+    for (size_t i = 0; i < n_rects; i++)
+        foff[i + 1] = foff[i] + (uint32_t)(rects[i].right - rects[i].left + 1) + (uint32_t)(rects[i].bottom - rects[i].top + 1);
+    const uint32_t n_frame = foff[n_rects];
+    if ((unsigned long long)n_px * 2 + n_frame > 0xFFFFFFF0ull) return fail(PVGPU_E_INVALID, "too many pixels in one anti-aliased call");
+    // SupersampleOnePixel's offsets: the reference's own floating-point loop (tracetask.cpp:862-869)
+    std::vector<double2> offsets;
+    {
+        const double step = 1.0 / (double)aa.depth, range = 0.5 - (step * 0.5);
+        for (double yy = -range; yy <= (range + PV_EPSILON); yy += step)
+            for (double xx = -range; xx <= (range + PV_EPSILON); xx += step) offsets.push_back(make_double2(xx, yy));
+    }
+    const uint32_t n_off = (uint32_t)offsets.size();
+    const AAParams ap = make_aa_params(aa);
+
+    Scratch sc;
+    float4* accum = nullptr; uint32_t* d_foff = nullptr; double2* d_fcoords = nullptr; int32_t* s_slot = nullptr; uint32_t* cand = nullptr;
+    unsigned int* counters = nullptr; uint8_t* flag = nullptr; double2* d_offsets = nullptr; double2* d_coords = nullptr; uint32_t* d_slots = nullptr;
+    const size_t n_slots = (size_t)n_px * 2 + n_frame;
+    const uint32_t cand_chunk = std::max<uint32_t>(1u, (uint32_t)(kBatchSamples / n_off));
+    AA_TRY(sc.alloc(accum, n_slots)); AA_TRY(sc.alloc(d_foff, n_rects + 1)); AA_TRY(sc.alloc(d_fcoords, n_frame));
+    AA_TRY(sc.alloc(s_slot, n_px)); AA_TRY(sc.alloc(cand, n_px)); AA_TRY(sc.alloc(counters, 4)); AA_TRY(sc.alloc(flag, n_px));
+    AA_TRY(sc.alloc(d_offsets, n_off)); AA_TRY(sc.alloc(d_coords, (size_t)cand_chunk * n_off)); AA_TRY(sc.alloc(d_slots, (size_t)cand_chunk * n_off));
+    CUDA_TRY(cudaMemsetAsync(accum, 0, n_slots * sizeof(float4), stream));
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream));
+    CUDA_TRY(cudaMemcpyAsync(d_foff, foff.data(), foff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_offsets, offsets.data(), n_off * sizeof(double2), cudaMemcpyHostToDevice, stream));
+    f.accum = accum;
+    AALayout L{};
+    L.rects = d.rects; L.rect_off = d.rect_off; L.frame_off = d_foff; L.corner_off = nullptr;
+    L.n_rects = (uint32_t)n_rects; L.n_px = n_px; L.n_frame = n_frame; L.n_corner = 0; L.s_base = n_px + n_frame;
+
+    // 1. pixel centres, 2. the frame above / left of every rectangle
+    SampleSource src{};
+    src.rects = d.rects; src.rect_off = d.rect_off; src.n_rects = (uint32_t)n_rects;
+    AA_TRY(trace_samples(f, src, n_px, true));
+    { TimedLaunch t(d, stream, KIND_AA, n_frame); launch_aa1_frame_coords(L, d_fcoords, stream); }
+    SampleSource fsrc{};
+    fsrc.coords = d_fcoords; fsrc.slot_base = n_px;
+    AA_TRY(trace_samples(f, fsrc, n_frame, true));
+    // 3. candidates from un-supersampled colours
+    { TimedLaunch t(d, stream, KIND_AA, n_px); launch_aa1_candidates(L, ap, accum, s_slot, cand, counters, stream); }
+    unsigned int n_cand = 0, n_done = 0;
+    AA_TRY(read_counter(counters, stream, n_cand));
+    // 4. trace what is queued, replay the sequential walk, repeat while the walk queues more
+    for (int round = 0; round < 64; round++) {
+        while (n_done < n_cand) {
+            const uint32_t cn = std::min<uint32_t>(cand_chunk, n_cand - n_done);
+            { TimedLaunch t(d, stream, KIND_AA, cn); launch_aa1_sample_coords(L, ap, d.view.noise.hash, cand, n_done, cn, d_offsets, n_off, d_coords, d_slots, stream); }
+            SampleSource ssrc{};
+            ssrc.coords = d_coords; ssrc.slots = d_slots;
+            AA_TRY(trace_samples(f, ssrc, cn * n_off, false));
+            n_done += cn;
+            n_extra_samples += (unsigned long long)cn * n_off;
+        }
+        CUDA_TRY(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned int), stream));
+        { TimedLaunch t(d, stream, KIND_AA, n_rects); launch_aa1_decide(L, ap, accum, s_slot, cand, counters, d_out, flag, counters + 1, stream); }
+        AA_TRY(read_counter(counters, stream, n_cand));
+        if (n_cand == n_done) return PVGPU_OK;
+    }
+    return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 1 did not settle");
+}
+
+// AdaptiveSupersamplingM2 (tracetask.cpp:604-657, 892-1074) for all rectangles of the call; see k_aa.cu.
+static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, size_t n_rects, const std::vector<uint32_t>& off, float4* d_out,
+                      unsigned long long& n_extra_samples)
+{
+    Scene& s = f.s;
+    DeviceScene& d = *s.dev;
+    cudaStream_t stream = f.stream;
+    const uint32_t n_px = off[n_rects];
+    std::vector<uint32_t> coff(n_rects + 1, 0);
+    for (size_t i = 0; i < n_rects; i++) {
+        unsigned long long c = (unsigned long long)(rects[i].right - rects[i].left + 2) * (unsigned long long)(rects[i].bottom - rects[i].top + 2);
+        if (coff[i] + c > 0xFFFFFFF0ull) return fail(PVGPU_E_INVALID, "too many pixels in one anti-aliased call");
+        coff[i + 1] = coff[i] + (uint32_t)c;
+    }
+    const uint32_t n_corner = coff[n_rects];
+    const AAParams ap = make_aa_params(aa);
+    const uint32_t S1 = (1u << aa.depth) + 1u, per = S1 * S1, words = (per + 31) / 32;
+
+    Scratch sc;
+    float4* corners = nullptr; uint32_t* d_coff = nullptr; double2* d_ccoords = nullptr; int32_t* act_idx = nullptr; uint32_t* act_list = nullptr;
+    unsigned int* counters = nullptr;
+    AA_TRY(sc.alloc(corners, n_corner)); AA_TRY(sc.alloc(d_coff, n_rects + 1)); AA_TRY(sc.alloc(d_ccoords, n_corner));
+    AA_TRY(sc.alloc(act_idx, n_px)); AA_TRY(sc.alloc(act_list, n_px)); AA_TRY(sc.alloc(counters, 4));
+    CUDA_TRY(cudaMemsetAsync(corners, 0, (size_t)n_corner * sizeof(float4), stream));
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream));
+    CUDA_TRY(cudaMemcpyAsync(d_coff, coff.data(), coff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    AALayout L{};
+    L.rects = d.rects; L.rect_off = d.rect_off; L.frame_off = nullptr; L.corner_off = d_coff;
+    L.n_rects = (uint32_t)n_rects; L.n_px = n_px; L.n_frame = 0; L.n_corner = n_corner; L.s_base = n_corner;
+
+    // 1. pixel corners
+    { TimedLaunch t(d, stream, KIND_AA, n_corner); launch_aa2_corner_coords(L, d_ccoords, stream); }
+    f.accum = corners;
+    SampleSource csrc{};
+    csrc.coords = d_ccoords;
+    AA_TRY(trace_samples(f, csrc, n_corner, true));
+    // 2. pixels that subdivide get a sample buffer
+    { TimedLaunch t(d, stream, KIND_AA, n_px); launch_aa2_mark(L, ap, corners, act_idx, act_list, counters, stream); }
+    unsigned int n_active = 0;
+    AA_TRY(read_counter(counters, stream, n_active));
+    float4* accum = corners;
+    if (n_active) {
+        const unsigned long long n_slots = (unsigned long long)n_corner + (unsigned long long)n_active * per;
+        if (n_slots > 0xFFFFFFF0ull) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: %u subdividing pixels x %u samples exceed the slot range; render fewer rectangles per call", n_active, per);
+        uint32_t* sampled = nullptr;
+        AA_TRY(sc.alloc(accum, (size_t)n_slots)); AA_TRY(sc.alloc(sampled, (size_t)n_active * words));
+        CUDA_TRY(cudaMemsetAsync(accum, 0, (size_t)n_slots * sizeof(float4), stream));
+        CUDA_TRY(cudaMemcpyAsync(accum, corners, (size_t)n_corner * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemsetAsync(sampled, 0, (size_t)n_active * words * sizeof(uint32_t), stream));
+        f.accum = accum;
+        // 3. one tracing round per subdivision level
+        unsigned long long per_pixel = 5;
+        for (uint32_t round = 0; round + 1 < aa.depth; round++, per_pixel *= 4) {
+            const unsigned long long cap64 = std::min<unsigned long long>((unsigned long long)n_active * per_pixel, 0xFFFFFFF0ull);
+            const uint32_t cap = (uint32_t)cap64;
+            double2* d_coords = nullptr; uint32_t* d_slots = nullptr;
+            Scratch rs;
+            AA_TRY(rs.alloc(d_coords, cap)); AA_TRY(rs.alloc(d_slots, cap));
+            CUDA_TRY(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned int), stream));
+            { TimedLaunch t(d, stream, KIND_AA, n_active); launch_aa2_expand(L, ap, d.view.noise.hash, accum, act_list, n_active, (int)round, sampled, d_coords, d_slots, counters + 1, cap, stream); }
+            unsigned int n_new = 0;
+            AA_TRY(read_counter(counters + 1, stream, n_new));
+            if (n_new > cap) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: sample list overflow");
+            if (n_new == 0) break;
+            SampleSource ssrc{};
+            ssrc.coords = d_coords; ssrc.slots = d_slots;
+            AA_TRY(trace_samples(f, ssrc, n_new, false));
+            n_extra_samples += n_new;
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+    }
+    // 4. combine
+    { TimedLaunch t(d, stream, KIND_AA, n_px); launch_aa2_resolve(L, ap, accum, act_idx, d_out, stream); }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    return PVGPU_OK;
+}
+
 static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, const pvgpu_rect* rects, size_t n_rects,
                        float* d_out, pvgpu_stats* stats, cudaStream_t stream, int (*cooperate)(void*), void* user)
 {
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     if (width <= 0 || height <= 0 || !rects || !n_rects || !d_out) return fail(PVGPU_E_INVALID, "pvgpu_render: bad arguments");
-    if (aa && aa->method != 0) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method %u not available yet", aa->method);
+    const unsigned int method = aa ? aa->method : 0u;
+    if (method > 2) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method %u (stochastic supersampling) is outside the GPU trace path", method);
+    if (method && (aa->depth < 1 || aa->depth > 9)) return fail(PVGPU_E_INVALID, "anti-aliasing depth %u out of range 1..9", aa->depth);
+    if (method == 2 && aa->depth > 5) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method 2 is limited to depth 5 on the GPU path (sample buffers of (2^depth + 1)^2 per pixel)");
     CUDA_TRY(cudaSetDevice(s.device));
     DeviceScene& d = *s.dev;
     std::vector<uint32_t> off(n_rects + 1, 0);
@@ -443,9 +634,13 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
     CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)n_samples * 4 * sizeof(float), stream));
 
     FrameCtx f{ s, stream, width, height, reinterpret_cast<float4*>(d_out), pvgpu_stats{}, cooperate, user };
-    SampleSource src{};
-    src.rects = d.rects; src.rect_off = d.rect_off; src.n_rects = (uint32_t)n_rects;
-    rc = trace_samples(f, src, n_samples, true);
+    unsigned long long n_extra_samples = 0;
+    if (method == 0) {
+        SampleSource src{};
+        src.rects = d.rects; src.rect_off = d.rect_off; src.n_rects = (uint32_t)n_rects;
+        rc = trace_samples(f, src, n_samples, true);
+    } else if (method == 1) rc = render_aa1(f, *aa, rects, n_rects, off, reinterpret_cast<float4*>(d_out), n_extra_samples);
+    else rc = render_aa2(f, *aa, rects, n_rects, off, reinterpret_cast<float4*>(d_out), n_extra_samples);
     if (rc != PVGPU_OK) return rc;
 
     Counters hc;
@@ -458,7 +653,7 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
     pvgpu_stats& st = f.st;
     st.rays = hc.rays; st.shadow_ray_tests = hc.shadow_tests; st.reflected_rays = hc.reflected;
     st.refracted_rays = hc.refracted; st.transmitted_rays = hc.transmitted; st.tir_rays = hc.tir;
-    st.adc_saves = hc.adc_saves; st.samples = 0; st.max_trace_level = hc.max_level; st.overflow = hc.overflow;
+    st.adc_saves = hc.adc_saves; st.samples = n_extra_samples; st.max_trace_level = hc.max_level; st.overflow = hc.overflow;
     st.kernel_launches = d.kernel_launches - launches0;
     st.device_ms = ms;
     for (const DeviceScene::Timed& t : d.timed) {
