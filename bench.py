@@ -185,11 +185,12 @@ def ours(args):
     scene.finalize(local_rank)
     t_upload = time.time() - t0
 
+    from povray_b200 import shard
     all_tiles = pv.tiles(W, H, BLOCK)
-    mine = all_tiles[rank::world]                      # round-robin deal: statistically balanced, no exchange needed
+    mine = shard.deal(all_tiles, rank, world)          # round-robin deal: statistically balanced, no exchange needed
     rect_arr = _rect_array(mine)
     n_px = _area(mine)
-    max_px = max(_area(all_tiles[r::world]) for r in range(world))
+    max_px = shard.padded_pixels(all_tiles, world)
     dev = torch.device("cuda", local_rank)
     out = torch.zeros(max_px * 4, dtype=torch.float32, device=dev)
     gathered = [torch.empty_like(out) for _ in range(world)] if (world > 1 and rank == 0) else None
