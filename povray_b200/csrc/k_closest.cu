@@ -52,7 +52,7 @@ __device__ inline void container_state(const DScene& sc, const V3& p, uint16_t* 
     stack.set(sp++, make_uint2(0u, 0u));
     while (sp > 0) {
         const uint32_t ni = stack.get(--sp).y;
-        const NodeL nd = load_node(sc.nodes + ni);
+        const pvgpu_node nd = sc.nodes[ni];
         if (!inside_bbox(nd.lo, nd.size)) continue;
         if (nd.count == 0) test_object(nd.first, sp);
         else for (uint32_t c = nd.count; c-- > 0 && sp < PV_STACK_SIZE;) stack.set(sp++, make_uint2(0u, nd.first + c));

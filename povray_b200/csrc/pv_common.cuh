@@ -56,8 +56,23 @@ struct __align__(16) DTri {
 };
 static_assert(sizeof(DTri) == 64, "DTri must be 64 bytes");
 
+// Traversal copy of a BBOX_TREE node (derived at upload from pvgpu_node): 32 bytes = one sector.
+//   hi   = lowerLeft + size rounded in FP32 - the very sum the reference forms at every slab test (boundingbox.cpp:576-591)
+//   code = what a traversal stack entry needs: [31:28] number of children (0 = leaf), [27] BBOX_TREE::Infinite,
+//          [26:0] first child (inner node) or object / triangle index (leaf).  Nodes with more than 14 children (only
+//          the node collecting the infinite objects can have that many) are split at upload into groups that repeat
+//          the parent's box, which changes no test result.
+#define PV_CODE_INFINITE 0x08000000u
+#define PV_CODE_INDEX    0x07FFFFFFu
+struct __align__(16) DNode {
+    float    lo[3], hi[3];
+    uint32_t code;
+    uint32_t aux;
+};
+static_assert(sizeof(DNode) == 32, "DNode must be 32 bytes");
+
 struct DMesh {                   // pvgpu_mesh with absolute offsets resolved
-    uint32_t tri_first, tri_count, node_first, node_count;
+    uint32_t tri_first, tri_count, node_first, node_count;    // node_first: root of the mesh tree in dmnodes
     uint32_t vertex_first, normal_first, texture_first, texture_count;
     uint32_t has_inside_vector;
     double inside_vector[3];
@@ -77,13 +92,14 @@ struct DScene {
     const pvgpu_transform*   xf;
     const uint32_t*          index_list;
     const uint32_t*          frame;
-    const pvgpu_node*        nodes;         // scene tree, root 0
+    const pvgpu_node*        nodes;         // scene tree, root 0 (verbatim; container state only)
+    const DNode*             dnodes;        // scene tree, traversal copy
+    const DNode*             dmnodes;       // mesh trees, traversal copy (node_first of a mesh indexes this array)
     const DMesh*             meshes;
     const DTri*              dtris;
     const pvgpu_triangle*    tris;
     const float*             verts;
     const float*             norms;
-    const pvgpu_node*        mnodes;
     const pvgpu_light*       lights;
     const pvgpu_texture*     textures;
     const pvgpu_pigment*     pigments;

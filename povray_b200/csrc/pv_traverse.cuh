@@ -50,33 +50,20 @@ __device__ __forceinline__ RayInfo make_rayinfo(const V3& o, const V3& d)
 #define PV_EPSILON_F32   1.0e-10f      // (double)1.0e-10f = 1.00000001335e-10 >= 1e-10; checked in device_upload()
 #define PV_BOUND_HUGE_F  2.0e10f
 
-// One BBOX_TREE node as it sits in HBM (pvgpu_node, 32 bytes = one sector), fetched with two 128-bit loads.
+// One traversal node (DNode, 32 bytes = one sector), fetched with two 128-bit loads.
 struct NodeL {
-    float lo[3], size[3];
-    uint32_t first;
-    uint32_t count;      // BBOX_TREE::Entries
-    uint32_t flags;      // PVGPU_NODE_*
+    float lo[3], hi[3];
+    uint32_t code;       // doubles as the stack entry: children count | infinite flag | first child or leaf payload
 };
-__device__ __forceinline__ NodeL load_node(const pvgpu_node* p)
+__device__ __forceinline__ NodeL load_node(const DNode* p)
 {
     const uint4* q = reinterpret_cast<const uint4*>(p);
     const uint4 a = __ldg(q), b = __ldg(q + 1);
     NodeL n;
     n.lo[0] = __uint_as_float(a.x); n.lo[1] = __uint_as_float(a.y); n.lo[2] = __uint_as_float(a.z);
-    n.size[0] = __uint_as_float(a.w); n.size[1] = __uint_as_float(b.x); n.size[2] = __uint_as_float(b.y);
-    n.first = b.z;
-    n.count = b.w & 0xFFFFu;
-    n.flags = b.w >> 16;
+    n.hi[0] = __uint_as_float(a.w); n.hi[1] = __uint_as_float(b.x); n.hi[2] = __uint_as_float(b.y);
+    n.code = b.z;
     return n;
-}
-
-// Traversal stack entry: x = entry depth (FP32 bits), y = what to do when popped:
-//   top nibble 0      : leaf, low 28 bits = object / triangle index
-//   top nibble 1..14  : inner node with that many children starting at node (low 28 bits)
-//   top nibble 15     : inner node with >= 15 children (only the node of infinite objects): low 28 bits = node index, reloaded
-__device__ __forceinline__ uint32_t stack_code(const NodeL& n, uint32_t index)
-{
-    return (n.count < 15u) ? (n.first | (n.count << 28)) : (index | 0xF0000000u);
 }
 
 // Branch-free form: the reference's cascade of early exits is, as its own comment says (boundingbox.cpp:597-603),
@@ -86,13 +73,11 @@ __device__ __forceinline__ uint32_t stack_code(const NodeL& n, uint32_t index)
 // Axes with a zero direction component do not take part in the reference (containment test instead): their
 // products are 0 * finite = 0 here and the per-ray constants cmin / cmax (-/+BOUND_HUGE) neutralise them, while for
 // all other axes the constants are 0 and adding them changes nothing.
-__device__ __forceinline__ bool slab_test(const float* lo, const float* size, const RayInfo& ri, float& dmin_out)
+__device__ __forceinline__ bool slab_test(const float* lo, const float* hi, const RayInfo& ri, float& dmin_out)
 {
     float dmin = -PV_BOUND_HUGE_F, dmax = PV_BOUND_HUGE_F;
-    float hi[3];
     #pragma unroll
     for (int k = 0; k < 3; k++) {
-        hi[k] = __fadd_rn(lo[k], size[k]);
         const float near_p = ri.positive[k] ? lo[k] : hi[k];
         const float far_p = ri.positive[k] ? hi[k] : lo[k];
         const float tmin = __fadd_rn(__fmul_rn(__fsub_rn(near_p, ri.org[k]), ri.inv[k]), ri.cmin[k]);
@@ -151,7 +136,7 @@ __device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
 //   limit: children entered beyond this depth are not pushed at all (a conservative FP32 upper bound of the best depth
 //   so far; the exact test is repeated when an entry is popped, so this only saves stack traffic).
 template <bool ALLOW_INFINITE, bool ORDERED>
-__device__ __forceinline__ void push_children(const pvgpu_node* __restrict__ nodes, uint32_t first, uint32_t count, const RayInfo& ri,
+__device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, uint32_t first, uint32_t count, const RayInfo& ri,
                                               const TStack& stack, int& sp, unsigned int* overflow, float limit = 3.0e38f)
 {
     const float kInvalid = __int_as_float(0x7f800000);     // +inf: sorts first, never pushed
@@ -164,11 +149,11 @@ __device__ __forceinline__ void push_children(const pvgpu_node* __restrict__ nod
         #pragma unroll
         for (int k = 0; k < 4; k++) {
             float dmin;
-            bool ok = slab_test(ch[k].lo, ch[k].size, ri, dmin);
-            if (ALLOW_INFINITE && (ch[k].flags & PVGPU_NODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
+            bool ok = slab_test(ch[k].lo, ch[k].hi, ri, dmin);
+            if (ALLOW_INFINITE && (ch[k].code & PV_CODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
             ok = ok && (c0 + k < count) && !(dmin > limit);
             key[k] = ok ? dmin : kInvalid;
-            val[k] = stack_code(ch[k], first + c0 + k);
+            val[k] = ch[k].code;
         }
         if (ORDERED) {
             // descending by entry depth; equal depths keep the child order (the ordinal rides in the comparison)
@@ -321,13 +306,13 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
         return;
     }
     const RayInfo ri = make_rayinfo(mo, md);
-    const pvgpu_node* __restrict__ nodes = sc.mnodes + me.node_first;
+    const DNode* __restrict__ nodes = sc.dmnodes + me.node_first;
     int sp = sp0;
     {
         const NodeL root = load_node(nodes);
         float dmin;
-        if (!slab_test(root.lo, root.size, ri, dmin)) return;
-        stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
+        if (!slab_test(root.lo, root.hi, ri, dmin)) return;
+        stack.set(sp++, make_uint2(__float_as_uint(dmin), root.code));
     }
     // "while-while" traversal: every lane first walks inner nodes until it holds a leaf (or runs out of work); the
     // warp reconverges behind that loop and the lanes that found a triangle run the FP64 test together, instead of
@@ -339,10 +324,9 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
         while (sp > sp0) {
             const uint2 e = stack.get(--sp);
             if ((double)__uint_as_float(e.x) > acc.closest * len) continue;
-            const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+            const uint32_t code = e.y >> 28, idx = e.y & PV_CODE_INDEX;
             if (code == 0u) { leaf = idx; break; }
-            uint32_t first = idx, count = code;
-            if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+            const uint32_t first = idx, count = code;
             push_children<false, true>(nodes, first, count, ri, stack, sp, overflow);
         }
         if (leaf == 0xFFFFFFFFu) break;
@@ -362,6 +346,11 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
 // provably reconverges between the two phases: every lane walks inner nodes until it holds a triangle (or runs out
 // of work), then the lanes that found one run the FP64 triangle test together.
 #define PV_FULL_MASK 0xffffffffu
+// phase vote: leaves are served when (#lanes holding a leaf) * NUM > (#lanes wanting a node visit) * DEN
+#ifndef PV_LEAF_BIAS_NUM
+#define PV_LEAF_BIAS_NUM 2
+#define PV_LEAF_BIAS_DEN 1
+#endif
 #define PV_NONE      0xFFFFFFFFu
 template <bool ANY_HIT>
 __device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t obj_index, const V3& o, const V3& d,
@@ -370,7 +359,7 @@ __device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t ob
     V3 mo = o, md = d;
     double len = 1.0;
     RayInfo ri;
-    const pvgpu_node* __restrict__ nodes = sc.mnodes;
+    const DNode* __restrict__ nodes = sc.dmnodes;
     uint32_t tri_first = 0;
     bool any_ok = false, clipped = false;
     int sp = sp0;
@@ -390,45 +379,43 @@ __device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t ob
                 md = md / len;
             }
             ri = make_rayinfo(mo, md);
-            nodes = sc.mnodes + me.node_first;
+            nodes = sc.dmnodes + me.node_first;
             tri_first = me.tri_first;
             clipped = ob.clip_count != 0;
             any_ok = ANY_HIT && (ob.flags & PVGPU_OPAQUE_FLAG) && !clipped;
             const NodeL root = load_node(nodes);
             float dmin;
-            if (slab_test(root.lo, root.size, ri, dmin)) stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
+            if (slab_test(root.lo, root.hi, ri, dmin)) stack.set(sp++, make_uint2(__float_as_uint(dmin), root.code));
         }
     }
+    // Every turn of the loop the warp votes: the lanes that want to walk an inner node and the lanes that hold a
+    // triangle are counted, and the larger group is served (node visit or FP64 triangle test); the others wait for
+    // their turn.  Both branches are warp-uniform, so the lanes served run converged.
     uint32_t tri = PV_NONE;
     for (;;) {
-        for (;;) {
-            const bool want = active && tri == PV_NONE && sp > sp0;
-            if (!__any_sync(PV_FULL_MASK, want)) break;
-            if (want) {
-                const uint2 e = stack.get(--sp);
-                // entries further than the closest accepted hit cannot improve it; compared in mesh space (t = world * len)
-                if (!((double)__uint_as_float(e.x) > fmin(acc.closest, limit0) * len)) {
-                    const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
-                    if (code == 0u) tri = idx;
-                    else {
-                        uint32_t first = idx, count = code;
-                        if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
-                        const double lim = fmin(acc.closest, limit0) * len;
-                        push_children<false, !ANY_HIT>(nodes, first, count, ri, stack, sp, overflow, (lim < 3.0e38) ? __double2float_ru(lim) : 3.0e38f);
-                    }
+        const bool want = active && tri == PV_NONE && sp > sp0;
+        const unsigned want_m = __ballot_sync(PV_FULL_MASK, want), hold_m = __ballot_sync(PV_FULL_MASK, tri != PV_NONE);
+        if ((want_m | hold_m) == 0u) break;
+        if (__popc(hold_m) * PV_LEAF_BIAS_NUM > __popc(want_m) * PV_LEAF_BIAS_DEN || want_m == 0u) {
+            if (tri != PV_NONE) {
+                double t;
+                const uint32_t ti = tri_first + tri;
+                tri = PV_NONE;
+                if (tri_intersect(sc.dtris[ti], mo, md, t)) {
+                    const double wd = t / len;
+                    const V3 ip = evaluate(o, d, wd);
+                    if (!clipped || point_in_clip(sc, sc.objs[obj_index], ip, stack, sp)) consider(acc, wd, ip, obj_index, ti, -1);
+                    if (any_ok && acc.found && acc.closest > PV_SHADOW_TOLERANCE && acc.closest < any_limit) sp = sp0;   // blocked: drop the rest
                 }
             }
-        }
-        if (!__any_sync(PV_FULL_MASK, tri != PV_NONE)) break;
-        if (tri != PV_NONE) {
-            double t;
-            const uint32_t ti = tri_first + tri;
-            tri = PV_NONE;
-            if (tri_intersect(sc.dtris[ti], mo, md, t)) {
-                const double wd = t / len;
-                const V3 ip = evaluate(o, d, wd);
-                if (!clipped || point_in_clip(sc, sc.objs[obj_index], ip, stack, sp)) consider(acc, wd, ip, obj_index, ti, -1);
-                if (any_ok && acc.found && acc.closest > PV_SHADOW_TOLERANCE && acc.closest < any_limit) sp = sp0;   // blocked: drop the rest
+        } else if (want) {
+            const uint2 e = stack.get(--sp);
+            // entries further than the closest accepted hit cannot improve it; compared in mesh space (t = world * len)
+            const double lim = fmin(acc.closest, limit0) * len;
+            if (!((double)__uint_as_float(e.x) > lim)) {
+                const uint32_t code = e.y >> 28, idx = e.y & PV_CODE_INDEX;
+                if (code == 0u) tri = idx;
+                else push_children<false, !ANY_HIT>(nodes, idx, code, ri, stack, sp, overflow, (lim < 3.0e38) ? __double2float_ru(lim) : 3.0e38f);
             }
         }
     }
@@ -453,18 +440,17 @@ __device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, con
         }
     } else {
         const RayInfo ri = make_rayinfo(mo, md);
-        const pvgpu_node* __restrict__ nodes = sc.mnodes + me.node_first;
+        const DNode* __restrict__ nodes = sc.dmnodes + me.node_first;
         int sp = sp0;
         float dmin;
         unsigned int ovf = 0;
         const NodeL root = load_node(nodes);
-        if (slab_test(root.lo, root.size, ri, dmin)) stack.set(sp++, make_uint2(0u, stack_code(root, 0u)));
+        if (slab_test(root.lo, root.hi, ri, dmin)) stack.set(sp++, make_uint2(0u, root.code));
         while (sp > sp0) {
             const uint2 e = stack.get(--sp);
-            const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+            const uint32_t code = e.y >> 28, idx = e.y & PV_CODE_INDEX;
             if (code) {
-                uint32_t first = idx, count = code;
-                if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+                const uint32_t first = idx, count = code;
                 push_children<false, false>(nodes, first, count, ri, stack, sp, &ovf);
             } else {
                 double t;
@@ -624,24 +610,23 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
         return found;
     }
     const RayInfo ri = make_rayinfo(o, d);
-    const pvgpu_node* __restrict__ nodes = sc.nodes;
+    const DNode* __restrict__ nodes = sc.dnodes;
     int sp = 0;
     {
         const NodeL root = load_node(nodes);
         float dmin;
-        if (root.flags & PVGPU_NODE_INFINITE) dmin = -PV_MAX_DISTANCE_F;
-        else if (!slab_test(root.lo, root.size, ri, dmin)) return false;
-        stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
+        if (root.code & PV_CODE_INFINITE) dmin = -PV_MAX_DISTANCE_F;
+        else if (!slab_test(root.lo, root.hi, ri, dmin)) return false;
+        stack.set(sp++, make_uint2(__float_as_uint(dmin), root.code));
     }
     for (;;) {
         uint32_t leaf = 0xFFFFFFFFu;
         while (sp > 0) {
             const uint2 e = stack.get(--sp);
             if ((double)__uint_as_float(e.x) > best.depth) continue;      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
-            const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
+            const uint32_t code = e.y >> 28, idx = e.y & PV_CODE_INDEX;
             if (code == 0u) { leaf = idx; break; }
-            uint32_t first = idx, count = code;
-            if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
+            const uint32_t first = idx, count = code;
             push_children<true, true>(nodes, first, count, ri, stack, sp, overflow);
         }
         if (leaf == 0xFFFFFFFFu) break;
@@ -711,38 +696,33 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
         return found;
     }
     RayInfo ri;
-    const pvgpu_node* __restrict__ nodes = sc.nodes;
+    const DNode* __restrict__ nodes = sc.dnodes;
     if (alive) {
         ri = make_rayinfo(o, d);
         const NodeL root = load_node(nodes);
         float dmin;
         bool ok = true;
-        if (root.flags & PVGPU_NODE_INFINITE) dmin = -PV_MAX_DISTANCE_F;
-        else ok = slab_test(root.lo, root.size, ri, dmin);
-        if (ok) stack.set(sp++, make_uint2(__float_as_uint(dmin), stack_code(root, 0u)));
+        if (root.code & PV_CODE_INFINITE) dmin = -PV_MAX_DISTANCE_F;
+        else ok = slab_test(root.lo, root.hi, ri, dmin);
+        if (ok) stack.set(sp++, make_uint2(__float_as_uint(dmin), root.code));
     }
     uint32_t leaf = PV_NONE;
     for (;;) {
-        for (;;) {
-            const bool want = alive && leaf == PV_NONE && sp > 0;
-            if (!__any_sync(PV_FULL_MASK, want)) break;
-            if (want) {
-                const uint2 e = stack.get(--sp);
-                if (!((double)__uint_as_float(e.x) > best.depth)) {      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
-                    const uint32_t code = e.y >> 28, idx = e.y & 0x0FFFFFFFu;
-                    if (code == 0u) { if (precondition(sc.objs[idx].flags, rflags, shadow_ray)) leaf = idx; }
-                    else {
-                        uint32_t first = idx, count = code;
-                        if (code == 15u) { const NodeL n = load_node(nodes + idx); first = n.first; count = n.count; }
-                        push_children<true, !ANY_OPAQUE>(nodes, first, count, ri, stack, sp, overflow, (best.depth < 3.0e38) ? __double2float_ru(best.depth) : 3.0e38f);
-                    }
-                }
+        const bool want = alive && leaf == PV_NONE && sp > 0;
+        const unsigned want_m = __ballot_sync(PV_FULL_MASK, want), hold_m = __ballot_sync(PV_FULL_MASK, leaf != PV_NONE);
+        if ((want_m | hold_m) == 0u) break;
+        if (__popc(hold_m) * PV_LEAF_BIAS_NUM > __popc(want_m) * PV_LEAF_BIAS_DEN || want_m == 0u) {
+            const uint32_t cur = leaf;
+            leaf = PV_NONE;
+            if (leaf_phase(cur != PV_NONE, cur)) { alive = false; sp = 0; }
+        } else if (want) {
+            const uint2 e = stack.get(--sp);
+            if (!((double)__uint_as_float(e.x) > best.depth)) {      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
+                const uint32_t code = e.y >> 28, idx = e.y & PV_CODE_INDEX;
+                if (code == 0u) { if (precondition(sc.objs[idx].flags, rflags, shadow_ray)) leaf = idx; }
+                else push_children<true, !ANY_OPAQUE>(nodes, idx, code, ri, stack, sp, overflow, (best.depth < 3.0e38) ? __double2float_ru(best.depth) : 3.0e38f);
             }
         }
-        if (!__any_sync(PV_FULL_MASK, leaf != PV_NONE)) break;
-        const uint32_t cur = leaf;
-        leaf = PV_NONE;
-        if (leaf_phase(cur != PV_NONE, cur)) { alive = false; sp = 0; }
     }
     return found;
 }

@@ -65,6 +65,49 @@ static int upload(DeviceScene& d, const std::vector<T>& v, const T*& out, size_t
     return PVGPU_OK;
 }
 
+// Traversal copy of a node array (see DNode in pv_common.cuh).  `base` is added to child indices (mesh trees are stored
+// back to back in one array with indices relative to their own root).  Nodes with more than 14 children are split
+// into groups of <= 14 appended at the end of this tree's range; the groups repeat the parent's box and flags.
+static int make_dnodes(const pvgpu_node* nodes, size_t n, std::vector<DNode>& out)
+{
+    const size_t base = out.size();
+    out.resize(base + n);
+    // appended group nodes need contiguous children: children of `nodes` already are, so a group is a sub-range
+    std::vector<DNode> extra;
+    auto fill = [&](DNode& dn, const pvgpu_node& nd) {
+        for (int k = 0; k < 3; k++) { dn.lo[k] = nd.lo[k]; dn.hi[k] = nd.lo[k] + nd.size[k]; }     // FP32 add, as the reference does per test
+        dn.aux = 0;
+    };
+    for (size_t i = 0; i < n; i++) {
+        const pvgpu_node& nd = nodes[i];
+        DNode& dn = out[base + i];
+        fill(dn, nd);
+        const uint32_t inf = (nd.flags & PVGPU_NODE_INFINITE) ? PV_CODE_INFINITE : 0u;
+        if (nd.count == 0) {
+            if (nd.first > PV_CODE_INDEX) return fail(PVGPU_E_UNSUPPORTED, "more than 2^27 objects / triangles");
+            dn.code = inf | nd.first;
+        } else if (nd.count <= 14) {
+            dn.code = ((uint32_t)nd.count << 28) | inf | (uint32_t)(nd.first);
+        } else {
+            // groups of <= 14 children; a group node has the parent's box.  Up to 14 groups (196 children) per level.
+            std::vector<std::pair<uint32_t, uint32_t>> ranges;      // (first, count) at the current level, indices into this tree
+            for (uint32_t c = 0; c < nd.count; c += 14) ranges.push_back({ nd.first + c, std::min<uint32_t>(14u, nd.count - c) });
+            while (ranges.size() > 14) return fail(PVGPU_E_UNSUPPORTED, "a bounding node with more than 196 children");
+            const uint32_t gfirst = (uint32_t)(n + extra.size());
+            for (auto& r : ranges) {
+                DNode g;
+                fill(g, nd);
+                g.code = (r.second << 28) | inf | r.first;
+                extra.push_back(g);
+            }
+            dn.code = ((uint32_t)ranges.size() << 28) | inf | gfirst;
+        }
+    }
+    out.insert(out.end(), extra.begin(), extra.end());
+    if (out.size() - base > PV_CODE_INDEX) return fail(PVGPU_E_UNSUPPORTED, "more than 2^27 bounding nodes");
+    return PVGPU_OK;
+}
+
 // Noise tables: InitTextureTable (noise.cpp:231-255), RTable fill (noise.cpp:181-182),
 // InitSolidNoise (noise.cpp:306-348).
 static const double kRTableEven[267] = {
@@ -143,8 +186,8 @@ int device_upload(Scene& s, int device)
     // the FP32 stand-in for EPSILON in the slab test must be the smallest float >= 1e-10 (pv_traverse.cuh)
     if (!((double)1.0e-10f >= 1.0e-10 && (double)std::nextafterf(1.0e-10f, 0.0f) < 1.0e-10))
         return fail(PVGPU_E_INVALID, "internal: FP32 epsilon of the slab test is not the smallest float >= 1e-10");
-    if (s.nodes.size() >= (1u << 28) || s.mesh_nodes.size() >= (1u << 28) || s.triangles.size() >= (1u << 28) || s.objects.size() >= (1u << 28))
-        return fail(PVGPU_E_UNSUPPORTED, "more than 2^28 nodes / triangles / objects");
+    if (s.nodes.size() >= (1u << 27) || s.mesh_nodes.size() >= (1u << 27) || s.triangles.size() >= (1u << 27) || s.objects.size() >= (1u << 27))
+        return fail(PVGPU_E_UNSUPPORTED, "more than 2^27 nodes / triangles / objects");
     DeviceScene* d = new DeviceScene();
     s.dev = d;
     size_t total = 0;
@@ -204,12 +247,23 @@ int device_upload(Scene& s, int device)
     std::vector<uint16_t> hash, perm;
     std::vector<double> rtable, grad;
     build_noise_tables(hash, rtable, perm, grad);
+    // traversal copies of the trees; every mesh tree gets its own index space (children relative to its root)
+    std::vector<DNode> dnodes, dmnodes;
+    {
+        int rc = make_dnodes(s.nodes.data(), s.nodes.size(), dnodes);
+        for (size_t m = 0; m < s.meshes.size() && rc == PVGPU_OK; m++) {
+            const pvgpu_mesh& me = s.meshes[m];
+            dmeshes[m].node_first = (uint32_t)dmnodes.size();
+            rc = make_dnodes(s.mesh_nodes.data() + me.node_first, me.node_count, dmnodes);
+        }
+        if (rc != PVGPU_OK) { device_release(s); return rc; }
+    }
 
     int rc = PVGPU_OK;
     #define UP(vec, field) if (rc == PVGPU_OK) rc = upload(*d, vec, field, total)
     UP(s.objects, v.objs); UP(s.transforms, v.xf); UP(s.index_list, v.index_list); UP(s.frame, v.frame);
-    UP(s.nodes, v.nodes); UP(dmeshes, v.meshes); UP(dtris, v.dtris); UP(s.triangles, v.tris);
-    UP(s.vertices, v.verts); UP(s.normals, v.norms); UP(s.mesh_nodes, v.mnodes); UP(s.lights, v.lights);
+    UP(s.nodes, v.nodes); UP(dnodes, v.dnodes); UP(dmnodes, v.dmnodes); UP(dmeshes, v.meshes); UP(dtris, v.dtris); UP(s.triangles, v.tris);
+    UP(s.vertices, v.verts); UP(s.normals, v.norms); UP(s.lights, v.lights);
     UP(s.textures, v.textures); UP(s.pigments, v.pigments); UP(s.finishes, v.finishes); UP(s.blend_maps, v.maps);
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
     UP(leaves, v.csg_leaves); UP(leaf_range, v.csg_leaf_range);
