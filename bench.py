@@ -227,18 +227,25 @@ def ours(args):
     kern_ms = {k: sum(s.get(k, 0.0) for s in stats) for k in ("closest_ms", "shadow_ms", "shade_ms", "primary_ms")}
     kern_n = {k: sum(s.get(k, 0) for s in stats) for k in ("closest_launches", "shadow_launches", "closest_rays", "shadow_rays")}
 
-    # end to end: host buffers through the C-ABI call, wall clock (rank-local frame share; at N > 1 the host-side
-    # gather is the caller's memcpy of disjoint tiles and is not part of the library)
-    px = None
+    # end to end: HOST buffers through the C-ABI call (rectangle list in, RGBT float frame out), wall clock.  The frame
+    # lands in page-locked memory obtained from pvgpu_host_alloc (what the adapter uses); the same call with an ordinary
+    # pageable numpy array goes through the library's staging copy and is reported as e2e.pageable_ms_per_step.
+    # At N > 1 every rank delivers its own tiles to its host (the caller's scatter of disjoint tiles is not part of the library).
+    hb = pv.HostBuffer(max_px * 4)
     for _ in range(2):
-        px, _ = scene.render(W, H, mine)
+        scene.render(W, H, mine, out=hb.array)
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
     for _ in range(args.steps):
-        px, st = scene.render(W, H, mine)
+        px, st = scene.render(W, H, mine, out=hb.array)
         e2e_rays += st["rays"] + st["shadow_ray_tests"]
     e2e_s = time.perf_counter() - t0
+    scene.render(W, H, mine)
+    t0 = time.perf_counter()
+    for _ in range(min(args.steps, 3)):
+        scene.render(W, H, mine)
+    e2e_pageable_s = (time.perf_counter() - t0) / min(args.steps, 3)
 
     vals = torch.tensor([ms, float(rays), float(launches), e2e_s, float(e2e_rays), kern_ms["closest_ms"], kern_ms["shadow_ms"],
                          float(kern_n["closest_rays"]), float(kern_n["shadow_rays"]), float(kern_n["closest_launches"]), float(kern_n["shadow_launches"]),
@@ -266,7 +273,8 @@ def ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "h2d_bytes_per_step": len(mine) * 16, "d2h_bytes_per_step": n_px * 16}}
+                    "h2d_bytes_per_step": len(mine) * 16, "d2h_bytes_per_step": n_px * 16,
+                    "pageable_ms_per_step": 1e3 * e2e_pageable_s}}
 
     # roofline of the dominant kernel, timed live with CUDA events inside the library (same stream as the launches)
     peaks = {}
@@ -280,9 +288,18 @@ def ours(args):
         dom = "k_closest" if t_ms >= s_ms else "k_shadow"
         d_ms, d_rays, d_n = (t_ms, float(vals[7]), float(vals[9])) if dom == "k_closest" else (s_ms, float(vals[8]), float(vals[10]))
         bpr = ALG_BYTES_PER_RAY[args.workload]
+        traffic = None
+        try:      # DRAM bytes per launch of this kernel family from the committed ncu --set full capture (config 2 only)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if args.workload == "cfg2":
+                b = tj[dom]["dram_bytes_per_launch"]
+                traffic = sum(b) / len(b)
+        except Exception:
+            pass
         achieved = d_rays * bpr / (d_ms * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "peak_source": which, "traffic": None, "alg_bytes_per_ray": bpr, "rays_per_launch": d_rays / max(d_n, 1),
+                            "peak_source": which, "traffic": traffic, "traffic_note": "mean DRAM bytes of the two launches captured in profiles/r1_traffic.json",
+                            "alg_bytes_per_launch": bpr * d_rays / max(d_n, 1), "alg_bytes_per_ray": bpr, "rays_per_launch": d_rays / max(d_n, 1),
                             "avg_launch_ms": d_ms / max(d_n, 1), "share_of_step": d_ms / ms,
                             "kernel_ms_per_step": {"k_primary": float(vals[12]) / args.steps, "k_closest": t_ms / args.steps,
                                                    "k_shade": float(vals[11]) / args.steps, "k_shadow": s_ms / args.steps}}

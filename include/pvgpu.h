@@ -397,6 +397,11 @@ int  pvgpu_render(pvgpu_scene* s, const pvgpu_aa* aa, int width, int height,
                   const pvgpu_rect* rects, size_t n_rects, float* rgbt_out,
                   pvgpu_stats* stats, int (*cooperate)(void*), void* user);
 
+/* Page-locked host memory for rgbt_out: pvgpu_render copies the frame straight into such a buffer with one DMA
+ * transfer; any other host pointer is served through an internal pinned staging buffer and an extra memcpy. */
+void* pvgpu_host_alloc(size_t bytes);
+void  pvgpu_host_free(void* p);
+
 /* Same, but the result stays in DEVICE memory (`d_rgbt_out` is a device pointer with room for the
  * rect-area sum x 4 floats) and the work is enqueued on `cuda_stream` (a cudaStream_t, 0 = default). */
 int  pvgpu_render_device(pvgpu_scene* s, const pvgpu_aa* aa, int width, int height,

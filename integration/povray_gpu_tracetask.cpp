@@ -595,7 +595,8 @@ void TraceTask::Run()
     if (dump_gpu) frame_gpu.assign((size_t)width * height * 4, 0.0f);
     if (dump_rays) frame_rays.assign((size_t)width * height, RayDumpRecord{});
 
-    vector<float> gpu_pixels;
+    // page-locked frame buffer from the library: pvgpu_render then needs no staging copy
+    std::unique_ptr<float, void (*)(float*)> gpu_pixels(nullptr, [](float* p) { pvgpu_host_free(p); });
     if (use_gpu) {
         vector<pvgpu_rect> pr(rects.size());
         size_t total = 0;
@@ -604,7 +605,8 @@ void TraceTask::Run()
             pr[i].right = (int32_t)rects[i].right; pr[i].bottom = (int32_t)rects[i].bottom;
             total += rects[i].GetArea();
         }
-        gpu_pixels.resize(total * 4);
+        gpu_pixels.reset(static_cast<float*>(pvgpu_host_alloc(total * 4 * sizeof(float))));
+        if (!gpu_pixels) throw POV_EXCEPTION_STRING("pvgpu: out of page-locked host memory");
         pvgpu_aa aa{};
         aa.method = tracingMethod;
         aa.depth = aaDepth;
@@ -612,7 +614,7 @@ void TraceTask::Run()
         aa.jitter_scale = jitterScale;
         aa.gamma = aa_decoding_gamma;
         pvgpu_stats st{};
-        check(pvgpu_render(gv->scene, &aa, (int)width, (int)height, pr.data(), pr.size(), gpu_pixels.data(), &st, nullptr, nullptr), "render");
+        check(pvgpu_render(gv->scene, &aa, (int)width, (int)height, pr.data(), pr.size(), gpu_pixels.get(), &st, nullptr, nullptr), "render");
         // the stock statistics page keeps working: counters the device kept in the reference's units
         GetViewDataPtr()->Stats()[Number_Of_Rays] += st.rays;
         GetViewDataPtr()->Stats()[Shadow_Ray_Tests] += st.shadow_ray_tests;
@@ -657,7 +659,7 @@ void TraceTask::Run()
                     }
                 }
                 if (use_gpu) {
-                    const float* g = &gpu_pixels[4 * cursor];
+                    const float* g = gpu_pixels.get() + 4 * cursor;
                     pixels.push_back(RGBTColour(g[0], g[1], g[2], g[3]));
                     if (dump_gpu) memcpy(&frame_gpu[4 * fi], g, 4 * sizeof(float));
                 } else pixels.push_back(ref);

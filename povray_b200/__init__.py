@@ -6,6 +6,6 @@ sm_100a CUDA); nothing here computes pixels on the CPU.
 """
 from . import _abi as abi
 from ._abi import PvgpuError
-from .scene import Scene, tiles, assemble
+from .scene import Scene, HostBuffer, tiles, assemble
 
-__all__ = ["abi", "PvgpuError", "Scene", "tiles", "assemble"]
+__all__ = ["abi", "PvgpuError", "Scene", "HostBuffer", "tiles", "assemble"]

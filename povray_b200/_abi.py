@@ -184,6 +184,8 @@ SIGNATURES = {
     "pvgpu_scene_save": (C.c_int, [VP, C.c_char_p]),
     "pvgpu_scene_load": (C.c_int, [P(VP), C.c_char_p]),
     "pvgpu_render": (C.c_int, [VP, P(AA), C.c_int, C.c_int, P(Rect), C.c_size_t, P(f32), P(Stats), VP, VP]),
+    "pvgpu_host_alloc": (VP, [C.c_size_t]),
+    "pvgpu_host_free": (None, [VP]),
     "pvgpu_render_device": (C.c_int, [VP, P(AA), C.c_int, C.c_int, P(Rect), C.c_size_t, VP, P(Stats), VP]),
     "pvgpu_trace_rays": (C.c_int, [VP, P(f64), C.c_size_t, P(u32), P(f64), P(u32)]),
     "pvgpu_camera_rays": (C.c_int, [VP, C.c_int, C.c_int, P(f64), C.c_size_t, P(f64)]),

@@ -16,6 +16,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace pvgpu {
@@ -761,38 +763,68 @@ int pvgpu_render(pvgpu_scene* sc, const pvgpu_aa* aa, int width, int height,
         if (d.h_frame) cudaFreeHost(d.h_frame);
         d.h_frame = nullptr; d.frame_cap = 0;
         CUDA_TRY(cudaMalloc(&d.d_frame, bytes));
-        CUDA_TRY(cudaMallocHost(&d.h_frame, bytes));
         d.frame_cap = bytes;
     }
     int rc = render_impl(s, aa, width, height, rects, n_rects, d.d_frame, stats, 0, cooperate, user);
-    if (rc == PVGPU_OK) {
-        // D2H into pinned memory in slices, each copied to the caller's buffer while the next slice is in flight
-        const size_t total = n * 4 * sizeof(float), slice = 4u << 20;
-        cudaEvent_t evs[2];
-        cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming);
-        cudaError_t e = cudaSuccess;
-        size_t issued = 0, done = 0;
-        int k = 0;
-        auto issue = [&]() {
-            const size_t len = std::min(slice, total - issued);
-            e = cudaMemcpyAsync(reinterpret_cast<char*>(d.h_frame) + issued, reinterpret_cast<const char*>(d.d_frame) + issued, len, cudaMemcpyDeviceToHost, 0);
-            cudaEventRecord(evs[k & 1], 0);
-            issued += len; k++;
-        };
-        if (total) issue();
-        int kd = 0;
-        while (done < total && e == cudaSuccess) {
-            if (issued < total) issue();
-            e = cudaEventSynchronize(evs[kd & 1]);
-            const size_t len = std::min(slice, total - done);
-            std::memcpy(reinterpret_cast<char*>(rgbt_out) + done, reinterpret_cast<const char*>(d.h_frame) + done, len);
-            done += len; kd++;
-        }
-        cudaEventDestroy(evs[0]); cudaEventDestroy(evs[1]);
-        if (e != cudaSuccess) rc = fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
+    if (rc != PVGPU_OK) return rc;
+    const size_t total = n * 4 * sizeof(float);
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, rgbt_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        // the caller's buffer is page-locked (pvgpu_host_alloc): one DMA transfer, no staging
+        cudaError_t e = cudaMemcpyAsync(rgbt_out, d.d_frame, total, cudaMemcpyDeviceToHost, 0);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+        if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
+        return PVGPU_OK;
     }
-    return rc;
+    // pageable destination: D2H into the pinned staging buffer in slices; a few host threads copy the slices that
+    // have landed into the caller's buffer while the next ones are in flight
+    if (d.h_frame == nullptr) {
+        CUDA_TRY(cudaMallocHost(&d.h_frame, d.frame_cap));
+    }
+    const size_t slice = 2u << 20;
+    const size_t n_slices = (total + slice - 1) / slice;
+    std::vector<cudaEvent_t> evs(n_slices);
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < n_slices && e == cudaSuccess; k++) {
+        const size_t off = k * slice, len = std::min(slice, total - off);
+        cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming);
+        e = cudaMemcpyAsync(reinterpret_cast<char*>(d.h_frame) + off, reinterpret_cast<const char*>(d.d_frame) + off, len, cudaMemcpyDeviceToHost, 0);
+        cudaEventRecord(evs[k], 0);
+    }
+    if (e == cudaSuccess) {
+        const int n_workers = (int)std::min<size_t>(4, n_slices);
+        std::atomic<int> failed(0);
+        auto worker = [&](int w) {
+            cudaSetDevice(s.device);
+            for (size_t k = (size_t)w; k < n_slices; k += (size_t)n_workers) {
+                if (cudaEventSynchronize(evs[k]) != cudaSuccess) { failed = 1; return; }
+                const size_t off = k * slice, len = std::min(slice, total - off);
+                std::memcpy(reinterpret_cast<char*>(rgbt_out) + off, reinterpret_cast<const char*>(d.h_frame) + off, len);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int w = 1; w < n_workers; w++) pool.emplace_back(worker, w);
+        worker(0);
+        for (auto& t : pool) t.join();
+        if (failed) e = cudaErrorUnknown;
+    }
+    for (size_t k = 0; k < n_slices; k++) if (evs[k]) cudaEventDestroy(evs[k]);
+    if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
+    return PVGPU_OK;
+}
+
+void* pvgpu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void pvgpu_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
 }
 
 int pvgpu_trace_rays(pvgpu_scene* sc, const double* org_dir, size_t n, uint32_t* obj, double* depth, uint32_t* aux)

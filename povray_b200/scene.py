@@ -43,6 +43,28 @@ def assemble(pixels, rects, width, height):
     return img
 
 
+class HostBuffer:
+    """Page-locked host memory from `pvgpu_host_alloc`, exposed as a float32 numpy array (`.array`)."""
+
+    def __init__(self, n_floats):
+        self._p = A.lib().pvgpu_host_alloc(int(n_floats) * 4)
+        if not self._p:
+            raise MemoryError("pvgpu_host_alloc failed")
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_float)), shape=(int(n_floats),))
+
+    def close(self):
+        if self._p:
+            self.array = None
+            A.lib().pvgpu_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Scene:
     """Owns a `pvgpu_scene*`."""
 
@@ -102,12 +124,16 @@ class Scene:
         return int(A.lib().pvgpu_scene_device_bytes(self._h))
 
     # -- rendering ------------------------------------------------------------------------------
-    def render(self, width, height, rects=None, aa=None):
-        """Host-buffer render (pvgpu_render): returns (rect-major pixels [n,4] float32, stats dict)."""
+    def render(self, width, height, rects=None, aa=None, out=None):
+        """Host-buffer render (pvgpu_render): returns (rect-major pixels [n,4] float32, stats dict).  `out`: optional
+        float32 array with room for n * 4 values (e.g. a `HostBuffer(...).array`, which avoids the staging copy)."""
         if rects is None:
             rects = tiles(width, height)
         n = _area(rects)
-        out = np.empty((n, 4), dtype=np.float32)
+        if out is None:
+            out = np.empty((n, 4), dtype=np.float32)
+        else:
+            out = out.reshape(-1)[:n * 4].reshape(n, 4)
         st = A.Stats()
         ra = _rect_array(rects)
         A.check(A.lib().pvgpu_render(self._h, C.byref(aa) if aa is not None else None, int(width), int(height), ra, len(rects),
