@@ -36,14 +36,47 @@ W, H, BLOCK = 1920, 1080, 32
 WORKLOADS = {
     "cfg2": "synthetic 999698-triangle mesh2 height field + BBox tree, 2 lights with shadows, reflection max_trace_level 5, 1920x1080 -A",
     "cfg1": "synthetic 1024 spheres + checker plane, 1 point light with shadows, 1920x1080 -A",
+    "cfg3": "synthetic 4096 CSG objects (difference / intersection / merge of boxes, spheres, quadrics), refraction ior 1.3-1.6, "
+            "2 lights, max_trace_level 6, 1920x1080 +A0.3 +AM2 +R3 +J (scene tables from the reference parser through the adapter)",
+    "cfg3_noaa": "config 3 without anti-aliasing (-A)",
+    "cfg4": "synthetic 2048 tori (half sturm) with granite / bozo pigments, colour maps, turbulence, noise_generator 2 and 3, 1920x1080 -A "
+            "(scene tables from the reference parser through the adapter)",
 }
+# anti-aliasing of the workload: (method, depth, threshold, jitter amount) and the reference's switches for it
+WORKLOAD_AA = {"cfg3": ((2, 3, 0.3, 1.0), ["+A0.3", "+AM2", "+R3", "+J"])}
 # algorithmic bytes per ray (SURVEY.md section 8d / DESIGN.md "Roofline"): node tests x 32 B + primitive records + ray record I/O
-ALG_BYTES_PER_RAY = {"cfg2": 101 * 32 + 10 * 64 + 128, "cfg1": 30 * 32 + 2 * 168 + 128}
+ALG_BYTES_PER_RAY = {"cfg2": 101 * 32 + 10 * 64 + 128, "cfg1": 30 * 32 + 2 * 168 + 128,
+                     "cfg3": 30 * 32 + 2 * 3 * 168 + 128, "cfg3_noaa": 30 * 32 + 2 * 3 * 168 + 128, "cfg4": 30 * 32 + 2 * (168 + 256) + 128}
+ADAPTER = os.path.join(ROOT, "oracle", "_ref", "parity", "povray-gpu")
 
 
 def make_builder(workload):
     from povray_b200 import synth
     return synth.mesh_scene(708) if workload == "cfg2" else synth.spheres_scene(1024)
+
+
+def pov_text(workload):
+    from povray_b200 import synth
+    return synth.csg_scene_pov(4096) if workload.startswith("cfg3") else synth.torus_scene_pov(2048)
+
+
+def build_scene(workload):
+    """The flattened scene of the workload: configs 1 and 2 from the Python table builder, configs 3 and 4 from the reference
+    parser through the reference-side adapter (povray-gpu dumps the tables it hands to pvgpu_scene_* and renders 8x8 pixels)."""
+    import povray_b200 as pv
+    if workload in ("cfg1", "cfg2"):
+        return make_builder(workload).build()
+    if not os.path.exists(ADAPTER):
+        raise SystemExit(f"bench.py: workload {workload} needs the reference-side adapter {ADAPTER}")
+    with tempfile.TemporaryDirectory() as d:
+        pov, pvs = os.path.join(d, "s.pov"), os.path.join(d, "s.pvs")
+        open(pov, "w").write(pov_text(workload))
+        r = subprocess.run([ADAPTER, "+I" + pov, "+O" + os.path.join(d, "o.png"), "+W8", "+H8", "-A", "-D", "+WT1", "-GA"],
+                           env=dict(os.environ, PVGPU_RENDER="gpu", PVGPU_DUMP_SCENE=pvs, PVGPU_DEVICE=os.environ.get("LOCAL_RANK", "0")),
+                           capture_output=True, text=True, cwd=d)
+        if r.returncode != 0 or not os.path.exists(pvs):
+            raise SystemExit("bench.py: adapter failed:\n" + (r.stdout + r.stderr)[-2000:])
+        return pv.Scene.load(pvs)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -102,11 +135,11 @@ def reference_binary():
     return None, None
 
 
-def run_reference_once(binary, pov, threads, width=W, height=H):
+def run_reference_once(binary, pov, threads, width=W, height=H, aa_flags=("-A",)):
     """One render of `pov` by the unmodified reference; returns (trace seconds, rays, shadow tests, parse seconds)."""
     with tempfile.TemporaryDirectory() as d:
-        r = subprocess.run([binary, "+I" + pov, "+O" + os.path.join(d, "o.png"), f"+W{width}", f"+H{height}", "-A", "-D", f"+WT{threads}",
-                            "-GD", "-GR", "-GW", "-GF", "+GS"], capture_output=True, text=True, cwd=d)
+        r = subprocess.run([binary, "+I" + pov, "+O" + os.path.join(d, "o.png"), f"+W{width}", f"+H{height}", "-D", f"+WT{threads}",
+                            "-GD", "-GR", "-GW", "-GF", "+GS"] + list(aa_flags), capture_output=True, text=True, cwd=d)
     out = (r.stdout + r.stderr).replace("\r", "\n")
     if r.returncode != 0:
         raise RuntimeError("reference render failed:\n" + out[-2000:])
@@ -121,8 +154,15 @@ def run_reference_once(binary, pov, threads, width=W, height=H):
 def write_pov(workload, directory):
     path = os.path.join(directory, workload + ".pov")
     with open(path, "w") as f:
-        make_builder(workload).to_pov(f)
+        if workload in ("cfg1", "cfg2"):
+            make_builder(workload).to_pov(f)
+        else:
+            f.write(pov_text(workload))
     return path
+
+
+def aa_flags(workload):
+    return WORKLOAD_AA[workload][1] if workload in WORKLOAD_AA else ["-A"]
 
 
 def reference_arm(args):
@@ -133,7 +173,7 @@ def reference_arm(args):
     threads = os.cpu_count() or 1
     base = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": "none", "tile": BLOCK}}
+            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": " ".join(aa_flags(args.workload)), "tile": BLOCK}}
     if binary is None:
         base["unavailable"] = "oracle/_ref/*/povray not built (needs /root/reference at build time)"
         print(json.dumps(base))
@@ -141,10 +181,10 @@ def reference_arm(args):
     with tempfile.TemporaryDirectory() as d:
         pov = write_pov(args.workload, d)
         for _ in range(args.warmup):
-            run_reference_once(binary, pov, threads)
+            run_reference_once(binary, pov, threads, aa_flags=aa_flags(args.workload))
         t, rays, shadow, parse = 0.0, 0, 0, 0.0
         for _ in range(args.steps):
-            tr, r, s, p = run_reference_once(binary, pov, threads)
+            tr, r, s, p = run_reference_once(binary, pov, threads, aa_flags=aa_flags(args.workload))
             t += tr; rays += r; shadow += s; parse += p
     value = (rays + shadow) / t / 1e6
     flags = "-O3 -march=x86-64-v3 -fno-fast-math" if variant == "fast" else "-O2 -fno-fast-math -ffp-contract=off"
@@ -179,8 +219,13 @@ def ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t0 = time.time()
-    scene = make_builder(args.workload).build()
+    scene = build_scene(args.workload)
     t_build = time.time() - t0
+    aa = None
+    if args.workload in WORKLOAD_AA:
+        m, dep, thr, jit = WORKLOAD_AA[args.workload][0]
+        aa = A.AA()
+        aa.method, aa.depth, aa.threshold, aa.jitter_scale, aa.gamma = m, dep, thr, jit, 2.5
     t0 = time.time()
     scene.finalize(local_rank)
     t_upload = time.time() - t0
@@ -198,7 +243,7 @@ def ours(args):
     stream = torch.cuda.current_stream()
 
     def step_device():
-        st = scene.render_device(W, H, rect_arr, out.data_ptr(), stream.cuda_stream)
+        st = scene.render_device(W, H, rect_arr, out.data_ptr(), stream.cuda_stream, aa=aa)
         if world > 1:
             dist.gather(out, gathered, dst=0)
         return st
@@ -233,18 +278,18 @@ def ours(args):
     # At N > 1 every rank delivers its own tiles to its host (the caller's scatter of disjoint tiles is not part of the library).
     hb = pv.HostBuffer(max_px * 4)
     for _ in range(2):
-        scene.render(W, H, mine, out=hb.array)
+        scene.render(W, H, mine, out=hb.array, aa=aa)
     barrier()
     t0 = time.perf_counter()
     e2e_rays = 0
     for _ in range(args.steps):
-        px, st = scene.render(W, H, mine, out=hb.array)
+        px, st = scene.render(W, H, mine, out=hb.array, aa=aa)
         e2e_rays += st["rays"] + st["shadow_ray_tests"]
     e2e_s = time.perf_counter() - t0
-    scene.render(W, H, mine)
+    scene.render(W, H, mine, aa=aa)
     t0 = time.perf_counter()
     for _ in range(min(args.steps, 3)):
-        scene.render(W, H, mine)
+        scene.render(W, H, mine, aa=aa)
     e2e_pageable_s = (time.perf_counter() - t0) / min(args.steps, 3)
 
     vals = torch.tensor([ms, float(rays), float(launches), e2e_s, float(e2e_rays), kern_ms["closest_ms"], kern_ms["shadow_ms"],
@@ -265,7 +310,7 @@ def ours(args):
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "sec_per_frame": ms / args.steps / 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": "none", "tile": BLOCK,
+            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": " ".join(aa_flags(args.workload)), "tile": BLOCK,
                        "sharding": f"{len(all_tiles)} tiles dealt round-robin over {world} GPU(s), scene replicated, gather to rank 0",
                        "l2": "256 MB flush write between timed frames; scene tables + ray queues exceed the 126 MB L2",
                        "scene_device_bytes": scene.device_bytes, "scene_build_s": round(t_build, 2), "scene_upload_s": round(t_upload, 3),
@@ -315,7 +360,7 @@ def ours(args):
                 raise RuntimeError("reference binary not built")
             with tempfile.TemporaryDirectory() as d:
                 pov = write_pov(args.workload, d)
-                tr, r, s, parse = run_reference_once(binary, pov, threads)
+                tr, r, s, parse = run_reference_once(binary, pov, threads, aa_flags=aa_flags(args.workload))
             line["cpu_baseline"] = {"value": (r + s) / tr / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "reference",
                                     "sec_per_frame": tr, "parse_s": parse,
                                     "sample": f"1 full {W}x{H} frame by oracle/_ref/{variant}/povray +WT{threads}, the reference's own Trace Time"}
@@ -327,7 +372,7 @@ def ours(args):
                 scene.save(p)
                 o = oracle_lib.OracleScene(p)
                 t0 = time.perf_counter()
-                _, ost = o.render(W, H, rect=(0, 476, W - 1, 603), threads=threads)      # 128 rows through the middle of the frame
+                _, ost = o.render(W, H, rect=(0, 476, W - 1, 603), threads=threads)      # 128 rows through the middle of the frame (no AA)
                 dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": (ost["rays"] + ost["shadow_ray_tests"]) / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
                                     "sample": f"rows 476-603 of the {W}x{H} frame by oracle/libpvoracle.so with {threads} threads ({e})"}

@@ -427,6 +427,7 @@ struct GpuView
 };
 
 std::mutex g_mutex;
+std::mutex g_drain_mutex;
 std::map<const void*, std::shared_ptr<GpuView>> g_views;     // keyed by SceneData
 
 void check(int rc, const char* what)
@@ -583,6 +584,8 @@ void TraceTask::Run()
     vector<POVRect> rects;
     vector<unsigned int> serials;
     {
+        // one task takes the whole queue (the device renders all tiles in one call); tasks arriving later find it empty
+        std::lock_guard<std::mutex> lock(g_drain_mutex);
         POVRect r; unsigned int serial;
         while (vd->GetNextRectangle(r, serial)) { rects.push_back(r); serials.push_back(serial); }
     }

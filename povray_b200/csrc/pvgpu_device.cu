@@ -657,6 +657,7 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
 {
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     if (width <= 0 || height <= 0 || !rects || !n_rects || !d_out) return fail(PVGPU_E_INVALID, "pvgpu_render: bad arguments");
+    std::lock_guard<std::recursive_mutex> device_lock(s.device_mutex);
     const unsigned int method = aa ? aa->method : 0u;
     if (method > 2) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method %u (stochastic supersampling) is outside the GPU trace path", method);
     if (method && (aa->depth < 1 || aa->depth > 9)) return fail(PVGPU_E_INVALID, "anti-aliasing depth %u out of range 1..9", aa->depth);
@@ -750,6 +751,7 @@ int pvgpu_render(pvgpu_scene* sc, const pvgpu_aa* aa, int width, int height,
     if (!sc || !rgbt_out || !rects) return fail(PVGPU_E_INVALID, "pvgpu_render: null argument");
     Scene& s = *reinterpret_cast<Scene*>(sc);
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
+    std::lock_guard<std::recursive_mutex> frame_lock(s.device_mutex);      // the device frame + staging buffer are per scene
     CUDA_TRY(cudaSetDevice(s.device));
     DeviceScene& d = *s.dev;
     size_t n = 0;
@@ -835,6 +837,7 @@ int pvgpu_trace_rays(pvgpu_scene* sc, const double* org_dir, size_t n, uint32_t*
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     if (n == 0) return PVGPU_OK;
     if (n > 0xFFFFFFF0ull) return fail(PVGPU_E_INVALID, "too many rays");
+    std::lock_guard<std::recursive_mutex> device_lock(s.device_mutex);
     CUDA_TRY(cudaSetDevice(s.device));
     DeviceScene& d = *s.dev;
     const size_t chunk = 1u << 22;

@@ -3,6 +3,7 @@
 // pvgpu_device.cu (upload + kernels).  Nothing here is part of the public ABI.
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "pvgpu.h"
@@ -42,6 +43,7 @@ struct Scene {
     int      device = -1;
     size_t   device_bytes = 0;
     DeviceScene* dev = nullptr;
+    std::recursive_mutex device_mutex;        // the device-side work buffers of a scene serve one render / trace call at a time
 };
 
 // error plumbing (thread-local message)

@@ -323,3 +323,87 @@ def mesh_scene(grid=708):
     b.sphere((-2.5, 2.2, 1.0), 0.9, b.texture((0.9, 0.3, 0.2), diffuse=0.5, specular=0.6, roughness=0.02, reflection=0.4))
     b.sphere((2.6, 2.0, -0.5), 0.8, b.texture((0.2, 0.8, 0.3), diffuse=0.5, specular=0.6, roughness=0.02, reflection=0.4))
     return b
+
+
+# ------------------------------------------------------------------------------------------------
+# Configs 3 and 4 as SDL text only: these scenes use constructs (CSG, quadrics, tori, interiors, noise pigments with
+# colour maps) whose tables come from the reference parser through the adapter, not from build().
+# ------------------------------------------------------------------------------------------------
+def csg_scene_pov(n_objects=4096, seed=777, max_trace_level=6):
+    """Config 3: `n_objects` CSG objects, each a difference / intersection / merge of 2-4 of {box, sphere, quadric
+    (cylinder, cone, ellipsoid forms)}, glass-like (filter 0.7, ior 1.3-1.6), on a jittered grid over a checker floor."""
+    rng = np.random.RandomState(seed)
+    side = int(math.ceil(math.sqrt(n_objects)))
+    out = ["#version 3.7;",
+           f"global_settings {{ assumed_gamma 1 max_trace_level {max_trace_level} }}",
+           "background { rgb <0.05, 0.07, 0.12> }",
+           "camera { perspective location <0, 14, -30> direction <0, 0, 1.6> up <0, 1, 0> right <1.7777777777777777, 0, 0> look_at <0, 0, 2> }",
+           "light_source { <40, 60, -40> rgb <1, 1, 1> }",
+           "light_source { <-30, 25, -10> rgb <0.4, 0.4, 0.5> }",
+           "plane { y, -0.5078125 pigment { checker rgb <0.9, 0.9, 0.9>, rgb <0.25, 0.3, 0.35> } finish { ambient 0.1 diffuse 0.7 } }"]
+
+    def prim(kind, c, s):
+        x, y, z = c
+        if kind == 0:
+            return f"box {{ <{x - s:.6f}, {y - s:.6f}, {z - s:.6f}>, <{x + s:.6f}, {y + s:.6f}, {z + s:.6f}> }}"
+        if kind == 1:
+            return f"sphere {{ <{x:.6f}, {y:.6f}, {z:.6f}>, {s * 1.2:.6f} }}"
+        if kind == 2:      # cylinder along y as a quadric: x^2 + z^2 = r^2
+            return f"quadric {{ <1, 0, 1>, <0, 0, 0>, <0, 0, 0>, {-(s * 0.8) ** 2:.6f} translate <{x:.6f}, {y:.6f}, {z:.6f}> }}"
+        if kind == 3:      # ellipsoid as a quadric
+            return f"quadric {{ <1, 2.5, 1.5>, <0, 0, 0>, <0, 0, 0>, {-(s * 1.1) ** 2:.6f} translate <{x:.6f}, {y:.6f}, {z:.6f}> }}"
+        return f"quadric {{ <1, -0.6, 1>, <0, 0, 0>, <0, 0, 0>, 0 translate <{x:.6f}, {y + s:.6f}, {z:.6f}> }}"      # cone
+
+    n = 0
+    for iz in range(side):
+        for ix in range(side):
+            if n >= n_objects:
+                break
+            n += 1
+            cx = (ix - side / 2.0) * 1.1 + rng.uniform(-0.15, 0.15)
+            cz = (iz - side / 2.0) * 1.1 + 8.0 + rng.uniform(-0.15, 0.15)
+            s = rng.uniform(0.28, 0.42)
+            cy = s - 0.3 + rng.uniform(0.0, 0.4)
+            op = ("difference", "intersection", "merge")[rng.randint(0, 3)]
+            k = rng.randint(2, 5)
+            # every object stays finite: a merge gets finite children only (box, sphere, ellipsoid), the first child of a
+            # difference / intersection is a box or a sphere (its box bounds the whole object, csg.cpp Compute_BBox)
+            finite = (0, 1, 3)
+            kinds = [rng.randint(0, 2)] + [(finite[rng.randint(0, 3)] if op == "merge" else rng.randint(0, 5)) for _ in range(k - 1)]
+            parts = []
+            for j, kd in enumerate(kinds):
+                off = (0.0, 0.0, 0.0) if j == 0 else tuple(rng.uniform(-0.5, 0.5) * s for _ in range(3))
+                parts.append(prim(kd, (cx + off[0], cy + off[1], cz + off[2]), s * (1.0 if j == 0 else rng.uniform(0.6, 0.95))))
+            col = rng.uniform(0.3, 1.0, size=3)
+            ior = rng.uniform(1.3, 1.6)
+            body = " ".join(parts)
+            bound = f" bounded_by {{ sphere {{ <{cx:.6f}, {cy:.6f}, {cz:.6f}>, {s * 2.6:.6f} }} }}" if op != "merge" and rng.rand() < 0.3 else ""
+            out.append(f"{op} {{ {body}{bound} pigment {{ rgbf <{col[0]:.4f}, {col[1]:.4f}, {col[2]:.4f}, 0.7> }} "
+                       f"finish {{ ambient 0.05 diffuse 0.5 specular 0.4 roughness 0.03 reflection 0.08 }} interior {{ ior {ior:.4f} }} }}")
+    return "\n".join(out) + "\n"
+
+
+def torus_scene_pov(n_tori=2048, seed=4242):
+    """Config 4 (torus part): `n_tori` tori (half of them `sturm`), random rotation / translation, granite and bozo
+    pigments with colour maps and turbulence, noise_generator 2 for one half of the pigments and 3 for the other."""
+    rng = np.random.RandomState(seed)
+    out = ["#version 3.7;",
+           "global_settings { assumed_gamma 1 max_trace_level 5 noise_generator 2 }",
+           "background { rgb <0.1, 0.12, 0.18> }",
+           "camera { perspective location <0, 18, -34> direction <0, 0, 1.5> up <0, 1, 0> right <1.7777777777777777, 0, 0> look_at <0, 2, 4> }",
+           "light_source { <30, 50, -40> rgb <1, 1, 1> }",
+           "plane { y, -0.2578125 pigment { checker rgb <0.8, 0.8, 0.8>, rgb <0.3, 0.3, 0.3> } finish { ambient 0.1 diffuse 0.7 } }"]
+    for i in range(n_tori):
+        R, r = rng.uniform(0.5, 1.0), rng.uniform(0.1, 0.3)
+        rot = rng.uniform(0.0, 360.0, size=3)
+        pos = (rng.uniform(-22.0, 22.0), rng.uniform(0.4, 9.0), rng.uniform(-10.0, 34.0))
+        c1, c2, c3 = rng.uniform(0.05, 1.0, size=(3, 3))
+        pat = "granite" if i % 2 == 0 else "bozo"
+        gen = "" if i % 4 < 2 else " noise_generator 3"
+        turb = f" turbulence {rng.uniform(0.1, 0.6):.3f}" if i % 3 == 0 else ""
+        sturm = " sturm" if i % 2 == 1 else ""
+        out.append(f"torus {{ {R:.6f}, {r:.6f}{sturm} pigment {{ {pat}{gen}{turb} scale {rng.uniform(0.15, 0.6):.4f} color_map {{ "
+                   f"[0 rgb <{c1[0]:.4f}, {c1[1]:.4f}, {c1[2]:.4f}>] [0.5 rgb <{c2[0]:.4f}, {c2[1]:.4f}, {c2[2]:.4f}>] "
+                   f"[1 rgb <{c3[0]:.4f}, {c3[1]:.4f}, {c3[2]:.4f}>] }} }} finish {{ ambient 0.1 diffuse 0.65 phong 0.4 }} "
+                   f"rotate <{rot[0]:.4f}, {rot[1]:.4f}, {rot[2]:.4f}> translate <{pos[0]:.6f}, {pos[1]:.6f}, {pos[2]:.6f}> }}")
+    return "\n".join(out) + "\n"

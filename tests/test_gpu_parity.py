@@ -315,3 +315,25 @@ def test_drop_in_adapter_antialiased_vs_unmodified_reference(pv, flags):
             outs[name] = read_ppm(out)
         d8 = np.abs(outs["gpu"] - outs["ref"]).max(axis=2)
         assert (d8 <= 1.0).mean() >= PIXEL_FRAC, f"{(d8 > 1).sum()} pixels differ by more than one 8-bit level"
+
+
+@pytest.mark.parametrize("which,flags", [("cfg3", ["-A"]), ("cfg3", ["+A0.3", "+AM2", "+R3", "+J"]), ("cfg4", ["-A"]), ("cfg4", ["+A0.3", "+AM1", "+R3", "+J"])])
+def test_configs_3_and_4_full_scene_through_the_adapter(pv, which, flags):
+    """BASELINE.json configs 3 (4096 CSG objects, refraction, AA) and 4 (2048 tori, half sturm, granite / bozo noise) at full
+    object count: reference front end + pvgpu trace path against the UNMODIFIED reference binary, 8-bit images."""
+    if not (os.path.exists(ADAPTER) and os.path.exists(REF_BINARY)):
+        pytest.skip("reference binaries not built (need the reference sources at build time)")
+    from povray_b200 import synth
+    text = synth.csg_scene_pov(4096) if which == "cfg3" else synth.torus_scene_pov(2048)
+    with tempfile.TemporaryDirectory() as d:
+        pov = os.path.join(d, which + ".pov")
+        open(pov, "w").write(text)
+        outs = {}
+        for name, binary in (("ref", REF_BINARY), ("gpu", ADAPTER)):
+            out = os.path.join(d, name + ".ppm")
+            r = subprocess.run([binary, "+I" + pov, "+O" + out, "+FP", "+W480", "+H270", "-D", f"+WT{os.cpu_count() or 2}", "-GA"] + flags,
+                               env=dict(os.environ, PVGPU_RENDER="gpu"), capture_output=True, text=True, timeout=900, cwd=d)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            outs[name] = read_ppm(out)
+        d8 = np.abs(outs["gpu"] - outs["ref"]).max(axis=2)
+        assert (d8 <= 1.0).mean() >= PIXEL_FRAC, f"{(d8 > 1).sum()} of {d8.size} pixels differ by more than one 8-bit level (max {d8.max()})"
