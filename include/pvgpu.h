@@ -54,8 +54,11 @@ enum {
     PVGPU_OBJ_MESH             = 6,  /* mesh.h:107     mesh = index into mesh table                         */
     PVGPU_OBJ_CSG_UNION        = 7,  /* csg.h CSGUnion        children in index list                        */
     PVGPU_OBJ_CSG_INTERSECTION = 8,  /* csg.h CSGIntersection (difference = intersection + inverted kids)   */
-    PVGPU_OBJ_CSG_MERGE        = 9   /* csg.h CSGMerge                                                      */
+    PVGPU_OBJ_CSG_MERGE        = 9,  /* csg.h CSGMerge                                                      */
+    PVGPU_OBJ_BLOB             = 10  /* blob.h:142     mesh = index into the blob table                     */
 };
+
+#define PVGPU_IS_CSG(type) ((type) >= PVGPU_OBJ_CSG_UNION && (type) <= PVGPU_OBJ_CSG_MERGE)
 
 /* Object flags: the reference's ObjectBase::Flags bits verbatim (source/core/scene/object.h:88-117). */
 #define PVGPU_NO_SHADOW_FLAG          0x00000001u
@@ -85,7 +88,7 @@ typedef struct pvgpu_object {
     uint32_t clip_first,  clip_count;    /* ObjectBase::Clip         -> range in the index list     */
     uint32_t bound_first, bound_count;   /* ObjectBase::Bound        -> range in the index list     */
     int32_t  mesh;               /* PVGPU_OBJ_MESH: mesh table index                                */
-    uint32_t aux;                /* see PVGPU_OBJ_* comments                                        */
+    uint32_t aux;                /* see PVGPU_OBJ_* comments; blob: 1 = IS_CHILD_OBJECT                */
     float    bbox[6];            /* ObjectBase::BBox: lowerLeft xyz, size xyz (boundingbox.h:93)    */
     uint32_t reserved;
     double   p[10];              /* see PVGPU_OBJ_* comments                                        */
@@ -141,6 +144,40 @@ typedef struct pvgpu_mesh {
     uint32_t reserved;
     double   inside_vector[3];
 } pvgpu_mesh;
+
+/* ---- blobs ------------------------------------------------------------------------------- */
+
+/* Blob_Element::Type (source/core/shape/blob.h:66-72) */
+#define PVGPU_BLOB_SPHERE          2
+#define PVGPU_BLOB_CYLINDER        4
+#define PVGPU_BLOB_ELLIPSOID       8
+#define PVGPU_BLOB_BASE_HEMISPHERE 16
+#define PVGPU_BLOB_APEX_HEMISPHERE 32
+
+/* Blob_Element (blob.h:85-100) as Blob::Make_Blob left it (coefficients c[] and transforms already resolved). */
+typedef struct pvgpu_blob_element {
+    uint32_t type;               /* PVGPU_BLOB_*                                   */
+    int32_t  transform;          /* Blob_Element::Trans -> transform table, or -1  */
+    double   o[3];               /* O                                              */
+    double   len, rad2;          /* len, rad2                                      */
+    double   c[3];               /* c[0..2]                                        */
+} pvgpu_blob_element;
+
+/* BSPHERE_TREE node (source/core/bounding/boundingsphere.h:66-72), children stored contiguously.
+ * count > 0: inner node, children are nodes [first, first+count) of the blob's node range;
+ * count == 0: leaf, `first` is the element index (relative to the blob's element range). */
+typedef struct pvgpu_blob_node {
+    double   c[3];               /* C  */
+    double   r2;                 /* r2 */
+    uint32_t first, count;
+} pvgpu_blob_node;
+
+/* Blob_Data (blob.h:102-118). */
+typedef struct pvgpu_blob {
+    uint32_t element_first, element_count;
+    uint32_t node_first, node_count;         /* node_count == 0: no bounding hierarchy (Blob_Data::Tree == nullptr) */
+    double   threshold;                      /* Threshold */
+} pvgpu_blob;
 
 /* ---- lights ------------------------------------------------------------------------------ */
 enum { PVGPU_LIGHT_POINT = 1, PVGPU_LIGHT_SPOT = 2, PVGPU_LIGHT_FILL = 3, PVGPU_LIGHT_CYLINDER = 4 };
@@ -359,6 +396,11 @@ int  pvgpu_scene_set_meshes(pvgpu_scene* s, const pvgpu_mesh* meshes, size_t n_m
                             const float* normals, size_t n_normals,
                             const pvgpu_triangle* tris, size_t n_tris,
                             const pvgpu_node* nodes, size_t n_nodes);
+/* Blobs: element c[] / transforms as computed by Blob::Make_Blob, bounding-sphere trees as built by
+ * Blob::build_bounding_hierarchy (blob.cpp:2516-2766). */
+int  pvgpu_scene_set_blobs(pvgpu_scene* s, const pvgpu_blob* blobs, size_t n_blobs,
+                           const pvgpu_blob_element* elements, size_t n_elements,
+                           const pvgpu_blob_node* nodes, size_t n_nodes);
 int  pvgpu_scene_set_lights(pvgpu_scene* s, const pvgpu_light* l, size_t n);
 int  pvgpu_scene_set_materials(pvgpu_scene* s,
                                const pvgpu_texture* tex, size_t n_tex,

@@ -53,6 +53,8 @@
 #include "core/scene/object.h"
 #include "core/scene/scenedata.h"
 #include "core/scene/tracethreaddata.h"
+#include "core/bounding/boundingsphere.h"
+#include "core/shape/blob.h"
 #include "core/shape/box.h"
 #include "core/shape/csg.h"
 #include "core/shape/mesh.h"
@@ -88,6 +90,9 @@ struct Flattener
     vector<pvgpu_transform> transforms;
     vector<pvgpu_node> nodes, mesh_nodes;
     vector<pvgpu_mesh> meshes;
+    vector<pvgpu_blob> blobs;
+    vector<pvgpu_blob_element> blob_elements;
+    vector<pvgpu_blob_node> blob_nodes;
     vector<float> vertices, normals;
     vector<pvgpu_triangle> triangles;
     vector<pvgpu_light> lights;
@@ -304,6 +309,51 @@ struct Flattener
         return (int32_t)meshes.size() - 1;
     }
 
+    // Blob_Data as Make_Blob / build_bounding_hierarchy left it (blob.cpp:2516-2766)
+    int32_t add_blob(Blob* b)
+    {
+        const Blob_Data* D = b->Data;
+        for (TEXTURE* t : b->Element_Texture) if (t != nullptr) unsupported("blob with per-component textures");
+        pvgpu_blob pb{};
+        pb.threshold = D->Threshold;
+        pb.element_first = (uint32_t)blob_elements.size();
+        pb.element_count = (uint32_t)D->Entry.size();
+        for (const Blob_Element& e : D->Entry) {
+            pvgpu_blob_element pe{};
+            pe.type = (uint32_t)e.Type;
+            pe.transform = add_transform(e.Trans);
+            for (int k = 0; k < 3; k++) { pe.o[k] = e.O[k]; pe.c[k] = e.c[k]; }
+            pe.len = e.len; pe.rad2 = e.rad2;
+            if (e.Texture != nullptr) unsupported("blob with per-component textures");
+            blob_elements.push_back(pe);
+        }
+        pb.node_first = (uint32_t)blob_nodes.size();
+        if (D->Tree != nullptr) {
+            // breadth-first so that the children of a node are contiguous; a leaf's Node points at its Blob_Element
+            vector<const BSPHERE_TREE*> order{ D->Tree };
+            vector<pvgpu_blob_node> tree(1);
+            for (size_t qi = 0; qi < order.size(); qi++) {
+                const BSPHERE_TREE* n = order[qi];
+                pvgpu_blob_node pn{};
+                for (int k = 0; k < 3; k++) pn.c[k] = n->C[k];
+                pn.r2 = n->r2;
+                if (n->Entries <= 0) {
+                    pn.count = 0;
+                    pn.first = (uint32_t)(reinterpret_cast<const Blob_Element*>(n->Node) - D->Entry.data());
+                } else {
+                    pn.count = (uint32_t)n->Entries;
+                    pn.first = (uint32_t)order.size();
+                    for (int i = 0; i < (int)n->Entries; i++) { order.push_back(n->Node[i]); tree.push_back(pvgpu_blob_node{}); }
+                }
+                tree[qi] = pn;
+            }
+            pb.node_count = (uint32_t)tree.size();
+            blob_nodes.insert(blob_nodes.end(), tree.begin(), tree.end());
+        }
+        blobs.push_back(pb);
+        return (int32_t)blobs.size() - 1;
+    }
+
     int32_t add_object(ObjectPtr o, int32_t parent)
     {
         auto it = object_ids.find(o);
@@ -350,6 +400,11 @@ struct Flattener
             p.type = PVGPU_OBJ_MESH;
             p.mesh = add_mesh(m);
             p.transform = add_transform(m->Trans);
+        } else if (Blob* bl = dynamic_cast<Blob*>(o)) {
+            p.type = PVGPU_OBJ_BLOB;
+            p.mesh = add_blob(bl);
+            p.transform = add_transform(bl->Trans);
+            p.aux = (bl->Type & IS_CHILD_OBJECT) ? 1u : 0u;
         } else if (CSG* c = dynamic_cast<CSG*>(o)) {
             if (dynamic_cast<CSGMerge*>(o)) p.type = PVGPU_OBJ_CSG_MERGE;
             else if (dynamic_cast<CSGUnion*>(o)) p.type = PVGPU_OBJ_CSG_UNION;
@@ -357,7 +412,7 @@ struct Flattener
             else unsupported("unknown CSG class");
             add_index_range(c->children, self, true, p.child_first, p.child_count);
         } else {
-            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, CSG)");
+            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, blob, CSG)");
             p.type = 0;
         }
         add_index_range(o->Clip, self, false, p.clip_first, p.clip_count);
@@ -494,6 +549,8 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
                                   fl.frame.data(), fl.frame.size()), "set_objects");
     check(pvgpu_scene_set_transforms(gv.scene, fl.transforms.data(), fl.transforms.size()), "set_transforms");
     check(pvgpu_scene_set_tree(gv.scene, fl.nodes.data(), fl.nodes.size()), "set_tree");
+    check(pvgpu_scene_set_blobs(gv.scene, fl.blobs.data(), fl.blobs.size(), fl.blob_elements.data(), fl.blob_elements.size(),
+                                fl.blob_nodes.data(), fl.blob_nodes.size()), "set_blobs");
     check(pvgpu_scene_set_meshes(gv.scene, fl.meshes.data(), fl.meshes.size(), fl.vertices.data(), fl.vertices.size() / 3,
                                  fl.normals.data(), fl.normals.size() / 3, fl.triangles.data(), fl.triangles.size(),
                                  fl.mesh_nodes.data(), fl.mesh_nodes.size()), "set_meshes");

@@ -77,6 +77,9 @@ struct Scene {
     std::vector<pvgpu_blend_entry> entries;
     std::vector<pvgpu_warp> warps;
     std::vector<pvgpu_interior> interiors;
+    std::vector<pvgpu_blob> blobs;
+    std::vector<pvgpu_blob_element> blob_elements;
+    std::vector<pvgpu_blob_node> blob_nodes;
     // noise tables
     std::vector<unsigned short> hashTable;
     std::vector<double> RTable;
@@ -526,6 +529,11 @@ public:
     bool tri_intersect(const pvgpu_mesh& me, const pvgpu_triangle& tr, V3 o, V3 d, double* Depth) const;
     bool mesh_intersect(uint32_t idx, const Ray& ray, IStack& stack) const;
     bool mesh_inside(const pvgpu_object& ob, V3 p) const;
+    bool blob_intersect(uint32_t idx, const Ray& ray, IStack& stack) const;
+    bool blob_element_hit(const pvgpu_blob_element& e, V3 P, V3 D, double mindist, double* tmin, double* tmax) const;
+    double blob_element_field(const pvgpu_blob_element& e, V3 P) const;
+    void blob_element_normal(const pvgpu_blob_element& e, V3 P, V3& Result) const;
+    template <class F> void blob_walk_point(const pvgpu_blob& bl, V3 P, F&& leaf) const;
     V3 Normal(const Intersection& isect) const;
 
     // ---- tree ----
@@ -770,6 +778,13 @@ bool Tracer::Inside(V3 p, uint32_t idx) const
             return inside ? !inv : inv;
         }
         case PVGPU_OBJ_MESH: return mesh_inside(ob, p);
+        case PVGPU_OBJ_BLOB: {                                                                            // blob.cpp:1502-1624
+            const pvgpu_blob& bl = S.blobs[ob.mesh];
+            V3 P = (ob.transform >= 0) ? MInvTransPoint(S.xf[ob.transform], p) : p;
+            double density = 0.0;
+            blob_walk_point(bl, P, [&](const pvgpu_blob_element& e) { density += blob_element_field(e, P); });
+            return (density > bl.threshold - 1.0e-6) ? !inv : inv;
+        }
         case PVGPU_OBJ_CSG_UNION:
         case PVGPU_OBJ_CSG_MERGE:                                                                         // csg.cpp:393-410
             for (uint32_t i = 0; i < ob.child_count; i++) if (Inside_Object(p, S.index_list[ob.child_first + i])) return true;
@@ -906,6 +921,7 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
             return found;
         }
         case PVGPU_OBJ_MESH: return mesh_intersect(idx, ray, Depth_Stack);
+        case PVGPU_OBJ_BLOB: return blob_intersect(idx, ray, Depth_Stack);
         case PVGPU_OBJ_CSG_UNION: {                                                                       // csg.cpp:128-189
             for (uint32_t i = 0; i < ob.child_count; i++) {
                 uint32_t ch = S.index_list[ob.child_first + i];
@@ -1037,6 +1053,233 @@ bool Tracer::FindIntersection(Intersection& best, const Ray& ray, double post_mi
     return found;
 }
 
+// ---- blob (blob.cpp) -------------------------------------------------------------------------------------
+// intersect_element and the four component intersectors (blob.cpp:716-1267)
+bool Tracer::blob_element_hit(const pvgpu_blob_element& e, V3 P, V3 D, double mindist, double* tmin, double* tmax) const
+{
+    *tmin = BOUND_HUGE; *tmax = -BOUND_HUGE;
+    double b, d, t, length = 1.0;
+    V3 PP = P, DD = D;
+    if (e.type != PVGPU_BLOB_SPHERE) {
+        const pvgpu_transform& tr = S.xf[e.transform];
+        PP = MInvTransPoint(tr, P); DD = MInvTransDirection(tr, D);
+        length = len(DD); DD = DD / length;
+    }
+    switch (e.type) {
+        case PVGPU_BLOB_SPHERE:
+        case PVGPU_BLOB_ELLIPSOID: {
+            V3 V1 = PP - v3(e.o);
+            b = dot(V1, DD); t = len2(V1); d = b * b - t + e.rad2;
+            if (d < EPSILON) return false;
+            d = std::sqrt(d);
+            if (e.type == PVGPU_BLOB_SPHERE) { *tmax = -b + d; *tmin = -b - d; } else { *tmax = (-b + d) / length; *tmin = (-b - d) / length; }
+            if (*tmax < mindist) *tmax = 0.0;
+            if (*tmin < mindist) *tmin = 0.0;
+            if (*tmax == *tmin) return false;
+            if (*tmax < *tmin) std::swap(*tmin, *tmax);
+            return true;
+        }
+        case PVGPU_BLOB_BASE_HEMISPHERE:
+        case PVGPU_BLOB_APEX_HEMISPHERE: {
+            const bool base = e.type == PVGPU_BLOB_BASE_HEMISPHERE;
+            if (!base) PP.z -= e.len;
+            b = dot(PP, DD); t = len2(PP); d = b * b - t + e.rad2;
+            if (d < EPSILON) return false;
+            d = std::sqrt(d);
+            *tmax = -b + d; *tmin = -b - d;
+            if (*tmax < *tmin) std::swap(*tmin, *tmax);
+            double z1 = PP.z + *tmin * DD.z, z2 = PP.z + *tmax * DD.z;
+            bool in1 = base ? (z1 >= 0.0) : (z1 <= 0.0), in2 = base ? (z2 >= 0.0) : (z2 <= 0.0);      // "inside" = beyond the cutting plane
+            bool out1 = base ? (z1 < 0.0) : (z1 > 0.0), out2 = base ? (z2 < 0.0) : (z2 > 0.0);
+            if (in1 && in2) return false;
+            if (out1 && out2) { *tmin /= length; *tmax /= length; return true; }
+            t = -PP.z / DD.z;
+            if (in1) *tmin = (t < mindist) ? 0.0 : t; else *tmax = (t < mindist) ? 0.0 : t;
+            *tmin /= length; *tmax /= length;
+            return true;
+        }
+        default: {      // cylinder
+            double a = DD.x * DD.x + DD.y * DD.y, u, v, w;
+            auto take = [&](double tt) { if (tt < *tmin) *tmin = tt; if (tt > *tmax) *tmax = tt; };
+            if (a > EPSILON) {
+                b = PP.x * DD.x + PP.y * DD.y;
+                double c = PP.x * PP.x + PP.y * PP.y - e.rad2;
+                d = b * b - a * c;
+                if (d > EPSILON) {
+                    d = std::sqrt(d);
+                    t = (-b + d) / a; w = PP.z + t * DD.z; if ((w >= 0.0) && (w <= e.len)) take(t);
+                    t = (-b - d) / a; w = PP.z + t * DD.z; if ((w >= 0.0) && (w <= e.len)) take(t);
+                }
+            }
+            if (std::fabs(DD.z) > EPSILON) {
+                t = -PP.z / DD.z; u = PP.x + t * DD.x; v = PP.y + t * DD.y; if ((u * u + v * v) <= e.rad2) take(t);
+                t = (e.len - PP.z) / DD.z; u = PP.x + t * DD.x; v = PP.y + t * DD.y; if ((u * u + v * v) <= e.rad2) take(t);
+            }
+            *tmin /= length; *tmax /= length;
+            if (*tmin < mindist) *tmin = 0.0;
+            if (*tmax < mindist) *tmax = 0.0;
+            return !(*tmin >= *tmax);
+        }
+    }
+}
+
+// calculate_element_field (blob.cpp:1379-1500)
+double Tracer::blob_element_field(const pvgpu_blob_element& e, V3 P) const
+{
+    auto f = [&](double rad2) { return rad2 * (rad2 * e.c[0] + e.c[1]) + e.c[2]; };
+    if (e.type == PVGPU_BLOB_SPHERE) { double r2 = len2(P - v3(e.o)); return (r2 < e.rad2) ? f(r2) : 0.0; }
+    V3 PP = MInvTransPoint(S.xf[e.transform], P);
+    switch (e.type) {
+        case PVGPU_BLOB_ELLIPSOID: { double r2 = len2(PP - v3(e.o)); return (r2 < e.rad2) ? f(r2) : 0.0; }
+        case PVGPU_BLOB_BASE_HEMISPHERE: if (PP.z <= 0.0) { double r2 = len2(PP); if (r2 <= e.rad2) return f(r2); } return 0.0;
+        case PVGPU_BLOB_APEX_HEMISPHERE: PP.z -= e.len; if (PP.z >= 0.0) { double r2 = len2(PP); if (r2 <= e.rad2) return f(r2); } return 0.0;
+        default: if ((PP.z >= 0.0) && (PP.z <= e.len)) { double r2 = sqr(PP.x) + sqr(PP.y); if (r2 <= e.rad2) return f(r2); } return 0.0;
+    }
+}
+
+// element_normal (blob.cpp:1677-1813)
+void Tracer::blob_element_normal(const pvgpu_blob_element& e, V3 P, V3& Result) const
+{
+    auto val = [&](double dist) { return -2.0 * e.c[0] * dist - e.c[1]; };
+    if (e.type == PVGPU_BLOB_SPHERE) { V3 V1 = P - v3(e.o); double dist = len2(V1); if (dist <= e.rad2) Result = Result + V1 * val(dist); return; }
+    const pvgpu_transform& tr = S.xf[e.transform];
+    V3 PP = MInvTransPoint(tr, P);
+    switch (e.type) {
+        case PVGPU_BLOB_ELLIPSOID: { V3 V1 = PP - v3(e.o); double dist = len2(V1); if (dist <= e.rad2) Result = Result + MTransNormal(tr, V1) * val(dist); return; }
+        case PVGPU_BLOB_BASE_HEMISPHERE: if (PP.z <= 0.0) { double dist = len2(PP); if (dist <= e.rad2) Result = Result + MTransNormal(tr, PP) * val(dist); } return;
+        case PVGPU_BLOB_APEX_HEMISPHERE: PP.z -= e.len; if (PP.z >= 0.0) { double dist = len2(PP); if (dist <= e.rad2) Result = Result + MTransNormal(tr, PP) * val(dist); } return;
+        default:
+            if ((PP.z >= 0.0) && (PP.z <= e.len)) {
+                double dist = sqr(PP.x) + sqr(PP.y);
+                if (dist <= e.rad2) { double vv = val(dist); PP.z = 0.0; Result = Result + MTransNormal(tr, PP) * vv; }
+            }
+    }
+}
+
+// the point walks of calculate_field_value / Normal (blob.cpp:1502-1594, 1815-1905): all components, or the leaves of the
+// bounding-sphere tree whose spheres contain the point, in the reference's LIFO order
+template <class F> void Tracer::blob_walk_point(const pvgpu_blob& bl, V3 P, F&& leaf) const
+{
+    const pvgpu_blob_element* el = S.blob_elements.data() + bl.element_first;
+    if (bl.node_count == 0) { for (uint32_t i = 0; i < bl.element_count; i++) leaf(el[i]); return; }
+    const pvgpu_blob_node* nodes = S.blob_nodes.data() + bl.node_first;
+    std::vector<uint32_t> queue{ 0u };
+    while (!queue.empty()) {
+        const pvgpu_blob_node& nd = nodes[queue.back()]; queue.pop_back();
+        if (nd.count == 0) leaf(el[nd.first]);
+        else for (uint32_t i = 0; i < nd.count; i++) if (len2(P - v3(nodes[nd.first + i].c)) <= nodes[nd.first + i].r2) queue.push_back(nd.first + i);
+    }
+}
+
+// Blob::All_Intersections (blob.cpp:239-610) with determine_influences (:1269-1377) and insert_hit (:616-714)
+bool Tracer::blob_intersect(uint32_t idx, const Ray& ray, IStack& Depth_Stack) const
+{
+    const pvgpu_object& ob = S.objects[idx];
+    const pvgpu_blob& bl = S.blobs[ob.mesh];
+    const pvgpu_blob_element* el = S.blob_elements.data() + bl.element_first;
+    const double depthTolerance = 1.0e-2;
+    V3 P = ray.Origin, D = ray.Direction;
+    double length = 1.0;
+    if (ob.transform >= 0) { const pvgpu_transform& t = S.xf[ob.transform]; P = MInvTransPoint(t, ray.Origin); D = MInvTransDirection(t, ray.Direction); length = len(D); D = D / length; }
+    struct Interval { int type; double bound; uint32_t elem; };
+    std::vector<Interval> iv;
+    auto insert_hit = [&](uint32_t e, double t0, double t1) {
+        // sorted insertion; a bound goes in front of the first stored bound that is not smaller
+        size_t k = 0;
+        while (k < iv.size() && t0 > iv[k].bound) k++;
+        const bool appended = (k == iv.size());
+        iv.insert(iv.begin() + k, Interval{ (int)el[e].type | 0, t0, e });
+        if (appended) { iv.push_back(Interval{ (int)el[e].type | 1, t1, e }); return; }
+        k++;
+        while (k < iv.size() && t1 > iv[k].bound) k++;
+        iv.insert(iv.begin() + k, Interval{ (int)el[e].type | 1, t1, e });
+    };
+    if (bl.node_count == 0) {
+        for (uint32_t i = 0; i < bl.element_count; i++) { double t0, t1; if (blob_element_hit(el[i], P, D, depthTolerance, &t0, &t1)) insert_hit(i, t0, t1); }
+    } else {
+        const pvgpu_blob_node* nodes = S.blob_nodes.data() + bl.node_first;
+        std::vector<uint32_t> queue{ 0u };
+        while (!queue.empty()) {
+            const pvgpu_blob_node& nd = nodes[queue.back()]; queue.pop_back();
+            if (nd.count == 0) { double t0, t1; if (blob_element_hit(el[nd.first], P, D, depthTolerance, &t0, &t1)) insert_hit(nd.first, t0, t1); }
+            else for (uint32_t i = 0; i < nd.count; i++) {
+                V3 V1 = v3(nodes[nd.first + i].c) - P;
+                double b = dot(V1, D), t = len2(V1);
+                if ((t - sqr(b)) <= nodes[nd.first + i].r2) queue.push_back(nd.first + i);
+            }
+        }
+    }
+    const int cnt = (int)iv.size();
+    if (cnt == 0) return false;
+    double start_dist = iv[0].bound;
+    if (start_dist < SMALL_TOLERANCE) start_dist = 0.0;
+    for (auto& x : iv) x.bound -= start_dist;
+    P = P + D * start_dist;
+    double max_bound = iv[0].bound;
+    for (auto& x : iv) if (x.bound > max_bound) max_bound = x.bound;
+    if (max_bound != 0) { D = D * max_bound; for (auto& x : iv) x.bound /= max_bound; } else max_bound = 1;
+    double coeffs[5] = { 0.0, 0.0, 0.0, 0.0, -bl.threshold };
+    std::vector<double> fcoeffs((size_t)bl.element_count * 5, 0.0);
+    bool found = false;
+    int in_flag = 0;
+    for (int i = 0; i < cnt; i++) {
+        double* f = &fcoeffs[(size_t)iv[i].elem * 5];
+        if ((iv[i].type & 1) == 0) {
+            in_flag++;
+            const pvgpu_blob_element& e = el[iv[i].elem];
+            double t0, t1, t2;
+            if (e.type == PVGPU_BLOB_SPHERE) { V3 V1 = P - v3(e.o); t0 = len2(V1); t1 = dot(V1, D); t2 = max_bound * max_bound; }
+            else {
+                const pvgpu_transform& tr = S.xf[e.transform];
+                V3 PP = MInvTransPoint(tr, P), DD = MInvTransDirection(tr, D);
+                if (e.type == PVGPU_BLOB_ELLIPSOID) { V3 V1 = PP - v3(e.o); t0 = len2(V1); t1 = dot(V1, DD); t2 = len2(DD); }
+                else if (e.type == PVGPU_BLOB_CYLINDER) { t0 = PP.x * PP.x + PP.y * PP.y; t1 = PP.x * DD.x + PP.y * DD.y; t2 = DD.x * DD.x + DD.y * DD.y; }
+                else { if (e.type == PVGPU_BLOB_APEX_HEMISPHERE) PP.z -= e.len; t0 = len2(PP); t1 = dot(PP, DD); t2 = len2(DD); }
+            }
+            const double c0 = e.c[0], c1 = e.c[1], c2 = e.c[2];
+            f[0] = c0 * t2 * t2;
+            f[1] = 4.0 * c0 * t1 * t2;
+            f[2] = 2.0 * c0 * (2.0 * t1 * t1 + t0 * t2) + c1 * t2;
+            f[3] = 2.0 * t1 * (2.0 * c0 * t0 + c1);
+            f[4] = t0 * (c0 * t0 + c1) + c2;
+            for (int j = 0; j < 5; j++) coeffs[j] += f[j];
+        } else {
+            for (int j = 0; j < 5; j++) coeffs[j] -= f[j];
+            if (--in_flag == 0) continue;
+        }
+        if ((i + 1 < cnt) && (std::fabs(iv[i].bound - iv[i + 1].bound) < EPSILON)) continue;
+        const double l = iv[i].bound, w = iv[i + 1].bound - l;
+        double nc[5], dk[5];
+        nc[0] = coeffs[0] * w * w * w * w;
+        nc[1] = (coeffs[1] + 4.0 * coeffs[0] * l) * w * w * w;
+        nc[2] = (3.0 * l * (2.0 * coeffs[0] * l + coeffs[1]) + coeffs[2]) * w * w;
+        nc[3] = (2.0 * l * (2.0 * l * (coeffs[0] * l + 0.75 * coeffs[1]) + coeffs[2]) + coeffs[3]) * w;
+        nc[4] = l * (l * (l * (coeffs[0] * l + coeffs[1]) + coeffs[2]) + coeffs[3]) + coeffs[4];
+        dk[0] = nc[4];
+        dk[1] = nc[4] + 0.25 * nc[3];
+        dk[2] = nc[4] + 0.50 * (nc[3] + nc[2] / 3.0);
+        dk[3] = nc[4] + 0.50 * (1.5 * nc[3] + nc[2] + 0.5 * nc[1]);
+        dk[4] = nc[4] + nc[3] + nc[2] + nc[1] + nc[0];
+        bool all_pos = true, all_neg = true;
+        for (int j = 0; j < 5; j++) { all_pos = all_pos && (dk[j] >= 0.0); all_neg = all_neg && (dk[j] <= 0.0); }
+        if (all_pos || all_neg) continue;
+        double roots[4];
+        int root_count = Solve_Polynomial(4, coeffs, roots, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, 1.0e-11);
+        for (int j = 0; j < root_count; j++) {
+            double dist = roots[j];
+            if ((dist >= iv[i].bound) && (dist <= iv[i + 1].bound)) {
+                dist = (dist * max_bound + start_dist) / length;
+                if ((dist > depthTolerance) && (dist < MAX_DISTANCE)) {
+                    V3 ip = ray.Evaluate(dist);
+                    if (clip_ok(ob, ip)) { Intersection is; is.Depth = dist; is.IPoint = ip; is.Object = (int)idx; is.aux = 0; Depth_Stack.push_back(is); found = true; }
+                }
+            }
+        }
+        if (!(ob.aux & 1u) && found) break;       // not a CSG child
+    }
+    return found;
+}
+
 // <Primitive>::Normal
 V3 Tracer::Normal(const Intersection& isect) const
 {
@@ -1070,6 +1313,17 @@ V3 Tracer::Normal(const Intersection& isect) const
             if (dist > EPSILON) { M.x = ob.p[0] * P.x / dist; M.z = ob.p[0] * P.z / dist; }
             V3 N = isect.aux ? P + M : P - M;
             return unit(MTransNormal(t, N));
+        }
+        case PVGPU_OBJ_BLOB: {                                                                            // blob.cpp:1815-1933
+            const pvgpu_blob& bl = S.blobs[ob.mesh];
+            V3 P = (ob.transform >= 0) ? MInvTransPoint(S.xf[ob.transform], isect.IPoint) : isect.IPoint;
+            V3 Result = v3(0, 0, 0);
+            blob_walk_point(bl, P, [&](const pvgpu_blob_element& e) { blob_element_normal(e, P, Result); });
+            double val = len2(Result);
+            if (val == 0.0) Result = v3(1, 0, 0);
+            else { val = 1.0 / std::sqrt(val); Result = Result * val; }
+            if (ob.transform >= 0) Result = unit(MTransNormal(S.xf[ob.transform], Result));
+            return Result;
         }
         case PVGPU_OBJ_MESH: {                                                                            // mesh.cpp:283-375
             const pvgpu_mesh& me = S.meshes[ob.mesh];
@@ -1676,6 +1930,7 @@ void* pvo_scene_load(const char* path)
               get(f, s->objects) && get(f, s->index_list) && get(f, s->frame) && get(f, s->xf) && get(f, s->nodes) && get(f, s->meshes) &&
               get(f, s->verts) && get(f, s->norms) && get(f, s->tris) && get(f, s->mnodes) && get(f, s->lights) && get(f, s->textures) &&
               get(f, s->pigments) && get(f, s->finishes) && get(f, s->maps) && get(f, s->entries) && get(f, s->warps) && get(f, s->interiors);
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->blobs) && get(f, s->blob_elements) && get(f, s->blob_nodes); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());

@@ -16,7 +16,7 @@ ABI_VERSION = 2
 OK, E_INVALID, E_UNSUPPORTED, E_NO_DEVICE, E_CUDA, E_IO, E_ABORTED, E_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
 
 # object kinds
-OBJ_SPHERE, OBJ_BOX, OBJ_PLANE, OBJ_QUADRIC, OBJ_TORUS, OBJ_MESH, OBJ_CSG_UNION, OBJ_CSG_INTERSECTION, OBJ_CSG_MERGE = range(1, 10)
+OBJ_SPHERE, OBJ_BOX, OBJ_PLANE, OBJ_QUADRIC, OBJ_TORUS, OBJ_MESH, OBJ_CSG_UNION, OBJ_CSG_INTERSECTION, OBJ_CSG_MERGE, OBJ_BLOB = range(1, 11)
 
 # object flags (source/core/scene/object.h:88-117)
 NO_SHADOW_FLAG = 0x00000001
@@ -75,6 +75,18 @@ class Mesh(C.Structure):
                 ("triangle_first", u32), ("triangle_count", u32), ("node_first", u32), ("node_count", u32),
                 ("texture_first", u32), ("texture_count", u32), ("has_inside_vector", u32), ("reserved", u32),
                 ("inside_vector", f64 * 3)]
+
+
+class BlobElement(C.Structure):
+    _fields_ = [("type", u32), ("transform", i32), ("o", f64 * 3), ("len", f64), ("rad2", f64), ("c", f64 * 3)]
+
+
+class BlobNode(C.Structure):
+    _fields_ = [("c", f64 * 3), ("r2", f64), ("first", u32), ("count", u32)]
+
+
+class Blob(C.Structure):
+    _fields_ = [("element_first", u32), ("element_count", u32), ("node_first", u32), ("node_count", u32), ("threshold", f64)]
 
 
 class Light(C.Structure):
@@ -170,6 +182,7 @@ SIGNATURES = {
     "pvgpu_scene_set_transforms": (C.c_int, [VP, P(Transform), C.c_size_t]),
     "pvgpu_scene_set_tree": (C.c_int, [VP, P(Node), C.c_size_t]),
     "pvgpu_scene_build_tree": (C.c_int, [VP]),
+    "pvgpu_scene_set_blobs": (C.c_int, [VP, P(Blob), C.c_size_t, P(BlobElement), C.c_size_t, P(BlobNode), C.c_size_t]),
     "pvgpu_scene_set_meshes": (C.c_int, [VP, P(Mesh), C.c_size_t, P(f32), C.c_size_t, P(f32), C.c_size_t,
                                          P(Triangle), C.c_size_t, P(Node), C.c_size_t]),
     "pvgpu_scene_set_lights": (C.c_int, [VP, P(Light), C.c_size_t]),

@@ -108,6 +108,9 @@ struct DScene {
     const pvgpu_blend_entry* entries;
     const pvgpu_warp*        warps;
     const pvgpu_interior*    interiors;
+    const pvgpu_blob*        blobs;
+    const pvgpu_blob_element* blob_elements;
+    const pvgpu_blob_node*   blob_nodes;
     const uint32_t*          csg_leaves;    // per top-level CSG object: its primitive descendants (DFS order)
     const uint2*             csg_leaf_range;// per object: (first, count) into csg_leaves
     NoiseTables              noise;

@@ -9,6 +9,7 @@
 // factors (`w`, `wt`) and adds its own local terms straight into the sample's accumulator.
 #pragma once
 #include "pv_shapes.cuh"
+#include "pv_blob.cuh"
 #include "pv_noise.cuh"
 #include "pv_kernels.hpp"
 
@@ -379,6 +380,7 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_QUADRIC: return quadric_normal(ob, hit.ip);
         case PVGPU_OBJ_TORUS:   return torus_normal(sc, ob, hit.ip, hit.aux);
         case PVGPU_OBJ_MESH:    return mesh_normal(sc, ob, hit);
+        case PVGPU_OBJ_BLOB:    return blob_normal(sc, ob, hit.ip);
     }
     return mk(0.0, 1.0, 0.0);
 }

@@ -10,6 +10,7 @@
 // for exact ties between different objects (first visited wins in both schemes, visit order differs).
 #pragma once
 #include "pv_shapes.cuh"
+#include "pv_blob.cuh"
 
 namespace pvgpu {
 
@@ -187,6 +188,7 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
         case PVGPU_OBJ_MESH:    return mesh_inside(sc, ob, p, stack, sp0);
+        case PVGPU_OBJ_BLOB:    return blob_inside(sc, ob, p);
     }
     return false;
 }
@@ -205,7 +207,7 @@ static __device__ __noinline__ bool inside_object(const DScene& sc, uint32_t roo
         Frame& f = st[sp];
         const pvgpu_object& o = sc.objs[f.obj];
         const uint32_t nclip = (sp == 0 && !root_clip) ? 0u : o.clip_count;   // Object->Inside() alone for the root if asked
-        const bool is_csg = o.type >= PVGPU_OBJ_CSG_UNION;
+        const bool is_csg = PVGPU_IS_CSG(o.type);
         if (have_ret) {
             have_ret = false;
             const uint32_t e = f.cur - 1;
@@ -253,9 +255,10 @@ __device__ __forceinline__ void consider(HitAcc& acc, double depth, const V3& ip
     }
 }
 
-__device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+__device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr)
 {
     switch (ob.type) {
+        case PVGPU_OBJ_BLOB:    if (!blob_hits(sc, ob, o, d, h) && overflow) atomicOr(overflow, 32u); break;
         case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_PLANE:   plane_hits(sc, ob, o, d, h); break;
@@ -541,11 +544,11 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     }
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
-    if (ob.type >= PVGPU_OBJ_CSG_UNION) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow);
+    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow);
     else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
     else {
         PrimHits h;
-        prim_hits(sc, ob, o, d, h);
+        prim_hits(sc, ob, o, d, h, overflow);
         for (int i = 0; i < h.n; i++)
             if (ob.clip_count == 0 || point_in_clip(sc, ob, h.ip[i], stack, sp0)) consider(acc, h.depth[i], h.ip[i], idx, h.aux[i], -1);
     }
@@ -562,11 +565,11 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
     if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL)) return false;
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = -1.0; acc.found = false;
-    if (ob.type >= PVGPU_OBJ_CSG_UNION) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow);
+    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow);
     else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
     else {
         PrimHits h;
-        prim_hits(sc, ob, o, d, h);
+        prim_hits(sc, ob, o, d, h, overflow);
         for (int i = 0; i < h.n; i++)
             if (ob.clip_count == 0 || point_in_clip(sc, ob, h.ip[i], stack, sp0)) consider(acc, h.depth[i], h.ip[i], idx, h.aux[i], -1);
     }

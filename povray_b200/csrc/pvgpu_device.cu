@@ -200,13 +200,13 @@ int device_upload(Scene& s, int device)
     std::vector<uint2> leaf_range(s.objects.size(), make_uint2(0, 0));
     for (size_t i = 0; i < s.objects.size(); i++) {
         const pvgpu_object& o = s.objects[i];
-        if (o.type < PVGPU_OBJ_CSG_UNION || o.parent >= 0) continue;
+        if (!PVGPU_IS_CSG(o.type) || o.parent >= 0) continue;
         uint32_t first = (uint32_t)leaves.size();
         std::vector<uint32_t> st{ (uint32_t)i };
         while (!st.empty()) {
             uint32_t c = st.back(); st.pop_back();
             const pvgpu_object& co = s.objects[c];
-            if (co.type >= PVGPU_OBJ_CSG_UNION) {
+            if (PVGPU_IS_CSG(co.type)) {
                 for (uint32_t k = co.child_count; k-- > 0;) {
                     uint32_t ch = s.index_list[co.child_first + k];
                     if (ch >= s.objects.size() || s.objects[ch].parent != (int32_t)c) {
@@ -268,6 +268,7 @@ int device_upload(Scene& s, int device)
     UP(s.vertices, v.verts); UP(s.normals, v.norms); UP(s.lights, v.lights);
     UP(s.textures, v.textures); UP(s.pigments, v.pigments); UP(s.finishes, v.finishes); UP(s.blend_maps, v.maps);
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
+    UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes);
     UP(leaves, v.csg_leaves); UP(leaf_range, v.csg_leaf_range);
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP
@@ -289,8 +290,8 @@ int device_upload(Scene& s, int device)
         device_release(s);
         return fail(PVGPU_E_CUDA, "cudaMalloc of counters failed");
     }
-    // the deepest Inside()/sturm paths keep a few small arrays per thread
-    cudaDeviceSetLimit(cudaLimitStackSize, 4096);
+    // the deepest Inside()/sturm paths keep a few small arrays per thread; blobs add their per-ray interval lists
+    cudaDeviceSetLimit(cudaLimitStackSize, s.blobs.empty() ? 4096 : 12288);
     d->camera_dirty = true;
     return PVGPU_OK;
 }
@@ -723,7 +724,7 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
     st.kernel_items[KIND_SHADOW] = hc.shadow_rays;
     if (stats) *stats = st;
     if (hc.overflow & ~(8u | 16u))
-        return fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x: 1 traversal stack, 2 mesh in CSG, 4 interior list)", hc.overflow);
+        return fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x: 1 traversal stack, 2 mesh in CSG, 4 interior list, 32 blob components per ray)", hc.overflow);
     return PVGPU_OK;
 }
 

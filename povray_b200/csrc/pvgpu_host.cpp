@@ -243,7 +243,7 @@ int validate_scene(Scene& s)
         if (f >= no) return fail(PVGPU_E_INVALID, "frame object index %u out of range", f);
     for (size_t i = 0; i < no; i++) {
         const pvgpu_object& o = s.objects[i];
-        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_CSG_MERGE)
+        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_BLOB)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: primitive type %u is outside the hot-path scope", i, o.type);
         if (!range_ok(o.child_first, o.child_count, s.index_list.size()) ||
             !range_ok(o.clip_first, o.clip_count, s.index_list.size()) ||
@@ -258,14 +258,36 @@ int validate_scene(Scene& s)
         if (o.parent >= (int32_t)no) return fail(PVGPU_E_INVALID, "object %zu: parent out of range", i);
         if (o.type == PVGPU_OBJ_MESH && (o.mesh < 0 || o.mesh >= (int32_t)s.meshes.size()))
             return fail(PVGPU_E_INVALID, "object %zu: mesh index out of range", i);
+        if (o.type == PVGPU_OBJ_BLOB) {
+            if (o.mesh < 0 || o.mesh >= (int32_t)s.blobs.size()) return fail(PVGPU_E_INVALID, "object %zu: blob index out of range", i);
+            if (o.parent >= 0 || (o.aux & 1u)) return fail(PVGPU_E_UNSUPPORTED, "object %zu: a blob inside CSG is outside the hot-path scope", i);
+        }
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
         if ((o.flags & PVGPU_UV_FLAG))
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: uv_mapping is outside the hot-path scope", i);
         if ((o.flags & PVGPU_CUTAWAY_TEXTURES_FLAG) && o.texture < 0)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: cutaway_textures is outside the hot-path scope", i);
-        if (o.type >= PVGPU_OBJ_CSG_UNION && o.parent >= 0 && o.bound_count)
+        if (PVGPU_IS_CSG(o.type) && o.parent >= 0 && o.bound_count)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: bounded_by on a nested CSG child", i);
+    }
+    for (size_t i = 0; i < s.blobs.size(); i++) {
+        const pvgpu_blob& b = s.blobs[i];
+        if (!range_ok(b.element_first, b.element_count, s.blob_elements.size()) || !range_ok(b.node_first, b.node_count, s.blob_nodes.size()) || b.element_count == 0)
+            return fail(PVGPU_E_INVALID, "blob %zu: element / node range out of bounds", i);
+        for (uint32_t k = 0; k < b.element_count; k++) {
+            const pvgpu_blob_element& e = s.blob_elements[b.element_first + k];
+            const bool known = e.type == PVGPU_BLOB_SPHERE || e.type == PVGPU_BLOB_CYLINDER || e.type == PVGPU_BLOB_ELLIPSOID ||
+                               e.type == PVGPU_BLOB_BASE_HEMISPHERE || e.type == PVGPU_BLOB_APEX_HEMISPHERE;
+            if (!known) return fail(PVGPU_E_UNSUPPORTED, "blob %zu: component type %u", i, e.type);
+            if (e.transform >= (int32_t)s.transforms.size() || (e.type != PVGPU_BLOB_SPHERE && e.transform < 0))
+                return fail(PVGPU_E_INVALID, "blob %zu: component transform out of range", i);
+        }
+        for (uint32_t k = 0; k < b.node_count; k++) {
+            const pvgpu_blob_node& n = s.blob_nodes[b.node_first + k];
+            if (n.count ? !range_ok(n.first, n.count, b.node_count) : n.first >= b.element_count)
+                return fail(PVGPU_E_INVALID, "blob %zu: bounding-sphere node %u out of range", i, k);
+        }
     }
     for (uint32_t v : s.index_list)
         if (v >= no && v >= s.textures.size())
@@ -374,7 +396,7 @@ int validate_scene(Scene& s)
     // otherwise the reference's closest-hit filter loop is followed (trace.cpp:2025-2075)
     s.all_shadow_casters_opaque = true;
     for (const pvgpu_object& o : s.objects)
-        if (o.type < PVGPU_OBJ_CSG_UNION && !(o.flags & PVGPU_NO_SHADOW_FLAG) && !(o.flags & PVGPU_OPAQUE_FLAG))
+        if (!PVGPU_IS_CSG(o.type) && !(o.flags & PVGPU_NO_SHADOW_FLAG) && !(o.flags & PVGPU_OPAQUE_FLAG))
             s.all_shadow_casters_opaque = false;
     return PVGPU_OK;
 }
@@ -475,6 +497,19 @@ int pvgpu_scene_build_tree(pvgpu_scene* sc)
         ((o.flags & PVGPU_INFINITE_FLAG) ? inf : fin).push_back(b);
     }
     build_bbox_tree(fin, inf, s.nodes);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_blobs(pvgpu_scene* sc, const pvgpu_blob* blobs, size_t n_blobs, const pvgpu_blob_element* elements, size_t n_elements,
+                          const pvgpu_blob_node* nodes, size_t n_nodes)
+{
+    clear_error();
+    if (!sc || (!blobs && n_blobs) || (!elements && n_elements) || (!nodes && n_nodes))
+        return fail(PVGPU_E_INVALID, "pvgpu_scene_set_blobs: null array");
+    Scene& s = *reinterpret_cast<Scene*>(sc);
+    s.blobs.assign(blobs, blobs + n_blobs);
+    s.blob_elements.assign(elements, elements + n_elements);
+    s.blob_nodes.assign(nodes, nodes + n_nodes);
     return PVGPU_OK;
 }
 
@@ -680,6 +715,8 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.triangles) && put(f, s.mesh_nodes) && put(f, s.lights) && put(f, s.textures) &&
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
+    // optional trailing section (files without it simply end here)
+    if (ok && !s.blobs.empty()) ok = put(f, s.blobs) && put(f, s.blob_elements) && put(f, s.blob_nodes);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -701,6 +738,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
               get(f, s->triangles) && get(f, s->mesh_nodes) && get(f, s->lights) && get(f, s->textures) &&
               get(f, s->pigments) && get(f, s->finishes) && get(f, s->blend_maps) && get(f, s->blend_entries) &&
               get(f, s->warps) && get(f, s->interiors);
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->blobs) && get(f, s->blob_elements) && get(f, s->blob_nodes); }
+    }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }
     s->have_camera = have_cam != 0;

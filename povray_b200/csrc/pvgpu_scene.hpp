@@ -29,6 +29,10 @@ struct Scene {
     std::vector<pvgpu_triangle>    triangles;
     std::vector<pvgpu_node>        mesh_nodes;
 
+    std::vector<pvgpu_blob>         blobs;
+    std::vector<pvgpu_blob_element> blob_elements;
+    std::vector<pvgpu_blob_node>    blob_nodes;
+
     std::vector<pvgpu_light>       lights;
     std::vector<pvgpu_texture>     textures;
     std::vector<pvgpu_pigment>     pigments;
