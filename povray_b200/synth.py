@@ -383,9 +383,10 @@ def csg_scene_pov(n_objects=4096, seed=777, max_trace_level=6):
     return "\n".join(out) + "\n"
 
 
-def torus_scene_pov(n_tori=2048, seed=4242):
-    """Config 4 (torus part): `n_tori` tori (half of them `sturm`), random rotation / translation, granite and bozo
-    pigments with colour maps and turbulence, noise_generator 2 for one half of the pigments and 3 for the other."""
+def torus_scene_pov(n_tori=2048, seed=4242, n_blobs=64):
+    """Config 4: `n_tori` tori (half of them `sturm`), random rotation / translation, granite and bozo pigments with
+    colour maps and turbulence, noise_generator 2 for one half of the pigments and 3 for the other; plus `n_blobs` blobs of
+    8 components each (spheres and cylinders, every fourth blob `sturm`)."""
     rng = np.random.RandomState(seed)
     out = ["#version 3.7;",
            "global_settings { assumed_gamma 1 max_trace_level 5 noise_generator 2 }",
@@ -406,4 +407,17 @@ def torus_scene_pov(n_tori=2048, seed=4242):
                    f"[0 rgb <{c1[0]:.4f}, {c1[1]:.4f}, {c1[2]:.4f}>] [0.5 rgb <{c2[0]:.4f}, {c2[1]:.4f}, {c2[2]:.4f}>] "
                    f"[1 rgb <{c3[0]:.4f}, {c3[1]:.4f}, {c3[2]:.4f}>] }} }} finish {{ ambient 0.1 diffuse 0.65 phong 0.4 }} "
                    f"rotate <{rot[0]:.4f}, {rot[1]:.4f}, {rot[2]:.4f}> translate <{pos[0]:.6f}, {pos[1]:.6f}, {pos[2]:.6f}> }}")
+    for i in range(n_blobs):
+        cx, cy, cz = rng.uniform(-20.0, 20.0), rng.uniform(1.0, 6.0), rng.uniform(-8.0, 30.0)
+        comps = []
+        for k in range(8):
+            px, py, pz = cx + rng.uniform(-1.0, 1.0), cy + rng.uniform(-0.8, 0.8), cz + rng.uniform(-1.0, 1.0)
+            if k % 3 == 2:
+                comps.append(f"cylinder {{ <{px:.5f}, {py:.5f}, {pz:.5f}>, <{px + rng.uniform(-0.9, 0.9):.5f}, {py + rng.uniform(0.3, 0.9):.5f}, "
+                             f"{pz + rng.uniform(-0.9, 0.9):.5f}>, {rng.uniform(0.4, 0.7):.5f}, {rng.uniform(0.7, 1.2):.4f} }}")
+            else:
+                comps.append(f"sphere {{ <{px:.5f}, {py:.5f}, {pz:.5f}>, {rng.uniform(0.7, 1.3):.5f}, {rng.uniform(0.7, 1.2):.4f} }}")
+        col = rng.uniform(0.2, 1.0, size=3)
+        out.append(f"blob {{ threshold {rng.uniform(0.45, 0.65):.4f} {' '.join(comps)}{' sturm' if i % 4 == 0 else ''} "
+                   f"pigment {{ rgb <{col[0]:.4f}, {col[1]:.4f}, {col[2]:.4f}> }} finish {{ ambient 0.1 diffuse 0.65 specular 0.4 roughness 0.03 }} }}")
     return "\n".join(out) + "\n"
