@@ -21,6 +21,7 @@ struct RayInfo {
     float cmin[3], cmax[3];       // 0 for axes the ray moves along; -/+BOUND_HUGE for axes with a zero direction component
     bool  nonzero[3], positive[3];
     bool  any_zero;               // some direction component is exactly zero (containment test needed)
+    bool  special;                // any_zero, or a reciprocal overflowed to +-inf: such rays take the general slab test
 };
 
 __device__ __forceinline__ RayInfo make_rayinfo(const V3& o, const V3& d)
@@ -39,6 +40,7 @@ __device__ __forceinline__ RayInfo make_rayinfo(const V3& o, const V3& d)
         ri.cmax[k] = ri.nonzero[k] ? 0.0f : 2.0e10f;
         ri.any_zero = ri.any_zero || !ri.nonzero[k];
     }
+    ri.special = ri.any_zero || isinf(ri.inv[0]) || isinf(ri.inv[1]) || isinf(ri.inv[2]);
     return ri;
 }
 
@@ -74,6 +76,25 @@ __device__ __forceinline__ NodeL load_node(const DNode* p)
 // Axes with a zero direction component do not take part in the reference (containment test instead): their
 // products are 0 * finite = 0 here and the per-ray constants cmin / cmax (-/+BOUND_HUGE) neutralise them, while for
 // all other axes the constants are 0 and adding them changes nothing.
+// Fast form for rays whose direction components are all non-zero with finite FP32 reciprocals (every ray in practice):
+// no NaN can arise, (lo - org) * inv and (hi - org) * inv are ordered by the sign of inv (rounding is monotone), so
+// tmin / tmax are the min / max of the pair - the same two products the reference assigns by the sign of the direction.
+__device__ __forceinline__ bool slab_test_fast(const float* lo, const float* hi, const RayInfo& ri, float& dmin_out)
+{
+    float tn[3], tf[3];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float a = __fmul_rn(__fsub_rn(lo[k], ri.org[k]), ri.inv[k]);
+        const float b = __fmul_rn(__fsub_rn(hi[k], ri.org[k]), ri.inv[k]);
+        tn[k] = fminf(a, b);
+        tf[k] = fmaxf(a, b);
+    }
+    const float dmin = fmaxf(fmaxf(fmaxf(tn[0], tn[1]), tn[2]), -PV_BOUND_HUGE_F);
+    const float dmax = fminf(fminf(fminf(tf[0], tf[1]), tf[2]), PV_BOUND_HUGE_F);
+    dmin_out = dmin;
+    return !(dmax < PV_EPSILON_F32) && !(dmin > dmax);
+}
+
 __device__ __forceinline__ bool slab_test(const float* lo, const float* hi, const RayInfo& ri, float& dmin_out)
 {
     float dmin = -PV_BOUND_HUGE_F, dmax = PV_BOUND_HUGE_F;
@@ -147,14 +168,26 @@ __device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, u
         for (int k = 0; k < 4; k++) ch[k] = load_node(nodes + first + min(c0 + (uint32_t)k, count - 1u));
         float key[4];
         uint32_t val[4];
-        #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float dmin;
-            bool ok = slab_test(ch[k].lo, ch[k].hi, ri, dmin);
-            if (ALLOW_INFINITE && (ch[k].code & PV_CODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
-            ok = ok && (c0 + k < count) && !(dmin > limit);
-            key[k] = ok ? dmin : kInvalid;
-            val[k] = ch[k].code;
+        if (!ri.special) {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float dmin;
+                bool ok = slab_test_fast(ch[k].lo, ch[k].hi, ri, dmin);
+                if (ALLOW_INFINITE && (ch[k].code & PV_CODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
+                ok = ok && (c0 + k < count) && !(dmin > limit);
+                key[k] = ok ? dmin : kInvalid;
+                val[k] = ch[k].code;
+            }
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float dmin;
+                bool ok = slab_test(ch[k].lo, ch[k].hi, ri, dmin);
+                if (ALLOW_INFINITE && (ch[k].code & PV_CODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }
+                ok = ok && (c0 + k < count) && !(dmin > limit);
+                key[k] = ok ? dmin : kInvalid;
+                val[k] = ch[k].code;
+            }
         }
         if (ORDERED) {
             // descending by entry depth; equal depths keep the child order (the ordinal rides in the comparison)
@@ -166,12 +199,14 @@ __device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, u
             PV_CSWAP(0, 1) PV_CSWAP(2, 3) PV_CSWAP(0, 2) PV_CSWAP(1, 3) PV_CSWAP(1, 2)
             #undef PV_CSWAP
         }
+        // branch-free pushes: every entry is stored at the current top, the top only advances past valid ones (an invalid
+        // entry is overwritten by the next store); the last slot of the stack absorbs an overflow, which is flagged
         #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (key[k] != kInvalid) {
-                if (sp >= PV_STACK_SIZE) atomicOr(overflow, 1u);
-                else stack.set(sp++, make_uint2(__float_as_uint(key[k]), val[k]));
-            }
+            const bool ok = key[k] != kInvalid;
+            stack.set(sp, make_uint2(__float_as_uint(key[k]), val[k]));
+            if (ok && sp >= PV_STACK_SIZE - 1) atomicOr(overflow, 1u);
+            sp += (ok && sp < PV_STACK_SIZE - 1) ? 1 : 0;
         }
     }
 }
