@@ -228,6 +228,19 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
     return false;
 }
 
+// Inside() of the primitives that need no traversal stack (sphere.cpp:262, box.cpp:538, plane.cpp:208, quadric.cpp:248, torus.cpp:348)
+__device__ __forceinline__ bool simple_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
+        case PVGPU_OBJ_BOX:     return box_inside(sc, ob, p);
+        case PVGPU_OBJ_PLANE:   return plane_inside(sc, ob, p);
+        case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
+        case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
+    }
+    return false;
+}
+
 // Inside_Object (object.cpp:346-355) = every clipped_by object contains the point AND Object->Inside();
 // CSGUnion/CSGMerge::Inside = any child, CSGIntersection::Inside = all children (csg.cpp:393-454).
 // Evaluated iteratively with short-circuit over the object graph (the reference recurses).
@@ -509,7 +522,44 @@ __device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, con
 __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
                                 HitAcc& acc, TStack stack, int sp0, unsigned int* overflow)
 {
-    const uint2 range = sc.csg_leaf_range[top];
+    uint2 range = sc.csg_leaf_range[top];
+    if (range.y & 0x80000000u) {
+        // fast path for the common shape: one CSG level whose children are simple primitives without clip lists, so
+        // Inside_Object(sibling) is the primitive's own Inside() and needs no walk over an object graph
+        const pvgpu_object& po = sc.objs[top];
+        const uint32_t n = range.y & 0x7FFFFFFFu;
+        for (uint32_t li = 0; li < n; li++) {
+            const uint32_t leaf = sc.csg_leaves[range.x + li];
+            const pvgpu_object& lo = sc.objs[leaf];
+            if (po.type == PVGPU_OBJ_CSG_UNION && !test_ray_flags(lo.flags, rflags, shadow_ray, false)) continue;
+            if (po.type == PVGPU_OBJ_CSG_MERGE && !test_ray_flags(lo.flags, rflags, shadow_ray, true)) continue;
+            PrimHits h;
+            prim_hits(sc, lo, o, d, h);
+            for (int i = 0; i < h.n; i++) {
+                const V3 ip = h.ip[i];
+                bool keep = true;
+                int32_t csg = (int32_t)top;
+                if (po.type == PVGPU_OBJ_CSG_INTERSECTION) {
+                    for (uint32_t k = 0; k < n && keep; k++) {
+                        const uint32_t sib = sc.csg_leaves[range.x + k];
+                        if (sib != leaf && !simple_inside(sc, sc.objs[sib], ip)) keep = false;
+                    }
+                    if (keep && po.clip_count && !point_in_clip(sc, po, ip, stack, sp0)) keep = false;
+                } else if (po.type == PVGPU_OBJ_CSG_MERGE) {
+                    if (po.clip_count && !point_in_clip(sc, po, ip, stack, sp0)) keep = false;
+                    for (uint32_t k = 0; k < n && keep; k++) {
+                        const uint32_t sib = sc.csg_leaves[range.x + k];
+                        if (sib != leaf && test_ray_flags(sc.objs[sib].flags, rflags, shadow_ray, true) && simple_inside(sc, sc.objs[sib], ip)) keep = false;
+                    }
+                } else {   // union: Intersection::Csg is only set when the union clips (csg.cpp:137-150)
+                    if (po.clip_count) { if (!point_in_clip(sc, po, ip, stack, sp0)) keep = false; }
+                    else csg = -1;
+                }
+                if (keep) consider(acc, h.depth[i], ip, leaf, h.aux[i], csg);
+            }
+        }
+        return;
+    }
     for (uint32_t li = 0; li < range.y; li++) {
         const uint32_t leaf = sc.csg_leaves[range.x + li];
         const pvgpu_object& lo = sc.objs[leaf];

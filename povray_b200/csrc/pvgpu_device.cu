@@ -221,7 +221,13 @@ int device_upload(Scene& s, int device)
                 leaves.push_back(c);
             }
         }
-        leaf_range[i] = make_uint2(first, (uint32_t)leaves.size() - first);
+        // "flat" CSG: every child is a simple primitive without its own clipped_by list -> csg_hits' fast path (bit 31)
+        bool flat = true;
+        for (uint32_t k = 0; k < o.child_count && flat; k++) {
+            const pvgpu_object& co = s.objects[s.index_list[o.child_first + k]];
+            flat = co.type >= PVGPU_OBJ_SPHERE && co.type <= PVGPU_OBJ_TORUS && co.clip_count == 0;
+        }
+        leaf_range[i] = make_uint2(first, ((uint32_t)leaves.size() - first) | (flat ? 0x80000000u : 0u));
     }
 
     // packed triangles + resolved mesh descriptors
