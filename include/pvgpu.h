@@ -457,6 +457,16 @@ int  pvgpu_render_device(pvgpu_scene* s, const pvgpu_aa* aa, int width, int heig
 int  pvgpu_trace_rays(pvgpu_scene* s, const double* org_dir, size_t n,
                       uint32_t* obj, double* depth, uint32_t* aux);
 
+/* Component-level harnesses (device code of the trace path run on explicit inputs; host arrays):
+ *  pvgpu_solve_polynomial mirrors Solve_Polynomial(n, c, r, sturm, epsilon) (source/core/math/polynomialsolver.h:73) for
+ *    n_polys polynomials of degree <= 4: coeffs = 5 doubles each (c[4 - degree ..] used, highest power first), degree / sturm per
+ *    polynomial; roots = 4 doubles each, counts = number of roots.
+ *  pvgpu_noise mirrors Noise / DNoise / Turbulence (source/core/material/noise.h:196-202) at n points: xyz = 3 doubles each,
+ *    generator and octaves per point (lambda 2, omega 0.5); out = 5 doubles each: noise, dnoise xyz, turbulence. */
+int  pvgpu_solve_polynomial(pvgpu_scene* s, size_t n_polys, const int32_t* degree, const int32_t* sturm, const double* epsilon,
+                            const double* coeffs, double* roots, int32_t* counts);
+int  pvgpu_noise(pvgpu_scene* s, size_t n, const double* xyz, const int32_t* generator, const int32_t* octaves, double* out);
+
 /* Camera rays exactly as TracePixel::CreateCameraRay makes them for pixel-space (x, y): 6 doubles each. */
 int  pvgpu_camera_rays(pvgpu_scene* s, int width, int height, const double* xy, size_t n, double* org_dir);
 

@@ -17,6 +17,8 @@
 //   PVGPU_DUMP_RAYS=<file>   per pixel: stock camera ray + stock Trace::FindIntersection result
 //   PVGPU_DUMP_RGBT=<file>   per pixel float RGBT from the stock TracePixel
 //   PVGPU_DUMP_GPU=<file>    per pixel float RGBT from pvgpu_render
+//   PVGPU_PROBE_IN=<file> PVGPU_PROBE_OUT=<file>   known-answer vectors: the reference's own Solve_Polynomial / Noise / DNoise /
+//                            Turbulence on the inputs of <in> (format: tests/golden/make_golden_probe.py), written once
 // Dumps cover the whole render area and are written when the tile queue is empty (run with +WT1).
 //
 // Build recipe: oracle/Makefile (target adapter).  See INTEGRATION.md.
@@ -49,6 +51,8 @@
 #include "core/material/texture.h"
 #include "core/material/warp.h"
 #include "core/math/matrix.h"
+#include "core/math/polynomialsolver.h"
+#include "core/material/noise.h"
 #include "core/render/ray.h"
 #include "core/scene/object.h"
 #include "core/scene/scenedata.h"
@@ -607,8 +611,48 @@ TraceTask::TraceTask(ViewData *vd, unsigned int tm, DBL js, DBL aat, DBL aac, un
 
 TraceTask::~TraceTask() {}
 
+// Known-answer vectors straight from the reference's functions (tests/golden/make_golden_probe.py).
+// in:  u32 n_poly, n_poly x { i32 degree, i32 sturm, f64 epsilon, f64 c[5] }, u32 n_pts, n_pts x { f64 x, y, z, i32 generator, i32 octaves }
+// out: n_poly x { i32 count, f64 roots[4] }, n_pts x { f64 noise, f64 dnoise[3], f64 turbulence (lambda 2, omega 0.5) }
+static void run_probe(const char* in_path, const char* out_path, TraceThreadData* td)
+{
+    static std::mutex m;
+    static bool done = false;
+    std::lock_guard<std::mutex> lock(m);
+    if (done) return;
+    done = true;
+    FILE* f = fopen(in_path, "rb");
+    FILE* g = fopen(out_path, "wb");
+    if (!f || !g) throw POV_EXCEPTION_STRING("pvgpu adapter: cannot open the probe files");
+    uint32_t n = 0;
+    if (fread(&n, 4, 1, f) != 1) n = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        int32_t hdr[2]; double eps, c[5], r[4] = { 0, 0, 0, 0 };
+        if (fread(hdr, 4, 2, f) != 2 || fread(&eps, 8, 1, f) != 1 || fread(c, 8, 5, f) != 5) break;
+        int32_t cnt = Solve_Polynomial(hdr[0], c + (4 - hdr[0]), r, hdr[1], eps, td->Stats());
+        for (int k = cnt; k < 4; k++) r[k] = 0.0;
+        fwrite(&cnt, 4, 1, g); fwrite(r, 8, 4, g);
+    }
+    if (fread(&n, 4, 1, f) != 1) n = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        double p[3]; int32_t gen[2];
+        if (fread(p, 8, 3, f) != 3 || fread(gen, 4, 2, f) != 2) break;
+        Vector3d P(p[0], p[1], p[2]), D;
+        double out[5];
+        out[0] = Noise(P, gen[0]);
+        DNoise(D, P);
+        out[1] = D[X]; out[2] = D[Y]; out[3] = D[Z];
+        ClassicTurbulence tw(false);
+        tw.Octaves = gen[1]; tw.Lambda = 2.0; tw.Omega = 0.5;
+        out[4] = Turbulence(P, &tw, gen[0]);
+        fwrite(out, 8, 5, g);
+    }
+    fclose(f); fclose(g);
+}
+
 void TraceTask::Run()
 {
+    if (getenv("PVGPU_PROBE_IN") && getenv("PVGPU_PROBE_OUT")) run_probe(getenv("PVGPU_PROBE_IN"), getenv("PVGPU_PROBE_OUT"), GetViewDataPtr());
     ViewData* vd = GetViewData();
     const unsigned int width = vd->GetWidth(), height = vd->GetHeight();
     const char* mode_env = getenv("PVGPU_RENDER");

@@ -2206,6 +2206,11 @@ int pvo_camera_rays(void* sc, int width, int height, const double* xy, size_t n,
 // Solve_Polynomial / Noise / DNoise probes for unit tests
 int pvo_solve_polynomial(int n, const double* c, double* r, int sturm, double epsilon) { return Solve_Polynomial(n, c, r, sturm, epsilon); }
 double pvo_noise(void* sc, double x, double y, double z, int gen) { return Noise(*reinterpret_cast<Scene*>(sc), v3(x, y, z), gen); }
+double pvo_turbulence(void* sc, double x, double y, double z, int gen, int octaves)
+{
+    pvgpu_warp w{}; w.octaves = octaves; w.lambda = 2.0f; w.omega = 0.5f;
+    return Turbulence(*reinterpret_cast<Scene*>(sc), v3(x, y, z), w, gen);
+}
 void pvo_dnoise(void* sc, double x, double y, double z, double* out) { V3 r = DNoise(*reinterpret_cast<Scene*>(sc), v3(x, y, z)); out[0] = r.x; out[1] = r.y; out[2] = r.z; }
 
 }  // extern "C"

@@ -197,6 +197,8 @@ SIGNATURES = {
     "pvgpu_scene_save": (C.c_int, [VP, C.c_char_p]),
     "pvgpu_scene_load": (C.c_int, [P(VP), C.c_char_p]),
     "pvgpu_render": (C.c_int, [VP, P(AA), C.c_int, C.c_int, P(Rect), C.c_size_t, P(f32), P(Stats), VP, VP]),
+    "pvgpu_solve_polynomial": (C.c_int, [VP, C.c_size_t, P(i32), P(i32), P(f64), P(f64), P(f64), P(i32)]),
+    "pvgpu_noise": (C.c_int, [VP, C.c_size_t, P(f64), P(i32), P(i32), P(f64)]),
     "pvgpu_host_alloc": (VP, [C.c_size_t]),
     "pvgpu_host_free": (None, [VP]),
     "pvgpu_render_device": (C.c_int, [VP, P(AA), C.c_int, C.c_int, P(Rect), C.c_size_t, VP, P(Stats), VP]),

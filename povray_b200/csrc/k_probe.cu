@@ -1,0 +1,41 @@
+// Component-level harness kernels: the device Solve_Polynomial and Noise / DNoise / Turbulence on explicit inputs
+// (pvgpu_solve_polynomial, pvgpu_noise in include/pvgpu.h), so that they can be checked against known-answer vectors
+// taken from the reference's own functions (tests/golden/make_golden_probe.py).
+#include "pv_solver.cuh"
+#include "pv_noise.cuh"
+#include "pv_kernels.hpp"
+
+namespace pvgpu {
+
+__global__ void k_probe_solver(uint32_t n, const int32_t* degree, const int32_t* sturm, const double* epsilon, const double* coeffs,
+                               double* roots, int32_t* counts)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double c[5], r[4] = { 0.0, 0.0, 0.0, 0.0 };
+        const int deg = degree[i];
+        for (int k = 0; k <= deg; k++) c[k] = coeffs[5 * (size_t)i + (4 - deg) + k];
+        const int cnt = solve_polynomial(deg, c, r, sturm[i], epsilon[i]);
+        counts[i] = cnt;
+        for (int k = 0; k < 4; k++) roots[4 * (size_t)i + k] = (k < cnt) ? r[k] : 0.0;
+    }
+}
+
+__global__ void k_probe_noise(NoiseTables nt, uint32_t n, const double* xyz, const int32_t* gen, const int32_t* octaves, double* out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const V3 p = mk(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]);
+        double* o = out + 5 * (size_t)i;
+        o[0] = noise3(nt, p, gen[i]);
+        const V3 dn = dnoise3(nt, p);
+        o[1] = dn.x; o[2] = dn.y; o[3] = dn.z;
+        o[4] = turbulence(nt, p, octaves[i], 2.0, 0.5, gen[i]);
+    }
+}
+
+void launch_probe_solver(uint32_t n, const int32_t* degree, const int32_t* sturm, const double* epsilon, const double* coeffs,
+                         double* roots, int32_t* counts, cudaStream_t st)
+{ k_probe_solver<<<grid_for(n, 128, 8), 128, 0, st>>>(n, degree, sturm, epsilon, coeffs, roots, counts); }
+void launch_probe_noise(const NoiseTables& nt, uint32_t n, const double* xyz, const int32_t* gen, const int32_t* octaves, double* out, cudaStream_t st)
+{ k_probe_noise<<<grid_for(n, 128, 8), 128, 0, st>>>(nt, n, xyz, gen, octaves, out); }
+
+}  // namespace pvgpu

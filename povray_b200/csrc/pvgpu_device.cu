@@ -736,6 +736,14 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
 
 }  // namespace pvgpu
 
+// device buffer holding a copy of a host array; freed on scope exit
+template <class T> struct DevCopy {
+    T* p = nullptr;
+    cudaError_t e;
+    DevCopy(const T* h, size_t n, bool upload) { e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess && upload && n) e = cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice); }
+    ~DevCopy() { cudaFree(p); }
+};
+
 using namespace pvgpu;
 
 extern "C" {
@@ -880,6 +888,45 @@ int pvgpu_trace_rays(pvgpu_scene* sc, const double* org_dir, size_t n, uint32_t*
     }
     cleanup();
     return rc;
+}
+
+int pvgpu_solve_polynomial(pvgpu_scene* sc, size_t n, const int32_t* degree, const int32_t* sturm, const double* epsilon,
+                           const double* coeffs, double* roots, int32_t* counts)
+{
+    clear_error();
+    if (!sc || !degree || !sturm || !epsilon || !coeffs || !roots || !counts) return fail(PVGPU_E_INVALID, "pvgpu_solve_polynomial: null argument");
+    Scene& s = *reinterpret_cast<Scene*>(sc);
+    if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
+    if (n == 0) return PVGPU_OK;
+    for (size_t i = 0; i < n; i++) if (degree[i] < 1 || degree[i] > 4) return fail(PVGPU_E_INVALID, "polynomial %zu: degree %d outside 1..4", i, degree[i]);
+    std::lock_guard<std::recursive_mutex> lock(s.device_mutex);
+    CUDA_TRY(cudaSetDevice(s.device));
+    DevCopy<int32_t> d_deg(degree, n, true), d_st(sturm, n, true), d_cnt(nullptr, n, false);
+    DevCopy<double> d_eps(epsilon, n, true), d_c(coeffs, 5 * n, true), d_r(nullptr, 4 * n, false);
+    if (d_deg.e || d_st.e || d_cnt.e || d_eps.e || d_c.e || d_r.e) return fail(PVGPU_E_CUDA, "pvgpu_solve_polynomial: device allocation failed");
+    launch_probe_solver((uint32_t)n, d_deg.p, d_st.p, d_eps.p, d_c.p, d_r.p, d_cnt.p, 0);
+    s.dev->kernel_launches++;
+    CUDA_TRY(cudaMemcpy(roots, d_r.p, 4 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(counts, d_cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return PVGPU_OK;
+}
+
+int pvgpu_noise(pvgpu_scene* sc, size_t n, const double* xyz, const int32_t* generator, const int32_t* octaves, double* out)
+{
+    clear_error();
+    if (!sc || !xyz || !generator || !octaves || !out) return fail(PVGPU_E_INVALID, "pvgpu_noise: null argument");
+    Scene& s = *reinterpret_cast<Scene*>(sc);
+    if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
+    if (n == 0) return PVGPU_OK;
+    std::lock_guard<std::recursive_mutex> lock(s.device_mutex);
+    CUDA_TRY(cudaSetDevice(s.device));
+    DevCopy<double> d_p(xyz, 3 * n, true), d_o(nullptr, 5 * n, false);
+    DevCopy<int32_t> d_g(generator, n, true), d_oct(octaves, n, true);
+    if (d_p.e || d_o.e || d_g.e || d_oct.e) return fail(PVGPU_E_CUDA, "pvgpu_noise: device allocation failed");
+    launch_probe_noise(s.dev->view.noise, (uint32_t)n, d_p.p, d_g.p, d_oct.p, d_o.p, 0);
+    s.dev->kernel_launches++;
+    CUDA_TRY(cudaMemcpy(out, d_o.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return PVGPU_OK;
 }
 
 int pvgpu_camera_rays(pvgpu_scene* sc, int width, int height, const double* xy, size_t n, double* org_dir)

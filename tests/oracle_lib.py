@@ -34,6 +34,8 @@ def lib():
         l.pvo_solve_polynomial.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_double]
         l.pvo_noise.restype = C.c_double
         l.pvo_noise.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int]
+        l.pvo_turbulence.restype = C.c_double
+        l.pvo_turbulence.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
         l.pvo_dnoise.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
         _lib = l
     return _lib

@@ -1,0 +1,106 @@
+"""Known-answer vectors for Solve_Polynomial and Noise / DNoise / Turbulence taken from the UNMODIFIED reference functions
+(tests/golden/make_golden_probe.py -> probe.in / probe.out): the oracle must reproduce them on the CPU, the device code
+through pvgpu_solve_polynomial / pvgpu_noise on the GPU (CUDA libm may differ from glibc by an ulp in acos / cos / pow / cbrt)."""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, has_gpu
+
+
+def load_probe():
+    raw = open(os.path.join(GOLDEN, "probe.in"), "rb").read()
+    n = struct.unpack_from("<I", raw, 0)[0]
+    pd = np.dtype([("degree", "<i4"), ("sturm", "<i4"), ("eps", "<f8"), ("c", "<f8", 5)])
+    polys = np.frombuffer(raw, dtype=pd, count=n, offset=4)
+    off = 4 + n * pd.itemsize
+    m = struct.unpack_from("<I", raw, off)[0]
+    qd = np.dtype([("p", "<f8", 3), ("gen", "<i4"), ("oct", "<i4")])
+    pts = np.frombuffer(raw, dtype=qd, count=m, offset=off + 4)
+    out = open(os.path.join(GOLDEN, "probe.out"), "rb").read()
+    rd = np.dtype([("count", "<i4"), ("roots", "<f8", 4)])
+    roots = np.frombuffer(out, dtype=rd, count=n, offset=0)
+    noise = np.frombuffer(out, dtype="<f8", count=5 * m, offset=n * rd.itemsize).reshape(m, 5)
+    return polys, pts, roots, noise
+
+
+def compare_roots(count, roots, ref, rtol, what):
+    """Same number of roots, and the same roots in the same order (the solvers are deterministic)."""
+    same = count == ref["count"]
+    assert same.mean() >= 0.999, f"{what}: root counts differ for {(~same).sum()} of {len(same)} polynomials"
+    worst = 0.0
+    for i in np.where(same)[0]:
+        k = ref["count"][i]
+        if k:
+            a, b = roots[i, :k], ref["roots"][i, :k]
+            worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))))
+    assert worst <= rtol, f"{what}: roots differ by {worst:.3e}"
+
+
+def test_oracle_solver_matches_reference_vectors(oracle):
+    polys, _, ref, _ = load_probe()
+    l = oracle.lib()
+    count = np.zeros(len(polys), dtype=np.int32)
+    roots = np.zeros((len(polys), 4))
+    r = (C.c_double * 4)()
+    for i, p in enumerate(polys):
+        deg = int(p["degree"])
+        cc = (C.c_double * (deg + 1))(*p["c"][4 - deg:])
+        count[i] = l.pvo_solve_polynomial(deg, cc, r, int(p["sturm"]), float(p["eps"]))
+        roots[i, :count[i]] = r[:count[i]]
+    assert np.array_equal(count, ref["count"])
+    compare_roots(count, roots, ref, 0.0, "oracle")          # same compiler flags, same libm: bit-identical
+
+
+def test_oracle_noise_matches_reference_vectors(oracle):
+    _, pts, _, ref = load_probe()
+    l = oracle.lib()
+    o = oracle.OracleScene(os.path.join(GOLDEN, "spheres64.pvs"))
+    out = np.zeros((len(pts), 5))
+    d = (C.c_double * 3)()
+    for i, q in enumerate(pts):
+        x, y, z = (float(v) for v in q["p"])
+        out[i, 0] = l.pvo_noise(o._h, x, y, z, int(q["gen"]))
+        l.pvo_dnoise(o._h, x, y, z, d)
+        out[i, 1:4] = d[:]
+        out[i, 4] = l.pvo_turbulence(o._h, x, y, z, int(q["gen"]), int(q["oct"]))
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.gpu
+def test_device_solver_matches_reference_vectors():
+    if not has_gpu():
+        pytest.skip("no CUDA device")
+    import povray_b200 as pv
+    from povray_b200 import _abi as A
+    polys, _, ref, _ = load_probe()
+    s = pv.Scene.load(os.path.join(GOLDEN, "spheres64.pvs")).finalize(0)
+    n = len(polys)
+    deg = np.ascontiguousarray(polys["degree"]); st = np.ascontiguousarray(polys["sturm"]); eps = np.ascontiguousarray(polys["eps"])
+    c = np.ascontiguousarray(polys["c"]).reshape(-1)
+    roots = np.zeros((n, 4)); count = np.zeros(n, dtype=np.int32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    A.check(A.lib().pvgpu_solve_polynomial(s.handle, n, P(deg, C.c_int32), P(st, C.c_int32), P(eps, C.c_double), P(c, C.c_double),
+                                           P(roots, C.c_double), P(count, C.c_int32)))
+    compare_roots(count, roots, ref, 1e-9, "device")
+
+
+@pytest.mark.gpu
+def test_device_noise_matches_reference_vectors():
+    if not has_gpu():
+        pytest.skip("no CUDA device")
+    import povray_b200 as pv
+    from povray_b200 import _abi as A
+    _, pts, _, ref = load_probe()
+    s = pv.Scene.load(os.path.join(GOLDEN, "spheres64.pvs")).finalize(0)
+    n = len(pts)
+    xyz = np.ascontiguousarray(pts["p"]).reshape(-1); gen = np.ascontiguousarray(pts["gen"]); octv = np.ascontiguousarray(pts["oct"])
+    out = np.zeros((n, 5))
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    A.check(A.lib().pvgpu_noise(s.handle, n, P(xyz, C.c_double), P(gen, C.c_int32), P(octv, C.c_int32), P(out, C.c_double)))
+    # table-driven lattice noise with +, -, * only: identical to the reference's doubles
+    assert np.array_equal(out[:, :4], ref[:, :4])
+    assert np.allclose(out[:, 4], ref[:, 4], rtol=0, atol=1e-14)
