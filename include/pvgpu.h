@@ -55,14 +55,17 @@ enum {
     PVGPU_OBJ_CSG_UNION        = 7,  /* csg.h CSGUnion        children in index list                        */
     PVGPU_OBJ_CSG_INTERSECTION = 8,  /* csg.h CSGIntersection (difference = intersection + inverted kids)   */
     PVGPU_OBJ_CSG_MERGE        = 9,  /* csg.h CSGMerge                                                      */
-    PVGPU_OBJ_BLOB             = 10  /* blob.h:142     mesh = index into the blob table                     */
+    PVGPU_OBJ_BLOB             = 10, /* blob.h:142     mesh = index into the blob table                     */
+    PVGPU_OBJ_CONE             = 11  /* cone.h:66      cone / cylinder in canonical space (transform required); p[0]=dist; CYLINDER / CLOSED flags */
 };
 
 #define PVGPU_IS_CSG(type) ((type) >= PVGPU_OBJ_CSG_UNION && (type) <= PVGPU_OBJ_CSG_MERGE)
 
 /* Object flags: the reference's ObjectBase::Flags bits verbatim (source/core/scene/object.h:88-117). */
 #define PVGPU_NO_SHADOW_FLAG          0x00000001u
+#define PVGPU_CLOSED_FLAG             0x00000002u
 #define PVGPU_INVERTED_FLAG           0x00000004u
+#define PVGPU_CYLINDER_FLAG           0x00000010u
 #define PVGPU_STURM_FLAG              0x00000040u
 #define PVGPU_OPAQUE_FLAG             0x00000080u
 #define PVGPU_MULTITEXTURE_FLAG       0x00000100u

@@ -60,6 +60,7 @@
 #include "core/bounding/boundingsphere.h"
 #include "core/shape/blob.h"
 #include "core/shape/box.h"
+#include "core/shape/cone.h"
 #include "core/shape/csg.h"
 #include "core/shape/mesh.h"
 #include "core/shape/plane.h"
@@ -404,6 +405,10 @@ struct Flattener
             p.type = PVGPU_OBJ_MESH;
             p.mesh = add_mesh(m);
             p.transform = add_transform(m->Trans);
+        } else if (Cone* cn = dynamic_cast<Cone*>(o)) {
+            p.type = PVGPU_OBJ_CONE;
+            p.p[0] = cn->dist;
+            p.transform = add_transform(cn->Trans);
         } else if (Blob* bl = dynamic_cast<Blob*>(o)) {
             p.type = PVGPU_OBJ_BLOB;
             p.mesh = add_blob(bl);
@@ -416,7 +421,7 @@ struct Flattener
             else unsupported("unknown CSG class");
             add_index_range(c->children, self, true, p.child_first, p.child_count);
         } else {
-            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, blob, CSG)");
+            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, blob, CSG; cone / cylinder from 8f)");
             p.type = 0;
         }
         add_index_range(o->Clip, self, false, p.clip_first, p.clip_count);

@@ -777,6 +777,14 @@ bool Tracer::Inside(V3 p, uint32_t idx) const
             }
             return inside ? !inv : inv;
         }
+        case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:333-390
+            const double offset = (ob.flags & PVGPU_CLOSED_FLAG) ? -EPSILON : EPSILON;
+            V3 q = MInvTransPoint(S.xf[ob.transform], p);
+            double w2 = q.x * q.x + q.y * q.y;
+            bool outside = (ob.flags & PVGPU_CYLINDER_FLAG) ? ((w2 > 1.0 + offset) || (q.z < 0.0 - offset) || (q.z > 1.0 + offset))
+                                                            : ((w2 > q.z * q.z + offset) || (q.z < ob.p[0] - offset) || (q.z > 1.0 + offset));
+            return outside ? inv : !inv;
+        }
         case PVGPU_OBJ_MESH: return mesh_inside(ob, p);
         case PVGPU_OBJ_BLOB: {                                                                            // blob.cpp:1502-1624
             const pvgpu_blob& bl = S.blobs[ob.mesh];
@@ -918,6 +926,35 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
                     found |= push(depth, ip, aux);
                 }
             }
+            return found;
+        }
+        case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:103-330
+            const pvgpu_transform& t = S.xf[ob.transform];
+            V3 P = MInvTransPoint(t, o), D = MInvTransDirection(t, d);
+            const double length = len(D), dist = ob.p[0], tol = 1.0e-9;
+            D = D / length;
+            const bool cyl = (ob.flags & PVGPU_CYLINDER_FLAG) != 0;
+            const double zlo = cyl ? 0.0 : dist;
+            struct { double d; uint32_t t; } I[4]; int n = 0;
+            auto side = [&](double tt) { double z = P.z + tt * D.z; if ((tt > tol) && (tt < MAX_DISTANCE) && (z >= zlo) && (z <= 1.0)) { I[n].d = tt / length; I[n++].t = 3; } };
+            if (cyl) {
+                double a = D.x * D.x + D.y * D.y;
+                if (a > EPSILON) {
+                    double b = P.x * D.x + P.y * D.y, c = P.x * P.x + P.y * P.y - 1.0, dd = b * b - a * c;
+                    if (dd >= 0.0) { dd = std::sqrt(dd); side((-b + dd) / a); side((-b - dd) / a); }
+                }
+            } else {
+                double a = D.x * D.x + D.y * D.y - D.z * D.z, b = D.x * P.x + D.y * P.y - D.z * P.z, c = P.x * P.x + P.y * P.y - P.z * P.z;
+                if (std::fabs(a) < EPSILON) { if (std::fabs(b) > EPSILON) side(-0.5 * c / b); }
+                else { double dd = b * b - a * c; if (dd >= 0.0) { dd = std::sqrt(dd); side((-b - dd) / a); side((-b + dd) / a); } }
+            }
+            if ((ob.flags & PVGPU_CLOSED_FLAG) && (std::fabs(D.z) > EPSILON)) {
+                double dd = (1.0 - P.z) / D.z, a = P.x + dd * D.x, b = P.y + dd * D.y;
+                if (((sqr(a) + sqr(b)) <= 1.0) && (dd > tol) && (dd < MAX_DISTANCE)) { I[n].d = dd / length; I[n++].t = 2; }
+                dd = (dist - P.z) / D.z; a = P.x + dd * D.x; b = P.y + dd * D.y;
+                if ((sqr(a) + sqr(b)) <= (cyl ? 1.0 : sqr(dist)) && (dd > tol) && (dd < MAX_DISTANCE)) { I[n].d = dd / length; I[n++].t = 1; }
+            }
+            for (int i = 0; i < n; i++) found |= push(I[i].d, ray.Evaluate(I[i].d), I[i].t);
             return found;
         }
         case PVGPU_OBJ_MESH: return mesh_intersect(idx, ray, Depth_Stack);
@@ -1313,6 +1350,14 @@ V3 Tracer::Normal(const Intersection& isect) const
             if (dist > EPSILON) { M.x = ob.p[0] * P.x / dist; M.z = ob.p[0] * P.z / dist; }
             V3 N = isect.aux ? P + M : P - M;
             return unit(MTransNormal(t, N));
+        }
+        case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:408-445
+            const pvgpu_transform& t = S.xf[ob.transform];
+            V3 r = MInvTransPoint(t, isect.IPoint);
+            if (isect.aux == 3) { if (ob.flags & PVGPU_CYLINDER_FLAG) r.z = 0.0; else r.z = -r.z; }
+            else if (isect.aux == 1) r = v3(0, 0, -1);
+            else if (isect.aux == 2) r = v3(0, 0, 1);
+            return unit(MTransNormal(t, r));
         }
         case PVGPU_OBJ_BLOB: {                                                                            // blob.cpp:1815-1933
             const pvgpu_blob& bl = S.blobs[ob.mesh];

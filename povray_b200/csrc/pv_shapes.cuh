@@ -285,6 +285,100 @@ __device__ inline V3 quadric_normal(const pvgpu_object& ob, const V3& ip)
     return n / len;
 }
 
+// ---- cone / cylinder ------------------------------------------------------------------------------
+#define PV_CONE_TOLERANCE 1.0e-9      // Cone_Tolerance  cone.cpp:65
+#define PV_CONE_BASE_HIT 1u           // cone.cpp:71-73
+#define PV_CONE_CAP_HIT  2u
+#define PV_CONE_SIDE_HIT 3u
+
+// Cone::Intersect + All_Intersections (cone.cpp:103-330): canonical space, z in [dist, 1] (cylinder: [0, 1])
+__device__ inline void cone_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const V3 P = inv_trans_point(tr, o);
+    V3 D = inv_trans_direction(tr, d);
+    const double len = length(D);
+    D = D / len;
+    const double dist = ob.p[0];
+    const bool cyl = (ob.flags & PVGPU_CYLINDER_FLAG) != 0;
+    auto push = [&](double t, uint32_t kind) { const double w = t / len; h.depth[h.n] = w; h.ip[h.n] = evaluate(o, d, w); h.aux[h.n] = kind; h.n++; };
+    double a, b, c, dd, t1, t2, z;
+    if (cyl) {
+        a = D.x * D.x + D.y * D.y;
+        if (a > PV_EPSILON) {
+            b = P.x * D.x + P.y * D.y;
+            c = P.x * P.x + P.y * P.y - 1.0;
+            dd = b * b - a * c;
+            if (dd >= 0.0) {
+                dd = sqrt(dd);
+                t1 = (-b + dd) / a;
+                t2 = (-b - dd) / a;
+                z = P.z + t1 * D.z;
+                if ((t1 > PV_CONE_TOLERANCE) && (t1 < PV_MAX_DISTANCE) && (z >= 0.0) && (z <= 1.0)) push(t1, PV_CONE_SIDE_HIT);
+                z = P.z + t2 * D.z;
+                if ((t2 > PV_CONE_TOLERANCE) && (t2 < PV_MAX_DISTANCE) && (z >= 0.0) && (z <= 1.0)) push(t2, PV_CONE_SIDE_HIT);
+            }
+        }
+    } else {
+        a = D.x * D.x + D.y * D.y - D.z * D.z;
+        b = D.x * P.x + D.y * P.y - D.z * P.z;
+        c = P.x * P.x + P.y * P.y - P.z * P.z;
+        if (fabs(a) < PV_EPSILON) {
+            if (fabs(b) > PV_EPSILON) {
+                t1 = -0.5 * c / b;
+                z = P.z + t1 * D.z;
+                if ((t1 > PV_CONE_TOLERANCE) && (t1 < PV_MAX_DISTANCE) && (z >= dist) && (z <= 1.0)) push(t1, PV_CONE_SIDE_HIT);
+            }
+        } else {
+            dd = b * b - a * c;
+            if (dd >= 0.0) {
+                dd = sqrt(dd);
+                t1 = (-b - dd) / a;
+                t2 = (-b + dd) / a;
+                z = P.z + t1 * D.z;
+                if ((t1 > PV_CONE_TOLERANCE) && (t1 < PV_MAX_DISTANCE) && (z >= dist) && (z <= 1.0)) push(t1, PV_CONE_SIDE_HIT);
+                z = P.z + t2 * D.z;
+                if ((t2 > PV_CONE_TOLERANCE) && (t2 < PV_MAX_DISTANCE) && (z >= dist) && (z <= 1.0)) push(t2, PV_CONE_SIDE_HIT);
+            }
+        }
+    }
+    if ((ob.flags & PVGPU_CLOSED_FLAG) && (fabs(D.z) > PV_EPSILON)) {
+        dd = (1.0 - P.z) / D.z;
+        a = (P.x + dd * D.x);
+        b = (P.y + dd * D.y);
+        if (((sqr(a) + sqr(b)) <= 1.0) && (dd > PV_CONE_TOLERANCE) && (dd < PV_MAX_DISTANCE)) push(dd, PV_CONE_CAP_HIT);
+        dd = (dist - P.z) / D.z;
+        a = (P.x + dd * D.x);
+        b = (P.y + dd * D.y);
+        if ((sqr(a) + sqr(b)) <= (cyl ? 1.0 : sqr(dist)) && (dd > PV_CONE_TOLERANCE) && (dd < PV_MAX_DISTANCE)) push(dd, PV_CONE_BASE_HIT);
+    }
+}
+
+// Cone::Inside (cone.cpp:333-390)
+__device__ inline bool cone_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    const double offset = (ob.flags & PVGPU_CLOSED_FLAG) ? -PV_EPSILON : PV_EPSILON;
+    const V3 q = inv_trans_point(sc.xf[ob.transform], p);
+    const double w2 = q.x * q.x + q.y * q.y;
+    bool outside;
+    if (ob.flags & PVGPU_CYLINDER_FLAG) outside = (w2 > 1.0 + offset) || (q.z < 0.0 - offset) || (q.z > 1.0 + offset);
+    else outside = (w2 > q.z * q.z + offset) || (q.z < ob.p[0] - offset) || (q.z > 1.0 + offset);
+    const bool inv = (ob.flags & PVGPU_INVERTED_FLAG) != 0;
+    return outside ? inv : !inv;
+}
+
+// Cone::Normal (cone.cpp:408-445)
+__device__ inline V3 cone_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip, uint32_t kind)
+{
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    V3 r = inv_trans_point(tr, ip);
+    if (kind == PV_CONE_SIDE_HIT) { if (ob.flags & PVGPU_CYLINDER_FLAG) r.z = 0.0; else r.z = -r.z; }
+    else if (kind == PV_CONE_BASE_HIT) r = mk(0.0, 0.0, -1.0);
+    else if (kind == PV_CONE_CAP_HIT) r = mk(0.0, 0.0, 1.0);
+    return normalized(trans_normal(tr, r));
+}
+
 // ---- torus --------------------------------------------------------------------------------------
 // Torus::Test_Thick_Cylinder (torus.cpp:932-1059)
 __device__ inline bool torus_thick_cylinder(const V3& P, const V3& D, double h1, double h2, double r1, double r2)

@@ -224,6 +224,7 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
         case PVGPU_OBJ_MESH:    return mesh_inside(sc, ob, p, stack, sp0);
         case PVGPU_OBJ_BLOB:    return blob_inside(sc, ob, p);
+        case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
     }
     return false;
 }
@@ -237,6 +238,7 @@ __device__ __forceinline__ bool simple_inside(const DScene& sc, const pvgpu_obje
         case PVGPU_OBJ_PLANE:   return plane_inside(sc, ob, p);
         case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
+        case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
     }
     return false;
 }
@@ -312,6 +314,7 @@ __device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const
         case PVGPU_OBJ_PLANE:   plane_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_QUADRIC: quadric_hits(ob, o, d, h); break;
         case PVGPU_OBJ_TORUS:   torus_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_CONE:    cone_hits(sc, ob, o, d, h); break;
         default: h.n = 0; break;
     }
 }
