@@ -9,7 +9,10 @@ CSRC      := povray_b200/csrc
 OBJDIR    := build/obj
 CU        := $(wildcard $(CSRC)/*.cu)
 CPP       := $(wildcard $(CSRC)/*.cpp)
-OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP))
+# the hot kernels are compiled a second time with -DPV_LEAN (see PV_VARIANT in pv_common.cuh)
+LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
+OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
+             $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC))
 HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) include/pvgpu.h
 
 .PHONY: all oracle clean
@@ -18,6 +21,10 @@ all: povray_b200/libpvgpu.so
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(OBJDIR)/%_lean.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -DPV_LEAN -c $< -o $@
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDR)
 	@mkdir -p $(OBJDIR)

@@ -6,6 +6,8 @@
 
 namespace pvgpu {
 
+#ifndef PV_LEAN
+
 int sm_count()
 {
     static int n = 0;
@@ -156,9 +158,11 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
     }
 }
 
+#endif  // !PV_LEAN
+
 // Trace::TraceRay's entry (trace.cpp:142-160) + FindIntersection for every ray of the wave.
 __global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
-k_closest(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRec* __restrict__ hits, Counters* cnt)
+PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRec* __restrict__ hits, Counters* cnt)
 {
 #if PV_SSTACK > 0
     __shared__ uint2 stack_sh[PV_SSTACK * PV_TRAV_BLOCK];
@@ -222,6 +226,7 @@ k_closest(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRec* __restric
     }
 }
 
+#ifndef PV_LEAN
 // ray-level harness: explicit rays under primary-ray conditions (Trace::FindIntersection(Intersection&, const Ray&), trace.h:255)
 __global__ void k_probe_rays(const double* org_dir, uint32_t n, PRay* out)
 {
@@ -267,10 +272,12 @@ void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, u
 {
     k_primary<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, src, first, n, width, height, out, cnt);
 }
-void launch_closest(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st)
+#endif  // !PV_LEAN
+void PV_VARIANT(launch_closest)(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st)
 {
-    k_closest<<<grid_for(n, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, n, hits, cnt);
+    PV_VARIANT(k_closest)<<<grid_for(n, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, n, hits, cnt);
 }
+#ifndef PV_LEAN
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st)
 {
     k_probe_rays<<<grid_for(n, 256, 8), 256, 0, st>>>(org_dir, n, out);
@@ -283,5 +290,7 @@ void launch_camera_rays(const DScene& sc, const double* xy, uint32_t n, double w
 {
     k_camera_rays<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, xy, n, width, height, org_dir);
 }
+
+#endif  // !PV_LEAN
 
 }  // namespace pvgpu

@@ -6,7 +6,7 @@
 namespace pvgpu {
 
 __global__ void __launch_bounds__(128)
-k_shade(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits, uint32_t n, WaveCtx ctx)
+PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits, uint32_t n, WaveCtx ctx)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const HitRec h = hits[i];
@@ -24,9 +24,9 @@ k_shade(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits
     }
 }
 
-void launch_shade(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st)
+void PV_VARIANT(launch_shade)(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st)
 {
-    k_shade<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, cur, hits, n, ctx);
+    PV_VARIANT(k_shade)<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, cur, hits, n, ctx);
 }
 
 }  // namespace pvgpu

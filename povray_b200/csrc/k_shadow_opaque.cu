@@ -4,7 +4,7 @@
 namespace pvgpu {
 
 __global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
-k_shadow_opaque(DScene sc, const SRay* __restrict__ rays, float4* accum, Counters* cnt)
+PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, float4* accum, Counters* cnt)
 {
 #if PV_SSTACK > 0
     __shared__ uint2 stack_sh[PV_SSTACK * PV_TRAV_BLOCK];
@@ -32,9 +32,9 @@ k_shadow_opaque(DScene sc, const SRay* __restrict__ rays, float4* accum, Counter
     if ((threadIdx.x & 31) == 0 && tests) atomicAdd(&cnt->shadow_tests, tests);
 }
 
-void launch_shadow_opaque(const DScene& sc, const SRay* rays, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st)
+void PV_VARIANT(launch_shadow_opaque)(const DScene& sc, const SRay* rays, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st)
 {
-    k_shadow_opaque<<<grid_for(n_max, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, rays, accum, cnt);
+    PV_VARIANT(k_shadow_opaque)<<<grid_for(n_max, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, rays, accum, cnt);
 }
 
 }  // namespace pvgpu

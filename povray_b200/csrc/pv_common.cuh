@@ -27,6 +27,17 @@ namespace pvgpu {
 #define PV_CSG_STACK      16            // nesting depth of Inside() evaluation
 #define PV_NO_OBJECT      0xFFFFFFFFu
 
+// Every hot kernel is compiled twice: the full variant knows all primitives, the lean variant (-DPV_LEAN) only spheres,
+// boxes, planes and meshes - scenes made of those (BASELINE configs 1 and 2) then run kernels that carry no quartic
+// solver, CSG, blob or cone code (fewer registers spilled, smaller local frames).  The host picks per scene.
+#ifdef PV_LEAN
+#define PV_HEAVY 0
+#define PV_VARIANT(name) name##_lean
+#else
+#define PV_HEAVY 1
+#define PV_VARIANT(name) name
+#endif
+
 struct V3 { double x, y, z; };
 
 // Per-ray traversal stack.  The first `nsh` entries of a thread live in shared memory (entry-major, one 8-byte

@@ -54,6 +54,11 @@ void launch_shade(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_
 // n_max: upper bound of the shadow-ray count (the exact count is read from cnt->n_shadow on the device)
 void launch_shadow_opaque(const DScene& sc, const SRay* rays, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_shadow_filter(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
+// lean variants (spheres, boxes, planes, meshes only; compiled from the same sources with -DPV_LEAN)
+void launch_closest_lean(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st);
+void launch_shade_lean(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st);
+void launch_shadow_opaque_lean(const DScene& sc, const SRay* rays, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_shadow_filter_lean(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st);
 void launch_probe_results(const HitRec* hits, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux, cudaStream_t st);
 void launch_aa1_frame_coords(const AALayout& L, double2* coords, cudaStream_t st);

@@ -9,7 +9,9 @@
 // factors (`w`, `wt`) and adds its own local terms straight into the sample's accumulator.
 #pragma once
 #include "pv_shapes.cuh"
+#if PV_HEAVY
 #include "pv_blob.cuh"
+#endif
 #include "pv_noise.cuh"
 #include "pv_kernels.hpp"
 
@@ -377,11 +379,13 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_SPHERE:  return sphere_normal(sc, ob, hit.ip);
         case PVGPU_OBJ_BOX:     return box_normal(sc, ob, hit.aux);
         case PVGPU_OBJ_PLANE:   return plane_normal(sc, ob);
+        case PVGPU_OBJ_MESH:    return mesh_normal(sc, ob, hit);
+#if PV_HEAVY
         case PVGPU_OBJ_QUADRIC: return quadric_normal(ob, hit.ip);
         case PVGPU_OBJ_TORUS:   return torus_normal(sc, ob, hit.ip, hit.aux);
-        case PVGPU_OBJ_MESH:    return mesh_normal(sc, ob, hit);
         case PVGPU_OBJ_BLOB:    return blob_normal(sc, ob, hit.ip);
         case PVGPU_OBJ_CONE:    return cone_normal(sc, ob, hit.ip, hit.aux);
+#endif
     }
     return mk(0.0, 1.0, 0.0);
 }

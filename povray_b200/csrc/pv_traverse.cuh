@@ -10,7 +10,9 @@
 // for exact ties between different objects (first visited wins in both schemes, visit order differs).
 #pragma once
 #include "pv_shapes.cuh"
+#if PV_HEAVY
 #include "pv_blob.cuh"
+#endif
 
 namespace pvgpu {
 
@@ -220,11 +222,13 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
         case PVGPU_OBJ_BOX:     return box_inside(sc, ob, p);
         case PVGPU_OBJ_PLANE:   return plane_inside(sc, ob, p);
+        case PVGPU_OBJ_MESH:    return mesh_inside(sc, ob, p, stack, sp0);
+#if PV_HEAVY
         case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
-        case PVGPU_OBJ_MESH:    return mesh_inside(sc, ob, p, stack, sp0);
         case PVGPU_OBJ_BLOB:    return blob_inside(sc, ob, p);
         case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
+#endif
     }
     return false;
 }
@@ -236,9 +240,11 @@ __device__ __forceinline__ bool simple_inside(const DScene& sc, const pvgpu_obje
         case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
         case PVGPU_OBJ_BOX:     return box_inside(sc, ob, p);
         case PVGPU_OBJ_PLANE:   return plane_inside(sc, ob, p);
+#if PV_HEAVY
         case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
         case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
+#endif
     }
     return false;
 }
@@ -308,13 +314,15 @@ __device__ __forceinline__ void consider(HitAcc& acc, double depth, const V3& ip
 __device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr)
 {
     switch (ob.type) {
+#if PV_HEAVY
         case PVGPU_OBJ_BLOB:    if (!blob_hits(sc, ob, o, d, h) && overflow) atomicOr(overflow, 32u); break;
-        case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_PLANE:   plane_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_QUADRIC: quadric_hits(ob, o, d, h); break;
         case PVGPU_OBJ_TORUS:   torus_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_CONE:    cone_hits(sc, ob, o, d, h); break;
+#endif
+        case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_PLANE:   plane_hits(sc, ob, o, d, h); break;
         default: h.n = 0; break;
     }
 }
@@ -632,8 +640,11 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     }
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
+#if PV_HEAVY
     if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow);
-    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
+    else
+#endif
+    if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
     else {
         PrimHits h;
         prim_hits(sc, ob, o, d, h, overflow);
@@ -653,8 +664,11 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
     if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL)) return false;
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = -1.0; acc.found = false;
+#if PV_HEAVY
     if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow);
-    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
+    else
+#endif
+    if (ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
     else {
         PrimHits h;
         prim_hits(sc, ob, o, d, h, overflow);

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <thread>
@@ -41,6 +42,7 @@ struct DeviceScene {
     size_t q_cap = 0, sq_cap = 0, rect_cap = 0;
     uint16_t* d_cam_int = nullptr;       // container-state result
     unsigned long long kernel_launches = 0;
+    bool lean = false;                   // only spheres, boxes, planes and meshes: the lean kernel variants serve the scene
     bool camera_dirty = true;
     // host-side staging of pvgpu_render (pinned) and its device frame
     float* d_frame = nullptr;
@@ -280,6 +282,10 @@ int device_upload(Scene& s, int device)
     #undef UP
     if (rc != PVGPU_OK) { device_release(s); return rc; }
 
+    d->lean = true;
+    for (const pvgpu_object& o : s.objects)
+        if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH)) d->lean = false;
+    if (const char* e = getenv("PVGPU_LEAN")) if (e[0] == '0') d->lean = false;
     v.n_objs = (uint32_t)s.objects.size();
     v.n_frame = (uint32_t)s.frame.size();
     v.n_nodes = (uint32_t)s.nodes.size();
@@ -417,18 +423,18 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
             ctx.next_cap = q_cap; ctx.shadow_cap = sq_cap;
             {
                 TimedLaunch t(d, stream, KIND_CLOSEST, cn);
-                launch_closest(d.view, d.q[cur] + c0, cn, d.hits + c0, d.cnt, stream);
+                (d.lean ? launch_closest_lean : launch_closest)(d.view, d.q[cur] + c0, cn, d.hits + c0, d.cnt, stream);
             }
             {
                 TimedLaunch t(d, stream, KIND_SHADE, cn);
-                launch_shade(d.view, d.q[cur] + c0, d.hits + c0, cn, ctx, stream);
+                (d.lean ? launch_shade_lean : launch_shade)(d.view, d.q[cur] + c0, d.hits + c0, cn, ctx, stream);
             }
             if (!s.lights.empty()) {
                 // the shadow kernel reads its count on the device; its grid is sized for the worst case of this chunk
                 const uint32_t worst = (uint32_t)std::min<unsigned long long>((unsigned long long)cn * n_lights, sq_cap);
                 TimedLaunch t(d, stream, KIND_SHADOW, 0);
-                if (d.view.all_opaque) launch_shadow_opaque(d.view, d.sq, worst, f.accum, d.cnt, stream);
-                else launch_shadow_filter(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, stream);
+                if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : launch_shadow_opaque)(d.view, d.sq, worst, f.accum, d.cnt, stream);
+                else (d.lean ? launch_shadow_filter_lean : launch_shadow_filter)(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, stream);
             }
         }
         unsigned int h[4];     // n_next, n_shadow, max_level, overflow
