@@ -3,9 +3,13 @@
 // reflection / refraction rays of the next wave.
 #include "pv_shade.cuh"
 
+#ifndef PV_SHADE_MIN_BLOCKS
+#define PV_SHADE_MIN_BLOCKS 4       // 128 registers: measured best (2 / 3 / 4 / 6 CTAs per SM: 1.63 / 1.5 / 1.28 / 1.57 ms on config 2)
+#endif
+
 namespace pvgpu {
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PV_SHADE_MIN_BLOCKS)
 PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits, uint32_t n, WaveCtx ctx)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
