@@ -17,11 +17,16 @@ namespace pvgpu {
 #define PV_TORUS_ROOT_TOL     1.0e-4   // torus.cpp:81
 
 // Candidate hits of one primitive, in the order the reference pushes them on the IStack.
+#if PV_HEAVY
+#define PV_MAX_PRIM_HITS 4          // torus / blob quartics
+#else
+#define PV_MAX_PRIM_HITS 2          // sphere, box, plane
+#endif
 struct PrimHits {
     int    n;
-    double depth[4];
-    V3     ip[4];
-    uint32_t aux[4];
+    double depth[PV_MAX_PRIM_HITS];
+    V3     ip[PV_MAX_PRIM_HITS];
+    uint32_t aux[PV_MAX_PRIM_HITS];
 };
 
 // ---- sphere -------------------------------------------------------------------------------------

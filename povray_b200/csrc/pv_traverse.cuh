@@ -287,9 +287,11 @@ static __device__ __noinline__ bool inside_object(const DScene& sc, uint32_t roo
 // Point_In_Clip (object.cpp:430-443)
 __device__ inline bool point_in_clip(const DScene& sc, const pvgpu_object& o, const V3& p, TStack stack, int sp0)
 {
+#if PV_HEAVY
     for (uint32_t i = 0; i < o.clip_count; i++)
         if (!inside_object(sc, sc.index_list[o.clip_first + i], p, stack, sp0)) return false;
-    return true;
+#endif
+    return true;       // (the lean variant only serves scenes without clipped_by / bounded_by lists: device_upload)
 }
 
 // ---- per-object candidate collection ----------------------------------------------------------------
@@ -634,10 +636,12 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     const pvgpu_object& ob = sc.objs[idx];
     if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, bbox_maxd)) return false;
     // Ray_In_Bound (object.cpp:385-400)
+#if PV_HEAVY
     for (uint32_t i = 0; i < ob.bound_count; i++) {
         const uint32_t b = sc.index_list[ob.bound_first + i];
         if (!object_find_simple(sc, b, o, d, rflags, stack, sp0, overflow) && !inside_object(sc, b, o, stack, sp0)) return false;
     }
+#endif
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
 #if PV_HEAVY
@@ -767,10 +771,12 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
             if (ob.type == PVGPU_OBJ_MESH) {
                 // object_find's prelude: FP32 box test and Ray_In_Bound (object.cpp:186-193, 385-400)
                 is_mesh = object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL);
+#if PV_HEAVY
                 for (uint32_t i = 0; is_mesh && i < ob.bound_count; i++) {
                     const uint32_t b = sc.index_list[ob.bound_first + i];
                     if (!object_find_simple(sc, b, o, d, rflags, stack, sp, overflow) && !inside_object(sc, b, o, stack, sp)) is_mesh = false;
                 }
+#endif
             } else {
                 Hit h;
                 if (object_find<ANY_OPAQUE>(sc, leaf, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow, opaque_limit) && h.depth < best.depth) {

@@ -42,7 +42,7 @@ struct DeviceScene {
     size_t q_cap = 0, sq_cap = 0, rect_cap = 0;
     uint16_t* d_cam_int = nullptr;       // container-state result
     unsigned long long kernel_launches = 0;
-    bool lean = false;                   // only spheres, boxes, planes and meshes: the lean kernel variants serve the scene
+    bool lean = false;                   // only spheres, boxes, planes, meshes and no clipped_by / bounded_by: lean kernel variants
     bool camera_dirty = true;
     // host-side staging of pvgpu_render (pinned) and its device frame
     float* d_frame = nullptr;
@@ -284,7 +284,8 @@ int device_upload(Scene& s, int device)
 
     d->lean = true;
     for (const pvgpu_object& o : s.objects)
-        if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH)) d->lean = false;
+        if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH) ||
+            o.clip_count || o.bound_count) d->lean = false;
     if (const char* e = getenv("PVGPU_LEAN")) if (e[0] == '0') d->lean = false;
     v.n_objs = (uint32_t)s.objects.size();
     v.n_frame = (uint32_t)s.frame.size();
