@@ -430,11 +430,14 @@ __device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t ob
     if (active) {
         const pvgpu_object& ob = sc.objs[obj_index];
         const DMesh& me = sc.meshes[ob.mesh];
+#if PV_HEAVY
         if (me.node_count == 0) {
-            // a mesh without its own tree (mesh.cpp:1490-1500): the generic, divergent form does it
+            // a mesh without its own tree (mesh.cpp:1490-1500): the generic, divergent form does it (lean scenes have none)
             mesh_hits<ANY_HIT>(sc, obj_index, ob, o, d, acc, -1, stack, sp0, overflow, any_limit);
             active = false;
-        } else {
+        } else
+#endif
+        {
             if (ob.transform >= 0) {
                 const pvgpu_transform& t = sc.xf[ob.transform];
                 mo = inv_trans_point(t, o);
@@ -645,11 +648,12 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
 #if PV_HEAVY
+    // (the lean variant walks meshes only through mesh_hits_sync and serves no CSG)
     if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow);
+    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
     else
 #endif
-    if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
-    else {
+    {
         PrimHits h;
         prim_hits(sc, ob, o, d, h, overflow);
         for (int i = 0; i < h.n; i++)

@@ -286,6 +286,7 @@ int device_upload(Scene& s, int device)
     for (const pvgpu_object& o : s.objects)
         if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH) ||
             o.clip_count || o.bound_count) d->lean = false;
+    for (const pvgpu_mesh& me : s.meshes) if (me.node_count == 0) d->lean = false;       // `hierarchy off` meshes take the generic walk
     if (const char* e = getenv("PVGPU_LEAN")) if (e[0] == '0') d->lean = false;
     v.n_objs = (uint32_t)s.objects.size();
     v.n_frame = (uint32_t)s.frame.size();
