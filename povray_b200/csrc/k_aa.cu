@@ -249,6 +249,11 @@ __global__ void k_aa2_expand(AALayout L, AAParams aa, const uint16_t* hash, cons
         uint32_t* bits = sampled + (size_t)a * words;
         Square st[48];
         int depth_of[48];
+        // the samples this pixel requests are collected first and appended as ONE contiguous run, so that the camera rays
+        // of a pixel (and of the neighbouring pixels of its warp) stay together in the wave
+        double2 lc[80];
+        uint32_t ls[80];
+        int ln = 0;
         int sp = 0;
         st[0].x = buf.pc.x; st[0].y = buf.pc.y; st[0].d = 0.5; st[0].bx = 0; st[0].by = 0; st[0].bs = S; st[0].level = aa.depth - 1;
         depth_of[0] = 0;
@@ -278,9 +283,19 @@ __global__ void k_aa2_expand(AALayout L, AAParams aa, const uint16_t* hash, cons
                     sx = q.x + 0.5 + ox[k] + (rx * aa.jitter_scale);
                     sy = q.y + 0.5 + oy[k] + (ry * aa.jitter_scale);
                 }
-                const unsigned int idx = atomicAdd(n_samples, 1u);
-                if (idx < cap) { coords[idx] = make_double2(sx, sy); slots[idx] = buf.base + bit; }
+                if (ln == 80) {       // flush a full run (only deep levels can exceed it)
+                    const unsigned int base = atomicAdd(n_samples, 80u);
+                    for (int m = 0; m < 80; m++) if (base + m < cap) { coords[base + m] = lc[m]; slots[base + m] = ls[m]; }
+                    ln = 0;
+                }
+                lc[ln] = make_double2(sx, sy);
+                ls[ln] = buf.base + bit;
+                ln++;
             }
+        }
+        if (ln) {
+            const unsigned int base = atomicAdd(n_samples, (unsigned int)ln);
+            for (int m = 0; m < ln; m++) if (base + m < cap) { coords[base + m] = lc[m]; slots[base + m] = ls[m]; }
         }
     }
 }
