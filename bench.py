@@ -173,7 +173,7 @@ def reference_arm(args):
     threads = os.cpu_count() or 1
     base = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": " ".join(aa_flags(args.workload)), "tile": BLOCK}}
+            "config": {"workload": WORKLOADS[args.workload].replace("1920x1080", f"{W}x{H}"), "width": W, "height": H, "aa": " ".join(aa_flags(args.workload)), "tile": BLOCK}}
     if binary is None:
         base["unavailable"] = "oracle/_ref/*/povray not built (needs /root/reference at build time)"
         print(json.dumps(base))
@@ -323,7 +323,7 @@ def ours(args):
     line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "sec_per_frame": ms / args.steps / 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "width": W, "height": H, "aa": " ".join(aa_flags(args.workload)), "tile": BLOCK,
+            "config": {"workload": WORKLOADS[args.workload].replace("1920x1080", f"{W}x{H}"), "width": W, "height": H, "aa": " ".join(aa_flags(args.workload)), "tile": BLOCK,
                        "sharding": f"{len(all_tiles)} tiles dealt round-robin over {world} GPU(s), scene replicated, gather to rank 0",
                        "l2": "256 MB flush write between timed frames; scene tables + ray queues exceed the 126 MB L2",
                        "scene_device_bytes": scene.device_bytes, "scene_build_s": round(t_build, 2), "scene_upload_s": round(t_upload, 3),
@@ -402,7 +402,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--width", type=int, default=1920, help="frame width (BASELINE.json's metric is quoted at 1920x1080)")
+    ap.add_argument("--height", type=int, default=1080)
     args = ap.parse_args()
+    global W, H
+    W, H = args.width, args.height
     if args.impl == "reference":
         reference_arm(args)
     else:
