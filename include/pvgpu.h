@@ -56,7 +56,8 @@ enum {
     PVGPU_OBJ_CSG_INTERSECTION = 8,  /* csg.h CSGIntersection (difference = intersection + inverted kids)   */
     PVGPU_OBJ_CSG_MERGE        = 9,  /* csg.h CSGMerge                                                      */
     PVGPU_OBJ_BLOB             = 10, /* blob.h:142     mesh = index into the blob table                     */
-    PVGPU_OBJ_CONE             = 11  /* cone.h:66      cone / cylinder in canonical space (transform required); p[0]=dist; CYLINDER / CLOSED flags */
+    PVGPU_OBJ_CONE             = 11, /* cone.h:66      cone / cylinder in canonical space (transform required); p[0]=dist; CYLINDER / CLOSED flags */
+    PVGPU_OBJ_DISC             = 12  /* disc.h:73      p[0..2]=normal p[3]=iradius2 p[4]=oradius2 (transform required)      */
 };
 
 #define PVGPU_IS_CSG(type) ((type) >= PVGPU_OBJ_CSG_UNION && (type) <= PVGPU_OBJ_CSG_MERGE)

@@ -61,6 +61,7 @@
 #include "core/shape/blob.h"
 #include "core/shape/box.h"
 #include "core/shape/cone.h"
+#include "core/shape/disc.h"
 #include "core/shape/csg.h"
 #include "core/shape/mesh.h"
 #include "core/shape/plane.h"
@@ -405,6 +406,11 @@ struct Flattener
             p.type = PVGPU_OBJ_MESH;
             p.mesh = add_mesh(m);
             p.transform = add_transform(m->Trans);
+        } else if (Disc* dc = dynamic_cast<Disc*>(o)) {
+            p.type = PVGPU_OBJ_DISC;
+            for (int k = 0; k < 3; k++) p.p[k] = dc->normal[k];
+            p.p[3] = dc->iradius2; p.p[4] = dc->oradius2;
+            p.transform = add_transform(dc->Trans);
         } else if (Cone* cn = dynamic_cast<Cone*>(o)) {
             p.type = PVGPU_OBJ_CONE;
             p.p[0] = cn->dist;

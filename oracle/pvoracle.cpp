@@ -777,6 +777,8 @@ bool Tracer::Inside(V3 p, uint32_t idx) const
             }
             return inside ? !inv : inv;
         }
+        case PVGPU_OBJ_DISC:                                                                              // disc.cpp:200-224
+            return (MInvTransPoint(S.xf[ob.transform], p).z >= 0.0) ? inv : !inv;
         case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:333-390
             const double offset = (ob.flags & PVGPU_CLOSED_FLAG) ? -EPSILON : EPSILON;
             V3 q = MInvTransPoint(S.xf[ob.transform], p);
@@ -924,6 +926,23 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
                         aux = on ? 1u : 0u;
                     }
                     found |= push(depth, ip, aux);
+                }
+            }
+            return found;
+        }
+        case PVGPU_OBJ_DISC: {                                                                            // disc.cpp:90-180
+            const pvgpu_transform& t = S.xf[ob.transform];
+            V3 P = MInvTransPoint(t, o), D = MInvTransDirection(t, d);
+            const double length = len(D);
+            D = D / length;
+            if (std::fabs(D.z) > EPSILON) {
+                double tt = -P.z / D.z;
+                if (tt >= 0.0) {
+                    double u = P.x + tt * D.x, v = P.y + tt * D.y, r2 = sqr(u) + sqr(v);
+                    if ((r2 >= ob.p[3]) && (r2 <= ob.p[4])) {
+                        double Depth = tt / length;
+                        if ((Depth > 1.0e-6) && (Depth < MAX_DISTANCE)) found |= push(Depth, ray.Evaluate(Depth), 0);
+                    }
                 }
             }
             return found;
@@ -1351,6 +1370,7 @@ V3 Tracer::Normal(const Intersection& isect) const
             V3 N = isect.aux ? P + M : P - M;
             return unit(MTransNormal(t, N));
         }
+        case PVGPU_OBJ_DISC: return v3(ob.p);                                                             // disc.cpp:226-229
         case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:408-445
             const pvgpu_transform& t = S.xf[ob.transform];
             V3 r = MInvTransPoint(t, isect.IPoint);

@@ -385,6 +385,7 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_TORUS:   return torus_normal(sc, ob, hit.ip, hit.aux);
         case PVGPU_OBJ_BLOB:    return blob_normal(sc, ob, hit.ip);
         case PVGPU_OBJ_CONE:    return cone_normal(sc, ob, hit.ip, hit.aux);
+        case PVGPU_OBJ_DISC:    return ld3(ob.p);       // Disc::Normal (disc.cpp:226-229)
 #endif
     }
     return mk(0.0, 1.0, 0.0);

@@ -290,6 +290,33 @@ __device__ inline V3 quadric_normal(const pvgpu_object& ob, const V3& ip)
     return n / len;
 }
 
+// ---- disc ------------------------------------------------------------------------------------------
+// Disc::Intersect / All_Intersections / Inside / Normal (disc.cpp:90-230): the plane z = 0 of the disc's space
+__device__ inline void disc_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const V3 P = inv_trans_point(tr, o);
+    V3 D = inv_trans_direction(tr, d);
+    const double len = length(D);
+    D = D / len;
+    if (fabs(D.z) > PV_EPSILON) {
+        const double t = -P.z / D.z;
+        if (t >= 0.0) {
+            const double u = P.x + t * D.x, v = P.y + t * D.y, r2 = sqr(u) + sqr(v);
+            if ((r2 >= ob.p[3]) && (r2 <= ob.p[4])) {
+                const double depth = t / len;
+                if ((depth > 1.0e-6) && (depth < PV_MAX_DISTANCE)) { h.depth[0] = depth; h.ip[0] = evaluate(o, d, depth); h.aux[0] = 0; h.n = 1; }
+            }
+        }
+    }
+}
+__device__ inline bool disc_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    const bool inv = (ob.flags & PVGPU_INVERTED_FLAG) != 0;
+    return (inv_trans_point(sc.xf[ob.transform], p).z >= 0.0) ? inv : !inv;
+}
+
 // ---- cone / cylinder ------------------------------------------------------------------------------
 #define PV_CONE_TOLERANCE 1.0e-9      // Cone_Tolerance  cone.cpp:65
 #define PV_CONE_BASE_HIT 1u           // cone.cpp:71-73

@@ -228,6 +228,7 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
         case PVGPU_OBJ_BLOB:    return blob_inside(sc, ob, p);
         case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
+        case PVGPU_OBJ_DISC:    return disc_inside(sc, ob, p);
 #endif
     }
     return false;
@@ -244,6 +245,7 @@ __device__ __forceinline__ bool simple_inside(const DScene& sc, const pvgpu_obje
         case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
         case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
+        case PVGPU_OBJ_DISC:    return disc_inside(sc, ob, p);
 #endif
     }
     return false;
@@ -321,6 +323,7 @@ __device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const
         case PVGPU_OBJ_QUADRIC: quadric_hits(ob, o, d, h); break;
         case PVGPU_OBJ_TORUS:   torus_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_CONE:    cone_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_DISC:    disc_hits(sc, ob, o, d, h); break;
 #endif
         case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;

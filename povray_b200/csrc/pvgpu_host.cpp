@@ -243,7 +243,7 @@ int validate_scene(Scene& s)
         if (f >= no) return fail(PVGPU_E_INVALID, "frame object index %u out of range", f);
     for (size_t i = 0; i < no; i++) {
         const pvgpu_object& o = s.objects[i];
-        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_CONE)
+        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_DISC)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: primitive type %u is outside the hot-path scope", i, o.type);
         if (!range_ok(o.child_first, o.child_count, s.index_list.size()) ||
             !range_ok(o.clip_first, o.clip_count, s.index_list.size()) ||
@@ -262,8 +262,8 @@ int validate_scene(Scene& s)
             if (o.mesh < 0 || o.mesh >= (int32_t)s.blobs.size()) return fail(PVGPU_E_INVALID, "object %zu: blob index out of range", i);
             if (o.parent >= 0 || (o.aux & 1u)) return fail(PVGPU_E_UNSUPPORTED, "object %zu: a blob inside CSG is outside the hot-path scope", i);
         }
-        if (o.type == PVGPU_OBJ_CONE && o.transform < 0)
-            return fail(PVGPU_E_INVALID, "object %zu: cone / cylinder without transform", i);
+        if ((o.type == PVGPU_OBJ_CONE || o.type == PVGPU_OBJ_DISC) && o.transform < 0)
+            return fail(PVGPU_E_INVALID, "object %zu: cone / cylinder / disc without transform", i);
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
         if ((o.flags & PVGPU_UV_FLAG))

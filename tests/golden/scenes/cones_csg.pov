@@ -19,3 +19,7 @@ intersection { cone { <-3.2, 0, -3>, 1.0, <-3.2, 2.0, -3>, 0.1 } cylinder { <-3.
   pigment { rgbf <0.85, 0.95, 1.0, 0.7> } finish { ambient 0.02 diffuse 0.3 specular 0.5 roughness 0.02 } interior { ior 1.4 } }
 merge { cylinder { <-5.5, 0, -2.5>, <-5.5, 1.2, -2.5>, 0.5 } cone { <-5.5, 1.0, -2.5>, 0.7, <-5.5, 1.9, -2.5>, 0.0 }
   pigment { rgbf <1.0, 0.8, 0.8, 0.6> } finish { ambient 0.02 diffuse 0.4 } interior { ior 1.3 } }
+disc { <1.8, 0.6, -5.0>, <0.2, 1, -0.3>, 0.9 pigment { rgb <0.9, 0.6, 0.7> } finish { ambient 0.1 diffuse 0.7 } }
+disc { <-1.6, 1.1, -5.2>, <0.5, 0.4, -1>, 0.8, 0.35 pigment { rgb <0.5, 0.8, 0.9> } finish { ambient 0.1 diffuse 0.6 specular 0.3 } }
+intersection { sphere { <5.4, 0.9, -3.4>, 0.9 } disc { <5.4, 1.2, -3.4>, <0, 1, 0.2>, 5 }
+  pigment { rgb <0.9, 0.9, 0.4> } finish { ambient 0.1 diffuse 0.6 } }
