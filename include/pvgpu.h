@@ -57,8 +57,14 @@ enum {
     PVGPU_OBJ_CSG_MERGE        = 9,  /* csg.h CSGMerge                                                      */
     PVGPU_OBJ_BLOB             = 10, /* blob.h:142     mesh = index into the blob table                     */
     PVGPU_OBJ_CONE             = 11, /* cone.h:66      cone / cylinder in canonical space (transform required); p[0]=dist; CYLINDER / CLOSED flags */
-    PVGPU_OBJ_DISC             = 12  /* disc.h:73      p[0..2]=normal p[3]=iradius2 p[4]=oradius2 (transform required)      */
+    PVGPU_OBJ_DISC             = 12, /* disc.h:73      p[0..2]=normal p[3]=iradius2 p[4]=oradius2 (transform required)      */
+    PVGPU_OBJ_TRIANGLE         = 13, /* triangle.h:73 / :103  mesh = offset into the shape-data table: P1 P2 P3 Normal_Vector Distance
+                                        (13 doubles), smooth_triangle: + N1 N2 N3 Perp (25 doubles);
+                                        aux = Dominant_Axis | vAxis << 2 | PVGPU_TRIANGLE_SMOOTH                 */
+    PVGPU_OBJ_POLYGON          = 14  /* polygon.h:83   p[0..2]=S_Normal; aux = Data->Number; mesh = offset into the shape-data table
+                                        (2 doubles per point, Data->Points); transform required                   */
 };
+#define PVGPU_TRIANGLE_SMOOTH 0x10u
 
 #define PVGPU_IS_CSG(type) ((type) >= PVGPU_OBJ_CSG_UNION && (type) <= PVGPU_OBJ_CSG_MERGE)
 
@@ -67,6 +73,7 @@ enum {
 #define PVGPU_CLOSED_FLAG             0x00000002u
 #define PVGPU_INVERTED_FLAG           0x00000004u
 #define PVGPU_CYLINDER_FLAG           0x00000010u
+#define PVGPU_DEGENERATE_FLAG         0x00000020u
 #define PVGPU_STURM_FLAG              0x00000040u
 #define PVGPU_OPAQUE_FLAG             0x00000080u
 #define PVGPU_MULTITEXTURE_FLAG       0x00000100u
@@ -405,6 +412,9 @@ int  pvgpu_scene_set_meshes(pvgpu_scene* s, const pvgpu_mesh* meshes, size_t n_m
 int  pvgpu_scene_set_blobs(pvgpu_scene* s, const pvgpu_blob* blobs, size_t n_blobs,
                            const pvgpu_blob_element* elements, size_t n_elements,
                            const pvgpu_blob_node* nodes, size_t n_nodes);
+/* Shape-data table: FP64 parameters of the primitives whose record does not fit pvgpu_object::p (triangle, smooth_triangle,
+ * polygon); an object's `mesh` field is its offset into this array. */
+int  pvgpu_scene_set_shape_data(pvgpu_scene* s, const double* data, size_t n);
 int  pvgpu_scene_set_lights(pvgpu_scene* s, const pvgpu_light* l, size_t n);
 int  pvgpu_scene_set_materials(pvgpu_scene* s,
                                const pvgpu_texture* tex, size_t n_tex,

@@ -65,9 +65,11 @@
 #include "core/shape/csg.h"
 #include "core/shape/mesh.h"
 #include "core/shape/plane.h"
+#include "core/shape/polygon.h"
 #include "core/shape/quadric.h"
 #include "core/shape/sphere.h"
 #include "core/shape/torus.h"
+#include "core/shape/triangle.h"
 #include "core/support/statistics.h"
 #undef private
 #undef protected
@@ -100,6 +102,7 @@ struct Flattener
     vector<pvgpu_blob_element> blob_elements;
     vector<pvgpu_blob_node> blob_nodes;
     vector<float> vertices, normals;
+    vector<double> shape_data;
     vector<pvgpu_triangle> triangles;
     vector<pvgpu_light> lights;
     vector<pvgpu_texture> textures;
@@ -411,6 +414,23 @@ struct Flattener
             for (int k = 0; k < 3; k++) p.p[k] = dc->normal[k];
             p.p[3] = dc->iradius2; p.p[4] = dc->oradius2;
             p.transform = add_transform(dc->Trans);
+        } else if (Triangle* tr = dynamic_cast<Triangle*>(o)) {
+            p.type = PVGPU_OBJ_TRIANGLE;
+            p.mesh = (int32_t)shape_data.size();
+            p.aux = tr->Dominant_Axis | (tr->vAxis << 2);
+            for (const Vector3d* v : { &tr->P1, &tr->P2, &tr->P3, &tr->Normal_Vector }) for (int k = 0; k < 3; k++) shape_data.push_back((*v)[k]);
+            shape_data.push_back(tr->Distance);
+            if (SmoothTriangle* st = dynamic_cast<SmoothTriangle*>(o)) {
+                p.aux |= PVGPU_TRIANGLE_SMOOTH;
+                for (const Vector3d* v : { &st->N1, &st->N2, &st->N3, &st->Perp }) for (int k = 0; k < 3; k++) shape_data.push_back((*v)[k]);
+            }
+        } else if (Polygon* pg = dynamic_cast<Polygon*>(o)) {
+            p.type = PVGPU_OBJ_POLYGON;
+            for (int k = 0; k < 3; k++) p.p[k] = pg->S_Normal[k];
+            p.mesh = (int32_t)shape_data.size();
+            p.aux = (uint32_t)pg->Data->Number;
+            for (int i = 0; i < pg->Data->Number; i++) { shape_data.push_back(pg->Data->Points[i][X]); shape_data.push_back(pg->Data->Points[i][Y]); }
+            p.transform = add_transform(pg->Trans);
         } else if (Cone* cn = dynamic_cast<Cone*>(o)) {
             p.type = PVGPU_OBJ_CONE;
             p.p[0] = cn->dist;
@@ -427,7 +447,7 @@ struct Flattener
             else unsupported("unknown CSG class");
             add_index_range(c->children, self, true, p.child_first, p.child_count);
         } else {
-            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, blob, CSG; cone / cylinder from 8f)");
+            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, blob, CSG; cone / cylinder / disc / triangle / polygon from 8f)");
             p.type = 0;
         }
         add_index_range(o->Clip, self, false, p.clip_first, p.clip_count);
@@ -566,6 +586,7 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
     check(pvgpu_scene_set_tree(gv.scene, fl.nodes.data(), fl.nodes.size()), "set_tree");
     check(pvgpu_scene_set_blobs(gv.scene, fl.blobs.data(), fl.blobs.size(), fl.blob_elements.data(), fl.blob_elements.size(),
                                 fl.blob_nodes.data(), fl.blob_nodes.size()), "set_blobs");
+    check(pvgpu_scene_set_shape_data(gv.scene, fl.shape_data.data(), fl.shape_data.size()), "set_shape_data");
     check(pvgpu_scene_set_meshes(gv.scene, fl.meshes.data(), fl.meshes.size(), fl.vertices.data(), fl.vertices.size() / 3,
                                  fl.normals.data(), fl.normals.size() / 3, fl.triangles.data(), fl.triangles.size(),
                                  fl.mesh_nodes.data(), fl.mesh_nodes.size()), "set_meshes");

@@ -80,6 +80,7 @@ struct Scene {
     std::vector<pvgpu_blob> blobs;
     std::vector<pvgpu_blob_element> blob_elements;
     std::vector<pvgpu_blob_node> blob_nodes;
+    std::vector<double> shape_data;
     // noise tables
     std::vector<unsigned short> hashTable;
     std::vector<double> RTable;
@@ -947,6 +948,55 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
             }
             return found;
         }
+        case PVGPU_OBJ_TRIANGLE: {                                                                        // triangle.cpp:447-590
+            if (ob.flags & PVGPU_DEGENERATE_FLAG) return false;
+            const double* T = S.shape_data.data() + ob.mesh;
+            const V3 Normal_Vector = v3(T + 9), P1 = v3(T), P2 = v3(T + 3), P3 = v3(T + 6);
+            double NormalDotDirection = dot(Normal_Vector, d);
+            if (std::fabs(NormalDotDirection) < EPSILON) return false;
+            double NormalDotOrigin = dot(Normal_Vector, o);
+            double Depth = -(T[12] + NormalDotOrigin) / NormalDotDirection;
+            if ((Depth < 1.0e-6) || (Depth > MAX_DISTANCE)) return false;
+            const int dom = ob.aux & 3;
+            const int A = (dom == 0) ? 1 : 0, B = (dom == 2) ? 1 : 2;
+            double ss = o[A] + Depth * d[A], tt = o[B] + Depth * d[B];
+            if ((P2[A] - ss) * (P2[B] - P1[B]) < (P2[B] - tt) * (P2[A] - P1[A])) return false;
+            if ((P3[A] - ss) * (P3[B] - P2[B]) < (P3[B] - tt) * (P3[A] - P2[A])) return false;
+            if ((P1[A] - ss) * (P1[B] - P3[B]) < (P1[B] - tt) * (P1[A] - P3[A])) return false;
+            return push(Depth, ray.Evaluate(Depth), 0);
+        }
+        case PVGPU_OBJ_POLYGON: {                                                                         // polygon.cpp:131-260, 905-980
+            if (ob.flags & PVGPU_DEGENERATE_FLAG) return false;
+            const pvgpu_transform& t = S.xf[ob.transform];
+            V3 P = MInvTransPoint(t, o), D = MInvTransDirection(t, d);
+            const double length = len(D);
+            D = D / length;
+            if (std::fabs(D.z) < 1.0e-10) return false;
+            double Depth = -P.z / D.z;
+            if ((Depth < 1.0e-8) || (Depth > MAX_DISTANCE)) return false;
+            const double tx = P.x + Depth * D.x, ty = P.y + Depth * D.y;
+            const int number = (int)ob.aux;
+            const double (*points)[2] = reinterpret_cast<const double (*)[2]>(S.shape_data.data() + ob.mesh);
+            const double *vtx0 = points[0], *vtx1 = points[1], *first = vtx0;
+            int yflag0 = (vtx0[1] >= ty), yflag1;
+            bool inside_flag = false;
+            for (int i = 1; i < number; ) {
+                yflag1 = (vtx1[1] >= ty);
+                if (yflag0 != yflag1)
+                    if (((vtx1[1] - ty) * (vtx0[0] - vtx1[0]) >= (vtx1[0] - tx) * (vtx0[1] - vtx1[1])) == yflag1) inside_flag = !inside_flag;
+                if ((i < number - 2) && (vtx1[0] == first[0]) && (vtx1[1] == first[1])) {
+                    vtx0 = points[++i]; vtx1 = points[++i];
+                    yflag0 = (vtx0[1] >= ty);
+                    first = vtx0;
+                } else {
+                    vtx0 = vtx1; vtx1 = points[++i];
+                    yflag0 = yflag1;
+                }
+            }
+            if (!inside_flag) return false;
+            Depth /= length;
+            return push(Depth, ray.Evaluate(Depth), 0);
+        }
         case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:103-330
             const pvgpu_transform& t = S.xf[ob.transform];
             V3 P = MInvTransPoint(t, o), D = MInvTransDirection(t, d);
@@ -1045,6 +1095,7 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
 static bool Intersect_BBox(const pvgpu_object& ob, V3 o, V3 d, float maxd)
 {
     if (ob.type < PVGPU_OBJ_QUADRIC) return true;          // Sphere / Box / Plane override it (sphere.cpp:753, box.cpp:1079, plane.cpp:629)
+    if (ob.type == PVGPU_OBJ_TRIANGLE) return true;        // and so does Triangle (triangle.cpp:1419)
     float origin[3] = { (float)o.x, (float)o.y, (float)o.z };
     float invdir[3] = { (float)(1.0 / d.x), (float)(1.0 / d.y), (float)(1.0 / d.z) };
     float b[2][3] = { { ob.bbox[0], ob.bbox[1], ob.bbox[2] }, { ob.bbox[0] + ob.bbox[3], ob.bbox[1] + ob.bbox[4], ob.bbox[2] + ob.bbox[5] } };
@@ -1371,6 +1422,17 @@ V3 Tracer::Normal(const Intersection& isect) const
             return unit(MTransNormal(t, N));
         }
         case PVGPU_OBJ_DISC: return v3(ob.p);                                                             // disc.cpp:226-229
+        case PVGPU_OBJ_POLYGON: return v3(ob.p);                                                          // polygon.cpp:308-311
+        case PVGPU_OBJ_TRIANGLE: {                                                                        // triangle.cpp:640-700
+            const double* T = S.shape_data.data() + ob.mesh;
+            if (!(ob.aux & PVGPU_TRIANGLE_SMOOTH)) return v3(T + 9);
+            V3 PIMinusP1 = isect.IPoint - v3(T);
+            double u = dot(PIMinusP1, v3(T + 22));
+            if (u < EPSILON) return v3(T + 13);
+            int Axis = (ob.aux >> 2) & 3;
+            double v = (PIMinusP1[Axis] / u + T[Axis] - T[3 + Axis]) / (T[6 + Axis] - T[3 + Axis]);
+            return unit(v3(T + 13) + u * (v3(T + 16) - v3(T + 13) + v * (v3(T + 19) - v3(T + 16))));
+        }
         case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:408-445
             const pvgpu_transform& t = S.xf[ob.transform];
             V3 r = MInvTransPoint(t, isect.IPoint);
@@ -1996,6 +2058,7 @@ void* pvo_scene_load(const char* path)
               get(f, s->verts) && get(f, s->norms) && get(f, s->tris) && get(f, s->mnodes) && get(f, s->lights) && get(f, s->textures) &&
               get(f, s->pigments) && get(f, s->finishes) && get(f, s->maps) && get(f, s->entries) && get(f, s->warps) && get(f, s->interiors);
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->blobs) && get(f, s->blob_elements) && get(f, s->blob_nodes); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->shape_data); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());

@@ -16,7 +16,7 @@ ABI_VERSION = 2
 OK, E_INVALID, E_UNSUPPORTED, E_NO_DEVICE, E_CUDA, E_IO, E_ABORTED, E_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
 
 # object kinds
-OBJ_SPHERE, OBJ_BOX, OBJ_PLANE, OBJ_QUADRIC, OBJ_TORUS, OBJ_MESH, OBJ_CSG_UNION, OBJ_CSG_INTERSECTION, OBJ_CSG_MERGE, OBJ_BLOB, OBJ_CONE, OBJ_DISC = range(1, 13)
+OBJ_SPHERE, OBJ_BOX, OBJ_PLANE, OBJ_QUADRIC, OBJ_TORUS, OBJ_MESH, OBJ_CSG_UNION, OBJ_CSG_INTERSECTION, OBJ_CSG_MERGE, OBJ_BLOB, OBJ_CONE, OBJ_DISC, OBJ_TRIANGLE, OBJ_POLYGON = range(1, 15)
 
 # object flags (source/core/scene/object.h:88-117)
 NO_SHADOW_FLAG = 0x00000001
@@ -185,6 +185,7 @@ SIGNATURES = {
     "pvgpu_scene_set_blobs": (C.c_int, [VP, P(Blob), C.c_size_t, P(BlobElement), C.c_size_t, P(BlobNode), C.c_size_t]),
     "pvgpu_scene_set_meshes": (C.c_int, [VP, P(Mesh), C.c_size_t, P(f32), C.c_size_t, P(f32), C.c_size_t,
                                          P(Triangle), C.c_size_t, P(Node), C.c_size_t]),
+    "pvgpu_scene_set_shape_data": (C.c_int, [VP, P(f64), C.c_size_t]),
     "pvgpu_scene_set_lights": (C.c_int, [VP, P(Light), C.c_size_t]),
     "pvgpu_scene_set_materials": (C.c_int, [VP, P(Texture), C.c_size_t, P(Pigment), C.c_size_t, P(Finish), C.c_size_t,
                                             P(BlendMap), C.c_size_t, P(BlendEntry), C.c_size_t, P(Warp), C.c_size_t,

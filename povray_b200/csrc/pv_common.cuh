@@ -122,6 +122,7 @@ struct DScene {
     const pvgpu_blob*        blobs;
     const pvgpu_blob_element* blob_elements;
     const pvgpu_blob_node*   blob_nodes;
+    const double*            shape_data;    // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
     const uint32_t*          csg_leaves;    // per top-level CSG object: its primitive descendants (DFS order)
     const uint2*             csg_leaf_range;// per object: (first, count) into csg_leaves
     NoiseTables              noise;

@@ -386,6 +386,8 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_BLOB:    return blob_normal(sc, ob, hit.ip);
         case PVGPU_OBJ_CONE:    return cone_normal(sc, ob, hit.ip, hit.aux);
         case PVGPU_OBJ_DISC:    return ld3(ob.p);       // Disc::Normal (disc.cpp:226-229)
+        case PVGPU_OBJ_TRIANGLE: return triangle_normal(sc, ob, hit.ip);
+        case PVGPU_OBJ_POLYGON: return ld3(ob.p);       // Polygon::Normal (polygon.cpp:308-311)
 #endif
     }
     return mk(0.0, 1.0, 0.0);

@@ -317,6 +317,85 @@ __device__ inline bool disc_inside(const DScene& sc, const pvgpu_object& ob, con
     return (inv_trans_point(sc.xf[ob.transform], p).z >= 0.0) ? inv : !inv;
 }
 
+// ---- triangle / smooth_triangle ----------------------------------------------------------------------
+// Triangle::Intersect / All_Intersections (triangle.cpp:447-590); record layout: see PVGPU_OBJ_TRIANGLE.
+__device__ inline void triangle_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    if (ob.flags & PVGPU_DEGENERATE_FLAG) return;
+    const double* T = sc.shape_data + ob.mesh;
+    const V3 N = ld3(T + 9);
+    const double ndd = dot(N, d);
+    if (fabs(ndd) < PV_EPSILON) return;
+    const double ndo = dot(N, o);
+    const double depth = -(T[12] + ndo) / ndd;
+    if ((depth < 1.0e-6) || (depth > PV_MAX_DISTANCE)) return;
+    const int dom = (int)(ob.aux & 3u);
+    const int a = (dom == 0) ? 1 : 0, b = (dom == 2) ? 1 : 2;       // X: (Y, Z)   Y: (X, Z)   Z: (X, Y)
+    const double s = comp(o, a) + depth * comp(d, a);
+    const double t = comp(o, b) + depth * comp(d, b);
+    const double p1a = T[a], p1b = T[b], p2a = T[3 + a], p2b = T[3 + b], p3a = T[6 + a], p3b = T[6 + b];
+    if ((p2a - s) * (p2b - p1b) < (p2b - t) * (p2a - p1a)) return;
+    if ((p3a - s) * (p3b - p2b) < (p3b - t) * (p3a - p2a)) return;
+    if ((p1a - s) * (p1b - p3b) < (p1b - t) * (p1a - p3a)) return;
+    h.depth[0] = depth; h.ip[0] = evaluate(o, d, depth); h.aux[0] = 0; h.n = 1;
+}
+// Triangle::Normal / SmoothTriangle::Normal (triangle.cpp:640-700)
+__device__ inline V3 triangle_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip)
+{
+    const double* T = sc.shape_data + ob.mesh;
+    if (!(ob.aux & PVGPU_TRIANGLE_SMOOTH)) return ld3(T + 9);
+    const V3 P1 = ld3(T), N1 = ld3(T + 13), N2 = ld3(T + 16), N3 = ld3(T + 19), Perp = ld3(T + 22);
+    const V3 pmp1 = ip - P1;
+    const double u = dot(pmp1, Perp);
+    if (u < PV_EPSILON) return N1;
+    const int axis = (int)((ob.aux >> 2) & 3u);
+    const double v = (comp(pmp1, axis) / u + T[axis] - T[3 + axis]) / (T[6 + axis] - T[3 + axis]);
+    return normalized(N1 + u * (N2 - N1 + v * (N3 - N2)));
+}
+
+// ---- polygon -----------------------------------------------------------------------------------------
+// Polygon::in_polygon (polygon.cpp:905-980): crossings test over the closed sub-polygons of the point list
+__device__ inline bool in_polygon(int number, const double* pts, double tx, double ty)
+{
+    int v0 = 0, v1 = 1, first = 0;
+    bool yflag0 = (pts[2 * v0 + 1] >= ty), inside_flag = false;
+    for (int i = 1; i < number; ) {
+        const bool yflag1 = (pts[2 * v1 + 1] >= ty);
+        if (yflag0 != yflag1) {
+            if (((pts[2 * v1 + 1] - ty) * (pts[2 * v0] - pts[2 * v1]) >= (pts[2 * v1] - tx) * (pts[2 * v0 + 1] - pts[2 * v1 + 1])) == yflag1)
+                inside_flag = !inside_flag;
+        }
+        if ((i < number - 2) && (pts[2 * v1] == pts[2 * first]) && (pts[2 * v1 + 1] == pts[2 * first + 1])) {
+            v0 = ++i; v1 = ++i;
+            yflag0 = (pts[2 * v0 + 1] >= ty);
+            first = v0;
+        } else {
+            v0 = v1; v1 = ++i;
+            yflag0 = yflag1;
+        }
+    }
+    return inside_flag;
+}
+// Polygon::Intersect / All_Intersections (polygon.cpp:131-260)
+__device__ inline void polygon_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    if (ob.flags & PVGPU_DEGENERATE_FLAG) return;
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const V3 P = inv_trans_point(tr, o);
+    V3 D = inv_trans_direction(tr, d);
+    const double len = length(D);
+    D = D / len;
+    if (fabs(D.z) < 1.0e-10) return;                   // ZERO_TOLERANCE polygon.cpp:93
+    double depth = -P.z / D.z;
+    if ((depth < 1.0e-8) || (depth > PV_MAX_DISTANCE)) return;      // DEPTH_TOLERANCE polygon.cpp:90
+    const double x = P.x + depth * D.x, y = P.y + depth * D.y;
+    if (!in_polygon((int)ob.aux, sc.shape_data + ob.mesh, x, y)) return;
+    depth /= len;
+    h.depth[0] = depth; h.ip[0] = evaluate(o, d, depth); h.aux[0] = 0; h.n = 1;
+}
+
 // ---- cone / cylinder ------------------------------------------------------------------------------
 #define PV_CONE_TOLERANCE 1.0e-9      // Cone_Tolerance  cone.cpp:65
 #define PV_CONE_BASE_HIT 1u           // cone.cpp:71-73

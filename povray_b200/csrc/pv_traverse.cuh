@@ -146,7 +146,8 @@ __device__ inline bool object_bbox_test(const float* bbox, const V3& o, const V3
 __device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
 {
     // Sphere, Box and Plane override Intersect_BBox to return true (sphere.cpp:753, box.cpp:1079, plane.cpp:629)
-    return type >= PVGPU_OBJ_QUADRIC;
+    // ... and so does Triangle (triangle.cpp:1419)
+    return type >= PVGPU_OBJ_QUADRIC && type != PVGPU_OBJ_TRIANGLE;
 }
 
 #define PV_MAX_DISTANCE_F 1.0e7f
@@ -324,6 +325,8 @@ __device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const
         case PVGPU_OBJ_TORUS:   torus_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_CONE:    cone_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_DISC:    disc_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_TRIANGLE: triangle_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_POLYGON: polygon_hits(sc, ob, o, d, h); break;
 #endif
         case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;

@@ -227,7 +227,7 @@ int device_upload(Scene& s, int device)
         bool flat = true;
         for (uint32_t k = 0; k < o.child_count && flat; k++) {
             const pvgpu_object& co = s.objects[s.index_list[o.child_first + k]];
-            flat = ((co.type >= PVGPU_OBJ_SPHERE && co.type <= PVGPU_OBJ_TORUS) || co.type == PVGPU_OBJ_CONE || co.type == PVGPU_OBJ_DISC) && co.clip_count == 0;
+            flat = ((co.type >= PVGPU_OBJ_SPHERE && co.type <= PVGPU_OBJ_TORUS) || (co.type >= PVGPU_OBJ_CONE && co.type <= PVGPU_OBJ_POLYGON)) && co.clip_count == 0;
         }
         leaf_range[i] = make_uint2(first, ((uint32_t)leaves.size() - first) | (flat ? 0x80000000u : 0u));
     }
@@ -276,7 +276,7 @@ int device_upload(Scene& s, int device)
     UP(s.vertices, v.verts); UP(s.normals, v.norms); UP(s.lights, v.lights);
     UP(s.textures, v.textures); UP(s.pigments, v.pigments); UP(s.finishes, v.finishes); UP(s.blend_maps, v.maps);
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
-    UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes);
+    UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes); UP(s.shape_data, v.shape_data);
     UP(leaves, v.csg_leaves); UP(leaf_range, v.csg_leaf_range);
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP

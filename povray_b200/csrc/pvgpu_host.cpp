@@ -243,7 +243,7 @@ int validate_scene(Scene& s)
         if (f >= no) return fail(PVGPU_E_INVALID, "frame object index %u out of range", f);
     for (size_t i = 0; i < no; i++) {
         const pvgpu_object& o = s.objects[i];
-        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_DISC)
+        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_POLYGON)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: primitive type %u is outside the hot-path scope", i, o.type);
         if (!range_ok(o.child_first, o.child_count, s.index_list.size()) ||
             !range_ok(o.clip_first, o.clip_count, s.index_list.size()) ||
@@ -264,6 +264,12 @@ int validate_scene(Scene& s)
         }
         if ((o.type == PVGPU_OBJ_CONE || o.type == PVGPU_OBJ_DISC) && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: cone / cylinder / disc without transform", i);
+        if (o.type == PVGPU_OBJ_TRIANGLE &&
+            (o.mesh < 0 || !range_ok((uint32_t)o.mesh, (o.aux & PVGPU_TRIANGLE_SMOOTH) ? 25u : 13u, s.shape_data.size()) || (o.aux & 3u) > 2u || ((o.aux >> 2) & 3u) > 2u))
+            return fail(PVGPU_E_INVALID, "object %zu: triangle record outside the shape-data table", i);
+        if (o.type == PVGPU_OBJ_POLYGON &&
+            (o.transform < 0 || o.mesh < 0 || o.aux > (1u << 24) || !range_ok((uint32_t)o.mesh, 2u * o.aux, s.shape_data.size())))
+            return fail(PVGPU_E_INVALID, "object %zu: polygon without transform or with points outside the shape-data table", i);
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
         if ((o.flags & PVGPU_UV_FLAG))
@@ -515,6 +521,14 @@ int pvgpu_scene_set_blobs(pvgpu_scene* sc, const pvgpu_blob* blobs, size_t n_blo
     return PVGPU_OK;
 }
 
+int pvgpu_scene_set_shape_data(pvgpu_scene* sc, const double* data, size_t n)
+{
+    SCENE_OR_FAIL(sc);
+    if (!data && n) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_shape_data: null array");
+    s.shape_data.assign(data, data + n);
+    return PVGPU_OK;
+}
+
 int pvgpu_scene_set_meshes(pvgpu_scene* sc, const pvgpu_mesh* meshes, size_t n_meshes,
                            const float* vertices, size_t n_vertices,
                            const float* normals, size_t n_normals,
@@ -717,8 +731,11 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.triangles) && put(f, s.mesh_nodes) && put(f, s.lights) && put(f, s.textures) &&
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
-    // optional trailing section (files without it simply end here)
-    if (ok && !s.blobs.empty()) ok = put(f, s.blobs) && put(f, s.blob_elements) && put(f, s.blob_nodes);
+    // optional trailing sections in fixed order; a section is written when it or a later one holds data
+    const bool sec2 = !s.shape_data.empty();
+    const bool sec1 = sec2 || !s.blobs.empty();
+    if (ok && sec1) ok = put(f, s.blobs) && put(f, s.blob_elements) && put(f, s.blob_nodes);
+    if (ok && sec2) ok = put(f, s.shape_data);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -743,6 +760,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->blobs) && get(f, s->blob_elements) && get(f, s->blob_nodes); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->shape_data); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

@@ -33,6 +33,8 @@ struct Scene {
     std::vector<pvgpu_blob_element> blob_elements;
     std::vector<pvgpu_blob_node>    blob_nodes;
 
+    std::vector<double>            shape_data;     // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
+
     std::vector<pvgpu_light>       lights;
     std::vector<pvgpu_texture>     textures;
     std::vector<pvgpu_pigment>     pigments;
