@@ -294,13 +294,43 @@ typedef struct pvgpu_finish {
     int32_t use_subsurface;
 } pvgpu_finish;
 
+/* ---- normal perturbation (source/core/material/normal.cpp, normal.h:118-123) ---------------- */
+enum {
+    PVGPU_NORM_BUMPS    = 1,     /* bumps    normal.cpp:235 */
+    PVGPU_NORM_DENTS    = 2,     /* dents    normal.cpp:272 */
+    PVGPU_NORM_RIPPLES  = 3,     /* ripples  normal.cpp:130 (wave sources: Initialize_Waves, noise.cpp:189) */
+    PVGPU_NORM_WAVES    = 4,     /* waves    normal.cpp:180 */
+    PVGPU_NORM_WRINKLES = 5,     /* wrinkles normal.cpp:325 */
+    PVGPU_NORM_QUILTED  = 6,     /* quilted  normal.cpp:371, carrier p[0..1] = Control0, Control1 */
+    PVGPU_NORM_PATTERN  = 7      /* any continuous pattern: 4 samples on Pyramid_Vect + slope map (normal.cpp:893-918) */
+};
+#define PVGPU_DONT_SCALE_BUMPS_FLAG 8u   /* pattern.h:106 */
+
+/* BlendMapEntry<Vector2d> of a SlopeBlendMap (normal.h:84-96). */
+typedef struct pvgpu_slope_entry {
+    float    value;
+    uint32_t reserved;
+    double   height, slope;      /* Vals[0], Vals[1] */
+} pvgpu_slope_entry;
+
+/* TNORMAL (normal.h:118-123).  The TPATTERN base it shares with PIGMENT (pattern kind, waveform, frequency / phase, warps,
+ * noise generator, pattern parameters) is stored as a pvgpu_pigment record used as pattern carrier (its colours are unused). */
+typedef struct pvgpu_tnormal {
+    uint32_t type;               /* PVGPU_NORM_*                                         */
+    uint32_t flags;              /* PVGPU_DONT_SCALE_BUMPS_FLAG                          */
+    int32_t  pattern;            /* pigment table index of the pattern carrier           */
+    uint32_t slope_first, slope_count;   /* slope_map entries, count 0 = none            */
+    float    amount, delta;      /* Amount, Delta                                        */
+    uint32_t reserved;
+} pvgpu_tnormal;
+
 /* TEXTURE (texture.h:108-117): one layer; `next` chains the layers of a layered texture. */
 typedef struct pvgpu_texture {
     uint32_t type;               /* PVGPU_PAT_PLAIN only (texture maps are out of scope) */
     int32_t  next;               /* TEXTURE::Next, -1 = last layer                       */
     int32_t  pigment;
     int32_t  finish;
-    int32_t  tnormal;            /* -1 (normal perturbation is a "next" row, section 8f)  */
+    int32_t  tnormal;            /* TEXTURE::Tnormal -> tnormal table index, -1 = none     */
     uint32_t reserved;
 } pvgpu_texture;
 
@@ -424,6 +454,8 @@ int  pvgpu_scene_set_materials(pvgpu_scene* s,
                                const pvgpu_blend_entry* entries, size_t n_entries,
                                const pvgpu_warp* warps, size_t n_warps,
                                const pvgpu_interior* interiors, size_t n_interiors);
+/* Normal perturbations referenced by pvgpu_texture::tnormal, and the slope_map entries they use. */
+int  pvgpu_scene_set_normals(pvgpu_scene* s, const pvgpu_tnormal* tn, size_t n_tn, const pvgpu_slope_entry* slopes, size_t n_slopes);
 int  pvgpu_scene_set_camera(pvgpu_scene* s, const pvgpu_camera* cam);
 int  pvgpu_scene_get_camera(const pvgpu_scene* s, pvgpu_camera* cam);
 

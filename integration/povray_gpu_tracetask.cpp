@@ -47,6 +47,7 @@
 #include "core/material/blendmap.h"
 #include "core/material/interior.h"
 #include "core/material/pattern.h"
+#include "core/material/normal.h"
 #include "core/material/pigment.h"
 #include "core/material/texture.h"
 #include "core/material/warp.h"
@@ -112,6 +113,8 @@ struct Flattener
     vector<pvgpu_blend_entry> entries;
     vector<pvgpu_warp> warps;
     vector<pvgpu_interior> interiors;
+    vector<pvgpu_tnormal> tnormals;
+    vector<pvgpu_slope_entry> slope_entries;
     std::map<const void*, int32_t> object_ids, texture_ids, interior_ids;
     std::string error;
 
@@ -164,6 +167,79 @@ struct Flattener
         }
     }
 
+    // the TPATTERN part PIGMENT and TNORMAL share: pattern kind + parameters, waveform, noise generator, warps
+    void fill_pattern(const BasicPattern* bp, pvgpu_pigment& p, const char* user)
+    {
+        if (dynamic_cast<const CheckerPattern*>(bp)) p.pattern = PVGPU_PAT_CHECKER;
+        else if (dynamic_cast<const BozoPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;
+        else if (dynamic_cast<const SpottedPattern*>(bp)) p.pattern = PVGPU_PAT_SPOTTED;
+        else if (dynamic_cast<const GranitePattern*>(bp)) p.pattern = PVGPU_PAT_GRANITE;
+        else if (const GradientPattern* g = dynamic_cast<const GradientPattern*>(bp)) { p.pattern = PVGPU_PAT_GRADIENT; for (int k = 0; k < 3; k++) p.p[k] = g->gradient[k]; }
+        else if (dynamic_cast<const MarblePattern*>(bp)) p.pattern = PVGPU_PAT_MARBLE;
+        else if (dynamic_cast<const OnionPattern*>(bp)) p.pattern = PVGPU_PAT_ONION;
+        else if (dynamic_cast<const WrinklesPattern*>(bp)) p.pattern = PVGPU_PAT_WRINKLES;
+        else if (const AgatePattern* a = dynamic_cast<const AgatePattern*>(bp)) { p.pattern = PVGPU_PAT_AGATE; p.p[0] = a->agateTurbScale; }
+        else unsupported(std::string(user) + " pattern outside the hot-path scope");
+        if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {
+            p.wave_type = cp->waveType; p.frequency = cp->waveFrequency; p.phase = cp->wavePhase; p.exponent = cp->waveExponent;
+        }
+        p.noise_generator = bp->noiseGenerator;
+        add_warps(bp->warps, p.warp_first, p.warp_count);
+    }
+
+    // TNORMAL (normal.h:118-123)
+    int32_t add_tnormal(const TNORMAL* tn)
+    {
+        pvgpu_tnormal t{};
+        pvgpu_pigment carrier{};
+        carrier.blend_map = -1;
+        carrier.pattern = PVGPU_PAT_PLAIN;
+        carrier.wave_type = PVGPU_WAVE_RAMP; carrier.frequency = 1.0f; carrier.exponent = 1.0f;
+        const BasicPattern* bp = tn->pattern.get();
+        t.flags = tn->Flags & PVGPU_DONT_SCALE_BUMPS_FLAG;
+        t.amount = tn->Amount; t.delta = tn->Delta;
+        const SlopeBlendMap* sm = dynamic_cast<const SlopeBlendMap*>(tn->Blend_Map.get());
+        if (tn->Blend_Map != nullptr && sm == nullptr) unsupported("normal_map");
+        bool special = true;
+        switch (tn->Type) {
+            case BUMPS_PATTERN:    t.type = PVGPU_NORM_BUMPS; break;
+            case DENTS_PATTERN:    t.type = PVGPU_NORM_DENTS; break;
+            case RIPPLES_PATTERN:  t.type = PVGPU_NORM_RIPPLES; break;
+            case WAVES_PATTERN:    t.type = PVGPU_NORM_WAVES; break;
+            case WRINKLES_PATTERN: t.type = PVGPU_NORM_WRINKLES; break;
+            case QUILTED_PATTERN:  t.type = PVGPU_NORM_QUILTED; break;
+            default:
+                special = false;
+                if (tn->Type <= LAST_SPECIAL_NORM_PATTERN) unsupported("normal type outside the hot-path scope (bump_map, facets, average, uv_mapping)");
+                else t.type = PVGPU_NORM_PATTERN;
+        }
+        if (special) {
+            if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {
+                carrier.wave_type = cp->waveType; carrier.frequency = cp->waveFrequency; carrier.phase = cp->wavePhase; carrier.exponent = cp->waveExponent;
+            }
+            if (const QuiltedPattern* q = dynamic_cast<const QuiltedPattern*>(bp)) { carrier.p[0] = q->Control0; carrier.p[1] = q->Control1; }
+            carrier.noise_generator = bp->noiseGenerator;
+            add_warps(bp->warps, carrier.warp_first, carrier.warp_count);
+        } else if (t.type == PVGPU_NORM_PATTERN) {
+            fill_pattern(bp, carrier, "normal");
+            if (carrier.pattern == PVGPU_PAT_CHECKER) unsupported("block-pattern normal (needs a normal_map)");
+        }
+        // WarpNormal exists for transform warps only (warp.cpp:582-640): any other warp leaves the normal as it is
+        if (sm != nullptr) {
+            t.slope_first = (uint32_t)slope_entries.size();
+            t.slope_count = (uint32_t)sm->Blend_Map_Entries.size();
+            for (const auto& e : sm->Blend_Map_Entries) {
+                pvgpu_slope_entry se{};
+                se.value = e.value; se.height = e.Vals[0]; se.slope = e.Vals[1];
+                slope_entries.push_back(se);
+            }
+        }
+        pigments.push_back(carrier);
+        t.pattern = (int32_t)pigments.size() - 1;
+        tnormals.push_back(t);
+        return (int32_t)tnormals.size() - 1;
+    }
+
     int32_t add_pigment(const PIGMENT* pg)
     {
         pvgpu_pigment p{};
@@ -176,21 +252,7 @@ struct Flattener
         if (pg->Type == PLAIN_PATTERN) p.pattern = PVGPU_PAT_PLAIN;
         else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern (image_map, average, uv_mapping ...)");
         else {
-            if (dynamic_cast<const CheckerPattern*>(bp)) p.pattern = PVGPU_PAT_CHECKER;
-            else if (dynamic_cast<const BozoPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;
-            else if (dynamic_cast<const SpottedPattern*>(bp)) p.pattern = PVGPU_PAT_SPOTTED;
-            else if (dynamic_cast<const GranitePattern*>(bp)) p.pattern = PVGPU_PAT_GRANITE;
-            else if (const GradientPattern* g = dynamic_cast<const GradientPattern*>(bp)) { p.pattern = PVGPU_PAT_GRADIENT; for (int k = 0; k < 3; k++) p.p[k] = g->gradient[k]; }
-            else if (dynamic_cast<const MarblePattern*>(bp)) p.pattern = PVGPU_PAT_MARBLE;
-            else if (dynamic_cast<const OnionPattern*>(bp)) p.pattern = PVGPU_PAT_ONION;
-            else if (dynamic_cast<const WrinklesPattern*>(bp)) p.pattern = PVGPU_PAT_WRINKLES;
-            else if (const AgatePattern* a = dynamic_cast<const AgatePattern*>(bp)) { p.pattern = PVGPU_PAT_AGATE; p.p[0] = a->agateTurbScale; }
-            else unsupported("pigment pattern outside the hot-path scope");
-            if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {
-                p.wave_type = cp->waveType; p.frequency = cp->waveFrequency; p.phase = cp->wavePhase; p.exponent = cp->waveExponent;
-            }
-            p.noise_generator = bp->noiseGenerator;
-            add_warps(bp->warps, p.warp_first, p.warp_count);
+            fill_pattern(bp, p, "pigment");
             const ColourBlendMap* cm = dynamic_cast<const ColourBlendMap*>(pg->Blend_Map.get());
             if (cm == nullptr) unsupported("pigment without a colour blend map (pigment_map ...)");
             else {
@@ -253,7 +315,7 @@ struct Flattener
                 p.type = PVGPU_PAT_PLAIN;
                 p.pigment = add_pigment(l->Pigment);
                 p.finish = add_finish(l->Finish);
-                if (l->Tnormal != nullptr) unsupported("normal perturbation (SURVEY 8f 'next')");
+                if (l->Tnormal != nullptr) p.tnormal = add_tnormal(l->Tnormal);
             }
             textures[first + i] = p;
             texture_ids[l] = first + (int32_t)i;
@@ -595,6 +657,7 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
                                     fl.finishes.data(), fl.finishes.size(), fl.maps.data(), fl.maps.size(),
                                     fl.entries.data(), fl.entries.size(), fl.warps.data(), fl.warps.size(),
                                     fl.interiors.data(), fl.interiors.size()), "set_materials");
+    check(pvgpu_scene_set_normals(gv.scene, fl.tnormals.data(), fl.tnormals.size(), fl.slope_entries.data(), fl.slope_entries.size()), "set_normals");
     check(pvgpu_scene_set_camera(gv.scene, &c), "set_camera");
     if (const char* path = getenv("PVGPU_DUMP_SCENE")) check(pvgpu_scene_save(gv.scene, path), "scene_save");
     if (!gv.error.empty()) fprintf(stderr, "pvgpu adapter: scene uses a feature outside the GPU trace path: %s\n", gv.error.c_str());

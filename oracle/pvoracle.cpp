@@ -81,6 +81,10 @@ struct Scene {
     std::vector<pvgpu_blob_element> blob_elements;
     std::vector<pvgpu_blob_node> blob_nodes;
     std::vector<double> shape_data;
+    std::vector<pvgpu_tnormal> tnormals;
+    std::vector<pvgpu_slope_entry> slope_entries;
+    std::vector<V3> waveSources;                 // TraceThreadData::waveSources / waveFrequencies (tracethreaddata.cpp:110-111)
+    std::vector<double> waveFrequencies;
     // noise tables
     std::vector<unsigned short> hashTable;
     std::vector<double> RTable;
@@ -619,6 +623,9 @@ public:
     void ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect);
     void ComputeSky(const Ray& ray, const Ticket& tk, Col& colour, float& transm) const;
     void Compute_Pigment(float col[5], int pigment, V3 EPoint) const;
+    V3 Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const;
+    double Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const;
+    V3 Perturb_Normal(V3 Layer_Normal, int tnormal, V3 EPoint) const;
     double relative_ior(const Ray& ray, int interior) const;
     void ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight);
     bool ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight);
@@ -1494,11 +1501,8 @@ static double Triangle_Wave(double value)                                       
     return (offset >= 0.5) ? 2.0 * (1.0 - offset) : 2.0 * offset;
 }
 
-void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const                                  // pigment.cpp:395-466
+V3 Tracer::Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const                                          // warp.cpp:103-122
 {
-    const pvgpu_pigment& pg = S.pigments[pigment];
-    if (pg.pattern == PVGPU_PAT_PLAIN) { for (int k = 0; k < 5; k++) col[k] = pg.colour[k]; return; }
-    // Warp_EPoint (warp.cpp:103-122)
     V3 p = EPoint;
     for (int i = (int)pg.warp_count - 1; i >= 0; i--) {
         const pvgpu_warp& w = S.warps[pg.warp_first + i];
@@ -1507,6 +1511,11 @@ void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const        
     }
     auto clampc = [](double& c) { if (c > COORDINATE_LIMIT) c = COORDINATE_LIMIT; else if (c < -COORDINATE_LIMIT) c = -COORDINATE_LIMIT; };
     clampc(p.x); clampc(p.y); clampc(p.z);
+    return p;
+}
+
+double Tracer::Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const                                         // pattern.cpp:354-392 + EvaluateRaw
+{
     const int gen = pg.noise_generator ? pg.noise_generator : S.g.noise_generator;
     const pvgpu_warp* turb = (pg.warp_count && S.warps[pg.warp_first].type == PVGPU_WARP_CLASSIC_TURBULENCE) ? &S.warps[pg.warp_first] : nullptr;
     double value = 0.0;
@@ -1555,6 +1564,122 @@ void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const        
             case PVGPU_WAVE_POLY: value = std::pow(value, (double)pg.exponent); break;
         }
     }
+    return value;
+}
+
+static double FLOOR(double x) { return x >= 0.0 ? std::floor(x) : (0.0 - std::floor(0.0 - x) - 1.0); }    // texture.h:73
+
+V3 Tracer::Perturb_Normal(V3 Layer_Normal, int tnormal, V3 EPoint) const                                  // normal.cpp:784-927
+{
+    const pvgpu_tnormal& tn = S.tnormals[tnormal];
+    const pvgpu_pigment& pat = S.pigments[tn.pattern];
+    const bool DontScaleBumps = (tn.flags & PVGPU_DONT_SCALE_BUMPS_FLAG) != 0;
+    // Warp_Normal (warp.cpp:563-580)
+    if (!DontScaleBumps) Layer_Normal = unit(Layer_Normal);
+    for (int i = (int)pat.warp_count - 1; i >= 0; i--) {
+        const pvgpu_warp& w = S.warps[pat.warp_first + i];
+        if (w.type == PVGPU_WARP_TRANSFORM) Layer_Normal = mtransposed(S.xf[w.transform].matrix, Layer_Normal);      // MInvTransNormal
+    }
+    if (!DontScaleBumps) Layer_Normal = unit(Layer_Normal);
+    const V3 TPoint = Warp_EPoint(pat, EPoint);
+    const double Amount = (double)tn.amount;
+    switch (tn.type) {
+        case PVGPU_NORM_BUMPS: Layer_Normal = Layer_Normal + DNoise(S, TPoint) * Amount; break;             // normal.cpp:235-246
+        case PVGPU_NORM_DENTS: {                                                                          // normal.cpp:272-288
+            double noise = Noise(S, TPoint, pat.noise_generator ? pat.noise_generator : S.g.noise_generator);
+            noise = noise * noise * noise * tn.amount;
+            Layer_Normal = Layer_Normal + DNoise(S, TPoint) * noise;
+            break;
+        }
+        case PVGPU_NORM_RIPPLES:                                                                          // normal.cpp:130-155
+            for (unsigned i = 0; i < S.g.number_of_waves; i++) {
+                V3 point = TPoint - S.waveSources[i];
+                double length = len(point);
+                if (length == 0.0) length = 1.0;
+                double index = length * pat.frequency + pat.phase;
+                double scalar = cycloidal(index) * tn.amount;
+                Layer_Normal = Layer_Normal + point * (scalar / (length * (double)S.g.number_of_waves));
+            }
+            break;
+        case PVGPU_NORM_WAVES:                                                                            // normal.cpp:180-209
+            for (unsigned i = 0; i < S.g.number_of_waves; i++) {
+                V3 point = TPoint - S.waveSources[i];
+                double length = len(point);
+                if (length == 0.0) length = 1.0;
+                double index = length * pat.frequency * S.waveFrequencies[i] + pat.phase;
+                double sinValue = cycloidal(index);
+                double scalar = sinValue * tn.amount / S.waveFrequencies[i];
+                Layer_Normal = Layer_Normal + point * (scalar / (length * (double)S.g.number_of_waves));
+            }
+            break;
+        case PVGPU_NORM_WRINKLES: {                                                                       // normal.cpp:325-347
+            double scale = 1.0;
+            V3 result = v3(0.0, 0.0, 0.0);
+            for (int i = 0; i < 10; scale *= 2.0, i++) {
+                V3 value = DNoise(S, TPoint * scale);
+                result = v3(result.x + std::fabs(value.x / scale), result.y + std::fabs(value.y / scale), result.z + std::fabs(value.z / scale));
+            }
+            Layer_Normal = Layer_Normal + result * Amount;
+            break;
+        }
+        case PVGPU_NORM_QUILTED: {                                                                        // normal.cpp:371-391, pattern.cpp:8949-8969
+            V3 value = v3(TPoint.x - FLOOR(TPoint.x) - 0.5, TPoint.y - FLOOR(TPoint.y) - 0.5, TPoint.z - FLOOR(TPoint.z) - 0.5);
+            double t = len(value);
+            const double p1 = pat.p[0], p2 = pat.p[1];
+            double it = (1 - t), itsqrd = it * it, tsqrd = t * t, tcubed = t * tsqrd;
+            t = (tcubed + 3.0 * t * itsqrd * p1 + 3.0 * tsqrd * it * p2) * 1.154700538;
+            value = value * t;
+            Layer_Normal = Layer_Normal + value * Amount;
+            break;
+        }
+        default: {                                                                                        // normal.cpp:893-918
+            static const V3 Pyramid_Vect[4] = { { 0.942809041, -0.333333333, 0.0 }, { -0.471404521, -0.333333333, 0.816496581 },
+                                                { -0.471404521, -0.333333333, -0.816496581 }, { 0.0, 1.0, 0.0 } };
+            double Amt = tn.amount * -5.0;
+            Amt *= 0.02 / tn.delta;
+            for (int i = 0; i <= 3; i++) {
+                V3 P1 = TPoint + Pyramid_Vect[i] * (double)tn.delta;
+                double value1 = Evaluate_TPat(pat, P1);
+                if (tn.slope_count) {                                                                     // Do_Slope_Map / Hermite_Cubic normal.cpp:929-1001
+                    const pvgpu_slope_entry* e = S.slope_entries.data() + tn.slope_first;
+                    const uint32_t Max_Ent = tn.slope_count - 1;
+                    uint32_t iP, iN; double prevW = 0.0, curW = 1.0;
+                    if (value1 >= e[Max_Ent].value) iP = iN = Max_Ent;
+                    else {
+                        iP = iN = 0;
+                        while (value1 > e[iN].value) { iP = iN; iN++; }
+                        if ((value1 == e[iN].value) || (iP == iN)) iP = iN;
+                        else { prevW = (e[iN].value - value1) / (e[iN].value - e[iP].value); curW = 1.0 - prevW; }
+                    }
+                    if (iP == iN) value1 = e[iN].height;
+                    else {
+                        const double T1 = curW, TT = T1 * T1, TTT = TT * T1;
+                        double rv = TTT * (e[iP].slope + e[iN].slope + 2.0 * (e[iP].height - e[iN].height));
+                        rv += -TT * (2.0 * e[iP].slope + e[iN].slope + 3.0 * (e[iP].height - e[iN].height));
+                        rv += T1 * e[iP].slope + e[iP].height;
+                        value1 = rv;
+                    }
+                }
+                Layer_Normal = Layer_Normal + Pyramid_Vect[i] * (value1 * Amt);
+            }
+            break;
+        }
+    }
+    // UnWarp_Normal (warp.cpp:603-620)
+    if (!DontScaleBumps) Layer_Normal = unit(Layer_Normal);
+    for (uint32_t i = 0; i < pat.warp_count; i++) {
+        const pvgpu_warp& w = S.warps[pat.warp_first + i];
+        if (w.type == PVGPU_WARP_TRANSFORM) Layer_Normal = MTransNormal(S.xf[w.transform], Layer_Normal);
+    }
+    if (!DontScaleBumps) Layer_Normal = unit(Layer_Normal);
+    return Layer_Normal;
+}
+
+void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const                                  // pigment.cpp:395-466
+{
+    const pvgpu_pigment& pg = S.pigments[pigment];
+    if (pg.pattern == PVGPU_PAT_PLAIN) { for (int k = 0; k < 5; k++) col[k] = pg.colour[k]; return; }
+    const double value = Evaluate_TPat(pg, Warp_EPoint(pg, EPoint));
     // BlendMap::Search + ColourBlendMap::Compute (pattern.cpp:1068-1112, pigment.cpp:513-530)
     const pvgpu_blend_map& m = S.maps[pg.blend_map];
     const pvgpu_blend_entry* e = S.entries.data() + m.entry_first;
@@ -1623,10 +1748,12 @@ static double Attenuate_Light(const pvgpu_light& L, const Ray& ray, double Dista
 double Tracer::relative_ior(const Ray& ray, int interior) const                                           // trace.cpp:2595-2625
 {
     if (interior < 0) return 1.0;
-    double ior = S.interiors[interior].ior;
-    if (ray.interiors.empty()) return ior / S.g.atmosphere_ior;
+    // SceneData::atmosphereIOR is DBL, Interior::IOR is SNGL: atmosphere ratios divide in FP64, object / object ratios in FP32
+    const float ior = S.interiors[interior].ior;
+    const double atmosphereIOR = S.g.atmosphere_ior;
+    if (ray.interiors.empty()) return ior / atmosphereIOR;
     if (ray.IsInterior(interior)) {
-        if (ray.interiors.size() == 1) return S.g.atmosphere_ior / ior;
+        if (ray.interiors.size() == 1) return atmosphereIOR / ior;
         return S.interiors[ray.interiors.back()].ior / ior;
     }
     return ior / S.interiors[ray.interiors.back()].ior;
@@ -1708,6 +1835,10 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
     for (int layer = texture; (layer >= 0) && (trans > tk.adcBailout); layer_number++, layer = S.textures[layer].next) {
         const pvgpu_finish& fn = S.finishes[S.textures[layer].finish];
         V3 layNormal = rawnormal;
+        if ((S.g.quality_flags & PVGPU_Q_NORMALS) && S.textures[layer].tnormal >= 0) {                    // trace.cpp:814-828
+            layNormal = Perturb_Normal(layNormal, S.textures[layer].tnormal, ipoint);
+            if (S.tnormals[S.textures[layer].tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) layNormal = unit(layNormal);
+        }
         if (layer_number == 0) topNormal = layNormal;
         double new_Weight = weight * trans;
         float lc[5];
@@ -1820,10 +1951,11 @@ bool Tracer::ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3
     nray.flags = RAY_REFRACTION | (ray.flags & RAY_REFLECTION);
     nray.Origin = ipoint;
     double ior;
-    if (nray.interiors.empty()) { nray.interiors.push_back(interior); ior = S.g.atmosphere_ior / in.ior; }
+    const double atmosphereIOR = S.g.atmosphere_ior;      // DBL in the reference (scenedata.h:103); Interior::IOR is SNGL
+    if (nray.interiors.empty()) { nray.interiors.push_back(interior); ior = atmosphereIOR / in.ior; }
     else if (interior == nray.interiors.back()) {
         nray.RemoveInterior(interior);
-        if (nray.interiors.empty()) ior = in.ior / S.g.atmosphere_ior;
+        if (nray.interiors.empty()) ior = in.ior / atmosphereIOR;
         else ior = in.ior / S.interiors[nray.interiors.back()].ior;
     } else if (nray.RemoveInterior(interior)) ior = 1.0;
     else { ior = S.interiors[nray.interiors.back()].ior / in.ior; nray.interiors.push_back(interior); }
@@ -1978,7 +2110,15 @@ void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& t
         float lc[5];
         Compute_Pigment(lc, S.textures[layer].pigment, isect.IPoint);
         tmpCol = tmpCol * Col{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
-        if (in && in->caustics != 0.0f) { double k = 1.0 + std::pow(std::fabs(dot(raw, lray.Direction)), (double)in->caustics); tmpCol = tmpCol * (float)k; }
+        if (in && in->caustics != 0.0f) {                                                                 // trace.cpp:1208-1234
+            V3 layer_Normal = raw;
+            if ((S.g.quality_flags & PVGPU_Q_NORMALS) && S.textures[layer].tnormal >= 0) {
+                layer_Normal = Perturb_Normal(layer_Normal, S.textures[layer].tnormal, isect.IPoint);
+                if (S.tnormals[S.textures[layer].tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) layer_Normal = unit(layer_Normal);
+            }
+            double k = 1.0 + std::pow(std::fabs(dot(layer_Normal, lray.Direction)), (double)in->caustics);
+            tmpCol = tmpCol * (float)k;
+        }
     }
     Col refraction{ 1, 1, 1 };
     if (in && lray.IsInterior(ob.interior) && (in->fade_power > 0.0f) && (std::fabs(in->fade_distance) > EPSILON)) {
@@ -2059,10 +2199,17 @@ void* pvo_scene_load(const char* path)
               get(f, s->pigments) && get(f, s->finishes) && get(f, s->maps) && get(f, s->entries) && get(f, s->warps) && get(f, s->interiors);
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->blobs) && get(f, s->blob_elements) && get(f, s->blob_nodes); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->shape_data); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->tnormals) && get(f, s->slope_entries); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());
     init_noise(*s);
+    // Initialize_Waves (noise.cpp:189-205)
+    for (int i = 0, next_rand = -560851967; i < (int)s->g.number_of_waves; i++) {
+        s->waveSources.push_back(unit(DNoise(*s, v3((double)i, 0.0, 0.0))));
+        next_rand = (int)((long long)next_rand * 1812433253LL + 12345LL);
+        s->waveFrequencies.push_back((double((int)(next_rand >> 16) & 0x7FFF) * 0.000030518509476) + 0.01);
+    }
     return s;
 }
 

@@ -128,6 +128,15 @@ class Texture(C.Structure):
     _fields_ = [("type", u32), ("next", i32), ("pigment", i32), ("finish", i32), ("tnormal", i32), ("reserved", u32)]
 
 
+class SlopeEntry(C.Structure):
+    _fields_ = [("value", f32), ("reserved", u32), ("height", f64), ("slope", f64)]
+
+
+class TNormal(C.Structure):
+    _fields_ = [("type", u32), ("flags", u32), ("pattern", i32), ("slope_first", u32), ("slope_count", u32),
+                ("amount", f32), ("delta", f32), ("reserved", u32)]
+
+
 class Interior(C.Structure):
     _fields_ = [("hollow", i32), ("disp_nelems", i32), ("ior", f32), ("dispersion", f32), ("caustics", f32),
                 ("old_refract", f32), ("fade_distance", f32), ("fade_power", f32), ("fade_colour", f32 * 3), ("reserved", u32)]
@@ -190,6 +199,7 @@ SIGNATURES = {
     "pvgpu_scene_set_materials": (C.c_int, [VP, P(Texture), C.c_size_t, P(Pigment), C.c_size_t, P(Finish), C.c_size_t,
                                             P(BlendMap), C.c_size_t, P(BlendEntry), C.c_size_t, P(Warp), C.c_size_t,
                                             P(Interior), C.c_size_t]),
+    "pvgpu_scene_set_normals": (C.c_int, [VP, P(TNormal), C.c_size_t, P(SlopeEntry), C.c_size_t]),
     "pvgpu_scene_set_camera": (C.c_int, [VP, P(Camera)]),
     "pvgpu_scene_get_camera": (C.c_int, [VP, P(Camera)]),
     "pvgpu_scene_add_mesh2": (C.c_int, [VP, P(f64), C.c_size_t, P(i32), C.c_size_t, P(i32)]),

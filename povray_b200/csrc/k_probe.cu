@@ -32,6 +32,21 @@ __global__ void k_probe_noise(NoiseTables nt, uint32_t n, const double* xyz, con
     }
 }
 
+// Initialize_Waves (noise.cpp:189-205): wave sources = normalised DNoise(<i, 0, 0>), frequencies from the reference's LCG
+__global__ void k_init_waves(NoiseTables nt, uint32_t n, double* sources, double* freqs)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const V3 s = normalized(dnoise3(nt, mk((double)i, 0.0, 0.0)));
+        sources[3 * i] = s.x; sources[3 * i + 1] = s.y; sources[3 * i + 2] = s.z;
+        int next_rand = -560851967;
+        for (uint32_t k = 0; k <= i; k++) next_rand = (int)((long long)next_rand * 1812433253LL + 12345LL);
+        freqs[i] = ((double)((int)(next_rand >> 16) & 0x7FFF) * 0.000030518509476) + 0.01;
+    }
+}
+
+void launch_init_waves(const NoiseTables& nt, uint32_t n, double* sources, double* freqs, cudaStream_t st)
+{ if (n) k_init_waves<<<grid_for(n, 128, 8), 128, 0, st>>>(nt, n, sources, freqs); }
+
 void launch_probe_solver(uint32_t n, const int32_t* degree, const int32_t* sturm, const double* epsilon, const double* coeffs,
                          double* roots, int32_t* counts, cudaStream_t st)
 { k_probe_solver<<<grid_for(n, 128, 8), 128, 0, st>>>(n, degree, sturm, epsilon, coeffs, roots, counts); }

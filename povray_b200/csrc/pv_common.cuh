@@ -123,6 +123,10 @@ struct DScene {
     const pvgpu_blob_element* blob_elements;
     const pvgpu_blob_node*   blob_nodes;
     const double*            shape_data;    // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
+    const pvgpu_tnormal*     tnormals;
+    const pvgpu_slope_entry* slopes;
+    const double*            wave_sources;  // TraceThreadData::waveSources (xyz per wave), Initialize_Waves (noise.cpp:189)
+    const double*            wave_freqs;    // TraceThreadData::waveFrequencies
     const uint32_t*          csg_leaves;    // per top-level CSG object: its primitive descendants (DFS order)
     const uint2*             csg_leaf_range;// per object: (first, count) into csg_leaves
     NoiseTables              noise;

@@ -75,6 +75,7 @@ void launch_aa2_resolve(const AALayout& L, const AAParams& aa, const float4* acc
 void launch_probe_solver(uint32_t n, const int32_t* degree, const int32_t* sturm, const double* epsilon, const double* coeffs,
                          double* roots, int32_t* counts, cudaStream_t st);
 void launch_probe_noise(const NoiseTables& nt, uint32_t n, const double* xyz, const int32_t* gen, const int32_t* octaves, double* out, cudaStream_t st);
+void launch_init_waves(const NoiseTables& nt, uint32_t n, double* sources, double* freqs, cudaStream_t st);
 void launch_camera_rays(const DScene& sc, const double* xy, uint32_t n, double width, double height, double* org_dir, cudaStream_t st);
 
 }  // namespace pvgpu

@@ -57,6 +57,10 @@ __device__ __forceinline__ V3 inv_trans_point(const pvgpu_transform& t, const V3
 __device__ __forceinline__ V3 trans_direction(const pvgpu_transform& t, const V3& v) { return m_direction(t.matrix, v); }
 __device__ __forceinline__ V3 inv_trans_direction(const pvgpu_transform& t, const V3& v) { return m_direction(t.inverse, v); }
 __device__ __forceinline__ V3 trans_normal(const pvgpu_transform& t, const V3& v) { return m_transposed(t.inverse, v); }
+__device__ __forceinline__ V3 inv_trans_normal(const pvgpu_transform& t, const V3& v) { return m_transposed(t.matrix, v); }
+
+// FLOOR (texture.h:73)
+__device__ __forceinline__ double pv_floor(double x) { return (x >= 0.0) ? floor(x) : (0.0 - floor(0.0 - x) - 1.0); }
 
 struct Ray3 { V3 o, d; };
 

@@ -166,7 +166,7 @@ __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, cons
         while (value > (double)e[in].value) { ip = in; in++; }
         if ((value == (double)e[in].value) || (ip == in)) { ip = in; }
         else {
-            wp = ((double)e[in].value - value) / ((double)e[in].value - (double)e[ip].value);
+            wp = ((double)e[in].value - value) / (double)__fsub_rn(e[in].value, e[ip].value);     // SNGL - SNGL rounds to FP32 (pattern.cpp:1105)
             wn = 1.0 - wp;
         }
     }
@@ -179,6 +179,123 @@ __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, cons
         for (int k = 0; k < 5; k++) col[k] = (float)(e[ip].colour[k] * wp) + (float)(e[in].colour[k] * wn);
     }
 }
+
+// ---- normal perturbation: Perturb_Normal (normal.cpp:784-927) ---------------------------------------
+#if PV_HEAVY
+// Warp_Normal / UnWarp_Normal (warp.cpp:563-640): only transform warps act on normals
+__device__ inline V3 warp_normal(const DScene& sc, const pvgpu_pigment& c, V3 n, bool dont_scale)
+{
+    if (!dont_scale) n = normalized(n);
+    for (int i = (int)c.warp_count - 1; i >= 0; i--) {
+        const pvgpu_warp& w = sc.warps[c.warp_first + i];
+        if (w.type == PVGPU_WARP_TRANSFORM) n = inv_trans_normal(sc.xf[w.transform], n);
+    }
+    if (!dont_scale) n = normalized(n);
+    return n;
+}
+__device__ inline V3 unwarp_normal(const DScene& sc, const pvgpu_pigment& c, V3 n, bool dont_scale)
+{
+    if (!dont_scale) n = normalized(n);
+    for (uint32_t i = 0; i < c.warp_count; i++) {
+        const pvgpu_warp& w = sc.warps[c.warp_first + i];
+        if (w.type == PVGPU_WARP_TRANSFORM) n = trans_normal(sc.xf[w.transform], n);
+    }
+    if (!dont_scale) n = normalized(n);
+    return n;
+}
+// Do_Slope_Map + Hermite_Cubic (normal.cpp:929-1001), BlendMap::Search (pattern.cpp:1068-1112)
+__device__ inline double do_slope_map(const DScene& sc, const pvgpu_tnormal& tn, double value)
+{
+    if (tn.slope_count == 0) return value;
+    const pvgpu_slope_entry* e = sc.slopes + tn.slope_first;
+    const uint32_t last = tn.slope_count - 1;
+    if (value >= (double)e[last].value) return e[last].height;
+    uint32_t ip = 0, in = 0;
+    while (value > (double)e[in].value) { ip = in; in++; }
+    if ((value == (double)e[in].value) || (ip == in)) return e[in].height;
+    const double wp = ((double)e[in].value - value) / (double)__fsub_rn(e[in].value, e[ip].value);
+    const double t1 = 1.0 - wp;
+    const double tt = t1 * t1, ttt = tt * t1;
+    double rv = ttt * (e[ip].slope + e[in].slope + 2.0 * (e[ip].height - e[in].height));
+    rv += -tt * (2.0 * e[ip].slope + e[in].slope + 3.0 * (e[ip].height - e[in].height));
+    rv += t1 * e[ip].slope + e[ip].height;
+    return rv;
+}
+__device__ inline V3 perturb_normal(const DScene& sc, int32_t tn_index, V3 n, const V3& epoint)
+{
+    const pvgpu_tnormal& tn = sc.tnormals[tn_index];
+    const pvgpu_pigment& c = sc.pigments[tn.pattern];
+    const bool dont_scale = (tn.flags & PVGPU_DONT_SCALE_BUMPS_FLAG) != 0;
+    const double amount = (double)tn.amount;
+    n = warp_normal(sc, c, n, dont_scale);
+    const V3 tp = warp_epoint(sc, c, epoint);
+    switch (tn.type) {
+        case PVGPU_NORM_BUMPS:                         // normal.cpp:235-246
+            n = n + amount * dnoise3(sc.noise, tp);
+            break;
+        case PVGPU_NORM_DENTS: {                       // normal.cpp:272-288
+            const int gen = c.noise_generator ? c.noise_generator : sc.g.noise_generator;
+            double noise = noise3(sc.noise, tp, gen);
+            noise = noise * noise * noise * amount;
+            n = n + noise * dnoise3(sc.noise, tp);
+            break;
+        }
+        case PVGPU_NORM_RIPPLES:                       // normal.cpp:130-155
+        case PVGPU_NORM_WAVES: {                       // normal.cpp:180-209
+            const uint32_t nw = sc.g.number_of_waves;
+            for (uint32_t i = 0; i < nw; i++) {
+                const V3 point = tp - ld3(sc.wave_sources + 3 * i);
+                double len = length(point);
+                if (len == 0.0) len = 1.0;
+                double scalar;
+                if (tn.type == PVGPU_NORM_RIPPLES) {
+                    const double index = len * (double)c.frequency + (double)c.phase;
+                    scalar = cycloidal(index) * amount;
+                } else {
+                    const double f = sc.wave_freqs[i];
+                    const double index = len * (double)c.frequency * f + (double)c.phase;
+                    scalar = cycloidal(index) * amount / f;
+                }
+                n = n + (scalar / (len * (double)nw)) * point;
+            }
+            break;
+        }
+        case PVGPU_NORM_WRINKLES: {                    // normal.cpp:325-347
+            double scale = 1.0;
+            V3 result = mk(0.0, 0.0, 0.0);
+            for (int i = 0; i < 10; scale *= 2.0, i++) {
+                const V3 value = dnoise3(sc.noise, tp * scale);
+                result.x += fabs(value.x / scale); result.y += fabs(value.y / scale); result.z += fabs(value.z / scale);
+            }
+            n = n + amount * result;
+            break;
+        }
+        case PVGPU_NORM_QUILTED: {                     // normal.cpp:371-391, quilt_cubic pattern.cpp:8949
+            V3 value = mk(tp.x - pv_floor(tp.x) - 0.5, tp.y - pv_floor(tp.y) - 0.5, tp.z - pv_floor(tp.z) - 0.5);
+            double t = length(value);
+            const double p1 = (double)(float)c.p[0], p2 = (double)(float)c.p[1];
+            const double it = 1 - t, itsqrd = it * it, tsqrd = t * t, tcubed = t * tsqrd;
+            t = (tcubed + 3.0 * t * itsqrd * p1 + 3.0 * tsqrd * it * p2) * 1.154700538;
+            n = n + amount * (value * t);
+            break;
+        }
+        default: {                                     // PVGPU_NORM_PATTERN: normal.cpp:893-918
+            const double pyr[4][3] = { { 0.942809041, -0.333333333, 0.0 }, { -0.471404521, -0.333333333, 0.816496581 },
+                                       { -0.471404521, -0.333333333, -0.816496581 }, { 0.0, 1.0, 0.0 } };
+            double am = amount * -5.0;
+            am *= 0.02 / (double)tn.delta;
+            for (int i = 0; i <= 3; i++) {
+                const V3 pv = mk(pyr[i][0], pyr[i][1], pyr[i][2]);
+                const V3 p1 = tp + (double)tn.delta * pv;
+                const double value1 = do_slope_map(sc, tn, evaluate_pattern(sc, c, p1));
+                n = n + (value1 * am) * pv;
+            }
+            break;
+        }
+    }
+    return unwarp_normal(sc, c, n, dont_scale);
+}
+#endif
 
 // ---- finish helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float greyscale(const float* c) { return (float)(0.297 * c[0] + 0.589 * c[1] + 0.114 * c[2]); }   // colour.h:1366
@@ -320,13 +437,15 @@ __device__ __forceinline__ void ray_append_interior(PRay& r, int32_t interior, u
 __device__ inline double relative_ior(const DScene& sc, const PRay& ray, int32_t interior)
 {
     if (interior < 0) return 1.0;
-    const double ior = sc.interiors[interior].ior;
+    // SceneData::atmosphereIOR is DBL, Interior::IOR is SNGL: atmosphere ratios divide in FP64, object / object ratios in FP32
+    const float iorf = sc.interiors[interior].ior;
+    const double ior = iorf;
     if (ray.n_int == 0) return ior / (double)sc.g.atmosphere_ior;
     if (ray_is_interior(ray, interior)) {
         if (ray.n_int == 1) return (double)sc.g.atmosphere_ior / ior;
-        return (double)sc.interiors[ray.interiors[ray.n_int - 1]].ior / ior;
+        return (double)__fdiv_rn(sc.interiors[ray.interiors[ray.n_int - 1]].ior, iorf);
     }
-    return ior / (double)sc.interiors[ray.interiors[ray.n_int - 1]].ior;
+    return (double)__fdiv_rn(iorf, sc.interiors[ray.interiors[ray.n_int - 1]].ior);
 }
 
 // ---- queues --------------------------------------------------------------------------------------
@@ -470,19 +589,38 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
 
     const double rel_ior = relative_ior(sc, ray, ob.interior);
 
-    struct Layer { float col[3]; float fil[3]; float refl[3]; double att; double rweight; int32_t finish; };
+    struct Layer {
+        float col[3]; float fil[3]; float refl[3]; double att; double rweight; int32_t finish;
+#if PV_HEAVY
+        V3 n;                 // layNormal of the layer (trace.cpp:812-828); the lean variant serves scenes without normal{}
+#endif
+    };
     Layer layers[PV_MAX_LAYERS];
     int nlayers = 0;
     float fil[3] = { 1.0f, 1.0f, 1.0f };
     double trans = 1.0;
     float amb[3] = { 0.0f, 0.0f, 0.0f };
-    const V3 lay_normal = rawnormal;      // no normal perturbation on this path
-    const double cos_inc = -dot(dir, lay_normal);
+    V3 top_normal = rawnormal;
+#if PV_HEAVY
+    #define LAYER_NORMAL(L) ((L).n)
+#else
+    #define LAYER_NORMAL(L) rawnormal
+#endif
 
     for (int32_t li = tex0; li >= 0 && trans > adc && nlayers < PV_MAX_LAYERS; li = sc.textures[li].next) {
         const pvgpu_texture& tx = sc.textures[li];
         const pvgpu_finish& fn = sc.finishes[tx.finish];
         Layer& L = layers[nlayers];
+#if PV_HEAVY
+        L.n = rawnormal;
+        if ((sc.g.quality_flags & PVGPU_Q_NORMALS) && tx.tnormal >= 0) {          // trace.cpp:814-828
+            L.n = perturb_normal(sc, tx.tnormal, L.n, ipoint);
+            if (sc.tnormals[tx.tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) L.n = normalized(L.n);
+        }
+        if (nlayers == 0) top_normal = L.n;
+#endif
+        const V3 lay_normal = LAYER_NORMAL(L);
+        const double cos_inc = -dot(dir, lay_normal);
         float lc[5];
         compute_pigment(sc, tx.pigment, ipoint, lc);
         L.col[0] = lc[0]; L.col[1] = lc[1]; L.col[2] = lc[2];
@@ -535,6 +673,7 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
                 const pvgpu_finish& fn = sc.finishes[L.finish];
                 if (!((fn.diffuse != 0.0f) || (fn.diffuse_back != 0.0f) || (fn.specular != 0.0f) || (fn.phong != 0.0f))) continue;
                 if (fn.alpha_knockout && L.att == 0.0) continue;
+                const V3 lay_normal = LAYER_NORMAL(L);
                 bool backside = false;
                 if (!(ob.flags & PVGPU_DOUBLE_ILLUMINATE_FLAG)) {
                     double cos_shadow = dot(lay_normal, ldir);
@@ -649,14 +788,13 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
         } else if ((uint16_t)ob.interior == nr.interiors[nr.n_int - 1]) {
             ray_remove_interior(nr, ob.interior);
             if (nr.n_int == 0) ior = (double)in.ior / (double)sc.g.atmosphere_ior;
-            else ior = (double)in.ior / (double)sc.interiors[nr.interiors[nr.n_int - 1]].ior;
+            else ior = (double)__fdiv_rn(in.ior, sc.interiors[nr.interiors[nr.n_int - 1]].ior);     // SNGL / SNGL (trace.cpp:1371)
         } else if (ray_remove_interior(nr, ob.interior)) {
             ior = 1.0;
         } else {
-            ior = (double)sc.interiors[nr.interiors[nr.n_int - 1]].ior / (double)in.ior;
+            ior = (double)__fdiv_rn(sc.interiors[nr.interiors[nr.n_int - 1]].ior, in.ior);         // SNGL / SNGL (trace.cpp:1388)
             ray_append_interior(nr, ob.interior, &ctx.cnt->overflow);
         }
-        const V3 top_normal = lay_normal;
         bool spawn = true;
         if (fabs(ior - 1.0) < PV_EPSILON) {
             nr.flags |= PV_RAY_CONTINUED;     // TraceRay(nray, ..., continuedRay = true)
@@ -702,7 +840,10 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
     if (sc.g.quality_flags & PVGPU_Q_REFLECTIONS) {
         for (int i = 0; i < nlayers; i++) {
             const Layer& L = layers[i];
-            if (tir) continue;      // all layer normals equal topNormal on this path
+            const V3 lay_normal = LAYER_NORMAL(L);
+            // after total internal reflection the reflections that use topNormal are skipped (trace.cpp:1155-1159)
+            if (tir && !((fabs(top_normal.x - lay_normal.x) > PV_EPSILON) || (fabs(top_normal.y - lay_normal.y) > PV_EPSILON) ||
+                         (fabs(top_normal.z - lay_normal.z) > PV_EPSILON))) continue;
             if (L.refl[0] == 0.0f && L.refl[1] == 0.0f && L.refl[2] == 0.0f) continue;
             PRay rr = ray;
             V3 rd = reflect_direction(dir, lay_normal, rawnormal);
@@ -717,6 +858,7 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
             push_ray(ctx, rr);
         }
     }
+    #undef LAYER_NORMAL
 }
 
 }  // namespace pvgpu

@@ -277,15 +277,27 @@ int device_upload(Scene& s, int device)
     UP(s.textures, v.textures); UP(s.pigments, v.pigments); UP(s.finishes, v.finishes); UP(s.blend_maps, v.maps);
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
     UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes); UP(s.shape_data, v.shape_data);
+    UP(s.tnormals, v.tnormals); UP(s.slope_entries, v.slopes);
     UP(leaves, v.csg_leaves); UP(leaf_range, v.csg_leaf_range);
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP
     if (rc != PVGPU_OK) { device_release(s); return rc; }
+    if (!s.tnormals.empty() && s.globals.number_of_waves) {       // TraceThreadData::waveSources / waveFrequencies, computed with the device's own DNoise
+        const uint32_t nw = s.globals.number_of_waves;
+        std::vector<double> zeros(4 * (size_t)nw, 0.0);
+        const double* d_waves = nullptr;
+        rc = upload(*d, zeros, d_waves, total);
+        if (rc != PVGPU_OK) { device_release(s); return rc; }
+        v.wave_sources = d_waves; v.wave_freqs = d_waves + 3 * (size_t)nw;
+        launch_init_waves(v.noise, nw, const_cast<double*>(v.wave_sources), const_cast<double*>(v.wave_freqs), 0);
+        if (cudaDeviceSynchronize() != cudaSuccess) { device_release(s); return fail(PVGPU_E_CUDA, "wave source initialisation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    }
 
     d->lean = true;
     for (const pvgpu_object& o : s.objects)
         if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH) ||
             o.clip_count || o.bound_count) d->lean = false;
+    for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->lean = false;
     for (const pvgpu_mesh& me : s.meshes) if (me.node_count == 0) d->lean = false;       // `hierarchy off` meshes take the generic walk
     if (const char* e = getenv("PVGPU_LEAN")) if (e[0] == '0') d->lean = false;
     v.n_objs = (uint32_t)s.objects.size();

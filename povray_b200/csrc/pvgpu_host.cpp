@@ -341,8 +341,11 @@ int validate_scene(Scene& s)
         if (t.pigment < 0 || t.pigment >= (int32_t)s.pigments.size() || t.finish < 0 ||
             t.finish >= (int32_t)s.finishes.size() || t.next >= (int32_t)s.textures.size())
             return fail(PVGPU_E_INVALID, "texture %zu: bad pigment / finish / next index", i);
-        if (t.tnormal >= 0)
-            return fail(PVGPU_E_UNSUPPORTED, "texture %zu: normal perturbation is outside the hot-path scope", i);
+        if (t.tnormal >= (int32_t)s.tnormals.size())
+            return fail(PVGPU_E_INVALID, "texture %zu: bad tnormal index", i);
+        const pvgpu_pigment& tp = s.pigments[t.pigment];
+        if (tp.pattern != PVGPU_PAT_PLAIN && (tp.blend_map < 0 || tp.blend_map >= (int32_t)s.blend_maps.size()))
+            return fail(PVGPU_E_INVALID, "texture %zu: patterned pigment without blend map", i);
         int depth = 0;
         for (int32_t k = (int32_t)i; k >= 0; k = s.textures[k].next)
             if (++depth > 8) return fail(PVGPU_E_UNSUPPORTED, "texture %zu: more than 8 layers", i);
@@ -351,10 +354,24 @@ int validate_scene(Scene& s)
         const pvgpu_pigment& p = s.pigments[i];
         if (p.pattern < PVGPU_PAT_PLAIN || p.pattern > PVGPU_PAT_RADIAL)
             return fail(PVGPU_E_UNSUPPORTED, "pigment %zu: pattern %u unsupported", i, p.pattern);
-        if (p.pattern != PVGPU_PAT_PLAIN && (p.blend_map < 0 || p.blend_map >= (int32_t)s.blend_maps.size()))
-            return fail(PVGPU_E_INVALID, "pigment %zu: patterned pigment without blend map", i);
+        if (p.blend_map >= (int32_t)s.blend_maps.size())        // (-1 is legal for the pattern carrier of a tnormal)
+            return fail(PVGPU_E_INVALID, "pigment %zu: bad blend map index", i);
         if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
+    }
+    for (size_t i = 0; i < s.tnormals.size(); i++) {
+        const pvgpu_tnormal& t = s.tnormals[i];
+        if (t.type < PVGPU_NORM_BUMPS || t.type > PVGPU_NORM_PATTERN)
+            return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: type %u unsupported", i, t.type);
+        if (t.pattern < 0 || t.pattern >= (int32_t)s.pigments.size() || !range_ok(t.slope_first, t.slope_count, s.slope_entries.size()))
+            return fail(PVGPU_E_INVALID, "tnormal %zu: bad pattern carrier / slope map range", i);
+        const pvgpu_pigment& c = s.pigments[t.pattern];
+        if (t.type == PVGPU_NORM_PATTERN && (c.pattern <= PVGPU_PAT_CHECKER || c.pattern == PVGPU_PAT_BRICK || c.pattern == PVGPU_PAT_HEXAGON))
+            return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: block patterns need a normal_map (outside the hot-path scope)", i);
+        for (uint32_t k = 0; k < c.warp_count; k++)
+            if (s.warps[c.warp_first + k].type != PVGPU_WARP_TRANSFORM && s.warps[c.warp_first + k].type != PVGPU_WARP_CLASSIC_TURBULENCE &&
+                s.warps[c.warp_first + k].type != PVGPU_WARP_TURBULENCE)
+                return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: warp unsupported", i);
     }
     for (size_t i = 0; i < s.blend_maps.size(); i++) {
         const pvgpu_blend_map& m = s.blend_maps[i];
@@ -518,6 +535,15 @@ int pvgpu_scene_set_blobs(pvgpu_scene* sc, const pvgpu_blob* blobs, size_t n_blo
     s.blobs.assign(blobs, blobs + n_blobs);
     s.blob_elements.assign(elements, elements + n_elements);
     s.blob_nodes.assign(nodes, nodes + n_nodes);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_normals(pvgpu_scene* sc, const pvgpu_tnormal* tn, size_t n_tn, const pvgpu_slope_entry* slopes, size_t n_slopes)
+{
+    SCENE_OR_FAIL(sc);
+    if ((!tn && n_tn) || (!slopes && n_slopes)) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_normals: null array");
+    s.tnormals.assign(tn, tn + n_tn);
+    s.slope_entries.assign(slopes, slopes + n_slopes);
     return PVGPU_OK;
 }
 
@@ -732,10 +758,12 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
     // optional trailing sections in fixed order; a section is written when it or a later one holds data
-    const bool sec2 = !s.shape_data.empty();
+    const bool sec3 = !s.tnormals.empty();
+    const bool sec2 = sec3 || !s.shape_data.empty();
     const bool sec1 = sec2 || !s.blobs.empty();
     if (ok && sec1) ok = put(f, s.blobs) && put(f, s.blob_elements) && put(f, s.blob_nodes);
     if (ok && sec2) ok = put(f, s.shape_data);
+    if (ok && sec3) ok = put(f, s.tnormals) && put(f, s.slope_entries);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -764,6 +792,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->shape_data); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->tnormals) && get(f, s->slope_entries); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

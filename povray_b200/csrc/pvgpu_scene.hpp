@@ -43,6 +43,8 @@ struct Scene {
     std::vector<pvgpu_blend_entry> blend_entries;
     std::vector<pvgpu_warp>        warps;
     std::vector<pvgpu_interior>    interiors;
+    std::vector<pvgpu_tnormal>     tnormals;
+    std::vector<pvgpu_slope_entry> slope_entries;
 
     // derived at finalize
     bool     all_shadow_casters_opaque = true;
