@@ -231,11 +231,18 @@ enum {
     PVGPU_PAT_SPOTTED  = 11,     /* SpottedPattern (== bozo noise)                        */
     PVGPU_PAT_AGATE    = 12,     /* AgatePattern     pattern.cpp:5396, p[0]=agateTurbScale */
     PVGPU_PAT_WOOD     = 13,     /* WoodPattern      pattern.cpp:8651                     */
-    PVGPU_PAT_LEOPARD  = 14,
-    PVGPU_PAT_SPHERICAL= 15,
-    PVGPU_PAT_BOXED    = 16,
-    PVGPU_PAT_RADIAL   = 17
+    PVGPU_PAT_LEOPARD  = 14,     /* LeopardPattern   pattern.cpp:7179                     */
+    PVGPU_PAT_SPHERICAL= 15,     /* SphericalPattern pattern.cpp:8551                     */
+    PVGPU_PAT_BOXED    = 16,     /* BoxedPattern     pattern.cpp:5454                     */
+    PVGPU_PAT_RADIAL   = 17,     /* RadialPattern    pattern.cpp:8115                     */
+    PVGPU_PAT_CYLINDRICAL = 18,  /* CylindricalPattern pattern.cpp:6025                   */
+    PVGPU_PAT_PLANAR   = 19,     /* PlanarPattern    pattern.cpp:8024                     */
+    PVGPU_PAT_DENTS    = 20,     /* DentsPattern     pattern.cpp:6307                     */
+    PVGPU_PAT_RIPPLES  = 21,     /* RipplesPattern   pattern.cpp:8163                     */
+    PVGPU_PAT_WAVES    = 22,     /* WavesPattern     pattern.cpp:8593                     */
+    PVGPU_PAT_QUILTED  = 23      /* QuiltedPattern   pattern.cpp:8067, p[0..1] = Control0, Control1 */
 };
+#define PVGPU_PAT_LAST PVGPU_PAT_QUILTED
 /* ContinuousPattern::waveType (pattern.h:108-117) */
 enum { PVGPU_WAVE_RAW = 0, PVGPU_WAVE_RAMP = 1, PVGPU_WAVE_SINE = 2, PVGPU_WAVE_TRIANGLE = 3,
        PVGPU_WAVE_SCALLOP = 4, PVGPU_WAVE_CUBIC = 5, PVGPU_WAVE_POLY = 6 };

@@ -179,6 +179,20 @@ struct Flattener
         else if (dynamic_cast<const OnionPattern*>(bp)) p.pattern = PVGPU_PAT_ONION;
         else if (dynamic_cast<const WrinklesPattern*>(bp)) p.pattern = PVGPU_PAT_WRINKLES;
         else if (const AgatePattern* a = dynamic_cast<const AgatePattern*>(bp)) { p.pattern = PVGPU_PAT_AGATE; p.p[0] = a->agateTurbScale; }
+        else if (const BrickPattern* b = dynamic_cast<const BrickPattern*>(bp)) { p.pattern = PVGPU_PAT_BRICK; for (int k = 0; k < 3; k++) p.p[k] = b->brickSize[k]; p.p[3] = b->mortar; }
+        else if (dynamic_cast<const HexagonPattern*>(bp)) p.pattern = PVGPU_PAT_HEXAGON;
+        else if (dynamic_cast<const WoodPattern*>(bp)) p.pattern = PVGPU_PAT_WOOD;
+        else if (dynamic_cast<const LeopardPattern*>(bp)) p.pattern = PVGPU_PAT_LEOPARD;
+        else if (dynamic_cast<const SphericalPattern*>(bp)) p.pattern = PVGPU_PAT_SPHERICAL;
+        else if (dynamic_cast<const BoxedPattern*>(bp)) p.pattern = PVGPU_PAT_BOXED;
+        else if (dynamic_cast<const RadialPattern*>(bp)) p.pattern = PVGPU_PAT_RADIAL;
+        else if (dynamic_cast<const CylindricalPattern*>(bp)) p.pattern = PVGPU_PAT_CYLINDRICAL;
+        else if (dynamic_cast<const PlanarPattern*>(bp)) p.pattern = PVGPU_PAT_PLANAR;
+        else if (dynamic_cast<const DentsPattern*>(bp)) p.pattern = PVGPU_PAT_DENTS;
+        else if (dynamic_cast<const RipplesPattern*>(bp)) p.pattern = PVGPU_PAT_RIPPLES;
+        else if (dynamic_cast<const WavesPattern*>(bp)) p.pattern = PVGPU_PAT_WAVES;
+        else if (const QuiltedPattern* q = dynamic_cast<const QuiltedPattern*>(bp)) { p.pattern = PVGPU_PAT_QUILTED; p.p[0] = q->Control0; p.p[1] = q->Control1; }
+        else if (dynamic_cast<const BumpsPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;      // BumpsPattern is a NoisePattern (pattern.h:989)
         else unsupported(std::string(user) + " pattern outside the hot-path scope");
         if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {
             p.wave_type = cp->waveType; p.frequency = cp->waveFrequency; p.phase = cp->wavePhase; p.exponent = cp->waveExponent;
@@ -222,7 +236,8 @@ struct Flattener
             add_warps(bp->warps, carrier.warp_first, carrier.warp_count);
         } else if (t.type == PVGPU_NORM_PATTERN) {
             fill_pattern(bp, carrier, "normal");
-            if (carrier.pattern == PVGPU_PAT_CHECKER) unsupported("block-pattern normal (needs a normal_map)");
+            if (carrier.pattern == PVGPU_PAT_CHECKER || carrier.pattern == PVGPU_PAT_BRICK || carrier.pattern == PVGPU_PAT_HEXAGON)
+                unsupported("block-pattern normal (needs a normal_map)");
         }
         // WarpNormal exists for transform warps only (warp.cpp:582-640): any other warp leaves the normal as it is
         if (sm != nullptr) {

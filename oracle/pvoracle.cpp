@@ -1501,6 +1501,8 @@ static double Triangle_Wave(double value)                                       
     return (offset >= 0.5) ? 2.0 * (1.0 - offset) : 2.0 * offset;
 }
 
+static double FLOOR(double x) { return x >= 0.0 ? std::floor(x) : (0.0 - std::floor(0.0 - x) - 1.0); }    // texture.h:73
+
 V3 Tracer::Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const                                          // warp.cpp:103-122
 {
     V3 p = EPoint;
@@ -1552,6 +1554,99 @@ double Tracer::Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const               
             if (noise < 0.0) noise = 0.0; else { noise = std::min(1.0, noise); noise = std::pow(noise, 0.77); }
             value = noise; break;
         }
+        case PVGPU_PAT_BRICK: {     // BrickPattern::Evaluate (pattern.cpp:5495-5608): discrete
+            const double mortar = pg.p[3], fudgit = EPSILON + mortar;
+            const double x = p.x + fudgit, y = p.y + fudgit, z = p.z + fudgit;
+            const double bw = pg.p[0], bh = pg.p[1], bd = pg.p[2];
+            const double mw = mortar / bw, mh = mortar / bh, md = mortar / bd;
+            double by = y / bh; by -= (double)(int)by; if (by < 0.0) by += 1.0;
+            if (by <= mh) { value = 0.0; discrete = true; break; }
+            by = (y / bh) * 0.5; by -= (double)(int)by; if (by < 0.0) by += 1.0;
+            double bx = x / bw; bx -= (double)(int)bx; if (bx < 0.0) bx += 1.0;
+            if ((bx <= mw) && (by <= 0.5)) { value = 0.0; discrete = true; break; }
+            bx = (x / bw) + 0.5; bx -= (double)(int)bx; if (bx < 0.0) bx += 1.0;
+            if ((bx <= mw) && (by > 0.5)) { value = 0.0; discrete = true; break; }
+            double bz = z / bd; bz -= (double)(int)bz; if (bz < 0.0) bz += 1.0;
+            if ((bz <= md) && (by > 0.5)) { value = 0.0; discrete = true; break; }
+            bz = (z / bd) + 0.5; bz -= (double)(int)bz; if (bz < 0.0) bz += 1.0;
+            if ((bz <= md) && (by <= 0.5)) { value = 0.0; discrete = true; break; }
+            value = 1.0; discrete = true; break;
+        }
+        case PVGPU_PAT_HEXAGON: {   // HexagonPattern::Evaluate (pattern.cpp:6512-6655): discrete 0 / 1 / 2
+            double x = fabs(p.x), z = (p.z < 0.0) ? 5.196152424 - fabs(p.z) : p.z;
+            double xs = x / 0.5, zs = z / 0.866025404;
+            xs -= floor(xs / 6.0) * 6.0;
+            zs -= floor(zs / 6.0) * 6.0;
+            const int xm = (int)FLOOR(xs) % 6, zm = (int)FLOOR(zs) % 6;
+            int v = 0;
+            if (xm == 0 || xm == 5) v = (zm == 0 || zm == 5) ? 0 : ((zm == 1 || zm == 2) ? 1 : 2);
+            else if (xm == 2 || xm == 3) v = (zm == 0 || zm == 1) ? 2 : ((zm == 2 || zm == 3) ? 0 : 1);
+            else {
+                double xl = xs - xm, zl = zs - zm;
+                if (((xm + zm) % 2) == 1) xl = 1.0 - xl;
+                if (xl == 0.0) xl = 0.0001;
+                const bool brk = (zl / xl) < 1.0;
+                const int zc = zm % 3;                 // (0,3) (1,4) (2,5)
+                if (brk) v = (zc == 0) ? 0 : ((zc == 2) ? 1 : 2);
+                else     v = (zc == 0) ? 2 : ((zc == 2) ? 0 : 1);
+            }
+            value = std::fmod((double)v, 3.0); discrete = true; break;
+        }
+        case PVGPU_PAT_WOOD: {      // WoodPattern::EvaluateRaw (pattern.cpp:8651-8683)
+            double px = 0.0, py = 0.0;
+            if (turb) {
+                const V3 wt = DTurbulence(S, p, *turb);
+                px = cycloidal((p.x + wt.x) * turb->turbulence[0]);
+                py = cycloidal((p.y + wt.y) * turb->turbulence[1]);
+            }
+            px += p.x; py += p.y;
+            value = len(v3(px, py, 0.0));
+            break;
+        }
+        case PVGPU_PAT_LEOPARD:     // LeopardPattern::EvaluateRaw (pattern.cpp:7179-7193)
+            value = sqr((sin(p.x) + sin(p.y) + sin(p.z)) / 3.0);
+            break;
+        case PVGPU_PAT_SPHERICAL:   // SphericalPattern / BoxedPattern / CylindricalPattern / PlanarPattern + CLIP_DENSITY (pattern.cpp:85)
+        case PVGPU_PAT_BOXED:
+        case PVGPU_PAT_CYLINDRICAL:
+        case PVGPU_PAT_PLANAR:
+            if (pg.pattern == PVGPU_PAT_SPHERICAL) value = len(p);
+            else if (pg.pattern == PVGPU_PAT_BOXED) value = fmax(fabs(p.x), fmax(fabs(p.y), fabs(p.z)));
+            else if (pg.pattern == PVGPU_PAT_CYLINDRICAL) value = sqrt(sqr(p.x) + sqr(p.z));
+            else value = fabs(p.y);
+            if (value < 0.0) value = 1.0; else if (value > 1.0) value = 0.0; else value = 1.0 - value;
+            break;
+        case PVGPU_PAT_RADIAL:      // RadialPattern::EvaluateRaw (pattern.cpp:8115-8129)
+            if ((fabs(p.x) < 0.001) && (fabs(p.z) < 0.001)) value = 0.25;
+            else value = 0.25 + (atan2(p.x, p.z) + 3.1415926535897932384626) / 6.283185307179586476925286766560;
+            break;
+        case PVGPU_PAT_DENTS: {     // DentsPattern::EvaluateRaw (pattern.cpp:6307-6313)
+            const double n = Noise(S, p, gen);
+            value = n * n * n;
+            break;
+        }
+        case PVGPU_PAT_RIPPLES:     // RipplesPattern::EvaluateRaw (pattern.cpp:8163-8186)
+        case PVGPU_PAT_WAVES: {     // WavesPattern::EvaluateRaw (pattern.cpp:8593-8618)
+            const uint32_t nw = S.g.number_of_waves;
+            double scalar = 0.0;
+            for (uint32_t i = 0; i < nw; i++) {
+                double length = len(p - S.waveSources[i]);
+                if (length == 0.0) length = 1.0;
+                if (pg.pattern == PVGPU_PAT_RIPPLES) scalar += cycloidal(length * (double)pg.frequency + (double)pg.phase);
+                else { const double f = S.waveFrequencies[i]; scalar += cycloidal(length * (double)pg.frequency * f + (double)pg.phase) / f; }
+            }
+            value = (pg.pattern == PVGPU_PAT_RIPPLES) ? 0.5 * (1.0 + (scalar / (double)nw)) : 0.2 * (2.5 + (scalar / (double)nw));
+            break;
+        }
+        case PVGPU_PAT_QUILTED: {   // QuiltedPattern::EvaluateRaw (pattern.cpp:8067-8083)
+            V3 v = v3(p.x - FLOOR(p.x) - 0.5, p.y - FLOOR(p.y) - 0.5, p.z - FLOOR(p.z) - 0.5);
+            double t = len(v);
+            const double it = 1 - t, itsqrd = it * it, tsqrd = t * t, tcubed = t * tsqrd;
+            t = (tcubed + 3.0 * t * itsqrd * pg.p[0] + 3.0 * tsqrd * it * pg.p[1]) * 1.154700538;
+            v = v * t;
+            value = (fabs(v.x) + fabs(v.y) + fabs(v.z)) / 3.0;
+            break;
+        }
     }
     if (!discrete && pg.wave_type != PVGPU_WAVE_RAW) {                                                    // pattern.cpp:354-392
         if (pg.frequency != 0.0f) value = std::fmod(value * (double)pg.frequency + (double)pg.phase, 1.00001);
@@ -1566,8 +1661,6 @@ double Tracer::Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const               
     }
     return value;
 }
-
-static double FLOOR(double x) { return x >= 0.0 ? std::floor(x) : (0.0 - std::floor(0.0 - x) - 1.0); }    // texture.h:73
 
 V3 Tracer::Perturb_Normal(V3 Layer_Normal, int tnormal, V3 EPoint) const                                  // normal.cpp:784-927
 {

@@ -125,6 +125,99 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
             value = noise;
             break;
         }
+        case PVGPU_PAT_BRICK: {     // BrickPattern::Evaluate (pattern.cpp:5495-5608): discrete
+            const double mortar = pg.p[3], fudgit = PV_EPSILON + mortar;
+            const double x = p.x + fudgit, y = p.y + fudgit, z = p.z + fudgit;
+            const double bw = pg.p[0], bh = pg.p[1], bd = pg.p[2];
+            const double mw = mortar / bw, mh = mortar / bh, md = mortar / bd;
+            double by = y / bh; by -= (double)(int)by; if (by < 0.0) by += 1.0;
+            if (by <= mh) return 0.0;
+            by = (y / bh) * 0.5; by -= (double)(int)by; if (by < 0.0) by += 1.0;
+            double bx = x / bw; bx -= (double)(int)bx; if (bx < 0.0) bx += 1.0;
+            if ((bx <= mw) && (by <= 0.5)) return 0.0;
+            bx = (x / bw) + 0.5; bx -= (double)(int)bx; if (bx < 0.0) bx += 1.0;
+            if ((bx <= mw) && (by > 0.5)) return 0.0;
+            double bz = z / bd; bz -= (double)(int)bz; if (bz < 0.0) bz += 1.0;
+            if ((bz <= md) && (by > 0.5)) return 0.0;
+            bz = (z / bd) + 0.5; bz -= (double)(int)bz; if (bz < 0.0) bz += 1.0;
+            if ((bz <= md) && (by <= 0.5)) return 0.0;
+            return 1.0;
+        }
+        case PVGPU_PAT_HEXAGON: {   // HexagonPattern::Evaluate (pattern.cpp:6512-6655): discrete 0 / 1 / 2
+            double x = fabs(p.x), z = (p.z < 0.0) ? 5.196152424 - fabs(p.z) : p.z;
+            double xs = x / 0.5, zs = z / 0.866025404;
+            xs -= floor(xs / 6.0) * 6.0;
+            zs -= floor(zs / 6.0) * 6.0;
+            const int xm = (int)pv_floor(xs) % 6, zm = (int)pv_floor(zs) % 6;
+            int v = 0;
+            if (xm == 0 || xm == 5) v = (zm == 0 || zm == 5) ? 0 : ((zm == 1 || zm == 2) ? 1 : 2);
+            else if (xm == 2 || xm == 3) v = (zm == 0 || zm == 1) ? 2 : ((zm == 2 || zm == 3) ? 0 : 1);
+            else {
+                double xl = xs - xm, zl = zs - zm;
+                if (((xm + zm) % 2) == 1) xl = 1.0 - xl;
+                if (xl == 0.0) xl = 0.0001;
+                const bool brk = (zl / xl) < 1.0;
+                const int zc = zm % 3;                 // (0,3) (1,4) (2,5)
+                if (brk) v = (zc == 0) ? 0 : ((zc == 2) ? 1 : 2);
+                else     v = (zc == 0) ? 2 : ((zc == 2) ? 0 : 1);
+            }
+            return fmod((double)v, 3.0);
+        }
+        case PVGPU_PAT_WOOD: {      // WoodPattern::EvaluateRaw (pattern.cpp:8651-8683)
+            double px = 0.0, py = 0.0;
+            if (turb) {
+                const V3 wt = dturbulence(sc.noise, p, turb->octaves, (double)turb->lambda, (double)turb->omega);
+                px = cycloidal((p.x + wt.x) * turb->turbulence[0]);
+                py = cycloidal((p.y + wt.y) * turb->turbulence[1]);
+            }
+            px += p.x; py += p.y;
+            value = length(mk(px, py, 0.0));
+            break;
+        }
+        case PVGPU_PAT_LEOPARD:     // LeopardPattern::EvaluateRaw (pattern.cpp:7179-7193)
+            value = sqr((sin(p.x) + sin(p.y) + sin(p.z)) / 3.0);
+            break;
+        case PVGPU_PAT_SPHERICAL:   // SphericalPattern / BoxedPattern / CylindricalPattern / PlanarPattern + CLIP_DENSITY (pattern.cpp:85)
+        case PVGPU_PAT_BOXED:
+        case PVGPU_PAT_CYLINDRICAL:
+        case PVGPU_PAT_PLANAR:
+            if (pg.pattern == PVGPU_PAT_SPHERICAL) value = length(p);
+            else if (pg.pattern == PVGPU_PAT_BOXED) value = fmax(fabs(p.x), fmax(fabs(p.y), fabs(p.z)));
+            else if (pg.pattern == PVGPU_PAT_CYLINDRICAL) value = sqrt(sqr(p.x) + sqr(p.z));
+            else value = fabs(p.y);
+            if (value < 0.0) value = 1.0; else if (value > 1.0) value = 0.0; else value = 1.0 - value;
+            break;
+        case PVGPU_PAT_RADIAL:      // RadialPattern::EvaluateRaw (pattern.cpp:8115-8129)
+            if ((fabs(p.x) < 0.001) && (fabs(p.z) < 0.001)) value = 0.25;
+            else value = 0.25 + (atan2(p.x, p.z) + 3.1415926535897932384626) / 6.283185307179586476925286766560;
+            break;
+        case PVGPU_PAT_DENTS: {     // DentsPattern::EvaluateRaw (pattern.cpp:6307-6313)
+            const double n = noise3(sc.noise, p, gen);
+            value = n * n * n;
+            break;
+        }
+        case PVGPU_PAT_RIPPLES:     // RipplesPattern::EvaluateRaw (pattern.cpp:8163-8186)
+        case PVGPU_PAT_WAVES: {     // WavesPattern::EvaluateRaw (pattern.cpp:8593-8618)
+            const uint32_t nw = sc.g.number_of_waves;
+            double scalar = 0.0;
+            for (uint32_t i = 0; i < nw; i++) {
+                double len = length(p - ld3(sc.wave_sources + 3 * i));
+                if (len == 0.0) len = 1.0;
+                if (pg.pattern == PVGPU_PAT_RIPPLES) scalar += cycloidal(len * (double)pg.frequency + (double)pg.phase);
+                else { const double f = sc.wave_freqs[i]; scalar += cycloidal(len * (double)pg.frequency * f + (double)pg.phase) / f; }
+            }
+            value = (pg.pattern == PVGPU_PAT_RIPPLES) ? 0.5 * (1.0 + (scalar / (double)nw)) : 0.2 * (2.5 + (scalar / (double)nw));
+            break;
+        }
+        case PVGPU_PAT_QUILTED: {   // QuiltedPattern::EvaluateRaw (pattern.cpp:8067-8083)
+            V3 v = mk(p.x - pv_floor(p.x) - 0.5, p.y - pv_floor(p.y) - 0.5, p.z - pv_floor(p.z) - 0.5);
+            double t = length(v);
+            const double it = 1 - t, itsqrd = it * it, tsqrd = t * t, tcubed = t * tsqrd;
+            t = (tcubed + 3.0 * t * itsqrd * pg.p[0] + 3.0 * tsqrd * it * pg.p[1]) * 1.154700538;
+            v = v * t;
+            value = (fabs(v.x) + fabs(v.y) + fabs(v.z)) / 3.0;
+            break;
+        }
         default:
             value = 0.0;
             break;

@@ -282,7 +282,7 @@ int device_upload(Scene& s, int device)
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP
     if (rc != PVGPU_OK) { device_release(s); return rc; }
-    if (!s.tnormals.empty() && s.globals.number_of_waves) {       // TraceThreadData::waveSources / waveFrequencies, computed with the device's own DNoise
+    if (s.globals.number_of_waves) {       // TraceThreadData::waveSources / waveFrequencies, computed with the device's own DNoise
         const uint32_t nw = s.globals.number_of_waves;
         std::vector<double> zeros(4 * (size_t)nw, 0.0);
         const double* d_waves = nullptr;

@@ -352,7 +352,7 @@ int validate_scene(Scene& s)
     }
     for (size_t i = 0; i < s.pigments.size(); i++) {
         const pvgpu_pigment& p = s.pigments[i];
-        if (p.pattern < PVGPU_PAT_PLAIN || p.pattern > PVGPU_PAT_RADIAL)
+        if (p.pattern < PVGPU_PAT_PLAIN || p.pattern > PVGPU_PAT_LAST)
             return fail(PVGPU_E_UNSUPPORTED, "pigment %zu: pattern %u unsupported", i, p.pattern);
         if (p.blend_map >= (int32_t)s.blend_maps.size())        // (-1 is legal for the pattern carrier of a tnormal)
             return fail(PVGPU_E_INVALID, "pigment %zu: bad blend map index", i);
