@@ -350,6 +350,26 @@ typedef struct pvgpu_interior {
     uint32_t reserved;
 } pvgpu_interior;
 
+/* ---- atmosphere: sky_sphere and fog (source/core/scene/atmosphere.h) ---------------------- */
+
+/* Skysphere_Struct (atmosphere.h:110-117). */
+typedef struct pvgpu_sky_sphere {
+    uint32_t pigment_first, pigment_count;   /* Pigments -> range in the index list (entries = pigment table indices) */
+    int32_t  transform;                      /* Trans -> transform table index, -1 = none                            */
+    float    emission[3];                    /* Emission                                                             */
+} pvgpu_sky_sphere;
+
+enum { PVGPU_FOG_CONSTANT = 1, PVGPU_FOG_GROUND = 2 };   /* ORIG_FOG, GROUND_MIST (atmosphere.h:71-72) */
+/* Fog_Struct (atmosphere.h:81-94); the list SceneData::fog is passed in list order. */
+typedef struct pvgpu_fog {
+    uint32_t type;               /* PVGPU_FOG_*                                                   */
+    int32_t  turbulence;         /* Turb -> warp table index of a turbulence warp, -1 = none      */
+    double   distance, alt, offset;
+    double   up[3];
+    float    colour[5];          /* rgb, filter, transmit                                         */
+    float    turb_depth;
+} pvgpu_fog;
+
 /* ---- frame-level ------------------------------------------------------------------------- */
 
 /* QualityFlags (source/core/coretypes.h:558-585) */
@@ -360,7 +380,8 @@ typedef struct pvgpu_interior {
 #define PVGPU_Q_REFRACTIONS  0x010u
 #define PVGPU_Q_REFLECTIONS  0x020u
 #define PVGPU_Q_NORMALS      0x040u
-#define PVGPU_Q_DEFAULT (PVGPU_Q_SHADOWS | PVGPU_Q_AREA_LIGHTS | PVGPU_Q_REFRACTIONS | PVGPU_Q_REFLECTIONS | PVGPU_Q_NORMALS)
+#define PVGPU_Q_MEDIA        0x080u   /* gates fog (trace.cpp:207-216); participating media itself is out of scope */
+#define PVGPU_Q_DEFAULT (PVGPU_Q_SHADOWS | PVGPU_Q_AREA_LIGHTS | PVGPU_Q_REFRACTIONS | PVGPU_Q_REFLECTIONS | PVGPU_Q_NORMALS | PVGPU_Q_MEDIA)
 
 /* The SceneData scalars the trace path reads (scenedata.h:85-263). */
 typedef struct pvgpu_globals {
@@ -463,6 +484,8 @@ int  pvgpu_scene_set_materials(pvgpu_scene* s,
                                const pvgpu_interior* interiors, size_t n_interiors);
 /* Normal perturbations referenced by pvgpu_texture::tnormal, and the slope_map entries they use. */
 int  pvgpu_scene_set_normals(pvgpu_scene* s, const pvgpu_tnormal* tn, size_t n_tn, const pvgpu_slope_entry* slopes, size_t n_slopes);
+/* SceneData::skysphere (NULL = none) and SceneData::fog (list order). */
+int  pvgpu_scene_set_atmosphere(pvgpu_scene* s, const pvgpu_sky_sphere* sky, const pvgpu_fog* fogs, size_t n_fogs);
 int  pvgpu_scene_set_camera(pvgpu_scene* s, const pvgpu_camera* cam);
 int  pvgpu_scene_get_camera(const pvgpu_scene* s, pvgpu_camera* cam);
 

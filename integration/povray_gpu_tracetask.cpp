@@ -55,6 +55,7 @@
 #include "core/math/polynomialsolver.h"
 #include "core/material/noise.h"
 #include "core/render/ray.h"
+#include "core/scene/atmosphere.h"
 #include "core/scene/object.h"
 #include "core/scene/scenedata.h"
 #include "core/scene/tracethreaddata.h"
@@ -582,7 +583,7 @@ int quality_bits(const QualityFlags& q)
 {
     return (q.ambientOnly ? PVGPU_Q_AMBIENT_ONLY : 0) | (q.quickColour ? PVGPU_Q_QUICK_COLOUR : 0) | (q.shadows ? PVGPU_Q_SHADOWS : 0) |
            (q.areaLights ? PVGPU_Q_AREA_LIGHTS : 0) | (q.refractions ? PVGPU_Q_REFRACTIONS : 0) | (q.reflections ? PVGPU_Q_REFLECTIONS : 0) |
-           (q.normals ? PVGPU_Q_NORMALS : 0);
+           (q.normals ? PVGPU_Q_NORMALS : 0) | (q.media ? PVGPU_Q_MEDIA : 0);
 }
 
 struct GpuView
@@ -612,8 +613,8 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
     slot.reset(new GpuView());
     GpuView& gv = *slot;
 
-    if (sd->skysphere != nullptr || sd->fog != nullptr || sd->rainbow != nullptr || !sd->atmosphere.empty())
-        gv.error = "sky_sphere / fog / rainbow / atmospheric media (SURVEY 8f 'next')";
+    if (sd->rainbow != nullptr || !sd->atmosphere.empty())
+        gv.error = "rainbow / atmospheric media (SURVEY 8f 'next')";
     if (sd->radiositySettings.radiosityEnabled) gv.error = "radiosity";
     if (sd->photonSettings.photonsEnabled) gv.error = "photons";
     if (sd->boundingMethod == 2) gv.error = "BSP bounding (+BM2)";
@@ -629,6 +630,37 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
     }
     for (const LightSource* l : sd->lightSources) fl.add_light(l);
     if (!sd->lightGroupLightSources.empty()) fl.unsupported("light_group");
+    // sky_sphere and fog (atmosphere.h:81-117)
+    pvgpu_sky_sphere sky{};
+    if (sd->skysphere != nullptr) {
+        sky.pigment_first = (uint32_t)fl.index_list.size();
+        sky.pigment_count = (uint32_t)sd->skysphere->Pigments.size();
+        vector<uint32_t> ids;
+        for (const PIGMENT* pg : sd->skysphere->Pigments) ids.push_back((uint32_t)fl.add_pigment(pg));
+        sky.pigment_first = (uint32_t)fl.index_list.size();
+        fl.index_list.insert(fl.index_list.end(), ids.begin(), ids.end());
+        sky.transform = fl.add_transform(sd->skysphere->Trans);
+        for (int k = 0; k < 3; k++) sky.emission[k] = sd->skysphere->Emission[k];
+    }
+    vector<pvgpu_fog> fogs;
+    for (const FOG* fog = sd->fog; fog != nullptr; fog = fog->Next) {
+        pvgpu_fog f{};
+        f.type = (uint32_t)fog->Type;
+        f.turbulence = -1;
+        if (fog->Turb != nullptr) {
+            pvgpu_warp w{};
+            w.type = PVGPU_WARP_TURBULENCE; w.transform = -1;
+            for (int k = 0; k < 3; k++) w.turbulence[k] = fog->Turb->Turbulence[k];
+            w.octaves = fog->Turb->Octaves; w.lambda = fog->Turb->Lambda; w.omega = fog->Turb->Omega;
+            fl.warps.push_back(w);
+            f.turbulence = (int32_t)fl.warps.size() - 1;
+        }
+        f.distance = fog->Distance; f.alt = fog->Alt; f.offset = fog->Offset;
+        for (int k = 0; k < 3; k++) { f.up[k] = fog->Up[k]; f.colour[k] = fog->colour.colour()[k]; }
+        f.colour[3] = fog->colour.filter(); f.colour[4] = fog->colour.transm();
+        f.turb_depth = fog->Turb_Depth;
+        fogs.push_back(f);
+    }
     if (sd->boundingSlabs != nullptr)
         fl.flatten_tree(sd->boundingSlabs, fl.nodes, [&](const BBOX_TREE* leaf) { return (uint32_t)fl.object_ids.at(reinterpret_cast<const void*>(leaf->Node)); });
     if (gv.error.empty()) gv.error = fl.error;
@@ -673,6 +705,7 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
                                     fl.entries.data(), fl.entries.size(), fl.warps.data(), fl.warps.size(),
                                     fl.interiors.data(), fl.interiors.size()), "set_materials");
     check(pvgpu_scene_set_normals(gv.scene, fl.tnormals.data(), fl.tnormals.size(), fl.slope_entries.data(), fl.slope_entries.size()), "set_normals");
+    check(pvgpu_scene_set_atmosphere(gv.scene, sd->skysphere != nullptr ? &sky : nullptr, fogs.data(), fogs.size()), "set_atmosphere");
     check(pvgpu_scene_set_camera(gv.scene, &c), "set_camera");
     if (const char* path = getenv("PVGPU_DUMP_SCENE")) check(pvgpu_scene_save(gv.scene, path), "scene_save");
     if (!gv.error.empty()) fprintf(stderr, "pvgpu adapter: scene uses a feature outside the GPU trace path: %s\n", gv.error.c_str());

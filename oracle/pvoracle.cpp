@@ -83,6 +83,8 @@ struct Scene {
     std::vector<double> shape_data;
     std::vector<pvgpu_tnormal> tnormals;
     std::vector<pvgpu_slope_entry> slope_entries;
+    std::vector<pvgpu_sky_sphere> sky_spheres;
+    std::vector<pvgpu_fog> fogs;
     std::vector<V3> waveSources;                 // TraceThreadData::waveSources / waveFrequencies (tracethreaddata.cpp:110-111)
     std::vector<double> waveFrequencies;
     // noise tables
@@ -483,6 +485,7 @@ struct Ray {
     bool IsInterior(int i) const { return std::find(interiors.begin(), interiors.end(), i) != interiors.end(); }
     bool RemoveInterior(int i) { auto it = std::find(interiors.begin(), interiors.end(), i); if (it == interiors.end()) return false; interiors.erase(it); return true; }
     V3 Evaluate(double t) const { return v3(Origin.x + Direction.x * t, Origin.y + Direction.y * t, Origin.z + Direction.z * t); }
+    bool IsHollowRay(const Scene& S) const { for (int i : interiors) if (!S.interiors[i].hollow) return false; return true; }   // ray.cpp:59-115
 };
 struct Ticket { unsigned traceLevel = 0, maxAllowedTraceLevel; double adcBailout; bool alphaBackground; unsigned maxFound = 0; };
 struct Intersection { double Depth = BOUND_HUGE; V3 IPoint{ 0, 0, 0 }; int Object = -1, Csg = -1; uint32_t aux = 0; };
@@ -622,6 +625,7 @@ public:
     void ComputeTextureColour(Intersection& isect, Col& colour, float& transm, Ray& ray, Ticket& tk, float weight);
     void ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect);
     void ComputeSky(const Ray& ray, const Ticket& tk, Col& colour, float& transm) const;
+    void ComputeFog(const Ray& ray, double Depth, Col& colour, float& transm) const;
     void Compute_Pigment(float col[5], int pigment, V3 EPoint) const;
     V3 Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const;
     double Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const;
@@ -1864,19 +1868,103 @@ int Tracer::hit_texture(const pvgpu_object& ob, const Intersection& isect, bool 
     return (backside && ob.interior_texture >= 0) ? ob.interior_texture : ob.texture;                     // trace.cpp:513-530
 }
 
-void Tracer::ComputeSky(const Ray&, const Ticket& tk, Col& colour, float& transm) const                   // trace.cpp:2769-2890 (no sky_sphere)
+// GenericColour::operator*=(double) rounds to FP32 after the FP64 product (colour.h:1681)
+static inline Col cmul(Col a, double b) { return Col{ (float)(a.r * b), (float)(a.g * b), (float)(a.b * b) }; }
+static inline Col cadd(Col a, double b) { return Col{ (float)(a.r + b), (float)(a.g + b), (float)(a.b + b) }; }
+
+void Tracer::ComputeSky(const Ray& ray, const Ticket& tk, Col& colour, float& transm) const               // trace.cpp:2769-2890
 {
     const float* bg = S.g.background;
+    const pvgpu_sky_sphere* sky = S.sky_spheres.empty() ? nullptr : &S.sky_spheres[0];
+    V3 p = ray.Direction;
+    if (sky && sky->transform >= 0) p = MInvTransPoint(S.xf[sky->transform], ray.Direction);
     if (S.g.language_version < 370) {
         if (tk.alphaBackground) { colour = Col{ 0, 0, 0 }; transm = 1.0f; return; }
         colour = Col{ bg[0], bg[1], bg[2] }; transm = bg[4];
+        if (!sky) return;
+        Col col{ 0, 0, 0 }, filterc_colour{ 1, 1, 1 };
+        float filterc_filter = 1.0f, filterc_transm = 1.0f;
+        double trans = 1.0;
+        for (int i = (int)sky->pigment_count - 1; i >= 0; i--) {
+            float t[5];
+            Compute_Pigment(t, (int)S.index_list[sky->pigment_first + i], p);
+            double att = trans * (float)(1.0 - t[3] - t[4]);
+            col = col + cmul(Col{ t[0], t[1], t[2] }, att);
+            filterc_colour = filterc_colour * Col{ t[0], t[1], t[2] };
+            filterc_filter *= t[3]; filterc_transm *= t[4];
+            trans = std::fabs(filterc_filter) + std::fabs(filterc_transm);
+        }
+        col = col * Col{ sky->emission[0], sky->emission[1], sky->emission[2] };
+        Col transColour = cadd(cmul(filterc_colour, filterc_filter), filterc_transm);
+        colour = colour * transColour + col;
+        transm *= filterc_transm;
         return;
     }
+    Col filCol{ 1, 1, 1 }, col{ 0, 0, 0 };
+    if (sky) {
+        const Col Emission{ sky->emission[0], sky->emission[1], sky->emission[2] };
+        for (int i = (int)sky->pigment_count - 1; i >= 0; i--) {
+            float t[5];
+            Compute_Pigment(t, (int)S.index_list[sky->pigment_first + i], p);
+            double att = (float)(1.0 - t[3] - t[4]);
+            col = col + cmul(Col{ t[0], t[1], t[2] }, att) * filCol * Emission;
+            filCol = filCol * cadd(cmul(Col{ t[0], t[1], t[2] }, t[3]), t[4]);
+        }
+    }
     float f = tk.alphaBackground ? bg[3] : 0.0f, t = tk.alphaBackground ? bg[4] : 0.0f;
-    float att = (float)(1.0 - f - t);
-    colour = Col{ bg[0] * att, bg[1] * att, bg[2] * att };
-    Col fil{ bg[0] * f + t, bg[1] * f + t, bg[2] * f + t };
-    transm = std::min(1.0f, std::fabs(grey(fil)));
+    double att = (float)(1.0 - f - t);
+    col = col + cmul(Col{ bg[0], bg[1], bg[2] }, att) * filCol;
+    filCol = filCol * cadd(cmul(Col{ bg[0], bg[1], bg[2] }, f), t);
+    colour = col;
+    transm = std::min(1.0f, std::fabs(grey(filCol)));
+}
+
+void Tracer::ComputeFog(const Ray& ray, double Depth, Col& colour, float& transm) const                   // trace.cpp:2892-3044
+{
+    Col sum_att{ 1, 1, 1 }, sum_col{ 0, 0, 0 };
+    for (const pvgpu_fog& fog : S.fogs) {
+        if (!(std::fabs(fog.distance) > EPSILON)) continue;
+        double width = Depth, att;
+        const pvgpu_warp* Turb = fog.turbulence >= 0 ? &S.warps[fog.turbulence] : nullptr;
+        if (fog.type == PVGPU_FOG_GROUND) {                                                               // ComputeGroundFogDepth
+            V3 p1 = ray.Evaluate(0.0), p2 = p1 + ray.Direction * width;
+            double y1 = dot(p1, v3(fog.up)), y2 = dot(p2, v3(fog.up));
+            double start = (y1 - fog.offset) / fog.alt, end = (y2 - fog.offset) / fog.alt, fog_density;
+            if (start <= 0.0) {
+                if (end <= 0.0) fog_density = 1.0;
+                else fog_density = (std::atan(end) - start) / (end - start);
+            } else {
+                if (end <= 0.0) fog_density = (std::atan(start) - end) / (start - end);
+                else {
+                    double delta = start - end;
+                    if (std::fabs(delta) > EPSILON) fog_density = (std::atan(start) - std::atan(end)) / delta;
+                    else fog_density = 1.0 / (sqr(start) + 1.0);
+                }
+            }
+            if (Turb) {
+                V3 p = (p1 + p2) * 0.5;
+                p = v3(p.x * Turb->turbulence[0], p.y * Turb->turbulence[1], p.z * Turb->turbulence[2]);
+                double k = std::exp(-width / fog.distance);
+                width *= (1.0 - k * std::min(1.0, Turbulence(S, p, *Turb, S.g.noise_generator) * fog.turb_depth));
+            }
+            att = std::exp(-width * fog_density / fog.distance);
+        } else {                                                                                          // ComputeConstantFogDepth
+            if (Turb) {
+                V3 p = ray.Evaluate(width / 2.0);
+                p = v3(p.x * Turb->turbulence[0], p.y * Turb->turbulence[1], p.z * Turb->turbulence[2]);
+                double k = std::exp(-width / fog.distance);
+                width *= (1.0 - k * std::min(1.0, Turbulence(S, p, *Turb, S.g.noise_generator) * fog.turb_depth));
+            }
+            att = std::exp(-width / fog.distance);
+        }
+        const Col col_fog{ fog.colour[0], fog.colour[1], fog.colour[2] };
+        const float filter_fog = fog.colour[3], transm_fog = fog.colour[4];
+        if (att < transm_fog) att = transm_fog;
+        sum_att = sum_att * cmul(cadd(cmul(col_fog, filter_fog), 1.0 - filter_fog), att);
+        sum_col = sum_col + cmul(col_fog, 1.0 - att);
+    }
+    colour = sum_col + sum_att * colour;
+    transm *= grey(sum_att);
 }
 
 double Tracer::TraceRay(Ray& ray, Ticket& tk, Col& colour, float& transm, float weight, bool continuedRay, double maxDepth)   // trace.cpp:135-228
@@ -1890,6 +1978,7 @@ double Tracer::TraceRay(Ray& ray, Ticket& tk, Col& colour, float& transm, float 
     if (inc) { tk.traceLevel++; tk.maxFound = std::max(tk.maxFound, tk.traceLevel); }
     if (found) ComputeTextureColour(bestisect, colour, transm, ray, tk, weight);
     else ComputeSky(ray, tk, colour, transm);
+    if ((S.g.quality_flags & PVGPU_Q_MEDIA) && !S.fogs.empty() && ray.IsHollowRay(S)) ComputeFog(ray, bestisect.Depth, colour, transm);   // trace.cpp:207-216
     if (inc) tk.traceLevel--;
     st.max_level = std::max(st.max_level, tk.maxFound);
     return found ? bestisect.Depth : HUGE_VALUE;
@@ -2293,6 +2382,7 @@ void* pvo_scene_load(const char* path)
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->blobs) && get(f, s->blob_elements) && get(f, s->blob_nodes); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->shape_data); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->tnormals) && get(f, s->slope_entries); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->sky_spheres) && get(f, s->fogs); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());

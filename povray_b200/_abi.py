@@ -42,8 +42,8 @@ LIGHT_AREA, LIGHT_PARALLEL, LIGHT_MEDIA_ATTEN, LIGHT_MEDIA_INTERACT = 0x001, 0x0
  PAT_HEXAGON, PAT_SPOTTED, PAT_AGATE) = range(1, 13)
 WAVE_RAW, WAVE_RAMP, WAVE_SINE, WAVE_TRIANGLE, WAVE_SCALLOP, WAVE_CUBIC, WAVE_POLY = range(7)
 WARP_TRANSFORM, WARP_TURBULENCE, WARP_CLASSIC_TURBULENCE = 1, 2, 3
-Q_AMBIENT_ONLY, Q_QUICK_COLOUR, Q_SHADOWS, Q_AREA_LIGHTS, Q_REFRACTIONS, Q_REFLECTIONS, Q_NORMALS = 1, 2, 4, 8, 16, 32, 64
-Q_DEFAULT = Q_SHADOWS | Q_AREA_LIGHTS | Q_REFRACTIONS | Q_REFLECTIONS | Q_NORMALS
+Q_AMBIENT_ONLY, Q_QUICK_COLOUR, Q_SHADOWS, Q_AREA_LIGHTS, Q_REFRACTIONS, Q_REFLECTIONS, Q_NORMALS, Q_MEDIA = 1, 2, 4, 8, 16, 32, 64, 128
+Q_DEFAULT = Q_SHADOWS | Q_AREA_LIGHTS | Q_REFRACTIONS | Q_REFLECTIONS | Q_NORMALS | Q_MEDIA
 CAMERA_PERSPECTIVE, CAMERA_ORTHOGRAPHIC = 1, 2
 
 u8, u16, u32, i32, u64, f32, f64 = C.c_uint8, C.c_uint16, C.c_uint32, C.c_int32, C.c_uint64, C.c_float, C.c_double
@@ -137,6 +137,15 @@ class TNormal(C.Structure):
                 ("amount", f32), ("delta", f32), ("reserved", u32)]
 
 
+class SkySphere(C.Structure):
+    _fields_ = [("pigment_first", u32), ("pigment_count", u32), ("transform", i32), ("emission", f32 * 3)]
+
+
+class Fog(C.Structure):
+    _fields_ = [("type", u32), ("turbulence", i32), ("distance", f64), ("alt", f64), ("offset", f64), ("up", f64 * 3),
+                ("colour", f32 * 5), ("turb_depth", f32)]
+
+
 class Interior(C.Structure):
     _fields_ = [("hollow", i32), ("disp_nelems", i32), ("ior", f32), ("dispersion", f32), ("caustics", f32),
                 ("old_refract", f32), ("fade_distance", f32), ("fade_power", f32), ("fade_colour", f32 * 3), ("reserved", u32)]
@@ -200,6 +209,7 @@ SIGNATURES = {
                                             P(BlendMap), C.c_size_t, P(BlendEntry), C.c_size_t, P(Warp), C.c_size_t,
                                             P(Interior), C.c_size_t]),
     "pvgpu_scene_set_normals": (C.c_int, [VP, P(TNormal), C.c_size_t, P(SlopeEntry), C.c_size_t]),
+    "pvgpu_scene_set_atmosphere": (C.c_int, [VP, P(SkySphere), P(Fog), C.c_size_t]),
     "pvgpu_scene_set_camera": (C.c_int, [VP, P(Camera)]),
     "pvgpu_scene_get_camera": (C.c_int, [VP, P(Camera)]),
     "pvgpu_scene_add_mesh2": (C.c_int, [VP, P(f64), C.c_size_t, P(i32), C.c_size_t, P(i32)]),

@@ -15,7 +15,18 @@ PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __res
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const HitRec h = hits[i];
         if (h.obj == PV_HIT_STOPPED) continue;
-        const PRay ray = cur[i];
+        PRay ray = cur[i];
+#if PV_HEAVY
+        // fog between the ray's origin and its hit (trace.cpp:207-216): colour' = sum_col + sum_att * colour, so the fog's own
+        // light is added here and everything this ray still collects is weighted by sum_att
+        if (sc.n_fogs && (sc.g.quality_flags & PVGPU_Q_MEDIA) && ray_is_hollow(sc, ray)) {
+            float sum_att[3], sum_col[3];
+            compute_fog(sc, ld3(ray.o), ld3(ray.d), (h.obj == PV_HIT_MISS) ? PV_BOUND_HUGE : h.depth, sum_att, sum_col);
+            accum_add(ctx.accum, ray.sample, ray.w[0] * sum_col[0], ray.w[1] * sum_col[1], ray.w[2] * sum_col[2], 0.0f);
+            ray.w[0] *= sum_att[0]; ray.w[1] *= sum_att[1]; ray.w[2] *= sum_att[2];
+            ray.wt *= greyscale(sum_att);
+        }
+#endif
         if (h.obj == PV_HIT_MISS) {
             float col[3], transm;
             compute_sky(sc, ray, col, transm);

@@ -127,6 +127,9 @@ struct DScene {
     const pvgpu_slope_entry* slopes;
     const double*            wave_sources;  // TraceThreadData::waveSources (xyz per wave), Initialize_Waves (noise.cpp:189)
     const double*            wave_freqs;    // TraceThreadData::waveFrequencies
+    const pvgpu_fog*         fogs;          // SceneData::fog in list order
+    uint32_t                 n_fogs, has_sky;
+    pvgpu_sky_sphere         sky;           // SceneData::skysphere (has_sky)
     const uint32_t*          csg_leaves;    // per top-level CSG object: its primitive descendants (DFS order)
     const uint2*             csg_leaf_range;// per object: (first, count) into csg_leaves
     NoiseTables              noise;

@@ -620,8 +620,8 @@ __device__ inline int32_t hit_texture(const DScene& sc, const pvgpu_object& ob, 
     return (backside && ob.interior_texture >= 0) ? ob.interior_texture : ob.texture;
 }
 
-// Trace::ComputeSky for language version >= 3.7 without sky_sphere (trace.cpp:2848-2890) and the
-// legacy branch (trace.cpp:2771-2800).
+// Trace::ComputeSky (trace.cpp:2769-2890): background and sky_sphere pigments, both language-version branches.
+// Colour * double rounds to FP32 after every product (GenericColour::operator*=(double), colour.h:1681).
 __device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[3], float& transm)
 {
     const bool alpha_bg = (ray.flags & PV_RAY_ALPHA_BG) != 0;
@@ -630,14 +630,124 @@ __device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[
         if (alpha_bg) { col[0] = col[1] = col[2] = 0.0f; transm = 1.0f; return; }
         col[0] = bg[0]; col[1] = bg[1]; col[2] = bg[2];
         transm = bg[4];
+#if PV_HEAVY
+        if (sc.has_sky) {
+            float c[3] = { 0.0f, 0.0f, 0.0f }, fc[3] = { 1.0f, 1.0f, 1.0f }, ff = 1.0f, ft = 1.0f;
+            double trans = 1.0;
+            V3 p = ld3(ray.d);
+            if (sc.sky.transform >= 0) p = inv_trans_point(sc.xf[sc.sky.transform], p);
+            for (int i = (int)sc.sky.pigment_count - 1; i >= 0; i--) {
+                float t[5];
+                compute_pigment(sc, (int32_t)sc.index_list[sc.sky.pigment_first + i], p, t);
+                const double att = trans * (double)(float)(1.0 - (double)t[3] - (double)t[4]);
+                #pragma unroll
+                for (int k = 0; k < 3; k++) { c[k] += (float)((double)t[k] * att); fc[k] *= t[k]; }
+                ff *= t[3]; ft *= t[4];
+                trans = fabs((double)ff) + fabs((double)ft);
+            }
+            #pragma unroll
+            for (int k = 0; k < 3; k++) {
+                c[k] *= sc.sky.emission[k];
+                const float tc = (float)((double)(float)((double)fc[k] * (double)ff) + (double)ft);
+                col[k] = col[k] * tc + c[k];
+            }
+            transm *= ft;
+        }
+#endif
         return;
     }
-    float f = alpha_bg ? bg[3] : 0.0f, t = alpha_bg ? bg[4] : 0.0f;
-    float att = (float)(1.0 - f - t);                       // TransColour::Opacity
-    col[0] = bg[0] * att; col[1] = bg[1] * att; col[2] = bg[2] * att;
-    float fil[3] = { bg[0] * f + t, bg[1] * f + t, bg[2] * f + t };   // TransmittedColour
+    float c[3] = { 0.0f, 0.0f, 0.0f }, fil[3] = { 1.0f, 1.0f, 1.0f };
+#if PV_HEAVY
+    if (sc.has_sky) {
+        V3 p = ld3(ray.d);
+        if (sc.sky.transform >= 0) p = inv_trans_point(sc.xf[sc.sky.transform], p);
+        for (int i = (int)sc.sky.pigment_count - 1; i >= 0; i--) {
+            float t[5];
+            compute_pigment(sc, (int32_t)sc.index_list[sc.sky.pigment_first + i], p, t);
+            const double att = (double)(float)(1.0 - (double)t[3] - (double)t[4]);      // TransColour::Opacity
+            #pragma unroll
+            for (int k = 0; k < 3; k++) {
+                c[k] += ((float)((double)t[k] * att) * fil[k]) * sc.sky.emission[k];
+                fil[k] *= (float)((double)(float)((double)t[k] * (double)t[3]) + (double)t[4]);   // TransmittedColour
+            }
+        }
+    }
+#endif
+    const float f = alpha_bg ? bg[3] : 0.0f, t = alpha_bg ? bg[4] : 0.0f;
+    const double att = (double)(float)(1.0 - (double)f - (double)t);
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        c[k] += (float)((double)bg[k] * att) * fil[k];
+        fil[k] *= (float)((double)(float)((double)bg[k] * (double)f) + (double)t);
+        col[k] = c[k];
+    }
     transm = fminf(1.0f, fabsf(greyscale(fil)));
 }
+
+#if PV_HEAVY
+// Ray::IsHollowRay (ray.cpp:59-115): every interior the ray is inside of is hollow
+__device__ __forceinline__ bool ray_is_hollow(const DScene& sc, const PRay& r)
+{
+    for (int i = 0; i < r.n_int; i++) if (!sc.interiors[r.interiors[i]].hollow) return false;
+    return true;
+}
+// Trace::ComputeFog + ComputeConstantFogDepth + ComputeGroundFogDepth (trace.cpp:2892-3044) for a non-shadow ray:
+// the caller's colour becomes sum_col + sum_att * colour, its transmittance is scaled by greyscale(sum_att).
+__device__ inline void compute_fog(const DScene& sc, const V3& o, const V3& d, double depth, float sum_att[3], float sum_col[3])
+{
+    sum_att[0] = sum_att[1] = sum_att[2] = 1.0f;
+    sum_col[0] = sum_col[1] = sum_col[2] = 0.0f;
+    for (uint32_t i = 0; i < sc.n_fogs; i++) {
+        const pvgpu_fog& fog = sc.fogs[i];
+        if (!(fabs(fog.distance) > PV_EPSILON)) continue;
+        double width = depth, att;
+        const pvgpu_warp* turb = (fog.turbulence >= 0) ? &sc.warps[fog.turbulence] : nullptr;
+        if (fog.type == PVGPU_FOG_GROUND) {
+            const V3 p1 = o;                                   // ray.Evaluate(0.0)
+            const V3 p2 = p1 + d * width;
+            const double y1 = dot(p1, ld3(fog.up)), y2 = dot(p2, ld3(fog.up));
+            const double start = (y1 - fog.offset) / fog.alt, end = (y2 - fog.offset) / fog.alt;
+            double fog_density;
+            if (start <= 0.0) {
+                if (end <= 0.0) fog_density = 1.0;
+                else fog_density = (atan(end) - start) / (end - start);
+            } else {
+                if (end <= 0.0) fog_density = (atan(start) - end) / (start - end);
+                else {
+                    const double delta = start - end;
+                    if (fabs(delta) > PV_EPSILON) fog_density = (atan(start) - atan(end)) / delta;
+                    else fog_density = 1.0 / (sqr(start) + 1.0);
+                }
+            }
+            if (turb) {
+                V3 p = (p1 + p2) * 0.5;
+                p = mk(p.x * turb->turbulence[0], p.y * turb->turbulence[1], p.z * turb->turbulence[2]);
+                const double k = exp(-width / fog.distance);
+                width *= (1.0 - k * fmin(1.0, turbulence(sc.noise, p, turb->octaves, (double)turb->lambda, (double)turb->omega, sc.g.noise_generator) * (double)fog.turb_depth));
+            }
+            att = exp(-width * fog_density / fog.distance);
+        } else {
+            if (turb) {
+                V3 p = evaluate(o, d, width / 2.0);
+                p = mk(p.x * turb->turbulence[0], p.y * turb->turbulence[1], p.z * turb->turbulence[2]);
+                const double k = exp(-width / fog.distance);
+                width *= (1.0 - k * fmin(1.0, turbulence(sc.noise, p, turb->octaves, (double)turb->lambda, (double)turb->omega, sc.g.noise_generator) * (double)fog.turb_depth));
+            }
+            att = exp(-width / fog.distance);
+        }
+        const float filter_fog = fog.colour[3], transm_fog = fog.colour[4];
+        if (att < (double)transm_fog) att = (double)transm_fog;
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float t = (float)((double)fog.colour[k] * (double)filter_fog);              // filter_fog * col_fog
+            t = (float)((double)t + (1.0 - (double)filter_fog));                        // (1.0 - filter_fog) + ...
+            t = (float)((double)t * att);                                               // att * (...)
+            sum_att[k] *= t;
+            sum_col[k] += (float)((double)fog.colour[k] * (1.0 - att));
+        }
+    }
+}
+#endif
 
 // ComputeReflection's direction rule (trace.cpp:1264-1300)
 __device__ inline V3 reflect_direction(const V3& dir, const V3& normal, const V3& rawnormal)

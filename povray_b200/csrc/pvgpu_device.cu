@@ -277,7 +277,7 @@ int device_upload(Scene& s, int device)
     UP(s.textures, v.textures); UP(s.pigments, v.pigments); UP(s.finishes, v.finishes); UP(s.blend_maps, v.maps);
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
     UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes); UP(s.shape_data, v.shape_data);
-    UP(s.tnormals, v.tnormals); UP(s.slope_entries, v.slopes);
+    UP(s.tnormals, v.tnormals); UP(s.slope_entries, v.slopes); UP(s.fogs, v.fogs);
     UP(leaves, v.csg_leaves); UP(leaf_range, v.csg_leaf_range);
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP
@@ -298,6 +298,10 @@ int device_upload(Scene& s, int device)
         if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH) ||
             o.clip_count || o.bound_count) d->lean = false;
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->lean = false;
+    if (!s.fogs.empty() || !s.sky_spheres.empty()) d->lean = false;
+    v.n_fogs = (uint32_t)s.fogs.size();
+    v.has_sky = s.sky_spheres.empty() ? 0u : 1u;
+    if (v.has_sky) v.sky = s.sky_spheres[0];
     for (const pvgpu_mesh& me : s.meshes) if (me.node_count == 0) d->lean = false;       // `hierarchy off` meshes take the generic walk
     if (const char* e = getenv("PVGPU_LEAN")) if (e[0] == '0') d->lean = false;
     v.n_objs = (uint32_t)s.objects.size();

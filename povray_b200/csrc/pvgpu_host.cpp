@@ -298,7 +298,7 @@ int validate_scene(Scene& s)
         }
     }
     for (uint32_t v : s.index_list)
-        if (v >= no && v >= s.textures.size())
+        if (v >= no && v >= s.textures.size() && v >= s.pigments.size())
             return fail(PVGPU_E_INVALID, "index list entry %u out of range", v);
     for (size_t i = 0; i < s.nodes.size(); i++) {
         const pvgpu_node& n = s.nodes[i];
@@ -359,6 +359,26 @@ int validate_scene(Scene& s)
         if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
     }
+    if (s.sky_spheres.size() > 1) return fail(PVGPU_E_INVALID, "more than one sky_sphere");
+    for (const pvgpu_sky_sphere& k : s.sky_spheres) {
+        if (!range_ok(k.pigment_first, k.pigment_count, s.index_list.size()) || k.transform >= (int32_t)s.transforms.size())
+            return fail(PVGPU_E_INVALID, "sky_sphere: bad pigment range / transform");
+        for (uint32_t i = 0; i < k.pigment_count; i++) {
+            const uint32_t pi = s.index_list[k.pigment_first + i];
+            if (pi >= s.pigments.size() || (s.pigments[pi].pattern != PVGPU_PAT_PLAIN && s.pigments[pi].blend_map < 0))
+                return fail(PVGPU_E_INVALID, "sky_sphere: bad pigment %u", pi);
+        }
+    }
+    for (size_t i = 0; i < s.fogs.size(); i++) {
+        const pvgpu_fog& f = s.fogs[i];
+        if (f.type != PVGPU_FOG_CONSTANT && f.type != PVGPU_FOG_GROUND) return fail(PVGPU_E_UNSUPPORTED, "fog %zu: type %u unsupported", i, f.type);
+        if (f.turbulence >= (int32_t)s.warps.size() || (f.turbulence >= 0 && s.warps[f.turbulence].type == PVGPU_WARP_TRANSFORM))
+            return fail(PVGPU_E_INVALID, "fog %zu: bad turbulence warp", i);
+    }
+    if (!s.fogs.empty())
+        for (size_t i = 0; i < s.lights.size(); i++)
+            if ((s.lights[i].flags & PVGPU_LIGHT_MEDIA_ATTEN) && (s.lights[i].flags & PVGPU_LIGHT_MEDIA_INTERACT))
+                return fail(PVGPU_E_UNSUPPORTED, "light %zu: media_attenuation with fog (fog on shadow rays) is outside the hot-path scope", i);
     for (size_t i = 0; i < s.tnormals.size(); i++) {
         const pvgpu_tnormal& t = s.tnormals[i];
         if (t.type < PVGPU_NORM_BUMPS || t.type > PVGPU_NORM_PATTERN)
@@ -544,6 +564,16 @@ int pvgpu_scene_set_normals(pvgpu_scene* sc, const pvgpu_tnormal* tn, size_t n_t
     if ((!tn && n_tn) || (!slopes && n_slopes)) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_normals: null array");
     s.tnormals.assign(tn, tn + n_tn);
     s.slope_entries.assign(slopes, slopes + n_slopes);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_atmosphere(pvgpu_scene* sc, const pvgpu_sky_sphere* sky, const pvgpu_fog* fogs, size_t n_fogs)
+{
+    SCENE_OR_FAIL(sc);
+    if (!fogs && n_fogs) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_atmosphere: null array");
+    s.sky_spheres.clear();
+    if (sky) s.sky_spheres.push_back(*sky);
+    s.fogs.assign(fogs, fogs + n_fogs);
     return PVGPU_OK;
 }
 
@@ -758,12 +788,14 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
     // optional trailing sections in fixed order; a section is written when it or a later one holds data
-    const bool sec3 = !s.tnormals.empty();
+    const bool sec4 = !s.sky_spheres.empty() || !s.fogs.empty();
+    const bool sec3 = sec4 || !s.tnormals.empty();
     const bool sec2 = sec3 || !s.shape_data.empty();
     const bool sec1 = sec2 || !s.blobs.empty();
     if (ok && sec1) ok = put(f, s.blobs) && put(f, s.blob_elements) && put(f, s.blob_nodes);
     if (ok && sec2) ok = put(f, s.shape_data);
     if (ok && sec3) ok = put(f, s.tnormals) && put(f, s.slope_entries);
+    if (ok && sec4) ok = put(f, s.sky_spheres) && put(f, s.fogs);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -796,6 +828,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->tnormals) && get(f, s->slope_entries); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->sky_spheres) && get(f, s->fogs); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

@@ -45,6 +45,8 @@ struct Scene {
     std::vector<pvgpu_interior>    interiors;
     std::vector<pvgpu_tnormal>     tnormals;
     std::vector<pvgpu_slope_entry> slope_entries;
+    std::vector<pvgpu_sky_sphere>  sky_spheres;    // 0 or 1 entry
+    std::vector<pvgpu_fog>         fogs;
 
     // derived at finalize
     bool     all_shadow_casters_opaque = true;
