@@ -48,6 +48,7 @@ inline V3 operator/(V3 a, double s) { return v3(a.x / s, a.y / s, a.z / s); }
 inline double dot(V3 a, V3 b) { return ((a.x * b.x) + (a.y * b.y)) + (a.z * b.z); }        // vector.h:568
 inline double len2(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 inline double len(V3 a) { return std::sqrt(len2(a)); }
+inline V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 inline V3 unit(V3 a) { double l = len(a); return l != 0.0 ? a / l : a; }                     // vector.h:531
 inline double sqr(double x) { return x * x; }
 
@@ -637,6 +638,11 @@ public:
                                 Col layer_pigment_colour, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor,
                                 std::pair<bool, Col>* light_cache);
     void TraceShadowRay(const pvgpu_light& L, double depth, Ray& lightsourceray, Ticket& tk, Col& colour);
+    void TracePointLightShadowRay(double& lightsourcedepth, Ray& newray, Ticket& tk, Col& colour);
+    void TraceAreaLightShadowRay(const pvgpu_light& L, double& lightsourcedepth, Ray& lightsourceray, V3 ipoint, Ticket& tk, Col& lightcolour);
+    void TraceAreaLightSubsetShadowRay(const pvgpu_light& L, double& lightsourcedepth, Ray& lightsourceray, V3 ipoint, Ticket& tk, Col& lightcolour,
+                                       int u1, int v1, int u2, int v2, int level, V3 axis1, V3 axis2, std::vector<Col>& lightGrid);
+    void ComputeOneWhiteLightRay(const pvgpu_light& L, double& depth, Ray& lray, V3 ipoint, V3 jitter) const;
     void ComputeShadowColour(Intersection& isect, Ray& lightsourceray, const Ticket& tk, Col& colour);
     int hit_texture(const pvgpu_object& ob, const Intersection& isect, bool backside) const;
 };
@@ -2164,14 +2170,9 @@ bool Tracer::ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3
     return false;
 }
 
-void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn, V3 ipoint, const Ray& eye, Ticket& tk, V3 layer_normal,
-                                    Col pig, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor,
-                                    std::pair<bool, Col>* light_cache)     // trace.cpp:1637-1728
+void Tracer::ComputeOneWhiteLightRay(const pvgpu_light& L, double& depth, Ray& lray, V3 ipoint, V3 jitter) const             // trace.cpp:2710-2767
 {
-    Ray lray(eye);
-    double depth;
-    // ComputeOneWhiteLightRay (trace.cpp:2710-2767)
-    V3 center = v3(L.center);
+    V3 center = v3(L.center) + jitter;
     lray.Origin = ipoint;
     if (L.type == PVGPU_LIGHT_CYLINDER) {
         lray.Direction = center - v3(L.points_at);
@@ -2181,7 +2182,23 @@ void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn
         depth /= distToPointsAt;
         lray.Direction = unit(lray.Direction);
     } else { lray.Direction = center - ipoint; depth = len(lray.Direction); lray.Direction = lray.Direction / depth; }
-    if (L.flags & PVGPU_LIGHT_PARALLEL) { double a = dot(v3(L.direction), lray.Direction); depth *= (-a); lray.Direction = -v3(L.direction); }
+    if (L.flags & PVGPU_LIGHT_PARALLEL) {
+        if (L.flags & PVGPU_LIGHT_AREA) {
+            V3 v1 = unit(center - v3(L.points_at));
+            double a = dot(v1, lray.Direction);
+            depth *= a;
+            lray.Direction = v1;
+        } else { double a = dot(v3(L.direction), lray.Direction); depth *= (-a); lray.Direction = -v3(L.direction); }
+    }
+}
+
+void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn, V3 ipoint, const Ray& eye, Ticket& tk, V3 layer_normal,
+                                    Col pig, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor,
+                                    std::pair<bool, Col>* light_cache)     // trace.cpp:1637-1728
+{
+    Ray lray(eye);
+    double depth;
+    ComputeOneWhiteLightRay(L, depth, lray, ipoint, v3(0.0, 0.0, 0.0));
     double latt = Attenuate_Light(L, lray, depth);
     Col lightcolour{ (float)(L.colour[0] * latt), (float)(L.colour[1] * latt), (float)(L.colour[2] * latt) };
     if (near_zero(lightcolour, (float)EPSILON)) return;
@@ -2249,14 +2266,22 @@ void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn
     colour = colour + tmpCol;
 }
 
-void Tracer::TraceShadowRay(const pvgpu_light&, double depth, Ray& lightsourceray, Ticket& tk, Col& colour)                  // trace.cpp:1892-2076 (no caches)
+void Tracer::TraceShadowRay(const pvgpu_light& L, double depth, Ray& lightsourceray, Ticket& tk, Col& colour)                // trace.cpp:1892-1933
 {
     if (tk.traceLevel > tk.maxAllowedTraceLevel) { colour = Col{ 0, 0, 0 }; return; }
     tk.maxFound = std::max(tk.maxFound, tk.traceLevel);
     tk.traceLevel++;
     Ray newray(lightsourceray);
     newray.flags = 0; newray.shadowTest = true;
-    double lightsourcedepth = depth;
+    double newdepth = depth;
+    if ((L.flags & PVGPU_LIGHT_AREA) && (S.g.quality_flags & PVGPU_Q_AREA_LIGHTS)) TraceAreaLightShadowRay(L, newdepth, newray, lightsourceray.Origin, tk, colour);
+    else TracePointLightShadowRay(newdepth, newray, tk, colour);
+    tk.traceLevel--;
+    st.max_level = std::max(st.max_level, tk.maxFound);
+}
+
+void Tracer::TracePointLightShadowRay(double& lightsourcedepth, Ray& newray, Ticket& tk, Col& colour)                         // trace.cpp:1946-2076 (no caches)
+{
     while (true) {
         Intersection bi;
         bi.Depth = lightsourcedepth;
@@ -2271,8 +2296,76 @@ void Tracer::TraceShadowRay(const pvgpu_light&, double depth, Ray& lightsourcera
             newray.Origin = bi.IPoint;
         } else break;
     }
-    tk.traceLevel--;
-    st.max_level = std::max(st.max_level, tk.maxFound);
+}
+
+void Tracer::TraceAreaLightShadowRay(const pvgpu_light& L, double& lightsourcedepth, Ray& lightsourceray, V3 ipoint, Ticket& tk, Col& lightcolour)   // trace.cpp:2078-2131
+{
+    std::vector<Col> lightGrid((size_t)L.area_size1 * L.area_size2, Col{ std::nanf(""), 0.0f, 0.0f });       // Invalidate(): NaN in the first channel (colour.h:71-73)
+    V3 axis1Temp = v3(L.axis1), axis2Temp = v3(L.axis2);
+    if (L.flags & PVGPU_LIGHT_ORIENT) {
+        ComputeOneWhiteLightRay(L, lightsourcedepth, lightsourceray, ipoint, v3(0.0, 0.0, 0.0));
+        double axis1_Length = len(axis1Temp);
+        V3 temp = (std::fabs(std::fabs(lightsourceray.Direction.z) - 1.0) < 0.01) ? v3(0.0, 1.0, 0.0) : v3(0.0, 0.0, 1.0);
+        axis1Temp = unit(cross(lightsourceray.Direction, temp));
+        axis2Temp = unit(cross(lightsourceray.Direction, axis1Temp));
+        axis1Temp = axis1Temp * axis1_Length;
+        axis2Temp = axis2Temp * axis1_Length;
+    }
+    TraceAreaLightSubsetShadowRay(L, lightsourcedepth, lightsourceray, ipoint, tk, lightcolour, 0, 0, L.area_size1 - 1, L.area_size2 - 1, 0, axis1Temp, axis2Temp, lightGrid);
+}
+
+void Tracer::TraceAreaLightSubsetShadowRay(const pvgpu_light& L, double& lightsourcedepth, Ray& lightsourceray, V3 ipoint, Ticket& tk, Col& lightcolour,
+                                           int u1, int v1, int u2, int v2, int level, V3 axis1, V3 axis2, std::vector<Col>& lightGrid)   // trace.cpp:2133-2271
+{
+    Col sample_Colour[4];
+    auto ColourDistance = [](Col a, Col b) { return std::fabs(a.r - b.r) + std::fabs(a.g - b.g) + std::fabs(a.b - b.b); };
+    for (int i = 0; i < 4; i++) {
+        Ray lsr(lightsourceray);
+        const int u = (i == 1 || i == 3) ? u2 : u1, v = (i >= 2) ? v2 : v1;
+        Col& cell = lightGrid[(size_t)u * L.area_size2 + v];
+        if (!std::isnan(cell.r)) sample_Colour[i] = cell;
+        else {
+            V3 jitterAxis1, jitterAxis2;
+            double jitter_u = (double)u, jitter_v = (double)v, scaleFactor;
+            // (jitter draws from the thread's random number generator: not reproducible, rejected at scene validation)
+            if (L.flags & PVGPU_LIGHT_CIRCULAR) {
+                jitter_u = jitter_u / (L.area_size1 - 1) - 0.5 + 0.001;
+                jitter_v = jitter_v / (L.area_size2 - 1) - 0.5 + 0.001;
+                scaleFactor = ((std::fabs(jitter_u) > std::fabs(jitter_v)) ? std::fabs(jitter_u) : std::fabs(jitter_v));
+                scaleFactor /= std::sqrt(jitter_u * jitter_u + jitter_v * jitter_v);
+                jitter_u *= scaleFactor;
+                jitter_v *= scaleFactor;
+                jitterAxis1 = axis1 * jitter_u;
+                jitterAxis2 = axis2 * jitter_v;
+            } else {
+                if (L.area_size1 > 1) { scaleFactor = jitter_u / (double)(L.area_size1 - 1) - 0.5; jitterAxis1 = axis1 * scaleFactor; }
+                else jitterAxis1 = v3(0.0, 0.0, 0.0);
+                if (L.area_size2 > 1) { scaleFactor = jitter_v / (double)(L.area_size2 - 1) - 0.5; jitterAxis2 = axis2 * scaleFactor; }
+                else jitterAxis2 = v3(0.0, 0.0, 0.0);
+            }
+            ComputeOneWhiteLightRay(L, lightsourcedepth, lsr, ipoint, jitterAxis1 + jitterAxis2);
+            sample_Colour[i] = lightcolour;
+            TracePointLightShadowRay(lightsourcedepth, lsr, tk, sample_Colour[i]);
+            cell = sample_Colour[i];
+        }
+    }
+    if ((u2 - u1 > 1) || (v2 - v1 > 1)) {
+        if ((level < L.adaptive_level) || (ColourDistance(sample_Colour[0], sample_Colour[1]) > 0.1) || (ColourDistance(sample_Colour[1], sample_Colour[3]) > 0.1) ||
+            (ColourDistance(sample_Colour[3], sample_Colour[2]) > 0.1) || (ColourDistance(sample_Colour[2], sample_Colour[0]) > 0.1)) {
+            for (int i = 0; i < 4; i++) {
+                int new_u1, new_v1, new_u2, new_v2;
+                switch (i) {
+                    case 0: new_u1 = u1; new_v1 = v1; new_u2 = (int)std::floor((u1 + u2) / 2.0); new_v2 = (int)std::floor((v1 + v2) / 2.0); break;
+                    case 1: new_u1 = (int)std::ceil((u1 + u2) / 2.0); new_v1 = v1; new_u2 = u2; new_v2 = (int)std::floor((v1 + v2) / 2.0); break;
+                    case 2: new_u1 = u1; new_v1 = (int)std::ceil((v1 + v2) / 2.0); new_u2 = (int)std::floor((u1 + u2) / 2.0); new_v2 = v2; break;
+                    default: new_u1 = (int)std::ceil((u1 + u2) / 2.0); new_v1 = (int)std::ceil((v1 + v2) / 2.0); new_u2 = u2; new_v2 = v2; break;
+                }
+                sample_Colour[i] = lightcolour;
+                TraceAreaLightSubsetShadowRay(L, lightsourcedepth, lightsourceray, ipoint, tk, sample_Colour[i], new_u1, new_v1, new_u2, new_v2, level + 1, axis1, axis2, lightGrid);
+            }
+        }
+    }
+    lightcolour = (((sample_Colour[0] + sample_Colour[1]) + sample_Colour[2]) + sample_Colour[3]) * 0.25f;
 }
 
 void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& tk, Col& colour)           // trace.cpp:2274-2439 + ComputeShadowTexture :1181-1262

@@ -21,8 +21,11 @@ PV_VARIANT(k_shadow_filter)(DScene sc, const SRay* __restrict__ rays, const PRay
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + lane;
-        const bool alive = i < n;
+        bool alive = i < n;
         const SRay s = rays[alive ? i : 0u];
+#if PV_HEAVY
+        if (sc.has_area_lights && (sc.lights[s.light].flags & PVGPU_LIGHT_AREA)) alive = false;        // served by k_shadow_area
+#endif
         float f[3];
         trace_shadow<false>(alive, sc, ld3(s.o), ld3(s.d), s.depth, wave, s.parent, stack, cnt, f, tests);
         if (alive) accum_add(accum, s.sample, s.a[0] * f[0], s.a[1] * f[1], s.a[2] * f[2], 0.0f);

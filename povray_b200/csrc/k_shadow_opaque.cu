@@ -20,8 +20,11 @@ PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, float4* ac
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + lane;
-        const bool alive = i < n;
+        bool alive = i < n;
         const SRay* sp = rays + (alive ? i : 0u);
+#if PV_HEAVY
+        if (sc.has_area_lights && (sc.lights[sp->light].flags & PVGPU_LIGHT_AREA)) alive = false;      // served by k_shadow_area
+#endif
         const V3 o = ld3(sp->o), d = ld3(sp->d);
         const double depth = sp->depth;
         float f[3];

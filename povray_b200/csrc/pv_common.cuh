@@ -129,6 +129,8 @@ struct DScene {
     const double*            wave_freqs;    // TraceThreadData::waveFrequencies
     const pvgpu_fog*         fogs;          // SceneData::fog in list order
     uint32_t                 n_fogs, has_sky;
+    uint32_t                 has_area_lights;   // some light is an area light and QualityFlags::areaLights is on
+    uint32_t                 area_grid_max;     // largest Area_Size1 * Area_Size2
     pvgpu_sky_sphere         sky;           // SceneData::skysphere (has_sky)
     const uint32_t*          csg_leaves;    // per top-level CSG object: its primitive descendants (DFS order)
     const uint2*             csg_leaf_range;// per object: (first, count) into csg_leaves

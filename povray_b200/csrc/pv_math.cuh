@@ -23,6 +23,7 @@ __device__ __forceinline__ V3 normalized(const V3& a)
     double l = length(a);
     return (l != 0.0) ? mk(a.x / l, a.y / l, a.z / l) : a;
 }
+__device__ __forceinline__ V3 cross(const V3& a, const V3& b) { return mk((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x)); }   // vector.h:575
 __device__ __forceinline__ double comp(const V3& a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 __device__ __forceinline__ V3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 __device__ __forceinline__ V3 ld3f(const float* p) { return mk((double)p[0], (double)p[1], (double)p[2]); }

@@ -481,10 +481,10 @@ __device__ inline double attenuate_light(const pvgpu_light& L, const V3& ray_o, 
     return att;
 }
 
-// ComputeOneWhiteLightRay (trace.cpp:2710-2767) for non-area lights
-__device__ inline void light_ray(const pvgpu_light& L, const V3& ipoint, V3& dir, double& depth)
+// ComputeOneWhiteLightRay (trace.cpp:2710-2767); `jitter` = offset of the sampled point of an area light from its centre
+__device__ inline void light_ray(const pvgpu_light& L, const V3& ipoint, V3& dir, double& depth, const V3& jitter)
 {
-    V3 center = ld3(L.center);
+    V3 center = ld3(L.center) + jitter;
     if (L.type == PVGPU_LIGHT_CYLINDER) {
         dir = center - ld3(L.points_at);
         V3 to_ctr = center - ipoint;
@@ -498,10 +498,20 @@ __device__ inline void light_ray(const pvgpu_light& L, const V3& ipoint, V3& dir
         dir = dir / depth;
     }
     if (L.flags & PVGPU_LIGHT_PARALLEL) {
-        double a = dot(ld3(L.direction), dir);
-        depth *= (-a);
-        dir = -ld3(L.direction);
+        if (L.flags & PVGPU_LIGHT_AREA) {
+            const V3 v1 = normalized(center - ld3(L.points_at));
+            depth *= dot(v1, dir);
+            dir = v1;
+        } else {
+            double a = dot(ld3(L.direction), dir);
+            depth *= (-a);
+            dir = -ld3(L.direction);
+        }
     }
+}
+__device__ inline void light_ray(const pvgpu_light& L, const V3& ipoint, V3& dir, double& depth)
+{
+    light_ray(L, ipoint, dir, depth, mk(0.0, 0.0, 0.0));
 }
 
 // ---- interiors -----------------------------------------------------------------------------------
@@ -949,6 +959,10 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
             if (a[0] == 0.0f && a[1] == 0.0f && a[2] == 0.0f) continue;
             const bool shadowed = (sc.g.quality_flags & PVGPU_Q_SHADOWS) && (Lt.type != PVGPU_LIGHT_FILL);
             if (!shadowed) { accum_add(ctx.accum, ray.sample, a[0], a[1], a[2], 0.0f); continue; }
+#if PV_HEAVY
+            // area light: k_shadow_area averages the light colour over the sampled grid and multiplies it in (trace.cpp:2078-2271)
+            if ((Lt.flags & PVGPU_LIGHT_AREA) && (sc.g.quality_flags & PVGPU_Q_AREA_LIGHTS)) { a[0] = ray.w[0] * K[0]; a[1] = ray.w[1] * K[1]; a[2] = ray.w[2] * K[2]; }
+#endif
             SRay s;
             s.o[0] = ipoint.x; s.o[1] = ipoint.y; s.o[2] = ipoint.z;
             s.d[0] = ldir.x; s.d[1] = ldir.y; s.d[2] = ldir.z;

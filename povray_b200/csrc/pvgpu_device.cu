@@ -44,6 +44,7 @@ struct DeviceScene {
     unsigned long long kernel_launches = 0;
     bool lean = false;                   // only spheres, boxes, planes, meshes and no clipped_by / bounded_by: lean kernel variants
     bool camera_dirty = true;
+    float* area_grid = nullptr;          // lightGrid scratch of k_shadow_area (3 floats x area_grid_max per resident thread)
     // host-side staging of pvgpu_render (pinned) and its device frame
     float* d_frame = nullptr;
     float* h_frame = nullptr;
@@ -299,6 +300,17 @@ int device_upload(Scene& s, int device)
             o.clip_count || o.bound_count) d->lean = false;
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->lean = false;
     if (!s.fogs.empty() || !s.sky_spheres.empty()) d->lean = false;
+    v.has_area_lights = 0; v.area_grid_max = 0;
+    if (s.globals.quality_flags & PVGPU_Q_AREA_LIGHTS)
+        for (const pvgpu_light& l : s.lights)
+            if (l.flags & PVGPU_LIGHT_AREA) { v.has_area_lights = 1; v.area_grid_max = std::max<uint32_t>(v.area_grid_max, (uint32_t)(l.area_size1 * l.area_size2)); }
+    if (v.has_area_lights) {
+        d->lean = false;
+        void* p = nullptr;
+        if (cudaMalloc(&p, (size_t)area_threads() * v.area_grid_max * 3 * sizeof(float)) != cudaSuccess) { device_release(s); return fail(PVGPU_E_CUDA, "cudaMalloc of the area-light sample grids failed"); }
+        d->allocs.push_back(p);
+        d->area_grid = reinterpret_cast<float*>(p);
+    }
     v.n_fogs = (uint32_t)s.fogs.size();
     v.has_sky = s.sky_spheres.empty() ? 0u : 1u;
     if (v.has_sky) v.sky = s.sky_spheres[0];
@@ -453,6 +465,7 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
                 TimedLaunch t(d, stream, KIND_SHADOW, 0);
                 if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : launch_shadow_opaque)(d.view, d.sq, worst, f.accum, d.cnt, stream);
                 else (d.lean ? launch_shadow_filter_lean : launch_shadow_filter)(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, stream);
+                if (d.view.has_area_lights) { d.kernel_launches++; launch_shadow_area(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, d.area_grid, stream); }
             }
         }
         unsigned int h[4];     // n_next, n_shadow, max_level, overflow

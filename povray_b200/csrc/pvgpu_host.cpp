@@ -419,8 +419,16 @@ int validate_scene(Scene& s)
         const pvgpu_light& l = s.lights[i];
         if (l.type < PVGPU_LIGHT_POINT || l.type > PVGPU_LIGHT_CYLINDER)
             return fail(PVGPU_E_INVALID, "light %zu: bad type", i);
-        if (l.flags & PVGPU_LIGHT_AREA)
-            return fail(PVGPU_E_UNSUPPORTED, "light %zu: area lights are a 'next' row (SURVEY 8f)", i);
+        if (l.flags & PVGPU_LIGHT_AREA) {
+            if (l.area_size1 < 1 || l.area_size2 < 1 || l.area_size1 > 2048 || l.area_size2 > 2048 || (long long)l.area_size1 * l.area_size2 > 4096)
+                return fail(PVGPU_E_UNSUPPORTED, "light %zu: area light grid %d x %d (supported: up to 4096 samples)", i, l.area_size1, l.area_size2);
+            if (l.flags & PVGPU_LIGHT_JITTER)
+                return fail(PVGPU_E_UNSUPPORTED, "light %zu: area light jitter is excluded from parity (per-thread RNG)", i);
+            if (l.flags & PVGPU_LIGHT_FULL_AREA)
+                return fail(PVGPU_E_UNSUPPORTED, "light %zu: area_illumination is outside the hot-path scope", i);
+            if ((l.flags & PVGPU_LIGHT_CIRCULAR) && (l.area_size1 < 2 || l.area_size2 < 2))
+                return fail(PVGPU_E_INVALID, "light %zu: circular area light needs at least 2 x 2 samples", i);
+        }
         if (l.projected_through >= 0)
             return fail(PVGPU_E_UNSUPPORTED, "light %zu: projected_through is outside the hot-path scope", i);
         if (l.flags & PVGPU_LIGHT_GROUP)

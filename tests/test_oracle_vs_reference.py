@@ -48,8 +48,13 @@ def test_oracle_pixels_match_reference(oracle, name):
     d = np.abs(img - rgbt).max(axis=2)
     assert (d > 1.0 / 255.0).mean() <= 0.001   # the contract
     # what the restatement actually achieves on these scenes: identical to ~1e-7 everywhere, except one pixel of the
-    # refracting blob (1.4e-4)
-    assert d.max() < 2e-4 and (d > 1e-5).sum() <= 1
+    # refracting blob (1.4e-4) and, with area lights, the few samples the reference's light-source shadow cache answers
+    # differently from its own uncached search (the cached object is tested without the
+    # SMALL_TOLERANCE post-condition, trace.cpp:1989-2013, so the result depends on which object was cached last)
+    if name == "area_lights":
+        assert d.max() < 1e-3 and (d > 1e-5).sum() <= 8
+    else:
+        assert d.max() < 2e-4 and (d > 1e-5).sum() <= 1
     assert st["rays"] >= W * H
 
 
