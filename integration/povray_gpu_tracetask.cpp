@@ -28,6 +28,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <typeinfo>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -194,7 +195,7 @@ struct Flattener
         else if (dynamic_cast<const WavesPattern*>(bp)) p.pattern = PVGPU_PAT_WAVES;
         else if (const QuiltedPattern* q = dynamic_cast<const QuiltedPattern*>(bp)) { p.pattern = PVGPU_PAT_QUILTED; p.p[0] = q->Control0; p.p[1] = q->Control1; }
         else if (dynamic_cast<const BumpsPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;      // BumpsPattern is a NoisePattern (pattern.h:989)
-        else unsupported(std::string(user) + " pattern outside the hot-path scope");
+        else unsupported(std::string(user) + " pattern outside the hot-path scope: " + typeid(*bp).name());
         if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {
             p.wave_type = cp->waveType; p.frequency = cp->waveFrequency; p.phase = cp->wavePhase; p.exponent = cp->waveExponent;
         }
@@ -495,11 +496,11 @@ struct Flattener
         } else if (Triangle* tr = dynamic_cast<Triangle*>(o)) {
             p.type = PVGPU_OBJ_TRIANGLE;
             p.mesh = (int32_t)shape_data.size();
-            p.aux = tr->Dominant_Axis | (tr->vAxis << 2);
+            p.aux = tr->Dominant_Axis;                  // (vAxis is only initialised for smooth triangles)
             for (const Vector3d* v : { &tr->P1, &tr->P2, &tr->P3, &tr->Normal_Vector }) for (int k = 0; k < 3; k++) shape_data.push_back((*v)[k]);
             shape_data.push_back(tr->Distance);
             if (SmoothTriangle* st = dynamic_cast<SmoothTriangle*>(o)) {
-                p.aux |= PVGPU_TRIANGLE_SMOOTH;
+                p.aux |= PVGPU_TRIANGLE_SMOOTH | (tr->vAxis << 2);
                 for (const Vector3d* v : { &st->N1, &st->N2, &st->N3, &st->Perp }) for (int k = 0; k < 3; k++) shape_data.push_back((*v)[k]);
             }
         } else if (Polygon* pg = dynamic_cast<Polygon*>(o)) {
@@ -525,7 +526,7 @@ struct Flattener
             else unsupported("unknown CSG class");
             add_index_range(c->children, self, true, p.child_first, p.child_count);
         } else {
-            unsupported("primitive outside the hot-path scope (SURVEY 8a lists sphere, box, plane, quadric, torus, mesh, blob, CSG; cone / cylinder / disc / triangle / polygon from 8f)");
+            unsupported(std::string("primitive outside the hot-path scope: ") + typeid(*o).name());
             p.type = 0;
         }
         add_index_range(o->Clip, self, false, p.clip_first, p.clip_count);

@@ -265,7 +265,7 @@ int validate_scene(Scene& s)
         if ((o.type == PVGPU_OBJ_CONE || o.type == PVGPU_OBJ_DISC) && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: cone / cylinder / disc without transform", i);
         if (o.type == PVGPU_OBJ_TRIANGLE &&
-            (o.mesh < 0 || !range_ok((uint32_t)o.mesh, (o.aux & PVGPU_TRIANGLE_SMOOTH) ? 25u : 13u, s.shape_data.size()) || (o.aux & 3u) > 2u || ((o.aux >> 2) & 3u) > 2u))
+            (o.mesh < 0 || !range_ok((uint32_t)o.mesh, (o.aux & PVGPU_TRIANGLE_SMOOTH) ? 25u : 13u, s.shape_data.size()) || (o.aux & 3u) > 2u || ((o.aux & PVGPU_TRIANGLE_SMOOTH) && ((o.aux >> 2) & 3u) > 2u)))
             return fail(PVGPU_E_INVALID, "object %zu: triangle record outside the shape-data table", i);
         if (o.type == PVGPU_OBJ_POLYGON &&
             (o.transform < 0 || o.mesh < 0 || o.aux > (1u << 24) || !range_ok((uint32_t)o.mesh, 2u * o.aux, s.shape_data.size())))
