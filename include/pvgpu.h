@@ -61,8 +61,10 @@ enum {
     PVGPU_OBJ_TRIANGLE         = 13, /* triangle.h:73 / :103  mesh = offset into the shape-data table: P1 P2 P3 Normal_Vector Distance
                                         (13 doubles), smooth_triangle: + N1 N2 N3 Perp (25 doubles);
                                         aux = Dominant_Axis | vAxis << 2 | PVGPU_TRIANGLE_SMOOTH                 */
-    PVGPU_OBJ_POLYGON          = 14  /* polygon.h:83   p[0..2]=S_Normal; aux = Data->Number; mesh = offset into the shape-data table
+    PVGPU_OBJ_POLYGON          = 14, /* polygon.h:83   p[0..2]=S_Normal; aux = Data->Number; mesh = offset into the shape-data table
                                         (2 doubles per point, Data->Points); transform required                   */
+    PVGPU_OBJ_POLY             = 15  /* polynomial.h:78 poly / cubic / quartic of Order <= 4: aux = Order, mesh = offset into the shape-data table
+                                        ((Order+1)(Order+2)(Order+3)/6 coefficients, Coeffs); transform required; STURM flag */
 };
 #define PVGPU_TRIANGLE_SMOOTH 0x10u
 

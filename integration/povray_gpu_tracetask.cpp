@@ -69,6 +69,7 @@
 #include "core/shape/mesh.h"
 #include "core/shape/plane.h"
 #include "core/shape/polygon.h"
+#include "core/shape/polynomial.h"
 #include "core/shape/quadric.h"
 #include "core/shape/sphere.h"
 #include "core/shape/torus.h"
@@ -503,6 +504,13 @@ struct Flattener
                 p.aux |= PVGPU_TRIANGLE_SMOOTH | (tr->vAxis << 2);
                 for (const Vector3d* v : { &st->N1, &st->N2, &st->N3, &st->Perp }) for (int k = 0; k < 3; k++) shape_data.push_back((*v)[k]);
             }
+        } else if (Poly* po = dynamic_cast<Poly*>(o)) {
+            p.type = PVGPU_OBJ_POLY;
+            p.aux = (uint32_t)po->Order;
+            p.mesh = (int32_t)shape_data.size();
+            if (po->Order < 1 || po->Order > 4) unsupported("poly of order > 4");
+            else for (int k = 0; k < (po->Order + 1) * (po->Order + 2) * (po->Order + 3) / 6; k++) shape_data.push_back(po->Coeffs[k]);
+            p.transform = add_transform(po->Trans);
         } else if (Polygon* pg = dynamic_cast<Polygon*>(o)) {
             p.type = PVGPU_OBJ_POLYGON;
             for (int k = 0; k < 3; k++) p.p[k] = pg->S_Normal[k];

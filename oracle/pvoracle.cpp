@@ -795,6 +795,25 @@ bool Tracer::Inside(V3 p, uint32_t idx) const
             }
             return inside ? !inv : inv;
         }
+        case PVGPU_OBJ_POLY: {                                                                            // polynomial.cpp:590-654, 1131-1178
+            const double* a = S.shape_data.data() + ob.mesh;
+            const int order = (int)ob.aux;
+            const V3 P = MInvTransPoint(S.xf[ob.transform], p);
+    double xp[5], yp[5], zp[5];
+    xp[0] = 1.0; yp[0] = 1.0; zp[0] = 1.0;
+    xp[1] = P.x; yp[1] = P.y; zp[1] = P.z;
+    for (int i = 2; i <= order; i++) { xp[i] = xp[1] * xp[i - 1]; yp[i] = yp[1] * yp[i - 1]; zp[i] = zp[1] * zp[i - 1]; }
+    double result = 0.0;
+    int term = 0;
+    for (int i = order; i >= 0; i--)
+        for (int j = order - i; j >= 0; j--)
+            for (int k = order - (i + j); k >= 0; k--) {
+                const double c = a[term];
+                if (c != 0.0) result += c * xp[i] * yp[j] * zp[k];
+                term++;
+            }
+            return (result < 1.0e-4) ? !inv : inv;
+        }
         case PVGPU_OBJ_DISC:                                                                              // disc.cpp:200-224
             return (MInvTransPoint(S.xf[ob.transform], p).z >= 0.0) ? inv : !inv;
         case PVGPU_OBJ_CONE: {                                                                            // cone.cpp:333-390
@@ -965,6 +984,92 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
             }
             return found;
         }
+        case PVGPU_OBJ_POLY: {                                                                            // polynomial.cpp:211-290, 656-947
+            const pvgpu_transform& t = S.xf[ob.transform];
+            const double* a = S.shape_data.data() + ob.mesh;
+            const int order = (int)ob.aux;
+            V3 O = MInvTransPoint(t, o), D = MInvTransDirection(t, d);
+            const double length = len(D);
+            D = D / length;
+            double depths[4];
+            int cnt = 0;
+            if (order == 1) {
+                double t0 = a[0] * O.x + a[1] * O.y + a[2] * O.z;
+                double t1 = a[0] * D.x + a[1] * D.y + a[2] * D.z;
+                if (std::fabs(t1) < EPSILON) return false;
+                depths[0] = -(a[3] + t0) / t1;
+                cnt = 1;
+            } else if (order == 2) cnt = [&]() -> int {
+    const double x = O.x, y = O.y, z = O.z, xx = D.x, yy = D.y, zz = D.z;
+    const double x2 = x * x, y2 = y * y, z2 = z * z, xx2 = xx * xx, yy2 = yy * yy, zz2 = zz * zz;
+    double ac = (a[0]*xx2 + a[1]*xx*yy + a[2]*xx*zz + a[4]*yy2 + a[5]*yy*zz + a[7]*zz2);
+    double bc = (2*a[0]*x*xx + a[1]*(x*yy + xx*y) + a[2]*(x*zz + xx*z) +
+                 a[3]*xx + 2*a[4]*y*yy + a[5]*(y*zz + yy*z) + a[6]*yy +
+                 2*a[7]*z*zz + a[8]*zz);
+    double cc = a[0]*x2 + a[1]*x*y + a[2]*x*z + a[3]*x + a[4]*y2 +
+                a[5]*y*z + a[6]*y + a[7]*z2 + a[8]*z + a[9];
+    if (std::fabs(ac) < 1.0e-20) {
+        if (std::fabs(bc) < 1.0e-20) return 0;
+        depths[0] = -cc / bc;
+        return 1;
+    }
+    double dd = bc * bc - 4.0 * ac * cc;
+    if (dd < 0.0) return 0;
+    dd = std::sqrt(dd);
+    bc = -bc;
+    const double t = 2.0 * ac;
+    depths[0] = (bc + dd) / t;
+    depths[1] = (bc - dd) / t;
+    return 2;
+            }();
+            else cnt = [&]() -> int {
+    // Poly::intersect (polynomial.cpp:656-800): substitute the ray into every term, collect powers of t
+    double eqn_v[3][5], eqn_vt[3][5], eqn[5], tt[3][5];
+    for (int i = 0; i < 3; i++) { eqn_v[i][0] = 1.0; eqn_vt[i][0] = 1.0; }
+    eqn_v[0][1] = O.x; eqn_v[1][1] = O.y; eqn_v[2][1] = O.z;
+    eqn_vt[0][1] = D.x; eqn_vt[1][1] = D.y; eqn_vt[2][1] = D.z;
+    for (int i = 2; i <= order; i++)
+        for (int j = 0; j < 3; j++) { eqn_v[j][i] = eqn_v[j][1] * eqn_v[j][i - 1]; eqn_vt[j][i] = eqn_vt[j][1] * eqn_vt[j][i - 1]; }
+    for (int i = 0; i <= order; i++) eqn[i] = 0.0;
+    const unsigned int binom[5][5] = { { 1, 0, 0, 0, 0 }, { 1, 1, 0, 0, 0 }, { 1, 2, 1, 0, 0 }, { 1, 3, 3, 1, 0 }, { 1, 4, 6, 4, 1 } };
+    int term = 0;
+    for (int i = order; i >= 0; i--) {
+        for (int h = 0; h <= i; h++) tt[0][h] = binom[i][h] * eqn_vt[0][i - h] * eqn_v[0][h];
+        for (int j = order - i; j >= 0; j--) {
+            for (int h = 0; h <= j; h++) tt[1][h] = binom[j][h] * eqn_vt[1][j - h] * eqn_v[1][h];
+            for (int k = order - (i + j); k >= 0; k--) {
+                if (a[term] != 0) {
+                    for (int h = 0; h <= k; h++) tt[2][h] = binom[k][h] * eqn_vt[2][k - h] * eqn_v[2][h];
+                    const int offset = order - (i + j + k);
+                    for (int i1 = 0; i1 <= i; i1++)
+                        for (int j1 = 0; j1 <= j; j1++)
+                            for (int k1 = 0; k1 <= k; k1++) {
+                                double val = a[term];
+                                val *= tt[0][i1];
+                                val *= tt[1][j1];
+                                val *= tt[2][k1];
+                                eqn[offset + i1 + j1 + k1] += val;
+                            }
+                }
+                term++;
+            }
+        }
+    }
+    int lead = 0, deg = order;
+    for (; lead <= order; lead++) { if (eqn[lead] != 0.0) break; else deg--; }
+    if (deg <= 1) return 0;
+                return Solve_Polynomial(deg, &eqn[lead], depths, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, 1.0e-4);
+            }();
+            for (int i = 0; i < cnt; i++) {
+                if (!(depths[i] > 1.0e-4)) continue;
+                bool same_root = false;
+                for (int j = 0; j < i; j++) if (depths[i] == depths[j]) { same_root = true; break; }
+                if (same_root) continue;
+                V3 IPoint = MTransPoint(t, v3(O.x + D.x * depths[i], O.y + D.y * depths[i], O.z + D.z * depths[i]));
+                found |= push(depths[i] / length, IPoint, 0);
+            }
+            return found;
+        }
         case PVGPU_OBJ_TRIANGLE: {                                                                        // triangle.cpp:447-590
             if (ob.flags & PVGPU_DEGENERATE_FLAG) return false;
             const double* T = S.shape_data.data() + ob.mesh;
@@ -1112,7 +1217,7 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
 static bool Intersect_BBox(const pvgpu_object& ob, V3 o, V3 d, float maxd)
 {
     if (ob.type < PVGPU_OBJ_QUADRIC) return true;          // Sphere / Box / Plane override it (sphere.cpp:753, box.cpp:1079, plane.cpp:629)
-    if (ob.type == PVGPU_OBJ_TRIANGLE) return true;        // and so does Triangle (triangle.cpp:1419)
+    if (ob.type == PVGPU_OBJ_TRIANGLE || ob.type == PVGPU_OBJ_POLY) return true;   // and so do Triangle (triangle.cpp:1419) and Poly (polynomial.cpp:1510)
     float origin[3] = { (float)o.x, (float)o.y, (float)o.z };
     float invdir[3] = { (float)(1.0 / d.x), (float)(1.0 / d.y), (float)(1.0 / d.z) };
     float b[2][3] = { { ob.bbox[0], ob.bbox[1], ob.bbox[2] }, { ob.bbox[0] + ob.bbox[3], ob.bbox[1] + ob.bbox[4], ob.bbox[2] + ob.bbox[5] } };
@@ -1440,6 +1545,48 @@ V3 Tracer::Normal(const Intersection& isect) const
         }
         case PVGPU_OBJ_DISC: return v3(ob.p);                                                             // disc.cpp:226-229
         case PVGPU_OBJ_POLYGON: return v3(ob.p);                                                          // polygon.cpp:308-311
+        case PVGPU_OBJ_POLY: {                                                                            // polynomial.cpp:1035-1129, 1180-1244
+            const pvgpu_transform& t = S.xf[ob.transform];
+            const double* a = S.shape_data.data() + ob.mesh;
+            const int order = (int)ob.aux;
+            const V3 P = MInvTransPoint(t, isect.IPoint);
+    const double x = P.x, y = P.y, z = P.z;
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    switch (order) {
+        case 1: rx = a[0]; ry = a[1]; rz = a[2]; break;
+        case 2:
+            rx = 2*a[0]*x+a[1]*y+a[2]*z+a[3];
+            ry = a[1]*x+2*a[4]*y+a[5]*z+a[6];
+            rz = a[2]*x+a[5]*y+2*a[7]*z+a[8];
+            break;
+        case 3: {
+            const double x2 = x * x, y2 = y * y, z2 = z * z;
+            rx = 3*a[0]*x2 + 2*x*(a[1]*y + a[2]*z + a[3]) + a[4]*y2 + y*(a[5]*z + a[6]) + a[7]*z2 + a[8]*z + a[9];
+            ry = a[1]*x2 + x*(2*a[4]*y + a[5]*z + a[6]) + 3*a[10]*y2 + 2*y*(a[11]*z + a[12]) + a[13]*z2 + a[14]*z + a[15];
+            rz = a[2]*x2 + x*(a[5]*y + 2*a[7]*z + a[8]) + a[11]*y2 + y*(2*a[13]*z + a[14]) + 3*a[16]*z2 + 2*a[17]*z + a[18];
+            break;
+        }
+        default: {
+            const double x2 = x * x, y2 = y * y, z2 = z * z, x3 = x * x2, y3 = y * y2, z3 = z * z2;
+            rx = 4*a[ 0]*x3+3*x2*(a[ 1]*y+a[ 2]*z+a[ 3])+
+                 2*x*(a[ 4]*y2+y*(a[ 5]*z+a[ 6])+a[ 7]*z2+a[ 8]*z+a[ 9])+
+                 a[10]*y3+y2*(a[11]*z+a[12])+y*(a[13]*z2+a[14]*z+a[15])+
+                 a[16]*z3+a[17]*z2+a[18]*z+a[19];
+            ry = a[ 1]*x3+x2*(2*a[ 4]*y+a[ 5]*z+a[ 6])+
+                 x*(3*a[10]*y2+2*y*(a[11]*z+a[12])+a[13]*z2+a[14]*z+a[15])+
+                 4*a[20]*y3+3*y2*(a[21]*z+a[22])+2*y*(a[23]*z2+a[24]*z+a[25])+
+                 a[26]*z3+a[27]*z2+a[28]*z+a[29];
+            rz = a[ 2]*x3+x2*(a[ 5]*y+2*a[ 7]*z+a[ 8])+
+                 x*(a[11]*y2+y*(2*a[13]*z+a[14])+3*a[16]*z2+2*a[17]*z+a[18])+
+                 a[21]*y3+y2*(2*a[23]*z+a[24])+y*(3*a[26]*z2+2*a[27]*z+a[28])+
+                 4*a[30]*z3+3*a[31]*z2+2*a[32]*z+a[33];
+        }
+    }
+            V3 r = MTransNormal(t, v3(rx, ry, rz));
+            double val = len2(r);
+            if (val > 0.0) { val = 1.0 / std::sqrt(val); return r * val; }
+            return v3(1.0, 0.0, 0.0);
+        }
         case PVGPU_OBJ_TRIANGLE: {                                                                        // triangle.cpp:640-700
             const double* T = S.shape_data.data() + ob.mesh;
             if (!(ob.aux & PVGPU_TRIANGLE_SMOOTH)) return v3(T + 9);

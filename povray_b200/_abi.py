@@ -16,7 +16,7 @@ ABI_VERSION = 2
 OK, E_INVALID, E_UNSUPPORTED, E_NO_DEVICE, E_CUDA, E_IO, E_ABORTED, E_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7
 
 # object kinds
-OBJ_SPHERE, OBJ_BOX, OBJ_PLANE, OBJ_QUADRIC, OBJ_TORUS, OBJ_MESH, OBJ_CSG_UNION, OBJ_CSG_INTERSECTION, OBJ_CSG_MERGE, OBJ_BLOB, OBJ_CONE, OBJ_DISC, OBJ_TRIANGLE, OBJ_POLYGON = range(1, 15)
+OBJ_SPHERE, OBJ_BOX, OBJ_PLANE, OBJ_QUADRIC, OBJ_TORUS, OBJ_MESH, OBJ_CSG_UNION, OBJ_CSG_INTERSECTION, OBJ_CSG_MERGE, OBJ_BLOB, OBJ_CONE, OBJ_DISC, OBJ_TRIANGLE, OBJ_POLYGON, OBJ_POLY = range(1, 16)
 
 # object flags (source/core/scene/object.h:88-117)
 NO_SHADOW_FLAG = 0x00000001

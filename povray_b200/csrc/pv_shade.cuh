@@ -610,6 +610,7 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_DISC:    return ld3(ob.p);       // Disc::Normal (disc.cpp:226-229)
         case PVGPU_OBJ_TRIANGLE: return triangle_normal(sc, ob, hit.ip);
         case PVGPU_OBJ_POLYGON: return ld3(ob.p);       // Polygon::Normal (polygon.cpp:308-311)
+        case PVGPU_OBJ_POLY:    return poly_normal(sc, ob, hit.ip);
 #endif
     }
     return mk(0.0, 1.0, 0.0);

@@ -396,6 +396,168 @@ __device__ inline void polygon_hits(const DScene& sc, const pvgpu_object& ob, co
     h.depth[0] = depth; h.ip[0] = evaluate(o, d, depth); h.aux[0] = 0; h.n = 1;
 }
 
+// ---- poly / cubic / quartic (order <= 4) ------------------------------------------------------------
+// Poly (polynomial.cpp:211-1245); coefficients in the shape-data table at ob.mesh, ob.aux = Order, transform required.
+#define PV_POLY_DEPTH_TOLERANCE 1.0e-4      // DEPTH_TOLERANCE, INSIDE_TOLERANCE, ROOT_TOLERANCE  polynomial.cpp:96-98
+__device__ inline int poly_quadratic(const double* a, const V3& O, const V3& D, double* depths)      // intersect_quadratic :852-947
+{
+    const double x = O.x, y = O.y, z = O.z, xx = D.x, yy = D.y, zz = D.z;
+    const double x2 = x * x, y2 = y * y, z2 = z * z, xx2 = xx * xx, yy2 = yy * yy, zz2 = zz * zz;
+    double ac = (a[0]*xx2 + a[1]*xx*yy + a[2]*xx*zz + a[4]*yy2 + a[5]*yy*zz + a[7]*zz2);
+    double bc = (2*a[0]*x*xx + a[1]*(x*yy + xx*y) + a[2]*(x*zz + xx*z) +
+                 a[3]*xx + 2*a[4]*y*yy + a[5]*(y*zz + yy*z) + a[6]*yy +
+                 2*a[7]*z*zz + a[8]*zz);
+    double cc = a[0]*x2 + a[1]*x*y + a[2]*x*z + a[3]*x + a[4]*y2 +
+                a[5]*y*z + a[6]*y + a[7]*z2 + a[8]*z + a[9];
+    if (fabs(ac) < 1.0e-20) {
+        if (fabs(bc) < 1.0e-20) return 0;
+        depths[0] = -cc / bc;
+        return 1;
+    }
+    double dd = bc * bc - 4.0 * ac * cc;
+    if (dd < 0.0) return 0;
+    dd = sqrt(dd);
+    bc = -bc;
+    const double t = 2.0 * ac;
+    depths[0] = (bc + dd) / t;
+    depths[1] = (bc - dd) / t;
+    return 2;
+}
+__device__ inline int poly_general(const double* a, int order, bool sturm, const V3& O, const V3& D, double* depths)
+{
+    // Poly::intersect (polynomial.cpp:656-800): substitute the ray into every term, collect powers of t
+    double eqn_v[3][5], eqn_vt[3][5], eqn[5], tt[3][5];
+    for (int i = 0; i < 3; i++) { eqn_v[i][0] = 1.0; eqn_vt[i][0] = 1.0; }
+    eqn_v[0][1] = O.x; eqn_v[1][1] = O.y; eqn_v[2][1] = O.z;
+    eqn_vt[0][1] = D.x; eqn_vt[1][1] = D.y; eqn_vt[2][1] = D.z;
+    for (int i = 2; i <= order; i++)
+        for (int j = 0; j < 3; j++) { eqn_v[j][i] = eqn_v[j][1] * eqn_v[j][i - 1]; eqn_vt[j][i] = eqn_vt[j][1] * eqn_vt[j][i - 1]; }
+    for (int i = 0; i <= order; i++) eqn[i] = 0.0;
+    const unsigned int binom[5][5] = { { 1, 0, 0, 0, 0 }, { 1, 1, 0, 0, 0 }, { 1, 2, 1, 0, 0 }, { 1, 3, 3, 1, 0 }, { 1, 4, 6, 4, 1 } };
+    int term = 0;
+    for (int i = order; i >= 0; i--) {
+        for (int h = 0; h <= i; h++) tt[0][h] = binom[i][h] * eqn_vt[0][i - h] * eqn_v[0][h];
+        for (int j = order - i; j >= 0; j--) {
+            for (int h = 0; h <= j; h++) tt[1][h] = binom[j][h] * eqn_vt[1][j - h] * eqn_v[1][h];
+            for (int k = order - (i + j); k >= 0; k--) {
+                if (a[term] != 0) {
+                    for (int h = 0; h <= k; h++) tt[2][h] = binom[k][h] * eqn_vt[2][k - h] * eqn_v[2][h];
+                    const int offset = order - (i + j + k);
+                    for (int i1 = 0; i1 <= i; i1++)
+                        for (int j1 = 0; j1 <= j; j1++)
+                            for (int k1 = 0; k1 <= k; k1++) {
+                                double val = a[term];
+                                val *= tt[0][i1];
+                                val *= tt[1][j1];
+                                val *= tt[2][k1];
+                                eqn[offset + i1 + j1 + k1] += val;
+                            }
+                }
+                term++;
+            }
+        }
+    }
+    int lead = 0, deg = order;
+    for (; lead <= order; lead++) { if (eqn[lead] != 0.0) break; else deg--; }
+    if (deg <= 1) return 0;
+    return solve_polynomial(deg, &eqn[lead], depths, sturm ? 1 : 0, PV_POLY_DEPTH_TOLERANCE);
+}
+__device__ inline void poly_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+{
+    h.n = 0;
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const double* a = sc.shape_data + ob.mesh;
+    const int order = (int)ob.aux;
+    const V3 O = inv_trans_point(tr, o);
+    V3 D = inv_trans_direction(tr, d);
+    const double len = length(D);
+    D = D / len;
+    double depths[4];
+    int cnt;
+    if (order == 1) {                                   // intersect_linear :804-850
+        const double t0 = a[0] * O.x + a[1] * O.y + a[2] * O.z;
+        const double t1 = a[0] * D.x + a[1] * D.y + a[2] * D.z;
+        if (fabs(t1) < PV_EPSILON) return;
+        depths[0] = -(a[3] + t0) / t1;
+        cnt = 1;
+    } else if (order == 2) cnt = poly_quadratic(a, O, D, depths);
+    else cnt = poly_general(a, order, (ob.flags & PVGPU_STURM_FLAG) != 0, O, D, depths);
+    for (int i = 0; i < cnt; i++) {
+        if (!(depths[i] > PV_POLY_DEPTH_TOLERANCE)) continue;
+        bool same_root = false;
+        for (int j = 0; j < i; j++) if (depths[i] == depths[j]) { same_root = true; break; }
+        if (same_root) continue;
+        h.depth[h.n] = depths[i] / len;
+        h.ip[h.n] = trans_point(tr, evaluate(O, D, depths[i]));
+        h.aux[h.n] = 0;
+        h.n++;
+    }
+}
+__device__ inline bool poly_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)     // Poly::Inside + inside :590-654, 1131-1178
+{
+    const double* a = sc.shape_data + ob.mesh;
+    const int order = (int)ob.aux;
+    const V3 P = inv_trans_point(sc.xf[ob.transform], p);
+    double xp[5], yp[5], zp[5];
+    xp[0] = 1.0; yp[0] = 1.0; zp[0] = 1.0;
+    xp[1] = P.x; yp[1] = P.y; zp[1] = P.z;
+    for (int i = 2; i <= order; i++) { xp[i] = xp[1] * xp[i - 1]; yp[i] = yp[1] * yp[i - 1]; zp[i] = zp[1] * zp[i - 1]; }
+    double result = 0.0;
+    int term = 0;
+    for (int i = order; i >= 0; i--)
+        for (int j = order - i; j >= 0; j--)
+            for (int k = order - (i + j); k >= 0; k--) {
+                const double c = a[term];
+                if (c != 0.0) result += c * xp[i] * yp[j] * zp[k];
+                term++;
+            }
+    const bool inv = (ob.flags & PVGPU_INVERTED_FLAG) != 0;
+    return (result < PV_POLY_DEPTH_TOLERANCE) ? !inv : inv;
+}
+__device__ inline V3 poly_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip)      // Poly::Normal + normal1 :1035-1129, 1180-1244
+{
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const double* a = sc.shape_data + ob.mesh;
+    const int order = (int)ob.aux;
+    const V3 P = inv_trans_point(tr, ip);
+    const double x = P.x, y = P.y, z = P.z;
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    switch (order) {
+        case 1: rx = a[0]; ry = a[1]; rz = a[2]; break;
+        case 2:
+            rx = 2*a[0]*x+a[1]*y+a[2]*z+a[3];
+            ry = a[1]*x+2*a[4]*y+a[5]*z+a[6];
+            rz = a[2]*x+a[5]*y+2*a[7]*z+a[8];
+            break;
+        case 3: {
+            const double x2 = x * x, y2 = y * y, z2 = z * z;
+            rx = 3*a[0]*x2 + 2*x*(a[1]*y + a[2]*z + a[3]) + a[4]*y2 + y*(a[5]*z + a[6]) + a[7]*z2 + a[8]*z + a[9];
+            ry = a[1]*x2 + x*(2*a[4]*y + a[5]*z + a[6]) + 3*a[10]*y2 + 2*y*(a[11]*z + a[12]) + a[13]*z2 + a[14]*z + a[15];
+            rz = a[2]*x2 + x*(a[5]*y + 2*a[7]*z + a[8]) + a[11]*y2 + y*(2*a[13]*z + a[14]) + 3*a[16]*z2 + 2*a[17]*z + a[18];
+            break;
+        }
+        default: {
+            const double x2 = x * x, y2 = y * y, z2 = z * z, x3 = x * x2, y3 = y * y2, z3 = z * z2;
+            rx = 4*a[ 0]*x3+3*x2*(a[ 1]*y+a[ 2]*z+a[ 3])+
+                 2*x*(a[ 4]*y2+y*(a[ 5]*z+a[ 6])+a[ 7]*z2+a[ 8]*z+a[ 9])+
+                 a[10]*y3+y2*(a[11]*z+a[12])+y*(a[13]*z2+a[14]*z+a[15])+
+                 a[16]*z3+a[17]*z2+a[18]*z+a[19];
+            ry = a[ 1]*x3+x2*(2*a[ 4]*y+a[ 5]*z+a[ 6])+
+                 x*(3*a[10]*y2+2*y*(a[11]*z+a[12])+a[13]*z2+a[14]*z+a[15])+
+                 4*a[20]*y3+3*y2*(a[21]*z+a[22])+2*y*(a[23]*z2+a[24]*z+a[25])+
+                 a[26]*z3+a[27]*z2+a[28]*z+a[29];
+            rz = a[ 2]*x3+x2*(a[ 5]*y+2*a[ 7]*z+a[ 8])+
+                 x*(a[11]*y2+y*(2*a[13]*z+a[14])+3*a[16]*z2+2*a[17]*z+a[18])+
+                 a[21]*y3+y2*(2*a[23]*z+a[24])+y*(3*a[26]*z2+2*a[27]*z+a[28])+
+                 4*a[30]*z3+3*a[31]*z2+2*a[32]*z+a[33];
+        }
+    }
+    V3 r = trans_normal(tr, mk(rx, ry, rz));
+    double val = dot(r, r);
+    if (val > 0.0) { val = 1.0 / sqrt(val); return r * val; }
+    return mk(1.0, 0.0, 0.0);
+}
+
 // ---- cone / cylinder ------------------------------------------------------------------------------
 #define PV_CONE_TOLERANCE 1.0e-9      // Cone_Tolerance  cone.cpp:65
 #define PV_CONE_BASE_HIT 1u           // cone.cpp:71-73

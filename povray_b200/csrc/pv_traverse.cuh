@@ -147,7 +147,8 @@ __device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
 {
     // Sphere, Box and Plane override Intersect_BBox to return true (sphere.cpp:753, box.cpp:1079, plane.cpp:629)
     // ... and so does Triangle (triangle.cpp:1419)
-    return type >= PVGPU_OBJ_QUADRIC && type != PVGPU_OBJ_TRIANGLE;
+    // ... and Poly (polynomial.cpp:1510)
+    return type >= PVGPU_OBJ_QUADRIC && type != PVGPU_OBJ_TRIANGLE && type != PVGPU_OBJ_POLY;
 }
 
 #define PV_MAX_DISTANCE_F 1.0e7f
@@ -230,6 +231,7 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_BLOB:    return blob_inside(sc, ob, p);
         case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
         case PVGPU_OBJ_DISC:    return disc_inside(sc, ob, p);
+        case PVGPU_OBJ_POLY:    return poly_inside(sc, ob, p);
 #endif
     }
     return false;
@@ -247,6 +249,7 @@ __device__ __forceinline__ bool simple_inside(const DScene& sc, const pvgpu_obje
         case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
         case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
         case PVGPU_OBJ_DISC:    return disc_inside(sc, ob, p);
+        case PVGPU_OBJ_POLY:    return poly_inside(sc, ob, p);
 #endif
     }
     return false;
@@ -327,6 +330,7 @@ __device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const
         case PVGPU_OBJ_DISC:    disc_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_TRIANGLE: triangle_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_POLYGON: polygon_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_POLY:    poly_hits(sc, ob, o, d, h); break;
 #endif
         case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
         case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;

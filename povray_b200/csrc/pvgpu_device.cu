@@ -228,7 +228,7 @@ int device_upload(Scene& s, int device)
         bool flat = true;
         for (uint32_t k = 0; k < o.child_count && flat; k++) {
             const pvgpu_object& co = s.objects[s.index_list[o.child_first + k]];
-            flat = ((co.type >= PVGPU_OBJ_SPHERE && co.type <= PVGPU_OBJ_TORUS) || (co.type >= PVGPU_OBJ_CONE && co.type <= PVGPU_OBJ_POLYGON)) && co.clip_count == 0;
+            flat = ((co.type >= PVGPU_OBJ_SPHERE && co.type <= PVGPU_OBJ_TORUS) || (co.type >= PVGPU_OBJ_CONE && co.type <= PVGPU_OBJ_POLY)) && co.clip_count == 0;
         }
         leaf_range[i] = make_uint2(first, ((uint32_t)leaves.size() - first) | (flat ? 0x80000000u : 0u));
     }

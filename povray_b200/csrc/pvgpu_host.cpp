@@ -243,7 +243,7 @@ int validate_scene(Scene& s)
         if (f >= no) return fail(PVGPU_E_INVALID, "frame object index %u out of range", f);
     for (size_t i = 0; i < no; i++) {
         const pvgpu_object& o = s.objects[i];
-        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_POLYGON)
+        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_POLY)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: primitive type %u is outside the hot-path scope", i, o.type);
         if (!range_ok(o.child_first, o.child_count, s.index_list.size()) ||
             !range_ok(o.clip_first, o.clip_count, s.index_list.size()) ||
@@ -270,6 +270,11 @@ int validate_scene(Scene& s)
         if (o.type == PVGPU_OBJ_POLYGON &&
             (o.transform < 0 || o.mesh < 0 || o.aux > (1u << 24) || !range_ok((uint32_t)o.mesh, 2u * o.aux, s.shape_data.size())))
             return fail(PVGPU_E_INVALID, "object %zu: polygon without transform or with points outside the shape-data table", i);
+        if (o.type == PVGPU_OBJ_POLY) {
+            if (o.aux < 1 || o.aux > 4) return fail(PVGPU_E_UNSUPPORTED, "object %zu: poly of order %u (the device solver handles order <= 4)", i, o.aux);
+            if (o.transform < 0 || o.mesh < 0 || !range_ok((uint32_t)o.mesh, (o.aux + 1) * (o.aux + 2) * (o.aux + 3) / 6, s.shape_data.size()))
+                return fail(PVGPU_E_INVALID, "object %zu: poly without transform or with coefficients outside the shape-data table", i);
+        }
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
         if ((o.flags & PVGPU_UV_FLAG))
