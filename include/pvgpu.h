@@ -242,9 +242,10 @@ enum {
     PVGPU_PAT_DENTS    = 20,     /* DentsPattern     pattern.cpp:6307                     */
     PVGPU_PAT_RIPPLES  = 21,     /* RipplesPattern   pattern.cpp:8163                     */
     PVGPU_PAT_WAVES    = 22,     /* WavesPattern     pattern.cpp:8593                     */
-    PVGPU_PAT_QUILTED  = 23      /* QuiltedPattern   pattern.cpp:8067, p[0..1] = Control0, Control1 */
+    PVGPU_PAT_QUILTED  = 23,     /* QuiltedPattern   pattern.cpp:8067, p[0..1] = Control0, Control1 */
+    PVGPU_PAT_AVERAGE  = 24      /* AVERAGE_PATTERN pigment: weighted mean of the blend map's entries (pigment.cpp:566-596) */
 };
-#define PVGPU_PAT_LAST PVGPU_PAT_QUILTED
+#define PVGPU_PAT_LAST PVGPU_PAT_AVERAGE
 /* ContinuousPattern::waveType (pattern.h:108-117) */
 enum { PVGPU_WAVE_RAW = 0, PVGPU_WAVE_RAMP = 1, PVGPU_WAVE_SINE = 2, PVGPU_WAVE_TRIANGLE = 3,
        PVGPU_WAVE_SCALLOP = 4, PVGPU_WAVE_CUBIC = 5, PVGPU_WAVE_POLY = 6 };
@@ -266,7 +267,10 @@ typedef struct pvgpu_blend_entry {
     float colour[5];
 } pvgpu_blend_entry;
 
-/* ColourBlendMap: contiguous entry range + GenericPigmentBlendMap::blendMode/blendGamma. */
+/* ColourBlendMap / PigmentBlendMap: contiguous entry range + GenericPigmentBlendMap::blendMode/blendGamma.
+ * blend_mode & PVGPU_BLEND_PIGMENT_MAP: a pigment_map (BlendMapEntry<PIGMENT*>, pigment.h:113-123) - every entry's colour[0]
+ * holds the pigment table index of its PIGMENT (exact in FP32, indices < 2^24), evaluated at the parent's warped point. */
+#define PVGPU_BLEND_PIGMENT_MAP 0x100
 typedef struct pvgpu_blend_map {
     uint32_t entry_first, entry_count;
     int32_t  blend_mode;

@@ -258,6 +258,39 @@ struct Flattener
         return (int32_t)tnormals.size() - 1;
     }
 
+    // PIGMENT::Blend_Map: a colour_map (ColourBlendMap) or a pigment_map (PigmentBlendMap, entries are pigments of their own)
+    void add_pigment_map(const PIGMENT* pg, pvgpu_pigment& p)
+    {
+        const ColourBlendMap* cm = dynamic_cast<const ColourBlendMap*>(pg->Blend_Map.get());
+        const PigmentBlendMap* pm = dynamic_cast<const PigmentBlendMap*>(pg->Blend_Map.get());
+        const GenericPigmentBlendMap* gm = dynamic_cast<const GenericPigmentBlendMap*>(pg->Blend_Map.get());
+        if (cm == nullptr && pm == nullptr) { unsupported("pigment without a colour / pigment blend map"); return; }
+        if (gm != nullptr && gm->blendMode != 0) unsupported("colour_map blend_mode other than 0");
+        vector<pvgpu_blend_entry> own;
+        if (cm != nullptr)
+            for (const auto& e : cm->Blend_Map_Entries) {
+                pvgpu_blend_entry be;
+                be.value = e.value;
+                for (int k = 0; k < 3; k++) be.colour[k] = e.Vals.colour()[k];
+                be.colour[3] = e.Vals.filter(); be.colour[4] = e.Vals.transm();
+                own.push_back(be);
+            }
+        else
+            for (const auto& e : pm->Blend_Map_Entries) {
+                pvgpu_blend_entry be{};
+                be.value = e.value;
+                be.colour[0] = (float)add_pigment(e.Vals);      // nested pigments first: their own maps' entries stay contiguous
+                own.push_back(be);
+            }
+        pvgpu_blend_map m{};
+        m.entry_first = (uint32_t)entries.size();
+        m.entry_count = (uint32_t)own.size();
+        m.blend_mode = (pm != nullptr) ? PVGPU_BLEND_PIGMENT_MAP : 0;
+        entries.insert(entries.end(), own.begin(), own.end());
+        maps.push_back(m);
+        p.blend_map = (int32_t)maps.size() - 1;
+    }
+
     int32_t add_pigment(const PIGMENT* pg)
     {
         pvgpu_pigment p{};
@@ -268,27 +301,15 @@ struct Flattener
         p.wave_type = PVGPU_WAVE_RAMP; p.frequency = 1.0f; p.exponent = 1.0f;
         const BasicPattern* bp = pg->pattern.get();
         if (pg->Type == PLAIN_PATTERN) p.pattern = PVGPU_PAT_PLAIN;
-        else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern (image_map, average, uv_mapping ...)");
+        else if (pg->Type == AVERAGE_PATTERN) {
+            p.pattern = PVGPU_PAT_AVERAGE;
+            add_warps(pg->pattern->warps, p.warp_first, p.warp_count);
+            add_pigment_map(pg, p);
+        }
+        else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern / average (image_map, uv_mapping ...)");
         else {
             fill_pattern(bp, p, "pigment");
-            const ColourBlendMap* cm = dynamic_cast<const ColourBlendMap*>(pg->Blend_Map.get());
-            if (cm == nullptr) unsupported("pigment without a colour blend map (pigment_map ...)");
-            else {
-                pvgpu_blend_map m{};
-                m.entry_first = (uint32_t)entries.size();
-                m.entry_count = (uint32_t)cm->Blend_Map_Entries.size();
-                m.blend_mode = cm->blendMode;
-                if (cm->blendMode != 0) unsupported("colour_map blend_mode other than 0");
-                for (const auto& e : cm->Blend_Map_Entries) {
-                    pvgpu_blend_entry be;
-                    be.value = e.value;
-                    for (int k = 0; k < 3; k++) be.colour[k] = e.Vals.colour()[k];
-                    be.colour[3] = e.Vals.filter(); be.colour[4] = e.Vals.transm();
-                    entries.push_back(be);
-                }
-                maps.push_back(m);
-                p.blend_map = (int32_t)maps.size() - 1;
-            }
+            add_pigment_map(pg, p);
         }
         pigments.push_back(p);
         return (int32_t)pigments.size() - 1;

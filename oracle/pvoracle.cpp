@@ -1929,10 +1929,28 @@ void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const        
 {
     const pvgpu_pigment& pg = S.pigments[pigment];
     if (pg.pattern == PVGPU_PAT_PLAIN) { for (int k = 0; k < 5; k++) col[k] = pg.colour[k]; return; }
-    const double value = Evaluate_TPat(pg, Warp_EPoint(pg, EPoint));
-    // BlendMap::Search + ColourBlendMap::Compute (pattern.cpp:1068-1112, pigment.cpp:513-530)
+    const V3 TPoint = Warp_EPoint(pg, EPoint);
     const pvgpu_blend_map& m = S.maps[pg.blend_map];
     const pvgpu_blend_entry* e = S.entries.data() + m.entry_first;
+    const bool pmap = (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) != 0;
+    auto entry_colour = [&](uint32_t i, float out[5]) {                    // BlendMapEntry<TransColour> or BlendMapEntry<PIGMENT*>
+        if (pmap) Compute_Pigment(out, (int)e[i].colour[0], TPoint);
+        else for (int k = 0; k < 5; k++) out[k] = e[i].colour[k];
+    };
+    if (pg.pattern == PVGPU_PAT_AVERAGE) {                                                                // pigment.cpp:566-596
+        float Total = 0.0f;
+        for (int k = 0; k < 5; k++) col[k] = 0.0f;
+        for (uint32_t i = 0; i < m.entry_count; i++) {
+            float t[5];
+            entry_colour(i, t);
+            for (int k = 0; k < 5; k++) col[k] += (float)(t[k] * (double)e[i].value);
+            Total += e[i].value;
+        }
+        for (int k = 0; k < 5; k++) col[k] = (float)(col[k] / (double)Total);
+        return;
+    }
+    const double value = Evaluate_TPat(pg, TPoint);
+    // BlendMap::Search + ColourBlendMap / PigmentBlendMap::Compute (pattern.cpp:1068-1112, pigment.cpp:513-564)
     const uint32_t Max_Ent = m.entry_count - 1;
     uint32_t iP, iN; double prevW = 0.0, nextW = 1.0;
     if (value >= e[Max_Ent].value) iP = iN = Max_Ent;
@@ -1942,8 +1960,12 @@ void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const        
         if ((value == e[iN].value) || (iP == iN)) iP = iN;
         else { prevW = (e[iN].value - value) / (e[iN].value - e[iP].value); nextW = 1.0 - prevW; }
     }
-    if (iP == iN) for (int k = 0; k < 5; k++) col[k] = e[iN].colour[k];
-    else for (int k = 0; k < 5; k++) col[k] = (float)(e[iP].colour[k] * prevW) + (float)(e[iN].colour[k] * nextW);
+    entry_colour(iN, col);
+    if (iP != iN) {
+        float t[5];
+        entry_colour(iP, t);
+        for (int k = 0; k < 5; k++) col[k] = (float)(t[k] * prevW) + (float)(col[k] * nextW);
+    }
 }
 
 static double FresnelR(double cosTi, double n)                                                            // trace.cpp:2680-2708

@@ -237,8 +237,64 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
     return value;
 }
 
-// Compute_Pigment (pigment.cpp:395-466) + ColourBlendMap::Compute / BlendMap::Search
-// (pigment.cpp:513-530, pattern.cpp:1068-1112).  col = rgb, filter, transmit.
+// BlendMap::Search (pattern.cpp:1068-1112): previous / next entry and the previous entry's weight (next = 1 - wp)
+__device__ __forceinline__ void blend_search(const pvgpu_blend_entry* e, uint32_t count, double value, uint32_t& ip, uint32_t& in, double& wp)
+{
+    const uint32_t last = count - 1;
+    ip = in = last;
+    wp = 0.0;
+    if (!(value >= (double)e[last].value)) {
+        ip = in = 0;
+        while (value > (double)e[in].value) { ip = in; in++; }
+        if ((value == (double)e[in].value) || (ip == in)) { ip = in; }
+        else wp = ((double)e[in].value - value) / (double)__fsub_rn(e[in].value, e[ip].value);     // SNGL - SNGL rounds to FP32 (pattern.cpp:1105)
+    }
+}
+
+#if PV_HEAVY
+// pigment_map / average pigments: Compute_Pigment recursing through PigmentBlendMap::Compute / ComputeAverage
+// (pigment.cpp:395-466, 546-596); nesting depth is bounded at validation.
+static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
+{
+    const pvgpu_pigment& pg = sc.pigments[pig_index];
+    if (pg.pattern == PVGPU_PAT_PLAIN) {
+        for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
+        return;
+    }
+    const V3 tp = warp_epoint(sc, pg, ep);
+    const pvgpu_blend_map& m = sc.maps[pg.blend_map];
+    const pvgpu_blend_entry* e = sc.entries + m.entry_first;
+    const bool pmap = (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) != 0;
+    if (pg.pattern == PVGPU_PAT_AVERAGE) {          // ColourBlendMap / PigmentBlendMap::ComputeAverage
+        float total = 0.0f;
+        for (int k = 0; k < 5; k++) col[k] = 0.0f;
+        for (uint32_t i = 0; i < m.entry_count; i++) {
+            float t[5];
+            if (pmap) compute_pigment_rec(sc, (int32_t)e[i].colour[0], tp, t);
+            else for (int k = 0; k < 5; k++) t[k] = e[i].colour[k];
+            for (int k = 0; k < 5; k++) col[k] += (float)((double)t[k] * (double)e[i].value);
+            total += e[i].value;
+        }
+        for (int k = 0; k < 5; k++) col[k] = (float)((double)col[k] / (double)total);
+        return;
+    }
+    const double value = evaluate_pattern(sc, pg, tp);
+    uint32_t ip, in;
+    double wp;
+    blend_search(e, m.entry_count, value, ip, in, wp);
+    if (pmap) compute_pigment_rec(sc, (int32_t)e[in].colour[0], tp, col);
+    else for (int k = 0; k < 5; k++) col[k] = e[in].colour[k];
+    if (ip != in) {
+        float t[5];
+        if (pmap) compute_pigment_rec(sc, (int32_t)e[ip].colour[0], tp, t);
+        else for (int k = 0; k < 5; k++) t[k] = e[ip].colour[k];
+        const double wn = 1.0 - wp;
+        for (int k = 0; k < 5; k++) col[k] = (float)((double)t[k] * wp) + (float)((double)col[k] * wn);
+    }
+}
+#endif
+
+// Compute_Pigment (pigment.cpp:395-466) + ColourBlendMap::Compute (pigment.cpp:513-530).  col = rgb, filter, transmit.
 __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
 {
     const pvgpu_pigment& pg = sc.pigments[pig_index];
@@ -247,27 +303,22 @@ __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, cons
         for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
         return;
     }
+    const pvgpu_blend_map& m = sc.maps[pg.blend_map];
+#if PV_HEAVY
+    if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) { compute_pigment_rec(sc, pig_index, ep, col); return; }
+#endif
     const V3 tp = warp_epoint(sc, pg, ep);
     const double value = evaluate_pattern(sc, pg, tp);
-    const pvgpu_blend_map& m = sc.maps[pg.blend_map];
     const pvgpu_blend_entry* e = sc.entries + m.entry_first;
-    const uint32_t last = m.entry_count - 1;
-    uint32_t ip = last, in = last;
-    double wp = 0.0, wn = 1.0;
-    if (!(value >= (double)e[last].value)) {
-        ip = in = 0;
-        while (value > (double)e[in].value) { ip = in; in++; }
-        if ((value == (double)e[in].value) || (ip == in)) { ip = in; }
-        else {
-            wp = ((double)e[in].value - value) / (double)__fsub_rn(e[in].value, e[ip].value);     // SNGL - SNGL rounds to FP32 (pattern.cpp:1105)
-            wn = 1.0 - wp;
-        }
-    }
+    uint32_t ip, in;
+    double wp;
+    blend_search(e, m.entry_count, value, ip, in, wp);
     if (ip == in) {
         #pragma unroll
         for (int k = 0; k < 5; k++) col[k] = e[in].colour[k];
     } else {
         // GenericPigmentBlendMap::Blend, default blend mode (pigment.cpp:468-511): colour1*w1 + colour2*w2
+        const double wn = 1.0 - wp;
         #pragma unroll
         for (int k = 0; k < 5; k++) col[k] = (float)(e[ip].colour[k] * wp) + (float)(e[in].colour[k] * wn);
     }

@@ -300,6 +300,8 @@ int device_upload(Scene& s, int device)
             o.clip_count || o.bound_count) d->lean = false;
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->lean = false;
     if (!s.fogs.empty() || !s.sky_spheres.empty()) d->lean = false;
+    for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->lean = false;
+    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE) d->lean = false;
     v.has_area_lights = 0; v.area_grid_max = 0;
     if (s.globals.quality_flags & PVGPU_Q_AREA_LIGHTS)
         for (const pvgpu_light& l : s.lights)

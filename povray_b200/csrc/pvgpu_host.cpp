@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <limits>
 
 namespace pvgpu {
@@ -364,6 +365,24 @@ int validate_scene(Scene& s)
         if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
     }
+    {   // pigment_map nesting: bounded depth, no cycles
+        std::vector<int> depth(s.pigments.size(), -1);
+        std::function<int(size_t, int)> walk = [&](size_t pi, int level) -> int {
+            if (level > 6) return -1;
+            const pvgpu_pigment& p = s.pigments[pi];
+            if (p.blend_map < 0 || !(s.blend_maps[p.blend_map].blend_mode & PVGPU_BLEND_PIGMENT_MAP)) return 0;
+            const pvgpu_blend_map& m = s.blend_maps[p.blend_map];
+            int worst = 0;
+            for (uint32_t k = 0; k < m.entry_count; k++) {
+                int dch = walk((size_t)s.blend_entries[m.entry_first + k].colour[0], level + 1);
+                if (dch < 0) return -1;
+                worst = std::max(worst, dch + 1);
+            }
+            return worst;
+        };
+        for (size_t i = 0; i < s.pigments.size(); i++)
+            if (walk(i, 0) < 0) return fail(PVGPU_E_UNSUPPORTED, "pigment %zu: pigment_map nested deeper than 6 levels", i);
+    }
     if (s.sky_spheres.size() > 1) return fail(PVGPU_E_INVALID, "more than one sky_sphere");
     for (const pvgpu_sky_sphere& k : s.sky_spheres) {
         if (!range_ok(k.pigment_first, k.pigment_count, s.index_list.size()) || k.transform >= (int32_t)s.transforms.size())
@@ -402,6 +421,14 @@ int validate_scene(Scene& s)
         const pvgpu_blend_map& m = s.blend_maps[i];
         if (m.entry_count == 0 || !range_ok(m.entry_first, m.entry_count, s.blend_entries.size()))
             return fail(PVGPU_E_INVALID, "blend map %zu: bad entry range", i);
+        if ((m.blend_mode & ~PVGPU_BLEND_PIGMENT_MAP) != 0)
+            return fail(PVGPU_E_UNSUPPORTED, "blend map %zu: blend_mode %d is outside the hot-path scope", i, m.blend_mode & ~PVGPU_BLEND_PIGMENT_MAP);
+        if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP)
+            for (uint32_t k = 0; k < m.entry_count; k++) {
+                const float pi = s.blend_entries[m.entry_first + k].colour[0];
+                if (!(pi >= 0.0f) || pi >= (float)s.pigments.size() || pi != std::floor(pi))
+                    return fail(PVGPU_E_INVALID, "blend map %zu: entry %u is not a pigment index", i, k);
+            }
     }
     for (size_t i = 0; i < s.warps.size(); i++) {
         const pvgpu_warp& w = s.warps[i];
