@@ -253,9 +253,16 @@ __device__ __forceinline__ void blend_search(const pvgpu_blend_entry* e, uint32_
 
 #if PV_HEAVY
 // pigment_map / average pigments: Compute_Pigment recursing through PigmentBlendMap::Compute / ComputeAverage
-// (pigment.cpp:395-466, 546-596); nesting depth is bounded at validation.
+// (pigment.cpp:395-466, 546-596).  The recursion is unrolled over LEVEL (maps nest at most 6 deep: validated on the host), so the
+// call graph stays acyclic and ptxas sizes the stack statically.
+#define PV_PIGMENT_MAP_LEVELS 6
+template <int LEVEL>
 static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
 {
+    auto child = [&](int32_t idx, const V3& p, float out[5]) {
+        if constexpr (LEVEL > 0) compute_pigment_rec<LEVEL - 1>(sc, idx, p, out);
+        else { for (int k = 0; k < 5; k++) out[k] = sc.pigments[idx].colour[k]; }     // unreachable: nesting depth is validated
+    };
     const pvgpu_pigment& pg = sc.pigments[pig_index];
     if (pg.pattern == PVGPU_PAT_PLAIN) {
         for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
@@ -270,7 +277,7 @@ static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_
         for (int k = 0; k < 5; k++) col[k] = 0.0f;
         for (uint32_t i = 0; i < m.entry_count; i++) {
             float t[5];
-            if (pmap) compute_pigment_rec(sc, (int32_t)e[i].colour[0], tp, t);
+            if (pmap) child((int32_t)e[i].colour[0], tp, t);
             else for (int k = 0; k < 5; k++) t[k] = e[i].colour[k];
             for (int k = 0; k < 5; k++) col[k] += (float)((double)t[k] * (double)e[i].value);
             total += e[i].value;
@@ -282,11 +289,11 @@ static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_
     uint32_t ip, in;
     double wp;
     blend_search(e, m.entry_count, value, ip, in, wp);
-    if (pmap) compute_pigment_rec(sc, (int32_t)e[in].colour[0], tp, col);
+    if (pmap) child((int32_t)e[in].colour[0], tp, col);
     else for (int k = 0; k < 5; k++) col[k] = e[in].colour[k];
     if (ip != in) {
         float t[5];
-        if (pmap) compute_pigment_rec(sc, (int32_t)e[ip].colour[0], tp, t);
+        if (pmap) child((int32_t)e[ip].colour[0], tp, t);
         else for (int k = 0; k < 5; k++) t[k] = e[ip].colour[k];
         const double wn = 1.0 - wp;
         for (int k = 0; k < 5; k++) col[k] = (float)((double)t[k] * wp) + (float)((double)col[k] * wn);
@@ -305,7 +312,7 @@ __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, cons
     }
     const pvgpu_blend_map& m = sc.maps[pg.blend_map];
 #if PV_HEAVY
-    if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) { compute_pigment_rec(sc, pig_index, ep, col); return; }
+    if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) { compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col); return; }
 #endif
     const V3 tp = warp_epoint(sc, pg, ep);
     const double value = evaluate_pattern(sc, pg, tp);

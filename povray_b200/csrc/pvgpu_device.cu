@@ -335,11 +335,7 @@ int device_upload(Scene& s, int device)
         return fail(PVGPU_E_CUDA, "cudaMalloc of counters failed");
     }
     // the deepest Inside()/sturm paths keep a few small arrays per thread; blobs add their per-ray interval lists
-    // ... and pigment_map / average pigments recurse (compute_pigment_rec: ~1 KB per level, <= 7 levels below k_shade's 2.3 KB frame)
-    bool nested_pigments = false;
-    for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) nested_pigments = true;
-    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE) nested_pigments = true;
-    cudaDeviceSetLimit(cudaLimitStackSize, (s.blobs.empty() && !nested_pigments) ? 4096 : 12288);
+    cudaDeviceSetLimit(cudaLimitStackSize, s.blobs.empty() ? 4096 : 12288);
     d->camera_dirty = true;
     return PVGPU_OK;
 }

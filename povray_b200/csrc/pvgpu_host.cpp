@@ -368,9 +368,9 @@ int validate_scene(Scene& s)
     {   // pigment_map nesting: bounded depth, no cycles
         std::vector<int> depth(s.pigments.size(), -1);
         std::function<int(size_t, int)> walk = [&](size_t pi, int level) -> int {
-            if (level > 6) return -1;
             const pvgpu_pigment& p = s.pigments[pi];
             if (p.blend_map < 0 || !(s.blend_maps[p.blend_map].blend_mode & PVGPU_BLEND_PIGMENT_MAP)) return 0;
+            if (level >= 6) return -1;          // PV_PIGMENT_MAP_LEVELS of the device code
             const pvgpu_blend_map& m = s.blend_maps[p.blend_map];
             int worst = 0;
             for (uint32_t k = 0; k < m.entry_count; k++) {

@@ -22,5 +22,5 @@ sphere { <3.5, 1.2, 0.5>, 1.2
   pigment { bozo turbulence 0.3 pigment_map { [0.3 wrinkles color_map { [0 rgb <0.9, 0.5, 0.1>] [1 rgb <0.3, 0.1, 0>] } scale 0.2]
                                               [0.7 gradient y pigment_map { [0 rgb <0.1, 0.6, 0.9>] [1 hexagon rgb <1, 1, 1>, rgb <0.5, 0.5, 0.5>, rgb <0.1, 0.1, 0.1> scale 0.2 rotate x*90] } scale 0.8] } scale 0.7 }
   finish { ambient 0.1 diffuse 0.7 specular 0.3 } }
-box { <-1.2, 0, -3.8>, <1.2, 0.9, -2.6>
+box { <-1.2, 0.05, -3.8>, <1.2, 0.95, -2.6>
   pigment { average pigment_map { [1 rgbf <1, 0.5, 0.2, 0.3>] [3 rgbf <0.2, 0.5, 1, 0.6>] } } finish { ambient 0.1 diffuse 0.6 } interior { ior 1.2 } }
