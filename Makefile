@@ -11,8 +11,10 @@ CU        := $(wildcard $(CSRC)/*.cu)
 CPP       := $(wildcard $(CSRC)/*.cpp)
 # the hot kernels are compiled a second time with -DPV_LEAN (see PV_VARIANT in pv_common.cuh)
 LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
+# ... and the shading-side kernels a third time with -DPV_FULL (normal perturbation, pigment maps, sky_sphere, fog, area lights)
+FULL_SRC  := k_shade k_shadow_filter
 OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
-             $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC))
+             $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC))
 HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) include/pvgpu.h
 
 .PHONY: all oracle clean
@@ -25,6 +27,10 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
 $(OBJDIR)/%_lean.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -DPV_LEAN -c $< -o $@
+
+$(OBJDIR)/%_full.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -DPV_FULL -c $< -o $@
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDR)
 	@mkdir -p $(OBJDIR)

@@ -9,23 +9,39 @@
 
 namespace pvgpu {
 
+#if PV_FULL_MATERIALS
+// A ray that travelled through fog (trace.cpp:207-216): colour' = sum_col + sum_att * colour, so the fog's own light is added
+// here and everything the ray still collects is weighted by sum_att.  Out of line, so that scenes without fog keep the ray record
+// a read-only copy the compiler may re-read instead of spilling.
+static __device__ __noinline__ void shade_fogged(const DScene& sc, const PRay& ray0, uint32_t i, const HitRec& h, WaveCtx& ctx)
+{
+    PRay ray = ray0;
+    float sum_att[3], sum_col[3];
+    compute_fog(sc, ld3(ray.o), ld3(ray.d), (h.obj == PV_HIT_MISS) ? PV_BOUND_HUGE : h.depth, sum_att, sum_col);
+    accum_add(ctx.accum, ray.sample, ray.w[0] * sum_col[0], ray.w[1] * sum_col[1], ray.w[2] * sum_col[2], 0.0f);
+    ray.w[0] *= sum_att[0]; ray.w[1] *= sum_att[1]; ray.w[2] *= sum_att[2];
+    ray.wt *= greyscale(sum_att);
+    if (h.obj == PV_HIT_MISS) {
+        float col[3], transm;
+        compute_sky(sc, ray, col, transm);
+        accum_add(ctx.accum, ray.sample, ray.w[0] * col[0], ray.w[1] * col[1], ray.w[2] * col[2], ray.wt * transm);
+        return;
+    }
+    Hit hit;
+    hit.depth = h.depth; hit.ip = mk(h.ip[0], h.ip[1], h.ip[2]); hit.obj = h.obj; hit.aux = h.aux; hit.csg = h.csg;
+    shade_hit(sc, ray, i, hit, ctx);
+}
+#endif
+
 __global__ void __launch_bounds__(128, PV_SHADE_MIN_BLOCKS)
 PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits, uint32_t n, WaveCtx ctx)
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const HitRec h = hits[i];
         if (h.obj == PV_HIT_STOPPED) continue;
-        PRay ray = cur[i];
-#if PV_HEAVY
-        // fog between the ray's origin and its hit (trace.cpp:207-216): colour' = sum_col + sum_att * colour, so the fog's own
-        // light is added here and everything this ray still collects is weighted by sum_att
-        if (sc.n_fogs && (sc.g.quality_flags & PVGPU_Q_MEDIA) && ray_is_hollow(sc, ray)) {
-            float sum_att[3], sum_col[3];
-            compute_fog(sc, ld3(ray.o), ld3(ray.d), (h.obj == PV_HIT_MISS) ? PV_BOUND_HUGE : h.depth, sum_att, sum_col);
-            accum_add(ctx.accum, ray.sample, ray.w[0] * sum_col[0], ray.w[1] * sum_col[1], ray.w[2] * sum_col[2], 0.0f);
-            ray.w[0] *= sum_att[0]; ray.w[1] *= sum_att[1]; ray.w[2] *= sum_att[2];
-            ray.wt *= greyscale(sum_att);
-        }
+        const PRay ray = cur[i];
+#if PV_FULL_MATERIALS
+        if (sc.n_fogs && (sc.g.quality_flags & PVGPU_Q_MEDIA) && ray_is_hollow(sc, ray)) { shade_fogged(sc, ray, i, h, ctx); continue; }
 #endif
         if (h.obj == PV_HIT_MISS) {
             float col[3], transm;

@@ -3,6 +3,7 @@
 // shadow rays (cached in `lightGrid`), the region is split in four while it is coarser than Adaptive_Level or its corner colours
 // differ by more than 0.1, and the four results are averaged.  Here every lane runs that recursion as an explicit state machine and
 // the warp meets at each sample, because the traversal underneath (trace_shadow) is warp-synchronous.
+#define PV_FULL 1          // area lights imply the full-material variant (see PV_FULL_MATERIALS in pv_common.cuh)
 #include "pv_shadow.cuh"
 
 namespace pvgpu {

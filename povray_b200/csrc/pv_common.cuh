@@ -30,11 +30,21 @@ namespace pvgpu {
 // Every hot kernel is compiled twice: the full variant knows all primitives, the lean variant (-DPV_LEAN) only spheres,
 // boxes, planes and meshes - scenes made of those (BASELINE configs 1 and 2) then run kernels that carry no quartic
 // solver, CSG, blob or cone code (fewer registers spilled, smaller local frames).  The host picks per scene.
+// The shading-side kernels (k_shade, k_shadow_filter) exist a third time (-DPV_FULL): the material features few scenes use -
+// normal perturbation, pigment_map / average pigments, sky_sphere, fog, area lights - are compiled only there.  Their mere
+// presence costs the other scenes dearly (config 3: 171 -> 305 ms per frame with them in the one heavy variant: larger local
+// frames and code in the kernels that write the next wave's queues).
 #ifdef PV_LEAN
 #define PV_HEAVY 0
+#define PV_FULL_MATERIALS 0
 #define PV_VARIANT(name) name##_lean
+#elif defined(PV_FULL)
+#define PV_HEAVY 1
+#define PV_FULL_MATERIALS 1
+#define PV_VARIANT(name) name##_full
 #else
 #define PV_HEAVY 1
+#define PV_FULL_MATERIALS 0
 #define PV_VARIANT(name) name
 #endif
 
@@ -129,6 +139,7 @@ struct DScene {
     const double*            wave_freqs;    // TraceThreadData::waveFrequencies
     const pvgpu_fog*         fogs;          // SceneData::fog in list order
     uint32_t                 n_fogs, has_sky;
+    uint32_t                 has_tnormals;      // some texture layer has a normal{} (per-layer normals are kept only then)
     uint32_t                 has_area_lights;   // some light is an area light and QualityFlags::areaLights is on
     uint32_t                 area_grid_max;     // largest Area_Size1 * Area_Size2
     pvgpu_sky_sphere         sky;           // SceneData::skysphere (has_sky)

@@ -61,6 +61,9 @@ void launch_shadow_opaque_lean(const DScene& sc, const SRay* rays, uint32_t n_ma
 void launch_shadow_filter_lean(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
 uint32_t area_threads();
 void launch_shadow_area(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st);
+// full-material variants (normal perturbation, pigment maps, sky_sphere, fog, area lights; -DPV_FULL)
+void launch_shade_full(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st);
+void launch_shadow_filter_full(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st);
 void launch_probe_results(const HitRec* hits, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux, cudaStream_t st);
 void launch_aa1_frame_coords(const AALayout& L, double2* coords, cudaStream_t st);

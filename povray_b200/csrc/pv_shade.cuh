@@ -60,7 +60,13 @@ __device__ inline V3 warp_epoint(const DScene& sc, const pvgpu_pigment& pg, cons
 }
 
 // Pattern value for a warped point: Evaluate_TPat -> <Pattern>::Evaluate.
+// (out of line in the heavy variants: the pattern switch is large and only patterned pigments / normals come here; the lean
+//  variant serves scenes whose pigments use the first pattern set only - device_upload - and keeps it inline)
+#if PV_HEAVY
+static __device__ __noinline__ double evaluate_pattern(const DScene& sc, const pvgpu_pigment& pg, const V3& p)
+#else
 __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment& pg, const V3& p)
+#endif
 {
     const int gen = pg.noise_generator ? pg.noise_generator : sc.g.noise_generator;   // BasicPattern::GetNoiseGen
     // first warp is a ClassicTurbulence? (GetTurb, pattern.cpp:1135)
@@ -125,6 +131,7 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
             value = noise;
             break;
         }
+#if PV_HEAVY
         case PVGPU_PAT_BRICK: {     // BrickPattern::Evaluate (pattern.cpp:5495-5608): discrete
             const double mortar = pg.p[3], fudgit = PV_EPSILON + mortar;
             const double x = p.x + fudgit, y = p.y + fudgit, z = p.z + fudgit;
@@ -218,6 +225,7 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
             value = (fabs(v.x) + fabs(v.y) + fabs(v.z)) / 3.0;
             break;
         }
+#endif
         default:
             value = 0.0;
             break;
@@ -251,7 +259,7 @@ __device__ __forceinline__ void blend_search(const pvgpu_blend_entry* e, uint32_
     }
 }
 
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
 // pigment_map / average pigments: Compute_Pigment recursing through PigmentBlendMap::Compute / ComputeAverage
 // (pigment.cpp:395-466, 546-596).  The recursion is unrolled over LEVEL (maps nest at most 6 deep: validated on the host), so the
 // call graph stays acyclic and ptxas sizes the stack statically.
@@ -311,7 +319,7 @@ __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, cons
         return;
     }
     const pvgpu_blend_map& m = sc.maps[pg.blend_map];
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
     if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) { compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col); return; }
 #endif
     const V3 tp = warp_epoint(sc, pg, ep);
@@ -332,7 +340,7 @@ __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, cons
 }
 
 // ---- normal perturbation: Perturb_Normal (normal.cpp:784-927) ---------------------------------------
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
 // Warp_Normal / UnWarp_Normal (warp.cpp:563-640): only transform warps act on normals
 __device__ inline V3 warp_normal(const DScene& sc, const pvgpu_pigment& c, V3 n, bool dont_scale)
 {
@@ -372,7 +380,7 @@ __device__ inline double do_slope_map(const DScene& sc, const pvgpu_tnormal& tn,
     rv += t1 * e[ip].slope + e[ip].height;
     return rv;
 }
-__device__ inline V3 perturb_normal(const DScene& sc, int32_t tn_index, V3 n, const V3& epoint)
+static __device__ __noinline__ V3 perturb_normal(const DScene& sc, int32_t tn_index, V3 n, const V3& epoint)
 {
     const pvgpu_tnormal& tn = sc.tnormals[tn_index];
     const pvgpu_pigment& c = sc.pigments[tn.pattern];
@@ -699,7 +707,7 @@ __device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[
         if (alpha_bg) { col[0] = col[1] = col[2] = 0.0f; transm = 1.0f; return; }
         col[0] = bg[0]; col[1] = bg[1]; col[2] = bg[2];
         transm = bg[4];
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
         if (sc.has_sky) {
             float c[3] = { 0.0f, 0.0f, 0.0f }, fc[3] = { 1.0f, 1.0f, 1.0f }, ff = 1.0f, ft = 1.0f;
             double trans = 1.0;
@@ -726,7 +734,7 @@ __device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[
         return;
     }
     float c[3] = { 0.0f, 0.0f, 0.0f }, fil[3] = { 1.0f, 1.0f, 1.0f };
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
     if (sc.has_sky) {
         V3 p = ld3(ray.d);
         if (sc.sky.transform >= 0) p = inv_trans_point(sc.xf[sc.sky.transform], p);
@@ -753,7 +761,7 @@ __device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[
     transm = fminf(1.0f, fabsf(greyscale(fil)));
 }
 
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
 // Ray::IsHollowRay (ray.cpp:59-115): every interior the ray is inside of is hollow
 __device__ __forceinline__ bool ray_is_hollow(const DScene& sc, const PRay& r)
 {
@@ -762,7 +770,7 @@ __device__ __forceinline__ bool ray_is_hollow(const DScene& sc, const PRay& r)
 }
 // Trace::ComputeFog + ComputeConstantFogDepth + ComputeGroundFogDepth (trace.cpp:2892-3044) for a non-shadow ray:
 // the caller's colour becomes sum_col + sum_att * colour, its transmittance is scaled by greyscale(sum_att).
-__device__ inline void compute_fog(const DScene& sc, const V3& o, const V3& d, double depth, float sum_att[3], float sum_col[3])
+static __device__ __noinline__ void compute_fog(const DScene& sc, const V3& o, const V3& d, double depth, float sum_att[3], float sum_col[3])
 {
     sum_att[0] = sum_att[1] = sum_att[2] = 1.0f;
     sum_col[0] = sum_col[1] = sum_col[2] = 0.0f;
@@ -863,7 +871,7 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
 
     struct Layer {
         float col[3]; float fil[3]; float refl[3]; double att; double rweight; int32_t finish;
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
         V3 n;                 // layNormal of the layer (trace.cpp:812-828); the lean variant serves scenes without normal{}
 #endif
     };
@@ -873,8 +881,9 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
     double trans = 1.0;
     float amb[3] = { 0.0f, 0.0f, 0.0f };
     V3 top_normal = rawnormal;
-#if PV_HEAVY
-    #define LAYER_NORMAL(L) ((L).n)
+#if PV_FULL_MATERIALS
+    const bool has_tn = (sc.has_tnormals != 0u) && (sc.g.quality_flags & PVGPU_Q_NORMALS);
+    #define LAYER_NORMAL(L) (has_tn ? (L).n : rawnormal)
 #else
     #define LAYER_NORMAL(L) rawnormal
 #endif
@@ -883,13 +892,15 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
         const pvgpu_texture& tx = sc.textures[li];
         const pvgpu_finish& fn = sc.finishes[tx.finish];
         Layer& L = layers[nlayers];
-#if PV_HEAVY
-        L.n = rawnormal;
-        if ((sc.g.quality_flags & PVGPU_Q_NORMALS) && tx.tnormal >= 0) {          // trace.cpp:814-828
-            L.n = perturb_normal(sc, tx.tnormal, L.n, ipoint);
-            if (sc.tnormals[tx.tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) L.n = normalized(L.n);
+#if PV_FULL_MATERIALS
+        if (has_tn) {
+            L.n = rawnormal;
+            if (tx.tnormal >= 0) {                                                    // trace.cpp:814-828
+                L.n = perturb_normal(sc, tx.tnormal, L.n, ipoint);
+                if (sc.tnormals[tx.tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) L.n = normalized(L.n);
+            }
+            if (nlayers == 0) top_normal = L.n;
         }
-        if (nlayers == 0) top_normal = L.n;
 #endif
         const V3 lay_normal = LAYER_NORMAL(L);
         const double cos_inc = -dot(dir, lay_normal);
@@ -1018,7 +1029,7 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
             if (a[0] == 0.0f && a[1] == 0.0f && a[2] == 0.0f) continue;
             const bool shadowed = (sc.g.quality_flags & PVGPU_Q_SHADOWS) && (Lt.type != PVGPU_LIGHT_FILL);
             if (!shadowed) { accum_add(ctx.accum, ray.sample, a[0], a[1], a[2], 0.0f); continue; }
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
             // area light: k_shadow_area averages the light colour over the sampled grid and multiplies it in (trace.cpp:2078-2271)
             if ((Lt.flags & PVGPU_LIGHT_AREA) && (sc.g.quality_flags & PVGPU_Q_AREA_LIGHTS)) { a[0] = ray.w[0] * K[0]; a[1] = ray.w[1] * K[1]; a[2] = ray.w[2] * K[2]; }
 #endif

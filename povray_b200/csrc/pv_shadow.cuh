@@ -26,7 +26,7 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
         for (int k = 0; k < 3; k++) tmp[k] *= (lc[k] * lc[3] + lc[4]);
         if (in && in->caustics != 0.0f) {
             V3 layer_normal = rawnormal;
-#if PV_HEAVY
+#if PV_FULL_MATERIALS
             if ((sc.g.quality_flags & PVGPU_Q_NORMALS) && sc.textures[li].tnormal >= 0) {       // trace.cpp:1208-1227
                 layer_normal = perturb_normal(sc, sc.textures[li].tnormal, layer_normal, hit.ip);
                 if (sc.tnormals[sc.textures[li].tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) layer_normal = normalized(layer_normal);

@@ -378,7 +378,7 @@ __device__ inline bool in_polygon(int number, const double* pts, double tx, doub
     return inside_flag;
 }
 // Polygon::Intersect / All_Intersections (polygon.cpp:131-260)
-__device__ inline void polygon_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+static __device__ __noinline__ void polygon_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
 {
     h.n = 0;
     if (ob.flags & PVGPU_DEGENERATE_FLAG) return;
@@ -462,7 +462,7 @@ __device__ inline int poly_general(const double* a, int order, bool sturm, const
     if (deg <= 1) return 0;
     return solve_polynomial(deg, &eqn[lead], depths, sturm ? 1 : 0, PV_POLY_DEPTH_TOLERANCE);
 }
-__device__ inline void poly_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+static __device__ __noinline__ void poly_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
 {
     h.n = 0;
     const pvgpu_transform& tr = sc.xf[ob.transform];
@@ -493,7 +493,7 @@ __device__ inline void poly_hits(const DScene& sc, const pvgpu_object& ob, const
         h.n++;
     }
 }
-__device__ inline bool poly_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)     // Poly::Inside + inside :590-654, 1131-1178
+static __device__ __noinline__ bool poly_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)     // Poly::Inside + inside :590-654, 1131-1178
 {
     const double* a = sc.shape_data + ob.mesh;
     const int order = (int)ob.aux;
@@ -514,7 +514,7 @@ __device__ inline bool poly_inside(const DScene& sc, const pvgpu_object& ob, con
     const bool inv = (ob.flags & PVGPU_INVERTED_FLAG) != 0;
     return (result < PV_POLY_DEPTH_TOLERANCE) ? !inv : inv;
 }
-__device__ inline V3 poly_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip)      // Poly::Normal + normal1 :1035-1129, 1180-1244
+static __device__ __noinline__ V3 poly_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip)      // Poly::Normal + normal1 :1035-1129, 1180-1244
 {
     const pvgpu_transform& tr = sc.xf[ob.transform];
     const double* a = sc.shape_data + ob.mesh;

@@ -294,7 +294,8 @@ __device__ inline int polysolve(int order, const double* coeffs, double* roots)
 }
 
 // Solve_Polynomial for n <= 4.
-__device__ inline int solve_polynomial(int n, const double* c0, double* r, int sturm, double epsilon)
+// (out of line: torus, poly and blob all come here; three inlined copies were 40 % of the heavy kernels' code)
+static __device__ __noinline__ int solve_polynomial(int n, const double* c0, double* r, int sturm, double epsilon)
 {
     int roots = 0, i = 0;
     while ((i < n) && (fabs(c0[i]) < PV_SMALL_ENOUGH)) i++;

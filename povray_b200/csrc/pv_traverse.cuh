@@ -218,7 +218,11 @@ __device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, u
 // ---- Inside --------------------------------------------------------------------------------------
 __device__ bool mesh_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, TStack stack, int sp0);
 
+#if PV_HEAVY
+static __device__ __noinline__ bool prim_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, TStack stack, int sp0)
+#else
 __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, const V3& p, TStack stack, int sp0)
+#endif
 {
     switch (ob.type) {
         case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
@@ -319,7 +323,13 @@ __device__ __forceinline__ void consider(HitAcc& acc, double depth, const V3& ip
     }
 }
 
+// (one out-of-line copy in the full variant: the switch carries every primitive incl. the quartic solver, and it is reached from
+//  object_find and from both CSG paths - inlined copies made the heavy kernels instruction-fetch bound)
+#if PV_HEAVY
+static __device__ __noinline__ void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr)
+#else
 __device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr)
+#endif
 {
     switch (ob.type) {
 #if PV_HEAVY

@@ -43,6 +43,7 @@ struct DeviceScene {
     uint16_t* d_cam_int = nullptr;       // container-state result
     unsigned long long kernel_launches = 0;
     bool lean = false;                   // only spheres, boxes, planes, meshes and no clipped_by / bounded_by: lean kernel variants
+    bool full = false;                   // normal{}, pigment_map / average, sky_sphere, fog or area lights: full-material shading variants
     bool camera_dirty = true;
     float* area_grid = nullptr;          // lightGrid scratch of k_shadow_area (3 floats x area_grid_max per resident thread)
     // host-side staging of pvgpu_render (pinned) and its device frame
@@ -187,6 +188,15 @@ int device_upload(Scene& s, int device)
         return fail(PVGPU_E_NO_DEVICE, "no CUDA device available (pvgpu has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(PVGPU_E_INVALID, "device %d out of range (have %d)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
+    {   // The traversal / shading kernels have different (large) local-memory frames.  By default the driver re-sizes the device's
+        // local-memory pool whenever the next kernel needs more than the last one left behind - a device-wide synchronising
+        // re-allocation on nearly every launch of the wave loop (measured: 170 -> 300 ms per frame on config 3).  Keep the pool
+        // at its high-water mark instead.
+        unsigned int flags = 0;
+        if (cudaGetDeviceFlags(&flags) == cudaSuccess && !(flags & cudaDeviceLmemResizeToMax)) {
+            if (cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();
+        }
+    }
     s.device = device;
     // the FP32 stand-in for EPSILON in the slab test must be the smallest float >= 1e-10 (pv_traverse.cuh)
     if (!((double)1.0e-10f >= 1.0e-10 && (double)std::nextafterf(1.0e-10f, 0.0f) < 1.0e-10))
@@ -299,9 +309,12 @@ int device_upload(Scene& s, int device)
         if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH) ||
             o.clip_count || o.bound_count) d->lean = false;
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->lean = false;
+    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern > PVGPU_PAT_AGATE || pg.pattern == PVGPU_PAT_BRICK || pg.pattern == PVGPU_PAT_HEXAGON) d->lean = false;
     if (!s.fogs.empty() || !s.sky_spheres.empty()) d->lean = false;
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->lean = false;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE) d->lean = false;
+    v.has_tnormals = 0;
+    for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) v.has_tnormals = 1;
     v.has_area_lights = 0; v.area_grid_max = 0;
     if (s.globals.quality_flags & PVGPU_Q_AREA_LIGHTS)
         for (const pvgpu_light& l : s.lights)
@@ -318,6 +331,12 @@ int device_upload(Scene& s, int device)
     if (v.has_sky) v.sky = s.sky_spheres[0];
     for (const pvgpu_mesh& me : s.meshes) if (me.node_count == 0) d->lean = false;       // `hierarchy off` meshes take the generic walk
     if (const char* e = getenv("PVGPU_LEAN")) if (e[0] == '0') d->lean = false;
+    d->full = false;
+    for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->full = true;
+    for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->full = true;
+    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE) d->full = true;
+    if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights) d->full = true;
+    if (const char* e = getenv("PVGPU_FULL")) if (e[0] == '1') d->full = true;
     v.n_objs = (uint32_t)s.objects.size();
     v.n_frame = (uint32_t)s.frame.size();
     v.n_nodes = (uint32_t)s.nodes.size();
@@ -459,14 +478,14 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
             }
             {
                 TimedLaunch t(d, stream, KIND_SHADE, cn);
-                (d.lean ? launch_shade_lean : launch_shade)(d.view, d.q[cur] + c0, d.hits + c0, cn, ctx, stream);
+                (d.lean ? launch_shade_lean : d.full ? launch_shade_full : launch_shade)(d.view, d.q[cur] + c0, d.hits + c0, cn, ctx, stream);
             }
             if (!s.lights.empty()) {
                 // the shadow kernel reads its count on the device; its grid is sized for the worst case of this chunk
                 const uint32_t worst = (uint32_t)std::min<unsigned long long>((unsigned long long)cn * n_lights, sq_cap);
                 TimedLaunch t(d, stream, KIND_SHADOW, 0);
                 if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : launch_shadow_opaque)(d.view, d.sq, worst, f.accum, d.cnt, stream);
-                else (d.lean ? launch_shadow_filter_lean : launch_shadow_filter)(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, stream);
+                else (d.lean ? launch_shadow_filter_lean : d.full ? launch_shadow_filter_full : launch_shadow_filter)(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, stream);
                 if (d.view.has_area_lights) { d.kernel_launches++; launch_shadow_area(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, d.area_grid, stream); }
             }
         }
