@@ -406,7 +406,10 @@ typedef struct pvgpu_globals {
 } pvgpu_globals;
 
 /* Camera (source/core/scene/camera.h:84-136), the members TracePixel reads (tracepixel.cpp:235-391). */
-enum { PVGPU_CAMERA_PERSPECTIVE = 1, PVGPU_CAMERA_ORTHOGRAPHIC = 2 };
+/* camera.h:71-81; types 3..11 additionally read Camera::Angle / H_Angle / V_Angle (pvgpu_scene_set_camera_angles) */
+enum { PVGPU_CAMERA_PERSPECTIVE = 1, PVGPU_CAMERA_ORTHOGRAPHIC = 2, PVGPU_CAMERA_FISHEYE = 3, PVGPU_CAMERA_ULTRA_WIDE_ANGLE = 4,
+       PVGPU_CAMERA_OMNIMAX = 5, PVGPU_CAMERA_PANORAMIC = 6, PVGPU_CAMERA_CYL_1 = 7, PVGPU_CAMERA_CYL_2 = 8, PVGPU_CAMERA_CYL_3 = 9,
+       PVGPU_CAMERA_CYL_4 = 10, PVGPU_CAMERA_SPHERICAL = 11 };
 typedef struct pvgpu_camera {
     uint32_t type;
     uint32_t reserved;
@@ -494,6 +497,8 @@ int  pvgpu_scene_set_normals(pvgpu_scene* s, const pvgpu_tnormal* tn, size_t n_t
 int  pvgpu_scene_set_atmosphere(pvgpu_scene* s, const pvgpu_sky_sphere* sky, const pvgpu_fog* fogs, size_t n_fogs);
 int  pvgpu_scene_set_camera(pvgpu_scene* s, const pvgpu_camera* cam);
 int  pvgpu_scene_get_camera(const pvgpu_scene* s, pvgpu_camera* cam);
+/* Camera::Angle, H_Angle, V_Angle (camera.h:105-107, degrees) for the fisheye / ultra_wide_angle / cylinder / spherical cameras. */
+int  pvgpu_scene_set_camera_angles(pvgpu_scene* s, double angle, double h_angle, double v_angle);
 
 /* Host-side mesh helper mirroring the parser's mesh2 post-processing (Mesh::Compute_Mesh_Triangle,
  * mesh.cpp:838-954, and Mesh::Build_Mesh_BBox_Tree, mesh.cpp:1376-1413): fills triangle records

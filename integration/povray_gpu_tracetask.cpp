@@ -737,6 +737,7 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
     check(pvgpu_scene_set_normals(gv.scene, fl.tnormals.data(), fl.tnormals.size(), fl.slope_entries.data(), fl.slope_entries.size()), "set_normals");
     check(pvgpu_scene_set_atmosphere(gv.scene, sd->skysphere != nullptr ? &sky : nullptr, fogs.data(), fogs.size()), "set_atmosphere");
     check(pvgpu_scene_set_camera(gv.scene, &c), "set_camera");
+    if (cam.Type > ORTHOGRAPHIC_CAMERA) check(pvgpu_scene_set_camera_angles(gv.scene, cam.Angle, cam.H_Angle, cam.V_Angle), "set_camera_angles");
     if (const char* path = getenv("PVGPU_DUMP_SCENE")) check(pvgpu_scene_save(gv.scene, path), "scene_save");
     if (!gv.error.empty()) fprintf(stderr, "pvgpu adapter: scene uses a feature outside the GPU trace path: %s\n", gv.error.c_str());
     if (need_device) {

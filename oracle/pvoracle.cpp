@@ -86,6 +86,7 @@ struct Scene {
     std::vector<pvgpu_slope_entry> slope_entries;
     std::vector<pvgpu_sky_sphere> sky_spheres;
     std::vector<pvgpu_fog> fogs;
+    std::vector<double> camera_ext;
     std::vector<V3> waveSources;                 // TraceThreadData::waveSources / waveFrequencies (tracethreaddata.cpp:110-111)
     std::vector<double> waveFrequencies;
     // noise tables
@@ -2583,13 +2584,104 @@ void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& t
 }
 
 // TracePixel::CreateCameraRay (tracepixel.cpp:341-391, 917-927)
-void camera_ray(const pvgpu_camera& cam, double x, double y, double width, double height, V3& o, V3& d)
+bool camera_ray(const Scene& S, double x, double y, double width, double height, V3& o, V3& d)
 {
-    double x0 = x / width - 0.5, y0 = 0.5 - y / height;
+    const pvgpu_camera& cam = S.cam;
     V3 loc = v3(cam.location), dir = v3(cam.direction), right = v3(cam.right), up = v3(cam.up);
-    if (cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) { d = dir; o = (loc + x0 * right) + y0 * up; }
-    else { o = loc; d = (dir + x0 * right) + y0 * up; }
+    o = loc;
+    if (cam.type <= PVGPU_CAMERA_ORTHOGRAPHIC) {
+        double x0 = x / width - 0.5, y0 = 0.5 - y / height;
+        if (cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) { d = dir; o = (loc + x0 * right) + y0 * up; }
+        else d = (dir + x0 * right) + y0 * up;
+        d = unit(d);
+        return true;
+    }
+    // SetupCamera (tracepixel.cpp:235-309)
+    const double cameraLengthRight = len(right), cameraLengthUp = len(up);
+    double aspectRatio;
+    switch (cam.type) {
+        case PVGPU_CAMERA_CYL_1: case PVGPU_CAMERA_CYL_3: aspectRatio = cameraLengthUp; break;
+        case PVGPU_CAMERA_CYL_2: case PVGPU_CAMERA_CYL_4: aspectRatio = cameraLengthRight; break;
+        case PVGPU_CAMERA_ULTRA_WIDE_ANGLE: aspectRatio = cameraLengthUp / cameraLengthRight; break;
+        default: aspectRatio = cameraLengthRight / cameraLengthUp; break;
+    }
+    if (cam.type != PVGPU_CAMERA_PANORAMIC && cam.type != PVGPU_CAMERA_SPHERICAL) { right = unit(right); up = unit(up); dir = unit(dir); }
+    const double Angle = S.camera_ext.size() == 3 ? S.camera_ext[0] : 0.0, H_Angle = S.camera_ext.size() == 3 ? S.camera_ext[1] : 0.0,
+                 V_Angle = S.camera_ext.size() == 3 ? S.camera_ext[2] : 0.0;
+    const double M_PI_ = 3.1415926535897932384626, M_PI_180_ = 0.01745329251994329576, M_PI_360_ = 0.00872664625997164788, M_PI_2_ = 1.57079632679489661923,
+                 TWO_M_PI_ = 6.283185307179586476925286766560;
+    double x0, y0, cx, sx, cy, sy, rad, phi, ty;
+    switch (cam.type) {
+        case PVGPU_CAMERA_FISHEYE:                                                                        // tracepixel.cpp:394-436
+            x0 = 2.0 * (x / width - 0.5); y0 = 2.0 * (0.5 - y / height);
+            x0 *= cameraLengthRight; y0 *= cameraLengthUp;
+            rad = std::sqrt(x0 * x0 + y0 * y0);
+            if (rad > 1.0) return false;
+            if (rad == 0.0) phi = 0.0; else if (x0 < 0.0) phi = M_PI_ - std::asin(y0 / rad); else phi = std::asin(y0 / rad);
+            x0 = phi; y0 = rad * Angle * M_PI_360_;
+            cx = std::cos(x0); sx = std::sin(x0); cy = std::cos(y0); sy = std::sin(y0);
+            d = ((cx * sy) * right + (sx * sy) * up) + cy * dir;
+            break;
+        case PVGPU_CAMERA_OMNIMAX:                                                                        // :438-492
+            x0 = 2.0 * (x / width - 0.5); y0 = 2.0 * (0.5 - y / height);
+            if (aspectRatio > 1.0) {
+                if (aspectRatio > 1.283458) { x0 *= aspectRatio / 1.283458; y0 = (y0 - 1.0) / 1.283458 + 1.0; }
+                else y0 = (y0 - 1.0) / aspectRatio + 1.0;
+            } else y0 /= aspectRatio;
+            rad = std::sqrt(x0 * x0 + y0 * y0);
+            if (rad > 1.0) return false;
+            if (rad == 0.0) phi = 0.0; else if (x0 < 0.0) phi = M_PI_ - std::asin(y0 / rad); else phi = std::asin(y0 / rad);
+            x0 = phi;
+            y0 = 1.411269 * rad - 0.09439 * rad * rad * rad + 0.25674 * rad * rad * rad * rad * rad;
+            cx = std::cos(x0); sx = std::sin(x0); cy = std::cos(y0); sy = std::sin(y0);
+            if (sx * sy < std::tan(135.0 * M_PI_180_) * cy) return false;
+            d = ((cx * sy) * right + (sx * sy) * up) + cy * dir;
+            break;
+        case PVGPU_CAMERA_PANORAMIC:                                                                      // :494-526
+            x0 = x / width; y0 = 2.0 * (0.5 - y / height);
+            x0 = (1.0 - x0) * M_PI_; y0 = M_PI_2_ * y0;
+            cx = std::cos(x0); sx = std::sin(x0);
+            if (std::fabs(M_PI_2_ - std::fabs(y0)) < EPSILON) ty = (y0 > 0.0) ? BOUND_HUGE : -BOUND_HUGE; else ty = std::tan(y0);
+            d = (cx * right + ty * up) + sx * dir;
+            break;
+        case PVGPU_CAMERA_ULTRA_WIDE_ANGLE:                                                               // :528-551
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            x0 *= Angle * M_PI_180_; y0 *= Angle * aspectRatio * M_PI_180_;
+            cx = std::cos(x0); sx = std::sin(x0); cy = std::cos(y0); sy = std::sin(y0);
+            d = (sx * right + sy * up) + (cx * cy) * dir;
+            break;
+        case PVGPU_CAMERA_CYL_1: case PVGPU_CAMERA_CYL_3:                                                 // :553-574, 598-621
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            x0 *= Angle * M_PI_180_; y0 *= aspectRatio;
+            cx = std::cos(x0); sx = std::sin(x0);
+            if (cam.type == PVGPU_CAMERA_CYL_1) d = (sx * right + y0 * up) + cx * dir;
+            else { d = sx * right + cx * dir; o = loc + y0 * up; }
+            break;
+        case PVGPU_CAMERA_CYL_2: case PVGPU_CAMERA_CYL_4:                                                 // :576-596, 623-646
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            y0 *= Angle * M_PI_180_; x0 *= aspectRatio;
+            cy = std::cos(y0); sy = std::sin(y0);
+            if (cam.type == PVGPU_CAMERA_CYL_2) d = (x0 * right + sy * up) + cy * dir;
+            else { d = sy * up + cy * dir; o = loc + x0 * right; }
+            break;
+        default: {                                                                                        // spherical :648-673
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            y0 *= (V_Angle / 360) * TWO_M_PI_; x0 *= (H_Angle / 360) * TWO_M_PI_;
+            auto rotate = [](V3 axis, double angle, V3 p) {                                               // matrix.cpp:825-850 + MTransPoint
+                V3 a = unit(axis);
+                double cosx = std::cos(angle), sinx = std::sin(angle);
+                double m00 = a.x * a.x + cosx * (1.0 - a.x * a.x), m01 = a.x * a.y * (1.0 - cosx) + a.z * sinx, m02 = a.x * a.z * (1.0 - cosx) - a.y * sinx;
+                double m10 = a.x * a.y * (1.0 - cosx) - a.z * sinx, m11 = a.y * a.y + cosx * (1.0 - a.y * a.y), m12 = a.y * a.z * (1.0 - cosx) + a.x * sinx;
+                double m20 = a.x * a.z * (1.0 - cosx) + a.y * sinx, m21 = a.y * a.z * (1.0 - cosx) - a.x * sinx, m22 = a.z * a.z + cosx * (1.0 - a.z * a.z);
+                return v3(p.x * m00 + p.y * m10 + p.z * m20 + 0.0, p.x * m01 + p.y * m11 + p.z * m21 + 0.0, p.x * m02 + p.y * m12 + p.z * m22 + 0.0);
+            };
+            V3 V1 = rotate(right, -y0, dir);
+            d = rotate(up, x0, V1);
+            break;
+        }
+    }
     d = unit(d);
+    return true;
 }
 
 // TracePixel::InitRayContainerState (tracepixel.cpp:929-1006)
@@ -2645,6 +2737,7 @@ void* pvo_scene_load(const char* path)
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->shape_data); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->tnormals) && get(f, s->slope_entries); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->sky_spheres) && get(f, s->fogs); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->camera_ext); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());
@@ -2672,7 +2765,7 @@ int pvo_render(void* sc, int width, int height, int left, int top, int right, in
     auto worker = [&](int ti) {
         Tracer T(S);
         std::vector<int> cam_interiors;
-        if (S.cam.type == PVGPU_CAMERA_PERSPECTIVE) container_state(S, T, v3(S.cam.location), cam_interiors);
+        if (!(S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC || S.cam.type == PVGPU_CAMERA_CYL_3 || S.cam.type == PVGPU_CAMERA_CYL_4)) container_state(S, T, v3(S.cam.location), cam_interiors);
         const int w = right - left + 1;
         for (;;) {
             int y = next_row.fetch_add(1);
@@ -2680,11 +2773,12 @@ int pvo_render(void* sc, int width, int height, int left, int top, int right, in
             for (int x = left; x <= right; x++) {
                 Ticket tk; tk.maxAllowedTraceLevel = S.g.max_trace_level; tk.adcBailout = S.g.adc_bailout; tk.alphaBackground = S.g.output_alpha != 0;
                 Ray ray;
-                camera_ray(S.cam, x + 0.5, y + 0.5, width, height, ray.Origin, ray.Direction);
-                if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) container_state(S, T, ray.Origin, cam_interiors);
-                ray.interiors = cam_interiors;
                 Col col{ 0, 0, 0 }; float transm = 0.0f;
-                T.TraceRay(ray, tk, col, transm, 1.0f, false, S.cam.max_ray_distance);
+                if (camera_ray(S, x + 0.5, y + 0.5, width, height, ray.Origin, ray.Direction)) {
+                    if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC || S.cam.type == PVGPU_CAMERA_CYL_3 || S.cam.type == PVGPU_CAMERA_CYL_4) container_state(S, T, ray.Origin, cam_interiors);
+                    ray.interiors = cam_interiors;
+                    T.TraceRay(ray, tk, col, transm, 1.0f, false, S.cam.max_ray_distance);
+                } else transm = 1.0f;                     // numTraced == 0 (tracepixel.cpp:332-335)
                 float* o = rgbt + 4 * ((size_t)(y - top) * w + (x - left));
                 o[0] = col.r; o[1] = col.g; o[2] = col.b; o[3] = transm;
             }
@@ -2737,10 +2831,10 @@ struct AATracer {
     {
         Ticket tk; tk.maxAllowedTraceLevel = S.g.max_trace_level; tk.adcBailout = S.g.adc_bailout; tk.alphaBackground = S.g.output_alpha != 0;
         Ray ray;
-        camera_ray(S.cam, x, y, width, height, ray.Origin, ray.Direction);
-        if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) container_state(S, T, ray.Origin, cam_interiors);
-        ray.interiors = cam_interiors;
         Col col{ 0, 0, 0 }; float transm = 0.0f;
+        if (!camera_ray(S, x, y, width, height, ray.Origin, ray.Direction)) return Px{ 0.0f, 0.0f, 0.0f, 1.0f };
+        if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC || S.cam.type == PVGPU_CAMERA_CYL_3 || S.cam.type == PVGPU_CAMERA_CYL_4) container_state(S, T, ray.Origin, cam_interiors);
+        ray.interiors = cam_interiors;
         T.TraceRay(ray, tk, col, transm, 1.0f, false, S.cam.max_ray_distance);
         return Px{ col.r, col.g, col.b, transm };
     }
@@ -2864,7 +2958,7 @@ int pvo_render_aa(void* sc, int width, int height, const int* rects, int n_rects
     auto worker = [&](int ti) {
         Tracer T(S);
         std::vector<int> cam_interiors;
-        if (S.cam.type == PVGPU_CAMERA_PERSPECTIVE) container_state(S, T, v3(S.cam.location), cam_interiors);
+        if (!(S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC || S.cam.type == PVGPU_CAMERA_CYL_3 || S.cam.type == PVGPU_CAMERA_CYL_4)) container_state(S, T, v3(S.cam.location), cam_interiors);
         AATracer A{ S, T, width, height, cam_interiors, 1.0f, true, AAParams{ method, depth, threshold, jitter_scale, gamma }, 0.0 };
         if (gamma > 0.0 && gamma != 1.0) { A.enc_gamma = 1.0f / (float)gamma; A.neutral = false; }
         // jitterScale = jitterScale / aaDepth (M1, tracetask.cpp:526) or / ((1 << aaDepth) + 1) (M2, tracetask.cpp:611)
@@ -2916,7 +3010,7 @@ int pvo_camera_rays(void* sc, int width, int height, const double* xy, size_t n,
     const Scene& S = *reinterpret_cast<Scene*>(sc);
     for (size_t i = 0; i < n; i++) {
         V3 o, d;
-        camera_ray(S.cam, xy[2 * i], xy[2 * i + 1], width, height, o, d);
+        if (!camera_ray(S, xy[2 * i], xy[2 * i + 1], width, height, o, d)) { o = v3(0.0, 0.0, 0.0); d = v3(0.0, 0.0, 0.0); }
         double* r = org_dir + 6 * i;
         r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
     }

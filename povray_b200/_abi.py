@@ -212,6 +212,7 @@ SIGNATURES = {
     "pvgpu_scene_set_atmosphere": (C.c_int, [VP, P(SkySphere), P(Fog), C.c_size_t]),
     "pvgpu_scene_set_camera": (C.c_int, [VP, P(Camera)]),
     "pvgpu_scene_get_camera": (C.c_int, [VP, P(Camera)]),
+    "pvgpu_scene_set_camera_angles": (C.c_int, [VP, C.c_double, C.c_double, C.c_double]),
     "pvgpu_scene_add_mesh2": (C.c_int, [VP, P(f64), C.c_size_t, P(i32), C.c_size_t, P(i32)]),
     "pvgpu_scene_finalize": (C.c_int, [VP, C.c_int]),
     "pvgpu_scene_device_bytes": (C.c_size_t, [VP]),

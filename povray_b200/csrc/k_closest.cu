@@ -73,20 +73,110 @@ __global__ void k_container_state(DScene sc, uint16_t* out, Counters* cnt)
     out[PV_MAX_INTERIORS] = (uint16_t)n;
 }
 
-// TracePixel::CreateCameraRay (tracepixel.cpp:341-391, 917-927): perspective and orthographic cameras.
-__device__ __forceinline__ void camera_ray(const pvgpu_camera& cam, double x, double y, double width, double height, V3& o, V3& d)
+// TracePixel::CreateCameraRay (tracepixel.cpp:341-674, 917-927): every camera type except mesh_camera / user_defined.
+// Returns false where the reference traces no ray (fisheye / omnimax pixels outside the image circle).
+__device__ inline bool camera_ray(const DScene& sc, double x, double y, double width, double height, V3& o, V3& d)
 {
-    const double x0 = x / width - 0.5;
-    const double y0 = 0.5 - y / height;
-    const V3 loc = ld3(cam.location), dirv = ld3(cam.direction), right = ld3(cam.right), up = ld3(cam.up);
-    if (cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) {
-        d = dirv;
-        o = (loc + x0 * right) + y0 * up;
-    } else {
-        o = loc;
-        d = (dirv + x0 * right) + y0 * up;
+    const pvgpu_camera& cam = sc.cam;
+    const V3 loc = ld3(cam.location);
+    o = loc;
+    if (cam.type <= PVGPU_CAMERA_ORTHOGRAPHIC) {
+        const double x0 = x / width - 0.5;
+        const double y0 = 0.5 - y / height;
+        const V3 dirv = ld3(cam.direction), right = ld3(cam.right), up = ld3(cam.up);
+        if (cam.type == PVGPU_CAMERA_ORTHOGRAPHIC) {
+            d = dirv;
+            o = (loc + x0 * right) + y0 * up;
+        } else d = (dirv + x0 * right) + y0 * up;
+        d = normalized(d);
+        return true;
+    }
+#ifndef PV_LEAN
+    const V3 right = ld3(sc.cam_right), up = ld3(sc.cam_up), dirv = ld3(sc.cam_dir);
+    const double pi = 3.1415926535897932384626, pi_180 = 0.01745329251994329576, pi_360 = 0.00872664625997164788, pi_2 = 1.57079632679489661923;
+    double x0, y0, cx, sx, cy, sy;
+    switch (cam.type) {
+        case PVGPU_CAMERA_FISHEYE:
+        case PVGPU_CAMERA_OMNIMAX: {
+            x0 = 2.0 * (x / width - 0.5);
+            y0 = 2.0 * (0.5 - y / height);
+            if (cam.type == PVGPU_CAMERA_FISHEYE) { x0 *= sc.cam_len_right; y0 *= sc.cam_len_up; }
+            else if (sc.cam_aspect > 1.0) {
+                if (sc.cam_aspect > 1.283458) { x0 *= sc.cam_aspect / 1.283458; y0 = (y0 - 1.0) / 1.283458 + 1.0; }
+                else y0 = (y0 - 1.0) / sc.cam_aspect + 1.0;
+            } else y0 /= sc.cam_aspect;
+            const double rad = sqrt(x0 * x0 + y0 * y0);
+            if (rad > 1.0) return false;
+            double phi;
+            if (rad == 0.0) phi = 0.0;
+            else if (x0 < 0.0) phi = pi - asin(y0 / rad);
+            else phi = asin(y0 / rad);
+            x0 = phi;
+            if (cam.type == PVGPU_CAMERA_FISHEYE) y0 = rad * sc.cam_angle * pi_360;
+            else y0 = 1.411269 * rad - 0.09439 * rad * rad * rad + 0.25674 * rad * rad * rad * rad * rad;
+            cx = cos(x0); sx = sin(x0); cy = cos(y0); sy = sin(y0);
+            if (cam.type == PVGPU_CAMERA_OMNIMAX && (sx * sy < tan(135.0 * pi_180) * cy)) return false;
+            d = ((cx * sy) * right + (sx * sy) * up) + cy * dirv;
+            break;
+        }
+        case PVGPU_CAMERA_PANORAMIC: {
+            x0 = x / width;
+            y0 = 2.0 * (0.5 - y / height);
+            x0 = (1.0 - x0) * pi;
+            y0 = pi_2 * y0;
+            cx = cos(x0); sx = sin(x0);
+            double ty;
+            if (fabs(pi_2 - fabs(y0)) < PV_EPSILON) ty = (y0 > 0.0) ? PV_BOUND_HUGE : -PV_BOUND_HUGE;
+            else ty = tan(y0);
+            d = (cx * right + ty * up) + sx * dirv;
+            break;
+        }
+        case PVGPU_CAMERA_ULTRA_WIDE_ANGLE:
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            x0 *= sc.cam_angle * pi_180;
+            y0 *= sc.cam_angle * sc.cam_aspect * pi_180;
+            cx = cos(x0); sx = sin(x0); cy = cos(y0); sy = sin(y0);
+            d = (sx * right + sy * up) + (cx * cy) * dirv;
+            break;
+        case PVGPU_CAMERA_CYL_1:
+        case PVGPU_CAMERA_CYL_3:
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            x0 *= sc.cam_angle * pi_180;
+            y0 *= sc.cam_aspect;
+            cx = cos(x0); sx = sin(x0);
+            if (cam.type == PVGPU_CAMERA_CYL_1) d = (sx * right + y0 * up) + cx * dirv;
+            else { d = sx * right + cx * dirv; o = loc + y0 * up; }
+            break;
+        case PVGPU_CAMERA_CYL_2:
+        case PVGPU_CAMERA_CYL_4:
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            y0 *= sc.cam_angle * pi_180;
+            x0 *= sc.cam_aspect;
+            cy = cos(y0); sy = sin(y0);
+            if (cam.type == PVGPU_CAMERA_CYL_2) d = (x0 * right + sy * up) + cy * dirv;
+            else { d = sy * up + cy * dirv; o = loc + x0 * right; }
+            break;
+        default: {      // PVGPU_CAMERA_SPHERICAL: two axis rotations (Compute_Axis_Rotation_Transform, matrix.cpp:825-850)
+            x0 = x / width - 0.5; y0 = 0.5 - y / height;
+            y0 *= (sc.cam_v_angle / 360) * 6.283185307179586476925286766560;
+            x0 *= (sc.cam_h_angle / 360) * 6.283185307179586476925286766560;
+            auto rotate = [](const V3& axis, double angle, const V3& p) {
+                const V3 a = normalized(axis);
+                const double cosx = cos(angle), sinx = sin(angle);
+                const double m00 = a.x * a.x + cosx * (1.0 - a.x * a.x), m01 = a.x * a.y * (1.0 - cosx) + a.z * sinx, m02 = a.x * a.z * (1.0 - cosx) - a.y * sinx;
+                const double m10 = a.x * a.y * (1.0 - cosx) - a.z * sinx, m11 = a.y * a.y + cosx * (1.0 - a.y * a.y), m12 = a.y * a.z * (1.0 - cosx) + a.x * sinx;
+                const double m20 = a.x * a.z * (1.0 - cosx) + a.y * sinx, m21 = a.y * a.z * (1.0 - cosx) - a.x * sinx, m22 = a.z * a.z + cosx * (1.0 - a.z * a.z);
+                // MTransPoint with a zero translation row (matrix.cpp:415-430)
+                return mk(p.x * m00 + p.y * m10 + p.z * m20 + 0.0, p.x * m01 + p.y * m11 + p.z * m21 + 0.0, p.x * m02 + p.y * m12 + p.z * m22 + 0.0);
+            };
+            const V3 v1 = rotate(right, -y0, dirv);
+            d = rotate(up, x0, v1);
+            break;
+        }
     }
     d = normalized(d);
+#endif
+    return true;
 }
 
 // sample i -> (rectangle, x, y) and its accumulator slot.  Slots are row-major inside a rectangle (the layout
@@ -118,7 +208,7 @@ __device__ __forceinline__ void sample_xy(const pvgpu_rect* rects, const uint32_
 
 // TracePixel::operator() (tracepixel.cpp:311-339): one new ticket + camera ray per sample.
 __global__ void __launch_bounds__(256)
-k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width, double height, PRay* out, Counters* cnt)
+k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width, double height, PRay* out, Counters* cnt, float4* accum)
 {
     uint2 stack_mem[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_mem, 0 };
@@ -133,8 +223,8 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
             sample_xy(src.rects, src.rect_off, src.n_rects, first + i, x, y, slot);
             slot += src.slot_base;
         }
-        V3 o, d;
-        camera_ray(sc.cam, x, y, width, height, o, d);
+        V3 o = mk(0.0, 0.0, 0.0), d = mk(0.0, 0.0, 1.0);
+        const bool have_ray = camera_ray(sc, x, y, width, height, o, d);
         PRay r;
         r.o[0] = o.x; r.o[1] = o.y; r.o[2] = o.z;
         r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
@@ -144,11 +234,15 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
         r.sample = slot;
         r.level = 0;
         r.flags = (uint8_t)(PV_RAY_PRIMARY | (sc.g.output_alpha ? PV_RAY_ALPHA_BG : 0));
+        if (!have_ray) {        // TracePixel::operator(): numTraced == 0 -> colour stays black, transm = 1 (tracepixel.cpp:332-335)
+            r.flags |= PV_RAY_DEAD;
+            atomicAdd(reinterpret_cast<float*>(accum + slot) + 3, 1.0f);
+        }
         r.n_int = (uint8_t)sc.n_cam_interiors;
         r.pad = 0;
         #pragma unroll
         for (int k = 0; k < PV_MAX_INTERIORS; k++) r.interiors[k] = sc.cam_interiors[k];
-        if (sc.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC && sc.has_interiors) {
+        if ((sc.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC || sc.cam.type == PVGPU_CAMERA_CYL_3 || sc.cam.type == PVGPU_CAMERA_CYL_4) && sc.has_interiors) {
             // InitRayContainerState(ray, true): recomputed per ray when the origin moves with the pixel
             uint32_t nci;
             container_state(sc, o, r.interiors, nci, stack, &cnt->overflow);
@@ -189,7 +283,8 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRe
             const float adcw = rp->adc;
             const uint32_t level = rp->level;
             flags = rp->flags;
-            if (!(flags & PV_RAY_PROBE)) {
+            if (flags & PV_RAY_DEAD) { out.obj = PV_HIT_STOPPED; alive = false; }
+            else if (!(flags & PV_RAY_PROBE)) {
                 n_rays++;
                 // max. trace level / ADC bailout (trace.cpp:147-155)
                 if ((level >= sc.g.max_trace_level) || ((double)adcw < sc.g.adc_bailout)) {
@@ -257,7 +352,7 @@ __global__ void k_camera_rays(DScene sc, const double* xy, uint32_t n, double wi
 {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         V3 o, d;
-        camera_ray(sc.cam, xy[2 * (size_t)i], xy[2 * (size_t)i + 1], width, height, o, d);
+        if (!camera_ray(sc, xy[2 * (size_t)i], xy[2 * (size_t)i + 1], width, height, o, d)) { o = mk(0.0, 0.0, 0.0); d = mk(0.0, 0.0, 0.0); }
         double* r = org_dir + 6 * (size_t)i;
         r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
     }
@@ -268,9 +363,9 @@ void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cuda
     k_container_state<<<1, 32, 0, st>>>(sc, out, cnt);
 }
 void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,
-                    PRay* out, Counters* cnt, cudaStream_t st)
+                    PRay* out, Counters* cnt, float4* accum, cudaStream_t st)
 {
-    k_primary<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, src, first, n, width, height, out, cnt);
+    k_primary<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, src, first, n, width, height, out, cnt, accum);
 }
 #endif  // !PV_LEAN
 void PV_VARIANT(launch_closest)(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st)

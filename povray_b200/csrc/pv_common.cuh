@@ -152,6 +152,9 @@ struct DScene {
     uint32_t has_interiors;                 // the interior table is not empty
     pvgpu_globals g;
     pvgpu_camera  cam;
+    // TracePixel::SetupCamera (tracepixel.cpp:235-309) for the non-pinhole cameras: normalised axes, aspectRatio, axis lengths, angles
+    double cam_right[3], cam_up[3], cam_dir[3];
+    double cam_aspect, cam_len_right, cam_len_up, cam_angle, cam_h_angle, cam_v_angle;
     uint16_t cam_interiors[PV_MAX_INTERIORS];   // TracePixel::InitRayContainerState result
     uint32_t n_cam_interiors;
 };
@@ -162,7 +165,8 @@ struct DScene {
 #define PV_RAY_REFRACTION  0x04u
 #define PV_RAY_CONTINUED   0x08u    // TraceRay(..., continuedRay = true): trace level is not incremented
 #define PV_RAY_ALPHA_BG    0x10u    // TraceTicket::alphaBackground
-#define PV_RAY_PROBE       0x20u    // ray of the ray-level harness: Trace::FindIntersection without the camera's Max_Ray_Distance
+#define PV_RAY_PROBE       0x20u
+#define PV_RAY_DEAD        0x40u    // CreateCameraRay returned false (fisheye / omnimax pixel outside the image circle): nothing is traced    // ray of the ray-level harness: Trace::FindIntersection without the camera's Max_Ray_Distance
 
 // One pending TraceRay call (trace.cpp:135): 96 bytes.
 struct __align__(16) PRay {

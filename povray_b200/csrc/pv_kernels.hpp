@@ -48,7 +48,7 @@ int  grid_for(uint32_t n, int block, int per_sm);
 
 void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cudaStream_t st);
 void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,
-                    PRay* out, Counters* cnt, cudaStream_t st);
+                    PRay* out, Counters* cnt, float4* accum, cudaStream_t st);
 void launch_closest(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st);
 void launch_shade(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st);
 // n_max: upper bound of the shadow-ray count (the exact count is read from cnt->n_shadow on the device)

@@ -422,7 +422,29 @@ static int refresh_camera(Scene& s, cudaStream_t stream)
     DeviceScene& d = *s.dev;
     d.view.cam = s.camera;
     d.view.n_cam_interiors = 0;
-    if (!s.interiors.empty() && s.camera.type == PVGPU_CAMERA_PERSPECTIVE) {
+    {   // TracePixel::SetupCamera (tracepixel.cpp:235-309)
+        DScene& v = d.view;
+        auto len3 = [](const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
+        auto norm3 = [&](const double* a, double* out) { double l = len3(a); for (int k = 0; k < 3; k++) out[k] = (l != 0.0) ? a[k] / l : a[k]; };
+        v.cam_len_right = len3(s.camera.right);
+        v.cam_len_up = len3(s.camera.up);
+        bool normalise = true;
+        switch (s.camera.type) {
+            case PVGPU_CAMERA_CYL_1: case PVGPU_CAMERA_CYL_3: v.cam_aspect = v.cam_len_up; break;
+            case PVGPU_CAMERA_CYL_2: case PVGPU_CAMERA_CYL_4: v.cam_aspect = v.cam_len_right; break;
+            case PVGPU_CAMERA_ULTRA_WIDE_ANGLE: v.cam_aspect = v.cam_len_up / v.cam_len_right; break;
+            case PVGPU_CAMERA_OMNIMAX: case PVGPU_CAMERA_FISHEYE: v.cam_aspect = v.cam_len_right / v.cam_len_up; break;
+            default: v.cam_aspect = v.cam_len_right / v.cam_len_up; normalise = false; break;
+        }
+        for (int k = 0; k < 3; k++) { v.cam_right[k] = s.camera.right[k]; v.cam_up[k] = s.camera.up[k]; v.cam_dir[k] = s.camera.direction[k]; }
+        if (normalise) { norm3(s.camera.right, v.cam_right); norm3(s.camera.up, v.cam_up); norm3(s.camera.direction, v.cam_dir); }
+        v.cam_angle = s.camera_ext.size() == 3 ? s.camera_ext[0] : 0.0;
+        v.cam_h_angle = s.camera_ext.size() == 3 ? s.camera_ext[1] : 0.0;
+        v.cam_v_angle = s.camera_ext.size() == 3 ? s.camera_ext[2] : 0.0;
+    }
+    // pinhole-style cameras: the containing interiors are found once (InitRayContainerState(ray, false)); orthographic and the
+    // cylinder cameras 3 / 4 move the origin with the pixel and recompute per ray (k_primary)
+    if (!s.interiors.empty() && s.camera.type != PVGPU_CAMERA_ORTHOGRAPHIC && s.camera.type != PVGPU_CAMERA_CYL_3 && s.camera.type != PVGPU_CAMERA_CYL_4) {
         launch_container_state(d.view, d.d_cam_int, d.cnt, stream);
         d.kernel_launches++;
         uint16_t h[PV_MAX_INTERIORS + 1];
@@ -459,7 +481,7 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
     const uint32_t chunk_max = std::max<uint32_t>(1, sq_cap / n_lights);
     {
         TimedLaunch t(d, stream, KIND_PRIMARY, n);
-        launch_primary(d.view, src, first, n, (double)f.width, (double)f.height, d.q[0], d.cnt, stream);
+        launch_primary(d.view, src, first, n, (double)f.width, (double)f.height, d.q[0], d.cnt, f.accum, stream);
     }
     uint32_t n_cur = n;
     int cur = 0;

@@ -472,8 +472,10 @@ int validate_scene(Scene& s)
     if (std::fabs((double)s.globals.atmosphere_dispersion - 1.0) >= 1e-10)
         return fail(PVGPU_E_UNSUPPORTED, "atmosphere dispersion is outside the hot-path scope");
     if (!s.have_camera) return fail(PVGPU_E_INVALID, "no camera set");
-    if (s.camera.type != PVGPU_CAMERA_PERSPECTIVE && s.camera.type != PVGPU_CAMERA_ORTHOGRAPHIC)
+    if (s.camera.type < PVGPU_CAMERA_PERSPECTIVE || s.camera.type > PVGPU_CAMERA_SPHERICAL)
         return fail(PVGPU_E_UNSUPPORTED, "camera type %u is outside the hot-path scope", s.camera.type);
+    if (s.camera.type > PVGPU_CAMERA_ORTHOGRAPHIC && s.camera_ext.size() != 3)
+        return fail(PVGPU_E_INVALID, "camera type %u needs pvgpu_scene_set_camera_angles", s.camera.type);
     if (s.globals.bounding_method == 1 && s.nodes.empty())
         return fail(PVGPU_E_INVALID, "bounding_method 1 without a tree (call pvgpu_scene_set_tree or pvgpu_scene_build_tree)");
 
@@ -604,6 +606,14 @@ int pvgpu_scene_set_normals(pvgpu_scene* sc, const pvgpu_tnormal* tn, size_t n_t
     if ((!tn && n_tn) || (!slopes && n_slopes)) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_normals: null array");
     s.tnormals.assign(tn, tn + n_tn);
     s.slope_entries.assign(slopes, slopes + n_slopes);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_camera_angles(pvgpu_scene* sc, double angle, double h_angle, double v_angle)
+{
+    SCENE_OR_FAIL(sc);
+    s.camera_ext = { angle, h_angle, v_angle };
+    if (s.dev) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_camera_angles: call before pvgpu_scene_finalize");
     return PVGPU_OK;
 }
 
@@ -828,7 +838,8 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
     // optional trailing sections in fixed order; a section is written when it or a later one holds data
-    const bool sec4 = !s.sky_spheres.empty() || !s.fogs.empty();
+    const bool sec5 = !s.camera_ext.empty();
+    const bool sec4 = sec5 || !s.sky_spheres.empty() || !s.fogs.empty();
     const bool sec3 = sec4 || !s.tnormals.empty();
     const bool sec2 = sec3 || !s.shape_data.empty();
     const bool sec1 = sec2 || !s.blobs.empty();
@@ -836,6 +847,7 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
     if (ok && sec2) ok = put(f, s.shape_data);
     if (ok && sec3) ok = put(f, s.tnormals) && put(f, s.slope_entries);
     if (ok && sec4) ok = put(f, s.sky_spheres) && put(f, s.fogs);
+    if (ok && sec5) ok = put(f, s.camera_ext);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -872,6 +884,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->sky_spheres) && get(f, s->fogs); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->camera_ext); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

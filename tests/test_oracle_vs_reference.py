@@ -55,7 +55,8 @@ def test_oracle_pixels_match_reference(oracle, name):
         assert d.max() < 1e-3 and (d > 1e-5).sum() <= 8
     else:
         assert d.max() < 2e-4 and (d > 1e-5).sum() <= 1
-    assert st["rays"] >= W * H
+    # (fisheye / omnimax: pixels outside the image circle trace nothing, tracepixel.cpp:408-411)
+    assert st["rays"] >= (W * H if name not in ("cam_fisheye", "cam_omnimax") else 1000)
 
 
 def test_oracle_rect_and_thread_invariance(oracle):
