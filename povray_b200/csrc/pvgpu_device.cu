@@ -417,13 +417,9 @@ static int ensure_work_buffers(DeviceScene& d, size_t q_cap, size_t sq_cap, size
 }
 
 // camera-dependent part of the device view (camera interiors for the pinhole case)
-static int refresh_camera(Scene& s, cudaStream_t stream)
+// TracePixel::SetupCamera (tracepixel.cpp:235-309): normalised axes, aspectRatio and axis lengths of the non-pinhole cameras
+static void setup_camera(const Scene& s, DScene& v)
 {
-    DeviceScene& d = *s.dev;
-    d.view.cam = s.camera;
-    d.view.n_cam_interiors = 0;
-    {   // TracePixel::SetupCamera (tracepixel.cpp:235-309)
-        DScene& v = d.view;
         auto len3 = [](const double* a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); };
         auto norm3 = [&](const double* a, double* out) { double l = len3(a); for (int k = 0; k < 3; k++) out[k] = (l != 0.0) ? a[k] / l : a[k]; };
         v.cam_len_right = len3(s.camera.right);
@@ -441,7 +437,14 @@ static int refresh_camera(Scene& s, cudaStream_t stream)
         v.cam_angle = s.camera_ext.size() == 3 ? s.camera_ext[0] : 0.0;
         v.cam_h_angle = s.camera_ext.size() == 3 ? s.camera_ext[1] : 0.0;
         v.cam_v_angle = s.camera_ext.size() == 3 ? s.camera_ext[2] : 0.0;
-    }
+}
+
+static int refresh_camera(Scene& s, cudaStream_t stream)
+{
+    DeviceScene& d = *s.dev;
+    d.view.cam = s.camera;
+    d.view.n_cam_interiors = 0;
+    setup_camera(s, d.view);
     // pinhole-style cameras: the containing interiors are found once (InitRayContainerState(ray, false)); orthographic and the
     // cylinder cameras 3 / 4 move the origin with the pixel and recompute per ray (k_primary)
     if (!s.interiors.empty() && s.camera.type != PVGPU_CAMERA_ORTHOGRAPHIC && s.camera.type != PVGPU_CAMERA_CYL_3 && s.camera.type != PVGPU_CAMERA_CYL_4) {
@@ -1019,6 +1022,8 @@ int pvgpu_camera_rays(pvgpu_scene* sc, int width, int height, const double* xy, 
     CUDA_TRY(cudaSetDevice(s.device));
     DeviceScene& d = *s.dev;
     d.view.cam = s.camera;
+    setup_camera(s, d.view);
+    d.camera_dirty = true;
     double *d_xy = nullptr, *d_out = nullptr;
     if (cudaMalloc(&d_xy, n * 2 * sizeof(double)) != cudaSuccess || cudaMalloc(&d_out, n * 6 * sizeof(double)) != cudaSuccess) {
         cudaFree(d_xy); cudaFree(d_out);
