@@ -243,9 +243,12 @@ enum {
     PVGPU_PAT_RIPPLES  = 21,     /* RipplesPattern   pattern.cpp:8163                     */
     PVGPU_PAT_WAVES    = 22,     /* WavesPattern     pattern.cpp:8593                     */
     PVGPU_PAT_QUILTED  = 23,     /* QuiltedPattern   pattern.cpp:8067, p[0..1] = Control0, Control1 */
-    PVGPU_PAT_AVERAGE  = 24      /* AVERAGE_PATTERN pigment: weighted mean of the blend map's entries (pigment.cpp:566-596) */
+    PVGPU_PAT_AVERAGE  = 24,     /* AVERAGE_PATTERN pigment: weighted mean of the blend map's entries (pigment.cpp:566-596) */
+    PVGPU_PAT_CRACKLE  = 25,     /* CracklePattern   pattern.cpp:5760; `data` = offset into the shape-data table of 9 doubles:
+                                    crackleForm xyz, crackleMetric, crackleOffset, crackleIsSolid, repeat xyz */
+    PVGPU_PAT_CELLS    = 26      /* CellsPattern     pattern.cpp:5652 */
 };
-#define PVGPU_PAT_LAST PVGPU_PAT_AVERAGE
+#define PVGPU_PAT_LAST PVGPU_PAT_CELLS
 /* ContinuousPattern::waveType (pattern.h:108-117) */
 enum { PVGPU_WAVE_RAW = 0, PVGPU_WAVE_RAMP = 1, PVGPU_WAVE_SINE = 2, PVGPU_WAVE_TRIANGLE = 3,
        PVGPU_WAVE_SCALLOP = 4, PVGPU_WAVE_CUBIC = 5, PVGPU_WAVE_POLY = 6 };
@@ -287,7 +290,7 @@ typedef struct pvgpu_pigment {
     int32_t  blend_map;          /* Blend_Map -> blend map index, -1 = none         */
     float    colour[5];          /* PIGMENT::colour                                 */
     float    quick_colour[5];    /* PIGMENT::Quick_Colour (NaN red = invalid)       */
-    uint32_t reserved;
+    uint32_t data;               /* pattern parameters that do not fit p[]: offset into the shape-data table (crackle) */
     double   p[4];               /* pattern-specific, see PVGPU_PAT_*               */
 } pvgpu_pigment;
 

@@ -195,6 +195,14 @@ struct Flattener
         else if (dynamic_cast<const RipplesPattern*>(bp)) p.pattern = PVGPU_PAT_RIPPLES;
         else if (dynamic_cast<const WavesPattern*>(bp)) p.pattern = PVGPU_PAT_WAVES;
         else if (const QuiltedPattern* q = dynamic_cast<const QuiltedPattern*>(bp)) { p.pattern = PVGPU_PAT_QUILTED; p.p[0] = q->Control0; p.p[1] = q->Control1; }
+        else if (const CracklePattern* cr = dynamic_cast<const CracklePattern*>(bp)) {
+            p.pattern = PVGPU_PAT_CRACKLE;
+            p.data = (uint32_t)shape_data.size();
+            for (int k = 0; k < 3; k++) shape_data.push_back(cr->crackleForm[k]);
+            shape_data.push_back(cr->crackleMetric); shape_data.push_back(cr->crackleOffset); shape_data.push_back(cr->crackleIsSolid ? 1.0 : 0.0);
+            shape_data.push_back(cr->repeat.x()); shape_data.push_back(cr->repeat.y()); shape_data.push_back(cr->repeat.z());
+        }
+        else if (dynamic_cast<const CellsPattern*>(bp)) p.pattern = PVGPU_PAT_CELLS;
         else if (dynamic_cast<const BumpsPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;      // BumpsPattern is a NoisePattern (pattern.h:989)
         else unsupported(std::string(user) + " pattern outside the hot-path scope: " + typeid(*bp).name());
         if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {

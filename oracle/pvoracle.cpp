@@ -23,6 +23,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <random>
 #include <vector>
 
 #include "pvgpu.h"
@@ -90,6 +91,7 @@ struct Scene {
     std::vector<V3> waveSources;                 // TraceThreadData::waveSources / waveFrequencies (tracethreaddata.cpp:110-111)
     std::vector<double> waveFrequencies;
     // noise tables
+    std::vector<double> patternRands;            // gPatternRands (pattern.cpp:91): mt19937 / 2^32, 32768 entries
     std::vector<unsigned short> hashTable;
     std::vector<double> RTable;
     std::vector<int> NoisePermutation;
@@ -1674,6 +1676,85 @@ V3 Tracer::Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const                
     return p;
 }
 
+static double crackle_pattern(const Scene& S, const pvgpu_pigment& pg, V3 ep, int gen)                      // pattern.cpp:5760-5987 (no cell cache)
+{
+    const double* cp = S.shape_data.data() + pg.data;
+    const double form_x = cp[0], form_y = cp[1], form_z = cp[2], metric = cp[3], offset = cp[4];
+    const bool is_solid = cp[5] != 0.0;
+    const int rep[3] = { (int)cp[6], (int)cp[7], (int)cp[8] };
+    const bool use_square = (metric == 2), use_unity = (metric == 1);
+    auto wrap = [](double val, double upper) {                       // wrap() mathutil.h:102-121
+        double t = std::fmod(val, upper);
+        if (t < 0.0) t += upper;
+        if (t >= upper) t = 0.0;
+        return t;
+    };
+    V3 tp = ep;
+    if (rep[0]) tp.x = wrap(tp.x, (double)rep[0]);
+    if (rep[1]) tp.y = wrap(tp.y, (double)rep[1]);
+    if (rep[2]) tp.z = wrap(tp.z, (double)rep[2]);
+    const int flo[3] = { (int)std::floor(tp.x - EPSILON), (int)std::floor(tp.y - EPSILON), (int)std::floor(tp.z - EPSILON) };
+    // nucleus of cube `index` of gaCrackleCubeTable (pattern.cpp:9349-9374) around the point: IntPickInCube (pattern.cpp:8808-8819)
+    auto nucleus = [&](int ax, int ay, int az) {
+        int c[3] = { flo[0] + ax, flo[1] + ay, flo[2] + az };
+        double woff[3] = { 0.0, 0.0, 0.0 };
+        for (int k = 0; k < 3; k++)
+            if (rep[k]) { int w = c[k] % rep[k]; if (w < 0) w += rep[k]; woff[k] += (c[k] - w); c[k] = w; }     // wrapInt
+        const unsigned seed = S.hashTable[S.hashTable[S.hashTable[c[0] & 0xfff] ^ (c[1] & 0xfff)] ^ (c[2] & 0xfff)];                  // Hash3d texture.h:75
+        double nx = c[0] + S.patternRands[seed % 32768u], ny = c[1] + S.patternRands[(seed + 1u) % 32768u], nz = c[2] + S.patternRands[(seed + 2u) % 32768u];
+        nx += woff[0]; ny += woff[1]; nz += woff[2];
+        return v3(nx, ny, nz);
+    };
+    auto dist = [&](const V3& n) {
+        const double dx = n.x - tp.x, dy = n.y - tp.y, dz = n.z - tp.z;
+        if (use_square) return dx * dx + dy * dy + dz * dz;
+        if (use_unity) return std::fabs(dx) + std::fabs(dy) + std::fabs(dz);
+        return std::pow(std::fabs(dx), metric) + std::pow(std::fabs(dy), metric) + std::pow(std::fabs(dz), metric);
+    };
+    double minsum = 0.0, minsum2 = 0.0, minsum3 = 0.0, tf;
+    int min_idx = 0, i = 0;
+    for (int ax = -2; ax <= 2; ax++)
+        for (int ay = -2; ay <= 2; ay++)
+            for (int az = -2; az <= 2; az++) {
+                if ((std::abs(ax) == 2) + (std::abs(ay) == 2) + (std::abs(az) == 2) > 1) continue;
+                const double sum = dist(nucleus(ax, ay, az));
+                if (i == 0) minsum = sum;
+                else if (i == 1) minsum2 = sum;
+                else if (i == 2) {
+                    minsum3 = sum;
+                    if (minsum2 < minsum) { tf = minsum; minsum = minsum2; minsum2 = tf; min_idx = 1; }
+                    if (minsum3 < minsum) { tf = minsum; minsum = minsum3; minsum3 = tf; min_idx = 2; }
+                    if (minsum3 < minsum2) { tf = minsum2; minsum2 = minsum3; minsum3 = tf; }
+                } else {
+                    if (sum < minsum) { minsum3 = minsum2; minsum2 = minsum; minsum = sum; min_idx = i; }
+                    else if (sum < minsum2) { minsum3 = minsum2; minsum2 = sum; }
+                    else if (sum < minsum3) { minsum3 = sum; }
+                }
+                i++;
+            }
+    if (offset != 0.0) {
+        if (use_square) { minsum += offset * offset; minsum2 += offset * offset; minsum3 += offset * offset; }
+        else if (use_unity) { minsum += offset; minsum2 += offset; minsum3 += offset; }
+        else { minsum += std::pow(offset, metric); minsum2 += std::pow(offset, metric); minsum3 += std::pow(offset, metric); }
+    }
+    if (is_solid) {
+        V3 minvec = v3(0.0, 0.0, 0.0);
+        i = 0;
+        for (int ax = -2; ax <= 2; ax++)
+            for (int ay = -2; ay <= 2; ay++)
+                for (int az = -2; az <= 2; az++) {
+                    if ((std::abs(ax) == 2) + (std::abs(ay) == 2) + (std::abs(az) == 2) > 1) continue;
+                    if (i == min_idx) minvec = nucleus(ax, ay, az);
+                    i++;
+                }
+        tf = Noise(S, minvec, gen);
+    }
+    else if (use_square) tf = form_x * std::sqrt(minsum) + form_y * std::sqrt(minsum2) + form_z * std::sqrt(minsum3);
+    else if (use_unity) tf = form_x * minsum + form_y * minsum2 + form_z * minsum3;
+    else tf = form_x * std::pow(minsum, 1.0 / metric) + form_y * std::pow(minsum2, 1.0 / metric) + form_z * std::pow(minsum3, 1.0 / metric);
+    return std::max(std::min(tf, 1.), 0.);
+}
+
 double Tracer::Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const                                         // pattern.cpp:354-392 + EvaluateRaw
 {
     const int gen = pg.noise_generator ? pg.noise_generator : S.g.noise_generator;
@@ -1806,6 +1887,10 @@ double Tracer::Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const               
             break;
         }
     }
+    if (pg.pattern == PVGPU_PAT_CRACKLE) value = crackle_pattern(S, pg, p, gen);
+    else if (pg.pattern == PVGPU_PAT_CELLS)                                                               // pattern.cpp:5652-5660
+        value = std::min(S.patternRands[S.hashTable[S.hashTable[S.hashTable[(int)std::floor(p.x + EPSILON) & 0xfff] ^ ((int)std::floor(p.y + EPSILON) & 0xfff)] ^
+                                                    ((int)std::floor(p.z + EPSILON) & 0xfff)] % 32768u], 1.0);
     if (!discrete && pg.wave_type != PVGPU_WAVE_RAW) {                                                    // pattern.cpp:354-392
         if (pg.frequency != 0.0f) value = std::fmod(value * (double)pg.frequency + (double)pg.phase, 1.00001);
         if (value < 0.0) value -= std::floor(value);
@@ -2742,6 +2827,7 @@ void* pvo_scene_load(const char* path)
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());
     init_noise(*s);
+    { std::mt19937 gen; s->patternRands.resize(32768); for (double& v : s->patternRands) v = gen() / 4294967296.0; }     // RandomDoubles (randomsequence.cpp:138-149)
     // Initialize_Waves (noise.cpp:189-205)
     for (int i = 0, next_rand = -560851967; i < (int)s->g.number_of_waves; i++) {
         s->waveSources.push_back(unit(DNoise(*s, v3((double)i, 0.0, 0.0))));

@@ -112,7 +112,7 @@ class BlendMap(C.Structure):
 class Pigment(C.Structure):
     _fields_ = [("pattern", u32), ("wave_type", u32), ("frequency", f32), ("phase", f32), ("exponent", f32),
                 ("noise_generator", i32), ("warp_first", u32), ("warp_count", u32), ("blend_map", i32),
-                ("colour", f32 * 5), ("quick_colour", f32 * 5), ("reserved", u32), ("p", f64 * 4)]
+                ("colour", f32 * 5), ("quick_colour", f32 * 5), ("data", u32), ("p", f64 * 4)]
 
 
 class Finish(C.Structure):

@@ -137,6 +137,7 @@ struct DScene {
     const pvgpu_slope_entry* slopes;
     const double*            wave_sources;  // TraceThreadData::waveSources (xyz per wave), Initialize_Waves (noise.cpp:189)
     const double*            wave_freqs;    // TraceThreadData::waveFrequencies
+    const double*            pattern_rands; // gPatternRands (pattern.cpp:91): 32768 x mt19937 / 2^32; crackle and cells
     const pvgpu_fog*         fogs;          // SceneData::fog in list order
     uint32_t                 n_fogs, has_sky;
     uint32_t                 has_tnormals;      // some texture layer has a normal{} (per-layer normals are kept only then)

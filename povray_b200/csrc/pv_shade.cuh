@@ -59,6 +59,89 @@ __device__ inline V3 warp_epoint(const DScene& sc, const pvgpu_pigment& pg, cons
     return p;
 }
 
+#if PV_FULL_MATERIALS
+// CracklePattern::EvaluateRaw (pattern.cpp:5760-5987) without the (result-neutral) per-thread cell cache: the 81 nuclei of the
+// cubes around the point come straight from IntPickInCube = Hash3d + three entries of gPatternRands (mt19937 / 2^32).
+static __device__ __noinline__ double crackle_pattern(const DScene& sc, const pvgpu_pigment& pg, const V3& ep, int gen)
+{
+    const double* cp = sc.shape_data + pg.data;
+    const double form_x = cp[0], form_y = cp[1], form_z = cp[2], metric = cp[3], offset = cp[4];
+    const bool is_solid = cp[5] != 0.0;
+    const int rep[3] = { (int)cp[6], (int)cp[7], (int)cp[8] };
+    const bool use_square = (metric == 2), use_unity = (metric == 1);
+    auto wrap = [](double val, double upper) {                       // wrap() mathutil.h:102-121
+        double t = fmod(val, upper);
+        if (t < 0.0) t += upper;
+        if (t >= upper) t = 0.0;
+        return t;
+    };
+    V3 tp = ep;
+    if (rep[0]) tp.x = wrap(tp.x, (double)rep[0]);
+    if (rep[1]) tp.y = wrap(tp.y, (double)rep[1]);
+    if (rep[2]) tp.z = wrap(tp.z, (double)rep[2]);
+    const int flo[3] = { (int)floor(tp.x - PV_EPSILON), (int)floor(tp.y - PV_EPSILON), (int)floor(tp.z - PV_EPSILON) };
+    // nucleus of cube `index` of gaCrackleCubeTable (pattern.cpp:9349-9374) around the point: IntPickInCube (pattern.cpp:8808-8819)
+    auto nucleus = [&](int ax, int ay, int az) {
+        int c[3] = { flo[0] + ax, flo[1] + ay, flo[2] + az };
+        double woff[3] = { 0.0, 0.0, 0.0 };
+        for (int k = 0; k < 3; k++)
+            if (rep[k]) { int w = c[k] % rep[k]; if (w < 0) w += rep[k]; woff[k] += (c[k] - w); c[k] = w; }     // wrapInt
+        const unsigned seed = sc.noise.hash[sc.noise.hash[sc.noise.hash[c[0] & 0xfff] ^ (c[1] & 0xfff)] ^ (c[2] & 0xfff)];                  // Hash3d texture.h:75
+        double nx = c[0] + sc.pattern_rands[seed % 32768u], ny = c[1] + sc.pattern_rands[(seed + 1u) % 32768u], nz = c[2] + sc.pattern_rands[(seed + 2u) % 32768u];
+        nx += woff[0]; ny += woff[1]; nz += woff[2];
+        return mk(nx, ny, nz);
+    };
+    auto dist = [&](const V3& n) {
+        const double dx = n.x - tp.x, dy = n.y - tp.y, dz = n.z - tp.z;
+        if (use_square) return dx * dx + dy * dy + dz * dz;
+        if (use_unity) return fabs(dx) + fabs(dy) + fabs(dz);
+        return pow(fabs(dx), metric) + pow(fabs(dy), metric) + pow(fabs(dz), metric);
+    };
+    double minsum = 0.0, minsum2 = 0.0, minsum3 = 0.0, tf;
+    int min_idx = 0, i = 0;
+    for (int ax = -2; ax <= 2; ax++)
+        for (int ay = -2; ay <= 2; ay++)
+            for (int az = -2; az <= 2; az++) {
+                if ((abs(ax) == 2) + (abs(ay) == 2) + (abs(az) == 2) > 1) continue;
+                const double sum = dist(nucleus(ax, ay, az));
+                if (i == 0) minsum = sum;
+                else if (i == 1) minsum2 = sum;
+                else if (i == 2) {
+                    minsum3 = sum;
+                    if (minsum2 < minsum) { tf = minsum; minsum = minsum2; minsum2 = tf; min_idx = 1; }
+                    if (minsum3 < minsum) { tf = minsum; minsum = minsum3; minsum3 = tf; min_idx = 2; }
+                    if (minsum3 < minsum2) { tf = minsum2; minsum2 = minsum3; minsum3 = tf; }
+                } else {
+                    if (sum < minsum) { minsum3 = minsum2; minsum2 = minsum; minsum = sum; min_idx = i; }
+                    else if (sum < minsum2) { minsum3 = minsum2; minsum2 = sum; }
+                    else if (sum < minsum3) { minsum3 = sum; }
+                }
+                i++;
+            }
+    if (offset != 0.0) {
+        if (use_square) { minsum += offset * offset; minsum2 += offset * offset; minsum3 += offset * offset; }
+        else if (use_unity) { minsum += offset; minsum2 += offset; minsum3 += offset; }
+        else { minsum += pow(offset, metric); minsum2 += pow(offset, metric); minsum3 += pow(offset, metric); }
+    }
+    if (is_solid) {
+        V3 minvec = mk(0.0, 0.0, 0.0);
+        i = 0;
+        for (int ax = -2; ax <= 2; ax++)
+            for (int ay = -2; ay <= 2; ay++)
+                for (int az = -2; az <= 2; az++) {
+                    if ((abs(ax) == 2) + (abs(ay) == 2) + (abs(az) == 2) > 1) continue;
+                    if (i == min_idx) minvec = nucleus(ax, ay, az);
+                    i++;
+                }
+        tf = noise3(sc.noise, minvec, gen);
+    }
+    else if (use_square) tf = form_x * sqrt(minsum) + form_y * sqrt(minsum2) + form_z * sqrt(minsum3);
+    else if (use_unity) tf = form_x * minsum + form_y * minsum2 + form_z * minsum3;
+    else tf = form_x * pow(minsum, 1.0 / metric) + form_y * pow(minsum2, 1.0 / metric) + form_z * pow(minsum3, 1.0 / metric);
+    return fmax(fmin(tf, 1.), 0.);
+}
+#endif
+
 // Pattern value for a warped point: Evaluate_TPat -> <Pattern>::Evaluate.
 // (out of line in the heavy variants: the pattern switch is large and only patterned pigments / normals come here; the lean
 //  variant serves scenes whose pigments use the first pattern set only - device_upload - and keeps it inline)
@@ -225,6 +308,15 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
             value = (fabs(v.x) + fabs(v.y) + fabs(v.z)) / 3.0;
             break;
         }
+#endif
+#if PV_FULL_MATERIALS
+        case PVGPU_PAT_CRACKLE:
+            value = crackle_pattern(sc, pg, p, gen);
+            break;
+        case PVGPU_PAT_CELLS:       // CellsPattern::EvaluateRaw (pattern.cpp:5652-5660)
+            value = fmin(sc.pattern_rands[sc.noise.hash[sc.noise.hash[sc.noise.hash[(int)floor(p.x + PV_EPSILON) & 0xfff] ^ ((int)floor(p.y + PV_EPSILON) & 0xfff)] ^
+                                                        ((int)floor(p.z + PV_EPSILON) & 0xfff)] % 32768u], 1.0);
+            break;
 #endif
         default:
             value = 0.0;

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <atomic>
 #include <thread>
+#include <random>
 #include <vector>
 
 namespace pvgpu {
@@ -289,6 +290,14 @@ int device_upload(Scene& s, int device)
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
     UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes); UP(s.shape_data, v.shape_data);
     UP(s.tnormals, v.tnormals); UP(s.slope_entries, v.slopes); UP(s.fogs, v.fogs);
+    std::vector<double> pattern_rands;
+    for (const pvgpu_pigment& pg : s.pigments)
+        if ((pg.pattern == PVGPU_PAT_CRACKLE || pg.pattern == PVGPU_PAT_CELLS) && pattern_rands.empty()) {
+            std::mt19937 gen;                                   // RandomDoubles (randomsequence.cpp:138-149): boost mt19937 + uniform_real<double>(0, 1)
+            pattern_rands.resize(32768);
+            for (double& r : pattern_rands) r = gen() / 4294967296.0;
+        }
+    UP(pattern_rands, v.pattern_rands);
     UP(leaves, v.csg_leaves); UP(leaf_range, v.csg_leaf_range);
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP
@@ -334,7 +343,7 @@ int device_upload(Scene& s, int device)
     d->full = false;
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->full = true;
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->full = true;
-    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE) d->full = true;
+    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
     if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights) d->full = true;
     if (const char* e = getenv("PVGPU_FULL")) if (e[0] == '1') d->full = true;
     v.n_objs = (uint32_t)s.objects.size();

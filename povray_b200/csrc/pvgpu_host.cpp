@@ -364,6 +364,8 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "pigment %zu: bad blend map index", i);
         if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
+        if (p.pattern == PVGPU_PAT_CRACKLE && !range_ok(p.data, 9, s.shape_data.size()))
+            return fail(PVGPU_E_INVALID, "pigment %zu: crackle parameters outside the shape-data table", i);
     }
     {   // pigment_map nesting: bounded depth, no cycles
         std::vector<int> depth(s.pigments.size(), -1);

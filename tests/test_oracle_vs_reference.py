@@ -53,6 +53,11 @@ def test_oracle_pixels_match_reference(oracle, name):
     # SMALL_TOLERANCE post-condition, trace.cpp:1989-2013, so the result depends on which object was cached last)
     if name == "area_lights":
         assert d.max() < 1e-3 and (d > 1e-5).sum() <= 8
+    elif name == "crackle_cells":
+        # the reference's per-thread crackle cache is keyed by the cell coordinates only (CrackleCellCoord::operator==,
+        # cracklecache.h:74-77) and shared by every crackle pattern of the scene: a pattern with `repeat` leaves wrapped nuclei
+        # behind that another pattern then picks up for the same cell (history dependent; one pixel here)
+        assert d.max() < 0.05 and (d > 1e-5).sum() <= 2
     else:
         assert d.max() < 2e-4 and (d > 1e-5).sum() <= 1
     # (fisheye / omnimax: pixels outside the image circle trace nothing, tracepixel.cpp:408-411)
