@@ -189,10 +189,9 @@ int device_upload(Scene& s, int device)
         return fail(PVGPU_E_NO_DEVICE, "no CUDA device available (pvgpu has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(PVGPU_E_INVALID, "device %d out of range (have %d)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
-    {   // The traversal / shading kernels have different (large) local-memory frames.  By default the driver re-sizes the device's
-        // local-memory pool whenever the next kernel needs more than the last one left behind - a device-wide synchronising
-        // re-allocation on nearly every launch of the wave loop (measured: 170 -> 300 ms per frame on config 3).  Keep the pool
-        // at its high-water mark instead.
+    {   // The traversal / shading kernels have different (large) local-memory frames; ask the driver to keep the device's local-memory
+        // pool at its high-water mark instead of re-sizing it between launches (cudaDeviceLmemResizeToMax).  Harmless where the
+        // context already exists (torch created it first in bench.py: the flag is then ignored, and no difference was measured).
         unsigned int flags = 0;
         if (cudaGetDeviceFlags(&flags) == cudaSuccess && !(flags & cudaDeviceLmemResizeToMax)) {
             if (cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();
