@@ -60,6 +60,12 @@ def one(pov):
         except Exception as e:
             return rel, dict(status="oracle_error", detail=str(e)[:200])
         diff = np.abs(img - ref).max(axis=2)
+        save = os.environ.get("PVGPU_CORPUS_SAVE")
+        if save:        # keep the flattened scene + the reference's pixels as a fixture (tests/golden/corpus, test_gpu_parity.py)
+            import shutil
+            stem = os.path.join(save, rel[:-4].replace("/", "__"))
+            shutil.copy(os.path.join(d, "s.pvs"), stem + ".pvs")
+            shutil.copy(os.path.join(d, "s.rgbt"), stem + ".rgbt")
         return rel, dict(status="accepted", max_abs=float(diff.max()), frac_within_1_255=float((diff <= 1 / 255).mean()))
 
 
