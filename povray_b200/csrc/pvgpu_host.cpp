@@ -239,7 +239,7 @@ static bool range_ok(uint32_t first, uint32_t count, size_t n) { return (size_t)
 int validate_scene(Scene& s)
 {
     const size_t no = s.objects.size();
-    if (s.frame.empty()) return fail(PVGPU_E_INVALID, "scene has no frame-level objects");
+    // (a scene without objects is legal: every ray ends in ComputeSky)
     for (uint32_t f : s.frame)
         if (f >= no) return fail(PVGPU_E_INVALID, "frame object index %u out of range", f);
     for (size_t i = 0; i < no; i++) {

@@ -67,3 +67,24 @@ def test_device_reproduces_the_corpus():
                 bad.append((name, int((diff > 1 / 255).sum()), float(diff.max())))
             os.remove(path)
     assert not bad, f"{len(bad)} corpus scenes outside the pixel contract on the device: {bad[:10]}"
+
+
+# ---- a scene without any object (6 of the distribution scenes are like that at clock 0): everything is ComputeSky -----------
+def _empty_golden():
+    ref = np.fromfile(os.path.join(GOLDEN, "empty_sky.rgbt"), dtype=np.float32).reshape(54, 96, 4)
+    return os.path.join(GOLDEN, "empty_sky.pvs"), ref
+
+
+def test_oracle_renders_a_scene_without_objects(oracle):
+    path, ref = _empty_golden()
+    img, st = oracle.OracleScene(path).render(96, 54, threads=1)
+    assert np.abs(img - ref).max() < 1e-6 and st["rays"] == 96 * 54 and st["shadow_ray_tests"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not has_gpu(), reason="needs a CUDA device")
+def test_device_renders_a_scene_without_objects():
+    import povray_b200 as pv
+    path, ref = _empty_golden()
+    img, st = pv.Scene.load(path).finalize(0).render_image(96, 54)
+    assert np.abs(img - ref).max() < 1e-6 and st["rays"] == 96 * 54 and st["shadow_ray_tests"] == 0
