@@ -56,10 +56,12 @@ def test_error_reporting_and_validation(pvlib):
     assert b"null" in pvlib.pvgpu_last_error()
     assert pvlib.pvgpu_scene_load(C.byref(h), b"/nonexistent/file.pvs") == A.E_IO
     g = A.Globals()
+    g.atmosphere_ior = 1.0
+    g.atmosphere_dispersion = 1.0
     s = Scene.create(g)
-    with pytest.raises(PvgpuError) as e:          # empty scene
+    with pytest.raises(PvgpuError) as e:          # no camera (a scene without objects alone would be legal)
         s.finalize(0)
-    assert e.value.code == A.E_INVALID
+    assert e.value.code == A.E_INVALID and "camera" in str(e.value)
     # rendering a scene that was never finalized is refused
     with pytest.raises(PvgpuError):
         s.render(8, 8)
