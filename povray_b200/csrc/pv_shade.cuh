@@ -710,15 +710,32 @@ __device__ inline double relative_ior(const DScene& sc, const PRay& ray, int32_t
 }
 
 // ---- queues --------------------------------------------------------------------------------------
+// Queue slots are taken warp-aggregated: the lanes that arrive at a push together take one atomic and consecutive slots in lane
+// order, so the rays of a warp's 8 x 4 pixel block stay neighbours in the next wave (coherent node fetches in the traversal
+// kernels that follow) whatever order the warps of the grid finish in.
+__device__ __forceinline__ unsigned int take_slot(unsigned int* counter)
+{
+#ifdef PV_PLAIN_PUSH
+    return atomicAdd(counter, 1u);
+#else
+    const unsigned mask = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(mask) - 1;
+    unsigned int base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (unsigned int)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (unsigned int)__popc(mask & ((1u << lane) - 1u));
+#endif
+}
 __device__ __forceinline__ void push_ray(WaveCtx& ctx, const PRay& r)
 {
-    unsigned int slot = atomicAdd(&ctx.cnt->n_next, 1u);
+    unsigned int slot = take_slot(&ctx.cnt->n_next);
     if (slot < ctx.next_cap) ctx.next[slot] = r;
     else atomicOr(&ctx.cnt->overflow, 8u);
 }
 __device__ __forceinline__ void push_shadow(WaveCtx& ctx, const SRay& r)
 {
-    unsigned int slot = atomicAdd(&ctx.cnt->n_shadow, 1u);
+    unsigned int slot = take_slot(&ctx.cnt->n_shadow);
     if (slot < ctx.shadow_cap) ctx.shadow[slot] = r;
     else atomicOr(&ctx.cnt->overflow, 16u);
 }
