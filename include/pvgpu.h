@@ -274,6 +274,8 @@ typedef struct pvgpu_blend_entry {
  * blend_mode & PVGPU_BLEND_PIGMENT_MAP: a pigment_map (BlendMapEntry<PIGMENT*>, pigment.h:113-123) - every entry's colour[0]
  * holds the pigment table index of its PIGMENT (exact in FP32, indices < 2^24), evaluated at the parent's warped point. */
 #define PVGPU_BLEND_PIGMENT_MAP 0x100
+/* blend_mode & PVGPU_BLEND_TEXTURE_MAP: a texture_map (BlendMapEntry<TexturePtr>, texture.h:96-104): colour[0] = texture table index */
+#define PVGPU_BLEND_TEXTURE_MAP 0x200
 typedef struct pvgpu_blend_map {
     uint32_t entry_first, entry_count;
     int32_t  blend_mode;
@@ -342,12 +344,14 @@ typedef struct pvgpu_tnormal {
 
 /* TEXTURE (texture.h:108-117): one layer; `next` chains the layers of a layered texture. */
 typedef struct pvgpu_texture {
-    uint32_t type;               /* PVGPU_PAT_PLAIN only (texture maps are out of scope) */
+    uint32_t type;               /* PVGPU_PAT_PLAIN: one layer (pigment / finish / tnormal).  Any other PVGPU_PAT_*: a patterned texture
+                                    (texture_map; PVGPU_PAT_AVERAGE: average texture_map) - `pigment` then is the pattern carrier
+                                    (a pvgpu_pigment record holding the TPATTERN part) and `blend_map` the texture map        */
     int32_t  next;               /* TEXTURE::Next, -1 = last layer                       */
     int32_t  pigment;
     int32_t  finish;
     int32_t  tnormal;            /* TEXTURE::Tnormal -> tnormal table index, -1 = none     */
-    uint32_t reserved;
+    int32_t  blend_map;          /* patterned textures: blend map index (PVGPU_BLEND_TEXTURE_MAP); plain layers: unused (0) */
 } pvgpu_texture;
 
 /* Interior (source/core/coretypes.h:193-214). */

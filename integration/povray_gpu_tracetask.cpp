@@ -357,7 +357,37 @@ struct Flattener
             pvgpu_texture p{};
             p.next = (i + 1 < chain.size()) ? first + (int32_t)i + 1 : -1;
             p.tnormal = -1;
-            if (l->Type != PLAIN_PATTERN) { unsupported("patterned texture / texture_map / material_map"); p.type = 0; }
+            if (l->Type != PLAIN_PATTERN) {
+                // texture_map / average texture_map (texture.h:96-117): pattern carrier + map of whole textures
+                const TextureBlendMap* tm = dynamic_cast<const TextureBlendMap*>(l->Blend_Map.get());
+                if (l->Type == BITMAP_PATTERN || l->Type == UV_MAP_PATTERN || tm == nullptr) { unsupported("material_map / uv_mapping texture"); p.type = 0; }
+                else if (l->Flags & PVGPU_DONT_SCALE_BUMPS_FLAG) { unsupported("no_bump_scale on a patterned texture"); p.type = 0; }
+                else {
+                    pvgpu_pigment carrier{};
+                    carrier.blend_map = -1;
+                    carrier.pattern = PVGPU_PAT_PLAIN;
+                    carrier.wave_type = PVGPU_WAVE_RAMP; carrier.frequency = 1.0f; carrier.exponent = 1.0f;
+                    if (l->Type == AVERAGE_PATTERN) { p.type = PVGPU_PAT_AVERAGE; add_warps(l->pattern->warps, carrier.warp_first, carrier.warp_count); }
+                    else { fill_pattern(l->pattern.get(), carrier, "texture"); p.type = carrier.pattern; }
+                    vector<pvgpu_blend_entry> own;
+                    for (const auto& e : tm->Blend_Map_Entries) {
+                        pvgpu_blend_entry be{};
+                        be.value = e.value;
+                        be.colour[0] = (float)add_texture(e.Vals);
+                        own.push_back(be);
+                    }
+                    pvgpu_blend_map m{};
+                    m.entry_first = (uint32_t)entries.size();
+                    m.entry_count = (uint32_t)own.size();
+                    m.blend_mode = PVGPU_BLEND_TEXTURE_MAP;
+                    entries.insert(entries.end(), own.begin(), own.end());
+                    maps.push_back(m);
+                    p.blend_map = (int32_t)maps.size() - 1;
+                    pigments.push_back(carrier);
+                    p.pigment = (int32_t)pigments.size() - 1;
+                    p.finish = -1;
+                }
+            }
             else {
                 p.type = PVGPU_PAT_PLAIN;
                 p.pigment = add_pigment(l->Pigment);

@@ -627,7 +627,12 @@ public:
     // ---- shading ----
     double TraceRay(Ray& ray, Ticket& tk, Col& colour, float& transm, float weight, bool continuedRay, double maxDepth = 0.0);
     void ComputeTextureColour(Intersection& isect, Col& colour, float& transm, Ray& ray, Ticket& tk, float weight);
-    void ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect);
+    void ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect,
+                               const std::vector<int>& warps = std::vector<int>());
+    void ComputeOneTextureColour(Col& resultColour, float& resultTransm, int texture, std::vector<int>& warps, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk,
+                                 float weight, Intersection& isect, bool shadowflag);
+    void ComputeShadowTexture(Col& filtercolour, int texture, const std::vector<int>& warps, V3 ipoint, V3 rawnormal, Ray& lray, Intersection& isect);
+    V3 Warp_Normal_Chain(V3 n, const std::vector<int>& warps, bool unwarp) const;
     void ComputeSky(const Ray& ray, const Ticket& tk, Col& colour, float& transm) const;
     void ComputeFog(const Ray& ray, double Depth, Col& colour, float& transm) const;
     void Compute_Pigment(float col[5], int pigment, V3 EPoint) const;
@@ -2257,13 +2262,82 @@ void Tracer::ComputeTextureColour(Intersection& isect, Col& colour, float& trans
     Col tmpCol{ 0, 0, 0 }; float tmpTransm = 0.0f;
     if (!(1.0 < tk.adcBailout)) {
         Col c1{ 0, 0, 0 }; float t1 = 0.0f;
-        ComputeLightedTexture(c1, t1, tex, isect.IPoint, rawnormal, ray, tk, weight, isect);
+        std::vector<int> warps;
+        ComputeOneTextureColour(c1, t1, tex, warps, isect.IPoint, rawnormal, ray, tk, weight, isect, false);
         tmpCol = tmpCol + c1 * 1.0f; tmpTransm += 1.0f * t1;
     }
     colour = colour + tmpCol; transm += tmpTransm;
 }
 
-void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect)   // trace.cpp:739-1179
+// Warp_Normal / UnWarp_Normal through the patterned textures that enclose a layer (trace.cpp:816-827): transform warps only
+V3 Tracer::Warp_Normal_Chain(V3 n, const std::vector<int>& warps, bool unwarp) const
+{
+    auto one = [&](int tex, V3 v) {
+        const pvgpu_pigment& pat = S.pigments[S.textures[tex].pigment];
+        v = unit(v);
+        if (!unwarp) { for (int i = (int)pat.warp_count - 1; i >= 0; i--) { const pvgpu_warp& w = S.warps[pat.warp_first + i]; if (w.type == PVGPU_WARP_TRANSFORM) v = mtransposed(S.xf[w.transform].matrix, v); } }
+        else { for (uint32_t i = 0; i < pat.warp_count; i++) { const pvgpu_warp& w = S.warps[pat.warp_first + i]; if (w.type == PVGPU_WARP_TRANSFORM) v = MTransNormal(S.xf[w.transform], v); } }
+        return unit(v);
+    };
+    if (!unwarp) for (size_t i = 0; i < warps.size(); i++) n = one(warps[i], n);
+    else for (size_t i = warps.size(); i-- > 0;) n = one(warps[i], n);
+    return n;
+}
+
+void Tracer::ComputeOneTextureColour(Col& resultColour, float& resultTransm, int texture, std::vector<int>& warps, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk,
+                                     float weight, Intersection& isect, bool shadowflag)                  // trace.cpp:588-694
+{
+    const pvgpu_texture& tx = S.textures[texture];
+    if (tx.type == PVGPU_PAT_PLAIN) {
+        if (shadowflag) ComputeShadowTexture(resultColour, texture, warps, ipoint, rawnormal, ray, isect);
+        else ComputeLightedTexture(resultColour, resultTransm, texture, ipoint, rawnormal, ray, tk, weight, isect, warps);
+        return;
+    }
+    warps.push_back(texture);
+    const pvgpu_pigment& pat = S.pigments[tx.pigment];
+    const pvgpu_blend_map& m = S.maps[tx.blend_map];
+    const pvgpu_blend_entry* e = S.entries.data() + m.entry_first;
+    const V3 tpoint = Warp_EPoint(pat, ipoint);
+    if (tx.type == PVGPU_PAT_AVERAGE) {                                                                   // ComputeAverageTextureColours trace.cpp:697-737
+        float total = 0.0f;
+        resultColour = Col{ 0, 0, 0 }; resultTransm = 0.0f;
+        for (uint32_t i = 0; i < m.entry_count; i++) {
+            Col lc{ 0, 0, 0 }; float lt = 0.0f;
+            const float val = e[i].value;
+            std::vector<int> w2(warps);
+            ComputeOneTextureColour(lc, lt, (int)e[i].colour[0], w2, tpoint, rawnormal, ray, tk, weight, isect, shadowflag);
+            resultColour = resultColour + cmul(lc, val); resultTransm += (float)(lt * (double)val);
+            total += val;
+        }
+        resultColour = Col{ (float)(resultColour.r / (double)total), (float)(resultColour.g / (double)total), (float)(resultColour.b / (double)total) };
+        resultTransm = (float)(resultTransm / (double)total);
+        return;
+    }
+    const double value1 = Evaluate_TPat(pat, tpoint);
+    const uint32_t Max_Ent = m.entry_count - 1;
+    uint32_t iP, iN; double prevW = 0.0, curW = 1.0;
+    if (value1 >= e[Max_Ent].value) iP = iN = Max_Ent;
+    else {
+        iP = iN = 0;
+        while (value1 > e[iN].value) { iP = iN; iN++; }
+        if ((value1 == e[iN].value) || (iP == iN)) iP = iN;
+        else { prevW = (e[iN].value - value1) / (e[iN].value - e[iP].value); curW = 1.0 - prevW; }
+    }
+    {
+        std::vector<int> w2(warps);
+        ComputeOneTextureColour(resultColour, resultTransm, (int)e[iN].colour[0], w2, tpoint, rawnormal, ray, tk, weight, isect, shadowflag);
+    }
+    if (iP != iN) {
+        Col c2{ 0, 0, 0 }; float t2 = 0.0f;
+        std::vector<int> w2(warps);
+        ComputeOneTextureColour(c2, t2, (int)e[iP].colour[0], w2, tpoint, rawnormal, ray, tk, weight, isect, shadowflag);
+        resultColour = cmul(resultColour, curW) + cmul(c2, prevW);
+        resultTransm = (float)(curW * resultTransm + prevW * t2);
+    }
+}
+
+void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int texture, V3 ipoint, V3 rawnormal, Ray& ray, Ticket& tk, float weight, Intersection& isect,
+                                   const std::vector<int>& warps)   // trace.cpp:739-1179
 {
     const pvgpu_object& ob = S.objects[isect.Object];
     const double relativeIor = relative_ior(ray, ob.interior);
@@ -2279,8 +2353,10 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
         const pvgpu_finish& fn = S.finishes[S.textures[layer].finish];
         V3 layNormal = rawnormal;
         if ((S.g.quality_flags & PVGPU_Q_NORMALS) && S.textures[layer].tnormal >= 0) {                    // trace.cpp:814-828
+            layNormal = Warp_Normal_Chain(layNormal, warps, false);
             layNormal = Perturb_Normal(layNormal, S.textures[layer].tnormal, ipoint);
             if (S.tnormals[S.textures[layer].tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) layNormal = unit(layNormal);
+            layNormal = Warp_Normal_Chain(layNormal, warps, true);
         }
         if (layer_number == 0) topNormal = layNormal;
         double new_Weight = weight * trans;
@@ -2623,28 +2699,22 @@ void Tracer::TraceAreaLightSubsetShadowRay(const pvgpu_light& L, double& lightso
     lightcolour = (((sample_Colour[0] + sample_Colour[1]) + sample_Colour[2]) + sample_Colour[3]) * 0.25f;
 }
 
-void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& tk, Col& colour)           // trace.cpp:2274-2439 + ComputeShadowTexture :1181-1262
+void Tracer::ComputeShadowTexture(Col& filtercolour, int tex, const std::vector<int>& warps, V3 ipoint, V3 raw, Ray& lray, Intersection& isect)   // trace.cpp:1181-1262
 {
     const pvgpu_object& ob = S.objects[isect.Object];
-    if (!(S.g.quality_flags & PVGPU_Q_SHADOWS)) return;
-    if (ob.flags & PVGPU_OPAQUE_FLAG) { colour = Col{ 0, 0, 0 }; return; }
-    V3 raw = Normal(isect);
-    if (ob.flags & PVGPU_INVERTED_FLAG) raw = -raw;
-    double nd = dot(raw, lray.Direction);
-    if (nd > 0.0) raw = -raw;
-    int tex = hit_texture(ob, isect, nd > 0.0);
-    if (tex < 0) return;
     Col tmpCol{ 1, 1, 1 };
     const pvgpu_interior* in = ob.interior >= 0 ? &S.interiors[ob.interior] : nullptr;
     for (int layer = tex; layer >= 0; layer = S.textures[layer].next) {
         float lc[5];
-        Compute_Pigment(lc, S.textures[layer].pigment, isect.IPoint);
+        Compute_Pigment(lc, S.textures[layer].pigment, ipoint);
         tmpCol = tmpCol * Col{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
         if (in && in->caustics != 0.0f) {                                                                 // trace.cpp:1208-1234
             V3 layer_Normal = raw;
             if ((S.g.quality_flags & PVGPU_Q_NORMALS) && S.textures[layer].tnormal >= 0) {
-                layer_Normal = Perturb_Normal(layer_Normal, S.textures[layer].tnormal, isect.IPoint);
+                layer_Normal = Warp_Normal_Chain(layer_Normal, warps, false);
+                layer_Normal = Perturb_Normal(layer_Normal, S.textures[layer].tnormal, ipoint);
                 if (S.tnormals[S.textures[layer].tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) layer_Normal = unit(layer_Normal);
+                layer_Normal = Warp_Normal_Chain(layer_Normal, warps, true);
             }
             double k = 1.0 + std::pow(std::fabs(dot(layer_Normal, lray.Direction)), (double)in->caustics);
             tmpCol = tmpCol * (float)k;
@@ -2660,7 +2730,25 @@ void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& t
             refraction = refraction * Col{ (float)(in->fade_colour[0] + (1.0 - in->fade_colour[0]) / k), (float)(in->fade_colour[1] + (1.0 - in->fade_colour[1]) / k), (float)(in->fade_colour[2] + (1.0 - in->fade_colour[2]) / k) };
         }
     }
-    Col temp = tmpCol * refraction;
+    filtercolour = tmpCol * refraction;
+}
+
+void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& tk, Col& colour)           // trace.cpp:2274-2439 + ComputeShadowTexture :1181-1262
+{
+    const pvgpu_object& ob = S.objects[isect.Object];
+    if (!(S.g.quality_flags & PVGPU_Q_SHADOWS)) return;
+    if (ob.flags & PVGPU_OPAQUE_FLAG) { colour = Col{ 0, 0, 0 }; return; }
+    V3 raw = Normal(isect);
+    if (ob.flags & PVGPU_INVERTED_FLAG) raw = -raw;
+    double nd = dot(raw, lray.Direction);
+    if (nd > 0.0) raw = -raw;
+    int tex = hit_texture(ob, isect, nd > 0.0);
+    if (tex < 0) return;
+    // texture list of one entry (weight 1): ComputeOneTextureColour(..., shadowflag = true) (trace.cpp:2399-2417)
+    Col temp{ 0, 0, 0 }; float dummy = 0.0f;
+    std::vector<int> warps;
+    Ticket tk2 = tk;
+    ComputeOneTextureColour(temp, dummy, tex, warps, isect.IPoint, raw, lray, tk2, 0.0f, isect, true);
     if (std::fabs((std::fabs(temp.r) + std::fabs(temp.g) + std::fabs(temp.b)) / 3.0f) < tk.adcBailout) { colour = Col{ 0, 0, 0 }; return; }
     colour = colour * temp;
     // ComputeShadowMedia (trace.cpp:3046-3071): toggle the blocker's interior on the light ray

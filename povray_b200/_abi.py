@@ -125,7 +125,7 @@ class Finish(C.Structure):
 
 
 class Texture(C.Structure):
-    _fields_ = [("type", u32), ("next", i32), ("pigment", i32), ("finish", i32), ("tnormal", i32), ("reserved", u32)]
+    _fields_ = [("type", u32), ("next", i32), ("pigment", i32), ("finish", i32), ("tnormal", i32), ("blend_map", i32)]
 
 
 class SlopeEntry(C.Structure):

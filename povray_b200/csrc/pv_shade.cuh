@@ -957,7 +957,63 @@ __device__ inline V3 reflect_direction(const V3& dir, const V3& normal, const V3
 // ---- the shading of one closest hit ---------------------------------------------------------------
 // ray:      the TraceRay call being served (already past the level / ADC test)
 // ray_slot: its index in the current wave (shadow records point back at it)
-__device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx)
+// One plain (layered) texture a hit's texture tree resolves to: ComputeOneTextureColour (trace.cpp:588-694) walks texture_map /
+// average textures down to plain textures, each evaluated at the point its enclosing patterns warped and weighted by the product
+// of the blend weights on the way; `chain` = the enclosing patterned textures (their transform warps act on the layer normals).
+#define PV_MAX_TEX_LEAVES 16
+#define PV_MAX_TEX_DEPTH  4
+struct TexLeaf { int32_t tex; int32_t n_chain; double w; V3 p; int32_t chain[PV_MAX_TEX_DEPTH]; };
+
+#if PV_FULL_MATERIALS
+// Resolves texture `tex0` at `ipoint` into plain leaves (explicit stack; depth and leaf count are validated on the host).
+static __device__ __noinline__ int resolve_texture(const DScene& sc, int32_t tex0, const V3& ipoint, TexLeaf* leaves)
+{
+    TexLeaf st[PV_MAX_TEX_LEAVES];
+    int sp = 0, n = 0;
+    st[sp].tex = tex0; st[sp].n_chain = 0; st[sp].w = 1.0; st[sp].p = ipoint; sp++;
+    while (sp > 0) {
+        const TexLeaf cur = st[--sp];
+        const pvgpu_texture& tx = sc.textures[cur.tex];
+        if (tx.type == PVGPU_PAT_PLAIN) { if (n < PV_MAX_TEX_LEAVES) leaves[n++] = cur; continue; }
+        const pvgpu_pigment& pat = sc.pigments[tx.pigment];
+        const pvgpu_blend_map& m = sc.maps[tx.blend_map];
+        const pvgpu_blend_entry* e = sc.entries + m.entry_first;
+        TexLeaf child = cur;
+        if (child.n_chain < PV_MAX_TEX_DEPTH) child.chain[child.n_chain++] = tx.pigment;
+        child.p = warp_epoint(sc, pat, cur.p);
+        if (tx.type == PVGPU_PAT_AVERAGE) {                      // ComputeAverageTextureColours (trace.cpp:697-737)
+            float total = 0.0f;
+            for (uint32_t i = 0; i < m.entry_count; i++) total += e[i].value;
+            for (uint32_t i = 0; i < m.entry_count && sp < PV_MAX_TEX_LEAVES; i++) {
+                child.tex = (int32_t)e[i].colour[0];
+                child.w = cur.w * ((double)e[i].value / (double)total);
+                st[sp++] = child;
+            }
+            continue;
+        }
+        const double value = evaluate_pattern(sc, pat, child.p);
+        uint32_t ip, in;
+        double wp;
+        blend_search(e, m.entry_count, value, ip, in, wp);
+        if (sp < PV_MAX_TEX_LEAVES) { child.tex = (int32_t)e[in].colour[0]; child.w = (ip != in) ? cur.w * (1.0 - wp) : cur.w; st[sp++] = child; }
+        if (ip != in && sp < PV_MAX_TEX_LEAVES) { child.tex = (int32_t)e[ip].colour[0]; child.w = cur.w * wp; st[sp++] = child; }
+    }
+    return n;
+}
+// Warp_Normal / UnWarp_Normal through the enclosing patterned textures (trace.cpp:816-827)
+__device__ inline V3 warp_normal_chain(const DScene& sc, const TexLeaf* leaf, V3 n, bool unwarp)
+{
+    if (!leaf) return n;
+    if (!unwarp) for (int i = 0; i < leaf->n_chain; i++) n = warp_normal(sc, sc.pigments[leaf->chain[i]], n, false);
+    else for (int i = leaf->n_chain - 1; i >= 0; i--) n = unwarp_normal(sc, sc.pigments[leaf->chain[i]], n, false);
+    return n;
+}
+template <bool LEAF> __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx, const TexLeaf* leaf);
+static __device__ __noinline__ void shade_texture_map(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx, int32_t tex0);
+#endif
+
+template <bool LEAF>
+__device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx, const TexLeaf* leaf)
 {
     const pvgpu_object& ob = sc.objs[hit.obj];
     const V3 dir = ld3(ray.d);
@@ -971,10 +1027,14 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
     const double normaldirection = dot(rawnormal, dir);
     if (normaldirection > 0.0) rawnormal = -rawnormal;
 
-    const int32_t tex0 = hit_texture(sc, ob, hit, normaldirection > 0.0);
+    const int32_t tex0 = (LEAF && leaf) ? leaf->tex : hit_texture(sc, ob, hit, normaldirection > 0.0);
     if (tex0 < 0) return;
     // a single WeightedTexture of weight 1.0: skipped if 1.0 < adcBailout (trace.cpp:541)
     if (1.0 < adc) return;
+#if PV_FULL_MATERIALS
+    if (!LEAF && sc.textures[tex0].type != PVGPU_PAT_PLAIN) { shade_texture_map(sc, ray, ray_slot, hit, ctx, tex0); return; }
+#endif
+    const V3 epoint = (LEAF && leaf) ? leaf->p : ipoint;       // where pigments and normals are evaluated (trace.cpp:588-694)
 
     const double rel_ior = relative_ior(sc, ray, ob.interior);
 
@@ -1005,8 +1065,10 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
         if (has_tn) {
             L.n = rawnormal;
             if (tx.tnormal >= 0) {                                                    // trace.cpp:814-828
-                L.n = perturb_normal(sc, tx.tnormal, L.n, ipoint);
+                L.n = warp_normal_chain(sc, LEAF ? leaf : nullptr, L.n, false);
+                L.n = perturb_normal(sc, tx.tnormal, L.n, epoint);
                 if (sc.tnormals[tx.tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) L.n = normalized(L.n);
+                L.n = warp_normal_chain(sc, LEAF ? leaf : nullptr, L.n, true);
             }
             if (nlayers == 0) top_normal = L.n;
         }
@@ -1014,7 +1076,7 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
         const V3 lay_normal = LAYER_NORMAL(L);
         const double cos_inc = -dot(dir, lay_normal);
         float lc[5];
-        compute_pigment(sc, tx.pigment, ipoint, lc);
+        compute_pigment(sc, tx.pigment, epoint, lc);
         L.col[0] = lc[0]; L.col[1] = lc[1]; L.col[2] = lc[2];
         L.fil[0] = fil[0]; L.fil[1] = fil[1]; L.fil[2] = fil[2];
         L.finish = tx.finish;
@@ -1255,6 +1317,27 @@ __device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray
         }
     }
     #undef LAYER_NORMAL
+}
+
+#if PV_FULL_MATERIALS
+// texture_map / average texture: every resolved plain texture is shaded like a texture of its own with the ray's weights scaled
+// by its blend weight (the reference blends the finished colours, trace.cpp:671-692; everything downstream is linear in them)
+static __device__ __noinline__ void shade_texture_map(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx, int32_t tex0)
+{
+    TexLeaf leaves[PV_MAX_TEX_LEAVES];
+    const int n = resolve_texture(sc, tex0, hit.ip, leaves);
+    for (int i = 0; i < n; i++) {
+        PRay sr = ray;
+        const float w = (float)leaves[i].w;
+        sr.w[0] *= w; sr.w[1] *= w; sr.w[2] *= w; sr.wt *= w;
+        shade_hit_impl<true>(sc, sr, ray_slot, hit, ctx, &leaves[i]);
+    }
+}
+#endif
+
+__device__ inline void shade_hit(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx)
+{
+    shade_hit_impl<false>(sc, ray, ray_slot, hit, ctx, nullptr);
 }
 
 }  // namespace pvgpu

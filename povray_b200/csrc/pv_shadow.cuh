@@ -7,29 +7,24 @@
 namespace pvgpu {
 
 // ---- shadow rays ----------------------------------------------------------------------------------
-// Trace::ComputeShadowTexture (trace.cpp:1181-1262) for a transparent blocker.
-__device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3& dir, const PRay* parent, bool inside_now, float f[3])
+// Trace::ComputeShadowTexture (trace.cpp:1181-1262) for one plain (layered) texture evaluated at `epoint`: filter colour x fade
+__device__ inline void shadow_texture(const DScene& sc, const pvgpu_object& ob, const pvgpu_interior* in, const Hit& hit, const V3& dir, const V3& rawnormal,
+                                      bool inside_now, int32_t tex0, const V3& epoint, const TexLeaf* leaf, float tc[3])
 {
-    const pvgpu_object& ob = sc.objs[hit.obj];
-    V3 rawnormal = object_normal(sc, ob, hit);
-    if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
-    const double nd = dot(rawnormal, dir);
-    if (nd > 0.0) rawnormal = -rawnormal;
-    const int32_t tex0 = hit_texture(sc, ob, hit, nd > 0.0);
-    if (tex0 < 0) return;       // texture list empty: colour unchanged (trace.cpp:2391-2397)
     float tmp[3] = { 1.0f, 1.0f, 1.0f };
-    const pvgpu_interior* in = (ob.interior >= 0) ? &sc.interiors[ob.interior] : nullptr;
     for (int32_t li = tex0; li >= 0; li = sc.textures[li].next) {
         float lc[5];
-        compute_pigment(sc, sc.textures[li].pigment, hit.ip, lc);
+        compute_pigment(sc, sc.textures[li].pigment, epoint, lc);
         #pragma unroll
         for (int k = 0; k < 3; k++) tmp[k] *= (lc[k] * lc[3] + lc[4]);
         if (in && in->caustics != 0.0f) {
             V3 layer_normal = rawnormal;
 #if PV_FULL_MATERIALS
             if ((sc.g.quality_flags & PVGPU_Q_NORMALS) && sc.textures[li].tnormal >= 0) {       // trace.cpp:1208-1227
-                layer_normal = perturb_normal(sc, sc.textures[li].tnormal, layer_normal, hit.ip);
+                layer_normal = warp_normal_chain(sc, leaf, layer_normal, false);
+                layer_normal = perturb_normal(sc, sc.textures[li].tnormal, layer_normal, epoint);
                 if (sc.tnormals[sc.textures[li].tnormal].flags & PVGPU_DONT_SCALE_BUMPS_FLAG) layer_normal = normalized(layer_normal);
+                layer_normal = warp_normal_chain(sc, leaf, layer_normal, true);
             }
 #endif
             double dotval = dot(layer_normal, dir);
@@ -48,7 +43,37 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
             for (int k = 0; k < 3; k++) refr[k] *= (float)((double)in->fade_colour[k] + (1.0 - (double)in->fade_colour[k]) / kk);
         }
     }
-    float tc[3] = { tmp[0] * refr[0], tmp[1] * refr[1], tmp[2] * refr[2] };
+    tc[0] = tmp[0] * refr[0]; tc[1] = tmp[1] * refr[1]; tc[2] = tmp[2] * refr[2];
+}
+
+
+// Trace::ComputeShadowTexture (trace.cpp:1181-1262) for a transparent blocker.
+__device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3& dir, const PRay* parent, bool inside_now, float f[3])
+{
+    const pvgpu_object& ob = sc.objs[hit.obj];
+    V3 rawnormal = object_normal(sc, ob, hit);
+    if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
+    const double nd = dot(rawnormal, dir);
+    if (nd > 0.0) rawnormal = -rawnormal;
+    const int32_t tex0 = hit_texture(sc, ob, hit, nd > 0.0);
+    if (tex0 < 0) return;       // texture list empty: colour unchanged (trace.cpp:2391-2397)
+    float tc[3];
+    const pvgpu_interior* in = (ob.interior >= 0) ? &sc.interiors[ob.interior] : nullptr;
+#if PV_FULL_MATERIALS
+    if (sc.textures[tex0].type != PVGPU_PAT_PLAIN) {
+        // texture_map: weighted sum of the leaves' filter colours (ComputeOneTextureColour with shadowflag, trace.cpp:671-692)
+        TexLeaf leaves[PV_MAX_TEX_LEAVES];
+        const int n = resolve_texture(sc, tex0, hit.ip, leaves);
+        tc[0] = tc[1] = tc[2] = 0.0f;
+        for (int i = 0; i < n; i++) {
+            float t1[3];
+            shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, leaves[i].tex, leaves[i].p, &leaves[i], t1);
+            #pragma unroll
+            for (int k = 0; k < 3; k++) tc[k] += (float)((double)t1[k] * leaves[i].w);
+        }
+    } else
+#endif
+    shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, tex0, hit.ip, nullptr, tc);
     // ComputeShadowColour: "close enough to full shadow" (trace.cpp:2419-2424)
     if (fabsf((fabsf(tc[0]) + fabsf(tc[1]) + fabsf(tc[2])) / 3.0f) < (float)sc.g.adc_bailout) { f[0] = f[1] = f[2] = 0.0f; return; }
     f[0] *= tc[0]; f[1] *= tc[1]; f[2] *= tc[2];

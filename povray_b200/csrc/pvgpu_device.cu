@@ -316,7 +316,7 @@ int device_upload(Scene& s, int device)
     for (const pvgpu_object& o : s.objects)
         if (!(o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_MESH) ||
             o.clip_count || o.bound_count) d->lean = false;
-    for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->lean = false;
+    for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0 || t.type != PVGPU_PAT_PLAIN) d->lean = false;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern > PVGPU_PAT_AGATE || pg.pattern == PVGPU_PAT_BRICK || pg.pattern == PVGPU_PAT_HEXAGON) d->lean = false;
     if (!s.fogs.empty() || !s.sky_spheres.empty()) d->lean = false;
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->lean = false;
@@ -340,7 +340,7 @@ int device_upload(Scene& s, int device)
     for (const pvgpu_mesh& me : s.meshes) if (me.node_count == 0) d->lean = false;       // `hierarchy off` meshes take the generic walk
     if (const char* e = getenv("PVGPU_LEAN")) if (e[0] == '0') d->lean = false;
     d->full = false;
-    for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) d->full = true;
+    for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0 || t.type != PVGPU_PAT_PLAIN) d->full = true;
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->full = true;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
     if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights) d->full = true;

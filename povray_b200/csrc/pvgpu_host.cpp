@@ -342,8 +342,19 @@ int validate_scene(Scene& s)
     }
     for (size_t i = 0; i < s.textures.size(); i++) {
         const pvgpu_texture& t = s.textures[i];
-        if (t.type != PVGPU_PAT_PLAIN)
-            return fail(PVGPU_E_UNSUPPORTED, "texture %zu: patterned textures / texture maps are outside the hot-path scope", i);
+        if (t.type != PVGPU_PAT_PLAIN) {
+            // texture_map / average texture_map: pattern carrier + a blend map whose entries are texture indices
+            if (t.type > PVGPU_PAT_LAST || t.pigment < 0 || t.pigment >= (int32_t)s.pigments.size() || t.blend_map < 0 || t.blend_map >= (int32_t)s.blend_maps.size() ||
+                !(s.blend_maps[t.blend_map].blend_mode & PVGPU_BLEND_TEXTURE_MAP))
+                return fail(PVGPU_E_INVALID, "texture %zu: patterned texture without pattern carrier / texture map", i);
+            const pvgpu_blend_map& m = s.blend_maps[t.blend_map];
+            for (uint32_t k = 0; k < m.entry_count; k++) {
+                const float ti = s.blend_entries[m.entry_first + k].colour[0];
+                if (!(ti >= 0.0f) || ti >= (float)s.textures.size() || ti != std::floor(ti))
+                    return fail(PVGPU_E_INVALID, "texture %zu: map entry %u is not a texture index", i, k);
+            }
+            continue;
+        }
         if (t.pigment < 0 || t.pigment >= (int32_t)s.pigments.size() || t.finish < 0 ||
             t.finish >= (int32_t)s.finishes.size() || t.next >= (int32_t)s.textures.size())
             return fail(PVGPU_E_INVALID, "texture %zu: bad pigment / finish / next index", i);
@@ -385,6 +396,25 @@ int validate_scene(Scene& s)
         for (size_t i = 0; i < s.pigments.size(); i++)
             if (walk(i, 0) < 0) return fail(PVGPU_E_UNSUPPORTED, "pigment %zu: pigment_map nested deeper than 6 levels", i);
     }
+    {   // texture_map nesting: bounded depth (the device resolves a hit's texture tree into at most 16 weighted plain textures)
+        std::function<int(size_t, int)> leaves = [&](size_t ti, int level) -> int {
+            const pvgpu_texture& t = s.textures[ti];
+            if (t.type == PVGPU_PAT_PLAIN) return 1;
+            if (level >= 4) return -1;
+            const pvgpu_blend_map& m = s.blend_maps[t.blend_map];
+            int worst = 0, sum = 0;
+            for (uint32_t k = 0; k < m.entry_count; k++) {
+                int n = leaves((size_t)s.blend_entries[m.entry_first + k].colour[0], level + 1);
+                if (n < 0) return -1;
+                worst = std::max(worst, n); sum += n;
+            }
+            return (t.type == PVGPU_PAT_AVERAGE) ? sum : 2 * worst;      // a map blends two neighbouring entries
+        };
+        for (size_t i = 0; i < s.textures.size(); i++) {
+            int n = leaves(i, 0);
+            if (n < 0 || n > 16) return fail(PVGPU_E_UNSUPPORTED, "texture %zu: texture_map nested deeper than 4 levels / more than 16 blended textures", i);
+        }
+    }
     if (s.sky_spheres.size() > 1) return fail(PVGPU_E_INVALID, "more than one sky_sphere");
     for (const pvgpu_sky_sphere& k : s.sky_spheres) {
         if (!range_ok(k.pigment_first, k.pigment_count, s.index_list.size()) || k.transform >= (int32_t)s.transforms.size())
@@ -423,8 +453,8 @@ int validate_scene(Scene& s)
         const pvgpu_blend_map& m = s.blend_maps[i];
         if (m.entry_count == 0 || !range_ok(m.entry_first, m.entry_count, s.blend_entries.size()))
             return fail(PVGPU_E_INVALID, "blend map %zu: bad entry range", i);
-        if ((m.blend_mode & ~PVGPU_BLEND_PIGMENT_MAP) != 0)
-            return fail(PVGPU_E_UNSUPPORTED, "blend map %zu: blend_mode %d is outside the hot-path scope", i, m.blend_mode & ~PVGPU_BLEND_PIGMENT_MAP);
+        if ((m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP)) != 0)
+            return fail(PVGPU_E_UNSUPPORTED, "blend map %zu: blend_mode %d is outside the hot-path scope", i, m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP));
         if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP)
             for (uint32_t k = 0; k < m.entry_count; k++) {
                 const float pi = s.blend_entries[m.entry_first + k].colour[0];
