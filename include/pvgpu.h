@@ -276,6 +276,8 @@ typedef struct pvgpu_blend_entry {
 #define PVGPU_BLEND_PIGMENT_MAP 0x100
 /* blend_mode & PVGPU_BLEND_TEXTURE_MAP: a texture_map (BlendMapEntry<TexturePtr>, texture.h:96-104): colour[0] = texture table index */
 #define PVGPU_BLEND_TEXTURE_MAP 0x200
+/* blend_mode & PVGPU_BLEND_NORMAL_MAP: a normal_map (BlendMapEntry<TNORMAL*>, normal.h:98-110): colour[0] = tnormal table index */
+#define PVGPU_BLEND_NORMAL_MAP  0x400
 typedef struct pvgpu_blend_map {
     uint32_t entry_first, entry_count;
     int32_t  blend_mode;
@@ -320,7 +322,9 @@ enum {
     PVGPU_NORM_WAVES    = 4,     /* waves    normal.cpp:180 */
     PVGPU_NORM_WRINKLES = 5,     /* wrinkles normal.cpp:325 */
     PVGPU_NORM_QUILTED  = 6,     /* quilted  normal.cpp:371, carrier p[0..1] = Control0, Control1 */
-    PVGPU_NORM_PATTERN  = 7      /* any continuous pattern: 4 samples on Pyramid_Vect + slope map (normal.cpp:893-918) */
+    PVGPU_NORM_PATTERN  = 7,     /* any continuous pattern: 4 samples on Pyramid_Vect + slope map (normal.cpp:893-918); with `normal_map`
+                                    set: any pattern (block patterns too) selecting / blending whole normals (normal.cpp:824-848) */
+    PVGPU_NORM_AVERAGE  = 8      /* average normal_map (NormalBlendMap::ComputeAverage, normal.cpp:1033-1059) */
 };
 #define PVGPU_DONT_SCALE_BUMPS_FLAG 8u   /* pattern.h:106 */
 
@@ -339,7 +343,7 @@ typedef struct pvgpu_tnormal {
     int32_t  pattern;            /* pigment table index of the pattern carrier           */
     uint32_t slope_first, slope_count;   /* slope_map entries, count 0 = none            */
     float    amount, delta;      /* Amount, Delta                                        */
-    uint32_t reserved;
+    uint32_t normal_map;         /* 0 = none, else blend map index + 1 of a normal_map (PVGPU_BLEND_NORMAL_MAP) */
 } pvgpu_tnormal;
 
 /* TEXTURE (texture.h:108-117): one layer; `next` chains the layers of a layered texture. */

@@ -224,7 +224,32 @@ struct Flattener
         t.flags = tn->Flags & PVGPU_DONT_SCALE_BUMPS_FLAG;
         t.amount = tn->Amount; t.delta = tn->Delta;
         const SlopeBlendMap* sm = dynamic_cast<const SlopeBlendMap*>(tn->Blend_Map.get());
-        if (tn->Blend_Map != nullptr && sm == nullptr) unsupported("normal_map");
+        const NormalBlendMap* nm = dynamic_cast<const NormalBlendMap*>(tn->Blend_Map.get());
+        if (tn->Blend_Map != nullptr && sm == nullptr && nm == nullptr) unsupported("normal blend map of unknown kind");
+        if (nm != nullptr) {
+            // normal_map: the entries are normals of their own (normal.cpp:824-848, 1033-1059)
+            if (tn->Type == UV_MAP_PATTERN) unsupported("uv_mapping normal");
+            vector<pvgpu_blend_entry> own;
+            for (const auto& e : nm->Blend_Map_Entries) {
+                pvgpu_blend_entry be{};
+                be.value = e.value;
+                be.colour[0] = (float)add_tnormal(e.Vals);
+                own.push_back(be);
+            }
+            pvgpu_blend_map m{};
+            m.entry_first = (uint32_t)entries.size();
+            m.entry_count = (uint32_t)own.size();
+            m.blend_mode = PVGPU_BLEND_NORMAL_MAP;
+            entries.insert(entries.end(), own.begin(), own.end());
+            maps.push_back(m);
+            t.normal_map = (uint32_t)maps.size();
+            if (tn->Type == AVERAGE_PATTERN) { t.type = PVGPU_NORM_AVERAGE; add_warps(bp->warps, carrier.warp_first, carrier.warp_count); }
+            else { t.type = PVGPU_NORM_PATTERN; fill_pattern(bp, carrier, "normal"); }
+            pigments.push_back(carrier);
+            t.pattern = (int32_t)pigments.size() - 1;
+            tnormals.push_back(t);
+            return (int32_t)tnormals.size() - 1;
+        }
         bool special = true;
         switch (tn->Type) {
             case BUMPS_PATTERN:    t.type = PVGPU_NORM_BUMPS; break;

@@ -1922,6 +1922,50 @@ V3 Tracer::Perturb_Normal(V3 Layer_Normal, int tnormal, V3 EPoint) const        
         if (w.type == PVGPU_WARP_TRANSFORM) Layer_Normal = mtransposed(S.xf[w.transform].matrix, Layer_Normal);      // MInvTransNormal
     }
     if (!DontScaleBumps) Layer_Normal = unit(Layer_Normal);
+    if (tn.normal_map) {
+        const pvgpu_blend_map& m = S.maps[tn.normal_map - 1];
+        const pvgpu_blend_entry* e = S.entries.data() + m.entry_first;
+        auto warpn = [&](V3 v) {                                                                          // Warp_Normal
+            if (!DontScaleBumps) v = unit(v);
+            for (int i = (int)pat.warp_count - 1; i >= 0; i--) { const pvgpu_warp& w = S.warps[pat.warp_first + i]; if (w.type == PVGPU_WARP_TRANSFORM) v = mtransposed(S.xf[w.transform].matrix, v); }
+            if (!DontScaleBumps) v = unit(v);
+            return v;
+        };
+        auto unwarpn = [&](V3 v) {                                                                        // UnWarp_Normal
+            if (!DontScaleBumps) v = unit(v);
+            for (uint32_t i = 0; i < pat.warp_count; i++) { const pvgpu_warp& w = S.warps[pat.warp_first + i]; if (w.type == PVGPU_WARP_TRANSFORM) v = MTransNormal(S.xf[w.transform], v); }
+            if (!DontScaleBumps) v = unit(v);
+            return v;
+        };
+        // (Layer_Normal was already put through Warp_Normal above)
+        if (tn.type == PVGPU_NORM_AVERAGE) {                                                              // normal.cpp:861-883, 1033-1059
+            const V3 TPointA = Warp_EPoint(pat, EPoint);
+            V3 V1 = v3(0.0, 0.0, 0.0);
+            float Total = 0.0f;
+            for (uint32_t i = 0; i < m.entry_count; i++) {
+                V3 V2 = Perturb_Normal(Layer_Normal, (int)e[i].colour[0], TPointA);
+                V1 = V1 + V2 * (double)e[i].value;
+                Total += e[i].value;
+            }
+            return unwarpn(V1 / (double)Total);
+        }
+        const V3 TPointM = Warp_EPoint(pat, EPoint);                                                      // normal.cpp:824-848
+        const double value1 = Evaluate_TPat(pat, TPointM);
+        const uint32_t Max_Ent = m.entry_count - 1;
+        uint32_t iP, iN; double prevW = 0.0, curW = 1.0;
+        if (value1 >= e[Max_Ent].value) iP = iN = Max_Ent;
+        else {
+            iP = iN = 0;
+            while (value1 > e[iN].value) { iP = iN; iN++; }
+            if ((value1 == e[iN].value) || (iP == iN)) iP = iN;
+            else { prevW = (e[iN].value - value1) / (e[iN].value - e[iP].value); curW = 1.0 - prevW; }
+        }
+        V3 P1 = Layer_Normal;
+        Layer_Normal = Perturb_Normal(Layer_Normal, (int)e[iN].colour[0], TPointM);
+        if (iP != iN) { P1 = Perturb_Normal(P1, (int)e[iP].colour[0], TPointM); Layer_Normal = prevW * P1 + curW * Layer_Normal; }
+        (void)warpn;
+        return unit(unwarpn(Layer_Normal));
+    }
     const V3 TPoint = Warp_EPoint(pat, EPoint);
     const double Amount = (double)tn.amount;
     switch (tn.type) {

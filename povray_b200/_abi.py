@@ -134,7 +134,7 @@ class SlopeEntry(C.Structure):
 
 class TNormal(C.Structure):
     _fields_ = [("type", u32), ("flags", u32), ("pattern", i32), ("slope_first", u32), ("slope_count", u32),
-                ("amount", f32), ("delta", f32), ("reserved", u32)]
+                ("amount", f32), ("delta", f32), ("normal_map", u32)]
 
 
 class SkySphere(C.Structure):

@@ -472,12 +472,51 @@ __device__ inline double do_slope_map(const DScene& sc, const pvgpu_tnormal& tn,
     rv += t1 * e[ip].slope + e[ip].height;
     return rv;
 }
-static __device__ __noinline__ V3 perturb_normal(const DScene& sc, int32_t tn_index, V3 n, const V3& epoint)
+// (LEVEL unrolls the recursion through normal_maps, nesting depth validated on the host: the call graph stays acyclic)
+#define PV_NORMAL_MAP_LEVELS 3
+template <int LEVEL>
+static __device__ __noinline__ V3 perturb_normal_t(const DScene& sc, int32_t tn_index, V3 n, const V3& epoint)
 {
     const pvgpu_tnormal& tn = sc.tnormals[tn_index];
     const pvgpu_pigment& c = sc.pigments[tn.pattern];
     const bool dont_scale = (tn.flags & PVGPU_DONT_SCALE_BUMPS_FLAG) != 0;
     const double amount = (double)tn.amount;
+    if (tn.normal_map) {
+        auto child = [&](int32_t idx, const V3& v, const V3& p) -> V3 {
+            if constexpr (LEVEL > 0) return perturb_normal_t<LEVEL - 1>(sc, idx, v, p);
+            else return v;          // unreachable: nesting depth is validated
+        };
+        const pvgpu_blend_map& m = sc.maps[tn.normal_map - 1];
+        const pvgpu_blend_entry* e = sc.entries + m.entry_first;
+        if (tn.type == PVGPU_NORM_AVERAGE) {            // normal.cpp:861-883 (special branch) + NormalBlendMap::ComputeAverage :1033-1059
+            n = warp_normal(sc, c, n, dont_scale);
+            const V3 tpa = warp_epoint(sc, c, epoint);
+            V3 v1 = mk(0.0, 0.0, 0.0);
+            float total = 0.0f;
+            for (uint32_t i = 0; i < m.entry_count; i++) {
+                const V3 v2 = child((int32_t)e[i].colour[0], n, tpa);
+                v1 = v1 + (double)e[i].value * v2;
+                total += e[i].value;
+            }
+            n = v1 / (double)total;
+            return unwarp_normal(sc, c, n, dont_scale);
+        }
+        // normal_map selected by a pattern (normal.cpp:824-848)
+        const V3 tpm = warp_epoint(sc, c, epoint);
+        const double value1 = evaluate_pattern(sc, c, tpm);
+        uint32_t ip, in;
+        double wp;
+        blend_search(e, m.entry_count, value1, ip, in, wp);
+        n = warp_normal(sc, c, n, dont_scale);
+        const V3 p1 = n;
+        n = child((int32_t)e[in].colour[0], n, tpm);
+        if (ip != in) {
+            const V3 q = child((int32_t)e[ip].colour[0], p1, tpm);
+            n = wp * q + (1.0 - wp) * n;
+        }
+        n = unwarp_normal(sc, c, n, dont_scale);
+        return normalized(n);
+    }
     n = warp_normal(sc, c, n, dont_scale);
     const V3 tp = warp_epoint(sc, c, epoint);
     switch (tn.type) {
@@ -545,6 +584,10 @@ static __device__ __noinline__ V3 perturb_normal(const DScene& sc, int32_t tn_in
         }
     }
     return unwarp_normal(sc, c, n, dont_scale);
+}
+__device__ __forceinline__ V3 perturb_normal(const DScene& sc, int32_t tn_index, const V3& n, const V3& epoint)
+{
+    return perturb_normal_t<PV_NORMAL_MAP_LEVELS>(sc, tn_index, n, epoint);
 }
 #endif
 

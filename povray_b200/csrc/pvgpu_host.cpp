@@ -396,6 +396,19 @@ int validate_scene(Scene& s)
         for (size_t i = 0; i < s.pigments.size(); i++)
             if (walk(i, 0) < 0) return fail(PVGPU_E_UNSUPPORTED, "pigment %zu: pigment_map nested deeper than 6 levels", i);
     }
+    {   // normal_map nesting: at most 3 levels (PV_NORMAL_MAP_LEVELS of the device code)
+        std::function<int(size_t, int)> depth = [&](size_t ni, int level) -> int {
+            const pvgpu_tnormal& t = s.tnormals[ni];
+            if (!t.normal_map) return 0;
+            if (level >= 3) return -1;
+            const pvgpu_blend_map& m = s.blend_maps[t.normal_map - 1];
+            for (uint32_t k = 0; k < m.entry_count; k++)
+                if (depth((size_t)s.blend_entries[m.entry_first + k].colour[0], level + 1) < 0) return -1;
+            return 1;
+        };
+        for (size_t i = 0; i < s.tnormals.size(); i++)
+            if (depth(i, 0) < 0) return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: normal_map nested deeper than 3 levels", i);
+    }
     {   // texture_map nesting: bounded depth (the device resolves a hit's texture tree into at most 16 weighted plain textures)
         std::function<int(size_t, int)> leaves = [&](size_t ti, int level) -> int {
             const pvgpu_texture& t = s.textures[ti];
@@ -437,12 +450,23 @@ int validate_scene(Scene& s)
                 return fail(PVGPU_E_UNSUPPORTED, "light %zu: media_attenuation with fog (fog on shadow rays) is outside the hot-path scope", i);
     for (size_t i = 0; i < s.tnormals.size(); i++) {
         const pvgpu_tnormal& t = s.tnormals[i];
-        if (t.type < PVGPU_NORM_BUMPS || t.type > PVGPU_NORM_PATTERN)
+        if (t.type < PVGPU_NORM_BUMPS || t.type > PVGPU_NORM_AVERAGE)
             return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: type %u unsupported", i, t.type);
+        if (t.normal_map) {
+            if (t.normal_map > s.blend_maps.size() || !(s.blend_maps[t.normal_map - 1].blend_mode & PVGPU_BLEND_NORMAL_MAP) ||
+                (t.type != PVGPU_NORM_PATTERN && t.type != PVGPU_NORM_AVERAGE))
+                return fail(PVGPU_E_INVALID, "tnormal %zu: bad normal_map", i);
+            const pvgpu_blend_map& m = s.blend_maps[t.normal_map - 1];
+            for (uint32_t k = 0; k < m.entry_count; k++) {
+                const float ni = s.blend_entries[m.entry_first + k].colour[0];
+                if (!(ni >= 0.0f) || ni >= (float)s.tnormals.size() || ni != std::floor(ni))
+                    return fail(PVGPU_E_INVALID, "tnormal %zu: normal_map entry %u is not a tnormal index", i, k);
+            }
+        } else if (t.type == PVGPU_NORM_AVERAGE) return fail(PVGPU_E_INVALID, "tnormal %zu: average without normal_map", i);
         if (t.pattern < 0 || t.pattern >= (int32_t)s.pigments.size() || !range_ok(t.slope_first, t.slope_count, s.slope_entries.size()))
             return fail(PVGPU_E_INVALID, "tnormal %zu: bad pattern carrier / slope map range", i);
         const pvgpu_pigment& c = s.pigments[t.pattern];
-        if (t.type == PVGPU_NORM_PATTERN && (c.pattern <= PVGPU_PAT_CHECKER || c.pattern == PVGPU_PAT_BRICK || c.pattern == PVGPU_PAT_HEXAGON))
+        if (t.type == PVGPU_NORM_PATTERN && !t.normal_map && (c.pattern <= PVGPU_PAT_CHECKER || c.pattern == PVGPU_PAT_BRICK || c.pattern == PVGPU_PAT_HEXAGON))
             return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: block patterns need a normal_map (outside the hot-path scope)", i);
         for (uint32_t k = 0; k < c.warp_count; k++)
             if (s.warps[c.warp_first + k].type != PVGPU_WARP_TRANSFORM && s.warps[c.warp_first + k].type != PVGPU_WARP_CLASSIC_TURBULENCE &&
@@ -453,8 +477,8 @@ int validate_scene(Scene& s)
         const pvgpu_blend_map& m = s.blend_maps[i];
         if (m.entry_count == 0 || !range_ok(m.entry_first, m.entry_count, s.blend_entries.size()))
             return fail(PVGPU_E_INVALID, "blend map %zu: bad entry range", i);
-        if ((m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP)) != 0)
-            return fail(PVGPU_E_UNSUPPORTED, "blend map %zu: blend_mode %d is outside the hot-path scope", i, m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP));
+        if ((m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP | PVGPU_BLEND_NORMAL_MAP)) != 0)
+            return fail(PVGPU_E_UNSUPPORTED, "blend map %zu: blend_mode %d is outside the hot-path scope", i, m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP | PVGPU_BLEND_NORMAL_MAP));
         if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP)
             for (uint32_t k = 0; k < m.entry_count; k++) {
                 const float pi = s.blend_entries[m.entry_first + k].colour[0];
