@@ -18,8 +18,16 @@ namespace pvgpu {
 #define PV_SHADOW_TOLERANCE 1.0e-3      // SHADOW_TOLERANCE trace.cpp:81
 #define PV_COORDINATE_LIMIT 1.0e17      // COORDINATE_LIMIT warp.h
 
+// Resident CTAs per SM the traversal kernels are compiled for (register budget).  Measured per variant: the lean kernels are best
+// at 8 (64 registers; 6 / 7 / 10: slower), the heavy ones at 16 (32 registers, full occupancy): their hot path is ~50 KB of
+// instructions, two thirds of the warp samples wait on instruction fetch (profiles/r1_ncu_source_footprint_cfg3.txt), and more
+// resident warps hide that better than registers help (config 3: 212 / 175 / 157 / 135 / 133 ms at 4 / 6 / 8 / 12 / 16).
 #ifndef PV_TRAV_MIN_BLOCKS
-#define PV_TRAV_MIN_BLOCKS 8           // resident CTAs per SM the traversal kernels are compiled for (register budget)
+#ifdef PV_LEAN
+#define PV_TRAV_MIN_BLOCKS 8
+#else
+#define PV_TRAV_MIN_BLOCKS 16
+#endif
 #endif
 #define PV_STACK_SIZE     96            // traversal stack entries per ray (scene tree + nested mesh tree)
 #define PV_MAX_LAYERS     8             // layers of a layered texture
