@@ -504,6 +504,8 @@ int  pvgpu_scene_set_materials(pvgpu_scene* s,
                                const pvgpu_interior* interiors, size_t n_interiors);
 /* Normal perturbations referenced by pvgpu_texture::tnormal, and the slope_map entries they use. */
 int  pvgpu_scene_set_normals(pvgpu_scene* s, const pvgpu_tnormal* tn, size_t n_tn, const pvgpu_slope_entry* slopes, size_t n_slopes);
+/* SceneData::iridWavelengths (scenedata.h:113; global_settings irid_wavelength) for finishes with iridescence. */
+int  pvgpu_scene_set_irid_wavelengths(pvgpu_scene* s, const float wavelengths[3]);
 /* SceneData::skysphere (NULL = none) and SceneData::fog (list order). */
 int  pvgpu_scene_set_atmosphere(pvgpu_scene* s, const pvgpu_sky_sphere* sky, const pvgpu_fog* fogs, size_t n_fogs);
 int  pvgpu_scene_set_camera(pvgpu_scene* s, const pvgpu_camera* cam);

@@ -799,6 +799,12 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
                                     fl.interiors.data(), fl.interiors.size()), "set_materials");
     check(pvgpu_scene_set_normals(gv.scene, fl.tnormals.data(), fl.tnormals.size(), fl.slope_entries.data(), fl.slope_entries.size()), "set_normals");
     check(pvgpu_scene_set_atmosphere(gv.scene, sd->skysphere != nullptr ? &sky : nullptr, fogs.data(), fogs.size()), "set_atmosphere");
+    {
+        const float wl[3] = { (float)sd->iridWavelengths[0], (float)sd->iridWavelengths[1], (float)sd->iridWavelengths[2] };
+        bool any_irid = false;
+        for (const pvgpu_finish& f : fl.finishes) if (f.irid > 0.0f) any_irid = true;
+        if (any_irid) check(pvgpu_scene_set_irid_wavelengths(gv.scene, wl), "set_irid_wavelengths");
+    }
     check(pvgpu_scene_set_camera(gv.scene, &c), "set_camera");
     if (cam.Type > ORTHOGRAPHIC_CAMERA) check(pvgpu_scene_set_camera_angles(gv.scene, cam.Angle, cam.H_Angle, cam.V_Angle), "set_camera_angles");
     if (const char* path = getenv("PVGPU_DUMP_SCENE")) check(pvgpu_scene_save(gv.scene, path), "scene_save");

@@ -88,6 +88,7 @@ struct Scene {
     std::vector<pvgpu_sky_sphere> sky_spheres;
     std::vector<pvgpu_fog> fogs;
     std::vector<double> camera_ext;
+    std::vector<float> irid_wavelengths;
     std::vector<V3> waveSources;                 // TraceThreadData::waveSources / waveFrequencies (tracethreaddata.cpp:110-111)
     std::vector<double> waveFrequencies;
     // noise tables
@@ -640,8 +641,9 @@ public:
     double Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const;
     V3 Perturb_Normal(V3 Layer_Normal, int tnormal, V3 EPoint) const;
     double relative_ior(const Ray& ray, int interior) const;
-    void ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight);
-    bool ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight);
+    void ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight, int finish = -1);
+    void ComputeIridColour(const pvgpu_finish& fn, V3 lightDirection, V3 eyeDirection, V3 layer_normal, V3 ipoint, Col& colour) const;
+    bool ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight, int finish = -1);
     void ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn, V3 ipoint, const Ray& eye, Ticket& tk, V3 layer_normal,
                                 Col layer_pigment_colour, Col& colour, double attenuation, const pvgpu_object& object, double relativeIor,
                                 std::pair<bool, Col>* light_cache);
@@ -2385,7 +2387,7 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
 {
     const pvgpu_object& ob = S.objects[isect.Object];
     const double relativeIor = relative_ior(ray, ob.interior);
-    struct WNRX { double weight; V3 normal; Col reflec; float reflex; };
+    struct WNRX { double weight; V3 normal; Col reflec; float reflex; int finish; };
     std::vector<WNRX> listWNRX;
     resultColour = Col{ 0, 0, 0 }; resultTransm = 0.0f;
     Col filCol{ 1, 1, 1 };
@@ -2407,7 +2409,7 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
         float lc[5];
         Compute_Pigment(lc, S.textures[layer].pigment, ipoint);
         Col layCol{ lc[0], lc[1], lc[2] };
-        listWNRX.push_back(WNRX{ new_Weight, layNormal, Col{ 0, 0, 0 }, fn.reflect_exp });
+        listWNRX.push_back(WNRX{ new_Weight, layNormal, Col{ 0, 0, 0 }, fn.reflect_exp, S.textures[layer].finish });
         double cos_Angle_Incidence = -dot(ray.Direction, layNormal);
         // ComputeReflectivity (trace.cpp:2627-2654)
         WNRX& W = listWNRX.back();
@@ -2455,7 +2457,7 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
         double w1 = std::max(std::max((double)std::fabs(filCol.r), (double)std::fabs(filCol.g)), (double)std::fabs(filCol.b));
         double new_Weight = weight * w1;
         Col rfrCol{ 0, 0, 0 }; float rfrTransm = 0.0f;
-        tir_occured = ComputeRefraction(ob.interior, isect.IPoint, ray, tk, topNormal, rawnormal, rfrCol, rfrTransm, (float)new_Weight);
+        tir_occured = ComputeRefraction(ob.interior, isect.IPoint, ray, tk, topNormal, rawnormal, rfrCol, rfrTransm, (float)new_Weight, S.textures[texture].finish);
         Col attCol{ in.old_refract, in.old_refract, in.old_refract };
         if (ray.IsInterior(ob.interior) && std::fabs(in.fade_distance) > EPSILON) {
             if (in.fade_power >= 1000) {
@@ -2475,7 +2477,7 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
             if ((!tir_occured) || (std::fabs(topNormal.x - W.normal.x) > EPSILON) || (std::fabs(topNormal.y - W.normal.y) > EPSILON) || (std::fabs(topNormal.z - W.normal.z) > EPSILON)) {
                 if (!(W.reflec.r == 0.0f && W.reflec.g == 0.0f && W.reflec.b == 0.0f)) {
                     Col rflCol{ 0, 0, 0 };
-                    ComputeReflection(isect.IPoint, ray, tk, W.normal, rawnormal, rflCol, (float)W.weight);
+                    ComputeReflection(isect.IPoint, ray, tk, W.normal, rawnormal, rflCol, (float)W.weight, W.finish);
                     if (W.reflex != 1.0f) resultColour = resultColour + W.reflec * Col{ std::pow(rflCol.r, W.reflex), std::pow(rflCol.g, W.reflex), std::pow(rflCol.b, W.reflex) };
                     else resultColour = resultColour + W.reflec * rflCol;
                 }
@@ -2484,7 +2486,25 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
     }
 }
 
-void Tracer::ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight)           // trace.cpp:1264-1321
+void Tracer::ComputeIridColour(const pvgpu_finish& fn, V3 lightDirection, V3 eyeDirection, V3 layer_normal, V3 ipoint, Col& colour) const   // trace.cpp:2486-2518
+{
+    double film_thickness = fn.irid_film_thickness;
+    if (fn.irid_turb != 0) {
+        pvgpu_warp turb{};
+        turb.omega = 0.5f; turb.lambda = 2.0f; turb.octaves = 5;
+        double noise = Turbulence(S, ipoint, turb, S.g.noise_generator);
+        noise = 2.0 * noise - 1.0;
+        noise = 1.0 + noise * fn.irid_turb;
+        film_thickness *= noise;
+    }
+    double cl = std::fabs(dot(layer_normal, lightDirection)), ce = std::fabs(dot(layer_normal, eyeDirection));
+    double interference = 2.0 * 3.1415926535897932384626 * film_thickness * (cl + ce);
+    const float w[3] = { S.irid_wavelengths.size() == 3 ? S.irid_wavelengths[0] : 1.0f, S.irid_wavelengths.size() == 3 ? S.irid_wavelengths[1] : 1.0f, S.irid_wavelengths.size() == 3 ? S.irid_wavelengths[2] : 1.0f };
+    auto factor = [&](float wl) { float q = (float)interference / wl; float cs = (float)std::cos((double)q); return (float)((double)(float)((double)cs * (double)fn.irid) + 1.0); };
+    colour = Col{ colour.r * factor(w[0]), colour.g * factor(w[1]), colour.b * factor(w[2]) };
+}
+
+void Tracer::ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float weight, int finish)           // trace.cpp:1264-1321
 {
     Ray nray(ray);
     nray.flags = RAY_REFLECTION | (ray.flags & RAY_REFRACTION);
@@ -2503,11 +2523,12 @@ void Tracer::ComputeReflection(V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 ra
     float dummyTransm = 0.0f;
     Col c{ 0, 0, 0 };
     TraceRay(nray, tk, c, dummyTransm, weight, false);
+    if (finish >= 0 && S.finishes[finish].irid > 0.0f) ComputeIridColour(S.finishes[finish], nray.Direction, ray.Direction, normal, ipoint, c);   // trace.cpp:1306-1314
     colour = colour + c;
     tk.alphaBackground = alphaBackground;
 }
 
-bool Tracer::ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight)   // trace.cpp:1323-1485
+bool Tracer::ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3 normal, V3 rawnormal, Col& colour, float& transm, float weight, int finish)   // trace.cpp:1323-1485
 {
     const pvgpu_interior& in = S.interiors[interior];
     Ray nray(ray);
@@ -2534,7 +2555,7 @@ bool Tracer::ComputeRefraction(int interior, V3 ipoint, Ray& ray, Ticket& tk, V3
     double t = 1.0 + sqr(ior) * (sqr(n) - 1.0);                                                           // TraceRefractionRay trace.cpp:1456-1485
     if (t < 0.0) {
         Col tempcolour{ 0, 0, 0 };
-        ComputeReflection(ipoint, ray, tk, normal, rawnormal, tempcolour, weight);
+        ComputeReflection(ipoint, ray, tk, normal, rawnormal, tempcolour, weight, finish);
         colour = colour + tempcolour;
         return true;
     }
@@ -2638,6 +2659,7 @@ void Tracer::ComputeOneDiffuseLight(const pvgpu_light& L, const pvgpu_finish& fn
             }
         }
     }
+    if (fn.irid > 0.0f) ComputeIridColour(fn, lray.Direction, eye.Direction, layer_normal, ipoint, tmpCol);        // trace.cpp:1723-1724
     colour = colour + tmpCol;
 }
 
@@ -2955,6 +2977,7 @@ void* pvo_scene_load(const char* path)
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->tnormals) && get(f, s->slope_entries); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->sky_spheres) && get(f, s->fogs); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->camera_ext); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->irid_wavelengths); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());

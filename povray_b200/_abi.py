@@ -209,6 +209,7 @@ SIGNATURES = {
                                             P(BlendMap), C.c_size_t, P(BlendEntry), C.c_size_t, P(Warp), C.c_size_t,
                                             P(Interior), C.c_size_t]),
     "pvgpu_scene_set_normals": (C.c_int, [VP, P(TNormal), C.c_size_t, P(SlopeEntry), C.c_size_t]),
+    "pvgpu_scene_set_irid_wavelengths": (C.c_int, [VP, P(f32)]),
     "pvgpu_scene_set_atmosphere": (C.c_int, [VP, P(SkySphere), P(Fog), C.c_size_t]),
     "pvgpu_scene_set_camera": (C.c_int, [VP, P(Camera)]),
     "pvgpu_scene_get_camera": (C.c_int, [VP, P(Camera)]),

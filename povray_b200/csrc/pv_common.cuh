@@ -148,6 +148,7 @@ struct DScene {
     const double*            pattern_rands; // gPatternRands (pattern.cpp:91): 32768 x mt19937 / 2^32; crackle and cells
     const pvgpu_fog*         fogs;          // SceneData::fog in list order
     uint32_t                 n_fogs, has_sky;
+    float                    irid_wavelengths[3];   // SceneData::iridWavelengths
     uint32_t                 has_tnormals;      // some texture layer has a normal{} (per-layer normals are kept only then)
     uint32_t                 has_area_lights;   // some light is an area light and QualityFlags::areaLights is on
     uint32_t                 area_grid_max;     // largest Area_Size1 * Area_Size2

@@ -642,6 +642,30 @@ __device__ inline void compute_reflectivity(double& weight, float refl[3], const
     }
 }
 
+#if PV_FULL_MATERIALS
+// Trace::ComputeIridColour (trace.cpp:2486-2518): per-channel interference factor of a thin film; c[] is multiplied in place.
+// MathColour arithmetic: FP32 channels, every colour-times-double product rounds to FP32 (colour.h:1681).
+__device__ inline void irid_colour(const DScene& sc, const pvgpu_finish& fn, const V3& light_dir, const V3& eye_dir, const V3& layer_normal, const V3& ipoint, float c[3])
+{
+    double film_thickness = (double)fn.irid_film_thickness;
+    if (fn.irid_turb != 0.0f) {
+        double noise = turbulence(sc.noise, ipoint, 5, 2.0, 0.5, sc.g.noise_generator);
+        noise = 2.0 * noise - 1.0;
+        noise = 1.0 + noise * (double)fn.irid_turb;
+        film_thickness *= noise;
+    }
+    const double cl = fabs(dot(layer_normal, light_dir)), ce = fabs(dot(layer_normal, eye_dir));
+    const double interference = 2.0 * 3.1415926535897932384626 * film_thickness * (cl + ce);
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float q = __fdiv_rn((float)interference, sc.irid_wavelengths[k]);       // GenericColour(a) / b: FP32 division
+        const float cs = (float)cos((double)q);
+        const float f = (float)((double)(float)((double)cs * (double)fn.irid) + 1.0);
+        c[k] *= f;
+    }
+}
+#endif
+
 // cubic_spline (lightsource.cpp:501-517)
 __device__ inline double cubic_spline(double low, double high, double pos)
 {
@@ -1236,6 +1260,9 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
                         }
                     }
                 }
+#if PV_FULL_MATERIALS
+                if (fn.irid > 0.0f) irid_colour(sc, fn, ldir, dir, lay_normal, ipoint, k3);      // trace.cpp:1723-1724
+#endif
                 #pragma unroll
                 for (int k = 0; k < 3; k++) K[k] += L.fil[k] * k3[k];
             }
@@ -1320,6 +1347,10 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
                 rr.level = child_level;
                 rr.adc = (float)new_weight;
                 rr.w[0] = ray.w[0] * attc[0]; rr.w[1] = ray.w[1] * attc[1]; rr.w[2] = ray.w[2] * attc[2];
+#if PV_FULL_MATERIALS
+                // ComputeReflection(texture->Finish, ...) of the top layer (trace.cpp:1099, 1462-1470)
+                if (nlayers > 0 && sc.finishes[layers[0].finish].irid > 0.0f) irid_colour(sc, sc.finishes[layers[0].finish], rd, dir, top_normal, ipoint, rr.w);
+#endif
                 rr.wt = 0.0f;
                 push_ray(ctx, rr);
             } else {
@@ -1354,6 +1385,9 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
             rr.level = child_level;
             rr.adc = (float)L.rweight;
             rr.w[0] = ray.w[0] * L.refl[0]; rr.w[1] = ray.w[1] * L.refl[1]; rr.w[2] = ray.w[2] * L.refl[2];
+#if PV_FULL_MATERIALS
+            if (sc.finishes[L.finish].irid > 0.0f) irid_colour(sc, sc.finishes[L.finish], rd, dir, lay_normal, ipoint, rr.w);    // trace.cpp:1306-1314
+#endif
             rr.wt = 0.0f;
             atomicAdd(&ctx.cnt->reflected, 1ull);
             push_ray(ctx, rr);

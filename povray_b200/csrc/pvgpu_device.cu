@@ -321,6 +321,7 @@ int device_upload(Scene& s, int device)
     if (!s.fogs.empty() || !s.sky_spheres.empty()) d->lean = false;
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->lean = false;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE) d->lean = false;
+    for (int k = 0; k < 3; k++) v.irid_wavelengths[k] = (s.irid_wavelengths.size() == 3) ? s.irid_wavelengths[k] : 1.0f;
     v.has_tnormals = 0;
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) v.has_tnormals = 1;
     v.has_area_lights = 0; v.area_grid_max = 0;
@@ -344,6 +345,7 @@ int device_upload(Scene& s, int device)
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->full = true;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
     if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights) d->full = true;
+    for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }
     if (const char* e = getenv("PVGPU_FULL")) if (e[0] == '1') d->full = true;
     v.n_objs = (uint32_t)s.objects.size();
     v.n_frame = (uint32_t)s.frame.size();

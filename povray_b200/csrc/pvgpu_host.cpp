@@ -499,7 +499,8 @@ int validate_scene(Scene& s)
                           f.reflection_min[0] != 0 || f.reflection_min[1] != 0 || f.reflection_min[2] != 0;
         if (reflective && f.reflect_exp != 1.0f)
             return fail(PVGPU_E_UNSUPPORTED, "finish %zu: reflection exponent != 1 (non-linear in the child ray)", i);
-        if (f.irid > 0.0f) return fail(PVGPU_E_UNSUPPORTED, "finish %zu: iridescence is outside the hot-path scope", i);
+        if (f.irid > 0.0f && s.irid_wavelengths.size() != 3)
+            return fail(PVGPU_E_INVALID, "finish %zu: iridescence needs pvgpu_scene_set_irid_wavelengths", i);
         if (f.crand > 0.0f) return fail(PVGPU_E_UNSUPPORTED, "finish %zu: crand is excluded from parity (per-thread RNG)", i);
         if (f.use_subsurface) return fail(PVGPU_E_UNSUPPORTED, "finish %zu: subsurface is outside the hot-path scope", i);
     }
@@ -670,6 +671,14 @@ int pvgpu_scene_set_camera_angles(pvgpu_scene* sc, double angle, double h_angle,
     SCENE_OR_FAIL(sc);
     s.camera_ext = { angle, h_angle, v_angle };
     if (s.dev) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_camera_angles: call before pvgpu_scene_finalize");
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_irid_wavelengths(pvgpu_scene* sc, const float wavelengths[3])
+{
+    SCENE_OR_FAIL(sc);
+    if (!wavelengths) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_irid_wavelengths: null argument");
+    s.irid_wavelengths.assign(wavelengths, wavelengths + 3);
     return PVGPU_OK;
 }
 
@@ -894,7 +903,8 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
     // optional trailing sections in fixed order; a section is written when it or a later one holds data
-    const bool sec5 = !s.camera_ext.empty();
+    const bool sec6 = !s.irid_wavelengths.empty();
+    const bool sec5 = sec6 || !s.camera_ext.empty();
     const bool sec4 = sec5 || !s.sky_spheres.empty() || !s.fogs.empty();
     const bool sec3 = sec4 || !s.tnormals.empty();
     const bool sec2 = sec3 || !s.shape_data.empty();
@@ -904,6 +914,7 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
     if (ok && sec3) ok = put(f, s.tnormals) && put(f, s.slope_entries);
     if (ok && sec4) ok = put(f, s.sky_spheres) && put(f, s.fogs);
     if (ok && sec5) ok = put(f, s.camera_ext);
+    if (ok && sec6) ok = put(f, s.irid_wavelengths);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -944,6 +955,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->camera_ext); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->irid_wavelengths); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

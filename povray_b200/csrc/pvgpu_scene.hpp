@@ -47,6 +47,7 @@ struct Scene {
     std::vector<pvgpu_slope_entry> slope_entries;
     std::vector<pvgpu_sky_sphere>  sky_spheres;    // 0 or 1 entry
     std::vector<pvgpu_fog>         fogs;
+    std::vector<float>             irid_wavelengths; // SceneData::iridWavelengths (3 values; empty: no iridescent finish)
     std::vector<double>            camera_ext;     // Camera::Angle, H_Angle, V_Angle (empty: perspective / orthographic only)
 
     // derived at finalize
