@@ -4,9 +4,12 @@
 # -fmad=false: FP64 expressions must round like the reference built with -ffp-contract=off ("Numerics").
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Iinclude -Ipovray_b200/csrc
+# EXTRA / LIB / OBJDIR: experiment builds (tools/build_variants.sh) - extra -D switches into a separate library
+EXTRA     ?=
+NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Iinclude -Ipovray_b200/csrc $(EXTRA)
 CSRC      := povray_b200/csrc
-OBJDIR    := build/obj
+OBJDIR    ?= build/obj
+LIB       ?= povray_b200/libpvgpu.so
 CU        := $(wildcard $(CSRC)/*.cu)
 CPP       := $(wildcard $(CSRC)/*.cpp)
 # the hot kernels are compiled a second time with -DPV_LEAN (see PV_VARIANT in pv_common.cuh)
@@ -18,7 +21,7 @@ OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.c
 HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) include/pvgpu.h
 
 .PHONY: all oracle clean
-all: povray_b200/libpvgpu.so
+all: $(LIB)
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
@@ -36,7 +39,8 @@ $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
-povray_b200/libpvgpu.so: $(OBJ)
+$(LIB): $(OBJ)
+	@mkdir -p $(dir $@)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
 
 oracle:

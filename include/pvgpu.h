@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PVGPU_ABI_VERSION 2
+#define PVGPU_ABI_VERSION 3
 #define PVGPU_FILE_VERSION 1      /* layout of the table records as written by pvgpu_scene_save */
 
 /* ---- error codes ------------------------------------------------------------------------- */
@@ -451,6 +451,8 @@ typedef struct pvgpu_stats {
     uint64_t kernel_launches;    /* CUDA kernels launched by the call             */
     uint32_t max_trace_level;    /* highest level reached                         */
     uint32_t overflow;           /* non-zero: a device capacity was exceeded      */
+    uint64_t node_tests;         /* bounding-box slab tests of the traversal kernels (scene tree + mesh trees)     */
+    uint64_t prim_tests;         /* top-level primitive tests + mesh triangle tests of the traversal kernels        */
     double   device_ms;          /* CUDA-event time of the device work            */
     /* per kernel family, timed with CUDA events on the launching stream:
      * 0 camera rays (k_primary), 1 closest hit (k_closest), 2 shading (k_shade), 3 shadow rays (k_shadow_*),
@@ -522,6 +524,15 @@ int  pvgpu_scene_add_mesh2(pvgpu_scene* s, const double* vertices, size_t n_vert
 
 /* Validates, derives device layouts and uploads everything to CUDA device `device`. */
 int  pvgpu_scene_finalize(pvgpu_scene* s, int device);
+/* Same, but the scene tables are replicated on `n_devices` CUDA devices of this node (devices[] lists them, NULL = 0 .. n_devices - 1;
+ * n_devices <= 0 = every visible device).  pvgpu_render / pvgpu_render_device then shard the rectangles of a call over the
+ * devices: one host thread per device takes chunks of rectangles from one atomic counter - the GPU counterpart of the render
+ * threads of View::StartRender pulling from ViewData::GetNextRectangle (view.cpp:236-271, 1186-1190) - and finished tiles are
+ * gathered into the caller's frame (D2H, or peer copies into devices[0]'s memory for pvgpu_render_device).  Pixels do not depend
+ * on the number of devices. */
+int  pvgpu_scene_finalize_multi(pvgpu_scene* s, const int* devices, int n_devices);
+/* Number of devices the scene lives on (0 before finalize). */
+int  pvgpu_scene_device_count(const pvgpu_scene* s);
 /* Total bytes uploaded by finalize (the H2D traffic of one scene). */
 size_t pvgpu_scene_device_bytes(const pvgpu_scene* s);
 

@@ -812,8 +812,16 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
     if (need_device) {
         if (!gv.error.empty())
             throw POV_EXCEPTION_STRING((std::string("pvgpu: scene uses a feature outside the GPU trace path: ") + gv.error).c_str());
+        // PVGPU_DEVICES = "all" | "<n>" | "i,j,k": the scene is replicated on these devices and every frame is sharded over them
+        // behind pvgpu_render (one atomic tile counter, like the render threads' GetNextRectangle); PVGPU_DEVICE = one index
+        const char* devs = getenv("PVGPU_DEVICES");
         const char* dev = getenv("PVGPU_DEVICE");
-        check(pvgpu_scene_finalize(gv.scene, dev ? atoi(dev) : 0), "scene_finalize");
+        if (devs && *devs) {
+            std::vector<int> list;
+            if (strchr(devs, ',')) { for (const char* p = devs; *p;) { list.push_back(atoi(p)); p = strchr(p, ','); if (!p) break; p++; } }
+            if (!list.empty()) check(pvgpu_scene_finalize_multi(gv.scene, list.data(), (int)list.size()), "scene_finalize_multi");
+            else check(pvgpu_scene_finalize_multi(gv.scene, nullptr, strcmp(devs, "all") == 0 ? 0 : atoi(devs)), "scene_finalize_multi");
+        } else check(pvgpu_scene_finalize(gv.scene, dev ? atoi(dev) : 0), "scene_finalize");
         gv.finalized = true;
     }
     return slot;

@@ -252,11 +252,34 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
     }
 }
 
+// Start of a batch: the ring of per-wave records is cleared and wave 0 gets its ray count.
+__global__ void k_wave_init(WaveCounts* ring, uint32_t n_slots, uint32_t n0)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots * (uint32_t)(sizeof(WaveCounts) / 4); i += gridDim.x * blockDim.x)
+        reinterpret_cast<unsigned int*>(ring)[i] = (i == 0u) ? n0 : 0u;
+}
+
+// Clears the accumulator slots of samples [first, first + n) of a sample source (retry of a batch after a queue overflow): the slots
+// are recomputed like k_primary does, because a rectangle's samples are dealt to its pixels in 8 x 4 blocks (sample_xy).
+__global__ void k_clear_slots(SampleSource src, uint32_t first, uint32_t n, float4* accum)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t slot = src.slot_base + first + i;
+        if (src.coords) { if (src.slots) slot = src.slots[first + i]; }
+        else {
+            double x, y;
+            sample_xy(src.rects, src.rect_off, src.n_rects, first + i, x, y, slot);
+            slot += src.slot_base;
+        }
+        accum[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
 #endif  // !PV_LEAN
 
 // Trace::TraceRay's entry (trace.cpp:142-160) + FindIntersection for every ray of the wave.
 __global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
-PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRec* __restrict__ hits, Counters* cnt)
+PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, uint32_t cap, HitRec* __restrict__ hits, Counters* cnt)
 {
 #if PV_SSTACK > 0
     __shared__ uint2 stack_sh[PV_SSTACK * PV_TRAV_BLOCK];
@@ -266,12 +289,13 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRe
     uint2 stack_lo[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_lo, 0 };
 #endif
+    const uint32_t n = min(wc->n_rays, cap);
     unsigned long long n_rays = 0, n_adc = 0;
     unsigned int max_level = 0;
-    // warp-uniform trip count: all 32 lanes stay in the loop (and in the warp-synchronous traversal) together
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + lane;
+    TravCount tc{ 0u, 0u };
+    // all lanes of a warp (all threads of the block with PV_CTA_SYNC) stay in the loop and in the phase-voting traversal together
+    uint32_t i;
+    while (next_chunk(&wc->cur_closest, n, i)) {
         bool alive = i < n;
         V3 o = mk(0.0, 0.0, 0.0), d = mk(0.0, 0.0, 1.0);
         uint32_t flags = 0;
@@ -301,7 +325,7 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRe
         best.depth = ((flags & PV_RAY_PRIMARY) && !(flags & PV_RAY_PROBE) && sc.cam.max_ray_distance >= PV_EPSILON) ? sc.cam.max_ray_distance : PV_BOUND_HUGE;
         best.obj = PV_NO_OBJECT;
         best.aux = 0; best.csg = -1;
-        const bool found = find_intersection_sync<false>(alive, sc, o, d, flags & ~PV_RAY_PROBE, false, -1.0, best, stack, &cnt->overflow);
+        const bool found = find_intersection_sync<false>(alive, sc, o, d, flags & ~PV_RAY_PROBE, false, -1.0, best, stack, &cnt->overflow, tc);
         if (found) {
             out.depth = best.depth; out.ip[0] = best.ip.x; out.ip[1] = best.ip.y; out.ip[2] = best.ip.z;
             out.obj = best.obj; out.aux = best.aux; out.csg = best.csg;
@@ -309,12 +333,17 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, uint32_t n, HitRe
         if (i < n) hits[i] = out;
     }
     // one atomic per warp for the statistics
+    unsigned long long n_nodes = tc.nodes, n_prims = tc.prims;
     for (int off = 16; off > 0; off >>= 1) {
         n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
         n_adc += __shfl_down_sync(0xffffffffu, n_adc, off);
+        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+        n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
         max_level = max(max_level, __shfl_down_sync(0xffffffffu, max_level, off));
     }
     if ((threadIdx.x & 31) == 0) {
+        if (n_nodes) atomicAdd(&cnt->node_tests, n_nodes);
+        if (n_prims) atomicAdd(&cnt->prim_tests, n_prims);
         if (n_rays) atomicAdd(&cnt->rays, n_rays);
         if (n_adc) atomicAdd(&cnt->adc_saves, n_adc);
         if (max_level) atomicMax(&cnt->max_level, max_level);
@@ -362,15 +391,23 @@ void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cuda
 {
     k_container_state<<<1, 32, 0, st>>>(sc, out, cnt);
 }
+void launch_wave_init(WaveCounts* ring, uint32_t n_slots, uint32_t n0, cudaStream_t st)
+{
+    k_wave_init<<<1, 256, 0, st>>>(ring, n_slots, n0);
+}
+void launch_clear_slots(const SampleSource& src, uint32_t first, uint32_t n, float4* accum, cudaStream_t st)
+{
+    k_clear_slots<<<grid_for(n, 256, 8), 256, 0, st>>>(src, first, n, accum);
+}
 void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,
                     PRay* out, Counters* cnt, float4* accum, cudaStream_t st)
 {
     k_primary<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, src, first, n, width, height, out, cnt, accum);
 }
 #endif  // !PV_LEAN
-void PV_VARIANT(launch_closest)(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st)
+void PV_VARIANT(launch_closest)(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st)
 {
-    PV_VARIANT(k_closest)<<<grid_for(n, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, n, hits, cnt);
+    PV_VARIANT(k_closest)<<<grid_for(n_bound, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, wc, cap, hits, cnt);
 }
 #ifndef PV_LEAN
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st)

@@ -34,8 +34,9 @@ static __device__ __noinline__ void shade_fogged(const DScene& sc, const PRay& r
 #endif
 
 __global__ void __launch_bounds__(128, PV_SHADE_MIN_BLOCKS)
-PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits, uint32_t n, WaveCtx ctx)
+PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __restrict__ hits, const WaveCounts* wc, WaveCtx ctx)
 {
+    const uint32_t n = min(wc->n_rays, ctx.cur_cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const HitRec h = hits[i];
         if (h.obj == PV_HIT_STOPPED) continue;
@@ -55,9 +56,9 @@ PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __res
     }
 }
 
-void PV_VARIANT(launch_shade)(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st)
+void PV_VARIANT(launch_shade)(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st)
 {
-    PV_VARIANT(k_shade)<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, cur, hits, n, ctx);
+    PV_VARIANT(k_shade)<<<grid_for(n_bound, 128, 8), 128, 0, st>>>(sc, cur, hits, wc, ctx);
 }
 
 }  // namespace pvgpu

@@ -19,18 +19,18 @@ struct AreaFrame {
 
 template <bool ALL_OPAQUE>
 __global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
-k_shadow_area(DScene sc, const SRay* __restrict__ rays, const PRay* __restrict__ wave, float4* accum, Counters* cnt, float* __restrict__ grid_mem, uint32_t n_threads)
+k_shadow_area(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t cap, const PRay* __restrict__ wave, float4* accum, Counters* cnt, float* __restrict__ grid_mem, uint32_t n_threads)
 {
     uint2 stack_lo[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_lo, 0 };
     AreaFrame fr[PV_AREA_MAX_DEPTH];
-    const uint32_t n = cnt->n_shadow;
+    const uint32_t n = min(wc->n_shadow, cap);
     unsigned long long tests = 0;
-    const uint32_t lane = threadIdx.x & 31u;
+    TravCount tc{ 0u, 0u };
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     float* const grid = grid_mem + tid;                 // lightGrid of this thread: cell c, channel k at grid[(3 * c + k) * n_threads]
-    for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + lane;
+    uint32_t i;
+    while (next_chunk(&wc->cur_area, n, i)) {
         const SRay s = rays[(i < n) ? i : 0u];
         const pvgpu_light& Lt = sc.lights[s.light];
         bool active = (i < n) && (Lt.flags & PVGPU_LIGHT_AREA);
@@ -102,7 +102,7 @@ k_shadow_area(DScene sc, const SRay* __restrict__ rays, const PRay* __restrict__
                     }
                 }
             }
-            if (!__any_sync(PV_FULL_MASK, need)) break;
+            if (!vote_any(need)) break;
             // the sample's light ray (trace.cpp:2163-2213)
             V3 ldir = mk(0.0, 0.0, 1.0);
             double ldepth = 1.0;
@@ -123,7 +123,7 @@ k_shadow_area(DScene sc, const SRay* __restrict__ rays, const PRay* __restrict__
                 light_ray(Lt, ipoint, ldir, ldepth, j1 + j2);
             }
             float f[3];
-            trace_shadow<ALL_OPAQUE>(need, sc, ipoint, ldir, ldepth, wave, s.parent, stack, cnt, f, tests);
+            trace_shadow<ALL_OPAQUE>(need, sc, ipoint, ldir, ldepth, wave, s.parent, stack, cnt, f, tests, tc);
             if (need) {
                 AreaFrame& F = fr[sp];
                 const size_t cell = (size_t)(3 * (su * n2 + sv)) * n_threads;
@@ -135,18 +135,27 @@ k_shadow_area(DScene sc, const SRay* __restrict__ rays, const PRay* __restrict__
         if ((i < n) && (Lt.flags & PVGPU_LIGHT_AREA))
             accum_add(accum, s.sample, s.a[0] * result[0], s.a[1] * result[1], s.a[2] * result[2], 0.0f);
     }
-    for (int off = 16; off > 0; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
-    if ((threadIdx.x & 31) == 0 && tests) atomicAdd(&cnt->shadow_tests, tests);
+    unsigned long long n_nodes = tc.nodes, n_prims = tc.prims;
+    for (int off = 16; off > 0; off >>= 1) {
+        tests += __shfl_down_sync(0xffffffffu, tests, off);
+        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+        n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (tests) atomicAdd(&cnt->shadow_tests, tests);
+        if (n_nodes) atomicAdd(&cnt->node_tests, n_nodes);
+        if (n_prims) atomicAdd(&cnt->prim_tests, n_prims);
+    }
 }
 
 // grid_mem: 3 floats x area_grid_max cells for every thread of the launch (area_threads() threads)
 uint32_t area_threads() { return (uint32_t)(sm_count() * PV_TRAV_MIN_BLOCKS * PV_TRAV_BLOCK); }
 
-void launch_shadow_area(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st)
+void launch_shadow_area(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st)
 {
-    const int blocks = grid_for(n_max, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
-    if (sc.all_opaque) k_shadow_area<true><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wave, accum, cnt, grid_mem, area_threads());
-    else k_shadow_area<false><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wave, accum, cnt, grid_mem, area_threads());
+    const int blocks = grid_for(n_bound, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
+    if (sc.all_opaque) k_shadow_area<true><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
+    else k_shadow_area<false><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
 }
 
 }  // namespace pvgpu

@@ -4,7 +4,7 @@
 namespace pvgpu {
 
 __global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
-PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, float4* accum, Counters* cnt)
+PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t cap, float4* accum, Counters* cnt)
 {
 #if PV_SSTACK > 0
     __shared__ uint2 stack_sh[PV_SSTACK * PV_TRAV_BLOCK];
@@ -14,12 +14,13 @@ PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, float4* ac
     uint2 stack_lo[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_lo, 0 };
 #endif
-    const uint32_t n = cnt->n_shadow;
+    // the queue never holds more than `cap` records: push_shadow drops (and flags) what does not fit, the count keeps running
+    const uint32_t n = min(wc->n_shadow, cap);
     unsigned long long tests = 0;
+    TravCount tc{ 0u, 0u };
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&cnt->shadow_rays, (unsigned long long)n);
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t i0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); i0 < n; i0 += gridDim.x * blockDim.x) {
-        const uint32_t i = i0 + lane;
+    uint32_t i;
+    while (next_chunk(&wc->cur_shadow, n, i)) {
         bool alive = i < n;
         const SRay* sp = rays + (alive ? i : 0u);
 #if PV_HEAVY
@@ -28,16 +29,25 @@ PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, float4* ac
         const V3 o = ld3(sp->o), d = ld3(sp->d);
         const double depth = sp->depth;
         float f[3];
-        trace_shadow<true>(alive, sc, o, d, depth, nullptr, 0u, stack, cnt, f, tests);
+        trace_shadow<true>(alive, sc, o, d, depth, nullptr, 0u, stack, cnt, f, tests, tc);
         if (alive && f[0] != 0.0f) accum_add(accum, sp->sample, sp->a[0], sp->a[1], sp->a[2], 0.0f);
     }
-    for (int off = 16; off > 0; off >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, off);
-    if ((threadIdx.x & 31) == 0 && tests) atomicAdd(&cnt->shadow_tests, tests);
+    unsigned long long n_nodes = tc.nodes, n_prims = tc.prims;
+    for (int off = 16; off > 0; off >>= 1) {
+        tests += __shfl_down_sync(0xffffffffu, tests, off);
+        n_nodes += __shfl_down_sync(0xffffffffu, n_nodes, off);
+        n_prims += __shfl_down_sync(0xffffffffu, n_prims, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (tests) atomicAdd(&cnt->shadow_tests, tests);
+        if (n_nodes) atomicAdd(&cnt->node_tests, n_nodes);
+        if (n_prims) atomicAdd(&cnt->prim_tests, n_prims);
+    }
 }
 
-void PV_VARIANT(launch_shadow_opaque)(const DScene& sc, const SRay* rays, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st)
+void PV_VARIANT(launch_shadow_opaque)(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st)
 {
-    PV_VARIANT(k_shadow_opaque)<<<grid_for(n_max, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, rays, accum, cnt);
+    PV_VARIANT(k_shadow_opaque)<<<grid_for(n_bound, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, accum, cnt);
 }
 
 }  // namespace pvgpu

@@ -22,11 +22,17 @@ namespace pvgpu {
 // at 8 (64 registers; 6 / 7 / 10: slower), the heavy ones at 16 (32 registers, full occupancy): their hot path is ~50 KB of
 // instructions, two thirds of the warp samples wait on instruction fetch (profiles/r1_ncu_source_footprint_cfg3.txt), and more
 // resident warps hide that better than registers help (config 3: 212 / 175 / 157 / 135 / 133 ms at 4 / 6 / 8 / 12 / 16).
+#ifndef PV_TRAV_MIN_BLOCKS_LEAN
+#define PV_TRAV_MIN_BLOCKS_LEAN 8
+#endif
+#ifndef PV_TRAV_MIN_BLOCKS_HEAVY
+#define PV_TRAV_MIN_BLOCKS_HEAVY 16
+#endif
 #ifndef PV_TRAV_MIN_BLOCKS
 #ifdef PV_LEAN
-#define PV_TRAV_MIN_BLOCKS 8
+#define PV_TRAV_MIN_BLOCKS PV_TRAV_MIN_BLOCKS_LEAN
 #else
-#define PV_TRAV_MIN_BLOCKS 16
+#define PV_TRAV_MIN_BLOCKS PV_TRAV_MIN_BLOCKS_HEAVY
 #endif
 #endif
 #define PV_STACK_SIZE     96            // traversal stack entries per ray (scene tree + nested mesh tree)
@@ -60,7 +66,9 @@ struct V3 { double x, y, z; };
 
 // Per-ray traversal stack.  The first `nsh` entries of a thread live in shared memory (entry-major, one 8-byte
 // column per thread: lanes never collide on a bank whatever their stack depths are), deeper entries in local memory.
+#ifndef PV_TRAV_BLOCK
 #define PV_TRAV_BLOCK   128            // threads per CTA of the traversal kernels
+#endif
 #ifndef PV_SSTACK
 #define PV_SSTACK       0              // shared-memory entries per thread.  0: the whole stack stays in local memory - measured
                                        // faster on B200: 24 entries (24 KB per CTA, 8 CTAs per SM) shrink the L1 that serves the
@@ -208,11 +216,25 @@ static_assert(sizeof(SRay) == 96, "SRay must be 96 bytes");
 struct Counters {
     unsigned long long rays, shadow_tests, reflected, refracted, transmitted, tir, adc_saves;
     unsigned long long shadow_rays;   // shadow rays traced (TraceShadowRay calls)
-    unsigned int n_next;         // rays appended to the next wave
-    unsigned int n_shadow;       // shadow rays appended for the current chunk
+    unsigned long long node_tests;    // bounding-box slab tests of the traversal kernels (scene tree + mesh trees), PV_COUNT_TESTS builds
+    unsigned long long prim_tests;    // primitive All_Intersections calls incl. mesh triangles, PV_COUNT_TESTS builds
     unsigned int max_level;
     unsigned int overflow;
 };
+
+// Per-wave hand-over between the kernels of one batch, in a device-resident ring indexed by the wave number.  The ray counts
+// never travel through the host: k_shade of wave k appends into ring[k + 1].n_rays and ring[k].n_shadow, k_closest / k_shadow_*
+// read their counts (clamped to the queue capacities) from the ring, and the warps of the traversal kernels take their 32-ray
+// chunks from the cursors.  The host reads n_rays one wave behind the launches only to know when to stop (pvgpu_device.cu).
+struct WaveCounts {
+    unsigned int n_rays;          // rays of this wave
+    unsigned int n_shadow;        // shadow rays this wave emitted
+    unsigned int cur_closest;     // next unclaimed ray of k_closest
+    unsigned int cur_shadow;      // next unclaimed shadow ray of k_shadow_*
+    unsigned int cur_area;        // ... of k_shadow_area
+    unsigned int pad[3];
+};
+static_assert(sizeof(WaveCounts) == 32, "WaveCounts must be 32 bytes");
 
 struct Hit {
     double   depth;

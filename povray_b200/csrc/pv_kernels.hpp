@@ -8,9 +8,11 @@ namespace pvgpu {
 struct WaveCtx {
     float4*   accum;          // per-sample RGBT accumulators
     PRay*     next;           // next wave's queue
-    SRay*     shadow;         // shadow-ray queue of the current chunk
+    SRay*     shadow;         // shadow-ray queue of this wave
     Counters* cnt;
-    uint32_t  next_cap, shadow_cap;
+    unsigned int* n_next;     // ring[wave + 1].n_rays
+    unsigned int* n_shadow;   // ring[wave].n_shadow
+    uint32_t  cur_cap, next_cap, shadow_cap;
 };
 
 // Where the samples of a batch come from.
@@ -49,21 +51,24 @@ int  grid_for(uint32_t n, int block, int per_sm);
 void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cudaStream_t st);
 void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,
                     PRay* out, Counters* cnt, float4* accum, cudaStream_t st);
-void launch_closest(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st);
-void launch_shade(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st);
-// n_max: upper bound of the shadow-ray count (the exact count is read from cnt->n_shadow on the device)
-void launch_shadow_opaque(const DScene& sc, const SRay* rays, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
-void launch_shadow_filter(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
+// The wave kernels read their ray counts on the device (wc = this wave's record in the ring, clamped to the queue capacity `cap`);
+// n_bound is the host's upper bound of that count and only sizes the grid.
+void launch_wave_init(WaveCounts* ring, uint32_t n_slots, uint32_t n0, cudaStream_t st);
+void launch_closest(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st);
+void launch_shade(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st);
+void launch_shadow_opaque(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_shadow_filter(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
 // lean variants (spheres, boxes, planes, meshes only; compiled from the same sources with -DPV_LEAN)
-void launch_closest_lean(const DScene& sc, const PRay* cur, uint32_t n, HitRec* hits, Counters* cnt, cudaStream_t st);
-void launch_shade_lean(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st);
-void launch_shadow_opaque_lean(const DScene& sc, const SRay* rays, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
-void launch_shadow_filter_lean(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_closest_lean(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st);
+void launch_shade_lean(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st);
+void launch_shadow_opaque_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_shadow_filter_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
 uint32_t area_threads();
-void launch_shadow_area(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st);
+void launch_shadow_area(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st);
 // full-material variants (normal perturbation, pigment maps, sky_sphere, fog, area lights; -DPV_FULL)
-void launch_shade_full(const DScene& sc, const PRay* cur, const HitRec* hits, uint32_t n, const WaveCtx& ctx, cudaStream_t st);
-void launch_shadow_filter_full(const DScene& sc, const SRay* rays, const PRay* wave, uint32_t n_max, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_shade_full(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st);
+void launch_shadow_filter_full(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_clear_slots(const SampleSource& src, uint32_t first, uint32_t n, float4* accum, cudaStream_t st);
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st);
 void launch_probe_results(const HitRec* hits, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux, cudaStream_t st);
 void launch_aa1_frame_coords(const AALayout& L, double2* coords, cudaStream_t st);

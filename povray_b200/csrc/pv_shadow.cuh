@@ -86,7 +86,7 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
 //   window ends the search (any-hit) and no filtering code is needed.
 template <bool ALL_OPAQUE>
 __device__ inline void trace_shadow(bool alive, const DScene& sc, V3 o, const V3& d, double depth, const PRay* wave, uint32_t parent,
-                                    TStack stack, Counters* cnt, float f[3], unsigned long long& tests)
+                                    TStack stack, Counters* cnt, float f[3], unsigned long long& tests, TravCount& tc)
 {
     // all 32 lanes of the warp are here together (the traversal is warp-synchronous); `alive` lanes carry a shadow ray
     f[0] = f[1] = f[2] = 1.0f;
@@ -95,7 +95,7 @@ __device__ inline void trace_shadow(bool alive, const DScene& sc, V3 o, const V3
         best.depth = depth;
         best.obj = PV_NO_OBJECT;
         if (alive) tests++;
-        const bool found = find_intersection_sync<true>(alive, sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow, depth - PV_SHADOW_TOLERANCE);
+        const bool found = find_intersection_sync<true>(alive, sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow, tc, depth - PV_SHADOW_TOLERANCE);
         if (found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))
             f[0] = f[1] = f[2] = 0.0f;     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
         return;
@@ -105,12 +105,12 @@ __device__ inline void trace_shadow(bool alive, const DScene& sc, V3 o, const V3
     in_state.n_int = 0;
     bool have_state = false;
     for (int iter = 0; iter < 256; iter++) {
-        if (!__any_sync(PV_FULL_MASK, alive)) break;
+        if (!vote_any(alive)) break;
         Hit best;
         best.depth = depth;
         best.obj = PV_NO_OBJECT;
         if (alive) tests++;
-        const bool found = find_intersection_sync<false>(alive, sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow);
+        const bool found = find_intersection_sync<false>(alive, sc, o, d, 0u, true, PV_SMALL_TOLERANCE, best, stack, &cnt->overflow, tc);
         if (!alive) continue;
         if (!(found && (best.depth < depth - PV_SHADOW_TOLERANCE) && (depth - best.depth > 0.0) && (best.depth > PV_SHADOW_TOLERANCE))) { alive = false; continue; }
         const pvgpu_object& ob = sc.objs[best.obj];

@@ -307,6 +307,11 @@ __device__ inline bool point_in_clip(const DScene& sc, const pvgpu_object& o, co
 // ---- per-object candidate collection ----------------------------------------------------------------
 // Selection rule of Find_Intersection (object.cpp:203-215): the IStack is popped from the top with a
 // strict `<`, so among equal depths of ONE object the hit pushed LAST wins -> `<=` in push order.
+// Work counters of the hot traversal (per lane, summed into Counters::node_tests / prim_tests by the kernels): bounding-box slab tests
+// (children of visited nodes, scene tree and mesh trees) and primitive tests (top-level All_Intersections calls and mesh triangles).
+// bench.py derives the algorithmic bytes of the roofline from them.
+struct TravCount { uint32_t nodes, prims; };
+
 struct HitAcc {
     double closest;      // starts at HUGE_VAL per object
     double post_min;     // SmallToleranceRayObjectCondition: depth > post_min (shadow rays), else -1
@@ -436,9 +441,43 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
 #define PV_LEAF_BIAS_DEN 1
 #endif
 #define PV_NONE      0xFFFFFFFFu
+// Scope of the phase votes.  Warp scope: the 32 lanes of a warp agree on the phase.  CTA scope (-DPV_CTA_SYNC): all warps of the
+// thread block agree, so that the whole block runs the same few KB of code at a time - the heavy kernels are bound by
+// instruction fetch (their hot path is several times the 32 KB L1.5 instruction cache when every warp of an SM sits in a
+// different phase).  Every loop that contains a vote must then be uniform over the block.
+#ifdef PV_CTA_SYNC
+__device__ __forceinline__ int  vote_count(bool p) { return __syncthreads_count(p ? 1 : 0); }
+__device__ __forceinline__ bool vote_any(bool p)   { return __syncthreads_or(p ? 1 : 0) != 0; }
+#else
+__device__ __forceinline__ int  vote_count(bool p) { return __popc(__ballot_sync(PV_FULL_MASK, p)); }
+__device__ __forceinline__ bool vote_any(bool p)   { return __any_sync(PV_FULL_MASK, p); }
+#endif
+// The traversal kernels take their rays in chunks from a cursor in the wave's WaveCounts record: one chunk per warp (32 rays)
+// or, with block-wide phase votes, one per thread block.  Rays of a chunk are neighbours in the queue (an 8 x 4 pixel block of
+// the frame and what it spawned), whichever warp picks the chunk up; a warp whose rays end early simply fetches the next chunk
+// instead of idling until the slowest warp of a static partition is done.  Returns false when the wave is exhausted.
+__device__ __forceinline__ bool next_chunk(unsigned int* cursor, uint32_t n, uint32_t& i)
+{
+#ifdef PV_CTA_SYNC
+    __shared__ uint32_t s_base;
+    __syncthreads();                                   // everybody has consumed the previous value
+    if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned int)blockDim.x);
+    __syncthreads();
+    const uint32_t base = s_base;
+    i = base + threadIdx.x;
+    return base < n;
+#else
+    uint32_t base = 0;
+    if ((threadIdx.x & 31u) == 0u) base = atomicAdd(cursor, 32u);
+    base = __shfl_sync(PV_FULL_MASK, base, 0);
+    i = base + (threadIdx.x & 31u);
+    return base < n;
+#endif
+}
+
 template <bool ANY_HIT>
 __device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t obj_index, const V3& o, const V3& d,
-                                      HitAcc& acc, TStack stack, int sp0, unsigned int* overflow, double any_limit, double limit0)
+                                      HitAcc& acc, TStack stack, int sp0, unsigned int* overflow, double any_limit, double limit0, TravCount& tc)
 {
     V3 mo = o, md = d;
     double len = 1.0;
@@ -481,13 +520,14 @@ __device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t ob
     uint32_t tri = PV_NONE;
     for (;;) {
         const bool want = active && tri == PV_NONE && sp > sp0;
-        const unsigned want_m = __ballot_sync(PV_FULL_MASK, want), hold_m = __ballot_sync(PV_FULL_MASK, tri != PV_NONE);
-        if ((want_m | hold_m) == 0u) break;
-        if (__popc(hold_m) * PV_LEAF_BIAS_NUM > __popc(want_m) * PV_LEAF_BIAS_DEN || want_m == 0u) {
+        const int want_n = vote_count(want), hold_n = vote_count(tri != PV_NONE);
+        if ((want_n | hold_n) == 0) break;
+        if (hold_n * PV_LEAF_BIAS_NUM > want_n * PV_LEAF_BIAS_DEN || want_n == 0) {
             if (tri != PV_NONE) {
                 double t;
                 const uint32_t ti = tri_first + tri;
                 tri = PV_NONE;
+                tc.prims++;
                 if (tri_intersect(sc.dtris[ti], mo, md, t)) {
                     const double wd = t / len;
                     const V3 ip = evaluate(o, d, wd);
@@ -502,7 +542,7 @@ __device__ inline void mesh_hits_sync(bool active, const DScene& sc, uint32_t ob
             if (!((double)__uint_as_float(e.x) > lim)) {
                 const uint32_t code = e.y >> 28, idx = e.y & PV_CODE_INDEX;
                 if (code == 0u) tri = idx;
-                else push_children<false, !ANY_HIT>(nodes, idx, code, ri, stack, sp, overflow, (lim < 3.0e38) ? __double2float_ru(lim) : 3.0e38f);
+                else tc.nodes += code, push_children<false, !ANY_HIT>(nodes, idx, code, ri, stack, sp, overflow, (lim < 3.0e38) ? __double2float_ru(lim) : 3.0e38f);
             }
         }
     }
@@ -780,7 +820,7 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
 // converged as well).  Same results as find_intersection(); only the scheduling of the work inside the warp differs.
 template <bool ANY_OPAQUE>
 __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
-                                              double post_min, Hit& best, TStack stack, unsigned int* overflow,
+                                              double post_min, Hit& best, TStack stack, unsigned int* overflow, TravCount& tc,
                                               double opaque_limit = 0.0)
 {
     bool found = false;
@@ -792,6 +832,7 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
         acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
         if (has_leaf) {
             const pvgpu_object& ob = sc.objs[leaf];
+            tc.prims++;
             if (ob.type == PVGPU_OBJ_MESH) {
                 // object_find's prelude: FP32 box test and Ray_In_Bound (object.cpp:186-193, 385-400)
                 is_mesh = object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL);
@@ -810,8 +851,8 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
                 }
             }
         }
-        if (__any_sync(PV_FULL_MASK, is_mesh)) {
-            mesh_hits_sync<ANY_OPAQUE>(is_mesh, sc, leaf, o, d, acc, stack, sp, overflow, opaque_limit, best.depth);
+        if (vote_any(is_mesh)) {
+            mesh_hits_sync<ANY_OPAQUE>(is_mesh, sc, leaf, o, d, acc, stack, sp, overflow, opaque_limit, best.depth, tc);
             if (is_mesh && acc.found && acc.best.depth < best.depth) {
                 best = acc.best;
                 found = true;
@@ -844,9 +885,9 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
     uint32_t leaf = PV_NONE;
     for (;;) {
         const bool want = alive && leaf == PV_NONE && sp > 0;
-        const unsigned want_m = __ballot_sync(PV_FULL_MASK, want), hold_m = __ballot_sync(PV_FULL_MASK, leaf != PV_NONE);
-        if ((want_m | hold_m) == 0u) break;
-        if (__popc(hold_m) * PV_LEAF_BIAS_NUM > __popc(want_m) * PV_LEAF_BIAS_DEN || want_m == 0u) {
+        const int want_n = vote_count(want), hold_n = vote_count(leaf != PV_NONE);
+        if ((want_n | hold_n) == 0) break;
+        if (hold_n * PV_LEAF_BIAS_NUM > want_n * PV_LEAF_BIAS_DEN || want_n == 0) {
             const uint32_t cur = leaf;
             leaf = PV_NONE;
             if (leaf_phase(cur != PV_NONE, cur)) { alive = false; sp = 0; }
@@ -855,7 +896,7 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
             if (!((double)__uint_as_float(e.x) > best.depth)) {      // "Depth > Best_Intersection->Depth" (boundingbox.cpp:517)
                 const uint32_t code = e.y >> 28, idx = e.y & PV_CODE_INDEX;
                 if (code == 0u) { if (precondition(sc.objs[idx].flags, rflags, shadow_ray)) leaf = idx; }
-                else push_children<true, !ANY_OPAQUE>(nodes, idx, code, ri, stack, sp, overflow, (best.depth < 3.0e38) ? __double2float_ru(best.depth) : 3.0e38f);
+                else tc.nodes += code, push_children<true, !ANY_OPAQUE>(nodes, idx, code, ri, stack, sp, overflow, (best.depth < 3.0e38) ? __double2float_ru(best.depth) : 3.0e38f);
             }
         }
     }

@@ -6,18 +6,25 @@
 //                          the reflection / refraction rays that form the next wave
 //   k_shadow_*: per shadow ray - blocker search towards the light (any-hit when every caster is opaque,
 //                          else filtered through transparent objects), then the contribution is added
-// Queues live in HBM; slots are handed out with warp-aggregated atomics (the compiler turns the
-// uniform-address atomicAdd into REDUX + one atomic per warp).  The kernels live in k_*.cu; this file is
-// the host side.  There is no CPU fallback anywhere.
+// Queues live in HBM; slots are handed out with warp-aggregated atomics.  The ray counts stay on the device (a ring of
+// WaveCounts records): the host launches the kernels of wave k + 1 before it knows how many rays wave k produced and reads the
+// counts one wave behind only to know when to stop, so the GPU never waits for the host between waves.  k_shadow_* of wave k runs
+// on a second stream next to k_closest / k_shade of wave k + 1 (they are independent; shadow queues are double-, ray queues
+// triple-buffered for that).  A scene may be replicated on several devices; then one host thread per device pulls chunks of
+// rectangles from one atomic counter (the GetNextRectangle contract, view.cpp:236-271) and delivers its tiles into the caller's
+// frame.  The kernels live in k_*.cu; this file is the host side.  There is no CPU fallback anywhere.
 #include "pvgpu_scene.hpp"
 #include "pv_kernels.hpp"
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <memory>
+#include <string>
 #include <thread>
 #include <random>
 #include <vector>
@@ -30,32 +37,49 @@ namespace pvgpu {
 // ------------------------------------------------------------------------------------------------
 // device buffers
 // ------------------------------------------------------------------------------------------------
-struct DeviceScene {
-    DScene view{};
-    std::vector<void*> allocs;
-    // work buffers (grown on demand)
-    PRay* q[2] = { nullptr, nullptr };
+#define PV_RING_SLOTS 512          // WaveCounts records per batch: max_trace_level (<= 256) + continued rays + slack
+
+// Everything one in-flight render call needs on one device: streams, ray queues, counters, staging.  A device has one or more
+// of these (PVGPU_CTX_PER_DEVICE); each serves one call at a time.
+struct WorkCtx {
+    int device = -1;
+    cudaStream_t s_main = nullptr, s_shadow = nullptr;     // own non-blocking streams; pvgpu_render_device uses the caller's as main
+    PRay* q[3] = { nullptr, nullptr, nullptr };            // wave k lives in q[k % 3]
     HitRec* hits = nullptr;
-    SRay* sq = nullptr;
+    SRay* sq[2] = { nullptr, nullptr };                    // shadow rays of wave k in sq[k & 1]
     Counters* cnt = nullptr;
+    WaveCounts* ring = nullptr;
+    unsigned int* h_counts = nullptr;                      // pinned: n_rays of wave k + 1 as read back after k_shade of wave k
     pvgpu_rect* rects = nullptr;
     uint32_t* rect_off = nullptr;
     size_t q_cap = 0, sq_cap = 0, rect_cap = 0;
-    uint16_t* d_cam_int = nullptr;       // container-state result
-    unsigned long long kernel_launches = 0;
-    bool lean = false;                   // only spheres, boxes, planes, meshes and no clipped_by / bounded_by: lean kernel variants
-    bool full = false;                   // normal{}, pigment_map / average, sky_sphere, fog or area lights: full-material shading variants
-    bool camera_dirty = true;
     float* area_grid = nullptr;          // lightGrid scratch of k_shadow_area (3 floats x area_grid_max per resident thread)
     // host-side staging of pvgpu_render (pinned) and its device frame
     float* d_frame = nullptr;
     float* h_frame = nullptr;
-    size_t frame_cap = 0;
+    size_t frame_cap = 0, h_frame_cap = 0;
+    unsigned long long kernel_launches = 0;
     // per-launch timing (CUDA events on the launching stream)
     std::vector<cudaEvent_t> ev_pool;
     struct Timed { int kind; size_t e0, e1; unsigned long long items; };
     std::vector<Timed> timed;
     size_t ev_used = 0;
+    std::mutex in_use;
+};
+
+struct DeviceScene {
+    int device = -1;
+    DScene view{};
+    std::vector<void*> allocs;
+    std::vector<std::unique_ptr<WorkCtx>> ctx;
+    uint16_t* d_cam_int = nullptr;       // container-state result
+    bool lean = false;                   // only spheres, boxes, planes, meshes and no clipped_by / bounded_by: lean kernel variants
+    bool full = false;                   // normal{}, pigment_map / average, sky_sphere, fog or area lights: full-material shading variants
+    bool camera_dirty = true;
+    uint32_t spawn_factor = 0;           // upper bound of the rays one shaded ray adds to the next wave (0: the frame is one wave)
+    uint32_t shadow_factor = 1;          // upper bound of the shadow rays one shaded ray emits
+    size_t bytes = 0;
+    std::mutex camera_mutex;
 };
 
 template <class T>
@@ -169,21 +193,38 @@ static void build_noise_tables(std::vector<uint16_t>& hash, std::vector<double>&
     for (size_t i = 0; i < p.size(); i++) perm[i] = (uint16_t)p[i];
 }
 
+static void release_ctx(WorkCtx& c)
+{
+    cudaFree(c.q[0]); cudaFree(c.q[1]); cudaFree(c.q[2]); cudaFree(c.sq[0]); cudaFree(c.sq[1]); cudaFree(c.cnt); cudaFree(c.hits); cudaFree(c.ring);
+    cudaFree(c.rects); cudaFree(c.rect_off); cudaFree(c.area_grid); cudaFree(c.d_frame);
+    if (c.h_frame) cudaFreeHost(c.h_frame);
+    if (c.h_counts) cudaFreeHost(c.h_counts);
+    for (cudaEvent_t e : c.ev_pool) cudaEventDestroy(e);
+    if (c.s_main) cudaStreamDestroy(c.s_main);
+    if (c.s_shadow) cudaStreamDestroy(c.s_shadow);
+}
+
+static void release_one(DeviceScene* d)
+{
+    if (!d) return;
+    if (d->device >= 0) cudaSetDevice(d->device);
+    for (auto& c : d->ctx) release_ctx(*c);
+    for (void* p : d->allocs) cudaFree(p);
+    cudaFree(d->d_cam_int);
+    delete d;
+}
+
 void device_release(Scene& s)
 {
-    if (!s.dev) return;
-    if (s.device >= 0) cudaSetDevice(s.device);
-    for (void* p : s.dev->allocs) cudaFree(p);
-    cudaFree(s.dev->q[0]); cudaFree(s.dev->q[1]); cudaFree(s.dev->sq); cudaFree(s.dev->cnt); cudaFree(s.dev->hits);
-    cudaFree(s.dev->rects); cudaFree(s.dev->rect_off); cudaFree(s.dev->d_cam_int);
-    cudaFree(s.dev->d_frame); if (s.dev->h_frame) cudaFreeHost(s.dev->h_frame);
-    for (cudaEvent_t e : s.dev->ev_pool) cudaEventDestroy(e);
-    delete s.dev;
+    for (DeviceScene* d : s.devs) release_one(d);
+    s.devs.clear();
     s.dev = nullptr;
 }
 
-int device_upload(Scene& s, int device)
+// Replicates the host tables of `s` on `device` (called once per device of the scene).
+static int upload_one(Scene& s, int device, DeviceScene*& out)
 {
+    out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(PVGPU_E_NO_DEVICE, "no CUDA device available (pvgpu has no CPU fallback)");
@@ -197,14 +238,13 @@ int device_upload(Scene& s, int device)
             if (cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();
         }
     }
-    s.device = device;
     // the FP32 stand-in for EPSILON in the slab test must be the smallest float >= 1e-10 (pv_traverse.cuh)
     if (!((double)1.0e-10f >= 1.0e-10 && (double)std::nextafterf(1.0e-10f, 0.0f) < 1.0e-10))
         return fail(PVGPU_E_INVALID, "internal: FP32 epsilon of the slab test is not the smallest float >= 1e-10");
     if (s.nodes.size() >= (1u << 27) || s.mesh_nodes.size() >= (1u << 27) || s.triangles.size() >= (1u << 27) || s.objects.size() >= (1u << 27))
         return fail(PVGPU_E_UNSUPPORTED, "more than 2^27 nodes / triangles / objects");
     DeviceScene* d = new DeviceScene();
-    s.dev = d;
+    d->device = device;
     size_t total = 0;
     DScene& v = d->view;
 
@@ -223,14 +263,14 @@ int device_upload(Scene& s, int device)
                 for (uint32_t k = co.child_count; k-- > 0;) {
                     uint32_t ch = s.index_list[co.child_first + k];
                     if (ch >= s.objects.size() || s.objects[ch].parent != (int32_t)c) {
-                        device_release(s);
+                        release_one(d);
                         return fail(PVGPU_E_INVALID, "CSG object %u: child %u has inconsistent parent", c, ch);
                     }
                     st.push_back(ch);
                 }
             } else {
-                if (co.type == PVGPU_OBJ_MESH) { device_release(s); return fail(PVGPU_E_UNSUPPORTED, "mesh inside CSG is outside the hot-path scope"); }
-                if (co.bound_count) { device_release(s); return fail(PVGPU_E_UNSUPPORTED, "bounded_by on a CSG child is outside the hot-path scope"); }
+                if (co.type == PVGPU_OBJ_MESH) { release_one(d); return fail(PVGPU_E_UNSUPPORTED, "mesh inside CSG is outside the hot-path scope"); }
+                if (co.bound_count) { release_one(d); return fail(PVGPU_E_UNSUPPORTED, "bounded_by on a CSG child is outside the hot-path scope"); }
                 leaves.push_back(c);
             }
         }
@@ -277,7 +317,7 @@ int device_upload(Scene& s, int device)
             dmeshes[m].node_first = (uint32_t)dmnodes.size();
             rc = make_dnodes(s.mesh_nodes.data() + me.node_first, me.node_count, dmnodes);
         }
-        if (rc != PVGPU_OK) { device_release(s); return rc; }
+        if (rc != PVGPU_OK) { release_one(d); return rc; }
     }
 
     int rc = PVGPU_OK;
@@ -300,16 +340,16 @@ int device_upload(Scene& s, int device)
     UP(leaves, v.csg_leaves); UP(leaf_range, v.csg_leaf_range);
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP
-    if (rc != PVGPU_OK) { device_release(s); return rc; }
+    if (rc != PVGPU_OK) { release_one(d); return rc; }
     if (s.globals.number_of_waves) {       // TraceThreadData::waveSources / waveFrequencies, computed with the device's own DNoise
         const uint32_t nw = s.globals.number_of_waves;
         std::vector<double> zeros(4 * (size_t)nw, 0.0);
         const double* d_waves = nullptr;
         rc = upload(*d, zeros, d_waves, total);
-        if (rc != PVGPU_OK) { device_release(s); return rc; }
+        if (rc != PVGPU_OK) { release_one(d); return rc; }
         v.wave_sources = d_waves; v.wave_freqs = d_waves + 3 * (size_t)nw;
         launch_init_waves(v.noise, nw, const_cast<double*>(v.wave_sources), const_cast<double*>(v.wave_freqs), 0);
-        if (cudaDeviceSynchronize() != cudaSuccess) { device_release(s); return fail(PVGPU_E_CUDA, "wave source initialisation failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        if (cudaDeviceSynchronize() != cudaSuccess) { release_one(d); return fail(PVGPU_E_CUDA, "wave source initialisation failed: %s", cudaGetErrorString(cudaGetLastError())); }
     }
 
     d->lean = true;
@@ -328,13 +368,7 @@ int device_upload(Scene& s, int device)
     if (s.globals.quality_flags & PVGPU_Q_AREA_LIGHTS)
         for (const pvgpu_light& l : s.lights)
             if (l.flags & PVGPU_LIGHT_AREA) { v.has_area_lights = 1; v.area_grid_max = std::max<uint32_t>(v.area_grid_max, (uint32_t)(l.area_size1 * l.area_size2)); }
-    if (v.has_area_lights) {
-        d->lean = false;
-        void* p = nullptr;
-        if (cudaMalloc(&p, (size_t)area_threads() * v.area_grid_max * 3 * sizeof(float)) != cudaSuccess) { device_release(s); return fail(PVGPU_E_CUDA, "cudaMalloc of the area-light sample grids failed"); }
-        d->allocs.push_back(p);
-        d->area_grid = reinterpret_cast<float*>(p);
-    }
+    if (v.has_area_lights) d->lean = false;
     v.n_fogs = (uint32_t)s.fogs.size();
     v.has_sky = s.sky_spheres.empty() ? 0u : 1u;
     if (v.has_sky) v.sky = s.sky_spheres[0];
@@ -357,15 +391,86 @@ int device_upload(Scene& s, int device)
     v.g = s.globals;
     v.cam = s.camera;
     v.n_cam_interiors = 0;
-    s.device_bytes = total;
+    d->bytes = total;
+    // how a wave can grow: a shaded ray adds at most one transmitted ray (or its total internal reflection) when the scene has
+    // interiors, plus one reflected ray per reflective layer; and one shadow ray per light (per resolved texture_map leaf)
+    {
+        uint32_t refl_layers = 0;
+        for (size_t t = 0; t < s.textures.size(); t++) {
+            uint32_t nl = 0;
+            for (int32_t li = (int32_t)t; li >= 0 && nl < PV_MAX_LAYERS; li = s.textures[li].next) {
+                const pvgpu_texture& tx = s.textures[li];
+                if (tx.type != PVGPU_PAT_PLAIN || tx.finish < 0 || (size_t)tx.finish >= s.finishes.size()) { nl = PV_MAX_LAYERS; break; }
+                const pvgpu_finish& fi = s.finishes[tx.finish];
+                if (fi.reflection_max[0] != 0.0f || fi.reflection_max[1] != 0.0f || fi.reflection_max[2] != 0.0f ||
+                    fi.reflection_min[0] != 0.0f || fi.reflection_min[1] != 0.0f || fi.reflection_min[2] != 0.0f) nl++;
+            }
+            refl_layers = std::max(refl_layers, nl);
+        }
+        const bool leaves = d->full;     // texture_map: up to PV_MAX_TEX_LEAVES plain textures are shaded per hit
+        d->spawn_factor = (refl_layers + (s.interiors.empty() ? 0u : 1u)) * (leaves ? 16u : 1u);
+        d->shadow_factor = std::max<uint32_t>(1u, (uint32_t)s.lights.size()) * (leaves ? 16u : 1u);
+    }
 
-    if (cudaMalloc(&d->cnt, sizeof(Counters)) != cudaSuccess || cudaMalloc(&d->d_cam_int, 64) != cudaSuccess) {
-        device_release(s);
-        return fail(PVGPU_E_CUDA, "cudaMalloc of counters failed");
+    if (cudaMalloc(&d->d_cam_int, 64) != cudaSuccess) {
+        release_one(d);
+        return fail(PVGPU_E_CUDA, "cudaMalloc of the camera state failed");
     }
     // the deepest Inside()/sturm paths keep a few small arrays per thread; blobs add their per-ray interval lists
     cudaDeviceSetLimit(cudaLimitStackSize, s.blobs.empty() ? 4096 : 12288);
     d->camera_dirty = true;
+    // work contexts (streams, queues) of this device
+    int n_ctx = 1;
+    if (const char* e = getenv("PVGPU_CTX_PER_DEVICE")) n_ctx = std::max(1, std::min(4, atoi(e)));
+    for (int i = 0; i < n_ctx; i++) {
+        std::unique_ptr<WorkCtx> c(new WorkCtx());
+        c->device = device;
+        bool ok = cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&c->s_shadow, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaMalloc(&c->cnt, sizeof(Counters)) == cudaSuccess &&
+                  cudaMalloc(&c->ring, PV_RING_SLOTS * sizeof(WaveCounts)) == cudaSuccess &&
+                  cudaMallocHost(&c->h_counts, PV_RING_SLOTS * sizeof(unsigned int)) == cudaSuccess;
+        if (ok && v.has_area_lights)
+            ok = cudaMalloc(&c->area_grid, (size_t)area_threads() * v.area_grid_max * 3 * sizeof(float)) == cudaSuccess;
+        d->ctx.push_back(std::move(c));
+        if (!ok) { release_one(d); return fail(PVGPU_E_CUDA, "allocation of the work context failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    }
+    out = d;
+    return PVGPU_OK;
+}
+
+int device_upload(Scene& s, const int* devices, int n_devices)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(PVGPU_E_NO_DEVICE, "no CUDA device available (pvgpu has no CPU fallback)");
+    std::vector<int> list;
+    if (n_devices <= 0) for (int i = 0; i < ndev; i++) list.push_back(i);                 // all visible devices
+    else for (int i = 0; i < n_devices; i++) list.push_back(devices ? devices[i] : i);
+    for (size_t i = 0; i < list.size(); i++) {
+        if (list[i] < 0 || list[i] >= ndev) return fail(PVGPU_E_INVALID, "device %d out of range (have %d)", list[i], ndev);
+        for (size_t j = 0; j < i; j++) if (list[j] == list[i]) return fail(PVGPU_E_INVALID, "device %d listed twice", list[i]);
+    }
+    for (int dev : list) {
+        DeviceScene* d = nullptr;
+        int rc = upload_one(s, dev, d);
+        if (rc != PVGPU_OK) { device_release(s); return rc; }
+        s.devs.push_back(d);
+    }
+    s.dev = s.devs[0];
+    s.device = list[0];
+    s.device_bytes = s.devs[0]->bytes;
+    // finished tiles travel to the first device of the list (or to the host) with peer copies
+    for (size_t i = 1; i < list.size(); i++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, list[i], list[0]) == cudaSuccess && can) {
+            cudaSetDevice(list[i]);
+            if (cudaDeviceEnablePeerAccess(list[0], 0) != cudaSuccess) cudaGetLastError();
+            cudaSetDevice(list[0]);
+            if (cudaDeviceEnablePeerAccess(list[i], 0) != cudaSuccess) cudaGetLastError();
+        }
+    }
+    cudaSetDevice(list[0]);
     return PVGPU_OK;
 }
 
@@ -374,54 +479,55 @@ int device_upload(Scene& s, int device)
 // ------------------------------------------------------------------------------------------------
 enum { KIND_PRIMARY = 0, KIND_CLOSEST = 1, KIND_SHADE = 2, KIND_SHADOW = 3, KIND_AA = 4, KIND_COUNT = 5 };
 
-static size_t next_event(DeviceScene& d)
+static size_t next_event(WorkCtx& c)
 {
-    if (d.ev_used == d.ev_pool.size()) {
+    if (c.ev_used == c.ev_pool.size()) {
         cudaEvent_t e;
         cudaEventCreate(&e);
-        d.ev_pool.push_back(e);
+        c.ev_pool.push_back(e);
     }
-    return d.ev_used++;
+    return c.ev_used++;
 }
 
 // Brackets one kernel launch with CUDA events on the launching stream; the elapsed times are summed per kernel
 // kind when the frame is complete (pvgpu_stats::kernel_ms).
 struct TimedLaunch {
-    DeviceScene& d; cudaStream_t st; size_t e0;
+    WorkCtx& c; cudaStream_t st; size_t e0;
     int kind; unsigned long long items;
-    TimedLaunch(DeviceScene& d_, cudaStream_t st_, int kind_, unsigned long long items_) : d(d_), st(st_), kind(kind_), items(items_)
+    TimedLaunch(WorkCtx& c_, cudaStream_t st_, int kind_, unsigned long long items_) : c(c_), st(st_), kind(kind_), items(items_)
     {
-        e0 = next_event(d);
-        cudaEventRecord(d.ev_pool[e0], st);
+        e0 = next_event(c);
+        cudaEventRecord(c.ev_pool[e0], st);
     }
     ~TimedLaunch()
     {
-        size_t e1 = next_event(d);
-        cudaEventRecord(d.ev_pool[e1], st);
-        d.timed.push_back({ kind, e0, e1, items });
-        d.kernel_launches++;
+        size_t e1 = next_event(c);
+        cudaEventRecord(c.ev_pool[e1], st);
+        c.timed.push_back({ kind, e0, e1, items });
+        c.kernel_launches++;
     }
 };
 
-static int ensure_work_buffers(DeviceScene& d, size_t q_cap, size_t sq_cap, size_t n_rects)
+static int ensure_work_buffers(WorkCtx& c, size_t q_cap, size_t sq_cap, size_t n_rects)
 {
-    if (q_cap > d.q_cap) {
-        cudaFree(d.q[0]); cudaFree(d.q[1]); cudaFree(d.hits); d.q[0] = d.q[1] = nullptr; d.hits = nullptr; d.q_cap = 0;
-        CUDA_TRY(cudaMalloc(&d.q[0], q_cap * sizeof(PRay)));
-        CUDA_TRY(cudaMalloc(&d.q[1], q_cap * sizeof(PRay)));
-        CUDA_TRY(cudaMalloc(&d.hits, q_cap * sizeof(HitRec)));
-        d.q_cap = q_cap;
+    if (q_cap > c.q_cap) {
+        for (int k = 0; k < 3; k++) { cudaFree(c.q[k]); c.q[k] = nullptr; }
+        cudaFree(c.hits); c.hits = nullptr; c.q_cap = 0;
+        for (int k = 0; k < 3; k++) CUDA_TRY(cudaMalloc(&c.q[k], q_cap * sizeof(PRay)));
+        CUDA_TRY(cudaMalloc(&c.hits, q_cap * sizeof(HitRec)));
+        c.q_cap = q_cap;
     }
-    if (sq_cap > d.sq_cap) {
-        cudaFree(d.sq); d.sq = nullptr; d.sq_cap = 0;
-        CUDA_TRY(cudaMalloc(&d.sq, sq_cap * sizeof(SRay)));
-        d.sq_cap = sq_cap;
+    if (sq_cap > c.sq_cap) {
+        for (int k = 0; k < 2; k++) { cudaFree(c.sq[k]); c.sq[k] = nullptr; }
+        c.sq_cap = 0;
+        for (int k = 0; k < 2; k++) CUDA_TRY(cudaMalloc(&c.sq[k], sq_cap * sizeof(SRay)));
+        c.sq_cap = sq_cap;
     }
-    if (n_rects > d.rect_cap) {
-        cudaFree(d.rects); cudaFree(d.rect_off); d.rects = nullptr; d.rect_off = nullptr; d.rect_cap = 0;
-        CUDA_TRY(cudaMalloc(&d.rects, n_rects * sizeof(pvgpu_rect)));
-        CUDA_TRY(cudaMalloc(&d.rect_off, (n_rects + 1) * sizeof(uint32_t)));
-        d.rect_cap = n_rects;
+    if (n_rects > c.rect_cap) {
+        cudaFree(c.rects); cudaFree(c.rect_off); c.rects = nullptr; c.rect_off = nullptr; c.rect_cap = 0;
+        CUDA_TRY(cudaMalloc(&c.rects, n_rects * sizeof(pvgpu_rect)));
+        CUDA_TRY(cudaMalloc(&c.rect_off, (n_rects + 1) * sizeof(uint32_t)));
+        c.rect_cap = n_rects;
     }
     return PVGPU_OK;
 }
@@ -449,17 +555,16 @@ static void setup_camera(const Scene& s, DScene& v)
         v.cam_v_angle = s.camera_ext.size() == 3 ? s.camera_ext[2] : 0.0;
 }
 
-static int refresh_camera(Scene& s, cudaStream_t stream)
+static int refresh_camera(Scene& s, DeviceScene& d, WorkCtx& c, cudaStream_t stream)
 {
-    DeviceScene& d = *s.dev;
     d.view.cam = s.camera;
     d.view.n_cam_interiors = 0;
     setup_camera(s, d.view);
     // pinhole-style cameras: the containing interiors are found once (InitRayContainerState(ray, false)); orthographic and the
     // cylinder cameras 3 / 4 move the origin with the pixel and recompute per ray (k_primary)
     if (!s.interiors.empty() && s.camera.type != PVGPU_CAMERA_ORTHOGRAPHIC && s.camera.type != PVGPU_CAMERA_CYL_3 && s.camera.type != PVGPU_CAMERA_CYL_4) {
-        launch_container_state(d.view, d.d_cam_int, d.cnt, stream);
-        d.kernel_launches++;
+        launch_container_state(d.view, d.d_cam_int, c.cnt, stream);
+        c.kernel_launches++;
         uint16_t h[PV_MAX_INTERIORS + 1];
         CUDA_TRY(cudaMemcpyAsync(h, d.d_cam_int, sizeof h, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
@@ -471,10 +576,12 @@ static int refresh_camera(Scene& s, cudaStream_t stream)
 }
 
 static const size_t kBatchSamples = 1u << 22;          // samples traced per batch of waves
-static const size_t kShadowCap = 1u << 23;             // shadow-ray queue capacity (records)
+static const size_t kShadowCapMax = 1u << 24;          // shadow-ray queue capacity limit (records per buffer)
 
 struct FrameCtx {
     Scene& s;
+    DeviceScene& d;
+    WorkCtx& c;
     cudaStream_t stream;
     int width, height;
     float4* accum;
@@ -487,65 +594,93 @@ struct FrameCtx {
 static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint32_t n)
 {
     Scene& s = f.s;
-    DeviceScene& d = *s.dev;
-    cudaStream_t stream = f.stream;
-    const uint32_t q_cap = (uint32_t)d.q_cap, sq_cap = (uint32_t)d.sq_cap;
-    const uint32_t n_lights = std::max<uint32_t>(1, (uint32_t)s.lights.size());
-    const uint32_t chunk_max = std::max<uint32_t>(1, sq_cap / n_lights);
+    DeviceScene& d = f.d;
+    WorkCtx& c = f.c;
+    cudaStream_t S1 = f.stream, S2 = c.s_shadow;
+    const uint32_t q_cap = (uint32_t)c.q_cap, sq_cap = (uint32_t)c.sq_cap;
+    const uint32_t max_waves = std::min<uint32_t>(s.globals.max_trace_level + 64u, PV_RING_SLOTS - 2);     // continued rays do not consume a level
+    const bool have_lights = !s.lights.empty();
+    launch_wave_init(c.ring, PV_RING_SLOTS, n, S1);
+    c.kernel_launches++;
     {
-        TimedLaunch t(d, stream, KIND_PRIMARY, n);
-        launch_primary(d.view, src, first, n, (double)f.width, (double)f.height, d.q[0], d.cnt, f.accum, stream);
+        TimedLaunch t(c, S1, KIND_PRIMARY, n);
+        launch_primary(d.view, src, first, n, (double)f.width, (double)f.height, c.q[0], c.cnt, f.accum, S1);
     }
-    uint32_t n_cur = n;
-    int cur = 0;
-    const uint32_t max_waves = s.globals.max_trace_level + 64;     // continued rays do not consume a level
-    for (uint32_t wave = 0; n_cur > 0 && wave < max_waves; wave++) {
-        CUDA_TRY(cudaMemsetAsync(&d.cnt->n_next, 0, sizeof(unsigned int), stream));
-        for (uint32_t c0 = 0; c0 < n_cur; c0 += chunk_max) {
-            const uint32_t cn = std::min(chunk_max, n_cur - c0);
-            CUDA_TRY(cudaMemsetAsync(&d.cnt->n_shadow, 0, sizeof(unsigned int), stream));
-            WaveCtx ctx;
-            ctx.accum = f.accum; ctx.next = d.q[cur ^ 1]; ctx.shadow = d.sq; ctx.cnt = d.cnt;
-            ctx.next_cap = q_cap; ctx.shadow_cap = sq_cap;
-            {
-                TimedLaunch t(d, stream, KIND_CLOSEST, cn);
-                (d.lean ? launch_closest_lean : launch_closest)(d.view, d.q[cur] + c0, cn, d.hits + c0, d.cnt, stream);
-            }
-            {
-                TimedLaunch t(d, stream, KIND_SHADE, cn);
-                (d.lean ? launch_shade_lean : d.full ? launch_shade_full : launch_shade)(d.view, d.q[cur] + c0, d.hits + c0, cn, ctx, stream);
-            }
-            if (!s.lights.empty()) {
-                // the shadow kernel reads its count on the device; its grid is sized for the worst case of this chunk
-                const uint32_t worst = (uint32_t)std::min<unsigned long long>((unsigned long long)cn * n_lights, sq_cap);
-                TimedLaunch t(d, stream, KIND_SHADOW, 0);
-                if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : launch_shadow_opaque)(d.view, d.sq, worst, f.accum, d.cnt, stream);
-                else (d.lean ? launch_shadow_filter_lean : d.full ? launch_shadow_filter_full : launch_shadow_filter)(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, stream);
-                if (d.view.has_area_lights) { d.kernel_launches++; launch_shadow_area(d.view, d.sq, d.q[cur] + c0, worst, f.accum, d.cnt, d.area_grid, stream); }
-            }
+    std::vector<size_t> ev_rb, ev_shadow;           // per wave: count read back / shadow kernels done
+    unsigned long long bound = n;                   // upper bound of the wave's ray count (sizes the grids only)
+    uint32_t known = n;                             // last ray count the host has seen
+    uint32_t wave = 0;
+    int rc = PVGPU_OK;
+    for (;; wave++) {
+        if (wave >= 2) {
+            // n_rays of wave - 1 (read back after k_shade of wave - 2, which finished while wave - 1 was being traced)
+            CUDA_TRY(cudaEventSynchronize(c.ev_pool[ev_rb[wave - 2]]));
+            known = c.h_counts[wave - 2];
+            if (known == 0) break;                  // wave - 1 was empty, so is this one
+            bound = std::min<unsigned long long>(bound, (unsigned long long)std::min(known, q_cap) * std::max<uint32_t>(d.spawn_factor, 1u));
+            if (f.cooperate && f.cooperate(f.user)) { rc = fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback"); break; }
         }
-        unsigned int h[4];     // n_next, n_shadow, max_level, overflow
-        CUDA_TRY(cudaMemcpyAsync(h, &d.cnt->n_next, sizeof h, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (wave >= max_waves) { rc = fail(PVGPU_E_OVERFLOW, "rays still alive after %u waves (max_trace_level %u)", wave, s.globals.max_trace_level); break; }
+        WaveCounts* wc = c.ring + wave;
+        PRay* cur = c.q[wave % 3];
+        const uint32_t nb = (uint32_t)std::min<unsigned long long>(std::max<unsigned long long>(bound, 1), q_cap);
+        WaveCtx ctx;
+        ctx.accum = f.accum; ctx.next = c.q[(wave + 1) % 3]; ctx.shadow = c.sq[wave & 1]; ctx.cnt = c.cnt;
+        ctx.n_next = &wc[1].n_rays; ctx.n_shadow = &wc->n_shadow;
+        ctx.cur_cap = q_cap; ctx.next_cap = q_cap; ctx.shadow_cap = sq_cap;
+        {
+            TimedLaunch t(c, S1, KIND_CLOSEST, 0);
+            (d.lean ? launch_closest_lean : launch_closest)(d.view, cur, wc, nb, q_cap, c.hits, c.cnt, S1);
+        }
+        // k_shade of this wave writes sq[wave & 1] and q[(wave + 1) % 3]: k_shadow_* of wave - 2 read both (queue and parent rays)
+        if (wave >= 2 && have_lights) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[wave - 2]], 0));
+        {
+            TimedLaunch t(c, S1, KIND_SHADE, 0);
+            (d.lean ? launch_shade_lean : d.full ? launch_shade_full : launch_shade)(d.view, cur, c.hits, wc, nb, ctx, S1);
+        }
+        CUDA_TRY(cudaMemcpyAsync(&c.h_counts[wave], &wc[1].n_rays, sizeof(unsigned int), cudaMemcpyDeviceToHost, S1));
+        ev_rb.push_back(next_event(c));
+        CUDA_TRY(cudaEventRecord(c.ev_pool[ev_rb.back()], S1));
+        if (have_lights) {
+            CUDA_TRY(cudaStreamWaitEvent(S2, c.ev_pool[ev_rb.back()], 0));
+            const uint32_t sb = (uint32_t)std::min<unsigned long long>((unsigned long long)nb * d.shadow_factor, sq_cap);
+            {
+                TimedLaunch t(c, S2, KIND_SHADOW, 0);
+                if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : launch_shadow_opaque)(d.view, c.sq[wave & 1], wc, sb, sq_cap, f.accum, c.cnt, S2);
+                else (d.lean ? launch_shadow_filter_lean : d.full ? launch_shadow_filter_full : launch_shadow_filter)(d.view, c.sq[wave & 1], wc, sb, sq_cap, cur, f.accum, c.cnt, S2);
+                if (d.view.has_area_lights) { c.kernel_launches++; launch_shadow_area(d.view, c.sq[wave & 1], wc, sb, sq_cap, cur, f.accum, c.cnt, c.area_grid, S2); }
+            }
+            ev_shadow.push_back(next_event(c));
+            CUDA_TRY(cudaEventRecord(c.ev_pool[ev_shadow.back()], S2));
+        }
         f.st.waves++;
-        if (h[3] & (8u | 16u)) return PVGPU_E_OVERFLOW;
-        n_cur = h[0];
-        cur ^= 1;
-        if (f.cooperate && n_cur && f.cooperate(f.user)) return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback");
+        if (d.spawn_factor == 0) { wave++; break; }         // no reflective or refractive material: the frame is this one wave
+        bound = std::min<unsigned long long>(bound * d.spawn_factor, q_cap);
     }
+    // the shadow stream joins the main stream; queue overflows are known once everything has run
+    if (have_lights) for (size_t k = (ev_shadow.size() > 2 ? ev_shadow.size() - 2 : 0); k < ev_shadow.size(); k++) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[k]], 0));
+    if (rc != PVGPU_OK) { cudaStreamSynchronize(S1); return rc; }
+    unsigned int ovf = 0;
+    CUDA_TRY(cudaMemcpyAsync(&ovf, &c.cnt->overflow, sizeof ovf, cudaMemcpyDeviceToHost, S1));
+    CUDA_TRY(cudaStreamSynchronize(S1));
+    if (ovf & (8u | 16u)) return PVGPU_E_OVERFLOW;
     return PVGPU_OK;
 }
 
 // Traces samples [0, n) of `src` into the accumulators: batches of kBatchSamples; a batch whose ray queues overflow is
-// retried as two halves.  `slot_of` must be the identity (slot = sample index) for the retry to clear the right slots,
-// or `clear_slots` = false when several samples share one slot (anti-aliasing sums) - then an overflow is fatal.
+// retried as two halves (its accumulator slots are cleared by recomputing them, k_clear_slots), unless several samples share
+// one slot (`clear_slots` = false, anti-aliasing sums) - then an overflow is fatal.
 static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_samples, bool clear_slots)
 {
-    DeviceScene& d = *f.s.dev;
+    DeviceScene& d = f.d;
+    WorkCtx& c = f.c;
     if (n_samples == 0) return PVGPU_OK;
     const size_t batch = std::min<size_t>(kBatchSamples, n_samples);
     {
-        int rc = ensure_work_buffers(d, std::max<size_t>(3 * batch, 1024), kShadowCap, 0);
+        // a wave cannot outgrow the batch when a ray spawns at most one ray; otherwise leave room for growth
+        const size_t q_cap = std::max<size_t>((d.spawn_factor <= 1 ? 1 : 4) * batch, 1024);
+        const size_t sq_cap = std::min<size_t>(kShadowCapMax, std::max<size_t>(q_cap * d.shadow_factor, 1024));
+        int rc = ensure_work_buffers(c, q_cap, f.s.lights.empty() ? 0 : sq_cap, 0);
         if (rc != PVGPU_OK) return rc;
     }
     struct Span { uint32_t first, n; };
@@ -556,9 +691,10 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
         Span sp = todo.back(); todo.pop_back();
         if (f.cooperate && f.cooperate(f.user)) return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback");
         int rc = run_batch(f, src, sp.first, sp.n);
-        if (rc == PVGPU_E_OVERFLOW && sp.n > 1 && clear_slots && !src.slots) {
-            CUDA_TRY(cudaMemsetAsync(f.accum + src.slot_base + sp.first, 0, (size_t)sp.n * sizeof(float4), f.stream));
-            CUDA_TRY(cudaMemsetAsync(&d.cnt->overflow, 0, sizeof(unsigned int), f.stream));
+        if (rc == PVGPU_E_OVERFLOW && sp.n > 1 && clear_slots) {
+            launch_clear_slots(src, sp.first, sp.n, f.accum, f.stream);
+            c.kernel_launches++;
+            CUDA_TRY(cudaMemsetAsync(&c.cnt->overflow, 0, sizeof(unsigned int), f.stream));
             todo.push_back({ sp.first + sp.n / 2, sp.n - sp.n / 2 });
             todo.push_back({ sp.first, sp.n / 2 });
             continue;
@@ -608,8 +744,8 @@ static AAParams make_aa_params(const pvgpu_aa& aa)
 static int render_aa1(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, size_t n_rects, const std::vector<uint32_t>& off, float4* d_out,
                       unsigned long long& n_extra_samples)
 {
-    Scene& s = f.s;
-    DeviceScene& d = *s.dev;
+    DeviceScene& d = f.d;
+    WorkCtx& c = f.c;
     cudaStream_t stream = f.stream;
     const uint32_t n_px = off[n_rects];
     std::vector<uint32_t> foff(n_rects + 1, 0);
@@ -641,26 +777,26 @@ static int render_aa1(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
     CUDA_TRY(cudaMemcpyAsync(d_offsets, offsets.data(), n_off * sizeof(double2), cudaMemcpyHostToDevice, stream));
     f.accum = accum;
     AALayout L{};
-    L.rects = d.rects; L.rect_off = d.rect_off; L.frame_off = d_foff; L.corner_off = nullptr;
+    L.rects = c.rects; L.rect_off = c.rect_off; L.frame_off = d_foff; L.corner_off = nullptr;
     L.n_rects = (uint32_t)n_rects; L.n_px = n_px; L.n_frame = n_frame; L.n_corner = 0; L.s_base = n_px + n_frame;
 
     // 1. pixel centres, 2. the frame above / left of every rectangle
     SampleSource src{};
-    src.rects = d.rects; src.rect_off = d.rect_off; src.n_rects = (uint32_t)n_rects;
+    src.rects = c.rects; src.rect_off = c.rect_off; src.n_rects = (uint32_t)n_rects;
     AA_TRY(trace_samples(f, src, n_px, true));
-    { TimedLaunch t(d, stream, KIND_AA, n_frame); launch_aa1_frame_coords(L, d_fcoords, stream); }
+    { TimedLaunch t(c, stream, KIND_AA, n_frame); launch_aa1_frame_coords(L, d_fcoords, stream); }
     SampleSource fsrc{};
     fsrc.coords = d_fcoords; fsrc.slot_base = n_px;
     AA_TRY(trace_samples(f, fsrc, n_frame, true));
     // 3. candidates from un-supersampled colours
-    { TimedLaunch t(d, stream, KIND_AA, n_px); launch_aa1_candidates(L, ap, accum, s_slot, cand, counters, stream); }
+    { TimedLaunch t(c, stream, KIND_AA, n_px); launch_aa1_candidates(L, ap, accum, s_slot, cand, counters, stream); }
     unsigned int n_cand = 0, n_done = 0;
     AA_TRY(read_counter(counters, stream, n_cand));
     // 4. trace what is queued, replay the sequential walk, repeat while the walk queues more
     for (int round = 0; round < 64; round++) {
         while (n_done < n_cand) {
             const uint32_t cn = std::min<uint32_t>(cand_chunk, n_cand - n_done);
-            { TimedLaunch t(d, stream, KIND_AA, cn); launch_aa1_sample_coords(L, ap, d.view.noise.hash, cand, n_done, cn, d_offsets, n_off, d_coords, d_slots, stream); }
+            { TimedLaunch t(c, stream, KIND_AA, cn); launch_aa1_sample_coords(L, ap, d.view.noise.hash, cand, n_done, cn, d_offsets, n_off, d_coords, d_slots, stream); }
             SampleSource ssrc{};
             ssrc.coords = d_coords; ssrc.slots = d_slots;
             AA_TRY(trace_samples(f, ssrc, cn * n_off, false));
@@ -668,7 +804,7 @@ static int render_aa1(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
             n_extra_samples += (unsigned long long)cn * n_off;
         }
         CUDA_TRY(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned int), stream));
-        { TimedLaunch t(d, stream, KIND_AA, n_rects); launch_aa1_decide(L, ap, accum, s_slot, cand, counters, d_out, flag, counters + 1, stream); }
+        { TimedLaunch t(c, stream, KIND_AA, n_rects); launch_aa1_decide(L, ap, accum, s_slot, cand, counters, d_out, flag, counters + 1, stream); }
         AA_TRY(read_counter(counters, stream, n_cand));
         if (n_cand == n_done) return PVGPU_OK;
     }
@@ -679,8 +815,8 @@ static int render_aa1(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
 static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, size_t n_rects, const std::vector<uint32_t>& off, float4* d_out,
                       unsigned long long& n_extra_samples)
 {
-    Scene& s = f.s;
-    DeviceScene& d = *s.dev;
+    DeviceScene& d = f.d;
+    WorkCtx& c = f.c;
     cudaStream_t stream = f.stream;
     const uint32_t n_px = off[n_rects];
     std::vector<uint32_t> coff(n_rects + 1, 0);
@@ -702,17 +838,17 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
     CUDA_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream));
     CUDA_TRY(cudaMemcpyAsync(d_coff, coff.data(), coff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     AALayout L{};
-    L.rects = d.rects; L.rect_off = d.rect_off; L.frame_off = nullptr; L.corner_off = d_coff;
+    L.rects = c.rects; L.rect_off = c.rect_off; L.frame_off = nullptr; L.corner_off = d_coff;
     L.n_rects = (uint32_t)n_rects; L.n_px = n_px; L.n_frame = 0; L.n_corner = n_corner; L.s_base = n_corner;
 
     // 1. pixel corners
-    { TimedLaunch t(d, stream, KIND_AA, n_corner); launch_aa2_corner_coords(L, d_ccoords, stream); }
+    { TimedLaunch t(c, stream, KIND_AA, n_corner); launch_aa2_corner_coords(L, d_ccoords, stream); }
     f.accum = corners;
     SampleSource csrc{};
     csrc.coords = d_ccoords;
     AA_TRY(trace_samples(f, csrc, n_corner, true));
     // 2. pixels that subdivide get a sample buffer
-    { TimedLaunch t(d, stream, KIND_AA, n_px); launch_aa2_mark(L, ap, corners, act_idx, act_list, counters, stream); }
+    { TimedLaunch t(c, stream, KIND_AA, n_px); launch_aa2_mark(L, ap, corners, act_idx, act_list, counters, stream); }
     unsigned int n_active = 0;
     AA_TRY(read_counter(counters, stream, n_active));
     float4* accum = corners;
@@ -734,7 +870,7 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
             Scratch rs;
             AA_TRY(rs.alloc(d_coords, cap)); AA_TRY(rs.alloc(d_slots, cap));
             CUDA_TRY(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned int), stream));
-            { TimedLaunch t(d, stream, KIND_AA, n_active); launch_aa2_expand(L, ap, d.view.noise.hash, accum, act_list, n_active, (int)round, sampled, d_coords, d_slots, counters + 1, cap, stream); }
+            { TimedLaunch t(c, stream, KIND_AA, n_active); launch_aa2_expand(L, ap, d.view.noise.hash, accum, act_list, n_active, (int)round, sampled, d_coords, d_slots, counters + 1, cap, stream); }
             unsigned int n_new = 0;
             AA_TRY(read_counter(counters + 1, stream, n_new));
             if (n_new > cap) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: sample list overflow");
@@ -747,23 +883,20 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
         }
     }
     // 4. combine
-    { TimedLaunch t(d, stream, KIND_AA, n_px); launch_aa2_resolve(L, ap, accum, act_idx, d_out, stream); }
+    { TimedLaunch t(c, stream, KIND_AA, n_px); launch_aa2_resolve(L, ap, accum, act_idx, d_out, stream); }
     CUDA_TRY(cudaStreamSynchronize(stream));
     return PVGPU_OK;
 }
 
-static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, const pvgpu_rect* rects, size_t n_rects,
+static int render_impl(Scene& s, DeviceScene& d, WorkCtx& c, const pvgpu_aa* aa, int width, int height, const pvgpu_rect* rects, size_t n_rects,
                        float* d_out, pvgpu_stats* stats, cudaStream_t stream, int (*cooperate)(void*), void* user)
 {
-    if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     if (width <= 0 || height <= 0 || !rects || !n_rects || !d_out) return fail(PVGPU_E_INVALID, "pvgpu_render: bad arguments");
-    std::lock_guard<std::recursive_mutex> device_lock(s.device_mutex);
     const unsigned int method = aa ? aa->method : 0u;
     if (method > 2) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method %u (stochastic supersampling) is outside the GPU trace path", method);
     if (method && (aa->depth < 1 || aa->depth > 9)) return fail(PVGPU_E_INVALID, "anti-aliasing depth %u out of range 1..9", aa->depth);
     if (method == 2 && aa->depth > 5) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method 2 is limited to depth 5 on the GPU path (sample buffers of (2^depth + 1)^2 per pixel)");
-    CUDA_TRY(cudaSetDevice(s.device));
-    DeviceScene& d = *s.dev;
+    CUDA_TRY(cudaSetDevice(d.device));
     std::vector<uint32_t> off(n_rects + 1, 0);
     for (size_t i = 0; i < n_rects; i++) {
         const pvgpu_rect& r = rects[i];
@@ -773,57 +906,251 @@ static int render_impl(Scene& s, const pvgpu_aa* aa, int width, int height, cons
         off[i + 1] = off[i] + (uint32_t)area;
     }
     const uint32_t n_samples = off[n_rects];
-    const unsigned long long launches0 = d.kernel_launches;
-    d.ev_used = 0;
-    d.timed.clear();
-    const size_t ev0 = next_event(d);
-    CUDA_TRY(cudaEventRecord(d.ev_pool[ev0], stream));
-    CUDA_TRY(cudaMemsetAsync(d.cnt, 0, sizeof(Counters), stream));
-    if (d.camera_dirty || std::memcmp(&d.view.cam, &s.camera, sizeof s.camera) != 0) {
-        int rc = refresh_camera(s, stream);
-        if (rc != PVGPU_OK) return rc;
+    const unsigned long long launches0 = c.kernel_launches;
+    c.ev_used = 0;
+    c.timed.clear();
+    const size_t ev0 = next_event(c);
+    CUDA_TRY(cudaEventRecord(c.ev_pool[ev0], stream));
+    CUDA_TRY(cudaMemsetAsync(c.cnt, 0, sizeof(Counters), stream));
+    {
+        std::lock_guard<std::mutex> cam_lock(d.camera_mutex);
+        if (d.camera_dirty || std::memcmp(&d.view.cam, &s.camera, sizeof s.camera) != 0) {
+            int rc = refresh_camera(s, d, c, stream);
+            if (rc != PVGPU_OK) return rc;
+        }
     }
-    size_t batch = std::min<size_t>(kBatchSamples, n_samples);
-    int rc = ensure_work_buffers(d, std::max<size_t>(3 * batch, 1024), kShadowCap, n_rects);
+    int rc = ensure_work_buffers(c, 1024, 0, n_rects);
     if (rc != PVGPU_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d.rects, rects, n_rects * sizeof(pvgpu_rect), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(d.rect_off, off.data(), (n_rects + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(c.rects, rects, n_rects * sizeof(pvgpu_rect), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(c.rect_off, off.data(), (n_rects + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)n_samples * 4 * sizeof(float), stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));        // `off` and (possibly pageable) `rects` are consumed
 
-    FrameCtx f{ s, stream, width, height, reinterpret_cast<float4*>(d_out), pvgpu_stats{}, cooperate, user };
+    FrameCtx f{ s, d, c, stream, width, height, reinterpret_cast<float4*>(d_out), pvgpu_stats{}, cooperate, user };
     unsigned long long n_extra_samples = 0;
     if (method == 0) {
         SampleSource src{};
-        src.rects = d.rects; src.rect_off = d.rect_off; src.n_rects = (uint32_t)n_rects;
+        src.rects = c.rects; src.rect_off = c.rect_off; src.n_rects = (uint32_t)n_rects;
         rc = trace_samples(f, src, n_samples, true);
     } else if (method == 1) rc = render_aa1(f, *aa, rects, n_rects, off, reinterpret_cast<float4*>(d_out), n_extra_samples);
     else rc = render_aa2(f, *aa, rects, n_rects, off, reinterpret_cast<float4*>(d_out), n_extra_samples);
-    if (rc != PVGPU_OK) return rc;
+    if (rc != PVGPU_OK) { cudaStreamSynchronize(stream); cudaStreamSynchronize(c.s_shadow); return rc; }
 
     Counters hc;
-    CUDA_TRY(cudaMemcpyAsync(&hc, d.cnt, sizeof hc, cudaMemcpyDeviceToHost, stream));
-    const size_t ev1 = next_event(d);
-    CUDA_TRY(cudaEventRecord(d.ev_pool[ev1], stream));
-    CUDA_TRY(cudaEventSynchronize(d.ev_pool[ev1]));
+    CUDA_TRY(cudaMemcpyAsync(&hc, c.cnt, sizeof hc, cudaMemcpyDeviceToHost, stream));
+    const size_t ev1 = next_event(c);
+    CUDA_TRY(cudaEventRecord(c.ev_pool[ev1], stream));
+    CUDA_TRY(cudaEventSynchronize(c.ev_pool[ev1]));
     float ms = 0.0f;
-    cudaEventElapsedTime(&ms, d.ev_pool[ev0], d.ev_pool[ev1]);
+    cudaEventElapsedTime(&ms, c.ev_pool[ev0], c.ev_pool[ev1]);
     pvgpu_stats& st = f.st;
     st.rays = hc.rays; st.shadow_ray_tests = hc.shadow_tests; st.reflected_rays = hc.reflected;
     st.refracted_rays = hc.refracted; st.transmitted_rays = hc.transmitted; st.tir_rays = hc.tir;
     st.adc_saves = hc.adc_saves; st.samples = n_extra_samples; st.max_trace_level = hc.max_level; st.overflow = hc.overflow;
-    st.kernel_launches = d.kernel_launches - launches0;
+    st.node_tests = hc.node_tests; st.prim_tests = hc.prim_tests;
+    st.kernel_launches = c.kernel_launches - launches0;
     st.device_ms = ms;
-    for (const DeviceScene::Timed& t : d.timed) {
+    for (const WorkCtx::Timed& t : c.timed) {
         float k = 0.0f;
-        cudaEventElapsedTime(&k, d.ev_pool[t.e0], d.ev_pool[t.e1]);
+        cudaEventElapsedTime(&k, c.ev_pool[t.e0], c.ev_pool[t.e1]);
         st.kernel_ms[t.kind] += k;
         st.kernel_count[t.kind] += 1;
         st.kernel_items[t.kind] += t.items;
     }
+    st.kernel_items[KIND_CLOSEST] = hc.rays;
+    st.kernel_items[KIND_SHADE] = hc.rays;
     st.kernel_items[KIND_SHADOW] = hc.shadow_rays;
     if (stats) *stats = st;
     if (hc.overflow & ~(8u | 16u))
         return fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x: 1 traversal stack, 2 mesh in CSG, 4 interior list, 32 blob components per ray)", hc.overflow);
+    return PVGPU_OK;
+}
+
+static void merge_stats(pvgpu_stats& a, const pvgpu_stats& b)
+{
+    a.rays += b.rays; a.shadow_ray_tests += b.shadow_ray_tests; a.reflected_rays += b.reflected_rays; a.refracted_rays += b.refracted_rays;
+    a.transmitted_rays += b.transmitted_rays; a.tir_rays += b.tir_rays; a.adc_saves += b.adc_saves; a.samples += b.samples;
+    a.waves += b.waves; a.kernel_launches += b.kernel_launches; a.node_tests += b.node_tests; a.prim_tests += b.prim_tests;
+    a.max_trace_level = std::max(a.max_trace_level, b.max_trace_level); a.overflow |= b.overflow;
+    for (int k = 0; k < 5; k++) { a.kernel_ms[k] += b.kernel_ms[k]; a.kernel_count[k] += b.kernel_count[k]; a.kernel_items[k] += b.kernel_items[k]; }
+}
+
+// D2H of `bytes` from a device buffer of context `c` into caller memory: one DMA when the destination is page-locked
+// (pvgpu_host_alloc), else through the context's pinned staging buffer in slices that a few host threads copy out while the
+// next ones are in flight.
+static int deliver_to_host(WorkCtx& c, const float* d_src, float* dst, size_t bytes, cudaStream_t stream)
+{
+    if (bytes == 0) return PVGPU_OK;
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        cudaError_t e = cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
+        return PVGPU_OK;
+    }
+    if (c.h_frame_cap < bytes) {
+        if (c.h_frame) cudaFreeHost(c.h_frame);
+        c.h_frame = nullptr; c.h_frame_cap = 0;
+        CUDA_TRY(cudaMallocHost(&c.h_frame, bytes));
+        c.h_frame_cap = bytes;
+    }
+    const size_t slice = 2u << 20;
+    const size_t n_slices = (bytes + slice - 1) / slice;
+    std::vector<cudaEvent_t> evs(n_slices, nullptr);
+    cudaError_t e = cudaSuccess;
+    for (size_t k = 0; k < n_slices && e == cudaSuccess; k++) {
+        const size_t off = k * slice, len = std::min(slice, bytes - off);
+        cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming);
+        e = cudaMemcpyAsync(reinterpret_cast<char*>(c.h_frame) + off, reinterpret_cast<const char*>(d_src) + off, len, cudaMemcpyDeviceToHost, stream);
+        cudaEventRecord(evs[k], stream);
+    }
+    if (e == cudaSuccess) {
+        const int n_workers = (int)std::min<size_t>(4, n_slices);
+        std::atomic<int> failed(0);
+        const int device = c.device;
+        auto worker = [&](int w) {
+            cudaSetDevice(device);
+            for (size_t k = (size_t)w; k < n_slices; k += (size_t)n_workers) {
+                if (cudaEventSynchronize(evs[k]) != cudaSuccess) { failed = 1; return; }
+                const size_t off = k * slice, len = std::min(slice, bytes - off);
+                std::memcpy(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(c.h_frame) + off, len);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int w = 1; w < n_workers; w++) pool.emplace_back(worker, w);
+        worker(0);
+        for (auto& t : pool) t.join();
+        if (failed) e = cudaErrorUnknown;
+    }
+    for (size_t k = 0; k < n_slices; k++) if (evs[k]) cudaEventDestroy(evs[k]);
+    if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
+    return PVGPU_OK;
+}
+
+static int ensure_frame(WorkCtx& c, size_t bytes)
+{
+    if (bytes > c.frame_cap) {
+        cudaFree(c.d_frame); c.d_frame = nullptr; c.frame_cap = 0;
+        CUDA_TRY(cudaMalloc(&c.d_frame, bytes));
+        c.frame_cap = bytes;
+    }
+    return PVGPU_OK;
+}
+
+static int coop_flag(void* p) { return reinterpret_cast<std::atomic<int>*>(p)->load(std::memory_order_relaxed); }
+
+// One frame on all devices / work contexts of the scene.  The rectangles are cut into units of consecutive rectangles (a unit is
+// contiguous in the rect-major output); chunk j is made of the units j, j + C, j + 2C ... so that every chunk samples the whole
+// frame (sky and geometry alike), and the workers - one host thread per work context - take chunk numbers from ONE atomic
+// counter in page-locked host memory until none is left: whoever finishes early takes the next chunk, like the reference's
+// render threads do with ViewData::GetNextRectangle (view.cpp:236-271).  Each worker renders its chunk into its own device frame
+// and sends every unit to its place in the caller's frame: D2H for a host frame, cudaMemcpyPeerAsync into the first device's
+// memory for a device frame.
+static int render_multi(Scene& s, const pvgpu_aa* aa, int width, int height, const pvgpu_rect* rects, size_t n_rects,
+                        float* host_out, float* dev_out, pvgpu_stats* stats, int (*cooperate)(void*), void* user)
+{
+    std::vector<std::pair<DeviceScene*, WorkCtx*>> workers;
+    for (DeviceScene* d : s.devs) for (auto& c : d->ctx) workers.push_back({ d, c.get() });
+    const size_t n_workers = workers.size();
+    std::vector<size_t> off(n_rects + 1, 0);
+    for (size_t i = 0; i < n_rects; i++) {
+        const pvgpu_rect& r = rects[i];
+        if (r.right < r.left || r.bottom < r.top) return fail(PVGPU_E_INVALID, "rectangle %zu is empty", i);
+        off[i + 1] = off[i] + (size_t)(r.right - r.left + 1) * (size_t)(r.bottom - r.top + 1);
+    }
+    // chunk plan
+    size_t grabs = 2;                                           // chunks per worker: 1 = static deal, more = finer load balancing
+    if (const char* e = getenv("PVGPU_CHUNKS_PER_WORKER")) grabs = (size_t)std::max(1, std::min(64, atoi(e)));
+    const size_t n_chunks = std::max<size_t>(1, std::min(n_rects, n_workers * grabs));
+    const size_t unit = std::max<size_t>(1, std::min<size_t>(16, n_rects / (n_chunks * 8)));       // rectangles per unit
+    const size_t n_units = (n_rects + unit - 1) / unit;
+    unsigned int* counter = nullptr;                            // the work queue: next chunk to hand out
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&counter), sizeof(unsigned int), cudaHostAllocPortable));
+    *counter = 0;
+    std::atomic<int> abort_flag(0);
+    std::mutex merge_mutex;
+    pvgpu_stats total{};
+    int first_rc = PVGPU_OK;
+    std::string first_msg;
+    std::vector<double> worker_ms(n_workers, 0.0);
+    const int primary = s.devs[0]->device;
+
+    auto work = [&](size_t w) {
+        DeviceScene& d = *workers[w].first;
+        WorkCtx& c = *workers[w].second;
+        std::lock_guard<std::mutex> ctx_lock(c.in_use);
+        cudaSetDevice(d.device);
+        std::vector<pvgpu_rect> mine;
+        std::vector<std::pair<size_t, size_t>> runs;          // (first rectangle, count) of every unit of the chunk
+        for (;;) {
+            if (abort_flag.load()) break;
+            const unsigned int j = __atomic_fetch_add(counter, 1u, __ATOMIC_RELAXED);
+            if (j >= n_chunks) break;
+            mine.clear(); runs.clear();
+            size_t px = 0;
+            for (size_t u = j; u < n_units; u += n_chunks) {
+                const size_t r0 = u * unit, r1 = std::min(n_rects, r0 + unit);
+                runs.push_back({ r0, r1 - r0 });
+                mine.insert(mine.end(), rects + r0, rects + r1);
+                px += off[r1] - off[r0];
+            }
+            if (mine.empty()) continue;
+            pvgpu_stats st{};
+            int rc = ensure_frame(c, px * 4 * sizeof(float));
+            if (rc == PVGPU_OK) rc = render_impl(s, d, c, aa, width, height, mine.data(), mine.size(), c.d_frame, &st, c.s_main, coop_flag, &abort_flag);
+            // deliver the units
+            size_t src_px = 0;
+            for (size_t k = 0; k < runs.size() && rc == PVGPU_OK; k++) {
+                const size_t r0 = runs[k].first, r1 = r0 + runs[k].second, n_px = off[r1] - off[r0];
+                const float* src = c.d_frame + src_px * 4;
+                if (dev_out) {
+                    cudaError_t e = (d.device == primary) ? cudaMemcpyAsync(dev_out + off[r0] * 4, src, n_px * 16, cudaMemcpyDeviceToDevice, c.s_main)
+                                                          : cudaMemcpyPeerAsync(dev_out + off[r0] * 4, primary, src, d.device, n_px * 16, c.s_main);
+                    if (e != cudaSuccess) rc = fail(PVGPU_E_CUDA, "peer copy of finished tiles failed: %s", cudaGetErrorString(e));
+                } else {
+                    cudaError_t e = cudaMemcpyAsync(host_out + off[r0] * 4, src, n_px * 16, cudaMemcpyDeviceToHost, c.s_main);      // pinned or pageable (then staged by the driver)
+                    if (e != cudaSuccess) rc = fail(PVGPU_E_CUDA, "copy of finished tiles to the host failed: %s", cudaGetErrorString(e));
+                }
+                src_px += n_px;
+            }
+            if (rc == PVGPU_OK && cudaStreamSynchronize(c.s_main) != cudaSuccess) rc = fail(PVGPU_E_CUDA, "delivery of finished tiles failed: %s", cudaGetErrorString(cudaGetLastError()));
+            std::lock_guard<std::mutex> lock(merge_mutex);
+            if (rc != PVGPU_OK) {
+                if (first_rc == PVGPU_OK) { first_rc = rc; first_msg = pvgpu_last_error(); }
+                abort_flag = 1;
+                break;
+            }
+            merge_stats(total, st);
+            worker_ms[w] += st.device_ms;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (size_t w = 1; w < n_workers; w++) pool.emplace_back(work, w);
+    if (cooperate) {
+        // the caller's thread keeps polling its cooperate callback (Task::Cooperate is bound to that thread) and works as well
+        std::thread w0(work, 0);
+        std::atomic<int> done(0);
+        std::thread waiter([&] { w0.join(); for (auto& t : pool) t.join(); done = 1; });
+        while (!done.load()) {
+            if (!abort_flag.load() && cooperate(user)) {
+                std::lock_guard<std::mutex> lock(merge_mutex);
+                if (first_rc == PVGPU_OK) { first_rc = PVGPU_E_ABORTED; first_msg = "render aborted by the cooperate callback"; }
+                abort_flag = 1;
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+        }
+        waiter.join();
+    } else {
+        work(0);
+        for (auto& t : pool) t.join();
+    }
+    cudaFreeHost(counter);
+    cudaSetDevice(primary);
+    if (first_rc != PVGPU_OK) return fail(first_rc, "%s", first_msg.c_str());
+    total.device_ms = *std::max_element(worker_ms.begin(), worker_ms.end());
+    if (stats) *stats = total;
     return PVGPU_OK;
 }
 
@@ -841,13 +1168,29 @@ using namespace pvgpu;
 
 extern "C" {
 
+static bool multi_worker(const Scene& s)
+{
+    return s.devs.size() > 1 || (s.devs.size() == 1 && s.devs[0]->ctx.size() > 1);
+}
+
 int pvgpu_render_device(pvgpu_scene* sc, const pvgpu_aa* aa, int width, int height,
                         const pvgpu_rect* rects, size_t n_rects, float* d_rgbt_out,
                         pvgpu_stats* stats, void* cuda_stream)
 {
     clear_error();
     if (!sc) return fail(PVGPU_E_INVALID, "pvgpu_render_device: null scene");
-    return render_impl(*reinterpret_cast<Scene*>(sc), aa, width, height, rects, n_rects, d_rgbt_out, stats,
+    Scene& s = *reinterpret_cast<Scene*>(sc);
+    if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
+    if (multi_worker(s)) {
+        if (width <= 0 || height <= 0 || !rects || !n_rects || !d_rgbt_out) return fail(PVGPU_E_INVALID, "pvgpu_render_device: bad arguments");
+        // the output belongs to the first device of the scene; work already queued on the caller's stream comes first
+        CUDA_TRY(cudaSetDevice(s.devs[0]->device));
+        CUDA_TRY(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(cuda_stream)));
+        return render_multi(s, aa, width, height, rects, n_rects, nullptr, d_rgbt_out, stats, nullptr, nullptr);
+    }
+    WorkCtx& c = *s.dev->ctx[0];
+    std::lock_guard<std::mutex> lock(c.in_use);
+    return render_impl(s, *s.dev, c, aa, width, height, rects, n_rects, d_rgbt_out, stats,
                        reinterpret_cast<cudaStream_t>(cuda_stream), nullptr, nullptr);
 }
 
@@ -859,70 +1202,24 @@ int pvgpu_render(pvgpu_scene* sc, const pvgpu_aa* aa, int width, int height,
     if (!sc || !rgbt_out || !rects) return fail(PVGPU_E_INVALID, "pvgpu_render: null argument");
     Scene& s = *reinterpret_cast<Scene*>(sc);
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
-    std::lock_guard<std::recursive_mutex> frame_lock(s.device_mutex);      // the device frame + staging buffer are per scene
-    CUDA_TRY(cudaSetDevice(s.device));
+    if (multi_worker(s)) {
+        if (width <= 0 || height <= 0 || !n_rects) return fail(PVGPU_E_INVALID, "pvgpu_render: bad arguments");
+        return render_multi(s, aa, width, height, rects, n_rects, rgbt_out, nullptr, stats, cooperate, user);
+    }
     DeviceScene& d = *s.dev;
+    WorkCtx& c = *d.ctx[0];
+    std::lock_guard<std::mutex> frame_lock(c.in_use);      // the device frame + staging buffer serve one call at a time
+    CUDA_TRY(cudaSetDevice(d.device));
     size_t n = 0;
     for (size_t i = 0; i < n_rects; i++)
         if (rects[i].right >= rects[i].left && rects[i].bottom >= rects[i].top)
             n += (size_t)(rects[i].right - rects[i].left + 1) * (size_t)(rects[i].bottom - rects[i].top + 1);
     // device frame + pinned staging buffer are kept between calls (a frame sequence reuses them)
-    const size_t bytes = std::max<size_t>(n, 1) * 4 * sizeof(float);
-    if (bytes > d.frame_cap) {
-        cudaFree(d.d_frame); d.d_frame = nullptr;
-        if (d.h_frame) cudaFreeHost(d.h_frame);
-        d.h_frame = nullptr; d.frame_cap = 0;
-        CUDA_TRY(cudaMalloc(&d.d_frame, bytes));
-        d.frame_cap = bytes;
-    }
-    int rc = render_impl(s, aa, width, height, rects, n_rects, d.d_frame, stats, 0, cooperate, user);
+    int rc = ensure_frame(c, std::max<size_t>(n, 1) * 4 * sizeof(float));
     if (rc != PVGPU_OK) return rc;
-    const size_t total = n * 4 * sizeof(float);
-    cudaPointerAttributes attr{};
-    const bool pinned = cudaPointerGetAttributes(&attr, rgbt_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (pinned) {
-        // the caller's buffer is page-locked (pvgpu_host_alloc): one DMA transfer, no staging
-        cudaError_t e = cudaMemcpyAsync(rgbt_out, d.d_frame, total, cudaMemcpyDeviceToHost, 0);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-        if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
-        return PVGPU_OK;
-    }
-    // pageable destination: D2H into the pinned staging buffer in slices; a few host threads copy the slices that
-    // have landed into the caller's buffer while the next ones are in flight
-    if (d.h_frame == nullptr) {
-        CUDA_TRY(cudaMallocHost(&d.h_frame, d.frame_cap));
-    }
-    const size_t slice = 2u << 20;
-    const size_t n_slices = (total + slice - 1) / slice;
-    std::vector<cudaEvent_t> evs(n_slices);
-    cudaError_t e = cudaSuccess;
-    for (size_t k = 0; k < n_slices && e == cudaSuccess; k++) {
-        const size_t off = k * slice, len = std::min(slice, total - off);
-        cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming);
-        e = cudaMemcpyAsync(reinterpret_cast<char*>(d.h_frame) + off, reinterpret_cast<const char*>(d.d_frame) + off, len, cudaMemcpyDeviceToHost, 0);
-        cudaEventRecord(evs[k], 0);
-    }
-    if (e == cudaSuccess) {
-        const int n_workers = (int)std::min<size_t>(4, n_slices);
-        std::atomic<int> failed(0);
-        auto worker = [&](int w) {
-            cudaSetDevice(s.device);
-            for (size_t k = (size_t)w; k < n_slices; k += (size_t)n_workers) {
-                if (cudaEventSynchronize(evs[k]) != cudaSuccess) { failed = 1; return; }
-                const size_t off = k * slice, len = std::min(slice, total - off);
-                std::memcpy(reinterpret_cast<char*>(rgbt_out) + off, reinterpret_cast<const char*>(d.h_frame) + off, len);
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int w = 1; w < n_workers; w++) pool.emplace_back(worker, w);
-        worker(0);
-        for (auto& t : pool) t.join();
-        if (failed) e = cudaErrorUnknown;
-    }
-    for (size_t k = 0; k < n_slices; k++) if (evs[k]) cudaEventDestroy(evs[k]);
-    if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "copy of the frame to the host failed: %s", cudaGetErrorString(e));
-    return PVGPU_OK;
+    rc = render_impl(s, d, c, aa, width, height, rects, n_rects, c.d_frame, stats, c.s_main, cooperate, user);
+    if (rc != PVGPU_OK) return rc;
+    return deliver_to_host(c, c.d_frame, rgbt_out, n * 4 * sizeof(float), c.s_main);
 }
 
 void* pvgpu_host_alloc(size_t bytes)
@@ -945,11 +1242,13 @@ int pvgpu_trace_rays(pvgpu_scene* sc, const double* org_dir, size_t n, uint32_t*
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     if (n == 0) return PVGPU_OK;
     if (n > 0xFFFFFFF0ull) return fail(PVGPU_E_INVALID, "too many rays");
-    std::lock_guard<std::recursive_mutex> device_lock(s.device_mutex);
-    CUDA_TRY(cudaSetDevice(s.device));
     DeviceScene& d = *s.dev;
+    WorkCtx& c = *d.ctx[0];
+    std::lock_guard<std::mutex> device_lock(c.in_use);
+    CUDA_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = c.s_main;
     const size_t chunk = 1u << 22;
-    int rc = ensure_work_buffers(d, std::max<size_t>(std::min(n, chunk), 1024), 0, 0);
+    int rc = ensure_work_buffers(c, std::max<size_t>(std::min(n, chunk), 1024), 0, 0);
     if (rc != PVGPU_OK) return rc;
     double *d_rays = nullptr, *d_depth = nullptr;
     uint32_t *d_obj = nullptr, *d_aux = nullptr;
@@ -960,15 +1259,16 @@ int pvgpu_trace_rays(pvgpu_scene* sc, const double* org_dir, size_t n, uint32_t*
         cleanup();
         return fail(PVGPU_E_CUDA, "cudaMalloc failed in pvgpu_trace_rays");
     }
-    cudaMemset(d.cnt, 0, sizeof(Counters));
+    cudaMemsetAsync(c.cnt, 0, sizeof(Counters), st);
     for (size_t c0 = 0; c0 < n && rc == PVGPU_OK; c0 += chunk) {
         const uint32_t cn = (uint32_t)std::min(chunk, n - c0);
-        cudaMemcpy(d_rays, org_dir + 6 * c0, (size_t)cn * 6 * sizeof(double), cudaMemcpyHostToDevice);
-        launch_probe_rays(d_rays, cn, d.q[0], 0);
-        launch_closest(d.view, d.q[0], cn, d.hits, d.cnt, 0);
-        launch_probe_results(d.hits, cn, d_obj, d_depth, d_aux, 0);
-        d.kernel_launches += 3;
-        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpyAsync(d_rays, org_dir + 6 * c0, (size_t)cn * 6 * sizeof(double), cudaMemcpyHostToDevice, st);
+        launch_wave_init(c.ring, 2, cn, st);
+        launch_probe_rays(d_rays, cn, c.q[0], st);
+        launch_closest(d.view, c.q[0], c.ring, cn, (uint32_t)c.q_cap, c.hits, c.cnt, st);
+        launch_probe_results(c.hits, cn, d_obj, d_depth, d_aux, st);
+        c.kernel_launches += 4;
+        cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { rc = fail(PVGPU_E_CUDA, "k_closest failed: %s", cudaGetErrorString(e)); break; }
         cudaMemcpy(obj + c0, d_obj, (size_t)cn * sizeof(uint32_t), cudaMemcpyDeviceToHost);
         cudaMemcpy(depth + c0, d_depth, (size_t)cn * sizeof(double), cudaMemcpyDeviceToHost);
@@ -976,7 +1276,7 @@ int pvgpu_trace_rays(pvgpu_scene* sc, const double* org_dir, size_t n, uint32_t*
     }
     if (rc == PVGPU_OK) {
         Counters hc;
-        cudaMemcpy(&hc, d.cnt, sizeof hc, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&hc, c.cnt, sizeof hc, cudaMemcpyDeviceToHost);
         if (hc.overflow) rc = fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x)", hc.overflow);
     }
     cleanup();
@@ -992,13 +1292,13 @@ int pvgpu_solve_polynomial(pvgpu_scene* sc, size_t n, const int32_t* degree, con
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     if (n == 0) return PVGPU_OK;
     for (size_t i = 0; i < n; i++) if (degree[i] < 1 || degree[i] > 4) return fail(PVGPU_E_INVALID, "polynomial %zu: degree %d outside 1..4", i, degree[i]);
-    std::lock_guard<std::recursive_mutex> lock(s.device_mutex);
+    std::lock_guard<std::mutex> lock(s.dev->ctx[0]->in_use);
     CUDA_TRY(cudaSetDevice(s.device));
     DevCopy<int32_t> d_deg(degree, n, true), d_st(sturm, n, true), d_cnt(nullptr, n, false);
     DevCopy<double> d_eps(epsilon, n, true), d_c(coeffs, 5 * n, true), d_r(nullptr, 4 * n, false);
     if (d_deg.e || d_st.e || d_cnt.e || d_eps.e || d_c.e || d_r.e) return fail(PVGPU_E_CUDA, "pvgpu_solve_polynomial: device allocation failed");
     launch_probe_solver((uint32_t)n, d_deg.p, d_st.p, d_eps.p, d_c.p, d_r.p, d_cnt.p, 0);
-    s.dev->kernel_launches++;
+    s.dev->ctx[0]->kernel_launches++;
     CUDA_TRY(cudaMemcpy(roots, d_r.p, 4 * n * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(counts, d_cnt.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     return PVGPU_OK;
@@ -1011,13 +1311,13 @@ int pvgpu_noise(pvgpu_scene* sc, size_t n, const double* xyz, const int32_t* gen
     Scene& s = *reinterpret_cast<Scene*>(sc);
     if (!s.dev) return fail(PVGPU_E_INVALID, "scene not finalized");
     if (n == 0) return PVGPU_OK;
-    std::lock_guard<std::recursive_mutex> lock(s.device_mutex);
+    std::lock_guard<std::mutex> lock(s.dev->ctx[0]->in_use);
     CUDA_TRY(cudaSetDevice(s.device));
     DevCopy<double> d_p(xyz, 3 * n, true), d_o(nullptr, 5 * n, false);
     DevCopy<int32_t> d_g(generator, n, true), d_oct(octaves, n, true);
     if (d_p.e || d_o.e || d_g.e || d_oct.e) return fail(PVGPU_E_CUDA, "pvgpu_noise: device allocation failed");
     launch_probe_noise(s.dev->view.noise, (uint32_t)n, d_p.p, d_g.p, d_oct.p, d_o.p, 0);
-    s.dev->kernel_launches++;
+    s.dev->ctx[0]->kernel_launches++;
     CUDA_TRY(cudaMemcpy(out, d_o.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost));
     return PVGPU_OK;
 }
@@ -1031,6 +1331,7 @@ int pvgpu_camera_rays(pvgpu_scene* sc, int width, int height, const double* xy, 
     if (n == 0) return PVGPU_OK;
     CUDA_TRY(cudaSetDevice(s.device));
     DeviceScene& d = *s.dev;
+    std::lock_guard<std::mutex> lock(d.ctx[0]->in_use);
     d.view.cam = s.camera;
     setup_camera(s, d.view);
     d.camera_dirty = true;
@@ -1041,7 +1342,7 @@ int pvgpu_camera_rays(pvgpu_scene* sc, int width, int height, const double* xy, 
     }
     cudaMemcpy(d_xy, xy, n * 2 * sizeof(double), cudaMemcpyHostToDevice);
     launch_camera_rays(d.view, d_xy, (uint32_t)n, (double)width, (double)height, d_out, 0);
-    d.kernel_launches++;
+    d.ctx[0]->kernel_launches++;
     cudaError_t e = cudaMemcpy(org_dir, d_out, n * 6 * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_xy); cudaFree(d_out);
     if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "k_camera_rays failed: %s", cudaGetErrorString(e));

@@ -876,7 +876,20 @@ int pvgpu_scene_finalize(pvgpu_scene* sc, int device)
     SCENE_OR_FAIL(sc);
     int rc = validate_scene(s);
     if (rc != PVGPU_OK) return rc;
-    return device_upload(s, device);
+    return device_upload(s, &device, 1);
+}
+
+int pvgpu_scene_finalize_multi(pvgpu_scene* sc, const int* devices, int n_devices)
+{
+    SCENE_OR_FAIL(sc);
+    int rc = validate_scene(s);
+    if (rc != PVGPU_OK) return rc;
+    return device_upload(s, devices, n_devices);
+}
+
+int pvgpu_scene_device_count(const pvgpu_scene* sc)
+{
+    return sc ? (int)reinterpret_cast<const Scene*>(sc)->devs.size() : 0;
 }
 
 size_t pvgpu_scene_device_bytes(const pvgpu_scene* sc)

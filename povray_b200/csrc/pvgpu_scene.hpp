@@ -54,8 +54,8 @@ struct Scene {
     bool     all_shadow_casters_opaque = true;
     int      device = -1;
     size_t   device_bytes = 0;
-    DeviceScene* dev = nullptr;
-    std::recursive_mutex device_mutex;        // the device-side work buffers of a scene serve one render / trace call at a time
+    DeviceScene* dev = nullptr;               // first device of the scene (owner of device-side outputs); non-null once finalized
+    std::vector<DeviceScene*> devs;           // one replica of the tables per device (pvgpu_scene_finalize_multi)
 };
 
 // error plumbing (thread-local message)
@@ -73,7 +73,7 @@ void build_bbox_tree(const std::vector<LeafBox>& finite, const std::vector<LeafB
                      std::vector<pvgpu_node>& out);
 
 // device side (pvgpu_device.cu)
-int  device_upload(Scene& s, int device);
+int  device_upload(Scene& s, const int* devices, int n_devices);     // n_devices <= 0: every visible device
 void device_release(Scene& s);
 
 }  // namespace pvgpu

@@ -119,6 +119,21 @@ class Scene:
         self.finalized = True
         return self
 
+    def finalize_multi(self, devices=None, n_devices=0):
+        """Replicates the scene on several CUDA devices (pvgpu_scene_finalize_multi): `devices` = list of device indices, or
+        `n_devices` (0 = every visible device); render calls then shard their rectangles over the devices."""
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            A.check(A.lib().pvgpu_scene_finalize_multi(self._h, arr, len(devices)))
+        else:
+            A.check(A.lib().pvgpu_scene_finalize_multi(self._h, None, int(n_devices)))
+        self.finalized = True
+        return self
+
+    @property
+    def device_count(self):
+        return int(A.lib().pvgpu_scene_device_count(self._h))
+
     @property
     def device_bytes(self):
         return int(A.lib().pvgpu_scene_device_bytes(self._h))
