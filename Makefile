@@ -6,8 +6,9 @@ NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 # EXTRA / LIB / OBJDIR: experiment builds (tools/build_variants.sh) - extra -D switches into a separate library
 EXTRA     ?=
-NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -Iinclude -Ipovray_b200/csrc $(EXTRA)
-CSRC      := povray_b200/csrc
+CSRC      ?= povray_b200/csrc
+INCDIR    ?= include
+NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -I$(INCDIR) -I$(CSRC) $(EXTRA)
 OBJDIR    ?= build/obj
 LIB       ?= povray_b200/libpvgpu.so
 CU        := $(wildcard $(CSRC)/*.cu)
@@ -18,7 +19,7 @@ LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
 FULL_SRC  := k_shade k_shadow_filter
 OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
              $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC))
-HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) include/pvgpu.h
+HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) $(INCDIR)/pvgpu.h
 
 .PHONY: all oracle clean
 all: $(LIB)

@@ -14,7 +14,9 @@ e2e     = same frame through pvgpu_render() with HOST buffers (rectangle list in
           wall clock around the C-ABI call.
 N > 1   = one process per GPU (torchrun); the frame's 32x32 tiles are dealt round-robin to the ranks, the scene is
           replicated, and the finished tiles are gathered to rank 0 (the only NVLink traffic).  Total work is one
-          frame whatever N is -> "strong" scaling.
+          frame whatever N is -> "strong" scaling.  e2e at N > 1 ends with the ASSEMBLED frame in rank 0's host memory
+          (NCCL gather + one D2H inside the timed region).  --inproc-gpus M instead shards one process's frame over M
+          devices inside the library (pvgpu_scene_finalize_multi: atomic tile counter + peer copies).
 --impl reference = the UNMODIFIED reference binary (oracle/_ref/*/povray, built from /root/reference by
           oracle/build_ref.sh) rendering the same scene file with +WT<host threads>; its "Trace Time" and its
           Rays / Shadow Ray Tests counters give the same metric.  Rank 0 only.
@@ -44,9 +46,13 @@ WORKLOADS = {
 }
 # anti-aliasing of the workload: (method, depth, threshold, jitter amount) and the reference's switches for it
 WORKLOAD_AA = {"cfg3": ((2, 3, 0.3, 1.0), ["+A0.3", "+AM2", "+R3", "+J"])}
-# algorithmic bytes per ray (SURVEY.md section 8d / DESIGN.md "Roofline"): node tests x 32 B + primitive records + ray record I/O
-ALG_BYTES_PER_RAY = {"cfg2": 101 * 32 + 10 * 64 + 128, "cfg1": 30 * 32 + 2 * 168 + 128,
-                     "cfg3": 30 * 32 + 2 * 3 * 168 + 128, "cfg3_noaa": 30 * 32 + 2 * 3 * 168 + 128, "cfg4": 30 * 32 + 2 * (168 + 256) + 128}
+# Algorithmic work of a traversal kernel (SURVEY.md section 8d / DESIGN.md "Roofline"), from the DEVICE's own counters of the timed
+# frames: every bounding-box test reads one 32 B node and costs 24 flop (6 sub, 6 mul, 12 compares: boundingbox.cpp:566-625);
+# every primitive test reads the record(s) below and costs the FP64 flop below; every ray moves its queue records through HBM.
+NODE_BYTES, NODE_FLOP = 32, 24
+PRIM_BYTES = {"cfg1": 168, "cfg2": 64, "cfg3": 4 * 168, "cfg3_noaa": 4 * 168, "cfg4": 168 + 256}     # object / triangle record (+ transform)
+PRIM_FLOP = {"cfg1": 40, "cfg2": 45, "cfg3": 250, "cfg3_noaa": 250, "cfg4": 400}
+RAY_BYTES = {"k_closest": 96 + 48, "k_shadow": 96 + 16}        # PRay in + HitRec out; SRay in + one RGBT accumulation
 ADAPTER = os.path.join(ROOT, "oracle", "_ref", "parity", "povray-gpu")
 
 
@@ -127,6 +133,10 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # reference arm (CPU)
 # ----------------------------------------------------------------------------------------------------------
+REF_FLAGS = {"fast": "-O3 -march=x86-64-v3 -fno-fast-math, portable noise", "parity": "-O2 -fno-fast-math -ffp-contract=off, portable noise",
+             "stock": "-O3 -ffast-math -march=x86-64-v3 + the reference's AVX / AVX2-FMA3 noise (unix/configure.ac:750-763 defaults, -march=native replaced by the portable x86-64-v3)"}
+
+
 def reference_binary():
     for variant in ("fast", "parity"):
         p = os.path.join(ROOT, "oracle", "_ref", variant, "povray")
@@ -187,7 +197,7 @@ def reference_arm(args):
             tr, r, s, p = run_reference_once(binary, pov, threads, aa_flags=aa_flags(args.workload))
             t += tr; rays += r; shadow += s; parse += p
     value = (rays + shadow) / t / 1e6
-    flags = "-O3 -march=x86-64-v3 -fno-fast-math" if variant == "fast" else "-O2 -fno-fast-math -ffp-contract=off"
+    flags = REF_FLAGS[variant]
     base.update({"value": value, "ms_per_step": 1e3 * t / args.steps, "sec_per_frame": t / args.steps,
                  "rays_per_step": (rays + shadow) / args.steps, "gpu_launches": 0,
                  "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "reference",
@@ -200,12 +210,197 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------
 # our arm (GPU)
 # ----------------------------------------------------------------------------------------------------------
-def ours(args):
-    import numpy as np
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def roofline_of(workload, stats, steps, frame_ms, fp64_peak_tflops):
+    """Roofline entries of the two traversal kernel families from the library's own per-launch CUDA events and the device's own
+    node / primitive test counters (pvgpu_stats), for the frames that were timed."""
+    peaks = load_peaks()
+    peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    fam = {}
+    for name, ms_key, n_key, rays_key, node_key, prim_key in (
+            ("k_closest", "closest_ms", "closest_launches", "closest_rays", "node_tests_closest", "prim_tests_closest"),
+            ("k_shadow", "shadow_ms", "shadow_launches", "shadow_rays", "node_tests_shadow", "prim_tests_shadow")):
+        ms = sum(s[ms_key] for s in stats)
+        n = sum(s[n_key] for s in stats)
+        rays = sum(s[rays_key] for s in stats)
+        nodes = sum(s.get(node_key, 0) for s in stats)
+        prims = sum(s.get(prim_key, 0) for s in stats)
+        if ms <= 0 or n == 0:
+            continue
+        alg_bytes = nodes * NODE_BYTES + prims * PRIM_BYTES[workload] + rays * RAY_BYTES[name]
+        alg_flop = nodes * NODE_FLOP + prims * PRIM_FLOP[workload]
+        fam[name] = {"ms": ms, "launches": n, "rays": rays, "node_tests": nodes, "prim_tests": prims, "alg_bytes": alg_bytes, "alg_flop": alg_flop}
+    if not fam:
+        return None
+    dom = max(fam, key=lambda k: fam[k]["ms"])
+    f = fam[dom]
+    achieved = f["alg_bytes"] / (f["ms"] * 1e-3) / 1e9
+    traffic, traffic_note = None, "no ncu capture of this build committed"
+    try:      # DRAM bytes per launch of this kernel family from the committed ncu --set full capture of THIS source revision
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if workload in tj.get("workloads", {}) and dom in tj["workloads"][workload]:
+            b = tj["workloads"][workload][dom]["dram_bytes_per_launch"]
+            traffic = sum(b) / len(b)
+            traffic_note = f"mean dram__bytes_read+write of the launches captured by ncu --set full at commit {tj.get('commit', '?')} (profiles/r2_traffic.json)"
+    except Exception:
+        pass
+    out = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
+           "traffic": traffic, "traffic_note": traffic_note,
+           "achieved_dram_gbs": (traffic / (f["ms"] / f["launches"] * 1e-3) / 1e9) if traffic else None,
+           "alg_bytes_per_launch": f["alg_bytes"] / f["launches"], "alg_bytes_per_ray": f["alg_bytes"] / max(f["rays"], 1),
+           "node_tests_per_ray": f["node_tests"] / max(f["rays"], 1), "prim_tests_per_ray": f["prim_tests"] / max(f["rays"], 1),
+           "counts": "device counters of the timed frames (pvgpu_stats.node_tests_* / prim_tests_*)",
+           "rays_per_launch": f["rays"] / f["launches"], "avg_launch_ms": f["ms"] / f["launches"],
+           "share_of_step": f["ms"] / (frame_ms * steps),
+           "share_note": "k_shadow_* of wave k runs concurrently with k_closest / k_shade of wave k+1 on a second stream: the shares of the families add up to more than 1",
+           "kernel_ms_per_step": {"k_primary": sum(s["primary_ms"] for s in stats) / steps, "k_closest": sum(s["closest_ms"] for s in stats) / steps,
+                                  "k_shade": sum(s["shade_ms"] for s in stats) / steps, "k_shadow": sum(s["shadow_ms"] for s in stats) / steps}}
+    if fp64_peak_tflops:
+        fl = f["alg_flop"] / (f["ms"] * 1e-3) / 1e12
+        out["fp64"] = {"achieved": fl, "peak": fp64_peak_tflops, "unit": "TFLOP/s", "frac": fl / fp64_peak_tflops,
+                       "peak_source": "DFMA loop timed in this run (pvgpu_fp64_peak)", "alg_flop_per_ray": f["alg_flop"] / max(f["rays"], 1)}
+    return out
+
+
+def bench_workload(args, workload, steps, warmup, rank, local_rank, world, dist, inproc):
+    """Device-timed value + e2e of one workload; returns (dict for the JSON line, scene, aa) on rank 0 (None elsewhere)."""
     import torch
     import povray_b200 as pv
     from povray_b200 import _abi as A
+    from povray_b200 import shard
     from povray_b200.scene import _rect_array, _area
+
+    dev = torch.device("cuda", local_rank)
+    t0 = time.time()
+    scene = build_scene(workload)
+    t_build = time.time() - t0
+    aa = None
+    if workload in WORKLOAD_AA:
+        m, dep, thr, jit = WORKLOAD_AA[workload][0]
+        aa = A.AA()
+        aa.method, aa.depth, aa.threshold, aa.jitter_scale, aa.gamma = m, dep, thr, jit, 2.5
+    t0 = time.time()
+    if inproc > 1:
+        scene.finalize_multi(n_devices=inproc)
+    else:
+        scene.finalize(local_rank)
+    t_upload = time.time() - t0
+
+    all_tiles = pv.tiles(W, H, BLOCK)
+    mine = shard.deal(all_tiles, rank, world)          # round-robin deal: statistically balanced, no exchange needed
+    if world == 1 and args.emulate_world > 1:          # development aid: the share of rank 0 of an N-rank run, on one GPU
+        mine = shard.deal(all_tiles, 0, args.emulate_world)
+    rect_arr = _rect_array(mine)
+    n_px = _area(mine)
+    max_px = shard.padded_pixels(all_tiles, world)
+    out = torch.zeros(max_px * 4, dtype=torch.float32, device=dev)
+    gathered = [torch.empty_like(out) for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        st = scene.render_device(W, H, rect_arr, out.data_ptr(), stream.cuda_stream, aa=aa)
+        if world > 1:
+            dist.gather(out, gathered, dst=0)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        step_device()
+    barrier()
+    stats = []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with ClockSampler(local_rank) as clocks:
+        for k in range(steps):
+            flush.zero_()                              # evict the scene tables and queues from L2 between timed frames
+            barrier()
+            ev[k][0].record()
+            stats.append(step_device())
+            ev[k][1].record()
+        barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    rays = sum(s["rays"] + s["shadow_ray_tests"] for s in stats)
+    launches = sum(s["kernel_launches"] for s in stats)
+
+    # end to end: HOST buffers through the C-ABI call (rectangle list in, RGBT float frame out), wall clock.  The frame lands in
+    # page-locked memory obtained from pvgpu_host_alloc (what the adapter uses); the same call with an ordinary pageable numpy array
+    # goes through the library's staging copy and is reported as e2e.pageable_ms_per_step.  At N > 1 (torchrun) every rank renders
+    # its tiles into device memory, NCCL gathers them on rank 0, and rank 0 copies the assembled frame to its host: the region
+    # ends when the whole frame is in ONE host buffer.
+    e2e_rays = 0
+    if world == 1:
+        hb = pv.HostBuffer(max_px * 4)
+        for _ in range(2):
+            scene.render(W, H, mine, out=hb.array, aa=aa)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            px, st = scene.render(W, H, mine, out=hb.array, aa=aa)
+            e2e_rays += st["rays"] + st["shadow_ray_tests"]
+        e2e_s = time.perf_counter() - t0
+        scene.render(W, H, mine, aa=aa)
+        t0 = time.perf_counter()
+        for _ in range(min(steps, 3)):
+            scene.render(W, H, mine, aa=aa)
+        e2e_pageable_s = (time.perf_counter() - t0) / min(steps, 3)
+        d2h = n_px * 16
+    else:
+        host_frame = torch.empty(world * max_px * 4, dtype=torch.float32).pin_memory() if rank == 0 else None
+        frame_dev = torch.empty(world * max_px * 4, dtype=torch.float32, device=dev) if rank == 0 else None
+        chunks = list(frame_dev.split(max_px * 4)) if rank == 0 else None
+
+        def step_e2e():
+            st = scene.render_device(W, H, rect_arr, out.data_ptr(), stream.cuda_stream, aa=aa)
+            dist.gather(out, chunks, dst=0)
+            if rank == 0:
+                host_frame.copy_(frame_dev, non_blocking=True)
+            torch.cuda.synchronize()
+            return st
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            st = step_e2e()
+            e2e_rays += st["rays"] + st["shadow_ray_tests"]
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_pageable_s = None
+        d2h = world * max_px * 16
+
+    vals = torch.tensor([ms, float(rays), float(launches), e2e_s, float(e2e_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e2e_s = float(mx[0]), float(mx[3])
+        rays, launches, e2e_rays = float(sm[1]), float(sm[2]), float(sm[4])
+    if rank != 0:
+        return None, scene, aa
+    res = {"value": rays / (ms * 1e-3) / 1e6, "ms_per_step": ms / steps, "rays_per_frame": rays / steps, "gpu_launches": int(launches),
+           "clocks": clocks.summary(), "t_build": t_build, "t_upload": t_upload, "scene_device_bytes": scene.device_bytes,
+           "n_tiles": len(all_tiles), "stats": stats,
+           "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / steps,
+                   "h2d_bytes_per_step": len(mine) * 16 * world, "d2h_bytes_per_step": d2h,
+                   "region": ("pvgpu_render: rectangle list in, RGBT frame out into page-locked host memory" if world == 1 else
+                              "per rank pvgpu_render_device, NCCL gather to rank 0, D2H of the assembled frame into one pinned host buffer")}}
+    if e2e_pageable_s is not None:
+        res["e2e"]["pageable_ms_per_step"] = 1e3 * e2e_pageable_s
+    return res, scene, aa
+
+
+def ours(args):
+    import torch
+    from povray_b200 import _abi as A
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,153 +426,76 @@ def ours(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    t0 = time.time()
-    scene = build_scene(args.workload)
-    t_build = time.time() - t0
-    aa = None
-    if args.workload in WORKLOAD_AA:
-        m, dep, thr, jit = WORKLOAD_AA[args.workload][0]
-        aa = A.AA()
-        aa.method, aa.depth, aa.threshold, aa.jitter_scale, aa.gamma = m, dep, thr, jit, 2.5
-    t0 = time.time()
-    scene.finalize(local_rank)
-    t_upload = time.time() - t0
-
-    from povray_b200 import shard
-    all_tiles = pv.tiles(W, H, BLOCK)
-    mine = shard.deal(all_tiles, rank, world)          # round-robin deal: statistically balanced, no exchange needed
-    rect_arr = _rect_array(mine)
-    n_px = _area(mine)
-    max_px = shard.padded_pixels(all_tiles, world)
-    dev = torch.device("cuda", local_rank)
-    out = torch.zeros(max_px * 4, dtype=torch.float32, device=dev)
-    gathered = [torch.empty_like(out) for _ in range(world)] if (world > 1 and rank == 0) else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    stream = torch.cuda.current_stream()
-
-    def step_device():
-        st = scene.render_device(W, H, rect_arr, out.data_ptr(), stream.cuda_stream, aa=aa)
-        if world > 1:
-            dist.gather(out, gathered, dst=0)
-        return st
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
-    stats = []
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        for k in range(args.steps):
-            flush.zero_()                              # evict the scene tables and queues from L2 between timed frames
-            barrier()
-            ev[k][0].record()
-            stats.append(step_device())
-            ev[k][1].record()
-        barrier()
-    ms = sum(a.elapsed_time(b) for a, b in ev)
-    rays = sum(s["rays"] + s["shadow_ray_tests"] for s in stats)
-    launches = sum(s["kernel_launches"] for s in stats)
-    kern_ms = {k: sum(s.get(k, 0.0) for s in stats) for k in ("closest_ms", "shadow_ms", "shade_ms", "primary_ms")}
-    kern_n = {k: sum(s.get(k, 0) for s in stats) for k in ("closest_launches", "shadow_launches", "closest_rays", "shadow_rays")}
-
-    # end to end: HOST buffers through the C-ABI call (rectangle list in, RGBT float frame out), wall clock.  The frame
-    # lands in page-locked memory obtained from pvgpu_host_alloc (what the adapter uses); the same call with an ordinary
-    # pageable numpy array goes through the library's staging copy and is reported as e2e.pageable_ms_per_step.
-    # At N > 1 every rank delivers its own tiles to its host (the caller's scatter of disjoint tiles is not part of the library).
-    hb = pv.HostBuffer(max_px * 4)
-    for _ in range(2):
-        scene.render(W, H, mine, out=hb.array, aa=aa)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_rays = 0
-    for _ in range(args.steps):
-        px, st = scene.render(W, H, mine, out=hb.array, aa=aa)
-        e2e_rays += st["rays"] + st["shadow_ray_tests"]
-    e2e_s = time.perf_counter() - t0
-    scene.render(W, H, mine, aa=aa)
-    t0 = time.perf_counter()
-    for _ in range(min(args.steps, 3)):
-        scene.render(W, H, mine, aa=aa)
-    e2e_pageable_s = (time.perf_counter() - t0) / min(args.steps, 3)
-
-    vals = torch.tensor([ms, float(rays), float(launches), e2e_s, float(e2e_rays), kern_ms["closest_ms"], kern_ms["shadow_ms"],
-                         float(kern_n["closest_rays"]), float(kern_n["shadow_rays"]), float(kern_n["closest_launches"]), float(kern_n["shadow_launches"]),
-                         kern_ms["shade_ms"], kern_ms["primary_ms"]],
-                        dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, e2e_s = float(mx[0]), float(mx[3])
-        rays, launches, e2e_rays = float(sm[1]), float(sm[2]), float(sm[4])
+    inproc = args.inproc_gpus if world == 1 else 1
+    res, scene, aa = bench_workload(args, args.workload, args.steps, args.warmup, rank, local_rank, world, dist, inproc)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    value = rays / (ms * 1e-3) / 1e6
-    line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "sec_per_frame": ms / args.steps / 1e3, "higher_is_better": True, "scaling": "strong",
+    n_gpus = world if world > 1 else max(1, inproc)
+    sharding = (f"{res['n_tiles']} tiles dealt round-robin over {world} GPU(s) (one process each), scene replicated, NCCL gather to rank 0" if inproc <= 1 else
+                f"{res['n_tiles']} tiles sharded over {inproc} GPUs inside the library: one host thread per GPU, chunks from one atomic counter, peer-copy gather")
+    line = {"metric": "Mrays/s", "value": res["value"], "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": res["ms_per_step"], "sec_per_frame": res["ms_per_step"] / 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload].replace("1920x1080", f"{W}x{H}"), "width": W, "height": H, "aa": " ".join(aa_flags(args.workload)), "tile": BLOCK,
-                       "sharding": f"{len(all_tiles)} tiles dealt round-robin over {world} GPU(s), scene replicated, gather to rank 0",
+                       "sharding": sharding,
                        "l2": "256 MB flush write between timed frames; scene tables + ray queues exceed the 126 MB L2",
-                       "scene_device_bytes": scene.device_bytes, "scene_build_s": round(t_build, 2), "scene_upload_s": round(t_upload, 3),
-                       "rays_per_frame": rays / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
-            "e2e": {"value": e2e_rays / e2e_s / 1e6, "unit": "Mrays/s", "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "h2d_bytes_per_step": len(mine) * 16, "d2h_bytes_per_step": n_px * 16,
-                    "pageable_ms_per_step": 1e3 * e2e_pageable_s}}
+                       "scene_device_bytes": res["scene_device_bytes"], "scene_build_s": round(res["t_build"], 2), "scene_upload_s": round(res["t_upload"], 3),
+                       "rays_per_frame": res["rays_per_frame"]},
+            "gpu_launches": res["gpu_launches"], "clocks": res["clocks"], "e2e": res["e2e"]}
 
-    # roofline of the dominant kernel, timed live with CUDA events inside the library (same stream as the launches)
-    peaks = {}
+    # FP64 vector peak of this GPU, measured in this run by a DFMA loop of the library (the second roofline bound of SURVEY 8d)
+    fp64_peak = None
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        v = A.C.c_double(0.0)
+        if A.lib().pvgpu_fp64_peak(local_rank, A.C.byref(v)) == 0:
+            fp64_peak = v.value
     except Exception:
         pass
-    peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    t_ms, s_ms = float(vals[5]), float(vals[6])
-    if t_ms > 0 or s_ms > 0:
-        dom = "k_closest" if t_ms >= s_ms else "k_shadow"
-        d_ms, d_rays, d_n = (t_ms, float(vals[7]), float(vals[9])) if dom == "k_closest" else (s_ms, float(vals[8]), float(vals[10]))
-        bpr = ALG_BYTES_PER_RAY[args.workload]
-        traffic = None
-        try:      # DRAM bytes per launch of this kernel family from the committed ncu --set full capture (config 2 only)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if args.workload == "cfg2":
-                b = tj[dom]["dram_bytes_per_launch"]
-                traffic = sum(b) / len(b)
-        except Exception:
-            pass
-        achieved = d_rays * bpr / (d_ms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "peak_source": which, "traffic": traffic, "traffic_note": "mean DRAM bytes of the two launches captured in profiles/r1_traffic.json",
-                            "alg_bytes_per_launch": bpr * d_rays / max(d_n, 1), "alg_bytes_per_ray": bpr, "rays_per_launch": d_rays / max(d_n, 1),
-                            "avg_launch_ms": d_ms / max(d_n, 1), "share_of_step": d_ms / ms,
-                            "kernel_ms_per_step": {"k_primary": float(vals[12]) / args.steps, "k_closest": t_ms / args.steps,
-                                                   "k_shade": float(vals[11]) / args.steps, "k_shadow": s_ms / args.steps}}
-    else:
-        line["roofline"] = None
+    line["roofline"] = roofline_of(args.workload, res["stats"], args.steps, res["ms_per_step"], fp64_peak)
+
+    # the other BASELINE.json configurations at the same frame size, short runs, in the same line (N = 1 only)
+    if world == 1 and inproc <= 1 and not args.no_other_workloads:
+        others = {}
+        for wl in ("cfg1", "cfg3_noaa", "cfg3", "cfg4"):
+            if wl == args.workload:
+                continue
+            try:
+                del scene
+                r, scene, _ = bench_workload(args, wl, 3, 3, rank, local_rank, world, dist, 1)
+                rf = roofline_of(wl, r["stats"], 3, r["ms_per_step"], fp64_peak)
+                others[wl] = {"workload": WORKLOADS[wl], "value": r["value"], "unit": "Mrays/s", "ms_per_step": r["ms_per_step"], "steps": 3,
+                              "e2e_ms_per_step": r["e2e"]["ms_per_step"], "rays_per_frame": r["rays_per_frame"],
+                              "roofline": {k: rf[k] for k in ("kernel", "frac", "achieved", "alg_bytes_per_ray", "node_tests_per_ray", "prim_tests_per_ray", "kernel_ms_per_step")} if rf else None,
+                              "roofline_fp64_frac": rf["fp64"]["frac"] if rf and "fp64" in rf else None}
+            except BaseException as e:      # e.g. the reference-side adapter is missing for configs 3 / 4
+                others[wl] = {"error": str(e)[:200]}
+        line["config"]["other_workloads"] = others
 
     # CPU baseline on this box's host cores: the unmodified reference on a bounded sample of the same workload
     if world == 1 and not args.no_cpu_baseline:
-        binary, variant = reference_binary()
         threads = os.cpu_count() or 1
-        try:
-            if binary is None:
-                raise RuntimeError("reference binary not built")
-            with tempfile.TemporaryDirectory() as d:
-                pov = write_pov(args.workload, d)
-                tr, r, s, parse = run_reference_once(binary, pov, threads, aa_flags=aa_flags(args.workload))
-            line["cpu_baseline"] = {"value": (r + s) / tr / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "reference",
-                                    "sec_per_frame": tr, "parse_s": parse,
-                                    "sample": f"1 full {W}x{H} frame by oracle/_ref/{variant}/povray +WT{threads}, the reference's own Trace Time"}
-        except Exception as e:      # the oracle port is the fallback checker-as-baseline
+        base = []
+        for variant in ("fast", "stock"):
+            binary = os.path.join(ROOT, "oracle", "_ref", variant, "povray")
+            if not os.path.exists(binary):
+                continue
+            try:
+                with tempfile.TemporaryDirectory() as d:
+                    pov = write_pov(args.workload, d)
+                    tr, r, s, parse = run_reference_once(binary, pov, threads, aa_flags=aa_flags(args.workload))
+                base.append({"value": (r + s) / tr / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "reference", "build": REF_FLAGS[variant],
+                             "sec_per_frame": tr, "parse_s": parse,
+                             "sample": f"1 full {W}x{H} frame by oracle/_ref/{variant}/povray +WT{threads}, the reference's own Trace Time"})
+            except Exception as e:
+                base.append({"error": f"{variant}: {e}"[:300]})
+        good = [b for b in base if "value" in b]
+        if good:
+            line["cpu_baseline"] = good[0]
+            if len(good) > 1:
+                line["cpu_baseline_stock_flags"] = good[1]
+        else:      # the oracle port is the fallback checker-as-baseline
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib
             with tempfile.TemporaryDirectory() as d:
@@ -388,7 +506,7 @@ def ours(args):
                 _, ost = o.render(W, H, rect=(0, 476, W - 1, 603), threads=threads)      # 128 rows through the middle of the frame (no AA)
                 dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": (ost["rays"] + ost["shadow_ray_tests"]) / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-                                    "sample": f"rows 476-603 of the {W}x{H} frame by oracle/libpvoracle.so with {threads} threads ({e})"}
+                                    "sample": f"rows 476-603 of the {W}x{H} frame by oracle/libpvoracle.so with {threads} threads ({base})"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -402,6 +520,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the short runs of the other configurations (config.other_workloads)")
+    ap.add_argument("--emulate-world", type=int, default=1, help="development aid: render only rank 0's share of an N-rank run (one GPU)")
+    ap.add_argument("--inproc-gpus", type=int, default=1, help="shard the frame over this many GPUs inside ONE process (pvgpu_scene_finalize_multi)")
     ap.add_argument("--width", type=int, default=1920, help="frame width (BASELINE.json's metric is quoted at 1920x1080)")
     ap.add_argument("--height", type=int, default=1080)
     args = ap.parse_args()

@@ -451,8 +451,9 @@ typedef struct pvgpu_stats {
     uint64_t kernel_launches;    /* CUDA kernels launched by the call             */
     uint32_t max_trace_level;    /* highest level reached                         */
     uint32_t overflow;           /* non-zero: a device capacity was exceeded      */
-    uint64_t node_tests;         /* bounding-box slab tests of the traversal kernels (scene tree + mesh trees)     */
-    uint64_t prim_tests;         /* top-level primitive tests + mesh triangle tests of the traversal kernels        */
+    /* work counters of the traversal kernels: bounding-box slab tests (scene tree + mesh trees) and primitive tests (top-level
+     * All_Intersections calls + mesh triangles), separately for k_closest and k_shadow_*; bench.py's roofline uses them */
+    uint64_t node_tests_closest, prim_tests_closest, node_tests_shadow, prim_tests_shadow;
     double   device_ms;          /* CUDA-event time of the device work            */
     /* per kernel family, timed with CUDA events on the launching stream:
      * 0 camera rays (k_primary), 1 closest hit (k_closest), 2 shading (k_shade), 3 shadow rays (k_shadow_*),
@@ -580,6 +581,10 @@ int  pvgpu_noise(pvgpu_scene* s, size_t n, const double* xyz, const int32_t* gen
 
 /* Camera rays exactly as TracePixel::CreateCameraRay makes them for pixel-space (x, y): 6 doubles each. */
 int  pvgpu_camera_rays(pvgpu_scene* s, int width, int height, const double* xy, size_t n, double* org_dir);
+
+/* Measured FP64 vector peak of CUDA device `device` in TFLOP/s (independent DFMA chains, timed with CUDA events): the second
+ * roofline denominator of the trace path.  No scene needed. */
+int  pvgpu_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

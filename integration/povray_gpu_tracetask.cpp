@@ -679,17 +679,26 @@ int quality_bits(const QualityFlags& q)
            (q.normals ? PVGPU_Q_NORMALS : 0) | (q.media ? PVGPU_Q_MEDIA : 0);
 }
 
+// The flattened scene of one SceneData.  Its lifetime is tied to that SceneData: the cache entry keeps a weak_ptr, an entry whose
+// SceneData is gone (next frame of an animation, or a new SceneData allocated at the same address) is dropped and its device
+// scene destroyed; views of the same scene rendered with different quality settings get their own entry.
 struct GpuView
 {
     pvgpu_scene* scene = nullptr;
     std::map<const void*, int32_t> object_ids;
     bool finalized = false;
     std::string error;
+    std::weak_ptr<BackendSceneData> owner;
+    int quality = 0;
+    GpuView() = default;
+    GpuView(const GpuView&) = delete;
+    GpuView& operator=(const GpuView&) = delete;
+    ~GpuView() { if (scene) pvgpu_scene_destroy(scene); }
 };
 
 std::mutex g_mutex;
 std::mutex g_drain_mutex;
-std::map<const void*, std::shared_ptr<GpuView>> g_views;     // keyed by SceneData
+std::map<std::pair<const void*, int>, std::shared_ptr<GpuView>> g_views;     // keyed by (SceneData, quality flags), validated through GpuView::owner
 
 void check(int rc, const char* what)
 {
@@ -697,14 +706,59 @@ void check(int rc, const char* what)
         throw POV_EXCEPTION_STRING((std::string("pvgpu: ") + what + ": " + pvgpu_last_error()).c_str());
 }
 
+void finalize_view(GpuView& gv)
+{
+    if (!gv.error.empty())
+        throw POV_EXCEPTION_STRING((std::string("pvgpu: scene uses a feature outside the GPU trace path: ") + gv.error).c_str());
+    // PVGPU_DEVICES = "all" | "<n>" | "i,j,k": the scene is replicated on these devices and every frame is sharded over them
+    // behind pvgpu_render (one atomic tile counter, like the render threads' GetNextRectangle); PVGPU_DEVICE = one index
+    const char* devs = getenv("PVGPU_DEVICES");
+    const char* dev = getenv("PVGPU_DEVICE");
+    int rc;
+    if (devs && *devs) {
+        std::vector<int> list;
+        if (strchr(devs, ',')) { for (const char* p = devs; *p;) { list.push_back(atoi(p)); p = strchr(p, ','); if (!p) break; p++; } }
+        if (!list.empty()) rc = pvgpu_scene_finalize_multi(gv.scene, list.data(), (int)list.size());
+        else rc = pvgpu_scene_finalize_multi(gv.scene, nullptr, strcmp(devs, "all") == 0 ? 0 : atoi(devs));
+    } else rc = pvgpu_scene_finalize(gv.scene, dev ? atoi(dev) : 0);
+    if (rc != PVGPU_OK) throw POV_EXCEPTION_STRING((std::string("pvgpu: scene_finalize: ") + pvgpu_last_error()).c_str());
+    gv.finalized = true;
+}
+
+std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device);
+
 std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
+    // entries of scenes that no longer exist go first (and free their device memory)
+    for (auto it = g_views.begin(); it != g_views.end();)
+        if (it->second->owner.expired()) it = g_views.erase(it); else ++it;
+    const std::pair<const void*, int> key(vd->GetSceneData().get(), quality_bits(vd->GetQualityFeatureFlags()));
+    auto it = g_views.find(key);
+    if (it != g_views.end()) {
+        if (need_device && !it->second->finalized) {
+            try { finalize_view(*it->second); }
+            catch (...) { g_views.erase(it); throw; }
+        }
+        return it->second;
+    }
+    try {
+        std::shared_ptr<GpuView> gv = flatten_scene_locked(vd, need_device);
+        g_views[key] = gv;
+        return gv;
+    } catch (...) {
+        g_views.erase(key);        // nothing half-built stays behind for later tasks to pick up
+        throw;
+    }
+}
+
+std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
+{
     SceneData* sd = vd->GetSceneData().get();
-    std::shared_ptr<GpuView>& slot = g_views[sd];
-    if (slot) return slot;
-    slot.reset(new GpuView());
+    std::shared_ptr<GpuView> slot(new GpuView());
     GpuView& gv = *slot;
+    gv.owner = vd->GetSceneData();
+    gv.quality = quality_bits(vd->GetQualityFeatureFlags());
 
     if (sd->rainbow != nullptr || !sd->atmosphere.empty())
         gv.error = "rainbow / atmospheric media (SURVEY 8f 'next')";
@@ -809,21 +863,7 @@ std::shared_ptr<GpuView> flatten_scene(ViewData* vd, bool need_device)
     if (cam.Type > ORTHOGRAPHIC_CAMERA) check(pvgpu_scene_set_camera_angles(gv.scene, cam.Angle, cam.H_Angle, cam.V_Angle), "set_camera_angles");
     if (const char* path = getenv("PVGPU_DUMP_SCENE")) check(pvgpu_scene_save(gv.scene, path), "scene_save");
     if (!gv.error.empty()) fprintf(stderr, "pvgpu adapter: scene uses a feature outside the GPU trace path: %s\n", gv.error.c_str());
-    if (need_device) {
-        if (!gv.error.empty())
-            throw POV_EXCEPTION_STRING((std::string("pvgpu: scene uses a feature outside the GPU trace path: ") + gv.error).c_str());
-        // PVGPU_DEVICES = "all" | "<n>" | "i,j,k": the scene is replicated on these devices and every frame is sharded over them
-        // behind pvgpu_render (one atomic tile counter, like the render threads' GetNextRectangle); PVGPU_DEVICE = one index
-        const char* devs = getenv("PVGPU_DEVICES");
-        const char* dev = getenv("PVGPU_DEVICE");
-        if (devs && *devs) {
-            std::vector<int> list;
-            if (strchr(devs, ',')) { for (const char* p = devs; *p;) { list.push_back(atoi(p)); p = strchr(p, ','); if (!p) break; p++; } }
-            if (!list.empty()) check(pvgpu_scene_finalize_multi(gv.scene, list.data(), (int)list.size()), "scene_finalize_multi");
-            else check(pvgpu_scene_finalize_multi(gv.scene, nullptr, strcmp(devs, "all") == 0 ? 0 : atoi(devs)), "scene_finalize_multi");
-        } else check(pvgpu_scene_finalize(gv.scene, dev ? atoi(dev) : 0), "scene_finalize");
-        gv.finalized = true;
-    }
+    if (need_device) finalize_view(gv);
     return slot;
 }
 

@@ -7,8 +7,11 @@
 # g++ invocations, following SURVEY.md Appendix C.  Two variants:
 #   parity : -O2 -fno-fast-math -ffp-contract=off, portable noise  -> all parity checks
 #   fast   : -O3 -march=x86-64-v3 (no -ffast-math)                 -> reported CPU baseline (optional)
+#   stock  : -O3 -ffast-math -march=x86-64-v3 + BUILD_X86 (the reference's AVX / AVX2-FMA3 noise, picked by cpuid at run time):
+#            the flags unix/configure.ac:750-763,799 selects, with -march=native replaced by x86-64-v3 because the binary is built
+#            in one container and timed on another host                   -> second reported CPU baseline
 #
-# usage: oracle/build_ref.sh [parity|fast] [jobs]
+# usage: oracle/build_ref.sh [parity|fast|stock] [jobs]
 set -euo pipefail
 VARIANT=${1:-parity}
 JOBS=${2:-$(nproc)}
@@ -20,6 +23,7 @@ mkdir -p "$B/obj"
 case $VARIANT in
   parity) OPT="-O2 -fno-fast-math -ffp-contract=off";;
   fast)   OPT="-O3 -march=x86-64-v3 -fno-fast-math";;
+  stock)  OPT="-O3 -ffast-math -march=x86-64-v3";;
   *) echo "unknown variant"; exit 2;;
 esac
 cat > "$B/config.h" <<CFG
@@ -36,6 +40,7 @@ cat > "$B/config.h" <<CFG
 #define POV_COMPILER_INFO "g++ @ x86_64-pc-linux-gnu"
 #define CXXFLAGS "$OPT"
 #define USE_OFFICIAL_BOOST
+$( [ "$VARIANT" = stock ] && echo "#define BUILD_X86 1" )
 #define LIBJPEG_MISSING
 #define LIBTIFF_MISSING
 #define OPENEXR_MISSING

@@ -174,13 +174,13 @@ class Rect(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", u64), ("shadow_ray_tests", u64), ("reflected_rays", u64), ("refracted_rays", u64),
                 ("transmitted_rays", u64), ("tir_rays", u64), ("adc_saves", u64), ("samples", u64), ("waves", u64),
-                ("kernel_launches", u64), ("max_trace_level", u32), ("overflow", u32), ("node_tests", u64), ("prim_tests", u64), ("device_ms", f64),
+                ("kernel_launches", u64), ("max_trace_level", u32), ("overflow", u32), ("node_tests_closest", u64), ("prim_tests_closest", u64), ("node_tests_shadow", u64), ("prim_tests_shadow", u64), ("device_ms", f64),
                 ("kernel_ms", f64 * 5), ("kernel_count", u64 * 5), ("kernel_items", u64 * 5)]
 
     KERNELS = ("primary", "closest", "shade", "shadow", "aa")
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_[:15]}
+        d = {n: getattr(self, n) for n, _ in self._fields_[:17]}
         for i, k in enumerate(self.KERNELS):
             d[k + "_ms"] = self.kernel_ms[i]
             d[k + "_launches"] = int(self.kernel_count[i])
@@ -218,6 +218,7 @@ SIGNATURES = {
     "pvgpu_scene_finalize": (C.c_int, [VP, C.c_int]),
     "pvgpu_scene_finalize_multi": (C.c_int, [VP, P(C.c_int), C.c_int]),
     "pvgpu_scene_device_count": (C.c_int, [VP]),
+    "pvgpu_fp64_peak": (C.c_int, [C.c_int, P(C.c_double)]),
     "pvgpu_scene_device_bytes": (C.c_size_t, [VP]),
     "pvgpu_scene_save": (C.c_int, [VP, C.c_char_p]),
     "pvgpu_scene_load": (C.c_int, [P(VP), C.c_char_p]),

@@ -342,8 +342,8 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, u
         max_level = max(max_level, __shfl_down_sync(0xffffffffu, max_level, off));
     }
     if ((threadIdx.x & 31) == 0) {
-        if (n_nodes) atomicAdd(&cnt->node_tests, n_nodes);
-        if (n_prims) atomicAdd(&cnt->prim_tests, n_prims);
+        if (n_nodes) atomicAdd(&cnt->node_tests[0], n_nodes);
+        if (n_prims) atomicAdd(&cnt->prim_tests[0], n_prims);
         if (n_rays) atomicAdd(&cnt->rays, n_rays);
         if (n_adc) atomicAdd(&cnt->adc_saves, n_adc);
         if (max_level) atomicMax(&cnt->max_level, max_level);

@@ -44,6 +44,27 @@ __global__ void k_init_waves(NoiseTables nt, uint32_t n, double* sources, double
     }
 }
 
+// FP64 vector peak: eight independent DFMA chains per thread (explicit __fma_rn: the library is compiled with -fmad=false).
+__global__ void __launch_bounds__(256)
+k_fp64_peak(double* out, int iters)
+{
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9, a4 = a0 + 4e-9, a5 = a0 + 5e-9, a6 = a0 + 6e-9, a7 = a0 + 7e-9;
+    const double m = 1.0 - 1e-12, c = 1e-12;
+    for (int i = 0; i < iters; i++) {
+        a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+        a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) *out = r;       // never true: keeps the chains alive
+}
+
+unsigned long long launch_fp64_peak(double* out, int iters, cudaStream_t st)
+{
+    const int blocks = sm_count() * 8;
+    k_fp64_peak<<<blocks, 256, 0, st>>>(out, iters);
+    return 2ull * 8ull * (unsigned long long)iters * 256ull * (unsigned long long)blocks;
+}
+
 void launch_init_waves(const NoiseTables& nt, uint32_t n, double* sources, double* freqs, cudaStream_t st)
 { if (n) k_init_waves<<<grid_for(n, 128, 8), 128, 0, st>>>(nt, n, sources, freqs); }
 

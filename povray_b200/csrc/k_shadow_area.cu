@@ -143,8 +143,8 @@ k_shadow_area(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t
     }
     if ((threadIdx.x & 31) == 0) {
         if (tests) atomicAdd(&cnt->shadow_tests, tests);
-        if (n_nodes) atomicAdd(&cnt->node_tests, n_nodes);
-        if (n_prims) atomicAdd(&cnt->prim_tests, n_prims);
+        if (n_nodes) atomicAdd(&cnt->node_tests[1], n_nodes);
+        if (n_prims) atomicAdd(&cnt->prim_tests[1], n_prims);
     }
 }
 

@@ -216,8 +216,8 @@ static_assert(sizeof(SRay) == 96, "SRay must be 96 bytes");
 struct Counters {
     unsigned long long rays, shadow_tests, reflected, refracted, transmitted, tir, adc_saves;
     unsigned long long shadow_rays;   // shadow rays traced (TraceShadowRay calls)
-    unsigned long long node_tests;    // bounding-box slab tests of the traversal kernels (scene tree + mesh trees), PV_COUNT_TESTS builds
-    unsigned long long prim_tests;    // primitive All_Intersections calls incl. mesh triangles, PV_COUNT_TESTS builds
+    unsigned long long node_tests[2]; // bounding-box slab tests (scene tree + mesh trees): [0] k_closest, [1] k_shadow_*
+    unsigned long long prim_tests[2]; // top-level primitive tests + mesh triangle tests: [0] k_closest, [1] k_shadow_*
     unsigned int max_level;
     unsigned int overflow;
 };

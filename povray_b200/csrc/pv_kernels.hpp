@@ -86,6 +86,7 @@ void launch_probe_solver(uint32_t n, const int32_t* degree, const int32_t* sturm
                          double* roots, int32_t* counts, cudaStream_t st);
 void launch_probe_noise(const NoiseTables& nt, uint32_t n, const double* xyz, const int32_t* gen, const int32_t* octaves, double* out, cudaStream_t st);
 void launch_init_waves(const NoiseTables& nt, uint32_t n, double* sources, double* freqs, cudaStream_t st);
+unsigned long long launch_fp64_peak(double* out, int iters, cudaStream_t st);      // returns the flop the launch performs
 void launch_camera_rays(const DScene& sc, const double* xy, uint32_t n, double width, double height, double* org_dir, cudaStream_t st);
 
 }  // namespace pvgpu

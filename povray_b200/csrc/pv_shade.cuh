@@ -364,6 +364,10 @@ static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_
         else { for (int k = 0; k < 5; k++) out[k] = sc.pigments[idx].colour[k]; }     // unreachable: nesting depth is validated
     };
     const pvgpu_pigment& pg = sc.pigments[pig_index];
+    if ((sc.g.quality_flags & PVGPU_Q_QUICK_COLOUR) && pg.quick_colour[0] == pg.quick_colour[0]) {     // pigment.cpp:401-405
+        for (int k = 0; k < 5; k++) col[k] = pg.quick_colour[k];
+        return;
+    }
     if (pg.pattern == PVGPU_PAT_PLAIN) {
         for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
         return;
@@ -405,6 +409,12 @@ static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_
 __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
 {
     const pvgpu_pigment& pg = sc.pigments[pig_index];
+    // quickColour (+Q5 and below): Quick_Colour replaces the pigment where the scene gives one (pigment.cpp:401-405; NaN red = none)
+    if ((sc.g.quality_flags & PVGPU_Q_QUICK_COLOUR) && pg.quick_colour[0] == pg.quick_colour[0]) {
+        #pragma unroll
+        for (int k = 0; k < 5; k++) col[k] = pg.quick_colour[k];
+        return;
+    }
     if (pg.pattern == PVGPU_PAT_PLAIN) {
         #pragma unroll
         for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
@@ -1144,6 +1154,15 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
         const double cos_inc = -dot(dir, lay_normal);
         float lc[5];
         compute_pigment(sc, tx.pigment, epoint, lc);
+        if (sc.g.quality_flags & PVGPU_Q_AMBIENT_ONLY) {
+            // +Q0 / +Q1 (trace.cpp:848-853): the result IS the layer's pigment colour (the last layer reached wins), no transparency,
+            // no lights, no secondary rays; the filter colour still decides whether the next layer is looked at (trace.cpp:1059-1076)
+            amb[0] = lc[0]; amb[1] = lc[1]; amb[2] = lc[2];
+            #pragma unroll
+            for (int k = 0; k < 3; k++) fil[k] *= (lc[k] * lc[3] + lc[4]);
+            trans = fmin(1.0, (double)fabsf(greyscale(fil)));
+            continue;
+        }
         L.col[0] = lc[0]; L.col[1] = lc[1]; L.col[2] = lc[2];
         L.fil[0] = fil[0]; L.fil[1] = fil[1]; L.fil[2] = fil[2];
         L.finish = tx.finish;
@@ -1178,6 +1197,7 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
 
     // local (non-recursive) term
     accum_add(ctx.accum, ray.sample, ray.w[0] * amb[0], ray.w[1] * amb[1], ray.w[2] * amb[2], 0.0f);
+    if (sc.g.quality_flags & PVGPU_Q_AMBIENT_ONLY) return;       // resultTransm = 0, nothing else is computed
 
     // ---- classic lights: ComputeDiffuseLight / ComputeOneDiffuseLight (trace.cpp:1488-1510, 1637-1728)
     if (!(ob.flags & PVGPU_NO_GLOBAL_LIGHTS_FLAG)) {

@@ -41,7 +41,9 @@ __device__ inline int solve_quadratic(const double* x, double* y)
     return 2;
 }
 
-__device__ inline int solve_cubic(const double* x, double* y)
+// (the solver is one of the largest pieces of the heavy kernels' hot path, which is bound by instruction fetch: its building blocks are
+//  single out-of-line copies with rolled loops - measured on config 4, profiles/README.md - instead of inlined, unrolled ones)
+static __device__ __noinline__ int solve_cubic(const double* x, double* y)
 {
     double a0 = x[0], a1, a2, a3;
     if (a0 == 0.0) return solve_quadratic(&x[1], y);
@@ -123,9 +125,11 @@ __device__ inline int solve_quartic(const double* x, double* results)
 __device__ inline int difficult_coeffs(int n, const double* x)
 {
     double biggest = 0.0;
+    #pragma unroll 1
     for (int i = 0; i <= n; i++)
         if (fabs(x[i]) > biggest) biggest = x[i];
     if (biggest == 0.0) return 0;
+    #pragma unroll 1
     for (int i = 0; i <= n; i++)
         if (x[i] != 0.0)
             if (fabs(biggest / x[i]) > PV_FUDGE_FACTOR1) return 1;
@@ -134,9 +138,10 @@ __device__ inline int difficult_coeffs(int n, const double* x)
 
 struct Poly { int ord; double coef[PV_POLY_MAX_ORDER + 1]; };
 
-__device__ inline double polyeval(double x, int n, const double* c)
+__device__ __forceinline__ double polyeval(double x, int n, const double* c)
 {
     double val = c[n];
+    #pragma unroll 1
     for (int i = n - 1; i >= 0; i--) val = val * x + c[i];
     return val;
 }
@@ -145,14 +150,21 @@ __device__ inline int modp(const Poly* u, const Poly* v, Poly* r)
 {
     *r = *u;
     if (v->coef[v->ord] < 0.0) {
+        #pragma unroll 1
         for (int k = u->ord - v->ord - 1; k >= 0; k -= 2) r->coef[k] = -r->coef[k];
-        for (int k = u->ord - v->ord; k >= 0; k--)
+        #pragma unroll 1
+        for (int k = u->ord - v->ord; k >= 0; k--) {
+            #pragma unroll 1
             for (int j = v->ord + k - 1; j >= k; j--)
                 r->coef[j] = -r->coef[j] - r->coef[v->ord + k] * v->coef[j - k];
+        }
     } else {
-        for (int k = u->ord - v->ord; k >= 0; k--)
+        #pragma unroll 1
+        for (int k = u->ord - v->ord; k >= 0; k--) {
+            #pragma unroll 1
             for (int j = v->ord + k - 1; j >= k; j--)
                 r->coef[j] -= r->coef[v->ord + k] * v->coef[j - k];
+        }
     }
     int k = v->ord - 1;
     while (k >= 0 && fabs(r->coef[k]) < PV_SMALL_ENOUGH) { r->coef[k] = 0.0; k--; }
@@ -165,10 +177,13 @@ __device__ inline int buildsturm(int ord, Poly* sseq)
     sseq[0].ord = ord;
     sseq[1].ord = ord - 1;
     double f = fabs(sseq[0].coef[ord] * ord);
+    #pragma unroll 1
     for (int i = 1; i <= ord; i++) sseq[1].coef[i - 1] = sseq[0].coef[i] * i / f;
     int sp = 2;
+    #pragma unroll 1
     for (; modp(&sseq[sp - 2], &sseq[sp - 1], &sseq[sp]); sp++) {
         f = -fabs(sseq[sp].coef[sseq[sp].ord]);
+        #pragma unroll 1
         for (int k = sseq[sp].ord; k >= 0; k--) sseq[sp].coef[k] /= f;
     }
     sseq[sp].coef[0] = -sseq[sp].coef[0];
@@ -179,12 +194,14 @@ __device__ inline int visible_roots(int np, const Poly* sseq)
 {
     int atposinf = 0, atzero = 0;
     double lf = sseq[0].coef[sseq[0].ord];
+    #pragma unroll 1
     for (int s = 1; s <= np; s++) {
         double f = sseq[s].coef[sseq[s].ord];
         if (lf == 0.0 || lf * f < 0) atposinf++;
         lf = f;
     }
     lf = sseq[0].coef[0];
+    #pragma unroll 1
     for (int s = 1; s <= np; s++) {
         double f = sseq[s].coef[0];
         if (lf == 0.0 || lf * f < 0) atzero++;
@@ -193,10 +210,11 @@ __device__ inline int visible_roots(int np, const Poly* sseq)
     return atzero - atposinf;
 }
 
-__device__ inline int numchanges(int np, const Poly* sseq, double a)
+static __device__ __noinline__ int numchanges(int np, const Poly* sseq, double a)
 {
     int changes = 0;
     double lf = polyeval(a, sseq[0].ord, sseq[0].coef);
+    #pragma unroll 1
     for (int s = 1; s <= np; s++) {
         double f = polyeval(a, sseq[s].ord, sseq[s].coef);
         if (lf == 0.0 || lf * f < 0) changes++;
@@ -205,13 +223,14 @@ __device__ inline int numchanges(int np, const Poly* sseq, double a)
     return changes;
 }
 
-__device__ inline int regula_falsa(int order, const double* coef, double a, double b, double* val)
+static __device__ __noinline__ int regula_falsa(int order, const double* coef, double a, double b, double* val)
 {
     double fa = polyeval(a, order, coef), fb = polyeval(b, order, coef);
     if (fa * fb > 0.0) return 0;
     if (fabs(fa) < PV_SMALL_ENOUGH) { *val = a; return 1; }
     if (fabs(fb) < PV_SMALL_ENOUGH) { *val = b; return 1; }
     double lfx = fa;
+    #pragma unroll 1
     for (int its = 0; its < PV_MAX_ITERATIONS; its++) {
         double x = (fb * a - fa * b) / (fb - fa);
         double fx = polyeval(x, order, coef);
@@ -246,6 +265,7 @@ __device__ inline int sbisect(int np, const Poly* sseq, double min0, double max0
         if ((atmin - atmax) == 1) {
             if (regula_falsa(sseq[0].ord, sseq[0].coef, min_value, max_value, &roots[nroots])) { nroots++; continue; }
             bool done = false;
+            #pragma unroll 1
             for (int its = 0; its < PV_MAX_ITERATIONS; its++) {
                 mid = (min_value + max_value) / 2;
                 int atmid = numchanges(np, sseq, mid);
@@ -259,6 +279,7 @@ __device__ inline int sbisect(int np, const Poly* sseq, double min0, double max0
             continue;
         }
         bool done = false;
+        #pragma unroll 1
         for (int its = 0; its < PV_MAX_ITERATIONS; its++) {
             mid = (min_value + max_value) / 2;
             int atmid = numchanges(np, sseq, mid);
@@ -280,9 +301,10 @@ __device__ inline int sbisect(int np, const Poly* sseq, double min0, double max0
     return nroots;
 }
 
-__device__ inline int polysolve(int order, const double* coeffs, double* roots)
+static __device__ __noinline__ int polysolve(int order, const double* coeffs, double* roots)
 {
     Poly sseq[PV_POLY_MAX_ORDER + 1];
+    #pragma unroll 1
     for (int i = 0; i <= order; i++) sseq[0].coef[order - i] = coeffs[i] / coeffs[0];
     int np = buildsturm(order, sseq);
     if (visible_roots(np, sseq) == 0) return 0;

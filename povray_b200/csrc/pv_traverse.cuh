@@ -156,8 +156,8 @@ __device__ __forceinline__ bool type_uses_bbox_test(uint32_t type)
 // Tests the `count` children stored at nodes[first..] (Check_And_Enqueue per child, boundingbox.cpp:541-648) and
 // pushes those the ray may hit so that the nearest ends up on top (equal depths: the later child on top, the order
 // an insertion of one child after the other produces).  Children are fetched four at a time (the reference bunches
-// <= 4 entries per node): 8 x LDG.128 in flight, four branch-free slab tests, a 5-comparator sorting network, and
-// predicated pushes - no data-dependent loop, so the lanes of a warp stay converged through a node visit.
+// <= 4 entries per node): 8 x LDG.128 in flight, four branch-free slab tests, ranks from the six pairwise comparisons, and
+// predicated scattered pushes - no data-dependent loop, so the lanes of a warp stay converged through a node visit.
 //   ORDERED = false (any-hit searches): no sorting, children are pushed in storage order.
 //   limit: children entered beyond this depth are not pushed at all (a conservative FP32 upper bound of the best depth
 //   so far; the exact test is repeated when an entry is popped, so this only saves stack traffic).
@@ -165,13 +165,12 @@ template <bool ALLOW_INFINITE, bool ORDERED>
 __device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, uint32_t first, uint32_t count, const RayInfo& ri,
                                               const TStack& stack, int& sp, unsigned int* overflow, float limit = 3.0e38f)
 {
-    const float kInvalid = __int_as_float(0x7f800000);     // +inf: sorts first, never pushed
+    const float kInvalid = __int_as_float(0x7fc00000);     // NaN: every comparison with it is false, never pushed
     for (uint32_t c0 = 0; c0 < count; c0 += 4) {
         NodeL ch[4];
         #pragma unroll
         for (int k = 0; k < 4; k++) ch[k] = load_node(nodes + first + min(c0 + (uint32_t)k, count - 1u));
         float key[4];
-        uint32_t val[4];
         if (!ri.special) {
             #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -180,7 +179,6 @@ __device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, u
                 if (ALLOW_INFINITE && (ch[k].code & PV_CODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }   // boundingbox.cpp:643-647
                 ok = ok && (c0 + k < count) && !(dmin > limit);
                 key[k] = ok ? dmin : kInvalid;
-                val[k] = ch[k].code;
             }
         } else {
             #pragma unroll
@@ -190,28 +188,34 @@ __device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, u
                 if (ALLOW_INFINITE && (ch[k].code & PV_CODE_INFINITE)) { dmin = -PV_MAX_DISTANCE_F; ok = true; }
                 ok = ok && (c0 + k < count) && !(dmin > limit);
                 key[k] = ok ? dmin : kInvalid;
-                val[k] = ch[k].code;
             }
         }
+        // Where each child lands above the current top: the farthest at the bottom, the nearest on top, equal depths in child
+        // order (the later child on top) - the order a descending stable sort of the entry depths produces, computed as ranks from
+        // the six pairwise comparisons instead of a sorting network.  ORDERED = false: storage order.
+        int pos[4] = { 0, 0, 0, 0 };
+        int n_valid = 0;
         if (ORDERED) {
-            // descending by entry depth; equal depths keep the child order (the ordinal rides in the comparison)
-            uint32_t ord[4] = { 0u, 1u, 2u, 3u };
-            #define PV_CSWAP(i, j) { const bool sw = (key[i] < key[j]) || (key[i] == key[j] && ord[i] > ord[j]); \
-                                     const float tk = sw ? key[j] : key[i]; key[j] = sw ? key[i] : key[j]; key[i] = tk; \
-                                     const uint32_t tv = sw ? val[j] : val[i]; val[j] = sw ? val[i] : val[j]; val[i] = tv; \
-                                     const uint32_t to = sw ? ord[j] : ord[i]; ord[j] = sw ? ord[i] : ord[j]; ord[i] = to; }
-            PV_CSWAP(0, 1) PV_CSWAP(2, 3) PV_CSWAP(0, 2) PV_CSWAP(1, 3) PV_CSWAP(1, 2)
-            #undef PV_CSWAP
+            #pragma unroll
+            for (int k = 1; k < 4; k++) {
+                #pragma unroll
+                for (int j = 0; j < k; j++) {
+                    pos[k] += (key[j] >= key[k]) ? 1 : 0;      // j goes below k: farther, or as far and earlier
+                    pos[j] += (key[j] < key[k]) ? 1 : 0;       // k goes below j
+                }
+            }
+            #pragma unroll
+            for (int k = 0; k < 4; k++) n_valid += (key[k] == key[k]) ? 1 : 0;
+        } else {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) { pos[k] = n_valid; n_valid += (key[k] == key[k]) ? 1 : 0; }
         }
-        // branch-free pushes: every entry is stored at the current top, the top only advances past valid ones (an invalid
-        // entry is overwritten by the next store); the last slot of the stack absorbs an overflow, which is flagged
+        const int room = PV_STACK_SIZE - 1 - sp;               // the last slot is never used: an overflow is flagged instead
         #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const bool ok = key[k] != kInvalid;
-            stack.set(sp, make_uint2(__float_as_uint(key[k]), val[k]));
-            if (ok && sp >= PV_STACK_SIZE - 1) atomicOr(overflow, 1u);
-            sp += (ok && sp < PV_STACK_SIZE - 1) ? 1 : 0;
-        }
+        for (int k = 0; k < 4; k++)
+            if (key[k] == key[k] && pos[k] < room) stack.set(sp + pos[k], make_uint2(__float_as_uint(key[k]), ch[k].code));
+        if (n_valid > room) { atomicOr(overflow, 1u); n_valid = room > 0 ? room : 0; }
+        sp += n_valid;
     }
 }
 
@@ -595,8 +599,12 @@ __device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, con
 // point inside all other children, every merge ancestor has it inside none of the other children, and
 // every ancestor's clipped_by list contains it.  Intersection::Csg ends up as the outermost ancestor
 // that sets it (unions without clipped_by do not, csg.cpp:137-150).
+// `limit`: hits at or beyond this depth cannot win (the caller only takes a hit nearer than its best so far), so their Inside
+// tests - the expensive part - are skipped, as are those of hits consider() would drop anyway (too near, behind the post-condition,
+// farther than the object's closest accepted hit so far).  The tests are pure functions of the point: skipping them changes nothing.
+#define PV_CSG_HIT_CAN_WIN(depth) ((depth) <= acc.closest && (depth) < limit && (depth) >= PV_MIN_ISECT_DEPTH && (depth) > acc.post_min)
 __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
-                                HitAcc& acc, TStack stack, int sp0, unsigned int* overflow)
+                                HitAcc& acc, TStack stack, int sp0, unsigned int* overflow, double limit)
 {
     uint2 range = sc.csg_leaf_range[top];
     if (range.y & 0x80000000u) {
@@ -612,6 +620,7 @@ __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, con
             PrimHits h;
             prim_hits(sc, lo, o, d, h);
             for (int i = 0; i < h.n; i++) {
+                if (!PV_CSG_HIT_CAN_WIN(h.depth[i])) continue;
                 const V3 ip = h.ip[i];
                 bool keep = true;
                 int32_t csg = (int32_t)top;
@@ -651,6 +660,7 @@ __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, con
         PrimHits h;
         prim_hits(sc, lo, o, d, h);
         for (int i = 0; i < h.n; i++) {
+            if (!PV_CSG_HIT_CAN_WIN(h.depth[i])) continue;
             const V3 ip = h.ip[i];
             if (lo.clip_count && !point_in_clip(sc, lo, ip, stack, sp0)) continue;
             bool keep = true;
@@ -694,7 +704,7 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
 template <bool ANY_OPAQUE>
 __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, const V3& d, uint32_t rflags, bool shadow_ray,
                                    double post_min, float bbox_maxd, Hit& out, TStack stack, int sp0, unsigned int* overflow,
-                                   double opaque_limit = 0.0)
+                                   double opaque_limit = 0.0, double limit = PV_HUGE_VAL)
 {
     const pvgpu_object& ob = sc.objs[idx];
     if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, bbox_maxd)) return false;
@@ -709,7 +719,7 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
 #if PV_HEAVY
     // (the lean variant walks meshes only through mesh_hits_sync and serves no CSG)
-    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow);
+    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow, limit);
     else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
     else
 #endif
@@ -733,7 +743,7 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = -1.0; acc.found = false;
 #if PV_HEAVY
-    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow);
+    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow, PV_HUGE_VAL);
     else
 #endif
     if (ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
@@ -774,7 +784,7 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
             const uint32_t idx = sc.frame[i];
             if (!precondition(sc.objs[idx].flags, rflags, shadow_ray)) continue;
             Hit h;
-            if (object_find<ANY_OPAQUE>(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, 0, overflow, opaque_limit) && h.depth < best.depth) {
+            if (object_find<ANY_OPAQUE>(sc, idx, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, 0, overflow, opaque_limit, best.depth) && h.depth < best.depth) {
                 best = h;
                 found = true;
                 if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
@@ -805,7 +815,7 @@ __device__ inline bool find_intersection(const DScene& sc, const V3& o, const V3
         if (leaf == 0xFFFFFFFFu) break;
         if (!precondition(sc.objs[leaf].flags, rflags, shadow_ray)) continue;
         Hit h;
-        if (object_find<ANY_OPAQUE>(sc, leaf, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow, opaque_limit) && h.depth < best.depth) {
+        if (object_find<ANY_OPAQUE>(sc, leaf, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow, opaque_limit, best.depth) && h.depth < best.depth) {
             best = h;
             found = true;
             if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) return true;
@@ -844,7 +854,7 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
 #endif
             } else {
                 Hit h;
-                if (object_find<ANY_OPAQUE>(sc, leaf, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow, opaque_limit) && h.depth < best.depth) {
+                if (object_find<ANY_OPAQUE>(sc, leaf, o, d, rflags, shadow_ray, post_min, (float)PV_HUGE_VAL, h, stack, sp, overflow, opaque_limit, best.depth) && h.depth < best.depth) {
                     best = h;
                     found = true;
                     if (ANY_OPAQUE && (sc.objs[h.obj].flags & PVGPU_OPAQUE_FLAG) && h.depth > PV_SHADOW_TOLERANCE && h.depth < opaque_limit) done = true;

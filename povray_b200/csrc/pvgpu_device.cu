@@ -678,8 +678,13 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
     const size_t batch = std::min<size_t>(kBatchSamples, n_samples);
     {
         // a wave cannot outgrow the batch when a ray spawns at most one ray; otherwise leave room for growth
-        const size_t q_cap = std::max<size_t>((d.spawn_factor <= 1 ? 1 : 4) * batch, 1024);
-        const size_t sq_cap = std::min<size_t>(kShadowCapMax, std::max<size_t>(q_cap * d.shadow_factor, 1024));
+        size_t q_cap = std::max<size_t>((d.spawn_factor <= 1 ? 1 : 4) * batch, 1024);
+        size_t sq_cap = std::min<size_t>(kShadowCapMax, std::max<size_t>(q_cap * d.shadow_factor, 1024));
+        if (const char* e = getenv("PVGPU_TEST_QUEUE_CAP")) {       // tests: force small queues to exercise the clamp + overflow retry
+            const size_t cap = (size_t)std::max(64, atoi(e));
+            if (c.q_cap == 0) q_cap = std::min(q_cap, cap);
+            if (c.sq_cap == 0) sq_cap = std::min(sq_cap, cap);
+        }
         int rc = ensure_work_buffers(c, q_cap, f.s.lights.empty() ? 0 : sq_cap, 0);
         if (rc != PVGPU_OK) return rc;
     }
@@ -947,7 +952,7 @@ static int render_impl(Scene& s, DeviceScene& d, WorkCtx& c, const pvgpu_aa* aa,
     st.rays = hc.rays; st.shadow_ray_tests = hc.shadow_tests; st.reflected_rays = hc.reflected;
     st.refracted_rays = hc.refracted; st.transmitted_rays = hc.transmitted; st.tir_rays = hc.tir;
     st.adc_saves = hc.adc_saves; st.samples = n_extra_samples; st.max_trace_level = hc.max_level; st.overflow = hc.overflow;
-    st.node_tests = hc.node_tests; st.prim_tests = hc.prim_tests;
+    st.node_tests_closest = hc.node_tests[0]; st.prim_tests_closest = hc.prim_tests[0]; st.node_tests_shadow = hc.node_tests[1]; st.prim_tests_shadow = hc.prim_tests[1];
     st.kernel_launches = c.kernel_launches - launches0;
     st.device_ms = ms;
     for (const WorkCtx::Timed& t : c.timed) {
@@ -970,7 +975,8 @@ static void merge_stats(pvgpu_stats& a, const pvgpu_stats& b)
 {
     a.rays += b.rays; a.shadow_ray_tests += b.shadow_ray_tests; a.reflected_rays += b.reflected_rays; a.refracted_rays += b.refracted_rays;
     a.transmitted_rays += b.transmitted_rays; a.tir_rays += b.tir_rays; a.adc_saves += b.adc_saves; a.samples += b.samples;
-    a.waves += b.waves; a.kernel_launches += b.kernel_launches; a.node_tests += b.node_tests; a.prim_tests += b.prim_tests;
+    a.waves += b.waves; a.kernel_launches += b.kernel_launches;
+    a.node_tests_closest += b.node_tests_closest; a.prim_tests_closest += b.prim_tests_closest; a.node_tests_shadow += b.node_tests_shadow; a.prim_tests_shadow += b.prim_tests_shadow;
     a.max_trace_level = std::max(a.max_trace_level, b.max_trace_level); a.overflow |= b.overflow;
     for (int k = 0; k < 5; k++) { a.kernel_ms[k] += b.kernel_ms[k]; a.kernel_count[k] += b.kernel_count[k]; a.kernel_items[k] += b.kernel_items[k]; }
 }
@@ -1319,6 +1325,36 @@ int pvgpu_noise(pvgpu_scene* sc, size_t n, const double* xyz, const int32_t* gen
     launch_probe_noise(s.dev->view.noise, (uint32_t)n, d_p.p, d_g.p, d_oct.p, d_o.p, 0);
     s.dev->ctx[0]->kernel_launches++;
     CUDA_TRY(cudaMemcpy(out, d_o.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return PVGPU_OK;
+}
+
+int pvgpu_fp64_peak(int device, double* tflops)
+{
+    clear_error();
+    if (!tflops) return fail(PVGPU_E_INVALID, "pvgpu_fp64_peak: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(PVGPU_E_NO_DEVICE, "no CUDA device available");
+    if (device < 0 || device >= ndev) return fail(PVGPU_E_INVALID, "device %d out of range (have %d)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, 0);
+        const unsigned long long flop = launch_fp64_peak(d_out, iters, 0);
+        cudaEventRecord(e1, 0);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms > 0.0f) best = std::max(best, (double)flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    if (cudaGetLastError() != cudaSuccess || best == 0.0) return fail(PVGPU_E_CUDA, "pvgpu_fp64_peak: measurement kernel failed");
+    *tflops = best;
     return PVGPU_OK;
 }
 

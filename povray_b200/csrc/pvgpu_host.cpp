@@ -242,6 +242,31 @@ int validate_scene(Scene& s)
     // (a scene without objects is legal: every ray ends in ComputeSky)
     for (uint32_t f : s.frame)
         if (f >= no) return fail(PVGPU_E_INVALID, "frame object index %u out of range", f);
+    // Tables other tables index into are validated first (blend maps and their entries, warps), then the records that refer
+    // to them, then the nesting walks: nothing is dereferenced before its range has been checked.
+    for (size_t i = 0; i < s.blend_maps.size(); i++) {
+        const pvgpu_blend_map& m = s.blend_maps[i];
+        if (m.entry_count == 0 || !range_ok(m.entry_first, m.entry_count, s.blend_entries.size()))
+            return fail(PVGPU_E_INVALID, "blend map %zu: bad entry range", i);
+        if ((m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP | PVGPU_BLEND_NORMAL_MAP)) != 0)
+            return fail(PVGPU_E_UNSUPPORTED, "blend map %zu: blend_mode %d is outside the hot-path scope", i, m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP | PVGPU_BLEND_NORMAL_MAP));
+        // entries of pigment / texture / normal maps carry an index into the respective table in colour[0]
+        const size_t limit = (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) ? s.pigments.size() : (m.blend_mode & PVGPU_BLEND_TEXTURE_MAP) ? s.textures.size()
+                           : (m.blend_mode & PVGPU_BLEND_NORMAL_MAP) ? s.tnormals.size() : 0;
+        if (m.blend_mode & (PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP | PVGPU_BLEND_NORMAL_MAP))
+            for (uint32_t k = 0; k < m.entry_count; k++) {
+                const float pi = s.blend_entries[m.entry_first + k].colour[0];
+                if (!(pi >= 0.0f) || pi >= (float)limit || pi != std::floor(pi))
+                    return fail(PVGPU_E_INVALID, "blend map %zu: entry %u is not a valid table index", i, k);
+            }
+    }
+    for (size_t i = 0; i < s.warps.size(); i++) {
+        const pvgpu_warp& w = s.warps[i];
+        if (w.type < PVGPU_WARP_TRANSFORM || w.type > PVGPU_WARP_CLASSIC_TURBULENCE)
+            return fail(PVGPU_E_UNSUPPORTED, "warp %zu: type %u unsupported", i, w.type);
+        if (w.type == PVGPU_WARP_TRANSFORM && (w.transform < 0 || w.transform >= (int32_t)s.transforms.size()))
+            return fail(PVGPU_E_INVALID, "warp %zu: bad transform", i);
+    }
     for (size_t i = 0; i < no; i++) {
         const pvgpu_object& o = s.objects[i];
         if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_POLY)
@@ -303,9 +328,14 @@ int validate_scene(Scene& s)
                 return fail(PVGPU_E_INVALID, "blob %zu: bounding-sphere node %u out of range", i, k);
         }
     }
-    for (uint32_t v : s.index_list)
-        if (v >= no && v >= s.textures.size() && v >= s.pigments.size())
-            return fail(PVGPU_E_INVALID, "index list entry %u out of range", v);
+    // index-list ranges are checked against the table they refer to: children / clipped_by / bounded_by lists -> objects,
+    // mesh texture lists -> textures (below), the sky_sphere's pigment list -> pigments (below)
+    for (size_t i = 0; i < no; i++) {
+        const pvgpu_object& o = s.objects[i];
+        for (uint32_t k = 0; k < o.child_count; k++) if (s.index_list[o.child_first + k] >= no) return fail(PVGPU_E_INVALID, "object %zu: child index out of range", i);
+        for (uint32_t k = 0; k < o.clip_count; k++) if (s.index_list[o.clip_first + k] >= no) return fail(PVGPU_E_INVALID, "object %zu: clipped_by index out of range", i);
+        for (uint32_t k = 0; k < o.bound_count; k++) if (s.index_list[o.bound_first + k] >= no) return fail(PVGPU_E_INVALID, "object %zu: bounded_by index out of range", i);
+    }
     for (size_t i = 0; i < s.nodes.size(); i++) {
         const pvgpu_node& n = s.nodes[i];
         if (n.count ? !range_ok(n.first, n.count, s.nodes.size()) : n.first >= no)
@@ -319,6 +349,8 @@ int validate_scene(Scene& s)
             !range_ok(me.node_first, me.node_count, s.mesh_nodes.size()) ||
             !range_ok(me.texture_first, me.texture_count, s.index_list.size()))
             return fail(PVGPU_E_INVALID, "mesh %zu: range out of bounds", m);
+        for (uint32_t k = 0; k < me.texture_count; k++)
+            if (s.index_list[me.texture_first + k] >= s.textures.size()) return fail(PVGPU_E_INVALID, "mesh %zu: texture list entry %u out of range", m, k);
         for (uint32_t t = 0; t < me.triangle_count; t++) {
             const pvgpu_triangle& tr = s.triangles[me.triangle_first + t];
             if (tr.p1 < 0 || tr.p2 < 0 || tr.p3 < 0 || (uint32_t)tr.p1 >= me.vertex_count ||
@@ -377,6 +409,31 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
         if (p.pattern == PVGPU_PAT_CRACKLE && !range_ok(p.data, 9, s.shape_data.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: crackle parameters outside the shape-data table", i);
+    }
+    for (size_t i = 0; i < s.tnormals.size(); i++) {
+        const pvgpu_tnormal& t = s.tnormals[i];
+        if (t.type < PVGPU_NORM_BUMPS || t.type > PVGPU_NORM_AVERAGE)
+            return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: type %u unsupported", i, t.type);
+        if (t.normal_map) {
+            if (t.normal_map > s.blend_maps.size() || !(s.blend_maps[t.normal_map - 1].blend_mode & PVGPU_BLEND_NORMAL_MAP) ||
+                (t.type != PVGPU_NORM_PATTERN && t.type != PVGPU_NORM_AVERAGE))
+                return fail(PVGPU_E_INVALID, "tnormal %zu: bad normal_map", i);
+            const pvgpu_blend_map& m = s.blend_maps[t.normal_map - 1];
+            for (uint32_t k = 0; k < m.entry_count; k++) {
+                const float ni = s.blend_entries[m.entry_first + k].colour[0];
+                if (!(ni >= 0.0f) || ni >= (float)s.tnormals.size() || ni != std::floor(ni))
+                    return fail(PVGPU_E_INVALID, "tnormal %zu: normal_map entry %u is not a tnormal index", i, k);
+            }
+        } else if (t.type == PVGPU_NORM_AVERAGE) return fail(PVGPU_E_INVALID, "tnormal %zu: average without normal_map", i);
+        if (t.pattern < 0 || t.pattern >= (int32_t)s.pigments.size() || !range_ok(t.slope_first, t.slope_count, s.slope_entries.size()))
+            return fail(PVGPU_E_INVALID, "tnormal %zu: bad pattern carrier / slope map range", i);
+        const pvgpu_pigment& c = s.pigments[t.pattern];
+        if (t.type == PVGPU_NORM_PATTERN && !t.normal_map && (c.pattern <= PVGPU_PAT_CHECKER || c.pattern == PVGPU_PAT_BRICK || c.pattern == PVGPU_PAT_HEXAGON))
+            return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: block patterns need a normal_map (outside the hot-path scope)", i);
+        for (uint32_t k = 0; k < c.warp_count; k++)
+            if (s.warps[c.warp_first + k].type != PVGPU_WARP_TRANSFORM && s.warps[c.warp_first + k].type != PVGPU_WARP_CLASSIC_TURBULENCE &&
+                s.warps[c.warp_first + k].type != PVGPU_WARP_TURBULENCE)
+                return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: warp unsupported", i);
     }
     {   // pigment_map nesting: bounded depth, no cycles
         std::vector<int> depth(s.pigments.size(), -1);
@@ -448,51 +505,6 @@ int validate_scene(Scene& s)
         for (size_t i = 0; i < s.lights.size(); i++)
             if ((s.lights[i].flags & PVGPU_LIGHT_MEDIA_ATTEN) && (s.lights[i].flags & PVGPU_LIGHT_MEDIA_INTERACT))
                 return fail(PVGPU_E_UNSUPPORTED, "light %zu: media_attenuation with fog (fog on shadow rays) is outside the hot-path scope", i);
-    for (size_t i = 0; i < s.tnormals.size(); i++) {
-        const pvgpu_tnormal& t = s.tnormals[i];
-        if (t.type < PVGPU_NORM_BUMPS || t.type > PVGPU_NORM_AVERAGE)
-            return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: type %u unsupported", i, t.type);
-        if (t.normal_map) {
-            if (t.normal_map > s.blend_maps.size() || !(s.blend_maps[t.normal_map - 1].blend_mode & PVGPU_BLEND_NORMAL_MAP) ||
-                (t.type != PVGPU_NORM_PATTERN && t.type != PVGPU_NORM_AVERAGE))
-                return fail(PVGPU_E_INVALID, "tnormal %zu: bad normal_map", i);
-            const pvgpu_blend_map& m = s.blend_maps[t.normal_map - 1];
-            for (uint32_t k = 0; k < m.entry_count; k++) {
-                const float ni = s.blend_entries[m.entry_first + k].colour[0];
-                if (!(ni >= 0.0f) || ni >= (float)s.tnormals.size() || ni != std::floor(ni))
-                    return fail(PVGPU_E_INVALID, "tnormal %zu: normal_map entry %u is not a tnormal index", i, k);
-            }
-        } else if (t.type == PVGPU_NORM_AVERAGE) return fail(PVGPU_E_INVALID, "tnormal %zu: average without normal_map", i);
-        if (t.pattern < 0 || t.pattern >= (int32_t)s.pigments.size() || !range_ok(t.slope_first, t.slope_count, s.slope_entries.size()))
-            return fail(PVGPU_E_INVALID, "tnormal %zu: bad pattern carrier / slope map range", i);
-        const pvgpu_pigment& c = s.pigments[t.pattern];
-        if (t.type == PVGPU_NORM_PATTERN && !t.normal_map && (c.pattern <= PVGPU_PAT_CHECKER || c.pattern == PVGPU_PAT_BRICK || c.pattern == PVGPU_PAT_HEXAGON))
-            return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: block patterns need a normal_map (outside the hot-path scope)", i);
-        for (uint32_t k = 0; k < c.warp_count; k++)
-            if (s.warps[c.warp_first + k].type != PVGPU_WARP_TRANSFORM && s.warps[c.warp_first + k].type != PVGPU_WARP_CLASSIC_TURBULENCE &&
-                s.warps[c.warp_first + k].type != PVGPU_WARP_TURBULENCE)
-                return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: warp unsupported", i);
-    }
-    for (size_t i = 0; i < s.blend_maps.size(); i++) {
-        const pvgpu_blend_map& m = s.blend_maps[i];
-        if (m.entry_count == 0 || !range_ok(m.entry_first, m.entry_count, s.blend_entries.size()))
-            return fail(PVGPU_E_INVALID, "blend map %zu: bad entry range", i);
-        if ((m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP | PVGPU_BLEND_NORMAL_MAP)) != 0)
-            return fail(PVGPU_E_UNSUPPORTED, "blend map %zu: blend_mode %d is outside the hot-path scope", i, m.blend_mode & ~(PVGPU_BLEND_PIGMENT_MAP | PVGPU_BLEND_TEXTURE_MAP | PVGPU_BLEND_NORMAL_MAP));
-        if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP)
-            for (uint32_t k = 0; k < m.entry_count; k++) {
-                const float pi = s.blend_entries[m.entry_first + k].colour[0];
-                if (!(pi >= 0.0f) || pi >= (float)s.pigments.size() || pi != std::floor(pi))
-                    return fail(PVGPU_E_INVALID, "blend map %zu: entry %u is not a pigment index", i, k);
-            }
-    }
-    for (size_t i = 0; i < s.warps.size(); i++) {
-        const pvgpu_warp& w = s.warps[i];
-        if (w.type < PVGPU_WARP_TRANSFORM || w.type > PVGPU_WARP_CLASSIC_TURBULENCE)
-            return fail(PVGPU_E_UNSUPPORTED, "warp %zu: type %u unsupported", i, w.type);
-        if (w.type == PVGPU_WARP_TRANSFORM && (w.transform < 0 || w.transform >= (int32_t)s.transforms.size()))
-            return fail(PVGPU_E_INVALID, "warp %zu: bad transform", i);
-    }
     for (size_t i = 0; i < s.finishes.size(); i++) {
         const pvgpu_finish& f = s.finishes[i];
         bool reflective = f.reflection_max[0] != 0 || f.reflection_max[1] != 0 || f.reflection_max[2] != 0 ||

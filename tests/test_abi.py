@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 import tempfile
 
 import pytest
@@ -96,3 +97,38 @@ def test_no_cpu_fallback(pvlib):
         s.finalize(0)
     assert e.value.code == A.E_NO_DEVICE
     assert "no CPU fallback" in str(e.value)
+
+
+FUZZ = r"""
+import os, sys, random, tempfile
+sys.path.insert(0, sys.argv[1])
+from povray_b200.scene import Scene
+from povray_b200._abi import PvgpuError
+random.seed(int(sys.argv[3]))
+data = bytearray(open(sys.argv[2], "rb").read())
+n_err = 0
+with tempfile.TemporaryDirectory() as d:
+    p = os.path.join(d, "f.pvs")
+    for trial in range(int(sys.argv[4])):
+        b = bytearray(data)
+        for _ in range(random.choice((1, 1, 2, 4))):
+            off = random.randrange(16, len(b) - 4) & ~3
+            b[off:off + 4] = random.choice((b"\xf0\xff\xff\x7f", b"\xff\xff\xff\xff", b"\x00\x00\x00\x80", bytes(random.randrange(256) for _ in range(4)), b"\x00\x00\xc0\x7f"))
+        open(p, "wb").write(b)
+        try:
+            Scene.load(p).finalize(0)
+        except PvgpuError:
+            n_err += 1
+print("ok", n_err)
+"""
+
+
+@pytest.mark.parametrize("name", ["texture_maps", "normal_maps", "pigment_maps", "clipped_bounded", "sky_fog", "blob_mix", "mesh24"])
+def test_malformed_tables_are_rejected_not_dereferenced(pvlib, name):
+    """Advisor finding of round 1: validate_scene used to index tables before validating them.  Corrupted scene files
+    (random 32-bit fields overwritten with huge / negative / NaN values) must end in an error code, never in a crash:
+    every table is range-checked before anything is read through it."""
+    if has_gpu():
+        pytest.skip("a corrupted scene that still validates would be uploaded; this check is for the host-side validation")
+    r = subprocess.run([sys.executable, "-c", FUZZ, ROOT, os.path.join(GOLDEN, name + ".pvs"), "1234", "150"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), f"validation crashed (rc {r.returncode}): {r.stderr[-1500:]}"

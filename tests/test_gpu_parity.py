@@ -322,6 +322,41 @@ def test_drop_in_adapter_antialiased_vs_unmodified_reference(pv, flags):
         assert (d8 <= 1.0).mean() >= PIXEL_FRAC, f"{(d8 > 1).sum()} pixels differ by more than one 8-bit level"
 
 
+QUALITY_SCENE = """#version 3.7;
+global_settings { assumed_gamma 1 }
+camera { location <0,2,-6> look_at <0,1,0> }
+light_source { <5,8,-5> rgb 1 }
+plane { y, 0 pigment { checker rgb 1, rgb 0.2 quick_color rgb <0.9,0.1,0.1> } }
+sphere { <0,1,0>, 1
+  texture { pigment { rgbf <0.2,0.8,0.3,0.5> } finish { reflection 0.3 } }
+  texture { pigment { bozo color_map { [0 rgbt <1,0,0,1>] [1 rgbt <0,0,1,0.2>] } } }
+  interior { ior 1.4 } }
+box { <-3,0,1>, <-2,1,2> pigment { rgb <0.1,0.2,0.9> quick_color rgb <1,1,0> } }
+cylinder { <2,0,0>, <2,1.5,0>, 0.5 pigment { granite quick_color rgb <0,1,1> } normal { bumps 0.5 } finish { phong 0.8 } }
+"""
+
+
+@pytest.mark.parametrize("q", ["+Q0", "+Q1", "+Q3", "+Q5", "+Q7", "+Q9"])
+def test_drop_in_adapter_quality_levels(pv, q):
+    """+Q0 .. +Q9 (QualityFlags, coretypes.h:558-585): ambientOnly (trace.cpp:848), quickColour (pigment.cpp:401) and the
+    shadow / refraction / reflection / normal switches travel through pvgpu_globals::quality_flags; the frame equals the
+    UNMODIFIED reference's at every level (advisor finding of round 1: two of the bits used to be ignored)."""
+    if not (os.path.exists(ADAPTER) and os.path.exists(REF_BINARY)):
+        pytest.skip("reference binaries not built (need the reference sources at build time)")
+    with tempfile.TemporaryDirectory() as d:
+        pov = os.path.join(d, "q.pov")
+        open(pov, "w").write(QUALITY_SCENE)
+        outs = {}
+        for name, binary in (("ref", REF_BINARY), ("gpu", ADAPTER)):
+            out = os.path.join(d, name + ".ppm")
+            r = subprocess.run([binary, "+I" + pov, "+O" + out, "+FP", "+W160", "+H90", "-D", "+WT2", "-GA", "-A", q],
+                               env=dict(os.environ, PVGPU_RENDER="gpu"), capture_output=True, text=True, timeout=600, cwd=d)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            outs[name] = read_ppm(out)
+        d8 = np.abs(outs["gpu"] - outs["ref"]).max(axis=2)
+        assert (d8 <= 1.0).mean() >= PIXEL_FRAC, f"{q}: {(d8 > 1).sum()} pixels differ by more than one 8-bit level (max {d8.max()})"
+
+
 @pytest.mark.parametrize("which,flags", [("cfg3", ["-A"]), ("cfg3", ["+A0.3", "+AM2", "+R3", "+J"]), ("cfg4", ["-A"]), ("cfg4", ["+A0.3", "+AM1", "+R3", "+J"])])
 def test_configs_3_and_4_full_scene_through_the_adapter(pv, which, flags):
     """BASELINE.json configs 3 (4096 CSG objects, refraction, AA) and 4 (2048 tori, half sturm, granite / bozo noise) at full
