@@ -17,8 +17,10 @@ CPP       := $(wildcard $(CSRC)/*.cpp)
 LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
 # ... and the shading-side kernels a third time with -DPV_FULL (normal perturbation, pigment maps, sky_sphere, fog, area lights)
 FULL_SRC  := k_shade k_shadow_filter
+# ... and the traversal kernels a fourth time with -DPV_CSG (quadric-class primitives + CSG only: no solver, blob, mesh code)
+CSG_SRC   := k_closest k_shadow_opaque k_shadow_filter
 OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
-             $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC))
+             $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC)) $(patsubst %,$(OBJDIR)/%_csg.o,$(CSG_SRC))
 HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) $(INCDIR)/pvgpu.h
 
 .PHONY: all oracle clean
@@ -35,6 +37,10 @@ $(OBJDIR)/%_lean.o: $(CSRC)/%.cu $(HDR)
 $(OBJDIR)/%_full.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -DPV_FULL -c $< -o $@
+
+$(OBJDIR)/%_csg.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -DPV_CSG -c $< -o $@
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDR)
 	@mkdir -p $(OBJDIR)

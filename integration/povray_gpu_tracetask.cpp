@@ -119,6 +119,7 @@ struct Flattener
     vector<pvgpu_tnormal> tnormals;
     vector<pvgpu_slope_entry> slope_entries;
     std::map<const void*, int32_t> object_ids, texture_ids, interior_ids;
+    std::map<const void*, uint32_t> mesh_tri_first;          // Mesh object -> first triangle of its copy in the triangle table (ray dumps)
     std::string error;
 
     void unsupported(const std::string& what) { if (error.empty()) error = what; }
@@ -448,6 +449,7 @@ struct Flattener
         me.vertex_first = (uint32_t)(vertices.size() / 3); me.vertex_count = D->Number_Of_Vertices;
         me.normal_first = (uint32_t)(normals.size() / 3);  me.normal_count = D->Number_Of_Normals;
         me.triangle_first = (uint32_t)triangles.size();    me.triangle_count = D->Number_Of_Triangles;
+        mesh_tri_first[m] = me.triangle_first;
         for (int i = 0; i < D->Number_Of_Vertices; i++) for (int k = 0; k < 3; k++) vertices.push_back(D->Vertices[i][k]);
         for (int i = 0; i < D->Number_Of_Normals; i++) for (int k = 0; k < 3; k++) normals.push_back(D->Normals[i][k]);
         for (int i = 0; i < D->Number_Of_Triangles; i++) {
@@ -686,6 +688,7 @@ struct GpuView
 {
     pvgpu_scene* scene = nullptr;
     std::map<const void*, int32_t> object_ids;
+    std::map<const void*, uint32_t> mesh_tri_first;
     bool finalized = false;
     std::string error;
     std::weak_ptr<BackendSceneData> owner;
@@ -812,6 +815,7 @@ std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
         fl.flatten_tree(sd->boundingSlabs, fl.nodes, [&](const BBOX_TREE* leaf) { return (uint32_t)fl.object_ids.at(reinterpret_cast<const void*>(leaf->Node)); });
     if (gv.error.empty()) gv.error = fl.error;
     gv.object_ids = fl.object_ids;
+    gv.mesh_tri_first = fl.mesh_tri_first;
 
     pvgpu_globals g{};
     g.max_trace_level = sd->parsedMaxTraceLevel;
@@ -1048,7 +1052,10 @@ void TraceTask::Run()
                             auto it = gv->object_ids.find(isect.Object);
                             rec.object = (it == gv->object_ids.end()) ? -2 : it->second;
                             rec.depth = isect.Depth;
-                            if (Mesh* m = dynamic_cast<Mesh*>(isect.Object)) rec.aux = (int32_t)(reinterpret_cast<const MESH_TRIANGLE*>(isect.Pointer) - m->Data->Triangles);
+                            if (Mesh* m = dynamic_cast<Mesh*>(isect.Object)) {      // index into the flattened scene's triangle table
+                                auto mf = gv->mesh_tri_first.find(isect.Object);
+                                rec.aux = (int32_t)(reinterpret_cast<const MESH_TRIANGLE*>(isect.Pointer) - m->Data->Triangles) + (int32_t)(mf == gv->mesh_tri_first.end() ? 0u : mf->second);
+                            }
                             else rec.aux = isect.i1;
                         }
                     }

@@ -9,11 +9,14 @@
 #   fast   : -O3 -march=x86-64-v3 (no -ffast-math)                 -> reported CPU baseline (optional)
 #   stock  : -O3 -ffast-math -march=x86-64-v3 + BUILD_X86 (the reference's AVX / AVX2-FMA3 noise, picked by cpuid at run time):
 #            the flags unix/configure.ac:750-763,799 selects, with -march=native replaced by x86-64-v3 because the binary is built
-#            in one container and timed on another host                   -> second reported CPU baseline
+#            in one container and timed on another host.  -ffast-math is applied to source/core (every TU the trace time is
+#            spent in); with gcc 13 the parser does not survive -ffinite-math-only ("Cannot parse input" on any scene), so the
+#            remaining TUs are built with -O3 -march=x86-64-v3 only        -> second reported CPU baseline
 #
 # usage: oracle/build_ref.sh [parity|fast|stock] [jobs]
 set -euo pipefail
 VARIANT=${1:-parity}
+CORE_OPT=""
 JOBS=${2:-$(nproc)}
 R=${POV_REFERENCE:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -23,7 +26,7 @@ mkdir -p "$B/obj"
 case $VARIANT in
   parity) OPT="-O2 -fno-fast-math -ffp-contract=off";;
   fast)   OPT="-O3 -march=x86-64-v3 -fno-fast-math";;
-  stock)  OPT="-O3 -ffast-math -march=x86-64-v3";;
+  stock)  OPT="-O3 -march=x86-64-v3"; CORE_OPT="-ffast-math";;
   *) echo "unknown variant"; exit 2;;
 esac
 cat > "$B/config.h" <<CFG
@@ -100,6 +103,7 @@ MK=$B/Makefile.gen
   while read -r f; do
     o=$B/obj/$(echo "${f#$R/}" | tr '/' '_' | sed 's/\.cpp$/.o/')
     extra=""
+    case $f in */source/core/*) extra="${CORE_OPT:-}";; esac
     case $f in */avx/*) extra="-mavx";; */avxfma4/*) extra="-mavx -mfma4";; */avx2fma3/*) extra="-mavx2 -mfma";; esac
     echo "$o: $f"; printf '\tg++ %s %s %s -c $< -o $@\n' "$CXXF" "$extra" "$INC"
     OBJS="$OBJS $o"

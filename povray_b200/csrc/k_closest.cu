@@ -6,7 +6,7 @@
 
 namespace pvgpu {
 
-#ifndef PV_LEAN
+#if !PV_SECONDARY_TU
 
 int sm_count()
 {
@@ -275,6 +275,22 @@ __global__ void k_clear_slots(SampleSource src, uint32_t first, uint32_t n, floa
     }
 }
 
+// Continuation records of wave `wave` (see Cont in pv_common.cuh): parent += w * Pow(slot colour, exponent), colour.h Pow = powf per channel.
+__global__ void k_resolve_conts(float4* accum, const Cont* __restrict__ conts, const Counters* cnt, uint32_t cont_cap, uint32_t cont_base, uint32_t wave)
+{
+    const uint32_t n = min(cnt->n_cont, cont_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Cont c = conts[i];
+        if (c.wave != wave) continue;
+        const float4 v = accum[cont_base + i];
+        float* a = reinterpret_cast<float*>(accum + c.parent);
+        const float r = c.w[0] * powf(v.x, c.exponent), g = c.w[1] * powf(v.y, c.exponent), b = c.w[2] * powf(v.z, c.exponent);
+        if (r != 0.0f) atomicAdd(a + 0, r);
+        if (g != 0.0f) atomicAdd(a + 1, g);
+        if (b != 0.0f) atomicAdd(a + 2, b);
+    }
+}
+
 #endif  // !PV_LEAN
 
 // Trace::TraceRay's entry (trace.cpp:142-160) + FindIntersection for every ray of the wave.
@@ -294,8 +310,9 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, u
     unsigned int max_level = 0;
     TravCount tc{ 0u, 0u };
     // all lanes of a warp (all threads of the block with PV_CTA_SYNC) stay in the loop and in the phase-voting traversal together
+    const uint32_t cs = chunk_size(n);
     uint32_t i;
-    while (next_chunk(&wc->cur_closest, n, i)) {
+    while (next_chunk(&wc->cur_closest, n, cs, i)) {
         bool alive = i < n;
         V3 o = mk(0.0, 0.0, 0.0), d = mk(0.0, 0.0, 1.0);
         uint32_t flags = 0;
@@ -350,7 +367,7 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, u
     }
 }
 
-#ifndef PV_LEAN
+#if !PV_SECONDARY_TU
 // ray-level harness: explicit rays under primary-ray conditions (Trace::FindIntersection(Intersection&, const Ray&), trace.h:255)
 __global__ void k_probe_rays(const double* org_dir, uint32_t n, PRay* out)
 {
@@ -395,6 +412,10 @@ void launch_wave_init(WaveCounts* ring, uint32_t n_slots, uint32_t n0, cudaStrea
 {
     k_wave_init<<<1, 256, 0, st>>>(ring, n_slots, n0);
 }
+void launch_resolve_conts(float4* accum, const Cont* conts, const Counters* cnt, uint32_t cont_cap, uint32_t cont_base, uint32_t wave, cudaStream_t st)
+{
+    k_resolve_conts<<<grid_for(cont_cap, 256, 8), 256, 0, st>>>(accum, conts, cnt, cont_cap, cont_base, wave);
+}
 void launch_clear_slots(const SampleSource& src, uint32_t first, uint32_t n, float4* accum, cudaStream_t st)
 {
     k_clear_slots<<<grid_for(n, 256, 8), 256, 0, st>>>(src, first, n, accum);
@@ -407,9 +428,9 @@ void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, u
 #endif  // !PV_LEAN
 void PV_VARIANT(launch_closest)(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st)
 {
-    PV_VARIANT(k_closest)<<<grid_for(n_bound, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, wc, cap, hits, cnt);
+    PV_VARIANT(k_closest)<<<grid_for(trav_grid_bound(n_bound), PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, wc, cap, hits, cnt);
 }
-#ifndef PV_LEAN
+#if !PV_SECONDARY_TU
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st)
 {
     k_probe_rays<<<grid_for(n, 256, 8), 256, 0, st>>>(org_dir, n, out);

@@ -29,8 +29,9 @@ k_shadow_area(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t
     TravCount tc{ 0u, 0u };
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     float* const grid = grid_mem + tid;                 // lightGrid of this thread: cell c, channel k at grid[(3 * c + k) * n_threads]
+    const uint32_t cs = chunk_size(n);
     uint32_t i;
-    while (next_chunk(&wc->cur_area, n, i)) {
+    while (next_chunk(&wc->cur_area, n, cs, i)) {
         const SRay s = rays[(i < n) ? i : 0u];
         const pvgpu_light& Lt = sc.lights[s.light];
         bool active = (i < n) && (Lt.flags & PVGPU_LIGHT_AREA);
@@ -153,7 +154,7 @@ uint32_t area_threads() { return (uint32_t)(sm_count() * PV_TRAV_MIN_BLOCKS * PV
 
 void launch_shadow_area(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st)
 {
-    const int blocks = grid_for(n_bound, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
+    const int blocks = grid_for(trav_grid_bound(n_bound), PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
     if (sc.all_opaque) k_shadow_area<true><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
     else k_shadow_area<false><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
 }

@@ -1,11 +1,12 @@
 // Shadow-ray kernel for scenes with transparent shadow casters: closest-hit loop towards the light, the light
 // colour is filtered through every transparent blocker (ComputeShadowColour, trace.cpp:2274-2439).
 #include "pv_shadow.cuh"
+#include <algorithm>
 
 namespace pvgpu {
 
 __global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
-PV_VARIANT(k_shadow_filter)(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t cap, const PRay* __restrict__ wave, float4* accum, Counters* cnt)
+PV_VARIANT(k_shadow_filter)(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t cap, uint32_t max_chunks, const PRay* __restrict__ wave, float4* accum, Counters* cnt)
 {
 #if PV_SSTACK > 0
     __shared__ uint2 stack_sh[PV_SSTACK * PV_TRAV_BLOCK];
@@ -19,9 +20,12 @@ PV_VARIANT(k_shadow_filter)(DScene sc, const SRay* __restrict__ rays, WaveCounts
     const uint32_t n = min(wc->n_shadow, cap);
     unsigned long long tests = 0;
     TravCount tc{ 0u, 0u };
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&cnt->shadow_rays, (unsigned long long)n);
+    // (max_chunks: a warp leaves after that many chunks - see the launcher; 0 = stay until the queue is exhausted)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n && atomicExch(&wc->counted, 1u) == 0u) atomicAdd(&cnt->shadow_rays, (unsigned long long)n);
+    const uint32_t cs = chunk_size(n);
     uint32_t i;
-    while (next_chunk(&wc->cur_shadow, n, i)) {
+    uint32_t taken = 0;
+    while ((max_chunks == 0u || taken++ < max_chunks) && next_chunk(&wc->cur_shadow, n, cs, i)) {
         bool alive = i < n;
         const SRay s = rays[alive ? i : 0u];
 #if PV_HEAVY
@@ -44,9 +48,18 @@ PV_VARIANT(k_shadow_filter)(DScene sc, const SRay* __restrict__ rays, WaveCounts
     }
 }
 
+// The shadow kernels run on a low-priority stream next to k_closest / k_shade of the following wave, which are on the frame's
+// critical path.  A small wave does not spread over the whole machine: the grid is sized so that every warp has
+// PV_SHADOW_CHUNKS_PER_WARP chunks to work through, which leaves block slots for the critical kernels; large waves fill the machine
+// as before.  (Tried and rejected: rounds of short-lived blocks, which would let the block scheduler's stream priorities arbitrate,
+// lose more in the drain of every round - config 2: 10.0 -> 17.2 ms.)
+#ifndef PV_SHADOW_CHUNKS_PER_WARP
+#define PV_SHADOW_CHUNKS_PER_WARP 2
+#endif
 void PV_VARIANT(launch_shadow_filter)(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st)
 {
-    PV_VARIANT(k_shadow_filter)<<<grid_for(n_bound, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, wave, accum, cnt);
+    const int grid = grid_for(n_bound / PV_SHADOW_CHUNKS_PER_WARP + 1u, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
+    PV_VARIANT(k_shadow_filter)<<<grid, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, 0u, wave, accum, cnt);
 }
 
 }  // namespace pvgpu

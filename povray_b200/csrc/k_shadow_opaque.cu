@@ -1,10 +1,11 @@
 // Shadow-ray kernel for scenes in which every shadow caster is opaque: any-hit search, no filtering.
 #include "pv_shadow.cuh"
+#include <algorithm>
 
 namespace pvgpu {
 
 __global__ void __launch_bounds__(PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS)
-PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t cap, float4* accum, Counters* cnt)
+PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t cap, uint32_t max_chunks, float4* accum, Counters* cnt)
 {
 #if PV_SSTACK > 0
     __shared__ uint2 stack_sh[PV_SSTACK * PV_TRAV_BLOCK];
@@ -18,9 +19,12 @@ PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, WaveCounts
     const uint32_t n = min(wc->n_shadow, cap);
     unsigned long long tests = 0;
     TravCount tc{ 0u, 0u };
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&cnt->shadow_rays, (unsigned long long)n);
+    // (max_chunks: a warp leaves after that many chunks - see the launcher; 0 = stay until the queue is exhausted)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n && atomicExch(&wc->counted, 1u) == 0u) atomicAdd(&cnt->shadow_rays, (unsigned long long)n);
+    const uint32_t cs = chunk_size(n);
     uint32_t i;
-    while (next_chunk(&wc->cur_shadow, n, i)) {
+    uint32_t taken = 0;
+    while ((max_chunks == 0u || taken++ < max_chunks) && next_chunk(&wc->cur_shadow, n, cs, i)) {
         bool alive = i < n;
         const SRay* sp = rays + (alive ? i : 0u);
 #if PV_HEAVY
@@ -45,9 +49,14 @@ PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, WaveCounts
     }
 }
 
+#ifndef PV_SHADOW_CHUNKS_PER_WARP
+#define PV_SHADOW_CHUNKS_PER_WARP 2
+#endif
+// grid sized for PV_SHADOW_CHUNKS_PER_WARP chunks per warp: see launch_shadow_filter (k_shadow_filter.cu)
 void PV_VARIANT(launch_shadow_opaque)(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st)
 {
-    PV_VARIANT(k_shadow_opaque)<<<grid_for(n_bound, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, accum, cnt);
+    const int grid = grid_for(n_bound / PV_SHADOW_CHUNKS_PER_WARP + 1u, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
+    PV_VARIANT(k_shadow_opaque)<<<grid, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, 0u, accum, cnt);
 }
 
 }  // namespace pvgpu

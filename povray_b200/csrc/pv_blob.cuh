@@ -131,11 +131,15 @@ __device__ inline void blob_insert_hit(uint32_t elem, uint32_t type, double t0, 
     }
 }
 
-// Blob::All_Intersections (blob.cpp:239-610) for a blob that is not a CSG child (the search stops after the first
-// interval that produced a hit).  Returns false when a per-ray capacity was exceeded.
-static __device__ __noinline__ bool blob_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h)
+// Blob::All_Intersections (blob.cpp:239-610).  A blob that is not a CSG child stops after the first interval that produced a
+// hit (blob.cpp:596-599: every further intersection is further away).  A CSG child has to report them all: the caller passes
+// `resume` (start with 0) and calls again while it comes back >= 0 - every call reports the hits of the next interval that has
+// any (at most four, the roots of one quartic).  Returns false when a per-ray capacity was exceeded.
+static __device__ __noinline__ bool blob_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, int* resume = nullptr)
 {
     h.n = 0;
+    const uint32_t start = resume ? (uint32_t)*resume : 0u;
+    if (resume) *resume = -1;
     const pvgpu_blob& bl = sc.blobs[ob.mesh];
     const pvgpu_blob_element* el = sc.blob_elements + bl.element_first;
     V3 P = o, D = d;
@@ -246,6 +250,7 @@ static __device__ __noinline__ bool blob_hits(const DScene& sc, const pvgpu_obje
         }
         // next bound (almost) at the same place: add / subtract it first (blob.cpp:497-500)
         if ((i + 1 < cnt) && (fabs(iv[i].bound - iv[i + 1].bound) < PV_EPSILON)) continue;
+        if (i < start) continue;          // intervals already reported to the caller (their coefficients are accounted for above)
         // move the interval to [0, 1] and test the convex hull of the Bezier form (blob.cpp:507-537)
         const double l = iv[i].bound, w = iv[i + 1].bound - l;
         double nc[5], dk[5];
@@ -273,7 +278,10 @@ static __device__ __noinline__ bool blob_hits(const DScene& sc, const pvgpu_obje
                 }
             }
         }
-        if (found) break;       // not a CSG child: every further intersection is further away (blob.cpp:596-599)
+        if (found) {
+            if (resume) *resume = (int)i + 1;       // CSG child: the caller comes back for the intervals behind this one
+            break;                                  // not a CSG child: every further intersection is further away (blob.cpp:596-599)
+        }
     }
     return true;
 }

@@ -52,6 +52,14 @@ namespace pvgpu {
 #define PV_HEAVY 0
 #define PV_FULL_MATERIALS 0
 #define PV_VARIANT(name) name##_lean
+#elif defined(PV_CSG)
+// traversal kernels for scenes made of spheres, boxes, planes, quadrics, cones / cylinders and discs, alone or in CSG
+// (BASELINE config 3): no polynomial solver, blob, mesh or polygon code
+#define PV_HEAVY 1
+#define PV_FULL_MATERIALS 0
+#define PV_VARIANT(name) name##_csg
+#define PV_TYPES ((1u << PVGPU_OBJ_SPHERE) | (1u << PVGPU_OBJ_BOX) | (1u << PVGPU_OBJ_PLANE) | (1u << PVGPU_OBJ_QUADRIC) | (1u << PVGPU_OBJ_CONE) | \
+                  (1u << PVGPU_OBJ_DISC) | (1u << PVGPU_OBJ_CSG_UNION) | (1u << PVGPU_OBJ_CSG_INTERSECTION) | (1u << PVGPU_OBJ_CSG_MERGE))
 #elif defined(PV_FULL)
 #define PV_HEAVY 1
 #define PV_FULL_MATERIALS 1
@@ -60,6 +68,28 @@ namespace pvgpu {
 #define PV_HEAVY 1
 #define PV_FULL_MATERIALS 0
 #define PV_VARIANT(name) name
+#endif
+
+// Primitive kinds a kernel variant is compiled for (bit n = PVGPU_OBJ_* value n).  The heavy variants' hot path is bound by
+// instruction fetch, so a variant that serves a class of scenes carries only that class's code: tests on the mask are constant
+// folded and the code of the other primitives never reaches the kernel.
+#ifndef PV_TYPES
+#if PV_HEAVY
+#define PV_TYPES 0xFFFFu
+#else
+#define PV_TYPES ((1u << PVGPU_OBJ_SPHERE) | (1u << PVGPU_OBJ_BOX) | (1u << PVGPU_OBJ_PLANE) | (1u << PVGPU_OBJ_MESH))
+#endif
+#endif
+#define PV_HAS(type) ((PV_TYPES & (1u << (type))) != 0u)
+#ifndef PV_CLIPBOUND
+#define PV_CLIPBOUND PV_HEAVY          // clipped_by / bounded_by lists are served
+#endif
+
+// k_closest.cu also holds the kernels that exist once (camera rays, probes, queue bookkeeping): compiled in its default variant only
+#if defined(PV_LEAN) || defined(PV_CSG)
+#define PV_SECONDARY_TU 1
+#else
+#define PV_SECONDARY_TU 0
 #endif
 
 struct V3 { double x, y, z; };
@@ -220,6 +250,20 @@ struct Counters {
     unsigned long long prim_tests[2]; // top-level primitive tests + mesh triangle tests: [0] k_closest, [1] k_shadow_*
     unsigned int max_level;
     unsigned int overflow;
+    unsigned int n_cont;              // continuation records taken in this batch (reflection exponent != 1)
+    unsigned int pad;
+};
+
+// A reflected ray whose colour enters its parent NON-linearly: resultColour += reflec * Pow(rflCol, Reflect_Exp) (trace.cpp:1166-1168).
+// Such a ray gets an accumulator slot of its own (behind the slots of the call), its whole subtree adds into that slot, and when
+// the batch's waves are done the records are resolved from the last wave back to the first: the parent's slot receives
+// w * pow(slot colour, exponent).  A continuation created in wave k has a parent from an earlier wave, so one pass per wave,
+// latest first, sees every slot complete before it is read.
+struct Cont {
+    uint32_t parent;             // accumulator slot of the ray that was reflected
+    uint32_t wave;               // wave whose k_shade created the record
+    float    w[3];               // the parent's path weight x the layer's reflectivity
+    float    exponent;           // FINISH::Reflect_Exp
 };
 
 // Per-wave hand-over between the kernels of one batch, in a device-resident ring indexed by the wave number.  The ray counts
@@ -232,7 +276,8 @@ struct WaveCounts {
     unsigned int cur_closest;     // next unclaimed ray of k_closest
     unsigned int cur_shadow;      // next unclaimed shadow ray of k_shadow_*
     unsigned int cur_area;        // ... of k_shadow_area
-    unsigned int pad[3];
+    unsigned int counted;         // the wave's shadow rays have been added to Counters::shadow_rays (the queue is worked off by several launches)
+    unsigned int pad[2];
 };
 static_assert(sizeof(WaveCounts) == 32, "WaveCounts must be 32 bytes");
 

@@ -13,6 +13,8 @@ struct WaveCtx {
     unsigned int* n_next;     // ring[wave + 1].n_rays
     unsigned int* n_shadow;   // ring[wave].n_shadow
     uint32_t  cur_cap, next_cap, shadow_cap;
+    Cont*     conts;          // continuation records (scenes with a reflection exponent != 1), else nullptr
+    uint32_t  cont_cap, cont_base, wave;     // capacity, accumulator slot of record 0, number of the current wave
 };
 
 // Where the samples of a batch come from.
@@ -47,6 +49,8 @@ struct AALayout {
 
 int  sm_count();
 int  grid_for(uint32_t n, int block, int per_sm);
+// grid bound of a traversal kernel: small waves are spread over the warps in chunks of down to 8 rays (chunk_size, pv_traverse.cuh)
+inline uint32_t trav_grid_bound(uint32_t n_bound) { return n_bound > 0x3FFFFFFFu ? 0xFFFFFFFFu : n_bound * 4u; }
 
 void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cudaStream_t st);
 void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,
@@ -63,11 +67,16 @@ void launch_closest_lean(const DScene& sc, const PRay* cur, WaveCounts* wc, uint
 void launch_shade_lean(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st);
 void launch_shadow_opaque_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_shadow_filter_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
+// quadric-class + CSG variants of the traversal kernels (-DPV_CSG)
+void launch_closest_csg(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st);
+void launch_shadow_opaque_csg(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_shadow_filter_csg(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
 uint32_t area_threads();
 void launch_shadow_area(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st);
 // full-material variants (normal perturbation, pigment maps, sky_sphere, fog, area lights; -DPV_FULL)
 void launch_shade_full(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st);
 void launch_shadow_filter_full(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_resolve_conts(float4* accum, const Cont* conts, const Counters* cnt, uint32_t cont_cap, uint32_t cont_base, uint32_t wave, cudaStream_t st);
 void launch_clear_slots(const SampleSource& src, uint32_t first, uint32_t n, float4* accum, cudaStream_t st);
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st);
 void launch_probe_results(const HitRec* hits, uint32_t n, uint32_t* obj, double* depth, uint32_t* aux, cudaStream_t st);

@@ -850,19 +850,19 @@ __device__ inline V3 mesh_normal(const DScene& sc, const pvgpu_object& ob, const
 __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, const Hit& hit)
 {
     switch (ob.type) {
-        case PVGPU_OBJ_SPHERE:  return sphere_normal(sc, ob, hit.ip);
-        case PVGPU_OBJ_BOX:     return box_normal(sc, ob, hit.aux);
-        case PVGPU_OBJ_PLANE:   return plane_normal(sc, ob);
-        case PVGPU_OBJ_MESH:    return mesh_normal(sc, ob, hit);
+        case PVGPU_OBJ_SPHERE: if (PV_HAS(PVGPU_OBJ_SPHERE)) return sphere_normal(sc, ob, hit.ip); break;
+        case PVGPU_OBJ_BOX: if (PV_HAS(PVGPU_OBJ_BOX)) return box_normal(sc, ob, hit.aux); break;
+        case PVGPU_OBJ_PLANE: if (PV_HAS(PVGPU_OBJ_PLANE)) return plane_normal(sc, ob); break;
+        case PVGPU_OBJ_MESH: if (PV_HAS(PVGPU_OBJ_MESH)) return mesh_normal(sc, ob, hit); break;
 #if PV_HEAVY
-        case PVGPU_OBJ_QUADRIC: return quadric_normal(ob, hit.ip);
-        case PVGPU_OBJ_TORUS:   return torus_normal(sc, ob, hit.ip, hit.aux);
-        case PVGPU_OBJ_BLOB:    return blob_normal(sc, ob, hit.ip);
-        case PVGPU_OBJ_CONE:    return cone_normal(sc, ob, hit.ip, hit.aux);
-        case PVGPU_OBJ_DISC:    return ld3(ob.p);       // Disc::Normal (disc.cpp:226-229)
-        case PVGPU_OBJ_TRIANGLE: return triangle_normal(sc, ob, hit.ip);
-        case PVGPU_OBJ_POLYGON: return ld3(ob.p);       // Polygon::Normal (polygon.cpp:308-311)
-        case PVGPU_OBJ_POLY:    return poly_normal(sc, ob, hit.ip);
+        case PVGPU_OBJ_QUADRIC: if (PV_HAS(PVGPU_OBJ_QUADRIC)) return quadric_normal(ob, hit.ip); break;
+        case PVGPU_OBJ_TORUS: if (PV_HAS(PVGPU_OBJ_TORUS)) return torus_normal(sc, ob, hit.ip, hit.aux); break;
+        case PVGPU_OBJ_BLOB: if (PV_HAS(PVGPU_OBJ_BLOB)) return blob_normal(sc, ob, hit.ip); break;
+        case PVGPU_OBJ_CONE: if (PV_HAS(PVGPU_OBJ_CONE)) return cone_normal(sc, ob, hit.ip, hit.aux); break;
+        case PVGPU_OBJ_DISC: if (PV_HAS(PVGPU_OBJ_DISC)) return ld3(ob.p); break;       // Disc::Normal (disc.cpp:226-229)
+        case PVGPU_OBJ_TRIANGLE: if (PV_HAS(PVGPU_OBJ_TRIANGLE)) return triangle_normal(sc, ob, hit.ip); break;
+        case PVGPU_OBJ_POLYGON: if (PV_HAS(PVGPU_OBJ_POLYGON)) return ld3(ob.p); break;       // Polygon::Normal (polygon.cpp:308-311)
+        case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) return poly_normal(sc, ob, hit.ip); break;
 #endif
     }
     return mk(0.0, 1.0, 0.0);
@@ -1406,6 +1406,19 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
             rr.adc = (float)L.rweight;
             rr.w[0] = ray.w[0] * L.refl[0]; rr.w[1] = ray.w[1] * L.refl[1]; rr.w[2] = ray.w[2] * L.refl[2];
 #if PV_FULL_MATERIALS
+            const float rexp = sc.finishes[L.finish].reflect_exp;
+            if (rexp != 1.0f && ctx.conts != nullptr) {
+                // resultColour += reflec * Pow(rflCol, Reflect_Exp) (trace.cpp:1166-1168): the reflected subtree is gathered in a slot
+                // of its own and enters this ray's slot through a continuation record when the batch's waves are done
+                const unsigned int ci = atomicAdd(&ctx.cnt->n_cont, 1u);
+                if (ci >= ctx.cont_cap) { atomicOr(&ctx.cnt->overflow, 8u); continue; }
+                Cont cr;
+                cr.parent = ray.sample; cr.wave = ctx.wave; cr.exponent = rexp;
+                cr.w[0] = rr.w[0]; cr.w[1] = rr.w[1]; cr.w[2] = rr.w[2];
+                ctx.conts[ci] = cr;
+                rr.sample = ctx.cont_base + ci;
+                rr.w[0] = rr.w[1] = rr.w[2] = 1.0f;
+            }
             if (sc.finishes[L.finish].irid > 0.0f) irid_colour(sc, sc.finishes[L.finish], rd, dir, lay_normal, ipoint, rr.w);    // trace.cpp:1306-1314
 #endif
             rr.wt = 0.0f;

@@ -229,17 +229,17 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
 #endif
 {
     switch (ob.type) {
-        case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
-        case PVGPU_OBJ_BOX:     return box_inside(sc, ob, p);
-        case PVGPU_OBJ_PLANE:   return plane_inside(sc, ob, p);
-        case PVGPU_OBJ_MESH:    return mesh_inside(sc, ob, p, stack, sp0);
+        case PVGPU_OBJ_SPHERE: if (PV_HAS(PVGPU_OBJ_SPHERE)) return sphere_inside(sc, ob, p); break;
+        case PVGPU_OBJ_BOX: if (PV_HAS(PVGPU_OBJ_BOX)) return box_inside(sc, ob, p); break;
+        case PVGPU_OBJ_PLANE: if (PV_HAS(PVGPU_OBJ_PLANE)) return plane_inside(sc, ob, p); break;
+        case PVGPU_OBJ_MESH: if (PV_HAS(PVGPU_OBJ_MESH)) return mesh_inside(sc, ob, p, stack, sp0); break;
 #if PV_HEAVY
-        case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
-        case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
-        case PVGPU_OBJ_BLOB:    return blob_inside(sc, ob, p);
-        case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
-        case PVGPU_OBJ_DISC:    return disc_inside(sc, ob, p);
-        case PVGPU_OBJ_POLY:    return poly_inside(sc, ob, p);
+        case PVGPU_OBJ_QUADRIC: if (PV_HAS(PVGPU_OBJ_QUADRIC)) return quadric_inside(ob, p); break;
+        case PVGPU_OBJ_TORUS: if (PV_HAS(PVGPU_OBJ_TORUS)) return torus_inside(sc, ob, p); break;
+        case PVGPU_OBJ_BLOB: if (PV_HAS(PVGPU_OBJ_BLOB)) return blob_inside(sc, ob, p); break;
+        case PVGPU_OBJ_CONE: if (PV_HAS(PVGPU_OBJ_CONE)) return cone_inside(sc, ob, p); break;
+        case PVGPU_OBJ_DISC: if (PV_HAS(PVGPU_OBJ_DISC)) return disc_inside(sc, ob, p); break;
+        case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) return poly_inside(sc, ob, p); break;
 #endif
     }
     return false;
@@ -249,15 +249,15 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
 __device__ __forceinline__ bool simple_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
 {
     switch (ob.type) {
-        case PVGPU_OBJ_SPHERE:  return sphere_inside(sc, ob, p);
-        case PVGPU_OBJ_BOX:     return box_inside(sc, ob, p);
-        case PVGPU_OBJ_PLANE:   return plane_inside(sc, ob, p);
+        case PVGPU_OBJ_SPHERE: if (PV_HAS(PVGPU_OBJ_SPHERE)) return sphere_inside(sc, ob, p); break;
+        case PVGPU_OBJ_BOX: if (PV_HAS(PVGPU_OBJ_BOX)) return box_inside(sc, ob, p); break;
+        case PVGPU_OBJ_PLANE: if (PV_HAS(PVGPU_OBJ_PLANE)) return plane_inside(sc, ob, p); break;
 #if PV_HEAVY
-        case PVGPU_OBJ_QUADRIC: return quadric_inside(ob, p);
-        case PVGPU_OBJ_TORUS:   return torus_inside(sc, ob, p);
-        case PVGPU_OBJ_CONE:    return cone_inside(sc, ob, p);
-        case PVGPU_OBJ_DISC:    return disc_inside(sc, ob, p);
-        case PVGPU_OBJ_POLY:    return poly_inside(sc, ob, p);
+        case PVGPU_OBJ_QUADRIC: if (PV_HAS(PVGPU_OBJ_QUADRIC)) return quadric_inside(ob, p); break;
+        case PVGPU_OBJ_TORUS: if (PV_HAS(PVGPU_OBJ_TORUS)) return torus_inside(sc, ob, p); break;
+        case PVGPU_OBJ_CONE: if (PV_HAS(PVGPU_OBJ_CONE)) return cone_inside(sc, ob, p); break;
+        case PVGPU_OBJ_DISC: if (PV_HAS(PVGPU_OBJ_DISC)) return disc_inside(sc, ob, p); break;
+        case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) return poly_inside(sc, ob, p); break;
 #endif
     }
     return false;
@@ -301,7 +301,7 @@ static __device__ __noinline__ bool inside_object(const DScene& sc, uint32_t roo
 // Point_In_Clip (object.cpp:430-443)
 __device__ inline bool point_in_clip(const DScene& sc, const pvgpu_object& o, const V3& p, TStack stack, int sp0)
 {
-#if PV_HEAVY
+#if PV_CLIPBOUND
     for (uint32_t i = 0; i < o.clip_count; i++)
         if (!inside_object(sc, sc.index_list[o.clip_first + i], p, stack, sp0)) return false;
 #endif
@@ -335,25 +335,26 @@ __device__ __forceinline__ void consider(HitAcc& acc, double depth, const V3& ip
 // (one out-of-line copy in the full variant: the switch carries every primitive incl. the quartic solver, and it is reached from
 //  object_find and from both CSG paths - inlined copies made the heavy kernels instruction-fetch bound)
 #if PV_HEAVY
-static __device__ __noinline__ void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr)
+static __device__ __noinline__ void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr, int* resume = nullptr)
 #else
-__device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr)
+__device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, unsigned int* overflow = nullptr, int* resume = nullptr)
 #endif
 {
+    h.n = 0;
     switch (ob.type) {
 #if PV_HEAVY
-        case PVGPU_OBJ_BLOB:    if (!blob_hits(sc, ob, o, d, h) && overflow) atomicOr(overflow, 32u); break;
-        case PVGPU_OBJ_QUADRIC: quadric_hits(ob, o, d, h); break;
-        case PVGPU_OBJ_TORUS:   torus_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_CONE:    cone_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_DISC:    disc_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_TRIANGLE: triangle_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_POLYGON: polygon_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_POLY:    poly_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_BLOB: if (PV_HAS(PVGPU_OBJ_BLOB)) { if (!blob_hits(sc, ob, o, d, h, resume) && overflow) atomicOr(overflow, 32u); } break;
+        case PVGPU_OBJ_QUADRIC: if (PV_HAS(PVGPU_OBJ_QUADRIC)) { quadric_hits(ob, o, d, h); } break;
+        case PVGPU_OBJ_TORUS: if (PV_HAS(PVGPU_OBJ_TORUS)) { torus_hits(sc, ob, o, d, h); } break;
+        case PVGPU_OBJ_CONE: if (PV_HAS(PVGPU_OBJ_CONE)) { cone_hits(sc, ob, o, d, h); } break;
+        case PVGPU_OBJ_DISC: if (PV_HAS(PVGPU_OBJ_DISC)) { disc_hits(sc, ob, o, d, h); } break;
+        case PVGPU_OBJ_TRIANGLE: if (PV_HAS(PVGPU_OBJ_TRIANGLE)) { triangle_hits(sc, ob, o, d, h); } break;
+        case PVGPU_OBJ_POLYGON: if (PV_HAS(PVGPU_OBJ_POLYGON)) { polygon_hits(sc, ob, o, d, h); } break;
+        case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) { poly_hits(sc, ob, o, d, h); } break;
 #endif
-        case PVGPU_OBJ_SPHERE:  sphere_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_BOX:     box_hits(sc, ob, o, d, h); break;
-        case PVGPU_OBJ_PLANE:   plane_hits(sc, ob, o, d, h); break;
+        case PVGPU_OBJ_SPHERE: if (PV_HAS(PVGPU_OBJ_SPHERE)) { sphere_hits(sc, ob, o, d, h); } break;
+        case PVGPU_OBJ_BOX: if (PV_HAS(PVGPU_OBJ_BOX)) { box_hits(sc, ob, o, d, h); } break;
+        case PVGPU_OBJ_PLANE: if (PV_HAS(PVGPU_OBJ_PLANE)) { plane_hits(sc, ob, o, d, h); } break;
         default: h.n = 0; break;
     }
 }
@@ -373,9 +374,11 @@ __device__ __forceinline__ bool test_ray_flags(uint32_t oflags, uint32_t rflags,
 // Mesh::intersect_bbox_tree + test_hit (mesh.cpp:1452-1528, 1208-1243) with a LIFO stack.
 //   ANY_HIT (shadow rays, every caster opaque): return at the first accepted hit inside (SHADOW_TOLERANCE, any_limit) -
 //   the closest hit the reference would find is then inside the same window, i.e. the light is blocked either way.
-template <bool ANY_HIT>
-__device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvgpu_object& ob, const V3& o, const V3& d,
-                                 HitAcc& acc, int32_t csg, TStack stack, int sp0, unsigned int* overflow, double any_limit = 0.0)
+//   accept(depth, point, triangle, stack top): takes a triangle hit - by default Point_In_Clip + the selection rule of consider(); a mesh
+//   that is a CSG child passes the CSG filter instead (csg_hits).  Entries are pruned against acc.closest, which only accepted hits move.
+template <bool ANY_HIT, class Accept>
+__device__ inline void mesh_hits_f(const DScene& sc, uint32_t obj_index, const pvgpu_object& ob, const V3& o, const V3& d,
+                                   HitAcc& acc, TStack stack, int sp0, unsigned int* overflow, double any_limit, Accept accept)
 {
     const DMesh& me = sc.meshes[ob.mesh];
     V3 mo = o, md = d;
@@ -393,7 +396,7 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
             if (tri_intersect(sc.dtris[me.tri_first + i], mo, md, t)) {
                 double wd = t / len;
                 V3 ip = evaluate(o, d, wd);
-                if (ob.clip_count == 0 || point_in_clip(sc, ob, ip, stack, sp0)) consider(acc, wd, ip, obj_index, me.tri_first + i, csg);
+                accept(wd, ip, me.tri_first + i, sp0);
             }
         }
         return;
@@ -428,10 +431,19 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
         if (tri_intersect(sc.dtris[ti], mo, md, t)) {
             double wd = t / len;
             V3 ip = evaluate(o, d, wd);
-            if (ob.clip_count == 0 || point_in_clip(sc, ob, ip, stack, sp)) consider(acc, wd, ip, obj_index, ti, csg);
+            accept(wd, ip, ti, sp);
             if (any_ok && acc.found && acc.closest > PV_SHADOW_TOLERANCE && acc.closest < any_limit) return;
         }
     }
+}
+
+template <bool ANY_HIT>
+__device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvgpu_object& ob, const V3& o, const V3& d,
+                                 HitAcc& acc, int32_t csg, TStack stack, int sp0, unsigned int* overflow, double any_limit = 0.0)
+{
+    mesh_hits_f<ANY_HIT>(sc, obj_index, ob, o, d, acc, stack, sp0, overflow, any_limit, [&](double wd, const V3& ip, uint32_t ti, int sp_now) {
+        if (ob.clip_count == 0 || point_in_clip(sc, ob, ip, stack, sp_now)) consider(acc, wd, ip, obj_index, ti, csg);
+    });
 }
 
 // Warp-synchronous form of mesh_hits for the hot path.  ALL 32 lanes of the warp call it together; lanes with
@@ -456,25 +468,42 @@ __device__ __forceinline__ bool vote_any(bool p)   { return __syncthreads_or(p ?
 __device__ __forceinline__ int  vote_count(bool p) { return __popc(__ballot_sync(PV_FULL_MASK, p)); }
 __device__ __forceinline__ bool vote_any(bool p)   { return __any_sync(PV_FULL_MASK, p); }
 #endif
-// The traversal kernels take their rays in chunks from a cursor in the wave's WaveCounts record: one chunk per warp (32 rays)
-// or, with block-wide phase votes, one per thread block.  Rays of a chunk are neighbours in the queue (an 8 x 4 pixel block of
-// the frame and what it spawned), whichever warp picks the chunk up; a warp whose rays end early simply fetches the next chunk
-// instead of idling until the slowest warp of a static partition is done.  Returns false when the wave is exhausted.
-__device__ __forceinline__ bool next_chunk(unsigned int* cursor, uint32_t n, uint32_t& i)
+// The traversal kernels take their rays in chunks from a cursor in the wave's WaveCounts record: one chunk per warp or, with
+// block-wide phase votes, one per thread block.  Rays of a chunk are neighbours in the queue (an 8 x 4 pixel block of the frame and
+// what it spawned), whichever warp picks the chunk up; a warp whose rays end early simply fetches the next chunk instead of idling
+// until the slowest warp of a static partition is done.
+// A warp normally takes 32 rays.  When a wave is too small to give every warp of the grid a chunk (late waves, one GPU's share of
+// a frame sharded over eight), chunks shrink to 16 or 8 rays and the other lanes idle: the time of such a wave is the time of its
+// slowest warp, which is shorter the fewer (diverging) rays the warp has to serve turn by turn.
+__device__ __forceinline__ uint32_t chunk_size(uint32_t n)
+{
+#ifdef PV_CTA_SYNC
+    return blockDim.x;
+#else
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t cs = 32u;
+    while (cs > 8u && (n + cs - 1u) / cs < warps) cs >>= 1;
+    return cs;
+#endif
+}
+
+// Next chunk: `i` = this lane's ray, or 0xFFFFFFFF for a lane without one.  Returns false when the wave is exhausted.
+__device__ __forceinline__ bool next_chunk(unsigned int* cursor, uint32_t n, uint32_t cs, uint32_t& i)
 {
 #ifdef PV_CTA_SYNC
     __shared__ uint32_t s_base;
     __syncthreads();                                   // everybody has consumed the previous value
-    if (threadIdx.x == 0) s_base = atomicAdd(cursor, (unsigned int)blockDim.x);
+    if (threadIdx.x == 0) s_base = atomicAdd(cursor, cs);
     __syncthreads();
     const uint32_t base = s_base;
-    i = base + threadIdx.x;
+    i = (base + threadIdx.x < n) ? base + threadIdx.x : 0xFFFFFFFFu;
     return base < n;
 #else
+    const uint32_t lane = threadIdx.x & 31u;
     uint32_t base = 0;
-    if ((threadIdx.x & 31u) == 0u) base = atomicAdd(cursor, 32u);
+    if (lane == 0u) base = atomicAdd(cursor, cs);
     base = __shfl_sync(PV_FULL_MASK, base, 0);
-    i = base + (threadIdx.x & 31u);
+    i = (lane < cs && base + lane < n) ? base + lane : 0xFFFFFFFFu;
     return base < n;
 #endif
 }
@@ -599,6 +628,26 @@ __device__ inline bool mesh_inside(const DScene& sc, const pvgpu_object& ob, con
 // point inside all other children, every merge ancestor has it inside none of the other children, and
 // every ancestor's clipped_by list contains it.  Intersection::Csg ends up as the outermost ancestor
 // that sets it (unions without clipped_by do not, csg.cpp:137-150).
+// Ray_In_Bound (object.cpp:385-400) for the bounded_by list of a CSG child: the ray must hit, or start inside, every bounding object.
+// Bounding objects of CSG children are plain primitives (validated on the host), so no object graph is walked here.
+#if PV_CLIPBOUND
+static __device__ __noinline__ bool ray_in_prim_bounds(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, TStack stack, int sp0)
+{
+    for (uint32_t i = 0; i < ob.bound_count; i++) {
+        const uint32_t bi = sc.index_list[ob.bound_first + i];
+        const pvgpu_object& b = sc.objs[bi];
+        bool hit = false;
+        if (!type_uses_bbox_test(b.type) || object_bbox_test(b.bbox, o, d, (float)PV_HUGE_VAL)) {
+            PrimHits h;
+            prim_hits(sc, b, o, d, h);
+            for (int k = 0; k < h.n; k++) if (h.depth[k] >= PV_MIN_ISECT_DEPTH) hit = true;       // Find_Intersection(isect, object, ray): any hit counts
+        }
+        if (!hit && !inside_object(sc, bi, o, stack, sp0)) return false;
+    }
+    return true;
+}
+#endif
+
 // `limit`: hits at or beyond this depth cannot win (the caller only takes a hit nearer than its best so far), so their Inside
 // tests - the expensive part - are skipped, as are those of hits consider() would drop anyway (too near, behind the post-condition,
 // farther than the object's closest accepted hit so far).  The tests are pure functions of the point: skipping them changes nothing.
@@ -645,55 +694,77 @@ __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, con
         }
         return;
     }
+    // The general shape.  `survives`: a hit of `leaf` at `ip` passes every ancestor up to `top`; csg = what Intersection::Csg becomes.
+    auto survives = [&](uint32_t leaf, const V3& ip, int sp_now, int32_t& csg) -> bool {
+        bool keep = true;
+        csg = -1;
+        uint32_t child = leaf;
+        while (child != top && keep) {
+            const uint32_t par = (uint32_t)sc.objs[child].parent;
+            const pvgpu_object& po = sc.objs[par];
+            if (po.type == PVGPU_OBJ_CSG_INTERSECTION) {
+                for (uint32_t k = 0; k < po.child_count && keep; k++) {
+                    const uint32_t sib = sc.index_list[po.child_first + k];
+                    if (sib != child && !inside_object(sc, sib, ip, stack, sp_now)) keep = false;
+                }
+                if (keep && po.clip_count && !point_in_clip(sc, po, ip, stack, sp_now)) keep = false;
+                if (keep) csg = (int32_t)par;
+            } else if (po.type == PVGPU_OBJ_CSG_MERGE) {
+                if (po.clip_count && !point_in_clip(sc, po, ip, stack, sp_now)) keep = false;
+                for (uint32_t k = 0; k < po.child_count && keep; k++) {
+                    const uint32_t sib = sc.index_list[po.child_first + k];
+                    if (sib != child && test_ray_flags(sc.objs[sib].flags, rflags, shadow_ray, true) &&
+                        inside_object(sc, sib, ip, stack, sp_now)) keep = false;
+                }
+                if (keep) csg = (int32_t)par;
+            } else {   // union
+                if (po.clip_count) {
+                    if (!point_in_clip(sc, po, ip, stack, sp_now)) keep = false;
+                    else csg = (int32_t)par;
+                }
+            }
+            child = par;
+        }
+        return keep;
+    };
     for (uint32_t li = 0; li < range.y; li++) {
         const uint32_t leaf = sc.csg_leaves[range.x + li];
         const pvgpu_object& lo = sc.objs[leaf];
-        // ray-kind visibility of the leaf and of every ancestor below `top` (children of unions / merges only)
+        // ray-kind visibility of the leaf and of every ancestor below `top` (children of unions / merges only), and their
+        // bounded_by lists: a child is only intersected when the ray is in its bounds (Ray_In_Bound, csg.cpp:163-166, 226-229, 322-325)
         bool visible = true;
         for (uint32_t c = leaf; c != top && visible; c = (uint32_t)sc.objs[c].parent) {
             const uint32_t ptype = sc.objs[sc.objs[c].parent].type;
             if (ptype == PVGPU_OBJ_CSG_UNION) visible = test_ray_flags(sc.objs[c].flags, rflags, shadow_ray, false);
             else if (ptype == PVGPU_OBJ_CSG_MERGE) visible = test_ray_flags(sc.objs[c].flags, rflags, shadow_ray, true);
+#if PV_CLIPBOUND
+            if (visible && sc.objs[c].bound_count) visible = ray_in_prim_bounds(sc, sc.objs[c], o, d, stack, sp0);
+#endif
         }
         if (!visible) continue;
-        if (lo.type == PVGPU_OBJ_MESH) { atomicOr(overflow, 2u); continue; }   // mesh inside CSG: rejected at finalize
-        PrimHits h;
-        prim_hits(sc, lo, o, d, h);
-        for (int i = 0; i < h.n; i++) {
-            if (!PV_CSG_HIT_CAN_WIN(h.depth[i])) continue;
-            const V3 ip = h.ip[i];
-            if (lo.clip_count && !point_in_clip(sc, lo, ip, stack, sp0)) continue;
-            bool keep = true;
-            int32_t csg = -1;
-            uint32_t child = leaf;
-            while (child != top && keep) {
-                const uint32_t par = (uint32_t)sc.objs[child].parent;
-                const pvgpu_object& po = sc.objs[par];
-                if (po.type == PVGPU_OBJ_CSG_INTERSECTION) {
-                    for (uint32_t k = 0; k < po.child_count && keep; k++) {
-                        const uint32_t sib = sc.index_list[po.child_first + k];
-                        if (sib != child && !inside_object(sc, sib, ip, stack, sp0)) keep = false;
-                    }
-                    if (keep && po.clip_count && !point_in_clip(sc, po, ip, stack, sp0)) keep = false;
-                    if (keep) csg = (int32_t)par;
-                } else if (po.type == PVGPU_OBJ_CSG_MERGE) {
-                    if (po.clip_count && !point_in_clip(sc, po, ip, stack, sp0)) keep = false;
-                    for (uint32_t k = 0; k < po.child_count && keep; k++) {
-                        const uint32_t sib = sc.index_list[po.child_first + k];
-                        if (sib != child && test_ray_flags(sc.objs[sib].flags, rflags, shadow_ray, true) &&
-                            inside_object(sc, sib, ip, stack, sp0)) keep = false;
-                    }
-                    if (keep) csg = (int32_t)par;
-                } else {   // union
-                    if (po.clip_count) {
-                        if (!point_in_clip(sc, po, ip, stack, sp0)) keep = false;
-                        else csg = (int32_t)par;
-                    }
-                }
-                child = par;
-            }
-            if (keep) consider(acc, h.depth[i], ip, leaf, h.aux[i], csg);
+        if (lo.type == PVGPU_OBJ_MESH) {
+            // Mesh::All_Intersections of a CSG child (mesh.cpp:138-195): every triangle hit is a candidate
+            if (PV_HAS(PVGPU_OBJ_MESH))
+                mesh_hits_f<false>(sc, leaf, lo, o, d, acc, stack, sp0, overflow, 0.0, [&](double wd, const V3& ip, uint32_t ti, int sp_now) {
+                    if (!PV_CSG_HIT_CAN_WIN(wd)) return;
+                    if (lo.clip_count && !point_in_clip(sc, lo, ip, stack, sp_now)) return;
+                    int32_t csg;
+                    if (survives(leaf, ip, sp_now, csg)) consider(acc, wd, ip, leaf, ti, csg);
+                });
+            continue;
         }
+        int resume = (lo.type == PVGPU_OBJ_BLOB) ? 0 : -1;       // a blob child reports its hits interval by interval (blob_hits)
+        do {
+            PrimHits h;
+            prim_hits(sc, lo, o, d, h, overflow, (resume >= 0) ? &resume : nullptr);
+            for (int i = 0; i < h.n; i++) {
+                if (!PV_CSG_HIT_CAN_WIN(h.depth[i])) continue;
+                const V3 ip = h.ip[i];
+                if (lo.clip_count && !point_in_clip(sc, lo, ip, stack, sp0)) continue;
+                int32_t csg;
+                if (survives(leaf, ip, sp0, csg)) consider(acc, h.depth[i], ip, leaf, h.aux[i], csg);
+            }
+        } while (resume >= 0);
     }
 }
 
@@ -709,7 +780,7 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     const pvgpu_object& ob = sc.objs[idx];
     if (type_uses_bbox_test(ob.type) && !object_bbox_test(ob.bbox, o, d, bbox_maxd)) return false;
     // Ray_In_Bound (object.cpp:385-400)
-#if PV_HEAVY
+#if PV_CLIPBOUND
     for (uint32_t i = 0; i < ob.bound_count; i++) {
         const uint32_t b = sc.index_list[ob.bound_first + i];
         if (!object_find_simple(sc, b, o, d, rflags, stack, sp0, overflow) && !inside_object(sc, b, o, stack, sp0)) return false;
@@ -719,8 +790,8 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     acc.closest = PV_HUGE_VAL; acc.post_min = post_min; acc.found = false;
 #if PV_HEAVY
     // (the lean variant walks meshes only through mesh_hits_sync and serves no CSG)
-    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow, limit);
-    else if (ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
+    if (PVGPU_IS_CSG(ob.type)) { if (PV_HAS(PVGPU_OBJ_CSG_UNION)) csg_hits(sc, idx, o, d, rflags, shadow_ray, acc, stack, sp0, overflow, limit); }
+    else if (PV_HAS(PVGPU_OBJ_MESH) && ob.type == PVGPU_OBJ_MESH) mesh_hits<ANY_OPAQUE>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow, opaque_limit);
     else
 #endif
     {
@@ -743,10 +814,10 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
     HitAcc acc;
     acc.closest = PV_HUGE_VAL; acc.post_min = -1.0; acc.found = false;
 #if PV_HEAVY
-    if (PVGPU_IS_CSG(ob.type)) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow, PV_HUGE_VAL);
+    if (PVGPU_IS_CSG(ob.type)) { if (PV_HAS(PVGPU_OBJ_CSG_UNION)) csg_hits(sc, idx, o, d, rflags, false, acc, stack, sp0, overflow, PV_HUGE_VAL); }
     else
 #endif
-    if (ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
+    if (PV_HAS(PVGPU_OBJ_MESH) && ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
     else {
         PrimHits h;
         prim_hits(sc, ob, o, d, h, overflow);
@@ -843,10 +914,10 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
         if (has_leaf) {
             const pvgpu_object& ob = sc.objs[leaf];
             tc.prims++;
-            if (ob.type == PVGPU_OBJ_MESH) {
+            if (PV_HAS(PVGPU_OBJ_MESH) && ob.type == PVGPU_OBJ_MESH) {
                 // object_find's prelude: FP32 box test and Ray_In_Bound (object.cpp:186-193, 385-400)
                 is_mesh = object_bbox_test(ob.bbox, o, d, (float)PV_HUGE_VAL);
-#if PV_HEAVY
+#if PV_CLIPBOUND
                 for (uint32_t i = 0; is_mesh && i < ob.bound_count; i++) {
                     const uint32_t b = sc.index_list[ob.bound_first + i];
                     if (!object_find_simple(sc, b, o, d, rflags, stack, sp, overflow) && !inside_object(sc, b, o, stack, sp)) is_mesh = false;
@@ -861,7 +932,7 @@ __device__ inline bool find_intersection_sync(bool alive, const DScene& sc, cons
                 }
             }
         }
-        if (vote_any(is_mesh)) {
+        if (PV_HAS(PVGPU_OBJ_MESH) && vote_any(is_mesh)) {
             mesh_hits_sync<ANY_OPAQUE>(is_mesh, sc, leaf, o, d, acc, stack, sp, overflow, opaque_limit, best.depth, tc);
             if (is_mesh && acc.found && acc.best.depth < best.depth) {
                 best = acc.best;

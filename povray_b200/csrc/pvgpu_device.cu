@@ -44,16 +44,20 @@ namespace pvgpu {
 struct WorkCtx {
     int device = -1;
     cudaStream_t s_main = nullptr, s_shadow = nullptr;     // own non-blocking streams; pvgpu_render_device uses the caller's as main
-    PRay* q[3] = { nullptr, nullptr, nullptr };            // wave k lives in q[k % 3]
+    PRay* q[4] = { nullptr, nullptr, nullptr, nullptr };   // wave k lives in q[k % 4]
     HitRec* hits = nullptr;
-    SRay* sq[2] = { nullptr, nullptr };                    // shadow rays of wave k in sq[k & 1]
-    Counters* cnt = nullptr;
+    SRay* sq[3] = { nullptr, nullptr, nullptr };           // shadow rays of wave k in sq[k % 3]: k_shadow_* may lag two waves behind
+    Counters* cnt = nullptr;             // [0] live counters, [1] their state at the start of the current batch (restored when it is retried)
     WaveCounts* ring = nullptr;
     unsigned int* h_counts = nullptr;                      // pinned: n_rays of wave k + 1 as read back after k_shade of wave k
     pvgpu_rect* rects = nullptr;
     uint32_t* rect_off = nullptr;
     size_t q_cap = 0, sq_cap = 0, rect_cap = 0;
     float* area_grid = nullptr;          // lightGrid scratch of k_shadow_area (3 floats x area_grid_max per resident thread)
+    Cont* conts = nullptr;               // continuation records (reflection exponent != 1), cont_cap of them
+    size_t cont_cap = 0;
+    float4* accum_ext = nullptr;         // frame accumulators + continuation slots of a non-anti-aliased call with such records
+    size_t accum_ext_cap = 0;
     // host-side staging of pvgpu_render (pinned) and its device frame
     float* d_frame = nullptr;
     float* h_frame = nullptr;
@@ -75,9 +79,11 @@ struct DeviceScene {
     uint16_t* d_cam_int = nullptr;       // container-state result
     bool lean = false;                   // only spheres, boxes, planes, meshes and no clipped_by / bounded_by: lean kernel variants
     bool full = false;                   // normal{}, pigment_map / average, sky_sphere, fog or area lights: full-material shading variants
+    bool csg = false;                    // quadric-class primitives (+ CSG) only: the _csg traversal variants
     bool camera_dirty = true;
     uint32_t spawn_factor = 0;           // upper bound of the rays one shaded ray adds to the next wave (0: the frame is one wave)
     uint32_t shadow_factor = 1;          // upper bound of the shadow rays one shaded ray emits
+    bool has_reflect_exp = false;        // some reflective finish has Reflect_Exp != 1: continuation records (Cont, pv_common.cuh)
     size_t bytes = 0;
     std::mutex camera_mutex;
 };
@@ -195,8 +201,8 @@ static void build_noise_tables(std::vector<uint16_t>& hash, std::vector<double>&
 
 static void release_ctx(WorkCtx& c)
 {
-    cudaFree(c.q[0]); cudaFree(c.q[1]); cudaFree(c.q[2]); cudaFree(c.sq[0]); cudaFree(c.sq[1]); cudaFree(c.cnt); cudaFree(c.hits); cudaFree(c.ring);
-    cudaFree(c.rects); cudaFree(c.rect_off); cudaFree(c.area_grid); cudaFree(c.d_frame);
+    cudaFree(c.q[0]); cudaFree(c.q[1]); cudaFree(c.q[2]); cudaFree(c.q[3]); cudaFree(c.sq[0]); cudaFree(c.sq[1]); cudaFree(c.sq[2]); cudaFree(c.cnt); cudaFree(c.hits); cudaFree(c.ring);
+    cudaFree(c.rects); cudaFree(c.rect_off); cudaFree(c.area_grid); cudaFree(c.d_frame); cudaFree(c.conts); cudaFree(c.accum_ext);
     if (c.h_frame) cudaFreeHost(c.h_frame);
     if (c.h_counts) cudaFreeHost(c.h_counts);
     for (cudaEvent_t e : c.ev_pool) cudaEventDestroy(e);
@@ -269,8 +275,6 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
                     st.push_back(ch);
                 }
             } else {
-                if (co.type == PVGPU_OBJ_MESH) { release_one(d); return fail(PVGPU_E_UNSUPPORTED, "mesh inside CSG is outside the hot-path scope"); }
-                if (co.bound_count) { release_one(d); return fail(PVGPU_E_UNSUPPORTED, "bounded_by on a CSG child is outside the hot-path scope"); }
                 leaves.push_back(c);
             }
         }
@@ -278,7 +282,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
         bool flat = true;
         for (uint32_t k = 0; k < o.child_count && flat; k++) {
             const pvgpu_object& co = s.objects[s.index_list[o.child_first + k]];
-            flat = ((co.type >= PVGPU_OBJ_SPHERE && co.type <= PVGPU_OBJ_TORUS) || (co.type >= PVGPU_OBJ_CONE && co.type <= PVGPU_OBJ_POLY)) && co.clip_count == 0;
+            flat = ((co.type >= PVGPU_OBJ_SPHERE && co.type <= PVGPU_OBJ_TORUS) || (co.type >= PVGPU_OBJ_CONE && co.type <= PVGPU_OBJ_POLY)) && co.clip_count == 0 && co.bound_count == 0;
         }
         leaf_range[i] = make_uint2(first, ((uint32_t)leaves.size() - first) | (flat ? 0x80000000u : 0u));
     }
@@ -380,7 +384,19 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
     if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights) d->full = true;
     for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }
+    for (const pvgpu_finish& fi : s.finishes) {
+        const bool reflective = fi.reflection_max[0] != 0 || fi.reflection_max[1] != 0 || fi.reflection_max[2] != 0 ||
+                                fi.reflection_min[0] != 0 || fi.reflection_min[1] != 0 || fi.reflection_min[2] != 0;
+        if (reflective && fi.reflect_exp != 1.0f) { d->has_reflect_exp = true; d->full = true; d->lean = false; }
+    }
     if (const char* e = getenv("PVGPU_FULL")) if (e[0] == '1') d->full = true;
+    d->csg = !d->lean && !d->full;
+    for (const pvgpu_object& o : s.objects) {
+        const bool in_class = o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_QUADRIC ||
+                              o.type == PVGPU_OBJ_CONE || o.type == PVGPU_OBJ_DISC || PVGPU_IS_CSG(o.type);
+        if (!in_class) d->csg = false;
+    }
+    if (const char* e = getenv("PVGPU_CSG")) if (e[0] == '0') d->csg = false;
     v.n_objs = (uint32_t)s.objects.size();
     v.n_frame = (uint32_t)s.frame.size();
     v.n_nodes = (uint32_t)s.nodes.size();
@@ -425,9 +441,12 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     for (int i = 0; i < n_ctx; i++) {
         std::unique_ptr<WorkCtx> c(new WorkCtx());
         c->device = device;
-        bool ok = cudaStreamCreateWithFlags(&c->s_main, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&c->s_shadow, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaMalloc(&c->cnt, sizeof(Counters)) == cudaSuccess &&
+        // the shadow stream is a background filler: its kernels give way to k_closest / k_shade of the next wave (critical path)
+        int prio_low = 0, prio_high = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_low, &prio_high);
+        bool ok = cudaStreamCreateWithPriority(&c->s_main, cudaStreamNonBlocking, prio_high) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&c->s_shadow, cudaStreamNonBlocking, prio_low) == cudaSuccess &&
+                  cudaMalloc(&c->cnt, 2 * sizeof(Counters)) == cudaSuccess &&
                   cudaMalloc(&c->ring, PV_RING_SLOTS * sizeof(WaveCounts)) == cudaSuccess &&
                   cudaMallocHost(&c->h_counts, PV_RING_SLOTS * sizeof(unsigned int)) == cudaSuccess;
         if (ok && v.has_area_lights)
@@ -511,16 +530,16 @@ struct TimedLaunch {
 static int ensure_work_buffers(WorkCtx& c, size_t q_cap, size_t sq_cap, size_t n_rects)
 {
     if (q_cap > c.q_cap) {
-        for (int k = 0; k < 3; k++) { cudaFree(c.q[k]); c.q[k] = nullptr; }
+        for (int k = 0; k < 4; k++) { cudaFree(c.q[k]); c.q[k] = nullptr; }
         cudaFree(c.hits); c.hits = nullptr; c.q_cap = 0;
-        for (int k = 0; k < 3; k++) CUDA_TRY(cudaMalloc(&c.q[k], q_cap * sizeof(PRay)));
+        for (int k = 0; k < 4; k++) CUDA_TRY(cudaMalloc(&c.q[k], q_cap * sizeof(PRay)));
         CUDA_TRY(cudaMalloc(&c.hits, q_cap * sizeof(HitRec)));
         c.q_cap = q_cap;
     }
     if (sq_cap > c.sq_cap) {
-        for (int k = 0; k < 2; k++) { cudaFree(c.sq[k]); c.sq[k] = nullptr; }
+        for (int k = 0; k < 3; k++) { cudaFree(c.sq[k]); c.sq[k] = nullptr; }
         c.sq_cap = 0;
-        for (int k = 0; k < 2; k++) CUDA_TRY(cudaMalloc(&c.sq[k], sq_cap * sizeof(SRay)));
+        for (int k = 0; k < 3; k++) CUDA_TRY(cudaMalloc(&c.sq[k], sq_cap * sizeof(SRay)));
         c.sq_cap = sq_cap;
     }
     if (n_rects > c.rect_cap) {
@@ -588,6 +607,7 @@ struct FrameCtx {
     pvgpu_stats st{};
     int (*cooperate)(void*);
     void* user;
+    uint32_t cont_base = 0;          // first continuation slot in `accum` (scenes with a reflection exponent != 1): room for c.cont_cap slots
 };
 
 // Runs all waves for samples [first, first+n) of `src`.  Returns PVGPU_E_OVERFLOW if a queue was too small.
@@ -602,6 +622,11 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
     const bool have_lights = !s.lights.empty();
     launch_wave_init(c.ring, PV_RING_SLOTS, n, S1);
     c.kernel_launches++;
+    const bool conts = d.has_reflect_exp && c.conts != nullptr;
+    if (conts) {
+        CUDA_TRY(cudaMemsetAsync(&c.cnt->n_cont, 0, sizeof(unsigned int), S1));
+        CUDA_TRY(cudaMemsetAsync(f.accum + f.cont_base, 0, c.cont_cap * sizeof(float4), S1));
+    }
     {
         TimedLaunch t(c, S1, KIND_PRIMARY, n);
         launch_primary(d.view, src, first, n, (double)f.width, (double)f.height, c.q[0], c.cnt, f.accum, S1);
@@ -622,18 +647,19 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
         }
         if (wave >= max_waves) { rc = fail(PVGPU_E_OVERFLOW, "rays still alive after %u waves (max_trace_level %u)", wave, s.globals.max_trace_level); break; }
         WaveCounts* wc = c.ring + wave;
-        PRay* cur = c.q[wave % 3];
+        PRay* cur = c.q[wave % 4];
         const uint32_t nb = (uint32_t)std::min<unsigned long long>(std::max<unsigned long long>(bound, 1), q_cap);
         WaveCtx ctx;
-        ctx.accum = f.accum; ctx.next = c.q[(wave + 1) % 3]; ctx.shadow = c.sq[wave & 1]; ctx.cnt = c.cnt;
+        ctx.accum = f.accum; ctx.next = c.q[(wave + 1) % 4]; ctx.shadow = c.sq[wave % 3]; ctx.cnt = c.cnt;
         ctx.n_next = &wc[1].n_rays; ctx.n_shadow = &wc->n_shadow;
         ctx.cur_cap = q_cap; ctx.next_cap = q_cap; ctx.shadow_cap = sq_cap;
+        ctx.conts = conts ? c.conts : nullptr; ctx.cont_cap = (uint32_t)c.cont_cap; ctx.cont_base = f.cont_base; ctx.wave = wave;
         {
             TimedLaunch t(c, S1, KIND_CLOSEST, 0);
-            (d.lean ? launch_closest_lean : launch_closest)(d.view, cur, wc, nb, q_cap, c.hits, c.cnt, S1);
+            (d.lean ? launch_closest_lean : d.csg ? launch_closest_csg : launch_closest)(d.view, cur, wc, nb, q_cap, c.hits, c.cnt, S1);
         }
-        // k_shade of this wave writes sq[wave & 1] and q[(wave + 1) % 3]: k_shadow_* of wave - 2 read both (queue and parent rays)
-        if (wave >= 2 && have_lights) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[wave - 2]], 0));
+        // k_shade of this wave writes sq[wave % 3] and q[(wave + 1) % 4]: k_shadow_* of wave - 3 read both (queue and parent rays)
+        if (wave >= 3 && have_lights) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[wave - 3]], 0));
         {
             TimedLaunch t(c, S1, KIND_SHADE, 0);
             (d.lean ? launch_shade_lean : d.full ? launch_shade_full : launch_shade)(d.view, cur, c.hits, wc, nb, ctx, S1);
@@ -646,9 +672,9 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
             const uint32_t sb = (uint32_t)std::min<unsigned long long>((unsigned long long)nb * d.shadow_factor, sq_cap);
             {
                 TimedLaunch t(c, S2, KIND_SHADOW, 0);
-                if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : launch_shadow_opaque)(d.view, c.sq[wave & 1], wc, sb, sq_cap, f.accum, c.cnt, S2);
-                else (d.lean ? launch_shadow_filter_lean : d.full ? launch_shadow_filter_full : launch_shadow_filter)(d.view, c.sq[wave & 1], wc, sb, sq_cap, cur, f.accum, c.cnt, S2);
-                if (d.view.has_area_lights) { c.kernel_launches++; launch_shadow_area(d.view, c.sq[wave & 1], wc, sb, sq_cap, cur, f.accum, c.cnt, c.area_grid, S2); }
+                if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : d.csg ? launch_shadow_opaque_csg : launch_shadow_opaque)(d.view, c.sq[wave % 3], wc, sb, sq_cap, f.accum, c.cnt, S2);
+                else (d.lean ? launch_shadow_filter_lean : d.full ? launch_shadow_filter_full : d.csg ? launch_shadow_filter_csg : launch_shadow_filter)(d.view, c.sq[wave % 3], wc, sb, sq_cap, cur, f.accum, c.cnt, S2);
+                if (d.view.has_area_lights) { c.kernel_launches++; launch_shadow_area(d.view, c.sq[wave % 3], wc, sb, sq_cap, cur, f.accum, c.cnt, c.area_grid, S2); }
             }
             ev_shadow.push_back(next_event(c));
             CUDA_TRY(cudaEventRecord(c.ev_pool[ev_shadow.back()], S2));
@@ -658,8 +684,10 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
         bound = std::min<unsigned long long>(bound * d.spawn_factor, q_cap);
     }
     // the shadow stream joins the main stream; queue overflows are known once everything has run
-    if (have_lights) for (size_t k = (ev_shadow.size() > 2 ? ev_shadow.size() - 2 : 0); k < ev_shadow.size(); k++) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[k]], 0));
+    if (have_lights) for (size_t k = (ev_shadow.size() > 3 ? ev_shadow.size() - 3 : 0); k < ev_shadow.size(); k++) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[k]], 0));
     if (rc != PVGPU_OK) { cudaStreamSynchronize(S1); return rc; }
+    if (conts)       // everything has been gathered: fold the continuation slots into their parents, last wave first
+        for (uint32_t w = wave; w-- > 0;) { launch_resolve_conts(f.accum, c.conts, c.cnt, (uint32_t)c.cont_cap, f.cont_base, w, S1); c.kernel_launches++; }
     unsigned int ovf = 0;
     CUDA_TRY(cudaMemcpyAsync(&ovf, &c.cnt->overflow, sizeof ovf, cudaMemcpyDeviceToHost, S1));
     CUDA_TRY(cudaStreamSynchronize(S1));
@@ -687,6 +715,7 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
         }
         int rc = ensure_work_buffers(c, q_cap, f.s.lights.empty() ? 0 : sq_cap, 0);
         if (rc != PVGPU_OK) return rc;
+        if (d.has_reflect_exp && c.conts == nullptr) return fail(PVGPU_E_INVALID, "internal: continuation records not allocated");
     }
     struct Span { uint32_t first, n; };
     std::vector<Span> todo;
@@ -695,11 +724,13 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
     while (!todo.empty()) {
         Span sp = todo.back(); todo.pop_back();
         if (f.cooperate && f.cooperate(f.user)) return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback");
+        CUDA_TRY(cudaMemcpyAsync(c.cnt + 1, c.cnt, sizeof(Counters), cudaMemcpyDeviceToDevice, f.stream));
         int rc = run_batch(f, src, sp.first, sp.n);
         if (rc == PVGPU_E_OVERFLOW && sp.n > 1 && clear_slots) {
+            // the batch is traced again in two halves: its pixels and its share of the statistics are taken back
             launch_clear_slots(src, sp.first, sp.n, f.accum, f.stream);
             c.kernel_launches++;
-            CUDA_TRY(cudaMemsetAsync(&c.cnt->overflow, 0, sizeof(unsigned int), f.stream));
+            CUDA_TRY(cudaMemcpyAsync(c.cnt, c.cnt + 1, sizeof(Counters), cudaMemcpyDeviceToDevice, f.stream));
             todo.push_back({ sp.first + sp.n / 2, sp.n - sp.n / 2 });
             todo.push_back({ sp.first, sp.n / 2 });
             continue;
@@ -708,6 +739,9 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
     }
     return PVGPU_OK;
 }
+
+// Accumulator slots to add behind the slots of a call for the continuation records of scenes with a reflection exponent != 1
+static size_t cont_extra(const DeviceScene& d, const WorkCtx& c) { return d.has_reflect_exp ? c.cont_cap : 0; }
 
 // Device scratch of one anti-aliased call, freed on scope exit.
 struct Scratch {
@@ -773,14 +807,14 @@ static int render_aa1(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
     unsigned int* counters = nullptr; uint8_t* flag = nullptr; double2* d_offsets = nullptr; double2* d_coords = nullptr; uint32_t* d_slots = nullptr;
     const size_t n_slots = (size_t)n_px * 2 + n_frame;
     const uint32_t cand_chunk = std::max<uint32_t>(1u, (uint32_t)(kBatchSamples / n_off));
-    AA_TRY(sc.alloc(accum, n_slots)); AA_TRY(sc.alloc(d_foff, n_rects + 1)); AA_TRY(sc.alloc(d_fcoords, n_frame));
+    AA_TRY(sc.alloc(accum, n_slots + cont_extra(d, c))); AA_TRY(sc.alloc(d_foff, n_rects + 1)); AA_TRY(sc.alloc(d_fcoords, n_frame));
     AA_TRY(sc.alloc(s_slot, n_px)); AA_TRY(sc.alloc(cand, n_px)); AA_TRY(sc.alloc(counters, 4)); AA_TRY(sc.alloc(flag, n_px));
     AA_TRY(sc.alloc(d_offsets, n_off)); AA_TRY(sc.alloc(d_coords, (size_t)cand_chunk * n_off)); AA_TRY(sc.alloc(d_slots, (size_t)cand_chunk * n_off));
     CUDA_TRY(cudaMemsetAsync(accum, 0, n_slots * sizeof(float4), stream));
     CUDA_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream));
     CUDA_TRY(cudaMemcpyAsync(d_foff, foff.data(), foff.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_offsets, offsets.data(), n_off * sizeof(double2), cudaMemcpyHostToDevice, stream));
-    f.accum = accum;
+    f.accum = accum; f.cont_base = (uint32_t)n_slots;
     AALayout L{};
     L.rects = c.rects; L.rect_off = c.rect_off; L.frame_off = d_foff; L.corner_off = nullptr;
     L.n_rects = (uint32_t)n_rects; L.n_px = n_px; L.n_frame = n_frame; L.n_corner = 0; L.s_base = n_px + n_frame;
@@ -837,7 +871,7 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
     Scratch sc;
     float4* corners = nullptr; uint32_t* d_coff = nullptr; double2* d_ccoords = nullptr; int32_t* act_idx = nullptr; uint32_t* act_list = nullptr;
     unsigned int* counters = nullptr;
-    AA_TRY(sc.alloc(corners, n_corner)); AA_TRY(sc.alloc(d_coff, n_rects + 1)); AA_TRY(sc.alloc(d_ccoords, n_corner));
+    AA_TRY(sc.alloc(corners, n_corner + cont_extra(d, c))); AA_TRY(sc.alloc(d_coff, n_rects + 1)); AA_TRY(sc.alloc(d_ccoords, n_corner));
     AA_TRY(sc.alloc(act_idx, n_px)); AA_TRY(sc.alloc(act_list, n_px)); AA_TRY(sc.alloc(counters, 4));
     CUDA_TRY(cudaMemsetAsync(corners, 0, (size_t)n_corner * sizeof(float4), stream));
     CUDA_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned int), stream));
@@ -848,7 +882,7 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
 
     // 1. pixel corners
     { TimedLaunch t(c, stream, KIND_AA, n_corner); launch_aa2_corner_coords(L, d_ccoords, stream); }
-    f.accum = corners;
+    f.accum = corners; f.cont_base = n_corner;
     SampleSource csrc{};
     csrc.coords = d_ccoords;
     AA_TRY(trace_samples(f, csrc, n_corner, true));
@@ -861,11 +895,11 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
         const unsigned long long n_slots = (unsigned long long)n_corner + (unsigned long long)n_active * per;
         if (n_slots > 0xFFFFFFF0ull) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: %u subdividing pixels x %u samples exceed the slot range; render fewer rectangles per call", n_active, per);
         uint32_t* sampled = nullptr;
-        AA_TRY(sc.alloc(accum, (size_t)n_slots)); AA_TRY(sc.alloc(sampled, (size_t)n_active * words));
+        AA_TRY(sc.alloc(accum, (size_t)n_slots + cont_extra(d, c))); AA_TRY(sc.alloc(sampled, (size_t)n_active * words));
         CUDA_TRY(cudaMemsetAsync(accum, 0, (size_t)n_slots * sizeof(float4), stream));
         CUDA_TRY(cudaMemcpyAsync(accum, corners, (size_t)n_corner * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
         CUDA_TRY(cudaMemsetAsync(sampled, 0, (size_t)n_active * words * sizeof(uint32_t), stream));
-        f.accum = accum;
+        f.accum = accum; f.cont_base = (uint32_t)n_slots;
         // 3. one tracing round per subdivision level
         unsigned long long per_pixel = 5;
         for (uint32_t round = 0; round + 1 < aa.depth; round++, per_pixel *= 4) {
@@ -932,11 +966,28 @@ static int render_impl(Scene& s, DeviceScene& d, WorkCtx& c, const pvgpu_aa* aa,
     CUDA_TRY(cudaStreamSynchronize(stream));        // `off` and (possibly pageable) `rects` are consumed
 
     FrameCtx f{ s, d, c, stream, width, height, reinterpret_cast<float4*>(d_out), pvgpu_stats{}, cooperate, user };
+    if (d.has_reflect_exp && c.conts == nullptr) {
+        c.cont_cap = std::min<size_t>(1u << 23, std::max<size_t>(8 * (size_t)std::min<size_t>(kBatchSamples, n_samples), 65536));
+        if (const char* e = getenv("PVGPU_TEST_QUEUE_CAP")) c.cont_cap = std::min<size_t>(c.cont_cap, (size_t)std::max(64, atoi(e)));
+        CUDA_TRY(cudaMalloc(&c.conts, c.cont_cap * sizeof(Cont)));
+    }
     unsigned long long n_extra_samples = 0;
     if (method == 0) {
         SampleSource src{};
         src.rects = c.rects; src.rect_off = c.rect_off; src.n_rects = (uint32_t)n_rects;
+        if (d.has_reflect_exp) {
+            // the frame is gathered in a buffer with room for the continuation slots behind the pixels, then copied out
+            const size_t need = (size_t)n_samples + c.cont_cap;
+            if (need > c.accum_ext_cap) {
+                cudaFree(c.accum_ext); c.accum_ext = nullptr; c.accum_ext_cap = 0;
+                CUDA_TRY(cudaMalloc(&c.accum_ext, need * sizeof(float4)));
+                c.accum_ext_cap = need;
+            }
+            CUDA_TRY(cudaMemsetAsync(c.accum_ext, 0, (size_t)n_samples * sizeof(float4), stream));
+            f.accum = c.accum_ext; f.cont_base = n_samples;
+        }
         rc = trace_samples(f, src, n_samples, true);
+        if (rc == PVGPU_OK && d.has_reflect_exp) CUDA_TRY(cudaMemcpyAsync(d_out, c.accum_ext, (size_t)n_samples * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
     } else if (method == 1) rc = render_aa1(f, *aa, rects, n_rects, off, reinterpret_cast<float4*>(d_out), n_extra_samples);
     else rc = render_aa2(f, *aa, rects, n_rects, off, reinterpret_cast<float4*>(d_out), n_extra_samples);
     if (rc != PVGPU_OK) { cudaStreamSynchronize(stream); cudaStreamSynchronize(c.s_shadow); return rc; }
@@ -961,6 +1012,18 @@ static int render_impl(Scene& s, DeviceScene& d, WorkCtx& c, const pvgpu_aa* aa,
         st.kernel_ms[t.kind] += k;
         st.kernel_count[t.kind] += 1;
         st.kernel_items[t.kind] += t.items;
+    }
+    if (getenv("PVGPU_TRACE_WAVES")) {       // development aid: every timed launch of the call, in launch order
+        static const char* names[KIND_COUNT] = { "primary", "closest", "shade", "shadow", "aa" };
+        for (const WorkCtx::Timed& t : c.timed) {
+            float k = 0.0f, t0 = 0.0f;
+            cudaEventElapsedTime(&k, c.ev_pool[t.e0], c.ev_pool[t.e1]);
+            cudaEventElapsedTime(&t0, c.ev_pool[ev0], c.ev_pool[t.e0]);
+            fprintf(stderr, "pvgpu wave trace: %-8s start %8.3f ms  dur %8.3f ms\n", names[t.kind], t0, k);
+        }
+        fprintf(stderr, "pvgpu wave trace: rays of waves 1..: ");
+        for (uint32_t k = 0; k + 1 < (uint32_t)st.waves && k < 16; k++) fprintf(stderr, "%u ", c.h_counts[k]);
+        fprintf(stderr, "| frame %.3f ms\n", ms);
     }
     st.kernel_items[KIND_CLOSEST] = hc.rays;
     st.kernel_items[KIND_SHADE] = hc.rays;

@@ -286,7 +286,6 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "object %zu: mesh index out of range", i);
         if (o.type == PVGPU_OBJ_BLOB) {
             if (o.mesh < 0 || o.mesh >= (int32_t)s.blobs.size()) return fail(PVGPU_E_INVALID, "object %zu: blob index out of range", i);
-            if (o.parent >= 0 || (o.aux & 1u)) return fail(PVGPU_E_UNSUPPORTED, "object %zu: a blob inside CSG is outside the hot-path scope", i);
         }
         if ((o.type == PVGPU_OBJ_CONE || o.type == PVGPU_OBJ_DISC) && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: cone / cylinder / disc without transform", i);
@@ -307,8 +306,16 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: uv_mapping is outside the hot-path scope", i);
         if ((o.flags & PVGPU_CUTAWAY_TEXTURES_FLAG) && o.texture < 0)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: cutaway_textures is outside the hot-path scope", i);
-        if (PVGPU_IS_CSG(o.type) && o.parent >= 0 && o.bound_count)
-            return fail(PVGPU_E_UNSUPPORTED, "object %zu: bounded_by on a nested CSG child", i);
+        if (o.parent >= 0 && o.bound_count) {
+            // bounded_by on a CSG child: the device tests such lists without walking an object graph (ray_in_prim_bounds)
+            for (uint32_t k = 0; k < o.bound_count; k++) {
+                const uint32_t bi = s.index_list[o.bound_first + k];
+                if (bi >= no) return fail(PVGPU_E_INVALID, "object %zu: bounded_by index out of range", i);
+                const pvgpu_object& b = s.objects[bi];
+                if (PVGPU_IS_CSG(b.type) || b.type == PVGPU_OBJ_MESH || b.type == PVGPU_OBJ_BLOB || b.bound_count || b.clip_count)
+                    return fail(PVGPU_E_UNSUPPORTED, "object %zu: bounded_by on a CSG child with a compound bounding object", i);
+            }
+        }
     }
     for (size_t i = 0; i < s.blobs.size(); i++) {
         const pvgpu_blob& b = s.blobs[i];
@@ -507,10 +514,7 @@ int validate_scene(Scene& s)
                 return fail(PVGPU_E_UNSUPPORTED, "light %zu: media_attenuation with fog (fog on shadow rays) is outside the hot-path scope", i);
     for (size_t i = 0; i < s.finishes.size(); i++) {
         const pvgpu_finish& f = s.finishes[i];
-        bool reflective = f.reflection_max[0] != 0 || f.reflection_max[1] != 0 || f.reflection_max[2] != 0 ||
-                          f.reflection_min[0] != 0 || f.reflection_min[1] != 0 || f.reflection_min[2] != 0;
-        if (reflective && f.reflect_exp != 1.0f)
-            return fail(PVGPU_E_UNSUPPORTED, "finish %zu: reflection exponent != 1 (non-linear in the child ray)", i);
+        // (a reflection exponent != 1 is non-linear in the child ray's colour: continuation records, see Cont in pv_common.cuh)
         if (f.irid > 0.0f && s.irid_wavelengths.size() != 3)
             return fail(PVGPU_E_INVALID, "finish %zu: iridescence needs pvgpu_scene_set_irid_wavelengths", i);
         if (f.crand > 0.0f) return fail(PVGPU_E_UNSUPPORTED, "finish %zu: crand is excluded from parity (per-thread RNG)", i);
