@@ -493,6 +493,10 @@ int  pvgpu_scene_set_meshes(pvgpu_scene* s, const pvgpu_mesh* meshes, size_t n_m
 int  pvgpu_scene_set_blobs(pvgpu_scene* s, const pvgpu_blob* blobs, size_t n_blobs,
                            const pvgpu_blob_element* elements, size_t n_elements,
                            const pvgpu_blob_node* nodes, size_t n_nodes);
+/* Per-component textures of blobs (Blob::Element_Texture, blob.h:167): one texture index per blob element, -1 = the object's own
+ * texture.  Objects whose blob has any carry MULTITEXTURE_FLAG; Blob::Determine_Textures (blob.cpp:2768-2843) then blends the
+ * components' textures by their field contribution at the hit point.  n must equal the number of blob elements (or 0). */
+int  pvgpu_scene_set_blob_textures(pvgpu_scene* s, const int32_t* textures, size_t n);
 /* Shape-data table: FP64 parameters of the primitives whose record does not fit pvgpu_object::p (triangle, smooth_triangle,
  * polygon); an object's `mesh` field is its offset into this array. */
 int  pvgpu_scene_set_shape_data(pvgpu_scene* s, const double* data, size_t n);

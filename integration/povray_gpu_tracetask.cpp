@@ -120,6 +120,8 @@ struct Flattener
     vector<pvgpu_slope_entry> slope_entries;
     std::map<const void*, int32_t> object_ids, texture_ids, interior_ids;
     std::map<const void*, uint32_t> mesh_tri_first;          // Mesh object -> first triangle of its copy in the triangle table (ray dumps)
+    std::vector<int32_t> blob_textures;                      // per blob element (pvgpu_scene_set_blob_textures)
+    bool any_blob_texture = false;
     std::string error;
 
     void unsupported(const std::string& what) { if (error.empty()) error = what; }
@@ -488,7 +490,6 @@ struct Flattener
     int32_t add_blob(Blob* b)
     {
         const Blob_Data* D = b->Data;
-        for (TEXTURE* t : b->Element_Texture) if (t != nullptr) unsupported("blob with per-component textures");
         pvgpu_blob pb{};
         pb.threshold = D->Threshold;
         pb.element_first = (uint32_t)blob_elements.size();
@@ -499,7 +500,11 @@ struct Flattener
             pe.transform = add_transform(e.Trans);
             for (int k = 0; k < 3; k++) { pe.o[k] = e.O[k]; pe.c[k] = e.c[k]; }
             pe.len = e.len; pe.rad2 = e.rad2;
-            if (e.Texture != nullptr) unsupported("blob with per-component textures");
+            // Blob::Element_Texture (blob.h:167): the texture Determine_Textures blends for this component, or the blob's own
+            const size_t ei = blob_elements.size() - pb.element_first;
+            TEXTURE* et = (ei < b->Element_Texture.size()) ? b->Element_Texture[ei] : nullptr;
+            blob_textures.push_back(et != nullptr ? add_texture(et) : -1);
+            if (et != nullptr) any_blob_texture = true;
             blob_elements.push_back(pe);
         }
         pb.node_first = (uint32_t)blob_nodes.size();
@@ -846,6 +851,7 @@ std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
     check(pvgpu_scene_set_tree(gv.scene, fl.nodes.data(), fl.nodes.size()), "set_tree");
     check(pvgpu_scene_set_blobs(gv.scene, fl.blobs.data(), fl.blobs.size(), fl.blob_elements.data(), fl.blob_elements.size(),
                                 fl.blob_nodes.data(), fl.blob_nodes.size()), "set_blobs");
+    if (fl.any_blob_texture) check(pvgpu_scene_set_blob_textures(gv.scene, fl.blob_textures.data(), fl.blob_textures.size()), "set_blob_textures");
     check(pvgpu_scene_set_shape_data(gv.scene, fl.shape_data.data(), fl.shape_data.size()), "set_shape_data");
     check(pvgpu_scene_set_meshes(gv.scene, fl.meshes.data(), fl.meshes.size(), fl.vertices.data(), fl.vertices.size() / 3,
                                  fl.normals.data(), fl.normals.size() / 3, fl.triangles.data(), fl.triangles.size(),

@@ -81,6 +81,7 @@ struct Scene {
     std::vector<pvgpu_interior> interiors;
     std::vector<pvgpu_blob> blobs;
     std::vector<pvgpu_blob_element> blob_elements;
+    std::vector<int32_t> blob_textures;          // per blob element: texture or -1 (Blob::Element_Texture)
     std::vector<pvgpu_blob_node> blob_nodes;
     std::vector<double> shape_data;
     std::vector<pvgpu_tnormal> tnormals;
@@ -655,6 +656,7 @@ public:
     void ComputeOneWhiteLightRay(const pvgpu_light& L, double& depth, Ray& lray, V3 ipoint, V3 jitter) const;
     void ComputeShadowColour(Intersection& isect, Ray& lightsourceray, const Ticket& tk, Col& colour);
     int hit_texture(const pvgpu_object& ob, const Intersection& isect, bool backside) const;
+    std::vector<std::pair<float, int>> Determine_Textures(const pvgpu_object& ob, const Intersection& isect, bool backside) const;
 };
 
 // Box::Intersect (box.cpp:167-520)
@@ -2180,6 +2182,37 @@ int Tracer::hit_texture(const pvgpu_object& ob, const Intersection& isect, bool 
     return (backside && ob.interior_texture >= 0) ? ob.interior_texture : ob.texture;                     // trace.cpp:513-530
 }
 
+// The weighted texture list of a hit (trace.cpp:513-530): one texture of weight 1, or Blob::Determine_Textures (blob.cpp:2768-2880)
+// for a blob with per-component textures: every component with a non-zero field at the point, weight |field|, normalised.
+std::vector<std::pair<float, int>> Tracer::Determine_Textures(const pvgpu_object& ob, const Intersection& isect, bool backside) const
+{
+    std::vector<std::pair<float, int>> out;
+    if (ob.type == PVGPU_OBJ_BLOB && (ob.flags & PVGPU_MULTITEXTURE_FLAG) && !S.blob_textures.empty()) {
+        const pvgpu_blob& bl = S.blobs[ob.mesh];
+        const pvgpu_blob_element* el = S.blob_elements.data() + bl.element_first;
+        const V3 P = (ob.transform >= 0) ? MInvTransPoint(S.xf[ob.transform], isect.IPoint) : isect.IPoint;
+        auto add = [&](uint32_t ei) {
+            const double density = std::fabs(blob_element_field(el[ei], P));
+            if (density > 0.0) { const int t = S.blob_textures[bl.element_first + ei]; out.push_back({ (float)density, t >= 0 ? t : ob.texture }); }
+        };
+        if (bl.node_count == 0) for (uint32_t i = 0; i < bl.element_count; i++) add(i);
+        else {
+            const pvgpu_blob_node* nodes = S.blob_nodes.data() + bl.node_first;
+            std::vector<uint32_t> queue{ 0u };
+            while (!queue.empty()) {
+                const pvgpu_blob_node nd = nodes[queue.back()]; queue.pop_back();
+                if (nd.count == 0) { add(nd.first); continue; }
+                for (uint32_t i = 0; i < nd.count; i++) { const pvgpu_blob_node& ch = nodes[nd.first + i]; if (len2(P - v3(ch.c)) <= ch.r2) queue.push_back(nd.first + i); }
+            }
+        }
+        if (!out.empty()) { float sum = 0.0f; for (auto& e : out) sum += e.first; sum = 1.0f / sum; for (auto& e : out) e.first *= sum; }
+        return out;
+    }
+    const int tex = hit_texture(ob, isect, backside);
+    if (tex >= 0) out.push_back({ 1.0f, tex });
+    return out;
+}
+
 // GenericColour::operator*=(double) rounds to FP32 after the FP64 product (colour.h:1681)
 static inline Col cmul(Col a, double b) { return Col{ (float)(a.r * b), (float)(a.g * b), (float)(a.b * b) }; }
 static inline Col cadd(Col a, double b) { return Col{ (float)(a.r + b), (float)(a.g + b), (float)(a.b + b) }; }
@@ -2303,14 +2336,15 @@ void Tracer::ComputeTextureColour(Intersection& isect, Col& colour, float& trans
     if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
     double normaldirection = dot(rawnormal, ray.Direction);
     if (normaldirection > 0.0) rawnormal = -rawnormal;
-    int tex = hit_texture(ob, isect, normaldirection > 0.0);
-    if (tex < 0) return;
+    const std::vector<std::pair<float, int>> wtextures = Determine_Textures(ob, isect, normaldirection > 0.0);
+    if (wtextures.empty()) return;
     Col tmpCol{ 0, 0, 0 }; float tmpTransm = 0.0f;
-    if (!(1.0 < tk.adcBailout)) {
+    for (const auto& wt : wtextures) {
+        if ((wt.first < tk.adcBailout) || wt.second < 0) continue;                                         // trace.cpp:541
         Col c1{ 0, 0, 0 }; float t1 = 0.0f;
         std::vector<int> warps;
-        ComputeOneTextureColour(c1, t1, tex, warps, isect.IPoint, rawnormal, ray, tk, weight, isect, false);
-        tmpCol = tmpCol + c1 * 1.0f; tmpTransm += 1.0f * t1;
+        ComputeOneTextureColour(c1, t1, wt.second, warps, isect.IPoint, rawnormal, ray, tk, weight, isect, false);
+        tmpCol = tmpCol + c1 * wt.first; tmpTransm += wt.first * t1;
     }
     colour = colour + tmpCol; transm += tmpTransm;
 }
@@ -2808,13 +2842,18 @@ void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& t
     if (ob.flags & PVGPU_INVERTED_FLAG) raw = -raw;
     double nd = dot(raw, lray.Direction);
     if (nd > 0.0) raw = -raw;
-    int tex = hit_texture(ob, isect, nd > 0.0);
-    if (tex < 0) return;
-    // texture list of one entry (weight 1): ComputeOneTextureColour(..., shadowflag = true) (trace.cpp:2399-2417)
-    Col temp{ 0, 0, 0 }; float dummy = 0.0f;
-    std::vector<int> warps;
+    const std::vector<std::pair<float, int>> wtextures = Determine_Textures(ob, isect, nd > 0.0);
+    if (wtextures.empty() && !(ob.type == PVGPU_OBJ_BLOB && (ob.flags & PVGPU_MULTITEXTURE_FLAG))) return;
+    // ComputeOneTextureColour(..., shadowflag = true) per weighted texture (trace.cpp:2399-2417)
+    Col temp{ 0, 0, 0 };
     Ticket tk2 = tk;
-    ComputeOneTextureColour(temp, dummy, tex, warps, isect.IPoint, raw, lray, tk2, 0.0f, isect, true);
+    for (const auto& wt : wtextures) {
+        if ((wt.first < tk.adcBailout) || wt.second < 0) continue;
+        Col fc1{ 0, 0, 0 }; float dummy = 0.0f;
+        std::vector<int> warps;
+        ComputeOneTextureColour(fc1, dummy, wt.second, warps, isect.IPoint, raw, lray, tk2, 0.0f, isect, true);
+        temp = temp + fc1 * wt.first;
+    }
     if (std::fabs((std::fabs(temp.r) + std::fabs(temp.g) + std::fabs(temp.b)) / 3.0f) < tk.adcBailout) { colour = Col{ 0, 0, 0 }; return; }
     colour = colour * temp;
     // ComputeShadowMedia (trace.cpp:3046-3071): toggle the blocker's interior on the light ray
@@ -2978,6 +3017,7 @@ void* pvo_scene_load(const char* path)
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->sky_spheres) && get(f, s->fogs); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->camera_ext); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->irid_wavelengths); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->blob_textures); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());

@@ -203,6 +203,7 @@ SIGNATURES = {
     "pvgpu_scene_set_blobs": (C.c_int, [VP, P(Blob), C.c_size_t, P(BlobElement), C.c_size_t, P(BlobNode), C.c_size_t]),
     "pvgpu_scene_set_meshes": (C.c_int, [VP, P(Mesh), C.c_size_t, P(f32), C.c_size_t, P(f32), C.c_size_t,
                                          P(Triangle), C.c_size_t, P(Node), C.c_size_t]),
+    "pvgpu_scene_set_blob_textures": (C.c_int, [VP, P(i32), C.c_size_t]),
     "pvgpu_scene_set_shape_data": (C.c_int, [VP, P(f64), C.c_size_t]),
     "pvgpu_scene_set_lights": (C.c_int, [VP, P(Light), C.c_size_t]),
     "pvgpu_scene_set_materials": (C.c_int, [VP, P(Texture), C.c_size_t, P(Pigment), C.c_size_t, P(Finish), C.c_size_t,

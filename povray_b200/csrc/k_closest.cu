@@ -63,6 +63,7 @@ __device__ inline void container_state(const DScene& sc, const V3& p, uint16_t* 
 
 __global__ void k_container_state(DScene sc, uint16_t* out, Counters* cnt)
 {
+    PV_TREELET_STAGE(sc);
     if (threadIdx.x || blockIdx.x) return;
     uint2 stack_mem[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_mem, 0 };
@@ -212,6 +213,7 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
 {
     uint2 stack_mem[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_mem, 0 };
+    PV_TREELET_STAGE(sc);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double x, y;
         uint32_t slot = src.slot_base + first + i;
@@ -305,6 +307,7 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, u
     uint2 stack_lo[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_lo, 0 };
 #endif
+    PV_TREELET_STAGE(sc);
     const uint32_t n = min(wc->n_rays, cap);
     unsigned long long n_rays = 0, n_adc = 0;
     unsigned int max_level = 0;
@@ -406,7 +409,7 @@ __global__ void k_camera_rays(DScene sc, const double* xy, uint32_t n, double wi
 
 void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cudaStream_t st)
 {
-    k_container_state<<<1, 32, 0, st>>>(sc, out, cnt);
+    k_container_state<<<1, 32, PV_TREELET_SMEM, st>>>(sc, out, cnt);
 }
 void launch_wave_init(WaveCounts* ring, uint32_t n_slots, uint32_t n0, cudaStream_t st)
 {
@@ -423,12 +426,12 @@ void launch_clear_slots(const SampleSource& src, uint32_t first, uint32_t n, flo
 void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,
                     PRay* out, Counters* cnt, float4* accum, cudaStream_t st)
 {
-    k_primary<<<grid_for(n, 256, 8), 256, 0, st>>>(sc, src, first, n, width, height, out, cnt, accum);
+    k_primary<<<grid_for(n, 256, 8), 256, PV_TREELET_SMEM, st>>>(sc, src, first, n, width, height, out, cnt, accum);
 }
 #endif  // !PV_LEAN
 void PV_VARIANT(launch_closest)(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st)
 {
-    PV_VARIANT(k_closest)<<<grid_for(trav_grid_bound(n_bound), PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, 0, st>>>(sc, cur, wc, cap, hits, cnt);
+    PV_VARIANT(k_closest)<<<grid_for(trav_grid_bound(n_bound), PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS), PV_TRAV_BLOCK, PV_TREELET_SMEM, st>>>(sc, cur, wc, cap, hits, cnt);
 }
 #if !PV_SECONDARY_TU
 void launch_probe_rays(const double* org_dir, uint32_t n, PRay* out, cudaStream_t st)

@@ -24,6 +24,7 @@ k_shadow_area(DScene sc, const SRay* __restrict__ rays, WaveCounts* wc, uint32_t
     uint2 stack_lo[PV_STACK_SIZE];
     const TStack stack{ nullptr, stack_lo, 0 };
     AreaFrame fr[PV_AREA_MAX_DEPTH];
+    PV_TREELET_STAGE(sc);
     const uint32_t n = min(wc->n_shadow, cap);
     unsigned long long tests = 0;
     TravCount tc{ 0u, 0u };
@@ -155,8 +156,8 @@ uint32_t area_threads() { return (uint32_t)(sm_count() * PV_TRAV_MIN_BLOCKS * PV
 void launch_shadow_area(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, float* grid_mem, cudaStream_t st)
 {
     const int blocks = grid_for(trav_grid_bound(n_bound), PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
-    if (sc.all_opaque) k_shadow_area<true><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
-    else k_shadow_area<false><<<blocks, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
+    if (sc.all_opaque) k_shadow_area<true><<<blocks, PV_TRAV_BLOCK, PV_TREELET_SMEM, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
+    else k_shadow_area<false><<<blocks, PV_TRAV_BLOCK, PV_TREELET_SMEM, st>>>(sc, rays, wc, cap, wave, accum, cnt, grid_mem, area_threads());
 }
 
 }  // namespace pvgpu

@@ -17,6 +17,7 @@ PV_VARIANT(k_shadow_filter)(DScene sc, const SRay* __restrict__ rays, WaveCounts
     const TStack stack{ nullptr, stack_lo, 0 };
 #endif
     // the queue never holds more than `cap` records: push_shadow drops (and flags) what does not fit, the count keeps running
+    PV_TREELET_STAGE(sc);
     const uint32_t n = min(wc->n_shadow, cap);
     unsigned long long tests = 0;
     TravCount tc{ 0u, 0u };
@@ -59,7 +60,7 @@ PV_VARIANT(k_shadow_filter)(DScene sc, const SRay* __restrict__ rays, WaveCounts
 void PV_VARIANT(launch_shadow_filter)(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st)
 {
     const int grid = grid_for(n_bound / PV_SHADOW_CHUNKS_PER_WARP + 1u, PV_TRAV_BLOCK, PV_TRAV_MIN_BLOCKS);
-    PV_VARIANT(k_shadow_filter)<<<grid, PV_TRAV_BLOCK, 0, st>>>(sc, rays, wc, cap, 0u, wave, accum, cnt);
+    PV_VARIANT(k_shadow_filter)<<<grid, PV_TRAV_BLOCK, PV_TREELET_SMEM, st>>>(sc, rays, wc, cap, 0u, wave, accum, cnt);
 }
 
 }  // namespace pvgpu

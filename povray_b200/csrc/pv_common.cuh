@@ -178,6 +178,7 @@ struct DScene {
     const pvgpu_blob*        blobs;
     const pvgpu_blob_element* blob_elements;
     const pvgpu_blob_node*   blob_nodes;
+    const int32_t*           blob_textures; // per blob element: texture or -1; nullptr: no blob has per-component textures
     const double*            shape_data;    // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
     const pvgpu_tnormal*     tnormals;
     const pvgpu_slope_entry* slopes;
@@ -195,6 +196,7 @@ struct DScene {
     const uint2*             csg_leaf_range;// per object: (first, count) into csg_leaves
     NoiseTables              noise;
     uint32_t n_objs, n_frame, n_nodes, n_lights;
+    uint32_t n_mnodes;                      // nodes of all mesh trees (dmnodes)
     uint32_t use_tree;                      // boundingMethod == 1 && tree present
     uint32_t all_opaque;                    // every shadow caster has OPAQUE_FLAG
     uint32_t has_interiors;                 // the interior table is not empty

@@ -1043,11 +1043,12 @@ struct TexLeaf { int32_t tex; int32_t n_chain; double w; V3 p; int32_t chain[PV_
 
 #if PV_FULL_MATERIALS
 // Resolves texture `tex0` at `ipoint` into plain leaves (explicit stack; depth and leaf count are validated on the host).
-static __device__ __noinline__ int resolve_texture(const DScene& sc, int32_t tex0, const V3& ipoint, TexLeaf* leaves)
+//   n0 / w0: leaves already in the list and the weight of this texture (a list of weighted textures: Blob::Determine_Textures)
+static __device__ __noinline__ int resolve_texture(const DScene& sc, int32_t tex0, const V3& ipoint, TexLeaf* leaves, int n0 = 0, double w0 = 1.0)
 {
     TexLeaf st[PV_MAX_TEX_LEAVES];
-    int sp = 0, n = 0;
-    st[sp].tex = tex0; st[sp].n_chain = 0; st[sp].w = 1.0; st[sp].p = ipoint; sp++;
+    int sp = 0, n = n0;
+    st[sp].tex = tex0; st[sp].n_chain = 0; st[sp].w = w0; st[sp].p = ipoint; sp++;
     while (sp > 0) {
         const TexLeaf cur = st[--sp];
         const pvgpu_texture& tx = sc.textures[cur.tex];
@@ -1085,8 +1086,47 @@ __device__ inline V3 warp_normal_chain(const DScene& sc, const TexLeaf* leaf, V3
     else for (int i = leaf->n_chain - 1; i >= 0; i--) n = unwarp_normal(sc, sc.pigments[leaf->chain[i]], n, false);
     return n;
 }
+// Blob::Determine_Textures (blob.cpp:2768-2880): every component whose field is non-zero at the hit point contributes its texture
+// (or the blob's own) with weight |field|, normalised to sum 1.  Returns the number of (texture, weight) pairs, at most PV_MAX_TEX_LEAVES.
+static __device__ __noinline__ int blob_weighted_textures(const DScene& sc, const pvgpu_object& ob, const V3& ip, int32_t* tex, float* w, unsigned int* overflow)
+{
+    const pvgpu_blob& bl = sc.blobs[ob.mesh];
+    const pvgpu_blob_element* el = sc.blob_elements + bl.element_first;
+    const V3 P = (ob.transform >= 0) ? inv_trans_point(sc.xf[ob.transform], ip) : ip;
+    int n = 0;
+    auto add = [&](uint32_t ei) {
+        const double density = fabs(blob_element_field(sc, el[ei], P));
+        if (density > 0.0) {
+            if (n < PV_MAX_TEX_LEAVES) { const int32_t t = sc.blob_textures[bl.element_first + ei]; tex[n] = (t >= 0) ? t : ob.texture; w[n] = (float)density; n++; }
+            else if (overflow) atomicOr(overflow, 64u);
+        }
+    };
+    if (bl.node_count == 0) { for (uint32_t i = 0; i < bl.element_count; i++) add(i); }
+    else {
+        const pvgpu_blob_node* nodes = sc.blob_nodes + bl.node_first;
+        uint32_t queue[PV_BLOB_QUEUE];
+        uint32_t size = 0;
+        queue[size++] = 0u;
+        while (size > 0) {
+            const pvgpu_blob_node nd = nodes[queue[--size]];
+            if (nd.count == 0) { add(nd.first); continue; }
+            for (uint32_t i = 0; i < nd.count; i++) {
+                const pvgpu_blob_node& ch = nodes[nd.first + i];
+                if (length_sqr(P - ld3(ch.c)) <= ch.r2 && size < PV_BLOB_QUEUE) queue[size++] = nd.first + i;
+            }
+        }
+    }
+    if (n > 0) {
+        float sum = 0.0f;
+        for (int i = 0; i < n; i++) sum += w[i];
+        sum = 1.0f / sum;
+        for (int i = 0; i < n; i++) w[i] *= sum;
+    }
+    return n;
+}
 template <bool LEAF> __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx, const TexLeaf* leaf);
 static __device__ __noinline__ void shade_texture_map(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx, int32_t tex0);
+static __device__ __noinline__ void shade_blob_textures(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx);
 #endif
 
 template <bool LEAF>
@@ -1104,6 +1144,9 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
     const double normaldirection = dot(rawnormal, dir);
     if (normaldirection > 0.0) rawnormal = -rawnormal;
 
+#if PV_FULL_MATERIALS
+    if (!LEAF && ob.type == PVGPU_OBJ_BLOB && (ob.flags & PVGPU_MULTITEXTURE_FLAG) && sc.blob_textures != nullptr) { shade_blob_textures(sc, ray, ray_slot, hit, ctx); return; }
+#endif
     const int32_t tex0 = (LEAF && leaf) ? leaf->tex : hit_texture(sc, ob, hit, normaldirection > 0.0);
     if (tex0 < 0) return;
     // a single WeightedTexture of weight 1.0: skipped if 1.0 < adcBailout (trace.cpp:541)
@@ -1436,6 +1479,29 @@ static __device__ __noinline__ void shade_texture_map(const DScene& sc, const PR
 {
     TexLeaf leaves[PV_MAX_TEX_LEAVES];
     const int n = resolve_texture(sc, tex0, hit.ip, leaves);
+    for (int i = 0; i < n; i++) {
+        PRay sr = ray;
+        const float w = (float)leaves[i].w;
+        sr.w[0] *= w; sr.w[1] *= w; sr.w[2] *= w; sr.wt *= w;
+        shade_hit_impl<true>(sc, sr, ray_slot, hit, ctx, &leaves[i]);
+    }
+}
+#endif
+
+#if PV_FULL_MATERIALS
+// A blob with per-component textures: the weighted texture list of Blob::Determine_Textures, every texture resolved into plain leaves
+// and shaded like shade_texture_map does (textures whose weight is below the ADC bailout are skipped, trace.cpp:541)
+static __device__ __noinline__ void shade_blob_textures(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx)
+{
+    int32_t tex[PV_MAX_TEX_LEAVES];
+    float wt[PV_MAX_TEX_LEAVES];
+    const int nt = blob_weighted_textures(sc, sc.objs[hit.obj], hit.ip, tex, wt, &ctx.cnt->overflow);
+    TexLeaf leaves[PV_MAX_TEX_LEAVES];
+    int n = 0;
+    for (int i = 0; i < nt; i++) {
+        if (tex[i] < 0 || (double)wt[i] < sc.g.adc_bailout) continue;
+        n = resolve_texture(sc, tex[i], hit.ip, leaves, n, (double)wt[i]);
+    }
     for (int i = 0; i < n; i++) {
         PRay sr = ray;
         const float w = (float)leaves[i].w;

@@ -55,10 +55,31 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
     if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
     const double nd = dot(rawnormal, dir);
     if (nd > 0.0) rawnormal = -rawnormal;
-    const int32_t tex0 = hit_texture(sc, ob, hit, nd > 0.0);
-    if (tex0 < 0) return;       // texture list empty: colour unchanged (trace.cpp:2391-2397)
     float tc[3];
     const pvgpu_interior* in = (ob.interior >= 0) ? &sc.interiors[ob.interior] : nullptr;
+#if PV_FULL_MATERIALS
+    if (ob.type == PVGPU_OBJ_BLOB && (ob.flags & PVGPU_MULTITEXTURE_FLAG) && sc.blob_textures != nullptr) {
+        // Blob::Determine_Textures: weighted sum of the components' filter colours (trace.cpp:2382, 2399-2417)
+        int32_t tex[PV_MAX_TEX_LEAVES];
+        float wt[PV_MAX_TEX_LEAVES];
+        const int nt = blob_weighted_textures(sc, ob, hit.ip, tex, wt, nullptr);
+        TexLeaf leaves[PV_MAX_TEX_LEAVES];
+        int n = 0;
+        for (int i = 0; i < nt; i++) if (tex[i] >= 0 && !((double)wt[i] < sc.g.adc_bailout)) n = resolve_texture(sc, tex[i], hit.ip, leaves, n, (double)wt[i]);
+        tc[0] = tc[1] = tc[2] = 0.0f;
+        for (int i = 0; i < n; i++) {
+            float t1[3];
+            shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, leaves[i].tex, leaves[i].p, &leaves[i], t1);
+            #pragma unroll
+            for (int k = 0; k < 3; k++) tc[k] += (float)((double)t1[k] * leaves[i].w);
+        }
+        if (fabsf((fabsf(tc[0]) + fabsf(tc[1]) + fabsf(tc[2])) / 3.0f) < (float)sc.g.adc_bailout) { f[0] = f[1] = f[2] = 0.0f; return; }
+        f[0] *= tc[0]; f[1] *= tc[1]; f[2] *= tc[2];
+        return;
+    }
+#endif
+    const int32_t tex0 = hit_texture(sc, ob, hit, nd > 0.0);
+    if (tex0 < 0) return;       // texture list empty: colour unchanged (trace.cpp:2391-2397)
 #if PV_FULL_MATERIALS
     if (sc.textures[tex0].type != PVGPU_PAT_PLAIN) {
         // texture_map: weighted sum of the leaves' filter colours (ComputeOneTextureColour with shadowflag, trace.cpp:671-692)

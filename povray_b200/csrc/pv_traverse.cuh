@@ -60,16 +60,75 @@ struct NodeL {
     float lo[3], hi[3];
     uint32_t code;       // doubles as the stack entry: children count | infinite flag | first child or leaf payload
 };
-__device__ __forceinline__ NodeL load_node(const DNode* p)
+__device__ __forceinline__ NodeL unpack_node(const uint4 a, const uint4 b)
 {
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    const uint4 a = __ldg(q), b = __ldg(q + 1);
     NodeL n;
     n.lo[0] = __uint_as_float(a.x); n.lo[1] = __uint_as_float(a.y); n.lo[2] = __uint_as_float(a.z);
     n.hi[0] = __uint_as_float(a.w); n.hi[1] = __uint_as_float(b.x); n.hi[2] = __uint_as_float(b.y);
     n.code = b.z;
     return n;
 }
+__device__ __forceinline__ NodeL load_node(const DNode* p)
+{
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    return unpack_node(__ldg(q), __ldg(q + 1));
+}
+
+// ---- upper tree levels in shared memory ------------------------------------------------------------
+// The node arrays are laid out breadth first, so the first PV_TREELET_BYTES / 32 nodes of an array ARE the upper levels of the tree
+// every ray walks through.  Each thread block of a traversal kernel copies that prefix of the scene's hottest tree (the mesh tree
+// when the scene has meshes, else the scene tree) into shared memory with ONE bulk asynchronous copy of the TMA unit
+// (cp.async.bulk.shared::cluster.global, completion on an mbarrier; UBLKCP in the SASS) before it takes its first ray; node
+// fetches that fall into the prefix are then served from shared memory (LDS.128), the rest from global memory as before.
+#ifndef PV_TREELET_BYTES
+#define PV_TREELET_BYTES 0
+#endif
+#if PV_TREELET_BYTES > 0
+extern __shared__ __align__(128) unsigned char pv_dyn_smem[];
+struct TreeletHdr { const char* g_base; uint32_t bytes; uint32_t pad; unsigned long long mbar; };
+#define PV_TREELET_HDR 128
+__device__ __forceinline__ void treelet_stage(const DNode* g, uint32_t n_nodes)
+{
+    TreeletHdr* h = reinterpret_cast<TreeletHdr*>(pv_dyn_smem);
+    const uint32_t bytes = min(n_nodes * (uint32_t)sizeof(DNode), (uint32_t)PV_TREELET_BYTES);
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&h->mbar);
+    if (threadIdx.x == 0) {
+        h->g_base = reinterpret_cast<const char*>(g);
+        h->bytes = bytes;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (bytes) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(pv_dyn_smem + PV_TREELET_HDR);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(g), "r"(bytes), "r"(mbar) : "memory");
+        } else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(mbar) : "memory");
+    }
+    __syncthreads();                       // the barrier is initialised and armed
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar) : "memory");
+    } while (!done);
+}
+// the four children at p .. p + 3 (clamped duplicates included) lie inside the staged prefix
+__device__ __forceinline__ bool treelet_holds(const DNode* p, uint32_t& off)
+{
+    const TreeletHdr* h = reinterpret_cast<const TreeletHdr*>(pv_dyn_smem);
+    const size_t d = (size_t)(reinterpret_cast<const char*>(p) - h->g_base);
+    off = (uint32_t)d;
+    return d + 4u * sizeof(DNode) <= (size_t)h->bytes;
+}
+__device__ __forceinline__ NodeL load_node_sh(uint32_t off)
+{
+    const uint4* q = reinterpret_cast<const uint4*>(pv_dyn_smem + PV_TREELET_HDR + off);
+    return unpack_node(q[0], q[1]);
+}
+#define PV_TREELET_SMEM (PV_TREELET_HDR + PV_TREELET_BYTES)
+#define PV_TREELET_STAGE(sc) treelet_stage((sc).n_mnodes ? (sc).dmnodes : (sc).dnodes, (sc).n_mnodes ? (sc).n_mnodes : (sc).n_nodes)
+#else
+#define PV_TREELET_SMEM 0
+#define PV_TREELET_STAGE(sc)
+#endif
 
 // Branch-free form: the reference's cascade of early exits is, as its own comment says (boundingbox.cpp:597-603),
 // "if (tmax < dmax) dmax = tmax; if (tmin > dmin) dmin = tmin; if (dmin > dmax) return;" per axis.  dmin only grows and
@@ -168,8 +227,17 @@ __device__ __forceinline__ void push_children(const DNode* __restrict__ nodes, u
     const float kInvalid = __int_as_float(0x7fc00000);     // NaN: every comparison with it is false, never pushed
     for (uint32_t c0 = 0; c0 < count; c0 += 4) {
         NodeL ch[4];
-        #pragma unroll
-        for (int k = 0; k < 4; k++) ch[k] = load_node(nodes + first + min(c0 + (uint32_t)k, count - 1u));
+#if PV_TREELET_BYTES > 0
+        uint32_t sh_off;
+        if (treelet_holds(nodes + first + c0, sh_off)) {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) ch[k] = load_node_sh(sh_off + (uint32_t)sizeof(DNode) * min((uint32_t)k, count - 1u - c0));
+        } else
+#endif
+        {
+            #pragma unroll
+            for (int k = 0; k < 4; k++) ch[k] = load_node(nodes + first + min(c0 + (uint32_t)k, count - 1u));
+        }
         float key[4];
         if (!ri.special) {
             #pragma unroll

@@ -317,6 +317,10 @@ int validate_scene(Scene& s)
             }
         }
     }
+    if (!s.blob_textures.empty()) {
+        if (s.blob_textures.size() != s.blob_elements.size()) return fail(PVGPU_E_INVALID, "blob texture table: %zu entries for %zu blob elements", s.blob_textures.size(), s.blob_elements.size());
+        for (int32_t t : s.blob_textures) if (t >= (int32_t)s.textures.size()) return fail(PVGPU_E_INVALID, "blob texture table: texture index out of range");
+    }
     for (size_t i = 0; i < s.blobs.size(); i++) {
         const pvgpu_blob& b = s.blobs[i];
         if (!range_ok(b.element_first, b.element_count, s.blob_elements.size()) || !range_ok(b.node_first, b.node_count, s.blob_nodes.size()) || b.element_count == 0)
@@ -673,6 +677,14 @@ int pvgpu_scene_set_blobs(pvgpu_scene* sc, const pvgpu_blob* blobs, size_t n_blo
     return PVGPU_OK;
 }
 
+int pvgpu_scene_set_blob_textures(pvgpu_scene* sc, const int32_t* textures, size_t n)
+{
+    SCENE_OR_FAIL(sc);
+    if (!textures && n) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_blob_textures: null array");
+    s.blob_textures.assign(textures, textures + n);
+    return PVGPU_OK;
+}
+
 int pvgpu_scene_set_normals(pvgpu_scene* sc, const pvgpu_tnormal* tn, size_t n_tn, const pvgpu_slope_entry* slopes, size_t n_slopes)
 {
     SCENE_OR_FAIL(sc);
@@ -932,7 +944,8 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
     // optional trailing sections in fixed order; a section is written when it or a later one holds data
-    const bool sec6 = !s.irid_wavelengths.empty();
+    const bool sec7 = !s.blob_textures.empty();
+    const bool sec6 = sec7 || !s.irid_wavelengths.empty();
     const bool sec5 = sec6 || !s.camera_ext.empty();
     const bool sec4 = sec5 || !s.sky_spheres.empty() || !s.fogs.empty();
     const bool sec3 = sec4 || !s.tnormals.empty();
@@ -944,6 +957,7 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
     if (ok && sec4) ok = put(f, s.sky_spheres) && put(f, s.fogs);
     if (ok && sec5) ok = put(f, s.camera_ext);
     if (ok && sec6) ok = put(f, s.irid_wavelengths);
+    if (ok && sec7) ok = put(f, s.blob_textures);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -988,6 +1002,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->irid_wavelengths); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->blob_textures); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

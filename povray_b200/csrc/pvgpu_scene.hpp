@@ -32,6 +32,7 @@ struct Scene {
     std::vector<pvgpu_blob>         blobs;
     std::vector<pvgpu_blob_element> blob_elements;
     std::vector<pvgpu_blob_node>    blob_nodes;
+    std::vector<int32_t>            blob_textures;   // per blob element: texture index or -1 (empty: no per-component textures)
 
     std::vector<double>            shape_data;     // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
 
