@@ -246,9 +246,10 @@ enum {
     PVGPU_PAT_AVERAGE  = 24,     /* AVERAGE_PATTERN pigment: weighted mean of the blend map's entries (pigment.cpp:566-596) */
     PVGPU_PAT_CRACKLE  = 25,     /* CracklePattern   pattern.cpp:5760; `data` = offset into the shape-data table of 9 doubles:
                                     crackleForm xyz, crackleMetric, crackleOffset, crackleIsSolid, repeat xyz */
-    PVGPU_PAT_CELLS    = 26      /* CellsPattern     pattern.cpp:5652 */
+    PVGPU_PAT_CELLS    = 26,     /* CellsPattern     pattern.cpp:5652 */
+    PVGPU_PAT_IMAGE_MAP = 27     /* IMAGE_MAP_PATTERN pigment (ColourImagePattern, pattern.cpp:493-514); `data` = index into the image table */
 };
-#define PVGPU_PAT_LAST PVGPU_PAT_CELLS
+#define PVGPU_PAT_LAST PVGPU_PAT_IMAGE_MAP
 /* ContinuousPattern::waveType (pattern.h:108-117) */
 enum { PVGPU_WAVE_RAW = 0, PVGPU_WAVE_RAMP = 1, PVGPU_WAVE_SINE = 2, PVGPU_WAVE_TRIANGLE = 3,
        PVGPU_WAVE_SCALLOP = 4, PVGPU_WAVE_CUBIC = 5, PVGPU_WAVE_POLY = 6 };
@@ -297,6 +298,25 @@ typedef struct pvgpu_pigment {
     uint32_t data;               /* pattern parameters that do not fit p[]: offset into the shape-data table (crackle) */
     double   p[4];               /* pattern-specific, see PVGPU_PAT_*               */
 } pvgpu_pigment;
+
+/* ImageData (source/core/support/imageutil.h:104-131) of an image_map pigment.  The texels are handed over decoded: one
+ * r g b filter transmit float quintuple per pixel as Image::GetRGBFTValue returns it (file gamma, palette and per-index
+ * filter / transmit applied by the reference's image readers), row-major, row 0 = top row of the file. */
+#define PVGPU_IMAGE_ONCE          1u   /* Once_Flag                                                                            */
+#define PVGPU_IMAGE_PREMULTIPLIED 2u   /* texels are alpha-premultiplied (Image::IsPremultiplied): un-premultiplied after interpolation */
+#define PVGPU_IMAGE_TRANSMIT_ALL  4u   /* proper "transmit all / filter all" (imageutil.cpp:400-402): scaled by the image's alpha;
+                                          the legacy mode (added to every texel) is applied to the texels by the caller       */
+typedef struct pvgpu_image {
+    uint32_t width, height;      /* iwidth, iheight                                 */
+    uint32_t map_type;           /* Map_Type: 0 planar, 1 spherical, 2 cylindrical, 5 torus, 7 angular (imageutil.h:75-82) */
+    uint32_t interpolation;      /* Interpolation_Type: 0 none, 2 bilinear, 3 bicubic, 4 normalized distance (imageutil.h:89-93) */
+    uint32_t flags;              /* PVGPU_IMAGE_*                                   */
+    uint32_t data_first;         /* first texel of this image in the texel table    */
+    float    fwidth, fheight;    /* width, height (SNGL)                            */
+    float    all_filter, all_transmit;   /* AllFilter, AllTransmit                  */
+    double   gradient[3];        /* Gradient                                        */
+    double   offset[2];          /* Offset                                          */
+} pvgpu_image;
 
 /* FINISH (source/core/material/texture.h:119-142), same field order. */
 typedef struct pvgpu_finish {
@@ -497,6 +517,8 @@ int  pvgpu_scene_set_blobs(pvgpu_scene* s, const pvgpu_blob* blobs, size_t n_blo
  * texture.  Objects whose blob has any carry MULTITEXTURE_FLAG; Blob::Determine_Textures (blob.cpp:2768-2843) then blends the
  * components' textures by their field contribution at the hit point.  n must equal the number of blob elements (or 0). */
 int  pvgpu_scene_set_blob_textures(pvgpu_scene* s, const int32_t* textures, size_t n);
+/* image_map pigments: the image table and the texel table (5 floats per texel) its records point into. */
+int  pvgpu_scene_set_images(pvgpu_scene* s, const pvgpu_image* images, size_t n_images, const float* texels, size_t n_texel_floats);
 /* Shape-data table: FP64 parameters of the primitives whose record does not fit pvgpu_object::p (triangle, smooth_triangle,
  * polygon); an object's `mesh` field is its offset into this array. */
 int  pvgpu_scene_set_shape_data(pvgpu_scene* s, const double* data, size_t n);

@@ -47,6 +47,8 @@
 #include "core/lighting/lightsource.h"
 #include "core/material/blendmap.h"
 #include "core/material/interior.h"
+#include "core/support/imageutil.h"
+#include "base/image/image.h"
 #include "core/material/pattern.h"
 #include "core/material/normal.h"
 #include "core/material/pigment.h"
@@ -121,6 +123,9 @@ struct Flattener
     std::map<const void*, int32_t> object_ids, texture_ids, interior_ids;
     std::map<const void*, uint32_t> mesh_tri_first;          // Mesh object -> first triangle of its copy in the triangle table (ray dumps)
     std::vector<int32_t> blob_textures;                      // per blob element (pvgpu_scene_set_blob_textures)
+    std::vector<pvgpu_image> images;
+    std::vector<float> texels;
+    std::map<const void*, int32_t> image_ids;
     bool any_blob_texture = false;
     std::string error;
 
@@ -327,6 +332,39 @@ struct Flattener
         p.blend_map = (int32_t)maps.size() - 1;
     }
 
+    // ImageData of an image_map (imageutil.h:104-131).  The texels are decoded here through the reference's own Image interface
+    // (file gamma, palettes, per-index filter / transmit), in the space image_colour_at(..., premul = false) interpolates in
+    // (imageutil.cpp:400-409); the legacy "transmit / filter all" is added to every texel like no_interpolation does (:1042-1049).
+    int32_t add_image(const ImageData* id)
+    {
+        auto it = image_ids.find(id);
+        if (it != image_ids.end()) return it->second;
+        const Image* img = id->data;
+        pvgpu_image pi{};
+        pi.width = (uint32_t)id->iwidth; pi.height = (uint32_t)id->iheight;
+        pi.fwidth = id->width; pi.fheight = id->height;
+        pi.map_type = (uint32_t)id->Map_Type; pi.interpolation = (uint32_t)id->Interpolation_Type;
+        if (pi.interpolation == 1) pi.interpolation = 0;        // NEAREST_NEIGHBOR "would be essentially the same as NO_INTERPOLATION" (imageutil.h:90)
+        pi.all_filter = id->AllFilter; pi.all_transmit = id->AllTransmit;
+        for (int k = 0; k < 3; k++) pi.gradient[k] = id->Gradient[k];
+        pi.offset[0] = id->Offset[U]; pi.offset[1] = id->Offset[V];
+        const bool proper_all = img->HasTransparency() && !id->AllTransmitLegacyMode && !img->IsIndexed() && ((id->AllTransmit != 0.0) || (id->AllFilter != 0.0));
+        const bool get_premul = proper_all ? false : img->IsPremultiplied();
+        pi.flags = (id->Once_Flag ? PVGPU_IMAGE_ONCE : 0u) | (get_premul ? PVGPU_IMAGE_PREMULTIPLIED : 0u) | (proper_all ? PVGPU_IMAGE_TRANSMIT_ALL : 0u);
+        pi.data_first = (uint32_t)(texels.size() / 5);
+        const bool legacy_add = !img->IsIndexed() && id->AllTransmitLegacyMode;
+        for (int y = 0; y < id->iheight; y++)
+            for (int x = 0; x < id->iwidth; x++) {
+                RGBFTColour c;
+                img->GetRGBFTValue((unsigned int)x, (unsigned int)y, c, get_premul);
+                if (legacy_add) { c.transm() += id->AllTransmit; c.filter() += id->AllFilter; }
+                texels.push_back(c.red()); texels.push_back(c.green()); texels.push_back(c.blue()); texels.push_back(c.filter()); texels.push_back(c.transm());
+            }
+        images.push_back(pi);
+        image_ids[id] = (int32_t)images.size() - 1;
+        return (int32_t)images.size() - 1;
+    }
+
     int32_t add_pigment(const PIGMENT* pg)
     {
         pvgpu_pigment p{};
@@ -342,7 +380,13 @@ struct Flattener
             add_warps(pg->pattern->warps, p.warp_first, p.warp_count);
             add_pigment_map(pg, p);
         }
-        else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern / average (image_map, uv_mapping ...)");
+        else if (pg->Type == IMAGE_MAP_PATTERN && dynamic_cast<const ColourImagePattern*>(bp) != nullptr &&
+                 dynamic_cast<const ColourImagePattern*>(bp)->pImage != nullptr && dynamic_cast<const ColourImagePattern*>(bp)->pImage->data != nullptr) {
+            p.pattern = PVGPU_PAT_IMAGE_MAP;
+            add_warps(pg->pattern->warps, p.warp_first, p.warp_count);
+            p.data = (uint32_t)add_image(dynamic_cast<const ColourImagePattern*>(bp)->pImage);
+        }
+        else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern / average / image_map (uv_mapping ...)");
         else {
             fill_pattern(bp, p, "pigment");
             add_pigment_map(pg, p);
@@ -851,6 +895,7 @@ std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
     check(pvgpu_scene_set_tree(gv.scene, fl.nodes.data(), fl.nodes.size()), "set_tree");
     check(pvgpu_scene_set_blobs(gv.scene, fl.blobs.data(), fl.blobs.size(), fl.blob_elements.data(), fl.blob_elements.size(),
                                 fl.blob_nodes.data(), fl.blob_nodes.size()), "set_blobs");
+    if (!fl.images.empty()) check(pvgpu_scene_set_images(gv.scene, fl.images.data(), fl.images.size(), fl.texels.data(), fl.texels.size()), "set_images");
     if (fl.any_blob_texture) check(pvgpu_scene_set_blob_textures(gv.scene, fl.blob_textures.data(), fl.blob_textures.size()), "set_blob_textures");
     check(pvgpu_scene_set_shape_data(gv.scene, fl.shape_data.data(), fl.shape_data.size()), "set_shape_data");
     check(pvgpu_scene_set_meshes(gv.scene, fl.meshes.data(), fl.meshes.size(), fl.vertices.data(), fl.vertices.size() / 3,

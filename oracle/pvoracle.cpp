@@ -82,6 +82,8 @@ struct Scene {
     std::vector<pvgpu_blob> blobs;
     std::vector<pvgpu_blob_element> blob_elements;
     std::vector<int32_t> blob_textures;          // per blob element: texture or -1 (Blob::Element_Texture)
+    std::vector<pvgpu_image> images;             // image_map pigments
+    std::vector<float> texels;                   // r g b filter transmit per texel, row 0 = top row
     std::vector<pvgpu_blob_node> blob_nodes;
     std::vector<double> shape_data;
     std::vector<pvgpu_tnormal> tnormals;
@@ -637,7 +639,8 @@ public:
     V3 Warp_Normal_Chain(V3 n, const std::vector<int>& warps, bool unwarp) const;
     void ComputeSky(const Ray& ray, const Ticket& tk, Col& colour, float& transm) const;
     void ComputeFog(const Ray& ray, double Depth, Col& colour, float& transm) const;
-    void Compute_Pigment(float col[5], int pigment, V3 EPoint) const;
+    bool Compute_Pigment(float col[5], int pigment, V3 EPoint) const;
+    bool image_map_colour(const pvgpu_image& im, V3 p, float col[5]) const;
     V3 Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const;
     double Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const;
     V3 Perturb_Normal(V3 Layer_Normal, int tnormal, V3 EPoint) const;
@@ -2064,16 +2067,138 @@ V3 Tracer::Perturb_Normal(V3 Layer_Normal, int tnormal, V3 EPoint) const        
     return Layer_Normal;
 }
 
-void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const                                  // pigment.cpp:395-466
+// map_pos (imageutil.cpp:932-999) with its mappers (:557-930), then image_colour_at(..., premul = false) (:396-466) with
+// no_interpolation / Interp / InterpolateBicubic (:1001-1203) on the decoded texels.  false = outside the map (once).
+static double img_wrap(double val, double upperLimit)                                                     // mathutil.h:102-127
+{
+    double t = std::fmod(val, upperLimit);
+    if (t < 0.0) t += upperLimit;
+    if (t >= upperLimit) t = 0.0;
+    return t;
+}
+static double img_theta(double x, double z, double len)
+{
+    if (z == 0.0) return (x > 0) ? 0.0 : M_PI;
+    double theta = std::acos(x / len);
+    if (z < 0.0) theta = 2.0 * M_PI - theta;
+    return theta;
+}
+bool Tracer::image_map_colour(const pvgpu_image& im, V3 p, float col[5]) const
+{
+    const bool once = (im.flags & PVGPU_IMAGE_ONCE) != 0;
+    const double W = im.fwidth, H = im.fheight;
+    double x = p.x, y = p.y, z = p.z, u = 0.0, v = 0.0, len;
+    bool inside = true;
+    switch (im.map_type) {
+        case 1:                                                                                           // spherical_image_map
+            len = std::sqrt(x * x + y * y + z * z);
+            if (len == 0.0) { inside = false; break; }
+            x /= len; y /= len; z /= len;
+            v = (0.5 + std::asin(y) / M_PI) * H;
+            len = std::sqrt(x * x + z * z);
+            u = ((len == 0.0) ? 0.0 : img_theta(x, z, len) / (2.0 * M_PI)) * W;
+            break;
+        case 2:                                                                                           // cylindrical_image_map
+            if (once && ((y < 0.0) || (y > 1.0))) { inside = false; break; }
+            v = std::fmod(y * H, H);
+            len = std::sqrt(x * x + y * y + z * z);
+            if (len == 0.0) { inside = false; break; }
+            x /= len; z /= len;
+            len = std::sqrt(x * x + z * z);
+            if (len == 0.0) { inside = false; break; }
+            u = (img_theta(x, z, len) / (2.0 * M_PI)) * W;
+            break;
+        case 5: {                                                                                         // torus_image_map
+            const double r0 = im.gradient[0];
+            len = std::sqrt(x * x + z * z);
+            if (len == 0.0) { inside = false; break; }
+            double theta = 0.0 - img_theta(x, z, len);
+            x = len - r0;
+            len = std::sqrt(x * x + y * y);
+            double phi = std::acos(-x / len);
+            if (y > 0.0) phi = 2.0 * M_PI - phi;
+            theta /= 2.0 * M_PI; phi /= 2.0 * M_PI;
+            u = -theta * W; v = phi * H;
+            break;
+        }
+        case 7: {                                                                                         // angular_image_map
+            len = std::sqrt(x * x + y * y + z * z);
+            if (len == 0.0) { inside = false; break; }
+            x /= len; y /= len; z /= len;
+            const double r = ((x == 0) && (y == 0)) ? 0.0 : (1 / M_PI) * std::acos(z) / std::sqrt(x * x + y * y);
+            u = (x * r + 1) / 2 * W; v = (y * r + 1) / 2 * H;
+            break;
+        }
+        default: {                                                                                        // planar_image_map
+            const double c[3] = { x, y, z };
+            for (int k = 0; k < 3 && inside; k++)
+                if (im.gradient[k] != 0.0) {
+                    if (once && ((c[k] < 0.0) || (c[k] > 1.0))) { inside = false; break; }
+                    if (im.gradient[k] > 0) u = std::fmod(c[k] * W, W); else v = std::fmod(c[k] * H, H);
+                }
+        }
+    }
+    if (inside) {
+        u += im.offset[0] + EPSILON; v += im.offset[1] + EPSILON;
+        if (once && ((u >= (double)im.width) || (v >= (double)im.height) || (u < 0.0) || (v < 0.0))) inside = false;
+    }
+    if (!inside) { col[0] = col[1] = col[2] = 1.0f; col[3] = 0.0f; col[4] = 1.0f; return false; }       // pattern.cpp:502-506
+    double xcoor = img_wrap(u, (double)im.width), ycoor = img_wrap(-v, (double)im.height);
+    auto texel = [&](double xc, double yc) -> const float* {                                              // no_interpolation
+        int ix, iy;
+        if (once) {
+            ix = (xc < 0.0) ? 0 : (xc >= (double)im.width) ? (int)im.width - 1 : (int)xc;
+            iy = (yc < 0.0) ? 0 : (yc >= (double)im.height) ? (int)im.height - 1 : (int)yc;
+        } else { ix = (int)img_wrap(xc, (double)im.width); iy = (int)img_wrap(yc, (double)im.height); }
+        return S.texels.data() + 5 * ((size_t)im.data_first + (size_t)iy * im.width + (size_t)ix);
+    };
+    if (im.interpolation == 0) { const float* t = texel(xcoor, ycoor); for (int k = 0; k < 5; k++) col[k] = t[k]; }
+    else {
+        double acc[5] = { 0, 0, 0, 0, 0 };
+        xcoor += 0.5; ycoor += 0.5;
+        const int iy = (int)ycoor, ix = (int)xcoor;
+        if (im.interpolation == 3) {                                                                      // InterpolateBicubic
+            auto cubic = [](double* f, double xx) { double pp = xx - (int)xx, q = 1 - pp; f[0] = -0.5 * pp * q * q; f[1] = 0.5 * q * (q * (3 * pp + 1) + 1); f[2] = 0.5 * pp * (pp * (3 * q + 1) + 1); f[3] = -0.5 * q * pp * pp; };
+            double fx[4], fy[4];
+            cubic(fx, xcoor); cubic(fy, ycoor);
+            for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++) {
+                    const float* t = texel((double)ix + i - 2, (double)iy + j - 2);
+                    const double f = fx[i] * fy[j];
+                    for (int k = 0; k < 5; k++) acc[k] += (double)t[k] * f;
+                }
+        } else {                                                                                          // Interp: bilinear / norm_dist
+            const double pp = xcoor - (int)xcoor, q = ycoor - (int)ycoor;
+            double f[4];
+            if (im.interpolation == 2) { f[0] = pp * q; f[1] = (1 - pp) * q; f[2] = pp * (1 - q); f[3] = (1 - pp) * (1 - q); }
+            else {
+                double w[4] = { 1.0 / ((1 - pp) * (1 - pp) + (1 - q) * (1 - q)), 1.0 / (pp * pp + (1 - q) * (1 - q)), 1.0 / ((1 - pp) * (1 - pp) + q * q), 1.0 / (pp * pp + q * q) };
+                double sum = 0.0;
+                for (int i = 0; i < 4; i++) sum += w[i];
+                for (int i = 0; i < 4; i++) f[i] = w[i] / sum;
+            }
+            const double cx[4] = { (double)ix, (double)ix - 1, (double)ix, (double)ix - 1 }, cy[4] = { (double)iy, (double)iy, (double)iy - 1, (double)iy - 1 };
+            for (int i = 0; i < 4; i++) { const float* t = texel(cx[i], cy[i]); for (int k = 0; k < 5; k++) acc[k] += (double)t[k] * f[i]; }
+        }
+        for (int k = 0; k < 5; k++) col[k] = (float)acc[k];
+    }
+    if (im.flags & PVGPU_IMAGE_PREMULTIPLIED) { float a = 1.0f - col[4]; if (a == 0) a = 1.0e-6f; col[0] /= a; col[1] /= a; col[2] /= a; }      // AlphaUnPremultiply
+    if (im.flags & PVGPU_IMAGE_TRANSMIT_ALL) { const float alpha = 1.0f - col[4]; if (alpha != 0.0f) { col[4] += im.all_transmit * alpha; col[3] += im.all_filter * alpha; } }
+    return true;
+}
+
+bool Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const                                  // pigment.cpp:395-466
 {
     const pvgpu_pigment& pg = S.pigments[pigment];
-    if (pg.pattern == PVGPU_PAT_PLAIN) { for (int k = 0; k < 5; k++) col[k] = pg.colour[k]; return; }
+    if (pg.pattern == PVGPU_PAT_PLAIN) { for (int k = 0; k < 5; k++) col[k] = pg.colour[k]; return true; }
     const V3 TPoint = Warp_EPoint(pg, EPoint);
+    if (pg.pattern == PVGPU_PAT_IMAGE_MAP) return image_map_colour(S.images[pg.data], TPoint, col);      // ColourImagePattern::Evaluate
     const pvgpu_blend_map& m = S.maps[pg.blend_map];
     const pvgpu_blend_entry* e = S.entries.data() + m.entry_first;
     const bool pmap = (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) != 0;
+    bool found = !pmap;
     auto entry_colour = [&](uint32_t i, float out[5]) {                    // BlendMapEntry<TransColour> or BlendMapEntry<PIGMENT*>
-        if (pmap) Compute_Pigment(out, (int)e[i].colour[0], TPoint);
+        if (pmap) { if (Compute_Pigment(out, (int)e[i].colour[0], TPoint)) found = true; }
         else for (int k = 0; k < 5; k++) out[k] = e[i].colour[k];
     };
     if (pg.pattern == PVGPU_PAT_AVERAGE) {                                                                // pigment.cpp:566-596
@@ -2086,7 +2211,7 @@ void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const        
             Total += e[i].value;
         }
         for (int k = 0; k < 5; k++) col[k] = (float)(col[k] / (double)Total);
-        return;
+        return true;
     }
     const double value = Evaluate_TPat(pg, TPoint);
     // BlendMap::Search + ColourBlendMap / PigmentBlendMap::Compute (pattern.cpp:1068-1112, pigment.cpp:513-564)
@@ -2105,6 +2230,7 @@ void Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const        
         entry_colour(iP, t);
         for (int k = 0; k < 5; k++) col[k] = (float)(t[k] * prevW) + (float)(col[k] * nextW);
     }
+    return found;
 }
 
 static double FresnelR(double cosTi, double n)                                                            // trace.cpp:2680-2708
@@ -2426,6 +2552,7 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
     resultColour = Col{ 0, 0, 0 }; resultTransm = 0.0f;
     Col filCol{ 1, 1, 1 };
     double trans = 1.0;
+    bool one_colour_found = false;
     V3 topNormal = rawnormal;
     int layer_number = 0;
     std::vector<std::pair<bool, Col>> light_cache(S.lights.size(), std::make_pair(false, Col{ 0, 0, 0 }));
@@ -2441,7 +2568,8 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
         if (layer_number == 0) topNormal = layNormal;
         double new_Weight = weight * trans;
         float lc[5];
-        Compute_Pigment(lc, S.textures[layer].pigment, ipoint);
+        const bool colour_found = Compute_Pigment(lc, S.textures[layer].pigment, ipoint);
+        one_colour_found = one_colour_found || colour_found;                                              // trace.cpp:838-841
         Col layCol{ lc[0], lc[1], lc[2] };
         listWNRX.push_back(WNRX{ new_Weight, layNormal, Col{ 0, 0, 0 }, fn.reflect_exp, S.textures[layer].finish });
         double cos_Angle_Incidence = -dot(ray.Direction, layNormal);
@@ -2480,9 +2608,11 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
         }
         tmpCol = tmpCol * filCol;
         resultColour = resultColour + tmpCol;
-        Col tc{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
-        filCol = filCol * tc;
-        if (fn.conserve_energy != 0) filCol = filCol * Col{ std::min(1.0f - W.reflec.r, 1.0f), std::min(1.0f - W.reflec.g, 1.0f), std::min(1.0f - W.reflec.b, 1.0f) };
+        if (colour_found) {                                                                               // trace.cpp:1066-1075
+            Col tc{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
+            filCol = filCol * tc;
+            if (fn.conserve_energy != 0) filCol = filCol * Col{ std::min(1.0f - W.reflec.r, 1.0f), std::min(1.0f - W.reflec.g, 1.0f), std::min(1.0f - W.reflec.b, 1.0f) };
+        }
         trans = std::min(1.0, (double)std::fabs(grey(filCol)));
     }
     bool tir_occured = false;
@@ -2503,7 +2633,8 @@ void Tracer::ComputeLightedTexture(Col& resultColour, float& resultTransm, int t
             }
         }
         if (tir_occured) resultColour = resultColour + attCol * rfrCol;
-        else { resultColour = resultColour + attCol * rfrCol * filCol; resultTransm = grey(attCol) * rfrTransm * (float)trans; }
+        else if (one_colour_found) { resultColour = resultColour + attCol * rfrCol * filCol; resultTransm = grey(attCol) * rfrTransm * (float)trans; }
+        else { resultColour = resultColour + attCol * rfrCol; resultTransm = grey(attCol) * rfrTransm; }  // trace.cpp:1137-1142
     }
     if (S.g.quality_flags & PVGPU_Q_REFLECTIONS) {                                                        // trace.cpp:1151-1178
         for (int i = 0; i < layer_number; i++) {
@@ -2806,8 +2937,8 @@ void Tracer::ComputeShadowTexture(Col& filtercolour, int tex, const std::vector<
     const pvgpu_interior* in = ob.interior >= 0 ? &S.interiors[ob.interior] : nullptr;
     for (int layer = tex; layer >= 0; layer = S.textures[layer].next) {
         float lc[5];
-        Compute_Pigment(lc, S.textures[layer].pigment, ipoint);
-        tmpCol = tmpCol * Col{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
+        if (Compute_Pigment(lc, S.textures[layer].pigment, ipoint))                                       // trace.cpp:1198-1205
+            tmpCol = tmpCol * Col{ lc[0] * lc[3] + lc[4], lc[1] * lc[3] + lc[4], lc[2] * lc[3] + lc[4] };
         if (in && in->caustics != 0.0f) {                                                                 // trace.cpp:1208-1234
             V3 layer_Normal = raw;
             if ((S.g.quality_flags & PVGPU_Q_NORMALS) && S.textures[layer].tnormal >= 0) {
@@ -3018,6 +3149,7 @@ void* pvo_scene_load(const char* path)
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->camera_ext); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->irid_wavelengths); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->blob_textures); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->images) && get(f, s->texels); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());

@@ -171,6 +171,11 @@ class Rect(C.Structure):
     _fields_ = [("left", i32), ("top", i32), ("right", i32), ("bottom", i32)]
 
 
+class Image(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("map_type", u32), ("interpolation", u32), ("flags", u32), ("data_first", u32),
+                ("fwidth", f32), ("fheight", f32), ("all_filter", f32), ("all_transmit", f32), ("gradient", f64 * 3), ("offset", f64 * 2)]
+
+
 class Stats(C.Structure):
     _fields_ = [("rays", u64), ("shadow_ray_tests", u64), ("reflected_rays", u64), ("refracted_rays", u64),
                 ("transmitted_rays", u64), ("tir_rays", u64), ("adc_saves", u64), ("samples", u64), ("waves", u64),
@@ -203,6 +208,7 @@ SIGNATURES = {
     "pvgpu_scene_set_blobs": (C.c_int, [VP, P(Blob), C.c_size_t, P(BlobElement), C.c_size_t, P(BlobNode), C.c_size_t]),
     "pvgpu_scene_set_meshes": (C.c_int, [VP, P(Mesh), C.c_size_t, P(f32), C.c_size_t, P(f32), C.c_size_t,
                                          P(Triangle), C.c_size_t, P(Node), C.c_size_t]),
+    "pvgpu_scene_set_images": (C.c_int, [VP, P(Image), C.c_size_t, P(f32), C.c_size_t]),
     "pvgpu_scene_set_blob_textures": (C.c_int, [VP, P(i32), C.c_size_t]),
     "pvgpu_scene_set_shape_data": (C.c_int, [VP, P(f64), C.c_size_t]),
     "pvgpu_scene_set_lights": (C.c_int, [VP, P(Light), C.c_size_t]),

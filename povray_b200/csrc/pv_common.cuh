@@ -178,6 +178,8 @@ struct DScene {
     const pvgpu_blob*        blobs;
     const pvgpu_blob_element* blob_elements;
     const pvgpu_blob_node*   blob_nodes;
+    const pvgpu_image*       images;        // image_map pigments
+    const float*             texels;        // r g b filter transmit per texel
     const int32_t*           blob_textures; // per blob element: texture or -1; nullptr: no blob has per-component textures
     const double*            shape_data;    // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
     const pvgpu_tnormal*     tnormals;

@@ -13,6 +13,9 @@
 #include "pv_blob.cuh"
 #endif
 #include "pv_noise.cuh"
+#if PV_FULL_MATERIALS
+#include "pv_image.cuh"
+#endif
 #include "pv_kernels.hpp"
 
 namespace pvgpu {
@@ -357,22 +360,25 @@ __device__ __forceinline__ void blend_search(const pvgpu_blend_entry* e, uint32_
 // call graph stays acyclic and ptxas sizes the stack statically.
 #define PV_PIGMENT_MAP_LEVELS 6
 template <int LEVEL>
-static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
+static __device__ __noinline__ bool compute_pigment_rec(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
 {
+    // (the return value is Compute_Pigment's Colour_Found: false only where an image_map used `once` does not cover the point)
+    bool found = false;
     auto child = [&](int32_t idx, const V3& p, float out[5]) {
-        if constexpr (LEVEL > 0) compute_pigment_rec<LEVEL - 1>(sc, idx, p, out);
-        else { for (int k = 0; k < 5; k++) out[k] = sc.pigments[idx].colour[k]; }     // unreachable: nesting depth is validated
+        if constexpr (LEVEL > 0) { if (compute_pigment_rec<LEVEL - 1>(sc, idx, p, out)) found = true; }
+        else { for (int k = 0; k < 5; k++) out[k] = sc.pigments[idx].colour[k]; found = true; }     // unreachable: nesting depth is validated
     };
     const pvgpu_pigment& pg = sc.pigments[pig_index];
     if ((sc.g.quality_flags & PVGPU_Q_QUICK_COLOUR) && pg.quick_colour[0] == pg.quick_colour[0]) {     // pigment.cpp:401-405
         for (int k = 0; k < 5; k++) col[k] = pg.quick_colour[k];
-        return;
+        return true;
     }
     if (pg.pattern == PVGPU_PAT_PLAIN) {
         for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
-        return;
+        return true;
     }
     const V3 tp = warp_epoint(sc, pg, ep);
+    if (pg.pattern == PVGPU_PAT_IMAGE_MAP) return image_map_colour(sc, sc.images[pg.data], tp, col);
     const pvgpu_blend_map& m = sc.maps[pg.blend_map];
     const pvgpu_blend_entry* e = sc.entries + m.entry_first;
     const bool pmap = (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) != 0;
@@ -387,7 +393,7 @@ static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_
             total += e[i].value;
         }
         for (int k = 0; k < 5; k++) col[k] = (float)((double)col[k] / (double)total);
-        return;
+        return true;           // Do_Average_Pigments does not report Colour_Found (pigment.cpp:427-433)
     }
     const double value = evaluate_pattern(sc, pg, tp);
     uint32_t ip, in;
@@ -402,27 +408,31 @@ static __device__ __noinline__ void compute_pigment_rec(const DScene& sc, int32_
         const double wn = 1.0 - wp;
         for (int k = 0; k < 5; k++) col[k] = (float)((double)t[k] * wp) + (float)((double)col[k] * wn);
     }
+    return pmap ? found : true;
 }
 #endif
 
 // Compute_Pigment (pigment.cpp:395-466) + ColourBlendMap::Compute (pigment.cpp:513-530).  col = rgb, filter, transmit.
-__device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
+__device__ inline bool compute_pigment(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
 {
     const pvgpu_pigment& pg = sc.pigments[pig_index];
     // quickColour (+Q5 and below): Quick_Colour replaces the pigment where the scene gives one (pigment.cpp:401-405; NaN red = none)
     if ((sc.g.quality_flags & PVGPU_Q_QUICK_COLOUR) && pg.quick_colour[0] == pg.quick_colour[0]) {
         #pragma unroll
         for (int k = 0; k < 5; k++) col[k] = pg.quick_colour[k];
-        return;
+        return true;
     }
     if (pg.pattern == PVGPU_PAT_PLAIN) {
         #pragma unroll
         for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
-        return;
+        return true;
     }
+#if PV_FULL_MATERIALS
+    if (pg.pattern == PVGPU_PAT_IMAGE_MAP) return image_map_colour(sc, sc.images[pg.data], warp_epoint(sc, pg, ep), col);
+#endif
     const pvgpu_blend_map& m = sc.maps[pg.blend_map];
 #if PV_FULL_MATERIALS
-    if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) { compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col); return; }
+    if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) return compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col);
 #endif
     const V3 tp = warp_epoint(sc, pg, ep);
     const double value = evaluate_pattern(sc, pg, tp);
@@ -439,6 +449,7 @@ __device__ inline void compute_pigment(const DScene& sc, int32_t pig_index, cons
         #pragma unroll
         for (int k = 0; k < 5; k++) col[k] = (float)(e[ip].colour[k] * wp) + (float)(e[in].colour[k] * wn);
     }
+    return true;
 }
 
 // ---- normal perturbation: Perturb_Normal (normal.cpp:784-927) ---------------------------------------
@@ -1169,6 +1180,7 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
     float fil[3] = { 1.0f, 1.0f, 1.0f };
     double trans = 1.0;
     float amb[3] = { 0.0f, 0.0f, 0.0f };
+    bool one_colour_found = false;       // some layer's pigment returned a colour (false only outside an image_map used `once`, trace.cpp:838-841)
     V3 top_normal = rawnormal;
 #if PV_FULL_MATERIALS
     const bool has_tn = (sc.has_tnormals != 0u) && (sc.g.quality_flags & PVGPU_Q_NORMALS);
@@ -1196,13 +1208,16 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
         const V3 lay_normal = LAYER_NORMAL(L);
         const double cos_inc = -dot(dir, lay_normal);
         float lc[5];
-        compute_pigment(sc, tx.pigment, epoint, lc);
+        const bool colour_found = compute_pigment(sc, tx.pigment, epoint, lc);
+        one_colour_found = one_colour_found || colour_found;
         if (sc.g.quality_flags & PVGPU_Q_AMBIENT_ONLY) {
             // +Q0 / +Q1 (trace.cpp:848-853): the result IS the layer's pigment colour (the last layer reached wins), no transparency,
             // no lights, no secondary rays; the filter colour still decides whether the next layer is looked at (trace.cpp:1059-1076)
             amb[0] = lc[0]; amb[1] = lc[1]; amb[2] = lc[2];
-            #pragma unroll
-            for (int k = 0; k < 3; k++) fil[k] *= (lc[k] * lc[3] + lc[4]);
+            if (colour_found) {
+                #pragma unroll
+                for (int k = 0; k < 3; k++) fil[k] *= (lc[k] * lc[3] + lc[4]);
+            }
             trans = fmin(1.0, (double)fabsf(greyscale(fil)));
             continue;
         }
@@ -1229,11 +1244,13 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
         for (int k = 0; k < 3; k++) amb[k] += (L.col[k] * em[k] * (float)att) * fil[k];
         nlayers++;
         // new filter colour and remaining translucency (trace.cpp:1059-1076)
-        #pragma unroll
-        for (int k = 0; k < 3; k++) fil[k] *= (lc[k] * lc[3] + lc[4]);
-        if (fn.conserve_energy != 0) {
+        if (colour_found) {
             #pragma unroll
-            for (int k = 0; k < 3; k++) fil[k] *= fminf(1.0f - L.refl[k], 1.0f);
+            for (int k = 0; k < 3; k++) fil[k] *= (lc[k] * lc[3] + lc[4]);
+            if (fn.conserve_energy != 0) {
+                #pragma unroll
+                for (int k = 0; k < 3; k++) fil[k] *= fminf(1.0f - L.refl[k], 1.0f);
+            }
         }
         trans = fmin(1.0, (double)fabsf(greyscale(fil)));
     }
@@ -1252,6 +1269,7 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
             float lcol[3] = { (float)(Lt.colour[0] * latt), (float)(Lt.colour[1] * latt), (float)(Lt.colour[2] * latt) };
             if (fabsf(lcol[0]) < (float)PV_EPSILON && fabsf(lcol[1]) < (float)PV_EPSILON && fabsf(lcol[2]) < (float)PV_EPSILON) continue;
             float K[3] = { 0.0f, 0.0f, 0.0f };
+            bool lit = false;           // some layer got as far as the reference's TraceShadowRay call (trace.cpp:1668-1673)
             for (int i = 0; i < nlayers; i++) {
                 const Layer& L = layers[i];
                 const pvgpu_finish& fn = sc.finishes[L.finish];
@@ -1266,6 +1284,7 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
                         else continue;
                     }
                 }
+                lit = true;
                 float k3[3] = { 0.0f, 0.0f, 0.0f };
                 // ComputeDiffuseColour (trace.cpp:2441-2484)
                 {
@@ -1330,7 +1349,9 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
                 for (int k = 0; k < 3; k++) K[k] += L.fil[k] * k3[k];
             }
             float a[3] = { ray.w[0] * lcol[0] * K[0], ray.w[1] * lcol[1] * K[1], ray.w[2] * lcol[2] * K[2] };
-            if (a[0] == 0.0f && a[1] == 0.0f && a[2] == 0.0f) continue;
+            // a light that contributes nothing is still shadow-tested by the reference once a layer asked for it (a fully
+            // transparent texel of an image_map, say): the ray is traced so that Shadow_Ray_Tests counts the same
+            if (a[0] == 0.0f && a[1] == 0.0f && a[2] == 0.0f && !lit) continue;
             const bool shadowed = (sc.g.quality_flags & PVGPU_Q_SHADOWS) && (Lt.type != PVGPU_LIGHT_FILL);
             if (!shadowed) { accum_add(ctx.accum, ray.sample, a[0], a[1], a[2], 0.0f); continue; }
 #if PV_FULL_MATERIALS
@@ -1424,9 +1445,13 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
             }
         }
         if (spawn) {
-            // one_colour_found is always true on this path (no image maps)
-            nr.w[0] = ray.w[0] * attc[0] * fil[0]; nr.w[1] = ray.w[1] * attc[1] * fil[1]; nr.w[2] = ray.w[2] * attc[2] * fil[2];
-            nr.wt = ray.wt * (float)((double)greyscale(attc) * trans);
+            if (one_colour_found) {      // trace.cpp:1131-1143
+                nr.w[0] = ray.w[0] * attc[0] * fil[0]; nr.w[1] = ray.w[1] * attc[1] * fil[1]; nr.w[2] = ray.w[2] * attc[2] * fil[2];
+                nr.wt = ray.wt * (float)((double)greyscale(attc) * trans);
+            } else {
+                nr.w[0] = ray.w[0] * attc[0]; nr.w[1] = ray.w[1] * attc[1]; nr.w[2] = ray.w[2] * attc[2];
+                nr.wt = ray.wt * greyscale(attc);
+            }
             push_ray(ctx, nr);
         }
     }

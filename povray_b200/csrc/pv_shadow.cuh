@@ -14,9 +14,10 @@ __device__ inline void shadow_texture(const DScene& sc, const pvgpu_object& ob, 
     float tmp[3] = { 1.0f, 1.0f, 1.0f };
     for (int32_t li = tex0; li >= 0; li = sc.textures[li].next) {
         float lc[5];
-        compute_pigment(sc, sc.textures[li].pigment, epoint, lc);
-        #pragma unroll
-        for (int k = 0; k < 3; k++) tmp[k] *= (lc[k] * lc[3] + lc[4]);
+        if (compute_pigment(sc, sc.textures[li].pigment, epoint, lc)) {        // (not found: outside an image_map used `once`, trace.cpp:1198-1205)
+            #pragma unroll
+            for (int k = 0; k < 3; k++) tmp[k] *= (lc[k] * lc[3] + lc[4]);
+        }
         if (in && in->caustics != 0.0f) {
             V3 layer_normal = rawnormal;
 #if PV_FULL_MATERIALS

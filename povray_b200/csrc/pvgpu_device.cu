@@ -333,6 +333,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
     UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes); UP(s.shape_data, v.shape_data);
     if (!s.blob_textures.empty()) { UP(s.blob_textures, v.blob_textures); } else v.blob_textures = nullptr;
+    UP(s.images, v.images); UP(s.texels, v.texels);
     UP(s.tnormals, v.tnormals); UP(s.slope_entries, v.slopes); UP(s.fogs, v.fogs);
     std::vector<double> pattern_rands;
     for (const pvgpu_pigment& pg : s.pigments)
@@ -365,7 +366,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern > PVGPU_PAT_AGATE || pg.pattern == PVGPU_PAT_BRICK || pg.pattern == PVGPU_PAT_HEXAGON) d->lean = false;
     if (!s.fogs.empty() || !s.sky_spheres.empty()) d->lean = false;
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->lean = false;
-    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE) d->lean = false;
+    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_AVERAGE || pg.pattern == PVGPU_PAT_IMAGE_MAP) d->lean = false;
     for (int k = 0; k < 3; k++) v.irid_wavelengths[k] = (s.irid_wavelengths.size() == 3) ? s.irid_wavelengths[k] : 1.0f;
     v.has_tnormals = 0;
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0) v.has_tnormals = 1;
@@ -383,7 +384,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     for (const pvgpu_texture& t : s.textures) if (t.tnormal >= 0 || t.type != PVGPU_PAT_PLAIN) d->full = true;
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->full = true;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
-    if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights || !s.blob_textures.empty()) d->full = true;
+    if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights || !s.blob_textures.empty() || !s.images.empty()) d->full = true;
     for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }
     for (const pvgpu_finish& fi : s.finishes) {
         const bool reflective = fi.reflection_max[0] != 0 || fi.reflection_max[1] != 0 || fi.reflection_max[2] != 0 ||

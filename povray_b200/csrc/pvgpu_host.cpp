@@ -317,6 +317,15 @@ int validate_scene(Scene& s)
             }
         }
     }
+    for (size_t i = 0; i < s.images.size(); i++) {
+        const pvgpu_image& im = s.images[i];
+        if (im.width == 0 || im.height == 0 || (size_t)im.data_first + (size_t)im.width * im.height > s.texels.size() / 5)
+            return fail(PVGPU_E_INVALID, "image %zu: texels outside the texel table", i);
+        if (!(im.map_type == 0 || im.map_type == 1 || im.map_type == 2 || im.map_type == 5 || im.map_type == 7))
+            return fail(PVGPU_E_UNSUPPORTED, "image %zu: map_type %u", i, im.map_type);
+        if (!(im.interpolation == 0 || im.interpolation == 2 || im.interpolation == 3 || im.interpolation == 4))
+            return fail(PVGPU_E_UNSUPPORTED, "image %zu: interpolation %u", i, im.interpolation);
+    }
     if (!s.blob_textures.empty()) {
         if (s.blob_textures.size() != s.blob_elements.size()) return fail(PVGPU_E_INVALID, "blob texture table: %zu entries for %zu blob elements", s.blob_textures.size(), s.blob_elements.size());
         for (int32_t t : s.blob_textures) if (t >= (int32_t)s.textures.size()) return fail(PVGPU_E_INVALID, "blob texture table: texture index out of range");
@@ -404,7 +413,7 @@ int validate_scene(Scene& s)
         if (t.tnormal >= (int32_t)s.tnormals.size())
             return fail(PVGPU_E_INVALID, "texture %zu: bad tnormal index", i);
         const pvgpu_pigment& tp = s.pigments[t.pigment];
-        if (tp.pattern != PVGPU_PAT_PLAIN && (tp.blend_map < 0 || tp.blend_map >= (int32_t)s.blend_maps.size()))
+        if (tp.pattern != PVGPU_PAT_PLAIN && tp.pattern != PVGPU_PAT_IMAGE_MAP && (tp.blend_map < 0 || tp.blend_map >= (int32_t)s.blend_maps.size()))
             return fail(PVGPU_E_INVALID, "texture %zu: patterned pigment without blend map", i);
         int depth = 0;
         for (int32_t k = (int32_t)i; k >= 0; k = s.textures[k].next)
@@ -418,6 +427,8 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "pigment %zu: bad blend map index", i);
         if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
+        if (p.pattern == PVGPU_PAT_IMAGE_MAP && p.data >= s.images.size())
+            return fail(PVGPU_E_INVALID, "pigment %zu: image index out of range", i);
         if (p.pattern == PVGPU_PAT_CRACKLE && !range_ok(p.data, 9, s.shape_data.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: crackle parameters outside the shape-data table", i);
     }
@@ -502,7 +513,7 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "sky_sphere: bad pigment range / transform");
         for (uint32_t i = 0; i < k.pigment_count; i++) {
             const uint32_t pi = s.index_list[k.pigment_first + i];
-            if (pi >= s.pigments.size() || (s.pigments[pi].pattern != PVGPU_PAT_PLAIN && s.pigments[pi].blend_map < 0))
+            if (pi >= s.pigments.size() || (s.pigments[pi].pattern != PVGPU_PAT_PLAIN && s.pigments[pi].pattern != PVGPU_PAT_IMAGE_MAP && s.pigments[pi].blend_map < 0))
                 return fail(PVGPU_E_INVALID, "sky_sphere: bad pigment %u", pi);
         }
     }
@@ -674,6 +685,15 @@ int pvgpu_scene_set_blobs(pvgpu_scene* sc, const pvgpu_blob* blobs, size_t n_blo
     s.blobs.assign(blobs, blobs + n_blobs);
     s.blob_elements.assign(elements, elements + n_elements);
     s.blob_nodes.assign(nodes, nodes + n_nodes);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_images(pvgpu_scene* sc, const pvgpu_image* images, size_t n_images, const float* texels, size_t n_texel_floats)
+{
+    SCENE_OR_FAIL(sc);
+    if ((!images && n_images) || (!texels && n_texel_floats)) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_images: null array");
+    s.images.assign(images, images + n_images);
+    s.texels.assign(texels, texels + n_texel_floats);
     return PVGPU_OK;
 }
 
@@ -944,7 +964,8 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
     // optional trailing sections in fixed order; a section is written when it or a later one holds data
-    const bool sec7 = !s.blob_textures.empty();
+    const bool sec8 = !s.images.empty();
+    const bool sec7 = sec8 || !s.blob_textures.empty();
     const bool sec6 = sec7 || !s.irid_wavelengths.empty();
     const bool sec5 = sec6 || !s.camera_ext.empty();
     const bool sec4 = sec5 || !s.sky_spheres.empty() || !s.fogs.empty();
@@ -958,6 +979,7 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
     if (ok && sec5) ok = put(f, s.camera_ext);
     if (ok && sec6) ok = put(f, s.irid_wavelengths);
     if (ok && sec7) ok = put(f, s.blob_textures);
+    if (ok && sec8) ok = put(f, s.images) && put(f, s.texels);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -1006,6 +1028,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->blob_textures); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->images) && get(f, s->texels); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

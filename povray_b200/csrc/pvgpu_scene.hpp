@@ -34,6 +34,8 @@ struct Scene {
     std::vector<pvgpu_blob_node>    blob_nodes;
     std::vector<int32_t>            blob_textures;   // per blob element: texture index or -1 (empty: no per-component textures)
 
+    std::vector<pvgpu_image>       images;         // image_map pigments (pvgpu_pigment::data = index)
+    std::vector<float>             texels;         // r g b filter transmit per texel
     std::vector<double>            shape_data;     // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
 
     std::vector<pvgpu_light>       lights;

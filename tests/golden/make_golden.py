@@ -38,7 +38,7 @@ def main(names):
         env = dict(os.environ, PVGPU_RENDER="stock", PVGPU_DUMP_SCENE=os.path.join(HERE, name + ".pvs"),
                    PVGPU_DUMP_RAYS=os.path.join(HERE, name + ".rays"), PVGPU_DUMP_RGBT=os.path.join(HERE, name + ".rgbt"))
         r = subprocess.run([ADAPTER, "+I" + pov, "+O/tmp/golden_" + name + ".png", f"+W{W}", f"+H{H}", "-A", "-D", "+WT1", "-GA"],
-                           env=env, capture_output=True, text=True)
+                           env=env, capture_output=True, text=True, cwd=os.path.join(HERE, "scenes"))       # image files live next to the scenes
         if r.returncode != 0:
             print(name, "FAILED\n", r.stdout[-3000:], r.stderr[-3000:])
             sys.exit(1)

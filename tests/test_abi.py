@@ -38,7 +38,7 @@ def test_struct_sizes_match_the_c_compiler():
              "pvgpu_interior": A.Interior, "pvgpu_globals": A.Globals, "pvgpu_camera": A.Camera, "pvgpu_aa": A.AA,
              "pvgpu_rect": A.Rect, "pvgpu_stats": A.Stats, "pvgpu_blob": A.Blob, "pvgpu_blob_element": A.BlobElement,
              "pvgpu_blob_node": A.BlobNode, "pvgpu_slope_entry": A.SlopeEntry, "pvgpu_tnormal": A.TNormal,
-             "pvgpu_sky_sphere": A.SkySphere, "pvgpu_fog": A.Fog}
+             "pvgpu_sky_sphere": A.SkySphere, "pvgpu_fog": A.Fog, "pvgpu_image": A.Image}
     src = "#include <stdio.h>\n#include \"pvgpu.h\"\nint main(void){\n" + \
           "".join(f'printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "return 0;}\n"
     with tempfile.TemporaryDirectory() as d:
