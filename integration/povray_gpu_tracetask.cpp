@@ -861,7 +861,13 @@ std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
         fogs.push_back(f);
     }
     if (sd->boundingSlabs != nullptr)
-        fl.flatten_tree(sd->boundingSlabs, fl.nodes, [&](const BBOX_TREE* leaf) { return (uint32_t)fl.object_ids.at(reinterpret_cast<const void*>(leaf->Node)); });
+        fl.flatten_tree(sd->boundingSlabs, fl.nodes, [&](const BBOX_TREE* leaf) {
+            // (a leaf the flattener did not take - e.g. the object of a light source with looks_like - makes the scene unsupported,
+            //  it must not end the render with an out_of_range exception: 28 distribution scenes used to "fail" that way)
+            auto it = fl.object_ids.find(reinterpret_cast<const void*>(leaf->Node));
+            if (it == fl.object_ids.end()) { fl.unsupported("bounding-tree leaf that is not a flattened object (light source geometry, looks_like)"); return 0u; }
+            return (uint32_t)it->second;
+        });
     if (gv.error.empty()) gv.error = fl.error;
     gv.object_ids = fl.object_ids;
     gv.mesh_tri_first = fl.mesh_tri_first;
