@@ -250,7 +250,7 @@ k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width,
             container_state(sc, o, r.interiors, nci, stack, &cnt->overflow);
             r.n_int = (uint8_t)nci;
         }
-        out[i] = r;
+        store_cs(out + i, r);
     }
 }
 
@@ -322,11 +322,11 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, u
         HitRec out;
         out.pad = 0; out.csg = -1; out.aux = 0; out.depth = 0.0; out.ip[0] = out.ip[1] = out.ip[2] = 0.0; out.obj = PV_HIT_MISS;
         if (alive) {
-            const PRay* rp = cur + i;
-            o = ld3(rp->o); d = ld3(rp->d);
-            const float adcw = rp->adc;
-            const uint32_t level = rp->level;
-            flags = rp->flags;
+            const PRay r = load_cs(cur + i);
+            o = ld3(r.o); d = ld3(r.d);
+            const float adcw = r.adc;
+            const uint32_t level = r.level;
+            flags = r.flags;
             if (flags & PV_RAY_DEAD) { out.obj = PV_HIT_STOPPED; alive = false; }
             else if (!(flags & PV_RAY_PROBE)) {
                 n_rays++;
@@ -350,7 +350,7 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, u
             out.depth = best.depth; out.ip[0] = best.ip.x; out.ip[1] = best.ip.y; out.ip[2] = best.ip.z;
             out.obj = best.obj; out.aux = best.aux; out.csg = best.csg;
         }
-        if (i < n) hits[i] = out;
+        if (i < n) store_cs(hits + i, out);
     }
     // one atomic per warp for the statistics
     unsigned long long n_nodes = tc.nodes, n_prims = tc.prims;

@@ -38,7 +38,7 @@ PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __res
 {
     const uint32_t n = min(wc->n_rays, ctx.cur_cap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const HitRec h = hits[i];
+        const HitRec h = load_cs(hits + i);
         if (h.obj == PV_HIT_STOPPED) continue;
         const PRay ray = cur[i];
 #if PV_FULL_MATERIALS

@@ -27,7 +27,8 @@ PV_VARIANT(k_shadow_opaque)(DScene sc, const SRay* __restrict__ rays, WaveCounts
     uint32_t taken = 0;
     while ((max_chunks == 0u || taken++ < max_chunks) && next_chunk(&wc->cur_shadow, n, cs, i)) {
         bool alive = i < n;
-        const SRay* sp = rays + (alive ? i : 0u);
+        const SRay sr = load_cs(rays + (alive ? i : 0u));
+        const SRay* sp = &sr;
 #if PV_HEAVY
         if (sc.has_area_lights && (sc.lights[sp->light].flags & PVGPU_LIGHT_AREA)) alive = false;      // served by k_shadow_area
 #endif

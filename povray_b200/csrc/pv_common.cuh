@@ -26,7 +26,7 @@ namespace pvgpu {
 #define PV_TRAV_MIN_BLOCKS_LEAN 8
 #endif
 #ifndef PV_TRAV_MIN_BLOCKS_HEAVY
-#define PV_TRAV_MIN_BLOCKS_HEAVY 16
+#define PV_TRAV_MIN_BLOCKS_HEAVY 12
 #endif
 #ifndef PV_TRAV_MIN_BLOCKS
 #ifdef PV_LEAN
@@ -284,6 +284,27 @@ struct WaveCounts {
     unsigned int pad[2];
 };
 static_assert(sizeof(WaveCounts) == 32, "WaveCounts must be 32 bytes");
+
+// Queue records are written once and read once, megabytes apart in time: they go through the caches with the streaming hint
+// (ld.global.cs / st.global.cs) so that they do not push the tree nodes and the per-ray traversal stacks out of L2.
+template <class T> __device__ __forceinline__ T load_cs(const T* p)
+{
+    static_assert(sizeof(T) % 16 == 0, "16-byte records");
+    T v;
+    uint4* dst = reinterpret_cast<uint4*>(&v);
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    #pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); k++) dst[k] = __ldcs(src + k);
+    return v;
+}
+template <class T> __device__ __forceinline__ void store_cs(T* p, const T& v)
+{
+    static_assert(sizeof(T) % 16 == 0, "16-byte records");
+    const uint4* src = reinterpret_cast<const uint4*>(&v);
+    uint4* dst = reinterpret_cast<uint4*>(p);
+    #pragma unroll
+    for (int k = 0; k < (int)(sizeof(T) / 16); k++) __stcs(dst + k, src[k]);
+}
 
 struct Hit {
     double   depth;

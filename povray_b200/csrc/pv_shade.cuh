@@ -818,13 +818,13 @@ __device__ __forceinline__ unsigned int take_slot(unsigned int* counter)
 __device__ __forceinline__ void push_ray(WaveCtx& ctx, const PRay& r)
 {
     unsigned int slot = take_slot(ctx.n_next);
-    if (slot < ctx.next_cap) ctx.next[slot] = r;
+    if (slot < ctx.next_cap) store_cs(ctx.next + slot, r);
     else atomicOr(&ctx.cnt->overflow, 8u);
 }
 __device__ __forceinline__ void push_shadow(WaveCtx& ctx, const SRay& r)
 {
     unsigned int slot = take_slot(ctx.n_shadow);
-    if (slot < ctx.shadow_cap) ctx.shadow[slot] = r;
+    if (slot < ctx.shadow_cap) store_cs(ctx.shadow + slot, r);
     else atomicOr(&ctx.cnt->overflow, 16u);
 }
 

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <future>
 #include <functional>
 #include <limits>
 
@@ -52,22 +53,32 @@ struct BuildNode {
     bool infinite = false;
 };
 
+// One pass of the reference's sort_and_split over work[first, last) creates ONE level of new nodes (bunches of the current
+// level's entries), left to right; the passes repeat on the new level until a single node is left.  The two halves of a split
+// touch disjoint sub-ranges of `work`, so the upper levels of the recursion run as parallel tasks; each task collects its new
+// nodes in its own list and the lists are concatenated left before right, which is the order the sequential recursion creates
+// them in - node numbering, and with it the final table, is byte-identical to the reference's (tests/golden/make_golden_1080.py
+// checks that against the parser's own tree).  The comparator reads precomputed FP32 keys instead of re-deriving them.
 struct TreeBuilder {
     std::deque<BuildNode> pool;
     std::vector<int64_t>  work;           // the reference's `Finite` array (ids into pool)
-    std::vector<float>    area;
+    std::vector<float>    box;            // per pool id: lo[3], size[3]     (compact copy for the hot loops)
+    std::vector<float>    key[3];         // per pool id: compboxes<>' sort key on each axis
     int64_t root = -1;
 
-    static thread_local const TreeBuilder* sort_ctx;
-    static thread_local int sort_axis;
+    static thread_local const float* sort_key;
+
+    void note_box(const BuildNode& n)
+    {
+        for (int k = 0; k < 3; k++) box.push_back(n.lo[k]);
+        for (int k = 0; k < 3; k++) box.push_back(n.size[k]);
+        // compboxes<>: am = 2.0 * lowerLeft + size evaluated in double, stored as BBoxScalar
+        for (int k = 0; k < 3; k++) key[k].push_back((float)(2.0 * n.lo[k] + n.size[k]));
+    }
 
     static int cmp(const void* pa, const void* pb)
     {
-        const BuildNode& a = sort_ctx->pool[(size_t)*(const int64_t*)pa];
-        const BuildNode& b = sort_ctx->pool[(size_t)*(const int64_t*)pb];
-        // compboxes<>: am = 2.0 * lowerLeft + size evaluated in double, stored as BBoxScalar
-        float am = (float)(2.0 * a.lo[sort_axis] + a.size[sort_axis]);
-        float bm = (float)(2.0 * b.lo[sort_axis] + b.size[sort_axis]);
+        const float am = sort_key[(size_t)*(const int64_t*)pa], bm = sort_key[(size_t)*(const int64_t*)pb];
         if (am < bm) return -1;
         return (am == bm) ? 0 : 1;
     }
@@ -77,10 +88,10 @@ struct TreeBuilder {
         float mins[3], maxs[3];
         for (int k = 0; k < 3; k++) { mins[k] = (float)kBoundHuge; maxs[k] = (float)-kBoundHuge; }
         for (ptrdiff_t i = first; i < last; i++) {
-            const BuildNode& n = pool[(size_t)work[i]];
+            const float* n = box.data() + 6 * (size_t)work[i];
             for (int k = 0; k < 3; k++) {
-                if (n.lo[k] < mins[k]) mins[k] = n.lo[k];
-                float hi = n.lo[k] + n.size[k];
+                if (n[k] < mins[k]) mins[k] = n[k];
+                float hi = n[k] + n[3 + k];
                 if (hi > maxs[k]) maxs[k] = hi;
             }
         }
@@ -98,10 +109,10 @@ struct TreeBuilder {
         double bmin[3] = { kBoundHuge, kBoundHuge, kBoundHuge };
         double bmax[3] = { -kBoundHuge, -kBoundHuge, -kBoundHuge };
         for (int64_t id : ids) {
-            const BuildNode& n = pool[(size_t)id];
+            const float* n = box.data() + 6 * (size_t)id;
             for (int k = 0; k < 3; k++) {
-                double tmin = n.lo[k];
-                double tmax = tmin + n.size[k];
+                double tmin = n[k];
+                double tmax = tmin + n[3 + k];
                 if (tmin < bmin[k]) bmin[k] = tmin;
                 if (tmax > bmax[k]) bmax[k] = tmax;
             }
@@ -115,9 +126,9 @@ struct TreeBuilder {
         float bmin[3], bmax[3];
         for (int k = 0; k < 3; k++) { bmin[k] = (float)kBoundHuge; bmax[k] = (float)-kBoundHuge; }
         for (ptrdiff_t i = a; i != b + dir; i += dir) {
-            const BuildNode& n = pool[(size_t)work[i]];
+            const float* n = box.data() + 6 * (size_t)work[i];
             for (int k = 0; k < 3; k++) {
-                float tmin = n.lo[k], tmax = tmin + n.size[k];
+                float tmin = n[k], tmax = tmin + n[3 + k];
                 if (tmin < bmin[k]) bmin[k] = tmin;
                 if (tmax > bmax[k]) bmax[k] = tmax;
             }
@@ -126,15 +137,16 @@ struct TreeBuilder {
         }
     }
 
-    bool sort_and_split(ptrdiff_t first, ptrdiff_t last)
+    // the new nodes of work[first, last), left to right, as lists of their entries; returns true when the range was split
+    bool split(ptrdiff_t first, ptrdiff_t last, std::vector<std::vector<int64_t>>& made, int depth)
     {
         ptrdiff_t size = last - first, best_loc = -1;
         if (size <= 0) return false;
         if (size > kBunching) {
-            sort_axis = find_axis(first, last);
-            sort_ctx = this;
+            const int axis = find_axis(first, last);
+            sort_key = key[axis].data();
             std::qsort(work.data() + first, (size_t)size, sizeof(int64_t), cmp);   // same libc routine as the reference
-            if (area.size() < (size_t)(2 * size)) area.resize((size_t)(2 * size));
+            std::vector<float> area((size_t)(2 * size));
             float* area_left = area.data();
             float* area_right = area_left + size;
             area_table(first, last - 1, area_left);
@@ -146,21 +158,39 @@ struct TreeBuilder {
             }
         }
         if (best_loc < 0) {
+            made.emplace_back(work.begin() + first, work.begin() + last);
+            return false;
+        }
+        if (depth < 4 && size > 20000) {
+            std::vector<std::vector<int64_t>> right;
+            std::future<void> left = std::async(std::launch::async, [&] { split(first, best_loc, made, depth + 1); });
+            split(best_loc, last, right, depth + 1);
+            left.get();
+            for (auto& r : right) made.push_back(std::move(r));
+        } else {
+            split(first, best_loc, made, depth + 1);
+            split(best_loc, last, made, depth + 1);
+        }
+        return true;
+    }
+
+    bool sort_and_split(ptrdiff_t first, ptrdiff_t last)
+    {
+        std::vector<std::vector<int64_t>> made;
+        const bool was_split = split(first, last, made, 0);
+        for (auto& kids : made) {
             BuildNode n;
-            n.kids.assign(work.begin() + first, work.begin() + last);
+            n.kids = std::move(kids);
             calc_bbox(n, n.kids);
+            note_box(n);
             pool.push_back(std::move(n));
             root = (int64_t)pool.size() - 1;
             work.push_back(root);
-            return false;
         }
-        sort_and_split(first, best_loc);
-        sort_and_split(best_loc, last);
-        return true;
+        return was_split;
     }
 };
-thread_local const TreeBuilder* TreeBuilder::sort_ctx = nullptr;
-thread_local int TreeBuilder::sort_axis = 0;
+thread_local const float* TreeBuilder::sort_key = nullptr;
 
 }  // namespace
 
@@ -175,6 +205,7 @@ void build_bbox_tree(const std::vector<LeafBox>& finite, const std::vector<LeafB
         std::memcpy(n.size, b.size, sizeof n.size);
         n.payload = b.payload;
         n.infinite = inf;
+        tb.note_box(n);
         tb.pool.push_back(std::move(n));
         return (int64_t)tb.pool.size() - 1;
     };
@@ -191,6 +222,7 @@ void build_bbox_tree(const std::vector<LeafBox>& finite, const std::vector<LeafB
             cd.kids = inf_ids;
             tb.calc_bbox(cd, cd.kids);
             cd.infinite = true;
+            tb.note_box(cd);
             tb.pool.push_back(std::move(cd));
             int64_t cd_id = (int64_t)tb.pool.size() - 1;
             BuildNode& r = tb.pool[(size_t)tb.root];
@@ -203,6 +235,7 @@ void build_bbox_tree(const std::vector<LeafBox>& finite, const std::vector<LeafB
         cd.kids = inf_ids;
         tb.calc_bbox(cd, cd.kids);
         cd.infinite = true;
+        tb.note_box(cd);
         tb.pool.push_back(std::move(cd));
         tb.root = (int64_t)tb.pool.size() - 1;
     } else {
