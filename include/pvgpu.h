@@ -608,6 +608,11 @@ int  pvgpu_noise(pvgpu_scene* s, size_t n, const double* xyz, const int32_t* gen
 /* Camera rays exactly as TracePixel::CreateCameraRay makes them for pixel-space (x, y): 6 doubles each. */
 int  pvgpu_camera_rays(pvgpu_scene* s, int width, int height, const double* xy, size_t n, double* org_dir);
 
+/* Starts the CUDA driver / context initialisation of `device` on a background thread and returns at once (a one-shot program
+ * calls it first thing, so that the ~1 s of cuInit + context creation overlaps the parser instead of preceding the first frame);
+ * pvgpu_scene_finalize waits for it.  Optional: finalize initialises on demand. */
+void pvgpu_prewarm(int device);
+
 /* Measured FP64 vector peak of CUDA device `device` in TFLOP/s (independent DFMA chains, timed with CUDA events): the second
  * roofline denominator of the trace path.  No scene needed. */
 int  pvgpu_fp64_peak(int device, double* tflops);

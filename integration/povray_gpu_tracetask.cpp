@@ -750,6 +750,19 @@ struct GpuView
 
 std::mutex g_mutex;
 std::mutex g_drain_mutex;
+
+// The CUDA driver and context come up on a background thread while the parser runs (about a second that a one-shot render
+// would otherwise spend between parsing and the first frame).
+struct Prewarm
+{
+    Prewarm()
+    {
+        const char* mode = getenv("PVGPU_RENDER");
+        if (mode != nullptr && strcmp(mode, "stock") == 0) return;
+        const char* dev = getenv("PVGPU_DEVICE");
+        pvgpu_prewarm(dev ? atoi(dev) : 0);
+    }
+} g_prewarm;
 std::map<std::pair<const void*, int>, std::shared_ptr<GpuView>> g_views;     // keyed by (SceneData, quality flags), validated through GpuView::owner
 
 void check(int rc, const char* what)

@@ -225,6 +225,7 @@ SIGNATURES = {
     "pvgpu_scene_finalize": (C.c_int, [VP, C.c_int]),
     "pvgpu_scene_finalize_multi": (C.c_int, [VP, P(C.c_int), C.c_int]),
     "pvgpu_scene_device_count": (C.c_int, [VP]),
+    "pvgpu_prewarm": (None, [C.c_int]),
     "pvgpu_fp64_peak": (C.c_int, [C.c_int, P(C.c_double)]),
     "pvgpu_scene_device_bytes": (C.c_size_t, [VP]),
     "pvgpu_scene_save": (C.c_int, [VP, C.c_char_p]),

@@ -301,18 +301,25 @@ __global__ void k_aa2_expand(AALayout L, AAParams aa, const uint16_t* hash, cons
 }
 
 // SubdivideOnePixel's result for every pixel (tracetask.cpp:892-1074), iterative post-order over the sample buffer
-__global__ void k_aa2_resolve(AALayout L, AAParams aa, const float4* accum, const int32_t* act_idx, float4* out)
+//   group == nullptr: every pixel; the sample buffer of subdividing pixel number a starts at s_base + a * n1^2, or - skip_active - only
+//   the pixels that do not subdivide.   group != nullptr: the n_group subdividing pixels listed there, buffers numbered within the group
+//   (deep subdivision levels: the buffers of all subdividing pixels do not fit at once, so the pixels are worked off in groups)
+__global__ void k_aa2_resolve(AALayout L, AAParams aa, const float4* accum, const int32_t* act_idx, float4* out,
+                              const uint32_t* group, uint32_t n_group, int skip_active)
 {
     const uint32_t S = 1u << aa.depth, n1 = S + 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < L.n_px; i += gridDim.x * blockDim.x) {
+    const uint32_t n_items = group ? n_group : L.n_px;
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        const uint32_t i = group ? group[it] : it;
         SubBuf buf;
         buf.accum = accum; buf.n1 = n1; buf.S = S;
         buf.pc = pixel_corners(L, i);
-        const int32_t a = act_idx[i];
+        const int32_t a = group ? (int32_t)it : act_idx[i];
         if (a < 0) {
             out[i] = px_div(px_add(px_add(px_add(accum[buf.pc.c00], accum[buf.pc.c02]), accum[buf.pc.c20]), accum[buf.pc.c22]), 4.0);
             continue;
         }
+        if (skip_active) continue;
         buf.base = L.s_base + (uint32_t)a * n1 * n1;
         struct Frame { Square q; int next; float4 acc; };
         Frame fr[12];
@@ -372,7 +379,8 @@ void launch_aa2_mark(const AALayout& L, const AAParams& aa, const float4* accum,
 void launch_aa2_expand(const AALayout& L, const AAParams& aa, const uint16_t* hash, const float4* accum, const uint32_t* act_list, uint32_t n_active,
                        int target, uint32_t* sampled, double2* coords, uint32_t* slots, unsigned int* n_samples, uint32_t cap, cudaStream_t st)
 { if (n_active) k_aa2_expand<<<grid_for(n_active, 64, 16), 64, 0, st>>>(L, aa, hash, accum, act_list, n_active, target, sampled, coords, slots, n_samples, cap); }
-void launch_aa2_resolve(const AALayout& L, const AAParams& aa, const float4* accum, const int32_t* act_idx, float4* out, cudaStream_t st)
-{ k_aa2_resolve<<<grid_for(L.n_px, 128, 8), 128, 0, st>>>(L, aa, accum, act_idx, out); }
+void launch_aa2_resolve(const AALayout& L, const AAParams& aa, const float4* accum, const int32_t* act_idx, float4* out, cudaStream_t st,
+                        const uint32_t* group, uint32_t n_group, int skip_active)
+{ k_aa2_resolve<<<grid_for(group ? n_group : L.n_px, 128, 8), 128, 0, st>>>(L, aa, accum, act_idx, out, group, n_group, skip_active); }
 
 }  // namespace pvgpu

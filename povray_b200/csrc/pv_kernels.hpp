@@ -90,7 +90,8 @@ void launch_aa2_corner_coords(const AALayout& L, double2* coords, cudaStream_t s
 void launch_aa2_mark(const AALayout& L, const AAParams& aa, const float4* accum, int32_t* act_idx, uint32_t* act_list, unsigned int* n_active, cudaStream_t st);
 void launch_aa2_expand(const AALayout& L, const AAParams& aa, const uint16_t* hash, const float4* accum, const uint32_t* act_list, uint32_t n_active,
                        int target, uint32_t* sampled, double2* coords, uint32_t* slots, unsigned int* n_samples, uint32_t cap, cudaStream_t st);
-void launch_aa2_resolve(const AALayout& L, const AAParams& aa, const float4* accum, const int32_t* act_idx, float4* out, cudaStream_t st);
+void launch_aa2_resolve(const AALayout& L, const AAParams& aa, const float4* accum, const int32_t* act_idx, float4* out, cudaStream_t st,
+                        const uint32_t* group = nullptr, uint32_t n_group = 0, int skip_active = 0);
 void launch_probe_solver(uint32_t n, const int32_t* degree, const int32_t* sturm, const double* epsilon, const double* coeffs,
                          double* roots, int32_t* counts, cudaStream_t st);
 void launch_probe_noise(const NoiseTables& nt, uint32_t n, const double* xyz, const int32_t* gen, const int32_t* octaves, double* out, cudaStream_t st);

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <string>
 #include <thread>
@@ -228,9 +229,18 @@ void device_release(Scene& s)
 }
 
 // Replicates the host tables of `s` on `device` (called once per device of the scene).
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int upload_one(Scene& s, int device, DeviceScene*& out)
 {
     out = nullptr;
+    const bool trace_t = getenv("PVGPU_TRACE_TIMING") != nullptr;
+    const double t_begin = now_s();
+    double t_mark = t_begin;
+    auto mark = [&](const char* what) { if (trace_t) { const double t = now_s(); fprintf(stderr, "pvgpu upload: %-28s %.3f s\n", what, t - t_mark); t_mark = t; } };
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(PVGPU_E_NO_DEVICE, "no CUDA device available (pvgpu has no CPU fallback)");
@@ -254,6 +264,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     size_t total = 0;
     DScene& v = d->view;
 
+    mark("context + device flags");
     // CSG leaf lists: primitive descendants of every parentless CSG object, depth first (csg.cpp walks children in order)
     std::vector<uint32_t> leaves;
     std::vector<uint2> leaf_range(s.objects.size(), make_uint2(0, 0));
@@ -324,6 +335,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
         if (rc != PVGPU_OK) { release_one(d); return rc; }
     }
 
+    mark("host-side derived tables");
     int rc = PVGPU_OK;
     #define UP(vec, field) if (rc == PVGPU_OK) rc = upload(*d, vec, field, total)
     UP(s.objects, v.objs); UP(s.transforms, v.xf); UP(s.index_list, v.index_list); UP(s.frame, v.frame);
@@ -347,6 +359,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     UP(hash, v.noise.hash); UP(rtable, v.noise.rtable); UP(perm, v.noise.perm); UP(grad, v.noise.grad);
     #undef UP
     if (rc != PVGPU_OK) { release_one(d); return rc; }
+    mark("cudaMalloc + H2D of the tables");
     if (s.globals.number_of_waves) {       // TraceThreadData::waveSources / waveFrequencies, computed with the device's own DNoise
         const uint32_t nw = s.globals.number_of_waves;
         std::vector<double> zeros(4 * (size_t)nw, 0.0);
@@ -457,12 +470,25 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
         d->ctx.push_back(std::move(c));
         if (!ok) { release_one(d); return fail(PVGPU_E_CUDA, "allocation of the work context failed: %s", cudaGetErrorString(cudaGetLastError())); }
     }
+    mark("work contexts");
+    if (trace_t) fprintf(stderr, "pvgpu upload: total %.3f s\n", now_s() - t_begin);
     out = d;
     return PVGPU_OK;
 }
 
+static std::mutex g_prewarm_mutex;
+static std::thread g_prewarm_thread;
+static struct PrewarmGuard { ~PrewarmGuard() { if (g_prewarm_thread.joinable()) g_prewarm_thread.join(); } } g_prewarm_guard;
+
+static void join_prewarm()
+{
+    std::lock_guard<std::mutex> lock(g_prewarm_mutex);
+    if (g_prewarm_thread.joinable()) g_prewarm_thread.join();
+}
+
 int device_upload(Scene& s, const int* devices, int n_devices)
 {
+    join_prewarm();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
         return fail(PVGPU_E_NO_DEVICE, "no CUDA device available (pvgpu has no CPU fallback)");
@@ -893,26 +919,24 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
     { TimedLaunch t(c, stream, KIND_AA, n_px); launch_aa2_mark(L, ap, corners, act_idx, act_list, counters, stream); }
     unsigned int n_active = 0;
     AA_TRY(read_counter(counters, stream, n_active));
-    float4* accum = corners;
-    if (n_active) {
-        const unsigned long long n_slots = (unsigned long long)n_corner + (unsigned long long)n_active * per;
-        if (n_slots > 0xFFFFFFF0ull) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: %u subdividing pixels x %u samples exceed the slot range; render fewer rectangles per call", n_active, per);
-        uint32_t* sampled = nullptr;
-        AA_TRY(sc.alloc(accum, (size_t)n_slots + cont_extra(d, c))); AA_TRY(sc.alloc(sampled, (size_t)n_active * words));
-        CUDA_TRY(cudaMemsetAsync(accum, 0, (size_t)n_slots * sizeof(float4), stream));
-        CUDA_TRY(cudaMemcpyAsync(accum, corners, (size_t)n_corner * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
-        CUDA_TRY(cudaMemsetAsync(sampled, 0, (size_t)n_active * words * sizeof(uint32_t), stream));
-        f.accum = accum; f.cont_base = (uint32_t)n_slots;
-        // 3. one tracing round per subdivision level
+    // The sample buffers ((2^depth + 1)^2 slots per subdividing pixel, like the reference's SubdivisionBuffer) of all subdividing
+    // pixels are held at once when they fit the slot budget; deep levels (+R6 .. +R9: 4 k .. 263 k slots per pixel) work the pixels
+    // off in groups, each with its own buffers, rounds and resolve pass - the result does not depend on the grouping.
+    unsigned long long kSlotBudget = 1ull << 26;                // 1 GB of accumulators
+    if (const char* e = getenv("PVGPU_TEST_AA2_SLOTS")) kSlotBudget = (unsigned long long)std::max(1, atoi(e));      // tests: force the grouped path
+    const uint32_t group_max = (uint32_t)std::max<unsigned long long>(1, std::min<unsigned long long>(n_active ? n_active : 1, (kSlotBudget > n_corner ? kSlotBudget - n_corner : 1) / per));
+    const bool grouped = n_active > group_max;
+    auto refine = [&](float4* accum, uint32_t* sampled, const uint32_t* list, uint32_t n_list) -> int {
+        // one tracing round per subdivision level for the pixels of `list`
         unsigned long long per_pixel = 5;
-        for (uint32_t round = 0; round + 1 < aa.depth; round++, per_pixel *= 4) {
-            const unsigned long long cap64 = std::min<unsigned long long>((unsigned long long)n_active * per_pixel, 0xFFFFFFF0ull);
+        for (uint32_t round = 0; round + 1 < aa.depth; round++, per_pixel = std::min<unsigned long long>(per_pixel * 4, per)) {
+            const unsigned long long cap64 = std::min<unsigned long long>((unsigned long long)n_list * per_pixel, 0xFFFFFFF0ull);
             const uint32_t cap = (uint32_t)cap64;
             double2* d_coords = nullptr; uint32_t* d_slots = nullptr;
             Scratch rs;
             AA_TRY(rs.alloc(d_coords, cap)); AA_TRY(rs.alloc(d_slots, cap));
             CUDA_TRY(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned int), stream));
-            { TimedLaunch t(c, stream, KIND_AA, n_active); launch_aa2_expand(L, ap, d.view.noise.hash, accum, act_list, n_active, (int)round, sampled, d_coords, d_slots, counters + 1, cap, stream); }
+            { TimedLaunch t(c, stream, KIND_AA, n_list); launch_aa2_expand(L, ap, d.view.noise.hash, accum, list, n_list, (int)round, sampled, d_coords, d_slots, counters + 1, cap, stream); }
             unsigned int n_new = 0;
             AA_TRY(read_counter(counters + 1, stream, n_new));
             if (n_new > cap) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: sample list overflow");
@@ -923,9 +947,42 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
             n_extra_samples += n_new;
             CUDA_TRY(cudaStreamSynchronize(stream));
         }
+        return PVGPU_OK;
+    };
+    if (!grouped) {
+        float4* accum = corners;
+        if (n_active) {
+            const unsigned long long n_slots = (unsigned long long)n_corner + (unsigned long long)n_active * per;
+            if (n_slots > 0xFFFFFFF0ull) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: %u subdividing pixels x %u samples exceed the slot range; render fewer rectangles per call", n_active, per);
+            uint32_t* sampled = nullptr;
+            AA_TRY(sc.alloc(accum, (size_t)n_slots + cont_extra(d, c))); AA_TRY(sc.alloc(sampled, (size_t)n_active * words));
+            CUDA_TRY(cudaMemsetAsync(accum, 0, (size_t)n_slots * sizeof(float4), stream));
+            CUDA_TRY(cudaMemcpyAsync(accum, corners, (size_t)n_corner * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+            CUDA_TRY(cudaMemsetAsync(sampled, 0, (size_t)n_active * words * sizeof(uint32_t), stream));
+            f.accum = accum; f.cont_base = (uint32_t)n_slots;
+            AA_TRY(refine(accum, sampled, act_list, n_active));
+        }
+        // 4. combine
+        { TimedLaunch t(c, stream, KIND_AA, n_px); launch_aa2_resolve(L, ap, accum, act_idx, d_out, stream); }
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        return PVGPU_OK;
     }
-    // 4. combine
-    { TimedLaunch t(c, stream, KIND_AA, n_px); launch_aa2_resolve(L, ap, accum, act_idx, d_out, stream); }
+    // pixels that do not subdivide: the mean of their corners
+    { TimedLaunch t(c, stream, KIND_AA, n_px); launch_aa2_resolve(L, ap, corners, act_idx, d_out, stream, nullptr, 0, 1); }
+    const unsigned long long g_slots = (unsigned long long)n_corner + (unsigned long long)group_max * per;
+    if (g_slots > 0xFFFFFFF0ull) return fail(PVGPU_E_OVERFLOW, "anti-aliasing method 2: sample buffer of one pixel exceeds the slot range");
+    float4* accum = nullptr; uint32_t* sampled = nullptr;
+    AA_TRY(sc.alloc(accum, (size_t)g_slots + cont_extra(d, c))); AA_TRY(sc.alloc(sampled, (size_t)group_max * words));
+    f.accum = accum; f.cont_base = (uint32_t)g_slots;
+    for (uint32_t a0 = 0; a0 < n_active; a0 += group_max) {
+        const uint32_t ng = std::min(group_max, n_active - a0);
+        CUDA_TRY(cudaMemsetAsync(accum, 0, ((size_t)n_corner + (size_t)ng * per) * sizeof(float4), stream));
+        CUDA_TRY(cudaMemcpyAsync(accum, corners, (size_t)n_corner * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemsetAsync(sampled, 0, (size_t)ng * words * sizeof(uint32_t), stream));
+        AA_TRY(refine(accum, sampled, act_list + a0, ng));
+        { TimedLaunch t(c, stream, KIND_AA, ng); launch_aa2_resolve(L, ap, accum, act_idx, d_out, stream, act_list + a0, ng, 0); }
+        if (f.cooperate && f.cooperate(f.user)) return fail(PVGPU_E_ABORTED, "render aborted by the cooperate callback");
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
     return PVGPU_OK;
 }
@@ -937,7 +994,6 @@ static int render_impl(Scene& s, DeviceScene& d, WorkCtx& c, const pvgpu_aa* aa,
     const unsigned int method = aa ? aa->method : 0u;
     if (method > 2) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method %u (stochastic supersampling) is outside the GPU trace path", method);
     if (method && (aa->depth < 1 || aa->depth > 9)) return fail(PVGPU_E_INVALID, "anti-aliasing depth %u out of range 1..9", aa->depth);
-    if (method == 2 && aa->depth > 5) return fail(PVGPU_E_UNSUPPORTED, "anti-aliasing method 2 is limited to depth 5 on the GPU path (sample buffers of (2^depth + 1)^2 per pixel)");
     CUDA_TRY(cudaSetDevice(d.device));
     std::vector<uint32_t> off(n_rects + 1, 0);
     for (size_t i = 0; i < n_rects; i++) {
@@ -1395,6 +1451,18 @@ int pvgpu_noise(pvgpu_scene* sc, size_t n, const double* xyz, const int32_t* gen
     s.dev->ctx[0]->kernel_launches++;
     CUDA_TRY(cudaMemcpy(out, d_o.p, 5 * n * sizeof(double), cudaMemcpyDeviceToHost));
     return PVGPU_OK;
+}
+
+void pvgpu_prewarm(int device)
+{
+    std::lock_guard<std::mutex> lock(g_prewarm_mutex);
+    if (g_prewarm_thread.joinable()) return;
+    g_prewarm_thread = std::thread([device] {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return; }
+        if (cudaSetDevice(device) == cudaSuccess) cudaFree(nullptr);      // creates the primary context
+        cudaGetLastError();
+    });
 }
 
 int pvgpu_fp64_peak(int device, double* tflops)

@@ -317,6 +317,28 @@ def test_antialiasing_matches_oracle_and_reference(pv, oracle, scene, mode):
         assert st["samples"] <= 1.25 * ost["samples"] + 64
 
 
+def test_antialiasing_method2_deep_levels_and_pixel_groups(pv, oracle):
+    """+AM2 beyond +R5: the sample buffers of all subdividing pixels no longer fit at once, so the pixels are refined in groups
+    (render_aa2).  (a) +R6 against the oracle's sequential restatement; (b) the grouped path forced at +R3 (tiny slot budget) gives the
+    frame and the sample count of the ungrouped path."""
+    path = os.path.join(GOLDEN, "csg_glass.pvs")
+    rects = pv.tiles(W, H, 32)
+    s = pv.Scene.load(path).finalize(0)
+    px, st = s.render(W, H, rects, aa=make_aa(pv, 2, 6, 0.3, 1.0))
+    opx, ost = oracle.render_aa(oracle.OracleScene(path), W, H, rects, 2, 6, 0.3, 1.0, 2.5, threads=4)
+    d = np.abs(px - opx).max(axis=1)
+    assert (d > PIXEL_TOL).mean() <= 0.002, d.max()
+    assert st["samples"] == ost["samples"]
+    px3, st3 = s.render(W, H, rects, aa=make_aa(pv, 2, 3, 0.3, 1.0))
+    os.environ["PVGPU_TEST_AA2_SLOTS"] = str(W * H + 40 * 81)          # room for the corner samples + 40 pixels' buffers
+    try:
+        pxg, stg = s.render(W, H, rects, aa=make_aa(pv, 2, 3, 0.3, 1.0))
+    finally:
+        del os.environ["PVGPU_TEST_AA2_SLOTS"]
+    assert stg["samples"] == st3["samples"]
+    assert np.abs(pxg - px3).max() < 2e-5
+
+
 def test_antialiasing_rect_semantics(pv, oracle):
     """Tile-edge behaviour: the result depends on how the frame is cut into rectangles exactly like the reference's
     (left / top neighbours are re-traced per tile and never supersampled); ragged rectangles included."""
