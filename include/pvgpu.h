@@ -247,9 +247,17 @@ enum {
     PVGPU_PAT_CRACKLE  = 25,     /* CracklePattern   pattern.cpp:5760; `data` = offset into the shape-data table of 9 doubles:
                                     crackleForm xyz, crackleMetric, crackleOffset, crackleIsSolid, repeat xyz */
     PVGPU_PAT_CELLS    = 26,     /* CellsPattern     pattern.cpp:5652 */
-    PVGPU_PAT_IMAGE_MAP = 27     /* IMAGE_MAP_PATTERN pigment (ColourImagePattern, pattern.cpp:493-514); `data` = index into the image table */
+    PVGPU_PAT_IMAGE_MAP = 27,    /* IMAGE_MAP_PATTERN pigment (ColourImagePattern, pattern.cpp:493-514); `data` = index into the image table */
+    PVGPU_PAT_FRACTAL  = 28,     /* FractalPattern family (pattern.cpp:6895-7098, 7228-7751): `data` = offset into the shape-data table of
+                                    8 doubles: PVGPU_FRACTAL_* kind, maxIterations, exteriorType, interiorType, exteriorFactor,
+                                    interiorFactor, juliaCoord u v */
+    PVGPU_PAT_SPIRAL1  = 29,     /* Spiral1Pattern   pattern.cpp:8396, p[0] = arms */
+    PVGPU_PAT_SPIRAL2  = 30      /* Spiral2Pattern   pattern.cpp:8473, p[0] = arms */
 };
-#define PVGPU_PAT_LAST PVGPU_PAT_IMAGE_MAP
+#define PVGPU_PAT_LAST PVGPU_PAT_SPIRAL2
+/* iteration formulas of PVGPU_PAT_FRACTAL (exponents above 4 - MandelXPattern / JuliaXPattern - are not served) */
+enum { PVGPU_FRACTAL_MANDEL2 = 0, PVGPU_FRACTAL_MANDEL3 = 1, PVGPU_FRACTAL_MANDEL4 = 2, PVGPU_FRACTAL_JULIA2 = 3, PVGPU_FRACTAL_JULIA3 = 4,
+       PVGPU_FRACTAL_JULIA4 = 5, PVGPU_FRACTAL_MAGNET1M = 6, PVGPU_FRACTAL_MAGNET1J = 7, PVGPU_FRACTAL_MAGNET2M = 8, PVGPU_FRACTAL_MAGNET2J = 9 };
 /* ContinuousPattern::waveType (pattern.h:108-117) */
 enum { PVGPU_WAVE_RAW = 0, PVGPU_WAVE_RAMP = 1, PVGPU_WAVE_SINE = 2, PVGPU_WAVE_TRIANGLE = 3,
        PVGPU_WAVE_SCALLOP = 4, PVGPU_WAVE_CUBIC = 5, PVGPU_WAVE_POLY = 6 };

@@ -211,6 +211,32 @@ struct Flattener
             shape_data.push_back(cr->repeat.x()); shape_data.push_back(cr->repeat.y()); shape_data.push_back(cr->repeat.z());
         }
         else if (dynamic_cast<const CellsPattern*>(bp)) p.pattern = PVGPU_PAT_CELLS;
+        else if (const FractalPattern* fp = dynamic_cast<const FractalPattern*>(bp)) {
+            int kind = -1;
+            if (dynamic_cast<const Mandel2Pattern*>(bp)) kind = PVGPU_FRACTAL_MANDEL2;
+            else if (dynamic_cast<const Mandel3Pattern*>(bp)) kind = PVGPU_FRACTAL_MANDEL3;
+            else if (dynamic_cast<const Mandel4Pattern*>(bp)) kind = PVGPU_FRACTAL_MANDEL4;
+            else if (dynamic_cast<const Magnet1MPattern*>(bp)) kind = PVGPU_FRACTAL_MAGNET1M;
+            else if (dynamic_cast<const Magnet2MPattern*>(bp)) kind = PVGPU_FRACTAL_MAGNET2M;
+            else if (dynamic_cast<const Magnet1JPattern*>(bp)) kind = PVGPU_FRACTAL_MAGNET1J;
+            else if (dynamic_cast<const Magnet2JPattern*>(bp)) kind = PVGPU_FRACTAL_MAGNET2J;
+            else if (dynamic_cast<const Julia3Pattern*>(bp)) kind = PVGPU_FRACTAL_JULIA3;
+            else if (dynamic_cast<const Julia4Pattern*>(bp)) kind = PVGPU_FRACTAL_JULIA4;
+            else if (dynamic_cast<const JuliaXPattern*>(bp) == nullptr && typeid(*bp) == typeid(JuliaPattern)) kind = PVGPU_FRACTAL_JULIA2;
+            if (kind < 0 || fp->maxIterations < 1 || (fp->exteriorType == 7 && fp->exteriorFactor < 1.0) || (fp->exteriorType == 8 && fp->exteriorFactor < 0.0))
+                unsupported(std::string(user) + " pattern outside the hot-path scope: " + typeid(*bp).name());
+            else {
+                p.pattern = PVGPU_PAT_FRACTAL;
+                p.data = (uint32_t)shape_data.size();
+                const JuliaPattern* jp = dynamic_cast<const JuliaPattern*>(bp);
+                for (double v : { (double)kind, (double)fp->maxIterations, (double)fp->exteriorType, (double)fp->interiorType, (double)fp->exteriorFactor,
+                                  (double)fp->interiorFactor, jp ? (double)jp->juliaCoord[U] : 0.0, jp ? (double)jp->juliaCoord[V] : 0.0 }) shape_data.push_back(v);
+            }
+        }
+        else if (const SpiralPattern* sp = dynamic_cast<const SpiralPattern*>(bp)) {
+            p.pattern = dynamic_cast<const Spiral1Pattern*>(bp) ? PVGPU_PAT_SPIRAL1 : PVGPU_PAT_SPIRAL2;
+            p.p[0] = (double)sp->arms;
+        }
         else if (dynamic_cast<const BumpsPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;      // BumpsPattern is a NoisePattern (pattern.h:989)
         else unsupported(std::string(user) + " pattern outside the hot-path scope: " + typeid(*bp).name());
         if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {
@@ -835,7 +861,22 @@ std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
     Flattener fl;
     for (ObjectPtr o : sd->objects) {
         if ((o->Type & LIGHT_SOURCE_OBJECT) != 0) {
-            if (!(reinterpret_cast<LightSource*>(o))->children.empty()) fl.unsupported("light source with looks_like");
+            // looks_like.  With a slab tree the tree's leaf IS children[0] (Build_Bounding_Slabs, boundingbox.cpp:337-347, 390-396): the
+            // child is a frame-level object like any other.  Without one (boundingMethod 0, or too few objects for a tree) the loop over
+            // SceneData::objects meets the light source: its flags gate the ray kinds (trace.cpp:84-95, 1943), its All_Intersections hands
+            // the ray to children[0] behind that child's bounded_by list (lightsource.cpp:83-95), and InitRayContainerState looks at the
+            // light source's own (absent) interior (tracepixel.cpp:950-955).
+            LightSource* ls = reinterpret_cast<LightSource*>(o);
+            if (ls->children.empty()) continue;
+            ObjectPtr child = ls->children[0];
+            const int32_t id = fl.add_object(child, -1);
+            if (!(sd->boundingMethod == 1 && sd->boundingSlabs != nullptr)) {
+                if (child->interior != nullptr && child->Inside(vd->GetCamera().Location, nullptr))
+                    fl.unsupported("camera inside the interior of a looks_like object, no bounding tree");
+                const uint32_t ray_kind = PVGPU_NO_SHADOW_FLAG | PVGPU_NO_IMAGE_FLAG | PVGPU_NO_REFLECTION_FLAG;
+                fl.objects[id].flags = (fl.objects[id].flags & ~ray_kind) | ((uint32_t)o->Flags & ray_kind);
+            }
+            fl.frame.push_back((uint32_t)id);
             continue;
         }
         fl.frame.push_back((uint32_t)fl.add_object(o, -1));

@@ -1688,6 +1688,81 @@ V3 Tracer::Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const                
     return p;
 }
 
+// FractalPattern family: JuliaPattern .. Julia4Pattern (pattern.cpp:6895-7098), Magnet1M .. Magnet2J (7228-7550), Mandel2 .. Mandel4
+// (7551-7751), ExteriorColour / InteriorColour (8990-9056).  rec = kind, maxIterations, exteriorType, interiorType, exteriorFactor,
+// interiorFactor, juliaCoord.  Every kind is the same loop around its own iteration step.
+static double fractal_pattern(const double* rec, V3 EPoint)
+{
+    const int kind = (int)rec[0], it_max = (int)rec[1], exteriorType = (int)rec[2], interiorType = (int)rec[3];
+    const double exteriorFactor = rec[4], interiorFactor = rec[5];
+    double x = EPoint.x, y = EPoint.y;                 // the constant c of the iteration: the point (M kinds) or juliaCoord (J kinds)
+    double a, b, a2, b2, mindist2;
+    bool magnet = false;
+    switch (kind) {
+        case PVGPU_FRACTAL_JULIA2: case PVGPU_FRACTAL_JULIA3: case PVGPU_FRACTAL_JULIA4:
+            a = EPoint.x; b = EPoint.y; x = rec[6]; y = rec[7]; a2 = sqr(a); b2 = sqr(b); mindist2 = a2 + b2; break;
+        case PVGPU_FRACTAL_MAGNET1J: case PVGPU_FRACTAL_MAGNET2J:
+            magnet = true; a = EPoint.x; b = EPoint.y; x = rec[6]; y = rec[7]; a2 = sqr(a); b2 = sqr(b); mindist2 = a2 + b2; break;
+        case PVGPU_FRACTAL_MAGNET1M: case PVGPU_FRACTAL_MAGNET2M:
+            magnet = true; a = a2 = 0; b = b2 = 0; mindist2 = 10000; break;
+        default:
+            a = x; b = y; a2 = sqr(a); b2 = sqr(b); mindist2 = a2 + b2; break;
+    }
+    const double c1r = x - 1, c2r = x - 2, c1c2r = c1r * c2r - y * y, c1c2i = (c1r + c2r) * y;
+    int col;
+    double cf = 0.0;
+    for (col = 0; col < it_max; col++) {
+        double tmp, tmp1r, tmp1i, tmp2r, tmp2i;
+        switch (kind) {
+            case PVGPU_FRACTAL_MANDEL2: case PVGPU_FRACTAL_JULIA2: b = 2.0 * a * b + y; a = a2 - b2 + x; break;
+            case PVGPU_FRACTAL_MANDEL3: case PVGPU_FRACTAL_JULIA3: b = 3.0 * a2 * b - b2 * b + y; a = a2 * a - 3.0 * a * b2 + x; break;
+            case PVGPU_FRACTAL_MANDEL4: case PVGPU_FRACTAL_JULIA4: b = 4.0 * (a2 * a * b - a * b2 * b) + y; a = a2 * a2 - 6.0 * a2 * b2 + b2 * b2 + x; break;
+            case PVGPU_FRACTAL_MAGNET1M: case PVGPU_FRACTAL_MAGNET1J:
+                tmp1r = a2 - b2 + x - 1; tmp1i = 2 * a * b + y; tmp2r = 2 * a + x - 2; tmp2i = 2 * b + y;
+                tmp = tmp2r * tmp2r + tmp2i * tmp2i;
+                a = (tmp1r * tmp2r + tmp1i * tmp2i) / tmp; b = (tmp1i * tmp2r - tmp1r * tmp2i) / tmp;
+                b2 = b * b; b = 2 * a * b; a = a * a - b2;
+                break;
+            default:
+                tmp1r = a2 * a - 3 * a * b2 + 3 * (a * c1r - b * y) + c1c2r; tmp1i = 3 * a2 * b - b2 * b + 3 * (a * y + b * c1r) + c1c2i;
+                tmp2r = 3 * (a2 - b2) + 3 * (a * c2r - b * y) + c1c2r + 1; tmp2i = 6 * a * b + 3 * (a * y + b * c2r) + c1c2i;
+                tmp = tmp2r * tmp2r + tmp2i * tmp2i;
+                a = (tmp1r * tmp2r + tmp1i * tmp2i) / tmp; b = (tmp1i * tmp2r - tmp1r * tmp2i) / tmp;
+                b2 = b * b; b = 2 * a * b; a = a * a - b2;
+                break;
+        }
+        a2 = sqr(a); b2 = sqr(b);
+        const double dist2 = a2 + b2;
+        if (dist2 < mindist2) mindist2 = dist2;
+        const bool escaped = magnet ? (dist2 > 10000.0 || (a - 1) * (a - 1) + b2 < 1 / 10000.0) : (dist2 > 4.0);
+        if (escaped) {
+            switch (exteriorType) {                                                                           // pattern.cpp:8990-9015
+                case 0: cf = exteriorFactor; break;
+                case 1: cf = (double)col / (double)it_max; break;
+                case 2: cf = a * exteriorFactor; break;
+                case 3: cf = b * exteriorFactor; break;
+                case 4: cf = a * a * exteriorFactor; break;
+                case 5: cf = b * b * exteriorFactor; break;
+                case 6: cf = std::sqrt(a * a + b * b) * exteriorFactor; break;
+                case 7: cf = (double)(col % (unsigned int)exteriorFactor) / exteriorFactor; break;
+                case 8: cf = (double)(col % (unsigned int)(1 + exteriorFactor)) / exteriorFactor; break;
+            }
+            break;
+        }
+    }
+    if (col == it_max)
+        switch (interiorType) {                                                                               // pattern.cpp:9036-9056
+            case 0: cf = interiorFactor; break;
+            case 1: cf = std::sqrt(mindist2) * interiorFactor; break;
+            case 2: cf = a * interiorFactor; break;
+            case 3: cf = b * interiorFactor; break;
+            case 4: cf = a * a * interiorFactor; break;
+            case 5: cf = b * b * interiorFactor; break;
+            case 6: cf = a * a + b * b * interiorFactor; break;
+        }
+    return cf;
+}
+
 static double crackle_pattern(const Scene& S, const pvgpu_pigment& pg, V3 ep, int gen)                      // pattern.cpp:5760-5987 (no cell cache)
 {
     const double* cp = S.shape_data.data() + pg.data;
@@ -1900,6 +1975,18 @@ double Tracer::Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const               
         }
     }
     if (pg.pattern == PVGPU_PAT_CRACKLE) value = crackle_pattern(S, pg, p, gen);
+    else if (pg.pattern == PVGPU_PAT_FRACTAL) value = fractal_pattern(&S.shape_data[pg.data], p);
+    else if (pg.pattern == PVGPU_PAT_SPIRAL1 || pg.pattern == PVGPU_PAT_SPIRAL2) {                        // pattern.cpp:8396-8437, 8473-8517
+        const double M_PI_2_ = 1.57079632679489661923, TWO_M_PI = 6.283185307179586476925286766560;
+        const double turb_val = turb ? turb->turbulence[0] * Turbulence(S, p, *turb, gen) : 0.0;
+        const double rad = std::sqrt(p.x * p.x + p.y * p.y);
+        double phi;
+        if (rad == 0.0) phi = 0.0;
+        else if (p.x < 0.0) phi = 3.0 * M_PI_2_ - std::asin(p.y / rad);
+        else phi = M_PI_2_ + std::asin(p.y / rad);
+        const double spiral = p.z + rad + pg.p[0] * phi / TWO_M_PI + turb_val;
+        value = (pg.pattern == PVGPU_PAT_SPIRAL1) ? spiral : Triangle_Wave(rad) + Triangle_Wave(spiral);
+    }
     else if (pg.pattern == PVGPU_PAT_CELLS)                                                               // pattern.cpp:5652-5660
         value = std::min(S.patternRands[S.hashTable[S.hashTable[S.hashTable[(int)std::floor(p.x + EPSILON) & 0xfff] ^ ((int)std::floor(p.y + EPSILON) & 0xfff)] ^
                                                     ((int)std::floor(p.z + EPSILON) & 0xfff)] % 32768u], 1.0);

@@ -63,6 +63,104 @@ __device__ inline V3 warp_epoint(const DScene& sc, const pvgpu_pigment& pg, cons
 }
 
 #if PV_FULL_MATERIALS
+// The FractalPattern family (pattern.cpp:6895-7098 julia, 7228-7550 magnet, 7551-7751 mandel; ExteriorColour / InteriorColour 8990-9056):
+// one orbit loop, the iteration formula picked by the record's kind.  z starts at the point (julia kinds: c is the record's
+// constant; mandel kinds: c is the point) or at 0 (magnet "m" kinds, which also start mindist2 at 10000).
+static __device__ __noinline__ double fractal_pattern(const double* fd, const V3& p)
+{
+    const int kind = (int)fd[0], it_max = (int)fd[1], ext_type = (int)fd[2], int_type = (int)fd[3];
+    const double ext_f = fd[4], int_f = fd[5];
+    const bool julia = (kind == PVGPU_FRACTAL_JULIA2 || kind == PVGPU_FRACTAL_JULIA3 || kind == PVGPU_FRACTAL_JULIA4 ||
+                        kind == PVGPU_FRACTAL_MAGNET1J || kind == PVGPU_FRACTAL_MAGNET2J);
+    const bool magnet = kind >= PVGPU_FRACTAL_MAGNET1M;
+    const double cr = julia ? fd[6] : p.x, ci = julia ? fd[7] : p.y;
+    double a = p.x, b = p.y;
+    if (magnet && !julia) a = b = 0.0;
+    double a2 = a * a, b2 = b * b;
+    double mindist2 = (magnet && !julia) ? 10000.0 : a2 + b2;
+    const double c1r = cr - 1, c2r = cr - 2;
+    const double c1c2r = c1r * c2r - ci * ci, c1c2i = (c1r + c2r) * ci;           // magnet 2 only
+    int col;
+    for (col = 0; col < it_max; col++) {
+        if (!magnet) {
+            switch (kind) {
+                case PVGPU_FRACTAL_MANDEL2: case PVGPU_FRACTAL_JULIA2:
+                    b = 2.0 * a * b + ci;
+                    a = a2 - b2 + cr;
+                    break;
+                case PVGPU_FRACTAL_MANDEL3: case PVGPU_FRACTAL_JULIA3:
+                    b = 3.0 * a2 * b - b2 * b + ci;
+                    a = a2 * a - 3.0 * a * b2 + cr;
+                    break;
+                default:
+                    b = 4.0 * (a2 * a * b - a * b2 * b) + ci;
+                    a = a2 * a2 - 6.0 * a2 * b2 + b2 * b2 + cr;
+                    break;
+            }
+        } else {
+            double t1r, t1i, t2r, t2i;
+            if (kind <= PVGPU_FRACTAL_MAGNET1J) {
+                t1r = a2 - b2 + cr - 1;
+                t1i = 2 * a * b + ci;
+                t2r = 2 * a + cr - 2;
+                t2i = 2 * b + ci;
+            } else {
+                t1r = a2 * a - 3 * a * b2 + 3 * (a * c1r - b * ci) + c1c2r;
+                t1i = 3 * a2 * b - b2 * b + 3 * (a * ci + b * c1r) + c1c2i;
+                t2r = 3 * (a2 - b2) + 3 * (a * c2r - b * ci) + c1c2r + 1;
+                t2i = 6 * a * b + 3 * (a * ci + b * c2r) + c1c2i;
+            }
+            const double den = t2r * t2r + t2i * t2i;
+            a = (t1r * t2r + t1i * t2i) / den;
+            b = (t1i * t2r - t1r * t2i) / den;
+            b2 = b * b;
+            b = 2 * a * b;
+            a = a * a - b2;
+        }
+        a2 = a * a;
+        b2 = b * b;
+        const double dist2 = a2 + b2;
+        if (dist2 < mindist2) mindist2 = dist2;
+        bool out;
+        if (magnet) { const double am1 = a - 1; out = dist2 > 10000.0 || am1 * am1 + b2 < 1 / 10000.0; }
+        else out = dist2 > 4.0;
+        if (out) {
+            switch (ext_type) {
+                case 0: return ext_f;
+                case 1: return (double)col / (double)it_max;
+                case 2: return a * ext_f;
+                case 3: return b * ext_f;
+                case 4: return a * a * ext_f;
+                case 5: return b * b * ext_f;
+                case 6: return sqrt(a * a + b * b) * ext_f;
+                case 7: return (double)((unsigned int)col % (unsigned int)ext_f) / ext_f;
+                case 8: return (double)((unsigned int)col % (unsigned int)(1 + ext_f)) / ext_f;
+                default: return 0.0;
+            }
+        }
+    }
+    switch (int_type) {
+        case 0: return int_f;
+        case 1: return sqrt(mindist2) * int_f;
+        case 2: return a * int_f;
+        case 3: return b * int_f;
+        case 4: return a * a * int_f;
+        case 5: return b * b * int_f;
+        case 6: return a * a + b * b * int_f;
+        default: return 0.0;
+    }
+}
+
+// Spiral1Pattern / Spiral2Pattern::EvaluateRaw (pattern.cpp:8396-8437, 8473-8517); tv = the classic-turbulence term
+__device__ inline double spiral_pattern(const V3& p, double arms, double tv, bool second)
+{
+    const double rad = sqrt(p.x * p.x + p.y * p.y);
+    double phi = 0.0;
+    if (rad != 0.0) phi = (p.x < 0.0) ? 3.0 * 1.57079632679489661923 - asin(p.y / rad) : 1.57079632679489661923 + asin(p.y / rad);
+    const double s = p.z + rad + arms * phi / 6.283185307179586476925286766560 + tv;
+    return second ? triangle_wave(rad) + triangle_wave(s) : s;
+}
+
 // CracklePattern::EvaluateRaw (pattern.cpp:5760-5987) without the (result-neutral) per-thread cell cache: the 81 nuclei of the
 // cubes around the point come straight from IntPickInCube = Hash3d + three entries of gPatternRands (mt19937 / 2^32).
 static __device__ __noinline__ double crackle_pattern(const DScene& sc, const pvgpu_pigment& pg, const V3& ep, int gen)
@@ -316,6 +414,16 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
         case PVGPU_PAT_CRACKLE:
             value = crackle_pattern(sc, pg, p, gen);
             break;
+        case PVGPU_PAT_FRACTAL:
+            value = fractal_pattern(sc.shape_data + pg.data, p);
+            break;
+        case PVGPU_PAT_SPIRAL1:
+        case PVGPU_PAT_SPIRAL2: {
+            double tv = 0.0;
+            if (turb) tv = turb->turbulence[0] * turbulence(sc.noise, p, turb->octaves, (double)turb->lambda, (double)turb->omega, gen);
+            value = spiral_pattern(p, pg.p[0], tv, pg.pattern == PVGPU_PAT_SPIRAL2);
+            break;
+        }
         case PVGPU_PAT_CELLS:       // CellsPattern::EvaluateRaw (pattern.cpp:5652-5660)
             value = fmin(sc.pattern_rands[sc.noise.hash[sc.noise.hash[sc.noise.hash[(int)floor(p.x + PV_EPSILON) & 0xfff] ^ ((int)floor(p.y + PV_EPSILON) & 0xfff)] ^
                                                         ((int)floor(p.z + PV_EPSILON) & 0xfff)] % 32768u], 1.0);

@@ -462,6 +462,10 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
         if (p.pattern == PVGPU_PAT_IMAGE_MAP && p.data >= s.images.size())
             return fail(PVGPU_E_INVALID, "pigment %zu: image index out of range", i);
+        if (p.pattern == PVGPU_PAT_FRACTAL && (!range_ok(p.data, 8, s.shape_data.size()) || !(s.shape_data[p.data] >= 0.0 && s.shape_data[p.data] <= PVGPU_FRACTAL_MAGNET2J) ||
+                                               !(s.shape_data[p.data + 1] >= 1.0 && s.shape_data[p.data + 1] <= 1.0e6) ||
+                                               (s.shape_data[p.data + 2] == 7.0 && !(s.shape_data[p.data + 4] >= 1.0)) || (s.shape_data[p.data + 2] == 8.0 && !(s.shape_data[p.data + 4] >= 0.0))))
+            return fail(PVGPU_E_INVALID, "pigment %zu: fractal pattern record out of range", i);
         if (p.pattern == PVGPU_PAT_CRACKLE && !range_ok(p.data, 9, s.shape_data.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: crackle parameters outside the shape-data table", i);
     }
