@@ -76,6 +76,7 @@
 #include "core/shape/sphere.h"
 #include "core/shape/torus.h"
 #include "core/shape/triangle.h"
+#include "core/shape/truetype.h"
 #include "core/support/statistics.h"
 #undef private
 #undef protected
@@ -97,6 +98,16 @@ namespace
 // ------------------------------------------------------------------------------------------------
 // SceneData -> pvgpu tables
 // ------------------------------------------------------------------------------------------------
+
+// The outline of a glyph is private to truetype.cpp (GlyphHeader / Contour / GlyphStruct, truetype.cpp:231-271; TrueType::glyph is an
+// opaque pointer in truetype.h).  These mirrors repeat the members in order, so that the flattener can read the contours of the glyphs
+// the parser built; they are only valid next to reference objects built by the same compiler with the same flags (oracle/build_ref.sh).
+namespace ttf_mirror {
+struct GlyphHeader { POV_INT16 numContours, xMin, yMin, xMax, yMax; };
+struct Contour { POV_UINT8 inside_flag; POV_UINT16 count; std::vector<POV_UINT8> flags; std::vector<DBL> x, y; };
+struct GlyphStruct { GlyphHeader header; POV_UINT32 glyph_index; Contour* contours; POV_UINT16 unitsPerEm; POV_UINT32 myMetrics; };
+}
+
 struct Flattener
 {
     vector<pvgpu_object> objects;
@@ -604,6 +615,49 @@ struct Flattener
         return (int32_t)blobs.size() - 1;
     }
 
+    // Outline of a glyph as the segment list GlyphIntersect / Inside_Glyph walk (truetype.cpp:2406-2560, 2790-2920): a point with
+    // the on-curve flag ends a straight line, any other point is the control point of a parabola whose far end is the next point
+    // (wrapping to the first), moved to the midpoint when that one is off-curve too.  Lines of zero length (the step onto the end point
+    // of a parabola) are skipped by both walks (y0 == y1; |t0| < EPSILON) and left out.
+    std::map<const void*, int32_t> glyph_ids;
+    int32_t add_glyph(const TrueType* tt)
+    {
+        auto it = glyph_ids.find(tt->glyph);
+        if (it != glyph_ids.end()) return it->second;
+        const ttf_mirror::GlyphStruct* g = reinterpret_cast<const ttf_mirror::GlyphStruct*>(tt->glyph);
+        const int32_t first = (int32_t)shape_data.size();
+        glyph_ids[tt->glyph] = first;
+        shape_data.push_back(0.0);
+        if (g == nullptr || g->header.numContours < 0 || g->header.numContours > 4096) { unsupported("glyph outline not readable"); return first; }
+        size_t nseg = 0;
+        for (int i = 0; i < g->header.numContours; i++) {
+            const ttf_mirror::Contour& c = g->contours[i];
+            const size_t n1 = c.count;
+            if (n1 == 0) continue;
+            if (c.x.size() < n1 + 1 || c.y.size() < n1 + 1 || c.flags.size() < n1 + 1) { unsupported("glyph outline not readable"); return first; }
+            double x0 = c.x[0], y0 = c.y[0];
+            for (size_t j = 1; j <= n1; j++) {
+                const double x1 = c.x[j], y1 = c.y[j];
+                if (c.flags[j] & 0x01) {        // ONCURVE
+                    if (!(x0 == x1 && y0 == y1)) { for (double v : { 0.0, x0, y0, x1, y1, 0.0, 0.0 }) shape_data.push_back(v); nseg++; }
+                    x0 = x1; y0 = y1;
+                } else {
+                    double x2, y2;
+                    if (j == n1) { x2 = c.x[0]; y2 = c.y[0]; }
+                    else {
+                        x2 = c.x[j + 1]; y2 = c.y[j + 1];
+                        if (!(c.flags[j + 1] & 0x01)) { x2 = 0.5 * (x1 + x2); y2 = 0.5 * (y1 + y2); }
+                    }
+                    for (double v : { 1.0, x0, y0, x1, y1, x2, y2 }) shape_data.push_back(v);
+                    nseg++;
+                    x0 = x2; y0 = y2;
+                }
+            }
+        }
+        shape_data[first] = (double)nseg;
+        return first;
+    }
+
     int32_t add_object(ObjectPtr o, int32_t parent)
     {
         auto it = object_ids.find(o);
@@ -683,6 +737,11 @@ struct Flattener
             p.type = PVGPU_OBJ_CONE;
             p.p[0] = cn->dist;
             p.transform = add_transform(cn->Trans);
+        } else if (TrueType* tt = dynamic_cast<TrueType*>(o)) {
+            p.type = PVGPU_OBJ_GLYPH;
+            p.p[0] = tt->depth;
+            p.mesh = add_glyph(tt);
+            p.transform = add_transform(tt->Trans);
         } else if (Blob* bl = dynamic_cast<Blob*>(o)) {
             p.type = PVGPU_OBJ_BLOB;
             p.mesh = add_blob(bl);
@@ -1167,6 +1226,7 @@ void TraceTask::Run()
                                 auto mf = gv->mesh_tri_first.find(isect.Object);
                                 rec.aux = (int32_t)(reinterpret_cast<const MESH_TRIANGLE*>(isect.Pointer) - m->Data->Triangles) + (int32_t)(mf == gv->mesh_tri_first.end() ? 0u : mf->second);
                             }
+                            else if (dynamic_cast<TrueType*>(isect.Object)) rec.aux = -1;      // a glyph hit carries its normal, not an index: not comparable
                             else rec.aux = isect.i1;
                         }
                     }

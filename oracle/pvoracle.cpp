@@ -496,10 +496,76 @@ struct Ray {
     bool IsHollowRay(const Scene& S) const { for (int i : interiors) if (!S.interiors[i].hollow) return false; return true; }   // ray.cpp:59-115
 };
 struct Ticket { unsigned traceLevel = 0, maxAllowedTraceLevel; double adcBailout; bool alphaBackground; unsigned maxFound = 0; };
-struct Intersection { double Depth = BOUND_HUGE; V3 IPoint{ 0, 0, 0 }; int Object = -1, Csg = -1; uint32_t aux = 0; };
+struct Intersection { double Depth = BOUND_HUGE; V3 IPoint{ 0, 0, 0 }; int Object = -1, Csg = -1; uint32_t aux = 0; V3 INormal{ 0, 0, 0 }; };   // INormal: glyph hits only (truetype.cpp stores it with the hit)
 typedef std::vector<Intersection> IStack;
 
 struct Stats { unsigned long long rays = 0, shadow_tests = 0; unsigned max_level = 0; };
+
+// ---- TrueType glyph (truetype.cpp) ----------------------------------------------------------------------
+// outline record in the shape-data table: segment count, then kind (0 line / 1 curve), x0 y0, x1 y1, x2 y2 per segment
+static int ttf_solve_quad(const double* x, double* y, double mindist, double maxdist)                      // truetype.cpp:2567-2610
+{
+    const double COEFF_LIMIT = 1.0e-20;
+    double a = x[0], b = -x[1], c = x[2];
+    if (std::fabs(a) < COEFF_LIMIT) {
+        if (std::fabs(b) < COEFF_LIMIT) return 0;
+        double q = c / b;
+        if (q >= mindist && q <= maxdist) { y[0] = q; return 1; }
+        return 0;
+    }
+    double d = b * b - 4.0 * a * c;
+    if (d < EPSILON) return 0;
+    d = std::sqrt(d);
+    double t = 2.0 * a, q = (b + d) / t;
+    if (q >= mindist && q <= maxdist) {
+        y[0] = q;
+        q = (b - d) / t;
+        if (q >= mindist && q <= maxdist) { y[1] = q; return 2; }
+        return 1;
+    }
+    q = (b - d) / t;
+    if (q >= mindist && q <= maxdist) { y[0] = q; return 1; }
+    return 0;
+}
+static bool ttf_inside_glyph(const double* g, double x, double y)                                          // truetype.cpp:2392-2565
+{
+    int crossings = 0;
+    const int n = (int)g[0];
+    for (int j = 0; j < n; j++) {
+        const double* e = g + 1 + 7 * j;
+        double x0 = e[1], y0 = e[2], x1 = e[3], y1 = e[4];
+        if (e[0] == 0.0) {                                                          // straight line: the crossing test
+            if (y0 == y1) continue;
+            int qi = (y0 < y) ? 1 : 0, qj = (y1 < y) ? 1 : 0;
+            if (qi == qj) continue;
+            int ri = (x0 > x) ? 1 : 0, rj = (x1 > x) ? 1 : 0;
+            if (ri & rj) { crossings++; continue; }
+            if ((ri | rj) == 0) continue;
+            double m = (y1 - y0) / (x1 - x0), b = (y1 - y) - m * (x1 - x);
+            if ((b / m) < EPSILON) crossings++;
+        } else {
+            double x2 = e[5], y2 = e[6], yt[3], xt[3], roots[2];
+            if (((y0 < y) && (y1 < y) && (y2 < y)) || ((y0 > y) && (y1 > y) && (y2 > y))) continue;
+            yt[0] = y0 - 2.0 * y1 + y2; yt[1] = 2.0 * (y1 - y0); yt[2] = y0 - y;
+            int k = ttf_solve_quad(yt, roots, 0.0, 1.0);
+            for (int ri = 0; ri < k;) {
+                if (roots[ri] <= EPSILON) {
+                    if (((y <= y0) && (y < y1)) || ((y >= y0) && (y > y1))) { k--; if (k > ri) roots[ri] = roots[ri + 1]; continue; }
+                } else if (roots[ri] >= (1.0 - EPSILON)) {
+                    if (((y < y2) && (y < y1)) || ((y > y2) && (y > y1))) { k--; if (k > ri) roots[ri] = roots[ri + 1]; continue; }
+                }
+                ri++;
+            }
+            if (k > 0) {
+                xt[0] = x0 - 2.0 * x1 + x2; xt[1] = 2.0 * (x1 - x0); xt[2] = x0;
+                double t = roots[0];
+                if ((xt[0] * t + xt[1]) * t + xt[2] > x) crossings++;
+                if (k > 1) { t = roots[1]; if ((xt[0] * t + xt[1]) * t + xt[2] > x) crossings++; }
+            }
+        }
+    }
+    return (crossings & 1) != 0;
+}
 
 class Tracer {
 public:
@@ -828,6 +894,10 @@ bool Tracer::Inside(V3 p, uint32_t idx) const
                 term++;
             }
             return (result < 1.0e-4) ? !inv : inv;
+        }
+        case PVGPU_OBJ_GLYPH: {                                                                           // truetype.cpp:2957-2970
+            V3 q = MInvTransPoint(S.xf[ob.transform], p);
+            return (q.z >= 0.0 && q.z <= ob.p[0] && ttf_inside_glyph(S.shape_data.data() + ob.mesh, q.x, q.y)) ? !inv : inv;
         }
         case PVGPU_OBJ_DISC:                                                                              // disc.cpp:200-224
             return (MInvTransPoint(S.xf[ob.transform], p).z >= 0.0) ? inv : !inv;
@@ -1161,6 +1231,60 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
                 if ((sqr(a) + sqr(b)) <= (cyl ? 1.0 : sqr(dist)) && (dd > tol) && (dd < MAX_DISTANCE)) { I[n].d = dd / length; I[n++].t = 1; }
             }
             for (int i = 0; i < n; i++) found |= push(I[i].d, ray.Evaluate(I[i].d), I[i].t);
+            return found;
+        }
+        case PVGPU_OBJ_GLYPH: {                                                                           // truetype.cpp:2706-2955
+            const double TTF_Tolerance = 1.0e-6;
+            const pvgpu_transform& tr = S.xf[ob.transform];
+            const V3 P = MInvTransPoint(tr, o), D = MInvTransDirection(tr, d);
+            const double* g = S.shape_data.data() + ob.mesh;
+            const double glyph_depth = ob.p[0];
+            auto hit = [&](double Depth, V3 N, uint32_t aux) {
+                V3 IPoint = ray.Evaluate(Depth);
+                if (Depth > TTF_Tolerance && clip_ok(ob, IPoint)) {
+                    Intersection is; is.Depth = Depth; is.IPoint = IPoint; is.Object = (int)idx; is.aux = aux; is.INormal = unit(MTransNormal(tr, N));
+                    Depth_Stack.push_back(is); found = true;
+                }
+            };
+            double t0 = -1.0, t1 = -1.0;                                                                   // GetZeroOneHits, :2630-2660
+            if (!(std::fabs(D.z) < EPSILON)) {
+                double t = -P.z / D.z;
+                if (ttf_inside_glyph(g, P.x + t * D.x, P.y + t * D.y)) t0 = t;
+                t += (glyph_depth / D.z);
+                if (ttf_inside_glyph(g, P.x + t * D.x, P.y + t * D.y)) t1 = t;
+            }
+            if (t0 > 0.0) hit(t0, v3(0.0, 0.0, -1.0), 0u);
+            if (t1 > 0.0) hit(t1, v3(0.0, 0.0, 1.0), 1u);
+            int dirflag;
+            if (std::fabs(D.x) < EPSILON) { if (std::fabs(D.y) < EPSILON) return found; dirflag = 0; } else dirflag = 1;
+            const double a = D.y, b = -D.x, c = (P.y * D.x - P.x * D.y);
+            const int n = (int)g[0];
+            for (int j = 0; j < n; j++) {
+                const double* e = g + 1 + 7 * j;
+                const double x0 = e[1], y0 = e[2], x1 = e[3], y1 = e[4];
+                if (e[0] == 0.0) {
+                    double d0 = (x1 - x0), d1 = (y1 - y0);
+                    t0 = d1 * D.x - d0 * D.y;
+                    if (std::fabs(t0) < EPSILON) continue;
+                    double t = (D.x * (P.y - y0) - D.y * (P.x - x0)) / t0;
+                    if (t < 0.0 || t > 1.0) continue;
+                    if (dirflag) t = ((x0 + t * d0) - P.x) / D.x; else t = ((y0 + t * d1) - P.y) / D.y;
+                    double z = P.z + t * D.z;
+                    if (z >= 0 && z <= glyph_depth && t > TTF_Tolerance) hit(t, v3(-d1, d0, 0.0), 2u | ((uint32_t)j << 3));
+                } else {
+                    const double x2 = e[5], y2 = e[6];
+                    double xt2 = x0 - 2.0 * x1 + x2, xt1 = 2.0 * (x1 - x0), xt0 = x0, yt2 = y0 - 2.0 * y1 + y2, yt1 = 2.0 * (y1 - y0), yt0 = y0;
+                    double C[3] = { a * xt2 + b * yt2, a * xt1 + b * yt1, a * xt0 + b * yt0 + c }, Sr[2];
+                    int k = ttf_solve_quad(C, Sr, 0.0, 1.0);
+                    for (int l = 0; l < k; l++) {
+                        double t;
+                        if (dirflag) t = ((Sr[l] * Sr[l] * xt2 + Sr[l] * xt1 + xt0) - P.x) / D.x;
+                        else t = ((Sr[l] * Sr[l] * yt2 + Sr[l] * yt1 + yt0) - P.y) / D.y;
+                        double z = P.z + t * D.z;
+                        if (z >= 0 && z <= glyph_depth && t > TTF_Tolerance) hit(t, v3(-2.0 * yt2 * Sr[l] - yt1, 2.0 * xt2 * Sr[l] + xt1, 0.0), 2u | ((uint32_t)l << 2) | ((uint32_t)j << 3));
+                    }
+                }
+            }
             return found;
         }
         case PVGPU_OBJ_MESH: return mesh_intersect(idx, ray, Depth_Stack);
@@ -1558,6 +1682,7 @@ V3 Tracer::Normal(const Intersection& isect) const
             V3 N = isect.aux ? P + M : P - M;
             return unit(MTransNormal(t, N));
         }
+        case PVGPU_OBJ_GLYPH: return isect.INormal;                                                       // truetype.cpp:2972-2976
         case PVGPU_OBJ_DISC: return v3(ob.p);                                                             // disc.cpp:226-229
         case PVGPU_OBJ_POLYGON: return v3(ob.p);                                                          // polygon.cpp:308-311
         case PVGPU_OBJ_POLY: {                                                                            // polynomial.cpp:1035-1129, 1180-1244

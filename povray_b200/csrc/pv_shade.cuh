@@ -966,7 +966,8 @@ __device__ inline V3 mesh_normal(const DScene& sc, const pvgpu_object& ob, const
     return result;
 }
 
-__device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, const Hit& hit)
+// (ray_o, ray_d: the ray that found the hit - a glyph's wall normal is a function of the curve parameter the ray solved for)
+__device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, const Hit& hit, const V3& ray_o, const V3& ray_d)
 {
     switch (ob.type) {
         case PVGPU_OBJ_SPHERE: if (PV_HAS(PVGPU_OBJ_SPHERE)) return sphere_normal(sc, ob, hit.ip); break;
@@ -982,6 +983,7 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_TRIANGLE: if (PV_HAS(PVGPU_OBJ_TRIANGLE)) return triangle_normal(sc, ob, hit.ip); break;
         case PVGPU_OBJ_POLYGON: if (PV_HAS(PVGPU_OBJ_POLYGON)) return ld3(ob.p); break;       // Polygon::Normal (polygon.cpp:308-311)
         case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) return poly_normal(sc, ob, hit.ip); break;
+        case PVGPU_OBJ_GLYPH: if (PV_HAS(PVGPU_OBJ_GLYPH)) return glyph_normal(sc, ob, hit.aux, ray_o, ray_d); break;
 #endif
     }
     return mk(0.0, 1.0, 0.0);
@@ -1258,7 +1260,7 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
     const double adc = sc.g.adc_bailout;
     const double weight = (double)ray.adc;
 
-    V3 rawnormal = object_normal(sc, ob, hit);
+    V3 rawnormal = object_normal(sc, ob, hit, ld3(ray.o), dir);
     if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
     const double normaldirection = dot(rawnormal, dir);
     if (normaldirection > 0.0) rawnormal = -rawnormal;

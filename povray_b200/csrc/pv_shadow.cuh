@@ -49,10 +49,10 @@ __device__ inline void shadow_texture(const DScene& sc, const pvgpu_object& ob, 
 
 
 // Trace::ComputeShadowTexture (trace.cpp:1181-1262) for a transparent blocker.
-__device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3& dir, const PRay* parent, bool inside_now, float f[3])
+__device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3& org, const V3& dir, const PRay* parent, bool inside_now, float f[3])
 {
     const pvgpu_object& ob = sc.objs[hit.obj];
-    V3 rawnormal = object_normal(sc, ob, hit);
+    V3 rawnormal = object_normal(sc, ob, hit, org, dir);
     if (ob.flags & PVGPU_INVERTED_FLAG) rawnormal = -rawnormal;
     const double nd = dot(rawnormal, dir);
     if (nd > 0.0) rawnormal = -rawnormal;
@@ -138,7 +138,7 @@ __device__ inline void trace_shadow(bool alive, const DScene& sc, V3 o, const V3
         const pvgpu_object& ob = sc.objs[best.obj];
         if (ob.flags & PVGPU_OPAQUE_FLAG) { f[0] = f[1] = f[2] = 0.0f; alive = false; continue; }     // ComputeShadowColour: full shadow (trace.cpp:2318-2323)
         if (!have_state) { in_state = wave[parent]; have_state = true; }
-        shadow_filter(sc, best, d, &in_state, ob.interior >= 0 && ray_is_interior(in_state, ob.interior), f);
+        shadow_filter(sc, best, o, d, &in_state, ob.interior >= 0 && ray_is_interior(in_state, ob.interior), f);
         // ComputeShadowMedia (trace.cpp:3046-3071) toggles the blocker's interior on the light ray
         if (ob.interior >= 0) {
             if (!ray_remove_interior(in_state, ob.interior)) ray_append_interior(in_state, ob.interior, &cnt->overflow);

@@ -802,4 +802,176 @@ __device__ __forceinline__ bool tri_intersect(const DTri& tr, const V3& o, const
     return true;
 }
 
+#if PV_HEAVY
+// ---- TrueType glyph -------------------------------------------------------------------------------
+#define PV_TTF_TOLERANCE   1.0e-6     // TTF_Tolerance  truetype.cpp:79
+#define PV_TTF_COEFF_LIMIT 1.0e-20    // COEFF_LIMIT    truetype.cpp:82
+
+// TrueType::solve_quad (truetype.cpp:2567-2610): roots of c0 s^2 + c1 s + c2 inside [lo, hi], the "+" root first
+__device__ inline int glyph_solve_quad(double c0, double c1, double c2, double& r0, double& r1, double lo, double hi)
+{
+    const double a = c0, b = -c1, c = c2;
+    if (fabs(a) < PV_TTF_COEFF_LIMIT) {
+        if (fabs(b) < PV_TTF_COEFF_LIMIT) return 0;
+        const double q = c / b;
+        if (q >= lo && q <= hi) { r0 = q; return 1; }
+        return 0;
+    }
+    double dd = b * b - 4.0 * a * c;
+    if (dd < PV_EPSILON) return 0;
+    dd = sqrt(dd);
+    const double t = 2.0 * a;
+    int n = 0;
+    double q = (b + dd) / t;
+    if (q >= lo && q <= hi) { r0 = q; n = 1; }
+    q = (b - dd) / t;
+    if (q >= lo && q <= hi) { if (n) r1 = q; else r0 = q; n++; }
+    return n;
+}
+
+// TrueType::Inside_Glyph (truetype.cpp:2392-2565): crossings of the +x half line from (x, y) with the outline
+static __device__ __noinline__ bool glyph_inside_2d(const double* g, double x, double y)
+{
+    const uint32_t nseg = (uint32_t)g[0];
+    int crossings = 0;
+    for (uint32_t s = 0; s < nseg; s++) {
+        const double* e = g + 1 + 7 * s;
+        const double x0 = e[1], y0 = e[2], x1 = e[3], y1 = e[4];
+        if (e[0] == 0.0) {
+            if (y0 == y1) continue;
+            const bool below0 = y0 < y, below1 = y1 < y;
+            if (below0 == below1) continue;
+            const bool right0 = x0 > x, right1 = x1 > x;
+            if (right0 && right1) { crossings++; continue; }
+            if (!right0 && !right1) continue;
+            const double m = (y1 - y0) / (x1 - x0);
+            const double b = (y1 - y) - m * (x1 - x);
+            if ((b / m) < PV_EPSILON) crossings++;
+        } else {
+            const double x2 = e[5], y2 = e[6];
+            if (((y0 < y) && (y1 < y) && (y2 < y)) || ((y0 > y) && (y1 > y) && (y2 > y))) continue;
+            double r0 = 0.0, r1 = 0.0;
+            int k = glyph_solve_quad(y0 - 2.0 * y1 + y2, 2.0 * (y1 - y0), y0 - y, r0, r1, 0.0, 1.0);
+            // roots at the ends of the curve only count when y really is in the range of that end (truetype.cpp:2508-2530)
+            auto discard = [&](double r) {
+                if (r <= PV_EPSILON) return ((y <= y0) && (y < y1)) || ((y >= y0) && (y > y1));
+                if (r >= (1.0 - PV_EPSILON)) return ((y < y2) && (y < y1)) || ((y > y2) && (y > y1));
+                return false;
+            };
+            if (k == 2 && discard(r1)) k = 1;
+            if (k >= 1 && discard(r0)) { r0 = r1; k--; }
+            if (k > 0) {
+                const double xt0 = x0 - 2.0 * x1 + x2, xt1 = 2.0 * (x1 - x0), xt2 = x0;
+                if ((xt0 * r0 + xt1) * r0 + xt2 > x) crossings++;
+                if (k > 1 && (xt0 * r1 + xt1) * r1 + xt2 > x) crossings++;
+            }
+        }
+    }
+    return (crossings & 1) != 0;
+}
+
+// TrueType::Inside (truetype.cpp:2957-2970)
+__device__ inline bool glyph_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    const V3 q = inv_trans_point(sc.xf[ob.transform], p);
+    const bool in = q.z >= 0.0 && q.z <= ob.p[0] && glyph_inside_2d(sc.shape_data + ob.mesh, q.x, q.y);
+    return in != ((ob.flags & PVGPU_INVERTED_FLAG) != 0);
+}
+
+// TrueType::All_Intersections -> GlyphIntersect (truetype.cpp:2706-2955).  A glyph has as many candidate hits as the ray crosses
+// outline segments, so the hits come in batches: the caller starts with *resume = 0 and calls again while it comes back >= 0; the
+// order over all batches is the reference's push order (face z = 0, face z = depth, then the walls in outline order).
+static __device__ __noinline__ void glyph_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, int* resume)
+{
+    h.n = 0;
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const V3 P = inv_trans_point(tr, o);
+    const V3 D = inv_trans_direction(tr, d);              // not normalised: depths are the world ray's own parameter
+    const double* g = sc.shape_data + ob.mesh;
+    const double gdepth = ob.p[0];
+    const uint32_t nseg = (uint32_t)g[0];
+    uint32_t s = 0;
+    if (resume && *resume > 0) s = (uint32_t)*resume - 1u;
+    else if (fabs(D.z) >= PV_EPSILON) {                   // GetZeroOneHits (truetype.cpp:2630-2660)
+        double t = -P.z / D.z;
+        if (t > 0.0 && t > PV_TTF_TOLERANCE && glyph_inside_2d(g, P.x + t * D.x, P.y + t * D.y)) {
+            h.depth[h.n] = t; h.ip[h.n] = evaluate(o, d, t); h.aux[h.n] = 0u; h.n++;
+        }
+        t += (gdepth / D.z);
+        if (t > 0.0 && t > PV_TTF_TOLERANCE && glyph_inside_2d(g, P.x + t * D.x, P.y + t * D.y)) {
+            h.depth[h.n] = t; h.ip[h.n] = evaluate(o, d, t); h.aux[h.n] = 1u; h.n++;
+        }
+    }
+    if (resume) *resume = -1;
+    int dirflag = 1;
+    if (fabs(D.x) < PV_EPSILON) {
+        if (fabs(D.y) < PV_EPSILON) return;               // parallel to the walls
+        dirflag = 0;
+    }
+    const double a = D.y, b = -D.x, c = (P.y * D.x - P.x * D.y);
+    for (; s < nseg; s++) {
+        if (h.n + 2 > PV_MAX_PRIM_HITS) {                 // a segment reports up to two hits: come back for the rest
+            if (resume) *resume = (int)s + 1;
+            return;
+        }
+        const double* e = g + 1 + 7 * s;
+        const double x0 = e[1], y0 = e[2], x1 = e[3], y1 = e[4];
+        if (e[0] == 0.0) {
+            const double d0 = (x1 - x0), d1 = (y1 - y0);
+            const double t0 = d1 * D.x - d0 * D.y;
+            if (fabs(t0) < PV_EPSILON) continue;
+            double t = (D.x * (P.y - y0) - D.y * (P.x - x0)) / t0;
+            if (t < 0.0 || t > 1.0) continue;
+            if (dirflag) t = ((x0 + t * d0) - P.x) / D.x;
+            else t = ((y0 + t * d1) - P.y) / D.y;
+            const double z = P.z + t * D.z;
+            if (z >= 0 && z <= gdepth && t > PV_TTF_TOLERANCE) { h.depth[h.n] = t; h.ip[h.n] = evaluate(o, d, t); h.aux[h.n] = 2u | (s << 3); h.n++; }
+        } else {
+            const double x2 = e[5], y2 = e[6];
+            const double xt2 = x0 - 2.0 * x1 + x2, xt1 = 2.0 * (x1 - x0), xt0 = x0;
+            const double yt2 = y0 - 2.0 * y1 + y2, yt1 = 2.0 * (y1 - y0), yt0 = y0;
+            double S0 = 0.0, S1 = 0.0;
+            const int k = glyph_solve_quad(a * xt2 + b * yt2, a * xt1 + b * yt1, a * xt0 + b * yt0 + c, S0, S1, 0.0, 1.0);
+            for (int l = 0; l < k; l++) {
+                const double S = l ? S1 : S0;
+                double t;
+                if (dirflag) t = ((S * S * xt2 + S * xt1 + xt0) - P.x) / D.x;
+                else t = ((S * S * yt2 + S * yt1 + yt0) - P.y) / D.y;
+                const double z = P.z + t * D.z;
+                if (z >= 0 && z <= gdepth && t > PV_TTF_TOLERANCE) { h.depth[h.n] = t; h.ip[h.n] = evaluate(o, d, t); h.aux[h.n] = 2u | ((uint32_t)l << 2) | (s << 3); h.n++; }
+            }
+        }
+    }
+}
+
+// The normal GlyphIntersect stores with each hit (truetype.cpp:2734-2737, 2749-2752, 2830-2833, 2905-2908), recomputed from the hit's
+// aux and the ray that found it: the wall's curve parameter is solved again with the very same operands.
+static __device__ __noinline__ V3 glyph_normal(const DScene& sc, const pvgpu_object& ob, uint32_t aux, const V3& ray_o, const V3& ray_d)
+{
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    V3 N;
+    const uint32_t kind = aux & 3u;
+    if (kind == 0u) N = mk(0.0, 0.0, -1.0);
+    else if (kind == 1u) N = mk(0.0, 0.0, 1.0);
+    else {
+        const double* e = sc.shape_data + ob.mesh + 1 + 7 * (aux >> 3);
+        const double x0 = e[1], y0 = e[2], x1 = e[3], y1 = e[4];
+        if (e[0] == 0.0) N = mk(-(y1 - y0), (x1 - x0), 0.0);
+        else {
+            const V3 P = inv_trans_point(tr, ray_o);
+            const V3 D = inv_trans_direction(tr, ray_d);
+            const double x2 = e[5], y2 = e[6];
+            const double xt2 = x0 - 2.0 * x1 + x2, xt1 = 2.0 * (x1 - x0), xt0 = x0;
+            const double yt2 = y0 - 2.0 * y1 + y2, yt1 = 2.0 * (y1 - y0), yt0 = y0;
+            const double a = D.y, b = -D.x, c = (P.y * D.x - P.x * D.y);
+            double S0 = 0.0, S1 = 0.0;
+            glyph_solve_quad(a * xt2 + b * yt2, a * xt1 + b * yt1, a * xt0 + b * yt0 + c, S0, S1, 0.0, 1.0);
+            const double S = (aux & 4u) ? S1 : S0;
+            N = mk(-2.0 * yt2 * S - yt1, 2.0 * xt2 * S + xt1, 0.0);
+        }
+    }
+    return normalized(trans_normal(tr, N));
+}
+#endif  // PV_HEAVY
+
 }  // namespace pvgpu

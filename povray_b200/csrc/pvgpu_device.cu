@@ -1089,7 +1089,7 @@ static int render_impl(Scene& s, DeviceScene& d, WorkCtx& c, const pvgpu_aa* aa,
     st.kernel_items[KIND_SHADOW] = hc.shadow_rays;
     if (stats) *stats = st;
     if (hc.overflow & ~(8u | 16u))
-        return fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x: 1 traversal stack, 2 mesh in CSG, 4 interior list, 32 blob components per ray)", hc.overflow);
+        return fail(PVGPU_E_OVERFLOW, "device capacity exceeded (flags 0x%x: 1 traversal stack, 2 mesh in CSG, 4 interior list, 32 blob components per ray, 128 glyph hit batches)", hc.overflow);
     return PVGPU_OK;
 }
 

@@ -302,7 +302,7 @@ int validate_scene(Scene& s)
     }
     for (size_t i = 0; i < no; i++) {
         const pvgpu_object& o = s.objects[i];
-        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_POLY)
+        if (o.type < PVGPU_OBJ_SPHERE || o.type > PVGPU_OBJ_LAST)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: primitive type %u is outside the hot-path scope", i, o.type);
         if (!range_ok(o.child_first, o.child_count, s.index_list.size()) ||
             !range_ok(o.clip_first, o.clip_count, s.index_list.size()) ||
@@ -332,6 +332,13 @@ int validate_scene(Scene& s)
             if (o.aux < 1 || o.aux > 4) return fail(PVGPU_E_UNSUPPORTED, "object %zu: poly of order %u (the device solver handles order <= 4)", i, o.aux);
             if (o.transform < 0 || o.mesh < 0 || !range_ok((uint32_t)o.mesh, (o.aux + 1) * (o.aux + 2) * (o.aux + 3) / 6, s.shape_data.size()))
                 return fail(PVGPU_E_INVALID, "object %zu: poly without transform or with coefficients outside the shape-data table", i);
+        }
+        if (o.type == PVGPU_OBJ_GLYPH) {
+            if (o.transform < 0 || o.mesh < 0 || !range_ok((uint32_t)o.mesh, 1u, s.shape_data.size()))
+                return fail(PVGPU_E_INVALID, "object %zu: glyph without transform or with its outline outside the shape-data table", i);
+            const double nseg = s.shape_data[o.mesh];
+            if (!(nseg >= 0.0 && nseg <= (double)(1u << 24)) || nseg != (double)(uint32_t)nseg || !range_ok((uint32_t)o.mesh + 1u, 7u * (uint32_t)nseg, s.shape_data.size()))
+                return fail(PVGPU_E_INVALID, "object %zu: glyph outline outside the shape-data table", i);
         }
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
