@@ -18,7 +18,7 @@ LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
 # ... and the shading-side kernels a third time with -DPV_FULL (normal perturbation, pigment maps, sky_sphere, fog, area lights)
 FULL_SRC  := k_shade k_shadow_filter
 # ... and the traversal kernels a fourth time with -DPV_CSG (quadric-class primitives + CSG only: no solver, blob, mesh code)
-CSG_SRC   := k_closest k_shadow_opaque k_shadow_filter
+CSG_SRC   := k_closest k_shade k_shadow_opaque k_shadow_filter
 OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
              $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC)) $(patsubst %,$(OBJDIR)/%_csg.o,$(CSG_SRC))
 HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) $(INCDIR)/pvgpu.h

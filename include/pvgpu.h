@@ -65,15 +65,20 @@ enum {
                                         (2 doubles per point, Data->Points); transform required                   */
     PVGPU_OBJ_POLY             = 15, /* polynomial.h:78 poly / cubic / quartic of Order <= 4: aux = Order, mesh = offset into the shape-data table
                                         ((Order+1)(Order+2)(Order+3)/6 coefficients, Coeffs); transform required; STURM flag */
-    PVGPU_OBJ_GLYPH            = 16  /* truetype.h:95  one character of a text object (the text itself is a CSG union of these): p[0] = depth;
+    PVGPU_OBJ_GLYPH            = 16, /* truetype.h:95  one character of a text object (the text itself is a CSG union of these): p[0] = depth;
                                         transform required; mesh = offset into the shape-data table: the segment count, then per outline
                                         segment 7 doubles - kind (0 line, 1 quadratic curve), x0 y0, x1 y1, x2 y2 - in the order
                                         GlyphIntersect / Inside_Glyph walk the contours (truetype.cpp:2392-2925), the far end of a curve
                                         whose next point is off-curve already moved to the midpoint, zero-length lines dropped.
                                         Hit aux: bits 0-1 = 0 face z = 0, 1 face z = depth, 2 wall; bit 2 = which root of the wall's
                                         quadratic; bits 3.. = segment */
+    PVGPU_OBJ_PRISM            = 17  /* prism.h:98     p[0..1] = Height1 Height2, p[2..5] = x1 y1 x2 y2, p[6..9] = u1 v1 u2 v2 (the spline's
+                                        bounding rectangles); aux = Spline_Type (1 linear .. 4 bezier) | Sweep_Type (1 linear, 2 conic) << 4;
+                                        transform required; CLOSED / STURM / DEGENERATE flags; mesh = offset into the shape-data table:
+                                        Number, then per PRISM_SPLINE_ENTRY 15 doubles: x1 y1 x2 y2, v1 u2 v2, A B C D (x y each).
+                                        Hit aux: bits 0-1 = 0 base, 1 cap, 2 spline; bits 2-3 = root index; bits 4.. = segment */
 };
-#define PVGPU_OBJ_LAST PVGPU_OBJ_GLYPH
+#define PVGPU_OBJ_LAST PVGPU_OBJ_PRISM
 #define PVGPU_TRIANGLE_SMOOTH 0x10u
 
 #define PVGPU_IS_CSG(type) ((type) >= PVGPU_OBJ_CSG_UNION && (type) <= PVGPU_OBJ_CSG_MERGE)

@@ -72,6 +72,7 @@
 #include "core/shape/plane.h"
 #include "core/shape/polygon.h"
 #include "core/shape/polynomial.h"
+#include "core/shape/prism.h"
 #include "core/shape/quadric.h"
 #include "core/shape/sphere.h"
 #include "core/shape/torus.h"
@@ -737,6 +738,19 @@ struct Flattener
             p.type = PVGPU_OBJ_CONE;
             p.p[0] = cn->dist;
             p.transform = add_transform(cn->Trans);
+        } else if (Prism* pr = dynamic_cast<Prism*>(o)) {
+            p.type = PVGPU_OBJ_PRISM;
+            p.p[0] = pr->Height1; p.p[1] = pr->Height2;
+            p.p[2] = pr->x1; p.p[3] = pr->y1; p.p[4] = pr->x2; p.p[5] = pr->y2;
+            p.p[6] = pr->u1; p.p[7] = pr->v1; p.p[8] = pr->u2; p.p[9] = pr->v2;
+            p.aux = (uint32_t)pr->Spline_Type | ((uint32_t)pr->Sweep_Type << 4);
+            p.mesh = (int32_t)shape_data.size();
+            shape_data.push_back((double)pr->Number);
+            for (int k = 0; k < pr->Number; k++) {
+                const PRISM_SPLINE_ENTRY& e = pr->Spline->Entry[k];
+                for (double v : { e.x1, e.y1, e.x2, e.y2, e.v1, e.u2, e.v2, e.A[X], e.A[Y], e.B[X], e.B[Y], e.C[X], e.C[Y], e.D[X], e.D[Y] }) shape_data.push_back(v);
+            }
+            p.transform = add_transform(pr->Trans);
         } else if (TrueType* tt = dynamic_cast<TrueType*>(o)) {
             p.type = PVGPU_OBJ_GLYPH;
             p.p[0] = tt->depth;
@@ -1226,7 +1240,7 @@ void TraceTask::Run()
                                 auto mf = gv->mesh_tri_first.find(isect.Object);
                                 rec.aux = (int32_t)(reinterpret_cast<const MESH_TRIANGLE*>(isect.Pointer) - m->Data->Triangles) + (int32_t)(mf == gv->mesh_tri_first.end() ? 0u : mf->second);
                             }
-                            else if (dynamic_cast<TrueType*>(isect.Object)) rec.aux = -1;      // a glyph hit carries its normal, not an index: not comparable
+                            else if (dynamic_cast<TrueType*>(isect.Object) || dynamic_cast<Prism*>(isect.Object)) rec.aux = -1;      // a glyph hit carries its normal, a prism hit a spline parameter: not comparable
                             else rec.aux = isect.i1;
                         }
                     }

@@ -496,7 +496,7 @@ struct Ray {
     bool IsHollowRay(const Scene& S) const { for (int i : interiors) if (!S.interiors[i].hollow) return false; return true; }   // ray.cpp:59-115
 };
 struct Ticket { unsigned traceLevel = 0, maxAllowedTraceLevel; double adcBailout; bool alphaBackground; unsigned maxFound = 0; };
-struct Intersection { double Depth = BOUND_HUGE; V3 IPoint{ 0, 0, 0 }; int Object = -1, Csg = -1; uint32_t aux = 0; V3 INormal{ 0, 0, 0 }; };   // INormal: glyph hits only (truetype.cpp stores it with the hit)
+struct Intersection { double Depth = BOUND_HUGE; V3 IPoint{ 0, 0, 0 }; int Object = -1, Csg = -1; uint32_t aux = 0; V3 INormal{ 0, 0, 0 }; double d1 = 0.0; };   // INormal: glyph hits (truetype.cpp stores it with the hit); d1: prism hits (spline parameter)
 typedef std::vector<Intersection> IStack;
 
 struct Stats { unsigned long long rays = 0, shadow_tests = 0; unsigned max_level = 0; };
@@ -565,6 +565,61 @@ static bool ttf_inside_glyph(const double* g, double x, double y)               
         }
     }
     return (crossings & 1) != 0;
+}
+
+// ---- prism (prism.cpp) ---------------------------------------------------------------------------------
+// spline record in the shape-data table: Number, then per PRISM_SPLINE_ENTRY x1 y1 x2 y2, v1 u2 v2, A B C D (x y each)
+struct PrismEntry { double x1, y1, x2, y2, v1, u2, v2, A[2], B[2], C[2], D[2]; };
+static_assert(sizeof(PrismEntry) == 15 * sizeof(double), "PrismEntry mirrors 15 doubles of the shape-data table");
+static int prism_in_curve(const pvgpu_object& ob, const double* sp, double u, double v)                   // prism.cpp:1154-1201
+{
+    int NC = 0;
+    const double u1 = ob.p[6], v1 = ob.p[7], u2 = ob.p[8], v2 = ob.p[9];
+    if ((u >= u1) && (u <= u2) && (v >= v1) && (v <= v2)) {
+        const int Number = (int)sp[0];
+        const PrismEntry* Entry = reinterpret_cast<const PrismEntry*>(sp + 1);
+        for (int i = 0; i < Number; i++) {
+            const PrismEntry& E = Entry[i];
+            if ((v >= E.v1) && (v <= E.v2) && (u <= E.u2)) {
+                double x[4] = { E.A[1], E.B[1], E.C[1], E.D[1] - v }, y[3];
+                int n = Solve_Polynomial(3, x, y, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, 0.0);
+                while (n--) {
+                    double w = y[n];
+                    if ((w >= 0.0) && (w <= 1.0)) {
+                        double k = w * (w * (w * E.A[0] + E.B[0]) + E.C[0]) + E.D[0] - u;
+                        if (k >= 0.0) NC++;
+                    }
+                }
+            }
+        }
+    }
+    return NC & 1;
+}
+static bool prism_test_rectangle(V3 P, V3 D, double x1, double z1, double x2, double z2)                   // prism.cpp:1233-1345
+{
+    double dmin, dmax, tmin, tmax;
+    if (std::fabs(D.x) > EPSILON) {
+        if (D.x > 0.0) { dmin = (x1 - P.x) / D.x; dmax = (x2 - P.x) / D.x; if (dmax < EPSILON) return false; }
+        else { dmax = (x1 - P.x) / D.x; if (dmax < EPSILON) return false; dmin = (x2 - P.x) / D.x; }
+        if (dmin > dmax) return false;
+    } else {
+        if ((P.x < x1) || (P.x > x2)) return false;
+        dmin = -BOUND_HUGE; dmax = BOUND_HUGE;
+    }
+    if (std::fabs(D.z) > EPSILON) {
+        if (D.z > 0.0) { tmin = (z1 - P.z) / D.z; tmax = (z2 - P.z) / D.z; }
+        else { tmax = (z1 - P.z) / D.z; tmin = (z2 - P.z) / D.z; }
+        if (tmax < dmax) {
+            if (tmax < EPSILON) return false;
+            if (tmin > dmin) { if (tmin > tmax) return false; dmin = tmin; }
+            else { if (dmin > tmax) return false; }
+        } else {
+            if (tmin > dmin) { if (tmin > dmax) return false; }
+        }
+    } else {
+        if ((P.z < z1) || (P.z > z2)) return false;
+    }
+    return true;
 }
 
 class Tracer {
@@ -894,6 +949,16 @@ bool Tracer::Inside(V3 p, uint32_t idx) const
                 term++;
             }
             return (result < 1.0e-4) ? !inv : inv;
+        }
+        case PVGPU_OBJ_PRISM: {                                                                           // prism.cpp:640-672
+            V3 P = MInvTransPoint(S.xf[ob.transform], p);
+            if ((P.y >= ob.p[0]) && (P.y < ob.p[1])) {
+                if (((ob.aux >> 4) & 15u) == 2u) {
+                    if (std::fabs(P.y) > EPSILON) { P.x /= P.y; P.z /= P.y; } else P.x = P.z = HUGE_VALUE;
+                }
+                if (prism_in_curve(ob, S.shape_data.data() + ob.mesh, P.x, P.z)) return !inv;
+            }
+            return inv;
         }
         case PVGPU_OBJ_GLYPH: {                                                                           // truetype.cpp:2957-2970
             V3 q = MInvTransPoint(S.xf[ob.transform], p);
@@ -1282,6 +1347,82 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
                         else t = ((Sr[l] * Sr[l] * yt2 + Sr[l] * yt1 + yt0) - P.y) / D.y;
                         double z = P.z + t * D.z;
                         if (z >= 0 && z <= glyph_depth && t > TTF_Tolerance) hit(t, v3(-2.0 * yt2 * Sr[l] - yt1, 2.0 * xt2 * Sr[l] + xt1, 0.0), 2u | ((uint32_t)l << 2) | ((uint32_t)j << 3));
+                    }
+                }
+            }
+            return found;
+        }
+        case PVGPU_OBJ_PRISM: {                                                                           // prism.cpp:194-596
+            if (ob.flags & PVGPU_DEGENERATE_FLAG) return false;
+            const double DEPTH_TOLERANCE = 1.0e-4;
+            const pvgpu_transform& tr = S.xf[ob.transform];
+            V3 P = MInvTransPoint(tr, o), D = MInvTransDirection(tr, d);
+            const double length = len(D);
+            D = D / length;
+            const double Height1 = ob.p[0], Height2 = ob.p[1], x1 = ob.p[2], y1 = ob.p[3], x2 = ob.p[4], y2 = ob.p[5];
+            if (((D.x >= 0.0) && (P.x > x2)) || ((D.x <= 0.0) && (P.x < x1)) || ((D.z >= 0.0) && (P.z > y2)) || ((D.z <= 0.0) && (P.z < y1))) return false;
+            const double* sp = S.shape_data.data() + ob.mesh;
+            const int Number = (int)sp[0];
+            const PrismEntry* Entry = reinterpret_cast<const PrismEntry*>(sp + 1);
+            const uint32_t Spline_Type = ob.aux & 15u, Sweep_Type = (ob.aux >> 4) & 15u;
+            const int sturm = (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0;
+            auto hit = [&](double k, uint32_t aux, double w) {
+                double distance = k / length;
+                if ((distance > DEPTH_TOLERANCE) && (distance < MAX_DISTANCE)) {
+                    V3 IPoint = ray.Evaluate(distance);
+                    if (clip_ok(ob, IPoint)) { Intersection is; is.Depth = distance; is.IPoint = IPoint; is.Object = (int)idx; is.aux = aux; is.d1 = w; Depth_Stack.push_back(is); found = true; }
+                }
+            };
+            auto plane = [&](double Height, uint32_t aux) {                                                // cap / base plane
+                if (Sweep_Type == 2u && !(std::fabs(Height) > EPSILON)) return;
+                double k = (Height - P.y) / D.y;
+                if ((k > DEPTH_TOLERANCE) && (k < MAX_DISTANCE)) {
+                    double u = P.x + k * D.x, v = P.z + k * D.z;
+                    if (Sweep_Type == 2u) { u = u / Height; v = v / Height; }
+                    if (prism_in_curve(ob, sp, u, v)) hit(k, aux, 0.0);
+                }
+            };
+            if (std::fabs(D.y) < EPSILON) { if ((P.y < Height1) || (P.y > Height2)) return false; }
+            else if (ob.flags & PVGPU_CLOSED_FLAG) { plane(Height2, 1u); plane(Height1, 0u); }
+            const double k1 = P.z * D.y - P.y * D.z, k2 = P.y * D.x - P.x * D.y, k3 = P.x * D.z - P.z * D.x;
+            if (Sweep_Type == 1u && !((std::fabs(D.x) > EPSILON) || (std::fabs(D.z) > EPSILON))) return found;
+            for (int j = 0; j < Number; j++) {
+                const PrismEntry& E = Entry[j];
+                if (((D.x >= 0.0) && (P.x > E.x2)) || ((D.x <= 0.0) && (P.x < E.x1)) || ((D.z >= 0.0) && (P.z > E.y2)) || ((D.z <= 0.0) && (P.z < E.y1))) continue;
+                int n = 0;
+                double x[4], y[3];
+                // linear sweep: coefficient pairs (X, Y) weighted with (D.z, -D.x); conic sweep: with (k1, k2) and the constant k3
+                auto coef = [&](const double* c) { return (Sweep_Type == 1u) ? c[0] * D.z - c[1] * D.x : c[0] * k1 + c[1] * k2; };
+                const double last = (Sweep_Type == 1u) ? D.z * (E.D[0] - P.x) - D.x * (E.D[1] - P.z) : E.D[0] * k1 + E.D[1] * k2 + k3;
+                switch (Spline_Type) {
+                    case 1: x[0] = coef(E.C); x[1] = last; if (std::fabs(x[0]) > EPSILON) y[n++] = -x[1] / x[0]; break;
+                    case 2: x[0] = coef(E.B); x[1] = coef(E.C); x[2] = last; n = Solve_Polynomial(2, x, y, 0, 0.0); break;
+                    default:
+                        if (Sweep_Type == 2u || prism_test_rectangle(P, D, E.x1, E.y1, E.x2, E.y2)) {
+                            x[0] = coef(E.A); x[1] = coef(E.B); x[2] = coef(E.C); x[3] = last;
+                            n = Solve_Polynomial(3, x, y, sturm, 0.0);
+                        }
+                        break;
+                }
+                while (n--) {
+                    const double w = y[n];
+                    if ((w >= 0.0) && (w <= 1.0)) {
+                        double k, h;
+                        if (Sweep_Type == 1u) {
+                            if (std::fabs(D.x) > EPSILON) k = (w * (w * (w * E.A[0] + E.B[0]) + E.C[0]) + E.D[0] - P.x) / D.x;
+                            else k = (w * (w * (w * E.A[1] + E.B[1]) + E.C[1]) + E.D[1] - P.z) / D.z;
+                        } else {
+                            k = w * (w * (w * E.A[0] + E.B[0]) + E.C[0]) + E.D[0];
+                            h = D.x - k * D.y;
+                            if (std::fabs(h) > EPSILON) k = (k * P.y - P.x) / h;
+                            else {
+                                k = w * (w * (w * E.A[1] + E.B[1]) + E.C[1]) + E.D[1];
+                                h = D.z - k * D.y;
+                                if (std::fabs(h) > EPSILON) k = (k * P.y - P.z) / h; else continue;
+                            }
+                        }
+                        h = P.y + k * D.y;
+                        if ((h >= Height1) && (h <= Height2)) hit(k, 2u | ((uint32_t)n << 2) | ((uint32_t)j << 4), w);
                     }
                 }
             }
@@ -1683,6 +1824,30 @@ V3 Tracer::Normal(const Intersection& isect) const
             return unit(MTransNormal(t, N));
         }
         case PVGPU_OBJ_GLYPH: return isect.INormal;                                                       // truetype.cpp:2972-2976
+        case PVGPU_OBJ_PRISM: {                                                                           // prism.cpp:710-770
+            const pvgpu_transform& t = S.xf[ob.transform];
+            V3 N = v3(0, 0, 0);
+            const uint32_t side = isect.aux & 3u;
+            if (side == 0u) N = v3(0.0, -1.0, 0.0);
+            else if (side == 1u) N = v3(0.0, 1.0, 0.0);
+            else {
+                const PrismEntry& E = reinterpret_cast<const PrismEntry*>(S.shape_data.data() + ob.mesh + 1)[isect.aux >> 4];
+                const double d1 = isect.d1;
+                if (((ob.aux >> 4) & 15u) == 1u) {
+                    N.x = d1 * (3.0 * E.A[1] * d1 + 2.0 * E.B[1]) + E.C[1];
+                    N.y = 0.0;
+                    N.z = -(d1 * (3.0 * E.A[0] * d1 + 2.0 * E.B[0]) + E.C[0]);
+                } else {
+                    V3 P = MInvTransPoint(t, isect.IPoint);
+                    if (std::fabs(P.y) > EPSILON) {
+                        N.x = d1 * (3.0 * E.A[1] * d1 + 2.0 * E.B[1]) + E.C[1];
+                        N.z = -(d1 * (3.0 * E.A[0] * d1 + 2.0 * E.B[0]) + E.C[0]);
+                        N.y = -(P.x * N.x + P.z * N.z) / P.y;
+                    }
+                }
+            }
+            return unit(MTransNormal(t, N));
+        }
         case PVGPU_OBJ_DISC: return v3(ob.p);                                                             // disc.cpp:226-229
         case PVGPU_OBJ_POLYGON: return v3(ob.p);                                                          // polygon.cpp:308-311
         case PVGPU_OBJ_POLY: {                                                                            // polynomial.cpp:1035-1129, 1180-1244

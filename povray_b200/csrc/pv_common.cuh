@@ -75,7 +75,7 @@ namespace pvgpu {
 // folded and the code of the other primitives never reaches the kernel.
 #ifndef PV_TYPES
 #if PV_HEAVY
-#define PV_TYPES 0x1FFFFu
+#define PV_TYPES 0x3FFFFu
 #else
 #define PV_TYPES ((1u << PVGPU_OBJ_SPHERE) | (1u << PVGPU_OBJ_BOX) | (1u << PVGPU_OBJ_PLANE) | (1u << PVGPU_OBJ_MESH))
 #endif

@@ -983,7 +983,12 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_TRIANGLE: if (PV_HAS(PVGPU_OBJ_TRIANGLE)) return triangle_normal(sc, ob, hit.ip); break;
         case PVGPU_OBJ_POLYGON: if (PV_HAS(PVGPU_OBJ_POLYGON)) return ld3(ob.p); break;       // Polygon::Normal (polygon.cpp:308-311)
         case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) return poly_normal(sc, ob, hit.ip); break;
+#endif
+#if PV_FULL_MATERIALS
+        // (full variant only - device_upload picks it for scenes with these primitives: 50 KB of solver code behind these two calls
+        //  cost config 3 13 % when the plain heavy k_shade carried them)
         case PVGPU_OBJ_GLYPH: if (PV_HAS(PVGPU_OBJ_GLYPH)) return glyph_normal(sc, ob, hit.aux, ray_o, ray_d); break;
+        case PVGPU_OBJ_PRISM: if (PV_HAS(PVGPU_OBJ_PRISM)) return prism_normal(sc, ob, hit.ip, hit.aux, ray_o, ray_d); break;
 #endif
     }
     return mk(0.0, 1.0, 0.0);

@@ -974,4 +974,246 @@ static __device__ __noinline__ V3 glyph_normal(const DScene& sc, const pvgpu_obj
 }
 #endif  // PV_HEAVY
 
+#if PV_HEAVY
+// ---- prism ------------------------------------------------------------------------------------------
+#define PV_PRISM_DEPTH_TOL 1.0e-4     // DEPTH_TOLERANCE prism.cpp:150
+#define PV_PRISM_ENTRY 15             // doubles per spline segment: x1 y1 x2 y2, v1 u2 v2, A B C D (x, y each)
+
+// Prism::in_curve (prism.cpp:1154-1201): crossing number of the half line u' >= u at height v with the closed spline
+static __device__ __noinline__ bool prism_in_curve(const pvgpu_object& ob, const double* sp, double u, double v)
+{
+    int nc = 0;
+    if ((u >= ob.p[6]) && (u <= ob.p[8]) && (v >= ob.p[7]) && (v <= ob.p[9])) {
+        const uint32_t number = (uint32_t)sp[0];
+        for (uint32_t i = 0; i < number; i++) {
+            const double* e = sp + 1 + PV_PRISM_ENTRY * i;
+            if ((v >= e[4]) && (v <= e[6]) && (u <= e[5])) {
+                double x[4] = { e[8], e[10], e[12], e[14] - v }, y[3];
+                int n = solve_polynomial(3, x, y, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, 0.0);
+                while (n--) {
+                    const double w = y[n];
+                    if ((w >= 0.0) && (w <= 1.0)) {
+                        const double k = w * (w * (w * e[7] + e[9]) + e[11]) + e[13] - u;
+                        if (k >= 0.0) nc++;
+                    }
+                }
+            }
+        }
+    }
+    return (nc & 1) != 0;
+}
+
+// Prism::test_rectangle (prism.cpp:1233-1345)
+__device__ inline bool prism_test_rectangle(const V3& P, const V3& D, double x1, double z1, double x2, double z2)
+{
+    double dmin, dmax, tmin, tmax;
+    if (fabs(D.x) > PV_EPSILON) {
+        if (D.x > 0.0) {
+            dmin = (x1 - P.x) / D.x;
+            dmax = (x2 - P.x) / D.x;
+            if (dmax < PV_EPSILON) return false;
+        } else {
+            dmax = (x1 - P.x) / D.x;
+            if (dmax < PV_EPSILON) return false;
+            dmin = (x2 - P.x) / D.x;
+        }
+        if (dmin > dmax) return false;
+    } else {
+        if ((P.x < x1) || (P.x > x2)) return false;
+        dmin = -PV_BOUND_HUGE;
+        dmax = PV_BOUND_HUGE;
+    }
+    if (fabs(D.z) > PV_EPSILON) {
+        if (D.z > 0.0) { tmin = (z1 - P.z) / D.z; tmax = (z2 - P.z) / D.z; }
+        else { tmax = (z1 - P.z) / D.z; tmin = (z2 - P.z) / D.z; }
+        if (tmax < dmax) {
+            if (tmax < PV_EPSILON) return false;
+            if (tmin > dmin) { if (tmin > tmax) return false; }
+            else if (dmin > tmax) return false;
+        } else if (tmin > dmin) {
+            if (tmin > dmax) return false;
+        }
+    } else if ((P.z < z1) || (P.z > z2)) return false;
+    return true;
+}
+
+// The spline parameters at which the ray meets segment `e` (prism.cpp:310-350 linear sweep, 480-510 conic sweep): the roots in y[],
+// in the solver's order; k1..k3 are the conic sweep's ray constants.
+__device__ inline int prism_segment_roots(const pvgpu_object& ob, const double* e, const V3& P, const V3& D, bool conic, double k1, double k2, double k3, double* y)
+{
+    const uint32_t spline = ob.aux & 15u;
+    const double Ax = e[7], Ay = e[8], Bx = e[9], By = e[10], Cx = e[11], Cy = e[12], Dx = e[13], Dy = e[14];
+    double x[4];
+    int n = 0;
+    if (!conic) {
+        switch (spline) {
+            case 1:
+                x[0] = Cx * D.z - Cy * D.x;
+                x[1] = D.z * (Dx - P.x) - D.x * (Dy - P.z);
+                if (fabs(x[0]) > PV_EPSILON) y[n++] = -x[1] / x[0];
+                break;
+            case 2:
+                x[0] = Bx * D.z - By * D.x;
+                x[1] = Cx * D.z - Cy * D.x;
+                x[2] = D.z * (Dx - P.x) - D.x * (Dy - P.z);
+                n = solve_polynomial(2, x, y, 0, 0.0);
+                break;
+            default:
+                if (prism_test_rectangle(P, D, e[0], e[1], e[2], e[3])) {
+                    x[0] = Ax * D.z - Ay * D.x;
+                    x[1] = Bx * D.z - By * D.x;
+                    x[2] = Cx * D.z - Cy * D.x;
+                    x[3] = D.z * (Dx - P.x) - D.x * (Dy - P.z);
+                    n = solve_polynomial(3, x, y, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, 0.0);
+                }
+                break;
+        }
+    } else {
+        switch (spline) {
+            case 1:
+                x[0] = Cx * k1 + Cy * k2;
+                x[1] = Dx * k1 + Dy * k2 + k3;
+                if (fabs(x[0]) > PV_EPSILON) y[n++] = -x[1] / x[0];
+                break;
+            case 2:
+                x[0] = Bx * k1 + By * k2;
+                x[1] = Cx * k1 + Cy * k2;
+                x[2] = Dx * k1 + Dy * k2 + k3;
+                n = solve_polynomial(2, x, y, 0, 0.0);
+                break;
+            default:
+                x[0] = Ax * k1 + Ay * k2;
+                x[1] = Bx * k1 + By * k2;
+                x[2] = Cx * k1 + Cy * k2;
+                x[3] = Dx * k1 + Dy * k2 + k3;
+                n = solve_polynomial(3, x, y, (ob.flags & PVGPU_STURM_FLAG) ? 1 : 0, 0.0);
+                break;
+        }
+    }
+    return n;
+}
+
+// Prism::All_Intersections (prism.cpp:194-596).  Hits come in batches like a glyph's (resume protocol); over all batches they follow
+// the reference's push order: cap, base, then the segments in order, each segment's roots from the last to the first.
+static __device__ __noinline__ void prism_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, int* resume)
+{
+    h.n = 0;
+    uint32_t j = 0;
+    const bool first = !(resume && *resume > 0);
+    if (!first) j = (uint32_t)*resume - 1u;
+    if (resume) *resume = -1;
+    if (ob.flags & PVGPU_DEGENERATE_FLAG) return;
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const V3 P = inv_trans_point(tr, o);
+    V3 D = inv_trans_direction(tr, d);
+    const double len = length(D);
+    D = D / len;
+    if (((D.x >= 0.0) && (P.x > ob.p[4])) || ((D.x <= 0.0) && (P.x < ob.p[2])) || ((D.z >= 0.0) && (P.z > ob.p[5])) || ((D.z <= 0.0) && (P.z < ob.p[3]))) return;
+    const double* sp = sc.shape_data + ob.mesh;
+    const uint32_t number = (uint32_t)sp[0];
+    const double h1 = ob.p[0], h2 = ob.p[1];
+    const bool conic = ((ob.aux >> 4) & 15u) == 2u;
+    if (fabs(D.y) < PV_EPSILON) {
+        if ((P.y < h1) || (P.y > h2)) return;
+    } else if (first && (ob.flags & PVGPU_CLOSED_FLAG)) {
+        for (int cap = 1; cap >= 0; cap--) {               // cap plane (Height2) first, then the base plane
+            const double hh = cap ? h2 : h1;
+            if (conic && !(fabs(hh) > PV_EPSILON)) continue;
+            const double k = (hh - P.y) / D.y;
+            if ((k > PV_PRISM_DEPTH_TOL) && (k < PV_MAX_DISTANCE)) {
+                double u = P.x + k * D.x, v = P.z + k * D.z;
+                if (conic) { u = u / hh; v = v / hh; }
+                if (prism_in_curve(ob, sp, u, v)) {
+                    const double dist = k / len;
+                    if ((dist > PV_PRISM_DEPTH_TOL) && (dist < PV_MAX_DISTANCE)) { h.depth[h.n] = dist; h.ip[h.n] = evaluate(o, d, dist); h.aux[h.n] = (uint32_t)cap; h.n++; }
+                }
+            }
+        }
+    }
+    if (!conic && !((fabs(D.x) > PV_EPSILON) || (fabs(D.z) > PV_EPSILON))) return;          // parallel to all sides
+    const double k1 = P.z * D.y - P.y * D.z, k2 = P.y * D.x - P.x * D.y, k3 = P.x * D.z - P.z * D.x;
+    for (; j < number; j++) {
+        if (h.n + 3 > PV_MAX_PRIM_HITS) { if (resume) *resume = (int)j + 1; return; }
+        const double* e = sp + 1 + PV_PRISM_ENTRY * j;
+        if (((D.x >= 0.0) && (P.x > e[2])) || ((D.x <= 0.0) && (P.x < e[0])) || ((D.z >= 0.0) && (P.z > e[3])) || ((D.z <= 0.0) && (P.z < e[1]))) continue;
+        double y[3];
+        int n = prism_segment_roots(ob, e, P, D, conic, k1, k2, k3, y);
+        while (n--) {
+            const double w = y[n];
+            if (!((w >= 0.0) && (w <= 1.0))) continue;
+            double k;
+            if (!conic) {
+                if (fabs(D.x) > PV_EPSILON) k = (w * (w * (w * e[7] + e[9]) + e[11]) + e[13] - P.x) / D.x;
+                else k = (w * (w * (w * e[8] + e[10]) + e[12]) + e[14] - P.z) / D.z;
+            } else {
+                k = w * (w * (w * e[7] + e[9]) + e[11]) + e[13];
+                double hh = D.x - k * D.y;
+                if (fabs(hh) > PV_EPSILON) k = (k * P.y - P.x) / hh;
+                else {
+                    k = w * (w * (w * e[8] + e[10]) + e[12]) + e[14];
+                    hh = D.z - k * D.y;
+                    if (fabs(hh) > PV_EPSILON) k = (k * P.y - P.z) / hh;
+                    else continue;
+                }
+            }
+            const double hh = P.y + k * D.y;
+            if ((hh >= h1) && (hh <= h2)) {
+                const double dist = k / len;
+                if ((dist > PV_PRISM_DEPTH_TOL) && (dist < PV_MAX_DISTANCE)) { h.depth[h.n] = dist; h.ip[h.n] = evaluate(o, d, dist); h.aux[h.n] = 2u | ((uint32_t)n << 2) | (j << 4); h.n++; }
+            }
+        }
+    }
+}
+
+// Prism::Inside (prism.cpp:640-672)
+__device__ inline bool prism_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    V3 P = inv_trans_point(sc.xf[ob.transform], p);
+    const bool inv = (ob.flags & PVGPU_INVERTED_FLAG) != 0;
+    if ((P.y >= ob.p[0]) && (P.y < ob.p[1])) {
+        if (((ob.aux >> 4) & 15u) == 2u) {
+            if (fabs(P.y) > PV_EPSILON) { P.x = P.x / P.y; P.z = P.z / P.y; }
+            else P.x = P.z = PV_HUGE_VAL;
+        }
+        if (prism_in_curve(ob, sc.shape_data + ob.mesh, P.x, P.z)) return !inv;
+    }
+    return inv;
+}
+
+// Prism::Normal (prism.cpp:710-770); the spline parameter the reference keeps with the hit (Intersection::d1) is solved for again
+// with the ray that found the hit (same operands, same solver path).
+static __device__ __noinline__ V3 prism_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip, uint32_t aux, const V3& ray_o, const V3& ray_d)
+{
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    V3 N = mk(0.0, 0.0, 0.0);
+    const uint32_t kind = aux & 3u;
+    if (kind == 0u) N = mk(0.0, -1.0, 0.0);
+    else if (kind == 1u) N = mk(0.0, 1.0, 0.0);
+    else {
+        const double* e = sc.shape_data + ob.mesh + 1 + PV_PRISM_ENTRY * (aux >> 4);
+        const V3 P = inv_trans_point(tr, ray_o);
+        V3 D = inv_trans_direction(tr, ray_d);
+        D = D / length(D);
+        const bool conic = ((ob.aux >> 4) & 15u) == 2u;
+        const double k1 = P.z * D.y - P.y * D.z, k2 = P.y * D.x - P.x * D.y, k3 = P.x * D.z - P.z * D.x;
+        double y[3] = { 0.0, 0.0, 0.0 };
+        prism_segment_roots(ob, e, P, D, conic, k1, k2, k3, y);
+        const double w = y[(aux >> 2) & 3u];
+        if (!conic) {
+            N.x = w * (3.0 * e[8] * w + 2.0 * e[10]) + e[12];
+            N.y = 0.0;
+            N.z = -(w * (3.0 * e[7] * w + 2.0 * e[9]) + e[11]);
+        } else {
+            const V3 Q = inv_trans_point(tr, ip);
+            if (fabs(Q.y) > PV_EPSILON) {
+                N.x = w * (3.0 * e[8] * w + 2.0 * e[10]) + e[12];
+                N.z = -(w * (3.0 * e[7] * w + 2.0 * e[9]) + e[11]);
+                N.y = -(Q.x * N.x + Q.z * N.z) / Q.y;
+            }
+        }
+    }
+    return normalized(trans_normal(tr, N));
+}
+#endif  // PV_HEAVY
+
 }  // namespace pvgpu

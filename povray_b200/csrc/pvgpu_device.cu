@@ -398,6 +398,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->full = true;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
     if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights || !s.blob_textures.empty() || !s.images.empty()) d->full = true;
+    for (const pvgpu_object& o : s.objects) if (o.type == PVGPU_OBJ_GLYPH || o.type == PVGPU_OBJ_PRISM) d->full = true;      // their normals live in the full shading kernels
     for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }
     for (const pvgpu_finish& fi : s.finishes) {
         const bool reflective = fi.reflection_max[0] != 0 || fi.reflection_max[1] != 0 || fi.reflection_max[2] != 0 ||
@@ -640,6 +641,13 @@ struct FrameCtx {
 };
 
 // Runs all waves for samples [first, first+n) of `src`.  Returns PVGPU_E_OVERFLOW if a queue was too small.
+// PVGPU_SHADE_CSG=0: scenes of the `_csg` class shade with the plain heavy k_shade (A/B switch)
+static bool shade_csg_enabled()
+{
+    static const bool on = [] { const char* e = getenv("PVGPU_SHADE_CSG"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint32_t n)
 {
     Scene& s = f.s;
@@ -691,7 +699,7 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
         if (wave >= 3 && have_lights) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[wave - 3]], 0));
         {
             TimedLaunch t(c, S1, KIND_SHADE, 0);
-            (d.lean ? launch_shade_lean : d.full ? launch_shade_full : launch_shade)(d.view, cur, c.hits, wc, nb, ctx, S1);
+            (d.lean ? launch_shade_lean : d.full ? launch_shade_full : (d.csg && shade_csg_enabled()) ? launch_shade_csg : launch_shade)(d.view, cur, c.hits, wc, nb, ctx, S1);
         }
         CUDA_TRY(cudaMemcpyAsync(&c.h_counts[wave], &wc[1].n_rays, sizeof(unsigned int), cudaMemcpyDeviceToHost, S1));
         ev_rb.push_back(next_event(c));

@@ -340,6 +340,14 @@ int validate_scene(Scene& s)
             if (!(nseg >= 0.0 && nseg <= (double)(1u << 24)) || nseg != (double)(uint32_t)nseg || !range_ok((uint32_t)o.mesh + 1u, 7u * (uint32_t)nseg, s.shape_data.size()))
                 return fail(PVGPU_E_INVALID, "object %zu: glyph outline outside the shape-data table", i);
         }
+        if (o.type == PVGPU_OBJ_PRISM) {
+            const uint32_t spline = o.aux & 15u, sweep = (o.aux >> 4) & 15u;
+            if (o.transform < 0 || o.mesh < 0 || !range_ok((uint32_t)o.mesh, 1u, s.shape_data.size()) || spline < 1 || spline > 4 || sweep < 1 || sweep > 2 || (o.aux >> 8))
+                return fail(PVGPU_E_INVALID, "object %zu: prism without transform, with its spline outside the shape-data table or with an unknown spline / sweep type", i);
+            const double number = s.shape_data[o.mesh];
+            if (!(number >= 0.0 && number <= (double)(1u << 24)) || number != (double)(uint32_t)number || !range_ok((uint32_t)o.mesh + 1u, 15u * (uint32_t)number, s.shape_data.size()))
+                return fail(PVGPU_E_INVALID, "object %zu: prism spline outside the shape-data table", i);
+        }
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
         if ((o.flags & PVGPU_UV_FLAG))
