@@ -81,6 +81,11 @@ namespace pvgpu {
 #endif
 #endif
 #define PV_HAS(type) ((PV_TYPES & (1u << (type))) != 0u)
+// Pattern set of a variant.  PV_BASIC_PATTERNS: plain and checker pigments with transform warps only - no noise, turbulence or
+// waveform code reaches the shading-side kernels.
+#ifndef PV_BASIC_PATTERNS
+#define PV_BASIC_PATTERNS 0
+#endif
 #ifndef PV_CLIPBOUND
 #define PV_CLIPBOUND PV_HEAVY          // clipped_by / bounded_by lists are served
 #endif

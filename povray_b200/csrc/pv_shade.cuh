@@ -51,10 +51,12 @@ __device__ inline V3 warp_epoint(const DScene& sc, const pvgpu_pigment& pg, cons
     for (int i = (int)pg.warp_count - 1; i >= 0; i--) {
         const pvgpu_warp& w = sc.warps[pg.warp_first + i];
         if (w.type == PVGPU_WARP_TRANSFORM) p = inv_trans_point(sc.xf[w.transform], p);
+#if !PV_BASIC_PATTERNS
         else {   // GenericTurbulenceWarp::WarpPoint (warp.cpp:553-559)
             V3 t = dturbulence(sc.noise, p, w.octaves, (double)w.lambda, (double)w.omega);
             p = mk(p.x + t.x * w.turbulence[0], p.y + t.y * w.turbulence[1], p.z + t.z * w.turbulence[2]);
         }
+#endif
     }
     if (p.x > PV_COORDINATE_LIMIT) p.x = PV_COORDINATE_LIMIT; else if (p.x < -PV_COORDINATE_LIMIT) p.x = -PV_COORDINATE_LIMIT;
     if (p.y > PV_COORDINATE_LIMIT) p.y = PV_COORDINATE_LIMIT; else if (p.y < -PV_COORDINATE_LIMIT) p.y = -PV_COORDINATE_LIMIT;
@@ -261,6 +263,7 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
             int v = (int)(floor(p.x + PV_EPSILON) + floor(p.y + PV_EPSILON) + floor(p.z + PV_EPSILON));
             return (v & 1) ? 1.0 : 0.0;
         }
+#if !PV_BASIC_PATTERNS
         case PVGPU_PAT_BOZO:
         case PVGPU_PAT_SPOTTED:     // NoisePattern::EvaluateRaw (pattern.cpp:7858)
             value = noise3(sc.noise, p, gen);
@@ -410,6 +413,7 @@ __device__ inline double evaluate_pattern(const DScene& sc, const pvgpu_pigment&
             break;
         }
 #endif
+#endif  // !PV_BASIC_PATTERNS
 #if PV_FULL_MATERIALS
         case PVGPU_PAT_CRACKLE:
             value = crackle_pattern(sc, pg, p, gen);
