@@ -345,7 +345,14 @@ PV_VARIANT(k_closest)(DScene sc, const PRay* __restrict__ cur, WaveCounts* wc, u
         best.depth = ((flags & PV_RAY_PRIMARY) && !(flags & PV_RAY_PROBE) && sc.cam.max_ray_distance >= PV_EPSILON) ? sc.cam.max_ray_distance : PV_BOUND_HUGE;
         best.obj = PV_NO_OBJECT;
         best.aux = 0; best.csg = -1;
+#ifdef PV_DIAG_MAX_VISITS
+        const uint32_t diag_nodes0 = tc.nodes;
+#endif
         const bool found = find_intersection_sync<false>(alive, sc, o, d, flags & ~PV_RAY_PROBE, false, -1.0, best, stack, &cnt->overflow, tc);
+#ifdef PV_DIAG_MAX_VISITS
+        // diagnostic build: the largest number of box tests any single ray of the frame needed (Counters::pad, printed by PVGPU_TRACE_WAVES)
+        if (alive) atomicMax(&cnt->pad, tc.nodes - diag_nodes0);
+#endif
         if (found) {
             out.depth = best.depth; out.ip[0] = best.ip.x; out.ip[1] = best.ip.y; out.ip[2] = best.ip.z;
             out.obj = best.obj; out.aux = best.aux; out.csg = best.csg;

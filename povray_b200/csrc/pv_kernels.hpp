@@ -50,7 +50,10 @@ struct AALayout {
 int  sm_count();
 int  grid_for(uint32_t n, int block, int per_sm);
 // grid bound of a traversal kernel: small waves are spread over the warps in chunks of down to 8 rays (chunk_size, pv_traverse.cuh)
-inline uint32_t trav_grid_bound(uint32_t n_bound) { return n_bound > 0x3FFFFFFFu ? 0xFFFFFFFFu : n_bound * 4u; }
+#ifndef PV_GRID_PER_RAY
+#define PV_GRID_PER_RAY 4u
+#endif
+inline uint32_t trav_grid_bound(uint32_t n_bound) { return n_bound > 0xFFFFFFFFu / PV_GRID_PER_RAY ? 0xFFFFFFFFu : n_bound * PV_GRID_PER_RAY; }
 
 void launch_container_state(const DScene& sc, uint16_t* out, Counters* cnt, cudaStream_t st);
 void launch_primary(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height,

@@ -547,6 +547,9 @@ __device__ __forceinline__ bool vote_any(bool p)   { return __any_sync(PV_FULL_M
 // A warp normally takes 32 rays.  When a wave is too small to give every warp of the grid a chunk (late waves, one GPU's share of
 // a frame sharded over eight), chunks shrink to 16 or 8 rays and the other lanes idle: the time of such a wave is the time of its
 // slowest warp, which is shorter the fewer (diverging) rays the warp has to serve turn by turn.
+#ifndef PV_CHUNK_MIN
+#define PV_CHUNK_MIN 8u
+#endif
 __device__ __forceinline__ uint32_t chunk_size(uint32_t n)
 {
 #ifdef PV_CTA_SYNC
@@ -554,7 +557,7 @@ __device__ __forceinline__ uint32_t chunk_size(uint32_t n)
 #else
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     uint32_t cs = 32u;
-    while (cs > 8u && (n + cs - 1u) / cs < warps) cs >>= 1;
+    while (cs > PV_CHUNK_MIN && (n + cs - 1u) / cs < warps) cs >>= 1;
     return cs;
 #endif
 }

@@ -1090,7 +1090,9 @@ static int render_impl(Scene& s, DeviceScene& d, WorkCtx& c, const pvgpu_aa* aa,
         }
         fprintf(stderr, "pvgpu wave trace: rays of waves 1..: ");
         for (uint32_t k = 0; k + 1 < (uint32_t)st.waves && k < 16; k++) fprintf(stderr, "%u ", c.h_counts[k]);
-        fprintf(stderr, "| frame %.3f ms\n", ms);
+        fprintf(stderr, "| frame %.3f ms", ms);
+        if (hc.pad) fprintf(stderr, " | most box tests of one ray (diagnostic build): %u", hc.pad);
+        fprintf(stderr, "\n");
     }
     st.kernel_items[KIND_CLOSEST] = hc.rays;
     st.kernel_items[KIND_SHADE] = hc.rays;
