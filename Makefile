@@ -19,8 +19,11 @@ LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
 FULL_SRC  := k_shade k_shadow_filter
 # ... and the traversal kernels a fourth time with -DPV_CSG (quadric-class primitives + CSG only: no solver, blob, mesh code)
 CSG_SRC   := k_closest k_shade k_shadow_opaque k_shadow_filter
+# ... and a fifth time with -DPV_QUARTIC (spheres, boxes, planes, quadrics, tori, blobs; no CSG, mesh, cone, polygon, glyph, prism code)
+QUARTIC_SRC := k_closest k_shadow_opaque k_shadow_filter
 OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
-             $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC)) $(patsubst %,$(OBJDIR)/%_csg.o,$(CSG_SRC))
+             $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC)) $(patsubst %,$(OBJDIR)/%_csg.o,$(CSG_SRC)) \
+             $(patsubst %,$(OBJDIR)/%_quartic.o,$(QUARTIC_SRC))
 HDR       := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.inc) $(INCDIR)/pvgpu.h
 
 .PHONY: all oracle clean
@@ -41,6 +44,10 @@ $(OBJDIR)/%_full.o: $(CSRC)/%.cu $(HDR)
 $(OBJDIR)/%_csg.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -DPV_CSG -c $< -o $@
+
+$(OBJDIR)/%_quartic.o: $(CSRC)/%.cu $(HDR)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -DPV_QUARTIC -c $< -o $@
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDR)
 	@mkdir -p $(OBJDIR)

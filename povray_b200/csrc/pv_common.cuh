@@ -60,6 +60,13 @@ namespace pvgpu {
 #define PV_VARIANT(name) name##_csg
 #define PV_TYPES ((1u << PVGPU_OBJ_SPHERE) | (1u << PVGPU_OBJ_BOX) | (1u << PVGPU_OBJ_PLANE) | (1u << PVGPU_OBJ_QUADRIC) | (1u << PVGPU_OBJ_CONE) | \
                   (1u << PVGPU_OBJ_DISC) | (1u << PVGPU_OBJ_CSG_UNION) | (1u << PVGPU_OBJ_CSG_INTERSECTION) | (1u << PVGPU_OBJ_CSG_MERGE))
+#elif defined(PV_QUARTIC)
+// traversal kernels for scenes made of stand-alone spheres, boxes, planes, quadrics, tori and blobs (BASELINE config 4): the
+// polynomial solver stays, CSG, mesh, cone, disc, polygon, poly, glyph and prism code goes
+#define PV_HEAVY 1
+#define PV_FULL_MATERIALS 0
+#define PV_VARIANT(name) name##_quartic
+#define PV_TYPES ((1u << PVGPU_OBJ_SPHERE) | (1u << PVGPU_OBJ_BOX) | (1u << PVGPU_OBJ_PLANE) | (1u << PVGPU_OBJ_QUADRIC) | (1u << PVGPU_OBJ_TORUS) | (1u << PVGPU_OBJ_BLOB))
 #elif defined(PV_FULL)
 #define PV_HEAVY 1
 #define PV_FULL_MATERIALS 1
@@ -91,7 +98,7 @@ namespace pvgpu {
 #endif
 
 // k_closest.cu also holds the kernels that exist once (camera rays, probes, queue bookkeeping): compiled in its default variant only
-#if defined(PV_LEAN) || defined(PV_CSG)
+#if defined(PV_LEAN) || defined(PV_CSG) || defined(PV_QUARTIC)
 #define PV_SECONDARY_TU 1
 #else
 #define PV_SECONDARY_TU 0

@@ -71,6 +71,9 @@ void launch_shade_lean(const DScene& sc, const PRay* cur, const HitRec* hits, co
 void launch_shadow_opaque_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_shadow_filter_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
 // quadric-class + CSG variants of the traversal kernels (-DPV_CSG)
+void launch_closest_quartic(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st);
+void launch_shadow_opaque_quartic(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
+void launch_shadow_filter_quartic(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_shade_csg(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st);
 void launch_closest_csg(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st);
 void launch_shadow_opaque_csg(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);

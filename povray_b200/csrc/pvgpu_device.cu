@@ -81,6 +81,7 @@ struct DeviceScene {
     bool lean = false;                   // only spheres, boxes, planes, meshes and no clipped_by / bounded_by: lean kernel variants
     bool full = false;                   // normal{}, pigment_map / average, sky_sphere, fog or area lights: full-material shading variants
     bool csg = false;                    // quadric-class primitives (+ CSG) only: the _csg traversal variants
+    bool quartic = false;                // stand-alone spheres, boxes, planes, quadrics, tori, blobs: the _quartic traversal variants
     bool camera_dirty = true;
     uint32_t spawn_factor = 0;           // upper bound of the rays one shaded ray adds to the next wave (0: the frame is one wave)
     uint32_t shadow_factor = 1;          // upper bound of the shadow rays one shaded ray emits
@@ -413,6 +414,13 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
         if (!in_class) d->csg = false;
     }
     if (const char* e = getenv("PVGPU_CSG")) if (e[0] == '0') d->csg = false;
+    d->quartic = !d->lean && !d->full && !d->csg;
+    for (const pvgpu_object& o : s.objects) {
+        const bool in_class = o.type == PVGPU_OBJ_SPHERE || o.type == PVGPU_OBJ_BOX || o.type == PVGPU_OBJ_PLANE || o.type == PVGPU_OBJ_QUADRIC ||
+                              o.type == PVGPU_OBJ_TORUS || o.type == PVGPU_OBJ_BLOB;
+        if (!in_class) d->quartic = false;
+    }
+    if (const char* e = getenv("PVGPU_QUARTIC")) if (e[0] == '0') d->quartic = false;
     v.n_objs = (uint32_t)s.objects.size();
     v.n_frame = (uint32_t)s.frame.size();
     v.n_nodes = (uint32_t)s.nodes.size();
@@ -693,7 +701,7 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
         ctx.conts = conts ? c.conts : nullptr; ctx.cont_cap = (uint32_t)c.cont_cap; ctx.cont_base = f.cont_base; ctx.wave = wave;
         {
             TimedLaunch t(c, S1, KIND_CLOSEST, 0);
-            (d.lean ? launch_closest_lean : d.csg ? launch_closest_csg : launch_closest)(d.view, cur, wc, nb, q_cap, c.hits, c.cnt, S1);
+            (d.lean ? launch_closest_lean : d.csg ? launch_closest_csg : d.quartic ? launch_closest_quartic : launch_closest)(d.view, cur, wc, nb, q_cap, c.hits, c.cnt, S1);
         }
         // k_shade of this wave writes sq[wave % 3] and q[(wave + 1) % 4]: k_shadow_* of wave - 3 read both (queue and parent rays)
         if (wave >= 3 && have_lights) CUDA_TRY(cudaStreamWaitEvent(S1, c.ev_pool[ev_shadow[wave - 3]], 0));
@@ -709,8 +717,8 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
             const uint32_t sb = (uint32_t)std::min<unsigned long long>((unsigned long long)nb * d.shadow_factor, sq_cap);
             {
                 TimedLaunch t(c, S2, KIND_SHADOW, 0);
-                if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : d.csg ? launch_shadow_opaque_csg : launch_shadow_opaque)(d.view, c.sq[wave % 3], wc, sb, sq_cap, f.accum, c.cnt, S2);
-                else (d.lean ? launch_shadow_filter_lean : d.full ? launch_shadow_filter_full : d.csg ? launch_shadow_filter_csg : launch_shadow_filter)(d.view, c.sq[wave % 3], wc, sb, sq_cap, cur, f.accum, c.cnt, S2);
+                if (d.view.all_opaque) (d.lean ? launch_shadow_opaque_lean : d.csg ? launch_shadow_opaque_csg : d.quartic ? launch_shadow_opaque_quartic : launch_shadow_opaque)(d.view, c.sq[wave % 3], wc, sb, sq_cap, f.accum, c.cnt, S2);
+                else (d.lean ? launch_shadow_filter_lean : d.full ? launch_shadow_filter_full : d.csg ? launch_shadow_filter_csg : d.quartic ? launch_shadow_filter_quartic : launch_shadow_filter)(d.view, c.sq[wave % 3], wc, sb, sq_cap, cur, f.accum, c.cnt, S2);
                 if (d.view.has_area_lights) { c.kernel_launches++; launch_shadow_area(d.view, c.sq[wave % 3], wc, sb, sq_cap, cur, f.accum, c.cnt, c.area_grid, S2); }
             }
             ev_shadow.push_back(next_event(c));
