@@ -219,6 +219,10 @@ static void release_one(DeviceScene* d)
     for (auto& c : d->ctx) release_ctx(*c);
     for (void* p : d->allocs) cudaFree(p);
     cudaFree(d->d_cam_int);
+    if (d->device >= 0) {       // hand the pooled anti-aliasing scratch back with the scene
+        cudaMemPool_t pool;
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, d->device) != cudaSuccess || cudaMemPoolTrimTo(pool, 0) != cudaSuccess) cudaGetLastError();
+    }
     delete d;
 }
 
@@ -265,6 +269,11 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     size_t total = 0;
     DScene& v = d->view;
 
+    {   // the anti-aliasing scratch comes from the default memory pool (Scratch): keep what it frees
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess || cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) cudaGetLastError();
+    }
     mark("context + device flags");
     // CSG leaf lists: primitive descendants of every parentless CSG object, depth first (csg.cpp walks children in order)
     std::vector<uint32_t> leaves;
@@ -788,15 +797,30 @@ static int trace_samples(FrameCtx& f, const SampleSource& src, uint32_t n_sample
 // Accumulator slots to add behind the slots of a call for the continuation records of scenes with a reflection exponent != 1
 static size_t cont_extra(const DeviceScene& d, const WorkCtx& c) { return d.has_reflect_exp ? c.cont_cap : 0; }
 
-// Device scratch of one anti-aliased call, freed on scope exit.
+// Device scratch of one anti-aliased call, freed on scope exit.  Stream-ordered allocations from the device's default pool, whose
+// release threshold device_upload raises: after the first frame the buffers of a call (GBs at 1080p +R3) come out of the pool
+// instead of cudaMalloc / cudaFree, which cost config 3 with AA half a second of idle GPU per frame.  The buffers are freed in the
+// order of `stream` after it has been made to wait for the shadow stream (a wave loop that returns early with an error has not
+// joined the two).
 struct Scratch {
+    cudaStream_t stream, other;
     std::vector<void*> ptrs;
-    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    Scratch(cudaStream_t s, cudaStream_t o) : stream(s), other(o) {}
+    ~Scratch()
+    {
+        if (ptrs.empty()) return;
+        cudaEvent_t ev;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+            if (cudaEventRecord(ev, other) != cudaSuccess || cudaStreamWaitEvent(stream, ev, 0) != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(other); }
+            cudaEventDestroy(ev);
+        } else { cudaGetLastError(); cudaStreamSynchronize(other); }
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
+    }
     template <class T> int alloc(T*& out, size_t n)
     {
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), stream);
+        if (e != cudaSuccess) return fail(PVGPU_E_CUDA, "cudaMallocAsync of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
         ptrs.push_back(p);
         out = reinterpret_cast<T*>(p);
         return PVGPU_OK;
@@ -847,7 +871,7 @@ static int render_aa1(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
     const uint32_t n_off = (uint32_t)offsets.size();
     const AAParams ap = make_aa_params(aa);
 
-    Scratch sc;
+    Scratch sc(stream, c.s_shadow);
     float4* accum = nullptr; uint32_t* d_foff = nullptr; double2* d_fcoords = nullptr; int32_t* s_slot = nullptr; uint32_t* cand = nullptr;
     unsigned int* counters = nullptr; uint8_t* flag = nullptr; double2* d_offsets = nullptr; double2* d_coords = nullptr; uint32_t* d_slots = nullptr;
     const size_t n_slots = (size_t)n_px * 2 + n_frame;
@@ -913,7 +937,7 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
     const AAParams ap = make_aa_params(aa);
     const uint32_t S1 = (1u << aa.depth) + 1u, per = S1 * S1, words = (per + 31) / 32;
 
-    Scratch sc;
+    Scratch sc(stream, c.s_shadow);
     float4* corners = nullptr; uint32_t* d_coff = nullptr; double2* d_ccoords = nullptr; int32_t* act_idx = nullptr; uint32_t* act_list = nullptr;
     unsigned int* counters = nullptr;
     AA_TRY(sc.alloc(corners, n_corner + cont_extra(d, c))); AA_TRY(sc.alloc(d_coff, n_rects + 1)); AA_TRY(sc.alloc(d_ccoords, n_corner));
@@ -949,7 +973,7 @@ static int render_aa2(FrameCtx& f, const pvgpu_aa& aa, const pvgpu_rect* rects, 
             const unsigned long long cap64 = std::min<unsigned long long>((unsigned long long)n_list * per_pixel, 0xFFFFFFF0ull);
             const uint32_t cap = (uint32_t)cap64;
             double2* d_coords = nullptr; uint32_t* d_slots = nullptr;
-            Scratch rs;
+            Scratch rs(stream, c.s_shadow);
             AA_TRY(rs.alloc(d_coords, cap)); AA_TRY(rs.alloc(d_slots, cap));
             CUDA_TRY(cudaMemsetAsync(counters + 1, 0, sizeof(unsigned int), stream));
             { TimedLaunch t(c, stream, KIND_AA, n_list); launch_aa2_expand(L, ap, d.view.noise.hash, accum, list, n_list, (int)round, sampled, d_coords, d_slots, counters + 1, cap, stream); }
