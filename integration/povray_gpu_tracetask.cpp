@@ -317,9 +317,7 @@ struct Flattener
             carrier.noise_generator = bp->noiseGenerator;
             add_warps(bp->warps, carrier.warp_first, carrier.warp_count);
         } else if (t.type == PVGPU_NORM_PATTERN) {
-            fill_pattern(bp, carrier, "normal");
-            if (carrier.pattern == PVGPU_PAT_CHECKER || carrier.pattern == PVGPU_PAT_BRICK || carrier.pattern == PVGPU_PAT_HEXAGON)
-                unsupported("block-pattern normal (needs a normal_map)");
+            fill_pattern(bp, carrier, "normal");     // (a block pattern without a normal_map is sampled like any other pattern, normal.cpp:880-905)
         }
         // WarpNormal exists for transform warps only (warp.cpp:582-640): any other warp leaves the normal as it is
         if (sm != nullptr) {

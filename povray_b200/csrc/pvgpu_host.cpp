@@ -502,8 +502,9 @@ int validate_scene(Scene& s)
         if (t.pattern < 0 || t.pattern >= (int32_t)s.pigments.size() || !range_ok(t.slope_first, t.slope_count, s.slope_entries.size()))
             return fail(PVGPU_E_INVALID, "tnormal %zu: bad pattern carrier / slope map range", i);
         const pvgpu_pigment& c = s.pigments[t.pattern];
-        if (t.type == PVGPU_NORM_PATTERN && !t.normal_map && (c.pattern <= PVGPU_PAT_CHECKER || c.pattern == PVGPU_PAT_BRICK || c.pattern == PVGPU_PAT_HEXAGON))
-            return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: block patterns need a normal_map (outside the hot-path scope)", i);
+        // (a block pattern without a normal_map is sampled on the pyramid like any other pattern, normal.cpp:880-905)
+        if (t.type == PVGPU_NORM_PATTERN && !t.normal_map && c.pattern < PVGPU_PAT_CHECKER)
+            return fail(PVGPU_E_INVALID, "tnormal %zu: a pattern normal needs a pattern", i);
         for (uint32_t k = 0; k < c.warp_count; k++)
             if (s.warps[c.warp_first + k].type != PVGPU_WARP_TRANSFORM && s.warps[c.warp_first + k].type != PVGPU_WARP_CLASSIC_TURBULENCE &&
                 s.warps[c.warp_first + k].type != PVGPU_WARP_TURBULENCE)
