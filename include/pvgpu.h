@@ -72,13 +72,15 @@ enum {
                                         whose next point is off-curve already moved to the midpoint, zero-length lines dropped.
                                         Hit aux: bits 0-1 = 0 face z = 0, 1 face z = depth, 2 wall; bit 2 = which root of the wall's
                                         quadratic; bits 3.. = segment */
-    PVGPU_OBJ_PRISM            = 17  /* prism.h:98     p[0..1] = Height1 Height2, p[2..5] = x1 y1 x2 y2, p[6..9] = u1 v1 u2 v2 (the spline's
+    PVGPU_OBJ_PRISM            = 17, /* prism.h:98     p[0..1] = Height1 Height2, p[2..5] = x1 y1 x2 y2, p[6..9] = u1 v1 u2 v2 (the spline's
                                         bounding rectangles); aux = Spline_Type (1 linear .. 4 bezier) | Sweep_Type (1 linear, 2 conic) << 4;
                                         transform required; CLOSED / STURM / DEGENERATE flags; mesh = offset into the shape-data table:
                                         Number, then per PRISM_SPLINE_ENTRY 15 doubles: x1 y1 x2 y2, v1 u2 v2, A B C D (x y each).
                                         Hit aux: bits 0-1 = 0 base, 1 cap, 2 spline; bits 2-3 = root index; bits 4.. = segment */
+    PVGPU_OBJ_SUPERELLIPSOID   = 18  /* superellipsoid.h:78  p[0..2] = Power (2/e, e/n, 2/n); transform required; aux bit 0 = IS_CHILD_OBJECT
+                                        (a CSG operand reports every hit, a stand-alone object stops at the first); no clipped_by */
 };
-#define PVGPU_OBJ_LAST PVGPU_OBJ_PRISM
+#define PVGPU_OBJ_LAST PVGPU_OBJ_SUPERELLIPSOID
 #define PVGPU_TRIANGLE_SMOOTH 0x10u
 
 #define PVGPU_IS_CSG(type) ((type) >= PVGPU_OBJ_CSG_UNION && (type) <= PVGPU_OBJ_CSG_MERGE)

@@ -75,6 +75,7 @@
 #include "core/shape/prism.h"
 #include "core/shape/quadric.h"
 #include "core/shape/sphere.h"
+#include "core/shape/superellipsoid.h"
 #include "core/shape/torus.h"
 #include "core/shape/triangle.h"
 #include "core/shape/truetype.h"
@@ -736,6 +737,11 @@ struct Flattener
             p.type = PVGPU_OBJ_CONE;
             p.p[0] = cn->dist;
             p.transform = add_transform(cn->Trans);
+        } else if (Superellipsoid* se = dynamic_cast<Superellipsoid*>(o)) {
+            p.type = PVGPU_OBJ_SUPERELLIPSOID;
+            for (int k = 0; k < 3; k++) p.p[k] = se->Power[k];
+            p.aux = (se->Type & IS_CHILD_OBJECT) ? 1u : 0u;
+            p.transform = add_transform(se->Trans);
         } else if (Prism* pr = dynamic_cast<Prism*>(o)) {
             p.type = PVGPU_OBJ_PRISM;
             p.p[0] = pr->Height1; p.p[1] = pr->Height2;

@@ -622,6 +622,103 @@ static bool prism_test_rectangle(V3 P, V3 D, double x1, double z1, double x2, do
     return true;
 }
 
+// ---- superellipsoid (superellipsoid.cpp) ------------------------------------------------------------------
+namespace superq {
+const double DEPTH_TOLERANCE = 1.0e-4, ZERO_TOLERANCE = 1.0e-10, MIN_VALUE = -1.01, MAX_VALUE = 1.01;
+const int MAX_ITERATIONS = 20, PLANECOUNT = 9;
+const double planes[PLANECOUNT][4] = { { 1, 1, 0, 0 }, { 1, -1, 0, 0 }, { 1, 0, 1, 0 }, { 1, 0, -1, 0 }, { 0, 1, 1, 0 }, { 0, 1, -1, 0 }, { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 } };
+static double power(double x, double e)                                                                    // :1097-1150
+{
+    double b = x;
+    int i = (int)e;
+    if (e == (double)i) {
+        switch (i) {
+            case 0: return 1.0;
+            case 1: return b;
+            case 2: return sqr(b);
+            case 3: return sqr(b) * b;
+            case 4: b *= b; return sqr(b);
+            case 5: b *= b; return sqr(b) * x;
+            case 6: b *= b; return sqr(b) * b;
+            default: return std::pow(x, e);
+        }
+    }
+    return std::pow(x, e);
+}
+static double evaluate_g(double x, double y, double e)                                                     // :1003-1021
+{
+    double g = 0;
+    if (x > y) { g = 1 + power(y / x, e); if (g != 1) g = power(g, 1 / e); g *= x; }
+    else if (y != 0) { g = 1 + power(x / y, e); if (g != 1) g = power(g, 1 / e); g *= y; }
+    return g;
+}
+static double evaluate(const double* Power, V3 P) { return evaluate_g(evaluate_g(std::fabs(P.x), std::fabs(P.y), Power[0]), std::fabs(P.z), Power[2]) - 1; }   // :1059-1062
+static bool intersect_box(V3 P, V3 D, double* dmin, double* dmax)                                          // :832-1001
+{
+    double tmin = 0.0, tmax = 0.0;
+    if (std::fabs(D.x) > EPSILON) {
+        if (D.x > EPSILON) { *dmin = (MIN_VALUE - P.x) / D.x; *dmax = (MAX_VALUE - P.x) / D.x; if (*dmax < EPSILON) return false; }
+        else { *dmax = (MIN_VALUE - P.x) / D.x; if (*dmax < EPSILON) return false; *dmin = (MAX_VALUE - P.x) / D.x; }
+        if (*dmin > *dmax) return false;
+    } else {
+        if ((P.x < MIN_VALUE) || (P.x > MAX_VALUE)) return false;
+        *dmin = -BOUND_HUGE; *dmax = BOUND_HUGE;
+    }
+    const double Ps[2] = { P.y, P.z }, Ds[2] = { D.y, D.z };
+    for (int a = 0; a < 2; a++) {                                                      // top / bottom, front / back
+        if (std::fabs(Ds[a]) > EPSILON) {
+            if (Ds[a] > EPSILON) { tmin = (MIN_VALUE - Ps[a]) / Ds[a]; tmax = (MAX_VALUE - Ps[a]) / Ds[a]; }
+            else { tmax = (MIN_VALUE - Ps[a]) / Ds[a]; tmin = (MAX_VALUE - Ps[a]) / Ds[a]; }
+            if (tmax < *dmax) {
+                if (tmax < EPSILON) return false;
+                if (tmin > *dmin) { if (tmin > tmax) return false; *dmin = tmin; }
+                else { if (*dmin > tmax) return false; }
+                *dmax = tmax;
+            } else {
+                if (tmin > *dmin) { if (tmin > *dmax) return false; *dmin = tmin; }
+            }
+        } else {
+            if ((Ps[a] < MIN_VALUE) || (Ps[a] > MAX_VALUE)) return false;
+        }
+    }
+    return true;
+}
+static void solve_hit1(const double* Power, double v0, V3 tP0, double v1, V3 tP1, V3& P)                    // :1344-1450
+{
+    V3 P0 = tP0, P1 = tP1, P2, P3;
+    int i;
+    for (i = 0; i < MAX_ITERATIONS; i++) {
+        if (std::fabs(v0) < ZERO_TOLERANCE) { P = P0; break; }
+        if (std::fabs(v1) < ZERO_TOLERANCE) { P = P1; break; }
+        double x = std::fabs(v0) / std::fabs(v1 - v0);
+        P2 = P1 - P0; P2 = P0 + P2 * x;
+        double v2 = evaluate(Power, P2);
+        P3 = P1 - P0; P3 = P0 + P3 * 0.5;
+        double v3 = evaluate(Power, P3);
+        if (v2 * v3 < 0.0) { v0 = v2; P0 = P2; v1 = v3; P1 = P3; }
+        else if (std::fabs(v2) < std::fabs(v3)) { if (v0 * v2 < 0) { v1 = v2; P1 = P2; } else { v0 = v2; P0 = P2; } }
+        else { if (v0 * v3 < 0) { v1 = v3; P1 = P3; } else { v0 = v3; P0 = P3; } }
+    }
+    if (i == MAX_ITERATIONS) P = (std::fabs(v0) < std::fabs(v1)) ? P0 : P1;
+}
+static bool check_hit2(const double* Power, V3 P, V3 D, double t0, V3& P0, double v0, double t1, double* t, V3& Q)   // :1485-1560
+{
+    double dt0 = t0, dt1 = t0 + 0.0001 * (t1 - t0), v1, deltat, maxdelta = t1 - t0;
+    for (int i = 0; (dt0 < t1) && (i < MAX_ITERATIONS); i++) {
+        V3 P1 = P + D * dt1;
+        v1 = evaluate(Power, P1);
+        if (v0 * v1 < 0) { solve_hit1(Power, v0, P0, v1, P1, Q); P0 = Q - P; *t = len(P0); return true; }
+        if (std::fabs(v1) < ZERO_TOLERANCE) { Q = P + D * dt1; *t = dt1; return true; }
+        if (((v0 > 0.0) && (v1 > v0)) || ((v0 < 0.0) && (v1 < v0))) break;
+        if (v1 == v0) break;
+        deltat = v1 * (dt1 - dt0) / (v1 - v0);
+        if (std::fabs(deltat) > maxdelta) break;
+        v0 = v1; dt0 = dt1; dt1 -= deltat;
+    }
+    return false;
+}
+}  // namespace superq
+
 class Tracer {
 public:
     const Scene& S;
@@ -950,6 +1047,8 @@ bool Tracer::Inside(V3 p, uint32_t idx) const
             }
             return (result < 1.0e-4) ? !inv : inv;
         }
+        case PVGPU_OBJ_SUPERELLIPSOID:                                                                    // superellipsoid.cpp:396-420
+            return (superq::evaluate(ob.p, MInvTransPoint(S.xf[ob.transform], p)) < EPSILON) ? !inv : inv;
         case PVGPU_OBJ_PRISM: {                                                                           // prism.cpp:640-672
             V3 P = MInvTransPoint(S.xf[ob.transform], p);
             if ((P.y >= ob.p[0]) && (P.y < ob.p[1])) {
@@ -1428,6 +1527,56 @@ bool Tracer::All_Intersections(uint32_t idx, const Ray& ray, IStack& Depth_Stack
             }
             return found;
         }
+        case PVGPU_OBJ_SUPERELLIPSOID: {                                                                  // superellipsoid.cpp:213-394
+            using namespace superq;
+            const pvgpu_transform& tr = S.xf[ob.transform];
+            V3 P = MInvTransPoint(tr, o), D = MInvTransDirection(tr, d), P0, P1, P2, P3;
+            const double length = len(D);
+            D = D / length;
+            double t, t1, t2, v0, v1, dists[PLANECOUNT + 2];
+            if (!intersect_box(P, D, &t1, &t2)) return false;
+            if (t2 < DEPTH_TOLERANCE) return false;
+            int cnt = 0;
+            if (t1 < DEPTH_TOLERANCE) t1 = DEPTH_TOLERANCE;
+            dists[cnt++] = t1; dists[cnt++] = t2;
+            {                                                                                              // find_ray_plane_points :1271-1310
+                double mindist = t1, maxdist = t2;
+                t = EPSILON * (maxdist - mindist);
+                mindist -= t; maxdist += t;
+                for (int i = 0; i < PLANECOUNT; i++) {
+                    double dd = (D.x * planes[i][0] + D.y * planes[i][1] + D.z * planes[i][2]);
+                    if (std::fabs(dd) < EPSILON) continue;
+                    t = (planes[i][3] - (P.x * planes[i][0] + P.y * planes[i][1] + P.z * planes[i][2])) / dd;
+                    if ((t >= mindist) && (t <= maxdist)) dists[cnt++] = t;
+                }
+                std::sort(dists, dists + cnt);
+            }
+            if (cnt <= 1) return false;
+            const bool child = (ob.aux & 1u) != 0;
+            auto insert_hit = [&](double Depth) {                                                          // :1172-1190
+                if ((Depth > DEPTH_TOLERANCE) && (Depth < MAX_DISTANCE)) return push(Depth, ray.Evaluate(Depth), 0);
+                return false;
+            };
+            P0 = P + D * dists[0];
+            v0 = evaluate(ob.p, P0);
+            if (std::fabs(v0) < ZERO_TOLERANCE) { if (insert_hit(dists[0] / length)) { if (child) found = true; else return true; } }
+            for (int i = 1; i < cnt; i++) {
+                P1 = P + D * dists[i];
+                v1 = evaluate(ob.p, P1);
+                if (std::fabs(v1) < ZERO_TOLERANCE) { if (insert_hit(dists[i] / length)) { if (child) found = true; else return true; } }
+                else if (v0 * v1 < 0.0) {
+                    solve_hit1(ob.p, v0, P0, v1, P1, P2);
+                    P3 = P2 - P;
+                    t = len(P3);
+                    if (insert_hit(t / length)) { if (child) found = true; else return true; }
+                } else if (check_hit2(ob.p, P, D, dists[i - 1], P0, v0, dists[i], &t, P2)) {
+                    if (insert_hit(t / length)) { if (child) found = true; else return true; }
+                    else break;
+                }
+                v0 = v1; P0 = P1;
+            }
+            return found;
+        }
         case PVGPU_OBJ_MESH: return mesh_intersect(idx, ray, Depth_Stack);
         case PVGPU_OBJ_BLOB: return blob_intersect(idx, ray, Depth_Stack);
         case PVGPU_OBJ_CSG_UNION: {                                                                       // csg.cpp:128-189
@@ -1824,6 +1973,24 @@ V3 Tracer::Normal(const Intersection& isect) const
             return unit(MTransNormal(t, N));
         }
         case PVGPU_OBJ_GLYPH: return isect.INormal;                                                       // truetype.cpp:2972-2976
+        case PVGPU_OBJ_SUPERELLIPSOID: {                                                                  // superellipsoid.cpp:451-495
+            const pvgpu_transform& t = S.xf[ob.transform];
+            const double* E = ob.p;
+            V3 P = MInvTransPoint(t, isect.IPoint);
+            double r = 0.0, z2n = 0;
+            if (P.z != 0) { z2n = superq::power(std::fabs(P.z), E[2]); P.z = z2n / P.z; }
+            if (std::fabs(P.x) > std::fabs(P.y)) {
+                r = superq::power(std::fabs(P.y / P.x), E[0]);
+                P.x = (1 - z2n) / P.x;
+                P.y = P.y ? (1 - z2n) * r / P.y : 0;
+            } else if (P.y != 0) {
+                r = superq::power(std::fabs(P.x / P.y), E[0]);
+                P.x = P.x ? (1 - z2n) * r / P.x : 0;
+                P.y = (1 - z2n) / P.y;
+            }
+            if (P.z) P.z *= (1 + r);
+            return unit(MTransNormal(t, P));
+        }
         case PVGPU_OBJ_PRISM: {                                                                           // prism.cpp:710-770
             const pvgpu_transform& t = S.xf[ob.transform];
             V3 N = v3(0, 0, 0);

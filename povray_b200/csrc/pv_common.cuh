@@ -82,7 +82,7 @@ namespace pvgpu {
 // folded and the code of the other primitives never reaches the kernel.
 #ifndef PV_TYPES
 #if PV_HEAVY
-#define PV_TYPES 0x3FFFFu
+#define PV_TYPES 0x7FFFFu
 #else
 #define PV_TYPES ((1u << PVGPU_OBJ_SPHERE) | (1u << PVGPU_OBJ_BOX) | (1u << PVGPU_OBJ_PLANE) | (1u << PVGPU_OBJ_MESH))
 #endif

@@ -993,6 +993,7 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
         //  cost config 3 13 % when the plain heavy k_shade carried them)
         case PVGPU_OBJ_GLYPH: if (PV_HAS(PVGPU_OBJ_GLYPH)) return glyph_normal(sc, ob, hit.aux, ray_o, ray_d); break;
         case PVGPU_OBJ_PRISM: if (PV_HAS(PVGPU_OBJ_PRISM)) return prism_normal(sc, ob, hit.ip, hit.aux, ray_o, ray_d); break;
+        case PVGPU_OBJ_SUPERELLIPSOID: if (PV_HAS(PVGPU_OBJ_SUPERELLIPSOID)) return superellipsoid_normal(sc, ob, hit.ip); break;
 #endif
     }
     return mk(0.0, 1.0, 0.0);

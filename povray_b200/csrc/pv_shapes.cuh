@@ -1216,4 +1216,243 @@ static __device__ __noinline__ V3 prism_normal(const DScene& sc, const pvgpu_obj
 }
 #endif  // PV_HEAVY
 
+#if PV_HEAVY
+// ---- superellipsoid ---------------------------------------------------------------------------------
+#define PV_SE_DEPTH_TOL  1.0e-4      // DEPTH_TOLERANCE superellipsoid.cpp:97
+#define PV_SE_ZERO_TOL   1.0e-10     // ZERO_TOLERANCE  superellipsoid.cpp:101
+#define PV_SE_MIN       -1.01        // MIN_VALUE / MAX_VALUE superellipsoid.cpp:107-108
+#define PV_SE_MAX        1.01
+#define PV_SE_MAX_ITER   20          // MAX_ITERATIONS  superellipsoid.cpp:110
+#define PV_SE_MAX_HITS   12          // two box planes + nine cutting planes: at most 11 sample points, a hit per point / interval
+
+// Superellipsoid::power (superellipsoid.cpp:1097-1150): small integer exponents by multiplication
+__device__ inline double se_power(double x, double e)
+{
+    const int i = (int)e;
+    if (e == (double)i) {
+        double b = x;
+        switch (i) {
+            case 0: return 1.0;
+            case 1: return b;
+            case 2: return b * b;
+            case 3: return (b * b) * b;
+            case 4: b *= b; return b * b;
+            case 5: b *= b; return (b * b) * x;
+            case 6: b *= b; return (b * b) * b;
+            default: return pow(x, e);
+        }
+    }
+    return pow(x, e);
+}
+// evaluate_g / evaluate_superellipsoid (superellipsoid.cpp:1003-1062)
+__device__ inline double se_g(double x, double y, double e)
+{
+    double g = 0;
+    if (x > y) {
+        g = 1 + se_power(y / x, e);
+        if (g != 1) g = se_power(g, 1 / e);
+        g *= x;
+    } else if (y != 0) {
+        g = 1 + se_power(x / y, e);
+        if (g != 1) g = se_power(g, 1 / e);
+        g *= y;
+    }
+    return g;
+}
+static __device__ __noinline__ double se_value(const pvgpu_object& ob, const V3& P)
+{
+    return se_g(se_g(fabs(P.x), fabs(P.y), ob.p[0]), fabs(P.z), ob.p[2]) - 1;
+}
+
+// Superellipsoid::intersect_box (superellipsoid.cpp:832-1001): the ray against the cube [-1.01, 1.01]^3
+__device__ inline bool se_intersect_box(const V3& P, const V3& D, double& dmin, double& dmax)
+{
+    double tmin = 0.0, tmax = 0.0;
+    if (fabs(D.x) > PV_EPSILON) {
+        if (D.x > PV_EPSILON) { dmin = (PV_SE_MIN - P.x) / D.x; dmax = (PV_SE_MAX - P.x) / D.x; if (dmax < PV_EPSILON) return false; }
+        else { dmax = (PV_SE_MIN - P.x) / D.x; if (dmax < PV_EPSILON) return false; dmin = (PV_SE_MAX - P.x) / D.x; }
+        if (dmin > dmax) return false;
+    } else {
+        if ((P.x < PV_SE_MIN) || (P.x > PV_SE_MAX)) return false;
+        dmin = -PV_BOUND_HUGE; dmax = PV_BOUND_HUGE;
+    }
+    #pragma unroll
+    for (int axis = 1; axis < 3; axis++) {
+        const double Pa = axis == 1 ? P.y : P.z, Da = axis == 1 ? D.y : D.z;
+        if (fabs(Da) > PV_EPSILON) {
+            if (Da > PV_EPSILON) { tmin = (PV_SE_MIN - Pa) / Da; tmax = (PV_SE_MAX - Pa) / Da; }
+            else { tmax = (PV_SE_MIN - Pa) / Da; tmin = (PV_SE_MAX - Pa) / Da; }
+            if (tmax < dmax) {
+                if (tmax < PV_EPSILON) return false;
+                if (tmin > dmin) { if (tmin > tmax) return false; dmin = tmin; }
+                else if (dmin > tmax) return false;
+                dmax = tmax;
+            } else if (tmin > dmin) {
+                if (tmin > dmax) return false;
+                dmin = tmin;
+            }
+        } else if ((Pa < PV_SE_MIN) || (Pa > PV_SE_MAX)) return false;
+    }
+    return true;
+}
+
+// Superellipsoid::solve_hit1 (superellipsoid.cpp:1344-1450): secant and bisection steps on a bracketed root
+__device__ inline V3 se_solve_hit1(const pvgpu_object& ob, double v0, V3 P0, double v1, V3 P1)
+{
+    for (int i = 0; i < PV_SE_MAX_ITER; i++) {
+        if (fabs(v0) < PV_SE_ZERO_TOL) return P0;
+        if (fabs(v1) < PV_SE_ZERO_TOL) return P1;
+        const double x = fabs(v0) / fabs(v1 - v0);
+        V3 P2 = P1 - P0;
+        P2 = P0 + x * P2;
+        const double v2 = se_value(ob, P2);
+        V3 P3 = P1 - P0;
+        P3 = P0 + 0.5 * P3;
+        const double v3 = se_value(ob, P3);
+        if (v2 * v3 < 0.0) { v0 = v2; P0 = P2; v1 = v3; P1 = P3; }
+        else if (fabs(v2) < fabs(v3)) {
+            if (v0 * v2 < 0) { v1 = v2; P1 = P2; } else { v0 = v2; P0 = P2; }
+        } else {
+            if (v0 * v3 < 0) { v1 = v3; P1 = P3; } else { v0 = v3; P0 = P3; }
+        }
+    }
+    return (fabs(v0) < fabs(v1)) ? P0 : P1;
+}
+
+// Superellipsoid::check_hit2 (superellipsoid.cpp:1485-1560): no sign change between two sample points - walk towards the surface
+__device__ inline bool se_check_hit2(const pvgpu_object& ob, const V3& P, const V3& D, double t0, const V3& P0, double v0, double t1, double& t)
+{
+    double dt0 = t0, dt1 = t0 + 0.0001 * (t1 - t0);
+    const double maxdelta = t1 - t0;
+    for (int i = 0; (dt0 < t1) && (i < PV_SE_MAX_ITER); i++) {
+        const V3 P1 = P + dt1 * D;
+        const double v1 = se_value(ob, P1);
+        double deltat;
+        if (v0 * v1 < 0) {
+            const V3 Q = se_solve_hit1(ob, v0, P0, v1, P1);
+            t = length(Q - P);
+            return true;
+        }
+        if (fabs(v1) < PV_SE_ZERO_TOL) { t = dt1; return true; }
+        if (((v0 > 0.0) && (v1 > v0)) || ((v0 < 0.0) && (v1 < v0))) break;
+        if (v1 == v0) break;
+        deltat = v1 * (dt1 - dt0) / (v1 - v0);
+        if (fabs(deltat) > maxdelta) break;
+        v0 = v1;
+        dt0 = dt1;
+        dt1 -= deltat;
+    }
+    return false;
+}
+
+// Superellipsoid::Intersect (superellipsoid.cpp:213-394): depths of the hits in the order the reference pushes them.  A superellipsoid
+// that is not a CSG child stops at its first hit (`first_only`).  insert_hit's clip test steers that walk in the reference, so
+// superellipsoids with a clipped_by list are rejected at finalize instead of being served with a different hit order.
+static __device__ __noinline__ int se_depths(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, bool first_only, double* out)
+{
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    const V3 P = inv_trans_point(tr, o);
+    V3 D = inv_trans_direction(tr, d);
+    const double len = length(D);
+    D = D / len;
+    double t1, t2;
+    if (!se_intersect_box(P, D, t1, t2)) return 0;
+    if (t2 < PV_SE_DEPTH_TOL) return 0;
+    double dists[11];
+    int cnt = 0;
+    if (t1 < PV_SE_DEPTH_TOL) t1 = PV_SE_DEPTH_TOL;
+    dists[cnt++] = t1;
+    dists[cnt++] = t2;
+    {   // find_ray_plane_points (superellipsoid.cpp:1271-1310)
+        const double planes[9][3] = { { 1, 1, 0 }, { 1, -1, 0 }, { 1, 0, 1 }, { 1, 0, -1 }, { 0, 1, 1 }, { 0, 1, -1 }, { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } };
+        const double slack = PV_EPSILON * (t2 - t1);
+        const double mind = t1 - slack, maxd = t2 + slack;
+        for (int i = 0; i < 9; i++) {
+            const double dd = (D.x * planes[i][0] + D.y * planes[i][1] + D.z * planes[i][2]);
+            if (fabs(dd) < PV_EPSILON) continue;
+            const double t = (0.0 - (P.x * planes[i][0] + P.y * planes[i][1] + P.z * planes[i][2])) / dd;
+            if ((t >= mind) && (t <= maxd)) dists[cnt++] = t;
+        }
+        for (int i = 1; i < cnt; i++) {                    // (qsort by value)
+            const double v = dists[i];
+            int j = i - 1;
+            while (j >= 0 && dists[j] > v) { dists[j + 1] = dists[j]; j--; }
+            dists[j + 1] = v;
+        }
+    }
+    if (cnt <= 1) return 0;
+    int n = 0;
+    // insert_hit (superellipsoid.cpp:1172-1190)
+    auto insert = [&](double depth) -> bool {
+        if (!((depth > PV_SE_DEPTH_TOL) && (depth < PV_MAX_DISTANCE))) return false;
+        if (n < PV_SE_MAX_HITS) out[n++] = depth;
+        return true;
+    };
+    V3 P0 = P + dists[0] * D;
+    double v0 = se_value(ob, P0);
+    if (fabs(v0) < PV_SE_ZERO_TOL) { if (insert(dists[0] / len) && first_only) return n; }
+    for (int i = 1; i < cnt; i++) {
+        const V3 P1 = P + dists[i] * D;
+        const double v1 = se_value(ob, P1);
+        if (fabs(v1) < PV_SE_ZERO_TOL) { if (insert(dists[i] / len) && first_only) return n; }
+        else if (v0 * v1 < 0.0) {
+            const V3 P2 = se_solve_hit1(ob, v0, P0, v1, P1);
+            const double t = length(P2 - P);
+            if (insert(t / len) && first_only) return n;
+        } else {
+            double t;
+            if (se_check_hit2(ob, P, D, dists[i - 1], P0, v0, dists[i], t)) {
+                if (insert(t / len)) { if (first_only) return n; }
+                else break;
+            }
+        }
+        v0 = v1;
+        P0 = P1;
+    }
+    return n;
+}
+
+// Superellipsoid::All_Intersections: hits in batches (resume protocol of glyph_hits); aux bit 0 of the object = IS_CHILD_OBJECT
+static __device__ __noinline__ void superellipsoid_hits(const DScene& sc, const pvgpu_object& ob, const V3& o, const V3& d, PrimHits& h, int* resume)
+{
+    h.n = 0;
+    double depths[PV_SE_MAX_HITS];
+    const int n = se_depths(sc, ob, o, d, (ob.aux & 1u) == 0u, depths);
+    const int start = (resume && *resume > 0) ? *resume - 1 : 0;
+    if (resume) *resume = -1;
+    for (int i = start; i < n; i++) {
+        if (h.n == PV_MAX_PRIM_HITS) { if (resume) *resume = i + 1; return; }
+        h.depth[h.n] = depths[i]; h.ip[h.n] = evaluate(o, d, depths[i]); h.aux[h.n] = 0u; h.n++;
+    }
+}
+
+// Superellipsoid::Inside (superellipsoid.cpp:396-420)
+__device__ inline bool superellipsoid_inside(const DScene& sc, const pvgpu_object& ob, const V3& p)
+{
+    const double val = se_value(ob, inv_trans_point(sc.xf[ob.transform], p));
+    return (val < PV_EPSILON) != ((ob.flags & PVGPU_INVERTED_FLAG) != 0);
+}
+
+// Superellipsoid::Normal (superellipsoid.cpp:451-495)
+static __device__ __noinline__ V3 superellipsoid_normal(const DScene& sc, const pvgpu_object& ob, const V3& ip)
+{
+    const pvgpu_transform& tr = sc.xf[ob.transform];
+    V3 P = inv_trans_point(tr, ip);
+    const double Ex = ob.p[0], Ez = ob.p[2];
+    double r = 0.0, z2n = 0;          // (r is uninitialised in the reference when P.x == P.y == 0; its product with P.z is then the only use)
+    if (P.z != 0) { z2n = se_power(fabs(P.z), Ez); P.z = z2n / P.z; }
+    if (fabs(P.x) > fabs(P.y)) {
+        r = se_power(fabs(P.y / P.x), Ex);
+        P.x = (1 - z2n) / P.x;
+        P.y = (P.y != 0.0) ? (1 - z2n) * r / P.y : 0;
+    } else if (P.y != 0) {
+        r = se_power(fabs(P.x / P.y), Ex);
+        P.x = (P.x != 0.0) ? (1 - z2n) * r / P.x : 0;
+        P.y = (1 - z2n) / P.y;
+    }
+    if (P.z != 0.0) P.z *= (1 + r);
+    return normalized(trans_normal(tr, P));
+}
+#endif  // PV_HEAVY
+
 }  // namespace pvgpu

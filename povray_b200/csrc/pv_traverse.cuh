@@ -317,6 +317,7 @@ __device__ inline bool prim_inside(const DScene& sc, const pvgpu_object& ob, con
         case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) return poly_inside(sc, ob, p); break;
         case PVGPU_OBJ_GLYPH: if (PV_HAS(PVGPU_OBJ_GLYPH)) return glyph_inside(sc, ob, p); break;
         case PVGPU_OBJ_PRISM: if (PV_HAS(PVGPU_OBJ_PRISM)) return prism_inside(sc, ob, p); break;
+        case PVGPU_OBJ_SUPERELLIPSOID: if (PV_HAS(PVGPU_OBJ_SUPERELLIPSOID)) return superellipsoid_inside(sc, ob, p); break;
 #endif
     }
     return false;
@@ -430,6 +431,7 @@ __device__ inline void prim_hits(const DScene& sc, const pvgpu_object& ob, const
         case PVGPU_OBJ_POLY: if (PV_HAS(PVGPU_OBJ_POLY)) { poly_hits(sc, ob, o, d, h); } break;
         case PVGPU_OBJ_GLYPH: if (PV_HAS(PVGPU_OBJ_GLYPH)) { glyph_hits(sc, ob, o, d, h, resume); if (resume == nullptr && overflow) atomicOr(overflow, 128u); } break;
         case PVGPU_OBJ_PRISM: if (PV_HAS(PVGPU_OBJ_PRISM)) { prism_hits(sc, ob, o, d, h, resume); if (resume == nullptr && overflow) atomicOr(overflow, 128u); } break;
+        case PVGPU_OBJ_SUPERELLIPSOID: if (PV_HAS(PVGPU_OBJ_SUPERELLIPSOID)) { superellipsoid_hits(sc, ob, o, d, h, resume); if (resume == nullptr && overflow) atomicOr(overflow, 128u); } break;
 #endif
         case PVGPU_OBJ_SPHERE: if (PV_HAS(PVGPU_OBJ_SPHERE)) { sphere_hits(sc, ob, o, d, h); } break;
         case PVGPU_OBJ_BOX: if (PV_HAS(PVGPU_OBJ_BOX)) { box_hits(sc, ob, o, d, h); } break;
@@ -835,7 +837,7 @@ __device__ inline void csg_hits(const DScene& sc, uint32_t top, const V3& o, con
                 });
             continue;
         }
-        int resume = (lo.type == PVGPU_OBJ_BLOB || lo.type == PVGPU_OBJ_GLYPH || lo.type == PVGPU_OBJ_PRISM) ? 0 : -1;       // blob and glyph children report their hits in batches (blob_hits, glyph_hits)
+        int resume = (lo.type == PVGPU_OBJ_BLOB || lo.type == PVGPU_OBJ_GLYPH || lo.type == PVGPU_OBJ_PRISM || lo.type == PVGPU_OBJ_SUPERELLIPSOID) ? 0 : -1;       // blob and glyph children report their hits in batches (blob_hits, glyph_hits)
         do {
             PrimHits h;
             prim_hits(sc, lo, o, d, h, overflow, (resume >= 0) ? &resume : nullptr);
@@ -877,7 +879,7 @@ __device__ inline bool object_find(const DScene& sc, uint32_t idx, const V3& o, 
     else
 #endif
     {
-        int resume = (PV_HEAVY && PV_HAS(PVGPU_OBJ_GLYPH) && (ob.type == PVGPU_OBJ_GLYPH || ob.type == PVGPU_OBJ_PRISM)) ? 0 : -1;       // glyph / prism hits come in batches
+        int resume = (PV_HEAVY && PV_HAS(PVGPU_OBJ_GLYPH) && (ob.type == PVGPU_OBJ_GLYPH || ob.type == PVGPU_OBJ_PRISM || ob.type == PVGPU_OBJ_SUPERELLIPSOID)) ? 0 : -1;       // glyph / prism hits come in batches
         do {
             PrimHits h;
             prim_hits(sc, ob, o, d, h, overflow, (resume >= 0) ? &resume : nullptr);
@@ -904,7 +906,7 @@ static __device__ __noinline__ bool object_find_simple(const DScene& sc, uint32_
 #endif
     if (PV_HAS(PVGPU_OBJ_MESH) && ob.type == PVGPU_OBJ_MESH) mesh_hits<false>(sc, idx, ob, o, d, acc, -1, stack, sp0, overflow);
     else {
-        int resume = (PV_HEAVY && PV_HAS(PVGPU_OBJ_GLYPH) && (ob.type == PVGPU_OBJ_GLYPH || ob.type == PVGPU_OBJ_PRISM)) ? 0 : -1;       // glyph / prism hits come in batches
+        int resume = (PV_HEAVY && PV_HAS(PVGPU_OBJ_GLYPH) && (ob.type == PVGPU_OBJ_GLYPH || ob.type == PVGPU_OBJ_PRISM || ob.type == PVGPU_OBJ_SUPERELLIPSOID)) ? 0 : -1;       // glyph / prism hits come in batches
         do {
             PrimHits h;
             prim_hits(sc, ob, o, d, h, overflow, (resume >= 0) ? &resume : nullptr);

@@ -408,7 +408,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     for (const pvgpu_blend_map& m : s.blend_maps) if (m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) d->full = true;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
     if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights || !s.blob_textures.empty() || !s.images.empty()) d->full = true;
-    for (const pvgpu_object& o : s.objects) if (o.type == PVGPU_OBJ_GLYPH || o.type == PVGPU_OBJ_PRISM) d->full = true;      // their normals live in the full shading kernels
+    for (const pvgpu_object& o : s.objects) if (o.type == PVGPU_OBJ_GLYPH || o.type == PVGPU_OBJ_PRISM || o.type == PVGPU_OBJ_SUPERELLIPSOID) d->full = true;      // their normals live in the full shading kernels
     for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }
     for (const pvgpu_finish& fi : s.finishes) {
         const bool reflective = fi.reflection_max[0] != 0 || fi.reflection_max[1] != 0 || fi.reflection_max[2] != 0 ||

@@ -348,6 +348,10 @@ int validate_scene(Scene& s)
             if (!(number >= 0.0 && number <= (double)(1u << 24)) || number != (double)(uint32_t)number || !range_ok((uint32_t)o.mesh + 1u, 15u * (uint32_t)number, s.shape_data.size()))
                 return fail(PVGPU_E_INVALID, "object %zu: prism spline outside the shape-data table", i);
         }
+        if (o.type == PVGPU_OBJ_SUPERELLIPSOID) {
+            if (o.transform < 0) return fail(PVGPU_E_INVALID, "object %zu: superellipsoid without transform", i);
+            if (o.clip_count) return fail(PVGPU_E_UNSUPPORTED, "object %zu: clipped_by on a superellipsoid (the clip test steers the reference's hit walk) is outside the hot-path scope", i);
+        }
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
         if ((o.flags & PVGPU_UV_FLAG))
