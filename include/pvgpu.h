@@ -267,9 +267,11 @@ enum {
                                     8 doubles: PVGPU_FRACTAL_* kind, maxIterations, exteriorType, interiorType, exteriorFactor,
                                     interiorFactor, juliaCoord u v */
     PVGPU_PAT_SPIRAL1  = 29,     /* Spiral1Pattern   pattern.cpp:8396, p[0] = arms */
-    PVGPU_PAT_SPIRAL2  = 30      /* Spiral2Pattern   pattern.cpp:8473, p[0] = arms */
+    PVGPU_PAT_SPIRAL2  = 30,     /* Spiral2Pattern   pattern.cpp:8473, p[0] = arms */
+    PVGPU_PAT_UV_MAP   = 31      /* UV_MAP_PATTERN pigment (`pigment { uv_mapping ... }`, PigmentBlendMap::ComputeUVMapped, pigment.cpp:603-618):
+                                    `data` = index of the pigment that is evaluated at (u, v, 0) of the hit */
 };
-#define PVGPU_PAT_LAST PVGPU_PAT_SPIRAL2
+#define PVGPU_PAT_LAST PVGPU_PAT_UV_MAP
 /* iteration formulas of PVGPU_PAT_FRACTAL (exponents above 4 - MandelXPattern / JuliaXPattern - are not served) */
 enum { PVGPU_FRACTAL_MANDEL2 = 0, PVGPU_FRACTAL_MANDEL3 = 1, PVGPU_FRACTAL_MANDEL4 = 2, PVGPU_FRACTAL_JULIA2 = 3, PVGPU_FRACTAL_JULIA3 = 4,
        PVGPU_FRACTAL_JULIA4 = 5, PVGPU_FRACTAL_MAGNET1M = 6, PVGPU_FRACTAL_MAGNET1J = 7, PVGPU_FRACTAL_MAGNET2M = 8, PVGPU_FRACTAL_MAGNET2J = 9 };
@@ -540,6 +542,12 @@ int  pvgpu_scene_set_blobs(pvgpu_scene* s, const pvgpu_blob* blobs, size_t n_blo
  * texture.  Objects whose blob has any carry MULTITEXTURE_FLAG; Blob::Determine_Textures (blob.cpp:2768-2843) then blends the
  * components' textures by their field contribution at the hit point.  n must equal the number of blob elements (or 0). */
 int  pvgpu_scene_set_blob_textures(pvgpu_scene* s, const int32_t* textures, size_t n);
+/* UV vectors of meshes (MESH_DATA::UVCoords, MESH_TRIANGLE::UV1..UV3; Mesh::UVCoord, mesh.cpp:2256-2332): `uv` holds n_uv (u, v) pairs,
+   `tri_uv` three indices into it for every triangle of the triangle table (n_tri = 0: no mesh has UV vectors).  Used by objects with
+   PVGPU_UV_FLAG (`uv_mapping` in an object's texture: ObjectBase::UVCoord replaces the intersection point for every texture
+   evaluation, trace.cpp:500-512) and by PVGPU_PAT_UV_MAP pigments.  UVCoord is served for spheres, boxes, tori and meshes; every
+   other primitive takes ObjectBase::UVCoord (x, y of the point) except cones / cylinders, which are rejected with the flag. */
+int  pvgpu_scene_set_mesh_uv(pvgpu_scene* s, const double* uv, size_t n_uv, const uint32_t* tri_uv, size_t n_tri);
 /* image_map pigments: the image table and the texel table (5 floats per texel) its records point into. */
 int  pvgpu_scene_set_images(pvgpu_scene* s, const pvgpu_image* images, size_t n_images, const float* texels, size_t n_texel_floats);
 /* Shape-data table: FP64 parameters of the primitives whose record does not fit pvgpu_object::p (triangle, smooth_triangle,

@@ -136,6 +136,9 @@ struct Flattener
     std::map<const void*, int32_t> object_ids, texture_ids, interior_ids;
     std::map<const void*, uint32_t> mesh_tri_first;          // Mesh object -> first triangle of its copy in the triangle table (ray dumps)
     std::vector<int32_t> blob_textures;                      // per blob element (pvgpu_scene_set_blob_textures)
+    std::vector<double> mesh_uv;                             // (u, v) pairs + three indices per triangle (pvgpu_scene_set_mesh_uv)
+    std::vector<uint32_t> tri_uv;
+    bool any_mesh_uv = false;
     std::vector<pvgpu_image> images;
     std::vector<float> texels;
     std::map<const void*, int32_t> image_ids;
@@ -423,7 +426,13 @@ struct Flattener
             add_warps(pg->pattern->warps, p.warp_first, p.warp_count);
             p.data = (uint32_t)add_image(dynamic_cast<const ColourImagePattern*>(bp)->pImage);
         }
-        else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern / average / image_map (uv_mapping ...)");
+        else if (pg->Type == UV_MAP_PATTERN && std::dynamic_pointer_cast<PigmentBlendMap>(pg->Blend_Map) != nullptr &&
+                 !std::dynamic_pointer_cast<PigmentBlendMap>(pg->Blend_Map)->Blend_Map_Entries.empty()) {
+            // pigment { uv_mapping <pigment> }: the one entry of the blend list is evaluated at the hit's (u, v, 0) (pigment.cpp:603-618)
+            p.pattern = PVGPU_PAT_UV_MAP;
+            p.data = (uint32_t)add_pigment(std::dynamic_pointer_cast<PigmentBlendMap>(pg->Blend_Map)->Blend_Map_Entries[0].Vals);
+        }
+        else if (pg->Type <= LAST_SPECIAL_PATTERN) unsupported("pigment type other than plain / pattern / average / image_map / uv_mapping");
         else {
             fill_pattern(bp, p, "pigment");
             add_pigment_map(pg, p);
@@ -545,7 +554,14 @@ struct Flattener
             p.flags = (t.Smooth ? PVGPU_TRI_SMOOTH : 0) | (t.ThreeTex ? PVGPU_TRI_THREETEX : 0);
             p.dominant_axis = t.Dominant_Axis; p.v_axis = t.vAxis;
             triangles.push_back(p);
+            // UV1..UV3 as indices into the scene-wide UV table (Mesh::UVCoord, mesh.cpp:2328-2330)
+            const uint32_t uv0 = (uint32_t)(mesh_uv.size() / 2);
+            const bool has_uv = D->UVCoords != nullptr && D->Number_Of_UVCoords > 0;
+            for (MeshIndex u : { t.UV1, t.UV2, t.UV3 }) tri_uv.push_back(has_uv ? uv0 + (uint32_t)u : 0u);
+            any_mesh_uv = any_mesh_uv || has_uv;
         }
+        if (D->UVCoords != nullptr) for (int i = 0; i < D->Number_Of_UVCoords; i++) { mesh_uv.push_back(D->UVCoords[i][U]); mesh_uv.push_back(D->UVCoords[i][V]); }
+        if (mesh_uv.empty()) { mesh_uv.push_back(0.0); mesh_uv.push_back(0.0); }      // (entry 0: what a mesh without uv_vectors indexes)
         me.texture_first = (uint32_t)index_list.size();
         me.texture_count = (uint32_t)m->Number_Of_Textures;
         {
@@ -682,6 +698,7 @@ struct Flattener
             p.p[3] = s->Radius;
             p.aux = s->Do_Ellipsoid ? 1 : 0;
             if (s->Do_Ellipsoid) p.transform = add_transform(s->Trans);
+            else if (s->Trans != nullptr) p.transform = add_transform(s->Trans);       // kept for Sphere::UVCoord only (sphere.cpp:699-704)
         } else if (Box* b = dynamic_cast<Box*>(o)) {
             p.type = PVGPU_OBJ_BOX;
             for (int k = 0; k < 3; k++) { p.p[k] = b->bounds[0][k]; p.p[3 + k] = b->bounds[1][k]; }
@@ -1033,6 +1050,7 @@ std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
     check(pvgpu_scene_set_blobs(gv.scene, fl.blobs.data(), fl.blobs.size(), fl.blob_elements.data(), fl.blob_elements.size(),
                                 fl.blob_nodes.data(), fl.blob_nodes.size()), "set_blobs");
     if (!fl.images.empty()) check(pvgpu_scene_set_images(gv.scene, fl.images.data(), fl.images.size(), fl.texels.data(), fl.texels.size()), "set_images");
+    if (fl.any_mesh_uv) check(pvgpu_scene_set_mesh_uv(gv.scene, fl.mesh_uv.data(), fl.mesh_uv.size() / 2, fl.tri_uv.data(), fl.tri_uv.size() / 3), "set_mesh_uv");
     if (fl.any_blob_texture) check(pvgpu_scene_set_blob_textures(gv.scene, fl.blob_textures.data(), fl.blob_textures.size()), "set_blob_textures");
     check(pvgpu_scene_set_shape_data(gv.scene, fl.shape_data.data(), fl.shape_data.size()), "set_shape_data");
     check(pvgpu_scene_set_meshes(gv.scene, fl.meshes.data(), fl.meshes.size(), fl.vertices.data(), fl.vertices.size() / 3,

@@ -82,6 +82,8 @@ struct Scene {
     std::vector<pvgpu_blob> blobs;
     std::vector<pvgpu_blob_element> blob_elements;
     std::vector<int32_t> blob_textures;          // per blob element: texture or -1 (Blob::Element_Texture)
+    std::vector<double> mesh_uv;                 // MESH_DATA::UVCoords of all meshes, (u, v) pairs
+    std::vector<uint32_t> tri_uv;                // per triangle: UV1 UV2 UV3 as indices into mesh_uv
     std::vector<pvgpu_image> images;             // image_map pigments
     std::vector<float> texels;                   // r g b filter transmit per texel, row 0 = top row
     std::vector<pvgpu_blob_node> blob_nodes;
@@ -858,6 +860,9 @@ public:
     void ComputeSky(const Ray& ray, const Ticket& tk, Col& colour, float& transm) const;
     void ComputeFog(const Ray& ray, double Depth, Col& colour, float& transm) const;
     bool Compute_Pigment(float col[5], int pigment, V3 EPoint) const;
+    // the intersection whose textures are being evaluated (the reference hands `Intersect` down to Compute_Pigment for uv_mapping)
+    mutable const Intersection* cur_isect = nullptr;
+    V3 UVCoord(const Intersection& isect) const;
     bool image_map_colour(const pvgpu_image& im, V3 p, float col[5]) const;
     V3 Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const;
     double Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const;
@@ -2731,10 +2736,86 @@ bool Tracer::image_map_colour(const pvgpu_image& im, V3 p, float col[5]) const
     return true;
 }
 
+// <Object>::UVCoord as the point (u, v, 0): sphere.cpp:688-752, box.cpp:1028-1077, torus.cpp:1118-1147, mesh.cpp:2256-2332, object.cpp:882-886
+V3 Tracer::UVCoord(const Intersection& isect) const
+{
+    const pvgpu_object& ob = S.objects[isect.Object];
+    const double M_PI_ = 3.1415926535897932384626, TWO_M_PI = 6.283185307179586476925286766560;
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE: {
+            V3 New_Point;
+            if (ob.aux) New_Point = MInvTransPoint(S.xf[ob.transform], isect.IPoint);
+            else { New_Point = isect.IPoint - v3(ob.p); if (ob.transform >= 0) New_Point = MInvTransPoint(S.xf[ob.transform], New_Point); }
+            double x = New_Point.x, y = New_Point.y, z = New_Point.z, phi, theta;
+            double l = std::sqrt(x * x + y * y + z * z);
+            if (l == 0.0) return v3(0, 0, 0);
+            x /= l; y /= l; z /= l;
+            phi = 0.5 + std::asin(y) / M_PI_;
+            l = x * x + z * z;
+            if (l > EPSILON) {
+                l = std::sqrt(l);
+                if (z == 0.0) { if (x > 0) theta = 0.0; else theta = M_PI_; }
+                else { theta = std::acos(x / l); if (z < 0.0) theta = TWO_M_PI - theta; }
+                theta /= TWO_M_PI;
+            } else theta = 0;
+            return v3(theta, phi, 0.0);
+        }
+        case PVGPU_OBJ_BOX: {
+            V3 P = (ob.transform >= 0) ? MInvTransPoint(S.xf[ob.transform], isect.IPoint) : isect.IPoint;
+            V3 Box_Diff = v3(ob.p + 3) - v3(ob.p);
+            P = P - v3(ob.p);
+            P = v3(P.x / Box_Diff.x, P.y / Box_Diff.y, P.z / Box_Diff.z);
+            switch (isect.aux) {
+                case 1: return v3((P.z / 4.0), (1.0 / 3.0) + (P.y / 3.0), 0.0);
+                case 2: return v3((3.0 / 4.0) - (P.z / 4.0), (1.0 / 3.0) + (P.y / 3.0), 0.0);
+                case 3: return v3((1.0 / 4.0) + (P.x / 4.0), (P.z / 3.0), 0.0);
+                case 4: return v3((1.0 / 4.0) + (P.x / 4.0), (3.0 / 3.0) - (P.z / 3.0), 0.0);
+                case 5: return v3(1.0 - (P.x / 4.0), (1.0 / 3.0) + (P.y / 3.0), 0.0);
+                default: return v3((1.0 / 4.0) + (P.x / 4.0), (1.0 / 3.0) + (P.y / 3.0), 0.0);
+            }
+        }
+        case PVGPU_OBJ_TORUS: {
+            V3 P = MInvTransPoint(S.xf[ob.transform], isect.IPoint);
+            double x = P.x, y = P.y, z = P.z;
+            double u = (1.0 - (std::atan2(z, x) + M_PI_) / TWO_M_PI);
+            double l = std::sqrt(x * x + z * z);
+            x = l - ob.p[0];
+            double v = (std::atan2(y, x) + M_PI_) / TWO_M_PI;
+            return v3(u, v, 0.0);
+        }
+        case PVGPU_OBJ_MESH: {
+            if (S.tri_uv.empty()) return v3(0, 0, 0);
+            const pvgpu_mesh& me = S.meshes[ob.mesh];
+            V3 P = (ob.transform >= 0) ? MInvTransPoint(S.xf[ob.transform], isect.IPoint) : isect.IPoint;
+            const pvgpu_triangle& T = S.tris[isect.aux];
+            const float* V = S.verts.data() + 3 * (size_t)me.vertex_first;
+            auto vert = [&](int i) { return V + 3 * (size_t)i; };
+            auto sngl_diff = [](const float* a, const float* b) { return v3((double)(float)(a[0] - b[0]), (double)(float)(a[1] - b[1]), (double)(float)(a[2] - b[2])); };   // SNGL vectors
+            auto weight = [&](const float* far_a, const float* far_b, const float* own) {
+                V3 Side1 = sngl_diff(far_a, far_b), Side2 = sngl_diff(far_a, own);
+                V3 vA = P - v3((double)own[0], (double)own[1], (double)own[2]);
+                double t1 = dot(Side2, Side1), t2 = dot(Side1, Side1);
+                V3 vB = Side1 * (t1 / t2) - Side2;
+                t1 = dot(vA, vB); t2 = dot(vB, vB);
+                return 1 + t1 / t2;
+            };
+            const double w1 = weight(vert(T.p3), vert(T.p2), vert(T.p1)), w2 = weight(vert(T.p3), vert(T.p1), vert(T.p2)), w3 = weight(vert(T.p2), vert(T.p1), vert(T.p3));
+            const uint32_t* iu = S.tri_uv.data() + 3 * (size_t)isect.aux;
+            const double* uv = S.mesh_uv.data();
+            return v3((w1 * uv[2 * iu[0]] + w2 * uv[2 * iu[1]]) + w3 * uv[2 * iu[2]], (w1 * uv[2 * iu[0] + 1] + w2 * uv[2 * iu[1] + 1]) + w3 * uv[2 * iu[2] + 1], 0.0);
+        }
+        default: return v3(isect.IPoint.x, isect.IPoint.y, 0.0);
+    }
+}
+
 bool Tracer::Compute_Pigment(float col[5], int pigment, V3 EPoint) const                                  // pigment.cpp:395-466
 {
     const pvgpu_pigment& pg = S.pigments[pigment];
     if (pg.pattern == PVGPU_PAT_PLAIN) { for (int k = 0; k < 5; k++) col[k] = pg.colour[k]; return true; }
+    if (pg.pattern == PVGPU_PAT_UV_MAP) {                                                                 // PigmentBlendMap::ComputeUVMapped, pigment.cpp:603-618
+        if (cur_isect == nullptr) { for (int k = 0; k < 5; k++) col[k] = 0.0f; return false; }       // (the reference throws: no uv_mapping outside a hit)
+        return Compute_Pigment(col, (int)pg.data, UVCoord(*cur_isect));
+    }
     const V3 TPoint = Warp_EPoint(pg, EPoint);
     if (pg.pattern == PVGPU_PAT_IMAGE_MAP) return image_map_colour(S.images[pg.data], TPoint, col);      // ColourImagePattern::Evaluate
     const pvgpu_blend_map& m = S.maps[pg.blend_map];
@@ -3013,7 +3094,9 @@ void Tracer::ComputeTextureColour(Intersection& isect, Col& colour, float& trans
         if ((wt.first < tk.adcBailout) || wt.second < 0) continue;                                         // trace.cpp:541
         Col c1{ 0, 0, 0 }; float t1 = 0.0f;
         std::vector<int> warps;
-        ComputeOneTextureColour(c1, t1, wt.second, warps, isect.IPoint, rawnormal, ray, tk, weight, isect, false);
+        cur_isect = &isect;
+        const V3 ipoint = (ob.flags & PVGPU_UV_FLAG) ? UVCoord(isect) : isect.IPoint;                      // trace.cpp:500-512
+        ComputeOneTextureColour(c1, t1, wt.second, warps, ipoint, rawnormal, ray, tk, weight, isect, false);
         tmpCol = tmpCol + c1 * wt.first; tmpTransm += wt.first * t1;
     }
     colour = colour + tmpCol; transm += tmpTransm;
@@ -3526,7 +3609,9 @@ void Tracer::ComputeShadowColour(Intersection& isect, Ray& lray, const Ticket& t
         if ((wt.first < tk.adcBailout) || wt.second < 0) continue;
         Col fc1{ 0, 0, 0 }; float dummy = 0.0f;
         std::vector<int> warps;
-        ComputeOneTextureColour(fc1, dummy, wt.second, warps, isect.IPoint, raw, lray, tk2, 0.0f, isect, true);
+        cur_isect = &isect;
+        const V3 ipoint = (S.objects[isect.Object].flags & PVGPU_UV_FLAG) ? UVCoord(isect) : isect.IPoint;   // trace.cpp:2351-2362
+        ComputeOneTextureColour(fc1, dummy, wt.second, warps, ipoint, raw, lray, tk2, 0.0f, isect, true);
         temp = temp + fc1 * wt.first;
     }
     if (std::fabs((std::fabs(temp.r) + std::fabs(temp.g) + std::fabs(temp.b)) / 3.0f) < tk.adcBailout) { colour = Col{ 0, 0, 0 }; return; }
@@ -3694,6 +3779,7 @@ void* pvo_scene_load(const char* path)
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->irid_wavelengths); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->blob_textures); } }
     if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->images) && get(f, s->texels); } }
+    if (ok) { int c = fgetc(f); if (c != EOF) { ungetc(c, f); ok = get(f, s->mesh_uv) && get(f, s->tri_uv); } }
     fclose(f);
     if (!ok) { delete s; return nullptr; }
     s->use_tree = (s->g.bounding_method == 1 && !s->nodes.empty());

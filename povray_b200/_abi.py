@@ -210,6 +210,7 @@ SIGNATURES = {
                                          P(Triangle), C.c_size_t, P(Node), C.c_size_t]),
     "pvgpu_scene_set_images": (C.c_int, [VP, P(Image), C.c_size_t, P(f32), C.c_size_t]),
     "pvgpu_scene_set_blob_textures": (C.c_int, [VP, P(i32), C.c_size_t]),
+    "pvgpu_scene_set_mesh_uv": (C.c_int, [VP, P(C.c_double), C.c_size_t, P(C.c_uint32), C.c_size_t]),
     "pvgpu_scene_set_shape_data": (C.c_int, [VP, P(f64), C.c_size_t]),
     "pvgpu_scene_set_lights": (C.c_int, [VP, P(Light), C.c_size_t]),
     "pvgpu_scene_set_materials": (C.c_int, [VP, P(Texture), C.c_size_t, P(Pigment), C.c_size_t, P(Finish), C.c_size_t,

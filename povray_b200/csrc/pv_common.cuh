@@ -193,6 +193,10 @@ struct DScene {
     const pvgpu_image*       images;        // image_map pigments
     const float*             texels;        // r g b filter transmit per texel
     const int32_t*           blob_textures; // per blob element: texture or -1; nullptr: no blob has per-component textures
+    const double*            mesh_uv;       // (u, v) pairs of the meshes' UV vectors
+    const uint32_t*          tri_uv;        // per triangle: three indices into mesh_uv; nullptr: no mesh has UV vectors
+    uint32_t                 has_uv;        // an object with PVGPU_UV_FLAG or a PVGPU_PAT_UV_MAP pigment exists: hits compute their (u, v)
+    uint32_t                 pad_uv;
     const double*            shape_data;    // triangle / smooth_triangle / polygon parameters (pvgpu_object::mesh = offset)
     const pvgpu_tnormal*     tnormals;
     const pvgpu_slope_entry* slopes;

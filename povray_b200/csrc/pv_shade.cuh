@@ -472,12 +472,12 @@ __device__ __forceinline__ void blend_search(const pvgpu_blend_entry* e, uint32_
 // call graph stays acyclic and ptxas sizes the stack statically.
 #define PV_PIGMENT_MAP_LEVELS 6
 template <int LEVEL>
-static __device__ __noinline__ bool compute_pigment_rec(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
+static __device__ __noinline__ bool compute_pigment_rec(const DScene& sc, int32_t pig_index, const V3& ep, float col[5], const V3& uvp)
 {
     // (the return value is Compute_Pigment's Colour_Found: false only where an image_map used `once` does not cover the point)
     bool found = false;
     auto child = [&](int32_t idx, const V3& p, float out[5]) {
-        if constexpr (LEVEL > 0) { if (compute_pigment_rec<LEVEL - 1>(sc, idx, p, out)) found = true; }
+        if constexpr (LEVEL > 0) { if (compute_pigment_rec<LEVEL - 1>(sc, idx, p, out, uvp)) found = true; }
         else { for (int k = 0; k < 5; k++) out[k] = sc.pigments[idx].colour[k]; found = true; }     // unreachable: nesting depth is validated
     };
     const pvgpu_pigment& pg = sc.pigments[pig_index];
@@ -488,6 +488,10 @@ static __device__ __noinline__ bool compute_pigment_rec(const DScene& sc, int32_
     if (pg.pattern == PVGPU_PAT_PLAIN) {
         for (int k = 0; k < 5; k++) col[k] = pg.colour[k];
         return true;
+    }
+    if (pg.pattern == PVGPU_PAT_UV_MAP) {          // PigmentBlendMap::ComputeUVMapped (pigment.cpp:603-618): no warps, the hit's (u, v, 0)
+        child((int32_t)pg.data, uvp, col);
+        return found;
     }
     const V3 tp = warp_epoint(sc, pg, ep);
     if (pg.pattern == PVGPU_PAT_IMAGE_MAP) return image_map_colour(sc, sc.images[pg.data], tp, col);
@@ -525,7 +529,8 @@ static __device__ __noinline__ bool compute_pigment_rec(const DScene& sc, int32_
 #endif
 
 // Compute_Pigment (pigment.cpp:395-466) + ColourBlendMap::Compute (pigment.cpp:513-530).  col = rgb, filter, transmit.
-__device__ inline bool compute_pigment(const DScene& sc, int32_t pig_index, const V3& ep, float col[5])
+// (uvp: the hit's UVCoord as a point, for uv_mapping pigments - hit_uv; anything where there is no hit)
+__device__ inline bool compute_pigment(const DScene& sc, int32_t pig_index, const V3& ep, float col[5], const V3& uvp)
 {
     const pvgpu_pigment& pg = sc.pigments[pig_index];
     // quickColour (+Q5 and below): Quick_Colour replaces the pigment where the scene gives one (pigment.cpp:401-405; NaN red = none)
@@ -541,10 +546,11 @@ __device__ inline bool compute_pigment(const DScene& sc, int32_t pig_index, cons
     }
 #if PV_FULL_MATERIALS
     if (pg.pattern == PVGPU_PAT_IMAGE_MAP) return image_map_colour(sc, sc.images[pg.data], warp_epoint(sc, pg, ep), col);
+    if (pg.pattern == PVGPU_PAT_UV_MAP) return compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col, uvp);
 #endif
     const pvgpu_blend_map& m = sc.maps[pg.blend_map];
 #if PV_FULL_MATERIALS
-    if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) return compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col);
+    if ((m.blend_mode & PVGPU_BLEND_PIGMENT_MAP) || pg.pattern == PVGPU_PAT_AVERAGE) return compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col, uvp);
 #endif
     const V3 tp = warp_epoint(sc, pg, ep);
     const double value = evaluate_pattern(sc, pg, tp);
@@ -999,6 +1005,101 @@ __device__ inline V3 object_normal(const DScene& sc, const pvgpu_object& ob, con
     return mk(0.0, 1.0, 0.0);
 }
 
+#if PV_FULL_MATERIALS
+// <Object>::UVCoord of a hit as the point (u, v, 0) texture evaluation uses for it (trace.cpp:500-512, pigment.cpp:603-618):
+// Sphere (sphere.cpp:688-752), Box (box.cpp:1028-1077), Torus (torus.cpp:1118-1147), Mesh (mesh.cpp:2256-2332), every other
+// primitive ObjectBase::UVCoord (object.cpp:882-886).
+static __device__ __noinline__ V3 hit_uv(const DScene& sc, const pvgpu_object& ob, const Hit& hit)
+{
+    const double pi = 3.1415926535897932384626, two_pi = 6.283185307179586476925286766560;
+    switch (ob.type) {
+        case PVGPU_OBJ_SPHERE: {
+            V3 p;
+            if (ob.aux) p = inv_trans_point(sc.xf[ob.transform], hit.ip);
+            else { p = hit.ip - ld3(ob.p); if (ob.transform >= 0) p = inv_trans_point(sc.xf[ob.transform], p); }
+            double x = p.x, y = p.y, z = p.z;
+            double len = sqrt(x * x + y * y + z * z);
+            if (len == 0.0) return mk(0.0, 0.0, 0.0);
+            x /= len; y /= len; z /= len;
+            const double phi = 0.5 + asin(y) / pi;
+            double theta;
+            len = x * x + z * z;
+            if (len > PV_EPSILON) {
+                len = sqrt(len);
+                if (z == 0.0) theta = (x > 0) ? 0.0 : pi;
+                else { theta = acos(x / len); if (z < 0.0) theta = two_pi - theta; }
+                theta /= two_pi;
+            } else theta = 0;
+            return mk(theta, phi, 0.0);
+        }
+        case PVGPU_OBJ_BOX: {
+            V3 P = (ob.transform >= 0) ? inv_trans_point(sc.xf[ob.transform], hit.ip) : hit.ip;
+            const V3 b0 = ld3(ob.p), diff = ld3(ob.p + 3) - b0;
+            P = P - b0;
+            P = mk(P.x / diff.x, P.y / diff.y, P.z / diff.z);
+            double u = 0.0, v = 0.0;
+            switch (hit.aux) {                                  // kSideHit_X0 .. kSideHit_Z1 = 1 .. 6
+                case 1: u = (P.z / 4.0);               v = (1.0 / 3.0) + (P.y / 3.0); break;
+                case 2: u = (3.0 / 4.0) - (P.z / 4.0); v = (1.0 / 3.0) + (P.y / 3.0); break;
+                case 3: u = (1.0 / 4.0) + (P.x / 4.0); v = (P.z / 3.0); break;
+                case 4: u = (1.0 / 4.0) + (P.x / 4.0); v = (3.0 / 3.0) - (P.z / 3.0); break;
+                case 5: u = 1.0 - (P.x / 4.0);         v = (1.0 / 3.0) + (P.y / 3.0); break;
+                default: u = (1.0 / 4.0) + (P.x / 4.0); v = (1.0 / 3.0) + (P.y / 3.0); break;
+            }
+            return mk(u, v, 0.0);
+        }
+        case PVGPU_OBJ_TORUS: {
+            const V3 P = inv_trans_point(sc.xf[ob.transform], hit.ip);
+            const double u = (1.0 - (atan2(P.z, P.x) + pi) / two_pi);
+            const double len = sqrt(P.x * P.x + P.z * P.z);
+            const double v = (atan2(P.y, len - ob.p[0]) + pi) / two_pi;
+            return mk(u, v, 0.0);
+        }
+        case PVGPU_OBJ_MESH: {
+            if (sc.tri_uv == nullptr) return mk(0.0, 0.0, 0.0);
+            const V3 P = (ob.transform >= 0) ? inv_trans_point(sc.xf[ob.transform], hit.ip) : hit.ip;
+            const pvgpu_triangle& tr = sc.tris[hit.aux];
+            const float* V = sc.verts + 3 * (size_t)sc.meshes[ob.mesh].vertex_first;
+            // the vertices are SNGL vectors: their differences are taken in FP32 and then widened (mesh.cpp:2273-2314)
+            auto vert = [&](uint32_t i, float out[3]) { out[0] = V[3 * i]; out[1] = V[3 * i + 1]; out[2] = V[3 * i + 2]; };
+            float p1[3], p2[3], p3[3];
+            vert(tr.p1, p1); vert(tr.p2, p2); vert(tr.p3, p3);
+            auto diff = [](const float a[3], const float b[3]) { return mk((double)__fsub_rn(a[0], b[0]), (double)__fsub_rn(a[1], b[1]), (double)__fsub_rn(a[2], b[2])); };
+            auto weight = [&](const float far_a[3], const float far_b[3], const float own[3]) {
+                // Side1 = far_a - far_b is the opposite side, Side2 = far_a - own an adjacent one; vB = the part of Side1 scaled to reach it
+                const V3 side1 = diff(far_a, far_b), side2 = diff(far_a, own);
+                const V3 vA = P - mk((double)own[0], (double)own[1], (double)own[2]);
+                double t1 = dot(side2, side1), t2 = dot(side1, side1);
+                const V3 vB = side1 * (t1 / t2) - side2;
+                t1 = dot(vA, vB); t2 = dot(vB, vB);
+                return 1 + t1 / t2;
+            };
+            const double w1 = weight(p3, p2, p1), w2 = weight(p3, p1, p2), w3 = weight(p2, p1, p3);
+            const uint32_t* iu = sc.tri_uv + 3 * hit.aux;
+            const double* uv = sc.mesh_uv;
+            const double u = (w1 * uv[2 * iu[0]] + w2 * uv[2 * iu[1]]) + w3 * uv[2 * iu[2]];
+            const double v = (w1 * uv[2 * iu[0] + 1] + w2 * uv[2 * iu[1] + 1]) + w3 * uv[2 * iu[2] + 1];
+            return mk(u, v, 0.0);
+        }
+        default: return mk(hit.ip.x, hit.ip.y, 0.0);
+    }
+}
+#endif
+
+// Where the textures of a hit are evaluated (the intersection point, or (u, v, 0) for an object with `uv_mapping`: trace.cpp:500-512,
+// 2351-2362) and the hit's UVCoord for uv_mapping pigments.
+__device__ __forceinline__ void texture_points(const DScene& sc, const pvgpu_object& ob, const Hit& hit, V3& tex_ip, V3& uvp)
+{
+    tex_ip = hit.ip;
+    uvp = hit.ip;
+#if PV_FULL_MATERIALS
+    if (sc.has_uv) {
+        uvp = hit_uv(sc, ob, hit);
+        if (ob.flags & PVGPU_UV_FLAG) tex_ip = uvp;
+    }
+#endif
+}
+
 // Texture of the hit: ObjectBase::Texture / Interior_Texture (trace.cpp:513-530) or, for a
 // multi-textured mesh, the triangle's texture (Mesh::Determine_Textures, mesh.cpp:2421-2457).
 __device__ inline int32_t hit_texture(const DScene& sc, const pvgpu_object& ob, const Hit& hit, bool backside)
@@ -1032,7 +1133,7 @@ __device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[
             if (sc.sky.transform >= 0) p = inv_trans_point(sc.xf[sc.sky.transform], p);
             for (int i = (int)sc.sky.pigment_count - 1; i >= 0; i--) {
                 float t[5];
-                compute_pigment(sc, (int32_t)sc.index_list[sc.sky.pigment_first + i], p, t);
+                compute_pigment(sc, (int32_t)sc.index_list[sc.sky.pigment_first + i], p, t, p);
                 const double att = trans * (double)(float)(1.0 - (double)t[3] - (double)t[4]);
                 #pragma unroll
                 for (int k = 0; k < 3; k++) { c[k] += (float)((double)t[k] * att); fc[k] *= t[k]; }
@@ -1057,7 +1158,7 @@ __device__ inline void compute_sky(const DScene& sc, const PRay& ray, float col[
         if (sc.sky.transform >= 0) p = inv_trans_point(sc.xf[sc.sky.transform], p);
         for (int i = (int)sc.sky.pigment_count - 1; i >= 0; i--) {
             float t[5];
-            compute_pigment(sc, (int32_t)sc.index_list[sc.sky.pigment_first + i], p, t);
+            compute_pigment(sc, (int32_t)sc.index_list[sc.sky.pigment_first + i], p, t, p);
             const double att = (double)(float)(1.0 - (double)t[3] - (double)t[4]);      // TransColour::Opacity
             #pragma unroll
             for (int k = 0; k < 3; k++) {
@@ -1285,7 +1386,9 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
 #if PV_FULL_MATERIALS
     if (!LEAF && sc.textures[tex0].type != PVGPU_PAT_PLAIN) { shade_texture_map(sc, ray, ray_slot, hit, ctx, tex0); return; }
 #endif
-    const V3 epoint = (LEAF && leaf) ? leaf->p : ipoint;       // where pigments and normals are evaluated (trace.cpp:588-694)
+    V3 tex_ip, uvp;
+    texture_points(sc, ob, hit, tex_ip, uvp);
+    const V3 epoint = (LEAF && leaf) ? leaf->p : tex_ip;       // where pigments and normals are evaluated (trace.cpp:588-694)
 
     const double rel_ior = relative_ior(sc, ray, ob.interior);
 
@@ -1328,7 +1431,7 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
         const V3 lay_normal = LAYER_NORMAL(L);
         const double cos_inc = -dot(dir, lay_normal);
         float lc[5];
-        const bool colour_found = compute_pigment(sc, tx.pigment, epoint, lc);
+        const bool colour_found = compute_pigment(sc, tx.pigment, epoint, lc, uvp);
         one_colour_found = one_colour_found || colour_found;
         if (sc.g.quality_flags & PVGPU_Q_AMBIENT_ONLY) {
             // +Q0 / +Q1 (trace.cpp:848-853): the result IS the layer's pigment colour (the last layer reached wins), no transparency,
@@ -1623,7 +1726,9 @@ __device__ inline void shade_hit_impl(const DScene& sc, const PRay& ray, uint32_
 static __device__ __noinline__ void shade_texture_map(const DScene& sc, const PRay& ray, uint32_t ray_slot, const Hit& hit, WaveCtx& ctx, int32_t tex0)
 {
     TexLeaf leaves[PV_MAX_TEX_LEAVES];
-    const int n = resolve_texture(sc, tex0, hit.ip, leaves);
+    V3 tex_ip, uvp;
+    texture_points(sc, sc.objs[hit.obj], hit, tex_ip, uvp);
+    const int n = resolve_texture(sc, tex0, tex_ip, leaves);
     for (int i = 0; i < n; i++) {
         PRay sr = ray;
         const float w = (float)leaves[i].w;

@@ -9,12 +9,12 @@ namespace pvgpu {
 // ---- shadow rays ----------------------------------------------------------------------------------
 // Trace::ComputeShadowTexture (trace.cpp:1181-1262) for one plain (layered) texture evaluated at `epoint`: filter colour x fade
 __device__ inline void shadow_texture(const DScene& sc, const pvgpu_object& ob, const pvgpu_interior* in, const Hit& hit, const V3& dir, const V3& rawnormal,
-                                      bool inside_now, int32_t tex0, const V3& epoint, const TexLeaf* leaf, float tc[3])
+                                      bool inside_now, int32_t tex0, const V3& epoint, const V3& uvp, const TexLeaf* leaf, float tc[3])
 {
     float tmp[3] = { 1.0f, 1.0f, 1.0f };
     for (int32_t li = tex0; li >= 0; li = sc.textures[li].next) {
         float lc[5];
-        if (compute_pigment(sc, sc.textures[li].pigment, epoint, lc)) {        // (not found: outside an image_map used `once`, trace.cpp:1198-1205)
+        if (compute_pigment(sc, sc.textures[li].pigment, epoint, lc, uvp)) {        // (not found: outside an image_map used `once`, trace.cpp:1198-1205)
             #pragma unroll
             for (int k = 0; k < 3; k++) tmp[k] *= (lc[k] * lc[3] + lc[4]);
         }
@@ -58,6 +58,8 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
     if (nd > 0.0) rawnormal = -rawnormal;
     float tc[3];
     const pvgpu_interior* in = (ob.interior >= 0) ? &sc.interiors[ob.interior] : nullptr;
+    V3 tex_ip, uvp;
+    texture_points(sc, ob, hit, tex_ip, uvp);       // (ComputeShadowColour switches to UV like ComputeTextureColour, trace.cpp:2351-2362)
 #if PV_FULL_MATERIALS
     if (ob.type == PVGPU_OBJ_BLOB && (ob.flags & PVGPU_MULTITEXTURE_FLAG) && sc.blob_textures != nullptr) {
         // Blob::Determine_Textures: weighted sum of the components' filter colours (trace.cpp:2382, 2399-2417)
@@ -70,7 +72,7 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
         tc[0] = tc[1] = tc[2] = 0.0f;
         for (int i = 0; i < n; i++) {
             float t1[3];
-            shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, leaves[i].tex, leaves[i].p, &leaves[i], t1);
+            shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, leaves[i].tex, leaves[i].p, uvp, &leaves[i], t1);
             #pragma unroll
             for (int k = 0; k < 3; k++) tc[k] += (float)((double)t1[k] * leaves[i].w);
         }
@@ -85,17 +87,17 @@ __device__ inline void shadow_filter(const DScene& sc, const Hit& hit, const V3&
     if (sc.textures[tex0].type != PVGPU_PAT_PLAIN) {
         // texture_map: weighted sum of the leaves' filter colours (ComputeOneTextureColour with shadowflag, trace.cpp:671-692)
         TexLeaf leaves[PV_MAX_TEX_LEAVES];
-        const int n = resolve_texture(sc, tex0, hit.ip, leaves);
+        const int n = resolve_texture(sc, tex0, tex_ip, leaves);
         tc[0] = tc[1] = tc[2] = 0.0f;
         for (int i = 0; i < n; i++) {
             float t1[3];
-            shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, leaves[i].tex, leaves[i].p, &leaves[i], t1);
+            shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, leaves[i].tex, leaves[i].p, uvp, &leaves[i], t1);
             #pragma unroll
             for (int k = 0; k < 3; k++) tc[k] += (float)((double)t1[k] * leaves[i].w);
         }
     } else
 #endif
-    shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, tex0, hit.ip, nullptr, tc);
+    shadow_texture(sc, ob, in, hit, dir, rawnormal, inside_now, tex0, tex_ip, uvp, nullptr, tc);
     // ComputeShadowColour: "close enough to full shadow" (trace.cpp:2419-2424)
     if (fabsf((fabsf(tc[0]) + fabsf(tc[1]) + fabsf(tc[2])) / 3.0f) < (float)sc.g.adc_bailout) { f[0] = f[1] = f[2] = 0.0f; return; }
     f[0] *= tc[0]; f[1] *= tc[1]; f[2] *= tc[2];

@@ -355,6 +355,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     UP(s.blend_entries, v.entries); UP(s.warps, v.warps); UP(s.interiors, v.interiors);
     UP(s.blobs, v.blobs); UP(s.blob_elements, v.blob_elements); UP(s.blob_nodes, v.blob_nodes); UP(s.shape_data, v.shape_data);
     if (!s.blob_textures.empty()) { UP(s.blob_textures, v.blob_textures); } else v.blob_textures = nullptr;
+    if (!s.tri_uv.empty()) { UP(s.mesh_uv, v.mesh_uv); UP(s.tri_uv, v.tri_uv); } else { v.mesh_uv = nullptr; v.tri_uv = nullptr; }
     UP(s.images, v.images); UP(s.texels, v.texels);
     UP(s.tnormals, v.tnormals); UP(s.slope_entries, v.slopes); UP(s.fogs, v.fogs);
     std::vector<double> pattern_rands;
@@ -409,6 +410,10 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern >= PVGPU_PAT_AVERAGE) d->full = true;      // average, crackle, cells
     if (!s.fogs.empty() || !s.sky_spheres.empty() || v.has_area_lights || !s.blob_textures.empty() || !s.images.empty()) d->full = true;
     for (const pvgpu_object& o : s.objects) if (o.type == PVGPU_OBJ_GLYPH || o.type == PVGPU_OBJ_PRISM || o.type == PVGPU_OBJ_SUPERELLIPSOID) d->full = true;      // their normals live in the full shading kernels
+    v.has_uv = 0; v.pad_uv = 0;
+    for (const pvgpu_object& o : s.objects) if (o.flags & PVGPU_UV_FLAG) v.has_uv = 1;
+    for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_UV_MAP) v.has_uv = 1;
+    if (v.has_uv) { d->full = true; d->lean = false; }      // hit_uv / uv_mapping pigments are full-variant code
     for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }
     for (const pvgpu_finish& fi : s.finishes) {
         const bool reflective = fi.reflection_max[0] != 0 || fi.reflection_max[1] != 0 || fi.reflection_max[2] != 0 ||

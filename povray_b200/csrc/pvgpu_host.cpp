@@ -354,8 +354,8 @@ int validate_scene(Scene& s)
         }
         if (o.type == PVGPU_OBJ_TORUS && o.transform < 0)
             return fail(PVGPU_E_INVALID, "object %zu: torus without transform", i);
-        if ((o.flags & PVGPU_UV_FLAG))
-            return fail(PVGPU_E_UNSUPPORTED, "object %zu: uv_mapping is outside the hot-path scope", i);
+        if ((o.flags & PVGPU_UV_FLAG) && o.type == PVGPU_OBJ_CONE)
+            return fail(PVGPU_E_UNSUPPORTED, "object %zu: uv_mapping on a cone / cylinder is outside the hot-path scope", i);
         if ((o.flags & PVGPU_CUTAWAY_TEXTURES_FLAG) && o.texture < 0)
             return fail(PVGPU_E_UNSUPPORTED, "object %zu: cutaway_textures is outside the hot-path scope", i);
         if (o.parent >= 0 && o.bound_count) {
@@ -377,6 +377,10 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_UNSUPPORTED, "image %zu: map_type %u", i, im.map_type);
         if (!(im.interpolation == 0 || im.interpolation == 2 || im.interpolation == 3 || im.interpolation == 4))
             return fail(PVGPU_E_UNSUPPORTED, "image %zu: interpolation %u", i, im.interpolation);
+    }
+    if (!s.tri_uv.empty()) {
+        if (s.tri_uv.size() != 3 * s.triangles.size() || (s.mesh_uv.size() & 1)) return fail(PVGPU_E_INVALID, "mesh UV table: %zu indices for %zu triangles", s.tri_uv.size(), s.triangles.size());
+        for (uint32_t u : s.tri_uv) if ((size_t)u >= s.mesh_uv.size() / 2) return fail(PVGPU_E_INVALID, "mesh UV table: index out of range");
     }
     if (!s.blob_textures.empty()) {
         if (s.blob_textures.size() != s.blob_elements.size()) return fail(PVGPU_E_INVALID, "blob texture table: %zu entries for %zu blob elements", s.blob_textures.size(), s.blob_elements.size());
@@ -465,7 +469,7 @@ int validate_scene(Scene& s)
         if (t.tnormal >= (int32_t)s.tnormals.size())
             return fail(PVGPU_E_INVALID, "texture %zu: bad tnormal index", i);
         const pvgpu_pigment& tp = s.pigments[t.pigment];
-        if (tp.pattern != PVGPU_PAT_PLAIN && tp.pattern != PVGPU_PAT_IMAGE_MAP && (tp.blend_map < 0 || tp.blend_map >= (int32_t)s.blend_maps.size()))
+        if (tp.pattern != PVGPU_PAT_PLAIN && tp.pattern != PVGPU_PAT_IMAGE_MAP && tp.pattern != PVGPU_PAT_UV_MAP && (tp.blend_map < 0 || tp.blend_map >= (int32_t)s.blend_maps.size()))
             return fail(PVGPU_E_INVALID, "texture %zu: patterned pigment without blend map", i);
         int depth = 0;
         for (int32_t k = (int32_t)i; k >= 0; k = s.textures[k].next)
@@ -479,6 +483,12 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "pigment %zu: bad blend map index", i);
         if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
+        if (p.pattern == PVGPU_PAT_UV_MAP) {
+            if (p.data >= s.pigments.size()) return fail(PVGPU_E_INVALID, "pigment %zu: uv_mapping pigment index out of range", i);
+            const pvgpu_pigment& q = s.pigments[p.data];
+            if (q.pattern != PVGPU_PAT_PLAIN && q.pattern != PVGPU_PAT_IMAGE_MAP && q.pattern != PVGPU_PAT_UV_MAP && q.blend_map < 0)
+                return fail(PVGPU_E_INVALID, "pigment %zu: uv_mapping over a patterned pigment without blend map", i);
+        }
         if (p.pattern == PVGPU_PAT_IMAGE_MAP && p.data >= s.images.size())
             return fail(PVGPU_E_INVALID, "pigment %zu: image index out of range", i);
         if (p.pattern == PVGPU_PAT_FRACTAL && (!range_ok(p.data, 8, s.shape_data.size()) || !(s.shape_data[p.data] >= 0.0 && s.shape_data[p.data] <= PVGPU_FRACTAL_MAGNET2J) ||
@@ -518,6 +528,11 @@ int validate_scene(Scene& s)
         std::vector<int> depth(s.pigments.size(), -1);
         std::function<int(size_t, int)> walk = [&](size_t pi, int level) -> int {
             const pvgpu_pigment& p = s.pigments[pi];
+            if (p.pattern == PVGPU_PAT_UV_MAP) {           // one level of nesting like a pigment_map entry
+                if (level >= 6) return -1;
+                const int dch = walk((size_t)p.data, level + 1);
+                return dch < 0 ? -1 : dch + 1;
+            }
             if (p.blend_map < 0 || !(s.blend_maps[p.blend_map].blend_mode & PVGPU_BLEND_PIGMENT_MAP)) return 0;
             if (level >= 6) return -1;          // PV_PIGMENT_MAP_LEVELS of the device code
             const pvgpu_blend_map& m = s.blend_maps[p.blend_map];
@@ -570,7 +585,7 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "sky_sphere: bad pigment range / transform");
         for (uint32_t i = 0; i < k.pigment_count; i++) {
             const uint32_t pi = s.index_list[k.pigment_first + i];
-            if (pi >= s.pigments.size() || (s.pigments[pi].pattern != PVGPU_PAT_PLAIN && s.pigments[pi].pattern != PVGPU_PAT_IMAGE_MAP && s.pigments[pi].blend_map < 0))
+            if (pi >= s.pigments.size() || s.pigments[pi].pattern == PVGPU_PAT_UV_MAP || (s.pigments[pi].pattern != PVGPU_PAT_PLAIN && s.pigments[pi].pattern != PVGPU_PAT_IMAGE_MAP && s.pigments[pi].blend_map < 0))
                 return fail(PVGPU_E_INVALID, "sky_sphere: bad pigment %u", pi);
         }
     }
@@ -751,6 +766,15 @@ int pvgpu_scene_set_images(pvgpu_scene* sc, const pvgpu_image* images, size_t n_
     if ((!images && n_images) || (!texels && n_texel_floats)) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_images: null array");
     s.images.assign(images, images + n_images);
     s.texels.assign(texels, texels + n_texel_floats);
+    return PVGPU_OK;
+}
+
+int pvgpu_scene_set_mesh_uv(pvgpu_scene* sc, const double* uv, size_t n_uv, const uint32_t* tri_uv, size_t n_tri)
+{
+    SCENE_OR_FAIL(sc);
+    if ((!uv && n_uv) || (!tri_uv && n_tri)) return fail(PVGPU_E_INVALID, "pvgpu_scene_set_mesh_uv: null array");
+    s.mesh_uv.assign(uv, uv + 2 * n_uv);
+    s.tri_uv.assign(tri_uv, tri_uv + 3 * n_tri);
     return PVGPU_OK;
 }
 
@@ -1021,7 +1045,8 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
               put(f, s.pigments) && put(f, s.finishes) && put(f, s.blend_maps) && put(f, s.blend_entries) &&
               put(f, s.warps) && put(f, s.interiors);
     // optional trailing sections in fixed order; a section is written when it or a later one holds data
-    const bool sec8 = !s.images.empty();
+    const bool sec9 = !s.tri_uv.empty();
+    const bool sec8 = sec9 || !s.images.empty();
     const bool sec7 = sec8 || !s.blob_textures.empty();
     const bool sec6 = sec7 || !s.irid_wavelengths.empty();
     const bool sec5 = sec6 || !s.camera_ext.empty();
@@ -1037,6 +1062,7 @@ int pvgpu_scene_save(const pvgpu_scene* sc, const char* path)
     if (ok && sec6) ok = put(f, s.irid_wavelengths);
     if (ok && sec7) ok = put(f, s.blob_textures);
     if (ok && sec8) ok = put(f, s.images) && put(f, s.texels);
+    if (ok && sec9) ok = put(f, s.mesh_uv) && put(f, s.tri_uv);
     ok = (fclose(f) == 0) && ok;
     return ok ? PVGPU_OK : fail(PVGPU_E_IO, "short write to %s", path);
 }
@@ -1089,6 +1115,10 @@ int pvgpu_scene_load(pvgpu_scene** out, const char* path)
     if (ok) {
         const int c = fgetc(f);
         if (c != EOF) { ungetc(c, f); ok = get(f, s->images) && get(f, s->texels); }
+    }
+    if (ok) {
+        const int c = fgetc(f);
+        if (c != EOF) { ungetc(c, f); ok = get(f, s->mesh_uv) && get(f, s->tri_uv); }
     }
     fclose(f);
     if (!ok) { delete s; return fail(PVGPU_E_IO, "%s is not a pvgpu scene file of version %d", path, PVGPU_FILE_VERSION); }

@@ -32,6 +32,8 @@ struct Scene {
     std::vector<pvgpu_blob>         blobs;
     std::vector<pvgpu_blob_element> blob_elements;
     std::vector<pvgpu_blob_node>    blob_nodes;
+    std::vector<double>             mesh_uv;         // (u, v) pairs (MESH_DATA::UVCoords of all meshes)
+    std::vector<uint32_t>           tri_uv;          // per triangle of the triangle table: three indices into mesh_uv (empty: no UV vectors)
     std::vector<int32_t>            blob_textures;   // per blob element: texture index or -1 (empty: no per-component textures)
 
     std::vector<pvgpu_image>       images;         // image_map pigments (pvgpu_pigment::data = index)
