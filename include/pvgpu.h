@@ -268,10 +268,12 @@ enum {
                                     interiorFactor, juliaCoord u v */
     PVGPU_PAT_SPIRAL1  = 29,     /* Spiral1Pattern   pattern.cpp:8396, p[0] = arms */
     PVGPU_PAT_SPIRAL2  = 30,     /* Spiral2Pattern   pattern.cpp:8473, p[0] = arms */
+    PVGPU_PAT_PIGMENT  = 32,     /* PigmentPattern (`pigment_pattern { ... }`, pattern.cpp:7974-7990): `data` = index of the pigment whose
+                                    greyscale is the pattern value; as the pattern of a pigment or of a normal */
     PVGPU_PAT_UV_MAP   = 31      /* UV_MAP_PATTERN pigment (`pigment { uv_mapping ... }`, PigmentBlendMap::ComputeUVMapped, pigment.cpp:603-618):
                                     `data` = index of the pigment that is evaluated at (u, v, 0) of the hit */
 };
-#define PVGPU_PAT_LAST PVGPU_PAT_UV_MAP
+#define PVGPU_PAT_LAST PVGPU_PAT_PIGMENT
 /* iteration formulas of PVGPU_PAT_FRACTAL (exponents above 4 - MandelXPattern / JuliaXPattern - are not served) */
 enum { PVGPU_FRACTAL_MANDEL2 = 0, PVGPU_FRACTAL_MANDEL3 = 1, PVGPU_FRACTAL_MANDEL4 = 2, PVGPU_FRACTAL_JULIA2 = 3, PVGPU_FRACTAL_JULIA3 = 4,
        PVGPU_FRACTAL_JULIA4 = 5, PVGPU_FRACTAL_MAGNET1M = 6, PVGPU_FRACTAL_MAGNET1J = 7, PVGPU_FRACTAL_MAGNET2M = 8, PVGPU_FRACTAL_MAGNET2J = 9 };

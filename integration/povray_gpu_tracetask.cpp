@@ -253,6 +253,10 @@ struct Flattener
             p.pattern = dynamic_cast<const Spiral1Pattern*>(bp) ? PVGPU_PAT_SPIRAL1 : PVGPU_PAT_SPIRAL2;
             p.p[0] = (double)sp->arms;
         }
+        else if (const PigmentPattern* pp = dynamic_cast<const PigmentPattern*>(bp)) {
+            if (pp->pPigment == nullptr) unsupported(std::string(user) + " pigment_pattern without a pigment");
+            else { p.pattern = PVGPU_PAT_PIGMENT; p.data = (uint32_t)add_pigment(pp->pPigment); }
+        }
         else if (dynamic_cast<const BumpsPattern*>(bp)) p.pattern = PVGPU_PAT_BOZO;      // BumpsPattern is a NoisePattern (pattern.h:989)
         else unsupported(std::string(user) + " pattern outside the hot-path scope: " + typeid(*bp).name());
         if (const ContinuousPattern* cp = dynamic_cast<const ContinuousPattern*>(bp)) {

@@ -2437,6 +2437,11 @@ double Tracer::Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const               
         }
     }
     if (pg.pattern == PVGPU_PAT_CRACKLE) value = crackle_pattern(S, pg, p, gen);
+    else if (pg.pattern == PVGPU_PAT_PIGMENT) {                                                           // PigmentPattern::EvaluateRaw, pattern.cpp:7974-7990
+        float Col[5];
+        const bool colour_found = Compute_Pigment(Col, (int)pg.data, p);
+        value = colour_found ? (double)(float)(0.297 * Col[0] + 0.589 * Col[1] + 0.114 * Col[2]) : 0.0;      // TransColour::Greyscale (colour.h:232-237)
+    }
     else if (pg.pattern == PVGPU_PAT_FRACTAL) value = fractal_pattern(&S.shape_data[pg.data], p);
     else if (pg.pattern == PVGPU_PAT_SPIRAL1 || pg.pattern == PVGPU_PAT_SPIRAL2) {                        // pattern.cpp:8396-8437, 8473-8517
         const double M_PI_2_ = 1.57079632679489661923, TWO_M_PI = 6.283185307179586476925286766560;

@@ -37,6 +37,9 @@ __device__ inline double cycloidal(double value)
     if (value >= 0.0) return sin(((value - floor(value)) * 50000.0) / 50000.0 * two_pi);
     return 0.0 - sin(((0.0 - (value + floor(0.0 - value))) * 50000.0) / 50000.0 * two_pi);
 }
+// RGBColour::Greyscale (colour.h:232-237)
+__device__ __forceinline__ float greyscale_rgb(const float* c) { return (float)(0.297 * c[0] + 0.589 * c[1] + 0.114 * c[2]); }
+
 // Triangle_Wave (texture.cpp:128-150)
 __device__ inline double triangle_wave(double value)
 {
@@ -467,6 +470,25 @@ __device__ __forceinline__ void blend_search(const pvgpu_blend_entry* e, uint32_
 }
 
 #if PV_FULL_MATERIALS
+// ContinuousPattern::Evaluate (pattern.cpp:354-392) on a raw value computed elsewhere (pigment_pattern: the value is a pigment's greyscale)
+__device__ inline double pattern_waveform(const pvgpu_pigment& pg, double value)
+{
+    if (pg.wave_type == PVGPU_WAVE_RAW) return value;
+    if (pg.frequency != 0.0f) value = fmod(value * (double)pg.frequency + (double)pg.phase, 1.00001);
+    if (value < 0.0) value -= floor(value);
+    switch (pg.wave_type) {
+        case PVGPU_WAVE_SINE:     value = (1.0 + cycloidal(value)) * 0.5; break;
+        case PVGPU_WAVE_TRIANGLE: value = triangle_wave(value); break;
+        case PVGPU_WAVE_SCALLOP:  value = fabs(cycloidal(value * 0.5)); break;
+        case PVGPU_WAVE_CUBIC:    value = sqr(value) * ((-2.0 * value) + 3.0); break;
+        case PVGPU_WAVE_POLY:     value = pow(value, (double)pg.exponent); break;
+        default: break;
+    }
+    return value;
+}
+#endif
+
+#if PV_FULL_MATERIALS
 // pigment_map / average pigments: Compute_Pigment recursing through PigmentBlendMap::Compute / ComputeAverage
 // (pigment.cpp:395-466, 546-596).  The recursion is unrolled over LEVEL (maps nest at most 6 deep: validated on the host), so the
 // call graph stays acyclic and ptxas sizes the stack statically.
@@ -511,7 +533,13 @@ static __device__ __noinline__ bool compute_pigment_rec(const DScene& sc, int32_
         for (int k = 0; k < 5; k++) col[k] = (float)((double)col[k] / (double)total);
         return true;           // Do_Average_Pigments does not report Colour_Found (pigment.cpp:427-433)
     }
-    const double value = evaluate_pattern(sc, pg, tp);
+    double value;
+    if (pg.pattern == PVGPU_PAT_PIGMENT) {          // PigmentPattern::EvaluateRaw (pattern.cpp:7974-7990): greyscale of a pigment at the warped point
+        float pc[5] = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+        bool pf = false;
+        if constexpr (LEVEL > 0) pf = compute_pigment_rec<LEVEL - 1>(sc, (int32_t)pg.data, tp, pc, uvp);
+        value = pattern_waveform(pg, pf ? (double)greyscale_rgb(pc) : 0.0);
+    } else value = evaluate_pattern(sc, pg, tp);
     uint32_t ip, in;
     double wp;
     blend_search(e, m.entry_count, value, ip, in, wp);
@@ -546,7 +574,7 @@ __device__ inline bool compute_pigment(const DScene& sc, int32_t pig_index, cons
     }
 #if PV_FULL_MATERIALS
     if (pg.pattern == PVGPU_PAT_IMAGE_MAP) return image_map_colour(sc, sc.images[pg.data], warp_epoint(sc, pg, ep), col);
-    if (pg.pattern == PVGPU_PAT_UV_MAP) return compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col, uvp);
+    if (pg.pattern == PVGPU_PAT_UV_MAP || pg.pattern == PVGPU_PAT_PIGMENT) return compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, pig_index, ep, col, uvp);
 #endif
     const pvgpu_blend_map& m = sc.maps[pg.blend_map];
 #if PV_FULL_MATERIALS
@@ -572,6 +600,16 @@ __device__ inline bool compute_pigment(const DScene& sc, int32_t pig_index, cons
 
 // ---- normal perturbation: Perturb_Normal (normal.cpp:784-927) ---------------------------------------
 #if PV_FULL_MATERIALS
+// Evaluate_TPat of a normal's pattern carrier: pigment_pattern values come from Compute_Pigment, everything else from evaluate_pattern
+__device__ inline double evaluate_normal_pattern(const DScene& sc, const pvgpu_pigment& c, const V3& p)
+{
+    if (c.pattern == PVGPU_PAT_PIGMENT) {
+        float pc[5];
+        const bool pf = compute_pigment_rec<PV_PIGMENT_MAP_LEVELS>(sc, (int32_t)c.data, p, pc, p);
+        return pattern_waveform(c, pf ? (double)greyscale_rgb(pc) : 0.0);
+    }
+    return evaluate_pattern(sc, c, p);
+}
 // Warp_Normal / UnWarp_Normal (warp.cpp:563-640): only transform warps act on normals
 __device__ inline V3 warp_normal(const DScene& sc, const pvgpu_pigment& c, V3 n, bool dont_scale)
 {
@@ -642,7 +680,7 @@ static __device__ __noinline__ V3 perturb_normal_t(const DScene& sc, int32_t tn_
         }
         // normal_map selected by a pattern (normal.cpp:824-848)
         const V3 tpm = warp_epoint(sc, c, epoint);
-        const double value1 = evaluate_pattern(sc, c, tpm);
+        const double value1 = evaluate_normal_pattern(sc, c, tpm);
         uint32_t ip, in;
         double wp;
         blend_search(e, m.entry_count, value1, ip, in, wp);
@@ -716,7 +754,7 @@ static __device__ __noinline__ V3 perturb_normal_t(const DScene& sc, int32_t tn_
             for (int i = 0; i <= 3; i++) {
                 const V3 pv = mk(pyr[i][0], pyr[i][1], pyr[i][2]);
                 const V3 p1 = tp + (double)tn.delta * pv;
-                const double value1 = do_slope_map(sc, tn, evaluate_pattern(sc, c, p1));
+                const double value1 = do_slope_map(sc, tn, evaluate_normal_pattern(sc, c, p1));
                 n = n + (value1 * am) * pv;
             }
             break;

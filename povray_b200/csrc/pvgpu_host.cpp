@@ -452,6 +452,7 @@ int validate_scene(Scene& s)
         const pvgpu_texture& t = s.textures[i];
         if (t.type != PVGPU_PAT_PLAIN) {
             // texture_map / average texture_map: pattern carrier + a blend map whose entries are texture indices
+            if (t.type == PVGPU_PAT_PIGMENT || t.type == PVGPU_PAT_UV_MAP) return fail(PVGPU_E_UNSUPPORTED, "texture %zu: pigment_pattern / uv_mapping as the pattern of a texture_map is outside the hot-path scope", i);
             if (t.type > PVGPU_PAT_LAST || t.pigment < 0 || t.pigment >= (int32_t)s.pigments.size() || t.blend_map < 0 || t.blend_map >= (int32_t)s.blend_maps.size() ||
                 !(s.blend_maps[t.blend_map].blend_mode & PVGPU_BLEND_TEXTURE_MAP))
                 return fail(PVGPU_E_INVALID, "texture %zu: patterned texture without pattern carrier / texture map", i);
@@ -483,6 +484,8 @@ int validate_scene(Scene& s)
             return fail(PVGPU_E_INVALID, "pigment %zu: bad blend map index", i);
         if (!range_ok(p.warp_first, p.warp_count, s.warps.size()))
             return fail(PVGPU_E_INVALID, "pigment %zu: warp range out of bounds", i);
+        if (p.pattern == PVGPU_PAT_PIGMENT && p.data >= s.pigments.size())
+            return fail(PVGPU_E_INVALID, "pigment %zu: pigment_pattern pigment index out of range", i);
         if (p.pattern == PVGPU_PAT_UV_MAP) {
             if (p.data >= s.pigments.size()) return fail(PVGPU_E_INVALID, "pigment %zu: uv_mapping pigment index out of range", i);
             const pvgpu_pigment& q = s.pigments[p.data];
@@ -528,15 +531,17 @@ int validate_scene(Scene& s)
         std::vector<int> depth(s.pigments.size(), -1);
         std::function<int(size_t, int)> walk = [&](size_t pi, int level) -> int {
             const pvgpu_pigment& p = s.pigments[pi];
-            if (p.pattern == PVGPU_PAT_UV_MAP) {           // one level of nesting like a pigment_map entry
+            int worst = 0;
+            if (p.pattern == PVGPU_PAT_UV_MAP || p.pattern == PVGPU_PAT_PIGMENT) {           // one level of nesting like a pigment_map entry
                 if (level >= 6) return -1;
                 const int dch = walk((size_t)p.data, level + 1);
-                return dch < 0 ? -1 : dch + 1;
+                if (dch < 0) return -1;
+                worst = dch + 1;
+                if (p.pattern == PVGPU_PAT_UV_MAP) return worst;
             }
-            if (p.blend_map < 0 || !(s.blend_maps[p.blend_map].blend_mode & PVGPU_BLEND_PIGMENT_MAP)) return 0;
+            if (p.blend_map < 0 || !(s.blend_maps[p.blend_map].blend_mode & PVGPU_BLEND_PIGMENT_MAP)) return worst;
             if (level >= 6) return -1;          // PV_PIGMENT_MAP_LEVELS of the device code
             const pvgpu_blend_map& m = s.blend_maps[p.blend_map];
-            int worst = 0;
             for (uint32_t k = 0; k < m.entry_count; k++) {
                 int dch = walk((size_t)s.blend_entries[m.entry_first + k].colour[0], level + 1);
                 if (dch < 0) return -1;
