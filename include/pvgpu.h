@@ -470,7 +470,8 @@ enum { PVGPU_CAMERA_PERSPECTIVE = 1, PVGPU_CAMERA_ORTHOGRAPHIC = 2, PVGPU_CAMERA
        PVGPU_CAMERA_CYL_4 = 10, PVGPU_CAMERA_SPHERICAL = 11 };
 typedef struct pvgpu_camera {
     uint32_t type;
-    uint32_t reserved;
+    uint32_t reserved;           /* camera { normal { ... } } (Camera::Tnormal, tracepixel.cpp:917-924): index into the tnormal table + 1,
+                                    0 = none; perspective and orthographic cameras only */
     double   location[3], direction[3], up[3], right[3];
     double   max_ray_distance;
 } pvgpu_camera;

@@ -1042,7 +1042,14 @@ std::shared_ptr<GpuView> flatten_scene_locked(ViewData* vd, bool need_device)
     c.type = cam.Type;
     for (int k = 0; k < 3; k++) { c.location[k] = cam.Location[k]; c.direction[k] = cam.Direction[k]; c.up[k] = cam.Up[k]; c.right[k] = cam.Right[k]; }
     c.max_ray_distance = cam.Max_Ray_Distance;
-    if (cam.Tnormal != nullptr) gv.error = "camera normal perturbation";
+    if (cam.Tnormal != nullptr) {
+        // camera { normal { ... } }: the ray direction is perturbed like a surface normal (tracepixel.cpp:917-924)
+        if (cam.Type > ORTHOGRAPHIC_CAMERA) gv.error = "camera normal perturbation on a non-planar camera";
+        else {
+            c.reserved = (uint32_t)fl.add_tnormal(cam.Tnormal) + 1u;
+            if (gv.error.empty()) gv.error = fl.error;
+        }
+    }
     if ((cam.Aperture != 0.0) && (cam.Blur_Samples > 0)) gv.error = "focal blur";
     if (cam.Rays_Per_Pixel != 1) gv.error = "mesh camera";
 

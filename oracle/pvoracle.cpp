@@ -863,6 +863,14 @@ public:
     // the intersection whose textures are being evaluated (the reference hands `Intersect` down to Compute_Pigment for uv_mapping)
     mutable const Intersection* cur_isect = nullptr;
     V3 UVCoord(const Intersection& isect) const;
+    // camera { normal { ... } }: the tail of TracePixel::CreateCameraRay (tracepixel.cpp:917-924), perspective / orthographic cameras
+    void camera_normal(double x, double y, double width, double height, V3& Direction) const
+    {
+        if (!S.cam.reserved) return;
+        const double x0 = x / width - 0.5, y0 = 0.5 - y / height;
+        // (camera_ray has normalised the direction once, like the reference does before Perturb_Normal)
+        Direction = unit(Perturb_Normal(Direction, (int)S.cam.reserved - 1, v3(x0, y0, 0.0)));
+    }
     bool image_map_colour(const pvgpu_image& im, V3 p, float col[5]) const;
     V3 Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const;
     double Evaluate_TPat(const pvgpu_pigment& pg, V3 p) const;
@@ -3823,6 +3831,7 @@ int pvo_render(void* sc, int width, int height, int left, int top, int right, in
                 Ray ray;
                 Col col{ 0, 0, 0 }; float transm = 0.0f;
                 if (camera_ray(S, x + 0.5, y + 0.5, width, height, ray.Origin, ray.Direction)) {
+                    T.camera_normal(x + 0.5, y + 0.5, width, height, ray.Direction);
                     if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC || S.cam.type == PVGPU_CAMERA_CYL_3 || S.cam.type == PVGPU_CAMERA_CYL_4) container_state(S, T, ray.Origin, cam_interiors);
                     ray.interiors = cam_interiors;
                     T.TraceRay(ray, tk, col, transm, 1.0f, false, S.cam.max_ray_distance);
@@ -3881,6 +3890,7 @@ struct AATracer {
         Ray ray;
         Col col{ 0, 0, 0 }; float transm = 0.0f;
         if (!camera_ray(S, x, y, width, height, ray.Origin, ray.Direction)) return Px{ 0.0f, 0.0f, 0.0f, 1.0f };
+        T.camera_normal(x, y, width, height, ray.Direction);
         if (S.cam.type == PVGPU_CAMERA_ORTHOGRAPHIC || S.cam.type == PVGPU_CAMERA_CYL_3 || S.cam.type == PVGPU_CAMERA_CYL_4) container_state(S, T, ray.Origin, cam_interiors);
         ray.interiors = cam_interiors;
         T.TraceRay(ray, tk, col, transm, 1.0f, false, S.cam.max_ray_distance);
@@ -4059,6 +4069,7 @@ int pvo_camera_rays(void* sc, int width, int height, const double* xy, size_t n,
     for (size_t i = 0; i < n; i++) {
         V3 o, d;
         if (!camera_ray(S, xy[2 * i], xy[2 * i + 1], width, height, o, d)) { o = v3(0.0, 0.0, 0.0); d = v3(0.0, 0.0, 0.0); }
+        else Tracer(S).camera_normal(xy[2 * i], xy[2 * i + 1], width, height, d);
         double* r = org_dir + 6 * i;
         r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
     }

@@ -180,33 +180,6 @@ __device__ inline bool camera_ray(const DScene& sc, double x, double y, double w
     return true;
 }
 
-// sample i -> (rectangle, x, y) and its accumulator slot.  Slots are row-major inside a rectangle (the layout
-// ViewData::CompletedRectangle takes), but the ORDER in which a rectangle's pixels become rays is by 8 x 4 pixel blocks
-// when its size allows: the 32 rays of a warp then cover a compact patch of the image instead of a 32 x 1 strip and share
-// more of their tree nodes (the shadow / reflection rays they spawn inherit the order).
-__device__ __forceinline__ void sample_xy(const pvgpu_rect* rects, const uint32_t* rect_off, uint32_t n_rects, uint32_t i,
-                                          double& x, double& y, uint32_t& slot)
-{
-    uint32_t lo = 0, hi = n_rects;
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (rect_off[mid] <= i) lo = mid; else hi = mid; }
-    const pvgpu_rect r = rects[lo];
-    const uint32_t k = i - rect_off[lo], w = (uint32_t)(r.right - r.left + 1), h = (uint32_t)(r.bottom - r.top + 1);
-    uint32_t px = k % w, py = k / w;
-    if (((w & 15u) | (h & 7u)) == 0u) {
-        // 8 x 4 blocks per warp, 2 x 2 such blocks (16 x 8 pixels) per CTA of four warps
-        const uint32_t blk = k >> 5, in = k & 31u, grp = blk >> 2, gpr = w >> 4;
-        px = (grp % gpr) * 16u + (blk & 1u) * 8u + (in & 7u);
-        py = (grp / gpr) * 8u + ((blk >> 1) & 1u) * 4u + (in >> 3);
-    } else if (((w & 7u) | (h & 3u)) == 0u) {
-        const uint32_t blk = k >> 5, in = k & 31u, bpr = w >> 3;      // 8 x 4 blocks, row-major over the rectangle
-        px = (blk % bpr) * 8u + (in & 7u);
-        py = (blk / bpr) * 4u + (in >> 3);
-    }
-    slot = rect_off[lo] + py * w + px;
-    x = (double)(r.left + (int)px) + 0.5;       // SimpleSamplingM0: pixel centres (tracetask.cpp:438)
-    y = (double)(r.top + (int)py) + 0.5;
-}
-
 // TracePixel::operator() (tracepixel.cpp:311-339): one new ticket + camera ray per sample.
 __global__ void __launch_bounds__(256)
 k_primary(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width, double height, PRay* out, Counters* cnt, float4* accum)

@@ -56,6 +56,48 @@ PV_VARIANT(k_shade)(DScene sc, const PRay* __restrict__ cur, const HitRec* __res
     }
 }
 
+#ifdef PV_FULL
+// camera { normal { ... } }: the tail of TracePixel::CreateCameraRay (tracepixel.cpp:917-924) as a pass over the primary rays - the
+// direction is perturbed like a surface normal at the point (x0, y0, 0) of the image plane and normalised again.  Perspective and
+// orthographic cameras (x0 = x / width - 0.5, y0 = 0.5 - y / height); lives here because Perturb_Normal is shading code.
+__device__ __forceinline__ V3 camera_normal_dir(const DScene& sc, const V3& d, double x, double y, double width, double height)
+{
+    const double x0 = x / width - 0.5, y0 = 0.5 - y / height;
+    // (d has been normalised once by camera_ray, like the reference does before Perturb_Normal)
+    return normalized(perturb_normal(sc, (int32_t)sc.cam.reserved - 1, d, mk(x0, y0, 0.0)));
+}
+__global__ void k_camera_normal_rays(DScene sc, SampleSource src, uint32_t first, uint32_t n, double width, double height, PRay* rays)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double x, y;
+        uint32_t slot;
+        if (src.coords) { const double2 c = src.coords[first + i]; x = c.x; y = c.y; }
+        else sample_xy(src.rects, src.rect_off, src.n_rects, first + i, x, y, slot);
+        PRay& r = rays[i];
+        if (r.flags & PV_RAY_DEAD) continue;
+        const V3 d = camera_normal_dir(sc, ld3(r.d), x, y, width, height);
+        r.d[0] = d.x; r.d[1] = d.y; r.d[2] = d.z;
+    }
+}
+__global__ void k_camera_normal_probe(DScene sc, const double* xy, uint32_t n, double width, double height, double* org_dir)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double* r = org_dir + 6 * (size_t)i;
+        if (r[3] == 0.0 && r[4] == 0.0 && r[5] == 0.0) continue;       // no ray for this pixel
+        const V3 d = camera_normal_dir(sc, mk(r[3], r[4], r[5]), xy[2 * (size_t)i], xy[2 * (size_t)i + 1], width, height);
+        r[3] = d.x; r[4] = d.y; r[5] = d.z;
+    }
+}
+void launch_camera_normal_rays(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height, PRay* rays, cudaStream_t st)
+{
+    k_camera_normal_rays<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, src, first, n, width, height, rays);
+}
+void launch_camera_normal_probe(const DScene& sc, const double* xy, uint32_t n, double width, double height, double* org_dir, cudaStream_t st)
+{
+    k_camera_normal_probe<<<grid_for(n, 128, 8), 128, 0, st>>>(sc, xy, n, width, height, org_dir);
+}
+#endif
+
 void PV_VARIANT(launch_shade)(const DScene& sc, const PRay* cur, const HitRec* hits, const WaveCounts* wc, uint32_t n_bound, const WaveCtx& ctx, cudaStream_t st)
 {
     PV_VARIANT(k_shade)<<<grid_for(n_bound, 128, 8), 128, 0, st>>>(sc, cur, hits, wc, ctx);

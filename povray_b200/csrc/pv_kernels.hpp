@@ -71,6 +71,8 @@ void launch_shade_lean(const DScene& sc, const PRay* cur, const HitRec* hits, co
 void launch_shadow_opaque_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_shadow_filter_lean(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);
 // quadric-class + CSG variants of the traversal kernels (-DPV_CSG)
+void launch_camera_normal_rays(const DScene& sc, const SampleSource& src, uint32_t first, uint32_t n, double width, double height, PRay* rays, cudaStream_t st);
+void launch_camera_normal_probe(const DScene& sc, const double* xy, uint32_t n, double width, double height, double* org_dir, cudaStream_t st);
 void launch_closest_quartic(const DScene& sc, const PRay* cur, WaveCounts* wc, uint32_t n_bound, uint32_t cap, HitRec* hits, Counters* cnt, cudaStream_t st);
 void launch_shadow_opaque_quartic(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, float4* accum, Counters* cnt, cudaStream_t st);
 void launch_shadow_filter_quartic(const DScene& sc, const SRay* rays, WaveCounts* wc, uint32_t n_bound, uint32_t cap, const PRay* wave, float4* accum, Counters* cnt, cudaStream_t st);

@@ -413,6 +413,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     v.has_uv = 0; v.pad_uv = 0;
     for (const pvgpu_object& o : s.objects) if (o.flags & PVGPU_UV_FLAG) v.has_uv = 1;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_UV_MAP) v.has_uv = 1;
+    if (s.camera.reserved) { d->full = true; d->lean = false; }      // camera normal: Perturb_Normal is full-variant code
     if (v.has_uv) { d->full = true; d->lean = false; }      // hit_uv / uv_mapping pigments are full-variant code
     for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }
     for (const pvgpu_finish& fi : s.finishes) {
@@ -689,6 +690,7 @@ static int run_batch(FrameCtx& f, const SampleSource& src, uint32_t first, uint3
     {
         TimedLaunch t(c, S1, KIND_PRIMARY, n);
         launch_primary(d.view, src, first, n, (double)f.width, (double)f.height, c.q[0], c.cnt, f.accum, S1);
+        if (d.view.cam.reserved) { launch_camera_normal_rays(d.view, src, first, n, (double)f.width, (double)f.height, c.q[0], S1); c.kernel_launches++; }
     }
     std::vector<size_t> ev_rb, ev_shadow;           // per wave: count read back / shadow kernels done
     unsigned long long bound = n;                   // upper bound of the wave's ray count (sizes the grids only)
@@ -1562,6 +1564,7 @@ int pvgpu_camera_rays(pvgpu_scene* sc, int width, int height, const double* xy, 
     }
     cudaMemcpy(d_xy, xy, n * 2 * sizeof(double), cudaMemcpyHostToDevice);
     launch_camera_rays(d.view, d_xy, (uint32_t)n, (double)width, (double)height, d_out, 0);
+    if (d.view.cam.reserved) launch_camera_normal_probe(d.view, d_xy, (uint32_t)n, (double)width, (double)height, d_out, 0);
     d.ctx[0]->kernel_launches++;
     cudaError_t e = cudaMemcpy(org_dir, d_out, n * 6 * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d_xy); cudaFree(d_out);

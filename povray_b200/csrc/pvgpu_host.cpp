@@ -639,6 +639,10 @@ int validate_scene(Scene& s)
     if (!s.have_camera) return fail(PVGPU_E_INVALID, "no camera set");
     if (s.camera.type < PVGPU_CAMERA_PERSPECTIVE || s.camera.type > PVGPU_CAMERA_SPHERICAL)
         return fail(PVGPU_E_UNSUPPORTED, "camera type %u is outside the hot-path scope", s.camera.type);
+    if (s.camera.reserved) {
+        if (s.camera.reserved > s.tnormals.size()) return fail(PVGPU_E_INVALID, "camera: normal index out of range");
+        if (s.camera.type > PVGPU_CAMERA_ORTHOGRAPHIC) return fail(PVGPU_E_UNSUPPORTED, "camera: normal perturbation on camera type %u is outside the hot-path scope", s.camera.type);
+    }
     if (s.camera.type > PVGPU_CAMERA_ORTHOGRAPHIC && s.camera_ext.size() != 3)
         return fail(PVGPU_E_INVALID, "camera type %u needs pvgpu_scene_set_camera_angles", s.camera.type);
     if (s.globals.bounding_method == 1 && s.nodes.empty())
