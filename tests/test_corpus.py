@@ -1,6 +1,6 @@
 """The reference's own scene corpus (distribution/scenes) as parity fixtures.
 
-tests/golden/corpus.zip holds, for each of the 245 distribution scenes the adapter accepts (and whose flattened scene is
+tests/golden/corpus.zip holds, for each of the 250 distribution scenes the adapter accepts (and whose flattened scene is
 below 600 KB), the flattened scene exactly as the reference's parser produced it (.pvs) and the reference's own float RGBT
 pixels at 64 x 48 (.rgbt) - written by `PVGPU_CORPUS_SAVE=<dir> python tools/corpus_check.py` in the build container.
 The CPU test pins the oracle on them, the GPU test the CUDA path."""
