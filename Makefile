@@ -19,8 +19,12 @@ LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
 FULL_SRC  := k_shade k_shadow_filter
 # ... and the traversal kernels a fourth time with -DPV_CSG (quadric-class primitives + CSG only: no solver, blob, mesh code)
 CSG_SRC   := k_closest k_shade k_shadow_opaque k_shadow_filter
+CSG_FLAGS ?=
 # ... and a fifth time with -DPV_QUARTIC (spheres, boxes, planes, quadrics, tori, blobs; no CSG, mesh, cone, polygon, glyph, prism code)
 QUARTIC_SRC := k_closest k_shadow_opaque k_shadow_filter
+# this class is bound by instruction fetch over an 80 KB hot set (solver + blob code): block-wide phase votes in 512-thread blocks of
+# 64 registers keep the warps of a block in the same few KB at a time (config 4: measured 13 % faster; the other classes lose with it)
+QUARTIC_FLAGS ?= -DPV_CTA_SYNC -DPV_TRAV_BLOCK=512 -DPV_TRAV_MIN_BLOCKS_HEAVY=2
 OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
              $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC)) $(patsubst %,$(OBJDIR)/%_csg.o,$(CSG_SRC)) \
              $(patsubst %,$(OBJDIR)/%_quartic.o,$(QUARTIC_SRC))
@@ -43,11 +47,11 @@ $(OBJDIR)/%_full.o: $(CSRC)/%.cu $(HDR)
 
 $(OBJDIR)/%_csg.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVCCFLAGS) -DPV_CSG -c $< -o $@
+	$(NVCC) $(NVCCFLAGS) -DPV_CSG $(CSG_FLAGS) -c $< -o $@
 
 $(OBJDIR)/%_quartic.o: $(CSRC)/%.cu $(HDR)
 	@mkdir -p $(OBJDIR)
-	$(NVCC) $(NVCCFLAGS) -DPV_QUARTIC -c $< -o $@
+	$(NVCC) $(NVCCFLAGS) -DPV_QUARTIC $(QUARTIC_FLAGS) -c $< -o $@
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(HDR)
 	@mkdir -p $(OBJDIR)

@@ -282,10 +282,19 @@ enum { PVGPU_WAVE_RAW = 0, PVGPU_WAVE_RAMP = 1, PVGPU_WAVE_SINE = 2, PVGPU_WAVE_
        PVGPU_WAVE_SCALLOP = 4, PVGPU_WAVE_CUBIC = 5, PVGPU_WAVE_POLY = 6 };
 
 /* Warps (source/core/material/warp.h). */
-enum { PVGPU_WARP_TRANSFORM = 1, PVGPU_WARP_TURBULENCE = 2, PVGPU_WARP_CLASSIC_TURBULENCE = 3 };
+enum { PVGPU_WARP_TRANSFORM = 1, PVGPU_WARP_TURBULENCE = 2, PVGPU_WARP_CLASSIC_TURBULENCE = 3,
+       /* the point-mapping warps (warp.cpp:124-545): parameters as doubles in the shape-data table at offset `transform` */
+       PVGPU_WARP_BLACK_HOLE = 4,   /* Center xyz, Repeat_Vector xyz, Strength, Radius, Power, flags (1 Inverted, 2 Repeat), Type: 11 doubles;
+                                       `uncertain` black holes (WarpRands) are not served */
+       PVGPU_WARP_REPEAT = 5,       /* Axis, Width, Flip xyz, Offset xyz: 8 doubles */
+       PVGPU_WARP_CUBIC = 6,        /* no parameters */
+       PVGPU_WARP_CYLINDRICAL = 7,  /* Orientation_Vector xyz, DistExp: 4 doubles */
+       PVGPU_WARP_SPHERICAL = 8,    /* Orientation_Vector xyz, DistExp: 4 doubles */
+       PVGPU_WARP_TOROIDAL = 9,     /* Orientation_Vector xyz, DistExp, MajorRadius: 5 doubles */
+       PVGPU_WARP_PLANAR = 10 };    /* Orientation_Vector xyz, OffSet: 4 doubles */
 typedef struct pvgpu_warp {
     uint32_t type;
-    int32_t  transform;          /* TransformWarp::Trans -> transform table index */
+    int32_t  transform;          /* TransformWarp::Trans -> transform table index; warps >= PVGPU_WARP_BLACK_HOLE: shape-data offset */
     double   turbulence[3];      /* GenericTurbulenceWarp::Turbulence             */
     int32_t  octaves;
     float    lambda, omega;

@@ -188,7 +188,37 @@ struct Flattener
                 for (int k = 0; k < 3; k++) w.turbulence[k] = gt->Turbulence[k];
                 w.octaves = gt->Octaves; w.lambda = gt->Lambda; w.omega = gt->Omega;
                 w.handled_by_pattern = ct ? ct->handledByPattern : 0;
-            } else unsupported("warp type other than transform / turbulence");
+            } else if (dynamic_cast<const IdentityWarp*>(*i)) {
+                continue;                                   // maps every point onto itself
+            } else {
+                // the point-mapping warps: parameters as doubles in the shape-data table (pvgpu.h, PVGPU_WARP_*)
+                w.transform = (int32_t)shape_data.size();
+                if (const BlackHoleWarp* bh = dynamic_cast<const BlackHoleWarp*>(*i)) {
+                    w.type = PVGPU_WARP_BLACK_HOLE;
+                    if (bh->Uncertain) unsupported("black_hole warp with turbulence (WarpRands)");
+                    for (double v : { (double)bh->Center[X], (double)bh->Center[Y], (double)bh->Center[Z], (double)bh->Repeat_Vector[X], (double)bh->Repeat_Vector[Y],
+                                      (double)bh->Repeat_Vector[Z], (double)bh->Strength, (double)bh->Radius, (double)bh->Power,
+                                      (double)((bh->Inverted ? 1 : 0) | (bh->Repeat ? 2 : 0)), (double)bh->Type }) shape_data.push_back(v);
+                } else if (const RepeatWarp* rw = dynamic_cast<const RepeatWarp*>(*i)) {
+                    w.type = PVGPU_WARP_REPEAT;
+                    for (double v : { (double)rw->Axis, (double)rw->Width, (double)rw->Flip[X], (double)rw->Flip[Y], (double)rw->Flip[Z],
+                                      (double)rw->Offset[X], (double)rw->Offset[Y], (double)rw->Offset[Z] }) shape_data.push_back(v);
+                } else if (dynamic_cast<const CubicWarp*>(*i)) {
+                    w.type = PVGPU_WARP_CUBIC;
+                } else if (const CylindricalWarp* cw = dynamic_cast<const CylindricalWarp*>(*i)) {
+                    w.type = PVGPU_WARP_CYLINDRICAL;
+                    for (double v : { (double)cw->Orientation_Vector[X], (double)cw->Orientation_Vector[Y], (double)cw->Orientation_Vector[Z], (double)cw->DistExp }) shape_data.push_back(v);
+                } else if (const SphericalWarp* sw = dynamic_cast<const SphericalWarp*>(*i)) {
+                    w.type = PVGPU_WARP_SPHERICAL;
+                    for (double v : { (double)sw->Orientation_Vector[X], (double)sw->Orientation_Vector[Y], (double)sw->Orientation_Vector[Z], (double)sw->DistExp }) shape_data.push_back(v);
+                } else if (const ToroidalWarp* tw2 = dynamic_cast<const ToroidalWarp*>(*i)) {
+                    w.type = PVGPU_WARP_TOROIDAL;
+                    for (double v : { (double)tw2->Orientation_Vector[X], (double)tw2->Orientation_Vector[Y], (double)tw2->Orientation_Vector[Z], (double)tw2->DistExp, (double)tw2->MajorRadius }) shape_data.push_back(v);
+                } else if (const PlanarWarp* pw = dynamic_cast<const PlanarWarp*>(*i)) {
+                    w.type = PVGPU_WARP_PLANAR;
+                    for (double v : { (double)pw->Orientation_Vector[X], (double)pw->Orientation_Vector[Y], (double)pw->Orientation_Vector[Z], (double)pw->OffSet }) shape_data.push_back(v);
+                } else { unsupported("warp type outside the hot-path scope"); w.type = PVGPU_WARP_TRANSFORM; w.transform = -1; }
+            }
             warps.push_back(w);
             count++;
         }

@@ -2145,12 +2145,120 @@ static double Triangle_Wave(double value)                                       
 
 static double FLOOR(double x) { return x >= 0.0 ? std::floor(x) : (0.0 - std::floor(0.0 - x) - 1.0); }    // texture.h:73
 
+// BlackHoleWarp / RepeatWarp / CubicWarp / CylindricalWarp / SphericalWarp / ToroidalWarp / PlanarWarp::WarpPoint (warp.cpp:124-545);
+// q = the warp's parameters in the shape-data table (pvgpu.h, PVGPU_WARP_*)
+static bool WarpPoint_other(uint32_t type, const double* q, V3& TPoint)
+{
+    const double M_PI_ = 3.1415926535897932384626, TWO_M_PI = 6.283185307179586476925286766560;
+    auto orientation = [&](const double* Orientation_Vector, double x, double y, double z) {
+        if ((Orientation_Vector[0] == 0.0) && (Orientation_Vector[1] == 0.0) && (Orientation_Vector[2] == 1.0)) { TPoint = v3(x, y, z); return; }
+        TPoint = v3((Orientation_Vector[0] * z) + (Orientation_Vector[1] * x) + (Orientation_Vector[2] * x),
+                    (Orientation_Vector[0] * y) + (Orientation_Vector[1] * -z) + (Orientation_Vector[2] * y),
+                    (Orientation_Vector[0] * -x) + (Orientation_Vector[1] * y) + (Orientation_Vector[2] * z));
+    };
+    double x = TPoint.x, y = TPoint.y, z = TPoint.z, len, theta, phi;
+    switch (type) {
+        case PVGPU_WARP_BLACK_HOLE: {                                                                     // :124-205
+            V3 C = v3(q[0], q[1], q[2]);
+            const uint32_t flags = (uint32_t)q[9];
+            if (flags & 2u) {
+                int blockX = 0, blockY = 0, blockZ = 0;
+                if (q[3] >= EPSILON) blockX = (int)std::floor(TPoint.x / q[3]);
+                if (q[4] >= EPSILON) blockY = (int)std::floor(TPoint.y / q[4]);
+                if (q[5] >= EPSILON) blockZ = (int)std::floor(TPoint.z / q[5]);
+                C.x += q[3] * blockX; C.y += q[4] * blockY; C.z += q[5] * blockZ;
+            }
+            V3 Delta = TPoint - C;
+            double Length = ::len(Delta);
+            if (Length >= q[7]) return true;
+            if ((int)q[10] == 0) {
+                Length = (q[7] - Length) / q[7];
+                double Sv = std::pow(Length, q[8]) * q[6];
+                if (Sv > 1.0) Sv = 1.0;
+                Delta = Delta * ((flags & 1u) ? -Sv : Sv);
+                TPoint = TPoint + Delta;
+            }
+            return true;
+        }
+        case PVGPU_WARP_REPEAT: {                                                                         // :354-366
+            const int Axis = (int)q[0];
+            const float Width = (float)q[1];
+            double* T[3] = { &TPoint.x, &TPoint.y, &TPoint.z };
+            float BlkNum = (float)std::floor(*T[Axis] / Width);
+            *T[Axis] -= BlkNum * Width;
+            if (((int)BlkNum) & 1) {
+                TPoint = v3(TPoint.x * q[2], TPoint.y * q[3], TPoint.z * q[4]);
+                if (q[2 + Axis] < 0) *T[Axis] += Width;
+            }
+            TPoint = TPoint + v3(q[5], q[6], q[7]) * (double)BlkNum;
+            return true;
+        }
+        case PVGPU_WARP_CUBIC: {                                                                          // :207-253
+            const double ax = std::fabs(x), ay = std::fabs(y), az = std::fabs(z);
+            if (x >= 0 && x >= ay && x >= az) TPoint = v3(0.75 - 0.25 * (z / x + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / x + 1.0) / 2.0, x);
+            else if (y >= 0 && y >= ax && y >= az) TPoint = v3(0.25 + 0.25 * (x / y + 1.0) / 2.0, 1.0 - (1.0 / 3.0) * (z / y + 1.0) / 2.0, y);
+            else if (z >= 0 && z >= ax && z >= ay) TPoint = v3(0.25 + 0.25 * (x / z + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / z + 1.0) / 2.0, z);
+            else if (x < 0 && x <= -ay && x <= -az) { x = -x; TPoint = v3(0.25 * (z / x + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / x + 1.0) / 2.0, x); }
+            else if (y < 0 && y <= -ax && y <= -az) { y = -y; TPoint = v3(0.25 + 0.25 * (x / y + 1.0) / 2.0, (1.0 / 3.0) * (z / y + 1.0) / 2.0, y); }
+            else { z = -z; TPoint = v3(1.0 - 0.25 * (x / z + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / z + 1.0) / 2.0, z); }
+            return true;
+        }
+        case PVGPU_WARP_CYLINDRICAL:                                                                      // :255-310
+            len = std::sqrt(x * x + z * z);
+            if (len == 0.0) return false;
+            if (z == 0.0) { if (x > 0) theta = 0.0; else theta = M_PI_; }
+            else { theta = std::acos(x / len); if (z < 0.0) theta = TWO_M_PI - theta; }
+            theta /= TWO_M_PI;
+            if (q[3] == 1.0) theta *= len; else if (q[3] != 0.0) theta *= std::pow(len, q[3]);
+            orientation(q, theta, y, len);
+            return true;
+        case PVGPU_WARP_SPHERICAL: {                                                                      // :368-452
+            const double dist = std::sqrt(x * x + y * y + z * z);
+            if (dist == 0.0) return false;
+            x /= dist; y /= dist; z /= dist;
+            phi = 0.5 + std::asin(y) / M_PI_;
+            len = std::sqrt(x * x + z * z);
+            if (len == 0.0) theta = 0;
+            else {
+                if (z == 0.0) { if (x > 0) theta = 0.0; else theta = M_PI_; }
+                else { theta = std::acos(x / len); if (z < 0.0) theta = TWO_M_PI - theta; }
+                theta /= TWO_M_PI;
+            }
+            if (q[3] == 1.0) { theta *= dist; phi *= dist; }
+            else if (q[3] != 0.0) { theta *= std::pow(dist, q[3]); phi *= std::pow(dist, q[3]); }
+            orientation(q, theta, phi, dist);
+            return true;
+        }
+        case PVGPU_WARP_TOROIDAL:                                                                         // :454-545
+            len = std::sqrt(x * x + z * z);
+            if (len == 0.0) return false;
+            if (z == 0.0) { if (x > 0) theta = 0.0; else theta = M_PI_; }
+            else { theta = std::acos(x / len); if (z < 0.0) theta = TWO_M_PI - theta; }
+            theta = 0.0 - theta;
+            x = len - q[4];
+            len = std::sqrt(x * x + y * y);
+            phi = std::acos(-x / len);
+            if (y > 0.0) phi = TWO_M_PI - phi;
+            theta /= (-TWO_M_PI);
+            phi /= TWO_M_PI;
+            if (q[3] == 1.0) { theta *= len; phi *= len; }
+            else if (q[3] != 0.0) { theta *= std::pow(len, q[3]); phi *= std::pow(len, q[3]); }
+            orientation(q, theta, phi, len);
+            return true;
+        case PVGPU_WARP_PLANAR:                                                                           // :318-352
+            orientation(q, x, y, q[3]);
+            return true;
+    }
+    return false;
+}
+
 V3 Tracer::Warp_EPoint(const pvgpu_pigment& pg, V3 EPoint) const                                          // warp.cpp:103-122
 {
     V3 p = EPoint;
     for (int i = (int)pg.warp_count - 1; i >= 0; i--) {
         const pvgpu_warp& w = S.warps[pg.warp_first + i];
         if (w.type == PVGPU_WARP_TRANSFORM) p = MInvTransPoint(S.xf[w.transform], p);
+        else if (w.type > PVGPU_WARP_CLASSIC_TURBULENCE) WarpPoint_other(w.type, S.shape_data.data() + w.transform, p);
         else { V3 t = DTurbulence(S, p, w); p = v3(p.x + t.x * w.turbulence[0], p.y + t.y * w.turbulence[1], p.z + t.z * w.turbulence[2]); }
     }
     auto clampc = [](double& c) { if (c > COORDINATE_LIMIT) c = COORDINATE_LIMIT; else if (c < -COORDINATE_LIMIT) c = -COORDINATE_LIMIT; };

@@ -47,6 +47,111 @@ __device__ inline double triangle_wave(double value)
     return (offset >= 0.5) ? 2.0 * (1.0 - offset) : 2.0 * offset;
 }
 
+#if PV_FULL_MATERIALS
+// The point-mapping warps: BlackHoleWarp, RepeatWarp, CubicWarp, CylindricalWarp, SphericalWarp, ToroidalWarp, PlanarWarp::WarpPoint
+// (warp.cpp:124-545).  A warp that cannot map the point (a cylindrical warp on its axis ...) leaves it as it is.
+static __device__ __noinline__ V3 warp_point_other(const DScene& sc, const pvgpu_warp& w, const V3& p)
+{
+    const double pi = 3.1415926535897932384626, two_pi = 6.283185307179586476925286766560;
+    const double* q = sc.shape_data + w.transform;
+    // the orientation step the cylindrical / spherical / toroidal / planar warps end with
+    auto orient = [](const double* O, double x, double y, double z) {
+        if ((O[0] == 0.0) && (O[1] == 0.0) && (O[2] == 1.0)) return mk(x, y, z);
+        return mk((O[0] * z) + (O[1] * x) + (O[2] * x), (O[0] * y) + (O[1] * -z) + (O[2] * y), (O[0] * -x) + (O[1] * y) + (O[2] * z));
+    };
+    // angle of (x, z) from (1, 0) in the x-z plane, 0 .. 2 pi
+    auto azimuth = [&](double x, double z, double len) {
+        if (z == 0.0) return (x > 0) ? 0.0 : pi;
+        const double t = acos(x / len);
+        return (z < 0.0) ? two_pi - t : t;
+    };
+    double x = p.x, y = p.y, z = p.z;
+    switch (w.type) {
+        case PVGPU_WARP_BLACK_HOLE: {
+            V3 C = mk(q[0], q[1], q[2]);
+            const uint32_t flags = (uint32_t)q[9];
+            if (flags & 2u) {
+                int bx = 0, by = 0, bz = 0;
+                if (q[3] >= PV_EPSILON) bx = (int)floor(p.x / q[3]);
+                if (q[4] >= PV_EPSILON) by = (int)floor(p.y / q[4]);
+                if (q[5] >= PV_EPSILON) bz = (int)floor(p.z / q[5]);
+                C.x += q[3] * bx; C.y += q[4] * by; C.z += q[5] * bz;
+            }
+            V3 delta = p - C;
+            double len = length(delta);
+            if (len >= q[7]) return p;
+            if ((int)q[10] == 0) {
+                len = (q[7] - len) / q[7];
+                double S = pow(len, q[8]) * q[6];
+                if (S > 1.0) S = 1.0;
+                delta = delta * ((flags & 1u) ? -S : S);
+                return p + delta;
+            }
+            return p;
+        }
+        case PVGPU_WARP_REPEAT: {
+            const int axis = (int)q[0];
+            const float width = (float)q[1];
+            V3 t = p;
+            double ta = comp(t, axis);
+            const float blk = (float)floor(ta / (double)width);
+            ta -= (double)(blk * width);
+            if (axis == 0) t.x = ta; else if (axis == 1) t.y = ta; else t.z = ta;
+            if (((int)blk) & 1) {
+                t = mk(t.x * q[2], t.y * q[3], t.z * q[4]);
+                if (q[2 + axis] < 0) { if (axis == 0) t.x += (double)width; else if (axis == 1) t.y += (double)width; else t.z += (double)width; }
+            }
+            return t + (double)blk * mk(q[5], q[6], q[7]);
+        }
+        case PVGPU_WARP_CUBIC: {
+            const double ax = fabs(x), ay = fabs(y), az = fabs(z);
+            if (x >= 0 && x >= ay && x >= az) return mk(0.75 - 0.25 * (z / x + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / x + 1.0) / 2.0, x);
+            if (y >= 0 && y >= ax && y >= az) return mk(0.25 + 0.25 * (x / y + 1.0) / 2.0, 1.0 - (1.0 / 3.0) * (z / y + 1.0) / 2.0, y);
+            if (z >= 0 && z >= ax && z >= ay) return mk(0.25 + 0.25 * (x / z + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / z + 1.0) / 2.0, z);
+            if (x < 0 && x <= -ay && x <= -az) { x = -x; return mk(0.25 * (z / x + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / x + 1.0) / 2.0, x); }
+            if (y < 0 && y <= -ax && y <= -az) { y = -y; return mk(0.25 + 0.25 * (x / y + 1.0) / 2.0, (1.0 / 3.0) * (z / y + 1.0) / 2.0, y); }
+            z = -z;
+            return mk(1.0 - 0.25 * (x / z + 1.0) / 2.0, 1.0 / 3.0 + (1.0 / 3.0) * (y / z + 1.0) / 2.0, z);
+        }
+        case PVGPU_WARP_CYLINDRICAL: {
+            const double len = sqrt(x * x + z * z);
+            if (len == 0.0) return p;
+            double theta = azimuth(x, z, len) / two_pi;
+            if (q[3] == 1.0) theta *= len; else if (q[3] != 0.0) theta *= pow(len, q[3]);
+            return orient(q, theta, y, len);
+        }
+        case PVGPU_WARP_SPHERICAL: {
+            const double dist = sqrt(x * x + y * y + z * z);
+            if (dist == 0.0) return p;
+            x /= dist; y /= dist; z /= dist;
+            double phi = 0.5 + asin(y) / pi, theta;
+            double len = sqrt(x * x + z * z);
+            if (len == 0.0) theta = 0;            // at a pole: "any value of theta will do"
+            else theta = azimuth(x, z, len) / two_pi;
+            if (q[3] == 1.0) { theta *= dist; phi *= dist; }
+            else if (q[3] != 0.0) { theta *= pow(dist, q[3]); phi *= pow(dist, q[3]); }
+            return orient(q, theta, phi, dist);
+        }
+        case PVGPU_WARP_TOROIDAL: {
+            double len = sqrt(x * x + z * z);
+            if (len == 0.0) return p;
+            double theta = 0.0 - azimuth(x, z, len);
+            x = len - q[4];
+            len = sqrt(x * x + y * y);
+            double phi = acos(-x / len);
+            if (y > 0.0) phi = two_pi - phi;
+            theta /= (-two_pi);
+            phi /= two_pi;
+            if (q[3] == 1.0) { theta *= len; phi *= len; }
+            else if (q[3] != 0.0) { theta *= pow(len, q[3]); phi *= pow(len, q[3]); }
+            return orient(q, theta, phi, len);
+        }
+        case PVGPU_WARP_PLANAR: return orient(q, x, y, q[3]);
+        default: return p;
+    }
+}
+#endif
+
 // Warp_EPoint (warp.cpp:103-122): warps applied last-to-first, then clamped to COORDINATE_LIMIT.
 __device__ inline V3 warp_epoint(const DScene& sc, const pvgpu_pigment& pg, const V3& ep)
 {
@@ -54,6 +159,9 @@ __device__ inline V3 warp_epoint(const DScene& sc, const pvgpu_pigment& pg, cons
     for (int i = (int)pg.warp_count - 1; i >= 0; i--) {
         const pvgpu_warp& w = sc.warps[pg.warp_first + i];
         if (w.type == PVGPU_WARP_TRANSFORM) p = inv_trans_point(sc.xf[w.transform], p);
+#if PV_FULL_MATERIALS
+        else if (w.type > PVGPU_WARP_CLASSIC_TURBULENCE) p = warp_point_other(sc, w, p);
+#endif
 #if !PV_BASIC_PATTERNS
         else {   // GenericTurbulenceWarp::WarpPoint (warp.cpp:553-559)
             V3 t = dturbulence(sc.noise, p, w.octaves, (double)w.lambda, (double)w.omega);

@@ -413,6 +413,7 @@ static int upload_one(Scene& s, int device, DeviceScene*& out)
     v.has_uv = 0; v.pad_uv = 0;
     for (const pvgpu_object& o : s.objects) if (o.flags & PVGPU_UV_FLAG) v.has_uv = 1;
     for (const pvgpu_pigment& pg : s.pigments) if (pg.pattern == PVGPU_PAT_UV_MAP) v.has_uv = 1;
+    for (const pvgpu_warp& w : s.warps) if (w.type > PVGPU_WARP_CLASSIC_TURBULENCE) { d->full = true; d->lean = false; }      // point-mapping warps
     if (s.camera.reserved) { d->full = true; d->lean = false; }      // camera normal: Perturb_Normal is full-variant code
     if (v.has_uv) { d->full = true; d->lean = false; }      // hit_uv / uv_mapping pigments are full-variant code
     for (const pvgpu_finish& fi : s.finishes) if (fi.irid > 0.0f) { d->full = true; d->lean = false; }

@@ -295,8 +295,15 @@ int validate_scene(Scene& s)
     }
     for (size_t i = 0; i < s.warps.size(); i++) {
         const pvgpu_warp& w = s.warps[i];
-        if (w.type < PVGPU_WARP_TRANSFORM || w.type > PVGPU_WARP_CLASSIC_TURBULENCE)
+        if (w.type < PVGPU_WARP_TRANSFORM || w.type > PVGPU_WARP_PLANAR)
             return fail(PVGPU_E_UNSUPPORTED, "warp %zu: type %u unsupported", i, w.type);
+        if (w.type >= PVGPU_WARP_BLACK_HOLE) {
+            static const uint32_t n_par[] = { 11, 8, 0, 4, 4, 5, 4 };
+            if (w.transform < 0 || !range_ok((uint32_t)w.transform, n_par[w.type - PVGPU_WARP_BLACK_HOLE], s.shape_data.size()))
+                return fail(PVGPU_E_INVALID, "warp %zu: parameters outside the shape-data table", i);
+            if (w.type == PVGPU_WARP_REPEAT && !(s.shape_data[w.transform] >= 0.0 && s.shape_data[w.transform] <= 2.0))
+                return fail(PVGPU_E_INVALID, "warp %zu: repeat axis out of range", i);
+        }
         if (w.type == PVGPU_WARP_TRANSFORM && (w.transform < 0 || w.transform >= (int32_t)s.transforms.size()))
             return fail(PVGPU_E_INVALID, "warp %zu: bad transform", i);
     }
@@ -523,8 +530,7 @@ int validate_scene(Scene& s)
         if (t.type == PVGPU_NORM_PATTERN && !t.normal_map && c.pattern < PVGPU_PAT_CHECKER)
             return fail(PVGPU_E_INVALID, "tnormal %zu: a pattern normal needs a pattern", i);
         for (uint32_t k = 0; k < c.warp_count; k++)
-            if (s.warps[c.warp_first + k].type != PVGPU_WARP_TRANSFORM && s.warps[c.warp_first + k].type != PVGPU_WARP_CLASSIC_TURBULENCE &&
-                s.warps[c.warp_first + k].type != PVGPU_WARP_TURBULENCE)
+            if (s.warps[c.warp_first + k].type < PVGPU_WARP_TRANSFORM || s.warps[c.warp_first + k].type > PVGPU_WARP_PLANAR)
                 return fail(PVGPU_E_UNSUPPORTED, "tnormal %zu: warp unsupported", i);
     }
     {   // pigment_map nesting: bounded depth, no cycles
@@ -597,7 +603,7 @@ int validate_scene(Scene& s)
     for (size_t i = 0; i < s.fogs.size(); i++) {
         const pvgpu_fog& f = s.fogs[i];
         if (f.type != PVGPU_FOG_CONSTANT && f.type != PVGPU_FOG_GROUND) return fail(PVGPU_E_UNSUPPORTED, "fog %zu: type %u unsupported", i, f.type);
-        if (f.turbulence >= (int32_t)s.warps.size() || (f.turbulence >= 0 && s.warps[f.turbulence].type == PVGPU_WARP_TRANSFORM))
+        if (f.turbulence >= (int32_t)s.warps.size() || (f.turbulence >= 0 && s.warps[f.turbulence].type != PVGPU_WARP_TURBULENCE && s.warps[f.turbulence].type != PVGPU_WARP_CLASSIC_TURBULENCE))
             return fail(PVGPU_E_INVALID, "fog %zu: bad turbulence warp", i);
     }
     if (!s.fogs.empty())

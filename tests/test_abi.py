@@ -123,7 +123,7 @@ print("ok", n_err)
 """
 
 
-@pytest.mark.parametrize("name", ["texture_maps", "normal_maps", "pigment_maps", "clipped_bounded", "sky_fog", "blob_mix", "mesh24", "text", "prisms", "superquadrics", "uv_mapping", "pigment_pattern", "fractals", "image_maps", "csg_children", "blob_textures"])
+@pytest.mark.parametrize("name", ["texture_maps", "normal_maps", "pigment_maps", "clipped_bounded", "sky_fog", "blob_mix", "mesh24", "text", "prisms", "superquadrics", "uv_mapping", "pigment_pattern", "warps", "fractals", "image_maps", "csg_children", "blob_textures"])
 def test_malformed_tables_are_rejected_not_dereferenced(pvlib, name):
     """Advisor finding of round 1: validate_scene used to index tables before validating them.  Corrupted scene files
     (random 32-bit fields overwritten with huge / negative / NaN values) must end in an error code, never in a crash:
