@@ -19,7 +19,9 @@ LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
 FULL_SRC  := k_shade k_shadow_filter
 # ... and the traversal kernels a fourth time with -DPV_CSG (quadric-class primitives + CSG only: no solver, blob, mesh code)
 CSG_SRC   := k_closest k_shade k_shadow_opaque k_shadow_filter
-CSG_FLAGS ?=
+# block-wide phase votes in 512-thread blocks of 64 registers, as for the _quartic class: config 3 103.4 -> 97.7 ms (the filtered-shadow
+# kernel 88 -> 71 ms); 256 x 4: 110.8, 1024 x 1: 103.0, 512 x 3 at 40 registers: 99.7
+CSG_FLAGS ?= -DPV_CTA_SYNC -DPV_TRAV_BLOCK=512 -DPV_TRAV_MIN_BLOCKS_HEAVY=2
 # ... and a fifth time with -DPV_QUARTIC (spheres, boxes, planes, quadrics, tori, blobs; no CSG, mesh, cone, polygon, glyph, prism code)
 QUARTIC_SRC := k_closest k_shadow_opaque k_shadow_filter
 # this class is bound by instruction fetch over an 80 KB hot set (solver + blob code): block-wide phase votes in 512-thread blocks of
