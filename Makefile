@@ -19,14 +19,16 @@ LEAN_SRC  := k_closest k_shade k_shadow_opaque k_shadow_filter
 FULL_SRC  := k_shade k_shadow_filter
 # ... and the traversal kernels a fourth time with -DPV_CSG (quadric-class primitives + CSG only: no solver, blob, mesh code)
 CSG_SRC   := k_closest k_shade k_shadow_opaque k_shadow_filter
-# block-wide phase votes in 512-thread blocks of 64 registers, as for the _quartic class: config 3 103.4 -> 97.7 ms (the filtered-shadow
-# kernel 88 -> 71 ms); 256 x 4: 110.8, 1024 x 1: 103.0, 512 x 3 at 40 registers: 99.7
-CSG_FLAGS ?= -DPV_CTA_SYNC -DPV_TRAV_BLOCK=512 -DPV_TRAV_MIN_BLOCKS_HEAVY=2
+# Build option, NOT the default: block-wide phase votes in 512-thread blocks of 64 registers
+#   make CSG_FLAGS="-DPV_CTA_SYNC -DPV_TRAV_BLOCK=512 -DPV_TRAV_MIN_BLOCKS_HEAVY=2" (same for QUARTIC_FLAGS)
+# measured config 3 103.4 -> 97.7 ms and config 4 17.4 -> 14.6 ms with all parity tests green and memcheck clean, but compute-sanitizer's
+# synccheck reports "Divergent thread(s) in block" at the __syncthreads_count votes on small frames (profiles/README.md, "block-wide
+# votes"); until that is explained the shipped kernels vote per warp.
+CSG_FLAGS ?=
 # ... and a fifth time with -DPV_QUARTIC (spheres, boxes, planes, quadrics, tori, blobs; no CSG, mesh, cone, polygon, glyph, prism code)
 QUARTIC_SRC := k_closest k_shadow_opaque k_shadow_filter
-# this class is bound by instruction fetch over an 80 KB hot set (solver + blob code): block-wide phase votes in 512-thread blocks of
-# 64 registers keep the warps of a block in the same few KB at a time (config 4: measured 13 % faster; the other classes lose with it)
-QUARTIC_FLAGS ?= -DPV_CTA_SYNC -DPV_TRAV_BLOCK=512 -DPV_TRAV_MIN_BLOCKS_HEAVY=2
+# (this class is bound by instruction fetch over an 80 KB hot set - solver + blob code; see the build option above)
+QUARTIC_FLAGS ?=
 OBJ       := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU)) $(patsubst $(CSRC)/%.cpp,$(OBJDIR)/%.o,$(CPP)) \
              $(patsubst %,$(OBJDIR)/%_lean.o,$(LEAN_SRC)) $(patsubst %,$(OBJDIR)/%_full.o,$(FULL_SRC)) $(patsubst %,$(OBJDIR)/%_csg.o,$(CSG_SRC)) \
              $(patsubst %,$(OBJDIR)/%_quartic.o,$(QUARTIC_SRC))
