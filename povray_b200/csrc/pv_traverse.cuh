@@ -547,8 +547,26 @@ __device__ inline void mesh_hits(const DScene& sc, uint32_t obj_index, const pvg
 // memcheck-clean, but compute-sanitizer's synccheck reports "Divergent thread(s) in block" at these barriers on small frames although
 // every loop around a vote is block-uniform at source level (ptxas peels the first turn of the vote loops, so the barriers exist twice
 // in SASS).  The __syncwarp() in front of the warp-aligned barriers did not clear the report.  Open item - see profiles/README.md.
+#ifdef PV_CTA_SYNC_UNALIGNED
+// experiment: the barrier forms without .aligned, which PTX allows the lanes of a warp to reach one by one
+__device__ __forceinline__ int vote_count(bool p)
+{
+    int r;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.cta.red.popc.u32 %0, 0, q;\n\t}" : "=r"(r) : "r"(p ? 1u : 0u) : "memory");
+    return r;
+}
+__device__ __forceinline__ bool vote_any(bool p)
+{
+    unsigned r;
+    asm volatile("{\n\t.reg .pred q, o;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.cta.red.or.pred o, 0, q;\n\tselp.u32 %0, 1, 0, o;\n\t}" : "=r"(r) : "r"(p ? 1u : 0u) : "memory");
+    return r != 0u;
+}
+__device__ __forceinline__ void cta_barrier() { asm volatile("barrier.cta.sync 0;" ::: "memory"); }
+#else
 __device__ __forceinline__ int  vote_count(bool p) { __syncwarp(); return __syncthreads_count(p ? 1 : 0); }
 __device__ __forceinline__ bool vote_any(bool p)   { __syncwarp(); return __syncthreads_or(p ? 1 : 0) != 0; }
+__device__ __forceinline__ void cta_barrier() { __syncwarp(); __syncthreads(); }
+#endif
 #else
 __device__ __forceinline__ int  vote_count(bool p) { return __popc(__ballot_sync(PV_FULL_MASK, p)); }
 __device__ __forceinline__ bool vote_any(bool p)   { return __any_sync(PV_FULL_MASK, p); }
@@ -580,10 +598,9 @@ __device__ __forceinline__ bool next_chunk(unsigned int* cursor, uint32_t n, uin
 {
 #ifdef PV_CTA_SYNC
     __shared__ uint32_t s_base;
-    __syncwarp();
-    __syncthreads();                                   // everybody has consumed the previous value
+    cta_barrier();                                     // everybody has consumed the previous value
     if (threadIdx.x == 0) s_base = atomicAdd(cursor, cs);
-    __syncthreads();
+    cta_barrier();
     const uint32_t base = s_base;
     i = (base + threadIdx.x < n) ? base + threadIdx.x : 0xFFFFFFFFu;
     return base < n;
